@@ -1,0 +1,200 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference,
+build container only) and, in the same run, assert that oracle/ref_port.py reproduces it.
+
+    python oracle/make_golden.py            # writes tests/golden/, prints the port-vs-reference table
+
+Weights come from ``idccrn_b200.synth.fill_state_dict`` (pure function of key/shape/seed), inputs
+from ``synth_waveform``, eps from ``synth_eps`` — so the fixtures hold only activations/outputs and
+every consumer regenerates weights/inputs bit-identically.  The reference has no eps hook
+(model/pvae_module.py:L2219-2220) so ``torch.randn_like`` is patched while it runs.
+"""
+import contextlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("IDV_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+
+import idccrn_b200  # noqa: E402
+from idccrn_b200.synth import fill_state_dict, synth_eps, synth_waveform  # noqa: E402
+from oracle import ref_port as P  # noqa: E402
+
+import model.causal_netconfig as ref_causal_cfg  # noqa: E402  (reference)
+import model.pvae_module as ref_mod  # noqa: E402  (reference)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+NFFT, HOP, WIN, ZDIM = 512, 100, 400, 128
+
+
+@contextlib.contextmanager
+def supplied_eps(eps_list):
+    """Make the reference's randn_like calls return the supplied tensors, in draw order."""
+    it = iter(eps_list)
+    orig = torch.randn_like
+
+    def fake(t, *a, **k):
+        e = next(it)
+        assert e.shape == t.shape, (e.shape, t.shape)
+        return e.to(t.dtype)
+    torch.randn_like = fake
+    try:
+        yield
+    finally:
+        torch.randn_like = orig
+
+
+def np32(t):
+    t = t.detach()
+    if t.is_complex():
+        t = torch.view_as_real(t)
+    return t.to(torch.float32).numpy()
+
+
+def check(name, a, b, tol=2e-6):
+    e = P.rel_l2(a, b)
+    print("  port-vs-reference %-28s rel_l2 = %.2e" % (name, e))
+    assert e < tol, (name, e)
+    return e
+
+
+def build_vae(latent_num, S, seed):
+    net = ref_causal_cfg.get_net_params()
+    enc = ref_mod.nsvae_pvae_dccrn_encoder_twophase(net, True, "cpu", ZDIM, NFFT, HOP, WIN, S, latent_num)
+    enc.load_state_dict(fill_state_dict(enc.state_dict(), seed), strict=True)
+    return net, enc.eval()
+
+
+def case_vae(tag, B, L, latent_num, S, dec_kind, recon_type, seed, full):
+    print("case", tag)
+    torch.manual_seed(0)
+    net, enc = build_vae(latent_num, S, seed)
+    if dec_kind == "skip_prepare":
+        dec = ref_mod.pvae_dccrn_decoder_skip_prepare(net, True, "cpu", S, ZDIM, NFFT, HOP, WIN, recon_type,
+                                                      [0, 1, 2, 3, 4, 5])
+        skip_mode = "zero"
+    else:
+        dec = ref_mod.nsvae_pvae_dccrn_decoder_twophase(net, True, "cpu", S, ZDIM, NFFT, HOP, WIN, recon_type,
+                                                        True, [0, 1, 2, 3, 4, 5], False)
+        skip_mode = "sig"
+    dec.load_state_dict(fill_state_dict(dec.state_dict(), seed + 1), strict=True)
+    dec.eval()
+    x = synth_waveform(B, L, seed=1234 + seed)
+    T = L // HOP + 1
+    eps = synth_eps((B, S, T, ZDIM), seed=7 + seed, n=2 * latent_num)
+    with torch.no_grad(), supplied_eps(eps):
+        r = enc(x, train=False)
+        z_s, mu_s, ls_s, de_s, z_n, mu_n, ls_n, de_n, skiper, C, Fq, stft_x = r
+        if dec_kind == "skip_prepare":
+            sig, pred = dec(stft_x, z_s, skiper, C, Fq, train=False)
+        else:
+            sig, pred = dec(stft_x, z_s, skiper, C, Fq, train=False, pad="sig")
+    # ---- oracle port on the same inputs
+    esd, dsd = enc.state_dict(), dec.state_dict()
+    with torch.no_grad():
+        st = P.vae_encoder_forward(esd, x, ZDIM, latent_num, S, eps)
+        dd = P.vae_decoder_forward(dsd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], S,
+                                   recon_type, skip_mode)
+        check("stft", st["stft_x"], stft_x)
+        check("stft_dense", P.stft_dense(x), stft_x, 1e-5)
+        for i in range(6):
+            check("enc%d" % i, st["skiper"][i], skiper[i])
+        check("miu", st["miu_speech"], mu_s)
+        check("log_sigma", st["log_sigma_speech"], ls_s)
+        check("delta", st["delta_speech"], de_s)
+        check("z_speech", st["z_speech"], z_s)
+        if latent_num == 2:
+            check("z_noise", st["z_noise"], z_n)
+        check("predict", dd["predict"], pred)
+        check("recon_sig", dd["recon_sig"], sig)
+        check("istft_dense", P.istft_dense(torch.view_as_real(pred)), sig, 1e-5)
+    g = {"B": B, "L": L, "S": S, "latent_num": latent_num, "seed": seed,
+         "stft_x": np32(stft_x), "miu": np32(mu_s), "log_sigma": np32(ls_s), "delta": np32(de_s),
+         "z_speech": np32(z_s), "predict": np32(pred), "recon_sig": np32(sig)}
+    if latent_num == 2:
+        g.update(z_noise=np32(z_n), miu_noise=np32(mu_n), log_sigma_noise=np32(ls_n), delta_noise=np32(de_n))
+    if full:
+        for i in range(6):
+            g["enc%d" % i] = np32(skiper[i])
+        if dec_kind == "skip_prepare":
+            for i, o in enumerate(dec.decoder_outputs):
+                g["dec%d" % i] = np32(o)
+        else:
+            for i, o in enumerate(dd["decoder_outputs"]):       # port already checked end-to-end above
+                g["dec%d" % i] = np32(o)
+    np.savez(os.path.join(OUT, tag + ".npz"), **g)
+
+
+def case_dccrn(tag, B, L, seed):
+    print("case", tag)
+    net = ref_causal_cfg.get_net_params()
+    m = ref_mod.DCCRN_(NFFT, HOP, net, True, "cpu", WIN, [0, 1, 2, 3, 4, 5], "mask", False, None, None)
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed), strict=True)
+    m.eval()
+    x = synth_waveform(B, L, seed=1234 + seed)
+    with torch.no_grad():
+        clean, pred = m(x, train=False)
+        d = P.dccrn_forward(m.state_dict(), x)
+        check("dccrn.latent", d["latent"], m.std_DCCRN.latent)
+        check("dccrn.predict", d["predict"], pred)
+        check("dccrn.clean", d["clean"], clean)
+    np.savez(os.path.join(OUT, tag + ".npz"), B=B, L=L, seed=seed, latent=np32(m.std_DCCRN.latent),
+             predict=np32(pred), clean=np32(clean))
+
+
+def case_primitives(tag, seed):
+    """Stand-alone complex primitives at odd shapes (reference classes called directly)."""
+    print("case", tag)
+    import model.complex_progress as cp
+    g = {}
+    gen = torch.Generator().manual_seed(100 + seed)
+    # causal complex conv + CBN(eval) + PReLU via the reference Encoder / Decoder blocks
+    enc = ref_mod.Encoder(3, 5, (5, 2), (2, 1), (5, 9, 1), padding=(2, 1), causal=True)
+    enc.load_state_dict(fill_state_dict(enc.state_dict(), seed))
+    x = torch.randn(2, 3, 11, 6, 2, generator=gen)
+    with torch.no_grad():
+        g["enc_in"], g["enc_out"] = np32(x), np32(enc(x, False))
+        check("Encoder block", P.encoder_block(x, enc.state_dict(), ""), enc(x, False))
+    dec = ref_mod.Decoder(4, 3, (5, 2), (2, 1), (3, 9, 1), padding=(2, 0), causal=True)
+    dec.load_state_dict(fill_state_dict(dec.state_dict(), seed))
+    x = torch.randn(2, 4, 5, 6, 2, generator=gen)
+    with torch.no_grad():
+        g["dec_in"], g["dec_out"] = np32(x), np32(dec(x, False))
+        check("Decoder block", P.decoder_block(x, dec.state_dict(), ""), dec(x, False))
+    lstm = cp.ComplexLSTM(20, 8, "cpu", num_layers=2)
+    lstm.load_state_dict(fill_state_dict(lstm.state_dict(), seed))
+    x = torch.randn(7, 3, 20, 2, generator=gen)
+    with torch.no_grad():
+        g["lstm_in"], g["lstm_out"] = np32(x), np32(lstm(x))
+        check("ComplexLSTM", P.complex_lstm(x, lstm.state_dict(), "", 8, 2), lstm(x))
+    dense = cp.ComplexDense(128, 24)
+    dense.load_state_dict(fill_state_dict(dense.state_dict(), seed))
+    x = torch.randn(9, 128, 2, generator=gen)
+    with torch.no_grad():
+        g["dense_in"], g["dense_out"] = np32(x), np32(dense(x))
+        check("ComplexDense", P.complex_dense(x, dense.state_dict(), ""), dense(x))
+    np.savez(os.path.join(OUT, tag + ".npz"), **g)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    case_primitives("primitives", seed=3)
+    # per-layer fixtures (tiny T, B=2 so the utterance boundary is exercised)
+    case_vae("vae_l1_zero_full", B=2, L=400, latent_num=1, S=1, dec_kind="skip_prepare",
+             recon_type="real_imag", seed=0, full=True)
+    case_vae("vae_l2_sig_mask_full", B=2, L=400, latent_num=2, S=1, dec_kind="twophase",
+             recon_type="mask", seed=1, full=True)
+    # end-to-end fixtures (T spans more than one 128-row tile; S>1 for the sample replication)
+    case_vae("vae_l1_zero_e2e", B=2, L=16000, latent_num=1, S=1, dec_kind="skip_prepare",
+             recon_type="real_imag", seed=2, full=False)
+    case_vae("vae_l2_sig_mask_s2_e2e", B=2, L=6400, latent_num=2, S=2, dec_kind="twophase",
+             recon_type="mask", seed=3, full=False)
+    case_vae("vae_l1_sig_ri_e2e", B=3, L=3200, latent_num=1, S=1, dec_kind="twophase",
+             recon_type="real_imag", seed=4, full=False)
+    case_dccrn("dccrn_mask_e2e", B=2, L=8000, seed=5)
+    print("golden fixtures written to", OUT)
