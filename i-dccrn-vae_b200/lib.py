@@ -1,0 +1,94 @@
+"""ctypes binding of libidv_b200.so (the C ABI declared in include/idv.h).
+
+There is deliberately no fallback: if the library is missing (and cannot be built because nvcc is
+absent) or a call fails, a RuntimeError is raised.  Tensors are passed as raw device pointers."""
+import ctypes
+import os
+
+import torch
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_f32p = ctypes.c_void_p
+i32, i64, u64, f32, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_void_p
+
+# name -> argtypes (all return int status)
+SIGNATURES = {
+    "idv_device_sm_count": [ctypes.POINTER(ctypes.c_int)],
+    "idv_tapgemm_f32": [vp, i32, i64, vp, i32, i64, i32, i32, vp, vp, i32, vp, vp, i32, vp, i32, i64, i32, f32, vp],
+    "idv_stft_fwd": [vp, i32, i32, vp, i32, i32, i32, vp, vp],
+    "idv_istft_fwd": [vp, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp],
+    "idv_enc0_fwd": [vp, i32, i32, i32, vp, vp, i32, f32, vp, vp],
+    "idv_dec5_head_fwd": [vp, i32, vp, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, i32, i32, vp],
+    "idv_lstm_recurrent_fwd": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp],
+    "idv_lstm_combine_fwd": [vp, i32, i32, i32, vp, vp],
+    "idv_reparam_fwd": [vp, i32, i32, i32, i32, i32, i32, vp, vp, u64, u64, vp, vp],
+    "idv_planes_to_user": [vp, i32, i32, i32, i32, vp, vp],
+    "idv_user_to_planes": [vp, i32, i32, i32, i32, vp, vp],
+    "idv_z_to_planes": [vp, i32, i32, i32, i32, i32, vp, vp],
+    "idv_cbn_eval_user": [vp, i64, i32, i64, vp, vp, vp],
+}
+EXPORTS = ["idv_abi_version", "idv_last_error"] + list(SIGNATURES)
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the sources are newer and nvcc exists) and type the library."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if _build.needs_build():
+        if os.path.exists(_build.NVCC):
+            _build.build()
+        elif not os.path.exists(path):
+            raise RuntimeError("libidv_b200.so is missing and nvcc is not available: the CUDA extension is "
+                               "mandatory, there is no CPU or PyTorch fallback")
+    lib = ctypes.CDLL(path)
+    lib.idv_abi_version.restype = ctypes.c_int
+    lib.idv_last_error.restype = ctypes.c_char_p
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = ctypes.c_int
+    _LIB = lib
+    return lib
+
+
+def call(name, *args):
+    """Call a C-ABI entry point.  torch tensors are passed as device pointers (they must be contiguous
+    CUDA tensors); the current CUDA stream is appended as the trailing ``stream`` argument."""
+    lib = load()
+    conv = [ptr(a) if isinstance(a, torch.Tensor) else a for a in args]
+    conv.append(torch.cuda.current_stream().cuda_stream)
+    rc = getattr(lib, name)(*conv)
+    if rc != 0:
+        raise RuntimeError("%s failed (code %d): %s" % (name, rc, lib.idv_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32/int32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("idccrn_b200 ops need CUDA tensors (no CPU fallback); got device %s" % t.device)
+    if not t.is_contiguous():
+        raise RuntimeError("idccrn_b200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_f32_cuda(t, what):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32:
+        raise RuntimeError("%s must be a float32 CUDA tensor (no CPU fallback), got %s %s" % (
+            what, getattr(t, "dtype", type(t)), getattr(t, "device", "")))
+    return t.contiguous()

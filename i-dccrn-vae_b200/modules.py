@@ -1,0 +1,760 @@
+"""torch.nn.Module surface of the reference, backed by libidv_b200.so.
+
+Same class names, constructor / forward signatures and state_dict keys as
+/root/reference/model/complex_progress.py and model/pvae_module.py (the hot-path classes listed in
+SURVEY §8(b)); ``load_state_dict(reference_state_dict, strict=True)`` works on every class.  The
+nn.Conv2d / nn.ConvTranspose2d / nn.LSTM / nn.Linear children exist only as parameter containers
+(same names, shapes and default init as the reference); their forward is never called – all compute
+goes through the C ABI (ops.py), and there is no CPU or eager fallback.
+
+North-star aliases: ConvSTFT = STFT, ConviSTFT = ISTFT, ComplexBatchNorm = ComplexBatchNormal,
+NavieComplexLSTM = ComplexLSTM.
+
+Not built yet (raise NotImplementedError): ``train=True`` (ComplexBatchNormal batch statistics,
+model/complex_progress.py:L131-160), the non-causal config (model/net_config.py) and data_norm.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops, pack
+from .ops import Planes
+
+_TRAIN_MSG = ("train=True (batch-statistics ComplexBatchNormal + autograd) is not built in this round; "
+              "call with train=False (the enhancement path of test_nsvae_se.py / test_se_cvaefinetune.py)")
+
+
+def _sd(module):
+    """leaf-name -> tensor dict of a child container module (no copies)."""
+    return dict(module.state_dict(keep_vars=True))
+
+
+class _PackCache:
+    """Caches packed operands; rebuilt when any watched parameter/buffer changes identity or version."""
+
+    def __init__(self):
+        self._stamp = None
+        self.items = {}
+
+    def check(self, module):
+        tensors = list(module.state_dict(keep_vars=True).values())
+        stamp = tuple((t.data_ptr(), t._version) for t in tensors)
+        if stamp != self._stamp:
+            self._stamp = stamp
+            self.items = {}
+        return self.items
+
+
+# --------------------------------------------------------------------------------------------------
+# STFT / ISTFT — model/pvae_module.py:L12-42
+# --------------------------------------------------------------------------------------------------
+class STFT(nn.Module):
+    def __init__(self, n_fft, hop_length, win_length, device):
+        super().__init__()
+        self.n_fft, self.hop_length = n_fft, hop_length
+        self.win_length = win_length
+        self.window = torch.hann_window(self.win_length).to(device)   # plain attribute like the reference
+        self._basis = None
+
+    def forward(self, signal):
+        if self._basis is None or self._basis.device != signal.device:
+            self._basis = pack.pack_stft_basis(self.n_fft, self.win_length, signal.device)
+        return ops.stft(signal, self._basis, self.n_fft, self.hop_length, self.win_length)
+
+
+class ISTFT(nn.Module):
+    def __init__(self, n_fft, hop_length, win_length, device):
+        super().__init__()
+        self.n_fft, self.hop_length, self.win_length = n_fft, hop_length, win_length
+        self.window = torch.hann_window(self.win_length).to(device)
+        self._basis = None
+
+    def _ensure(self, device):
+        if self._basis is None or self._basis[0].device != device:
+            self._basis = pack.pack_istft_basis(self.n_fft, self.win_length, device)
+        return self._basis
+
+    def forward_ri(self, spec_ri):
+        basis, wsq = self._ensure(spec_ri.device)
+        return ops.istft(spec_ri, basis, wsq, self.n_fft, self.hop_length, self.win_length)
+
+    def forward(self, x):
+        """x: complex (B, F, T) like torch.istft's input at model/pvae_module.py:L41."""
+        if not x.is_complex():
+            raise RuntimeError("ISTFT.forward expects a complex (B, F, T) tensor")
+        return self.forward_ri(torch.view_as_real(x).contiguous())
+
+
+# --------------------------------------------------------------------------------------------------
+# complex primitives — model/complex_progress.py
+# --------------------------------------------------------------------------------------------------
+def _pair(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+class _ComplexConvBase(nn.Module):
+    causal = True
+
+    def __init__(self, in_channel, out_channel, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True):
+        super().__init__()
+        self.conv_re = nn.Conv2d(in_channel, out_channel, kernel_size, stride=stride, padding=padding,
+                                 dilation=dilation, groups=groups, bias=bias)
+        self.conv_im = nn.Conv2d(in_channel, out_channel, kernel_size, stride=stride, padding=padding,
+                                 dilation=dilation, groups=groups, bias=bias)
+        self._cache = _PackCache()
+
+    def _geometry(self):
+        c = self.conv_re
+        if _pair(c.dilation) != (1, 1) or c.groups != 1 or c.bias is None:
+            raise NotImplementedError("complex conv kernels are built for dilation 1, groups 1, bias=True")
+        (kh, kw), (sf, st), (pf, pt) = _pair(c.kernel_size), _pair(c.stride), _pair(c.padding)
+        if not self.causal or kw != 2 or st != 1 or pt != 1:
+            raise NotImplementedError(
+                "only the causal time geometry (kernel (k,2), stride (s,1), padding (p,1), last column dropped: "
+                "model/complex_progress.py:L8-22) is built; got kernel %s stride %s padding %s causal=%s"
+                % ((kh, kw), (sf, st), (pf, pt), self.causal))
+        return kh, sf, pf
+
+    def _packed(self, f_in, device, bn=None, slope=None):
+        items = self._cache.check(self)
+        key = (f_in, str(device), id(bn), slope)
+        if key not in items:
+            kh, sf, pf = self._geometry()
+            items[key] = pack.pack_conv(self.conv_re.weight, self.conv_re.bias, self.conv_im.weight,
+                                        self.conv_im.bias, bn, slope, f_in, sf, pf, device)
+        return items[key]
+
+    def forward_planes(self, xp, bn=None, slope=None):
+        pk = self._packed(xp.F, xp.data.device, bn, slope)
+        out = ops.tapgemm(pk, xp, None, xp.NB, xp.T)
+        return Planes(out, xp.NB, pk.c_out, pk.f_out, xp.T)
+
+    def forward(self, x):
+        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x)))
+
+
+class causal_complex_conv2d(_ComplexConvBase):
+    """model/complex_progress.py:L8-22"""
+    causal = True
+
+
+class ComplexConv2d(_ComplexConvBase):
+    """model/complex_progress.py:L24-36 (non-causal time geometry: not built, raises)."""
+    causal = False
+
+
+class _ComplexConvTransposeBase(nn.Module):
+    causal = True
+
+    def __init__(self, in_channel, out_channel, kernel_size, stride=1, padding=0, output_padding=0, dilation=1,
+                 groups=1, bias=True):
+        super().__init__()
+        kw = dict(kernel_size=kernel_size, stride=stride, padding=padding, output_padding=output_padding,
+                  groups=groups, bias=bias, dilation=dilation)
+        self.tconv_re = nn.ConvTranspose2d(in_channel, out_channel, **kw)
+        self.tconv_im = nn.ConvTranspose2d(in_channel, out_channel, **kw)
+        self._cache = _PackCache()
+
+    def _geometry(self):
+        c = self.tconv_re
+        if _pair(c.dilation) != (1, 1) or c.groups != 1 or c.bias is None or _pair(c.output_padding) != (0, 0):
+            raise NotImplementedError("complex transposed conv kernels are built for dilation 1, groups 1, bias=True")
+        (kh, kw), (sf, st), (pf, pt) = _pair(c.kernel_size), _pair(c.stride), _pair(c.padding)
+        if not self.causal or kw != 2 or st != 1 or pt != 0:
+            raise NotImplementedError(
+                "only the causal time geometry (kernel (k,2), stride (s,1), padding (p,0), last column dropped: "
+                "model/complex_progress.py:L222-250) is built")
+        return kh, sf, pf
+
+    def _packed(self, f_in, c_p, c_skip, device, bn=None, slope=None):
+        items = self._cache.check(self)
+        key = (f_in, c_p, c_skip, str(device), id(bn), slope)
+        if key not in items:
+            kh, sf, pf = self._geometry()
+            items[key] = pack.pack_conv_transpose(self.tconv_re.weight, self.tconv_re.bias, self.tconv_im.weight,
+                                                  self.tconv_im.bias, bn, slope, f_in, c_p, c_skip, device, sf, pf)
+        return items[key]
+
+    def forward_planes(self, pp, skip=None, bn=None, slope=None):
+        c_skip = skip.C if skip is not None else 0
+        if pp.C + c_skip > self.tconv_re.in_channels:
+            raise RuntimeError("transposed conv got %d+%d input channels, layer has %d"
+                               % (pp.C, c_skip, self.tconv_re.in_channels))
+        pk = self._packed(pp.F, pp.C, c_skip, pp.data.device, bn, slope)
+        out = ops.tapgemm(pk, pp, skip, pp.NB, pp.T)
+        return Planes(out, pp.NB, pk.c_out, pk.f_out, pp.T)
+
+    def forward(self, x):
+        if x.shape[1] != self.tconv_re.in_channels:
+            raise RuntimeError("expected %d input channels, got %d" % (self.tconv_re.in_channels, x.shape[1]))
+        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x)))
+
+
+class causal_ComplexConvTranspose2d(_ComplexConvTransposeBase):
+    """model/complex_progress.py:L222-250"""
+    causal = True
+
+
+class ComplexConvTranspose2d(_ComplexConvTransposeBase):
+    """model/complex_progress.py:L253-279 (non-causal: not built, raises)."""
+    causal = False
+
+
+class ComplexBatchNormal(nn.Module):
+    """model/complex_progress.py:L92-209 (eval branch; parameters/buffers identical)."""
+
+    def __init__(self, C, H, W, momentum=0.9, dis_cbn=False):
+        super().__init__()
+        self.momentum = momentum
+        self.gamma_rr = nn.Parameter(torch.ones(C), requires_grad=True)
+        self.gamma_ri = nn.Parameter(torch.randn(C), requires_grad=True)
+        self.gamma_ii = nn.Parameter(torch.ones(C), requires_grad=True)
+        self.beta_r = nn.Parameter(torch.zeros(C), requires_grad=True)
+        self.beta_i = nn.Parameter(torch.zeros(C), requires_grad=True)
+        self.epsilon = 1e-5
+        self.register_buffer('running_mean_real', torch.zeros(1, C, 1, 1))
+        self.register_buffer('running_mean_imag', torch.zeros(1, C, 1, 1))
+        self.register_buffer('Vrr', torch.ones(1, C, 1, 1))
+        self.register_buffer('Vri', torch.zeros(1, C, 1, 1))
+        self.register_buffer('Vii', torch.ones(1, C, 1, 1))
+        self.init_flag = True
+        self.detect_anormal = True
+        self.dis_cbn = dis_cbn
+        self._cache = _PackCache()
+
+    def fold_inputs(self):
+        return _sd(self)
+
+    def forward(self, x, train=True):
+        if train:
+            raise NotImplementedError(_TRAIN_MSG)
+        items = self._cache.check(self)
+        key = str(x.device)
+        if key not in items:
+            Z, bp = pack.cbn_fold(self.fold_inputs())
+            items[key] = torch.cat((Z.reshape(-1, 4), bp), 1).to(torch.float32).contiguous().to(x.device)
+        return ops.cbn_eval_user(x, items[key])
+
+
+class ComplexLSTM(nn.Module):
+    """model/complex_progress.py:L39-74"""
+
+    def __init__(self, input_size, hidden_size, device, num_layers=1, bias=True, dropout=0, bidirectional=False):
+        super().__init__()
+        if bidirectional or not bias:
+            raise NotImplementedError("ComplexLSTM kernels are built for unidirectional LSTMs with bias")
+        self.num_layer = num_layers
+        self.hidden_size = hidden_size
+        self.device = device
+        self.lstm_re = nn.LSTM(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers, bias=bias,
+                               dropout=dropout, bidirectional=bidirectional)
+        self.lstm_im = nn.LSTM(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers, bias=bias,
+                               dropout=dropout, bidirectional=bidirectional)
+        self._cache = _PackCache()
+
+    def _packed(self, c_in, f_in, device):
+        items = self._cache.check(self)
+        key = (c_in, f_in, str(device))
+        if key not in items:
+            if c_in * f_in != self.lstm_re.input_size:
+                raise RuntimeError("LSTM input size %d != C*F = %d*%d" % (self.lstm_re.input_size, c_in, f_in))
+            re, im, H = _sd(self.lstm_re), _sd(self.lstm_im), self.hidden_size
+            layers = [(pack.pack_lstm_inproj0(re, im, H, c_in, f_in, device), pack.pack_lstm_whh(re, im, 0, device))]
+            for l in range(1, self.num_layer):
+                layers.append((pack.pack_lstm_inproj1(re, im, H, device, l), pack.pack_lstm_whh(re, im, l, device)))
+            items[key] = layers
+        return items[key]
+
+    def forward_planes(self, xp):
+        """xp: Planes with C*F == input_size (feature d = c*F + f).  Returns the latent (NB, T, H, 2)."""
+        layers = self._packed(xp.C, xp.F, xp.data.device)
+        NB, T, H = xp.NB, xp.T, self.hidden_size
+        R = NB * (T + 1)
+        src, hseq = xp, None
+        for l, (inproj, whh) in enumerate(layers):
+            g = ops.tapgemm(inproj, src, None, NB, T, zero_pad_rows=False)
+            if l == 0:
+                hseq = ops.lstm_recurrent(g, 4 * H, R * 8 * H, 8 * H, whh, NB, T, H)
+            else:
+                hseq = ops.lstm_recurrent(g, 2 * R * 4 * H, R * 4 * H, 4 * H, whh, NB, T, H)
+            src = Planes(hseq, NB, H, 4, T, cp=H)       # [4 streams][R][H]: plane = stream, row stride H
+        return ops.lstm_combine(hseq, NB, T, H)
+
+    def forward(self, x):
+        """x: (T, B, D, 2) -> (T, B, H, 2)"""
+        if x.dim() != 4 or x.shape[-1] != 2:
+            raise RuntimeError("ComplexLSTM expects (T, B, D, 2)")
+        if self.hidden_size % 4:
+            raise NotImplementedError("ComplexLSTM kernels need hidden_size %% 4 == 0")
+        xu = x.permute(1, 2, 0, 3).unsqueeze(2).contiguous()          # (B, D, 1, T, 2)
+        lat = self.forward_planes(ops.user_to_planes(xu))             # (B, T, H, 2)
+        return lat.permute(1, 0, 2, 3).contiguous()
+
+
+class ComplexDense(nn.Module):
+    """model/complex_progress.py:L77-89"""
+
+    def __init__(self, in_channel, out_channel):
+        super().__init__()
+        self.linear_read = nn.Linear(in_channel, out_channel)
+        self.linear_imag = nn.Linear(in_channel, out_channel)
+        self._cache = _PackCache()
+
+    def _packed(self, c_out, f_out, device):
+        items = self._cache.check(self)
+        key = (c_out, f_out, str(device))
+        if key not in items:
+            if c_out * f_out != self.linear_read.out_features:
+                raise RuntimeError("dense out_features %d != C*F = %d*%d" % (self.linear_read.out_features, c_out, f_out))
+            items[key] = pack.pack_dense(self.linear_read.weight, self.linear_read.bias, self.linear_imag.weight,
+                                         self.linear_imag.bias, c_out, f_out, device)
+        return items[key]
+
+    def forward_planes(self, zp, c_out, f_out):
+        pk = self._packed(c_out, f_out, zp.data.device)
+        out = ops.tapgemm(pk, zp, None, zp.NB, zp.T)
+        return Planes(out, zp.NB, c_out, f_out, zp.T)
+
+    def forward(self, x):
+        """x: (..., D, 2) -> (..., out, 2)"""
+        lead = x.shape[:-2]
+        D = x.shape[-2]
+        M = 1
+        for s in lead:
+            M *= s
+        xu = x.reshape(1, M, D, 2).permute(0, 2, 1, 3).unsqueeze(2).contiguous()       # (1, D, 1, M, 2)
+        outp = self.forward_planes(ops.user_to_planes(xu), self.linear_read.out_features, 1)
+        y = ops.planes_to_user(outp)                                                      # (1, out, 1, M, 2)
+        return y[0, :, 0].permute(1, 0, 2).reshape(*lead, self.linear_read.out_features, 2).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# Encoder / Decoder blocks — model/pvae_module.py:L45-93
+# --------------------------------------------------------------------------------------------------
+class Encoder(nn.Module):
+    def __init__(self, in_channel, out_channel, kernel_size, stride, chw, padding=None, causal=False):
+        super().__init__()
+        if padding is None:
+            padding = [int((i - 1) / 2) for i in kernel_size]
+        cls = causal_complex_conv2d if causal else ComplexConv2d
+        self.conv = cls(in_channel=in_channel, out_channel=out_channel, kernel_size=kernel_size, stride=stride,
+                        padding=padding)
+        self.bn = ComplexBatchNormal(chw[0], chw[1], chw[2])
+        self.prelu = nn.PReLU()
+        self._cache = _PackCache()
+
+    def _slope(self):
+        return float(self.prelu.weight.detach().reshape(-1)[0])
+
+    def forward_from_stft(self, stft_x):
+        """First layer (in_channel == 1): reads the user-layout STFT (B, F, T, 2) directly."""
+        items = self._cache.check(self)
+        key = ("enc0", str(stft_x.device))
+        if key not in items:
+            self.conv._geometry()
+            c = self.conv
+            items[key] = pack.pack_enc0(c.conv_re.weight, c.conv_re.bias, c.conv_im.weight, c.conv_im.bias,
+                                        self.bn.fold_inputs(), self._slope(), stft_x.device)
+        w, b, cout, slope = items[key]
+        return ops.enc0(stft_x, w, b, cout, slope)
+
+    def forward_planes(self, xp):
+        items = self._cache.check(self)          # invalidates the child's fold when bn / prelu change
+        key = ("fold", xp.F, str(xp.data.device))
+        if key not in items:
+            kh, sf, pf = self.conv._geometry()
+            c = self.conv
+            items[key] = pack.pack_conv(c.conv_re.weight, c.conv_re.bias, c.conv_im.weight, c.conv_im.bias,
+                                        self.bn.fold_inputs(), self._slope(), xp.F, sf, pf, xp.data.device)
+        pk = items[key]
+        out = ops.tapgemm(pk, xp, None, xp.NB, xp.T)
+        return Planes(out, xp.NB, pk.c_out, pk.f_out, xp.T)
+
+    def forward(self, x, train):
+        if train:
+            raise NotImplementedError(_TRAIN_MSG)
+        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x)))
+
+
+class Decoder(nn.Module):
+    def __init__(self, in_channel, out_channel, kernel_size, stride, chw, padding=None, causal=False, if_bn=True):
+        super().__init__()
+        cls = causal_ComplexConvTranspose2d if causal else ComplexConvTranspose2d
+        self.transconv = cls(in_channel=in_channel, out_channel=out_channel, kernel_size=kernel_size,
+                             stride=stride, padding=padding)
+        self.bn = ComplexBatchNormal(chw[0], chw[1], chw[2])
+        self.prelu = nn.PReLU()
+        self.if_bn = if_bn
+        self._cache = _PackCache()
+
+    def _slope(self):
+        return float(self.prelu.weight.detach().reshape(-1)[0])
+
+    def _fold(self):
+        return (self.bn.fold_inputs(), self._slope()) if self.if_bn else (None, None)
+
+    def forward_planes(self, pp, skip=None):
+        items = self._cache.check(self)
+        c_skip = skip.C if skip is not None else 0
+        key = ("fold", pp.F, pp.C, c_skip, str(pp.data.device))
+        if key not in items:
+            kh, sf, pf = self.transconv._geometry()
+            t = self.transconv
+            if pp.C + c_skip > t.tconv_re.in_channels:
+                raise RuntimeError("decoder layer got %d+%d input channels, has %d"
+                                   % (pp.C, c_skip, t.tconv_re.in_channels))
+            bn, slope = self._fold()
+            items[key] = pack.pack_conv_transpose(t.tconv_re.weight, t.tconv_re.bias, t.tconv_im.weight,
+                                                  t.tconv_im.bias, bn, slope, pp.F, pp.C, c_skip,
+                                                  pp.data.device, sf, pf)
+        pk = items[key]
+        out = ops.tapgemm(pk, pp, skip, pp.NB, pp.T)
+        return Planes(out, pp.NB, pk.c_out, pk.f_out, pp.T)
+
+    def forward_head(self, pp, skip, mask, stft_x, predict, out_bmul, out_boff):
+        """Last layer (out_channel == 1) fused with the reconstruction head; writes ``predict``."""
+        items = self._cache.check(self)
+        c_skip = skip.C if skip is not None else 0
+        key = ("head", pp.C, c_skip, str(pp.data.device))
+        if key not in items:
+            self.transconv._geometry()
+            t = self.transconv
+            bn, slope = self._fold()
+            items[key] = pack.pack_dec5(t.tconv_re.weight, t.tconv_re.bias, t.tconv_im.weight, t.tconv_im.bias,
+                                        bn, slope, pp.C, c_skip, pp.data.device)
+        w, b, slope = items[key]
+        ops.dec5_head(pp, skip, w, b, slope, mask, stft_x, predict, out_bmul, out_boff)
+
+    def forward(self, x, train=True):
+        if train and self.if_bn:
+            raise NotImplementedError(_TRAIN_MSG)
+        if x.shape[1] != self.transconv.tconv_re.in_channels:
+            raise RuntimeError("expected %d input channels" % self.transconv.tconv_re.in_channels)
+        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x)))
+
+
+# --------------------------------------------------------------------------------------------------
+# skip list: encoder outputs stay in planes; reference-layout tensors are materialised on access
+# --------------------------------------------------------------------------------------------------
+class SkipList(list):
+    """``skiper`` of the encoder return tuple (model/pvae_module.py:L2236-2240).  Behaves like the
+    reference's list of (B, C, F, T, 2) tensors (converted lazily, cached), while the decoders read the
+    planes directly (no torch.cat, no repeat: SURVEY §2.1 K8)."""
+
+    def __init__(self, planes):
+        super().__init__([None] * len(planes))
+        self.planes = list(planes)
+
+    def _get(self, i):
+        v = list.__getitem__(self, i)
+        if v is None:
+            v = ops.planes_to_user(self.planes[i])
+            list.__setitem__(self, i, v)
+        return v
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._get(j) for j in range(*i.indices(len(self)))]
+        return self._get(i if i >= 0 else len(self) + i)
+
+    def __iter__(self):
+        return (self._get(i) for i in range(len(self)))
+
+
+def _skip_planes(skiper, idx):
+    if isinstance(skiper, SkipList):
+        return skiper.planes[idx]
+    return ops.user_to_planes(skiper[idx])
+
+
+def _build_encoders(net_params, causal):
+    ch, ks = net_params["encoder_channels"], net_params["encoder_kernel_sizes"]
+    st, pd, chw = net_params["encoder_strides"], net_params["encoder_paddings"], net_params["encoder_chw"]
+    return [Encoder(in_channel=ch[i], out_channel=ch[i + 1], kernel_size=ks[i], stride=st[i], padding=pd[i],
+                    chw=chw[i], causal=causal) for i in range(len(ch) - 1)]
+
+
+def _build_decoders(net_params, causal, skip_to_use, use_sc=True):
+    en_ch, de_ch = net_params["encoder_channels"], net_params["decoder_channels"]
+    ks, st, pd = net_params["decoder_kernel_sizes"], net_params["decoder_strides"], net_params["decoder_paddings"]
+    chw = net_params["decoder_chw"]
+    out = []
+    for i in range(len(de_ch) - 1):
+        cin = de_ch[i] + (en_ch[len(en_ch) - 1 - i] if (use_sc and i in skip_to_use) else 0)
+        out.append(Decoder(in_channel=cin, out_channel=de_ch[i + 1], kernel_size=ks[i], stride=st[i],
+                           padding=pd[i], chw=chw[i], causal=causal))
+    return out
+
+
+def _run_encoder_stack(encoders, stft_x):
+    planes = [encoders[0].forward_from_stft(stft_x)]
+    for enc in encoders[1:]:
+        planes.append(enc.forward_planes(planes[-1]))
+    return planes
+
+
+_philox_calls = [0]
+
+
+def _next_philox():
+    _philox_calls[0] += 1
+    return torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, _philox_calls[0]
+
+
+# --------------------------------------------------------------------------------------------------
+# VAE encoders — model/pvae_module.py:L1791-1914, L2131-2268
+# --------------------------------------------------------------------------------------------------
+class _VaeEncoderBase(nn.Module):
+    def _init_common(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num):
+        if not causal:
+            raise NotImplementedError("only the causal network config (model/causal_netconfig.py) is built")
+        self.device = device
+        self.causal = causal
+        self.latent_num = latent_num
+        self.stft = STFT(n_fft, hop_len, win_length=win_length, device=device)
+        self.dense = ComplexDense(zdim, net_params["dense"][1])          # unused, present in the state_dict
+        self.zdim = zdim
+        self.num_samples = num_samples
+        encoders = _build_encoders(net_params, causal)
+        lstm_dims = net_params["lstm_dim"]
+        lstms = [ComplexLSTM(input_size=lstm_dims[i], hidden_size=int(3 * zdim * latent_num),
+                             num_layers=net_params["lstm_layer_num"], device=device)
+                 for i in range(len(lstm_dims) - 1)]
+        self.encoders = nn.ModuleList(encoders)
+        self.lstms = nn.ModuleList(lstms)
+        self.epsilon = 1e-6
+
+    def _encode(self, x, train, eps):
+        if train:
+            raise NotImplementedError(_TRAIN_MSG)
+        if len(self.lstms) != 1:
+            raise NotImplementedError("one ComplexLSTM stage expected (lstm_dim has two entries)")
+        stft_x = self.stft(x)
+        planes = _run_encoder_stack(self.encoders, stft_x)
+        top = planes[-1]
+        latent = self.lstms[0].forward_planes(top)                     # (B, T, 3*zdim*latent_num, 2)
+        z, S = self.zdim, self.num_samples
+        zs = []
+        for k in range(self.latent_num):
+            if eps is not None:
+                er, ei, seed, off = eps[2 * k], eps[2 * k + 1], 0, 0
+            else:
+                er = ei = None
+                seed, off = _next_philox()
+            zs.append(ops.reparam(latent, 3 * z * k, z, S, er, ei, seed, off))
+        return stft_x, SkipList(planes), latent, zs, top.C, top.F
+
+    def reparameterization(self, miu, log_sigma, delta, num_samples, eps=None):
+        """model/pvae_module.py:L2177-2231; eps = (eps_real, eps_imag) of shape (B, S, T, zdim) or None."""
+        latent = torch.cat((miu, log_sigma, delta), dim=2).contiguous()
+        er, ei = eps if eps is not None else (None, None)
+        seed, off = (0, 0) if eps is not None else _next_philox()
+        return ops.reparam(latent, 0, miu.shape[2], num_samples, er, ei, seed, off)
+
+
+class nsvae_pvae_dccrn_encoder_twophase(_VaeEncoderBase):
+    """model/pvae_module.py:L2131-2268.  Extra keyword ``eps``: list of supplied N(0,1) tensors
+    (B, S, T, zdim) in draw order [speech_real, speech_imag(, noise_real, noise_imag)]; default = Philox."""
+
+    def __init__(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num):
+        super().__init__()
+        if latent_num not in (1, 2):
+            raise ValueError("latent_num must be 1 or 2")
+        self._init_common(net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num)
+
+    def forward(self, x, train=True, eps=None):
+        stft_x, skiper, lat, zs, C, F = self._encode(x, train, eps)
+        z = self.zdim
+        miu_s, ls_s, de_s = lat[:, :, 0:z, :], lat[:, :, z:2 * z, :], lat[:, :, 2 * z:3 * z, :]
+        if self.latent_num == 1:
+            return zs[0], miu_s, ls_s, de_s, None, None, None, None, skiper, C, F, stft_x
+        miu_n, ls_n, de_n = lat[:, :, 3 * z:4 * z, :], lat[:, :, 4 * z:5 * z, :], lat[:, :, 5 * z:6 * z, :]
+        return zs[0], miu_s, ls_s, de_s, zs[1], miu_n, ls_n, de_n, skiper, C, F, stft_x
+
+
+class pvae_dccrn_encoder_skip_prepare(_VaeEncoderBase):
+    """model/pvae_module.py:L1791-1914"""
+
+    def __init__(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples):
+        super().__init__()
+        self._init_common(net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, 1)
+
+    def forward(self, x, train=True, eps=None):
+        stft_x, skiper, lat, zs, C, F = self._encode(x, train, eps)
+        z = self.zdim
+        return zs[0], lat[:, :, 0:z, :], lat[:, :, z:2 * z, :], lat[:, :, 2 * z:, :], skiper, C, F, stft_x
+
+
+# --------------------------------------------------------------------------------------------------
+# VAE decoders — model/pvae_module.py:L2045-2122, L2505-2619
+# --------------------------------------------------------------------------------------------------
+class _VaeDecoderBase(nn.Module):
+    def _init_common(self, net_params, causal, device, num_samples, zdim, n_fft, hop_len, win_length, recon_type,
+                     skip_to_use, use_sc):
+        if not causal:
+            raise NotImplementedError("only the causal network config (model/causal_netconfig.py) is built")
+        if recon_type not in ("real_imag", "mask"):
+            raise ValueError("recon_type must be 'real_imag' or 'mask'")
+        self.device = device
+        self.causal = causal
+        self.num_samples = num_samples
+        self.zdim = zdim
+        self.recon_type = recon_type
+        self.skip_to_use = skip_to_use
+        self.dense = ComplexDense(zdim, net_params["dense"][1])
+        self.use_sc = use_sc
+        self.decoders = nn.ModuleList(_build_decoders(net_params, causal, skip_to_use, use_sc))
+        self.istft = ISTFT(n_fft, hop_len, win_length=win_length, device=device)
+        self.keep_decoder_outputs = False
+
+    def _decode(self, stft_x, z, skiper, C, F, train, real_skips, mask):
+        if train:
+            raise NotImplementedError(_TRAIN_MSG)
+        BS, T, zdim, D = z.shape
+        S = self.num_samples
+        if BS % S:
+            raise RuntimeError("z batch %d is not a multiple of num_samples %d" % (BS, S))
+        B = BS // S
+        n = len(self.decoders)
+        skips = {}
+        if real_skips:
+            for i in range(n):
+                if self.use_sc and i in self.skip_to_use:
+                    skips[i] = _skip_planes(skiper, len(skiper) - i - 1)
+        n_bins = F
+        for _ in range(n):
+            n_bins = 2 * n_bins - 1          # kernel 5 / stride 2 / pad 2 transposed conv
+        predict = torch.empty((BS, n_bins, T, 2), dtype=torch.float32, device=z.device)
+        if mask:
+            stft_x = ops.lib.require_f32_cuda(stft_x, "stft_x")
+        self.decoder_outputs = []
+        for s in range(S):
+            zp = ops.z_to_planes(z, B, S, s)
+            p = self.dense.forward_planes(zp, C, F)
+            for i in range(n - 1):
+                p = self.decoders[i].forward_planes(p, skips.get(i))
+                if self.keep_decoder_outputs and S == 1:
+                    self.decoder_outputs.append(p)
+            self.decoders[n - 1].forward_head(p, skips.get(n - 1), mask, stft_x if mask else None, predict, S, s)
+        if self.keep_decoder_outputs and S == 1:
+            self.decoder_outputs = SkipList(self.decoder_outputs)
+        recon_sig = self.istft.forward_ri(predict)
+        return recon_sig, torch.view_as_complex(predict)
+
+
+class pvae_dccrn_decoder_skip_prepare(_VaeDecoderBase):
+    """model/pvae_module.py:L2045-2122: the skip slots are fed zeros (L2092-2097) – the skip half of
+    every K loop is skipped instead of multiplying zeros."""
+
+    def __init__(self, net_params, causal, device, num_samples, zdim, n_fft, hop_len, win_length, recon_type,
+                 skip_to_use):
+        super().__init__()
+        self._init_common(net_params, causal, device, num_samples, zdim, n_fft, hop_len, win_length, recon_type,
+                          skip_to_use, True)
+        if recon_type != "real_imag":
+            raise NotImplementedError("pvae_dccrn_decoder_skip_prepare only defines recon_type='real_imag' "
+                                      "(model/pvae_module.py:L2117-2120)")
+
+    def forward(self, stft_x, z, skiper, C, F, train=True):
+        return self._decode(stft_x, z, skiper, C, F, train, real_skips=False, mask=False)
+
+
+class nsvae_pvae_dccrn_decoder_twophase(_VaeDecoderBase):
+    """model/pvae_module.py:L2505-2619"""
+
+    def __init__(self, net_params, causal, device, num_samples, zdim, n_fft, hop_len, win_length, recon_type,
+                 use_sc, skip_to_use, resynthesis):
+        super().__init__()
+        self._init_common(net_params, causal, device, num_samples, zdim, n_fft, hop_len, win_length, recon_type,
+                          skip_to_use, use_sc)
+        self.resynthesis = resynthesis
+        self.stft = STFT(n_fft, hop_len, win_length=win_length, device=device)
+
+    def forward(self, stft_x, z, skiper, C, F, train=True, pad='zero'):
+        if pad not in ('zero', 'sig'):
+            raise ValueError("pad must be 'zero' or 'sig'")
+        sig, predict = self._decode(stft_x, z, skiper, C, F, train, real_skips=(pad == 'sig'),
+                                    mask=(self.recon_type == 'mask'))
+        if self.resynthesis:
+            predict = torch.view_as_complex(self.stft(sig))
+        return sig, predict
+
+
+# --------------------------------------------------------------------------------------------------
+# supervised DCCRN — model/pvae_module.py:L96-255
+# --------------------------------------------------------------------------------------------------
+class standard_DCCRN(nn.Module):
+    def __init__(self, net_params, causal, device, skip_to_use):
+        super().__init__()
+        if not causal:
+            raise NotImplementedError("only the causal network config (model/causal_netconfig.py) is built")
+        self.device = device
+        self.causal = causal
+        self.dense = ComplexDense(net_params["dense"][0], net_params["dense"][1])
+        self.skip_to_use = skip_to_use
+        lstm_dims = net_params["lstm_dim"]
+        lstms = [ComplexLSTM(input_size=lstm_dims[i], hidden_size=lstm_dims[i + 1],
+                             num_layers=net_params["lstm_layer_num"], device=device)
+                 for i in range(len(lstm_dims) - 1)]
+        self.encoders = nn.ModuleList(_build_encoders(net_params, causal))
+        self.lstms = nn.ModuleList(lstms)
+        self.decoders = nn.ModuleList(_build_decoders(net_params, causal, skip_to_use, True))
+        self.linear = ComplexConv2d(in_channel=1, out_channel=1, kernel_size=1, stride=1)   # unused, in state_dict
+        self.detect_anormal = True
+
+    def forward_spec(self, stft_x, train, mask):
+        """stft_x (B, F, T, 2) -> predict (B, F, T, 2): decoder output, optionally through the mask head."""
+        if train:
+            raise NotImplementedError(_TRAIN_MSG)
+        stft_x = ops.lib.require_f32_cuda(stft_x, "stft_x")
+        planes = _run_encoder_stack(self.encoders, stft_x)
+        top = planes[-1]
+        lat = self.lstms[0].forward_planes(top)                         # (B, T, H, 2)
+        self.latent = lat
+        B, T = lat.shape[0], lat.shape[1]
+        zp = ops.z_to_planes(lat, B, 1, 0)
+        p = self.dense.forward_planes(zp, top.C, top.F)
+        n = len(self.decoders)
+        for i in range(n - 1):
+            p = self.decoders[i].forward_planes(p, planes[n - 1 - i] if i in self.skip_to_use else None)
+        predict = torch.empty((B, stft_x.shape[1], T, 2), dtype=torch.float32, device=stft_x.device)
+        self.decoders[n - 1].forward_head(p, planes[0] if (n - 1) in self.skip_to_use else None, mask,
+                                          stft_x if mask else None, predict, 1, 0)
+        return predict
+
+    def forward(self, x, train=True):
+        """x: (B, 1, F, T, 2) -> (B, 1, F, T, 2) like model/pvae_module.py:L174-198."""
+        return self.forward_spec(x[:, 0].contiguous(), train, mask=False).unsqueeze(1)
+
+
+class DCCRN_(nn.Module):
+    def __init__(self, n_fft, hop_len, net_params, causal, device, win_length, skip_to_use, recon_type, resynthesis,
+                 data_mean, data_std):
+        super().__init__()
+        self.stft = STFT(n_fft, hop_len, win_length=win_length, device=device)
+        self.std_DCCRN = standard_DCCRN(net_params, causal, device=device, skip_to_use=skip_to_use)
+        self.istft = ISTFT(n_fft, hop_len, win_length=win_length, device=device)
+        self.recon_type = recon_type
+        self.resynthesis = resynthesis
+        self.register_buffer("data_mean", data_mean)
+        self.register_buffer("data_std", data_std)
+        self.datanorm = self.data_mean is not None and self.data_std is not None
+        if self.datanorm:
+            raise NotImplementedError("data_norm (model/pvae_module.py:L217-221) is off in every shipped run and "
+                                      "is not built")
+        if recon_type not in ("mask", "real_imag"):
+            raise ValueError("recon_type must be 'mask' or 'real_imag'")
+
+    def forward(self, signal, train=True):
+        stft_x = self.stft(signal)
+        predict = self.std_DCCRN.forward_spec(stft_x, train, mask=(self.recon_type == 'mask'))
+        clean = self.istft.forward_ri(predict)
+        if self.resynthesis:
+            predict = self.stft(clean)
+        return clean, torch.view_as_complex(predict)
+
+
+# north-star aliases
+ConvSTFT = STFT
+ConviSTFT = ISTFT
+ComplexBatchNorm = ComplexBatchNormal
+NavieComplexLSTM = ComplexLSTM

@@ -1,0 +1,304 @@
+"""Host-side weight pre-packing (done once per weight version, never per forward).
+
+Turns reference-layout parameters into the operands of the kernels in include/idv.h:
+  * complex (transposed) conv  -> block-real tap-GEMM weights with ComplexBatchNormal(eval) folded in
+    (SURVEY §9 V3/V4/V5): out = Z (W x + b - mu) + beta = (Z W) x + (Z (b - mu) + beta);
+  * nn.LSTM input projections and ComplexDense -> tap-GEMM weights;
+  * STFT / iSTFT windowed DFT bases.
+All folding is done in float64 and rounded once to float32.
+"""
+import math
+
+import torch
+
+EPS_CBN = 1e-5
+
+
+def round8(c):
+    return (c + 7) // 8 * 8
+
+
+class TapGemmPack:
+    """Operands of one idv_tapgemm_* launch (weights, bias, unit/tap tables)."""
+
+    def __init__(self, w, bias, units, taps, N, out_planes, out_ld, prelu, slope, device):
+        self.w = w.to(device=device, dtype=torch.float32).contiguous()
+        self.bias = bias.to(device=device, dtype=torch.float32).contiguous()
+        self.units = torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(device)
+        self.taps = torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(device)
+        self.n_units = len(units)
+        self.N = N
+        self.out_planes = out_planes
+        self.out_ld = out_ld
+        self.prelu = bool(prelu)
+        self.slope = float(slope)
+
+
+def cbn_fold(bn):
+    """Per-channel Z (C,2,2) and b' (C,2) of ComplexBatchNormal(train=False)
+    (model/complex_progress.py:L161-209).  ``bn`` maps leaf names to tensors."""
+    d = {k: v.detach().double().cpu().reshape(-1) for k, v in bn.items()}
+    vrr, vri, vii = d["Vrr"], d["Vri"], d["Vii"]
+    delta = torch.clamp(vrr * vii - vri ** 2 + EPS_CBN, min=1e-8)
+    s = torch.sqrt(delta)
+    t = torch.sqrt(vrr + vii + 2 * s + EPS_CBN)
+    ist = 1.0 / (s * t + EPS_CBN)
+    wrr, wii, wri = (vii + s) * ist, (vrr + s) * ist, -vri * ist
+    grr, gri, gii = d["gamma_rr"], d["gamma_ri"], d["gamma_ii"]
+    Z = torch.stack((torch.stack((grr * wrr + gri * wri, grr * wri + gri * wii), -1),
+                     torch.stack((gri * wrr + gii * wri, gri * wri + gii * wii), -1)), -2)   # (C,2,2)
+    mu = torch.stack((d["running_mean_real"], d["running_mean_imag"]), -1)                    # (C,2)
+    beta = torch.stack((d["beta_r"], d["beta_i"]), -1)
+    bprime = beta - torch.einsum("cij,cj->ci", Z, mu)
+    return Z, bprime
+
+
+def _identity_fold(C):
+    Z = torch.eye(2, dtype=torch.float64).repeat(C, 1, 1)
+    return Z, torch.zeros(C, 2, dtype=torch.float64)
+
+
+def _block_weights(m_re, m_im, b_re, b_im, Z, bprime, ch_in, ch_out):
+    """m_re/m_im: (taps, Cin, Cout) real matrices of the re/im sub-layers (input-major).
+    Returns W (taps, 2*ch_in, 2*ch_out) and bias (2*ch_out) with the 2x2 fold applied.
+    Raw block: y_re = m_re x_re - m_im x_im, y_im = m_re x_im + m_im x_re (complex_progress.py:L17-19)."""
+    taps, cin, cout = m_re.shape
+    m_re, m_im = m_re.double(), m_im.double()
+    zrr, zri, zir, zii = (Z[:, 0, 0], Z[:, 0, 1], Z[:, 1, 0], Z[:, 1, 1])
+    W = torch.zeros(taps, 2 * ch_in, 2 * ch_out, dtype=torch.float64)
+    # rows: [re-in | im-in], cols: [re-out | im-out]
+    W[:, :cin, :cout] = zrr * m_re + zri * m_im
+    W[:, ch_in:ch_in + cin, :cout] = -zrr * m_im + zri * m_re
+    W[:, :cin, ch_out:ch_out + cout] = zir * m_re + zii * m_im
+    W[:, ch_in:ch_in + cin, ch_out:ch_out + cout] = -zir * m_im + zii * m_re
+    yb_re = (b_re - b_im).double()
+    yb_im = (b_re + b_im).double()
+    bias = torch.zeros(2 * ch_out, dtype=torch.float64)
+    bias[:cout] = zrr * yb_re + zri * yb_im + bprime[:, 0]
+    bias[ch_out:ch_out + cout] = zir * yb_re + zii * yb_im + bprime[:, 1]
+    return W, bias
+
+
+def _cpu(t):
+    return t.detach().cpu()
+
+
+def pack_conv(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, f_in, stride_f, pad_f, device):
+    """Causal complex conv (kernel (kh,2), stride (stride_f,1), pad (pad_f,1)) [+ CBN + PReLU].
+    weights: (Cout, Cin, kh, 2).  Time tap kt reads x[t-1+kt]."""
+    wr, wi = _cpu(conv_re_w), _cpu(conv_im_w)
+    cout, cin, kh, kw = wr.shape
+    if kw != 2:
+        raise NotImplementedError("causal complex conv is built for a 2-tap time kernel (got %d)" % kw)
+    ch_in, ch_out = round8(cin), round8(cout)
+    Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(cout)
+    m_re = wr.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
+    m_im = wi.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
+    W, bias = _block_weights(m_re, m_im, _cpu(conv_re_b), _cpu(conv_im_b), Z, bp, ch_in, ch_out)
+    N, kc = 2 * ch_out, 2 * ch_in
+    f_out = (f_in + 2 * pad_f - kh) // stride_f + 1
+    units, taps = [], []
+    for fo in range(f_out):
+        begin = len(taps)
+        for kf in range(kh):
+            fi = stride_f * fo + kf - pad_f
+            if fi < 0 or fi >= f_in:
+                continue
+            for kt in range(2):
+                taps.append([0, fi, 1 - kt, 0, kc, (kf * 2 + kt) * kc * N])
+        units.append([begin, len(taps) - begin, fo, 0, 0, 0])
+    p = TapGemmPack(W.reshape(-1), bias, units, taps, N, f_out, N, slope is not None, slope or 0.0, device)
+    p.f_out, p.c_out = f_out, cout
+    return p
+
+
+def pack_conv_transpose(t_re_w, t_re_b, t_im_w, t_im_b, bn, slope, f_in, c_p, c_skip, device,
+                        stride_f=2, pad_f=2):
+    """Causal complex transposed conv in gather form over two sources: the running
+    activation p (c_p complex channels) and the skip tensor (c_skip, 0 = none / zero skip).
+    weights: (Cin_total, Cout, kh, 2); input channel order [p | skip] like torch.cat
+    (model/pvae_module.py:L2098).  Time tap kt reads x[t-kt]."""
+    wr, wi = _cpu(t_re_w), _cpu(t_im_w)
+    cin_tot, cout, kh, kw = wr.shape
+    if kw != 2:
+        raise NotImplementedError("causal complex transposed conv is built for a 2-tap time kernel")
+    ch_out = round8(cout)
+    Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(cout)
+    f_out = (f_in - 1) * stride_f - 2 * pad_f + kh
+    N = 2 * ch_out
+    srcs = [(0, 0, c_p)]
+    if c_skip:
+        srcs.append((1, c_p, c_skip))
+    Ws, w_offs, kcs, off = [], [], [], 0
+    bias = None
+    for (src, c0, cn) in srcs:
+        ch_in = round8(cn)
+        m_re = wr[c0:c0 + cn].permute(2, 3, 0, 1).reshape(kh * kw, cn, cout)
+        m_im = wi[c0:c0 + cn].permute(2, 3, 0, 1).reshape(kh * kw, cn, cout)
+        W, b = _block_weights(m_re, m_im, _cpu(t_re_b), _cpu(t_im_b), Z, bp, ch_in, ch_out)
+        if bias is None:
+            bias = b
+        Ws.append(W.reshape(-1))
+        w_offs.append(off)
+        kcs.append(2 * ch_in)
+        off += W.numel()
+    units, taps = [], []
+    for fo in range(f_out):
+        begin = len(taps)
+        for kf in range(kh):
+            num = fo + pad_f - kf
+            if num % stride_f:
+                continue
+            fi = num // stride_f
+            if fi < 0 or fi >= f_in:
+                continue
+            for kt in range(2):
+                for si, (src, _, _) in enumerate(srcs):
+                    taps.append([src, fi, kt, 0, kcs[si], w_offs[si] + (kf * 2 + kt) * kcs[si] * N])
+        units.append([begin, len(taps) - begin, fo, 0, 0, 0])
+    p = TapGemmPack(torch.cat(Ws), bias, units, taps, N, f_out, N, slope is not None, slope or 0.0, device)
+    p.f_out, p.c_out = f_out, cout
+    return p
+
+
+def pack_enc0(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, device):
+    """First encoder layer (Cin = 1): w [10][2][2*Cout], bias [2*Cout] for idv_enc0_fwd."""
+    wr, wi = _cpu(conv_re_w), _cpu(conv_im_w)
+    cout, cin, kh, kw = wr.shape
+    assert cin == 1 and kh == 5 and kw == 2 and cout % 16 == 0
+    Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(cout)
+    m_re = wr.permute(2, 3, 1, 0).reshape(10, 1, cout)
+    m_im = wi.permute(2, 3, 1, 0).reshape(10, 1, cout)
+    W = torch.zeros(10, 2, 2 * cout, dtype=torch.float64)
+    Wb, bias = _block_weights(m_re, m_im, _cpu(conv_re_b), _cpu(conv_im_b), Z, bp, 8, cout)
+    W[:, 0] = Wb[:, 0]           # re-in row
+    W[:, 1] = Wb[:, 8]           # im-in row (ch_in = 8 padding of one channel)
+    return (W.to(torch.float32).contiguous().to(device), bias.to(torch.float32).to(device), cout,
+            float(slope if slope is not None else 1.0))
+
+
+def pack_dec5(t_re_w, t_re_b, t_im_w, t_im_b, bn, slope, c_p, c_skip, device):
+    """Last decoder layer (Cout = 1): w [10][2*ch_p + 2*ch_skip][2], bias [2] for idv_dec5_head_fwd."""
+    wr, wi = _cpu(t_re_w), _cpu(t_im_w)
+    cin_tot, cout, kh, kw = wr.shape
+    assert cout == 1 and kh == 5 and kw == 2 and cin_tot >= c_p + c_skip
+    Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(1)
+    parts, bias = [], None
+    for (c0, cn) in ((0, c_p), (c_p, c_skip)):
+        if cn == 0:
+            continue
+        ch_in = round8(cn)
+        m_re = wr[c0:c0 + cn].permute(2, 3, 0, 1).reshape(10, cn, 1)
+        m_im = wi[c0:c0 + cn].permute(2, 3, 0, 1).reshape(10, cn, 1)
+        W, b = _block_weights(m_re, m_im, _cpu(t_re_b), _cpu(t_im_b), Z, bp, ch_in, 8)
+        bias = b if bias is None else bias
+        parts.append(torch.stack((W[:, :, 0], W[:, :, 8]), -1))      # (10, 2*ch_in, 2): re-out, im-out
+    w = torch.cat(parts, 1).to(torch.float32).contiguous().to(device)
+    b2 = torch.stack((bias[0], bias[8])).to(torch.float32).to(device)
+    return w, b2, float(slope if slope is not None else 1.0)
+
+
+def pack_lstm_inproj0(lstm_re, lstm_im, hidden, c_in, f_in, device):
+    """Layer-0 input projection of both nn.LSTM modules as one tap-GEMM: feature d = c*f_in + f
+    (the reshape at model/pvae_module.py:L2241).  N = 8H: [module re gates | module im gates];
+    unit p (input part x_re / x_im) writes plane p of G0[2][R][8H]."""
+    H, ch = hidden, round8(c_in)
+    N = 8 * H
+    W = torch.zeros(f_in, ch, N, dtype=torch.float64)
+    bias = torch.zeros(N, dtype=torch.float64)
+    for m, mod in enumerate((lstm_re, lstm_im)):
+        wih = _cpu(mod["weight_ih_l0"]).double()                     # (4H, c_in*f_in)
+        W[:, :c_in, m * 4 * H:(m + 1) * 4 * H] = wih.reshape(4 * H, c_in, f_in).permute(2, 1, 0)
+        bias[m * 4 * H:(m + 1) * 4 * H] = _cpu(mod["bias_ih_l0"]).double() + _cpu(mod["bias_hh_l0"]).double()
+    units, taps = [], []
+    for p in range(2):
+        begin = len(taps)
+        for f in range(f_in):
+            taps.append([0, f, 0, p * ch, ch, f * ch * N])
+        units.append([begin, f_in, p, 0, 0, 0])
+    return TapGemmPack(W.reshape(-1), bias, units, taps, N, 2, N, False, 0.0, device)
+
+
+def pack_lstm_inproj1(lstm_re, lstm_im, hidden, device, layer=1):
+    """Layer>=1 input projection: A = hseq of the previous layer [4 streams][R][H]; unit (m,p) uses
+    module m's weight_ih_l{layer} and writes plane m*2+p of G1[4][R][4H]."""
+    H = hidden
+    N = 4 * H
+    W = torch.zeros(2, H, N, dtype=torch.float64)
+    bias = torch.zeros(2 * N, dtype=torch.float64)
+    for m, mod in enumerate((lstm_re, lstm_im)):
+        W[m] = _cpu(mod["weight_ih_l%d" % layer]).double().t()
+        bias[m * N:(m + 1) * N] = _cpu(mod["bias_ih_l%d" % layer]).double() + _cpu(mod["bias_hh_l%d" % layer]).double()
+    units, taps = [], []
+    for m in range(2):
+        for p in range(2):
+            taps.append([0, m * 2 + p, 0, 0, H, m * H * N])
+            units.append([len(taps) - 1, 1, m * 2 + p, 0, m * N, 0])
+    return TapGemmPack(W.reshape(-1), bias, units, taps, N, 4, N, False, 0.0, device)
+
+
+def pack_lstm_whh(lstm_re, lstm_im, layer, device):
+    return torch.stack((_cpu(lstm_re["weight_hh_l%d" % layer]), _cpu(lstm_im["weight_hh_l%d" % layer]))) \
+        .to(torch.float32).contiguous().to(device)
+
+
+def pack_dense(w_read, b_read, w_imag, b_imag, c_out, f_out, device):
+    """ComplexDense (no cross terms, model/complex_progress.py:L83-89) followed by the reshape/permute
+    to (B, C, F, T) (model/pvae_module.py:L2085-2088): output feature n = c*f_out + f goes to plane f,
+    channel part*ch_c + c.  Input: z planes [1][R][2*ch_z]."""
+    zdim = w_read.shape[1]
+    ch_z, ch_c = round8(zdim), round8(c_out)
+    N = ch_c
+    W = torch.zeros(2, f_out, ch_z, N, dtype=torch.float64)
+    bias = torch.zeros(2, f_out, N, dtype=torch.float64)
+    for part, (w, b) in enumerate(((w_read, b_read), (w_imag, b_imag))):
+        w = _cpu(w).double().reshape(c_out, f_out, zdim)             # [c][f][k]
+        W[part, :, :zdim, :c_out] = w.permute(1, 2, 0)
+        bias[part, :, :c_out] = _cpu(b).double().reshape(c_out, f_out).t()
+    units, taps = [], []
+    for part in range(2):
+        for f in range(f_out):
+            taps.append([0, 0, 0, part * ch_z, ch_z, (part * f_out + f) * ch_z * N])
+            units.append([len(taps) - 1, 1, f, part * ch_c, (part * f_out + f) * N, 0])
+    return TapGemmPack(W.reshape(-1), bias.reshape(-1), units, taps, N, f_out, 2 * ch_c, False, 0.0, device)
+
+
+def hann_periodic(win):
+    n = torch.arange(win, dtype=torch.float64)
+    return 0.5 * (1.0 - torch.cos(2 * math.pi * n / win))
+
+
+def pack_stft_basis(n_fft, win, device):
+    """[win][ncol_pad] analysis basis: column 2k = cos(2 pi (j+off) k / n_fft) w[j], 2k+1 = -sin(..) w[j]."""
+    nb = n_fft // 2 + 1
+    ncol = 2 * nb
+    ncol_pad = (ncol + 127) // 128 * 128
+    off = (n_fft - win) // 2
+    j = torch.arange(win, dtype=torch.float64) + off
+    k = torch.arange(nb, dtype=torch.float64)
+    ang = 2 * math.pi * torch.outer(j, k) / n_fft
+    w = hann_periodic(win)[:, None]
+    basis = torch.zeros(win, ncol_pad, dtype=torch.float64)
+    basis[:, 0:ncol:2] = torch.cos(ang) * w
+    basis[:, 1:ncol:2] = -torch.sin(ang) * w
+    return basis.to(torch.float32).contiguous().to(device)
+
+
+def pack_istft_basis(n_fft, win, device):
+    """[kpad][ncol_pad] synthesis basis (rows 2k / 2k+1 = re / im of bin k) and w^2 [win]."""
+    nb = n_fft // 2 + 1
+    kpad = (2 * nb + 15) // 16 * 16
+    ncol_pad = (win + 127) // 128 * 128
+    off = (n_fft - win) // 2
+    j = torch.arange(win, dtype=torch.float64) + off
+    k = torch.arange(nb, dtype=torch.float64)
+    ck = torch.full((nb,), 2.0, dtype=torch.float64)
+    ck[0] = 1.0
+    ck[-1] = 1.0
+    ang = 2 * math.pi * torch.outer(k, j) / n_fft
+    w = hann_periodic(win)[None, :]
+    basis = torch.zeros(kpad, ncol_pad, dtype=torch.float64)
+    basis[0:2 * nb:2, :win] = ck[:, None] / n_fft * torch.cos(ang) * w
+    basis[1:2 * nb:2, :win] = -ck[:, None] / n_fft * torch.sin(ang) * w
+    wsq = (hann_periodic(win) ** 2)
+    return basis.to(torch.float32).contiguous().to(device), wsq.to(torch.float32).to(device)

@@ -1,0 +1,134 @@
+/*
+ * idv.h — C ABI of libidv_b200.so: the B200 (sm_100a) kernels behind the I-DCCRN-VAE enhancement
+ * forward path.  The reference (iris1997jiatong/I-DCCRN-VAE) is pure PyTorch and has no FFI; each
+ * entry point below names the reference call site (file:line under /root/reference) whose library
+ * kernels it replaces.  See INTEGRATION.md for the ctypes binding the Python wrappers use.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named h_*; nothing is allocated internally;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value: 0 = ok, otherwise an IDV_E_* code; idv_last_error() gives the message of the
+ *     last failure on the calling thread.  Nothing throws across the boundary;
+ *   - all floating point is IEEE fp32.
+ *
+ * Internal activation layout ("planes"): fp32 [F][R][Cp] with
+ *     R  = NB * Tp,  Tp = T + 1,  row(b, t) = b*Tp + 1 + t,  row(b, -1) = b*Tp is an all-zero
+ *          causal pad row (the reference's left time padding, model/complex_progress.py:L16-22);
+ *     Cp = 2*Ch, Ch = C rounded up to 8: real part of complex channel c at c, imaginary at Ch + c.
+ * "user" layout is the reference's (B, C, F, T, 2) fp32 with re/im interleaved innermost.
+ */
+#ifndef IDV_H_
+#define IDV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDV_OK 0
+#define IDV_E_ARG 1      /* bad argument / unsupported shape */
+#define IDV_E_CUDA 2     /* CUDA runtime error (message has the cudaError string) */
+#define IDV_E_RESOURCE 3 /* kernel cannot be made resident (cooperative launch too large) */
+
+#define IDV_ABI_VERSION 1
+
+int idv_abi_version(void);
+const char* idv_last_error(void);
+/* SM count of the current device (grids are sized against it). */
+int idv_device_sm_count(int* out);
+
+/* ---- tap-GEMM descriptors -------------------------------------------------------------------
+ * One launch computes, for every unit u, output rows r in [0,R) and columns n in [0,N):
+ *   out[u.out_f][r][u.out_ch_off + n] =
+ *       act( bias[u.bias_off + n] + sum_{tap in u} sum_{c < tap.kc}
+ *            A_{tap.src}[tap.f_in][r - tap.dt][tap.ch_off + c] * W[tap.w_off + c*N + n] )
+ * rows outside [0, R) read as zero; if Tp > 0, output rows with r % Tp == 0 are written as 0.
+ * act = PReLU(slope) if apply_prelu else identity.  A complex (transposed) convolution, the LSTM
+ * input projection and the complex dense layer are all instances (see pack.py).            */
+typedef struct {
+  int32_t src, f_in, dt, ch_off, kc, w_off;
+} idv_tap_t;
+typedef struct {
+  int32_t tap_begin, n_taps, out_f, out_ch_off, bias_off, reserved;
+} idv_unit_t;
+
+/* replaces nn.Conv2d x4 + sub/add/slice/stack + ComplexBatchNormal(eval) + nn.PReLU
+ * (model/complex_progress.py:L16-22, L161-209; model/pvae_module.py:L64-68), nn.ConvTranspose2d x4
+ * + torch.cat skip (complex_progress.py:L244-250; pvae_module.py:L2092-2099, L2556-2568), the
+ * nn.LSTM input projections (complex_progress.py:L58-61) and ComplexDense (L83-89).              */
+int idv_tapgemm_f32(const float* a0, int a0_ld, int64_t a0_plane,
+                    const float* a1, int a1_ld, int64_t a1_plane,
+                    int R, int Tp,
+                    const float* w, const float* bias, int N,
+                    const idv_unit_t* units, const idv_tap_t* taps, int n_units,
+                    float* out, int out_ld, int64_t out_plane,
+                    int apply_prelu, float prelu_slope, void* stream);
+
+/* ---- STFT / iSTFT -----------------------------------------------------------------------------
+ * replaces torch.stft at model/pvae_module.py:L22 (n_fft 512, hop, win, periodic Hann, center,
+ * reflect pad, onesided).  basis: [win][2*(n_fft/2+1)] fp32, column 2k = cos*w, 2k+1 = -sin*w
+ * (built by pack.py).  x: (B, L) -> out: (B, n_fft/2+1, T, 2), T = L/hop + 1.                    */
+int idv_stft_fwd(const float* x, int B, int L, const float* basis, int n_fft, int hop, int win,
+                 float* out, void* stream);
+/* replaces torch.istft at model/pvae_module.py:L41.  spec: (B, n_fft/2+1, T, 2) fp32;
+ * basis: [2*(n_fft/2+1)][win] (synthesis window, 1/n_fft and c_k folded); wsq: [win] = w^2;
+ * frames: workspace (B*T, win) fp32; out: (B, hop*(T-1)).                                        */
+int idv_istft_fwd(const float* spec, int B, int T, const float* basis, const float* wsq,
+                  int n_fft, int hop, int win, float* frames, float* out, void* stream);
+
+/* ---- first encoder layer (Cin = 1) -------------------------------------------------------------
+ * Encoder 0: causal ComplexConv2d(1 -> Cout, (5,2), stride (2,1), pad (2,1)) + CBN(eval) + PReLU,
+ * reading the user-layout STFT (B,257,T,2) and writing planes [Fout][R][2*Cout].
+ * w: [10 taps (kf*2+kt)][2 (re,im in)][2*Cout] with CBN folded, bias: [2*Cout].                 */
+int idv_enc0_fwd(const float* stft, int B, int Fin, int T, const float* w, const float* bias,
+                 int Cout, float prelu_slope, float* out, void* stream);
+
+/* ---- last decoder layer (Cout = 1) + reconstruction head ---------------------------------------
+ * Decoder 5: causal ComplexConvTranspose2d(Cin -> 1) + CBN(eval) + PReLU (+ mask head,
+ * model/pvae_module.py:L2594-2609 / L224-234) writing `predict` in user layout (NBdec, Fout, T, 2).
+ * p: planes [Fin][R][p_cp]; skip: planes [Fin][R][s_cp] or NULL (zero skip).
+ * w: [10 taps (kf*2+kt)][p_cp + s_cp][2], bias[2].  stft_x: (NBdec/?,Fout,T,2) noisy STFT rows
+ * for this pass (mask head only, may be NULL when mask == 0); out_bstride lets a pass write
+ * every S-th utterance of the (B*S) batch: out utterance index = b*out_bmul + out_boff.          */
+int idv_dec5_head_fwd(const float* p, int p_cp, const float* skip, int s_cp, int NB, int Fin, int T,
+                      const float* w, const float* bias, float prelu_slope, int mask,
+                      const float* stft_x, float* predict, int out_bmul, int out_boff, void* stream);
+
+/* ---- complex LSTM ------------------------------------------------------------------------------
+ * Recurrent part of one nn.LSTM layer for the four (module, input-part) streams of ComplexLSTM
+ * (model/complex_progress.py:L58-74), gates i,f,g,o.  g: pre-computed input projections incl. both
+ * biases; stream (m,p) starts at g + m*g_m_off + p*g_p_off, row stride g_ld.  whh: [2][4H][H]
+ * (lstm_re, lstm_im).  hseq: [4 streams (m*2+p)][R][H]; the kernel zeroes the pad rows itself.
+ * sync: 2 x uint32 workspace, zeroed by the call.  Cooperative launch.                           */
+int idv_lstm_recurrent_fwd(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld,
+                           const float* whh, int NB, int T, int H, float* hseq,
+                           unsigned int* sync, void* stream);
+/* Combine the four streams (real = rr - ii, imag = ir + ri), emit the user-layout latent
+ * (NB, T, H, 2).  Replaces the stack/permute at complex_progress.py:L62-73, pvae_module.py:L2247. */
+int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, float* latent, void* stream);
+/* reparameterization (model/pvae_module.py:L2177-2231).  latent: (NB,T,Htot,2); the (mu, log
+ * sigma, delta) triplet starts at channel ch0 (zdim each).  eps_r/eps_i: (NB,S,T,zdim) or NULL ->
+ * Philox4x32-10 N(0,1) from (seed, offset).  z: (NB*S, T, zdim, 2).                             */
+int idv_reparam_fwd(const float* latent, int NB, int T, int Htot, int ch0, int zdim, int S,
+                    const float* eps_r, const float* eps_i, uint64_t seed, uint64_t offset,
+                    float* z, void* stream);
+
+/* ---- layout conversion at the module boundary --------------------------------------------------*/
+/* planes [F][R][Cp] -> user (NB, C, F, T, 2) */
+int idv_planes_to_user(const float* planes, int NB, int C, int F, int T, float* user, void* stream);
+/* user (NB, C, F, T, 2) -> planes (pad rows and pad channels written as zero) */
+int idv_user_to_planes(const float* user, int NB, int C, int F, int T, float* planes, void* stream);
+/* z (NB*S, T, zdim, 2) sample s -> planes [1][NB*Tp][2*zdim] */
+int idv_z_to_planes(const float* z, int NB, int S, int s, int T, int zdim, float* planes, void* stream);
+
+/* stand-alone ComplexBatchNormal.forward(x, train=False) (model/complex_progress.py:L161-209) on the
+ * reference layout x: (outer, C, inner, 2).  zb: [C][6] = Zrr, Zri, Zir, Zii, b'_r, b'_i with
+ * b' = beta - Z mu.                                                                */
+int idv_cbn_eval_user(const float* x, int64_t outer, int C, int64_t inner, const float* zb, float* out,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDV_H_ */

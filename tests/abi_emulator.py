@@ -1,0 +1,213 @@
+"""TEST DOUBLE of the C ABI (include/idv.h) in plain torch on the CPU.
+
+Each function restates the *contract* written in the header (not the kernels) so that the host side
+of the package — weight packing, CBN folding, tap tables, plane layout, per-sample decoder passes,
+module wiring, state_dict handling — can be checked against the reference goldens in the CPU-only
+test tier.  It is injected by the ``emulated_abi`` fixture (tests/conftest.py) via monkeypatching
+``lib.call``; the product never imports this file and has no CPU path of its own.
+"""
+import math
+
+import torch
+
+D = torch.float64
+
+
+def _flat(t):
+    return t.view(-1)
+
+
+def idv_tapgemm_f32(a0, a0_ld, a0_plane, a1, a1_ld, a1_plane, R, Tp, w, bias, N, units, taps, n_units, out,
+                    out_ld, out_plane, apply_prelu, slope):
+    taps_l, units_l = taps.tolist(), units.tolist()
+    assert len(units_l) == n_units
+    for (tap_begin, n_taps, out_f, out_ch_off, bias_off, _) in units_l:
+        acc = torch.zeros(R, N, dtype=D)
+        for (src, f_in, dt, ch_off, kc, w_off) in taps_l[tap_begin:tap_begin + n_taps]:
+            a, ld, plane = (a0, a0_ld, a0_plane) if src == 0 else (a1, a1_ld, a1_plane)
+            A = _flat(a)[f_in * plane:f_in * plane + R * ld].view(R, ld)[:, ch_off:ch_off + kc].to(D)
+            if dt > 0:
+                A = torch.cat((torch.zeros(dt, kc, dtype=D), A[:R - dt]), 0)
+            elif dt < 0:
+                A = torch.cat((A[-dt:], torch.zeros(-dt, kc, dtype=D)), 0)
+            W = _flat(w)[w_off:w_off + kc * N].view(kc, N).to(D)
+            acc += A @ W
+        acc += _flat(bias)[bias_off:bias_off + N].to(D)
+        if apply_prelu:
+            acc = torch.where(acc > 0, acc, slope * acc)
+        if Tp > 0:
+            acc[torch.arange(R) % Tp == 0] = 0
+        _flat(out)[out_f * out_plane:out_f * out_plane + R * out_ld].view(R, out_ld)[:, out_ch_off:out_ch_off + N] = \
+            acc.to(torch.float32)
+
+
+def idv_stft_fwd(x, B, L, basis, n_fft, hop, win, out):
+    T = L // hop + 1
+    nb = n_fft // 2 + 1
+    off = (n_fft - win) // 2
+    xp = torch.nn.functional.pad(x.view(B, 1, L).to(D), (n_fft // 2, n_fft // 2), mode="reflect")[:, 0]
+    frames = xp.unfold(1, n_fft, hop)[:, :T, off:off + win]                      # (B, T, win)
+    y = frames @ basis[:, :2 * nb].to(D)                                          # (B, T, 2nb)
+    out.copy_(y.view(B, T, nb, 2).permute(0, 2, 1, 3).to(torch.float32))
+
+
+def idv_istft_fwd(spec, B, T, basis, wsq, n_fft, hop, win, frames, out):
+    nb = n_fft // 2 + 1
+    off = (n_fft - win) // 2
+    A = spec.view(B, nb, T, 2).permute(0, 2, 1, 3).reshape(B * T, 2 * nb).to(D)
+    fr = A @ basis[:2 * nb, :win].to(D)
+    frames.view(B * T, win).copy_(fr.to(torch.float32))
+    total = n_fft + hop * (T - 1)
+    y = torch.zeros(B, total, dtype=D)
+    env = torch.zeros(total, dtype=D)
+    fr = fr.view(B, T, win)
+    for t in range(T):
+        y[:, t * hop + off:t * hop + off + win] += fr[:, t]
+        env[t * hop + off:t * hop + off + win] += wsq.to(D)
+    h = n_fft // 2
+    out.copy_((y[:, h:total - h] / env[h:total - h]).to(torch.float32))
+
+
+def idv_enc0_fwd(stft, B, Fin, T, w, bias, Cout, slope, out):
+    N = 2 * Cout
+    Fout = (Fin + 4 - 5) // 2 + 1
+    Tp = T + 1
+    x = stft.view(B, Fin, T, 2).to(D)
+    xpad = torch.zeros(B, Fin + 4, T + 1, 2, dtype=D)                             # freq pad 2/2, time pad 1 left
+    xpad[:, 2:2 + Fin, 1:] = x
+    W = w.view(10, 2, N).to(D)
+    res = torch.zeros(Fout, B, Tp, N, dtype=D)
+    for kf in range(5):
+        for kt in range(2):
+            sl = xpad[:, kf:kf + 2 * Fout - 1:2, kt:kt + T]                       # (B, Fout, T, 2)
+            res[:, :, 1:] += torch.einsum("bftp,pn->fbtn", sl, W[kf * 2 + kt])
+    res[:, :, 1:] += bias.to(D)
+    res = torch.where(res > 0, res, slope * res)
+    res[:, :, 0] = 0
+    out.copy_(res.reshape(-1).to(torch.float32))
+
+
+def idv_dec5_head_fwd(p, p_cp, skip, s_cp, NB, Fin, T, w, bias, slope, mask, stft_x, predict, out_bmul, out_boff):
+    Tp = T + 1
+    R = NB * Tp
+    Fout = 2 * Fin - 1
+    if skip is None:
+        s_cp = 0
+    A = _flat(p)[:Fin * R * p_cp].view(Fin, R, p_cp).to(D)
+    if s_cp:
+        A = torch.cat((A, _flat(skip)[:Fin * R * s_cp].view(Fin, R, s_cp).to(D)), 2)
+    W = w.view(10, p_cp + s_cp, 2).to(D)
+    y = torch.zeros(Fout, R, 2, dtype=D)
+    for fo in range(Fout):
+        for kf in range(5):
+            if (fo + 2 - kf) % 2:
+                continue
+            fi = (fo + 2 - kf) // 2
+            if fi < 0 or fi >= Fin:
+                continue
+            for kt in range(2):
+                Ash = A[fi] if kt == 0 else torch.cat((torch.zeros(1, A.shape[2], dtype=D), A[fi, :R - 1]), 0)
+                y[fo] += Ash @ W[kf * 2 + kt]
+    y += bias.to(D)
+    y = torch.where(y > 0, y, slope * y)
+    y = y.view(Fout, NB, Tp, 2)[:, :, 1:].permute(1, 0, 2, 3)                     # (NB, Fout, T, 2)
+    if mask:
+        yr, yi = y[..., 0], y[..., 1]
+        mag = torch.tanh(torch.sqrt(yr ** 2 + yi ** 2))
+        ph = torch.atan2(yi / (mag + 1e-8), yr / (mag + 1e-8))
+        X = stft_x.view(-1, Fout, T, 2)[:NB].to(D)
+        in_mag = torch.sqrt(X[..., 0] ** 2 + X[..., 1] ** 2)
+        in_ph = torch.atan2(X[..., 1], X[..., 0])
+        y = torch.stack((in_mag * mag * torch.cos(in_ph + ph), in_mag * mag * torch.sin(in_ph + ph)), -1)
+    pv = predict.view(-1, Fout, T, 2)
+    pv[out_boff::out_bmul][:NB] = y.to(torch.float32)
+
+
+def idv_lstm_recurrent_fwd(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, hseq, sync):
+    Tp = T + 1
+    R = NB * Tp
+    hs = hseq.view(4, R, H)
+    W = whh.view(2, 4 * H, H).to(D)
+    gf = _flat(g)
+    rows0 = torch.arange(NB) * Tp
+    for m in range(2):
+        for p in range(2):
+            base = m * g_m_off + p * g_p_off
+            h = torch.zeros(NB, H, dtype=D)
+            c = torch.zeros(NB, H, dtype=D)
+            hs[m * 2 + p, rows0] = 0
+            for t in range(T):
+                rows = rows0 + 1 + t
+                idx = base + rows[:, None] * g_ld + torch.arange(4 * H)[None, :]
+                a = gf[idx].to(D) + h @ W[m].t()
+                i, f, gg, o = a[:, :H], a[:, H:2 * H], a[:, 2 * H:3 * H], a[:, 3 * H:]
+                c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+                h = torch.sigmoid(o) * torch.tanh(c)
+                hs[m * 2 + p, rows] = h.to(torch.float32)
+
+
+def idv_lstm_combine_fwd(hseq, NB, T, H, latent):
+    Tp = T + 1
+    hs = hseq.view(4, NB, Tp, H)[:, :, 1:]
+    rr, ir, ri, ii = hs[0], hs[1], hs[2], hs[3]
+    latent.copy_(torch.stack((rr - ii, ir + ri), -1))
+
+
+def idv_reparam_fwd(latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, seed, offset, z):
+    assert eps_r is not None, "the emulator only supports supplied eps"
+    e = 1e-6
+    lat = latent.view(NB, T, Htot, 2)
+    mu, ls, dl = lat[:, :, ch0:ch0 + zdim], lat[:, :, ch0 + zdim:ch0 + 2 * zdim], lat[:, :, ch0 + 2 * zdim:ch0 + 3 * zdim]
+    sig = torch.exp(ls[..., 0])
+    dr, di = dl[..., 0], dl[..., 1]
+    ad = torch.sqrt(dr * dr + di * di + e)
+    tmp = sig * 0.99 / (ad + e)
+    cl = ad >= sig - 1e-3
+    dr, di = torch.where(cl, dr * tmp, dr), torch.where(cl, di * tmp, di)
+    ad = torch.sqrt(dr * dr + di * di + e)
+    den = torch.sqrt(2 * (sig + dr) + e)
+    zr = mu[..., 0][:, None] + ((sig + dr) / (den + e))[:, None] * eps_r.view(NB, S, T, zdim)
+    zi = mu[..., 1][:, None] + (di / (den + e))[:, None] * eps_r.view(NB, S, T, zdim) + \
+        (torch.sqrt(sig * sig - ad * ad + e) / (den + e))[:, None] * eps_i.view(NB, S, T, zdim)
+    z.copy_(torch.stack((zr, zi), -1).view(NB * S, T, zdim, 2))
+
+
+def _r8(c):
+    return (c + 7) // 8 * 8
+
+
+def idv_planes_to_user(planes, NB, C, F, T, user):
+    Ch, Tp = _r8(C), T + 1
+    p = _flat(planes)[:F * NB * Tp * 2 * Ch].view(F, NB, Tp, 2, Ch)[:, :, 1:, :, :C]    # (F,NB,T,2,C)
+    user.copy_(p.permute(1, 4, 0, 2, 3))
+
+
+def idv_user_to_planes(user, NB, C, F, T, planes):
+    Ch, Tp = _r8(C), T + 1
+    n = F * NB * Tp * 2 * Ch
+    _flat(planes)[:n] = 0
+    p = _flat(planes)[:n].view(F, NB, Tp, 2, Ch)
+    p[:, :, 1:, :, :C] = user.view(NB, C, F, T, 2).permute(2, 0, 3, 4, 1)
+
+
+def idv_z_to_planes(z, NB, S, s, T, zdim, planes):
+    Ch, Tp = _r8(zdim), T + 1
+    n = NB * Tp * 2 * Ch
+    _flat(planes)[:n] = 0
+    p = _flat(planes)[:n].view(NB, Tp, 2, Ch)
+    p[:, 1:, :, :zdim] = z.view(NB, S, T, zdim, 2)[:, s].permute(0, 1, 3, 2)
+
+
+def idv_cbn_eval_user(x, outer, C, inner, zb, out):
+    v = x.view(outer, C, inner, 2)
+    k = zb.view(C, 6)[None, :, None, :]
+    o = out.view(outer, C, inner, 2)
+    o[..., 0] = k[..., 0] * v[..., 0] + k[..., 1] * v[..., 1] + k[..., 4]
+    o[..., 1] = k[..., 2] * v[..., 0] + k[..., 3] * v[..., 1] + k[..., 5]
+
+
+TABLE = {k: v for k, v in globals().items() if k.startswith("idv_")}
+
+
+def call(name, *args):
+    TABLE[name](*args)

@@ -1,0 +1,92 @@
+"""CPU tier: the package's host logic (packing, CBN fold, tap tables, plane layout, module wiring) run
+over the emulated C-ABI contract must reproduce the reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+import common as C
+
+TOL = 2e-5   # fp32 golden vs folded weights evaluated through an fp64 emulator
+
+
+@pytest.mark.parametrize("tag,latent_num,S,dec_kind,recon,seed", [
+    ("vae_l1_zero_full", 1, 1, "skip_prepare", "real_imag", 0),
+    ("vae_l2_sig_mask_full", 2, 1, "twophase", "mask", 1),
+])
+def test_vae_layers_match_reference(emulated_abi, golden, tag, latent_num, S, dec_kind, recon, seed):
+    g = golden(tag)
+    B, L = int(g["B"]), int(g["L"])
+    enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cpu")
+    dec.keep_decoder_outputs = True
+    x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cpu")
+    out = C.run_vae(enc, dec, x, eps, dec_kind)
+    errs = {"stft_x": C.rel_l2(out["stft_x"], g["stft_x"])}
+    for i in range(6):
+        errs["enc%d" % i] = C.rel_l2(out["skiper"][i], g["enc%d" % i])
+    for k in ("miu", "log_sigma", "delta", "z_speech", "predict", "recon_sig"):
+        errs[k] = C.rel_l2(out[k], g[k])
+    if latent_num == 2:
+        errs["z_noise"] = C.rel_l2(out["z_noise"], g["z_noise"])
+    for i in range(5):
+        errs["dec%d" % i] = C.rel_l2(dec.decoder_outputs[i], g["dec%d" % i])
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, errs
+
+
+@pytest.mark.parametrize("tag,latent_num,S,dec_kind,recon,seed", [
+    ("vae_l2_sig_mask_s2_e2e", 2, 2, "twophase", "mask", 3),
+    ("vae_l1_sig_ri_e2e", 1, 1, "twophase", "real_imag", 4),
+])
+def test_vae_e2e_match_reference(emulated_abi, golden, tag, latent_num, S, dec_kind, recon, seed):
+    g = golden(tag)
+    B, L = int(g["B"]), int(g["L"])
+    enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cpu")
+    x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cpu")
+    out = C.run_vae(enc, dec, x, eps, dec_kind)
+    errs = {k: C.rel_l2(out[k], g[k]) for k in ("stft_x", "miu", "log_sigma", "delta", "z_speech", "predict", "recon_sig")}
+    assert all(v < TOL for v in errs.values()), errs
+
+
+def test_dccrn_matches_reference(emulated_abi, golden):
+    import idccrn_b200 as M
+    from idccrn_b200.synth import fill_state_dict, synth_waveform
+    g = golden("dccrn_mask_e2e")
+    B, L, seed = int(g["B"]), int(g["L"]), int(g["seed"])
+    m = M.DCCRN_(C.NFFT, C.HOP, M.get_net_params(), True, "cpu", C.WIN, C.SKIPS, "mask", False, None, None)
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed), strict=True)
+    x = synth_waveform(B, L, seed=1234 + seed)
+    with torch.no_grad():
+        clean, pred = m(x, train=False)
+    errs = {"latent": C.rel_l2(m.std_DCCRN.latent, g["latent"]),
+            "predict": C.rel_l2(torch.view_as_real(pred), g["predict"]),
+            "clean": C.rel_l2(clean, g["clean"])}
+    assert all(v < TOL for v in errs.values()), errs
+
+
+def test_primitives_match_reference(emulated_abi, golden):
+    import idccrn_b200 as M
+    from idccrn_b200.synth import fill_state_dict
+    g = golden("primitives")
+    seed = 3
+    enc = M.Encoder(3, 5, (5, 2), (2, 1), (5, 9, 1), padding=(2, 1), causal=True)
+    enc.load_state_dict(fill_state_dict(enc.state_dict(), seed))
+    dec = M.Decoder(4, 3, (5, 2), (2, 1), (3, 9, 1), padding=(2, 0), causal=True)
+    dec.load_state_dict(fill_state_dict(dec.state_dict(), seed))
+    lstm = M.ComplexLSTM(20, 8, "cpu", num_layers=2)
+    lstm.load_state_dict(fill_state_dict(lstm.state_dict(), seed))
+    dense = M.ComplexDense(128, 24)
+    dense.load_state_dict(fill_state_dict(dense.state_dict(), seed))
+    t = lambda k: torch.from_numpy(g[k])
+    with torch.no_grad():
+        errs = {"enc": C.rel_l2(enc(t("enc_in"), False), g["enc_out"]),
+                "dec": C.rel_l2(dec(t("dec_in"), False), g["dec_out"]),
+                "lstm": C.rel_l2(lstm(t("lstm_in")), g["lstm_out"]),
+                "dense": C.rel_l2(dense(t("dense_in")), g["dense_out"])}
+    assert all(v < TOL for v in errs.values()), errs
+
+
+def test_train_mode_raises_loudly(emulated_abi):
+    enc, dec = C.build_vae(1, 1, "skip_prepare", "real_imag", 0, "cpu")
+    x, eps = C.vae_inputs(1, 400, 1, 1, 0, "cpu")
+    with pytest.raises(NotImplementedError):
+        enc(x)        # reference default is train=True
