@@ -61,15 +61,41 @@ def load():
     return lib
 
 
+# kernels launched by each entry point (memset nodes not counted)
+KERNELS_PER_CALL = {"idv_istft_fwd": 2}
+LAUNCHES = [0]          # running count of kernel launches issued through call()
+_PROFILE_HOOK = None
+
+
+def set_profile_hook(hook):
+    """hook(name, (start_event, end_event)) is invoked for every call (CUDA events recorded on the launching
+    stream); None disables.  Used by bench.py for the per-kernel device times."""
+    global _PROFILE_HOOK
+    _PROFILE_HOOK = hook
+
+
+def resolve_profile(prof):
+    """{name: [(e0, e1), ...]} -> {name: [ms, ...]} (call after a device synchronize)."""
+    return {k: [e0.elapsed_time(e1) for (e0, e1) in v] for k, v in prof.items()}
+
+
 def call(name, *args):
     """Call a C-ABI entry point.  torch tensors are passed as device pointers (they must be contiguous
     CUDA tensors); the current CUDA stream is appended as the trailing ``stream`` argument."""
     lib = load()
     conv = [ptr(a) if isinstance(a, torch.Tensor) else a for a in args]
     conv.append(torch.cuda.current_stream().cuda_stream)
+    hook = _PROFILE_HOOK
+    if hook is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib, name)(*conv)
     if rc != 0:
         raise RuntimeError("%s failed (code %d): %s" % (name, rc, lib.idv_last_error().decode()))
+    LAUNCHES[0] += KERNELS_PER_CALL.get(name, 1)
+    if hook is not None:
+        e1.record()
+        hook(name, (e0, e1))
 
 
 def ptr(t):

@@ -1,0 +1,129 @@
+"""GPU tier: every C-ABI entry point against the torch restatement of its contract (tests/abi_emulator.py)
+on edge-case shapes: row counts that are not tile multiples, N tails, K chunks that are not multiples of
+the K step, two-source taps, single-frame / single-utterance inputs."""
+import pytest
+import torch
+
+import abi_emulator as E
+import common as C
+from idccrn_b200 import lib, pack
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(name, args, outs):
+    """args: list of CPU tensors / scalars / None; outs: indices of output tensors.  Returns max rel_l2."""
+    cpu = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
+    E.call(name, *cpu)
+    gpu = [a.cuda() if isinstance(a, torch.Tensor) else a for a in args]
+    lib.call(name, *gpu)
+    torch.cuda.synchronize()
+    return max(C.rel_l2(gpu[i], cpu[i]) for i in outs)
+
+
+def _rand(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.mark.parametrize("R,Tp,N,kcs,dts,two_src,prelu", [
+    (300, 0, 128, [16, 32], [0, 1], False, False),
+    (130, 13, 64, [64, 24], [1, 0], True, True),       # kc not a multiple of 16, N = 64 path, two sources
+    (1, 0, 16, [8], [0], False, True),                  # single row, N tail (16 < 64)
+    (517, 47, 384, [128, 128, 128], [0, 1, 0], True, True),
+])
+def test_tapgemm(R, Tp, N, kcs, dts, two_src, prelu):
+    F0, ld0, ld1 = 3, 136, 136
+    a0 = _rand(F0, R, ld0, seed=1)
+    a1 = _rand(F0, R, ld1, seed=2) if two_src else None
+    taps, woff = [], 0
+    for i, (kc, dt) in enumerate(zip(kcs, dts)):
+        src = 1 if (two_src and i % 2) else 0
+        taps.append([src, i % F0, dt, 8 if src == 0 else 4, kc, woff])
+        woff += kc * N
+    units = [[0, len(taps), 1, 4, N, 0], [0, 1, 0, 4, 0, 0]]
+    w = _rand(woff, seed=3) * 0.1
+    bias = _rand(2 * N, seed=4)
+    out_ld = N + 8
+    out = torch.zeros(2, R, out_ld)
+    args = [a0, ld0, R * ld0, a1, ld1 if two_src else 0, R * ld1 if two_src else 0, R, Tp, w, bias, N,
+            torch.tensor(units, dtype=torch.int32), torch.tensor(taps, dtype=torch.int32), 2, out, out_ld,
+            R * out_ld, 1 if prelu else 0, 0.2]
+    assert _both("idv_tapgemm_f32", args, [14]) < 1e-5
+
+
+@pytest.mark.parametrize("B,L", [(1, 300), (3, 6400), (2, 12799)])
+def test_stft_istft(B, L):
+    basis = pack.pack_stft_basis(512, 400, "cpu")
+    T = L // 100 + 1
+    x = _rand(B, L, seed=5)
+    out = torch.zeros(B, 257, T, 2)
+    assert _both("idv_stft_fwd", [x, B, L, basis, 512, 100, 400, out], [7]) < 1e-5
+    ib, wsq = pack.pack_istft_basis(512, 400, "cpu")
+    spec = _rand(B, 257, T, 2, seed=6)
+    frames, y = torch.zeros(B * T, 400), torch.zeros(B, 100 * (T - 1))
+    assert _both("idv_istft_fwd", [spec, B, T, ib, wsq, 512, 100, 400, frames, y], [8, 9]) < 1e-5
+
+
+@pytest.mark.parametrize("B,Fin,T,Cout", [(1, 257, 1, 32), (3, 33, 70, 16)])
+def test_enc0(B, Fin, T, Cout):
+    Fout = (Fin - 1) // 2 + 1
+    args = [_rand(B, Fin, T, 2, seed=7), B, Fin, T, _rand(10, 2, 2 * Cout, seed=8), _rand(2 * Cout, seed=9), Cout, 0.3,
+            torch.zeros(Fout * B * (T + 1) * 2 * Cout)]
+    assert _both("idv_enc0_fwd", args, [8]) < 1e-5
+
+
+@pytest.mark.parametrize("NB,Fin,T,p_cp,s_cp,mask,S", [(2, 9, 40, 64, 64, 1, 1), (3, 5, 7, 32, 0, 0, 2)])
+def test_dec5_head(NB, Fin, T, p_cp, s_cp, mask, S):
+    R, Fout = NB * (T + 1), 2 * Fin - 1
+    p = _rand(Fin, R, p_cp, seed=10)
+    p.view(Fin, NB, T + 1, p_cp)[:, :, 0] = 0
+    skip = None
+    if s_cp:
+        skip = _rand(Fin, R, s_cp, seed=11)
+        skip.view(Fin, NB, T + 1, s_cp)[:, :, 0] = 0
+    args = [p, p_cp, skip, s_cp, NB, Fin, T, _rand(10, p_cp + s_cp, 2, seed=12) * 0.1, _rand(2, seed=13), 0.25, mask,
+            _rand(NB, Fout, T, 2, seed=14), torch.zeros(NB * S, Fout, T, 2), S, S - 1]
+    assert _both("idv_dec5_head_fwd", args, [12]) < 1e-5
+
+
+@pytest.mark.parametrize("NB,T,H", [(1, 5, 8), (3, 20, 384), (64, 3, 128), (5, 4, 768)])
+def test_lstm_recurrent_and_combine(NB, T, H):
+    R = NB * (T + 1)
+    g = _rand(2, R, 8 * H, seed=15)
+    whh = _rand(2, 4 * H, H, seed=16) / (H ** 0.5)
+    hseq = torch.full((4, R, H), 7.0)
+    sync = torch.zeros(2, dtype=torch.int32)
+    assert _both("idv_lstm_recurrent_fwd", [g, 4 * H, R * 8 * H, 8 * H, whh, NB, T, H, hseq, sync], [8]) < 1e-5
+    hs = _rand(4, R, H, seed=17)
+    assert _both("idv_lstm_combine_fwd", [hs, NB, T, H, torch.zeros(NB, T, H, 2)], [4]) < 1e-6
+
+
+def test_reparam_supplied_eps():
+    NB, T, z, S = 3, 11, 128, 2
+    lat = _rand(NB, T, 6 * z, 2, seed=18)
+    args = [lat, NB, T, 6 * z, 3 * z, z, S, _rand(NB, S, T, z, seed=19), _rand(NB, S, T, z, seed=20), 0, 0,
+            torch.zeros(NB * S, T, z, 2)]
+    assert _both("idv_reparam_fwd", args, [11]) < 1e-5
+
+
+@pytest.mark.parametrize("NB,C_,F,T", [(2, 3, 5, 7), (1, 32, 129, 33), (3, 1, 4, 65)])
+def test_layout_roundtrip(NB, C_, F, T):
+    Cp = 2 * ((C_ + 7) // 8 * 8)
+    x = _rand(NB, C_, F, T, 2, seed=21)
+    planes = torch.full((F * NB * (T + 1) * Cp,), 3.0)
+    assert _both("idv_user_to_planes", [x, NB, C_, F, T, planes], [5]) < 1e-7
+    E.call("idv_user_to_planes", x, NB, C_, F, T, planes)
+    assert _both("idv_planes_to_user", [planes, NB, C_, F, T, torch.zeros_like(x)], [5]) < 1e-7
+    z = _rand(NB * 2, T, 16, 2, seed=22)
+    assert _both("idv_z_to_planes", [z, NB, 2, 1, T, 16, torch.full((NB * (T + 1) * 32,), 5.0)], [6]) < 1e-7
+    zb = _rand(C_, 6, seed=23)
+    assert _both("idv_cbn_eval_user", [x, NB, C_, F * T, zb, torch.zeros_like(x)], [5]) < 1e-6
+
+
+def test_bad_arguments_return_error_codes():
+    with pytest.raises(RuntimeError, match="idv_stft_fwd"):
+        lib.call("idv_stft_fwd", torch.zeros(1, 100).cuda(), 1, 100, torch.zeros(4).cuda(), 512, 100, 400,
+                 torch.zeros(4).cuda())          # L <= n_fft/2: reflect padding impossible
+    with pytest.raises(RuntimeError, match="H"):
+        lib.call("idv_lstm_recurrent_fwd", torch.zeros(4).cuda(), 0, 0, 4, torch.zeros(4).cuda(), 1, 1, 6,
+                 torch.zeros(4).cuda(), torch.zeros(2, dtype=torch.int32).cuda())

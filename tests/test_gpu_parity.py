@@ -1,0 +1,196 @@
+"""GPU tier (-m gpu): parity of the CUDA path, called through the C ABI, against
+  (1) the reference goldens in tests/golden/ (outputs of the real reference),
+  (2) the CPU oracle port run live on the same seeded inputs at sizes it finishes in seconds,
+  (3) size-independent properties at BASELINE config-2 size (B=64 x 4 s).
+Tolerances (north_star): rel-L2(waveform) <= 1e-4 and |delta SI-SNR| <= 0.01 dB."""
+import pytest
+import torch
+
+import common as C
+import idccrn_b200 as M
+from idccrn_b200.synth import fill_state_dict, synth_eps, synth_waveform
+from oracle import ref_port as P
+
+pytestmark = pytest.mark.gpu
+
+WAVE_TOL = 1e-4      # north_star gate
+STAGE_TOL = 2e-5     # fp32 kernels: every intermediate stage
+
+
+def _sisnr_gap_db(ours, ref, anchor):
+    """|SI-SDR(ours, anchor) - SI-SDR(ref, anchor)| with the input signal as the common anchor, and the
+    SI-SDR of ours w.r.t. the reference output (utils/eval_metrics.py:L49-64 formula)."""
+    ours, ref, anchor = ours.detach().cpu(), torch.as_tensor(ref).cpu(), anchor.detach().cpu()
+    n = min(ours.shape[-1], anchor.shape[-1])
+    gap = (P.si_sdr_db(ours[..., :n], anchor[..., :n]) - P.si_sdr_db(ref[..., :n], anchor[..., :n])).abs().max()
+    return float(gap), float(P.si_sdr_db(ours, ref).min())
+
+
+def test_extension_is_loaded_and_native():
+    from idccrn_b200 import lib
+    l = lib.load()
+    assert l.idv_abi_version() == 1
+    import ctypes
+    n = ctypes.c_int(0)
+    assert l.idv_device_sm_count(ctypes.byref(n)) == 0 and n.value > 0
+
+
+@pytest.mark.parametrize("tag,latent_num,S,dec_kind,recon,seed,full", [
+    ("vae_l1_zero_full", 1, 1, "skip_prepare", "real_imag", 0, True),
+    ("vae_l2_sig_mask_full", 2, 1, "twophase", "mask", 1, True),
+    ("vae_l1_zero_e2e", 1, 1, "skip_prepare", "real_imag", 2, False),
+    ("vae_l2_sig_mask_s2_e2e", 2, 2, "twophase", "mask", 3, False),
+    ("vae_l1_sig_ri_e2e", 1, 1, "twophase", "real_imag", 4, False),
+])
+def test_vae_vs_reference_golden(golden, tag, latent_num, S, dec_kind, recon, seed, full):
+    g = golden(tag)
+    B, L = int(g["B"]), int(g["L"])
+    enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cuda")
+    dec.keep_decoder_outputs = full
+    x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cuda")
+    out = C.run_vae(enc, dec, x, eps, dec_kind)
+    torch.cuda.synchronize()
+    errs = {k: C.rel_l2(out[k], g[k]) for k in ("stft_x", "miu", "log_sigma", "delta", "z_speech", "predict")}
+    if latent_num == 2:
+        errs["z_noise"] = C.rel_l2(out["z_noise"], g["z_noise"])
+    if full:
+        for i in range(6):
+            errs["enc%d" % i] = C.rel_l2(out["skiper"][i], g["enc%d" % i])
+        for i in range(5):
+            errs["dec%d" % i] = C.rel_l2(dec.decoder_outputs[i], g["dec%d" % i])
+    wave = C.rel_l2(out["recon_sig"], g["recon_sig"])
+    xrep = x.repeat_interleave(S, 0)
+    gap, sdr = _sisnr_gap_db(out["recon_sig"], g["recon_sig"], xrep)
+    print(tag, "wave rel_l2 %.2e  sisnr gap %.4f dB  sdr-vs-ref %.1f dB" % (wave, gap, sdr), errs)
+    assert all(v < STAGE_TOL for v in errs.values()), errs
+    assert wave < WAVE_TOL and gap < 0.01, (wave, gap)
+
+
+def test_dccrn_vs_reference_golden(golden):
+    g = golden("dccrn_mask_e2e")
+    B, L, seed = int(g["B"]), int(g["L"]), int(g["seed"])
+    m = M.DCCRN_(C.NFFT, C.HOP, M.get_net_params(), True, "cuda", C.WIN, C.SKIPS, "mask", False, None, None)
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed), strict=True)
+    m = m.cuda().eval()
+    x = synth_waveform(B, L, seed=1234 + seed).cuda()
+    with torch.no_grad():
+        clean, pred = m(x, train=False)
+    errs = {"latent": C.rel_l2(m.std_DCCRN.latent, g["latent"]),
+            "predict": C.rel_l2(torch.view_as_real(pred), g["predict"]), "clean": C.rel_l2(clean, g["clean"])}
+    gap, sdr = _sisnr_gap_db(clean, g["clean"], x)
+    print("dccrn", errs, gap, sdr)
+    assert errs["latent"] < STAGE_TOL and errs["predict"] < STAGE_TOL
+    assert errs["clean"] < WAVE_TOL and gap < 0.01
+
+
+def test_primitives_vs_reference_golden(golden):
+    g = golden("primitives")
+    seed = 3
+    enc = M.Encoder(3, 5, (5, 2), (2, 1), (5, 9, 1), padding=(2, 1), causal=True)
+    enc.load_state_dict(fill_state_dict(enc.state_dict(), seed))
+    dec = M.Decoder(4, 3, (5, 2), (2, 1), (3, 9, 1), padding=(2, 0), causal=True)
+    dec.load_state_dict(fill_state_dict(dec.state_dict(), seed))
+    lstm = M.ComplexLSTM(20, 8, "cuda", num_layers=2)
+    lstm.load_state_dict(fill_state_dict(lstm.state_dict(), seed))
+    dense = M.ComplexDense(128, 24)
+    dense.load_state_dict(fill_state_dict(dense.state_dict(), seed))
+    enc, dec, lstm, dense = enc.cuda(), dec.cuda(), lstm.cuda(), dense.cuda()
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    with torch.no_grad():
+        errs = {"enc": C.rel_l2(enc(t("enc_in"), False), g["enc_out"]),
+                "dec": C.rel_l2(dec(t("dec_in"), False), g["dec_out"]),
+                "lstm": C.rel_l2(lstm(t("lstm_in")), g["lstm_out"]),
+                "dense": C.rel_l2(dense(t("dense_in")), g["dense_out"])}
+        cbn = M.ComplexBatchNormal(5, 1, 1)
+        cbn.load_state_dict(fill_state_dict(cbn.state_dict(), seed))
+        xin = torch.randn(2, 5, 7, 9, 2, generator=torch.Generator().manual_seed(5))
+        want = P.cbn_eval(xin, cbn.state_dict(), "")
+        errs["cbn"] = C.rel_l2(cbn.cuda()(xin.cuda(), train=False), want)
+    assert all(v < STAGE_TOL for v in errs.values()), errs
+
+
+@pytest.mark.parametrize("B,L,latent_num,S,dec_kind,recon", [
+    (3, 16000, 1, 1, "skip_prepare", "real_imag"),      # T = 161: crosses the 128-row tiles, odd batch
+    (2, 25700, 2, 1, "twophase", "mask"),               # T = 258, H = 768 recurrent config
+    (5, 1300, 1, 3, "twophase", "mask"),                # S = 3 sample replication, short ragged length
+])
+def test_vae_vs_live_oracle(B, L, latent_num, S, dec_kind, recon):
+    seed = 11
+    enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cuda")
+    x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cuda")
+    out = C.run_vae(enc, dec, x, eps, dec_kind)
+    esd = {k: v.cpu() for k, v in enc.state_dict().items()}
+    dsd = {k: v.cpu() for k, v in dec.state_dict().items()}
+    with torch.no_grad():
+        st = P.vae_encoder_forward(esd, x.cpu(), C.ZDIM, latent_num, S, [e.cpu() for e in eps])
+        dd = P.vae_decoder_forward(dsd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], S, recon,
+                                   "zero" if dec_kind == "skip_prepare" else "sig")
+    errs = {"stft_x": C.rel_l2(out["stft_x"], st["stft_x"]), "enc5": C.rel_l2(out["skiper"][5], st["skiper"][5]),
+            "miu": C.rel_l2(out["miu"], st["miu_speech"]), "z": C.rel_l2(out["z_speech"], st["z_speech"]),
+            "predict": C.rel_l2(out["predict"], torch.view_as_real(dd["predict"]))}
+    wave = C.rel_l2(out["recon_sig"], dd["recon_sig"])
+    gap, sdr = _sisnr_gap_db(out["recon_sig"], dd["recon_sig"], x.repeat_interleave(S, 0))
+    print("live", (B, L, latent_num, S), "wave %.2e gap %.4f dB sdr %.1f dB" % (wave, gap, sdr), errs)
+    assert all(v < STAGE_TOL for v in errs.values()), errs
+    assert wave < WAVE_TOL and gap < 0.01
+
+
+def test_stft_istft_properties_full_size():
+    """Config-2 size (64 x 4 s): STFT linearity, exact istft(stft(x)) = x round trip, Parseval-type check
+    against torch.stft on a slice."""
+    stft = M.STFT(C.NFFT, C.HOP, C.WIN, "cuda")
+    istft = M.ISTFT(C.NFFT, C.HOP, C.WIN, "cuda")
+    x = synth_waveform(64, 64000, seed=5).cuda()
+    y = synth_waveform(64, 64000, seed=6).cuda()
+    X, Y = stft(x), stft(y)
+    assert X.shape == (64, 257, 641, 2)
+    lin = stft(2.0 * x - 3.0 * y)
+    assert C.rel_l2(lin, 2.0 * X - 3.0 * Y) < 1e-5
+    xr = istft(torch.view_as_complex(X))
+    assert xr.shape == (64, 64000)
+    assert C.rel_l2(xr, x) < 1e-5
+    ref = P.stft(x[:2].cpu())
+    assert C.rel_l2(X[:2], ref) < 1e-5
+
+
+def test_full_size_batch_rows_match_small_oracle_run():
+    """Utterances are independent: rows of the B=64 x 4 s CUDA run must equal the oracle run on those rows."""
+    seed, B, L = 21, 64, 64000
+    enc, dec = C.build_vae(1, 1, "skip_prepare", "real_imag", seed, "cuda")
+    x, eps = C.vae_inputs(B, L, 1, 1, seed, "cuda")
+    out = C.run_vae(enc, dec, x, eps, "skip_prepare")
+    rows = [0, 63]
+    esd = {k: v.cpu() for k, v in enc.state_dict().items()}
+    dsd = {k: v.cpu() for k, v in dec.state_dict().items()}
+    with torch.no_grad():
+        st = P.vae_encoder_forward(esd, x[rows].cpu(), C.ZDIM, 1, 1, [e[rows].cpu() for e in eps])
+        dd = P.vae_decoder_forward(dsd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], 1,
+                                   "real_imag", "zero")
+    wave = C.rel_l2(out["recon_sig"][rows], dd["recon_sig"])
+    mu = C.rel_l2(out["miu"][rows], st["miu_speech"])
+    gap, sdr = _sisnr_gap_db(out["recon_sig"][rows], dd["recon_sig"], x[rows])
+    print("full-size rows: wave %.2e mu %.2e gap %.4f dB sdr %.1f" % (wave, mu, gap, sdr))
+    assert torch.isfinite(out["recon_sig"]).all()
+    assert wave < WAVE_TOL and mu < WAVE_TOL and gap < 0.01
+
+
+def test_philox_eps_statistics():
+    """Default (no eps supplied) path: on-device Philox N(0,1); z - mu must have the closed-form scale."""
+    enc, dec = C.build_vae(1, 1, "skip_prepare", "real_imag", 0, "cuda")
+    x, eps = C.vae_inputs(4, 3200, 1, 1, 0, "cuda")
+    with torch.no_grad():
+        r0 = enc(x, train=False, eps=[torch.zeros_like(eps[0]), torch.zeros_like(eps[1])])
+        r1 = enc(x, train=False)
+        r2 = enc(x, train=False)
+    assert C.rel_l2(r0[0], torch.stack((r0[1][..., 0], r0[1][..., 1]), -1)) < 1e-6     # eps = 0 -> z = mu
+    d1, d2 = (r1[0] - r0[0]), (r2[0] - r0[0])
+    assert float(d1.abs().mean()) > 1e-3 and C.rel_l2(d1, d2) > 0.5                      # random, and re-drawn
+    sig = torch.exp(r0[2][..., 0])
+    ratio = float((d1[..., 0] ** 2).mean() / ((sig + r0[3][..., 0]) / 2).mean())
+    assert 0.3 < ratio < 3.0, ratio
+
+
+def test_cpu_tensor_is_rejected():
+    enc, dec = C.build_vae(1, 1, "skip_prepare", "real_imag", 0, "cuda")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        enc(torch.zeros(1, 800), train=False)
