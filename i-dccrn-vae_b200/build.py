@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
-    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcuda"])
+    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs)
     return LIB
 
 

@@ -9,7 +9,8 @@ namespace idv {
 // grid: (row tiles of 32, Fout); block 256 = 32 rows x 8 column groups
 __global__ void __launch_bounds__(256) enc0_kernel(const float* __restrict__ stft, int NB, int Fin, int T,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
-                                                   int N, float slope, float* __restrict__ out, int Fout) {
+                                                   int N, float slope, void* __restrict__ outv, int Fout,
+                                                   int out_split) {
   extern __shared__ __align__(16) float ws[];       // [20][N] then bias [N]
   const int tid = threadIdx.x;
   for (int i = tid; i < 20 * N; i += 256) ws[i] = __ldg(w + i);
@@ -22,9 +23,15 @@ __global__ void __launch_bounds__(256) enc0_kernel(const float* __restrict__ stf
   const int fo = blockIdx.y;
   if (r >= R) return;
   const int b = r / Tp, t = r % Tp - 1;
-  float* orow = out + ((int64_t)fo * R + r) * N;
+  const long long oidx = ((long long)fo * R + r) * N;
+  const long long hl = (long long)Fout * R * N;
+  float* orow = reinterpret_cast<float*>(outv) + oidx;
+  unsigned short* osp = reinterpret_cast<unsigned short*>(outv);
   if (t < 0) {                                       // causal pad row
-    for (int n = cg * 4; n < N; n += 32) *reinterpret_cast<float4*>(orow + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = cg * 4; n < N; n += 32) {
+      if (out_split) st_split4(osp, hl, oidx + n, make_float4(0.f, 0.f, 0.f, 0.f));
+      else *reinterpret_cast<float4*>(orow + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     return;
   }
   float xin[20];                                     // [kf][kt][part]
@@ -54,14 +61,15 @@ __global__ void __launch_bounds__(256) enc0_kernel(const float* __restrict__ stf
     }
     acc.x = prelu_f(acc.x, slope); acc.y = prelu_f(acc.y, slope);
     acc.z = prelu_f(acc.z, slope); acc.w = prelu_f(acc.w, slope);
-    *reinterpret_cast<float4*>(orow + n) = acc;
+    if (out_split) st_split4(osp, hl, oidx + n, acc);
+    else *reinterpret_cast<float4*>(orow + n) = acc;
   }
 }
 
 // grid: (row tiles of 32, Fout); block 256 = 8 warps x 4 rows each; one warp per output bin
 constexpr int D5_ROWS = 32;
-__global__ void __launch_bounds__(256) dec5_head_kernel(const float* __restrict__ p, int p_cp,
-                                                        const float* __restrict__ skip, int s_cp, int NB,
+__global__ void __launch_bounds__(256) dec5_head_kernel(const void* __restrict__ pv, int p_cp,
+                                                        const void* __restrict__ skipv, int s_cp, int in_split, int NB,
                                                         int Fin, int T, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float slope, int mask,
                                                         const float* __restrict__ stft_x,
@@ -79,6 +87,11 @@ __global__ void __launch_bounds__(256) dec5_head_kernel(const float* __restrict_
   const float b_r = __ldg(bias), b_i = __ldg(bias + 1);
   const int nq = ktot / 4;                           // float4 chunks per input row (p then skip)
   const int pq = p_cp / 4;
+  const float* p = reinterpret_cast<const float*>(pv);
+  const float* skip = reinterpret_cast<const float*>(skipv);
+  const unsigned short* psp = reinterpret_cast<const unsigned short*>(pv);
+  const unsigned short* ssp = reinterpret_cast<const unsigned short*>(skipv);
+  const long long p_hl = (long long)Fin * R * p_cp, s_hl = (long long)Fin * R * s_cp;
   for (int rr = 0; rr < D5_ROWS / 8; ++rr) {
     const int r = blockIdx.x * D5_ROWS + warp * (D5_ROWS / 8) + rr;
     if (r >= R) break;                               // warp-uniform
@@ -95,8 +108,13 @@ __global__ void __launch_bounds__(256) dec5_head_kernel(const float* __restrict_
         const float* wt = ws + (kf * 2 + kt) * ktot * 2;
         for (int q = lane; q < nq; q += 32) {
           float4 a;
-          if (q < pq) a = ldg4(p + ((int64_t)fi * R + ra) * p_cp + q * 4);
-          else a = ldg4(skip + ((int64_t)fi * R + ra) * s_cp + (q - pq) * 4);
+          if (in_split) {
+            if (q < pq) a = ld_split4(psp, p_hl, ((long long)fi * R + ra) * p_cp + q * 4);
+            else a = ld_split4(ssp, s_hl, ((long long)fi * R + ra) * s_cp + (q - pq) * 4);
+          } else {
+            if (q < pq) a = ldg4(p + ((int64_t)fi * R + ra) * p_cp + q * 4);
+            else a = ldg4(skip + ((int64_t)fi * R + ra) * s_cp + (q - pq) * 4);
+          }
           const float4 w0 = *reinterpret_cast<const float4*>(wt + q * 8);
           const float4 w1 = *reinterpret_cast<const float4*>(wt + q * 8 + 4);
           yr = fmaf(a.x, w0.x, yr); yi = fmaf(a.x, w0.y, yi);
@@ -136,7 +154,7 @@ __global__ void __launch_bounds__(256) dec5_head_kernel(const float* __restrict_
 }  // namespace idv
 
 extern "C" int idv_enc0_fwd(const float* stft, int B, int Fin, int T, const float* w, const float* bias,
-                            int Cout, float prelu_slope, float* out, void* stream) {
+                            int Cout, float prelu_slope, void* out, int out_split, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(stft && w && bias && out, "idv_enc0_fwd: null pointer");
   IDV_CHECK_ARG(B > 0 && Fin >= 5 && T > 0, "idv_enc0_fwd: bad shape B=%d Fin=%d T=%d", B, Fin, T);
@@ -148,12 +166,13 @@ extern "C" int idv_enc0_fwd(const float* stft, int B, int Fin, int T, const floa
   const size_t smem = (size_t)21 * N * sizeof(float);
   IDV_CUDA(cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(R, 32), Fout);
-  enc0_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(stft, B, Fin, T, w, bias, N, prelu_slope, out, Fout);
+  enc0_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(stft, B, Fin, T, w, bias, N, prelu_slope, out, Fout,
+                                                         out_split);
   IDV_LAUNCH_CHECK("enc0_kernel");
   return IDV_OK;
 }
 
-extern "C" int idv_dec5_head_fwd(const float* p, int p_cp, const float* skip, int s_cp, int NB, int Fin, int T,
+extern "C" int idv_dec5_head_fwd(const void* p, int p_cp, const void* skip, int s_cp, int in_split, int NB, int Fin, int T,
                                  const float* w, const float* bias, float prelu_slope, int mask,
                                  const float* stft_x, float* predict, int out_bmul, int out_boff,
                                  void* stream) {
@@ -168,7 +187,7 @@ extern "C" int idv_dec5_head_fwd(const float* p, int p_cp, const float* skip, in
   IDV_CHECK_ARG(smem <= 200 * 1024, "idv_dec5_head_fwd: too many input channels");
   IDV_CUDA(cudaFuncSetAttribute(dec5_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(R, D5_ROWS), 2 * Fin - 1);
-  dec5_head_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, p_cp, skip, s_cp, NB, Fin, T, w, bias,
+  dec5_head_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, p_cp, skip, s_cp, in_split, NB, Fin, T, w, bias,
                                                              prelu_slope, mask, stft_x, predict, out_bmul,
                                                              out_boff);
   IDV_LAUNCH_CHECK("dec5_head_kernel");

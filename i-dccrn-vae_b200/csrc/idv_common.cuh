@@ -1,5 +1,6 @@
 // Shared helpers for the libidv_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -44,5 +45,40 @@ __device__ __forceinline__ float prelu_f(float v, float a) { return v > 0.f ? v 
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// ---- split-bf16 activation format: x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi) ----------------
+__device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(l);
+}
+__device__ __forceinline__ float bf16_bits_to_float(unsigned short b) { return __uint_as_float((unsigned int)b << 16); }
+// 4 consecutive channels of a split tensor -> float4 (hi + lo)
+__device__ __forceinline__ float4 ld_split4(const unsigned short* hi, long long hl, long long idx) {
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + idx));
+  const uint2 l = __ldg(reinterpret_cast<const uint2*>(hi + hl + idx));
+  float4 r;
+  r.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+  r.y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+  r.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+  r.w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+  return r;
+}
+__device__ __forceinline__ void st_split4(unsigned short* hi, long long hl, long long idx, float4 v) {
+  unsigned short h[4], l[4];
+  split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+  *reinterpret_cast<uint2*>(hi + idx) = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
+  *reinterpret_cast<uint2*>(hi + hl + idx) = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+}
+__device__ __forceinline__ float ld_split1(const unsigned short* hi, long long hl, long long idx) {
+  return bf16_bits_to_float(__ldg(hi + idx)) + bf16_bits_to_float(__ldg(hi + hl + idx));
+}
+__device__ __forceinline__ void st_split1(unsigned short* hi, long long hl, long long idx, float v) {
+  unsigned short h, l;
+  split_bf16(v, h, l);
+  hi[idx] = h;
+  hi[hl + idx] = l;
+}
 
 }  // namespace idv

@@ -23,6 +23,7 @@ struct LstmRecParams {
   const float* whh;               // [2][4H][H]
   int NB, T, H;
   float* hseq;                    // [4][R][H]
+  unsigned short* hsplit;         // optional bf16 [2][4][R][H] copy (hi, lo) for the next layer's tensor-core in-proj
   unsigned int* sync;
   int NU, NR, Hs, RC;             // unit slices, row slices, units per CTA, rows per CTA
 };
@@ -80,7 +81,9 @@ __global__ void lstm_rec_kernel(const LstmRecParams p) {
   for (int i = tid; i < (row1 - row0) * Hs; i += nthr) {
     const int q = row0 + i / Hs, jl = i % Hs;
     const int pp = q / p.NB, b = q % p.NB;
-    p.hseq[((int64_t)(m * 2 + pp) * R + (int64_t)b * Tp) * H + u0 + jl] = 0.f;
+    const int64_t zi = ((int64_t)(m * 2 + pp) * R + (int64_t)b * Tp) * H + u0 + jl;
+    p.hseq[zi] = 0.f;
+    if (p.hsplit) st_split1(p.hsplit, 4 * R * H, zi, 0.f);
   }
   unsigned int bar = 0;
   grid_barrier(p.sync, ++bar * nblk);
@@ -144,7 +147,9 @@ __global__ void lstm_rec_kernel(const LstmRecParams p) {
           const float og = sigmoid_f(acc[u][3]);
           const float c = fg * cp[u] + ig * gg;
           cp[u] = c;
-          hout[u] = og * tanhf(c);
+          const float hv = og * tanhf(c);
+          hout[u] = hv;
+          if (p.hsplit) st_split1(p.hsplit, 4 * R * H, (hout - p.hseq) + u, hv);
         }
       }
     }
@@ -279,7 +284,8 @@ static int launch_rec(const LstmRecParams& p, const RecCfg& c, cudaStream_t st) 
 }  // namespace idv
 
 extern "C" int idv_lstm_recurrent_fwd(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld, const float* whh,
-                                      int NB, int T, int H, float* hseq, unsigned int* sync, void* stream) {
+                                      int NB, int T, int H, float* hseq, void* hsplit, unsigned int* sync,
+                                      void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(g && whh && hseq && sync, "idv_lstm_recurrent_fwd: null pointer");
   IDV_CHECK_ARG(NB > 0 && T > 0 && H > 0 && H % 4 == 0, "idv_lstm_recurrent_fwd: need H %% 4 == 0 (NB=%d T=%d H=%d)", NB, T, H);
@@ -291,7 +297,7 @@ extern "C" int idv_lstm_recurrent_fwd(const float* g, int64_t g_m_off, int64_t g
   IDV_CHECK_ARG(pick_rec_cfg(H, NB, sms, (size_t)smem_optin, &c), "idv_lstm_recurrent_fwd: no launch config for H=%d NB=%d", H, NB);
   LstmRecParams p;
   p.g = g; p.g_m_off = g_m_off; p.g_p_off = g_p_off; p.g_ld = g_ld; p.whh = whh;
-  p.NB = NB; p.T = T; p.H = H; p.hseq = hseq; p.sync = sync;
+  p.NB = NB; p.T = T; p.H = H; p.hseq = hseq; p.hsplit = reinterpret_cast<unsigned short*>(hsplit); p.sync = sync;
   p.NU = c.NU; p.NR = c.NR; p.Hs = c.Hs; p.RC = c.RC;
   cudaStream_t st = (cudaStream_t)stream;
   IDV_CUDA(cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned int), st));

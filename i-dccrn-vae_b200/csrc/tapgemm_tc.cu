@@ -1,0 +1,421 @@
+// tap-GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), error-compensated bf16:
+//
+//   every fp32 operand x is held as two bf16 planes  hi = bf16(x), lo = bf16(x - hi)  (same bytes as
+//   fp32) and every product is issued as three MMAs  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  accumulated
+//   in fp32 in TMEM (single-pass TF32/BF16 misses the 1e-4 parity budget, this split
+//   measures 1.6e-5 end to end).
+//
+// Implicit GEMM without im2col: activations are planes [hl][F][R][Cp] (bf16), so the A tile of tap
+// (f_in, dt, ch_off, k0) for output rows [r0, r0+128) is the box {64 ch, 128 rows, 1 plane, 2 (hi,lo)} at
+// (ch_off+k0, r0-dt, f_in, 0) of a 4-D tensor map; rows outside [0,R) (the r = -1 causal tap of the first
+// tile, the tail of the last) are zero-filled by TMA.  Weights are [hl][slot][N][kc_max] (K-major), one
+// box {64, BN, 1, 2} per K step.  Both land 128B-swizzled, which is the UMMA K-major SW128 canonical
+// layout, so the MMA descriptors need no data movement.
+//
+// Persistent, warp-specialised CTA (one per SM):  warp 0 = TMA producer, warp 1 = MMA issuer (one
+// elected thread), warps 2-5 = epilogue (TMEM -> registers -> bias + PReLU + pad-row mask -> split bf16
+// or fp32 -> global).  STAGES-deep smem ring (full/empty mbarriers) and two TMEM accumulator stages
+// (tmem_full/tmem_empty) so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "idv_common.cuh"
+
+namespace idv {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;   // ~2 s: a stuck pipeline traps instead of hanging the GPU
+
+struct Params {
+  int R, Tp, N;
+  int n_units, n_row_tiles, n_col_tiles;
+  const idv_unit_t* units;
+  const idv_tap_t* taps;
+  const float* bias;
+  void* out;
+  int out_ld;
+  long long out_plane;        // elements between output planes
+  long long out_hl;           // elements between the hi and the lo plane set (split mode)
+  int out_split;              // 1: bf16 hi/lo planes, 0: fp32
+  int apply_prelu;
+  float slope;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 1023u) == 0) {            // never hang the device: surface a launch failure instead
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > WAIT_TIMEOUT_CYCLES) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp gets row (lane base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+//  version=1 [46,48), layout_type [61,64) with SWIZZLE_128B = 2)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                  // LBO (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;        // SBO = 1024 B
+  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;              // one of hi / lo
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 2 : (BN >= 128 ? 3 : 4);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages, power of two
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmW, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * C::STAGES;
+  const uint32_t tfull0 = empty0 + 8 * C::STAGES, tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  const uint32_t smem_base = smem_u32(smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.n_units * p.n_row_tiles * p.n_col_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4);      // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == EPI_WARP0) {
+    tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_col_tiles;
+        const int rt = (t / p.n_col_tiles) % p.n_row_tiles;
+        const idv_unit_t unit = p.units[t / (p.n_col_tiles * p.n_row_tiles)];
+        for (int ti = 0; ti < unit.n_taps; ++ti) {
+          const idv_tap_t tap = p.taps[unit.tap_begin + ti];
+          const CUtensorMap* am = tap.src ? &tmA1 : &tmA0;
+          for (int k0 = 0; k0 < tap.kc; k0 += BK) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+            mbar_expect_tx(full0 + 8 * stage, C::STAGE_BYTES);
+            tma_load_4d(am, full0 + 8 * stage, sa, tap.ch_off + k0, rt * BM - tap.dt, tap.f_in, 0);
+            tma_load_4d(&tmW, full0 + 8 * stage, sa + 2 * C::A_BYTES, k0, nt * BN, tap.w_off, 0);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      uint32_t stage = 0, phase = 0, local = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+        const idv_unit_t unit = p.units[t / (p.n_col_tiles * p.n_row_tiles)];
+        const int ksteps = unit.reserved;
+        const uint32_t acc = local & 1, aphase = (local >> 1) & 1;
+        mbar_wait(tempty0 + 8 * acc, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + C::A_BYTES);
+          const uint64_t b_hi = make_desc_sw128(sa + 2 * C::A_BYTES);
+          const uint64_t b_lo = make_desc_sw128(sa + 2 * C::A_BYTES + C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);      // +32 B per K step inside the swizzle row
+            umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, (ks | k) != 0);
+            umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+            umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1);
+          }
+          umma_commit(empty0 + 8 * stage);            // frees the smem slot when these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull0 + 8 * acc);                // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ================================ epilogue (4 warps) ================================
+    const int q = warp & 3;                           // TMEM lane quarter this warp may access
+    uint32_t local = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      const int nt = t % p.n_col_tiles;
+      const int rt = (t / p.n_col_tiles) % p.n_row_tiles;
+      const idv_unit_t unit = p.units[t / (p.n_col_tiles * p.n_row_tiles)];
+      const uint32_t acc = local & 1, aphase = (local >> 1) & 1;
+      mbar_wait(tfull0 + 8 * acc, aphase);
+      tc_fence_after();
+      const int r = rt * BM + q * 32 + lane;
+      const bool row_ok = r < p.R;
+      const bool pad_row = p.Tp > 0 && (r % p.Tp) == 0;
+      const float* bias = p.bias + unit.bias_off + nt * BN;
+      const long long obase = (long long)unit.out_f * p.out_plane + (long long)r * p.out_ld + unit.out_ch_off + nt * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]) + __ldg(bias + c0 + j);
+          if (p.apply_prelu) x = prelu_f(x, p.slope);
+          f[j] = pad_row ? 0.f : x;
+        }
+        if (row_ok) {
+          if (p.out_split) {
+            __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + c0;
+            __nv_bfloat16* ol = oh + p.out_hl;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(f[j + 2 * e]), h1 = __float2bfloat16_rn(f[j + 2 * e + 1]);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(f[j + 2 * e] - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(f[j + 2 * e + 1] - __bfloat162float(h1));
+                hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              *reinterpret_cast<uint4*>(oh + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(ol + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          } else {
+            float* of = reinterpret_cast<float*>(p.out) + obase + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(of + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARP0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+// cuTensorMapEncodeTiled is resolved through the runtime so the library has no link-time dependency on
+// libcuda.so (it must load on the GPU-less build box for the export checks).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int encode_map_4d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t hl_stride_el,
+                         uint32_t b0, uint32_t b1) {
+  // dims (elements): {d0 = channels/k, d1 = rows/n, d2 = planes/slots, 2 = hi/lo}
+  cuuint64_t dims[4] = {d0, d1, d2, 2};
+  cuuint64_t strides[3] = {d0 * 2, d0 * d1 * 2, hl_stride_el * 2};
+  cuuint32_t box[4] = {b0, b1, 1, 2};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return IDV_E_CUDA;
+  }
+  CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                                       box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (dims %llu %llu %llu box %u %u)", (int)rc, (unsigned long long)d0,
+              (unsigned long long)d1, (unsigned long long)d2, b0, b1);
+    return IDV_E_CUDA;
+  }
+  return IDV_OK;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const Params& p, int sms,
+                  cudaStream_t st) {
+  using C = Cfg<BN>;
+  IDV_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int total = p.n_units * p.n_row_tiles * p.n_col_tiles;
+  const int grid = total < sms ? total : sms;
+  tapgemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(a0, a1, w, p);
+  IDV_LAUNCH_CHECK("tapgemm_tc_kernel");
+  return IDV_OK;
+}
+
+}  // namespace tc
+}  // namespace idv
+
+extern "C" int idv_tapgemm_tc(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
+                              int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias, int N,
+                              const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
+                              int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu, float prelu_slope,
+                              void* stream) {
+  using namespace idv;
+  using namespace idv::tc;
+  IDV_CHECK_ARG(a0 && wt && bias && units && taps && out, "idv_tapgemm_tc: null pointer");
+  IDV_CHECK_ARG(R > 0 && n_units > 0 && a0_planes > 0 && n_slots > 0, "idv_tapgemm_tc: empty problem");
+  IDV_CHECK_ARG(N >= 32 && N % 32 == 0 && (N <= 256 ? (N == 32 || N == 64 || N == 128 || N == 256) : N % 256 == 0),
+                "idv_tapgemm_tc: N=%d must be 32, 64, 128, 256 or a multiple of 256", N);
+  IDV_CHECK_ARG(a0_cp % 8 == 0 && kc_max % 64 == 0 && out_ld % 8 == 0 && (!a1 || a1_cp % 8 == 0),
+                "idv_tapgemm_tc: channel counts must be multiples of 8 and kc_max of 64");
+  const int BN = N < 256 ? N : 256;
+  CUtensorMap mA0, mA1, mW;
+  int rc = encode_map_4d(&mA0, a0, a0_cp, R, a0_planes, (uint64_t)a0_planes * R * a0_cp, BK, BM);
+  if (rc) return rc;
+  if (a1) {
+    rc = encode_map_4d(&mA1, a1, a1_cp, R, a1_planes, (uint64_t)a1_planes * R * a1_cp, BK, BM);
+    if (rc) return rc;
+  } else {
+    mA1 = mA0;
+  }
+  rc = encode_map_4d(&mW, wt, kc_max, N, n_slots, (uint64_t)n_slots * N * kc_max, BK, BN);
+  if (rc) return rc;
+  Params p;
+  p.R = R; p.Tp = Tp; p.N = N; p.n_units = n_units;
+  p.n_row_tiles = cdiv(R, BM); p.n_col_tiles = N / BN;
+  p.units = units; p.taps = taps; p.bias = bias; p.out = out; p.out_ld = out_ld;
+  p.out_plane = out_plane; p.out_hl = out_hl; p.out_split = out_split; p.apply_prelu = apply_prelu; p.slope = prelu_slope;
+  int dev = 0, sms = 0;
+  IDV_CUDA(cudaGetDevice(&dev));
+  IDV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (BN) {
+    case 256: return launch<256>(mA0, mA1, mW, p, sms, st);
+    case 128: return launch<128>(mA0, mA1, mW, p, sms, st);
+    case 64: return launch<64>(mA0, mA1, mW, p, sms, st);
+    default: return launch<32>(mA0, mA1, mW, p, sms, st);
+  }
+}

@@ -21,14 +21,16 @@ SIGNATURES = {
     "idv_tapgemm_f32": [vp, i32, i64, vp, i32, i64, i32, i32, vp, vp, i32, vp, vp, i32, vp, i32, i64, i32, f32, vp],
     "idv_stft_fwd": [vp, i32, i32, vp, i32, i32, i32, vp, vp],
     "idv_istft_fwd": [vp, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp],
-    "idv_enc0_fwd": [vp, i32, i32, i32, vp, vp, i32, f32, vp, vp],
-    "idv_dec5_head_fwd": [vp, i32, vp, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, i32, i32, vp],
-    "idv_lstm_recurrent_fwd": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp],
+    "idv_tapgemm_tc": [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, vp, vp, i32, vp, i32, i64, i64,
+                       i32, i32, f32, vp],
+    "idv_enc0_fwd": [vp, i32, i32, i32, vp, vp, i32, f32, vp, i32, vp],
+    "idv_dec5_head_fwd": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, i32, i32, vp],
+    "idv_lstm_recurrent_fwd": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp],
     "idv_lstm_combine_fwd": [vp, i32, i32, i32, vp, vp],
     "idv_reparam_fwd": [vp, i32, i32, i32, i32, i32, i32, vp, vp, u64, u64, vp, vp],
-    "idv_planes_to_user": [vp, i32, i32, i32, i32, vp, vp],
-    "idv_user_to_planes": [vp, i32, i32, i32, i32, vp, vp],
-    "idv_z_to_planes": [vp, i32, i32, i32, i32, i32, vp, vp],
+    "idv_planes_to_user": [vp, i32, i32, i32, i32, i32, vp, vp],
+    "idv_user_to_planes": [vp, i32, i32, i32, i32, vp, i32, vp],
+    "idv_z_to_planes": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "idv_cbn_eval_user": [vp, i64, i32, i64, vp, vp, vp],
 }
 EXPORTS = ["idv_abi_version", "idv_last_error"] + list(SIGNATURES)

@@ -126,7 +126,7 @@ class _ComplexConvBase(nn.Module):
     def forward_planes(self, xp, bn=None, slope=None):
         pk = self._packed(xp.F, xp.data.device, bn, slope)
         out = ops.tapgemm(pk, xp, None, xp.NB, xp.T)
-        return Planes(out, xp.NB, pk.c_out, pk.f_out, xp.T)
+        return Planes(out, xp.NB, pk.c_out, pk.f_out, xp.T, split=xp.split)
 
     def forward(self, x):
         return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x)))
@@ -181,7 +181,7 @@ class _ComplexConvTransposeBase(nn.Module):
                                % (pp.C, c_skip, self.tconv_re.in_channels))
         pk = self._packed(pp.F, pp.C, c_skip, pp.data.device, bn, slope)
         out = ops.tapgemm(pk, pp, skip, pp.NB, pp.T)
-        return Planes(out, pp.NB, pk.c_out, pk.f_out, pp.T)
+        return Planes(out, pp.NB, pk.c_out, pk.f_out, pp.T, split=pp.split)
 
     def forward(self, x):
         if x.shape[1] != self.tconv_re.in_channels:
@@ -269,14 +269,16 @@ class ComplexLSTM(nn.Module):
         layers = self._packed(xp.C, xp.F, xp.data.device)
         NB, T, H = xp.NB, xp.T, self.hidden_size
         R = NB * (T + 1)
-        src, hseq = xp, None
+        src, hseq, split = xp, None, xp.split
         for l, (inproj, whh) in enumerate(layers):
-            g = ops.tapgemm(inproj, src, None, NB, T, zero_pad_rows=False)
+            g = ops.tapgemm(inproj, src, None, NB, T, zero_pad_rows=False, out_split=False)
+            more = split and l + 1 < len(layers)       # the next layer's tensor-core in-proj reads split h
             if l == 0:
-                hseq = ops.lstm_recurrent(g, 4 * H, R * 8 * H, 8 * H, whh, NB, T, H)
+                hseq, hsp = ops.lstm_recurrent(g, 4 * H, R * 8 * H, 8 * H, whh, NB, T, H, want_split=more)
             else:
-                hseq = ops.lstm_recurrent(g, 2 * R * 4 * H, R * 4 * H, 4 * H, whh, NB, T, H)
-            src = Planes(hseq, NB, H, 4, T, cp=H)       # [4 streams][R][H]: plane = stream, row stride H
+                hseq, hsp = ops.lstm_recurrent(g, 2 * R * 4 * H, R * 4 * H, 4 * H, whh, NB, T, H, want_split=more)
+            # [4 streams][R][H]: plane = stream, row stride H
+            src = Planes(hsp, NB, H, 4, T, cp=H, split=True) if split else Planes(hseq, NB, H, 4, T, cp=H)
         return ops.lstm_combine(hseq, NB, T, H)
 
     def forward(self, x):
@@ -312,7 +314,7 @@ class ComplexDense(nn.Module):
     def forward_planes(self, zp, c_out, f_out):
         pk = self._packed(c_out, f_out, zp.data.device)
         out = ops.tapgemm(pk, zp, None, zp.NB, zp.T)
-        return Planes(out, zp.NB, c_out, f_out, zp.T)
+        return Planes(out, zp.NB, c_out, f_out, zp.T, split=zp.split)
 
     def forward(self, x):
         """x: (..., D, 2) -> (..., out, 2)"""
@@ -355,7 +357,7 @@ class Encoder(nn.Module):
             items[key] = pack.pack_enc0(c.conv_re.weight, c.conv_re.bias, c.conv_im.weight, c.conv_im.bias,
                                         self.bn.fold_inputs(), self._slope(), stft_x.device)
         w, b, cout, slope = items[key]
-        return ops.enc0(stft_x, w, b, cout, slope)
+        return ops.enc0(stft_x, w, b, cout, slope, out_split=ops.use_split())
 
     def forward_planes(self, xp):
         items = self._cache.check(self)          # invalidates the child's fold when bn / prelu change
@@ -367,7 +369,7 @@ class Encoder(nn.Module):
                                         self.bn.fold_inputs(), self._slope(), xp.F, sf, pf, xp.data.device)
         pk = items[key]
         out = ops.tapgemm(pk, xp, None, xp.NB, xp.T)
-        return Planes(out, xp.NB, pk.c_out, pk.f_out, xp.T)
+        return Planes(out, xp.NB, pk.c_out, pk.f_out, xp.T, split=xp.split)
 
     def forward(self, x, train):
         if train:
@@ -408,7 +410,7 @@ class Decoder(nn.Module):
                                                   pp.data.device, sf, pf)
         pk = items[key]
         out = ops.tapgemm(pk, pp, skip, pp.NB, pp.T)
-        return Planes(out, pp.NB, pk.c_out, pk.f_out, pp.T)
+        return Planes(out, pp.NB, pk.c_out, pk.f_out, pp.T, split=pp.split)
 
     def forward_head(self, pp, skip, mask, stft_x, predict, out_bmul, out_boff):
         """Last layer (out_channel == 1) fused with the reconstruction head; writes ``predict``."""
@@ -460,10 +462,10 @@ class SkipList(list):
         return (self._get(i) for i in range(len(self)))
 
 
-def _skip_planes(skiper, idx):
-    if isinstance(skiper, SkipList):
+def _skip_planes(skiper, idx, split):
+    if isinstance(skiper, SkipList) and skiper.planes[idx].split == split:
         return skiper.planes[idx]
-    return ops.user_to_planes(skiper[idx])
+    return ops.user_to_planes(skiper[idx], split=split)
 
 
 def _build_encoders(net_params, causal):
@@ -615,11 +617,11 @@ class _VaeDecoderBase(nn.Module):
             raise RuntimeError("z batch %d is not a multiple of num_samples %d" % (BS, S))
         B = BS // S
         n = len(self.decoders)
-        skips = {}
+        skips, split = {}, ops.use_split()
         if real_skips:
             for i in range(n):
                 if self.use_sc and i in self.skip_to_use:
-                    skips[i] = _skip_planes(skiper, len(skiper) - i - 1)
+                    skips[i] = _skip_planes(skiper, len(skiper) - i - 1, split)
         n_bins = F
         for _ in range(n):
             n_bins = 2 * n_bins - 1          # kernel 5 / stride 2 / pad 2 transposed conv
@@ -628,7 +630,7 @@ class _VaeDecoderBase(nn.Module):
             stft_x = ops.lib.require_f32_cuda(stft_x, "stft_x")
         self.decoder_outputs = []
         for s in range(S):
-            zp = ops.z_to_planes(z, B, S, s)
+            zp = ops.z_to_planes(z, B, S, s, split=split)
             p = self.dense.forward_planes(zp, C, F)
             for i in range(n - 1):
                 p = self.decoders[i].forward_planes(p, skips.get(i))
@@ -711,7 +713,7 @@ class standard_DCCRN(nn.Module):
         lat = self.lstms[0].forward_planes(top)                         # (B, T, H, 2)
         self.latent = lat
         B, T = lat.shape[0], lat.shape[1]
-        zp = ops.z_to_planes(lat, B, 1, 0)
+        zp = ops.z_to_planes(lat, B, 1, 0, split=top.split)
         p = self.dense.forward_planes(zp, top.C, top.F)
         n = len(self.decoders)
         for i in range(n - 1):

@@ -1,18 +1,35 @@
 """Thin Python front of the C ABI: shape bookkeeping + output allocation (torch is used only for device
 memory and streams).  Every function ends in a ``lib.call`` – there is no other compute path."""
+import os
+
 import torch
 
 from . import lib
 from .pack import round8
 
+# "tc": tcgen05 tensor-core tap-GEMMs on split-bf16 activations (default); "simt": fp32 SIMT kernels on fp32
+# planes (bring-up / cross-check path).  Both are CUDA; neither is a fallback for the other at run time.
+GEMM_MODE = [os.environ.get("IDV_GEMM", "tc")]
+
+
+def set_gemm_mode(mode):
+    if mode not in ("tc", "simt"):
+        raise ValueError("mode must be 'tc' or 'simt'")
+    GEMM_MODE[0] = mode
+
+
+def use_split():
+    return GEMM_MODE[0] == "tc"
+
 
 class Planes:
     """Internal activation: fp32 [F][R][Cp], R = NB*(T+1) (row b*(T+1) is the causal zero row),
     Cp = 2*round8(C) with the real parts in [0, Ch) and the imaginary parts in [Ch, 2Ch)."""
-    __slots__ = ("data", "NB", "C", "F", "T", "_cp")
+    __slots__ = ("data", "NB", "C", "F", "T", "_cp", "split")
 
-    def __init__(self, data, NB, C, F, T, cp=None):
-        self.data, self.NB, self.C, self.F, self.T, self._cp = data, NB, C, F, T, cp
+    def __init__(self, data, NB, C, F, T, cp=None, split=False):
+        """split=True: data is bf16 [2 (hi, lo)][F][R][Cp] (x ~= hi + lo), else fp32 [F][R][Cp]."""
+        self.data, self.NB, self.C, self.F, self.T, self._cp, self.split = data, NB, C, F, T, cp, split
 
     @property
     def Ch(self):
@@ -32,6 +49,13 @@ class Planes:
 
 
 def _empty(n, device):
+    return torch.empty(int(n), dtype=torch.float32, device=device)
+
+
+def _empty_act(n, device, split):
+    """n logical fp32 elements: fp32 [n] or bf16 [2][n]."""
+    if split:
+        return torch.empty(2 * int(n), dtype=torch.bfloat16, device=device)
     return torch.empty(int(n), dtype=torch.float32, device=device)
 
 
@@ -58,10 +82,26 @@ def istft(spec_ri, basis, wsq, n_fft, hop, win):
     return out
 
 
-def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True):
+def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None):
     """Run one packed tap-GEMM.  a0/a1: Planes (a1 may be None).  Returns the flat output tensor
-    [pack.out_planes][R][pack.out_ld]."""
+    [pack.out_planes][R][pack.out_ld] (fp32, or bf16 [2][...] when out_split).  Split inputs run on the
+    tcgen05 kernel, fp32 inputs on the SIMT kernel."""
     R = NB * (T + 1)
+    if a0.split:
+        if a1 is not None and not a1.split:
+            raise RuntimeError("tap-GEMM sources must share one activation format")
+        out_split = True if out_split is None else out_split
+        tc = pack.tc()
+        n_out = pack.out_planes * R * pack.out_ld
+        out = _empty_act(n_out, a0.data.device, out_split)
+        lib.call("idv_tapgemm_tc", a0.data, a0.Cp, a0.F, a1.data if a1 is not None else None,
+                 a1.Cp if a1 is not None else 0, a1.F if a1 is not None else 0, R,
+                 (T + 1) if zero_pad_rows else 0, tc["wt"], tc["kc_max"], tc["n_slots"], pack.bias, pack.N,
+                 tc["units"], tc["taps"], pack.n_units, out, pack.out_ld, R * pack.out_ld, n_out,
+                 1 if out_split else 0, 1 if pack.prelu else 0, pack.slope)
+        return out
+    if out_split:
+        raise RuntimeError("the fp32 SIMT tap-GEMM writes fp32 planes only")
     out = _empty(pack.out_planes * R * pack.out_ld, a0.data.device)
     lib.call("idv_tapgemm_f32",
              a0.data, a0.Cp, a0.plane_stride,
@@ -73,25 +113,29 @@ def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True):
     return out
 
 
-def enc0(stft_x, w, bias, cout, slope):
+def enc0(stft_x, w, bias, cout, slope, out_split=False):
     B, Fin, T, _ = stft_x.shape
     Fout = (Fin + 4 - 5) // 2 + 1
-    out = _empty(Fout * B * (T + 1) * 2 * cout, stft_x.device)
-    lib.call("idv_enc0_fwd", stft_x, B, Fin, T, w, bias, cout, slope, out)
-    return Planes(out, B, cout, Fout, T)
+    out = _empty_act(Fout * B * (T + 1) * 2 * cout, stft_x.device, out_split)
+    lib.call("idv_enc0_fwd", stft_x, B, Fin, T, w, bias, cout, slope, out, 1 if out_split else 0)
+    return Planes(out, B, cout, Fout, T, split=out_split)
 
 
 def dec5_head(p, skip, w, bias, slope, mask, stft_x, predict, out_bmul, out_boff):
+    if skip is not None and skip.split != p.split:
+        raise RuntimeError("decoder sources must share one activation format")
     lib.call("idv_dec5_head_fwd", p.data, p.Cp, skip.data if skip is not None else None,
-             skip.Cp if skip is not None else 0, p.NB, p.F, p.T, w, bias, slope, 1 if mask else 0,
-             stft_x if mask else None, predict, out_bmul, out_boff)
+             skip.Cp if skip is not None else 0, 1 if p.split else 0, p.NB, p.F, p.T, w, bias, slope,
+             1 if mask else 0, stft_x if mask else None, predict, out_bmul, out_boff)
 
 
-def lstm_recurrent(g, g_m_off, g_p_off, g_ld, whh, NB, T, H):
+def lstm_recurrent(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, want_split=False):
+    """Returns (hseq fp32 [4][R][H], hsplit bf16 [2][4][R][H] or None)."""
     hseq = _empty(4 * NB * (T + 1) * H, g.device)
+    hsplit = _empty_act(4 * NB * (T + 1) * H, g.device, True) if want_split else None
     sync = torch.empty(2, dtype=torch.int32, device=g.device)
-    lib.call("idv_lstm_recurrent_fwd", g, g_m_off, g_p_off, g_ld, whh, NB, T, H, hseq, sync)
-    return hseq
+    lib.call("idv_lstm_recurrent_fwd", g, g_m_off, g_p_off, g_ld, whh, NB, T, H, hseq, hsplit, sync)
+    return hseq, hsplit
 
 
 def lstm_combine(hseq, NB, T, H):
@@ -114,26 +158,26 @@ def reparam(latent, ch0, zdim, S, eps_r, eps_i, seed, offset):
 
 def planes_to_user(p):
     out = torch.empty((p.NB, p.C, p.F, p.T, 2), dtype=torch.float32, device=p.data.device)
-    lib.call("idv_planes_to_user", p.data, p.NB, p.C, p.F, p.T, out)
+    lib.call("idv_planes_to_user", p.data, 1 if p.split else 0, p.NB, p.C, p.F, p.T, out)
     return out
 
 
-def user_to_planes(x):
+def user_to_planes(x, split=False):
     x = lib.require_f32_cuda(x, "activation")
     if x.dim() != 5 or x.shape[-1] != 2:
         raise RuntimeError("activation must be (B, C, F, T, 2), got %s" % (tuple(x.shape),))
     NB, C, F, T, _ = x.shape
-    data = _empty(F * NB * (T + 1) * 2 * round8(C), x.device)
-    lib.call("idv_user_to_planes", x, NB, C, F, T, data)
-    return Planes(data, NB, C, F, T)
+    data = _empty_act(F * NB * (T + 1) * 2 * round8(C), x.device, split)
+    lib.call("idv_user_to_planes", x, NB, C, F, T, data, 1 if split else 0)
+    return Planes(data, NB, C, F, T, split=split)
 
 
-def z_to_planes(z, NB, S, s):
+def z_to_planes(z, NB, S, s, split=False):
     z = lib.require_f32_cuda(z, "z")
     _, T, zdim, _ = z.shape
-    data = _empty(NB * (T + 1) * 2 * round8(zdim), z.device)
-    lib.call("idv_z_to_planes", z, NB, S, s, T, zdim, data)
-    return Planes(data, NB, zdim, 1, T)
+    data = _empty_act(NB * (T + 1) * 2 * round8(zdim), z.device, split)
+    lib.call("idv_z_to_planes", z, NB, S, s, T, zdim, data, 1 if split else 0)
+    return Planes(data, NB, zdim, 1, T, split=split)
 
 
 def cbn_eval_user(x, zb):

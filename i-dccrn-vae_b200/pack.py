@@ -32,6 +32,41 @@ class TapGemmPack:
         self.out_ld = out_ld
         self.prelu = bool(prelu)
         self.slope = float(slope)
+        self._tc = None
+        self._units_l, self._taps_l = [list(u) for u in units], [list(t) for t in taps]
+
+    def tc_eligible(self):
+        n_ok = self.N in (32, 64, 128, 256) or (self.N > 256 and self.N % 256 == 0)
+        return n_ok and all(t[4] % 64 == 0 and t[3] % 8 == 0 for t in self._taps_l) and self.out_ld % 8 == 0
+
+    def tc(self):
+        """Operands of idv_tapgemm_tc: K-major bf16 hi/lo weight slots [2][slots][N][kc_max], taps with
+        w_off -> slot, units with reserved -> number of 64-wide K steps."""
+        if self._tc is None:
+            if not self.tc_eligible():
+                raise RuntimeError("tap-GEMM (N=%d) does not fit the tensor-core kernel's shape rules" % self.N)
+            dev = self.w.device
+            w = self.w.detach().cpu()
+            slots, taps = {}, []
+            kc_max = max(t[4] for t in self._taps_l)
+            for t in self._taps_l:
+                key = (t[5], t[4])
+                if key not in slots:
+                    slots[key] = len(slots)
+                taps.append([t[0], t[1], t[2], t[3], t[4], slots[key]])
+            wt = torch.zeros(len(slots), self.N, kc_max, dtype=torch.float32)
+            for (w_off, kc), si in slots.items():
+                wt[si, :, :kc] = w[w_off:w_off + kc * self.N].view(kc, self.N).t()
+            hi = wt.to(torch.bfloat16)
+            lo = (wt - hi.to(torch.float32)).to(torch.bfloat16)
+            units = []
+            for u in self._units_l:
+                ks = sum(t[4] // 64 for t in self._taps_l[u[0]:u[0] + u[1]])
+                units.append([u[0], u[1], u[2], u[3], u[4], ks])
+            self._tc = dict(wt=torch.stack((hi, lo)).contiguous().to(dev), kc_max=kc_max, n_slots=len(slots),
+                            taps=torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(dev),
+                            units=torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(dev))
+        return self._tc
 
 
 def cbn_fold(bn):

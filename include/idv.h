@@ -11,7 +11,8 @@
  *     last failure on the calling thread.  Nothing throws across the boundary;
  *   - all floating point is IEEE fp32.
  *
- * Internal activation layout ("planes"): fp32 [F][R][Cp] with
+ * Internal activation layout ("planes"): fp32 [F][R][Cp], or split bf16 [2][F][R][Cp] (see
+ * idv_tapgemm_tc), with
  *     R  = NB * Tp,  Tp = T + 1,  row(b, t) = b*Tp + 1 + t,  row(b, -1) = b*Tp is an all-zero
  *          causal pad row (the reference's left time padding, model/complex_progress.py:L16-22);
  *     Cp = 2*Ch, Ch = C rounded up to 8: real part of complex channel c at c, imaginary at Ch + c.
@@ -31,7 +32,7 @@ extern "C" {
 #define IDV_E_CUDA 2     /* CUDA runtime error (message has the cudaError string) */
 #define IDV_E_RESOURCE 3 /* kernel cannot be made resident (cooperative launch too large) */
 
-#define IDV_ABI_VERSION 1
+#define IDV_ABI_VERSION 2
 
 int idv_abi_version(void);
 const char* idv_last_error(void);
@@ -65,6 +66,19 @@ int idv_tapgemm_f32(const float* a0, int a0_ld, int64_t a0_plane,
                     float* out, int out_ld, int64_t out_plane,
                     int apply_prelu, float prelu_slope, void* stream);
 
+/* Tensor-core version (tcgen05.mma kind::f16, TMEM accumulators, TMA-fed): same contract on the
+ * "split" activation format: every fp32 value x is stored as two bf16 planes hi = bf16(x),
+ * lo = bf16(x - hi), tensor = bf16 [2 (hi,lo)][planes][R][cp]; products are evaluated as
+ * a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation.
+ * wt: bf16 [2][n_slots][N][kc_max] (K-major), tap.w_off = slot index, tap.kc % 64 == 0,
+ * unit.reserved = number of 64-wide K steps of the unit.  out: split bf16 (out_hl = elements between
+ * the hi and lo sets) when out_split, else fp32.  N in {32,64,128,256} or a multiple of 256.        */
+int idv_tapgemm_tc(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
+                   int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias, int N,
+                   const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
+                   int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu, float prelu_slope,
+                   void* stream);
+
 /* ---- STFT / iSTFT -----------------------------------------------------------------------------
  * replaces torch.stft at model/pvae_module.py:L22 (n_fft 512, hop, win, periodic Hann, center,
  * reflect pad, onesided).  basis: [win][2*(n_fft/2+1)] fp32, column 2k = cos*w, 2k+1 = -sin*w
@@ -82,7 +96,7 @@ int idv_istft_fwd(const float* spec, int B, int T, const float* basis, const flo
  * reading the user-layout STFT (B,257,T,2) and writing planes [Fout][R][2*Cout].
  * w: [10 taps (kf*2+kt)][2 (re,im in)][2*Cout] with CBN folded, bias: [2*Cout].                 */
 int idv_enc0_fwd(const float* stft, int B, int Fin, int T, const float* w, const float* bias,
-                 int Cout, float prelu_slope, float* out, void* stream);
+                 int Cout, float prelu_slope, void* out, int out_split, void* stream);
 
 /* ---- last decoder layer (Cout = 1) + reconstruction head ---------------------------------------
  * Decoder 5: causal ComplexConvTranspose2d(Cin -> 1) + CBN(eval) + PReLU (+ mask head,
@@ -91,8 +105,8 @@ int idv_enc0_fwd(const float* stft, int B, int Fin, int T, const float* w, const
  * w: [10 taps (kf*2+kt)][p_cp + s_cp][2], bias[2].  stft_x: (NBdec/?,Fout,T,2) noisy STFT rows
  * for this pass (mask head only, may be NULL when mask == 0); out_bstride lets a pass write
  * every S-th utterance of the (B*S) batch: out utterance index = b*out_bmul + out_boff.          */
-int idv_dec5_head_fwd(const float* p, int p_cp, const float* skip, int s_cp, int NB, int Fin, int T,
-                      const float* w, const float* bias, float prelu_slope, int mask,
+int idv_dec5_head_fwd(const void* p, int p_cp, const void* skip, int s_cp, int in_split, int NB, int Fin,
+                      int T, const float* w, const float* bias, float prelu_slope, int mask,
                       const float* stft_x, float* predict, int out_bmul, int out_boff, void* stream);
 
 /* ---- complex LSTM ------------------------------------------------------------------------------
@@ -100,9 +114,10 @@ int idv_dec5_head_fwd(const float* p, int p_cp, const float* skip, int s_cp, int
  * (model/complex_progress.py:L58-74), gates i,f,g,o.  g: pre-computed input projections incl. both
  * biases; stream (m,p) starts at g + m*g_m_off + p*g_p_off, row stride g_ld.  whh: [2][4H][H]
  * (lstm_re, lstm_im).  hseq: [4 streams (m*2+p)][R][H]; the kernel zeroes the pad rows itself.
- * sync: 2 x uint32 workspace, zeroed by the call.  Cooperative launch.                           */
+ * hsplit: optional (NULL) split-bf16 copy [2][4][R][H] of hseq for a tensor-core in-proj of the next
+ * layer.  sync: 2 x uint32 workspace, zeroed by the call.  Cooperative launch.                     */
 int idv_lstm_recurrent_fwd(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld,
-                           const float* whh, int NB, int T, int H, float* hseq,
+                           const float* whh, int NB, int T, int H, float* hseq, void* hsplit,
                            unsigned int* sync, void* stream);
 /* Combine the four streams (real = rr - ii, imag = ir + ri), emit the user-layout latent
  * (NB, T, H, 2).  Replaces the stack/permute at complex_progress.py:L62-73, pvae_module.py:L2247. */
@@ -115,12 +130,15 @@ int idv_reparam_fwd(const float* latent, int NB, int T, int Htot, int ch0, int z
                     float* z, void* stream);
 
 /* ---- layout conversion at the module boundary --------------------------------------------------*/
-/* planes [F][R][Cp] -> user (NB, C, F, T, 2) */
-int idv_planes_to_user(const float* planes, int NB, int C, int F, int T, float* user, void* stream);
+/* planes [F][R][Cp] (fp32, or split bf16 when in_split) -> user (NB, C, F, T, 2) */
+int idv_planes_to_user(const void* planes, int in_split, int NB, int C, int F, int T, float* user,
+                       void* stream);
 /* user (NB, C, F, T, 2) -> planes (pad rows and pad channels written as zero) */
-int idv_user_to_planes(const float* user, int NB, int C, int F, int T, float* planes, void* stream);
+int idv_user_to_planes(const float* user, int NB, int C, int F, int T, void* planes, int out_split,
+                       void* stream);
 /* z (NB*S, T, zdim, 2) sample s -> planes [1][NB*Tp][2*zdim] */
-int idv_z_to_planes(const float* z, int NB, int S, int s, int T, int zdim, float* planes, void* stream);
+int idv_z_to_planes(const float* z, int NB, int S, int s, int T, int zdim, void* planes, int out_split,
+                    void* stream);
 
 /* stand-alone ComplexBatchNormal.forward(x, train=False) (model/complex_progress.py:L161-209) on the
  * reference layout x: (outer, C, inner, 2).  zb: [C][6] = Zrr, Zri, Zir, Zii, b'_r, b'_i with

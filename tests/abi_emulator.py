@@ -17,6 +17,81 @@ def _flat(t):
     return t.view(-1)
 
 
+def _rd(t, split, n=None):
+    """Logical fp64 values of an activation tensor: fp32 [n] or split bf16 [2][n] (hi + lo)."""
+    f = _flat(t)
+    if not split:
+        return f.to(D) if n is None else f[:n].to(D)
+    n = f.numel() // 2 if n is None else n
+    half = f.numel() // 2
+    return f[:n].to(D) + f[half:half + n].to(D)
+
+
+def _wr(t, split, vals):
+    """Store logical values (flat, fp64/fp32) into an activation tensor in its format."""
+    f = _flat(t)
+    v = vals.reshape(-1).to(torch.float32)
+    if not split:
+        f[:v.numel()] = v
+        return
+    half = f.numel() // 2
+    hi = v.to(torch.bfloat16)
+    lo = (v - hi.to(torch.float32)).to(torch.bfloat16)
+    f[:v.numel()] = hi
+    f[half:half + v.numel()] = lo
+
+
+def idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, N, units, taps,
+                   n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, slope):
+    """Contract of the tensor-core tap-GEMM incl. its arithmetic: a_hi*w_hi + a_hi*w_lo + a_lo*w_hi."""
+    taps_l, units_l = taps.tolist(), units.tolist()
+    W = wt.view(2, n_slots, N, kc_max).to(D)
+
+    def planes(a, cp, npl):
+        v = _flat(a).view(2, npl, R, cp).to(D)
+        return v[0], v[1]
+    A0 = planes(a0, a0_cp, a0_planes)
+    A1 = planes(a1, a1_cp, a1_planes) if a1 is not None else None
+    res = torch.zeros(out.numel() // (2 if out_split else 1), dtype=D)
+    res[:] = float("nan")
+    written = torch.zeros_like(res, dtype=torch.bool)
+    for (tap_begin, n_taps, out_f, out_ch_off, bias_off, ksteps) in units_l:
+        acc = torch.zeros(R, N, dtype=D)
+        assert ksteps == sum(t[4] // 64 for t in taps_l[tap_begin:tap_begin + n_taps])
+        for (src, f_in, dt, ch_off, kc, slot) in taps_l[tap_begin:tap_begin + n_taps]:
+            assert kc % 64 == 0
+            hi, lo = (A0 if src == 0 else A1)
+
+            def shifted(x):
+                x = x[f_in][:, ch_off:ch_off + kc]
+                if dt > 0:
+                    x = torch.cat((torch.zeros(dt, kc, dtype=D), x[:R - dt]), 0)
+                return x
+            ah, al = shifted(hi), shifted(lo)
+            wh, wl = W[0, slot, :, :kc].t(), W[1, slot, :, :kc].t()
+            acc += ah @ wh + ah @ wl + al @ wh
+        acc += _flat(bias)[bias_off:bias_off + N].to(D)
+        if apply_prelu:
+            acc = torch.where(acc > 0, acc, slope * acc)
+        if Tp > 0:
+            acc[torch.arange(R) % Tp == 0] = 0
+        view = res[out_f * out_plane:out_f * out_plane + R * out_ld].view(R, out_ld)
+        view[:, out_ch_off:out_ch_off + N] = acc
+        written[out_f * out_plane:out_f * out_plane + R * out_ld].view(R, out_ld)[:, out_ch_off:out_ch_off + N] = True
+    # only touch what the kernel writes
+    f = _flat(out)
+    vals = res[written].to(torch.float32)
+    if out_split:
+        half = f.numel() // 2
+        assert half == out_hl
+        hi = vals.to(torch.bfloat16)
+        lo = (vals - hi.to(torch.float32)).to(torch.bfloat16)
+        f[:half][written] = hi
+        f[half:][written] = lo
+    else:
+        f[written] = vals
+
+
 def idv_tapgemm_f32(a0, a0_ld, a0_plane, a1, a1_ld, a1_plane, R, Tp, w, bias, N, units, taps, n_units, out,
                     out_ld, out_plane, apply_prelu, slope):
     taps_l, units_l = taps.tolist(), units.tolist()
@@ -68,7 +143,7 @@ def idv_istft_fwd(spec, B, T, basis, wsq, n_fft, hop, win, frames, out):
     out.copy_((y[:, h:total - h] / env[h:total - h]).to(torch.float32))
 
 
-def idv_enc0_fwd(stft, B, Fin, T, w, bias, Cout, slope, out):
+def idv_enc0_fwd(stft, B, Fin, T, w, bias, Cout, slope, out, out_split=0):
     N = 2 * Cout
     Fout = (Fin + 4 - 5) // 2 + 1
     Tp = T + 1
@@ -84,18 +159,19 @@ def idv_enc0_fwd(stft, B, Fin, T, w, bias, Cout, slope, out):
     res[:, :, 1:] += bias.to(D)
     res = torch.where(res > 0, res, slope * res)
     res[:, :, 0] = 0
-    out.copy_(res.reshape(-1).to(torch.float32))
+    _wr(out, out_split, res)
 
 
-def idv_dec5_head_fwd(p, p_cp, skip, s_cp, NB, Fin, T, w, bias, slope, mask, stft_x, predict, out_bmul, out_boff):
+def idv_dec5_head_fwd(p, p_cp, skip, s_cp, in_split, NB, Fin, T, w, bias, slope, mask, stft_x, predict, out_bmul,
+                      out_boff):
     Tp = T + 1
     R = NB * Tp
     Fout = 2 * Fin - 1
     if skip is None:
         s_cp = 0
-    A = _flat(p)[:Fin * R * p_cp].view(Fin, R, p_cp).to(D)
+    A = _rd(p, in_split, Fin * R * p_cp).view(Fin, R, p_cp)
     if s_cp:
-        A = torch.cat((A, _flat(skip)[:Fin * R * s_cp].view(Fin, R, s_cp).to(D)), 2)
+        A = torch.cat((A, _rd(skip, in_split, Fin * R * s_cp).view(Fin, R, s_cp)), 2)
     W = w.view(10, p_cp + s_cp, 2).to(D)
     y = torch.zeros(Fout, R, 2, dtype=D)
     for fo in range(Fout):
@@ -123,7 +199,7 @@ def idv_dec5_head_fwd(p, p_cp, skip, s_cp, NB, Fin, T, w, bias, slope, mask, stf
     pv[out_boff::out_bmul][:NB] = y.to(torch.float32)
 
 
-def idv_lstm_recurrent_fwd(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, hseq, sync):
+def idv_lstm_recurrent_fwd(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, hseq, hsplit, sync):
     Tp = T + 1
     R = NB * Tp
     hs = hseq.view(4, R, H)
@@ -144,6 +220,8 @@ def idv_lstm_recurrent_fwd(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, hseq, sync)
                 c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
                 h = torch.sigmoid(o) * torch.tanh(c)
                 hs[m * 2 + p, rows] = h.to(torch.float32)
+    if hsplit is not None:
+        _wr(hsplit, 1, hs)
 
 
 def idv_lstm_combine_fwd(hseq, NB, T, H, latent):
@@ -176,26 +254,24 @@ def _r8(c):
     return (c + 7) // 8 * 8
 
 
-def idv_planes_to_user(planes, NB, C, F, T, user):
+def idv_planes_to_user(planes, in_split, NB, C, F, T, user):
     Ch, Tp = _r8(C), T + 1
-    p = _flat(planes)[:F * NB * Tp * 2 * Ch].view(F, NB, Tp, 2, Ch)[:, :, 1:, :, :C]    # (F,NB,T,2,C)
-    user.copy_(p.permute(1, 4, 0, 2, 3))
+    p = _rd(planes, in_split, F * NB * Tp * 2 * Ch).view(F, NB, Tp, 2, Ch)[:, :, 1:, :, :C]    # (F,NB,T,2,C)
+    user.copy_(p.permute(1, 4, 0, 2, 3).to(torch.float32))
 
 
-def idv_user_to_planes(user, NB, C, F, T, planes):
+def idv_user_to_planes(user, NB, C, F, T, planes, out_split=0):
     Ch, Tp = _r8(C), T + 1
-    n = F * NB * Tp * 2 * Ch
-    _flat(planes)[:n] = 0
-    p = _flat(planes)[:n].view(F, NB, Tp, 2, Ch)
-    p[:, :, 1:, :, :C] = user.view(NB, C, F, T, 2).permute(2, 0, 3, 4, 1)
+    p = torch.zeros(F, NB, Tp, 2, Ch, dtype=D)
+    p[:, :, 1:, :, :C] = user.view(NB, C, F, T, 2).permute(2, 0, 3, 4, 1).to(D)
+    _wr(planes, out_split, p)
 
 
-def idv_z_to_planes(z, NB, S, s, T, zdim, planes):
+def idv_z_to_planes(z, NB, S, s, T, zdim, planes, out_split=0):
     Ch, Tp = _r8(zdim), T + 1
-    n = NB * Tp * 2 * Ch
-    _flat(planes)[:n] = 0
-    p = _flat(planes)[:n].view(NB, Tp, 2, Ch)
-    p[:, 1:, :, :zdim] = z.view(NB, S, T, zdim, 2)[:, s].permute(0, 1, 3, 2)
+    p = torch.zeros(NB, Tp, 2, Ch, dtype=D)
+    p[:, 1:, :, :zdim] = z.view(NB, S, T, zdim, 2)[:, s].permute(0, 1, 3, 2).to(D)
+    _wr(planes, out_split, p)
 
 
 def idv_cbn_eval_user(x, outer, C, inner, zb, out):

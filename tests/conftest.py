@@ -45,3 +45,14 @@ def golden():
     def load(name):
         return {k: v for k, v in np.load(os.path.join(GOLDEN, name + ".npz")).items()}
     return load
+
+
+@pytest.fixture(params=["tc", "simt"])
+def gemm_mode(request):
+    """Run a test once per tap-GEMM implementation: tcgen05 on split-bf16 planes / fp32 SIMT on fp32 planes."""
+    import idccrn_b200
+    from idccrn_b200 import ops
+    old = ops.GEMM_MODE[0]
+    ops.set_gemm_mode(request.param)
+    yield request.param
+    ops.set_gemm_mode(old)

@@ -18,7 +18,13 @@ def _both(name, args, outs):
     gpu = [a.cuda() if isinstance(a, torch.Tensor) else a for a in args]
     lib.call(name, *gpu)
     torch.cuda.synchronize()
-    return max(C.rel_l2(gpu[i], cpu[i]) for i in outs)
+    def val(t):
+        t = t.detach().cpu()
+        if t.dtype == torch.bfloat16:                      # split activation: hi + lo
+            f = t.view(-1).to(torch.float64)
+            return f[:f.numel() // 2] + f[f.numel() // 2:]
+        return t
+    return max(C.rel_l2(val(gpu[i]), val(cpu[i])) for i in outs)
 
 
 def _rand(*shape, seed=0):
@@ -67,9 +73,18 @@ def test_stft_istft(B, L):
 @pytest.mark.parametrize("B,Fin,T,Cout", [(1, 257, 1, 32), (3, 33, 70, 16)])
 def test_enc0(B, Fin, T, Cout):
     Fout = (Fin - 1) // 2 + 1
+    n = Fout * B * (T + 1) * 2 * Cout
     args = [_rand(B, Fin, T, 2, seed=7), B, Fin, T, _rand(10, 2, 2 * Cout, seed=8), _rand(2 * Cout, seed=9), Cout, 0.3,
-            torch.zeros(Fout * B * (T + 1) * 2 * Cout)]
+            torch.zeros(n), 0]
     assert _both("idv_enc0_fwd", args, [8]) < 1e-5
+    args[8], args[9] = torch.zeros(2 * n, dtype=torch.bfloat16), 1
+    assert _both("idv_enc0_fwd", args, [8]) < 2e-5
+
+
+def _to_split(x):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.stack((hi.reshape(-1), lo.reshape(-1))).contiguous()
 
 
 @pytest.mark.parametrize("NB,Fin,T,p_cp,s_cp,mask,S", [(2, 9, 40, 64, 64, 1, 1), (3, 5, 7, 32, 0, 0, 2)])
@@ -81,9 +96,11 @@ def test_dec5_head(NB, Fin, T, p_cp, s_cp, mask, S):
     if s_cp:
         skip = _rand(Fin, R, s_cp, seed=11)
         skip.view(Fin, NB, T + 1, s_cp)[:, :, 0] = 0
-    args = [p, p_cp, skip, s_cp, NB, Fin, T, _rand(10, p_cp + s_cp, 2, seed=12) * 0.1, _rand(2, seed=13), 0.25, mask,
+    args = [p, p_cp, skip, s_cp, 0, NB, Fin, T, _rand(10, p_cp + s_cp, 2, seed=12) * 0.1, _rand(2, seed=13), 0.25, mask,
             _rand(NB, Fout, T, 2, seed=14), torch.zeros(NB * S, Fout, T, 2), S, S - 1]
-    assert _both("idv_dec5_head_fwd", args, [12]) < 1e-5
+    assert _both("idv_dec5_head_fwd", args, [13]) < 1e-5
+    args[0], args[2], args[4] = _to_split(p), (_to_split(skip) if skip is not None else None), 1
+    assert _both("idv_dec5_head_fwd", args, [13]) < 1e-5
 
 
 @pytest.mark.parametrize("NB,T,H", [(1, 5, 8), (3, 20, 384), (64, 3, 128), (5, 4, 768)])
@@ -93,7 +110,9 @@ def test_lstm_recurrent_and_combine(NB, T, H):
     whh = _rand(2, 4 * H, H, seed=16) / (H ** 0.5)
     hseq = torch.full((4, R, H), 7.0)
     sync = torch.zeros(2, dtype=torch.int32)
-    assert _both("idv_lstm_recurrent_fwd", [g, 4 * H, R * 8 * H, 8 * H, whh, NB, T, H, hseq, sync], [8]) < 1e-5
+    hsplit = torch.zeros(2 * 4 * R * H, dtype=torch.bfloat16)
+    assert _both("idv_lstm_recurrent_fwd", [g, 4 * H, R * 8 * H, 8 * H, whh, NB, T, H, hseq, hsplit, sync], [8, 9]) < 2e-5
+    assert _both("idv_lstm_recurrent_fwd", [g, 4 * H, R * 8 * H, 8 * H, whh, NB, T, H, hseq, None, sync], [8]) < 1e-5
     hs = _rand(4, R, H, seed=17)
     assert _both("idv_lstm_combine_fwd", [hs, NB, T, H, torch.zeros(NB, T, H, 2)], [4]) < 1e-6
 
@@ -111,11 +130,17 @@ def test_layout_roundtrip(NB, C_, F, T):
     Cp = 2 * ((C_ + 7) // 8 * 8)
     x = _rand(NB, C_, F, T, 2, seed=21)
     planes = torch.full((F * NB * (T + 1) * Cp,), 3.0)
-    assert _both("idv_user_to_planes", [x, NB, C_, F, T, planes], [5]) < 1e-7
-    E.call("idv_user_to_planes", x, NB, C_, F, T, planes)
-    assert _both("idv_planes_to_user", [planes, NB, C_, F, T, torch.zeros_like(x)], [5]) < 1e-7
+    assert _both("idv_user_to_planes", [x, NB, C_, F, T, planes, 0], [5]) < 1e-7
+    E.call("idv_user_to_planes", x, NB, C_, F, T, planes, 0)
+    assert _both("idv_planes_to_user", [planes, 0, NB, C_, F, T, torch.zeros_like(x)], [6]) < 1e-7
+    sp = torch.full((2 * planes.numel(),), 3.0, dtype=torch.bfloat16)
+    assert _both("idv_user_to_planes", [x, NB, C_, F, T, sp, 1], [5]) < 1e-7
+    E.call("idv_user_to_planes", x, NB, C_, F, T, sp, 1)
+    assert _both("idv_planes_to_user", [sp, 1, NB, C_, F, T, torch.zeros_like(x)], [6]) < 1e-7
     z = _rand(NB * 2, T, 16, 2, seed=22)
-    assert _both("idv_z_to_planes", [z, NB, 2, 1, T, 16, torch.full((NB * (T + 1) * 32,), 5.0)], [6]) < 1e-7
+    assert _both("idv_z_to_planes", [z, NB, 2, 1, T, 16, torch.full((NB * (T + 1) * 32,), 5.0), 0], [6]) < 1e-7
+    assert _both("idv_z_to_planes", [z, NB, 2, 1, T, 16, torch.zeros(2 * NB * (T + 1) * 32, dtype=torch.bfloat16), 1],
+                 [6]) < 1e-7
     zb = _rand(C_, 6, seed=23)
     assert _both("idv_cbn_eval_user", [x, NB, C_, F * T, zb, torch.zeros_like(x)], [5]) < 1e-6
 
@@ -126,4 +151,40 @@ def test_bad_arguments_return_error_codes():
                  torch.zeros(4).cuda())          # L <= n_fft/2: reflect padding impossible
     with pytest.raises(RuntimeError, match="H"):
         lib.call("idv_lstm_recurrent_fwd", torch.zeros(4).cuda(), 0, 0, 4, torch.zeros(4).cuda(), 1, 1, 6,
-                 torch.zeros(4).cuda(), torch.zeros(2, dtype=torch.int32).cuda())
+                 torch.zeros(4).cuda(), None, torch.zeros(2, dtype=torch.int32).cuda())
+
+
+# ---------------------------------------------------------------------------------------------------
+# tensor-core tap-GEMM (tcgen05 / TMEM / TMA) against the contract incl. its split arithmetic
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("R,Tp,N,kcs,dts,two_src,prelu,out_split", [
+    (128, 0, 64, [64], [0], False, False, 0),                # one tile, one K step, fp32 out
+    (128, 0, 64, [64], [0], False, False, 1),                # same, split out
+    (300, 0, 128, [64, 128], [0, 1], False, True, 1),        # row tail, shifted tap, 3 K steps
+    (517, 47, 256, [128, 64, 128], [0, 1, 0], True, True, 1),   # two sources, pad rows, BN = 256
+    (1000, 0, 512, [192], [1], False, False, 0),             # two N tiles, many row tiles (persistent loop)
+    (40000, 641, 32, [64, 64], [1, 0], False, True, 1),      # > 148 tiles: several tiles per CTA, both TMEM stages
+])
+def test_tapgemm_tc(R, Tp, N, kcs, dts, two_src, prelu, out_split):
+    F0, cp0, cp1 = 3, 264, 136
+    a0 = _to_split(_rand(F0, R, cp0, seed=1))
+    a1 = _to_split(_rand(2, R, cp1, seed=2)) if two_src else None
+    kc_max = max(kcs)
+    taps, nk = [], 0
+    for i, (kc, dt) in enumerate(zip(kcs, dts)):
+        src = 1 if (two_src and i % 2) else 0
+        taps.append([src, i % (2 if src else F0), dt, 8, kc, i])
+        nk += kc // 64
+    units = [[0, len(taps), 1, 8, N, nk], [0, 1, 0, 8, 0, kcs[0] // 64]]
+    w = _rand(len(taps), N, kc_max, seed=3) * 0.1
+    for i, kc in enumerate(kcs):
+        w[i, :, kc:] = 0
+    wt = _to_split(w)
+    bias = _rand(2 * N, seed=4)
+    out_ld = N + 16
+    n_out = 2 * R * out_ld
+    out = torch.zeros(2 * n_out, dtype=torch.bfloat16) if out_split else torch.zeros(n_out)
+    args = [a0, cp0, F0, a1, cp1 if two_src else 0, 2 if two_src else 0, R, Tp, wt, kc_max, len(taps), bias, N,
+            torch.tensor(units, dtype=torch.int32), torch.tensor(taps, dtype=torch.int32), 2, out, out_ld,
+            R * out_ld, n_out, out_split, 1 if prelu else 0, 0.2]
+    assert _both("idv_tapgemm_tc", args, [16]) < 1e-5

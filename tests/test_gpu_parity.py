@@ -14,7 +14,7 @@ from oracle import ref_port as P
 pytestmark = pytest.mark.gpu
 
 WAVE_TOL = 1e-4      # north_star gate
-STAGE_TOL = 2e-5     # fp32 kernels: every intermediate stage
+STAGE_TOL = {"simt": 2e-5, "tc": 5e-5}   # intermediate stages: fp32 kernels / error-compensated bf16x3 kernels
 
 
 def _sisnr_gap_db(ours, ref, anchor):
@@ -29,7 +29,7 @@ def _sisnr_gap_db(ours, ref, anchor):
 def test_extension_is_loaded_and_native():
     from idccrn_b200 import lib
     l = lib.load()
-    assert l.idv_abi_version() == 1
+    assert l.idv_abi_version() == 2
     import ctypes
     n = ctypes.c_int(0)
     assert l.idv_device_sm_count(ctypes.byref(n)) == 0 and n.value > 0
@@ -42,7 +42,7 @@ def test_extension_is_loaded_and_native():
     ("vae_l2_sig_mask_s2_e2e", 2, 2, "twophase", "mask", 3, False),
     ("vae_l1_sig_ri_e2e", 1, 1, "twophase", "real_imag", 4, False),
 ])
-def test_vae_vs_reference_golden(golden, tag, latent_num, S, dec_kind, recon, seed, full):
+def test_vae_vs_reference_golden(gemm_mode, golden, tag, latent_num, S, dec_kind, recon, seed, full):
     g = golden(tag)
     B, L = int(g["B"]), int(g["L"])
     enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cuda")
@@ -61,12 +61,12 @@ def test_vae_vs_reference_golden(golden, tag, latent_num, S, dec_kind, recon, se
     wave = C.rel_l2(out["recon_sig"], g["recon_sig"])
     xrep = x.repeat_interleave(S, 0)
     gap, sdr = _sisnr_gap_db(out["recon_sig"], g["recon_sig"], xrep)
-    print(tag, "wave rel_l2 %.2e  sisnr gap %.4f dB  sdr-vs-ref %.1f dB" % (wave, gap, sdr), errs)
-    assert all(v < STAGE_TOL for v in errs.values()), errs
+    print(gemm_mode, tag, "wave rel_l2 %.2e  sisnr gap %.4f dB  sdr-vs-ref %.1f dB" % (wave, gap, sdr), errs)
+    assert all(v < STAGE_TOL[gemm_mode] for v in errs.values()), errs
     assert wave < WAVE_TOL and gap < 0.01, (wave, gap)
 
 
-def test_dccrn_vs_reference_golden(golden):
+def test_dccrn_vs_reference_golden(gemm_mode, golden):
     g = golden("dccrn_mask_e2e")
     B, L, seed = int(g["B"]), int(g["L"]), int(g["seed"])
     m = M.DCCRN_(C.NFFT, C.HOP, M.get_net_params(), True, "cuda", C.WIN, C.SKIPS, "mask", False, None, None)
@@ -79,7 +79,7 @@ def test_dccrn_vs_reference_golden(golden):
             "predict": C.rel_l2(torch.view_as_real(pred), g["predict"]), "clean": C.rel_l2(clean, g["clean"])}
     gap, sdr = _sisnr_gap_db(clean, g["clean"], x)
     print("dccrn", errs, gap, sdr)
-    assert errs["latent"] < STAGE_TOL and errs["predict"] < STAGE_TOL
+    assert errs["latent"] < STAGE_TOL[gemm_mode] and errs["predict"] < STAGE_TOL[gemm_mode]
     assert errs["clean"] < WAVE_TOL and gap < 0.01
 
 
@@ -106,7 +106,7 @@ def test_primitives_vs_reference_golden(golden):
         xin = torch.randn(2, 5, 7, 9, 2, generator=torch.Generator().manual_seed(5))
         want = P.cbn_eval(xin, cbn.state_dict(), "")
         errs["cbn"] = C.rel_l2(cbn.cuda()(xin.cuda(), train=False), want)
-    assert all(v < STAGE_TOL for v in errs.values()), errs
+    assert all(v < STAGE_TOL["simt"] for v in errs.values()), errs
 
 
 @pytest.mark.parametrize("B,L,latent_num,S,dec_kind,recon", [
@@ -114,7 +114,7 @@ def test_primitives_vs_reference_golden(golden):
     (2, 25700, 2, 1, "twophase", "mask"),               # T = 258, H = 768 recurrent config
     (5, 1300, 1, 3, "twophase", "mask"),                # S = 3 sample replication, short ragged length
 ])
-def test_vae_vs_live_oracle(B, L, latent_num, S, dec_kind, recon):
+def test_vae_vs_live_oracle(gemm_mode, B, L, latent_num, S, dec_kind, recon):
     seed = 11
     enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cuda")
     x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cuda")
@@ -130,8 +130,8 @@ def test_vae_vs_live_oracle(B, L, latent_num, S, dec_kind, recon):
             "predict": C.rel_l2(out["predict"], torch.view_as_real(dd["predict"]))}
     wave = C.rel_l2(out["recon_sig"], dd["recon_sig"])
     gap, sdr = _sisnr_gap_db(out["recon_sig"], dd["recon_sig"], x.repeat_interleave(S, 0))
-    print("live", (B, L, latent_num, S), "wave %.2e gap %.4f dB sdr %.1f dB" % (wave, gap, sdr), errs)
-    assert all(v < STAGE_TOL for v in errs.values()), errs
+    print(gemm_mode, "live", (B, L, latent_num, S), "wave %.2e gap %.4f dB sdr %.1f dB" % (wave, gap, sdr), errs)
+    assert all(v < STAGE_TOL[gemm_mode] for v in errs.values()), errs
     assert wave < WAVE_TOL and gap < 0.01
 
 
@@ -153,7 +153,7 @@ def test_stft_istft_properties_full_size():
     assert C.rel_l2(X[:2], ref) < 1e-5
 
 
-def test_full_size_batch_rows_match_small_oracle_run():
+def test_full_size_batch_rows_match_small_oracle_run(gemm_mode):
     """Utterances are independent: rows of the B=64 x 4 s CUDA run must equal the oracle run on those rows."""
     seed, B, L = 21, 64, 64000
     enc, dec = C.build_vae(1, 1, "skip_prepare", "real_imag", seed, "cuda")
@@ -169,7 +169,7 @@ def test_full_size_batch_rows_match_small_oracle_run():
     wave = C.rel_l2(out["recon_sig"][rows], dd["recon_sig"])
     mu = C.rel_l2(out["miu"][rows], st["miu_speech"])
     gap, sdr = _sisnr_gap_db(out["recon_sig"][rows], dd["recon_sig"], x[rows])
-    print("full-size rows: wave %.2e mu %.2e gap %.4f dB sdr %.1f" % (wave, mu, gap, sdr))
+    print(gemm_mode, "full-size rows: wave %.2e mu %.2e gap %.4f dB sdr %.1f" % (wave, mu, gap, sdr))
     assert torch.isfinite(out["recon_sig"]).all()
     assert wave < WAVE_TOL and mu < WAVE_TOL and gap < 0.01
 
