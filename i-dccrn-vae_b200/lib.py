@@ -26,6 +26,7 @@ SIGNATURES = {
     "idv_enc0_fwd": [vp, i32, i32, i32, vp, vp, i32, f32, vp, i32, vp],
     "idv_dec5_head_fwd": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, i32, i32, vp],
     "idv_lstm_recurrent_fwd": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp],
+    "idv_lstm_recurrent_tc": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp],
     "idv_lstm_combine_fwd": [vp, i32, i32, i32, vp, vp],
     "idv_reparam_fwd": [vp, i32, i32, i32, i32, i32, i32, vp, vp, u64, u64, vp, vp],
     "idv_planes_to_user": [vp, i32, i32, i32, i32, i32, vp, vp],
@@ -33,7 +34,7 @@ SIGNATURES = {
     "idv_z_to_planes": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "idv_cbn_eval_user": [vp, i64, i32, i64, vp, vp, vp],
 }
-EXPORTS = ["idv_abi_version", "idv_last_error"] + list(SIGNATURES)
+EXPORTS = ["idv_abi_version", "idv_last_error", "idv_lstm_tc_config"] + list(SIGNATURES)
 
 
 def lib_path():
@@ -98,6 +99,17 @@ def call(name, *args):
     if hook is not None:
         e1.record()
         hook(name, (e0, e1))
+
+
+def lstm_tc_config(H):
+    """(gate columns per CTA, CTAs per module) of the tensor-core recurrence, or None if H is unsupported."""
+    lib = load()
+    n, c = ctypes.c_int(0), ctypes.c_int(0)
+    lib.idv_lstm_tc_config.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    lib.idv_lstm_tc_config.restype = ctypes.c_int
+    if lib.idv_lstm_tc_config(int(H), ctypes.byref(n), ctypes.byref(c)) != 0:
+        return None
+    return n.value, c.value
 
 
 def ptr(t):

@@ -264,21 +264,37 @@ class ComplexLSTM(nn.Module):
             items[key] = layers
         return items[key]
 
+    def _packed_tc(self, cfg, device):
+        items = self._cache.check(self)
+        key = ("whh_tc", cfg, str(device))
+        if key not in items:
+            re, im = _sd(self.lstm_re), _sd(self.lstm_im)
+            items[key] = [pack.pack_lstm_whh_tc(re, im, l, cfg[0], cfg[1], device) for l in range(self.num_layer)]
+        return items[key]
+
     def forward_planes(self, xp):
         """xp: Planes with C*F == input_size (feature d = c*F + f).  Returns the latent (NB, T, H, 2)."""
         layers = self._packed(xp.C, xp.F, xp.data.device)
         NB, T, H = xp.NB, xp.T, self.hidden_size
         R = NB * (T + 1)
         src, hseq, split = xp, None, xp.split
+        # tensor-core recurrence when the planes are split-bf16 and the cooperative grid fits the device;
+        # otherwise the fp32 SIMT recurrence (any batch size)
+        cfg = ops.lstm_tc_supported(H, NB, xp.data.device) if split else None
+        whh_tc = self._packed_tc(cfg, xp.data.device) if cfg else None
         for l, (inproj, whh) in enumerate(layers):
             g = ops.tapgemm(inproj, src, None, NB, T, zero_pad_rows=False, out_split=False)
-            more = split and l + 1 < len(layers)       # the next layer's tensor-core in-proj reads split h
-            if l == 0:
-                hseq, hsp = ops.lstm_recurrent(g, 4 * H, R * 8 * H, 8 * H, whh, NB, T, H, want_split=more)
+            last = l + 1 == len(layers)
+            more = split and not last                  # the next layer's tensor-core in-proj reads split h
+            offs = (4 * H, R * 8 * H, 8 * H) if l == 0 else (2 * R * 4 * H, R * 4 * H, 4 * H)
+            if cfg:
+                hseq, hsp = ops.lstm_recurrent_tc(g, offs[0], offs[1], offs[2], whh_tc[l], NB, T, H,
+                                                  want_f32=last, want_split=more)
             else:
-                hseq, hsp = ops.lstm_recurrent(g, 2 * R * 4 * H, R * 4 * H, 4 * H, whh, NB, T, H, want_split=more)
+                hseq, hsp = ops.lstm_recurrent(g, offs[0], offs[1], offs[2], whh, NB, T, H, want_split=more)
             # [4 streams][R][H]: plane = stream, row stride H
-            src = Planes(hsp, NB, H, 4, T, cp=H, split=True) if split else Planes(hseq, NB, H, 4, T, cp=H)
+            if not last:
+                src = Planes(hsp, NB, H, 4, T, cp=H, split=True) if split else Planes(hseq, NB, H, 4, T, cp=H)
         return ops.lstm_combine(hseq, NB, T, H)
 
     def forward(self, x):

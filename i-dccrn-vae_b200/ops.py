@@ -138,6 +138,27 @@ def lstm_recurrent(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, want_split=False):
     return hseq, hsplit
 
 
+def lstm_tc_supported(H, NB, device):
+    cfg = lib.lstm_tc_config(H)
+    if cfg is None:
+        return None
+    n_rg = (NB + 63) // 64
+    sms = torch.cuda.get_device_properties(device).multi_processor_count if torch.cuda.is_available() else 148
+    return cfg if n_rg * 2 * cfg[1] <= sms else None
+
+
+def lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, want_f32=True, want_split=False):
+    """Tensor-core recurrence.  Returns (hseq fp32 or None, hsplit bf16 or None)."""
+    n = 4 * NB * (T + 1) * H
+    hseq = _empty(n, g.device) if want_f32 else None
+    hsplit = _empty_act(n, g.device, True) if want_split else None
+    n_rg = (NB + 63) // 64
+    hx = torch.empty(n_rg * 2 * 2 * 2 * 128 * H, dtype=torch.bfloat16, device=g.device)
+    sync = torch.empty(n_rg * 2, dtype=torch.int32, device=g.device)
+    lib.call("idv_lstm_recurrent_tc", g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, hx, sync)
+    return hseq, hsplit
+
+
 def lstm_combine(hseq, NB, T, H):
     latent = torch.empty((NB, T, H, 2), dtype=torch.float32, device=hseq.device)
     lib.call("idv_lstm_combine_fwd", hseq, NB, T, H, latent)

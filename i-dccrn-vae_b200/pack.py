@@ -277,6 +277,22 @@ def pack_lstm_whh(lstm_re, lstm_im, layer, device):
         .to(torch.float32).contiguous().to(device)
 
 
+def pack_lstm_whh_tc(lstm_re, lstm_im, layer, n_cols, n_ctas, device):
+    """Recurrent weights for idv_lstm_recurrent_tc: bf16 [2 (hi,lo)][2 (module)][n_ctas][n_cols][H], CTA c holds
+    the rows W_hh[gate*H + c*Hs + j] at (gate*Hs + j), Hs = n_cols / 4."""
+    hs = n_cols // 4
+    mats = []
+    for mod in (lstm_re, lstm_im):
+        w = _cpu(mod["weight_hh_l%d" % layer]).to(torch.float32)          # (4H, H)
+        H = w.shape[1]
+        assert hs * n_ctas == H
+        mats.append(w.view(4, n_ctas, hs, H).permute(1, 0, 2, 3).reshape(n_ctas, n_cols, H))
+    w = torch.stack(mats)                                                 # (2, n_ctas, n_cols, H)
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.to(torch.float32)).to(torch.bfloat16)
+    return torch.stack((hi, lo)).contiguous().to(device)
+
+
 def pack_dense(w_read, b_read, w_imag, b_imag, c_out, f_out, device):
     """ComplexDense (no cross terms, model/complex_progress.py:L83-89) followed by the reshape/permute
     to (B, C, F, T) (model/pvae_module.py:L2085-2088): output feature n = c*f_out + f goes to plane f,

@@ -119,6 +119,17 @@ int idv_dec5_head_fwd(const void* p, int p_cp, const void* skip, int s_cp, int i
 int idv_lstm_recurrent_fwd(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld,
                            const float* whh, int NB, int T, int H, float* hseq, void* hsplit,
                            unsigned int* sync, void* stream);
+/* Tensor-core recurrence (tcgen05): same contract as idv_lstm_recurrent_fwd with the recurrent product
+ * evaluated as h_hi*W_hi + h_hi*W_lo + h_lo*W_hi on the split-bf16 value of h(t-1) (fp32 accumulate, fp32
+ * cell state).  idv_lstm_tc_config gives the gate columns per CTA (n_cols = 4*Hs) and CTAs per module for a
+ * hidden size; wpack: bf16 [2 (hi,lo)][2 (module)][n_ctas][n_cols (gate*Hs + j)][H] holds row
+ * W_hh^m[gate*H + c*Hs + j] at (c, gate*Hs + j).  hseq and/or hsplit may be NULL (not both).
+ * hx: workspace bf16 [ceil(NB/64)][2][2][2][128][H]; sync: ceil(NB/64)*2 x uint32; both zeroed by the call.
+ * H % 64 == 0; ceil(NB/64) * 2 * n_ctas must not exceed the SM count (cooperative launch).                  */
+int idv_lstm_tc_config(int H, int* n_cols, int* n_ctas);
+int idv_lstm_recurrent_tc(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* wpack,
+                          int NB, int T, int H, float* hseq, void* hsplit, void* hx, unsigned int* sync,
+                          void* stream);
 /* Combine the four streams (real = rr - ii, imag = ir + ri), emit the user-layout latent
  * (NB, T, H, 2).  Replaces the stack/permute at complex_progress.py:L62-73, pvae_module.py:L2247. */
 int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, float* latent, void* stream);

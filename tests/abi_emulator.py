@@ -224,6 +224,59 @@ def idv_lstm_recurrent_fwd(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, hseq, hspli
         _wr(hsplit, 1, hs)
 
 
+def _bf16_split(x):
+    hi = x.to(torch.float32).to(torch.bfloat16)
+    lo = (x.to(torch.float32) - hi.to(torch.float32)).to(torch.bfloat16)
+    return hi.to(D), lo.to(D)
+
+
+def idv_lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, hx, sync):
+    """Contract of the tensor-core recurrence: the recurrent product uses the split value of h(t-1)."""
+    n_cols, n_ctas = _lstm_tc_config(H)
+    hs = n_cols // 4
+    Tp = T + 1
+    R = NB * Tp
+    wp = wpack.view(2, 2, n_ctas, 4, hs, H).to(D)                     # [hl][m][c][gate][j][k]
+    W = wp.permute(0, 1, 3, 2, 4, 5).reshape(2, 2, 4 * H, H)          # [hl][m][gate*H + c*hs + j][k]
+    gf = _flat(g)
+    rows0 = torch.arange(NB) * Tp
+    out = torch.zeros(4, R, H, dtype=D)
+    for m in range(2):
+        for p in range(2):
+            base = m * g_m_off + p * g_p_off
+            h = torch.zeros(NB, H, dtype=D)
+            c = torch.zeros(NB, H, dtype=D)
+            for t in range(T):
+                rows = rows0 + 1 + t
+                idx = base + rows[:, None] * g_ld + torch.arange(4 * H)[None, :]
+                hh, hl = _bf16_split(h)
+                a = gf[idx].to(D) + hh @ W[0, m].t() + hh @ W[1, m].t() + hl @ W[0, m].t()
+                i, f, gg, o = a[:, :H], a[:, H:2 * H], a[:, 2 * H:3 * H], a[:, 3 * H:]
+                c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+                h = torch.sigmoid(o) * torch.tanh(c)
+                out[m * 2 + p, rows] = h
+    valid = torch.zeros(R, dtype=torch.bool)
+    valid[(rows0[:, None] + 1 + torch.arange(T)[None, :]).reshape(-1)] = True
+    if hseq is not None:
+        hseq.view(4, R, H)[:, valid] = out[:, valid].to(torch.float32)
+    if hsplit is not None:
+        hi, lo = _bf16_split(out)
+        hv = hsplit.view(2, 4, R, H)
+        hv[0][:, valid] = hi[:, valid].to(torch.bfloat16)
+        hv[1][:, valid] = lo[:, valid].to(torch.bfloat16)
+
+
+def _lstm_tc_config(H):
+    assert H % 64 == 0
+    if H <= 384 and H % 16 == 0:
+        n = 64
+    elif H <= 768 and H % 12 == 0:
+        n = 48
+    else:
+        n = 32
+    return n, H // (n // 4)
+
+
 def idv_lstm_combine_fwd(hseq, NB, T, H, latent):
     Tp = T + 1
     hs = hseq.view(4, NB, Tp, H)[:, :, 1:]

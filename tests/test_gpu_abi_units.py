@@ -188,3 +188,21 @@ def test_tapgemm_tc(R, Tp, N, kcs, dts, two_src, prelu, out_split):
             torch.tensor(units, dtype=torch.int32), torch.tensor(taps, dtype=torch.int32), 2, out, out_ld,
             R * out_ld, n_out, out_split, 1 if prelu else 0, 0.2]
     assert _both("idv_tapgemm_tc", args, [16]) < 1e-5
+
+
+@pytest.mark.parametrize("NB,T,H", [(3, 6, 128), (64, 40, 384), (5, 9, 768), (70, 5, 128)])
+def test_lstm_recurrent_tc(NB, T, H):
+    from idccrn_b200 import pack as PK
+    n_cols, n_ctas = lib.lstm_tc_config(H)
+    assert (n_cols, n_ctas) == E._lstm_tc_config(H)
+    R = NB * (T + 1)
+    g = _rand(2, R, 8 * H, seed=15)
+    whh = _rand(2, 4 * H, H, seed=16) / (H ** 0.5)
+    wp = PK.pack_lstm_whh_tc({"weight_hh_l0": whh[0]}, {"weight_hh_l0": whh[1]}, 0, n_cols, n_ctas, "cpu")
+    n_rg = (NB + 63) // 64
+    hseq = torch.zeros(4, R, H)
+    hsplit = torch.zeros(2 * 4 * R * H, dtype=torch.bfloat16)
+    hx = torch.zeros(n_rg * 2 * 2 * 2 * 128 * H, dtype=torch.bfloat16)
+    sync = torch.zeros(n_rg * 2, dtype=torch.int32)
+    args = [g, 4 * H, R * 8 * H, 8 * H, wp, NB, T, H, hseq, hsplit, hx, sync]
+    assert _both("idv_lstm_recurrent_tc", args, [8, 9]) < 2e-5
