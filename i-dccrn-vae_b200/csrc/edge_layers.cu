@@ -28,9 +28,14 @@ __global__ void __launch_bounds__(256) enc0_kernel(const float* __restrict__ stf
   float* orow = reinterpret_cast<float*>(outv) + oidx;
   unsigned short* osp = reinterpret_cast<unsigned short*>(outv);
   if (t < 0) {                                       // causal pad row
-    for (int n = cg * 4; n < N; n += 32) {
-      if (out_split) st_split4(osp, hl, oidx + n, make_float4(0.f, 0.f, 0.f, 0.f));
-      else *reinterpret_cast<float4*>(orow + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = cg * 8; n < N; n += 64) {
+      if (out_split) {
+        *reinterpret_cast<uint4*>(osp + oidx + n) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(osp + hl + oidx + n) = make_uint4(0u, 0u, 0u, 0u);
+      } else {
+        *reinterpret_cast<float4*>(orow + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(orow + n + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     return;
   }
@@ -49,20 +54,40 @@ __global__ void __launch_bounds__(256) enc0_kernel(const float* __restrict__ stf
       xin[(kf * 2 + kt) * 2 + 1] = v.y;
     }
   }
-  for (int n = cg * 4; n < N; n += 32) {
-    float4 acc = *reinterpret_cast<const float4*>(&ws[20 * N + n]);
+  // 8 consecutive channels per thread: one 16-byte store per plane (hi / lo) or two float4
+  for (int n = cg * 8; n < N; n += 64) {
+    float acc[8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(&ws[20 * N + n]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&ws[20 * N + n + 4]);
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
 #pragma unroll
     for (int k = 0; k < 20; ++k) {
-      const float4 wv = *reinterpret_cast<const float4*>(&ws[k * N + n]);
-      acc.x = fmaf(xin[k], wv.x, acc.x);
-      acc.y = fmaf(xin[k], wv.y, acc.y);
-      acc.z = fmaf(xin[k], wv.z, acc.z);
-      acc.w = fmaf(xin[k], wv.w, acc.w);
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[k * N + n]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&ws[k * N + n + 4]);
+      acc[0] = fmaf(xin[k], w0.x, acc[0]); acc[1] = fmaf(xin[k], w0.y, acc[1]);
+      acc[2] = fmaf(xin[k], w0.z, acc[2]); acc[3] = fmaf(xin[k], w0.w, acc[3]);
+      acc[4] = fmaf(xin[k], w1.x, acc[4]); acc[5] = fmaf(xin[k], w1.y, acc[5]);
+      acc[6] = fmaf(xin[k], w1.z, acc[6]); acc[7] = fmaf(xin[k], w1.w, acc[7]);
     }
-    acc.x = prelu_f(acc.x, slope); acc.y = prelu_f(acc.y, slope);
-    acc.z = prelu_f(acc.z, slope); acc.w = prelu_f(acc.w, slope);
-    if (out_split) st_split4(osp, hl, oidx + n, acc);
-    else *reinterpret_cast<float4*>(orow + n) = acc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = prelu_f(acc[j], slope);
+    if (out_split) {
+      unsigned short h[8], l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_bf16(acc[j], h[j], l[j]);
+      *reinterpret_cast<uint4*>(osp + oidx + n) =
+          make_uint4((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16),
+                     (unsigned)h[4] | ((unsigned)h[5] << 16), (unsigned)h[6] | ((unsigned)h[7] << 16));
+      *reinterpret_cast<uint4*>(osp + hl + oidx + n) =
+          make_uint4((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16),
+                     (unsigned)l[4] | ((unsigned)l[5] << 16), (unsigned)l[6] | ((unsigned)l[7] << 16));
+    } else {
+      *reinterpret_cast<float4*>(orow + n) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(orow + n + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
   }
 }
 

@@ -13,6 +13,8 @@
 //                   bf16 hi/lo into the exchange buffer (+ the sequence outputs), then release the step counter.
 // The exchange buffer hx[parity][m][hi/lo][128][H] (≈ 0.8 MB) stays in L2; the per-module step counter is the only
 // inter-CTA synchronisation (NC CTAs, not the whole grid).  Cooperative launch guarantees co-residency.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace idv {
@@ -32,7 +34,19 @@ struct LstmTcParams {
   unsigned short* hsplit;                   // optional bf16 [2][4][R][H]
   unsigned short* hx;                       // bf16 [n_rg][2 parity][2 m][2 hl][128][H]
   unsigned int* sync;                       // [n_rg][2 m] step counters (zeroed by the host)
+  unsigned long long* dbg;                  // optional phase timestamps (IDV_LSTM_DBG=1), CTA (0,0,0), steps [200,208)
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define LSTM_DBG(slot)                                                                            \
+  do {                                                                                            \
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && t >= 200 && t < 208)   \
+      p.dbg[(t - 200) * 16 + (slot)] = gtime();                                                   \
+  } while (0)
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
@@ -118,6 +132,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           }
           fence_proxy_async_global();          // generic-proxy writes of the peers -> visible to the TMA reads
         }
+        LSTM_DBG(0);
         const int par = t & 1;
         const int row_base = (((rg * 2 + par) * 2 + m) * 2) * L_ROWS;
         for (int kc = 0; kc < KC; ++kc) {
@@ -128,6 +143,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           tma_load_2d(&tmH, hfull0 + 8 * stage, sa + L_HTILE, kc * BK, row_base + L_ROWS);
           if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
         }
+        LSTM_DBG(1);
       }
     }
   } else if (warp == 1) {
@@ -142,6 +158,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(hfull0 + 8 * stage, phase);
           tc_fence_after();
+          if (kc == 0) LSTM_DBG(2);
           const uint32_t sa = smem_ring + stage * 2 * L_HTILE;
           const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + L_HTILE);
           const uint64_t b_hi = make_desc_sw128(smem_w + kc * W_TILE);
@@ -157,6 +174,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(accfull);
+        LSTM_DBG(3);
       }
     }
   } else {
@@ -190,6 +208,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       }
       mbar_wait(accfull, t & 1);
       tc_fence_after();
+      if (warp == L_EPI_WARP0 && lane == 0) LSTM_DBG(4);
       uint32_t v[N];
 #pragma unroll
       for (int c0 = 0; c0 < N; c0 += 16) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v + c0);
@@ -197,6 +216,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(accempty);           // accumulator drained -> next step's MMAs may start
+      if (warp == L_EPI_WARP0 && lane == 0) LSTM_DBG(5);
       float hn[HS];
 #pragma unroll
       for (int j = 0; j < HS; ++j) {
@@ -221,9 +241,14 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           if (p.hseq) *reinterpret_cast<float4*>(p.hseq + oidx + j) = hv;
         }
       }
+      if (warp == L_EPI_WARP0 && lane == 0) LSTM_DBG(6);
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == L_EPI_WARP0 && lane == 0) atomicAdd(ctr, 1u);
+      if (warp == L_EPI_WARP0 && lane == 0) {
+        LSTM_DBG(7);
+        atomicAdd(ctr, 1u);
+        LSTM_DBG(8);
+      }
     }
   }
 
@@ -306,9 +331,29 @@ extern "C" int idv_lstm_recurrent_tc(const float* g, int64_t g_m_off, int64_t g_
   p.NB = NB; p.T = T; p.H = H; p.NC = NC; p.KC = KC;
   p.hseq = hseq; p.hsplit = reinterpret_cast<unsigned short*>(hsplit);
   p.hx = reinterpret_cast<unsigned short*>(hx); p.sync = sync;
-  switch (N) {
-    case 64: return launch_lstm_tc<64>(mW, mH, p, n_rg, smem, st);
-    case 48: return launch_lstm_tc<48>(mW, mH, p, n_rg, smem, st);
-    default: return launch_lstm_tc<32>(mW, mH, p, n_rg, smem, st);
+  p.dbg = nullptr;
+  const bool dbg = getenv("IDV_LSTM_DBG") != nullptr && T > 208;
+  if (dbg) {
+    IDV_CUDA(cudaMalloc(&p.dbg, 8 * 16 * sizeof(unsigned long long)));
+    IDV_CUDA(cudaMemsetAsync(p.dbg, 0, 8 * 16 * sizeof(unsigned long long), st));
   }
+  switch (N) {
+    case 64: rc = launch_lstm_tc<64>(mW, mH, p, n_rg, smem, st); break;
+    case 48: rc = launch_lstm_tc<48>(mW, mH, p, n_rg, smem, st); break;
+    default: rc = launch_lstm_tc<32>(mW, mH, p, n_rg, smem, st); break;
+  }
+  if (dbg && rc == IDV_OK) {
+    unsigned long long h[8 * 16];
+    IDV_CUDA(cudaStreamSynchronize(st));
+    IDV_CUDA(cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg);
+    // slots: 0 step counter seen, 1 TMA issued, 2 first h tile landed, 3 last MMA issued, 4 accumulator ready,
+    //        5 TMEM drained, 6 gates+stores done, 7 fence+bar done, 8 counter published
+    for (int i = 0; i < 8; ++i) {
+      fprintf(stderr, "[lstm_tc dbg] step %d:", 200 + i);
+      for (int sl = 0; sl < 9; ++sl) fprintf(stderr, " %lld", (long long)(h[i * 16 + sl] - h[0]));
+      fprintf(stderr, "\n");
+    }
+  }
+  return rc;
 }

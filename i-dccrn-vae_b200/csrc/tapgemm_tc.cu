@@ -37,6 +37,13 @@ struct Params {
   int out_split;              // 1: bf16 hi/lo planes, 0: fp32
   int apply_prelu;
   float slope;
+  // head mode (last decoder layer, Cout = 1): unit q holds output bins fo = 2q (columns 0,1 = re,im) and
+  // fo = 2q+1 (columns 16,17); the epilogue applies bias + PReLU (+ mask head) and writes `predict`
+  // (NBtot, head_fout, T, 2) directly.  0 = off, 1 = real/imag, 2 = mask.
+  int head;
+  int head_fout, head_bmul, head_boff;
+  const float* stft_x;
+  float* predict;
 };
 
 template <int BN>
@@ -160,6 +167,43 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const bool row_ok = r < p.R;
       const bool pad_row = p.Tp > 0 && (r % p.Tp) == 0;
       const float* bias = p.bias + unit.bias_off + nt * BN;
+      if (p.head) {
+        // ---- fused reconstruction head: 2 output bins per unit, written to the reference layout
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        if (row_ok && !pad_row) {
+          const int T = p.Tp - 1;
+          const int b = r / p.Tp, t = r % p.Tp - 1;
+          const float b_r = __ldg(bias), b_i = __ldg(bias + 1);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int fo = 2 * unit.out_f + e;
+            if (fo >= p.head_fout) continue;
+            float yr = prelu_f(__uint_as_float(v[16 * e]) + b_r, p.slope);
+            float yi = prelu_f(__uint_as_float(v[16 * e + 1]) + b_i, p.slope);
+            if (p.head == 2) {
+              // model/pvae_module.py:L2594-2609 — operation order kept
+              const float mag = tanhf(sqrtf(yr * yr + yi * yi));
+              const float ph = atan2f(yi / (mag + 1e-8f), yr / (mag + 1e-8f));
+              const float2 X = __ldg(reinterpret_cast<const float2*>(p.stft_x + ((long long)(b * p.head_fout + fo) * T + t) * 2));
+              const float in_mag = sqrtf(X.x * X.x + X.y * X.y);
+              const float in_ph = atan2f(X.y, X.x);
+              float sn, cs;
+              sincosf(in_ph + ph, &sn, &cs);
+              const float gm = in_mag * mag;
+              yr = gm * cs;
+              yi = gm * sn;
+            }
+            const int bo = b * p.head_bmul + p.head_boff;
+            *reinterpret_cast<float2*>(p.predict + ((long long)(bo * p.head_fout + fo) * T + t) * 2) = make_float2(yr, yi);
+          }
+        }
+        continue;
+      }
       const long long obase = (long long)unit.out_f * p.out_plane + (long long)r * p.out_ld + unit.out_ch_off + nt * BN;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -290,13 +334,29 @@ extern "C" int idv_tapgemm_tc(const void* a0, int a0_cp, int a0_planes, const vo
                               const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
                               int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu, float prelu_slope,
                               void* stream) {
+  return idv_tapgemm_tc_head(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, N, units,
+                             taps, n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, prelu_slope, 0, 0,
+                             1, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
+                                   int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias, int N,
+                                   const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
+                                   int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu,
+                                   float prelu_slope, int head, int head_fout, int head_bmul, int head_boff,
+                                   const float* stft_x, float* predict, void* stream) {
   using namespace idv;
   using namespace idv::tc;
-  IDV_CHECK_ARG(a0 && wt && bias && units && taps && out, "idv_tapgemm_tc: null pointer");
+  IDV_CHECK_ARG(a0 && wt && bias && units && taps && (out || head), "idv_tapgemm_tc: null pointer");
+  IDV_CHECK_ARG(head >= 0 && head <= 2, "idv_tapgemm_tc: head mode must be 0, 1 or 2");
+  if (head) {
+    IDV_CHECK_ARG(N == 32 && Tp > 1 && predict && head_fout > 0 && head_bmul > 0 && head_boff >= 0 && (head != 2 || stft_x),
+                  "idv_tapgemm_tc: head mode needs N == 32, Tp, predict (and stft_x for the mask head)");
+  }
   IDV_CHECK_ARG(R > 0 && n_units > 0 && a0_planes > 0 && n_slots > 0, "idv_tapgemm_tc: empty problem");
   IDV_CHECK_ARG(N >= 32 && N % 32 == 0 && (N <= 256 ? (N == 32 || N == 64 || N == 128 || N == 256) : N % 256 == 0),
                 "idv_tapgemm_tc: N=%d must be 32, 64, 128, 256 or a multiple of 256", N);
-  IDV_CHECK_ARG(a0_cp % 8 == 0 && kc_max % 64 == 0 && out_ld % 8 == 0 && (!a1 || a1_cp % 8 == 0),
+  IDV_CHECK_ARG(a0_cp % 8 == 0 && kc_max % 64 == 0 && (head || out_ld % 8 == 0) && (!a1 || a1_cp % 8 == 0),
                 "idv_tapgemm_tc: channel counts must be multiples of 8 and kc_max of 64");
   const int BN = N < 256 ? N : 256;
   CUtensorMap mA0, mA1, mW;
@@ -315,6 +375,8 @@ extern "C" int idv_tapgemm_tc(const void* a0, int a0_cp, int a0_planes, const vo
   p.n_row_tiles = cdiv(R, BM); p.n_col_tiles = N / BN;
   p.units = units; p.taps = taps; p.bias = bias; p.out = out; p.out_ld = out_ld;
   p.out_plane = out_plane; p.out_hl = out_hl; p.out_split = out_split; p.apply_prelu = apply_prelu; p.slope = prelu_slope;
+  p.head = head; p.head_fout = head_fout; p.head_bmul = head_bmul; p.head_boff = head_boff;
+  p.stft_x = stft_x; p.predict = predict;
   int dev = 0, sms = 0;
   IDV_CUDA(cudaGetDevice(&dev));
   IDV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -440,7 +440,14 @@ class Decoder(nn.Module):
             items[key] = pack.pack_dec5(t.tconv_re.weight, t.tconv_re.bias, t.tconv_im.weight, t.tconv_im.bias,
                                         bn, slope, pp.C, c_skip, pp.data.device)
         w, b, slope = items[key]
-        ops.dec5_head(pp, skip, w, b, slope, mask, stft_x, predict, out_bmul, out_boff)
+        kcs = [pp.Cp] + ([skip.Cp] if skip is not None else [])
+        if pp.split and all(k % 64 == 0 for k in kcs):
+            tkey = ("head_tc", pp.C, c_skip, pp.F, str(pp.data.device))
+            if tkey not in items:
+                items[tkey] = pack.pack_dec5_tc(w, b, slope, pp.F, kcs, pp.data.device)
+            ops.dec5_head_tc(items[tkey], pp, skip, mask, stft_x, predict, out_bmul, out_boff)
+        else:
+            ops.dec5_head(pp, skip, w, b, slope, mask, stft_x, predict, out_bmul, out_boff)
 
     def forward(self, x, train=True):
         if train and self.if_bn:

@@ -129,6 +129,16 @@ def dec5_head(p, skip, w, bias, slope, mask, stft_x, predict, out_bmul, out_boff
              1 if mask else 0, stft_x if mask else None, predict, out_bmul, out_boff)
 
 
+def dec5_head_tc(hp, p, skip, mask, stft_x, predict, out_bmul, out_boff):
+    """Last decoder layer + head on the tensor-core kernel (hp = pack.pack_dec5_tc)."""
+    R = p.NB * (p.T + 1)
+    lib.call("idv_tapgemm_tc_head", p.data, p.Cp, p.F, skip.data if skip is not None else None,
+             skip.Cp if skip is not None else 0, skip.F if skip is not None else 0, R, p.T + 1,
+             hp["wt"], hp["kc_max"], hp["n_slots"], hp["bias"], hp["N"], hp["units"], hp["taps"], hp["n_units"],
+             None, 0, 0, 0, 0, 1, hp["slope"], 2 if mask else 1, predict.shape[1], out_bmul, out_boff,
+             stft_x if mask else None, predict)
+
+
 def lstm_recurrent(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, want_split=False):
     """Returns (hseq fp32 [4][R][H], hsplit bf16 [2][4][R][H] or None)."""
     hseq = _empty(4 * NB * (T + 1) * H, g.device)

@@ -233,6 +233,56 @@ def pack_dec5(t_re_w, t_re_b, t_im_w, t_im_b, bn, slope, c_p, c_skip, device):
     return w, b2, float(slope if slope is not None else 1.0)
 
 
+def pack_dec5_tc(w10, bias2, slope, f_in, kcs, device):
+    """Last decoder layer on the tensor-core kernel with the head fused (idv_tapgemm_tc_head).
+    w10: [10 (kf*2+kt)][sum(kcs)][2] folded weights of pack_dec5 (sources concatenated along k), bias2: [2].
+    Unit q -> output bins 2q (columns 0,1) and 2q+1 (columns 16,17); per source and time tap three weight slots
+    (input plane q+1, q, q-1):  q+1 feeds kf=0 (even) / kf=1 (odd), q feeds kf=2 / kf=3, q-1 feeds kf=4 (even)."""
+    w10 = w10.detach().cpu().to(torch.float32)
+    N = 32
+    ksum = sum(kcs)
+    assert w10.shape == (10, ksum, 2) and all(k % 64 == 0 for k in kcs)
+    k_off = [0]
+    for k in kcs:
+        k_off.append(k_off[-1] + k)
+    kc_max = max(kcs)
+    rel = (+1, 0, -1)
+    kf_even, kf_odd = {+1: 0, 0: 2, -1: 4}, {+1: 1, 0: 3}
+    slots, slot_id = [], {}
+    for si in range(len(kcs)):
+        for d in rel:
+            for kt in range(2):
+                W = torch.zeros(N, kc_max)
+                ks = slice(k_off[si], k_off[si + 1])
+                W[0:2, :kcs[si]] = w10[kf_even[d] * 2 + kt, ks].t()
+                if d in kf_odd:
+                    W[16:18, :kcs[si]] = w10[kf_odd[d] * 2 + kt, ks].t()
+                slot_id[(si, d, kt)] = len(slots)
+                slots.append(W)
+    wt = torch.stack(slots)
+    hi = wt.to(torch.bfloat16)
+    lo = (wt - hi.to(torch.float32)).to(torch.bfloat16)
+    n_units = (2 * f_in - 1 + 1) // 2
+    units, taps = [], []
+    for q in range(n_units):
+        begin = len(taps)
+        for d in rel:
+            fi = q + d
+            if fi < 0 or fi >= f_in:
+                continue
+            for kt in range(2):
+                for si in range(len(kcs)):
+                    taps.append([si, fi, kt, 0, kcs[si], slot_id[(si, d, kt)]])
+        ks = sum(t[4] // 64 for t in taps[begin:])
+        units.append([begin, len(taps) - begin, q, 0, 0, ks])
+    bias = torch.zeros(N)
+    bias[0:2] = bias2.detach().cpu().to(torch.float32)
+    return dict(wt=torch.stack((hi, lo)).contiguous().to(device), kc_max=kc_max, n_slots=len(slots),
+                taps=torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(device),
+                units=torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(device), n_units=n_units,
+                bias=bias.to(device), slope=float(slope), N=N)
+
+
 def pack_lstm_inproj0(lstm_re, lstm_im, hidden, c_in, f_in, device):
     """Layer-0 input projection of both nn.LSTM modules as one tap-GEMM: feature d = c*f_in + f
     (the reshape at model/pvae_module.py:L2241).  N = 8H: [module re gates | module im gates];

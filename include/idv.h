@@ -79,6 +79,19 @@ int idv_tapgemm_tc(const void* a0, int a0_cp, int a0_planes, const void* a1, int
                    int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu, float prelu_slope,
                    void* stream);
 
+/* Same kernel with the reconstruction head fused into the epilogue (last decoder layer, Cout = 1):
+ * N == 32, unit q produces the output bins fo = 2q (accumulator columns 0,1 = re,im) and fo = 2q+1 (columns
+ * 16,17); bias[unit.bias_off + {0,1}] = (re, im); PReLU(slope) is always applied; head = 1 writes the complex
+ * spectrum, head = 2 the mask head of model/pvae_module.py:L2594-2609 (needs stft_x (NB, head_fout, T, 2)).
+ * predict: (NBtot, head_fout, T, 2), utterance index b*head_bmul + head_boff.  `out` is unused (may be NULL).
+ * Replaces idv_dec5_head_fwd on split-bf16 planes.                                                        */
+int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
+                        int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias, int N,
+                        const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
+                        int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu, float prelu_slope,
+                        int head, int head_fout, int head_bmul, int head_boff, const float* stft_x,
+                        float* predict, void* stream);
+
 /* ---- STFT / iSTFT -----------------------------------------------------------------------------
  * replaces torch.stft at model/pvae_module.py:L22 (n_fft 512, hop, win, periodic Hann, center,
  * reflect pad, onesided).  basis: [win][2*(n_fft/2+1)] fp32, column 2k = cos*w, 2k+1 = -sin*w

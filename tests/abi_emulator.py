@@ -41,6 +41,40 @@ def _wr(t, split, vals):
     f[half:half + v.numel()] = lo
 
 
+def idv_tapgemm_tc_head(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, N, units, taps,
+                        n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, slope, head, head_fout,
+                        head_bmul, head_boff, stft_x, predict):
+    assert head in (1, 2) and N == 32
+    tmp = torch.zeros(n_units * R * 32)
+    un = units.clone()
+    un[:, 2] = torch.arange(n_units)          # plane per unit in the scratch output
+    un[:, 3] = 0
+    idv_tapgemm_tc._head_bias = True          # the head applies bias (re, im) to both bin pairs
+    try:
+        idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, 0, wt, kc_max, n_slots, bias, N, un, taps,
+                       n_units, tmp, 32, R * 32, 0, 0, 1, slope)
+    finally:
+        idv_tapgemm_tc._head_bias = False
+    T = Tp - 1
+    NB = R // Tp
+    acc = tmp.view(n_units, NB, Tp, 32)[:, :, 1:].to(D)             # (units, NB, T, 32), bias + PReLU applied
+    pv = predict.view(-1, head_fout, T, 2)
+    for ui, (tb, nt, q, _, _, _) in enumerate(units.tolist()):
+        for e in range(2):
+            fo = 2 * q + e
+            if fo >= head_fout:
+                continue
+            yr, yi = acc[ui, :, :, 16 * e], acc[ui, :, :, 16 * e + 1]
+            if head == 2:
+                mag = torch.tanh(torch.sqrt(yr ** 2 + yi ** 2))
+                ph = torch.atan2(yi / (mag + 1e-8), yr / (mag + 1e-8))
+                X = stft_x.view(-1, head_fout, T, 2)[:NB, fo].to(D)
+                in_mag = torch.sqrt(X[..., 0] ** 2 + X[..., 1] ** 2)
+                in_ph = torch.atan2(X[..., 1], X[..., 0])
+                yr, yi = in_mag * mag * torch.cos(in_ph + ph), in_mag * mag * torch.sin(in_ph + ph)
+            pv[head_boff::head_bmul][:NB, fo] = torch.stack((yr, yi), -1).to(torch.float32)
+
+
 def idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, N, units, taps,
                    n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, slope):
     """Contract of the tensor-core tap-GEMM incl. its arithmetic: a_hi*w_hi + a_hi*w_lo + a_lo*w_hi."""
@@ -70,7 +104,10 @@ def idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max
             ah, al = shifted(hi), shifted(lo)
             wh, wl = W[0, slot, :, :kc].t(), W[1, slot, :, :kc].t()
             acc += ah @ wh + ah @ wl + al @ wh
-        acc += _flat(bias)[bias_off:bias_off + N].to(D)
+        bvec = _flat(bias)[bias_off:bias_off + N].to(D).clone()
+        if getattr(idv_tapgemm_tc, "_head_bias", False):
+            bvec[16:18] = bvec[0:2]
+        acc += bvec
         if apply_prelu:
             acc = torch.where(acc > 0, acc, slope * acc)
         if Tp > 0:

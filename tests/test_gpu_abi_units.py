@@ -206,3 +206,34 @@ def test_lstm_recurrent_tc(NB, T, H):
     sync = torch.zeros(n_rg * 2, dtype=torch.int32)
     args = [g, 4 * H, R * 8 * H, 8 * H, wp, NB, T, H, hseq, hsplit, hx, sync]
     assert _both("idv_lstm_recurrent_tc", args, [8, 9]) < 2e-5
+
+
+@pytest.mark.parametrize("NB,Fin,T,two_src,mask,S", [(2, 9, 40, True, 2, 1), (3, 5, 130, False, 1, 2)])
+def test_tapgemm_tc_head(NB, Fin, T, two_src, mask, S):
+    """Last decoder layer + head fused in the tensor-core epilogue, packed by pack.pack_dec5_tc."""
+    from idccrn_b200 import pack as PK
+    R, Fout = NB * (T + 1), 2 * Fin - 1
+    kcs = [64, 64] if two_src else [64]
+
+    def planes(seed, cp):
+        x = _rand(Fin, NB, T + 1, cp, seed=seed)
+        x[:, :, 0] = 0
+        return _to_split(x)
+    p = planes(10, 64)
+    skip = planes(11, 64) if two_src else None
+    w10 = _rand(10, sum(kcs), 2, seed=12) * 0.1
+    hp = PK.pack_dec5_tc(w10, _rand(2, seed=13), 0.25, Fin, kcs, "cpu")
+    predict = torch.zeros(NB * S, Fout, T, 2)
+    args = [p, 64, Fin, skip, 64 if two_src else 0, Fin if two_src else 0, R, T + 1, hp["wt"], hp["kc_max"],
+            hp["n_slots"], hp["bias"], 32, hp["units"], hp["taps"], hp["n_units"], None, 0, 0, 0, 0, 1, hp["slope"],
+            mask, Fout, S, S - 1, _rand(NB, Fout, T, 2, seed=14), predict]
+    assert _both("idv_tapgemm_tc_head", args, [28]) < 1e-5
+    # and the packed form agrees with the SIMT head kernel's contract on the same folded weights
+    ref = torch.zeros(NB * S, Fout, T, 2)
+    E.call("idv_dec5_head_fwd", p, 64, skip, 64 if two_src else 0, 1, NB, Fin, T, w10, hp["bias"][:2].clone(), 0.25,
+           1 if mask == 2 else 0, args[27], ref, S, S - 1)
+    cpu = torch.zeros(NB * S, Fout, T, 2)
+    a2 = list(args)
+    a2[28] = cpu
+    E.call("idv_tapgemm_tc_head", *a2)
+    assert C.rel_l2(cpu, ref) < 2e-5
