@@ -123,6 +123,15 @@ def cpu_oracle_throughput(steps, warmup, batch=CPU_SAMPLE_BATCH):
     return batch * SECONDS / dt, dt, cores, "%d x %d s utterances per step, %d timed steps" % (batch, SECONDS, steps)
 
 
+def workload_config(B, world, T, g):
+    return {"workload": "config2: NSVAE encoder (nsvae_pvae_dccrn_encoder_twophase, latent_num=1, H=384) "
+                        "+ CVAE decoder (pvae_dccrn_decoder_skip_prepare, zero skips, real_imag)",
+            "batch_per_gpu": B, "global_batch": B * world, "utterance_s": SECONDS, "fs": FS, "frames": T,
+            "eps": "on-device Philox", "parallelism": "replica x%d (utterance shards)" % world,
+            "l2": "per-step activation working set ~12 GB >> 126 MB L2 (no flush needed)",
+            "gflop_per_utt_algorithmic": 2 * g["total"]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -133,8 +142,8 @@ def run_reference(args):
         "impl": "reference", "metric": "audio_seconds_enhanced_per_second", "value": val, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2: NSVAE encoder (latent_num=1, H=384) + CVAE decoder (zero skips, real_imag), "
-                               "4 s 16 kHz utterances; CPU sample batch %d" % CPU_SAMPLE_BATCH},
+        "config": workload_config(args.batch, args.gpus, FS * SECONDS // HOP + 1,
+                                  algorithmic_gmac_per_utt(FS * SECONDS // HOP + 1)),
         "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -143,7 +152,7 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     import idccrn_b200 as M
-    from idccrn_b200 import lib
+    from idccrn_b200 import lib, shard
     from idccrn_b200.synth import fill_state_dict, synth_waveform
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,11 +202,7 @@ def run_ours(args):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = shard.max_over_ranks(e0.elapsed_time(e1), dev)       # device time, MAX over ranks
         sync_all()
         return ms
 
@@ -255,12 +260,7 @@ def run_ours(args):
             "metric": "audio_seconds_enhanced_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split on the tensor pipe)" if tc_mode else "f32", "data": "synthetic",
-            "config": {"workload": "config2: NSVAE encoder (nsvae_pvae_dccrn_encoder_twophase, latent_num=1, H=384) "
-                                   "+ CVAE decoder (pvae_dccrn_decoder_skip_prepare, zero skips, real_imag)",
-                       "batch_per_gpu": B, "global_batch": B * world, "utterance_s": SECONDS, "fs": FS,
-                       "frames": T, "eps": "on-device Philox", "parallelism": "replica x%d (utterance shards)" % world,
-                       "l2": "per-step activation working set ~12 GB >> 126 MB L2 (no flush needed)",
-                       "gflop_per_utt_algorithmic": 2 * g["total"]},
+            "config": workload_config(B, world, T, g),
             "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": B * L * 4,
                     "d2h_bytes_per_step": B * L * 4, "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": launches,

@@ -6,87 +6,103 @@
 
 namespace idv {
 
-// grid: (row tiles of 32, Fout); block 256 = 32 rows x 8 column groups
-__global__ void __launch_bounds__(256) enc0_kernel(const float* __restrict__ stft, int NB, int Fin, int T,
+// grid: (row tiles of 128, Fout); block 256 = 32 row groups (4 consecutive rows each) x 8 channel groups.
+// Each thread computes 4 rows x 8 consecutive channels per 64-channel slab: the 4 rows share the weight loads
+// (2 LDS.128 per 32 FMA) and, being consecutive frames, 5 instead of 8 time samples of input.
+constexpr int E0_ROWS = 128;
+__global__ void __launch_bounds__(256, 2) enc0_kernel(const float* __restrict__ stft, int NB, int Fin, int T,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
                                                    int N, float slope, void* __restrict__ outv, int Fout,
                                                    int out_split) {
-  extern __shared__ __align__(16) float ws[];       // [20][N] then bias [N]
+  // weights [20][N] + bias [N]; inside every 64-channel slab the columns are stored as
+  // [cg*4 + j | 32 + cg*4 + j] so that the two float4 of channel group cg are bank-conflict free
+  extern __shared__ __align__(16) float ws[];
   const int tid = threadIdx.x;
-  for (int i = tid; i < 20 * N; i += 256) ws[i] = __ldg(w + i);
-  for (int i = tid; i < N; i += 256) ws[20 * N + i] = __ldg(bias + i);
-  __syncthreads();
+  for (int i = tid; i < 21 * N; i += 256) {
+    const int k = i / N, n = i % N;
+    const int slab = n & ~63, c = n & 63;
+    const int phys = slab + ((c & 4) ? 32 : 0) + (c >> 3) * 4 + (c & 3);
+    ws[k * N + phys] = (k < 20) ? __ldg(w + i) : __ldg(bias + n);
+  }
   const int Tp = T + 1;
   const int R = NB * Tp;
-  const int r = blockIdx.x * 32 + (tid >> 3);
   const int cg = tid & 7;
+  const int r0 = blockIdx.x * E0_ROWS + (tid >> 3) * 4;
   const int fo = blockIdx.y;
-  if (r >= R) return;
-  const int b = r / Tp, t = r % Tp - 1;
-  const long long oidx = ((long long)fo * R + r) * N;
+  // im2col of the block's 128 rows: xs[row][tap*2 + part], row stride 21 (bank-conflict free); pad rows,
+  // rows past R and out-of-range taps are zero
+  float* xs = ws + 21 * N;
+  for (int i = tid; i < E0_ROWS * 10; i += 256) {
+    const int rl = i / 10, tap = i % 10;
+    const int kf = tap >> 1, kt = tap & 1;
+    const int r = blockIdx.x * E0_ROWS + rl;
+    float2 v = make_float2(0.f, 0.f);
+    if (r < R) {
+      const int b = r / Tp, t = r % Tp - 1;
+      const int fi = 2 * fo + kf - 2, ti = t - 1 + kt;
+      if (t >= 0 && fi >= 0 && fi < Fin && ti >= 0)
+        v = __ldg(reinterpret_cast<const float2*>(stft + ((int64_t)(b * Fin + fi) * T + ti) * 2));
+    }
+    xs[rl * 21 + tap * 2] = v.x;
+    xs[rl * 21 + tap * 2 + 1] = v.y;
+  }
+  __syncthreads();
+  if (r0 >= R) return;
+  bool ok[4], pad[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ok[i] = r0 + i < R;
+    pad[i] = ((r0 + i) % Tp) == 0;
+  }
+  const float* xrow = xs + (tid >> 3) * 4 * 21;
   const long long hl = (long long)Fout * R * N;
-  float* orow = reinterpret_cast<float*>(outv) + oidx;
+  float* of32 = reinterpret_cast<float*>(outv);
   unsigned short* osp = reinterpret_cast<unsigned short*>(outv);
-  if (t < 0) {                                       // causal pad row
-    for (int n = cg * 8; n < N; n += 64) {
-      if (out_split) {
-        *reinterpret_cast<uint4*>(osp + oidx + n) = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(osp + hl + oidx + n) = make_uint4(0u, 0u, 0u, 0u);
-      } else {
-        *reinterpret_cast<float4*>(orow + n) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(orow + n + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int n0 = 0; n0 < N; n0 += 64) {
+    float acc[4][8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(&ws[20 * N + n0 + cg * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&ws[20 * N + n0 + 32 + cg * 4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = b0.x; acc[i][1] = b0.y; acc[i][2] = b0.z; acc[i][3] = b0.w;
+        acc[i][4] = b1.x; acc[i][5] = b1.y; acc[i][6] = b1.z; acc[i][7] = b1.w;
       }
     }
-    return;
-  }
-  float xin[20];                                     // [kf][kt][part]
-#pragma unroll
-  for (int kf = 0; kf < 5; ++kf) {
-    const int fi = 2 * fo + kf - 2;
-    const bool fok = (fi >= 0 && fi < Fin);
-    const float* xp = stft + ((int64_t)(b * Fin + (fok ? fi : 0)) * T) * 2;
-#pragma unroll
-    for (int kt = 0; kt < 2; ++kt) {
-      const int ti = t - 1 + kt;
-      float2 v = make_float2(0.f, 0.f);
-      if (fok && ti >= 0) v = __ldg(reinterpret_cast<const float2*>(xp + (int64_t)ti * 2));
-      xin[(kf * 2 + kt) * 2 + 0] = v.x;
-      xin[(kf * 2 + kt) * 2 + 1] = v.y;
-    }
-  }
-  // 8 consecutive channels per thread: one 16-byte store per plane (hi / lo) or two float4
-  for (int n = cg * 8; n < N; n += 64) {
-    float acc[8];
-    {
-      const float4 b0 = *reinterpret_cast<const float4*>(&ws[20 * N + n]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&ws[20 * N + n + 4]);
-      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-    }
-#pragma unroll
+#pragma unroll 4
     for (int k = 0; k < 20; ++k) {
-      const float4 w0 = *reinterpret_cast<const float4*>(&ws[k * N + n]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&ws[k * N + n + 4]);
-      acc[0] = fmaf(xin[k], w0.x, acc[0]); acc[1] = fmaf(xin[k], w0.y, acc[1]);
-      acc[2] = fmaf(xin[k], w0.z, acc[2]); acc[3] = fmaf(xin[k], w0.w, acc[3]);
-      acc[4] = fmaf(xin[k], w1.x, acc[4]); acc[5] = fmaf(xin[k], w1.y, acc[5]);
-      acc[6] = fmaf(xin[k], w1.z, acc[6]); acc[7] = fmaf(xin[k], w1.w, acc[7]);
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[k * N + n0 + cg * 4]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&ws[k * N + n0 + 32 + cg * 4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x = xrow[i * 21 + k];
+        acc[i][0] = fmaf(x, w0.x, acc[i][0]); acc[i][1] = fmaf(x, w0.y, acc[i][1]);
+        acc[i][2] = fmaf(x, w0.z, acc[i][2]); acc[i][3] = fmaf(x, w0.w, acc[i][3]);
+        acc[i][4] = fmaf(x, w1.x, acc[i][4]); acc[i][5] = fmaf(x, w1.y, acc[i][5]);
+        acc[i][6] = fmaf(x, w1.z, acc[i][6]); acc[i][7] = fmaf(x, w1.w, acc[i][7]);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = prelu_f(acc[j], slope);
-    if (out_split) {
-      unsigned short h[8], l[8];
+    for (int i = 0; i < 4; ++i) {
+      if (!ok[i]) continue;
+      const long long oidx = ((long long)fo * R + r0 + i) * N + n0 + cg * 8;
+      float v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) split_bf16(acc[j], h[j], l[j]);
-      *reinterpret_cast<uint4*>(osp + oidx + n) =
-          make_uint4((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16),
-                     (unsigned)h[4] | ((unsigned)h[5] << 16), (unsigned)h[6] | ((unsigned)h[7] << 16));
-      *reinterpret_cast<uint4*>(osp + hl + oidx + n) =
-          make_uint4((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16),
-                     (unsigned)l[4] | ((unsigned)l[5] << 16), (unsigned)l[6] | ((unsigned)l[7] << 16));
-    } else {
-      *reinterpret_cast<float4*>(orow + n) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(orow + n + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      for (int j = 0; j < 8; ++j) v[j] = pad[i] ? 0.f : prelu_f(acc[i][j], slope);
+      if (out_split) {
+        unsigned short h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_bf16(v[j], h[j], l[j]);
+        *reinterpret_cast<uint4*>(osp + oidx) =
+            make_uint4((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16),
+                       (unsigned)h[4] | ((unsigned)h[5] << 16), (unsigned)h[6] | ((unsigned)h[7] << 16));
+        *reinterpret_cast<uint4*>(osp + hl + oidx) =
+            make_uint4((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16),
+                       (unsigned)l[4] | ((unsigned)l[5] << 16), (unsigned)l[6] | ((unsigned)l[7] << 16));
+      } else {
+        *reinterpret_cast<float4*>(of32 + oidx) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(of32 + oidx + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
     }
   }
 }
@@ -183,14 +199,14 @@ extern "C" int idv_enc0_fwd(const float* stft, int B, int Fin, int T, const floa
   using namespace idv;
   IDV_CHECK_ARG(stft && w && bias && out, "idv_enc0_fwd: null pointer");
   IDV_CHECK_ARG(B > 0 && Fin >= 5 && T > 0, "idv_enc0_fwd: bad shape B=%d Fin=%d T=%d", B, Fin, T);
-  IDV_CHECK_ARG(Cout > 0 && Cout % 16 == 0, "idv_enc0_fwd: Cout=%d must be a multiple of 16", Cout);
+  IDV_CHECK_ARG(Cout > 0 && Cout % 32 == 0, "idv_enc0_fwd: Cout=%d must be a multiple of 32", Cout);
   const int N = 2 * Cout;
   const int Fout = (Fin + 4 - 5) / 2 + 1;
   IDV_CHECK_ARG(Fout <= 65535, "idv_enc0_fwd: Fout too large");
   const int R = B * (T + 1);
-  const size_t smem = (size_t)21 * N * sizeof(float);
+  const size_t smem = (size_t)(21 * N + E0_ROWS * 21) * sizeof(float);
   IDV_CUDA(cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(cdiv(R, 32), Fout);
+  dim3 grid(cdiv(R, E0_ROWS), Fout);
   enc0_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(stft, B, Fin, T, w, bias, N, prelu_slope, out, Fout,
                                                          out_split);
   IDV_LAUNCH_CHECK("enc0_kernel");

@@ -200,7 +200,7 @@ def pack_enc0(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, device):
     """First encoder layer (Cin = 1): w [10][2][2*Cout], bias [2*Cout] for idv_enc0_fwd."""
     wr, wi = _cpu(conv_re_w), _cpu(conv_im_w)
     cout, cin, kh, kw = wr.shape
-    assert cin == 1 and kh == 5 and kw == 2 and cout % 16 == 0
+    assert cin == 1 and kh == 5 and kw == 2 and cout % 32 == 0
     Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(cout)
     m_re = wr.permute(2, 3, 1, 0).reshape(10, 1, cout)
     m_im = wi.permute(2, 3, 1, 0).reshape(10, 1, cout)

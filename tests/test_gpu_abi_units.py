@@ -70,7 +70,7 @@ def test_stft_istft(B, L):
     assert _both("idv_istft_fwd", [spec, B, T, ib, wsq, 512, 100, 400, frames, y], [8, 9]) < 1e-5
 
 
-@pytest.mark.parametrize("B,Fin,T,Cout", [(1, 257, 1, 32), (3, 33, 70, 16)])
+@pytest.mark.parametrize("B,Fin,T,Cout", [(1, 257, 1, 32), (3, 33, 70, 64), (5, 17, 129, 32)])
 def test_enc0(B, Fin, T, Cout):
     Fout = (Fin - 1) // 2 + 1
     n = Fout * B * (T + 1) * 2 * Cout

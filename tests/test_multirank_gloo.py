@@ -1,0 +1,59 @@
+"""CPU tier: the N>1 host path (utterance sharding, result gather, max-over-ranks timing) with world_size 2 over
+gloo, compute through the emulated C-ABI contract."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import common as C
+from idccrn_b200 import shard
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 5, 64, 65, 256):
+        for w in (1, 2, 3, 8):
+            spans = [shard.shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [h - l for l, h in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard.shard_bounds(4, 2, 2)
+
+
+def _worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import abi_emulator
+    from idccrn_b200 import lib
+    lib.call = abi_emulator.call                       # test double of the C ABI (CPU tier only)
+    lib.require_f32_cuda = lambda t, what: t.contiguous()
+    torch.set_num_threads(2)
+    B, L, seed = 3, 400, 0
+    enc, dec = C.build_vae(1, 1, "skip_prepare", "real_imag", seed, "cpu")
+    x, eps = C.vae_inputs(B, L, 1, 1, seed, "cpu")
+    out, (lo, hi) = shard.enhance_sharded(x, enc, dec, "cpu", eps=eps, gather=True)
+    t = shard.max_over_ranks(10.0 + rank, "cpu")
+    if rank == 0:
+        torch.save({"out": out, "t": t}, tmp)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_enhancement_matches_single_process(emulated_abi, tmp_path):
+    B, L, seed = 3, 400, 0
+    enc, dec = C.build_vae(1, 1, "skip_prepare", "real_imag", seed, "cpu")
+    x, eps = C.vae_inputs(B, L, 1, 1, seed, "cpu")
+    want = C.run_vae(enc, dec, x, eps, "skip_prepare")["recon_sig"]
+    tmp = str(tmp_path / "rank0.pt")
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, tmp), nprocs=2, join=True)
+    got = torch.load(tmp)
+    assert got["out"].shape == want.shape
+    assert C.rel_l2(got["out"], want) < 1e-6            # ragged shards (2 + 1 utterances), same arithmetic
+    assert got["t"] == 11.0                             # MAX over ranks
