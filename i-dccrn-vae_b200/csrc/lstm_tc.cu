@@ -29,7 +29,7 @@ struct LstmTcParams {
   const float* g;
   long long g_m_off, g_p_off;
   int g_ld;
-  int NB, T, H, NC, KC;                     // KC = H / 64
+  int NB, T, H, NC, KC, stages;             // KC = H / 64; stages = depth of the h TMA ring (<= 8)
   float* hseq;                              // optional fp32 [4][R][H]
   unsigned short* hsplit;                   // optional bf16 [2][4][R][H]
   unsigned short* hx;                       // bf16 [n_rg][2 parity][2 m][2 hl][128][H]
@@ -69,13 +69,12 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int KC = p.KC;
   const int w_bytes = 2 * KC * W_TILE;
-  // ring depth from what is left of the 227 KB (host passes the same formula)
-  const int stages = p.H <= 384 ? 3 : 2;
+  const int stages = p.stages;              // as many 32 KB stages as fit next to the resident weights
   uint8_t* ring = smem + w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + stages * 2 * L_HTILE);
-  const uint32_t wfull = smem_u32(bars), hfull0 = wfull + 8, hempty0 = hfull0 + 8 * 4, accfull = hempty0 + 8 * 4,
+  const uint32_t wfull = smem_u32(bars), hfull0 = wfull + 8, hempty0 = hfull0 + 8 * 8, accfull = hempty0 + 8 * 8,
                  accempty = accfull + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   const uint32_t smem_w = smem_u32(smem), smem_ring = smem_u32(ring);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,7 +90,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   }
   if (warp == 1 && lane == 0) {
     mbar_init(wfull, 1);
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < 8; ++s) {
       mbar_init(hfull0 + 8 * s, 1);
       mbar_init(hempty0 + 8 * s, 1);
     }
@@ -232,22 +231,27 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const int par = (t + 1) & 1;
         unsigned short* hx = p.hx + ((((long long)(rg * 2 + par) * 2 + m) * 2) * L_ROWS + r) * H + u0;
         const long long hx_hl = (long long)L_ROWS * H;
-        const long long oidx = ((long long)(m * 2 + part) * R + rcur) * H + u0;
 #pragma unroll
-        for (int j = 0; j < HS; j += 4) {
-          const float4 hv = make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]);
-          st_split4(hx, hx_hl, j, hv);
-          if (p.hsplit) st_split4(p.hsplit, 4 * R * H, oidx + j, hv);
-          if (p.hseq) *reinterpret_cast<float4*>(p.hseq + oidx + j) = hv;
-        }
+        for (int j = 0; j < HS; j += 4)
+          st_split4(hx, hx_hl, j, make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]));
       }
       if (warp == L_EPI_WARP0 && lane == 0) LSTM_DBG(6);
+      // publish h(t): only the exchange-buffer stores are on the critical path of the other CTAs
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == L_EPI_WARP0 && lane == 0) {
         LSTM_DBG(7);
         atomicAdd(ctr, 1u);
         LSTM_DBG(8);
+      }
+      if (valid) {                                    // sequence outputs, off the critical path
+        const long long oidx = ((long long)(m * 2 + part) * R + rcur) * H + u0;
+#pragma unroll
+        for (int j = 0; j < HS; j += 4) {
+          const float4 hv = make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]);
+          if (p.hsplit) st_split4(p.hsplit, 4 * R * H, oidx + j, hv);
+          if (p.hseq) *reinterpret_cast<float4*>(p.hseq + oidx + j) = hv;
+        }
       }
     }
   }
@@ -287,9 +291,10 @@ extern "C" int idv_lstm_tc_config(int H, int* n_cols, int* n_ctas) {
   IDV_CHECK_ARG(n_cols && n_ctas, "idv_lstm_tc_config: null pointer");
   int N = 0;
   if (H % 64 == 0) {
-    if (H <= 384 && H % 16 == 0) N = 64;
+    // N = 32 (8 hidden units per CTA) keeps the resident slice small so the TMA ring can hold most of h(t-1)
+    // (the step is latency-bound on bytes in flight); H = 768 needs N = 48 to stay within 148 co-resident CTAs
+    if (H <= 512 && H % 8 == 0) N = 32;
     else if (H <= 768 && H % 12 == 0) N = 48;
-    else if (H % 8 == 0 && H <= 1024) N = 32;
   }
   IDV_CHECK_ARG(N > 0, "idv_lstm_tc_config: hidden size %d is not supported by the tensor-core recurrence", H);
   *n_cols = N;
@@ -309,12 +314,16 @@ extern "C" int idv_lstm_recurrent_tc(const float* g, int64_t g_m_off, int64_t g_
   if (rc) return rc;
   const int n_rg = cdiv(NB, 64);
   const int KC = H / 64;
-  const int stages = H <= 384 ? 3 : 2;
-  const size_t smem = (size_t)2 * KC * N * BK * 2 + (size_t)stages * 2 * L_HTILE + 1024 + 256;
   int dev = 0, sms = 0, smem_optin = 0;
   IDV_CUDA(cudaGetDevice(&dev));
   IDV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   IDV_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t w_bytes = (size_t)2 * KC * N * BK * 2;
+  int stages = (int)(((size_t)smem_optin - w_bytes - 1024 - 256) / (2 * L_HTILE));
+  if (stages > 8) stages = 8;
+  if (stages > KC) stages = KC;              // one step never has more than KC tiles in flight
+  IDV_CHECK_ARG(stages >= 2 || (stages >= 1 && KC == 1), "idv_lstm_recurrent_tc: not enough shared memory for H=%d", H);
+  const size_t smem = w_bytes + (size_t)stages * 2 * L_HTILE + 1024 + 256;
   IDV_CHECK_ARG((int)smem <= smem_optin, "idv_lstm_recurrent_tc: needs %zu B of shared memory", smem);
   IDV_CHECK_ARG(NC * 2 * n_rg <= sms, "idv_lstm_recurrent_tc: %d CTAs exceed the %d SMs (batch %d too large for one launch)",
                 NC * 2 * n_rg, sms, NB);
@@ -328,7 +337,7 @@ extern "C" int idv_lstm_recurrent_tc(const float* g, int64_t g_m_off, int64_t g_
   IDV_CUDA(cudaMemsetAsync(sync, 0, (size_t)n_rg * 2 * sizeof(unsigned int), st));
   LstmTcParams p;
   p.g = g; p.g_m_off = g_m_off; p.g_p_off = g_p_off; p.g_ld = g_ld;
-  p.NB = NB; p.T = T; p.H = H; p.NC = NC; p.KC = KC;
+  p.NB = NB; p.T = T; p.H = H; p.NC = NC; p.KC = KC; p.stages = stages;
   p.hseq = hseq; p.hsplit = reinterpret_cast<unsigned short*>(hsplit);
   p.hx = reinterpret_cast<unsigned short*>(hx); p.sync = sync;
   p.dbg = nullptr;

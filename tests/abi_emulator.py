@@ -305,12 +305,7 @@ def idv_lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hspl
 
 def _lstm_tc_config(H):
     assert H % 64 == 0
-    if H <= 384 and H % 16 == 0:
-        n = 64
-    elif H <= 768 and H % 12 == 0:
-        n = 48
-    else:
-        n = 32
+    n = 32 if H <= 512 else 48
     return n, H // (n // 4)
 
 
