@@ -1,0 +1,376 @@
+// Two-layer complex-LSTM recurrence as ONE wavefront kernel (tcgen05): layer 0, the layer-1 input projection and
+// layer 1 run concurrently, skewed by one time step each, so the sequential depth is T+2 steps instead of 2T and
+// the layer-1 gate pre-activations never go to HBM.
+//
+// CTA roles (grid = NC x (2 modules * 3 roles), one CTA per SM, cooperative launch):
+//   L0 : h0(t) = cell(G0(t) + h0(t-1) W_hh0^T)            reads hxA, writes hxA            publishes counter A
+//   IP : G1(t) = h0(t) W_ih1^T + (b_ih1 + b_hh1)          reads hxA, writes G1x (fp32)     publishes counter B
+//   L1 : h1(t) = cell(G1(t) + h1(t-1) W_hh1^T)            reads hxC + G1x, writes hxC, hseq publishes counter C
+// Every role is the same pipeline as csrc/lstm_tc.cu: its N = 4*Hs gate columns of the weight matrix resident in
+// shared memory (bf16 hi/lo), the 128 x H input rows streamed by TMA from an L2-resident exchange buffer, 3 MMAs
+// per K step into TMEM, thread = row epilogue.  Exchange buffers are 4 deep in time (hxA, G1x) / 2 deep (hxC) and
+// the per-(module, role) step counters carry both the data dependencies and the buffer-reuse back-pressure:
+//   L0(t) waits A >= NC*t            and B >= NC*(t-3)   (slot t%4 of hxA was last read by IP(t-4))
+//   IP(t) waits A >= NC*(t+1)        and C >= NC*(t-3)   (slot t%4 of G1x was last read by L1(t-4))
+//   L1(t) waits C >= NC*t            and B >= NC*(t+1)
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace idv {
+namespace tc {
+
+constexpr int W_THREADS = 192;
+constexpr int W_EPI_WARP0 = 2;
+constexpr int W_ROWS = 128;
+constexpr int W_HTILE = W_ROWS * BK * 2;
+
+struct WaveParams {
+  const float* g0;
+  long long g_m_off, g_p_off;
+  int g_ld;
+  const float* bias1;                       // [2 m][NC][N] CTA-major (gate*Hs + j)
+  int NB, T, H, NC, KC, stages;
+  float* hseq1;                             // fp32 [4][R][H] layer-1 output
+  unsigned short* hxA;                      // bf16 [4 slot][2 m][2 hl][128][H]   h0
+  unsigned short* hxC;                      // bf16 [2 slot][2 m][2 hl][128][H]   h1
+  float* g1x;                               // fp32 [4 slot][2 m][128][4H]        layer-1 gate pre-activations
+  unsigned int* sync;                       // [2 m][3] counters A, B, C
+};
+
+__device__ __forceinline__ unsigned int ldacq(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_counter(const unsigned int* ctr, long long target) {
+  if (target <= 0) return;
+  long long t0 = 0;
+  unsigned int spins = 0;
+  while ((long long)ldacq(ctr) < target) {
+    if ((++spins & 255u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > WAIT_TIMEOUT_CYCLES) __trap();
+    }
+  }
+}
+__device__ __forceinline__ float wsig(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float wtanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+template <int N>
+__global__ void __launch_bounds__(W_THREADS, 1)
+lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmWi,
+                    const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmHA,
+                    const __grid_constant__ CUtensorMap tmHC, const WaveParams p) {
+  constexpr int HS = N / 4;
+  constexpr int TMEM_COLS = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  constexpr int W_TILE = N * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int KC = p.KC, stages = p.stages;
+  const int w_bytes = 2 * KC * W_TILE;
+  uint8_t* ring = smem + w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + stages * 2 * W_HTILE);
+  const uint32_t wfull = smem_u32(bars), hfull0 = wfull + 8, hempty0 = hfull0 + 8 * 8, accfull = hempty0 + 8 * 8,
+                 accempty = accfull + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  const uint32_t smem_w = smem_u32(smem), smem_ring = smem_u32(ring);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x;
+  const int m = blockIdx.y / 3, role = blockIdx.y % 3;        // 0 = L0, 1 = IP, 2 = L1
+  const int NC = p.NC, H = p.H, T = p.T;
+  const int Tp = T + 1;
+  const long long R = (long long)p.NB * Tp;
+  unsigned int* cA = p.sync + m * 3 + 0;
+  unsigned int* cB = p.sync + m * 3 + 1;
+  unsigned int* cC = p.sync + m * 3 + 2;
+  unsigned int* my_ctr = role == 0 ? cA : (role == 1 ? cB : cC);
+  const CUtensorMap* tmW = role == 0 ? &tmW0 : (role == 1 ? &tmWi : &tmW1);
+  const CUtensorMap* tmH = role == 2 ? &tmHC : &tmHA;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(tmW);
+    prefetch_tmap(tmH);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(wfull, 1);
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(hfull0 + 8 * s, 1);
+      mbar_init(hempty0 + 8 * s, 1);
+    }
+    mbar_init(accfull, 1);
+    mbar_init(accempty, 4);
+    fence_barrier_init();
+  }
+  if (warp == W_EPI_WARP0) {
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_expect_tx(wfull, (uint32_t)w_bytes);
+      for (int hl = 0; hl < 2; ++hl)
+        for (int kc = 0; kc < KC; ++kc)
+          tma_load_2d(tmW, wfull, smem_w + (hl * KC + kc) * W_TILE, kc * BK, ((hl * 2 + m) * NC + c) * N);
+      uint32_t stage = 0, phase = 0;
+      for (int t = 0; t < T; ++t) {
+        int slot;
+        if (role == 0) {            // input h0(t-1): slot (t)%4 holds h0(t-1) (h0(t) is written to slot (t+1)%4)
+          wait_counter(cA, (long long)NC * t);
+          wait_counter(cB, (long long)NC * (t - 3));
+          slot = t & 3;
+        } else if (role == 1) {     // input h0(t): slot (t+1)%4
+          wait_counter(cA, (long long)NC * (t + 1));
+          wait_counter(cC, (long long)NC * (t - 3));
+          slot = (t + 1) & 3;
+        } else {                    // input h1(t-1): slot t%2
+          wait_counter(cC, (long long)NC * t);
+          wait_counter(cB, (long long)NC * (t + 1));
+          slot = t & 1;
+        }
+        fence_proxy_async_global();
+        const int row_base = ((slot * 2 + m) * 2) * W_ROWS;
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait(hempty0 + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_ring + stage * 2 * W_HTILE;
+          mbar_expect_tx(hfull0 + 8 * stage, 2 * W_HTILE);
+          tma_load_2d(tmH, hfull0 + 8 * stage, sa, kc * BK, row_base);
+          tma_load_2d(tmH, hfull0 + 8 * stage, sa + W_HTILE, kc * BK, row_base + W_ROWS);
+          if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(N);
+      mbar_wait(wfull, 0);
+      uint32_t stage = 0, phase = 0;
+      for (int t = 0; t < T; ++t) {
+        mbar_wait(accempty, (t & 1) ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait(hfull0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_ring + stage * 2 * W_HTILE;
+          const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + W_HTILE);
+          const uint64_t b_hi = make_desc_sw128(smem_w + kc * W_TILE);
+          const uint64_t b_lo = make_desc_sw128(smem_w + (KC + kc) * W_TILE);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+            umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, (kc | k) != 0);
+            umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
+            umma_bf16(tmem_base, a_hi + koff, b_hi + koff, idesc, 1);
+          }
+          umma_commit(hempty0 + 8 * stage);
+          if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(accfull);
+      }
+    }
+  } else {
+    // ================================ epilogue (thread = row) ================================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int part = r >> 6;
+    const int b = r & 63;
+    const bool valid = b < p.NB;
+    const int u0 = c * HS;
+    float cst[HS];
+#pragma unroll
+    for (int j = 0; j < HS; ++j) cst[j] = 0.f;
+    float bias[N];
+    if (role == 1) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) bias[j] = __ldg(p.bias1 + ((long long)m * NC + c) * N + j);
+    }
+    for (int t = 0; t < T; ++t) {
+      const long long rcur = (long long)b * Tp + 1 + t;
+      float gin[N];
+      if (role == 0) {
+        if (valid) {
+          const float* gp = p.g0 + m * p.g_m_off + part * p.g_p_off + u0 + rcur * p.g_ld;
+#pragma unroll
+          for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+            for (int j = 0; j < HS; j += 4) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(gp + gt * H + j));
+              gin[gt * HS + j] = v.x; gin[gt * HS + j + 1] = v.y; gin[gt * HS + j + 2] = v.z; gin[gt * HS + j + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < N; ++j) gin[j] = 0.f;
+        }
+      } else if (role == 2) {
+        // G1(t) is produced inside this kernel: acquire counter B, then coherent (L2) loads
+        if (lane == 0) wait_counter(cB, (long long)NC * (t + 1));
+        __syncwarp();
+        const float* gp = p.g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+          for (int j = 0; j < HS; j += 4) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(gp + gt * H + j));
+            gin[gt * HS + j] = v.x; gin[gt * HS + j + 1] = v.y; gin[gt * HS + j + 2] = v.z; gin[gt * HS + j + 3] = v.w;
+          }
+      }
+      mbar_wait(accfull, t & 1);
+      tc_fence_after();
+      uint32_t v[N];
+#pragma unroll
+      for (int c0 = 0; c0 < N; c0 += 16) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v + c0);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accempty);
+      if (role == 1) {
+        // ---- layer-1 input projection: G1(t) rows -> exchange buffer slot t%4
+        float* gp = p.g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+          for (int j = 0; j < HS; j += 4)
+            *reinterpret_cast<float4*>(gp + gt * H + j) =
+                make_float4(__uint_as_float(v[gt * HS + j]) + bias[gt * HS + j],
+                            __uint_as_float(v[gt * HS + j + 1]) + bias[gt * HS + j + 1],
+                            __uint_as_float(v[gt * HS + j + 2]) + bias[gt * HS + j + 2],
+                            __uint_as_float(v[gt * HS + j + 3]) + bias[gt * HS + j + 3]);
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == W_EPI_WARP0 && lane == 0) atomicAdd(my_ctr, 1u);
+        continue;
+      }
+      float hn[HS];
+#pragma unroll
+      for (int j = 0; j < HS; ++j) {
+        const float ig = wsig(__uint_as_float(v[j]) + gin[j]);
+        const float fg = wsig(__uint_as_float(v[HS + j]) + gin[HS + j]);
+        const float gg = wtanh(__uint_as_float(v[2 * HS + j]) + gin[2 * HS + j]);
+        const float og = wsig(__uint_as_float(v[3 * HS + j]) + gin[3 * HS + j]);
+        cst[j] = fg * cst[j] + ig * gg;
+        hn[j] = og * wtanh(cst[j]);
+      }
+      if (valid) {
+        // h(t) goes to the slot the consumers of step t+1 read: (t+1)%4 for h0, (t+1)%2 for h1
+        const int slot = role == 0 ? ((t + 1) & 3) : ((t + 1) & 1);
+        unsigned short* hx = (role == 0 ? p.hxA : p.hxC) + ((((long long)slot * 2 + m) * 2) * W_ROWS + r) * H + u0;
+#pragma unroll
+        for (int j = 0; j < HS; j += 4)
+          st_split4(hx, (long long)W_ROWS * H, j, make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]));
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == W_EPI_WARP0 && lane == 0) atomicAdd(my_ctr, 1u);
+      if (role == 2 && valid) {
+        const long long oidx = ((long long)(m * 2 + part) * R + rcur) * H + u0;
+#pragma unroll
+        for (int j = 0; j < HS; j += 4)
+          *reinterpret_cast<float4*>(p.hseq1 + oidx + j) = make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_EPI_WARP0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int N>
+static int launch_wave(const CUtensorMap* maps, const WaveParams& p, size_t smem, cudaStream_t st) {
+  IDV_CUDA(cudaFuncSetAttribute(lstm_wave_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(p.NC, 6, 1), block(W_THREADS);
+  void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&maps[4], (void*)&p};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)lstm_wave_tc_kernel<N>, grid, block, args, smem, st);
+  if (e == cudaErrorCooperativeLaunchTooLarge) {
+    set_error("idv_lstm2_wave_tc: cooperative grid %dx6 is not co-resident", p.NC);
+    return IDV_E_RESOURCE;
+  }
+  if (e != cudaSuccess) {
+    set_error("idv_lstm2_wave_tc: launch failed: %s", cudaGetErrorString(e));
+    return IDV_E_CUDA;
+  }
+  return IDV_OK;
+}
+
+static int wave_cols(int H) {
+  // gate columns per CTA such that 6 * (H / Hs) CTAs fit the device (148 SMs): N = 64 for H = 384, 128
+  if (H % 64 != 0) return 0;
+  if (H % 16 == 0 && 6 * (H / 16) <= 148) return 64;
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace idv
+
+extern "C" int idv_lstm2_wave_config(int H, int* n_cols, int* n_ctas, int64_t* work_bytes) {
+  using namespace idv;
+  IDV_CHECK_ARG(n_cols && n_ctas && work_bytes, "idv_lstm2_wave_config: null pointer");
+  const int N = tc::wave_cols(H);
+  IDV_CHECK_ARG(N > 0, "idv_lstm2_wave_config: hidden size %d is not supported by the wavefront kernel", H);
+  *n_cols = N;
+  *n_ctas = H / (N / 4);
+  // hxA (4 slots) + hxC (2 slots) bf16 [slot][2][2][128][H]  +  g1x fp32 [4][2][128][4H]
+  *work_bytes = (int64_t)(4 + 2) * 2 * 2 * 128 * H * 2 + (int64_t)4 * 2 * 128 * 4 * H * 4;
+  return IDV_OK;
+}
+
+extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
+                                 const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
+                                 float* hseq1, void* work, unsigned int* sync, void* stream) {
+  using namespace idv;
+  using namespace idv::tc;
+  IDV_CHECK_ARG(g0 && w_hh0 && w_ih1 && w_hh1 && bias1 && hseq1 && work && sync, "idv_lstm2_wave_tc: null pointer");
+  IDV_CHECK_ARG(NB > 0 && NB <= 64 && T > 0, "idv_lstm2_wave_tc: needs 1 <= NB <= 64 (got %d)", NB);
+  int N = 0, NC = 0;
+  int64_t work_bytes = 0;
+  int rc = idv_lstm2_wave_config(H, &N, &NC, &work_bytes);
+  if (rc) return rc;
+  const int KC = H / 64;
+  int dev = 0, sms = 0, smem_optin = 0;
+  IDV_CUDA(cudaGetDevice(&dev));
+  IDV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  IDV_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  IDV_CHECK_ARG(6 * NC <= sms, "idv_lstm2_wave_tc: %d CTAs exceed the %d SMs", 6 * NC, sms);
+  const size_t w_bytes = (size_t)2 * KC * N * BK * 2;
+  int stages = (int)(((size_t)smem_optin - w_bytes - 1024 - 256) / (2 * W_HTILE));
+  if (stages > 8) stages = 8;
+  if (stages > KC) stages = KC;
+  IDV_CHECK_ARG(stages >= 1, "idv_lstm2_wave_tc: not enough shared memory for H=%d", H);
+  const size_t smem = w_bytes + (size_t)stages * 2 * W_HTILE + 1024 + 256;
+  uint8_t* wk = reinterpret_cast<uint8_t*>(work);
+  const size_t hxA_bytes = (size_t)4 * 2 * 2 * 128 * H * 2, hxC_bytes = (size_t)2 * 2 * 2 * 128 * H * 2;
+  CUtensorMap maps[5];
+  const void* wp[3] = {w_hh0, w_ih1, w_hh1};
+  for (int i = 0; i < 3; ++i) {
+    rc = encode_map_2d(&maps[i], wp[i], H, (uint64_t)2 * 2 * NC * N, BK, N);
+    if (rc) return rc;
+  }
+  rc = encode_map_2d(&maps[3], wk, H, (uint64_t)4 * 2 * 2 * 128, BK, W_ROWS);
+  if (rc) return rc;
+  rc = encode_map_2d(&maps[4], wk + hxA_bytes, H, (uint64_t)2 * 2 * 2 * 128, BK, W_ROWS);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  IDV_CUDA(cudaMemsetAsync(work, 0, (size_t)work_bytes, st));
+  IDV_CUDA(cudaMemsetAsync(sync, 0, 6 * sizeof(unsigned int), st));
+  WaveParams p;
+  p.g0 = g0; p.g_m_off = g_m_off; p.g_p_off = g_p_off; p.g_ld = g_ld; p.bias1 = bias1;
+  p.NB = NB; p.T = T; p.H = H; p.NC = NC; p.KC = KC; p.stages = stages;
+  p.hseq1 = hseq1;
+  p.hxA = reinterpret_cast<unsigned short*>(wk);
+  p.hxC = reinterpret_cast<unsigned short*>(wk + hxA_bytes);
+  p.g1x = reinterpret_cast<float*>(wk + hxA_bytes + hxC_bytes);
+  p.sync = sync;
+  return launch_wave<64>(maps, p, smem, st);
+}

@@ -29,6 +29,7 @@ SIGNATURES = {
     "idv_dec5_head_fwd": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, i32, i32, vp],
     "idv_lstm_recurrent_fwd": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp],
     "idv_lstm_recurrent_tc": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp],
+    "idv_lstm2_wave_tc": [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp],
     "idv_lstm_combine_fwd": [vp, i32, i32, i32, vp, vp],
     "idv_reparam_fwd": [vp, i32, i32, i32, i32, i32, i32, vp, vp, u64, u64, vp, vp],
     "idv_planes_to_user": [vp, i32, i32, i32, i32, i32, vp, vp],
@@ -36,7 +37,7 @@ SIGNATURES = {
     "idv_z_to_planes": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "idv_cbn_eval_user": [vp, i64, i32, i64, vp, vp, vp],
 }
-EXPORTS = ["idv_abi_version", "idv_last_error", "idv_lstm_tc_config"] + list(SIGNATURES)
+EXPORTS = ["idv_abi_version", "idv_last_error", "idv_lstm_tc_config", "idv_lstm2_wave_config"] + list(SIGNATURES)
 
 
 def lib_path():
@@ -112,6 +113,18 @@ def lstm_tc_config(H):
     if lib.idv_lstm_tc_config(int(H), ctypes.byref(n), ctypes.byref(c)) != 0:
         return None
     return n.value, c.value
+
+
+def lstm2_wave_config(H):
+    """(gate columns per CTA, CTAs per (module, role), workspace bytes) of the 2-layer wavefront kernel or None."""
+    lib = load()
+    n, c, w = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int64(0)
+    lib.idv_lstm2_wave_config.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                          ctypes.POINTER(ctypes.c_int64)]
+    lib.idv_lstm2_wave_config.restype = ctypes.c_int
+    if lib.idv_lstm2_wave_config(int(H), ctypes.byref(n), ctypes.byref(c), ctypes.byref(w)) != 0:
+        return None
+    return n.value, c.value, w.value
 
 
 def ptr(t):

@@ -272,12 +272,29 @@ class ComplexLSTM(nn.Module):
             items[key] = [pack.pack_lstm_whh_tc(re, im, l, cfg[0], cfg[1], device) for l in range(self.num_layer)]
         return items[key]
 
+    def _packed_wave(self, cfg, device):
+        items = self._cache.check(self)
+        key = ("wave", cfg, str(device))
+        if key not in items:
+            re, im = _sd(self.lstm_re), _sd(self.lstm_im)
+            n, c = cfg[0], cfg[1]
+            items[key] = (pack.pack_lstm_whh_tc(re, im, 0, n, c, device), pack.pack_lstm_whh_tc(re, im, 1, n, c, device, "ih"),
+                          pack.pack_lstm_whh_tc(re, im, 1, n, c, device), pack.pack_lstm_bias_tc(re, im, 1, n, c, device))
+        return items[key]
+
     def forward_planes(self, xp):
         """xp: Planes with C*F == input_size (feature d = c*F + f).  Returns the latent (NB, T, H, 2)."""
         layers = self._packed(xp.C, xp.F, xp.data.device)
         NB, T, H = xp.NB, xp.T, self.hidden_size
         R = NB * (T + 1)
         src, hseq, split = xp, None, xp.split
+        # two layers, batch <= 64: one wavefront kernel (layer 0 | layer-1 input projection | layer 1)
+        wave = ops.lstm2_wave_supported(H, NB, xp.data.device) if (split and self.num_layer == 2 and ops.LSTM_WAVE[0]) else None
+        if wave:
+            w0, wi1, w1, b1 = self._packed_wave(wave, xp.data.device)
+            g = ops.tapgemm(layers[0][0], xp, None, NB, T, zero_pad_rows=False, out_split=False)
+            hseq = ops.lstm2_wave_tc(g, 4 * H, R * 8 * H, 8 * H, w0, wi1, w1, b1, NB, T, H, wave[2])
+            return ops.lstm_combine(hseq, NB, T, H)
         # tensor-core recurrence when the planes are split-bf16 and the cooperative grid fits the device;
         # otherwise the fp32 SIMT recurrence (any batch size)
         cfg = ops.lstm_tc_supported(H, NB, xp.data.device) if split else None

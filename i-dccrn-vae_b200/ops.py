@@ -12,6 +12,9 @@ from .pack import round8
 GEMM_MODE = [os.environ.get("IDV_GEMM", "tc")]
 
 
+LSTM_WAVE = [os.environ.get("IDV_LSTM_WAVE", "1") != "0"]     # 2-layer wavefront kernel (else one launch per layer)
+
+
 def set_gemm_mode(mode):
     if mode not in ("tc", "simt"):
         raise ValueError("mode must be 'tc' or 'simt'")
@@ -167,6 +170,23 @@ def lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, want_f32=True,
     sync = torch.empty(n_rg * 2, dtype=torch.int32, device=g.device)
     lib.call("idv_lstm_recurrent_tc", g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, hx, sync)
     return hseq, hsplit
+
+
+def lstm2_wave_supported(H, NB, device):
+    cfg = lib.lstm2_wave_config(H)
+    if cfg is None or NB > 64:
+        return None
+    sms = torch.cuda.get_device_properties(device).multi_processor_count if torch.cuda.is_available() else 148
+    return cfg if 6 * cfg[1] <= sms else None
+
+
+def lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, work_bytes):
+    """Both layers of the ComplexLSTM as one wavefront kernel.  Returns hseq1 fp32 [4][R][H]."""
+    hseq = _empty(4 * NB * (T + 1) * H, g0.device)
+    work = torch.empty(int(work_bytes), dtype=torch.uint8, device=g0.device)
+    sync = torch.empty(6, dtype=torch.int32, device=g0.device)
+    lib.call("idv_lstm2_wave_tc", g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq, work, sync)
+    return hseq
 
 
 def lstm_combine(hseq, NB, T, H):

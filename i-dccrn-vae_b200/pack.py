@@ -327,13 +327,24 @@ def pack_lstm_whh(lstm_re, lstm_im, layer, device):
         .to(torch.float32).contiguous().to(device)
 
 
-def pack_lstm_whh_tc(lstm_re, lstm_im, layer, n_cols, n_ctas, device):
-    """Recurrent weights for idv_lstm_recurrent_tc: bf16 [2 (hi,lo)][2 (module)][n_ctas][n_cols][H], CTA c holds
-    the rows W_hh[gate*H + c*Hs + j] at (gate*Hs + j), Hs = n_cols / 4."""
+def pack_lstm_bias_tc(lstm_re, lstm_im, layer, n_cols, n_ctas, device):
+    """b_ih + b_hh of one layer in the CTA-major order of pack_lstm_whh_tc: fp32 [2][n_ctas][n_cols]."""
+    hs = n_cols // 4
+    out = []
+    for mod in (lstm_re, lstm_im):
+        b = (_cpu(mod["bias_ih_l%d" % layer]).double() + _cpu(mod["bias_hh_l%d" % layer]).double())
+        out.append(b.view(4, n_ctas, hs).permute(1, 0, 2).reshape(n_ctas, n_cols))
+    return torch.stack(out).to(torch.float32).contiguous().to(device)
+
+
+def pack_lstm_whh_tc(lstm_re, lstm_im, layer, n_cols, n_ctas, device, kind="hh"):
+    """Recurrent (kind='hh') or layer>=1 input (kind='ih', square H x H) weights for the tensor-core LSTM
+    kernels: bf16 [2 (hi,lo)][2 (module)][n_ctas][n_cols][H], CTA c holds the rows W[gate*H + c*Hs + j] at
+    (gate*Hs + j), Hs = n_cols / 4."""
     hs = n_cols // 4
     mats = []
     for mod in (lstm_re, lstm_im):
-        w = _cpu(mod["weight_hh_l%d" % layer]).to(torch.float32)          # (4H, H)
+        w = _cpu(mod["weight_%s_l%d" % (kind, layer)]).to(torch.float32)          # (4H, H)
         H = w.shape[1]
         assert hs * n_ctas == H
         mats.append(w.view(4, n_ctas, hs, H).permute(1, 0, 2, 3).reshape(n_ctas, n_cols, H))

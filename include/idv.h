@@ -143,6 +143,17 @@ int idv_lstm_tc_config(int H, int* n_cols, int* n_ctas);
 int idv_lstm_recurrent_tc(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* wpack,
                           int NB, int T, int H, float* hseq, void* hsplit, void* hx, unsigned int* sync,
                           void* stream);
+/* Both layers of a 2-layer ComplexLSTM as one wavefront kernel (layer 0, the layer-1 input projection and layer 1
+ * run concurrently, one time step apart): same arithmetic as two idv_lstm_recurrent_tc calls around a tensor-core
+ * input projection, without materialising the layer-1 gate pre-activations.  g0: layer-0 input projection
+ * (as for idv_lstm_recurrent_tc).  w_hh0 / w_ih1 / w_hh1: packs in the layout of idv_lstm_recurrent_tc's wpack
+ * with (n_cols, n_ctas) from idv_lstm2_wave_config; bias1: fp32 [2][n_ctas][n_cols] = b_ih_l1 + b_hh_l1 in the
+ * same CTA-major order.  hseq1: fp32 [4][R][H] layer-1 output.  work: work_bytes workspace, sync: 6 x uint32
+ * (both zeroed by the call).  NB <= 64; 6 * n_ctas CTAs must be co-resident.                                  */
+int idv_lstm2_wave_config(int H, int* n_cols, int* n_ctas, int64_t* work_bytes);
+int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
+                      const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
+                      float* hseq1, void* work, unsigned int* sync, void* stream);
 /* Combine the four streams (real = rr - ii, imag = ir + ri), emit the user-layout latent
  * (NB, T, H, 2).  Replaces the stack/permute at complex_progress.py:L62-73, pvae_module.py:L2247. */
 int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, float* latent, void* stream);

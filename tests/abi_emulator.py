@@ -303,6 +303,47 @@ def idv_lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hspl
         hv[1][:, valid] = lo[:, valid].to(torch.bfloat16)
 
 
+def idv_lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq1, work, sync):
+    """Contract: layer 0 recurrence (split h), layer-1 input projection on the split h0 (3 products) + bias,
+    layer-1 recurrence (split h1)."""
+    n_cols, n_ctas = 64, H // 16
+    hs = n_cols // 4
+    Tp = T + 1
+    R = NB * Tp
+
+    def unpack(wp):
+        w = wp.view(2, 2, n_ctas, 4, hs, H).to(D)
+        return w.permute(0, 1, 3, 2, 4, 5).reshape(2, 2, 4 * H, H)
+    W0, Wi, W1 = unpack(w_hh0), unpack(w_ih1), unpack(w_hh1)
+    b1 = bias1.view(2, n_ctas, 4, hs).to(D).permute(0, 2, 1, 3).reshape(2, 4 * H)
+    gf = _flat(g0)
+    rows0 = torch.arange(NB) * Tp
+    out = hseq1.view(4, R, H)
+
+    def mm3(x, W, m):
+        xh, xl = _bf16_split(x)
+        return xh @ W[0, m].t() + xh @ W[1, m].t() + xl @ W[0, m].t()
+
+    def cell(a, c):
+        i, f, gg, o = a[:, :H], a[:, H:2 * H], a[:, 2 * H:3 * H], a[:, 3 * H:]
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        return torch.sigmoid(o) * torch.tanh(c), c
+    for m in range(2):
+        for p in range(2):
+            base = m * g_m_off + p * g_p_off
+            h0 = torch.zeros(NB, H, dtype=D)
+            c0 = torch.zeros(NB, H, dtype=D)
+            h1 = torch.zeros(NB, H, dtype=D)
+            c1 = torch.zeros(NB, H, dtype=D)
+            for t in range(T):
+                rows = rows0 + 1 + t
+                idx = base + rows[:, None] * g_ld + torch.arange(4 * H)[None, :]
+                h0, c0 = cell(gf[idx].to(D) + mm3(h0, W0, m), c0)
+                g1 = (mm3(h0, Wi, m) + b1[m]).to(torch.float32).to(D)        # G1 is stored as fp32
+                h1, c1 = cell(g1 + mm3(h1, W1, m), c1)
+                out[m * 2 + p, rows] = h1.to(torch.float32)
+
+
 def _lstm_tc_config(H):
     assert H % 64 == 0
     n = 32 if H <= 512 else 48

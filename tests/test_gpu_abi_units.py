@@ -237,3 +237,26 @@ def test_tapgemm_tc_head(NB, Fin, T, two_src, mask, S):
     a2[28] = cpu
     E.call("idv_tapgemm_tc_head", *a2)
     assert C.rel_l2(cpu, ref) < 2e-5
+
+
+@pytest.mark.parametrize("NB,T,H", [(3, 9, 128), (64, 30, 384), (17, 2, 384)])
+def test_lstm2_wave_tc(NB, T, H):
+    from idccrn_b200 import pack as PK
+    n_cols, n_ctas, work_bytes = lib.lstm2_wave_config(H)
+    R = NB * (T + 1)
+    g = _rand(2, R, 8 * H, seed=15)
+    mods = []
+    for mi in range(2):
+        mods.append({"weight_hh_l0": _rand(4 * H, H, seed=20 + mi) / (H ** 0.5),
+                     "weight_ih_l1": _rand(4 * H, H, seed=22 + mi) / (H ** 0.5),
+                     "weight_hh_l1": _rand(4 * H, H, seed=24 + mi) / (H ** 0.5),
+                     "bias_ih_l1": _rand(4 * H, seed=26 + mi) * 0.1, "bias_hh_l1": _rand(4 * H, seed=28 + mi) * 0.1})
+    w0 = PK.pack_lstm_whh_tc(mods[0], mods[1], 0, n_cols, n_ctas, "cpu")
+    wi = PK.pack_lstm_whh_tc(mods[0], mods[1], 1, n_cols, n_ctas, "cpu", "ih")
+    w1 = PK.pack_lstm_whh_tc(mods[0], mods[1], 1, n_cols, n_ctas, "cpu")
+    b1 = PK.pack_lstm_bias_tc(mods[0], mods[1], 1, n_cols, n_ctas, "cpu")
+    hseq = torch.zeros(4, R, H)
+    work = torch.zeros(work_bytes, dtype=torch.uint8)
+    sync = torch.zeros(6, dtype=torch.int32)
+    args = [g, 4 * H, R * 8 * H, 8 * H, w0, wi, w1, b1, NB, T, H, hseq, work, sync]
+    assert _both("idv_lstm2_wave_tc", args, [11]) < 2e-5
