@@ -27,15 +27,22 @@ __global__ void __launch_bounds__(256, 2) enc0_kernel(const float* __restrict__ 
   const int Tp = T + 1;
   const int R = NB * Tp;
   const int cg = tid & 7;
-  const int r0 = blockIdx.x * E0_ROWS + (tid >> 3) * 4;
   const int fo = blockIdx.y;
-  // im2col of the block's 128 rows: xs[row][tap*2 + part], row stride 21 (bank-conflict free); pad rows,
-  // rows past R and out-of-range taps are zero
+  const long long hl = (long long)Fout * R * N;
+  float* of32 = reinterpret_cast<float*>(outv);
+  unsigned short* osp = reinterpret_cast<unsigned short*>(outv);
   float* xs = ws + 21 * N;
+  const int n_tiles = (R + E0_ROWS - 1) / E0_ROWS;
+  // each block walks over row tiles blockIdx.x, blockIdx.x + gridDim.x, ... (weights staged once)
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int r0 = tile * E0_ROWS + (tid >> 3) * 4;
+  __syncthreads();                                   // previous tile's xs fully consumed (and ws visible)
+  // im2col of the tile's 128 rows: xs[row][tap*2 + part], row stride 21 (bank-conflict free); pad rows,
+  // rows past R and out-of-range taps are zero
   for (int i = tid; i < E0_ROWS * 10; i += 256) {
     const int rl = i / 10, tap = i % 10;
     const int kf = tap >> 1, kt = tap & 1;
-    const int r = blockIdx.x * E0_ROWS + rl;
+    const int r = tile * E0_ROWS + rl;
     float2 v = make_float2(0.f, 0.f);
     if (r < R) {
       const int b = r / Tp, t = r % Tp - 1;
@@ -47,7 +54,7 @@ __global__ void __launch_bounds__(256, 2) enc0_kernel(const float* __restrict__ 
     xs[rl * 21 + tap * 2 + 1] = v.y;
   }
   __syncthreads();
-  if (r0 >= R) return;
+  if (r0 >= R) continue;
   bool ok[4], pad[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -55,9 +62,6 @@ __global__ void __launch_bounds__(256, 2) enc0_kernel(const float* __restrict__ 
     pad[i] = ((r0 + i) % Tp) == 0;
   }
   const float* xrow = xs + (tid >> 3) * 4 * 21;
-  const long long hl = (long long)Fout * R * N;
-  float* of32 = reinterpret_cast<float*>(outv);
-  unsigned short* osp = reinterpret_cast<unsigned short*>(outv);
   for (int n0 = 0; n0 < N; n0 += 64) {
     float acc[4][8];
     {
@@ -105,6 +109,7 @@ __global__ void __launch_bounds__(256, 2) enc0_kernel(const float* __restrict__ 
       }
     }
   }
+  }   // tile loop
 }
 
 // grid: (row tiles of 32, Fout); block 256 = 8 warps x 4 rows each; one warp per output bin
@@ -206,7 +211,8 @@ extern "C" int idv_enc0_fwd(const float* stft, int B, int Fin, int T, const floa
   const int R = B * (T + 1);
   const size_t smem = (size_t)(21 * N + E0_ROWS * 21) * sizeof(float);
   IDV_CUDA(cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(cdiv(R, E0_ROWS), Fout);
+  const int n_tiles = cdiv(R, E0_ROWS);
+  dim3 grid(n_tiles < 16 ? n_tiles : cdiv(n_tiles, 8), Fout);      // ~8 row tiles per block
   enc0_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(stft, B, Fin, T, w, bias, N, prelu_slope, out, Fout,
                                                          out_split);
   IDV_LAUNCH_CHECK("enc0_kernel");

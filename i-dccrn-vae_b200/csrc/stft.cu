@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(ST_THREADS) istft_frames_kernel(const float* _
 }
 
 // overlap-add + window-envelope normalisation + centre trim (HBM-bound)
-__global__ void __launch_bounds__(256) ola_kernel(const float* __restrict__ frames, const float* __restrict__ wsq,
-                                                  int T, int n_fft, int hop, int win, int out_len,
-                                                  float* __restrict__ out) {
+__global__ void __launch_bounds__(256) ola_kernel(const float* __restrict__ frames, int frame_ld,
+                                                  const float* __restrict__ wsq, int T, int n_fft, int hop, int win,
+                                                  int out_len, float* __restrict__ out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (s >= out_len) return;
@@ -173,18 +173,111 @@ __global__ void __launch_bounds__(256) ola_kernel(const float* __restrict__ fram
   if (q - win + 1 <= 0) t_lo = 0;
   if (t_hi > T - 1) t_hi = T - 1;
   float acc = 0.f, env = 0.f;
-  const float* fb = frames + (int64_t)b * T * win;
+  const float* fb = frames + (int64_t)b * T * frame_ld;
   for (int t = t_lo; t <= t_hi; ++t) {
     const int j = q - hop * t;
     if (j >= 0 && j < win) {
-      acc += __ldg(fb + (int64_t)t * win + j);
+      acc += __ldg(fb + (int64_t)t * frame_ld + j);
       env += __ldg(wsq + j);
     }
   }
   out[(int64_t)b * out_len + s] = acc / env;
 }
 
+// ---- tensor-core path helpers: operands of the two DFT GEMMs in split-bf16, K-major -----------------------
+// frames[(b*T + t)][j] = xp[b][hop*t + off + j] for j < win, 0 for win <= j < kpad   (hi / lo planes)
+__global__ void __launch_bounds__(256) stft_frames_split_kernel(const float* __restrict__ x, int B, int L, int T,
+                                                                int n_fft, int hop, int win, int kpad,
+                                                                unsigned short* __restrict__ out) {
+  const long long n = (long long)B * T * (kpad / 4);
+  const long long hl = (long long)B * T * kpad;
+  const int off = (n_fft - win) / 2, half = n_fft / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j4 = (int)(i % (kpad / 4)) * 4;
+    const long long bt = i / (kpad / 4);
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = j4 + e;
+      int idx = hop * t + off + j - half;
+      if (idx < 0) idx = -idx;
+      if (idx >= L) idx = 2 * (L - 1) - idx;
+      v[e] = (j < win && idx >= 0 && idx < L) ? __ldg(x + (long long)b * L + idx) : 0.f;
+    }
+    st_split4(out, hl, bt * kpad + j4, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+// rows[(b*T + t)][2k + part] = spec[b][k][t][part], zero padded to kpad columns (hi / lo planes)
+// grid (ceil(T/32), ceil(nbins/32), B), block (32, 8)
+__global__ void __launch_bounds__(256) spec_rows_split_kernel(const float* __restrict__ spec, int B, int nbins, int T,
+                                                              int kpad, unsigned short* __restrict__ out) {
+  __shared__ float tile[2][32][33];
+  const int t0 = blockIdx.x * 32, k0 = blockIdx.y * 32, b = blockIdx.z;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int k = k0 + i, t = t0 + tx;
+    float2 v = make_float2(0.f, 0.f);
+    if (k < nbins && t < T) v = __ldg(reinterpret_cast<const float2*>(spec + ((long long)(b * nbins + k) * T + t) * 2));
+    tile[0][i][tx] = v.x;
+    tile[1][i][tx] = v.y;
+  }
+  __syncthreads();
+  const long long hl = (long long)B * T * kpad;
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, k = k0 + tx;
+    if (t < T && 2 * k + 1 < kpad) {
+      const long long idx = ((long long)b * T + t) * kpad + 2 * k;
+      unsigned short h0, l0, h1, l1;
+      split_bf16(tile[0][tx][i], h0, l0);
+      split_bf16(tile[1][tx][i], h1, l1);
+      *reinterpret_cast<unsigned int*>(out + idx) = (unsigned)h0 | ((unsigned)h1 << 16);
+      *reinterpret_cast<unsigned int*>(out + hl + idx) = (unsigned)l0 | ((unsigned)l1 << 16);
+    }
+  }
+}
+
 }  // namespace idv
+
+extern "C" int idv_stft_frames_split(const float* x, int B, int L, int n_fft, int hop, int win, int kpad, void* out,
+                                     void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(x && out && B > 0 && hop > 0 && win > 0 && n_fft >= win && kpad >= win && kpad % 64 == 0,
+                "idv_stft_frames_split: bad argument");
+  IDV_CHECK_ARG(L > n_fft / 2, "idv_stft_frames_split: reflect padding needs L > n_fft/2 (L=%d)", L);
+  const int T = L / hop + 1;
+  const long long n = (long long)B * T * (kpad / 4);
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  stft_frames_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, B, L, T, n_fft, hop, win, kpad,
+                                                                      reinterpret_cast<unsigned short*>(out));
+  IDV_LAUNCH_CHECK("stft_frames_split_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_spec_rows_split(const float* spec, int B, int nbins, int T, int kpad, void* out, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(spec && out && B > 0 && B <= 65535 && nbins > 0 && T > 0 && kpad % 64 == 0 && kpad >= 2 * nbins,
+                "idv_spec_rows_split: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  // zero the K padding (columns 2*nbins .. kpad) once: the kernel writes every (row, 2k) pair with 2k+1 < kpad,
+  // covering bins up to kpad/2 with zeros beyond nbins
+  dim3 grid(cdiv(T, 32), cdiv(kpad / 2, 32), B), block(32, 8);
+  spec_rows_split_kernel<<<grid, block, 0, st>>>(spec, B, nbins, T, kpad, reinterpret_cast<unsigned short*>(out));
+  IDV_LAUNCH_CHECK("spec_rows_split_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_ola_fwd(const float* frames, int frame_ld, const float* wsq, int B, int T, int n_fft, int hop,
+                           int win, float* out, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(frames && wsq && out && B > 0 && B <= 65535 && T > 1 && frame_ld >= win, "idv_ola_fwd: bad argument");
+  const int out_len = hop * (T - 1);
+  dim3 g2(cdiv(out_len, 256), B);
+  ola_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(frames, frame_ld, wsq, T, n_fft, hop, win, out_len, out);
+  IDV_LAUNCH_CHECK("ola_kernel");
+  return IDV_OK;
+}
 
 extern "C" int idv_stft_fwd(const float* x, int B, int L, const float* basis, int n_fft, int hop, int win,
                             float* out, void* stream) {
@@ -221,7 +314,7 @@ extern "C" int idv_istft_fwd(const float* spec, int B, int T, const float* basis
   IDV_LAUNCH_CHECK("istft_frames_kernel");
   const int out_len = hop * (T - 1);
   dim3 g2(cdiv(out_len, 256), B);
-  ola_kernel<<<g2, 256, 0, st>>>(frames, wsq, T, n_fft, hop, win, out_len, out);
+  ola_kernel<<<g2, 256, 0, st>>>(frames, win, wsq, T, n_fft, hop, win, out_len, out);
   IDV_LAUNCH_CHECK("ola_kernel");
   return IDV_OK;
 }

@@ -167,6 +167,31 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const bool row_ok = r < p.R;
       const bool pad_row = p.Tp > 0 && (r % p.Tp) == 0;
       const float* bias = p.bias + unit.bias_off + nt * BN;
+      if (p.head == 3) {
+        // ---- STFT epilogue: rows are (b, t) frames (Tp = frames per utterance, no pad rows), column pair
+        //      (2k, 2k+1) = (re, im) of bin k; written to the reference layout (B, nbins, T, 2)
+        const int T = p.Tp;
+        const int b = r / T, t = r % T;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const int bin = (nt * BN + c0 + j) >> 1;
+              if (bin < p.head_fout)
+                *reinterpret_cast<float2*>(p.predict + ((long long)(b * p.head_fout + bin) * T + t) * 2) =
+                    make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        continue;
+      }
       if (p.head) {
         // ---- fused reconstruction head: 2 output bins per unit, written to the reference layout
         uint32_t v[32];
@@ -348,8 +373,10 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
   using namespace idv;
   using namespace idv::tc;
   IDV_CHECK_ARG(a0 && wt && bias && units && taps && (out || head), "idv_tapgemm_tc: null pointer");
-  IDV_CHECK_ARG(head >= 0 && head <= 2, "idv_tapgemm_tc: head mode must be 0, 1 or 2");
-  if (head) {
+  IDV_CHECK_ARG(head >= 0 && head <= 3, "idv_tapgemm_tc: epilogue mode must be 0..3");
+  if (head == 3) {
+    IDV_CHECK_ARG(Tp > 0 && predict && head_fout > 0 && R % Tp == 0, "idv_tapgemm_tc: STFT epilogue needs Tp = frames per utterance");
+  } else if (head) {
     IDV_CHECK_ARG(N == 32 && Tp > 1 && predict && head_fout > 0 && head_bmul > 0 && head_boff >= 0 && (head != 2 || stft_x),
                   "idv_tapgemm_tc: head mode needs N == 32, Tp, predict (and stft_x for the mask head)");
   }

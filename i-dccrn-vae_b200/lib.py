@@ -25,6 +25,9 @@ SIGNATURES = {
                        i32, i32, f32, vp],
     "idv_tapgemm_tc_head": [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, vp, vp, i32, vp, i32, i64, i64,
                             i32, i32, f32, i32, i32, i32, i32, vp, vp, vp],
+    "idv_stft_frames_split": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    "idv_spec_rows_split": [vp, i32, i32, i32, i32, vp, vp],
+    "idv_ola_fwd": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp],
     "idv_enc0_fwd": [vp, i32, i32, i32, vp, vp, i32, f32, vp, i32, vp],
     "idv_dec5_head_fwd": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, i32, i32, vp],
     "idv_lstm_recurrent_fwd": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp],

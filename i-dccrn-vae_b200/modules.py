@@ -56,6 +56,10 @@ class STFT(nn.Module):
         self._basis = None
 
     def forward(self, signal):
+        if ops.use_split():                            # tensor-core DFT GEMM
+            if getattr(self, "_tc", None) is None or self._tc["bias"].device != signal.device:
+                self._tc = pack.pack_stft_tc(self.n_fft, self.win_length, signal.device)
+            return ops.stft_tc(signal, self._tc, self.n_fft, self.hop_length, self.win_length)
         if self._basis is None or self._basis.device != signal.device:
             self._basis = pack.pack_stft_basis(self.n_fft, self.win_length, signal.device)
         return ops.stft(signal, self._basis, self.n_fft, self.hop_length, self.win_length)
@@ -74,6 +78,10 @@ class ISTFT(nn.Module):
         return self._basis
 
     def forward_ri(self, spec_ri):
+        if ops.use_split():
+            if getattr(self, "_tc", None) is None or self._tc["bias"].device != spec_ri.device:
+                self._tc = pack.pack_istft_tc(self.n_fft, self.win_length, spec_ri.device)
+            return ops.istft_tc(spec_ri, self._tc, self.n_fft, self.hop_length, self.win_length)
         basis, wsq = self._ensure(spec_ri.device)
         return ops.istft(spec_ri, basis, wsq, self.n_fft, self.hop_length, self.win_length)
 

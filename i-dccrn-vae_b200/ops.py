@@ -85,6 +85,40 @@ def istft(spec_ri, basis, wsq, n_fft, hop, win):
     return out
 
 
+def stft_tc(x, hp, n_fft, hop, win):
+    """STFT on the tensor cores: frames (split bf16) -> one tap-GEMM against the windowed DFT basis whose
+    epilogue writes the reference layout (B, nbins, T, 2)."""
+    x = lib.require_f32_cuda(x, "signal")
+    if x.dim() != 2:
+        raise RuntimeError("signal must be (B, L), got %s" % (tuple(x.shape),))
+    B, L = x.shape
+    T = L // hop + 1
+    R = B * T
+    frames = torch.empty(2 * R * hp["kpad"], dtype=torch.bfloat16, device=x.device)
+    lib.call("idv_stft_frames_split", x, B, L, n_fft, hop, win, hp["kpad"], frames)
+    out = torch.empty((B, hp["nbins"], T, 2), dtype=torch.float32, device=x.device)
+    lib.call("idv_tapgemm_tc_head", frames, hp["kpad"], 1, None, 0, 0, R, T, hp["wt"], hp["kc_max"], 1, hp["bias"],
+             hp["N"], hp["units"], hp["taps"], 1, None, 0, 0, 0, 0, 0, 0.0, 3, hp["nbins"], 1, 0, None, out)
+    return out
+
+
+def istft_tc(spec_ri, hp, n_fft, hop, win):
+    spec_ri = lib.require_f32_cuda(spec_ri, "spectrum")
+    B, nb, T, _ = spec_ri.shape
+    if nb != hp["nbins"]:
+        raise RuntimeError("spectrum has %d bins, expected %d" % (nb, hp["nbins"]))
+    R = B * T
+    rows = torch.empty(2 * R * hp["kpad"], dtype=torch.bfloat16, device=spec_ri.device)
+    lib.call("idv_spec_rows_split", spec_ri, B, nb, T, hp["kpad"], rows)
+    N = hp["N"]
+    frames = _empty(R * N, spec_ri.device)
+    lib.call("idv_tapgemm_tc", rows, hp["kpad"], 1, None, 0, 0, R, 0, hp["wt"], hp["kc_max"], 1, hp["bias"], N,
+             hp["units"], hp["taps"], 1, frames, N, R * N, 0, 0, 0, 0.0)
+    out = torch.empty((B, hop * (T - 1)), dtype=torch.float32, device=spec_ri.device)
+    lib.call("idv_ola_fwd", frames, N, hp["wsq"], B, T, n_fft, hop, win, out)
+    return out
+
+
 def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None):
     """Run one packed tap-GEMM.  a0/a1: Planes (a1 may be None).  Returns the flat output tensor
     [pack.out_planes][R][pack.out_ld] (fp32, or bf16 [2][...] when out_split).  Split inputs run on the

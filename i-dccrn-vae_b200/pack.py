@@ -414,3 +414,38 @@ def pack_istft_basis(n_fft, win, device):
     basis[1:2 * nb:2, :win] = -ck[:, None] / n_fft * torch.sin(ang) * w
     wsq = (hann_periodic(win) ** 2)
     return basis.to(torch.float32).contiguous().to(device), wsq.to(torch.float32).to(device)
+
+
+def _split_rows(w):
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.to(torch.float32)).to(torch.bfloat16)
+    return torch.stack((hi, lo)).contiguous()
+
+
+def pack_stft_tc(n_fft, win, device):
+    """Analysis basis for the tensor-core STFT: one tap, K = win padded to 64, N = 2*nbins padded to 256.
+    wt: bf16 [2][1][N][kpad] (row n = 2k+part of pack_stft_basis)."""
+    nb = n_fft // 2 + 1
+    kpad = (win + 63) // 64 * 64
+    N = (2 * nb + 255) // 256 * 256
+    basis = pack_stft_basis(n_fft, win, "cpu")[:, :2 * nb]            # [win][2nb]
+    w = torch.zeros(N, kpad)
+    w[:2 * nb, :win] = basis.t()
+    return dict(wt=_split_rows(w.unsqueeze(0)).to(device), kc_max=kpad, n_slots=1, N=N, kpad=kpad, nbins=nb,
+                bias=torch.zeros(N, device=device),
+                taps=torch.tensor([[0, 0, 0, 0, kpad, 0]], dtype=torch.int32, device=device),
+                units=torch.tensor([[0, 1, 0, 0, 0, kpad // 64]], dtype=torch.int32, device=device))
+
+
+def pack_istft_tc(n_fft, win, device):
+    """Synthesis basis for the tensor-core iSTFT: K = 2*nbins padded to 64, N = win padded to 256."""
+    nb = n_fft // 2 + 1
+    kpad = (2 * nb + 63) // 64 * 64
+    N = (win + 255) // 256 * 256
+    basis, wsq = pack_istft_basis(n_fft, win, "cpu")                  # [>=2nb][>=win]
+    w = torch.zeros(N, kpad)
+    w[:win, :2 * nb] = basis[:2 * nb, :win].t()
+    return dict(wt=_split_rows(w.unsqueeze(0)).to(device), kc_max=kpad, n_slots=1, N=N, kpad=kpad, nbins=nb,
+                bias=torch.zeros(N, device=device), wsq=wsq.to(device),
+                taps=torch.tensor([[0, 0, 0, 0, kpad, 0]], dtype=torch.int32, device=device),
+                units=torch.tensor([[0, 1, 0, 0, 0, kpad // 64]], dtype=torch.int32, device=device))

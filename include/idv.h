@@ -104,6 +104,19 @@ int idv_stft_fwd(const float* x, int B, int L, const float* basis, int n_fft, in
 int idv_istft_fwd(const float* spec, int B, int T, const float* basis, const float* wsq,
                   int n_fft, int hop, int win, float* frames, float* out, void* stream);
 
+/* Tensor-core STFT / iSTFT = operand preparation + idv_tapgemm_tc_head (epilogue mode 3 for the STFT) + overlap-add:
+ *   idv_stft_frames_split: x (B, L) -> split-bf16 frames [2][B*T][kpad], frames[(b,t)][j] = reflect-padded signal
+ *                          at hop*t + (n_fft-win)/2 + j for j < win, 0 up to kpad (kpad % 64 == 0);
+ *   idv_tapgemm_tc_head(head = 3): D = frames . basis^T, column pair (2k, 2k+1) of row (b,t) is written to
+ *                          predict[(b*head_fout + k)*Tp + t] (Tp = frames per utterance; no bias, no pad rows);
+ *   idv_spec_rows_split:   spec (B, nbins, T, 2) -> split-bf16 rows [2][B*T][kpad], rows[(b,t)][2k+part];
+ *   idv_ola_fwd:           frames (B*T, frame_ld) -> overlap-add / window envelope / centre trim -> (B, hop*(T-1)). */
+int idv_stft_frames_split(const float* x, int B, int L, int n_fft, int hop, int win, int kpad, void* out,
+                          void* stream);
+int idv_spec_rows_split(const float* spec, int B, int nbins, int T, int kpad, void* out, void* stream);
+int idv_ola_fwd(const float* frames, int frame_ld, const float* wsq, int B, int T, int n_fft, int hop, int win,
+                float* out, void* stream);
+
 /* ---- first encoder layer (Cin = 1) -------------------------------------------------------------
  * Encoder 0: causal ComplexConv2d(1 -> Cout, (5,2), stride (2,1), pad (2,1)) + CBN(eval) + PReLU,
  * reading the user-layout STFT (B,257,T,2) and writing planes [Fout][R][2*Cout].

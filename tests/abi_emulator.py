@@ -44,6 +44,15 @@ def _wr(t, split, vals):
 def idv_tapgemm_tc_head(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, N, units, taps,
                         n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, slope, head, head_fout,
                         head_bmul, head_boff, stft_x, predict):
+    if head == 3:                                       # STFT epilogue: column pairs -> (B, nbins, Tp, 2)
+        tmp = torch.zeros(R * N)
+        idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, 0, wt, kc_max, n_slots, bias, N, units, taps,
+                       n_units, tmp, N, R * N, 0, 0, 0, 0.0)
+        T = Tp
+        B = R // T
+        predict.view(B, head_fout, T, 2).copy_(tmp.view(B, T, N)[:, :, :2 * head_fout].reshape(B, T, head_fout, 2)
+                                               .permute(0, 2, 1, 3))
+        return
     assert head in (1, 2) and N == 32
     tmp = torch.zeros(n_units * R * 32)
     un = units.clone()
@@ -173,6 +182,34 @@ def idv_istft_fwd(spec, B, T, basis, wsq, n_fft, hop, win, frames, out):
     y = torch.zeros(B, total, dtype=D)
     env = torch.zeros(total, dtype=D)
     fr = fr.view(B, T, win)
+    for t in range(T):
+        y[:, t * hop + off:t * hop + off + win] += fr[:, t]
+        env[t * hop + off:t * hop + off + win] += wsq.to(D)
+    h = n_fft // 2
+    out.copy_((y[:, h:total - h] / env[h:total - h]).to(torch.float32))
+
+
+def idv_stft_frames_split(x, B, L, n_fft, hop, win, kpad, out):
+    T = L // hop + 1
+    off = (n_fft - win) // 2
+    xp = torch.nn.functional.pad(x.view(B, 1, L).to(D), (n_fft // 2, n_fft // 2), mode="reflect")[:, 0]
+    fr = torch.zeros(B, T, kpad, dtype=D)
+    fr[:, :, :win] = xp.unfold(1, n_fft, hop)[:, :T, off:off + win]
+    _wr(out, 1, fr)
+
+
+def idv_spec_rows_split(spec, B, nbins, T, kpad, out):
+    rows = torch.zeros(B, T, kpad, dtype=D)
+    rows[:, :, :2 * nbins] = spec.view(B, nbins, T, 2).permute(0, 2, 1, 3).reshape(B, T, 2 * nbins).to(D)
+    _wr(out, 1, rows)
+
+
+def idv_ola_fwd(frames, frame_ld, wsq, B, T, n_fft, hop, win, out):
+    off = (n_fft - win) // 2
+    fr = frames.view(B, T, frame_ld)[:, :, :win].to(D)
+    total = n_fft + hop * (T - 1)
+    y = torch.zeros(B, total, dtype=D)
+    env = torch.zeros(total, dtype=D)
     for t in range(T):
         y[:, t * hop + off:t * hop + off + win] += fr[:, t]
         env[t * hop + off:t * hop + off + win] += wsq.to(D)

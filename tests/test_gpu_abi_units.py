@@ -260,3 +260,26 @@ def test_lstm2_wave_tc(NB, T, H):
     sync = torch.zeros(6, dtype=torch.int32)
     args = [g, 4 * H, R * 8 * H, 8 * H, w0, wi, w1, b1, NB, T, H, hseq, work, sync]
     assert _both("idv_lstm2_wave_tc", args, [11]) < 2e-5
+
+
+@pytest.mark.parametrize("B,L", [(1, 300), (3, 6400), (2, 12799)])
+def test_stft_istft_tensor_core_pieces(B, L):
+    """Operand preparation kernels, the STFT epilogue mode and the overlap-add against their contracts."""
+    from idccrn_b200 import pack as PK
+    T = L // 100 + 1
+    R = B * T
+    hp = PK.pack_stft_tc(512, 400, "cpu")
+    x = _rand(B, L, seed=5)
+    frames = torch.zeros(2 * R * hp["kpad"], dtype=torch.bfloat16)
+    assert _both("idv_stft_frames_split", [x, B, L, 512, 100, 400, hp["kpad"], frames], [7]) < 1e-7
+    E.call("idv_stft_frames_split", x, B, L, 512, 100, 400, hp["kpad"], frames)
+    out = torch.zeros(B, 257, T, 2)
+    args = [frames, hp["kpad"], 1, None, 0, 0, R, T, hp["wt"], hp["kc_max"], 1, hp["bias"], hp["N"], hp["units"],
+            hp["taps"], 1, None, 0, 0, 0, 0, 0, 0.0, 3, 257, 1, 0, None, out]
+    assert _both("idv_tapgemm_tc_head", args, [28]) < 1e-5
+    ip = PK.pack_istft_tc(512, 400, "cpu")
+    spec = _rand(B, 257, T, 2, seed=6)
+    rows = torch.zeros(2 * R * ip["kpad"], dtype=torch.bfloat16)
+    assert _both("idv_spec_rows_split", [spec, B, 257, T, ip["kpad"], rows], [5]) < 1e-7
+    fr = _rand(R, 512, seed=7)
+    assert _both("idv_ola_fwd", [fr, 512, ip["wsq"], B, T, 512, 100, 400, torch.zeros(B, 100 * (T - 1))], [8]) < 1e-5
