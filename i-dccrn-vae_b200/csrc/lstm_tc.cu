@@ -134,7 +134,8 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         LSTM_DBG(0);
         const int par = t & 1;
         const int row_base = (((rg * 2 + par) * 2 + m) * 2) * L_ROWS;
-        for (int kc = 0; kc < KC; ++kc) {
+        for (int kc0 = 0; kc0 < KC; ++kc0) {
+          const int kc = (kc0 + c) % KC;       // CTAs walk the K chunks in rotated order (spreads the L2 requests)
           mbar_wait(hempty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_ring + stage * 2 * L_HTILE;
           mbar_expect_tx(hfull0 + 8 * stage, 2 * L_HTILE);
@@ -154,10 +155,11 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       for (int t = 0; t < T; ++t) {
         mbar_wait(accempty, (t & 1) ^ 1);
         tc_fence_after();
-        for (int kc = 0; kc < KC; ++kc) {
+        for (int kc0 = 0; kc0 < KC; ++kc0) {
+          const int kc = (kc0 + c) % KC;
           mbar_wait(hfull0 + 8 * stage, phase);
           tc_fence_after();
-          if (kc == 0) LSTM_DBG(2);
+          if (kc0 == 0) LSTM_DBG(2);
           const uint32_t sa = smem_ring + stage * 2 * L_HTILE;
           const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + L_HTILE);
           const uint64_t b_hi = make_desc_sw128(smem_w + kc * W_TILE);
@@ -165,7 +167,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-            umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, (kc | k) != 0);
+            umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, (kc0 | k) != 0);
             umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
             umma_bf16(tmem_base, a_hi + koff, b_hi + koff, idesc, 1);
           }

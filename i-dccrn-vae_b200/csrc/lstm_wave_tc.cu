@@ -9,10 +9,11 @@
 // Every role is the same pipeline as csrc/lstm_tc.cu: its N = 4*Hs gate columns of the weight matrix resident in
 // shared memory (bf16 hi/lo), the 128 x H input rows streamed by TMA from an L2-resident exchange buffer, 3 MMAs
 // per K step into TMEM, thread = row epilogue.  Exchange buffers are 4 deep in time (hxA, G1x) / 2 deep (hxC) and
-// the per-(module, role) step counters carry both the data dependencies and the buffer-reuse back-pressure:
-//   L0(t) waits A >= NC*t            and B >= NC*(t-3)   (slot t%4 of hxA was last read by IP(t-4))
-//   IP(t) waits A >= NC*(t+1)        and C >= NC*(t-3)   (slot t%4 of G1x was last read by L1(t-4))
-//   L1(t) waits C >= NC*t            and B >= NC*(t+1)
+// the per-(module, role) step counters (one increment per epilogue warp: 4*NC per step) carry both the data
+// dependencies and the buffer-reuse back-pressure:
+//   L0(t) waits A >= 4NC*t           and B >= 4NC*(t-3)  (slot t%4 of hxA was last read by IP(t-4))
+//   IP(t) waits A >= 4NC*(t+1)       and C >= 4NC*(t-3)  (slot t%4 of G1x was last read by L1(t-4))
+//   L1(t) waits C >= 4NC*t           and B >= 4NC*(t+1)
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -124,21 +125,22 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       for (int t = 0; t < T; ++t) {
         int slot;
         if (role == 0) {            // input h0(t-1): slot (t)%4 holds h0(t-1) (h0(t) is written to slot (t+1)%4)
-          wait_counter(cA, (long long)NC * t);
-          wait_counter(cB, (long long)NC * (t - 3));
+          wait_counter(cA, (long long)NC * 4 * t);
+          wait_counter(cB, (long long)NC * 4 * (t - 3));
           slot = t & 3;
         } else if (role == 1) {     // input h0(t): slot (t+1)%4
-          wait_counter(cA, (long long)NC * (t + 1));
-          wait_counter(cC, (long long)NC * (t - 3));
+          wait_counter(cA, (long long)NC * 4 * (t + 1));
+          wait_counter(cC, (long long)NC * 4 * (t - 3));
           slot = (t + 1) & 3;
         } else {                    // input h1(t-1): slot t%2
-          wait_counter(cC, (long long)NC * t);
-          wait_counter(cB, (long long)NC * (t + 1));
+          wait_counter(cC, (long long)NC * 4 * t);
+          wait_counter(cB, (long long)NC * 4 * (t + 1));
           slot = t & 1;
         }
         fence_proxy_async_global();
         const int row_base = ((slot * 2 + m) * 2) * W_ROWS;
-        for (int kc = 0; kc < KC; ++kc) {
+        for (int kc0 = 0; kc0 < KC; ++kc0) {
+          const int kc = (kc0 + c) % KC;       // CTAs walk the K chunks in rotated order (spreads the L2 requests)
           mbar_wait(hempty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_ring + stage * 2 * W_HTILE;
           mbar_expect_tx(hfull0 + 8 * stage, 2 * W_HTILE);
@@ -157,7 +159,8 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       for (int t = 0; t < T; ++t) {
         mbar_wait(accempty, (t & 1) ^ 1);
         tc_fence_after();
-        for (int kc = 0; kc < KC; ++kc) {
+        for (int kc0 = 0; kc0 < KC; ++kc0) {
+          const int kc = (kc0 + c) % KC;
           mbar_wait(hfull0 + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_ring + stage * 2 * W_HTILE;
@@ -167,7 +170,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-            umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, (kc | k) != 0);
+            umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, (kc0 | k) != 0);
             umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
             umma_bf16(tmem_base, a_hi + koff, b_hi + koff, idesc, 1);
           }
@@ -212,7 +215,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         }
       } else if (role == 2) {
         // G1(t) is produced inside this kernel: acquire counter B, then coherent (L2) loads
-        if (lane == 0) wait_counter(cB, (long long)NC * (t + 1));
+        if (lane == 0) wait_counter(cB, (long long)NC * 4 * (t + 1));
         __syncwarp();
         const float* gp = p.g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
 #pragma unroll
@@ -244,9 +247,9 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
                             __uint_as_float(v[gt * HS + j + 1]) + bias[gt * HS + j + 1],
                             __uint_as_float(v[gt * HS + j + 2]) + bias[gt * HS + j + 2],
                             __uint_as_float(v[gt * HS + j + 3]) + bias[gt * HS + j + 3]);
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == W_EPI_WARP0 && lane == 0) atomicAdd(my_ctr, 1u);
+        __threadfence();                               // every warp publishes on its own (counters count warps)
+        __syncwarp();
+        if (lane == 0) atomicAdd(my_ctr, 1u);
         continue;
       }
       float hn[HS];
@@ -268,8 +271,8 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
           st_split4(hx, (long long)W_ROWS * H, j, make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]));
       }
       __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == W_EPI_WARP0 && lane == 0) atomicAdd(my_ctr, 1u);
+      __syncwarp();
+      if (lane == 0) atomicAdd(my_ctr, 1u);
       if (role == 2 && valid) {
         const long long oidx = ((long long)(m * 2 + part) * R + rcur) * H + u0;
 #pragma unroll

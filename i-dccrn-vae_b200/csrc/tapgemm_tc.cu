@@ -106,7 +106,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int nt = t % p.n_col_tiles;
         const int rt = (t / p.n_col_tiles) % p.n_row_tiles;
         const idv_unit_t unit = p.units[t / (p.n_col_tiles * p.n_row_tiles)];
-        for (int ti = 0; ti < unit.n_taps; ++ti) {
+        // co-resident CTAs work on the same unit: start each at a different tap so they do not all request the
+        // same weight tile (same L2 lines) at the same moment; the accumulation order is per-CTA but fixed
+        const int rot = (int)(blockIdx.x % (unsigned)unit.n_taps);
+        for (int ti0 = 0; ti0 < unit.n_taps; ++ti0) {
+          const int ti = ti0 + rot < unit.n_taps ? ti0 + rot : ti0 + rot - unit.n_taps;
           const idv_tap_t tap = p.taps[unit.tap_begin + ti];
           const CUtensorMap* am = tap.src ? &tmA1 : &tmA0;
           for (int k0 = 0; k0 < tap.kc; k0 += BK) {
