@@ -180,7 +180,6 @@ def run_ours(args):
     enc, dec = enc.to(dev).eval(), dec.to(dev).eval()
     x_host = synth_waveform(B, L, rank=rank).pin_memory()
     x_dev = x_host.to(dev)
-    out_host = torch.empty((B, L), dtype=torch.float32).pin_memory()
 
     def step(x):
         with torch.no_grad():
@@ -194,13 +193,28 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    from idccrn_b200.pipeline import StreamPipeline
+
+    def timed(fn, steps, n_streams=1):
+        """K steps bracketed by barrier + synchronize; device time by CUDA events on the current stream (the
+        pipeline streams fork after e0 and join before e1)."""
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
+        with StreamPipeline(dev, n_streams) as pipe:
+            for _ in range(2 if n_streams > 1 else 0):           # packs for the pipelined kernel configuration
+                with pipe.next_stream():
+                    fn()
+                torch.cuda.synchronize()
+            pipe.join()
+            torch.cuda.synchronize()
+            e0.record()
+            for s_ in pipe.streams:
+                s_.wait_stream(torch.cuda.current_stream())      # the timed region starts after e0
+            for _ in range(steps):
+                with pipe.next_stream():
+                    fn()
+            pipe.join()
+            e1.record()
         torch.cuda.synchronize()
         ms = shard.max_over_ranks(e0.elapsed_time(e1), dev)       # device time, MAX over ranks
         sync_all()
@@ -213,20 +227,29 @@ def run_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ms = timed(lambda: step(x_dev), args.steps)
+    ms = timed(lambda: step(x_dev), args.steps, args.streams)
     launches = lib.LAUNCHES[0]
+    ms_single = timed(lambda: step(x_dev), args.steps, 1) if args.streams > 1 else ms
     clk = clocks.stop() if rank == 0 else None
     value = world * B * SECONDS * args.steps / (ms / 1e3)
 
     # ---- end-to-end through the public API with host buffers
+    out_hosts = [torch.empty((B, L), dtype=torch.float32).pin_memory() for _ in range(max(2, args.streams))]
+    e2e_i = [0]
+
     def e2e_step():
+        # public API with host buffers: pinned H2D of the batch, forward, D2H of the enhanced waveforms; with
+        # several streams the copies of one batch overlap the compute of the other (results are complete when the
+        # timed region ends: the pipeline joins and the device is synchronised)
         xd = x_host.to(dev, non_blocking=True)
         sig = step(xd)
-        out_host.copy_(sig, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        out_hosts[e2e_i[0] % len(out_hosts)].copy_(sig, non_blocking=True)
+        e2e_i[0] += 1
+        if args.streams == 1:
+            torch.cuda.current_stream().synchronize()
     e2e_step()
     e2e_steps = max(1, args.steps)
-    ms_e2e = timed(e2e_step, e2e_steps)
+    ms_e2e = timed(e2e_step, e2e_steps, args.streams)
     e2e_val = world * B * SECONDS * e2e_steps / (ms_e2e / 1e3)
 
     # ---- per-kernel device time of one step (CUDA events on the launching stream), for the roofline
@@ -264,6 +287,8 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": B * L * 4,
                     "d2h_bytes_per_step": B * L * 4, "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": launches,
+            "streams": args.streams,
+            "single_stream": {"value": world * B * SECONDS * args.steps / (ms_single / 1e3), "ms_per_step": ms_single / args.steps},
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "tapgemm (complex conv / convT / LSTM in-proj / dense)",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
@@ -291,6 +316,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="utterances per GPU (config 2: 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="batches in flight: consecutive steps alternate over this many CUDA streams (1 = serial)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

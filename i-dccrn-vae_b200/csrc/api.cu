@@ -1,5 +1,6 @@
 // Error reporting and device queries of the C ABI (include/idv.h).
 #include <stdarg.h>
+#include <string.h>
 
 #include "idv_common.cuh"
 
@@ -11,7 +12,21 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static int g_lstm_ncols = 0;
+int option_lstm_ncols() { return g_lstm_ncols; }
 }  // namespace idv
+
+extern "C" int idv_set_option(const char* name, int value) {
+  using namespace idv;
+  IDV_CHECK_ARG(name, "idv_set_option: null name");
+  if (strcmp(name, "lstm_ncols") == 0) {
+    IDV_CHECK_ARG(value == 0 || value == 32 || value == 48 || value == 64, "idv_set_option: lstm_ncols must be 0, 32, 48 or 64");
+    g_lstm_ncols = value;
+    return IDV_OK;
+  }
+  set_error("idv_set_option: unknown option %s", name);
+  return IDV_E_ARG;
+}
 
 extern "C" int idv_abi_version(void) { return IDV_ABI_VERSION; }
 extern "C" const char* idv_last_error(void) { return idv::g_err; }

@@ -10,6 +10,7 @@
 namespace idv {
 
 void set_error(const char* fmt, ...);
+int option_lstm_ncols();
 
 #define IDV_CHECK_ARG(cond, ...)             \
   do {                                       \

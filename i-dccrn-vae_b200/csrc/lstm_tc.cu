@@ -295,7 +295,9 @@ extern "C" int idv_lstm_tc_config(int H, int* n_cols, int* n_ctas) {
   if (H % 64 == 0) {
     // N = 32 (8 hidden units per CTA) keeps the resident slice small so the TMA ring can hold most of h(t-1)
     // (the step is latency-bound on bytes in flight); H = 768 needs N = 48 to stay within 148 co-resident CTAs
-    if (H <= 512 && H % 8 == 0) N = 32;
+    // option "lstm_ncols" = 64: fewer, fatter CTAs (48 per layer at H = 384) — leaves SMs to kernels of other streams
+    if (idv::option_lstm_ncols() == 64 && H <= 384 && H % 16 == 0) N = 64;
+    else if (H <= 512 && H % 8 == 0) N = 32;
     else if (H <= 768 && H % 12 == 0) N = 48;
   }
   IDV_CHECK_ARG(N > 0, "idv_lstm_tc_config: hidden size %d is not supported by the tensor-core recurrence", H);

@@ -44,6 +44,7 @@ struct Params {
   int head_fout, head_bmul, head_boff;
   const float* stft_x;
   float* predict;
+  unsigned int* sched;        // [0] next tile, [1] CTAs finished (dynamic tile scheduler; self-resetting)
 };
 
 template <int BN>
@@ -64,10 +65,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address
+  // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tile-queue full[4] / empty[4], then the TMEM
+  // base address and the 4-entry tile queue
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * C::STAGES;
   const uint32_t tfull0 = empty0 + 8 * C::STAGES, tempty0 = tfull0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  const uint32_t qfull0 = tempty0 + 16, qempty0 = qfull0 + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 12);
+  volatile int* tq = reinterpret_cast<volatile int*>(tmem_slot + 1);
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -87,6 +91,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       mbar_init(tfull0 + 8 * a, 1);
       mbar_init(tempty0 + 8 * a, 4);      // one arrive per epilogue warp
     }
+    for (int qi = 0; qi < 4; ++qi) {
+      mbar_init(qfull0 + 8 * qi, 1);
+      mbar_init(qempty0 + 8 * qi, 5);     // MMA thread + 4 epilogue warps
+    }
     fence_barrier_init();
   }
   if (warp == EPI_WARP0) {
@@ -102,7 +110,17 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ================================ TMA producer ================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      // dynamic tile scheduler: tiles are claimed from a global counter so that any number of co-resident CTAs
+      // (other kernels may hold SMs) share the work evenly; the claimed ids are handed to the MMA / epilogue
+      // warps through a 4-entry shared-memory queue (-1 terminates)
+      for (uint32_t qi = 0;; ++qi) {
+        const uint32_t qs = qi & 3, qph = (qi >> 2) & 1;
+        mbar_wait(qempty0 + 8 * qs, qph ^ 1);
+        int t = (int)atomicAdd(p.sched, 1u);
+        if (t >= total_tiles) t = -1;
+        tq[qs] = t;
+        mbar_arrive(qfull0 + 8 * qs);
+        if (t < 0) break;
         const int nt = t % p.n_col_tiles;
         const int rt = (t / p.n_col_tiles) % p.n_row_tiles;
         const idv_unit_t unit = p.units[t / (p.n_col_tiles * p.n_row_tiles)];
@@ -128,8 +146,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ================================ MMA issuer ================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN);
-      uint32_t stage = 0, phase = 0, local = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t local = 0;; ++local) {
+        const uint32_t qs = local & 3, qph = (local >> 2) & 1;
+        mbar_wait(qfull0 + 8 * qs, qph);
+        const int t = tq[qs];
+        mbar_arrive(qempty0 + 8 * qs);
+        if (t < 0) break;
         const idv_unit_t unit = p.units[t / (p.n_col_tiles * p.n_row_tiles)];
         const int ksteps = unit.reserved;
         const uint32_t acc = local & 1, aphase = (local >> 1) & 1;
@@ -159,8 +182,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   } else {
     // ================================ epilogue (4 warps) ================================
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
-    uint32_t local = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+    for (uint32_t local = 0;; ++local) {
+      const uint32_t qs = local & 3, qph = (local >> 2) & 1;
+      mbar_wait(qfull0 + 8 * qs, qph);
+      const int t = tq[qs];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qempty0 + 8 * qs);
+      if (t < 0) break;
       const int nt = t % p.n_col_tiles;
       const int rt = (t / p.n_col_tiles) % p.n_row_tiles;
       const idv_unit_t unit = p.units[t / (p.n_col_tiles * p.n_row_tiles)];
@@ -284,6 +312,14 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
+  if (threadIdx.x == 0) {
+    // last CTA out re-arms the scheduler slot for its next user
+    if (atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {
+      p.sched[0] = 0;
+      p.sched[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -341,6 +377,22 @@ static int encode_map_4d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t
     return IDV_E_CUDA;
   }
   return IDV_OK;
+}
+
+// Pool of self-resetting scheduler slots (2 x u32 each), one pool per device, slots handed out round-robin so that
+// launches in flight on different streams never share one.
+constexpr int SCHED_SLOTS = 2048;
+static unsigned int* sched_slot() {
+  static unsigned int* pool[64] = {nullptr};
+  static unsigned int next[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!pool[dev]) {
+    if (cudaMalloc(&pool[dev], SCHED_SLOTS * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    if (cudaMemset(pool[dev], 0, SCHED_SLOTS * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+  }
+  const unsigned int i = __sync_fetch_and_add(&next[dev], 1u) % SCHED_SLOTS;
+  return pool[dev] + 2 * i;
 }
 
 template <int BN>
@@ -408,6 +460,8 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
   p.out_plane = out_plane; p.out_hl = out_hl; p.out_split = out_split; p.apply_prelu = apply_prelu; p.slope = prelu_slope;
   p.head = head; p.head_fout = head_fout; p.head_bmul = head_bmul; p.head_boff = head_boff;
   p.stft_x = stft_x; p.predict = predict;
+  p.sched = sched_slot();
+  IDV_CHECK_ARG(p.sched != nullptr, "idv_tapgemm_tc: could not allocate the tile-scheduler pool");
   int dev = 0, sms = 0;
   IDV_CUDA(cudaGetDevice(&dev));
   IDV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -40,7 +40,8 @@ SIGNATURES = {
     "idv_z_to_planes": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "idv_cbn_eval_user": [vp, i64, i32, i64, vp, vp, vp],
 }
-EXPORTS = ["idv_abi_version", "idv_last_error", "idv_lstm_tc_config", "idv_lstm2_wave_config"] + list(SIGNATURES)
+EXPORTS = ["idv_abi_version", "idv_last_error", "idv_lstm_tc_config", "idv_lstm2_wave_config", "idv_set_option"] + \
+    list(SIGNATURES)
 
 
 def lib_path():
@@ -105,6 +106,14 @@ def call(name, *args):
     if hook is not None:
         e1.record()
         hook(name, (e0, e1))
+
+
+def set_option(name, value):
+    lib = load()
+    lib.idv_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    lib.idv_set_option.restype = ctypes.c_int
+    if lib.idv_set_option(name.encode(), int(value)) != 0:
+        raise RuntimeError("idv_set_option failed: %s" % lib.idv_last_error().decode())
 
 
 def lstm_tc_config(H):

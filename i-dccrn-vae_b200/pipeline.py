@@ -1,0 +1,59 @@
+"""Throughput mode: consecutive batches alternate over several CUDA streams.
+
+A single forward is a dependency chain  encoder GEMMs -> LSTM recurrence (latency-bound, few SMs) -> decoder
+GEMMs, so on one stream the tensor pipe idles during the recurrence.  With two batches in flight the recurrence of
+batch i overlaps the tensor-core GEMMs of batch i+1 / i-1: the GEMM kernels claim their tiles from a global counter
+(any number of free SMs is used evenly) and the recurrence is configured to occupy only 48 SMs
+(``lstm_ncols = 64``, one launch per layer instead of the 144-CTA wavefront kernel).
+"""
+import contextlib
+
+import torch
+
+from . import lib, ops
+
+
+class StreamPipeline:
+    """with pipe.next_stream(): enc(...); dec(...)   — round-robins the batches over ``n_streams`` streams."""
+
+    def __init__(self, device, n_streams=2):
+        if n_streams < 1:
+            raise ValueError("n_streams must be >= 1")
+        self.device = torch.device(device)
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)] if n_streams > 1 else []
+        self._i = 0
+        self._saved = None
+
+    def __enter__(self):
+        # overlap-friendly kernel configuration (restored on exit)
+        self._saved = (ops.LSTM_WAVE[0],)
+        if self.streams:
+            ops.LSTM_WAVE[0] = False
+            lib.set_option("lstm_ncols", 64)
+            cur = torch.cuda.current_stream(self.device)
+            for s in self.streams:
+                s.wait_stream(cur)
+        return self
+
+    def __exit__(self, *exc):
+        self.join()
+        ops.LSTM_WAVE[0] = self._saved[0]
+        if self.streams:
+            lib.set_option("lstm_ncols", 0)
+        return False
+
+    @contextlib.contextmanager
+    def next_stream(self):
+        if not self.streams:
+            yield torch.cuda.current_stream(self.device)
+            return
+        s = self.streams[self._i % len(self.streams)]
+        self._i += 1
+        with torch.cuda.stream(s):
+            yield s
+
+    def join(self):
+        """Make the caller's current stream wait for everything submitted so far."""
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)

@@ -36,6 +36,9 @@ extern "C" {
 
 int idv_abi_version(void);
 const char* idv_last_error(void);
+/* Process-wide tuning options.  "lstm_ncols": gate columns per CTA of idv_lstm_recurrent_tc (0 = auto; 64 = half as
+ * many CTAs, leaves SMs free for kernels running concurrently on other streams).                              */
+int idv_set_option(const char* name, int value);
 /* SM count of the current device (grids are sized against it). */
 int idv_device_sm_count(int* out);
 

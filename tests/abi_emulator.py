@@ -383,8 +383,8 @@ def idv_lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB
 
 def _lstm_tc_config(H):
     assert H % 64 == 0
-    n = 32 if H <= 512 else 48
-    return n, H // (n // 4)
+    from idccrn_b200 import lib
+    return lib.lstm_tc_config(H)          # pure host function of the real library (no GPU needed)
 
 
 def idv_lstm_combine_fwd(hseq, NB, T, H, latent):
