@@ -316,7 +316,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="utterances per GPU (config 2: 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=1,
                     help="batches in flight: consecutive steps alternate over this many CUDA streams (1 = serial)")
     args = ap.parse_args()
     if args.impl == "reference":

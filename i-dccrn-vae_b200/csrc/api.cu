@@ -13,7 +13,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 static int g_lstm_ncols = 0;
+static int g_dynamic_tiles = 0;
 int option_lstm_ncols() { return g_lstm_ncols; }
+int option_dynamic_tiles() { return g_dynamic_tiles; }
 }  // namespace idv
 
 extern "C" int idv_set_option(const char* name, int value) {
@@ -22,6 +24,10 @@ extern "C" int idv_set_option(const char* name, int value) {
   if (strcmp(name, "lstm_ncols") == 0) {
     IDV_CHECK_ARG(value == 0 || value == 32 || value == 48 || value == 64, "idv_set_option: lstm_ncols must be 0, 32, 48 or 64");
     g_lstm_ncols = value;
+    return IDV_OK;
+  }
+  if (strcmp(name, "gemm_dynamic_tiles") == 0) {
+    g_dynamic_tiles = value != 0;
     return IDV_OK;
   }
   set_error("idv_set_option: unknown option %s", name);

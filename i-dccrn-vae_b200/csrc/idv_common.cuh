@@ -11,6 +11,7 @@ namespace idv {
 
 void set_error(const char* fmt, ...);
 int option_lstm_ncols();
+int option_dynamic_tiles();
 
 #define IDV_CHECK_ARG(cond, ...)             \
   do {                                       \

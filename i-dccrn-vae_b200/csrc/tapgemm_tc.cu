@@ -57,7 +57,9 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// DYN = false: tile i of CTA b is b + i*gridDim.x (lock-step CTAs, best when the kernel owns the GPU);
+// DYN = true : tiles are claimed from a global counter (kernels of other streams may hold SMs).
+template <int BN, bool DYN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW, const Params p) {
@@ -113,14 +115,19 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       // dynamic tile scheduler: tiles are claimed from a global counter so that any number of co-resident CTAs
       // (other kernels may hold SMs) share the work evenly; the claimed ids are handed to the MMA / epilogue
       // warps through a 4-entry shared-memory queue (-1 terminates)
+      int t_next = DYN ? (int)atomicAdd(p.sched, 1u) : (int)blockIdx.x;
       for (uint32_t qi = 0;; ++qi) {
-        const uint32_t qs = qi & 3, qph = (qi >> 2) & 1;
-        mbar_wait(qempty0 + 8 * qs, qph ^ 1);
-        int t = (int)atomicAdd(p.sched, 1u);
+        int t = t_next;
         if (t >= total_tiles) t = -1;
-        tq[qs] = t;
-        mbar_arrive(qfull0 + 8 * qs);
+        if (DYN) {
+          const uint32_t qs = qi & 3, qph = (qi >> 2) & 1;
+          mbar_wait(qempty0 + 8 * qs, qph ^ 1);
+          tq[qs] = t;
+          mbar_arrive(qfull0 + 8 * qs);
+        }
         if (t < 0) break;
+        // DYN: claimed one tile ahead, the atomic's latency hides behind this tile's loads
+        t_next = DYN ? (int)atomicAdd(p.sched, 1u) : t + (int)gridDim.x;
         const int nt = t % p.n_col_tiles;
         const int rt = (t / p.n_col_tiles) % p.n_row_tiles;
         const idv_unit_t unit = p.units[t / (p.n_col_tiles * p.n_row_tiles)];
@@ -148,10 +155,16 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       constexpr uint32_t idesc = make_idesc(BN);
       uint32_t stage = 0, phase = 0;
       for (uint32_t local = 0;; ++local) {
-        const uint32_t qs = local & 3, qph = (local >> 2) & 1;
-        mbar_wait(qfull0 + 8 * qs, qph);
-        const int t = tq[qs];
-        mbar_arrive(qempty0 + 8 * qs);
+        int t;
+        if (DYN) {
+          const uint32_t qs = local & 3, qph = (local >> 2) & 1;
+          mbar_wait(qfull0 + 8 * qs, qph);
+          t = tq[qs];
+          mbar_arrive(qempty0 + 8 * qs);
+        } else {
+          t = (int)(blockIdx.x + local * gridDim.x);
+          if (t >= total_tiles) t = -1;
+        }
         if (t < 0) break;
         const idv_unit_t unit = p.units[t / (p.n_col_tiles * p.n_row_tiles)];
         const int ksteps = unit.reserved;
@@ -183,11 +196,17 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ================================ epilogue (4 warps) ================================
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
     for (uint32_t local = 0;; ++local) {
-      const uint32_t qs = local & 3, qph = (local >> 2) & 1;
-      mbar_wait(qfull0 + 8 * qs, qph);
-      const int t = tq[qs];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(qempty0 + 8 * qs);
+      int t;
+      if (DYN) {
+        const uint32_t qs = local & 3, qph = (local >> 2) & 1;
+        mbar_wait(qfull0 + 8 * qs, qph);
+        t = tq[qs];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(qempty0 + 8 * qs);
+      } else {
+        t = (int)(blockIdx.x + local * gridDim.x);
+        if (t >= total_tiles) t = -1;
+      }
       if (t < 0) break;
       const int nt = t % p.n_col_tiles;
       const int rt = (t / p.n_col_tiles) % p.n_row_tiles;
@@ -312,7 +331,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
-  if (threadIdx.x == 0) {
+  if (DYN && threadIdx.x == 0) {
     // last CTA out re-arms the scheduler slot for its next user
     if (atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {
       p.sched[0] = 0;
@@ -395,16 +414,28 @@ static unsigned int* sched_slot() {
   return pool[dev] + 2 * i;
 }
 
-template <int BN>
-static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const Params& p, int sms,
-                  cudaStream_t st) {
+template <int BN, bool DYN>
+static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const Params& p, int sms,
+                   cudaStream_t st) {
   using C = Cfg<BN>;
-  IDV_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  IDV_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<BN, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int total = p.n_units * p.n_row_tiles * p.n_col_tiles;
   const int grid = total < sms ? total : sms;
-  tapgemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(a0, a1, w, p);
+  tapgemm_tc_kernel<BN, DYN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(a0, a1, w, p);
   IDV_LAUNCH_CHECK("tapgemm_tc_kernel");
   return IDV_OK;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, Params& p, int sms,
+                  cudaStream_t st) {
+  if (option_dynamic_tiles()) {
+    p.sched = sched_slot();
+    IDV_CHECK_ARG(p.sched != nullptr, "idv_tapgemm_tc: could not allocate the tile-scheduler pool");
+    return launch2<BN, true>(a0, a1, w, p, sms, st);
+  }
+  p.sched = nullptr;
+  return launch2<BN, false>(a0, a1, w, p, sms, st);
 }
 
 }  // namespace tc
@@ -460,8 +491,6 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
   p.out_plane = out_plane; p.out_hl = out_hl; p.out_split = out_split; p.apply_prelu = apply_prelu; p.slope = prelu_slope;
   p.head = head; p.head_fout = head_fout; p.head_bmul = head_bmul; p.head_boff = head_boff;
   p.stft_x = stft_x; p.predict = predict;
-  p.sched = sched_slot();
-  IDV_CHECK_ARG(p.sched != nullptr, "idv_tapgemm_tc: could not allocate the tile-scheduler pool");
   int dev = 0, sms = 0;
   IDV_CUDA(cudaGetDevice(&dev));
   IDV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

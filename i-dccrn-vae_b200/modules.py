@@ -301,6 +301,8 @@ class ComplexLSTM(nn.Module):
         if wave:
             w0, wi1, w1, b1 = self._packed_wave(wave, xp.data.device)
             g = ops.tapgemm(layers[0][0], xp, None, NB, T, zero_pad_rows=False, out_split=False)
+            if ops.GATE_HOOK[0] is not None:
+                ops.GATE_HOOK[0]()
             hseq = ops.lstm2_wave_tc(g, 4 * H, R * 8 * H, 8 * H, w0, wi1, w1, b1, NB, T, H, wave[2])
             return ops.lstm_combine(hseq, NB, T, H)
         # tensor-core recurrence when the planes are split-bf16 and the cooperative grid fits the device;
@@ -309,6 +311,8 @@ class ComplexLSTM(nn.Module):
         whh_tc = self._packed_tc(cfg, xp.data.device) if cfg else None
         for l, (inproj, whh) in enumerate(layers):
             g = ops.tapgemm(inproj, src, None, NB, T, zero_pad_rows=False, out_split=False)
+            if l == 0 and ops.GATE_HOOK[0] is not None:
+                ops.GATE_HOOK[0]()
             last = l + 1 == len(layers)
             more = split and not last                  # the next layer's tensor-core in-proj reads split h
             offs = (4 * H, R * 8 * H, 8 * H) if l == 0 else (2 * R * 4 * H, R * 4 * H, 4 * H)

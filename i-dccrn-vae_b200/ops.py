@@ -15,6 +15,9 @@ GEMM_MODE = [os.environ.get("IDV_GEMM", "tc")]
 LSTM_WAVE = [os.environ.get("IDV_LSTM_WAVE", "1") != "0"]     # 2-layer wavefront kernel (else one launch per layer)
 
 
+GATE_HOOK = [None]      # called right before the LSTM recurrence is launched (StreamPipeline staggers batches on it)
+
+
 def set_gemm_mode(mode):
     if mode not in ("tc", "simt"):
         raise ValueError("mode must be 'tc' or 'simt'")

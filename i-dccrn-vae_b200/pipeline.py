@@ -23,6 +23,8 @@ class StreamPipeline:
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)] if n_streams > 1 else []
         self._i = 0
         self._saved = None
+        self._gate = None          # event: the previous batch has reached its LSTM recurrence
+        self.stagger = True
 
     def __enter__(self):
         # overlap-friendly kernel configuration (restored on exit)
@@ -30,6 +32,7 @@ class StreamPipeline:
         if self.streams:
             ops.LSTM_WAVE[0] = False
             lib.set_option("lstm_ncols", 64)
+            lib.set_option("gemm_dynamic_tiles", 1)
             cur = torch.cuda.current_stream(self.device)
             for s in self.streams:
                 s.wait_stream(cur)
@@ -40,6 +43,7 @@ class StreamPipeline:
         ops.LSTM_WAVE[0] = self._saved[0]
         if self.streams:
             lib.set_option("lstm_ncols", 0)
+            lib.set_option("gemm_dynamic_tiles", 0)
         return False
 
     @contextlib.contextmanager
@@ -49,8 +53,27 @@ class StreamPipeline:
             return
         s = self.streams[self._i % len(self.streams)]
         self._i += 1
-        with torch.cuda.stream(s):
-            yield s
+        # stagger: a batch starts its encoder GEMMs only once the previous batch has entered its (latency-bound)
+        # recurrence, so the tensor pipe always has GEMM work from one batch while another one is in its LSTM
+        if self.stagger and self._gate is not None:
+            s.wait_event(self._gate)
+        gate = torch.cuda.Event()
+        fired = [False]
+
+        def hook():
+            if not fired[0]:
+                gate.record(torch.cuda.current_stream(self.device))
+                fired[0] = True
+        old = ops.GATE_HOOK[0]
+        ops.GATE_HOOK[0] = hook
+        try:
+            with torch.cuda.stream(s):
+                yield s
+                if not fired[0]:
+                    gate.record(s)
+        finally:
+            ops.GATE_HOOK[0] = old
+        self._gate = gate
 
     def join(self):
         """Make the caller's current stream wait for everything submitted so far."""

@@ -37,7 +37,9 @@ extern "C" {
 int idv_abi_version(void);
 const char* idv_last_error(void);
 /* Process-wide tuning options.  "lstm_ncols": gate columns per CTA of idv_lstm_recurrent_tc (0 = auto; 64 = half as
- * many CTAs, leaves SMs free for kernels running concurrently on other streams).                              */
+ * many CTAs, leaves SMs free for kernels running concurrently on other streams).  "gemm_dynamic_tiles": 1 = the
+ * tensor-core tap-GEMM claims its tiles from a global counter (for kernels sharing the GPU across streams),
+ * 0 (default) = static round-robin tiles.                                                                      */
 int idv_set_option(const char* name, int value);
 /* SM count of the current device (grids are sized against it). */
 int idv_device_sm_count(int* out);

@@ -165,7 +165,16 @@ def test_bad_arguments_return_error_codes():
     (1000, 0, 512, [192], [1], False, False, 0),             # two N tiles, many row tiles (persistent loop)
     (40000, 641, 32, [64, 64], [1, 0], False, True, 1),      # > 148 tiles: several tiles per CTA, both TMEM stages
 ])
-def test_tapgemm_tc(R, Tp, N, kcs, dts, two_src, prelu, out_split):
+@pytest.mark.parametrize("dynamic_tiles", [0, 1])
+def test_tapgemm_tc(R, Tp, N, kcs, dts, two_src, prelu, out_split, dynamic_tiles):
+    lib.set_option("gemm_dynamic_tiles", dynamic_tiles)
+    try:
+        _tapgemm_tc_case(R, Tp, N, kcs, dts, two_src, prelu, out_split)
+    finally:
+        lib.set_option("gemm_dynamic_tiles", 0)
+
+
+def _tapgemm_tc_case(R, Tp, N, kcs, dts, two_src, prelu, out_split):
     F0, cp0, cp1 = 3, 264, 136
     a0 = _to_split(_rand(F0, R, cp0, seed=1))
     a1 = _to_split(_rand(2, R, cp1, seed=2)) if two_src else None
