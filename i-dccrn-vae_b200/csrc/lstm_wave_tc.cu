@@ -9,11 +9,11 @@
 // Every role is the same pipeline as csrc/lstm_tc.cu: its N = 4*Hs gate columns of the weight matrix resident in
 // shared memory (bf16 hi/lo), the 128 x H input rows streamed by TMA from an L2-resident exchange buffer, 3 MMAs
 // per K step into TMEM, thread = row epilogue.  Exchange buffers are 4 deep in time (hxA, G1x) / 2 deep (hxC) and
-// the per-(module, role) step counters (one increment per epilogue warp: 4*NC per step) carry both the data
+// the per-(module, role) step counters (one increment per epilogue warp: 8*NC per step) carry both the data
 // dependencies and the buffer-reuse back-pressure:
-//   L0(t) waits A >= 4NC*t           and B >= 4NC*(t-3)  (slot t%4 of hxA was last read by IP(t-4))
-//   IP(t) waits A >= 4NC*(t+1)       and C >= 4NC*(t-3)  (slot t%4 of G1x was last read by L1(t-4))
-//   L1(t) waits C >= 4NC*t           and B >= 4NC*(t+1)
+//   L0(t) waits A >= 8NC*t           and B >= 8NC*(t-3)  (slot t%4 of hxA was last read by IP(t-4))
+//   IP(t) waits A >= 8NC*(t+1)       and C >= 8NC*(t-3)  (slot t%4 of G1x was last read by L1(t-4))
+//   L1(t) waits C >= 8NC*t           and B >= 8NC*(t+1)
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -21,7 +21,8 @@
 namespace idv {
 namespace tc {
 
-constexpr int W_THREADS = 192;
+constexpr int W_EPI_WARPS = 8;
+constexpr int W_THREADS = 64 + 32 * W_EPI_WARPS;
 constexpr int W_EPI_WARP0 = 2;
 constexpr int W_ROWS = 128;
 constexpr int W_HTILE = W_ROWS * BK * 2;
@@ -102,7 +103,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       mbar_init(hempty0 + 8 * s, 1);
     }
     mbar_init(accfull, 1);
-    mbar_init(accempty, 4);
+    mbar_init(accempty, W_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == W_EPI_WARP0) {
@@ -125,16 +126,16 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       for (int t = 0; t < T; ++t) {
         int slot;
         if (role == 0) {            // input h0(t-1): slot (t)%4 holds h0(t-1) (h0(t) is written to slot (t+1)%4)
-          wait_counter(cA, (long long)NC * 4 * t);
-          wait_counter(cB, (long long)NC * 4 * (t - 3));
+          wait_counter(cA, (long long)NC * W_EPI_WARPS * t);
+          wait_counter(cB, (long long)NC * W_EPI_WARPS * (t - 3));
           slot = t & 3;
         } else if (role == 1) {     // input h0(t): slot (t+1)%4
-          wait_counter(cA, (long long)NC * 4 * (t + 1));
-          wait_counter(cC, (long long)NC * 4 * (t - 3));
+          wait_counter(cA, (long long)NC * W_EPI_WARPS * (t + 1));
+          wait_counter(cC, (long long)NC * W_EPI_WARPS * (t - 3));
           slot = (t + 1) & 3;
         } else {                    // input h1(t-1): slot t%2
-          wait_counter(cC, (long long)NC * 4 * t);
-          wait_counter(cB, (long long)NC * 4 * (t + 1));
+          wait_counter(cC, (long long)NC * W_EPI_WARPS * t);
+          wait_counter(cB, (long long)NC * W_EPI_WARPS * (t + 1));
           slot = t & 1;
         }
         fence_proxy_async_global();
@@ -181,56 +182,62 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       }
     }
   } else {
-    // ================================ epilogue (thread = row) ================================
-    const int q = warp & 3;
+    // ================================ epilogue: 8 warps, thread = (row, half of the CTA's units) ===========
+    const int q = warp & 3;                           // TMEM lane quarter (rows q*32 .. q*32+31)
+    const int half = (warp - W_EPI_WARP0) >> 2;       // which half of the HS hidden units
+    constexpr int HU = HS / 2;                        // units per thread
     const int r = q * 32 + lane;
     const int part = r >> 6;
     const int b = r & 63;
     const bool valid = b < p.NB;
-    const int u0 = c * HS;
-    float cst[HS];
+    const int u0 = c * HS + half * HU;                // first hidden unit of this thread
+    float cst[HU];
 #pragma unroll
-    for (int j = 0; j < HS; ++j) cst[j] = 0.f;
-    float bias[N];
+    for (int j = 0; j < HU; ++j) cst[j] = 0.f;
+    float bias[4 * HU];
     if (role == 1) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) bias[j] = __ldg(p.bias1 + ((long long)m * NC + c) * N + j);
+      for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+        for (int j = 0; j < HU; ++j)
+          bias[gt * HU + j] = __ldg(p.bias1 + ((long long)m * NC + c) * N + gt * HS + half * HU + j);
     }
     for (int t = 0; t < T; ++t) {
       const long long rcur = (long long)b * Tp + 1 + t;
-      float gin[N];
+      float gin[4 * HU];
       if (role == 0) {
         if (valid) {
           const float* gp = p.g0 + m * p.g_m_off + part * p.g_p_off + u0 + rcur * p.g_ld;
 #pragma unroll
           for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
-            for (int j = 0; j < HS; j += 4) {
+            for (int j = 0; j < HU; j += 4) {
               const float4 v = __ldg(reinterpret_cast<const float4*>(gp + gt * H + j));
-              gin[gt * HS + j] = v.x; gin[gt * HS + j + 1] = v.y; gin[gt * HS + j + 2] = v.z; gin[gt * HS + j + 3] = v.w;
+              gin[gt * HU + j] = v.x; gin[gt * HU + j + 1] = v.y; gin[gt * HU + j + 2] = v.z; gin[gt * HU + j + 3] = v.w;
             }
         } else {
 #pragma unroll
-          for (int j = 0; j < N; ++j) gin[j] = 0.f;
+          for (int j = 0; j < 4 * HU; ++j) gin[j] = 0.f;
         }
       } else if (role == 2) {
         // G1(t) is produced inside this kernel: acquire counter B, then coherent (L2) loads
-        if (lane == 0) wait_counter(cB, (long long)NC * 4 * (t + 1));
+        if (lane == 0) wait_counter(cB, (long long)NC * W_EPI_WARPS * (t + 1));
         __syncwarp();
         const float* gp = p.g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
 #pragma unroll
         for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
-          for (int j = 0; j < HS; j += 4) {
+          for (int j = 0; j < HU; j += 4) {
             const float4 v = __ldcg(reinterpret_cast<const float4*>(gp + gt * H + j));
-            gin[gt * HS + j] = v.x; gin[gt * HS + j + 1] = v.y; gin[gt * HS + j + 2] = v.z; gin[gt * HS + j + 3] = v.w;
+            gin[gt * HU + j] = v.x; gin[gt * HU + j + 1] = v.y; gin[gt * HU + j + 2] = v.z; gin[gt * HU + j + 3] = v.w;
           }
       }
       mbar_wait(accfull, t & 1);
       tc_fence_after();
-      uint32_t v[N];
+      uint32_t v[4 * HU];                             // [gate][unit]: accumulator columns gate*HS + half*HU + j
 #pragma unroll
-      for (int c0 = 0; c0 < N; c0 += 16) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v + c0);
+      for (int gt = 0; gt < 4; ++gt)
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + gt * HS + half * HU, v + gt * HU);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -241,24 +248,24 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
 #pragma unroll
         for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
-          for (int j = 0; j < HS; j += 4)
+          for (int j = 0; j < HU; j += 4)
             *reinterpret_cast<float4*>(gp + gt * H + j) =
-                make_float4(__uint_as_float(v[gt * HS + j]) + bias[gt * HS + j],
-                            __uint_as_float(v[gt * HS + j + 1]) + bias[gt * HS + j + 1],
-                            __uint_as_float(v[gt * HS + j + 2]) + bias[gt * HS + j + 2],
-                            __uint_as_float(v[gt * HS + j + 3]) + bias[gt * HS + j + 3]);
+                make_float4(__uint_as_float(v[gt * HU + j]) + bias[gt * HU + j],
+                            __uint_as_float(v[gt * HU + j + 1]) + bias[gt * HU + j + 1],
+                            __uint_as_float(v[gt * HU + j + 2]) + bias[gt * HU + j + 2],
+                            __uint_as_float(v[gt * HU + j + 3]) + bias[gt * HU + j + 3]);
         __threadfence();                               // every warp publishes on its own (counters count warps)
         __syncwarp();
         if (lane == 0) atomicAdd(my_ctr, 1u);
         continue;
       }
-      float hn[HS];
+      float hn[HU];
 #pragma unroll
-      for (int j = 0; j < HS; ++j) {
+      for (int j = 0; j < HU; ++j) {
         const float ig = wsig(__uint_as_float(v[j]) + gin[j]);
-        const float fg = wsig(__uint_as_float(v[HS + j]) + gin[HS + j]);
-        const float gg = wtanh(__uint_as_float(v[2 * HS + j]) + gin[2 * HS + j]);
-        const float og = wsig(__uint_as_float(v[3 * HS + j]) + gin[3 * HS + j]);
+        const float fg = wsig(__uint_as_float(v[HU + j]) + gin[HU + j]);
+        const float gg = wtanh(__uint_as_float(v[2 * HU + j]) + gin[2 * HU + j]);
+        const float og = wsig(__uint_as_float(v[3 * HU + j]) + gin[3 * HU + j]);
         cst[j] = fg * cst[j] + ig * gg;
         hn[j] = og * wtanh(cst[j]);
       }
@@ -267,7 +274,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         const int slot = role == 0 ? ((t + 1) & 3) : ((t + 1) & 1);
         unsigned short* hx = (role == 0 ? p.hxA : p.hxC) + ((((long long)slot * 2 + m) * 2) * W_ROWS + r) * H + u0;
 #pragma unroll
-        for (int j = 0; j < HS; j += 4)
+        for (int j = 0; j < HU; j += 4)
           st_split4(hx, (long long)W_ROWS * H, j, make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]));
       }
       __threadfence();
@@ -276,7 +283,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       if (role == 2 && valid) {
         const long long oidx = ((long long)(m * 2 + part) * R + rcur) * H + u0;
 #pragma unroll
-        for (int j = 0; j < HS; j += 4)
+        for (int j = 0; j < HU; j += 4)
           *reinterpret_cast<float4*>(p.hseq1 + oidx + j) = make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]);
       }
     }
