@@ -26,6 +26,7 @@ constexpr int W_THREADS = 64 + 32 * W_EPI_WARPS;
 constexpr int W_EPI_WARP0 = 2;
 constexpr int W_ROWS = 128;
 constexpr int W_HTILE = W_ROWS * BK * 2;
+constexpr int W_REP = 1;                     // replicas of the h exchange buffers (measured on B200: replication does not help)
 
 struct WaveParams {
   const float* g0;
@@ -34,11 +35,25 @@ struct WaveParams {
   const float* bias1;                       // [2 m][NC][N] CTA-major (gate*Hs + j)
   int NB, T, H, NC, KC, stages;
   float* hseq1;                             // fp32 [4][R][H] layer-1 output
-  unsigned short* hxA;                      // bf16 [4 slot][2 m][2 hl][128][H]   h0
-  unsigned short* hxC;                      // bf16 [2 slot][2 m][2 hl][128][H]   h1
+  unsigned short* hxA;                      // bf16 [W_REP][4 slot][2 m][2 hl][128][H]   h0
+  unsigned short* hxC;                      // bf16 [W_REP][2 slot][2 m][2 hl][128][H]   h1
   float* g1x;                               // fp32 [4 slot][2 m][128][4H]        layer-1 gate pre-activations
   unsigned int* sync;                       // [2 m][3] counters A, B, C
+  unsigned long long* dbg;                  // optional phase timestamps (IDV_LSTM_DBG): CTA 0 of each role, module 0
 };
+
+__device__ __forceinline__ unsigned long long wgtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// slots per (role, step): 0 deps satisfied, 1 loads issued, 2 first tile landed, 3 MMAs issued, 4 accumulator ready,
+// 5 TMEM drained, 6 stores done, 7 published
+#define WAVE_DBG(slot)                                                                      \
+  do {                                                                                      \
+    if (p.dbg && blockIdx.x == 0 && m == 0 && t >= 300 && t < 304)                          \
+      p.dbg[(role * 4 + (t - 300)) * 8 + (slot)] = wgtime();                                \
+  } while (0)
 
 __device__ __forceinline__ unsigned int ldacq(const unsigned int* p) {
   unsigned int v;
@@ -139,16 +154,18 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
           slot = t & 1;
         }
         fence_proxy_async_global();
-        const int row_base = ((slot * 2 + m) * 2) * W_ROWS;
+        WAVE_DBG(0);
+        const int nslot = role == 2 ? 2 : 4;
+        const int blk = ((((c % W_REP) * nslot + slot) * 2 + m) * 2);      // block index of the hi tile (lo = +1)
         for (int kc0 = 0; kc0 < KC; ++kc0) {
-          const int kc = (kc0 + c) % KC;       // CTAs walk the K chunks in rotated order (spreads the L2 requests)
+          const int kc = kc0;                  // same order in every CTA (measured: rotating the order does not help)
           mbar_wait(hempty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_ring + stage * 2 * W_HTILE;
           mbar_expect_tx(hfull0 + 8 * stage, 2 * W_HTILE);
-          tma_load_2d(tmH, hfull0 + 8 * stage, sa, kc * BK, row_base);
-          tma_load_2d(tmH, hfull0 + 8 * stage, sa + W_HTILE, kc * BK, row_base + W_ROWS);
+          tma_load_3d(tmH, hfull0 + 8 * stage, sa, kc * BK, 0, blk);        // {64 k, 128 rows, hi+lo} = 32 KB
           if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
         }
+        WAVE_DBG(1);
       }
     }
   } else if (warp == 1) {
@@ -161,9 +178,12 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         mbar_wait(accempty, (t & 1) ^ 1);
         tc_fence_after();
         for (int kc0 = 0; kc0 < KC; ++kc0) {
-          const int kc = (kc0 + c) % KC;
+          const int kc = kc0;
           mbar_wait(hfull0 + 8 * stage, phase);
           tc_fence_after();
+          if (kc0 == 0) WAVE_DBG(2);
+          if (p.dbg && blockIdx.x == 0 && m == 0 && role == 0 && t >= 300 && t < 304 && kc0 < 8)
+            p.dbg[96 + (t - 300) * 8 + kc0] = wgtime();
           const uint32_t sa = smem_ring + stage * 2 * W_HTILE;
           const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + W_HTILE);
           const uint64_t b_hi = make_desc_sw128(smem_w + kc * W_TILE);
@@ -179,6 +199,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
           if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(accfull);
+        WAVE_DBG(3);
       }
     }
   } else {
@@ -234,6 +255,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       }
       mbar_wait(accfull, t & 1);
       tc_fence_after();
+      if (warp == W_EPI_WARP0 && lane == 0) WAVE_DBG(4);
       uint32_t v[4 * HU];                             // [gate][unit]: accumulator columns gate*HS + half*HU + j
 #pragma unroll
       for (int gt = 0; gt < 4; ++gt)
@@ -242,6 +264,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(accempty);
+      if (warp == W_EPI_WARP0 && lane == 0) WAVE_DBG(5);
       if (role == 1) {
         // ---- layer-1 input projection: G1(t) rows -> exchange buffer slot t%4
         float* gp = p.g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
@@ -272,14 +295,21 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       if (valid) {
         // h(t) goes to the slot the consumers of step t+1 read: (t+1)%4 for h0, (t+1)%2 for h1
         const int slot = role == 0 ? ((t + 1) & 3) : ((t + 1) & 1);
-        unsigned short* hx = (role == 0 ? p.hxA : p.hxC) + ((((long long)slot * 2 + m) * 2) * W_ROWS + r) * H + u0;
+        const int nslot = role == 0 ? 4 : 2;
 #pragma unroll
-        for (int j = 0; j < HU; j += 4)
-          st_split4(hx, (long long)W_ROWS * H, j, make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]));
+        for (int rep = 0; rep < W_REP; ++rep) {
+          unsigned short* hx = (role == 0 ? p.hxA : p.hxC) +
+                               (((((long long)rep * nslot + slot) * 2 + m) * 2) * W_ROWS + r) * H + u0;
+#pragma unroll
+          for (int j = 0; j < HU; j += 4)
+            st_split4(hx, (long long)W_ROWS * H, j, make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]));
+        }
       }
+      if (warp == W_EPI_WARP0 && lane == 0) WAVE_DBG(6);
       __threadfence();
       __syncwarp();
       if (lane == 0) atomicAdd(my_ctr, 1u);
+      if (warp == W_EPI_WARP0 && lane == 0) WAVE_DBG(7);
       if (role == 2 && valid) {
         const long long oidx = ((long long)(m * 2 + part) * R + rcur) * H + u0;
 #pragma unroll
@@ -332,7 +362,7 @@ extern "C" int idv_lstm2_wave_config(int H, int* n_cols, int* n_ctas, int64_t* w
   *n_cols = N;
   *n_ctas = H / (N / 4);
   // hxA (4 slots) + hxC (2 slots) bf16 [slot][2][2][128][H]  +  g1x fp32 [4][2][128][4H]
-  *work_bytes = (int64_t)(4 + 2) * 2 * 2 * 128 * H * 2 + (int64_t)4 * 2 * 128 * 4 * H * 4;
+  *work_bytes = (int64_t)tc::W_REP * (4 + 2) * 2 * 2 * 128 * H * 2 + (int64_t)4 * 2 * 128 * 4 * H * 4;
   return IDV_OK;
 }
 
@@ -360,16 +390,16 @@ extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_o
   IDV_CHECK_ARG(stages >= 1, "idv_lstm2_wave_tc: not enough shared memory for H=%d", H);
   const size_t smem = w_bytes + (size_t)stages * 2 * W_HTILE + 1024 + 256;
   uint8_t* wk = reinterpret_cast<uint8_t*>(work);
-  const size_t hxA_bytes = (size_t)4 * 2 * 2 * 128 * H * 2, hxC_bytes = (size_t)2 * 2 * 2 * 128 * H * 2;
+  const size_t hxA_bytes = (size_t)W_REP * 4 * 2 * 2 * 128 * H * 2, hxC_bytes = (size_t)W_REP * 2 * 2 * 2 * 128 * H * 2;
   CUtensorMap maps[5];
   const void* wp[3] = {w_hh0, w_ih1, w_hh1};
   for (int i = 0; i < 3; ++i) {
     rc = encode_map_2d(&maps[i], wp[i], H, (uint64_t)2 * 2 * NC * N, BK, N);
     if (rc) return rc;
   }
-  rc = encode_map_2d(&maps[3], wk, H, (uint64_t)4 * 2 * 2 * 128, BK, W_ROWS);
+  rc = encode_map_3d(&maps[3], wk, H, W_ROWS, (uint64_t)W_REP * 4 * 2 * 2, BK, W_ROWS, 2);
   if (rc) return rc;
-  rc = encode_map_2d(&maps[4], wk + hxA_bytes, H, (uint64_t)2 * 2 * 2 * 128, BK, W_ROWS);
+  rc = encode_map_3d(&maps[4], wk + hxA_bytes, H, W_ROWS, (uint64_t)W_REP * 2 * 2 * 2, BK, W_ROWS, 2);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   IDV_CUDA(cudaMemsetAsync(work, 0, (size_t)work_bytes, st));
@@ -382,5 +412,30 @@ extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_o
   p.hxC = reinterpret_cast<unsigned short*>(wk + hxA_bytes);
   p.g1x = reinterpret_cast<float*>(wk + hxA_bytes + hxC_bytes);
   p.sync = sync;
-  return launch_wave<64>(maps, p, smem, st);
+  p.dbg = nullptr;
+  const bool dbg = getenv("IDV_LSTM_DBG") != nullptr && T > 304;
+  if (dbg) {
+    IDV_CUDA(cudaMalloc(&p.dbg, (96 + 32) * sizeof(unsigned long long)));
+    IDV_CUDA(cudaMemsetAsync(p.dbg, 0, (96 + 32) * sizeof(unsigned long long), st));
+  }
+  rc = launch_wave<64>(maps, p, smem, st);
+  if (dbg && rc == IDV_OK) {
+    unsigned long long h[96 + 32];
+    IDV_CUDA(cudaStreamSynchronize(st));
+    IDV_CUDA(cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg);
+    const char* names[3] = {"L0", "IP", "L1"};
+    for (int ro = 0; ro < 3; ++ro)
+      for (int i = 0; i < 4; ++i) {
+        fprintf(stderr, "[wave dbg] %s t=%d:", names[ro], 300 + i);
+        for (int sl = 0; sl < 8; ++sl) fprintf(stderr, " %lld", (long long)(h[(ro * 4 + i) * 8 + sl] - h[0]));
+        fprintf(stderr, "\n");
+      }
+    for (int i = 0; i < 4; ++i) {
+      fprintf(stderr, "[wave dbg] L0 tile arrivals t=%d:", 300 + i);
+      for (int k = 0; k < 6; ++k) fprintf(stderr, " %lld", (long long)(h[96 + i * 8 + k] - h[0]));
+      fprintf(stderr, "\n");
+    }
+  }
+  return rc;
 }

@@ -124,6 +124,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 // 32 lanes x 16 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
@@ -152,6 +158,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode_fn();
 // bf16 2-D map over [rows][cols] (cols contiguous), 128B-swizzled boxes {box_cols, box_rows}
 int encode_map_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows);
+// bf16 3-D map over [blocks][rows][cols], boxes {box_cols, box_rows, box_blocks}
+int encode_map_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t blocks, uint32_t box_cols,
+                  uint32_t box_rows, uint32_t box_blocks);
 
 }  // namespace tc
 }  // namespace idv
