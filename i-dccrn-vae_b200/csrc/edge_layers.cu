@@ -31,30 +31,51 @@ __global__ void __launch_bounds__(256, 2) enc0_kernel(const float* __restrict__ 
   const long long hl = (long long)Fout * R * N;
   float* of32 = reinterpret_cast<float*>(outv);
   unsigned short* osp = reinterpret_cast<unsigned short*>(outv);
-  float* xs = ws + 21 * N;
+  float* xs0 = ws + 21 * N;                          // two im2col buffers [128 rows][21] (double buffered)
   const int n_tiles = (R + E0_ROWS - 1) / E0_ROWS;
-  // each block walks over row tiles blockIdx.x, blockIdx.x + gridDim.x, ... (weights staged once)
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-  const int r0 = tile * E0_ROWS + (tid >> 3) * 4;
-  __syncthreads();                                   // previous tile's xs fully consumed (and ws visible)
-  // im2col of the tile's 128 rows: xs[row][tap*2 + part], row stride 21 (bank-conflict free); pad rows,
-  // rows past R and out-of-range taps are zero
-  for (int i = tid; i < E0_ROWS * 10; i += 256) {
-    const int rl = i / 10, tap = i % 10;
-    const int kf = tap >> 1, kt = tap & 1;
-    const int r = tile * E0_ROWS + rl;
-    float2 v = make_float2(0.f, 0.f);
-    if (r < R) {
-      const int b = r / Tp, t = r % Tp - 1;
-      const int fi = 2 * fo + kf - 2, ti = t - 1 + kt;
-      if (t >= 0 && fi >= 0 && fi < Fin && ti >= 0)
-        v = __ldg(reinterpret_cast<const float2*>(stft + ((int64_t)(b * Fin + fi) * T + ti) * 2));
+  // im2col entry i = (row, tap) of a tile: xs[row][tap*2 + part]; pad rows, rows past R and out-of-range taps are 0.
+  // Every thread owns entries tid + j*256, j < 5; the next tile's entries are fetched into registers before the
+  // current tile is computed so the global-load latency hides behind the FMAs.
+  float2 pre[5];
+  auto fetch = [&](int tile) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int i = tid + j * 256;
+      const int rl = i / 10, tap = i % 10;
+      const int kf = tap >> 1, kt = tap & 1;
+      const int r = tile * E0_ROWS + rl;
+      float2 v = make_float2(0.f, 0.f);
+      if (r < R) {
+        const int b = r / Tp, t = r % Tp - 1;
+        const int fi = 2 * fo + kf - 2, ti = t - 1 + kt;
+        if (t >= 0 && fi >= 0 && fi < Fin && ti >= 0)
+          v = __ldg(reinterpret_cast<const float2*>(stft + ((int64_t)(b * Fin + fi) * T + ti) * 2));
+      }
+      pre[j] = v;
     }
-    xs[rl * 21 + tap * 2] = v.x;
-    xs[rl * 21 + tap * 2 + 1] = v.y;
+  };
+  auto stash = [&](float* xs) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int i = tid + j * 256;
+      const int rl = i / 10, tap = i % 10;
+      xs[rl * 21 + tap * 2] = pre[j].x;
+      xs[rl * 21 + tap * 2 + 1] = pre[j].y;
+    }
+  };
+  int cur = 0;
+  if ((int)blockIdx.x < n_tiles) {
+    fetch(blockIdx.x);
+    stash(xs0);
   }
-  __syncthreads();
-  if (r0 >= R) continue;
+  __syncthreads();                                   // weights + first tile visible
+  // each block walks over row tiles blockIdx.x, blockIdx.x + gridDim.x, ... (weights staged once)
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, cur ^= 1) {
+  const float* xs = xs0 + cur * (E0_ROWS * 21);
+  const int next = tile + gridDim.x;
+  if (next < n_tiles) fetch(next);
+  const int r0 = tile * E0_ROWS + (tid >> 3) * 4;
+  if (r0 < R) {
   bool ok[4], pad[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -109,6 +130,9 @@ __global__ void __launch_bounds__(256, 2) enc0_kernel(const float* __restrict__ 
       }
     }
   }
+  }   // r0 < R
+  if (next < n_tiles) stash(xs0 + (cur ^ 1) * (E0_ROWS * 21));
+  __syncthreads();
   }   // tile loop
 }
 
@@ -209,7 +233,7 @@ extern "C" int idv_enc0_fwd(const float* stft, int B, int Fin, int T, const floa
   const int Fout = (Fin + 4 - 5) / 2 + 1;
   IDV_CHECK_ARG(Fout <= 65535, "idv_enc0_fwd: Fout too large");
   const int R = B * (T + 1);
-  const size_t smem = (size_t)(21 * N + E0_ROWS * 21) * sizeof(float);
+  const size_t smem = (size_t)(21 * N + 2 * E0_ROWS * 21) * sizeof(float);
   IDV_CUDA(cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_tiles = cdiv(R, E0_ROWS);
   dim3 grid(n_tiles < 16 ? n_tiles : cdiv(n_tiles, 8), Fout);      // ~8 row tiles per block
