@@ -30,7 +30,7 @@ EPS_REPARAM = 1e-6  # model/pvae_module.py:L2175
 # ------------------------------------------------------------------------------------------------
 def stft(signal, n_fft=512, hop=100, win=400):
     """model/pvae_module.py:L21-27 — torch.stft, periodic Hann, center/reflect, onesided."""
-    w = torch.hann_window(win, dtype=signal.dtype)
+    w = torch.hann_window(win, dtype=signal.dtype, device=signal.device)
     spec = torch.stft(signal, n_fft=n_fft, hop_length=hop, win_length=win, window=w,
                       return_complex=True)
     return torch.view_as_real(spec)                         # (B, n_fft/2+1, T, 2)
@@ -38,7 +38,7 @@ def stft(signal, n_fft=512, hop=100, win=400):
 
 def istft(spec_c, n_fft=512, hop=100, win=400):
     """model/pvae_module.py:L38-42 — torch.istft on a complex (B, F, T) spectrum."""
-    w = torch.hann_window(win, dtype=spec_c.real.dtype)
+    w = torch.hann_window(win, dtype=spec_c.real.dtype, device=spec_c.device)
     return torch.istft(spec_c, n_fft=n_fft, hop_length=hop, win_length=win, window=w,
                        return_complex=False)
 
@@ -168,8 +168,10 @@ def decoder_block(x, sd, pre, causal=True):
 
 
 def _lstm_module(sd, pre, input_size, hidden, layers, dtype):
-    m = torch.nn.LSTM(input_size=input_size, hidden_size=hidden, num_layers=layers).to(dtype)
-    m.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+    sub = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+    dev = next(iter(sub.values())).device
+    m = torch.nn.LSTM(input_size=input_size, hidden_size=hidden, num_layers=layers).to(device=dev, dtype=dtype)
+    m.load_state_dict(sub)
     return m.eval()
 
 
@@ -285,7 +287,7 @@ def vae_decoder_forward(sd, stft_x, z, skiper, C, Fq, num_samples=1, recon_type=
         if i in skip_to_use:
             sk = skiper[len(skiper) - i - 1]
             if skip_mode == "zero":
-                sk = torch.zeros((BS,) + tuple(sk.shape[1:]), dtype=p.dtype)
+                sk = torch.zeros((BS,) + tuple(sk.shape[1:]), dtype=p.dtype, device=p.device)
             else:
                 sk = sk.unsqueeze(1).repeat(1, num_samples, 1, 1, 1, 1).view((BS,) + tuple(sk.shape[1:]))
             p = torch.cat([p, sk], dim=1)
