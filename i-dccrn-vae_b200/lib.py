@@ -39,6 +39,11 @@ SIGNATURES = {
     "idv_user_to_planes": [vp, i32, i32, i32, i32, vp, i32, vp],
     "idv_z_to_planes": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "idv_cbn_eval_user": [vp, i64, i32, i64, vp, vp, vp],
+    "idv_cbn_stats_planes": [vp, i32, i32, i32, i32, i32, vp, vp],
+    "idv_cbn_train_finalize": [vp, ctypes.c_double, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp],
+    "idv_cbn_apply_planes": [vp, i32, i32, i32, i32, i32, vp, i32, f32, vp],
+    "idv_cbn_stats_user": [vp, i64, i32, i64, vp, vp],
+    "idv_head_user": [vp, i64, i64, f32, i32, vp, i32, vp],
 }
 EXPORTS = ["idv_abi_version", "idv_last_error", "idv_lstm_tc_config", "idv_lstm2_wave_config", "idv_set_option"] + \
     list(SIGNATURES)

@@ -10,8 +10,9 @@ goes through the C ABI (ops.py), and there is no CPU or eager fallback.
 North-star aliases: ConvSTFT = STFT, ConviSTFT = ISTFT, ComplexBatchNorm = ComplexBatchNormal,
 NavieComplexLSTM = ComplexLSTM.
 
-Not built yet (raise NotImplementedError): ``train=True`` (ComplexBatchNormal batch statistics,
-model/complex_progress.py:L131-160), the non-causal config (model/net_config.py) and data_norm.
+``train=True`` runs the reference's train-mode FORWARD (ComplexBatchNormal batch statistics and running-buffer
+updates, model/complex_progress.py:L131-160) without building an autograd graph.  Not built (raise
+NotImplementedError): backward / optimiser, the non-causal config (model/net_config.py), data_norm.
 """
 import torch
 import torch.nn as nn
@@ -19,8 +20,10 @@ import torch.nn as nn
 from . import ops, pack
 from .ops import Planes
 
-_TRAIN_MSG = ("train=True (batch-statistics ComplexBatchNormal + autograd) is not built in this round; "
-              "call with train=False (the enhancement path of test_nsvae_se.py / test_se_cvaefinetune.py)")
+_TRAIN_MSG = ("train=True with num_samples > 1 is not built (the batch statistics would span the sample passes); "
+              "use num_samples == 1 or train=False")
+# train=True is FORWARD ONLY: ComplexBatchNormal uses batch statistics and updates its running buffers exactly like
+# the reference (first call copies, later calls EMA), but no autograd graph is built (backward kernels: next round).
 
 
 def _sd(module):
@@ -234,7 +237,7 @@ class ComplexBatchNormal(nn.Module):
 
     def forward(self, x, train=True):
         if train:
-            raise NotImplementedError(_TRAIN_MSG)
+            return ops.cbn_train_user(x, self)
         items = self._cache.check(self)
         key = str(x.device)
         if key not in items:
@@ -392,34 +395,35 @@ class Encoder(nn.Module):
     def _slope(self):
         return float(self.prelu.weight.detach().reshape(-1)[0])
 
-    def forward_from_stft(self, stft_x):
+    def forward_from_stft(self, stft_x, train=False):
         """First layer (in_channel == 1): reads the user-layout STFT (B, F, T, 2) directly."""
         items = self._cache.check(self)
-        key = ("enc0", str(stft_x.device))
+        key = ("enc0", bool(train), str(stft_x.device))
         if key not in items:
             self.conv._geometry()
             c = self.conv
             items[key] = pack.pack_enc0(c.conv_re.weight, c.conv_re.bias, c.conv_im.weight, c.conv_im.bias,
-                                        self.bn.fold_inputs(), self._slope(), stft_x.device)
+                                        None if train else self.bn.fold_inputs(), None if train else self._slope(),
+                                        stft_x.device)
         w, b, cout, slope = items[key]
-        return ops.enc0(stft_x, w, b, cout, slope, out_split=ops.use_split())
+        out = ops.enc0(stft_x, w, b, cout, slope, out_split=ops.use_split())
+        return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
-    def forward_planes(self, xp):
+    def forward_planes(self, xp, train=False):
         items = self._cache.check(self)          # invalidates the child's fold when bn / prelu change
-        key = ("fold", xp.F, str(xp.data.device))
+        key = ("raw" if train else "fold", xp.F, str(xp.data.device))
         if key not in items:
             kh, sf, pf = self.conv._geometry()
             c = self.conv
             items[key] = pack.pack_conv(c.conv_re.weight, c.conv_re.bias, c.conv_im.weight, c.conv_im.bias,
-                                        self.bn.fold_inputs(), self._slope(), xp.F, sf, pf, xp.data.device)
+                                        None if train else self.bn.fold_inputs(), None if train else self._slope(),
+                                        xp.F, sf, pf, xp.data.device)
         pk = items[key]
-        out = ops.tapgemm(pk, xp, None, xp.NB, xp.T)
-        return Planes(out, xp.NB, pk.c_out, pk.f_out, xp.T, split=xp.split)
+        out = Planes(ops.tapgemm(pk, xp, None, xp.NB, xp.T), xp.NB, pk.c_out, pk.f_out, xp.T, split=xp.split)
+        return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
     def forward(self, x, train):
-        if train:
-            raise NotImplementedError(_TRAIN_MSG)
-        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x)))
+        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x), train))
 
 
 class Decoder(nn.Module):
@@ -439,51 +443,57 @@ class Decoder(nn.Module):
     def _fold(self):
         return (self.bn.fold_inputs(), self._slope()) if self.if_bn else (None, None)
 
-    def forward_planes(self, pp, skip=None):
+    def forward_planes(self, pp, skip=None, train=False):
+        train = bool(train) and self.if_bn
         items = self._cache.check(self)
         c_skip = skip.C if skip is not None else 0
-        key = ("fold", pp.F, pp.C, c_skip, str(pp.data.device))
+        key = ("raw" if train else "fold", pp.F, pp.C, c_skip, str(pp.data.device))
         if key not in items:
             kh, sf, pf = self.transconv._geometry()
             t = self.transconv
             if pp.C + c_skip > t.tconv_re.in_channels:
                 raise RuntimeError("decoder layer got %d+%d input channels, has %d"
                                    % (pp.C, c_skip, t.tconv_re.in_channels))
-            bn, slope = self._fold()
+            bn, slope = (None, None) if train else self._fold()
             items[key] = pack.pack_conv_transpose(t.tconv_re.weight, t.tconv_re.bias, t.tconv_im.weight,
                                                   t.tconv_im.bias, bn, slope, pp.F, pp.C, c_skip,
                                                   pp.data.device, sf, pf)
         pk = items[key]
-        out = ops.tapgemm(pk, pp, skip, pp.NB, pp.T)
-        return Planes(out, pp.NB, pk.c_out, pk.f_out, pp.T, split=pp.split)
+        out = Planes(ops.tapgemm(pk, pp, skip, pp.NB, pp.T), pp.NB, pk.c_out, pk.f_out, pp.T, split=pp.split)
+        return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
-    def forward_head(self, pp, skip, mask, stft_x, predict, out_bmul, out_boff):
-        """Last layer (out_channel == 1) fused with the reconstruction head; writes ``predict``."""
+    def forward_head(self, pp, skip, mask, stft_x, predict, out_bmul, out_boff, train=False):
+        """Last layer (out_channel == 1) fused with the reconstruction head; writes ``predict``.  train=True: the raw
+        transposed conv is written first, then CBN with batch statistics + PReLU (+ mask head) run in place."""
+        train = bool(train) and self.if_bn
+        if train and out_bmul != 1:
+            raise NotImplementedError(_TRAIN_MSG)
         items = self._cache.check(self)
         c_skip = skip.C if skip is not None else 0
-        key = ("head", pp.C, c_skip, str(pp.data.device))
+        key = ("head", train, pp.C, c_skip, str(pp.data.device))
         if key not in items:
             self.transconv._geometry()
             t = self.transconv
-            bn, slope = self._fold()
+            bn, slope = (None, None) if train else self._fold()
             items[key] = pack.pack_dec5(t.tconv_re.weight, t.tconv_re.bias, t.tconv_im.weight, t.tconv_im.bias,
                                         bn, slope, pp.C, c_skip, pp.data.device)
         w, b, slope = items[key]
         kcs = [pp.Cp] + ([skip.Cp] if skip is not None else [])
+        fused_mask = mask and not train          # train: raw output first (slope 1 = identity), head applied after CBN
         if pp.split and all(k % 64 == 0 for k in kcs):
-            tkey = ("head_tc", pp.C, c_skip, pp.F, str(pp.data.device))
+            tkey = ("head_tc", train, pp.C, c_skip, pp.F, str(pp.data.device))
             if tkey not in items:
                 items[tkey] = pack.pack_dec5_tc(w, b, slope, pp.F, kcs, pp.data.device)
-            ops.dec5_head_tc(items[tkey], pp, skip, mask, stft_x, predict, out_bmul, out_boff)
+            ops.dec5_head_tc(items[tkey], pp, skip, fused_mask, stft_x, predict, out_bmul, out_boff)
         else:
-            ops.dec5_head(pp, skip, w, b, slope, mask, stft_x, predict, out_bmul, out_boff)
+            ops.dec5_head(pp, skip, w, b, slope, fused_mask, stft_x, predict, out_bmul, out_boff)
+        if train:
+            ops.head_train_user(predict, self.bn, self._slope(), mask, stft_x, 1)
 
     def forward(self, x, train=True):
-        if train and self.if_bn:
-            raise NotImplementedError(_TRAIN_MSG)
         if x.shape[1] != self.transconv.tconv_re.in_channels:
             raise RuntimeError("expected %d input channels" % self.transconv.tconv_re.in_channels)
-        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x)))
+        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x), None, train))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -539,10 +549,10 @@ def _build_decoders(net_params, causal, skip_to_use, use_sc=True):
     return out
 
 
-def _run_encoder_stack(encoders, stft_x):
-    planes = [encoders[0].forward_from_stft(stft_x)]
+def _run_encoder_stack(encoders, stft_x, train=False):
+    planes = [encoders[0].forward_from_stft(stft_x, train)]
     for enc in encoders[1:]:
-        planes.append(enc.forward_planes(planes[-1]))
+        planes.append(enc.forward_planes(planes[-1], train))
     return planes
 
 
@@ -578,12 +588,10 @@ class _VaeEncoderBase(nn.Module):
         self.epsilon = 1e-6
 
     def _encode(self, x, train, eps):
-        if train:
-            raise NotImplementedError(_TRAIN_MSG)
         if len(self.lstms) != 1:
             raise NotImplementedError("one ComplexLSTM stage expected (lstm_dim has two entries)")
         stft_x = self.stft(x)
-        planes = _run_encoder_stack(self.encoders, stft_x)
+        planes = _run_encoder_stack(self.encoders, stft_x, train)
         top = planes[-1]
         latent = self.lstms[0].forward_planes(top)                     # (B, T, 3*zdim*latent_num, 2)
         z, S = self.zdim, self.num_samples
@@ -661,10 +669,10 @@ class _VaeDecoderBase(nn.Module):
         self.keep_decoder_outputs = False
 
     def _decode(self, stft_x, z, skiper, C, F, train, real_skips, mask):
-        if train:
-            raise NotImplementedError(_TRAIN_MSG)
         BS, T, zdim, D = z.shape
         S = self.num_samples
+        if train and S != 1:
+            raise NotImplementedError(_TRAIN_MSG)
         if BS % S:
             raise RuntimeError("z batch %d is not a multiple of num_samples %d" % (BS, S))
         B = BS // S
@@ -685,10 +693,11 @@ class _VaeDecoderBase(nn.Module):
             zp = ops.z_to_planes(z, B, S, s, split=split)
             p = self.dense.forward_planes(zp, C, F)
             for i in range(n - 1):
-                p = self.decoders[i].forward_planes(p, skips.get(i))
+                p = self.decoders[i].forward_planes(p, skips.get(i), train)
                 if self.keep_decoder_outputs and S == 1:
                     self.decoder_outputs.append(p)
-            self.decoders[n - 1].forward_head(p, skips.get(n - 1), mask, stft_x if mask else None, predict, S, s)
+            self.decoders[n - 1].forward_head(p, skips.get(n - 1), mask, stft_x if mask else None, predict, S, s,
+                                              train)
         if self.keep_decoder_outputs and S == 1:
             self.decoder_outputs = SkipList(self.decoder_outputs)
         recon_sig = self.istft.forward_ri(predict)
@@ -757,22 +766,21 @@ class standard_DCCRN(nn.Module):
 
     def forward_spec(self, stft_x, train, mask):
         """stft_x (B, F, T, 2) -> predict (B, F, T, 2): decoder output, optionally through the mask head."""
-        if train:
-            raise NotImplementedError(_TRAIN_MSG)
         stft_x = ops.lib.require_f32_cuda(stft_x, "stft_x")
-        planes = _run_encoder_stack(self.encoders, stft_x)
+        planes = _run_encoder_stack(self.encoders, stft_x, train)
         top = planes[-1]
         lat = self.lstms[0].forward_planes(top)                         # (B, T, H, 2)
-        self.latent = lat
+        if not train:
+            self.latent = lat                                           # model/pvae_module.py:L187-188
         B, T = lat.shape[0], lat.shape[1]
         zp = ops.z_to_planes(lat, B, 1, 0, split=top.split)
         p = self.dense.forward_planes(zp, top.C, top.F)
         n = len(self.decoders)
         for i in range(n - 1):
-            p = self.decoders[i].forward_planes(p, planes[n - 1 - i] if i in self.skip_to_use else None)
+            p = self.decoders[i].forward_planes(p, planes[n - 1 - i] if i in self.skip_to_use else None, train)
         predict = torch.empty((B, stft_x.shape[1], T, 2), dtype=torch.float32, device=stft_x.device)
         self.decoders[n - 1].forward_head(p, planes[0] if (n - 1) in self.skip_to_use else None, mask,
-                                          stft_x if mask else None, predict, 1, 0)
+                                          stft_x if mask else None, predict, 1, 0, train)
         return predict
 
     def forward(self, x, train=True):

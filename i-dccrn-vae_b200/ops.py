@@ -275,3 +275,55 @@ def cbn_eval_user(x, zb):
     out = torch.empty_like(x)
     lib.call("idv_cbn_eval_user", x, B, C, inner, zb, out)
     return out
+
+
+# ---- ComplexBatchNormal(train=True), forward only ------------------------------------------------------------------
+def _cbn_finalize(bn, acc, count, device):
+    """Batch statistics -> running-buffer update (first call copies, then EMA: complex_progress.py:L144-159) and the
+    per-channel affine of the batch statistics.  ``bn`` is a modules.ComplexBatchNormal."""
+    C = bn.gamma_rr.numel()
+    zb = torch.empty(C * 6, dtype=torch.float32, device=device)
+    first = bool(bn.init_flag)
+    lib.call("idv_cbn_train_finalize", acc, float(count), C, bn.gamma_rr.detach(), bn.gamma_ri.detach(),
+             bn.gamma_ii.detach(), bn.beta_r.detach(), bn.beta_i.detach(), bn.running_mean_real, bn.running_mean_imag,
+             bn.Vrr, bn.Vri, bn.Vii, float(bn.momentum), 1 if first else 0, zb)
+    if first and not bn.dis_cbn:
+        bn.init_flag = False
+    return zb
+
+
+def cbn_train_planes(p, bn, slope):
+    """In place on planes: batch statistics over (B, F, T), running-stat update, normalise (+ PReLU if slope)."""
+    C = p.C
+    acc = torch.empty(C * 5, dtype=torch.float64, device=p.data.device)
+    lib.call("idv_cbn_stats_planes", p.data, 1 if p.split else 0, p.NB, C, p.F, p.T, acc)
+    zb = _cbn_finalize(bn, acc, p.NB * p.F * p.T, p.data.device)
+    lib.call("idv_cbn_apply_planes", p.data, 1 if p.split else 0, p.NB, C, p.F, p.T, zb,
+             0 if slope is None else 1, 0.0 if slope is None else float(slope))
+    return p
+
+
+def cbn_train_user(x, bn):
+    """Stand-alone ComplexBatchNormal.forward(x, train=True) on the reference layout (B, C, ..., 2)."""
+    x = lib.require_f32_cuda(x, "activation")
+    B, C = x.shape[0], x.shape[1]
+    inner = x[0, 0].numel() // 2
+    acc = torch.empty(C * 5, dtype=torch.float64, device=x.device)
+    lib.call("idv_cbn_stats_user", x, B, C, inner, acc)
+    zb = _cbn_finalize(bn, acc, B * inner, x.device)
+    out = torch.empty_like(x)
+    lib.call("idv_cbn_eval_user", x, B, C, inner, zb, out)
+    return out
+
+
+def head_train_user(y, bn, slope, mask, stft_x, s_rep):
+    """Last decoder layer in train mode: y (NB, F, T, 2) raw transposed-conv output in the reference layout ->
+    CBN with batch statistics (C = 1), PReLU, optional mask head; in place."""
+    NB = y.shape[0]
+    inner = y[0].numel() // 2
+    acc = torch.empty(5, dtype=torch.float64, device=y.device)
+    lib.call("idv_cbn_stats_user", y, NB, 1, inner, acc)
+    zb = _cbn_finalize(bn, acc, NB * inner, y.device)
+    lib.call("idv_cbn_eval_user", y, NB, 1, inner, zb, y)
+    lib.call("idv_head_user", y, inner, NB, float(slope), 1 if mask else 0, stft_x if mask else None, s_rep)
+    return y

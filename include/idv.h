@@ -199,6 +199,26 @@ int idv_z_to_planes(const float* z, int NB, int S, int s, int T, int zdim, void*
 int idv_cbn_eval_user(const float* x, int64_t outer, int C, int64_t inner, const float* zb, float* out,
                       void* stream);
 
+/* ---- ComplexBatchNormal(train=True), forward only (model/complex_progress.py:L131-160) -------------------------
+ * idv_cbn_stats_planes: acc[c][5] (double) = sum r, sum i, sum r^2, sum i^2, sum r*i over every plane and every
+ *   non-pad row of the planes tensor (fp32 or split bf16);
+ * idv_cbn_train_finalize: batch mean / biased (co)variances (eps added to Vrr, Vii as the reference does), update
+ *   of the running buffers (first != 0: copy, else EMA with `momentum`), zb[c][6] = Z, b' from the batch statistics;
+ * idv_cbn_apply_planes: y <- act(Z y + b') in place (pad rows untouched).                                       */
+int idv_cbn_stats_planes(const void* planes, int split, int NB, int C, int F, int T, double* acc, void* stream);
+int idv_cbn_train_finalize(const double* acc, double count, int C, const float* gamma_rr, const float* gamma_ri,
+                           const float* gamma_ii, const float* beta_r, const float* beta_i, float* run_mean_r,
+                           float* run_mean_i, float* run_vrr, float* run_vri, float* run_vii, float momentum,
+                           int first, float* zb, void* stream);
+int idv_cbn_apply_planes(void* planes, int split, int NB, int C, int F, int T, const float* zb, int apply_prelu,
+                         float prelu_slope, void* stream);
+/* statistics on the reference layout x (outer, C, inner, 2) (stand-alone ComplexBatchNormal(train=True); the last
+ * decoder layer whose raw output is written in the reference layout) and the in-place recon head on
+ * y (n_utt, n_per_utt, 2): PReLU(slope) then, if mask, the mask head with stft_x[b / s_rep].                       */
+int idv_cbn_stats_user(const float* x, int64_t outer, int C, int64_t inner, double* acc, void* stream);
+int idv_head_user(float* y, int64_t n_per_utt, int64_t n_utt, float prelu_slope, int mask, const float* stft_x,
+                  int s_rep, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,31 @@ def case_vae(tag, B, L, latent_num, S, dec_kind, recon_type, seed, full):
     np.savez(os.path.join(OUT, tag + ".npz"), **g)
 
 
+def case_vae_train(tag, B, L, seed):
+    """train=True FORWARD (batch-statistics CBN, running-buffer updates): two consecutive calls so both the
+    first-call copy and the EMA branch (model/complex_progress.py:L144-159) are pinned."""
+    print("case", tag)
+    net, enc = build_vae(1, 1, seed)
+    dec = ref_mod.nsvae_pvae_dccrn_decoder_twophase(net, True, "cpu", 1, ZDIM, NFFT, HOP, WIN, "mask", True,
+                                                    [0, 1, 2, 3, 4, 5], False)
+    dec.load_state_dict(fill_state_dict(dec.state_dict(), seed + 1), strict=True)
+    g = {"B": B, "L": L, "seed": seed}
+    T = L // HOP + 1
+    for call in range(2):
+        x = synth_waveform(B, L, seed=1234 + seed + call)
+        eps = synth_eps((B, 1, T, ZDIM), seed=7 + seed + call, n=2)
+        with torch.no_grad(), supplied_eps(eps):
+            r = enc(x, train=True)
+            sig, pred = dec(r[11], r[0], r[8], r[9], r[10], train=True, pad="sig")
+        g["miu_%d" % call], g["recon_sig_%d" % call], g["predict_%d" % call] = np32(r[1]), np32(sig), np32(pred)
+        g["enc5_%d" % call] = np32(r[8][5])
+        for name, mod in (("enc0", enc.encoders[0].bn), ("enc5", enc.encoders[5].bn), ("dec0", dec.decoders[0].bn),
+                          ("dec5", dec.decoders[5].bn)):
+            for buf in ("running_mean_real", "running_mean_imag", "Vrr", "Vri", "Vii"):
+                g["%s_%s_%d" % (name, buf, call)] = np32(getattr(mod, buf))
+    np.savez(os.path.join(OUT, tag + ".npz"), **g)
+
+
 def case_dccrn(tag, B, L, seed):
     print("case", tag)
     net = ref_causal_cfg.get_net_params()
@@ -183,6 +208,10 @@ def case_primitives(tag, seed):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-train" in sys.argv:
+        case_vae_train("vae_train_fwd", B=2, L=800, seed=6)
+        sys.exit(0)
+    case_vae_train("vae_train_fwd", B=2, L=800, seed=6)
     case_primitives("primitives", seed=3)
     # per-layer fixtures (tiny T, B=2 so the utterance boundary is exercised)
     case_vae("vae_l1_zero_full", B=2, L=400, latent_num=1, S=1, dec_kind="skip_prepare",

@@ -441,8 +441,80 @@ def idv_cbn_eval_user(x, outer, C, inner, zb, out):
     v = x.view(outer, C, inner, 2)
     k = zb.view(C, 6)[None, :, None, :]
     o = out.view(outer, C, inner, 2)
-    o[..., 0] = k[..., 0] * v[..., 0] + k[..., 1] * v[..., 1] + k[..., 4]
-    o[..., 1] = k[..., 2] * v[..., 0] + k[..., 3] * v[..., 1] + k[..., 5]
+    o_r = k[..., 0] * v[..., 0] + k[..., 1] * v[..., 1] + k[..., 4]          # x may alias out: compute both first
+    o_i = k[..., 2] * v[..., 0] + k[..., 3] * v[..., 1] + k[..., 5]
+    o[..., 0] = o_r
+    o[..., 1] = o_i
+
+
+def idv_cbn_stats_planes(planes, split, NB, C, F, T, acc):
+    Ch, Tp = _r8(C), T + 1
+    p = _rd(planes, split, F * NB * Tp * 2 * Ch).view(F, NB, Tp, 2, Ch)[:, :, 1:, :, :C]      # (F,NB,T,2,C)
+    re, im = p[:, :, :, 0], p[:, :, :, 1]
+    acc.view(C, 5).copy_(torch.stack((re.sum((0, 1, 2)), im.sum((0, 1, 2)), (re * re).sum((0, 1, 2)),
+                                      (im * im).sum((0, 1, 2)), (re * im).sum((0, 1, 2))), 1))
+
+
+def idv_cbn_stats_user(x, outer, C, inner, acc):
+    v = x.view(outer, C, inner, 2).to(D)
+    re, im = v[..., 0], v[..., 1]
+    acc.view(C, 5).copy_(torch.stack((re.sum((0, 2)), im.sum((0, 2)), (re * re).sum((0, 2)), (im * im).sum((0, 2)),
+                                      (re * im).sum((0, 2))), 1))
+
+
+def idv_cbn_train_finalize(acc, count, C, g_rr, g_ri, g_ii, beta_r, beta_i, run_mr, run_mi, run_vrr, run_vri, run_vii,
+                           momentum, first, zb):
+    a = acc.view(C, 5).to(D)
+    eps = 1e-5
+    mr, mi = a[:, 0] / count, a[:, 1] / count
+    f32 = lambda t: t.to(torch.float32)
+    mu_r, mu_i = f32(mr), f32(mi)
+    vrr = f32(a[:, 2] / count - mr * mr) + eps
+    vii = f32(a[:, 3] / count - mi * mi) + eps
+    vri = f32(a[:, 4] / count - mr * mi)
+    for buf, val in ((run_mr, mu_r), (run_mi, mu_i), (run_vrr, vrr), (run_vri, vri), (run_vii, vii)):
+        b = buf.view(-1)
+        b.copy_(val if first else momentum * b + (1 - momentum) * val)
+    delta = torch.clamp(vrr * vii - vri * vri + eps, min=1e-8)
+    s = torch.sqrt(delta)
+    t = torch.sqrt(vrr + vii + 2 * s + eps)
+    ist = 1.0 / (s * t + eps)
+    wrr, wii, wri = (vii + s) * ist, (vrr + s) * ist, -vri * ist
+    grr, gri, gii = g_rr.view(-1), g_ri.view(-1), g_ii.view(-1)
+    zrr, zri = grr * wrr + gri * wri, grr * wri + gri * wii
+    zir, zii = gri * wrr + gii * wri, gri * wri + gii * wii
+    zb.view(C, 6).copy_(torch.stack((zrr, zri, zir, zii, beta_r.view(-1) - (zrr * mu_r + zri * mu_i),
+                                     beta_i.view(-1) - (zir * mu_r + zii * mu_i)), 1))
+
+
+def idv_cbn_apply_planes(planes, split, NB, C, F, T, zb, apply_prelu, slope):
+    Ch, Tp = _r8(C), T + 1
+    n = F * NB * Tp * 2 * Ch
+    p = _rd(planes, split, n).view(F, NB, Tp, 2, Ch).clone()
+    k = zb.view(C, 6).to(D)
+    re, im = p[:, :, 1:, 0, :C].clone(), p[:, :, 1:, 1, :C].clone()
+    o_r = k[:, 0] * re + k[:, 1] * im + k[:, 4]
+    o_i = k[:, 2] * re + k[:, 3] * im + k[:, 5]
+    if apply_prelu:
+        o_r = torch.where(o_r > 0, o_r, slope * o_r)
+        o_i = torch.where(o_i > 0, o_i, slope * o_i)
+    p[:, :, 1:, 0, :C] = o_r
+    p[:, :, 1:, 1, :C] = o_i
+    _wr(planes, split, p)
+
+
+def idv_head_user(y, n_per_utt, n_utt, slope, mask, stft_x, s_rep):
+    v = y.view(n_utt, n_per_utt, 2).to(D)
+    yr = torch.where(v[..., 0] > 0, v[..., 0], slope * v[..., 0])
+    yi = torch.where(v[..., 1] > 0, v[..., 1], slope * v[..., 1])
+    if mask:
+        mag = torch.tanh(torch.sqrt(yr ** 2 + yi ** 2))
+        ph = torch.atan2(yi / (mag + 1e-8), yr / (mag + 1e-8))
+        X = stft_x.view(-1, n_per_utt, 2).to(D)[torch.arange(n_utt) // s_rep]
+        in_mag = torch.sqrt(X[..., 0] ** 2 + X[..., 1] ** 2)
+        in_ph = torch.atan2(X[..., 1], X[..., 0])
+        yr, yi = in_mag * mag * torch.cos(in_ph + ph), in_mag * mag * torch.sin(in_ph + ph)
+    y.view(n_utt, n_per_utt, 2).copy_(torch.stack((yr, yi), -1).to(torch.float32))
 
 
 TABLE = {k: v for k, v in globals().items() if k.startswith("idv_")}

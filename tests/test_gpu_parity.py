@@ -194,3 +194,29 @@ def test_cpu_tensor_is_rejected():
     enc, dec = C.build_vae(1, 1, "skip_prepare", "real_imag", 0, "cuda")
     with pytest.raises(RuntimeError, match="CUDA"):
         enc(torch.zeros(1, 800), train=False)
+
+
+def test_train_mode_forward_vs_reference_golden(gemm_mode, golden):
+    """train=True forward (batch-statistics CBN + running-buffer updates), two consecutive calls."""
+    from test_host_emulated import run_train_case
+    run_train_case(golden, "cuda", 5e-5)
+
+
+def test_standalone_cbn_train_vs_oracle_formula():
+    cbn = M.ComplexBatchNormal(5, 1, 1)
+    cbn.load_state_dict(fill_state_dict(cbn.state_dict(), 3))
+    cbn = cbn.cuda()
+    x = torch.randn(3, 5, 7, 9, 2, generator=torch.Generator().manual_seed(5))
+    # reference formulas (model/complex_progress.py:L131-160) restated on the CPU in float64
+    xr, xi = x[..., 0].double(), x[..., 1].double()
+    mr, mi = xr.mean((0, 2, 3), keepdim=True), xi.mean((0, 2, 3), keepdim=True)
+    rc, ic = xr - mr, xi - mi
+    sd = {k: v.detach().cpu().double() for k, v in cbn.state_dict().items()}
+    sd["Vrr"] = (rc * rc).mean((0, 2, 3), keepdim=True) + 1e-5
+    sd["Vii"] = (ic * ic).mean((0, 2, 3), keepdim=True) + 1e-5
+    sd["Vri"] = (rc * ic).mean((0, 2, 3), keepdim=True)
+    sd["running_mean_real"], sd["running_mean_imag"] = mr, mi
+    want = P.cbn_eval(x.double(), sd, "")
+    got = cbn(x.cuda(), train=True)
+    assert C.rel_l2(got, want) < 1e-5
+    assert C.rel_l2(cbn.Vri, sd["Vri"]) < 1e-4 and cbn.init_flag is False

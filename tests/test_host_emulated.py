@@ -86,8 +86,42 @@ def test_primitives_match_reference(emulated_abi, golden):
     assert all(v < TOL for v in errs.values()), errs
 
 
-def test_train_mode_raises_loudly(emulated_abi):
-    enc, dec = C.build_vae(1, 1, "skip_prepare", "real_imag", 0, "cpu")
-    x, eps = C.vae_inputs(1, 400, 1, 1, 0, "cpu")
+def run_train_case(golden, device, tol):
+    """train=True forward, two consecutive calls (first-call copy, then EMA of the running statistics)."""
+    import idccrn_b200 as M
+    from idccrn_b200.synth import fill_state_dict, synth_eps, synth_waveform
+    g = golden("vae_train_fwd")
+    B, L, seed = int(g["B"]), int(g["L"]), int(g["seed"])
+    enc, dec = C.build_vae(1, 1, "twophase", "mask", seed, device)
+    errs = {}
+    for call in range(2):
+        x = synth_waveform(B, L, seed=1234 + seed + call).to(device)
+        eps = [e.to(device) for e in synth_eps((B, 1, L // C.HOP + 1, C.ZDIM), seed=7 + seed + call, n=2)]
+        with torch.no_grad():
+            r = enc(x, train=True, eps=eps)
+            sig, pred = dec(r[11], r[0], r[8], r[9], r[10], train=True, pad="sig")
+        errs["miu_%d" % call] = C.rel_l2(r[1], g["miu_%d" % call])
+        errs["enc5_%d" % call] = C.rel_l2(r[8][5], g["enc5_%d" % call])
+        errs["predict_%d" % call] = C.rel_l2(torch.view_as_real(pred), g["predict_%d" % call])
+        errs["recon_sig_%d" % call] = C.rel_l2(sig, g["recon_sig_%d" % call])
+        for name, mod in (("enc0", enc.encoders[0].bn), ("enc5", enc.encoders[5].bn), ("dec0", dec.decoders[0].bn),
+                          ("dec5", dec.decoders[5].bn)):
+            for buf in ("running_mean_real", "running_mean_imag", "Vrr", "Vri", "Vii"):
+                errs["%s_%s_%d" % (name, buf, call)] = C.rel_l2(getattr(mod, buf), g["%s_%s_%d" % (name, buf, call)])
+    # running cross-covariances are small differences of larger moments: their relative error amplifies the
+    # activation noise of the split-bf16 path, so the statistics get a 10x looser bound than the activations
+    bad = {k: v for k, v in errs.items() if not v < (10 * tol if ("_V" in k or "running_mean" in k) else tol)}
+    assert not bad, bad
+    assert enc.encoders[0].bn.init_flag is False
+
+
+def test_train_mode_forward_matches_reference(emulated_abi, gemm_mode, golden):
+    run_train_case(golden, "cpu", 5e-5)
+
+
+def test_train_mode_rejects_multi_sample_decoder(emulated_abi):
+    enc, dec = C.build_vae(1, 2, "twophase", "mask", 0, "cpu")
+    x, eps = C.vae_inputs(1, 400, 2, 1, 0, "cpu")
+    r = enc(x, train=True, eps=eps)
     with pytest.raises(NotImplementedError):
-        enc(x)        # reference default is train=True
+        dec(r[11], r[0], r[8], r[9], r[10], train=True, pad="sig")
