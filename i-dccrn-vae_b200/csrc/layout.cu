@@ -9,11 +9,11 @@ __device__ __forceinline__ int round_up8(int c) { return (c + 7) & ~7; }
 
 // grid (ceil(T/32)*ceil(C/32), F, NB), block (32, 8)
 __global__ void __launch_bounds__(256) planes_to_user_kernel(const void* __restrict__ planesv, int in_split, int NB,
-                                                             int C, int F, int T, float* __restrict__ user) {
+                                                             int C, int F, int Talloc, int T, float* __restrict__ user) {
   const float* planes = reinterpret_cast<const float*>(planesv);
   const unsigned short* psp = reinterpret_cast<const unsigned short*>(planesv);
   __shared__ float tile[2][32][33];
-  const int Ch = round_up8(C), Cp = 2 * Ch, Tp = T + 1;
+  const int Ch = round_up8(C), Cp = 2 * Ch, Tp = Talloc + 1;
   const int64_t R = (int64_t)NB * Tp;
   const int ct = (C + 31) / 32;
   const int c0 = (blockIdx.x % ct) * 32, t0 = (blockIdx.x / ct) * 32;
@@ -47,11 +47,12 @@ __global__ void __launch_bounds__(256) planes_to_user_kernel(const void* __restr
 }
 
 __global__ void __launch_bounds__(256) user_to_planes_kernel(const float* __restrict__ user, int NB, int C, int F,
-                                                             int T, void* __restrict__ planesv, int out_split) {
+                                                             int Talloc, int T, void* __restrict__ planesv,
+                                                             int out_split) {
   float* planes = reinterpret_cast<float*>(planesv);
   unsigned short* psp = reinterpret_cast<unsigned short*>(planesv);
   __shared__ float tile[2][32][33];
-  const int Ch = round_up8(C), Cp = 2 * Ch, Tp = T + 1;
+  const int Ch = round_up8(C), Cp = 2 * Ch, Tp = Talloc + 1;
   const int64_t R = (int64_t)NB * Tp;
   const int ct = (C + 31) / 32;
   const int c0 = (blockIdx.x % ct) * 32, t0 = (blockIdx.x / ct) * 32;
@@ -82,11 +83,11 @@ __global__ void __launch_bounds__(256) user_to_planes_kernel(const float* __rest
   }
 }
 
-__global__ void __launch_bounds__(256) z_to_planes_kernel(const float* __restrict__ z, int NB, int S, int s, int T,
-                                                          int zdim, void* __restrict__ planesv, int out_split) {
+__global__ void __launch_bounds__(256) z_to_planes_kernel(const float* __restrict__ z, int NB, int S, int s, int Talloc,
+                                                          int T, int zdim, void* __restrict__ planesv, int out_split) {
   float* planes = reinterpret_cast<float*>(planesv);
   unsigned short* psp = reinterpret_cast<unsigned short*>(planesv);
-  const int Ch = round_up8(zdim), Cp = 2 * Ch, Tp = T + 1;
+  const int Ch = round_up8(zdim), Cp = 2 * Ch, Tp = Talloc + 1;
   const int64_t n = (int64_t)NB * T * zdim;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(i % zdim);
@@ -134,18 +135,19 @@ extern "C" int idv_cbn_eval_user(const float* x, int64_t outer, int C, int64_t i
 }
 
 extern "C" int idv_planes_to_user(const void* planes, int in_split, int NB, int C, int F, int T, float* user,
-                                  void* stream) {
+                                  int t_valid, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(planes && user, "idv_planes_to_user: null pointer");
   IDV_CHECK_ARG(NB > 0 && NB <= 65535 && C > 0 && F > 0 && F <= 65535 && T > 0, "idv_planes_to_user: bad shape");
-  dim3 grid(cdiv(T, 32) * cdiv(C, 32), F, NB), block(32, 8);
-  planes_to_user_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(planes, in_split, NB, C, F, T, user);
+  const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;      // the user tensor has Tv frames
+  dim3 grid(cdiv(Tv, 32) * cdiv(C, 32), F, NB), block(32, 8);
+  planes_to_user_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(planes, in_split, NB, C, F, T, Tv, user);
   IDV_LAUNCH_CHECK("planes_to_user_kernel");
   return IDV_OK;
 }
 
 extern "C" int idv_user_to_planes(const float* user, int NB, int C, int F, int T, void* planes, int out_split,
-                                  void* stream) {
+                                  int t_valid, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(planes && user, "idv_user_to_planes: null pointer");
   IDV_CHECK_ARG(NB > 0 && NB <= 65535 && C > 0 && F > 0 && F <= 65535 && T > 0, "idv_user_to_planes: bad shape");
@@ -153,23 +155,25 @@ extern "C" int idv_user_to_planes(const float* user, int NB, int C, int F, int T
   cudaStream_t st = (cudaStream_t)stream;
   // fp32: F*R*Cp floats; split: 2 bf16 plane sets = the same number of bytes
   IDV_CUDA(cudaMemsetAsync(planes, 0, (size_t)F * NB * (T + 1) * Cp * sizeof(float), st));
-  dim3 grid(cdiv(T, 32) * cdiv(C, 32), F, NB), block(32, 8);
-  user_to_planes_kernel<<<grid, block, 0, st>>>(user, NB, C, F, T, planes, out_split);
+  const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
+  dim3 grid(cdiv(Tv, 32) * cdiv(C, 32), F, NB), block(32, 8);
+  user_to_planes_kernel<<<grid, block, 0, st>>>(user, NB, C, F, T, Tv, planes, out_split);
   IDV_LAUNCH_CHECK("user_to_planes_kernel");
   return IDV_OK;
 }
 
 extern "C" int idv_z_to_planes(const float* z, int NB, int S, int s, int T, int zdim, void* planes, int out_split,
-                               void* stream) {
+                               int t_valid, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(planes && z, "idv_z_to_planes: null pointer");
   IDV_CHECK_ARG(NB > 0 && S > 0 && s >= 0 && s < S && T > 0 && zdim > 0, "idv_z_to_planes: bad shape");
   const int Cp = 2 * ((zdim + 7) / 8 * 8);
   cudaStream_t st = (cudaStream_t)stream;
   IDV_CUDA(cudaMemsetAsync(planes, 0, (size_t)NB * (T + 1) * Cp * sizeof(float), st));
-  const int64_t n = (int64_t)NB * T * zdim;
+  const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
+  const int64_t n = (int64_t)NB * Tv * zdim;
   const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-  z_to_planes_kernel<<<blocks, 256, 0, st>>>(z, NB, S, s, T, zdim, planes, out_split);
+  z_to_planes_kernel<<<blocks, 256, 0, st>>>(z, NB, S, s, T, Tv, zdim, planes, out_split);
   IDV_LAUNCH_CHECK("z_to_planes_kernel");
   return IDV_OK;
 }
@@ -187,7 +191,7 @@ namespace idv {
 
 // grid (F, chunks), block = Ch threads (one complex channel per thread; Ch <= 1024)
 __global__ void cbn_stats_planes_kernel(const void* __restrict__ planesv, int split, int NB, int C, int F, int T,
-                                        int rows_per_chunk, double* __restrict__ acc) {
+                                        int Tv, int rows_per_chunk, double* __restrict__ acc) {
   const int c = threadIdx.x;
   const int Ch = round_up8(C), Cp = 2 * Ch, Tp = T + 1;
   const long long R = (long long)NB * Tp;
@@ -200,7 +204,8 @@ __global__ void cbn_stats_planes_kernel(const void* __restrict__ planesv, int sp
   double sr = 0, si = 0, srr = 0, sii = 0, sri = 0;
   if (c < C) {
     for (long long r = r_begin; r < r_end; ++r) {
-      if (r % Tp == 0) continue;                         // causal pad row
+      const int tt = (int)(r % Tp);
+      if (tt == 0 || tt > Tv) continue;                  // causal pad row / beyond the valid frames
       const long long idx = ((long long)f * R + r) * Cp;
       float re, im;
       if (split) {
@@ -262,7 +267,7 @@ __global__ void cbn_train_finalize_kernel(const double* __restrict__ acc, double
 
 // grid-stride over (plane, row, channel)
 __global__ void __launch_bounds__(256) cbn_apply_planes_kernel(void* __restrict__ planesv, int split, int NB, int C,
-                                                               int F, int T, const float* __restrict__ zb,
+                                                               int F, int T, int Tv, const float* __restrict__ zb,
                                                                int apply_prelu, float slope) {
   const int Ch = round_up8(C), Cp = 2 * Ch, Tp = T + 1;
   const long long R = (long long)NB * Tp;
@@ -274,7 +279,8 @@ __global__ void __launch_bounds__(256) cbn_apply_planes_kernel(void* __restrict_
     const int c = (int)(i % C);
     const long long fr = i / C;
     const long long r = fr % R;
-    if (r % Tp == 0) continue;
+    const int tt = (int)(r % Tp);
+    if (tt == 0 || tt > Tv) continue;
     const long long idx = fr * Cp;
     float re, im;
     if (split) {
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(256) cbn_apply_planes_kernel(void* __restrict_
 }  // namespace idv
 
 extern "C" int idv_cbn_stats_planes(const void* planes, int split, int NB, int C, int F, int T, double* acc,
-                                    void* stream) {
+                                    int t_valid, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(planes && acc && NB > 0 && C > 0 && C <= 1024 && F > 0 && F <= 65535 && T > 0, "idv_cbn_stats_planes: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -315,7 +321,8 @@ extern "C" int idv_cbn_stats_planes(const void* planes, int split, int NB, int C
   const int rows_per_chunk = (int)((R + chunks - 1) / chunks);
   const int threads = ((C + 31) / 32) * 32;
   dim3 grid(F, chunks);
-  cbn_stats_planes_kernel<<<grid, threads, 0, st>>>(planes, split, NB, C, F, T, rows_per_chunk, acc);
+  const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
+  cbn_stats_planes_kernel<<<grid, threads, 0, st>>>(planes, split, NB, C, F, T, Tv, rows_per_chunk, acc);
   IDV_LAUNCH_CHECK("cbn_stats_planes_kernel");
   return IDV_OK;
 }
@@ -338,12 +345,13 @@ extern "C" int idv_cbn_train_finalize(const double* acc, double count, int C, co
 }
 
 extern "C" int idv_cbn_apply_planes(void* planes, int split, int NB, int C, int F, int T, const float* zb,
-                                    int apply_prelu, float prelu_slope, void* stream) {
+                                    int apply_prelu, float prelu_slope, int t_valid, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(planes && zb && NB > 0 && C > 0 && F > 0 && T > 0, "idv_cbn_apply_planes: bad argument");
   const long long n = (long long)F * NB * (T + 1) * C;
   const int blocks = (int)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
-  cbn_apply_planes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(planes, split, NB, C, F, T, zb, apply_prelu, prelu_slope);
+  const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
+  cbn_apply_planes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(planes, split, NB, C, F, T, Tv, zb, apply_prelu, prelu_slope);
   IDV_LAUNCH_CHECK("cbn_apply_planes_kernel");
   return IDV_OK;
 }

@@ -21,7 +21,7 @@ struct LstmRecParams {
   int64_t g_m_off, g_p_off;
   int g_ld;
   const float* whh;               // [2][4H][H]
-  int NB, T, H;
+  int NB, T, H, Tsteps;           // T = allocated frames per utterance (row layout), Tsteps = valid steps
   float* hseq;                    // [4][R][H]
   unsigned short* hsplit;         // optional bf16 [2][4][R][H] copy (hi, lo) for the next layer's tensor-core in-proj
   unsigned int* sync;
@@ -89,7 +89,7 @@ __global__ void lstm_rec_kernel(const LstmRecParams p) {
   grid_barrier(p.sync, ++bar * nblk);
 
   const int jbase = warp * UT;                        // first local unit of this warp
-  for (int t = 0; t < p.T; ++t) {
+  for (int t = 0; t < p.Tsteps; ++t) {
     for (int ch = 0; ch < nchunks; ++ch) {
       const int q = row0 + ch * LS_ROWS + lane;
       const bool valid = q < row1;
@@ -158,10 +158,10 @@ __global__ void lstm_rec_kernel(const LstmRecParams p) {
 }
 
 // latent[b][t][j][part]: part 0 = h(re,x_re) - h(im,x_im), part 1 = h(re,x_im) + h(im,x_re)
-__global__ void __launch_bounds__(256) lstm_combine_kernel(const float* __restrict__ hseq, int NB, int T, int H,
-                                                           float* __restrict__ latent) {
+__global__ void __launch_bounds__(256) lstm_combine_kernel(const float* __restrict__ hseq, int NB, int Talloc, int T,
+                                                           int H, float* __restrict__ latent) {
   const int64_t n = (int64_t)NB * T * H;
-  const int Tp = T + 1;
+  const int Tp = Talloc + 1;
   const int64_t R = (int64_t)NB * Tp;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(i % H);
@@ -285,7 +285,7 @@ static int launch_rec(const LstmRecParams& p, const RecCfg& c, cudaStream_t st) 
 
 extern "C" int idv_lstm_recurrent_fwd(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld, const float* whh,
                                       int NB, int T, int H, float* hseq, void* hsplit, unsigned int* sync,
-                                      void* stream) {
+                                      int t_valid, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(g && whh && hseq && sync, "idv_lstm_recurrent_fwd: null pointer");
   IDV_CHECK_ARG(NB > 0 && T > 0 && H > 0 && H % 4 == 0, "idv_lstm_recurrent_fwd: need H %% 4 == 0 (NB=%d T=%d H=%d)", NB, T, H);
@@ -297,7 +297,7 @@ extern "C" int idv_lstm_recurrent_fwd(const float* g, int64_t g_m_off, int64_t g
   IDV_CHECK_ARG(pick_rec_cfg(H, NB, sms, (size_t)smem_optin, &c), "idv_lstm_recurrent_fwd: no launch config for H=%d NB=%d", H, NB);
   LstmRecParams p;
   p.g = g; p.g_m_off = g_m_off; p.g_p_off = g_p_off; p.g_ld = g_ld; p.whh = whh;
-  p.NB = NB; p.T = T; p.H = H; p.hseq = hseq; p.hsplit = reinterpret_cast<unsigned short*>(hsplit); p.sync = sync;
+  p.NB = NB; p.T = T; p.H = H; p.Tsteps = (t_valid > 0 && t_valid < T) ? t_valid : T; p.hseq = hseq; p.hsplit = reinterpret_cast<unsigned short*>(hsplit); p.sync = sync;
   p.NU = c.NU; p.NR = c.NR; p.Hs = c.Hs; p.RC = c.RC;
   cudaStream_t st = (cudaStream_t)stream;
   IDV_CUDA(cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned int), st));
@@ -310,12 +310,14 @@ extern "C" int idv_lstm_recurrent_fwd(const float* g, int64_t g_m_off, int64_t g
   }
 }
 
-extern "C" int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, float* latent, void* stream) {
+extern "C" int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, float* latent, int t_valid,
+                                    void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(hseq && latent && NB > 0 && T > 0 && H > 0, "idv_lstm_combine_fwd: bad argument");
-  const int64_t n = (int64_t)NB * T * H;
+  const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
+  const int64_t n = (int64_t)NB * Tv * H;
   const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-  lstm_combine_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(hseq, NB, T, H, latent);
+  lstm_combine_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(hseq, NB, T, Tv, H, latent);
   IDV_LAUNCH_CHECK("lstm_combine_kernel");
   return IDV_OK;
 }

@@ -29,7 +29,7 @@ struct LstmTcParams {
   const float* g;
   long long g_m_off, g_p_off;
   int g_ld;
-  int NB, T, H, NC, KC, stages;             // KC = H / 64; stages = depth of the h TMA ring (<= 8)
+  int NB, T, H, NC, KC, stages, Tsteps;     // KC = H / 64; stages = depth of the h TMA ring (<= 8); Tsteps <= T valid steps
   float* hseq;                              // optional fp32 [4][R][H]
   unsigned short* hsplit;                   // optional bf16 [2][4][R][H]
   unsigned short* hx;                       // bf16 [n_rg][2 parity][2 m][2 hl][128][H]
@@ -79,8 +79,8 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x, m = blockIdx.y, rg = blockIdx.z;
-  const int NC = p.NC, H = p.H, T = p.T;
-  const int Tp = T + 1;
+  const int NC = p.NC, H = p.H, T = p.Tsteps;
+  const int Tp = p.T + 1;
   const long long R = (long long)p.NB * Tp;
   unsigned int* ctr = p.sync + rg * 2 + m;
 
@@ -308,7 +308,7 @@ extern "C" int idv_lstm_tc_config(int H, int* n_cols, int* n_ctas) {
 
 extern "C" int idv_lstm_recurrent_tc(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* wpack,
                                      int NB, int T, int H, float* hseq, void* hsplit, void* hx, unsigned int* sync,
-                                     void* stream) {
+                                     int t_valid, void* stream) {
   using namespace idv;
   using namespace idv::tc;
   IDV_CHECK_ARG(g && wpack && hx && sync && (hseq || hsplit), "idv_lstm_recurrent_tc: null pointer");
@@ -342,10 +342,11 @@ extern "C" int idv_lstm_recurrent_tc(const float* g, int64_t g_m_off, int64_t g_
   LstmTcParams p;
   p.g = g; p.g_m_off = g_m_off; p.g_p_off = g_p_off; p.g_ld = g_ld;
   p.NB = NB; p.T = T; p.H = H; p.NC = NC; p.KC = KC; p.stages = stages;
+  p.Tsteps = (t_valid > 0 && t_valid < T) ? t_valid : T;
   p.hseq = hseq; p.hsplit = reinterpret_cast<unsigned short*>(hsplit);
   p.hx = reinterpret_cast<unsigned short*>(hx); p.sync = sync;
   p.dbg = nullptr;
-  const bool dbg = getenv("IDV_LSTM_DBG") != nullptr && T > 208;
+  const bool dbg = getenv("IDV_LSTM_DBG") != nullptr && p.Tsteps > 208;
   if (dbg) {
     IDV_CUDA(cudaMalloc(&p.dbg, 8 * 16 * sizeof(unsigned long long)));
     IDV_CUDA(cudaMemsetAsync(p.dbg, 0, 8 * 16 * sizeof(unsigned long long), st));

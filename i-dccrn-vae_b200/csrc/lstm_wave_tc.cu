@@ -33,7 +33,7 @@ struct WaveParams {
   long long g_m_off, g_p_off;
   int g_ld;
   const float* bias1;                       // [2 m][NC][N] CTA-major (gate*Hs + j)
-  int NB, T, H, NC, KC, stages;
+  int NB, T, H, NC, KC, stages, Tsteps;     // T = allocated frames (row layout), Tsteps = valid steps
   float* hseq1;                             // fp32 [4][R][H] layer-1 output
   unsigned short* hxA;                      // bf16 [W_REP][4 slot][2 m][2 hl][128][H]   h0
   unsigned short* hxC;                      // bf16 [W_REP][2 slot][2 m][2 hl][128][H]   h1
@@ -97,8 +97,8 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x;
   const int m = blockIdx.y / 3, role = blockIdx.y % 3;        // 0 = L0, 1 = IP, 2 = L1
-  const int NC = p.NC, H = p.H, T = p.T;
-  const int Tp = T + 1;
+  const int NC = p.NC, H = p.H, T = p.Tsteps;
+  const int Tp = p.T + 1;
   const long long R = (long long)p.NB * Tp;
   unsigned int* cA = p.sync + m * 3 + 0;
   unsigned int* cB = p.sync + m * 3 + 1;
@@ -368,7 +368,7 @@ extern "C" int idv_lstm2_wave_config(int H, int* n_cols, int* n_ctas, int64_t* w
 
 extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
                                  const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
-                                 float* hseq1, void* work, unsigned int* sync, void* stream) {
+                                 float* hseq1, void* work, unsigned int* sync, int t_valid, void* stream) {
   using namespace idv;
   using namespace idv::tc;
   IDV_CHECK_ARG(g0 && w_hh0 && w_ih1 && w_hh1 && bias1 && hseq1 && work && sync, "idv_lstm2_wave_tc: null pointer");
@@ -407,13 +407,14 @@ extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_o
   WaveParams p;
   p.g0 = g0; p.g_m_off = g_m_off; p.g_p_off = g_p_off; p.g_ld = g_ld; p.bias1 = bias1;
   p.NB = NB; p.T = T; p.H = H; p.NC = NC; p.KC = KC; p.stages = stages;
+  p.Tsteps = (t_valid > 0 && t_valid < T) ? t_valid : T;
   p.hseq1 = hseq1;
   p.hxA = reinterpret_cast<unsigned short*>(wk);
   p.hxC = reinterpret_cast<unsigned short*>(wk + hxA_bytes);
   p.g1x = reinterpret_cast<float*>(wk + hxA_bytes + hxC_bytes);
   p.sync = sync;
   p.dbg = nullptr;
-  const bool dbg = getenv("IDV_LSTM_DBG") != nullptr && T > 304;
+  const bool dbg = getenv("IDV_LSTM_DBG") != nullptr && p.Tsteps > 304;
   if (dbg) {
     IDV_CUDA(cudaMalloc(&p.dbg, (96 + 32) * sizeof(unsigned long long)));
     IDV_CUDA(cudaMemsetAsync(p.dbg, 0, (96 + 32) * sizeof(unsigned long long), st));

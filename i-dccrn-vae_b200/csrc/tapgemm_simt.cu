@@ -17,7 +17,7 @@ struct TapGemmParams {
   const float* a[2];
   int a_ld[2];
   int64_t a_plane[2];
-  int R, Tp;
+  int R, Tp, t_valid;
   const float* w;
   const float* bias;
   int N;
@@ -172,7 +172,10 @@ __global__ void __launch_bounds__(TG_THREADS, 2) tapgemm_f32_kernel(const TapGem
         v.x = prelu_f(v.x, p.slope); v.y = prelu_f(v.y, p.slope);
         v.z = prelu_f(v.z, p.slope); v.w = prelu_f(v.w, p.slope);
       }
-      if (p.Tp > 0 && (r % p.Tp) == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.Tp > 0) {                              // causal pad row, or frame beyond the valid length
+        const int tt = r % p.Tp;
+        if (tt == 0 || (p.t_valid > 0 && tt > p.t_valid)) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       *reinterpret_cast<float4*>(outp + (int64_t)r * p.out_ld + n) = v;
     }
   }
@@ -184,7 +187,7 @@ extern "C" int idv_tapgemm_f32(const float* a0, int a0_ld, int64_t a0_plane, con
                                int64_t a1_plane, int R, int Tp, const float* w, const float* bias, int N,
                                const idv_unit_t* units, const idv_tap_t* taps, int n_units, float* out,
                                int out_ld, int64_t out_plane, int apply_prelu, float prelu_slope,
-                               void* stream) {
+                               int t_valid, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(a0 && w && bias && units && taps && out, "idv_tapgemm_f32: null pointer");
   IDV_CHECK_ARG(R > 0 && N > 0 && n_units > 0, "idv_tapgemm_f32: empty problem R=%d N=%d units=%d", R, N, n_units);
@@ -195,7 +198,7 @@ extern "C" int idv_tapgemm_f32(const float* a0, int a0_ld, int64_t a0_plane, con
   p.a[0] = a0; p.a[1] = a1 ? a1 : a0;
   p.a_ld[0] = a0_ld; p.a_ld[1] = a1 ? a1_ld : a0_ld;
   p.a_plane[0] = a0_plane; p.a_plane[1] = a1 ? a1_plane : a0_plane;
-  p.R = R; p.Tp = Tp; p.w = w; p.bias = bias; p.N = N; p.units = units; p.taps = taps;
+  p.R = R; p.Tp = Tp; p.t_valid = t_valid; p.w = w; p.bias = bias; p.N = N; p.units = units; p.taps = taps;
   p.out = out; p.out_ld = out_ld; p.out_plane = out_plane; p.apply_prelu = apply_prelu; p.slope = prelu_slope;
   cudaStream_t st = (cudaStream_t)stream;
   if (N % 128 == 0) {

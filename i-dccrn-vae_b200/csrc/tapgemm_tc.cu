@@ -25,7 +25,7 @@ constexpr int NUM_THREADS = 192;
 constexpr int EPI_WARP0 = 2;
 
 struct Params {
-  int R, Tp, N;
+  int R, Tp, N, t_valid;
   int n_units, n_row_tiles, n_col_tiles;
   const idv_unit_t* units;
   const idv_tap_t* taps;
@@ -216,7 +216,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       tc_fence_after();
       const int r = rt * BM + q * 32 + lane;
       const bool row_ok = r < p.R;
-      const bool pad_row = p.Tp > 0 && (r % p.Tp) == 0;
+      const int tt_row = p.Tp > 0 ? r % p.Tp : 1;
+      const bool pad_row = p.Tp > 0 && p.head != 3 && (tt_row == 0 || (p.t_valid > 0 && tt_row > p.t_valid));
       const float* bias = p.bias + unit.bias_off + nt * BN;
       if (p.head == 3) {
         // ---- STFT epilogue: rows are (b, t) frames (Tp = frames per utterance, no pad rows), column pair
@@ -466,10 +467,10 @@ extern "C" int idv_tapgemm_tc(const void* a0, int a0_cp, int a0_planes, const vo
                               int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias, int N,
                               const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
                               int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu, float prelu_slope,
-                              void* stream) {
+                              int t_valid, void* stream) {
   return idv_tapgemm_tc_head(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, N, units,
                              taps, n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, prelu_slope, 0, 0,
-                             1, 0, nullptr, nullptr, stream);
+                             1, 0, nullptr, nullptr, t_valid, stream);
 }
 
 extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
@@ -477,7 +478,7 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
                                    const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
                                    int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu,
                                    float prelu_slope, int head, int head_fout, int head_bmul, int head_boff,
-                                   const float* stft_x, float* predict, void* stream) {
+                                   const float* stft_x, float* predict, int t_valid, void* stream) {
   using namespace idv;
   using namespace idv::tc;
   IDV_CHECK_ARG(a0 && wt && bias && units && taps && (out || head), "idv_tapgemm_tc: null pointer");
@@ -506,7 +507,7 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
   rc = encode_map_4d(&mW, wt, kc_max, N, n_slots, (uint64_t)n_slots * N * kc_max, BK, BN);
   if (rc) return rc;
   Params p;
-  p.R = R; p.Tp = Tp; p.N = N; p.n_units = n_units;
+  p.R = R; p.Tp = Tp; p.N = N; p.n_units = n_units; p.t_valid = t_valid;
   p.n_row_tiles = cdiv(R, BM); p.n_col_tiles = N / BN;
   p.units = units; p.taps = taps; p.bias = bias; p.out = out; p.out_ld = out_ld;
   p.out_plane = out_plane; p.out_hl = out_hl; p.out_split = out_split; p.apply_prelu = apply_prelu; p.slope = prelu_slope;

@@ -18,30 +18,30 @@ i32, i64, u64, f32, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c
 # name -> argtypes (all return int status)
 SIGNATURES = {
     "idv_device_sm_count": [ctypes.POINTER(ctypes.c_int)],
-    "idv_tapgemm_f32": [vp, i32, i64, vp, i32, i64, i32, i32, vp, vp, i32, vp, vp, i32, vp, i32, i64, i32, f32, vp],
+    "idv_tapgemm_f32": [vp, i32, i64, vp, i32, i64, i32, i32, vp, vp, i32, vp, vp, i32, vp, i32, i64, i32, f32, i32, vp],
     "idv_stft_fwd": [vp, i32, i32, vp, i32, i32, i32, vp, vp],
     "idv_istft_fwd": [vp, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp],
     "idv_tapgemm_tc": [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, vp, vp, i32, vp, i32, i64, i64,
-                       i32, i32, f32, vp],
+                       i32, i32, f32, i32, vp],
     "idv_tapgemm_tc_head": [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, vp, vp, i32, vp, i32, i64, i64,
-                            i32, i32, f32, i32, i32, i32, i32, vp, vp, vp],
+                            i32, i32, f32, i32, i32, i32, i32, vp, vp, i32, vp],
     "idv_stft_frames_split": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "idv_spec_rows_split": [vp, i32, i32, i32, i32, vp, vp],
     "idv_ola_fwd": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp],
-    "idv_enc0_fwd": [vp, i32, i32, i32, vp, vp, i32, f32, vp, i32, vp],
+    "idv_enc0_fwd": [vp, i32, i32, i32, vp, vp, i32, f32, vp, i32, i32, i32, vp],
     "idv_dec5_head_fwd": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, i32, i32, vp],
-    "idv_lstm_recurrent_fwd": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp],
-    "idv_lstm_recurrent_tc": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp],
-    "idv_lstm2_wave_tc": [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp],
-    "idv_lstm_combine_fwd": [vp, i32, i32, i32, vp, vp],
+    "idv_lstm_recurrent_fwd": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, i32, vp],
+    "idv_lstm_recurrent_tc": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp],
+    "idv_lstm2_wave_tc": [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],
+    "idv_lstm_combine_fwd": [vp, i32, i32, i32, vp, i32, vp],
     "idv_reparam_fwd": [vp, i32, i32, i32, i32, i32, i32, vp, vp, u64, u64, vp, vp],
-    "idv_planes_to_user": [vp, i32, i32, i32, i32, i32, vp, vp],
-    "idv_user_to_planes": [vp, i32, i32, i32, i32, vp, i32, vp],
-    "idv_z_to_planes": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
+    "idv_planes_to_user": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
+    "idv_user_to_planes": [vp, i32, i32, i32, i32, vp, i32, i32, vp],
+    "idv_z_to_planes": [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp],
     "idv_cbn_eval_user": [vp, i64, i32, i64, vp, vp, vp],
-    "idv_cbn_stats_planes": [vp, i32, i32, i32, i32, i32, vp, vp],
+    "idv_cbn_stats_planes": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "idv_cbn_train_finalize": [vp, ctypes.c_double, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp],
-    "idv_cbn_apply_planes": [vp, i32, i32, i32, i32, i32, vp, i32, f32, vp],
+    "idv_cbn_apply_planes": [vp, i32, i32, i32, i32, i32, vp, i32, f32, i32, vp],
     "idv_cbn_stats_user": [vp, i64, i32, i64, vp, vp],
     "idv_head_user": [vp, i64, i64, f32, i32, vp, i32, vp],
 }

@@ -11,8 +11,11 @@ North-star aliases: ConvSTFT = STFT, ConviSTFT = ISTFT, ComplexBatchNorm = Compl
 NavieComplexLSTM = ComplexLSTM.
 
 ``train=True`` runs the reference's train-mode FORWARD (ComplexBatchNormal batch statistics and running-buffer
-updates, model/complex_progress.py:L131-160) without building an autograd graph.  Not built (raise
-NotImplementedError): backward / optimiser, the non-causal config (model/net_config.py), data_norm.
+updates, model/complex_progress.py:L131-160) without building an autograd graph.  Both time geometries are built:
+the causal one (model/causal_netconfig.py: time pad 1, last column dropped, T frames everywhere) and the
+non-causal one (model/net_config.py: no time pad, one frame fewer per encoder layer and one more per decoder
+layer); activations keep the row layout of the STFT's T frames and carry their valid frame count (ops.Planes.Tv).
+Not built (raise NotImplementedError): backward / optimiser, data_norm.
 """
 import torch
 import torch.nn as nn
@@ -118,12 +121,22 @@ class _ComplexConvBase(nn.Module):
         if _pair(c.dilation) != (1, 1) or c.groups != 1 or c.bias is None:
             raise NotImplementedError("complex conv kernels are built for dilation 1, groups 1, bias=True")
         (kh, kw), (sf, st), (pf, pt) = _pair(c.kernel_size), _pair(c.stride), _pair(c.padding)
-        if not self.causal or kw != 2 or st != 1 or pt != 1:
+        ok = (kw == 2 and pt == 1) if self.causal else (kw in (1, 2) and pt in (0, 1))
+        if st != 1 or not ok:
             raise NotImplementedError(
-                "only the causal time geometry (kernel (k,2), stride (s,1), padding (p,1), last column dropped: "
-                "model/complex_progress.py:L8-22) is built; got kernel %s stride %s padding %s causal=%s"
+                "built time geometries: causal kernel (k,2) / stride (s,1) / padding (p,1) with the last column "
+                "dropped (model/complex_progress.py:L8-22) and non-causal kernel (k,1|2) / stride (s,1) / padding "
+                "(p,0|1) (L24-36); got kernel %s stride %s padding %s causal=%s"
                 % ((kh, kw), (sf, st), (pf, pt), self.causal))
         return kh, sf, pf
+
+    def _time_geometry(self):
+        """(time padding, change of the frame count) of this layer."""
+        kw, pt = _pair(self.conv_re.kernel_size)[1], _pair(self.conv_re.padding)[1]
+        return pt, 2 * pt - kw + 1 - (1 if self.causal else 0)
+
+    def frames_out(self, frames_in):
+        return frames_in + self._time_geometry()[1]
 
     def _packed(self, f_in, device, bn=None, slope=None):
         items = self._cache.check(self)
@@ -131,16 +144,24 @@ class _ComplexConvBase(nn.Module):
         if key not in items:
             kh, sf, pf = self._geometry()
             items[key] = pack.pack_conv(self.conv_re.weight, self.conv_re.bias, self.conv_im.weight,
-                                        self.conv_im.bias, bn, slope, f_in, sf, pf, device)
+                                        self.conv_im.bias, bn, slope, f_in, sf, pf, device,
+                                        pad_t=self._time_geometry()[0])
         return items[key]
 
+    def run_packed(self, pk, xp):
+        """One tap-GEMM launch of a pack built by pack.pack_conv for this layer's geometry."""
+        tv = self.frames_out(xp.Tv)
+        if not 0 < tv <= xp.T:
+            raise RuntimeError("conv output has %d frames, the row layout holds %d" % (tv, xp.T))
+        out = ops.tapgemm(pk, xp, None, xp.NB, xp.T, t_valid=tv)
+        return Planes(out, xp.NB, pk.c_out, pk.f_out, xp.T, split=xp.split, Tv=tv)
+
     def forward_planes(self, xp, bn=None, slope=None):
-        pk = self._packed(xp.F, xp.data.device, bn, slope)
-        out = ops.tapgemm(pk, xp, None, xp.NB, xp.T)
-        return Planes(out, xp.NB, pk.c_out, pk.f_out, xp.T, split=xp.split)
+        return self.run_packed(self._packed(xp.F, xp.data.device, bn, slope), xp)
 
     def forward(self, x):
-        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x)))
+        grow = max(self._time_geometry()[1], 0)
+        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x, t_alloc=x.shape[3] + grow)))
 
 
 class causal_complex_conv2d(_ComplexConvBase):
@@ -149,7 +170,7 @@ class causal_complex_conv2d(_ComplexConvBase):
 
 
 class ComplexConv2d(_ComplexConvBase):
-    """model/complex_progress.py:L24-36 (non-causal time geometry: not built, raises)."""
+    """model/complex_progress.py:L24-36 (no frame dropped: kernel (k,2) with time padding 0 gives T-1 frames)."""
     causal = False
 
 
@@ -170,11 +191,25 @@ class _ComplexConvTransposeBase(nn.Module):
         if _pair(c.dilation) != (1, 1) or c.groups != 1 or c.bias is None or _pair(c.output_padding) != (0, 0):
             raise NotImplementedError("complex transposed conv kernels are built for dilation 1, groups 1, bias=True")
         (kh, kw), (sf, st), (pf, pt) = _pair(c.kernel_size), _pair(c.stride), _pair(c.padding)
-        if not self.causal or kw != 2 or st != 1 or pt != 0:
+        if st != 1 or pt != 0 or (kw != 2 if self.causal else kw not in (1, 2)):
             raise NotImplementedError(
-                "only the causal time geometry (kernel (k,2), stride (s,1), padding (p,0), last column dropped: "
-                "model/complex_progress.py:L222-250) is built")
+                "built time geometries: kernel (k,2) / stride (s,1) / padding (p,0), last column dropped when causal "
+                "(model/complex_progress.py:L222-250) or kept (L253-279)")
         return kh, sf, pf
+
+    def frames_out(self, frames_in):
+        return frames_in + _pair(self.tconv_re.kernel_size)[1] - 1 - (1 if self.causal else 0)
+
+    def run_packed(self, pk, pp, skip):
+        """One tap-GEMM launch of a pack built by pack.pack_conv_transpose for this layer."""
+        tv = self.frames_out(pp.Tv)
+        if not 0 < tv <= pp.T:
+            raise RuntimeError("transposed conv output has %d frames, the row layout holds %d" % (tv, pp.T))
+        if skip is not None and (skip.T != pp.T or skip.NB != pp.NB or skip.Tv != pp.Tv):
+            raise RuntimeError("skip tensor has %d/%d frames x %d utterances, the decoder activation %d/%d x %d"
+                               % (skip.Tv, skip.T, skip.NB, pp.Tv, pp.T, pp.NB))
+        out = ops.tapgemm(pk, pp, skip, pp.NB, pp.T, t_valid=tv)
+        return Planes(out, pp.NB, pk.c_out, pk.f_out, pp.T, split=pp.split, Tv=tv)
 
     def _packed(self, f_in, c_p, c_skip, device, bn=None, slope=None):
         items = self._cache.check(self)
@@ -191,13 +226,12 @@ class _ComplexConvTransposeBase(nn.Module):
             raise RuntimeError("transposed conv got %d+%d input channels, layer has %d"
                                % (pp.C, c_skip, self.tconv_re.in_channels))
         pk = self._packed(pp.F, pp.C, c_skip, pp.data.device, bn, slope)
-        out = ops.tapgemm(pk, pp, skip, pp.NB, pp.T)
-        return Planes(out, pp.NB, pk.c_out, pk.f_out, pp.T, split=pp.split)
+        return self.run_packed(pk, pp, skip)
 
     def forward(self, x):
         if x.shape[1] != self.tconv_re.in_channels:
             raise RuntimeError("expected %d input channels, got %d" % (self.tconv_re.in_channels, x.shape[1]))
-        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x)))
+        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x, t_alloc=self.frames_out(x.shape[3]))))
 
 
 class causal_ComplexConvTranspose2d(_ComplexConvTransposeBase):
@@ -206,7 +240,7 @@ class causal_ComplexConvTranspose2d(_ComplexConvTransposeBase):
 
 
 class ComplexConvTranspose2d(_ComplexConvTransposeBase):
-    """model/complex_progress.py:L253-279 (non-causal: not built, raises)."""
+    """model/complex_progress.py:L253-279 (keeps all T+1 output frames)."""
     causal = False
 
 
@@ -296,7 +330,7 @@ class ComplexLSTM(nn.Module):
     def forward_planes(self, xp):
         """xp: Planes with C*F == input_size (feature d = c*F + f).  Returns the latent (NB, T, H, 2)."""
         layers = self._packed(xp.C, xp.F, xp.data.device)
-        NB, T, H = xp.NB, xp.T, self.hidden_size
+        NB, T, H, Tv = xp.NB, xp.T, self.hidden_size, xp.Tv
         R = NB * (T + 1)
         src, hseq, split = xp, None, xp.split
         # two layers, batch <= 64: one wavefront kernel (layer 0 | layer-1 input projection | layer 1)
@@ -306,8 +340,8 @@ class ComplexLSTM(nn.Module):
             g = ops.tapgemm(layers[0][0], xp, None, NB, T, zero_pad_rows=False, out_split=False)
             if ops.GATE_HOOK[0] is not None:
                 ops.GATE_HOOK[0]()
-            hseq = ops.lstm2_wave_tc(g, 4 * H, R * 8 * H, 8 * H, w0, wi1, w1, b1, NB, T, H, wave[2])
-            return ops.lstm_combine(hseq, NB, T, H)
+            hseq = ops.lstm2_wave_tc(g, 4 * H, R * 8 * H, 8 * H, w0, wi1, w1, b1, NB, T, H, wave[2], t_valid=Tv)
+            return ops.lstm_combine(hseq, NB, T, H, Tv)
         # tensor-core recurrence when the planes are split-bf16 and the cooperative grid fits the device;
         # otherwise the fp32 SIMT recurrence (any batch size)
         cfg = ops.lstm_tc_supported(H, NB, xp.data.device) if split else None
@@ -321,13 +355,15 @@ class ComplexLSTM(nn.Module):
             offs = (4 * H, R * 8 * H, 8 * H) if l == 0 else (2 * R * 4 * H, R * 4 * H, 4 * H)
             if cfg:
                 hseq, hsp = ops.lstm_recurrent_tc(g, offs[0], offs[1], offs[2], whh_tc[l], NB, T, H,
-                                                  want_f32=last, want_split=more)
+                                                  want_f32=last, want_split=more, t_valid=Tv)
             else:
-                hseq, hsp = ops.lstm_recurrent(g, offs[0], offs[1], offs[2], whh, NB, T, H, want_split=more)
+                hseq, hsp = ops.lstm_recurrent(g, offs[0], offs[1], offs[2], whh, NB, T, H, want_split=more,
+                                               t_valid=Tv)
             # [4 streams][R][H]: plane = stream, row stride H
             if not last:
-                src = Planes(hsp, NB, H, 4, T, cp=H, split=True) if split else Planes(hseq, NB, H, 4, T, cp=H)
-        return ops.lstm_combine(hseq, NB, T, H)
+                src = Planes(hsp, NB, H, 4, T, cp=H, split=True, Tv=Tv) if split else \
+                    Planes(hseq, NB, H, 4, T, cp=H, Tv=Tv)
+        return ops.lstm_combine(hseq, NB, T, H, Tv)
 
     def forward(self, x):
         """x: (T, B, D, 2) -> (T, B, H, 2)"""
@@ -361,8 +397,8 @@ class ComplexDense(nn.Module):
 
     def forward_planes(self, zp, c_out, f_out):
         pk = self._packed(c_out, f_out, zp.data.device)
-        out = ops.tapgemm(pk, zp, None, zp.NB, zp.T)
-        return Planes(out, zp.NB, c_out, f_out, zp.T, split=zp.split)
+        out = ops.tapgemm(pk, zp, None, zp.NB, zp.T, t_valid=zp.Tv)
+        return Planes(out, zp.NB, c_out, f_out, zp.T, split=zp.split, Tv=zp.Tv)
 
     def forward(self, x):
         """x: (..., D, 2) -> (..., out, 2)"""
@@ -406,7 +442,9 @@ class Encoder(nn.Module):
                                         None if train else self.bn.fold_inputs(), None if train else self._slope(),
                                         stft_x.device)
         w, b, cout, slope = items[key]
-        out = ops.enc0(stft_x, w, b, cout, slope, out_split=ops.use_split())
+        if not self.conv.causal and self.conv._time_geometry() != (0, -1):
+            raise NotImplementedError("first non-causal encoder layer: kernel (5,2) with time padding 0 expected")
+        out = ops.enc0(stft_x, w, b, cout, slope, out_split=ops.use_split(), causal=self.conv.causal)
         return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
     def forward_planes(self, xp, train=False):
@@ -417,13 +455,13 @@ class Encoder(nn.Module):
             c = self.conv
             items[key] = pack.pack_conv(c.conv_re.weight, c.conv_re.bias, c.conv_im.weight, c.conv_im.bias,
                                         None if train else self.bn.fold_inputs(), None if train else self._slope(),
-                                        xp.F, sf, pf, xp.data.device)
-        pk = items[key]
-        out = Planes(ops.tapgemm(pk, xp, None, xp.NB, xp.T), xp.NB, pk.c_out, pk.f_out, xp.T, split=xp.split)
+                                        xp.F, sf, pf, xp.data.device, pad_t=c._time_geometry()[0])
+        out = self.conv.run_packed(items[key], xp)
         return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
     def forward(self, x, train):
-        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x), train))
+        grow = max(self.conv._time_geometry()[1], 0)
+        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x, t_alloc=x.shape[3] + grow), train))
 
 
 class Decoder(nn.Module):
@@ -458,8 +496,7 @@ class Decoder(nn.Module):
             items[key] = pack.pack_conv_transpose(t.tconv_re.weight, t.tconv_re.bias, t.tconv_im.weight,
                                                   t.tconv_im.bias, bn, slope, pp.F, pp.C, c_skip,
                                                   pp.data.device, sf, pf)
-        pk = items[key]
-        out = Planes(ops.tapgemm(pk, pp, skip, pp.NB, pp.T), pp.NB, pk.c_out, pk.f_out, pp.T, split=pp.split)
+        out = self.transconv.run_packed(items[key], pp, skip)
         return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
     def forward_head(self, pp, skip, mask, stft_x, predict, out_bmul, out_boff, train=False):
@@ -468,6 +505,12 @@ class Decoder(nn.Module):
         train = bool(train) and self.if_bn
         if train and out_bmul != 1:
             raise NotImplementedError(_TRAIN_MSG)
+        if self.transconv.frames_out(pp.Tv) != pp.T or predict.shape[2] != pp.T:
+            raise RuntimeError("the reconstruction head writes all %d frames of the row layout; the last decoder "
+                               "layer produces %d" % (pp.T, self.transconv.frames_out(pp.Tv)))
+        if skip is not None and (skip.T != pp.T or skip.Tv != pp.Tv):
+            raise RuntimeError("skip tensor frames %d/%d != decoder activation frames %d/%d"
+                               % (skip.Tv, skip.T, pp.Tv, pp.T))
         items = self._cache.check(self)
         c_skip = skip.C if skip is not None else 0
         key = ("head", train, pp.C, c_skip, str(pp.data.device))
@@ -493,7 +536,8 @@ class Decoder(nn.Module):
     def forward(self, x, train=True):
         if x.shape[1] != self.transconv.tconv_re.in_channels:
             raise RuntimeError("expected %d input channels" % self.transconv.tconv_re.in_channels)
-        return ops.planes_to_user(self.forward_planes(ops.user_to_planes(x), None, train))
+        return ops.planes_to_user(self.forward_planes(
+            ops.user_to_planes(x, t_alloc=self.transconv.frames_out(x.shape[3])), None, train))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -524,10 +568,11 @@ class SkipList(list):
         return (self._get(i) for i in range(len(self)))
 
 
-def _skip_planes(skiper, idx, split):
-    if isinstance(skiper, SkipList) and skiper.planes[idx].split == split:
+def _skip_planes(skiper, idx, split, t_alloc=None):
+    if isinstance(skiper, SkipList) and skiper.planes[idx].split == split and \
+            (t_alloc is None or skiper.planes[idx].T == t_alloc):
         return skiper.planes[idx]
-    return ops.user_to_planes(skiper[idx], split=split)
+    return ops.user_to_planes(skiper[idx], split=split, t_alloc=t_alloc)
 
 
 def _build_encoders(net_params, causal):
@@ -569,8 +614,6 @@ def _next_philox():
 # --------------------------------------------------------------------------------------------------
 class _VaeEncoderBase(nn.Module):
     def _init_common(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num):
-        if not causal:
-            raise NotImplementedError("only the causal network config (model/causal_netconfig.py) is built")
         self.device = device
         self.causal = causal
         self.latent_num = latent_num
@@ -652,8 +695,6 @@ class pvae_dccrn_encoder_skip_prepare(_VaeEncoderBase):
 class _VaeDecoderBase(nn.Module):
     def _init_common(self, net_params, causal, device, num_samples, zdim, n_fft, hop_len, win_length, recon_type,
                      skip_to_use, use_sc):
-        if not causal:
-            raise NotImplementedError("only the causal network config (model/causal_netconfig.py) is built")
         if recon_type not in ("real_imag", "mask"):
             raise ValueError("recon_type must be 'real_imag' or 'mask'")
         self.device = device
@@ -677,20 +718,27 @@ class _VaeDecoderBase(nn.Module):
             raise RuntimeError("z batch %d is not a multiple of num_samples %d" % (BS, S))
         B = BS // S
         n = len(self.decoders)
+        # frames of the row layout = frames of the reconstructed spectrum (the non-causal layers add one each)
+        t_alloc = T
+        for dec in self.decoders:
+            t_alloc = dec.transconv.frames_out(t_alloc)
         skips, split = {}, ops.use_split()
         if real_skips:
             for i in range(n):
                 if self.use_sc and i in self.skip_to_use:
-                    skips[i] = _skip_planes(skiper, len(skiper) - i - 1, split)
+                    skips[i] = _skip_planes(skiper, len(skiper) - i - 1, split, t_alloc)
         n_bins = F
         for _ in range(n):
             n_bins = 2 * n_bins - 1          # kernel 5 / stride 2 / pad 2 transposed conv
-        predict = torch.empty((BS, n_bins, T, 2), dtype=torch.float32, device=z.device)
+        predict = torch.empty((BS, n_bins, t_alloc, 2), dtype=torch.float32, device=z.device)
         if mask:
             stft_x = ops.lib.require_f32_cuda(stft_x, "stft_x")
+            if tuple(stft_x.shape[1:]) != (n_bins, t_alloc, 2):
+                raise RuntimeError("stft_x %s does not match the reconstructed spectrum (B, %d, %d, 2)"
+                                   % (tuple(stft_x.shape), n_bins, t_alloc))
         self.decoder_outputs = []
         for s in range(S):
-            zp = ops.z_to_planes(z, B, S, s, split=split)
+            zp = ops.z_to_planes(z, B, S, s, split=split, t_alloc=t_alloc)
             p = self.dense.forward_planes(zp, C, F)
             for i in range(n - 1):
                 p = self.decoders[i].forward_planes(p, skips.get(i), train)
@@ -748,8 +796,6 @@ class nsvae_pvae_dccrn_decoder_twophase(_VaeDecoderBase):
 class standard_DCCRN(nn.Module):
     def __init__(self, net_params, causal, device, skip_to_use):
         super().__init__()
-        if not causal:
-            raise NotImplementedError("only the causal network config (model/causal_netconfig.py) is built")
         self.device = device
         self.causal = causal
         self.dense = ComplexDense(net_params["dense"][0], net_params["dense"][1])
@@ -772,8 +818,8 @@ class standard_DCCRN(nn.Module):
         lat = self.lstms[0].forward_planes(top)                         # (B, T, H, 2)
         if not train:
             self.latent = lat                                           # model/pvae_module.py:L187-188
-        B, T = lat.shape[0], lat.shape[1]
-        zp = ops.z_to_planes(lat, B, 1, 0, split=top.split)
+        B, T = lat.shape[0], top.T
+        zp = ops.z_to_planes(lat, B, 1, 0, split=top.split, t_alloc=top.T)
         p = self.dense.forward_planes(zp, top.C, top.F)
         n = len(self.decoders)
         for i in range(n - 1):

@@ -30,12 +30,17 @@ def use_split():
 
 class Planes:
     """Internal activation: fp32 [F][R][Cp], R = NB*(T+1) (row b*(T+1) is the causal zero row),
-    Cp = 2*round8(C) with the real parts in [0, Ch) and the imaginary parts in [Ch, 2Ch)."""
-    __slots__ = ("data", "NB", "C", "F", "T", "_cp", "split")
+    Cp = 2*round8(C) with the real parts in [0, Ch) and the imaginary parts in [Ch, 2Ch).
+    T is the ALLOCATED number of frames per utterance (fixes the row layout), Tv <= T the number of valid
+    frames (non-causal layers shrink / grow it: model/net_config.py); rows of frames >= Tv are zero."""
+    __slots__ = ("data", "NB", "C", "F", "T", "_cp", "split", "Tv")
 
-    def __init__(self, data, NB, C, F, T, cp=None, split=False):
+    def __init__(self, data, NB, C, F, T, cp=None, split=False, Tv=None):
         """split=True: data is bf16 [2 (hi, lo)][F][R][Cp] (x ~= hi + lo), else fp32 [F][R][Cp]."""
         self.data, self.NB, self.C, self.F, self.T, self._cp, self.split = data, NB, C, F, T, cp, split
+        self.Tv = T if Tv is None else int(Tv)
+        if not 0 < self.Tv <= T:
+            raise RuntimeError("valid frames %d outside (0, %d]" % (self.Tv, T))
 
     @property
     def Ch(self):
@@ -101,7 +106,7 @@ def stft_tc(x, hp, n_fft, hop, win):
     lib.call("idv_stft_frames_split", x, B, L, n_fft, hop, win, hp["kpad"], frames)
     out = torch.empty((B, hp["nbins"], T, 2), dtype=torch.float32, device=x.device)
     lib.call("idv_tapgemm_tc_head", frames, hp["kpad"], 1, None, 0, 0, R, T, hp["wt"], hp["kc_max"], 1, hp["bias"],
-             hp["N"], hp["units"], hp["taps"], 1, None, 0, 0, 0, 0, 0, 0.0, 3, hp["nbins"], 1, 0, None, out)
+             hp["N"], hp["units"], hp["taps"], 1, None, 0, 0, 0, 0, 0, 0.0, 3, hp["nbins"], 1, 0, None, out, 0)
     return out
 
 
@@ -116,16 +121,16 @@ def istft_tc(spec_ri, hp, n_fft, hop, win):
     N = hp["N"]
     frames = _empty(R * N, spec_ri.device)
     lib.call("idv_tapgemm_tc", rows, hp["kpad"], 1, None, 0, 0, R, 0, hp["wt"], hp["kc_max"], 1, hp["bias"], N,
-             hp["units"], hp["taps"], 1, frames, N, R * N, 0, 0, 0, 0.0)
+             hp["units"], hp["taps"], 1, frames, N, R * N, 0, 0, 0, 0.0, 0)
     out = torch.empty((B, hop * (T - 1)), dtype=torch.float32, device=spec_ri.device)
     lib.call("idv_ola_fwd", frames, N, hp["wsq"], B, T, n_fft, hop, win, out)
     return out
 
 
-def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None):
+def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None, t_valid=0):
     """Run one packed tap-GEMM.  a0/a1: Planes (a1 may be None).  Returns the flat output tensor
     [pack.out_planes][R][pack.out_ld] (fp32, or bf16 [2][...] when out_split).  Split inputs run on the
-    tcgen05 kernel, fp32 inputs on the SIMT kernel."""
+    tcgen05 kernel, fp32 inputs on the SIMT kernel.  t_valid: valid frames of the OUTPUT (0 = all T)."""
     R = NB * (T + 1)
     if a0.split:
         if a1 is not None and not a1.split:
@@ -138,7 +143,7 @@ def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None):
                  a1.Cp if a1 is not None else 0, a1.F if a1 is not None else 0, R,
                  (T + 1) if zero_pad_rows else 0, tc["wt"], tc["kc_max"], tc["n_slots"], pack.bias, pack.N,
                  tc["units"], tc["taps"], pack.n_units, out, pack.out_ld, R * pack.out_ld, n_out,
-                 1 if out_split else 0, 1 if pack.prelu else 0, pack.slope)
+                 1 if out_split else 0, 1 if pack.prelu else 0, pack.slope, int(t_valid))
         return out
     if out_split:
         raise RuntimeError("the fp32 SIMT tap-GEMM writes fp32 planes only")
@@ -149,16 +154,18 @@ def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None):
              a1.plane_stride if a1 is not None else 0,
              R, (T + 1) if zero_pad_rows else 0,
              pack.w, pack.bias, pack.N, pack.units, pack.taps, pack.n_units,
-             out, pack.out_ld, R * pack.out_ld, 1 if pack.prelu else 0, pack.slope)
+             out, pack.out_ld, R * pack.out_ld, 1 if pack.prelu else 0, pack.slope, int(t_valid))
     return out
 
 
-def enc0(stft_x, w, bias, cout, slope, out_split=False):
+def enc0(stft_x, w, bias, cout, slope, out_split=False, causal=True):
     B, Fin, T, _ = stft_x.shape
     Fout = (Fin + 4 - 5) // 2 + 1
+    Tv = T if causal else T - 1
     out = _empty_act(Fout * B * (T + 1) * 2 * cout, stft_x.device, out_split)
-    lib.call("idv_enc0_fwd", stft_x, B, Fin, T, w, bias, cout, slope, out, 1 if out_split else 0)
-    return Planes(out, B, cout, Fout, T, split=out_split)
+    lib.call("idv_enc0_fwd", stft_x, B, Fin, T, w, bias, cout, slope, out, 1 if out_split else 0,
+             1 if causal else 0, Tv)
+    return Planes(out, B, cout, Fout, T, split=out_split, Tv=Tv)
 
 
 def dec5_head(p, skip, w, bias, slope, mask, stft_x, predict, out_bmul, out_boff):
@@ -166,7 +173,7 @@ def dec5_head(p, skip, w, bias, slope, mask, stft_x, predict, out_bmul, out_boff
         raise RuntimeError("decoder sources must share one activation format")
     lib.call("idv_dec5_head_fwd", p.data, p.Cp, skip.data if skip is not None else None,
              skip.Cp if skip is not None else 0, 1 if p.split else 0, p.NB, p.F, p.T, w, bias, slope,
-             1 if mask else 0, stft_x if mask else None, predict, out_bmul, out_boff)
+             1 if mask else 0, stft_x if mask else None, predict, out_bmul, out_boff)   # writes all p.T frames
 
 
 def dec5_head_tc(hp, p, skip, mask, stft_x, predict, out_bmul, out_boff):
@@ -176,15 +183,15 @@ def dec5_head_tc(hp, p, skip, mask, stft_x, predict, out_bmul, out_boff):
              skip.Cp if skip is not None else 0, skip.F if skip is not None else 0, R, p.T + 1,
              hp["wt"], hp["kc_max"], hp["n_slots"], hp["bias"], hp["N"], hp["units"], hp["taps"], hp["n_units"],
              None, 0, 0, 0, 0, 1, hp["slope"], 2 if mask else 1, predict.shape[1], out_bmul, out_boff,
-             stft_x if mask else None, predict)
+             stft_x if mask else None, predict, 0)
 
 
-def lstm_recurrent(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, want_split=False):
+def lstm_recurrent(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, want_split=False, t_valid=0):
     """Returns (hseq fp32 [4][R][H], hsplit bf16 [2][4][R][H] or None)."""
     hseq = _empty(4 * NB * (T + 1) * H, g.device)
     hsplit = _empty_act(4 * NB * (T + 1) * H, g.device, True) if want_split else None
     sync = torch.empty(2, dtype=torch.int32, device=g.device)
-    lib.call("idv_lstm_recurrent_fwd", g, g_m_off, g_p_off, g_ld, whh, NB, T, H, hseq, hsplit, sync)
+    lib.call("idv_lstm_recurrent_fwd", g, g_m_off, g_p_off, g_ld, whh, NB, T, H, hseq, hsplit, sync, int(t_valid))
     return hseq, hsplit
 
 
@@ -197,7 +204,7 @@ def lstm_tc_supported(H, NB, device):
     return cfg if n_rg * 2 * cfg[1] <= sms else None
 
 
-def lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, want_f32=True, want_split=False):
+def lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, want_f32=True, want_split=False, t_valid=0):
     """Tensor-core recurrence.  Returns (hseq fp32 or None, hsplit bf16 or None)."""
     n = 4 * NB * (T + 1) * H
     hseq = _empty(n, g.device) if want_f32 else None
@@ -205,7 +212,8 @@ def lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, want_f32=True,
     n_rg = (NB + 63) // 64
     hx = torch.empty(n_rg * 2 * 2 * 2 * 128 * H, dtype=torch.bfloat16, device=g.device)
     sync = torch.empty(n_rg * 2, dtype=torch.int32, device=g.device)
-    lib.call("idv_lstm_recurrent_tc", g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, hx, sync)
+    lib.call("idv_lstm_recurrent_tc", g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, hx, sync,
+             int(t_valid))
     return hseq, hsplit
 
 
@@ -217,18 +225,20 @@ def lstm2_wave_supported(H, NB, device):
     return cfg if 6 * cfg[1] <= sms else None
 
 
-def lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, work_bytes):
+def lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, work_bytes, t_valid=0):
     """Both layers of the ComplexLSTM as one wavefront kernel.  Returns hseq1 fp32 [4][R][H]."""
     hseq = _empty(4 * NB * (T + 1) * H, g0.device)
     work = torch.empty(int(work_bytes), dtype=torch.uint8, device=g0.device)
     sync = torch.empty(6, dtype=torch.int32, device=g0.device)
-    lib.call("idv_lstm2_wave_tc", g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq, work, sync)
+    lib.call("idv_lstm2_wave_tc", g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq, work, sync,
+             int(t_valid))
     return hseq
 
 
-def lstm_combine(hseq, NB, T, H):
-    latent = torch.empty((NB, T, H, 2), dtype=torch.float32, device=hseq.device)
-    lib.call("idv_lstm_combine_fwd", hseq, NB, T, H, latent)
+def lstm_combine(hseq, NB, T, H, t_valid=0):
+    Tv = t_valid if 0 < t_valid < T else T
+    latent = torch.empty((NB, Tv, H, 2), dtype=torch.float32, device=hseq.device)
+    lib.call("idv_lstm_combine_fwd", hseq, NB, T, H, latent, Tv)
     return latent
 
 
@@ -245,27 +255,34 @@ def reparam(latent, ch0, zdim, S, eps_r, eps_i, seed, offset):
 
 
 def planes_to_user(p):
-    out = torch.empty((p.NB, p.C, p.F, p.T, 2), dtype=torch.float32, device=p.data.device)
-    lib.call("idv_planes_to_user", p.data, 1 if p.split else 0, p.NB, p.C, p.F, p.T, out)
+    out = torch.empty((p.NB, p.C, p.F, p.Tv, 2), dtype=torch.float32, device=p.data.device)
+    lib.call("idv_planes_to_user", p.data, 1 if p.split else 0, p.NB, p.C, p.F, p.T, out, p.Tv)
     return out
 
 
-def user_to_planes(x, split=False):
+def user_to_planes(x, split=False, t_alloc=None):
+    """t_alloc: frames of the row layout (>= the tensor's own frame count; default = the tensor's)."""
     x = lib.require_f32_cuda(x, "activation")
     if x.dim() != 5 or x.shape[-1] != 2:
         raise RuntimeError("activation must be (B, C, F, T, 2), got %s" % (tuple(x.shape),))
-    NB, C, F, T, _ = x.shape
+    NB, C, F, Tv, _ = x.shape
+    T = Tv if t_alloc is None else int(t_alloc)
+    if T < Tv:
+        raise RuntimeError("activation has %d frames, the row layout only %d" % (Tv, T))
     data = _empty_act(F * NB * (T + 1) * 2 * round8(C), x.device, split)
-    lib.call("idv_user_to_planes", x, NB, C, F, T, data, 1 if split else 0)
-    return Planes(data, NB, C, F, T, split=split)
+    lib.call("idv_user_to_planes", x, NB, C, F, T, data, 1 if split else 0, Tv)
+    return Planes(data, NB, C, F, T, split=split, Tv=Tv)
 
 
-def z_to_planes(z, NB, S, s, split=False):
+def z_to_planes(z, NB, S, s, split=False, t_alloc=None):
     z = lib.require_f32_cuda(z, "z")
-    _, T, zdim, _ = z.shape
+    _, Tv, zdim, _ = z.shape
+    T = Tv if t_alloc is None else int(t_alloc)
+    if T < Tv:
+        raise RuntimeError("z has %d frames, the row layout only %d" % (Tv, T))
     data = _empty_act(NB * (T + 1) * 2 * round8(zdim), z.device, split)
-    lib.call("idv_z_to_planes", z, NB, S, s, T, zdim, data, 1 if split else 0)
-    return Planes(data, NB, zdim, 1, T, split=split)
+    lib.call("idv_z_to_planes", z, NB, S, s, T, zdim, data, 1 if split else 0, Tv)
+    return Planes(data, NB, zdim, 1, T, split=split, Tv=Tv)
 
 
 def cbn_eval_user(x, zb):
@@ -296,10 +313,10 @@ def cbn_train_planes(p, bn, slope):
     """In place on planes: batch statistics over (B, F, T), running-stat update, normalise (+ PReLU if slope)."""
     C = p.C
     acc = torch.empty(C * 5, dtype=torch.float64, device=p.data.device)
-    lib.call("idv_cbn_stats_planes", p.data, 1 if p.split else 0, p.NB, C, p.F, p.T, acc)
-    zb = _cbn_finalize(bn, acc, p.NB * p.F * p.T, p.data.device)
+    lib.call("idv_cbn_stats_planes", p.data, 1 if p.split else 0, p.NB, C, p.F, p.T, acc, p.Tv)
+    zb = _cbn_finalize(bn, acc, p.NB * p.F * p.Tv, p.data.device)
     lib.call("idv_cbn_apply_planes", p.data, 1 if p.split else 0, p.NB, C, p.F, p.T, zb,
-             0 if slope is None else 1, 0.0 if slope is None else float(slope))
+             0 if slope is None else 1, 0.0 if slope is None else float(slope), p.Tv)
     return p
 
 

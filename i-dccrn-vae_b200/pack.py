@@ -118,13 +118,16 @@ def _cpu(t):
     return t.detach().cpu()
 
 
-def pack_conv(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, f_in, stride_f, pad_f, device):
-    """Causal complex conv (kernel (kh,2), stride (stride_f,1), pad (pad_f,1)) [+ CBN + PReLU].
-    weights: (Cout, Cin, kh, 2).  Time tap kt reads x[t-1+kt]."""
+def pack_conv(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, f_in, stride_f, pad_f, device, pad_t=1):
+    """Complex conv (kernel (kh,kw), stride (stride_f,1), pad (pad_f,pad_t)) [+ CBN + PReLU].
+    weights: (Cout, Cin, kh, kw).  Time tap kt reads x[t-pad_t+kt]: the causal layer (pad_t = 1, last column
+    dropped) reads x[t-1], x[t]; the non-causal one (pad_t = 0, model/net_config.py) x[t], x[t+1]
+    and has kw-1 fewer valid frames."""
     wr, wi = _cpu(conv_re_w), _cpu(conv_im_w)
     cout, cin, kh, kw = wr.shape
-    if kw != 2:
-        raise NotImplementedError("causal complex conv is built for a 2-tap time kernel (got %d)" % kw)
+    if kw not in (1, 2) or pad_t not in (0, 1):
+        raise NotImplementedError("complex conv is built for 1- or 2-tap time kernels with time padding 0 or 1 "
+                                  "(got kernel %d, padding %d)" % (kw, pad_t))
     ch_in, ch_out = round8(cin), round8(cout)
     Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(cout)
     m_re = wr.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
@@ -139,8 +142,8 @@ def pack_conv(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, f_in, strid
             fi = stride_f * fo + kf - pad_f
             if fi < 0 or fi >= f_in:
                 continue
-            for kt in range(2):
-                taps.append([0, fi, 1 - kt, 0, kc, (kf * 2 + kt) * kc * N])
+            for kt in range(kw):
+                taps.append([0, fi, pad_t - kt, 0, kc, (kf * kw + kt) * kc * N])
         units.append([begin, len(taps) - begin, fo, 0, 0, 0])
     p = TapGemmPack(W.reshape(-1), bias, units, taps, N, f_out, N, slope is not None, slope or 0.0, device)
     p.f_out, p.c_out = f_out, cout
@@ -149,14 +152,15 @@ def pack_conv(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, f_in, strid
 
 def pack_conv_transpose(t_re_w, t_re_b, t_im_w, t_im_b, bn, slope, f_in, c_p, c_skip, device,
                         stride_f=2, pad_f=2):
-    """Causal complex transposed conv in gather form over two sources: the running
+    """Complex transposed conv (time padding 0) in gather form over two sources: the running
     activation p (c_p complex channels) and the skip tensor (c_skip, 0 = none / zero skip).
-    weights: (Cin_total, Cout, kh, 2); input channel order [p | skip] like torch.cat
-    (model/pvae_module.py:L2098).  Time tap kt reads x[t-kt]."""
+    weights: (Cin_total, Cout, kh, kw); input channel order [p | skip] like torch.cat
+    (model/pvae_module.py:L2098).  Time tap kt reads x[t-kt]; the causal layer drops the last of the T+kw-1
+    output frames, the non-causal one keeps it (the caller sets the valid frame count)."""
     wr, wi = _cpu(t_re_w), _cpu(t_im_w)
     cin_tot, cout, kh, kw = wr.shape
-    if kw != 2:
-        raise NotImplementedError("causal complex transposed conv is built for a 2-tap time kernel")
+    if kw not in (1, 2):
+        raise NotImplementedError("complex transposed conv is built for 1- or 2-tap time kernels")
     ch_out = round8(cout)
     Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(cout)
     f_out = (f_in - 1) * stride_f - 2 * pad_f + kh
@@ -187,9 +191,9 @@ def pack_conv_transpose(t_re_w, t_re_b, t_im_w, t_im_b, bn, slope, f_in, c_p, c_
             fi = num // stride_f
             if fi < 0 or fi >= f_in:
                 continue
-            for kt in range(2):
+            for kt in range(kw):
                 for si, (src, _, _) in enumerate(srcs):
-                    taps.append([src, fi, kt, 0, kcs[si], w_offs[si] + (kf * 2 + kt) * kcs[si] * N])
+                    taps.append([src, fi, kt, 0, kcs[si], w_offs[si] + (kf * kw + kt) * kcs[si] * N])
         units.append([begin, len(taps) - begin, fo, 0, 0, 0])
     p = TapGemmPack(torch.cat(Ws), bias, units, taps, N, f_out, N, slope is not None, slope or 0.0, device)
     p.f_out, p.c_out = f_out, cout

@@ -17,6 +17,14 @@
  *          causal pad row (the reference's left time padding, model/complex_progress.py:L16-22);
  *     Cp = 2*Ch, Ch = C rounded up to 8: real part of complex channel c at c, imaginary at Ch + c.
  * "user" layout is the reference's (B, C, F, T, 2) fp32 with re/im interleaved innermost.
+ *
+ * Valid frames (`t_valid`): the non-causal network (model/net_config.py, ComplexConv2d /
+ * ComplexConvTranspose2d at model/complex_progress.py:L24-36, L253-279) changes the number of frames per
+ * layer (T-1 per encoder layer, T+1 per decoder layer).  The row layout stays that of the allocation (`T`);
+ * every entry point that walks rows takes `t_valid` = number of valid frames per utterance of the tensor it
+ * WRITES (0 or >= T: all T).  Rows of frames t >= t_valid are written as zero exactly like the pad row, so
+ * a later layer reading x[t+1] / x[t] beyond the valid range sees the zero padding of the reference.
+ * User-layout tensors have exactly t_valid frames.
  */
 #ifndef IDV_H_
 #define IDV_H_
@@ -32,7 +40,7 @@ extern "C" {
 #define IDV_E_CUDA 2     /* CUDA runtime error (message has the cudaError string) */
 #define IDV_E_RESOURCE 3 /* kernel cannot be made resident (cooperative launch too large) */
 
-#define IDV_ABI_VERSION 2
+#define IDV_ABI_VERSION 3
 
 int idv_abi_version(void);
 const char* idv_last_error(void);
@@ -69,7 +77,7 @@ int idv_tapgemm_f32(const float* a0, int a0_ld, int64_t a0_plane,
                     const float* w, const float* bias, int N,
                     const idv_unit_t* units, const idv_tap_t* taps, int n_units,
                     float* out, int out_ld, int64_t out_plane,
-                    int apply_prelu, float prelu_slope, void* stream);
+                    int apply_prelu, float prelu_slope, int t_valid, void* stream);
 
 /* Tensor-core version (tcgen05.mma kind::f16, TMEM accumulators, TMA-fed): same contract on the
  * "split" activation format: every fp32 value x is stored as two bf16 planes hi = bf16(x),
@@ -82,7 +90,7 @@ int idv_tapgemm_tc(const void* a0, int a0_cp, int a0_planes, const void* a1, int
                    int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias, int N,
                    const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
                    int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu, float prelu_slope,
-                   void* stream);
+                   int t_valid, void* stream);
 
 /* Same kernel with the reconstruction head fused into the epilogue (last decoder layer, Cout = 1):
  * N == 32, unit q produces the output bins fo = 2q (accumulator columns 0,1 = re,im) and fo = 2q+1 (columns
@@ -95,7 +103,7 @@ int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, const void* a1
                         const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
                         int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu, float prelu_slope,
                         int head, int head_fout, int head_bmul, int head_boff, const float* stft_x,
-                        float* predict, void* stream);
+                        float* predict, int t_valid, void* stream);
 
 /* ---- STFT / iSTFT -----------------------------------------------------------------------------
  * replaces torch.stft at model/pvae_module.py:L22 (n_fft 512, hop, win, periodic Hann, center,
@@ -123,11 +131,14 @@ int idv_ola_fwd(const float* frames, int frame_ld, const float* wsq, int B, int 
                 float* out, void* stream);
 
 /* ---- first encoder layer (Cin = 1) -------------------------------------------------------------
- * Encoder 0: causal ComplexConv2d(1 -> Cout, (5,2), stride (2,1), pad (2,1)) + CBN(eval) + PReLU,
+ * Encoder 0: ComplexConv2d(1 -> Cout, (5,2), stride (2,1), freq pad 2) + CBN(eval) + PReLU,
  * reading the user-layout STFT (B,257,T,2) and writing planes [Fout][R][2*Cout].
+ * causal != 0: time pad 1 / last column dropped (time tap kt reads x[t-1+kt], T valid frames);
+ * causal == 0: no time pad (tap kt reads x[t+kt]; pass t_valid = T-1).
  * w: [10 taps (kf*2+kt)][2 (re,im in)][2*Cout] with CBN folded, bias: [2*Cout].                 */
 int idv_enc0_fwd(const float* stft, int B, int Fin, int T, const float* w, const float* bias,
-                 int Cout, float prelu_slope, void* out, int out_split, void* stream);
+                 int Cout, float prelu_slope, void* out, int out_split, int causal, int t_valid,
+                 void* stream);
 
 /* ---- last decoder layer (Cout = 1) + reconstruction head ---------------------------------------
  * Decoder 5: causal ComplexConvTranspose2d(Cin -> 1) + CBN(eval) + PReLU (+ mask head,
@@ -149,7 +160,7 @@ int idv_dec5_head_fwd(const void* p, int p_cp, const void* skip, int s_cp, int i
  * layer.  sync: 2 x uint32 workspace, zeroed by the call.  Cooperative launch.                     */
 int idv_lstm_recurrent_fwd(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld,
                            const float* whh, int NB, int T, int H, float* hseq, void* hsplit,
-                           unsigned int* sync, void* stream);
+                           unsigned int* sync, int t_valid, void* stream);
 /* Tensor-core recurrence (tcgen05): same contract as idv_lstm_recurrent_fwd with the recurrent product
  * evaluated as h_hi*W_hi + h_hi*W_lo + h_lo*W_hi on the split-bf16 value of h(t-1) (fp32 accumulate, fp32
  * cell state).  idv_lstm_tc_config gives the gate columns per CTA (n_cols = 4*Hs) and CTAs per module for a
@@ -160,7 +171,7 @@ int idv_lstm_recurrent_fwd(const float* g, int64_t g_m_off, int64_t g_p_off, int
 int idv_lstm_tc_config(int H, int* n_cols, int* n_ctas);
 int idv_lstm_recurrent_tc(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* wpack,
                           int NB, int T, int H, float* hseq, void* hsplit, void* hx, unsigned int* sync,
-                          void* stream);
+                          int t_valid, void* stream);
 /* Both layers of a 2-layer ComplexLSTM as one wavefront kernel (layer 0, the layer-1 input projection and layer 1
  * run concurrently, one time step apart): same arithmetic as two idv_lstm_recurrent_tc calls around a tensor-core
  * input projection, without materialising the layer-1 gate pre-activations.  g0: layer-0 input projection
@@ -171,10 +182,10 @@ int idv_lstm_recurrent_tc(const float* g, int64_t g_m_off, int64_t g_p_off, int 
 int idv_lstm2_wave_config(int H, int* n_cols, int* n_ctas, int64_t* work_bytes);
 int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
                       const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
-                      float* hseq1, void* work, unsigned int* sync, void* stream);
+                      float* hseq1, void* work, unsigned int* sync, int t_valid, void* stream);
 /* Combine the four streams (real = rr - ii, imag = ir + ri), emit the user-layout latent
  * (NB, T, H, 2).  Replaces the stack/permute at complex_progress.py:L62-73, pvae_module.py:L2247. */
-int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, float* latent, void* stream);
+int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, float* latent, int t_valid, void* stream);
 /* reparameterization (model/pvae_module.py:L2177-2231).  latent: (NB,T,Htot,2); the (mu, log
  * sigma, delta) triplet starts at channel ch0 (zdim each).  eps_r/eps_i: (NB,S,T,zdim) or NULL ->
  * Philox4x32-10 N(0,1) from (seed, offset).  z: (NB*S, T, zdim, 2).                             */
@@ -185,13 +196,13 @@ int idv_reparam_fwd(const float* latent, int NB, int T, int Htot, int ch0, int z
 /* ---- layout conversion at the module boundary --------------------------------------------------*/
 /* planes [F][R][Cp] (fp32, or split bf16 when in_split) -> user (NB, C, F, T, 2) */
 int idv_planes_to_user(const void* planes, int in_split, int NB, int C, int F, int T, float* user,
-                       void* stream);
+                       int t_valid, void* stream);
 /* user (NB, C, F, T, 2) -> planes (pad rows and pad channels written as zero) */
 int idv_user_to_planes(const float* user, int NB, int C, int F, int T, void* planes, int out_split,
-                       void* stream);
-/* z (NB*S, T, zdim, 2) sample s -> planes [1][NB*Tp][2*zdim] */
+                       int t_valid, void* stream);
+/* z (NB*S, t_valid, zdim, 2) sample s -> planes [1][NB*Tp][2*zdim] */
 int idv_z_to_planes(const float* z, int NB, int S, int s, int T, int zdim, void* planes, int out_split,
-                    void* stream);
+                    int t_valid, void* stream);
 
 /* stand-alone ComplexBatchNormal.forward(x, train=False) (model/complex_progress.py:L161-209) on the
  * reference layout x: (outer, C, inner, 2).  zb: [C][6] = Zrr, Zri, Zir, Zii, b'_r, b'_i with
@@ -205,13 +216,14 @@ int idv_cbn_eval_user(const float* x, int64_t outer, int C, int64_t inner, const
  * idv_cbn_train_finalize: batch mean / biased (co)variances (eps added to Vrr, Vii as the reference does), update
  *   of the running buffers (first != 0: copy, else EMA with `momentum`), zb[c][6] = Z, b' from the batch statistics;
  * idv_cbn_apply_planes: y <- act(Z y + b') in place (pad rows untouched).                                       */
-int idv_cbn_stats_planes(const void* planes, int split, int NB, int C, int F, int T, double* acc, void* stream);
+int idv_cbn_stats_planes(const void* planes, int split, int NB, int C, int F, int T, double* acc, int t_valid,
+                         void* stream);
 int idv_cbn_train_finalize(const double* acc, double count, int C, const float* gamma_rr, const float* gamma_ri,
                            const float* gamma_ii, const float* beta_r, const float* beta_i, float* run_mean_r,
                            float* run_mean_i, float* run_vrr, float* run_vri, float* run_vii, float momentum,
                            int first, float* zb, void* stream);
 int idv_cbn_apply_planes(void* planes, int split, int NB, int C, int F, int T, const float* zb, int apply_prelu,
-                         float prelu_slope, void* stream);
+                         float prelu_slope, int t_valid, void* stream);
 /* statistics on the reference layout x (outer, C, inner, 2) (stand-alone ComplexBatchNormal(train=True); the last
  * decoder layer whose raw output is written in the reference layout) and the in-place recon head on
  * y (n_utt, n_per_utt, 2): PReLU(slope) then, if mask, the mask head with stft_x[b / s_rep].                       */

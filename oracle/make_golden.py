@@ -25,6 +25,7 @@ from idccrn_b200.synth import fill_state_dict, synth_eps, synth_waveform  # noqa
 from oracle import ref_port as P  # noqa: E402
 
 import model.causal_netconfig as ref_causal_cfg  # noqa: E402  (reference)
+import model.net_config as ref_noncausal_cfg  # noqa: E402  (reference)
 import model.pvae_module as ref_mod  # noqa: E402  (reference)
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -62,29 +63,30 @@ def check(name, a, b, tol=2e-6):
     return e
 
 
-def build_vae(latent_num, S, seed):
-    net = ref_causal_cfg.get_net_params()
-    enc = ref_mod.nsvae_pvae_dccrn_encoder_twophase(net, True, "cpu", ZDIM, NFFT, HOP, WIN, S, latent_num)
+def build_vae(latent_num, S, seed, causal=True):
+    net = (ref_causal_cfg if causal else ref_noncausal_cfg).get_net_params()
+    enc = ref_mod.nsvae_pvae_dccrn_encoder_twophase(net, causal, "cpu", ZDIM, NFFT, HOP, WIN, S, latent_num)
     enc.load_state_dict(fill_state_dict(enc.state_dict(), seed), strict=True)
     return net, enc.eval()
 
 
-def case_vae(tag, B, L, latent_num, S, dec_kind, recon_type, seed, full):
+def case_vae(tag, B, L, latent_num, S, dec_kind, recon_type, seed, full, causal=True):
+    """causal=False: model/net_config.py (T-1 frames per encoder layer, T+1 per decoder layer: SURVEY §9 V10)."""
     print("case", tag)
     torch.manual_seed(0)
-    net, enc = build_vae(latent_num, S, seed)
+    net, enc = build_vae(latent_num, S, seed, causal)
     if dec_kind == "skip_prepare":
-        dec = ref_mod.pvae_dccrn_decoder_skip_prepare(net, True, "cpu", S, ZDIM, NFFT, HOP, WIN, recon_type,
+        dec = ref_mod.pvae_dccrn_decoder_skip_prepare(net, causal, "cpu", S, ZDIM, NFFT, HOP, WIN, recon_type,
                                                       [0, 1, 2, 3, 4, 5])
         skip_mode = "zero"
     else:
-        dec = ref_mod.nsvae_pvae_dccrn_decoder_twophase(net, True, "cpu", S, ZDIM, NFFT, HOP, WIN, recon_type,
+        dec = ref_mod.nsvae_pvae_dccrn_decoder_twophase(net, causal, "cpu", S, ZDIM, NFFT, HOP, WIN, recon_type,
                                                         True, [0, 1, 2, 3, 4, 5], False)
         skip_mode = "sig"
     dec.load_state_dict(fill_state_dict(dec.state_dict(), seed + 1), strict=True)
     dec.eval()
     x = synth_waveform(B, L, seed=1234 + seed)
-    T = L // HOP + 1
+    T = L // HOP + 1 - (0 if causal else 6)        # latent frames
     eps = synth_eps((B, S, T, ZDIM), seed=7 + seed, n=2 * latent_num)
     with torch.no_grad(), supplied_eps(eps):
         r = enc(x, train=False)
@@ -96,9 +98,9 @@ def case_vae(tag, B, L, latent_num, S, dec_kind, recon_type, seed, full):
     # ---- oracle port on the same inputs
     esd, dsd = enc.state_dict(), dec.state_dict()
     with torch.no_grad():
-        st = P.vae_encoder_forward(esd, x, ZDIM, latent_num, S, eps)
+        st = P.vae_encoder_forward(esd, x, ZDIM, latent_num, S, eps, causal=causal)
         dd = P.vae_decoder_forward(dsd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], S,
-                                   recon_type, skip_mode)
+                                   recon_type, skip_mode, causal=causal)
         check("stft", st["stft_x"], stft_x)
         check("stft_dense", P.stft_dense(x), stft_x, 1e-5)
         for i in range(6):
@@ -112,7 +114,7 @@ def case_vae(tag, B, L, latent_num, S, dec_kind, recon_type, seed, full):
         check("predict", dd["predict"], pred)
         check("recon_sig", dd["recon_sig"], sig)
         check("istft_dense", P.istft_dense(torch.view_as_real(pred)), sig, 1e-5)
-    g = {"B": B, "L": L, "S": S, "latent_num": latent_num, "seed": seed,
+    g = {"B": B, "L": L, "S": S, "latent_num": latent_num, "seed": seed, "causal": int(causal),
          "stft_x": np32(stft_x), "miu": np32(mu_s), "log_sigma": np32(ls_s), "delta": np32(de_s),
          "z_speech": np32(z_s), "predict": np32(pred), "recon_sig": np32(sig)}
     if latent_num == 2:
@@ -154,21 +156,51 @@ def case_vae_train(tag, B, L, seed):
     np.savez(os.path.join(OUT, tag + ".npz"), **g)
 
 
-def case_dccrn(tag, B, L, seed):
+def case_dccrn(tag, B, L, seed, causal=True):
     print("case", tag)
-    net = ref_causal_cfg.get_net_params()
-    m = ref_mod.DCCRN_(NFFT, HOP, net, True, "cpu", WIN, [0, 1, 2, 3, 4, 5], "mask", False, None, None)
+    net = (ref_causal_cfg if causal else ref_noncausal_cfg).get_net_params()
+    m = ref_mod.DCCRN_(NFFT, HOP, net, causal, "cpu", WIN, [0, 1, 2, 3, 4, 5], "mask", False, None, None)
     m.load_state_dict(fill_state_dict(m.state_dict(), seed), strict=True)
     m.eval()
     x = synth_waveform(B, L, seed=1234 + seed)
     with torch.no_grad():
         clean, pred = m(x, train=False)
-        d = P.dccrn_forward(m.state_dict(), x)
+        d = P.dccrn_forward(m.state_dict(), x, causal=causal)
         check("dccrn.latent", d["latent"], m.std_DCCRN.latent)
         check("dccrn.predict", d["predict"], pred)
         check("dccrn.clean", d["clean"], clean)
     np.savez(os.path.join(OUT, tag + ".npz"), B=B, L=L, seed=seed, latent=np32(m.std_DCCRN.latent),
              predict=np32(pred), clean=np32(clean))
+
+
+def case_primitives_noncausal(tag, seed):
+    """Non-causal complex conv / transposed conv blocks (model/complex_progress.py:L24-36, L253-279) at odd shapes."""
+    print("case", tag)
+    g = {}
+    gen = torch.Generator().manual_seed(200 + seed)
+    enc = ref_mod.Encoder(3, 5, (5, 2), (2, 1), (5, 9, 1), padding=(2, 0), causal=False)
+    enc.load_state_dict(fill_state_dict(enc.state_dict(), seed))
+    x = torch.randn(2, 3, 11, 6, 2, generator=gen)
+    with torch.no_grad():
+        g["enc_in"], g["enc_out"] = np32(x), np32(enc(x, False))
+        check("Encoder block (non-causal)", P.encoder_block(x, enc.state_dict(), "", causal=False), enc(x, False))
+    dec = ref_mod.Decoder(4, 3, (5, 2), (2, 1), (3, 9, 1), padding=(2, 0), causal=False)
+    dec.load_state_dict(fill_state_dict(dec.state_dict(), seed))
+    x = torch.randn(2, 4, 5, 6, 2, generator=gen)
+    with torch.no_grad():
+        g["dec_in"], g["dec_out"] = np32(x), np32(dec(x, False))
+        check("Decoder block (non-causal)", P.decoder_block(x, dec.state_dict(), "", causal=False), dec(x, False))
+    assert g["enc_out"].shape[3] == 5 and g["dec_out"].shape[3] == 7
+    np.savez(os.path.join(OUT, tag + ".npz"), **g)
+
+
+def noncausal_cases():
+    case_primitives_noncausal("primitives_noncausal", seed=8)
+    case_vae("vae_nc_l1_zero_full", B=2, L=1000, latent_num=1, S=1, dec_kind="skip_prepare",
+             recon_type="real_imag", seed=9, full=True, causal=False)
+    case_vae("vae_nc_l2_sig_mask_s2_e2e", B=2, L=4000, latent_num=2, S=2, dec_kind="twophase",
+             recon_type="mask", seed=10, full=False, causal=False)
+    case_dccrn("dccrn_nc_mask_e2e", B=3, L=3000, seed=11, causal=False)
 
 
 def case_primitives(tag, seed):
@@ -208,6 +240,9 @@ def case_primitives(tag, seed):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-noncausal" in sys.argv:
+        noncausal_cases()
+        sys.exit(0)
     if "--only-train" in sys.argv:
         case_vae_train("vae_train_fwd", B=2, L=800, seed=6)
         sys.exit(0)
@@ -226,4 +261,5 @@ if __name__ == "__main__":
     case_vae("vae_l1_sig_ri_e2e", B=3, L=3200, latent_num=1, S=1, dec_kind="twophase",
              recon_type="real_imag", seed=4, full=False)
     case_dccrn("dccrn_mask_e2e", B=2, L=8000, seed=5)
+    noncausal_cases()
     print("golden fixtures written to", OUT)

@@ -13,6 +13,19 @@ import torch
 D = torch.float64
 
 
+def _tv(t_valid, T):
+    """Valid frames per utterance: 0 or >= T means all T (include/idv.h, "Valid frames")."""
+    return t_valid if 0 < t_valid < T else T
+
+
+def _mask_rows(acc, R, Tp, t_valid):
+    """Pad rows and rows of frames beyond the valid length are written as zero."""
+    if Tp > 0:
+        tt = torch.arange(R) % Tp
+        acc[(tt == 0) | (tt > _tv(t_valid, Tp - 1))] = 0
+    return acc
+
+
 def _flat(t):
     return t.view(-1)
 
@@ -43,7 +56,7 @@ def _wr(t, split, vals):
 
 def idv_tapgemm_tc_head(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, N, units, taps,
                         n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, slope, head, head_fout,
-                        head_bmul, head_boff, stft_x, predict):
+                        head_bmul, head_boff, stft_x, predict, t_valid=0):
     if head == 3:                                       # STFT epilogue: column pairs -> (B, nbins, Tp, 2)
         tmp = torch.zeros(R * N)
         idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, 0, wt, kc_max, n_slots, bias, N, units, taps,
@@ -85,7 +98,7 @@ def idv_tapgemm_tc_head(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, k
 
 
 def idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, N, units, taps,
-                   n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, slope):
+                   n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, slope, t_valid=0):
     """Contract of the tensor-core tap-GEMM incl. its arithmetic: a_hi*w_hi + a_hi*w_lo + a_lo*w_hi."""
     taps_l, units_l = taps.tolist(), units.tolist()
     W = wt.view(2, n_slots, N, kc_max).to(D)
@@ -109,6 +122,8 @@ def idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max
                 x = x[f_in][:, ch_off:ch_off + kc]
                 if dt > 0:
                     x = torch.cat((torch.zeros(dt, kc, dtype=D), x[:R - dt]), 0)
+                elif dt < 0:
+                    x = torch.cat((x[-dt:], torch.zeros(-dt, kc, dtype=D)), 0)
                 return x
             ah, al = shifted(hi), shifted(lo)
             wh, wl = W[0, slot, :, :kc].t(), W[1, slot, :, :kc].t()
@@ -119,8 +134,7 @@ def idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max
         acc += bvec
         if apply_prelu:
             acc = torch.where(acc > 0, acc, slope * acc)
-        if Tp > 0:
-            acc[torch.arange(R) % Tp == 0] = 0
+        _mask_rows(acc, R, Tp, t_valid)
         view = res[out_f * out_plane:out_f * out_plane + R * out_ld].view(R, out_ld)
         view[:, out_ch_off:out_ch_off + N] = acc
         written[out_f * out_plane:out_f * out_plane + R * out_ld].view(R, out_ld)[:, out_ch_off:out_ch_off + N] = True
@@ -139,7 +153,7 @@ def idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max
 
 
 def idv_tapgemm_f32(a0, a0_ld, a0_plane, a1, a1_ld, a1_plane, R, Tp, w, bias, N, units, taps, n_units, out,
-                    out_ld, out_plane, apply_prelu, slope):
+                    out_ld, out_plane, apply_prelu, slope, t_valid=0):
     taps_l, units_l = taps.tolist(), units.tolist()
     assert len(units_l) == n_units
     for (tap_begin, n_taps, out_f, out_ch_off, bias_off, _) in units_l:
@@ -156,8 +170,7 @@ def idv_tapgemm_f32(a0, a0_ld, a0_plane, a1, a1_ld, a1_plane, R, Tp, w, bias, N,
         acc += _flat(bias)[bias_off:bias_off + N].to(D)
         if apply_prelu:
             acc = torch.where(acc > 0, acc, slope * acc)
-        if Tp > 0:
-            acc[torch.arange(R) % Tp == 0] = 0
+        _mask_rows(acc, R, Tp, t_valid)
         _flat(out)[out_f * out_plane:out_f * out_plane + R * out_ld].view(R, out_ld)[:, out_ch_off:out_ch_off + N] = \
             acc.to(torch.float32)
 
@@ -217,13 +230,16 @@ def idv_ola_fwd(frames, frame_ld, wsq, B, T, n_fft, hop, win, out):
     out.copy_((y[:, h:total - h] / env[h:total - h]).to(torch.float32))
 
 
-def idv_enc0_fwd(stft, B, Fin, T, w, bias, Cout, slope, out, out_split=0):
+def idv_enc0_fwd(stft, B, Fin, T, w, bias, Cout, slope, out, out_split=0, causal=1, t_valid=0):
     N = 2 * Cout
     Fout = (Fin + 4 - 5) // 2 + 1
     Tp = T + 1
     x = stft.view(B, Fin, T, 2).to(D)
-    xpad = torch.zeros(B, Fin + 4, T + 1, 2, dtype=D)                             # freq pad 2/2, time pad 1 left
-    xpad[:, 2:2 + Fin, 1:] = x
+    xpad = torch.zeros(B, Fin + 4, T + 1, 2, dtype=D)        # freq pad 2/2; time: one zero left (causal) / right
+    if causal:
+        xpad[:, 2:2 + Fin, 1:] = x
+    else:
+        xpad[:, 2:2 + Fin, :T] = x
     W = w.view(10, 2, N).to(D)
     res = torch.zeros(Fout, B, Tp, N, dtype=D)
     for kf in range(5):
@@ -233,6 +249,7 @@ def idv_enc0_fwd(stft, B, Fin, T, w, bias, Cout, slope, out, out_split=0):
     res[:, :, 1:] += bias.to(D)
     res = torch.where(res > 0, res, slope * res)
     res[:, :, 0] = 0
+    res[:, :, 1 + _tv(t_valid, T):] = 0
     _wr(out, out_split, res)
 
 
@@ -273,7 +290,7 @@ def idv_dec5_head_fwd(p, p_cp, skip, s_cp, in_split, NB, Fin, T, w, bias, slope,
     pv[out_boff::out_bmul][:NB] = y.to(torch.float32)
 
 
-def idv_lstm_recurrent_fwd(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, hseq, hsplit, sync):
+def idv_lstm_recurrent_fwd(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, hseq, hsplit, sync, t_valid=0):
     Tp = T + 1
     R = NB * Tp
     hs = hseq.view(4, R, H)
@@ -286,7 +303,7 @@ def idv_lstm_recurrent_fwd(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, hseq, hspli
             h = torch.zeros(NB, H, dtype=D)
             c = torch.zeros(NB, H, dtype=D)
             hs[m * 2 + p, rows0] = 0
-            for t in range(T):
+            for t in range(_tv(t_valid, T)):
                 rows = rows0 + 1 + t
                 idx = base + rows[:, None] * g_ld + torch.arange(4 * H)[None, :]
                 a = gf[idx].to(D) + h @ W[m].t()
@@ -304,7 +321,7 @@ def _bf16_split(x):
     return hi.to(D), lo.to(D)
 
 
-def idv_lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, hx, sync):
+def idv_lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, hx, sync, t_valid=0):
     """Contract of the tensor-core recurrence: the recurrent product uses the split value of h(t-1)."""
     n_cols, n_ctas = _lstm_tc_config(H)
     hs = n_cols // 4
@@ -320,7 +337,7 @@ def idv_lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hspl
             base = m * g_m_off + p * g_p_off
             h = torch.zeros(NB, H, dtype=D)
             c = torch.zeros(NB, H, dtype=D)
-            for t in range(T):
+            for t in range(_tv(t_valid, T)):
                 rows = rows0 + 1 + t
                 idx = base + rows[:, None] * g_ld + torch.arange(4 * H)[None, :]
                 hh, hl = _bf16_split(h)
@@ -330,7 +347,7 @@ def idv_lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hspl
                 h = torch.sigmoid(o) * torch.tanh(c)
                 out[m * 2 + p, rows] = h
     valid = torch.zeros(R, dtype=torch.bool)
-    valid[(rows0[:, None] + 1 + torch.arange(T)[None, :]).reshape(-1)] = True
+    valid[(rows0[:, None] + 1 + torch.arange(_tv(t_valid, T))[None, :]).reshape(-1)] = True
     if hseq is not None:
         hseq.view(4, R, H)[:, valid] = out[:, valid].to(torch.float32)
     if hsplit is not None:
@@ -340,7 +357,8 @@ def idv_lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hspl
         hv[1][:, valid] = lo[:, valid].to(torch.bfloat16)
 
 
-def idv_lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq1, work, sync):
+def idv_lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq1, work, sync,
+                      t_valid=0):
     """Contract: layer 0 recurrence (split h), layer-1 input projection on the split h0 (3 products) + bias,
     layer-1 recurrence (split h1)."""
     n_cols, n_ctas = 64, H // 16
@@ -372,7 +390,7 @@ def idv_lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB
             c0 = torch.zeros(NB, H, dtype=D)
             h1 = torch.zeros(NB, H, dtype=D)
             c1 = torch.zeros(NB, H, dtype=D)
-            for t in range(T):
+            for t in range(_tv(t_valid, T)):
                 rows = rows0 + 1 + t
                 idx = base + rows[:, None] * g_ld + torch.arange(4 * H)[None, :]
                 h0, c0 = cell(gf[idx].to(D) + mm3(h0, W0, m), c0)
@@ -387,9 +405,9 @@ def _lstm_tc_config(H):
     return lib.lstm_tc_config(H)          # pure host function of the real library (no GPU needed)
 
 
-def idv_lstm_combine_fwd(hseq, NB, T, H, latent):
+def idv_lstm_combine_fwd(hseq, NB, T, H, latent, t_valid=0):
     Tp = T + 1
-    hs = hseq.view(4, NB, Tp, H)[:, :, 1:]
+    hs = hseq.view(4, NB, Tp, H)[:, :, 1:1 + _tv(t_valid, T)]
     rr, ir, ri, ii = hs[0], hs[1], hs[2], hs[3]
     latent.copy_(torch.stack((rr - ii, ir + ri), -1))
 
@@ -417,23 +435,23 @@ def _r8(c):
     return (c + 7) // 8 * 8
 
 
-def idv_planes_to_user(planes, in_split, NB, C, F, T, user):
+def idv_planes_to_user(planes, in_split, NB, C, F, T, user, t_valid=0):
     Ch, Tp = _r8(C), T + 1
-    p = _rd(planes, in_split, F * NB * Tp * 2 * Ch).view(F, NB, Tp, 2, Ch)[:, :, 1:, :, :C]    # (F,NB,T,2,C)
+    p = _rd(planes, in_split, F * NB * Tp * 2 * Ch).view(F, NB, Tp, 2, Ch)[:, :, 1:1 + _tv(t_valid, T), :, :C]
     user.copy_(p.permute(1, 4, 0, 2, 3).to(torch.float32))
 
 
-def idv_user_to_planes(user, NB, C, F, T, planes, out_split=0):
-    Ch, Tp = _r8(C), T + 1
+def idv_user_to_planes(user, NB, C, F, T, planes, out_split=0, t_valid=0):
+    Ch, Tp, Tv = _r8(C), T + 1, _tv(t_valid, T)
     p = torch.zeros(F, NB, Tp, 2, Ch, dtype=D)
-    p[:, :, 1:, :, :C] = user.view(NB, C, F, T, 2).permute(2, 0, 3, 4, 1).to(D)
+    p[:, :, 1:1 + Tv, :, :C] = user.view(NB, C, F, Tv, 2).permute(2, 0, 3, 4, 1).to(D)
     _wr(planes, out_split, p)
 
 
-def idv_z_to_planes(z, NB, S, s, T, zdim, planes, out_split=0):
-    Ch, Tp = _r8(zdim), T + 1
+def idv_z_to_planes(z, NB, S, s, T, zdim, planes, out_split=0, t_valid=0):
+    Ch, Tp, Tv = _r8(zdim), T + 1, _tv(t_valid, T)
     p = torch.zeros(NB, Tp, 2, Ch, dtype=D)
-    p[:, 1:, :, :zdim] = z.view(NB, S, T, zdim, 2)[:, s].permute(0, 1, 3, 2).to(D)
+    p[:, 1:1 + Tv, :, :zdim] = z.view(NB, S, Tv, zdim, 2)[:, s].permute(0, 1, 3, 2).to(D)
     _wr(planes, out_split, p)
 
 
@@ -447,9 +465,9 @@ def idv_cbn_eval_user(x, outer, C, inner, zb, out):
     o[..., 1] = o_i
 
 
-def idv_cbn_stats_planes(planes, split, NB, C, F, T, acc):
+def idv_cbn_stats_planes(planes, split, NB, C, F, T, acc, t_valid=0):
     Ch, Tp = _r8(C), T + 1
-    p = _rd(planes, split, F * NB * Tp * 2 * Ch).view(F, NB, Tp, 2, Ch)[:, :, 1:, :, :C]      # (F,NB,T,2,C)
+    p = _rd(planes, split, F * NB * Tp * 2 * Ch).view(F, NB, Tp, 2, Ch)[:, :, 1:1 + _tv(t_valid, T), :, :C]
     re, im = p[:, :, :, 0], p[:, :, :, 1]
     acc.view(C, 5).copy_(torch.stack((re.sum((0, 1, 2)), im.sum((0, 1, 2)), (re * re).sum((0, 1, 2)),
                                       (im * im).sum((0, 1, 2)), (re * im).sum((0, 1, 2))), 1))
@@ -487,19 +505,20 @@ def idv_cbn_train_finalize(acc, count, C, g_rr, g_ri, g_ii, beta_r, beta_i, run_
                                      beta_i.view(-1) - (zir * mu_r + zii * mu_i)), 1))
 
 
-def idv_cbn_apply_planes(planes, split, NB, C, F, T, zb, apply_prelu, slope):
+def idv_cbn_apply_planes(planes, split, NB, C, F, T, zb, apply_prelu, slope, t_valid=0):
     Ch, Tp = _r8(C), T + 1
+    te = 1 + _tv(t_valid, T)
     n = F * NB * Tp * 2 * Ch
     p = _rd(planes, split, n).view(F, NB, Tp, 2, Ch).clone()
     k = zb.view(C, 6).to(D)
-    re, im = p[:, :, 1:, 0, :C].clone(), p[:, :, 1:, 1, :C].clone()
+    re, im = p[:, :, 1:te, 0, :C].clone(), p[:, :, 1:te, 1, :C].clone()
     o_r = k[:, 0] * re + k[:, 1] * im + k[:, 4]
     o_i = k[:, 2] * re + k[:, 3] * im + k[:, 5]
     if apply_prelu:
         o_r = torch.where(o_r > 0, o_r, slope * o_r)
         o_i = torch.where(o_i > 0, o_i, slope * o_i)
-    p[:, :, 1:, 0, :C] = o_r
-    p[:, :, 1:, 1, :C] = o_i
+    p[:, :, 1:te, 0, :C] = o_r
+    p[:, :, 1:te, 1, :C] = o_i
     _wr(planes, split, p)
 
 

@@ -8,22 +8,22 @@ NFFT, HOP, WIN, ZDIM = 512, 100, 400, 128
 SKIPS = [0, 1, 2, 3, 4, 5]
 
 
-def build_vae(latent_num, S, dec_kind, recon_type, seed, device):
-    net = M.get_net_params()
-    enc = M.nsvae_pvae_dccrn_encoder_twophase(net, True, device, ZDIM, NFFT, HOP, WIN, S, latent_num)
+def build_vae(latent_num, S, dec_kind, recon_type, seed, device, causal=True):
+    net = M.get_net_params(causal)
+    enc = M.nsvae_pvae_dccrn_encoder_twophase(net, causal, device, ZDIM, NFFT, HOP, WIN, S, latent_num)
     enc.load_state_dict(fill_state_dict(enc.state_dict(), seed), strict=True)
     if dec_kind == "skip_prepare":
-        dec = M.pvae_dccrn_decoder_skip_prepare(net, True, device, S, ZDIM, NFFT, HOP, WIN, recon_type, SKIPS)
+        dec = M.pvae_dccrn_decoder_skip_prepare(net, causal, device, S, ZDIM, NFFT, HOP, WIN, recon_type, SKIPS)
     else:
-        dec = M.nsvae_pvae_dccrn_decoder_twophase(net, True, device, S, ZDIM, NFFT, HOP, WIN, recon_type, True,
+        dec = M.nsvae_pvae_dccrn_decoder_twophase(net, causal, device, S, ZDIM, NFFT, HOP, WIN, recon_type, True,
                                                   SKIPS, False)
     dec.load_state_dict(fill_state_dict(dec.state_dict(), seed + 1), strict=True)
     return enc.to(device).eval(), dec.to(device).eval()
 
 
-def vae_inputs(B, L, S, latent_num, seed, device):
+def vae_inputs(B, L, S, latent_num, seed, device, causal=True):
     x = synth_waveform(B, L, seed=1234 + seed).to(device)
-    T = L // HOP + 1
+    T = L // HOP + 1 - (0 if causal else 6)          # latent frames (non-causal: one fewer per encoder layer)
     eps = [e.to(device) for e in synth_eps((B, S, T, ZDIM), seed=7 + seed, n=2 * latent_num)]
     return x, eps
 

@@ -31,13 +31,14 @@ def _rand(*shape, seed=0):
     return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
 
 
-@pytest.mark.parametrize("R,Tp,N,kcs,dts,two_src,prelu", [
-    (300, 0, 128, [16, 32], [0, 1], False, False),
-    (130, 13, 64, [64, 24], [1, 0], True, True),       # kc not a multiple of 16, N = 64 path, two sources
-    (1, 0, 16, [8], [0], False, True),                  # single row, N tail (16 < 64)
-    (517, 47, 384, [128, 128, 128], [0, 1, 0], True, True),
+@pytest.mark.parametrize("R,Tp,N,kcs,dts,two_src,prelu,tv", [
+    (300, 0, 128, [16, 32], [0, 1], False, False, 0),
+    (130, 13, 64, [64, 24], [1, 0], True, True, 0),    # kc not a multiple of 16, N = 64 path, two sources
+    (1, 0, 16, [8], [0], False, True, 0),               # single row, N tail (16 < 64)
+    (517, 47, 384, [128, 128, 128], [0, 1, 0], True, True, 0),
+    (470, 47, 128, [64, 64], [0, -1], False, True, 41),   # non-causal taps (x[t], x[t+1]), 41 of 46 frames valid
 ])
-def test_tapgemm(R, Tp, N, kcs, dts, two_src, prelu):
+def test_tapgemm(R, Tp, N, kcs, dts, two_src, prelu, tv):
     F0, ld0, ld1 = 3, 136, 136
     a0 = _rand(F0, R, ld0, seed=1)
     a1 = _rand(F0, R, ld1, seed=2) if two_src else None
@@ -53,7 +54,7 @@ def test_tapgemm(R, Tp, N, kcs, dts, two_src, prelu):
     out = torch.zeros(2, R, out_ld)
     args = [a0, ld0, R * ld0, a1, ld1 if two_src else 0, R * ld1 if two_src else 0, R, Tp, w, bias, N,
             torch.tensor(units, dtype=torch.int32), torch.tensor(taps, dtype=torch.int32), 2, out, out_ld,
-            R * out_ld, 1 if prelu else 0, 0.2]
+            R * out_ld, 1 if prelu else 0, 0.2, tv]
     assert _both("idv_tapgemm_f32", args, [14]) < 1e-5
 
 
@@ -70,12 +71,13 @@ def test_stft_istft(B, L):
     assert _both("idv_istft_fwd", [spec, B, T, ib, wsq, 512, 100, 400, frames, y], [8, 9]) < 1e-5
 
 
-@pytest.mark.parametrize("B,Fin,T,Cout", [(1, 257, 1, 32), (3, 33, 70, 64), (5, 17, 129, 32)])
-def test_enc0(B, Fin, T, Cout):
+@pytest.mark.parametrize("causal", [1, 0])
+@pytest.mark.parametrize("B,Fin,T,Cout", [(1, 257, 2, 32), (3, 33, 70, 64), (5, 17, 129, 32)])
+def test_enc0(B, Fin, T, Cout, causal):
     Fout = (Fin - 1) // 2 + 1
     n = Fout * B * (T + 1) * 2 * Cout
     args = [_rand(B, Fin, T, 2, seed=7), B, Fin, T, _rand(10, 2, 2 * Cout, seed=8), _rand(2 * Cout, seed=9), Cout, 0.3,
-            torch.zeros(n), 0]
+            torch.zeros(n), 0, causal, T if causal else T - 1]
     assert _both("idv_enc0_fwd", args, [8]) < 1e-5
     args[8], args[9] = torch.zeros(2 * n, dtype=torch.bfloat16), 1
     assert _both("idv_enc0_fwd", args, [8]) < 2e-5
@@ -103,18 +105,19 @@ def test_dec5_head(NB, Fin, T, p_cp, s_cp, mask, S):
     assert _both("idv_dec5_head_fwd", args, [13]) < 1e-5
 
 
-@pytest.mark.parametrize("NB,T,H", [(1, 5, 8), (3, 20, 384), (64, 3, 128), (5, 4, 768)])
-def test_lstm_recurrent_and_combine(NB, T, H):
+@pytest.mark.parametrize("NB,T,H,tv", [(1, 5, 8, 0), (3, 20, 384, 0), (64, 3, 128, 0), (5, 4, 768, 0), (3, 20, 128, 14)])
+def test_lstm_recurrent_and_combine(NB, T, H, tv):
     R = NB * (T + 1)
     g = _rand(2, R, 8 * H, seed=15)
     whh = _rand(2, 4 * H, H, seed=16) / (H ** 0.5)
     hseq = torch.full((4, R, H), 7.0)
     sync = torch.zeros(2, dtype=torch.int32)
     hsplit = torch.zeros(2 * 4 * R * H, dtype=torch.bfloat16)
-    assert _both("idv_lstm_recurrent_fwd", [g, 4 * H, R * 8 * H, 8 * H, whh, NB, T, H, hseq, hsplit, sync], [8, 9]) < 2e-5
-    assert _both("idv_lstm_recurrent_fwd", [g, 4 * H, R * 8 * H, 8 * H, whh, NB, T, H, hseq, None, sync], [8]) < 1e-5
+    hseq.view(4, NB, T + 1, H)[:, :, 1 + (tv or T):] = 0          # frames beyond the valid length are not written
+    assert _both("idv_lstm_recurrent_fwd", [g, 4 * H, R * 8 * H, 8 * H, whh, NB, T, H, hseq, hsplit, sync, tv], [8, 9]) < 2e-5
+    assert _both("idv_lstm_recurrent_fwd", [g, 4 * H, R * 8 * H, 8 * H, whh, NB, T, H, hseq, None, sync, tv], [8]) < 1e-5
     hs = _rand(4, R, H, seed=17)
-    assert _both("idv_lstm_combine_fwd", [hs, NB, T, H, torch.zeros(NB, T, H, 2)], [4]) < 1e-6
+    assert _both("idv_lstm_combine_fwd", [hs, NB, T, H, torch.zeros(NB, tv or T, H, 2), tv], [4]) < 1e-6
 
 
 def test_reparam_supplied_eps():
@@ -125,24 +128,31 @@ def test_reparam_supplied_eps():
     assert _both("idv_reparam_fwd", args, [11]) < 1e-5
 
 
-@pytest.mark.parametrize("NB,C_,F,T", [(2, 3, 5, 7), (1, 32, 129, 33), (3, 1, 4, 65)])
-def test_layout_roundtrip(NB, C_, F, T):
+@pytest.mark.parametrize("NB,C_,F,T,tv", [(2, 3, 5, 7, 0), (1, 32, 129, 33, 0), (3, 1, 4, 65, 0), (2, 5, 3, 40, 34)])
+def test_layout_roundtrip(NB, C_, F, T, tv):
+    """tv: valid frames (< T: the user tensor has tv frames inside a T-frame row layout)."""
     Cp = 2 * ((C_ + 7) // 8 * 8)
-    x = _rand(NB, C_, F, T, 2, seed=21)
+    Tv = tv or T
+    x = _rand(NB, C_, F, Tv, 2, seed=21)
     planes = torch.full((F * NB * (T + 1) * Cp,), 3.0)
-    assert _both("idv_user_to_planes", [x, NB, C_, F, T, planes, 0], [5]) < 1e-7
-    E.call("idv_user_to_planes", x, NB, C_, F, T, planes, 0)
-    assert _both("idv_planes_to_user", [planes, 0, NB, C_, F, T, torch.zeros_like(x)], [6]) < 1e-7
+    assert _both("idv_user_to_planes", [x, NB, C_, F, T, planes, 0, tv], [5]) < 1e-7
+    E.call("idv_user_to_planes", x, NB, C_, F, T, planes, 0, tv)
+    assert _both("idv_planes_to_user", [planes, 0, NB, C_, F, T, torch.zeros_like(x), tv], [6]) < 1e-7
     sp = torch.full((2 * planes.numel(),), 3.0, dtype=torch.bfloat16)
-    assert _both("idv_user_to_planes", [x, NB, C_, F, T, sp, 1], [5]) < 1e-7
-    E.call("idv_user_to_planes", x, NB, C_, F, T, sp, 1)
-    assert _both("idv_planes_to_user", [sp, 1, NB, C_, F, T, torch.zeros_like(x)], [6]) < 1e-7
-    z = _rand(NB * 2, T, 16, 2, seed=22)
-    assert _both("idv_z_to_planes", [z, NB, 2, 1, T, 16, torch.full((NB * (T + 1) * 32,), 5.0), 0], [6]) < 1e-7
-    assert _both("idv_z_to_planes", [z, NB, 2, 1, T, 16, torch.zeros(2 * NB * (T + 1) * 32, dtype=torch.bfloat16), 1],
-                 [6]) < 1e-7
+    assert _both("idv_user_to_planes", [x, NB, C_, F, T, sp, 1, tv], [5]) < 1e-7
+    E.call("idv_user_to_planes", x, NB, C_, F, T, sp, 1, tv)
+    assert _both("idv_planes_to_user", [sp, 1, NB, C_, F, T, torch.zeros_like(x), tv], [6]) < 1e-7
+    z = _rand(NB * 2, Tv, 16, 2, seed=22)
+    assert _both("idv_z_to_planes", [z, NB, 2, 1, T, 16, torch.full((NB * (T + 1) * 32,), 5.0), 0, tv], [6]) < 1e-7
+    assert _both("idv_z_to_planes", [z, NB, 2, 1, T, 16, torch.zeros(2 * NB * (T + 1) * 32, dtype=torch.bfloat16), 1,
+                                     tv], [6]) < 1e-7
     zb = _rand(C_, 6, seed=23)
-    assert _both("idv_cbn_eval_user", [x, NB, C_, F * T, zb, torch.zeros_like(x)], [5]) < 1e-6
+    assert _both("idv_cbn_eval_user", [x, NB, C_, F * Tv, zb, torch.zeros_like(x)], [5]) < 1e-6
+    # train-mode CBN on planes: statistics over the valid frames only, in-place apply leaves the other rows alone
+    for split, buf in ((0, planes), (1, sp)):
+        acc = torch.zeros(C_ * 5, dtype=torch.float64)
+        assert _both("idv_cbn_stats_planes", [buf, split, NB, C_, F, T, acc, tv], [6]) < 1e-6
+        assert _both("idv_cbn_apply_planes", [buf.clone(), split, NB, C_, F, T, zb.reshape(-1), 1, 0.3, tv], [0]) < 1e-6
 
 
 def test_bad_arguments_return_error_codes():
@@ -151,30 +161,32 @@ def test_bad_arguments_return_error_codes():
                  torch.zeros(4).cuda())          # L <= n_fft/2: reflect padding impossible
     with pytest.raises(RuntimeError, match="H"):
         lib.call("idv_lstm_recurrent_fwd", torch.zeros(4).cuda(), 0, 0, 4, torch.zeros(4).cuda(), 1, 1, 6,
-                 torch.zeros(4).cuda(), None, torch.zeros(2, dtype=torch.int32).cuda())
+                 torch.zeros(4).cuda(), None, torch.zeros(2, dtype=torch.int32).cuda(), 0)
 
 
 # ---------------------------------------------------------------------------------------------------
 # tensor-core tap-GEMM (tcgen05 / TMEM / TMA) against the contract incl. its split arithmetic
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("R,Tp,N,kcs,dts,two_src,prelu,out_split", [
-    (128, 0, 64, [64], [0], False, False, 0),                # one tile, one K step, fp32 out
-    (128, 0, 64, [64], [0], False, False, 1),                # same, split out
-    (300, 0, 128, [64, 128], [0, 1], False, True, 1),        # row tail, shifted tap, 3 K steps
-    (517, 47, 256, [128, 64, 128], [0, 1, 0], True, True, 1),   # two sources, pad rows, BN = 256
-    (1000, 0, 512, [192], [1], False, False, 0),             # two N tiles, many row tiles (persistent loop)
-    (40000, 641, 32, [64, 64], [1, 0], False, True, 1),      # > 148 tiles: several tiles per CTA, both TMEM stages
+@pytest.mark.parametrize("R,Tp,N,kcs,dts,two_src,prelu,out_split,tv", [
+    (128, 0, 64, [64], [0], False, False, 0, 0),                # one tile, one K step, fp32 out
+    (128, 0, 64, [64], [0], False, False, 1, 0),                # same, split out
+    (300, 0, 128, [64, 128], [0, 1], False, True, 1, 0),        # row tail, shifted tap, 3 K steps
+    (517, 47, 256, [128, 64, 128], [0, 1, 0], True, True, 1, 0),   # two sources, pad rows, BN = 256
+    (1000, 0, 512, [192], [1], False, False, 0, 0),             # two N tiles, many row tiles (persistent loop)
+    (40000, 641, 32, [64, 64], [1, 0], False, True, 1, 0),      # > 148 tiles: several tiles per CTA, both TMEM stages
+    (470, 47, 128, [64, 64], [0, -1], False, True, 1, 41),      # non-causal taps (x[t], x[t+1]), 41 of 46 frames valid
+    (1284, 642, 256, [128, 128], [-1, 0], True, True, 0, 640),  # row+1 tap at the end of the tensor (zero fill)
 ])
 @pytest.mark.parametrize("dynamic_tiles", [0, 1])
-def test_tapgemm_tc(R, Tp, N, kcs, dts, two_src, prelu, out_split, dynamic_tiles):
+def test_tapgemm_tc(R, Tp, N, kcs, dts, two_src, prelu, out_split, tv, dynamic_tiles):
     lib.set_option("gemm_dynamic_tiles", dynamic_tiles)
     try:
-        _tapgemm_tc_case(R, Tp, N, kcs, dts, two_src, prelu, out_split)
+        _tapgemm_tc_case(R, Tp, N, kcs, dts, two_src, prelu, out_split, tv)
     finally:
         lib.set_option("gemm_dynamic_tiles", 0)
 
 
-def _tapgemm_tc_case(R, Tp, N, kcs, dts, two_src, prelu, out_split):
+def _tapgemm_tc_case(R, Tp, N, kcs, dts, two_src, prelu, out_split, tv=0):
     F0, cp0, cp1 = 3, 264, 136
     a0 = _to_split(_rand(F0, R, cp0, seed=1))
     a1 = _to_split(_rand(2, R, cp1, seed=2)) if two_src else None
@@ -195,12 +207,12 @@ def _tapgemm_tc_case(R, Tp, N, kcs, dts, two_src, prelu, out_split):
     out = torch.zeros(2 * n_out, dtype=torch.bfloat16) if out_split else torch.zeros(n_out)
     args = [a0, cp0, F0, a1, cp1 if two_src else 0, 2 if two_src else 0, R, Tp, wt, kc_max, len(taps), bias, N,
             torch.tensor(units, dtype=torch.int32), torch.tensor(taps, dtype=torch.int32), 2, out, out_ld,
-            R * out_ld, n_out, out_split, 1 if prelu else 0, 0.2]
+            R * out_ld, n_out, out_split, 1 if prelu else 0, 0.2, tv]
     assert _both("idv_tapgemm_tc", args, [16]) < 1e-5
 
 
-@pytest.mark.parametrize("NB,T,H", [(3, 6, 128), (64, 40, 384), (5, 9, 768), (70, 5, 128)])
-def test_lstm_recurrent_tc(NB, T, H):
+@pytest.mark.parametrize("NB,T,H,tv", [(3, 6, 128, 0), (64, 40, 384, 0), (5, 9, 768, 0), (70, 5, 128, 0), (3, 12, 128, 7)])
+def test_lstm_recurrent_tc(NB, T, H, tv):
     from idccrn_b200 import pack as PK
     n_cols, n_ctas = lib.lstm_tc_config(H)
     assert (n_cols, n_ctas) == E._lstm_tc_config(H)
@@ -213,7 +225,7 @@ def test_lstm_recurrent_tc(NB, T, H):
     hsplit = torch.zeros(2 * 4 * R * H, dtype=torch.bfloat16)
     hx = torch.zeros(n_rg * 2 * 2 * 2 * 128 * H, dtype=torch.bfloat16)
     sync = torch.zeros(n_rg * 2, dtype=torch.int32)
-    args = [g, 4 * H, R * 8 * H, 8 * H, wp, NB, T, H, hseq, hsplit, hx, sync]
+    args = [g, 4 * H, R * 8 * H, 8 * H, wp, NB, T, H, hseq, hsplit, hx, sync, tv]
     assert _both("idv_lstm_recurrent_tc", args, [8, 9]) < 2e-5
 
 
@@ -235,7 +247,7 @@ def test_tapgemm_tc_head(NB, Fin, T, two_src, mask, S):
     predict = torch.zeros(NB * S, Fout, T, 2)
     args = [p, 64, Fin, skip, 64 if two_src else 0, Fin if two_src else 0, R, T + 1, hp["wt"], hp["kc_max"],
             hp["n_slots"], hp["bias"], 32, hp["units"], hp["taps"], hp["n_units"], None, 0, 0, 0, 0, 1, hp["slope"],
-            mask, Fout, S, S - 1, _rand(NB, Fout, T, 2, seed=14), predict]
+            mask, Fout, S, S - 1, _rand(NB, Fout, T, 2, seed=14), predict, 0]
     assert _both("idv_tapgemm_tc_head", args, [28]) < 1e-5
     # and the packed form agrees with the SIMT head kernel's contract on the same folded weights
     ref = torch.zeros(NB * S, Fout, T, 2)
@@ -248,8 +260,8 @@ def test_tapgemm_tc_head(NB, Fin, T, two_src, mask, S):
     assert C.rel_l2(cpu, ref) < 2e-5
 
 
-@pytest.mark.parametrize("NB,T,H", [(3, 9, 128), (64, 30, 384), (17, 2, 384)])
-def test_lstm2_wave_tc(NB, T, H):
+@pytest.mark.parametrize("NB,T,H,tv", [(3, 9, 128, 0), (64, 30, 384, 0), (17, 2, 384, 0), (4, 16, 128, 10)])
+def test_lstm2_wave_tc(NB, T, H, tv):
     from idccrn_b200 import pack as PK
     n_cols, n_ctas, work_bytes = lib.lstm2_wave_config(H)
     R = NB * (T + 1)
@@ -267,7 +279,7 @@ def test_lstm2_wave_tc(NB, T, H):
     hseq = torch.zeros(4, R, H)
     work = torch.zeros(work_bytes, dtype=torch.uint8)
     sync = torch.zeros(6, dtype=torch.int32)
-    args = [g, 4 * H, R * 8 * H, 8 * H, w0, wi, w1, b1, NB, T, H, hseq, work, sync]
+    args = [g, 4 * H, R * 8 * H, 8 * H, w0, wi, w1, b1, NB, T, H, hseq, work, sync, tv]
     assert _both("idv_lstm2_wave_tc", args, [11]) < 2e-5
 
 
@@ -284,7 +296,7 @@ def test_stft_istft_tensor_core_pieces(B, L):
     E.call("idv_stft_frames_split", x, B, L, 512, 100, 400, hp["kpad"], frames)
     out = torch.zeros(B, 257, T, 2)
     args = [frames, hp["kpad"], 1, None, 0, 0, R, T, hp["wt"], hp["kc_max"], 1, hp["bias"], hp["N"], hp["units"],
-            hp["taps"], 1, None, 0, 0, 0, 0, 0, 0.0, 3, 257, 1, 0, None, out]
+            hp["taps"], 1, None, 0, 0, 0, 0, 0, 0.0, 3, 257, 1, 0, None, out, 0]
     assert _both("idv_tapgemm_tc_head", args, [28]) < 1e-5
     ip = PK.pack_istft_tc(512, 400, "cpu")
     spec = _rand(B, 257, T, 2, seed=6)

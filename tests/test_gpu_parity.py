@@ -18,18 +18,31 @@ STAGE_TOL = {"simt": 2e-5, "tc": 5e-5}   # intermediate stages: fp32 kernels / e
 
 
 def _sisnr_gap_db(ours, ref, anchor):
-    """|SI-SDR(ours, anchor) - SI-SDR(ref, anchor)| with the input signal as the common anchor, and the
-    SI-SDR of ours w.r.t. the reference output (utils/eval_metrics.py:L49-64 formula)."""
-    ours, ref, anchor = ours.detach().cpu(), torch.as_tensor(ref).cpu(), anchor.detach().cpu()
+    """north_star gate |delta SI-SNR| <= 0.01 dB: the SI-SDR (utils/eval_metrics.py:L49-64 formula) of our output and
+    of the reference's output are taken against the same target and must agree.  Two targets:
+      * a pseudo-clean target = reference output + seeded noise at 10 dB (the regime an enhancement system is scored
+        in; always asserted);
+      * the input signal, as the scripts' noisy/clean pairs would be - only where that measurement is conditioned:
+        with random-init weights the output can be orthogonal to the input (SI-SDR < -20 dB), where a 1e-5 relative
+        change of the waveform moves the projection, hence the dB value, by more than the gate.
+    Returns (max gap in dB, min SI-SDR of ours w.r.t. the reference output)."""
+    ours, ref, anchor = ours.detach().cpu().double(), torch.as_tensor(ref).cpu().double(), anchor.detach().cpu().double()
+    noise = torch.randn(ref.shape, generator=torch.Generator().manual_seed(99), dtype=torch.float64)
+    noise = noise * (ref.pow(2).mean(-1, keepdim=True) / 10).sqrt()
+    tgt = ref + noise
+    gap = (P.si_sdr_db(ours, tgt) - P.si_sdr_db(ref, tgt)).abs().max()
     n = min(ours.shape[-1], anchor.shape[-1])
-    gap = (P.si_sdr_db(ours[..., :n], anchor[..., :n]) - P.si_sdr_db(ref[..., :n], anchor[..., :n])).abs().max()
+    s_ref = P.si_sdr_db(ref[..., :n], anchor[..., :n])
+    ok = s_ref > -20.0
+    if bool(ok.any()):
+        gap = torch.maximum(gap, (P.si_sdr_db(ours[..., :n], anchor[..., :n]) - s_ref).abs()[ok].max())
     return float(gap), float(P.si_sdr_db(ours, ref).min())
 
 
 def test_extension_is_loaded_and_native():
     from idccrn_b200 import lib
     l = lib.load()
-    assert l.idv_abi_version() == 2
+    assert l.idv_abi_version() == 3
     import ctypes
     n = ctypes.c_int(0)
     assert l.idv_device_sm_count(ctypes.byref(n)) == 0 and n.value > 0
@@ -41,13 +54,16 @@ def test_extension_is_loaded_and_native():
     ("vae_l1_zero_e2e", 1, 1, "skip_prepare", "real_imag", 2, False),
     ("vae_l2_sig_mask_s2_e2e", 2, 2, "twophase", "mask", 3, False),
     ("vae_l1_sig_ri_e2e", 1, 1, "twophase", "real_imag", 4, False),
+    ("vae_nc_l1_zero_full", 1, 1, "skip_prepare", "real_imag", 9, True),       # non-causal net (model/net_config.py)
+    ("vae_nc_l2_sig_mask_s2_e2e", 2, 2, "twophase", "mask", 10, False),
 ])
 def test_vae_vs_reference_golden(gemm_mode, golden, tag, latent_num, S, dec_kind, recon, seed, full):
     g = golden(tag)
     B, L = int(g["B"]), int(g["L"])
-    enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cuda")
+    causal = bool(int(g.get("causal", 1)))
+    enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cuda", causal)
     dec.keep_decoder_outputs = full
-    x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cuda")
+    x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cuda", causal)
     out = C.run_vae(enc, dec, x, eps, dec_kind)
     torch.cuda.synchronize()
     errs = {k: C.rel_l2(out[k], g[k]) for k in ("stft_x", "miu", "log_sigma", "delta", "z_speech", "predict")}
@@ -66,10 +82,11 @@ def test_vae_vs_reference_golden(gemm_mode, golden, tag, latent_num, S, dec_kind
     assert wave < WAVE_TOL and gap < 0.01, (wave, gap)
 
 
-def test_dccrn_vs_reference_golden(gemm_mode, golden):
-    g = golden("dccrn_mask_e2e")
+@pytest.mark.parametrize("tag,causal", [("dccrn_mask_e2e", True), ("dccrn_nc_mask_e2e", False)])
+def test_dccrn_vs_reference_golden(gemm_mode, golden, tag, causal):
+    g = golden(tag)
     B, L, seed = int(g["B"]), int(g["L"]), int(g["seed"])
-    m = M.DCCRN_(C.NFFT, C.HOP, M.get_net_params(), True, "cuda", C.WIN, C.SKIPS, "mask", False, None, None)
+    m = M.DCCRN_(C.NFFT, C.HOP, M.get_net_params(causal), causal, "cuda", C.WIN, C.SKIPS, "mask", False, None, None)
     m.load_state_dict(fill_state_dict(m.state_dict(), seed), strict=True)
     m = m.cuda().eval()
     x = synth_waveform(B, L, seed=1234 + seed).cuda()
@@ -109,22 +126,24 @@ def test_primitives_vs_reference_golden(golden):
     assert all(v < STAGE_TOL["simt"] for v in errs.values()), errs
 
 
-@pytest.mark.parametrize("B,L,latent_num,S,dec_kind,recon", [
-    (3, 16000, 1, 1, "skip_prepare", "real_imag"),      # T = 161: crosses the 128-row tiles, odd batch
-    (2, 25700, 2, 1, "twophase", "mask"),               # T = 258, H = 768 recurrent config
-    (5, 1300, 1, 3, "twophase", "mask"),                # S = 3 sample replication, short ragged length
+@pytest.mark.parametrize("B,L,latent_num,S,dec_kind,recon,causal", [
+    (3, 16000, 1, 1, "skip_prepare", "real_imag", True),      # T = 161: crosses the 128-row tiles, odd batch
+    (2, 25700, 2, 1, "twophase", "mask", True),               # T = 258, H = 768 recurrent config
+    (5, 1300, 1, 3, "twophase", "mask", True),                # S = 3 sample replication, short ragged length
+    (3, 19100, 1, 1, "twophase", "mask", False),              # non-causal: T = 192 -> 186 latent frames, real skips
+    (2, 12700, 1, 2, "skip_prepare", "real_imag", False),     # non-causal, zero skips, 2 samples
 ])
-def test_vae_vs_live_oracle(gemm_mode, B, L, latent_num, S, dec_kind, recon):
+def test_vae_vs_live_oracle(gemm_mode, B, L, latent_num, S, dec_kind, recon, causal):
     seed = 11
-    enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cuda")
-    x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cuda")
+    enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cuda", causal)
+    x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cuda", causal)
     out = C.run_vae(enc, dec, x, eps, dec_kind)
     esd = {k: v.cpu() for k, v in enc.state_dict().items()}
     dsd = {k: v.cpu() for k, v in dec.state_dict().items()}
     with torch.no_grad():
-        st = P.vae_encoder_forward(esd, x.cpu(), C.ZDIM, latent_num, S, [e.cpu() for e in eps])
+        st = P.vae_encoder_forward(esd, x.cpu(), C.ZDIM, latent_num, S, [e.cpu() for e in eps], causal=causal)
         dd = P.vae_decoder_forward(dsd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], S, recon,
-                                   "zero" if dec_kind == "skip_prepare" else "sig")
+                                   "zero" if dec_kind == "skip_prepare" else "sig", causal=causal)
     errs = {"stft_x": C.rel_l2(out["stft_x"], st["stft_x"]), "enc5": C.rel_l2(out["skiper"][5], st["skiper"][5]),
             "miu": C.rel_l2(out["miu"], st["miu_speech"]), "z": C.rel_l2(out["z_speech"], st["z_speech"]),
             "predict": C.rel_l2(out["predict"], torch.view_as_real(dd["predict"]))}
@@ -133,6 +152,22 @@ def test_vae_vs_live_oracle(gemm_mode, B, L, latent_num, S, dec_kind, recon):
     print(gemm_mode, "live", (B, L, latent_num, S), "wave %.2e gap %.4f dB sdr %.1f dB" % (wave, gap, sdr), errs)
     assert all(v < STAGE_TOL[gemm_mode] for v in errs.values()), errs
     assert wave < WAVE_TOL and gap < 0.01
+
+
+def test_noncausal_primitives_vs_reference_golden(gemm_mode, golden):
+    g = golden("primitives_noncausal")
+    seed = 8
+    enc = M.Encoder(3, 5, (5, 2), (2, 1), (5, 9, 1), padding=(2, 0), causal=False)
+    enc.load_state_dict(fill_state_dict(enc.state_dict(), seed))
+    dec = M.Decoder(4, 3, (5, 2), (2, 1), (3, 9, 1), padding=(2, 0), causal=False)
+    dec.load_state_dict(fill_state_dict(dec.state_dict(), seed))
+    enc, dec = enc.cuda(), dec.cuda()
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    with torch.no_grad():
+        eo, do = enc(t("enc_in"), False), dec(t("dec_in"), False)
+    assert tuple(eo.shape) == g["enc_out"].shape and tuple(do.shape) == g["dec_out"].shape
+    errs = {"enc": C.rel_l2(eo, g["enc_out"]), "dec": C.rel_l2(do, g["dec_out"])}
+    assert all(v < STAGE_TOL["simt"] for v in errs.values()), errs
 
 
 def test_stft_istft_properties_full_size():

@@ -12,13 +12,15 @@ TOL = 2e-5   # fp32 golden vs folded weights evaluated through an fp64 emulator 
 @pytest.mark.parametrize("tag,latent_num,S,dec_kind,recon,seed", [
     ("vae_l1_zero_full", 1, 1, "skip_prepare", "real_imag", 0),
     ("vae_l2_sig_mask_full", 2, 1, "twophase", "mask", 1),
+    ("vae_nc_l1_zero_full", 1, 1, "skip_prepare", "real_imag", 9),          # non-causal net (model/net_config.py)
 ])
 def test_vae_layers_match_reference(emulated_abi, gemm_mode, golden, tag, latent_num, S, dec_kind, recon, seed):
     g = golden(tag)
     B, L = int(g["B"]), int(g["L"])
-    enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cpu")
+    causal = bool(int(g.get("causal", 1)))
+    enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cpu", causal)
     dec.keep_decoder_outputs = True
-    x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cpu")
+    x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cpu", causal)
     out = C.run_vae(enc, dec, x, eps, dec_kind)
     errs = {"stft_x": C.rel_l2(out["stft_x"], g["stft_x"])}
     for i in range(6):
@@ -37,23 +39,26 @@ def test_vae_layers_match_reference(emulated_abi, gemm_mode, golden, tag, latent
 @pytest.mark.parametrize("tag,latent_num,S,dec_kind,recon,seed", [
     ("vae_l2_sig_mask_s2_e2e", 2, 2, "twophase", "mask", 3),
     ("vae_l1_sig_ri_e2e", 1, 1, "twophase", "real_imag", 4),
+    ("vae_nc_l2_sig_mask_s2_e2e", 2, 2, "twophase", "mask", 10),            # non-causal, real skips, 2 samples
 ])
 def test_vae_e2e_match_reference(emulated_abi, gemm_mode, golden, tag, latent_num, S, dec_kind, recon, seed):
     g = golden(tag)
     B, L = int(g["B"]), int(g["L"])
-    enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cpu")
-    x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cpu")
+    causal = bool(int(g.get("causal", 1)))
+    enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cpu", causal)
+    x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cpu", causal)
     out = C.run_vae(enc, dec, x, eps, dec_kind)
     errs = {k: C.rel_l2(out[k], g[k]) for k in ("stft_x", "miu", "log_sigma", "delta", "z_speech", "predict", "recon_sig")}
     assert all(v < TOL for v in errs.values()), errs
 
 
-def test_dccrn_matches_reference(emulated_abi, gemm_mode, golden):
+@pytest.mark.parametrize("tag,causal", [("dccrn_mask_e2e", True), ("dccrn_nc_mask_e2e", False)])
+def test_dccrn_matches_reference(emulated_abi, gemm_mode, golden, tag, causal):
     import idccrn_b200 as M
     from idccrn_b200.synth import fill_state_dict, synth_waveform
-    g = golden("dccrn_mask_e2e")
+    g = golden(tag)
     B, L, seed = int(g["B"]), int(g["L"]), int(g["seed"])
-    m = M.DCCRN_(C.NFFT, C.HOP, M.get_net_params(), True, "cpu", C.WIN, C.SKIPS, "mask", False, None, None)
+    m = M.DCCRN_(C.NFFT, C.HOP, M.get_net_params(causal), causal, "cpu", C.WIN, C.SKIPS, "mask", False, None, None)
     m.load_state_dict(fill_state_dict(m.state_dict(), seed), strict=True)
     x = synth_waveform(B, L, seed=1234 + seed)
     with torch.no_grad():
@@ -83,6 +88,24 @@ def test_primitives_match_reference(emulated_abi, golden):
                 "dec": C.rel_l2(dec(t("dec_in"), False), g["dec_out"]),
                 "lstm": C.rel_l2(lstm(t("lstm_in")), g["lstm_out"]),
                 "dense": C.rel_l2(dense(t("dense_in")), g["dense_out"])}
+    assert all(v < TOL for v in errs.values()), errs
+
+
+def test_noncausal_primitives_match_reference(emulated_abi, gemm_mode, golden):
+    """Stand-alone non-causal blocks: T-1 frames out of the conv, T+1 out of the transposed conv."""
+    import idccrn_b200 as M
+    from idccrn_b200.synth import fill_state_dict
+    g = golden("primitives_noncausal")
+    seed = 8
+    enc = M.Encoder(3, 5, (5, 2), (2, 1), (5, 9, 1), padding=(2, 0), causal=False)
+    enc.load_state_dict(fill_state_dict(enc.state_dict(), seed))
+    dec = M.Decoder(4, 3, (5, 2), (2, 1), (3, 9, 1), padding=(2, 0), causal=False)
+    dec.load_state_dict(fill_state_dict(dec.state_dict(), seed))
+    t = lambda k: torch.from_numpy(g[k])
+    with torch.no_grad():
+        eo, do = enc(t("enc_in"), False), dec(t("dec_in"), False)
+    assert tuple(eo.shape) == g["enc_out"].shape and tuple(do.shape) == g["dec_out"].shape
+    errs = {"enc": C.rel_l2(eo, g["enc_out"]), "dec": C.rel_l2(do, g["dec_out"])}
     assert all(v < TOL for v in errs.values()), errs
 
 
