@@ -13,7 +13,8 @@ constexpr int E0_ROWS = 128;
 __global__ void __launch_bounds__(256, 2) enc0_kernel(const float* __restrict__ stft, int NB, int Fin, int T,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
                                                    int N, float slope, void* __restrict__ outv, int Fout,
-                                                   int out_split, int causal, int t_valid) {
+                                                   int out_split, int causal, int t_valid,
+                                                   const float* __restrict__ prev, int keep_pad) {
   // weights [20][N] + bias [N]; inside every 64-channel slab the columns are stored as
   // [cg*4 + j | 32 + cg*4 + j] so that the two float4 of channel group cg are bank-conflict free
   extern __shared__ __align__(16) float ws[];
@@ -50,6 +51,8 @@ __global__ void __launch_bounds__(256, 2) enc0_kernel(const float* __restrict__ 
         const int fi = 2 * fo + kf - 2, ti = causal ? t - 1 + kt : t + kt;   // non-causal: x[t], x[t+1]
         if (t >= 0 && fi >= 0 && fi < Fin && ti >= 0 && ti < T)
           v = __ldg(reinterpret_cast<const float2*>(stft + ((int64_t)(b * Fin + fi) * T + ti) * 2));
+        else if (prev && t >= 0 && fi >= 0 && fi < Fin && ti == -1)       // streaming: x[-1] = last frame of the
+          v = __ldg(reinterpret_cast<const float2*>(prev + (int64_t)(b * Fin + fi) * 2));   // previous step
       }
       pre[j] = v;
     }
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(256, 2) enc0_kernel(const float* __restrict__ 
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if (!ok[i]) continue;
+      if (!ok[i] || (keep_pad && ((r0 + i) % Tp) == 0)) continue;      // keep_pad: pad rows carry state
       const long long oidx = ((long long)fo * R + r0 + i) * N + n0 + cg * 8;
       float v[8];
 #pragma unroll
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(256) dec5_head_kernel(const void* __restrict__
 
 extern "C" int idv_enc0_fwd(const float* stft, int B, int Fin, int T, const float* w, const float* bias,
                             int Cout, float prelu_slope, void* out, int out_split, int causal, int t_valid,
-                            void* stream) {
+                            const float* prev, int keep_pad, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(stft && w && bias && out, "idv_enc0_fwd: null pointer");
   IDV_CHECK_ARG(B > 0 && Fin >= 5 && T > 0, "idv_enc0_fwd: bad shape B=%d Fin=%d T=%d", B, Fin, T);
@@ -239,7 +242,7 @@ extern "C" int idv_enc0_fwd(const float* stft, int B, int Fin, int T, const floa
   const int n_tiles = cdiv(R, E0_ROWS);
   dim3 grid(n_tiles < 16 ? n_tiles : cdiv(n_tiles, 8), Fout);      // ~8 row tiles per block
   enc0_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(stft, B, Fin, T, w, bias, N, prelu_slope, out, Fout,
-                                                         out_split, causal, t_valid);
+                                                         out_split, causal, t_valid, prev, keep_pad);
   IDV_LAUNCH_CHECK("enc0_kernel");
   return IDV_OK;
 }

@@ -179,9 +179,11 @@ __global__ void __launch_bounds__(256) lstm_combine_kernel(const float* __restri
 __global__ void __launch_bounds__(256) reparam_kernel(const float* __restrict__ latent, int NB, int T, int Htot,
                                                       int ch0, int zdim, int S, const float* __restrict__ eps_r,
                                                       const float* __restrict__ eps_i, uint64_t seed,
-                                                      uint64_t offset, float* __restrict__ z) {
+                                                      uint64_t offset, const unsigned long long* __restrict__ offset_dev,
+                                                      float* __restrict__ z) {
   const int64_t n = (int64_t)NB * S * T * zdim;
   const float e = 1e-6f;
+  if (offset_dev) offset += *offset_dev;               // device-side draw counter (CUDA-graph replays)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(i % zdim);
     int64_t rem = i / zdim;
@@ -323,8 +325,8 @@ extern "C" int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, flo
 }
 
 extern "C" int idv_reparam_fwd(const float* latent, int NB, int T, int Htot, int ch0, int zdim, int S,
-                               const float* eps_r, const float* eps_i, uint64_t seed, uint64_t offset, float* z,
-                               void* stream) {
+                               const float* eps_r, const float* eps_i, uint64_t seed, uint64_t offset,
+                               const uint64_t* offset_dev, float* z, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(latent && z && NB > 0 && T > 0 && S > 0 && zdim > 0, "idv_reparam_fwd: bad argument");
   IDV_CHECK_ARG(ch0 >= 0 && ch0 + 3 * zdim <= Htot, "idv_reparam_fwd: latent slice out of range");
@@ -332,7 +334,8 @@ extern "C" int idv_reparam_fwd(const float* latent, int NB, int T, int Htot, int
   const int64_t n = (int64_t)NB * S * T * zdim;
   const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
   reparam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, seed,
-                                                           offset, z);
+                                                           offset, reinterpret_cast<const unsigned long long*>(offset_dev),
+                                                           z);
   IDV_LAUNCH_CHECK("reparam_kernel");
   return IDV_OK;
 }

@@ -17,7 +17,7 @@ struct TapGemmParams {
   const float* a[2];
   int a_ld[2];
   int64_t a_plane[2];
-  int R, Tp, t_valid;
+  int R, Tp, t_valid, keep_pad;
   const float* w;
   const float* bias;
   int N;
@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(TG_THREADS, 2) tapgemm_f32_kernel(const TapGem
       }
       if (p.Tp > 0) {                              // causal pad row, or frame beyond the valid length
         const int tt = r % p.Tp;
+        if (tt == 0 && p.keep_pad) continue;       // streaming: the pad row carries x[t-1] of the last step
         if (tt == 0 || (p.t_valid > 0 && tt > p.t_valid)) v = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       *reinterpret_cast<float4*>(outp + (int64_t)r * p.out_ld + n) = v;
@@ -198,7 +199,7 @@ extern "C" int idv_tapgemm_f32(const float* a0, int a0_ld, int64_t a0_plane, con
   p.a[0] = a0; p.a[1] = a1 ? a1 : a0;
   p.a_ld[0] = a0_ld; p.a_ld[1] = a1 ? a1_ld : a0_ld;
   p.a_plane[0] = a0_plane; p.a_plane[1] = a1 ? a1_plane : a0_plane;
-  p.R = R; p.Tp = Tp; p.t_valid = t_valid; p.w = w; p.bias = bias; p.N = N; p.units = units; p.taps = taps;
+  p.R = R; p.Tp = Tp < 0 ? -Tp : Tp; p.keep_pad = Tp < 0; p.t_valid = t_valid; p.w = w; p.bias = bias; p.N = N; p.units = units; p.taps = taps;
   p.out = out; p.out_ld = out_ld; p.out_plane = out_plane; p.apply_prelu = apply_prelu; p.slope = prelu_slope;
   cudaStream_t st = (cudaStream_t)stream;
   if (N % 128 == 0) {

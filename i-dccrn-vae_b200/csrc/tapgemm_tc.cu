@@ -25,7 +25,7 @@ constexpr int NUM_THREADS = 192;
 constexpr int EPI_WARP0 = 2;
 
 struct Params {
-  int R, Tp, N, t_valid;
+  int R, Tp, N, t_valid, keep_pad;
   int n_units, n_row_tiles, n_col_tiles;
   const idv_unit_t* units;
   const idv_tap_t* taps;
@@ -294,7 +294,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           if (p.apply_prelu) x = prelu_f(x, p.slope);
           f[j] = pad_row ? 0.f : x;
         }
-        if (row_ok) {
+        if (row_ok && !(p.keep_pad && tt_row == 0)) {     // keep_pad: the pad row carries x[t-1] of the last step
           if (p.out_split) {
             __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + c0;
             __nv_bfloat16* ol = oh + p.out_hl;
@@ -507,7 +507,7 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
   rc = encode_map_4d(&mW, wt, kc_max, N, n_slots, (uint64_t)n_slots * N * kc_max, BK, BN);
   if (rc) return rc;
   Params p;
-  p.R = R; p.Tp = Tp; p.N = N; p.n_units = n_units; p.t_valid = t_valid;
+  p.R = R; p.Tp = Tp < 0 ? -Tp : Tp; p.keep_pad = Tp < 0; p.N = N; p.n_units = n_units; p.t_valid = t_valid;
   p.n_row_tiles = cdiv(R, BM); p.n_col_tiles = N / BN;
   p.units = units; p.taps = taps; p.bias = bias; p.out = out; p.out_ld = out_ld;
   p.out_plane = out_plane; p.out_hl = out_hl; p.out_split = out_split; p.apply_prelu = apply_prelu; p.slope = prelu_slope;

@@ -28,13 +28,13 @@ SIGNATURES = {
     "idv_stft_frames_split": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "idv_spec_rows_split": [vp, i32, i32, i32, i32, vp, vp],
     "idv_ola_fwd": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp],
-    "idv_enc0_fwd": [vp, i32, i32, i32, vp, vp, i32, f32, vp, i32, i32, i32, vp],
+    "idv_enc0_fwd": [vp, i32, i32, i32, vp, vp, i32, f32, vp, i32, i32, i32, vp, i32, vp],
     "idv_dec5_head_fwd": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, i32, i32, vp],
     "idv_lstm_recurrent_fwd": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, i32, vp],
     "idv_lstm_recurrent_tc": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp],
     "idv_lstm2_wave_tc": [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],
     "idv_lstm_combine_fwd": [vp, i32, i32, i32, vp, i32, vp],
-    "idv_reparam_fwd": [vp, i32, i32, i32, i32, i32, i32, vp, vp, u64, u64, vp, vp],
+    "idv_reparam_fwd": [vp, i32, i32, i32, i32, i32, i32, vp, vp, u64, u64, vp, vp, vp],
     "idv_planes_to_user": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "idv_user_to_planes": [vp, i32, i32, i32, i32, vp, i32, i32, vp],
     "idv_z_to_planes": [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp],
@@ -44,6 +44,12 @@ SIGNATURES = {
     "idv_cbn_apply_planes": [vp, i32, i32, i32, i32, i32, vp, i32, f32, i32, vp],
     "idv_cbn_stats_user": [vp, i64, i32, i64, vp, vp],
     "idv_head_user": [vp, i64, i64, f32, i32, vp, i32, vp],
+    "idv_stream_frames_split": [vp, vp, i32, i32, i64, i32, i32, i32, vp, vp],
+    "idv_stream_hist_shift": [vp, vp, i32, i32, i32, i32, vp],
+    "idv_lstm_cell_step": [vp, i64, i64, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp],
+    "idv_carry_rows": [vp, i32, vp, vp],
+    "idv_stream_last_frame": [vp, i32, i32, i32, vp, vp],
+    "idv_stream_ola": [vp, i32, vp, vp, i32, i32, i64, i32, i32, vp, vp],
 }
 EXPORTS = ["idv_abi_version", "idv_last_error", "idv_lstm_tc_config", "idv_lstm2_wave_config", "idv_set_option"] + \
     list(SIGNATURES)
@@ -78,6 +84,13 @@ def load():
 
 # kernels launched by each entry point (memset nodes not counted)
 KERNELS_PER_CALL = {"idv_istft_fwd": 2}
+
+
+class CarryEntry(ctypes.Structure):
+    """idv_carry_t (include/idv.h)."""
+    _fields_ = [("base", ctypes.c_uint64), ("n_planes", ctypes.c_int64), ("plane_bytes", ctypes.c_int64),
+                ("row_bytes", ctypes.c_int32), ("NB", ctypes.c_int32), ("Tp", ctypes.c_int32),
+                ("src_row", ctypes.c_int32)]
 LAUNCHES = [0]          # running count of kernel launches issued through call()
 _PROFILE_HOOK = None
 

@@ -148,12 +148,13 @@ class _ComplexConvBase(nn.Module):
                                         pad_t=self._time_geometry()[0])
         return items[key]
 
-    def run_packed(self, pk, xp):
-        """One tap-GEMM launch of a pack built by pack.pack_conv for this layer's geometry."""
+    def run_packed(self, pk, xp, out=None):
+        """One tap-GEMM launch of a pack built by pack.pack_conv for this layer's geometry (out: static
+        streaming-state tensor, see ops.tapgemm)."""
         tv = self.frames_out(xp.Tv)
         if not 0 < tv <= xp.T:
             raise RuntimeError("conv output has %d frames, the row layout holds %d" % (tv, xp.T))
-        out = ops.tapgemm(pk, xp, None, xp.NB, xp.T, t_valid=tv)
+        out = ops.tapgemm(pk, xp, None, xp.NB, xp.T, t_valid=tv, out=out)
         return Planes(out, xp.NB, pk.c_out, pk.f_out, xp.T, split=xp.split, Tv=tv)
 
     def forward_planes(self, xp, bn=None, slope=None):
@@ -200,7 +201,7 @@ class _ComplexConvTransposeBase(nn.Module):
     def frames_out(self, frames_in):
         return frames_in + _pair(self.tconv_re.kernel_size)[1] - 1 - (1 if self.causal else 0)
 
-    def run_packed(self, pk, pp, skip):
+    def run_packed(self, pk, pp, skip, out=None):
         """One tap-GEMM launch of a pack built by pack.pack_conv_transpose for this layer."""
         tv = self.frames_out(pp.Tv)
         if not 0 < tv <= pp.T:
@@ -208,7 +209,7 @@ class _ComplexConvTransposeBase(nn.Module):
         if skip is not None and (skip.T != pp.T or skip.NB != pp.NB or skip.Tv != pp.Tv):
             raise RuntimeError("skip tensor has %d/%d frames x %d utterances, the decoder activation %d/%d x %d"
                                % (skip.Tv, skip.T, skip.NB, pp.Tv, pp.T, pp.NB))
-        out = ops.tapgemm(pk, pp, skip, pp.NB, pp.T, t_valid=tv)
+        out = ops.tapgemm(pk, pp, skip, pp.NB, pp.T, t_valid=tv, out=out)
         return Planes(out, pp.NB, pk.c_out, pk.f_out, pp.T, split=pp.split, Tv=tv)
 
     def _packed(self, f_in, c_p, c_skip, device, bn=None, slope=None):
@@ -395,9 +396,9 @@ class ComplexDense(nn.Module):
                                          self.linear_imag.bias, c_out, f_out, device)
         return items[key]
 
-    def forward_planes(self, zp, c_out, f_out):
+    def forward_planes(self, zp, c_out, f_out, out=None):
         pk = self._packed(c_out, f_out, zp.data.device)
-        out = ops.tapgemm(pk, zp, None, zp.NB, zp.T, t_valid=zp.Tv)
+        out = ops.tapgemm(pk, zp, None, zp.NB, zp.T, t_valid=zp.Tv, out=out)
         return Planes(out, zp.NB, c_out, f_out, zp.T, split=zp.split, Tv=zp.Tv)
 
     def forward(self, x):
@@ -431,8 +432,9 @@ class Encoder(nn.Module):
     def _slope(self):
         return float(self.prelu.weight.detach().reshape(-1)[0])
 
-    def forward_from_stft(self, stft_x, train=False):
-        """First layer (in_channel == 1): reads the user-layout STFT (B, F, T, 2) directly."""
+    def forward_from_stft(self, stft_x, train=False, out=None, prev=None):
+        """First layer (in_channel == 1): reads the user-layout STFT (B, F, T, 2) directly.  out / prev: streaming
+        state (ops.enc0)."""
         items = self._cache.check(self)
         key = ("enc0", bool(train), str(stft_x.device))
         if key not in items:
@@ -444,10 +446,11 @@ class Encoder(nn.Module):
         w, b, cout, slope = items[key]
         if not self.conv.causal and self.conv._time_geometry() != (0, -1):
             raise NotImplementedError("first non-causal encoder layer: kernel (5,2) with time padding 0 expected")
-        out = ops.enc0(stft_x, w, b, cout, slope, out_split=ops.use_split(), causal=self.conv.causal)
+        out = ops.enc0(stft_x, w, b, cout, slope, out_split=ops.use_split(), causal=self.conv.causal, out=out,
+                       prev=prev)
         return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
-    def forward_planes(self, xp, train=False):
+    def forward_planes(self, xp, train=False, out=None):
         items = self._cache.check(self)          # invalidates the child's fold when bn / prelu change
         key = ("raw" if train else "fold", xp.F, str(xp.data.device))
         if key not in items:
@@ -456,7 +459,7 @@ class Encoder(nn.Module):
             items[key] = pack.pack_conv(c.conv_re.weight, c.conv_re.bias, c.conv_im.weight, c.conv_im.bias,
                                         None if train else self.bn.fold_inputs(), None if train else self._slope(),
                                         xp.F, sf, pf, xp.data.device, pad_t=c._time_geometry()[0])
-        out = self.conv.run_packed(items[key], xp)
+        out = self.conv.run_packed(items[key], xp, out)
         return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
     def forward(self, x, train):
@@ -481,7 +484,7 @@ class Decoder(nn.Module):
     def _fold(self):
         return (self.bn.fold_inputs(), self._slope()) if self.if_bn else (None, None)
 
-    def forward_planes(self, pp, skip=None, train=False):
+    def forward_planes(self, pp, skip=None, train=False, out=None):
         train = bool(train) and self.if_bn
         items = self._cache.check(self)
         c_skip = skip.C if skip is not None else 0
@@ -496,7 +499,7 @@ class Decoder(nn.Module):
             items[key] = pack.pack_conv_transpose(t.tconv_re.weight, t.tconv_re.bias, t.tconv_im.weight,
                                                   t.tconv_im.bias, bn, slope, pp.F, pp.C, c_skip,
                                                   pp.data.device, sf, pf)
-        out = self.transconv.run_packed(items[key], pp, skip)
+        out = self.transconv.run_packed(items[key], pp, skip, out)
         return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
     def forward_head(self, pp, skip, mask, stft_x, predict, out_bmul, out_boff, train=False):

@@ -127,44 +127,53 @@ def istft_tc(spec_ri, hp, n_fft, hop, win):
     return out
 
 
-def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None, t_valid=0):
+def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None, t_valid=0, out=None):
     """Run one packed tap-GEMM.  a0/a1: Planes (a1 may be None).  Returns the flat output tensor
     [pack.out_planes][R][pack.out_ld] (fp32, or bf16 [2][...] when out_split).  Split inputs run on the
-    tcgen05 kernel, fp32 inputs on the SIMT kernel.  t_valid: valid frames of the OUTPUT (0 = all T)."""
+    tcgen05 kernel, fp32 inputs on the SIMT kernel.  t_valid: valid frames of the OUTPUT (0 = all T).
+    out: write into this (static) tensor and leave its pad rows untouched (streaming state, Tp < 0 in the ABI)."""
     R = NB * (T + 1)
+    tp = ((T + 1) if zero_pad_rows else 0) if out is None else -(T + 1)
     if a0.split:
         if a1 is not None and not a1.split:
             raise RuntimeError("tap-GEMM sources must share one activation format")
         out_split = True if out_split is None else out_split
         tc = pack.tc()
         n_out = pack.out_planes * R * pack.out_ld
-        out = _empty_act(n_out, a0.data.device, out_split)
+        if out is None:
+            out = _empty_act(n_out, a0.data.device, out_split)
+        elif out.numel() != (2 * n_out if out_split else n_out):
+            raise RuntimeError("static tap-GEMM output has %d elements, expected %d" % (out.numel(), n_out))
         lib.call("idv_tapgemm_tc", a0.data, a0.Cp, a0.F, a1.data if a1 is not None else None,
                  a1.Cp if a1 is not None else 0, a1.F if a1 is not None else 0, R,
-                 (T + 1) if zero_pad_rows else 0, tc["wt"], tc["kc_max"], tc["n_slots"], pack.bias, pack.N,
+                 tp, tc["wt"], tc["kc_max"], tc["n_slots"], pack.bias, pack.N,
                  tc["units"], tc["taps"], pack.n_units, out, pack.out_ld, R * pack.out_ld, n_out,
                  1 if out_split else 0, 1 if pack.prelu else 0, pack.slope, int(t_valid))
         return out
     if out_split:
         raise RuntimeError("the fp32 SIMT tap-GEMM writes fp32 planes only")
-    out = _empty(pack.out_planes * R * pack.out_ld, a0.data.device)
+    if out is None:
+        out = _empty(pack.out_planes * R * pack.out_ld, a0.data.device)
     lib.call("idv_tapgemm_f32",
              a0.data, a0.Cp, a0.plane_stride,
              a1.data if a1 is not None else None, a1.Cp if a1 is not None else 0,
              a1.plane_stride if a1 is not None else 0,
-             R, (T + 1) if zero_pad_rows else 0,
+             R, tp,
              pack.w, pack.bias, pack.N, pack.units, pack.taps, pack.n_units,
              out, pack.out_ld, R * pack.out_ld, 1 if pack.prelu else 0, pack.slope, int(t_valid))
     return out
 
 
-def enc0(stft_x, w, bias, cout, slope, out_split=False, causal=True):
+def enc0(stft_x, w, bias, cout, slope, out_split=False, causal=True, out=None, prev=None):
+    """out / prev: streaming (static output planes whose pad rows are kept, previous STFT frame (B, Fin, 2))."""
     B, Fin, T, _ = stft_x.shape
     Fout = (Fin + 4 - 5) // 2 + 1
     Tv = T if causal else T - 1
-    out = _empty_act(Fout * B * (T + 1) * 2 * cout, stft_x.device, out_split)
+    keep = out is not None
+    if out is None:
+        out = _empty_act(Fout * B * (T + 1) * 2 * cout, stft_x.device, out_split)
     lib.call("idv_enc0_fwd", stft_x, B, Fin, T, w, bias, cout, slope, out, 1 if out_split else 0,
-             1 if causal else 0, Tv)
+             1 if causal else 0, Tv, prev, 1 if keep else 0)
     return Planes(out, B, cout, Fout, T, split=out_split, Tv=Tv)
 
 
@@ -242,15 +251,15 @@ def lstm_combine(hseq, NB, T, H, t_valid=0):
     return latent
 
 
-def reparam(latent, ch0, zdim, S, eps_r, eps_i, seed, offset):
+def reparam(latent, ch0, zdim, S, eps_r, eps_i, seed, offset, offset_dev=None, out=None):
     NB, T, Htot, _ = latent.shape
-    z = torch.empty((NB * S, T, zdim, 2), dtype=torch.float32, device=latent.device)
+    z = out if out is not None else torch.empty((NB * S, T, zdim, 2), dtype=torch.float32, device=latent.device)
     if eps_r is not None:
         eps_r = lib.require_f32_cuda(eps_r, "eps_r")
         eps_i = lib.require_f32_cuda(eps_i, "eps_i")
         if tuple(eps_r.shape) != (NB, S, T, zdim) or tuple(eps_i.shape) != (NB, S, T, zdim):
             raise RuntimeError("eps must have shape (B, S, T, zdim) = %s" % ((NB, S, T, zdim),))
-    lib.call("idv_reparam_fwd", latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, int(seed), int(offset), z)
+    lib.call("idv_reparam_fwd", latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, int(seed), int(offset), offset_dev, z)
     return z
 
 

@@ -326,6 +326,37 @@ def pack_lstm_inproj1(lstm_re, lstm_im, hidden, device, layer=1):
     return TapGemmPack(W.reshape(-1), bias, units, taps, N, 4, N, False, 0.0, device)
 
 
+def pack_lstm_step(lstm_re, lstm_im, hidden, layer, device):
+    """One streaming time step of layer `layer` as a tap-GEMM on the carried h planes [4 streams][NB][H]
+    (frame streaming: nn.LSTM's carried state): unit s = (module m, part p) computes h_s W_hh^m^T; for layer >= 1
+    the same launch adds the input projection x W_ih^m^T of the layer below's new h (source 0) and both biases.
+    Output G [4][NB][4H] fp32."""
+    H = hidden
+    N = 4 * H
+    mats, bias = [], torch.zeros(2 * N, dtype=torch.float64)
+    for m, mod in enumerate((lstm_re, lstm_im)):
+        if layer > 0:
+            mats.append(_cpu(mod["weight_ih_l%d" % layer]).double().t())
+            bias[m * N:(m + 1) * N] = _cpu(mod["bias_ih_l%d" % layer]).double() + _cpu(mod["bias_hh_l%d" % layer]).double()
+        mats.append(_cpu(mod["weight_hh_l%d" % layer]).double().t())
+    W = torch.stack(mats)                                   # (2 or 4, H, 4H), K-major rows
+    per = 2 if layer > 0 else 1
+    units, taps = [], []
+    for m in range(2):
+        for p in range(2):
+            s = m * 2 + p
+            begin = len(taps)
+            if layer > 0:
+                taps.append([0, s, 0, 0, H, (m * per) * H * N])          # input projection: h of the layer below
+                taps.append([1, s, 0, 0, H, (m * per + 1) * H * N])      # recurrent: this layer's carried h
+            else:
+                taps.append([0, s, 0, 0, H, m * H * N])
+            units.append([begin, len(taps) - begin, s, 0, m * N if layer > 0 else 0, 0])
+    if layer == 0:
+        bias = torch.zeros(N, dtype=torch.float64)          # layer-0 biases are inside the input projection
+    return TapGemmPack(W.reshape(-1), bias, units, taps, N, 4, N, False, 0.0, device)
+
+
 def pack_lstm_whh(lstm_re, lstm_im, layer, device):
     return torch.stack((_cpu(lstm_re["weight_hh_l%d" % layer]), _cpu(lstm_im["weight_hh_l%d" % layer]))) \
         .to(torch.float32).contiguous().to(device)

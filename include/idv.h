@@ -57,7 +57,9 @@ int idv_device_sm_count(int* out);
  *   out[u.out_f][r][u.out_ch_off + n] =
  *       act( bias[u.bias_off + n] + sum_{tap in u} sum_{c < tap.kc}
  *            A_{tap.src}[tap.f_in][r - tap.dt][tap.ch_off + c] * W[tap.w_off + c*N + n] )
- * rows outside [0, R) read as zero; if Tp > 0, output rows with r % Tp == 0 are written as 0.
+ * rows outside [0, R) read as zero; if Tp > 0, output rows with r % Tp == 0 are written as 0; if Tp < 0 the
+ * row period is -Tp and the pad rows are NOT written (streaming: they carry x[t-1] of the previous step, see
+ * idv_carry_rows).
  * act = PReLU(slope) if apply_prelu else identity.  A complex (transposed) convolution, the LSTM
  * input projection and the complex dense layer are all instances (see pack.py).            */
 typedef struct {
@@ -135,10 +137,12 @@ int idv_ola_fwd(const float* frames, int frame_ld, const float* wsq, int B, int 
  * reading the user-layout STFT (B,257,T,2) and writing planes [Fout][R][2*Cout].
  * causal != 0: time pad 1 / last column dropped (time tap kt reads x[t-1+kt], T valid frames);
  * causal == 0: no time pad (tap kt reads x[t+kt]; pass t_valid = T-1).
- * w: [10 taps (kf*2+kt)][2 (re,im in)][2*Cout] with CBN folded, bias: [2*Cout].                 */
+ * w: [10 taps (kf*2+kt)][2 (re,im in)][2*Cout] with CBN folded, bias: [2*Cout].
+ * Streaming: prev (B, Fin, 2) or NULL = the STFT frame before frame 0 (x[-1]); keep_pad != 0 leaves the pad rows
+ * of `out` untouched (they carry this layer's previous output frame).                                 */
 int idv_enc0_fwd(const float* stft, int B, int Fin, int T, const float* w, const float* bias,
                  int Cout, float prelu_slope, void* out, int out_split, int causal, int t_valid,
-                 void* stream);
+                 const float* prev, int keep_pad, void* stream);
 
 /* ---- last decoder layer (Cout = 1) + reconstruction head ---------------------------------------
  * Decoder 5: causal ComplexConvTranspose2d(Cin -> 1) + CBN(eval) + PReLU (+ mask head,
@@ -188,10 +192,11 @@ int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_l
 int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, float* latent, int t_valid, void* stream);
 /* reparameterization (model/pvae_module.py:L2177-2231).  latent: (NB,T,Htot,2); the (mu, log
  * sigma, delta) triplet starts at channel ch0 (zdim each).  eps_r/eps_i: (NB,S,T,zdim) or NULL ->
- * Philox4x32-10 N(0,1) from (seed, offset).  z: (NB*S, T, zdim, 2).                             */
+ * Philox4x32-10 N(0,1) from (seed, offset + *offset_dev); offset_dev (device, may be NULL) lets a captured CUDA
+ * graph draw fresh noise on every replay.  z: (NB*S, T, zdim, 2).                                */
 int idv_reparam_fwd(const float* latent, int NB, int T, int Htot, int ch0, int zdim, int S,
                     const float* eps_r, const float* eps_i, uint64_t seed, uint64_t offset,
-                    float* z, void* stream);
+                    const uint64_t* offset_dev, float* z, void* stream);
 
 /* ---- layout conversion at the module boundary --------------------------------------------------*/
 /* planes [F][R][Cp] (fp32, or split bf16 when in_split) -> user (NB, C, F, T, 2) */
@@ -230,6 +235,40 @@ int idv_cbn_apply_planes(void* planes, int split, int NB, int C, int F, int T, c
 int idv_cbn_stats_user(const float* x, int64_t outer, int C, int64_t inner, double* acc, void* stream);
 int idv_head_user(float* y, int64_t n_per_utt, int64_t n_utt, float prelu_slope, int mask, const float* stft_x,
                   int s_rep, void* stream);
+
+/* ---- frame streaming (causal network; carried state instead of whole utterances) ------------------------------
+ * Hop-synchronous streams: a step consumes hop*k new samples per stream and runs the same tap-GEMMs on k-frame
+ * planes (Tp = -(k+1): pad rows kept) whose pad rows hold the last frame of the previous step.  The state kernels:
+ *   idv_stream_frames_split: window = [hist (NB, win-hop) | x_new (NB, hop*k)] = samples base .. of every stream;
+ *     frames [2][NB*k][kpad] split bf16, frame f = window[hop*f .. hop*f + win); a negative global sample index g
+ *     reads sample -g (torch.stft's reflect padding at the start, model/pvae_module.py:L22);
+ *   idv_stream_hist_shift:   hist <- the last win-hop samples of the window;
+ *   idv_lstm_cell_step:      one nn.LSTM time step for the 4 (module, part) streams: gates (i,f,g,o) =
+ *     g_in[stream row (b, frame)] (layout of idv_lstm_recurrent_fwd's g; NULL = none) + g_rec [4][NB][4H];
+ *     c fp32 [4][NB][H] and h_split bf16 [2][4][NB][H] are updated in place, hseq (may be NULL) [4][NB*(T+1)][H]
+ *     receives h at row b*(T+1)+1+frame;
+ *   idv_carry_rows:          for every table entry copy row b*Tp + src_row to row b*Tp of every plane (the causal
+ *     x[t-1] of the next step); *counter (may be NULL) += 1;
+ *   idv_stream_ola:          acc (NB, win-hop) carried partial sums; frames (NB*k, frame_ld) synthesis frames of the
+ *     global frames t0 .. t0+k-1; out (NB, hop*k) = the finished samples o = hop*t0 - win/2 + i divided by the
+ *     window envelope over all frames t >= 0 (o < 0 is pre-roll and is discarded by the caller).              */
+typedef struct {
+  uint64_t base;        /* device address of the first plane */
+  int64_t n_planes;     /* number of planes (the two bf16 halves of a split tensor count separately) */
+  int64_t plane_bytes;  /* bytes between planes */
+  int32_t row_bytes;    /* bytes per row, multiple of 16 */
+  int32_t NB, Tp, src_row;
+} idv_carry_t;
+int idv_stream_frames_split(const float* hist, const float* x_new, int NB, int k, int64_t base, int hop, int win,
+                            int kpad, void* frames, void* stream);
+int idv_stream_hist_shift(float* hist, const float* x_new, int NB, int k, int hop, int win, void* stream);
+int idv_lstm_cell_step(const float* g_in, int64_t g_m_off, int64_t g_p_off, int g_ld, const float* g_rec, int NB,
+                       int H, int T, int frame, float* c, void* h_split, float* hseq, void* stream);
+int idv_carry_rows(const idv_carry_t* table, int n_entries, uint64_t* counter, void* stream);
+/* prev (NB, F, 2) <- last frame of the user-layout STFT chunk stft (NB, F, k, 2) (x[-1] of idv_enc0_fwd's next step) */
+int idv_stream_last_frame(const float* stft, int NB, int F, int k, float* prev, void* stream);
+int idv_stream_ola(const float* frames, int frame_ld, const float* wsq, float* acc, int NB, int k, int64_t t0,
+                   int hop, int win, float* out, void* stream);
 
 #ifdef __cplusplus
 }

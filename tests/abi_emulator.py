@@ -20,10 +20,18 @@ def _tv(t_valid, T):
 
 def _mask_rows(acc, R, Tp, t_valid):
     """Pad rows and rows of frames beyond the valid length are written as zero."""
+    Tp = abs(Tp)
     if Tp > 0:
         tt = torch.arange(R) % Tp
         acc[(tt == 0) | (tt > _tv(t_valid, Tp - 1))] = 0
     return acc
+
+
+def _written_rows(R, Tp):
+    """Tp < 0 (streaming): pad rows are not written at all (they carry state)."""
+    if Tp < 0:
+        return (torch.arange(R) % (-Tp)) != 0
+    return torch.ones(R, dtype=torch.bool)
 
 
 def _flat(t):
@@ -137,7 +145,8 @@ def idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max
         _mask_rows(acc, R, Tp, t_valid)
         view = res[out_f * out_plane:out_f * out_plane + R * out_ld].view(R, out_ld)
         view[:, out_ch_off:out_ch_off + N] = acc
-        written[out_f * out_plane:out_f * out_plane + R * out_ld].view(R, out_ld)[:, out_ch_off:out_ch_off + N] = True
+        written[out_f * out_plane:out_f * out_plane + R * out_ld].view(R, out_ld)[:, out_ch_off:out_ch_off + N] = \
+            _written_rows(R, Tp)[:, None]
     # only touch what the kernel writes
     f = _flat(out)
     vals = res[written].to(torch.float32)
@@ -171,8 +180,9 @@ def idv_tapgemm_f32(a0, a0_ld, a0_plane, a1, a1_ld, a1_plane, R, Tp, w, bias, N,
         if apply_prelu:
             acc = torch.where(acc > 0, acc, slope * acc)
         _mask_rows(acc, R, Tp, t_valid)
-        _flat(out)[out_f * out_plane:out_f * out_plane + R * out_ld].view(R, out_ld)[:, out_ch_off:out_ch_off + N] = \
-            acc.to(torch.float32)
+        ov = _flat(out)[out_f * out_plane:out_f * out_plane + R * out_ld].view(R, out_ld)
+        wr = _written_rows(R, Tp)
+        ov[wr, out_ch_off:out_ch_off + N] = acc.to(torch.float32)[wr]
 
 
 def idv_stft_fwd(x, B, L, basis, n_fft, hop, win, out):
@@ -230,7 +240,7 @@ def idv_ola_fwd(frames, frame_ld, wsq, B, T, n_fft, hop, win, out):
     out.copy_((y[:, h:total - h] / env[h:total - h]).to(torch.float32))
 
 
-def idv_enc0_fwd(stft, B, Fin, T, w, bias, Cout, slope, out, out_split=0, causal=1, t_valid=0):
+def idv_enc0_fwd(stft, B, Fin, T, w, bias, Cout, slope, out, out_split=0, causal=1, t_valid=0, prev=None, keep_pad=0):
     N = 2 * Cout
     Fout = (Fin + 4 - 5) // 2 + 1
     Tp = T + 1
@@ -238,6 +248,8 @@ def idv_enc0_fwd(stft, B, Fin, T, w, bias, Cout, slope, out, out_split=0, causal
     xpad = torch.zeros(B, Fin + 4, T + 1, 2, dtype=D)        # freq pad 2/2; time: one zero left (causal) / right
     if causal:
         xpad[:, 2:2 + Fin, 1:] = x
+        if prev is not None:
+            xpad[:, 2:2 + Fin, 0] = prev.view(B, Fin, 2).to(D)
     else:
         xpad[:, 2:2 + Fin, :T] = x
     W = w.view(10, 2, N).to(D)
@@ -250,6 +262,9 @@ def idv_enc0_fwd(stft, B, Fin, T, w, bias, Cout, slope, out, out_split=0, causal
     res = torch.where(res > 0, res, slope * res)
     res[:, :, 0] = 0
     res[:, :, 1 + _tv(t_valid, T):] = 0
+    if keep_pad:
+        old = _rd(out, out_split, res.numel()).view(res.shape)
+        res[:, :, 0] = old[:, :, 0]
     _wr(out, out_split, res)
 
 
@@ -412,7 +427,7 @@ def idv_lstm_combine_fwd(hseq, NB, T, H, latent, t_valid=0):
     latent.copy_(torch.stack((rr - ii, ir + ri), -1))
 
 
-def idv_reparam_fwd(latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, seed, offset, z):
+def idv_reparam_fwd(latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, seed, offset, offset_dev, z):
     assert eps_r is not None, "the emulator only supports supplied eps"
     e = 1e-6
     lat = latent.view(NB, T, Htot, 2)
@@ -534,6 +549,78 @@ def idv_head_user(y, n_per_utt, n_utt, slope, mask, stft_x, s_rep):
         in_ph = torch.atan2(X[..., 1], X[..., 0])
         yr, yi = in_mag * mag * torch.cos(in_ph + ph), in_mag * mag * torch.sin(in_ph + ph)
     y.view(n_utt, n_per_utt, 2).copy_(torch.stack((yr, yi), -1).to(torch.float32))
+
+
+# ---- frame streaming --------------------------------------------------------------------------------------------
+def idv_stream_frames_split(hist, x_new, NB, k, base, hop, win, kpad, frames):
+    hl = win - hop
+    w = torch.cat((hist.view(NB, hl), x_new.view(NB, hop * k)), 1).to(D)
+    wlen = w.shape[1]
+    fr = torch.zeros(NB, k, kpad, dtype=D)
+    for f in range(k):
+        for j in range(win):
+            wi = hop * f + j
+            if base + wi < 0:
+                wi = -(base + wi) - base
+            if 0 <= wi < wlen:
+                fr[:, f, j] = w[:, wi]
+    _wr(frames, 1, fr)
+
+
+def idv_stream_hist_shift(hist, x_new, NB, k, hop, win):
+    hl = win - hop
+    w = torch.cat((hist.view(NB, hl), x_new.view(NB, hop * k)), 1)
+    hist.view(NB, hl).copy_(w[:, hop * k:hop * k + hl].clone())
+
+
+def idv_lstm_cell_step(g_in, g_m_off, g_p_off, g_ld, g_rec, NB, H, T, frame, c, h_split, hseq):
+    Tp = T + 1
+    a = g_rec.view(4, NB, 4 * H).to(D).clone()
+    if g_in is not None:
+        gf = _flat(g_in)
+        rows = torch.arange(NB) * Tp + 1 + frame
+        for s in range(4):
+            idx = (s >> 1) * g_m_off + (s & 1) * g_p_off + rows[:, None] * g_ld + torch.arange(4 * H)[None, :]
+            a[s] += gf[idx].to(D)
+    i, f, gg, o = a[..., :H], a[..., H:2 * H], a[..., 2 * H:3 * H], a[..., 3 * H:]
+    cn = torch.sigmoid(f) * c.view(4, NB, H).to(D) + torch.sigmoid(i) * torch.tanh(gg)
+    hn = torch.sigmoid(o) * torch.tanh(cn)
+    c.view(4, NB, H).copy_(cn.to(torch.float32))
+    _wr(h_split, 1, hn)
+    if hseq is not None:
+        hseq.view(4, NB, Tp, H)[:, :, 1 + frame] = hn.to(torch.float32)
+
+
+def idv_carry_rows(table, n_entries, counter):
+    """table: list of (tensor, n_planes, NB, Tp, src_row) in the emulator (the product passes idv_carry_t records)."""
+    for (t, n_planes, NB, Tp, src_row) in table._entries[:n_entries]:
+        v = _flat(t).view(n_planes, NB, Tp, -1)
+        v[:, :, 0] = v[:, :, src_row].clone()
+    if counter is not None:
+        counter += 1
+
+
+def idv_stream_last_frame(stft, NB, F, k, prev):
+    prev.view(NB, F, 2).copy_(stft.view(NB, F, k, 2)[:, :, k - 1])
+
+
+def idv_stream_ola(frames, frame_ld, wsq, acc, NB, k, t0, hop, win, out):
+    tl = win - hop
+    fr = frames.view(NB, k, frame_ld)[:, :, :win].to(D)
+    buf = torch.zeros(NB, hop * k + tl + win, dtype=D)
+    buf[:, :tl] = acc.view(NB, tl).to(D)
+    for f in range(k):
+        buf[:, hop * f:hop * f + win] += fr[:, f]
+    env = torch.zeros(hop * k, dtype=D)
+    for i in range(hop * k):
+        q = hop * t0 + i
+        for t in range(max(0, (q - win + hop) // hop if q - win + 1 > 0 else 0), q // hop + 1):
+            j = q - hop * t
+            if 0 <= j < win:
+                env[i] += wsq[j].to(D)
+    o = torch.where(env > 0, buf[:, :hop * k] / torch.where(env > 0, env, torch.ones_like(env)), torch.zeros_like(env))
+    out.view(NB, hop * k).copy_(o.to(torch.float32))
+    acc.view(NB, tl).copy_(buf[:, hop * k:hop * k + tl].to(torch.float32))
 
 
 TABLE = {k: v for k, v in globals().items() if k.startswith("idv_")}

@@ -77,10 +77,13 @@ def test_enc0(B, Fin, T, Cout, causal):
     Fout = (Fin - 1) // 2 + 1
     n = Fout * B * (T + 1) * 2 * Cout
     args = [_rand(B, Fin, T, 2, seed=7), B, Fin, T, _rand(10, 2, 2 * Cout, seed=8), _rand(2 * Cout, seed=9), Cout, 0.3,
-            torch.zeros(n), 0, causal, T if causal else T - 1]
+            torch.zeros(n), 0, causal, T if causal else T - 1, None, 0]
     assert _both("idv_enc0_fwd", args, [8]) < 1e-5
     args[8], args[9] = torch.zeros(2 * n, dtype=torch.bfloat16), 1
     assert _both("idv_enc0_fwd", args, [8]) < 2e-5
+    if causal:                                   # streaming: x[-1] supplied, pad rows of the output kept
+        args[8], args[12], args[13] = _to_split(_rand(n, seed=31)).reshape(-1), _rand(B, Fin, 2, seed=30), 1
+        assert _both("idv_enc0_fwd", args, [8]) < 2e-5
 
 
 def _to_split(x):
@@ -123,9 +126,9 @@ def test_lstm_recurrent_and_combine(NB, T, H, tv):
 def test_reparam_supplied_eps():
     NB, T, z, S = 3, 11, 128, 2
     lat = _rand(NB, T, 6 * z, 2, seed=18)
-    args = [lat, NB, T, 6 * z, 3 * z, z, S, _rand(NB, S, T, z, seed=19), _rand(NB, S, T, z, seed=20), 0, 0,
+    args = [lat, NB, T, 6 * z, 3 * z, z, S, _rand(NB, S, T, z, seed=19), _rand(NB, S, T, z, seed=20), 0, 0, None,
             torch.zeros(NB * S, T, z, 2)]
-    assert _both("idv_reparam_fwd", args, [11]) < 1e-5
+    assert _both("idv_reparam_fwd", args, [12]) < 1e-5
 
 
 @pytest.mark.parametrize("NB,C_,F,T,tv", [(2, 3, 5, 7, 0), (1, 32, 129, 33, 0), (3, 1, 4, 65, 0), (2, 5, 3, 40, 34)])
@@ -153,6 +156,59 @@ def test_layout_roundtrip(NB, C_, F, T, tv):
         acc = torch.zeros(C_ * 5, dtype=torch.float64)
         assert _both("idv_cbn_stats_planes", [buf, split, NB, C_, F, T, acc, tv], [6]) < 1e-6
         assert _both("idv_cbn_apply_planes", [buf.clone(), split, NB, C_, F, T, zb.reshape(-1), 1, 0.3, tv], [0]) < 1e-6
+
+
+def test_streaming_state_kernels():
+    """csrc/stream.cu against the contract: framing with the reflect start, history shift, LSTM cell step, carry,
+    carried overlap-add (start-of-stream envelope and steady state)."""
+    NB, k, hop, win, kpad = 3, 2, 100, 400, 448
+    hist, xn = _rand(NB, win - hop, seed=40), _rand(NB, hop * k, seed=41)
+    for base in (-200, -100, 0, 12300):
+        fr = torch.zeros(2 * NB * k * kpad, dtype=torch.bfloat16)
+        assert _both("idv_stream_frames_split", [hist, xn, NB, k, base, hop, win, kpad, fr], [8]) < 1e-7
+    assert _both("idv_stream_hist_shift", [hist.clone(), xn, NB, k, hop, win], [0]) < 1e-7
+    assert _both("idv_stream_hist_shift", [hist.clone(), _rand(NB, hop * 5, seed=42), NB, 5, hop, win], [0]) < 1e-7
+    H, T = 128, 3
+    R = NB * (T + 1)
+    g_in, g_rec = _rand(2, R, 8 * H, seed=43), _rand(4, NB, 4 * H, seed=44)
+    c, hs, hseq = _rand(4 * NB * H, seed=45), torch.zeros(2 * 4 * NB * H, dtype=torch.bfloat16), torch.zeros(4 * R * H)
+    assert _both("idv_lstm_cell_step", [g_in, 4 * H, R * 8 * H, 8 * H, g_rec, NB, H, T, 1, c, hs, hseq], [9, 10, 11]) < 1e-5
+    assert _both("idv_lstm_cell_step", [None, 0, 0, 0, g_rec, NB, H, T, 2, c, hs, None], [9, 10]) < 1e-5
+    frames, wsq = _rand(NB * k, 512, seed=46), pack.pack_istft_basis(512, 400, "cpu")[1]
+    for t0 in (0, 2, 4, 1000):
+        acc = _rand(NB, win - hop, seed=47)
+        assert _both("idv_stream_ola", [frames, 512, wsq, acc, NB, k, t0, hop, win, torch.zeros(NB, hop * k)], [3, 9]) < 1e-5
+    st = _rand(NB, 257, k, 2, seed=48)
+    assert _both("idv_stream_last_frame", [st, NB, 257, k, torch.zeros(NB, 257, 2)], [4]) < 1e-7
+
+
+def test_carry_rows_and_counter():
+    from idccrn_b200.streaming import _carry_table
+    NB, Tp = 3, 4
+    a = _rand(2 * 5, NB, Tp, 64, seed=50).to(torch.bfloat16).cuda()
+    b = _rand(7, NB, Tp, 16, seed=51).cuda()
+    wa, wb = a.clone(), b.clone()
+    wa[:, :, 0], wb[:, :, 0] = wa[:, :, Tp - 1].clone(), wb[:, :, Tp - 1].clone()
+    table = _carry_table([(a, 10, NB, Tp), (b, 7, NB, Tp)], "cuda")
+    counter = torch.zeros(1, dtype=torch.int64).cuda()
+    lib.call("idv_carry_rows", table, 2, counter)
+    lib.call("idv_carry_rows", table, 2, counter)
+    assert torch.equal(a, wa) and torch.equal(b, wb) and int(counter) == 2
+
+
+def test_tapgemm_keeps_pad_rows_when_streaming():
+    """Tp < 0: pad rows of the output are left untouched (they carry x[t-1] of the previous step)."""
+    R, Tp, N = 260, 13, 128
+    a0 = _to_split(_rand(1, R, 72, seed=1))
+    w = _to_split(_rand(1, N, 64, seed=3) * 0.1)
+    out0 = _to_split(_rand(1, R, N, seed=5)).reshape(-1)
+    args = [a0, 72, 1, None, 0, 0, R, -Tp, w, 64, 1, _rand(N, seed=4), N, torch.tensor([[0, 1, 0, 0, 0, 1]], dtype=torch.int32),
+            torch.tensor([[0, 0, 1, 8, 64, 0]], dtype=torch.int32), 1, out0, N, R * N, R * N, 1, 1, 0.2, 0]
+    assert _both("idv_tapgemm_tc", args, [16]) < 1e-5
+    a32, w32 = _rand(1, R, 72, seed=1), _rand(64 * N, seed=3) * 0.1
+    args = [a32, 72, R * 72, None, 0, 0, R, -Tp, w32, _rand(N, seed=4), N, torch.tensor([[0, 1, 0, 0, 0, 0]], dtype=torch.int32),
+            torch.tensor([[0, 0, 1, 8, 64, 0]], dtype=torch.int32), 1, _rand(R * N, seed=6), N, R * N, 1, 0.2, 0]
+    assert _both("idv_tapgemm_f32", args, [14]) < 1e-5
 
 
 def test_bad_arguments_return_error_codes():
