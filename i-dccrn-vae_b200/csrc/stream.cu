@@ -96,19 +96,36 @@ struct CarryEntry {
   int NB, Tp, src_row;          // row b*Tp + src_row -> row b*Tp
 };
 
-// grid (chunks, entries)
+// grid (chunks, entries): a chunk walks over (plane, stream) rows, the threads of a block over the 16-byte vectors of
+// 256/vec rows at a time; four independent row copies in flight per thread
 __global__ void __launch_bounds__(256) carry_rows_kernel(const CarryEntry* __restrict__ table,
                                                          unsigned long long* __restrict__ counter) {
   const CarryEntry e = table[blockIdx.y];
-  const int vec = e.row_bytes / 16;
-  const long long n = e.n_planes * e.NB * vec;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vec);
-    const int b = (int)((i / vec) % e.NB);
-    const long long pl = i / ((long long)vec * e.NB);
-    char* row0 = reinterpret_cast<char*>(e.base) + pl * e.plane_bytes + (long long)b * e.Tp * e.row_bytes;
-    const uint4 val = *reinterpret_cast<const uint4*>(row0 + (long long)e.src_row * e.row_bytes + v * 16);
-    *reinterpret_cast<uint4*>(row0 + v * 16) = val;
+  const int vec = e.row_bytes / 16;                        // vectors per row
+  const int rows_per_pass = 256 / vec > 0 ? 256 / vec : 1;
+  const int v = threadIdx.x % vec, rsub = threadIdx.x / vec;
+  const long long n_rows = e.n_planes * e.NB;
+  const long long stride = (long long)gridDim.x * rows_per_pass;
+  const long long src_off = (long long)e.src_row * e.row_bytes + v * 16;
+  char* base = reinterpret_cast<char*>(e.base);
+  if (vec <= 256 && rsub < rows_per_pass) {
+    long long r = (long long)blockIdx.x * rows_per_pass + rsub;
+    for (; r + 3 * stride < n_rows; r += 4 * stride) {
+      char* p[4];
+      uint4 val[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + u * stride;
+        p[u] = base + (rr / e.NB) * e.plane_bytes + (rr % e.NB) * (long long)e.Tp * e.row_bytes;
+        val[u] = *reinterpret_cast<const uint4*>(p[u] + src_off);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(p[u] + v * 16) = val[u];
+    }
+    for (; r < n_rows; r += stride) {
+      char* p = base + (r / e.NB) * e.plane_bytes + (r % e.NB) * (long long)e.Tp * e.row_bytes;
+      *reinterpret_cast<uint4*>(p + v * 16) = *reinterpret_cast<const uint4*>(p + src_off);
+    }
   }
   if (counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *counter += 1ULL;
 }
@@ -196,7 +213,7 @@ extern "C" int idv_carry_rows(const idv_carry_t* table, int n_entries, uint64_t*
   using namespace idv;
   static_assert(sizeof(idv_carry_t) == sizeof(CarryEntry), "idv_carry_t layout");
   IDV_CHECK_ARG(table && n_entries > 0 && n_entries <= 65535, "idv_carry_rows: bad argument");
-  dim3 grid(16, n_entries);
+  dim3 grid(48, n_entries);        // row_bytes <= 4096 (vec <= 256) is checked by the caller building the table
   carry_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const CarryEntry*>(table),
                                                             reinterpret_cast<unsigned long long*>(counter));
   IDV_LAUNCH_CHECK("carry_rows_kernel");

@@ -494,7 +494,15 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
                 "idv_tapgemm_tc: N=%d must be 32, 64, 128, 256 or a multiple of 256", N);
   IDV_CHECK_ARG(a0_cp % 8 == 0 && kc_max % 64 == 0 && (head || out_ld % 8 == 0) && (!a1 || a1_cp % 8 == 0),
                 "idv_tapgemm_tc: channel counts must be multiples of 8 and kc_max of 64");
-  const int BN = N < 256 ? N : 256;
+  int dev = 0, sms = 0;
+  IDV_CUDA(cudaGetDevice(&dev));
+  IDV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // Widest N tile by default (fewest A re-reads).  Small problems (streaming steps, short batches) would leave most
+  // SMs idle and, with one CTA streaming a whole weight slice through a 2-stage ring, run at the latency of single
+  // TMA round trips: narrow the tile (more CTAs, 3-4 stage ring) until every SM has a tile.
+  int BN = N < 256 ? N : 256;
+  if (head == 0 || head == 3)
+    while (BN > 64 && N % (BN / 2) == 0 && (long long)n_units * cdiv(R, BM) * (N / BN) < sms) BN /= 2;
   CUtensorMap mA0, mA1, mW;
   int rc = encode_map_4d(&mA0, a0, a0_cp, R, a0_planes, (uint64_t)a0_planes * R * a0_cp, BK, BM);
   if (rc) return rc;
@@ -513,9 +521,6 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
   p.out_plane = out_plane; p.out_hl = out_hl; p.out_split = out_split; p.apply_prelu = apply_prelu; p.slope = prelu_slope;
   p.head = head; p.head_fout = head_fout; p.head_bmul = head_bmul; p.head_boff = head_boff;
   p.stft_x = stft_x; p.predict = predict;
-  int dev = 0, sms = 0;
-  IDV_CUDA(cudaGetDevice(&dev));
-  IDV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   cudaStream_t st = (cudaStream_t)stream;
   switch (BN) {
     case 256: return launch<256>(mA0, mA1, mW, p, sms, st);

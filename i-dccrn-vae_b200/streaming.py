@@ -33,8 +33,8 @@ def _carry_table(bufs, device):
     for i, (t, n_planes, NB, Tp) in enumerate(bufs):
         plane_bytes = t.numel() * t.element_size() // n_planes
         row_bytes = plane_bytes // (NB * Tp)
-        if row_bytes % 16 or row_bytes * NB * Tp != plane_bytes:
-            raise RuntimeError("carry rows must be multiples of 16 bytes")
+        if row_bytes % 16 or row_bytes > 4096 or row_bytes * NB * Tp != plane_bytes:
+            raise RuntimeError("carry rows must be multiples of 16 bytes, at most 4096")
         recs[i] = lib.CarryEntry(t.data_ptr(), n_planes, plane_bytes, row_bytes, NB, Tp, Tp - 1)
         entries.append((t, n_planes, NB, Tp, Tp - 1))
     raw = torch.frombuffer(bytearray(bytes(recs)), dtype=torch.uint8).clone().to(device)

@@ -232,6 +232,8 @@ def test_bad_arguments_return_error_codes():
     (40000, 641, 32, [64, 64], [1, 0], False, True, 1, 0),      # > 148 tiles: several tiles per CTA, both TMEM stages
     (470, 47, 128, [64, 64], [0, -1], False, True, 1, 41),      # non-causal taps (x[t], x[t+1]), 41 of 46 frames valid
     (1284, 642, 256, [128, 128], [-1, 0], True, True, 0, 640),  # row+1 tap at the end of the tensor (zero fill)
+    (256, 2, 512, [128, 64], [1, 0], False, True, 1, 0),        # streaming-sized: few tiles -> narrow N tiles (BN 64)
+    (128, 0, 1536, [192, 64], [0, 0], False, False, 0, 0),        # one LSTM step: N = 4H in 24 narrow tiles
 ])
 @pytest.mark.parametrize("dynamic_tiles", [0, 1])
 def test_tapgemm_tc(R, Tp, N, kcs, dts, two_src, prelu, out_split, tv, dynamic_tiles):
