@@ -282,6 +282,7 @@ def run_ours(args):
         tg_flops = 2 * g["tapgemm"] * 1e9 * B
         achieved_tf = tg_flops / (tg["ms"] / 1e3) / 1e12 if tg["launches"] else None
         cpu_val, cpu_dt, cores, sample = cpu_oracle_throughput(2, 1) if not args.no_cpu else (None, None, 0, "skipped")
+        traffic, traffic_src = ncu_dram_traffic(B, tc_mode)
         line = {
             "metric": "audio_seconds_enhanced_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -295,7 +296,9 @@ def run_ours(args):
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "tapgemm_tc_kernel (complex conv / convT / LSTM layer-0 in-proj / dense / iSTFT DFT)",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": None,
+                         "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic,
+                         "traffic_unit": "GB per step (dram__bytes_read.sum + dram__bytes_write.sum over the kernel's launches)",
+                         "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_gflop_per_step": tg_flops / 1e9,
                          "kernel_ms_per_step": tg["ms"], "kernel_share_of_step": tg["ms"] / step_ms_prof if step_ms_prof else None,
                          "split_factor": 3 if tc_mode else None,
@@ -309,6 +312,20 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_dram_traffic(B, tc_mode):
+    """DRAM bytes of the dominant kernel's launches in one step, from the committed `ncu --set full` capture of this
+    workload (profiles/r01_ncu_tapgemm_tc_full.csv, taken at batch 64): a profiler figure, never measured here."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_tapgemm_tc_full.csv")
+    if not tc_mode or B != 64 or not os.path.exists(path):
+        return None, "no ncu capture for this configuration"
+    import csv
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]
+    ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    gb = sum(float(r[ir]) + float(r[iw]) for r in rows[2:] if len(r) > iw)
+    return gb, "profiles/r01_ncu_tapgemm_tc_full.csv (%d launches)" % (len(rows) - 2)
 
 
 def main():
