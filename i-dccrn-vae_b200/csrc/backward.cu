@@ -1,0 +1,461 @@
+// Backward of the NSVAE encoder (phase-1 training step, /root/reference i_dccrn_vae/nsvae_dccrn/train_nsvae.py:L505-566:
+// noisy encoder train=True -> closed-form KL -> loss.backward() -> Adam).  The GEMM-shaped parts of the backward
+// (data gradients of the complex convs and LSTM projections, all weight gradients) run on the tcgen05 tap-GEMM
+// (csrc/tapgemm_tc.cu) - weight gradients as GEMMs over the ROW dimension on transposed copies of the activations;
+// this file holds the HBM-bound pieces around them:
+//   planes_transpose_split : [F][R][Cp] -> split-bf16 [2][F][Cp][Rpad] (optionally row-shifted), the K-major operands
+//                            of the weight-gradient GEMMs
+//   cbn_bwd_*              : ComplexBatchNormal(train=True) + PReLU backward (model/complex_progress.py:L131-209,
+//                            differentiated through the batch mean and covariance like the reference's autograd)
+//   lstm_scan_c / lstm_cell_bwd_step / lstm_combine_bwd / colsum : BPTT of nn.LSTM (complex_progress.py:L58-74)
+//   enc0_wgrad             : weight gradient of the Cin = 1 first layer
+//   adam_step              : torch.optim.Adam(lr, weight_decay) update (train_nsvae.py:L200)
+#include "idv_common.cuh"
+
+namespace idv {
+
+__device__ __forceinline__ int r8(int c) { return (c + 7) & ~7; }
+__device__ __forceinline__ float sgm(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float ld_act(const void* p, int split, long long hl, long long idx) {
+  return split ? ld_split1(reinterpret_cast<const unsigned short*>(p), hl, idx)
+               : __ldg(reinterpret_cast<const float*>(p) + idx);
+}
+
+// out[f][c][k] = in[f][k + shift][c] for 0 <= k + shift < R, else 0;  k < Rpad.  grid (Rpad/32, Cp/32, F), block (32, 8)
+__global__ void __launch_bounds__(256) planes_transpose_split_kernel(const void* __restrict__ in, int in_split, int F,
+                                                                     int R, int Cp, int Rpad, int shift,
+                                                                     unsigned short* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32, f = blockIdx.z;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const long long hl_in = (long long)F * R * Cp, hl_out = (long long)F * Cp * Rpad;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = k0 + i + shift, c = c0 + tx;
+    tile[i][tx] = (r >= 0 && r < R && c < Cp) ? ld_act(in, in_split, hl_in, ((long long)f * R + r) * Cp + c) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, k = k0 + tx;
+    if (c < Cp && k < Rpad) st_split1(out, hl_out, ((long long)f * Cp + c) * Rpad + k, tile[tx][i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) f32_to_split_kernel(const float* __restrict__ x, long long n4,
+                                                           unsigned short* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    st_split4(out, n4 * 4, i * 4, ldg4(x + i * 4));
+}
+
+// ---- ComplexBatchNormal(train) + PReLU backward --------------------------------------------------------------------
+// pre = Z y + b' (b' = beta - Z mu), act = PReLU(pre).  gp = g * (pre > 0 ? 1 : slope), xc = y - mu.
+// acc[c][8] (double): sum gp_r, gp_i, gp_r xc_r, gp_r xc_i, gp_i xc_r, gp_i xc_i, sum g*pre over pre <= 0, (unused)
+// grid (F, chunks), block = round32(C) threads (one complex channel per thread)
+__global__ void cbn_bwd_reduce_kernel(const void* __restrict__ y, int y_split, const void* __restrict__ g, int g_split,
+                                      int NB, int C, int F, int T, int Tv, int rows_per_chunk,
+                                      const float* __restrict__ stats, const float* __restrict__ zb, float slope,
+                                      double* __restrict__ acc) {
+  const int c = threadIdx.x;
+  const int Ch = r8(C), Cp = 2 * Ch, Tp = T + 1;
+  const long long R = (long long)NB * Tp, hl = (long long)F * R * Cp;
+  const int f = blockIdx.x;
+  long long r_begin = (long long)blockIdx.y * rows_per_chunk, r_end = r_begin + rows_per_chunk;
+  if (r_end > R) r_end = R;
+  if (c >= C) return;
+  const float mu_r = stats[c * 5 + 0], mu_i = stats[c * 5 + 1];
+  const float zrr = zb[c * 6 + 0], zri = zb[c * 6 + 1], zir = zb[c * 6 + 2], zii = zb[c * 6 + 3];
+  const float br = zb[c * 6 + 4], bi = zb[c * 6 + 5];
+  double s[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (long long r = r_begin; r < r_end; ++r) {
+    const int tt = (int)(r % Tp);
+    if (tt == 0 || tt > Tv) continue;
+    const long long idx = ((long long)f * R + r) * Cp;
+    const float yr = ld_act(y, y_split, hl, idx + c), yi = ld_act(y, y_split, hl, idx + Ch + c);
+    const float gr = ld_act(g, g_split, hl, idx + c), gi = ld_act(g, g_split, hl, idx + Ch + c);
+    const float pr = fmaf(zrr, yr, fmaf(zri, yi, br)), pi = fmaf(zir, yr, fmaf(zii, yi, bi));
+    const float gpr = pr > 0.f ? gr : slope * gr, gpi = pi > 0.f ? gi : slope * gi;
+    const float xr = yr - mu_r, xi = yi - mu_i;
+    s[0] += gpr; s[1] += gpi;
+    s[2] += (double)gpr * xr; s[3] += (double)gpr * xi; s[4] += (double)gpi * xr; s[5] += (double)gpi * xi;
+    s[6] += (pr > 0.f ? 0.0 : (double)gr * pr) + (pi > 0.f ? 0.0 : (double)gi * pi);
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) atomicAdd(acc + c * 8 + k, s[k]);
+}
+
+// per channel: parameter gradients (+=) and the coefficients of the element-wise pass
+//   dy = Z^T gp + D xc - m,  coef[c][10] = Zrr, Zir, Zri, Zii (Z^T rows), Drr, Dri, Dii, m_r, m_i, (unused)
+__global__ void cbn_bwd_finalize_kernel(const double* __restrict__ acc, double n, int C, const float* __restrict__ stats,
+                                        const float* __restrict__ g_rr, const float* __restrict__ g_ri,
+                                        const float* __restrict__ g_ii, float* __restrict__ coef,
+                                        float* __restrict__ d_grr, float* __restrict__ d_gri, float* __restrict__ d_gii,
+                                        float* __restrict__ d_br, float* __restrict__ d_bi,
+                                        double* __restrict__ d_slope) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double slope_part = 0.0;
+  if (c < C) {
+    const double eps = 1e-5;
+    const double a = stats[c * 5 + 2], cri = stats[c * 5 + 3], b = stats[c * 5 + 4];      // Vrr, Vri, Vii (eps inside)
+    const double* s = acc + c * 8;
+    // forward quantities (model/complex_progress.py:L168-200)
+    double delta = a * b - cri * cri + eps;
+    const bool clamped = delta < 1e-8;
+    if (clamped) delta = 1e-8;
+    const double sq = sqrt(delta), t = sqrt(a + b + 2 * sq + eps), q = sq * t + eps;
+    const double wrr = (b + sq) / q, wii = (a + sq) / q, wri = -cri / q;
+    const double grr = g_rr[c], gri = g_ri[c], gii = g_ii[c];
+    const double zrr = grr * wrr + gri * wri, zri = grr * wri + gri * wii;
+    const double zir = gri * wrr + gii * wri, zii = gri * wri + gii * wii;
+    // dZ_ab = sum gp_a xc_b
+    const double dzrr = s[2], dzri = s[3], dzir = s[4], dzii = s[5];
+    d_grr[c] += (float)(dzrr * wrr + dzri * wri);
+    d_gri[c] += (float)(dzrr * wri + dzri * wii + dzir * wrr + dzii * wri);
+    d_gii[c] += (float)(dzir * wri + dzii * wii);
+    d_br[c] += (float)s[0];
+    d_bi[c] += (float)s[1];
+    const double dwrr = dzrr * grr + dzir * gri;
+    const double dwri = dzrr * gri + dzri * grr + dzir * gii + dzii * gri;
+    const double dwii = dzri * gri + dzii * gii;
+    // W(V): Wrr = (b + s)/q, Wii = (a + s)/q, Wri = -c/q, q = s t + eps, t = sqrt(a + b + 2 s + eps), s = sqrt(delta)
+    double ga = dwii / q, gb = dwrr / q, gc = -dwri / q;
+    double gs = (dwrr + dwii) / q;
+    const double gq = -(dwrr * (b + sq) + dwii * (a + sq) - dwri * cri) / (q * q);
+    gs += gq * t;
+    const double gt = gq * sq;
+    const double gin = gt / (2 * t);
+    ga += gin; gb += gin; gs += 2 * gin;
+    const double gdelta = clamped ? 0.0 : gs / (2 * sq);
+    ga += gdelta * b; gb += gdelta * a; gc += -2 * cri * gdelta;
+    // V = mean(xc xc^T): d/dxc_r = (2 ga xc_r + gc xc_i)/n, d/dxc_i = (2 gb xc_i + gc xc_r)/n
+    float* k = coef + c * 10;
+    k[0] = (float)zrr; k[1] = (float)zir; k[2] = (float)zri; k[3] = (float)zii;
+    k[4] = (float)(2 * ga / n); k[5] = (float)(gc / n); k[6] = (float)(2 * gb / n);
+    k[7] = (float)((zrr * s[0] + zir * s[1]) / n);
+    k[8] = (float)((zri * s[0] + zii * s[1]) / n);
+    k[9] = 0.f;
+    slope_part = s[6];
+  }
+  // one PReLU slope for the whole layer
+  for (int o = 16; o > 0; o >>= 1) slope_part += __shfl_down_sync(0xffffffffu, slope_part, o);
+  if ((threadIdx.x & 31) == 0 && d_slope) atomicAdd(d_slope, slope_part);
+}
+
+// dy (planes, pad rows and invalid frames = 0), fp32 or split
+__global__ void __launch_bounds__(256) cbn_bwd_apply_kernel(const void* __restrict__ y, int y_split,
+                                                            const void* __restrict__ g, int g_split, int NB, int C,
+                                                            int F, int T, int Tv, const float* __restrict__ stats,
+                                                            const float* __restrict__ zb, const float* __restrict__ coef,
+                                                            float slope, void* __restrict__ dy, int dy_split) {
+  const int Ch = r8(C), Cp = 2 * Ch, Tp = T + 1;
+  const long long R = (long long)NB * Tp, hl = (long long)F * R * Cp;
+  const long long n = (long long)F * R * Ch;
+  float* d32 = reinterpret_cast<float*>(dy);
+  unsigned short* dsp = reinterpret_cast<unsigned short*>(dy);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Ch);
+    const long long fr = i / Ch;
+    const int tt = (int)((fr % R) % Tp);
+    const long long idx = fr * Cp;
+    float dr = 0.f, di = 0.f;
+    if (c < C && tt != 0 && tt <= Tv) {
+      const float yr = ld_act(y, y_split, hl, idx + c), yi = ld_act(y, y_split, hl, idx + Ch + c);
+      const float gr = ld_act(g, g_split, hl, idx + c), gi = ld_act(g, g_split, hl, idx + Ch + c);
+      const float* z = zb + c * 6;
+      const float pr = fmaf(z[0], yr, fmaf(z[1], yi, z[4])), pi = fmaf(z[2], yr, fmaf(z[3], yi, z[5]));
+      const float gpr = pr > 0.f ? gr : slope * gr, gpi = pi > 0.f ? gi : slope * gi;
+      const float xr = yr - stats[c * 5 + 0], xi = yi - stats[c * 5 + 1];
+      const float* k = coef + c * 10;
+      dr = k[0] * gpr + k[1] * gpi + k[4] * xr + k[5] * xi - k[7];
+      di = k[2] * gpr + k[3] * gpi + k[5] * xr + k[6] * xi - k[8];
+    }
+    if (dy_split) {
+      st_split1(dsp, hl, idx + c, dr);
+      st_split1(dsp, hl, idx + Ch + c, di);
+    } else {
+      d32[idx + c] = dr;
+      d32[idx + Ch + c] = di;
+    }
+  }
+}
+
+// ---- LSTM backward -------------------------------------------------------------------------------------------------
+// P: gate pre-activations [4][R][4H] (i, f, g, o); cst[4][R][H] <- c_t (pad rows 0).  One thread per (stream, b, j).
+__global__ void __launch_bounds__(256) lstm_scan_c_kernel(const float* __restrict__ P, int NB, int T, int Tv, int H,
+                                                          float* __restrict__ cst) {
+  const long long n = 4LL * NB * H;
+  const int Tp = T + 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % H);
+    const long long sb = i / H;                                  // s*NB + b
+    const float* p = P + sb * Tp * 4 * H;
+    float* co = cst + sb * Tp * H;
+    float c = 0.f;
+    co[j] = 0.f;
+    for (int t = 0; t < Tv; ++t) {
+      const float* pt = p + (long long)(1 + t) * 4 * H;
+      c = sgm(__ldg(pt + H + j)) * c + sgm(__ldg(pt + j)) * tanhf(__ldg(pt + 2 * H + j));
+      co[(long long)(1 + t) * H + j] = c;
+    }
+  }
+}
+
+// one BPTT step (time t): dh = dH[t] + dh_rec; dP[t] <- gate gradients; dc carried.
+__global__ void __launch_bounds__(256) lstm_cell_bwd_step_kernel(const float* __restrict__ P,
+                                                                 const float* __restrict__ cst,
+                                                                 const float* __restrict__ dH,
+                                                                 const float* __restrict__ dh_rec, float* __restrict__ dc,
+                                                                 int NB, int T, int H, int t, int last,
+                                                                 float* __restrict__ dP,
+                                                                 unsigned short* __restrict__ dP_step) {
+  const long long n = 4LL * NB * H;
+  const int Tp = T + 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % H);
+    const long long sb = i / H;
+    const long long row = sb * Tp + 1 + t;
+    const float* pt = P + row * 4 * H;
+    const float ig = sgm(__ldg(pt + j)), fg = sgm(__ldg(pt + H + j)), gg = tanhf(__ldg(pt + 2 * H + j)),
+                og = sgm(__ldg(pt + 3 * H + j));
+    const float c = __ldg(cst + row * H + j), cprev = __ldg(cst + (row - 1) * H + j);   // row - 1 = pad row (0) at t = 0
+    const float tc = tanhf(c);
+    const float dh = __ldg(dH + row * H + j) + (last ? 0.f : __ldg(dh_rec + i));
+    const float dcv = (last ? 0.f : dc[i]) + dh * og * (1.f - tc * tc);
+    const float d_o = dh * tc * og * (1.f - og);
+    const float d_i = dcv * gg * ig * (1.f - ig);
+    const float d_g = dcv * ig * (1.f - gg * gg);
+    const float d_f = dcv * cprev * fg * (1.f - fg);
+    dc[i] = dcv * fg;
+    float* dp = dP + row * 4 * H;
+    dp[j] = d_i; dp[H + j] = d_f; dp[2 * H + j] = d_g; dp[3 * H + j] = d_o;
+    const long long hl = 4LL * NB * 4 * H, so = sb * 4 * H;
+    st_split1(dP_step, hl, so + j, d_i);
+    st_split1(dP_step, hl, so + H + j, d_f);
+    st_split1(dP_step, hl, so + 2 * H + j, d_g);
+    st_split1(dP_step, hl, so + 3 * H + j, d_o);
+  }
+}
+
+// dlatent (NB, Tv, H, 2) -> dH [4][R][H]: h_rr = +d_re, h_ir = +d_im, h_ri = +d_im, h_ii = -d_re (pad rows 0)
+__global__ void __launch_bounds__(256) lstm_combine_bwd_kernel(const float* __restrict__ dl, int NB, int T, int Tv, int H,
+                                                               float* __restrict__ dH) {
+  const int Tp = T + 1;
+  const long long R = (long long)NB * Tp, n = R * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % H);
+    const long long r = i / H;
+    const int tt = (int)(r % Tp), b = (int)(r / Tp);
+    float2 d = make_float2(0.f, 0.f);
+    if (tt != 0 && tt <= Tv) d = __ldg(reinterpret_cast<const float2*>(dl + (((long long)b * Tv + tt - 1) * H + j) * 2));
+    dH[i] = d.x;
+    dH[R * H + i] = d.y;
+    dH[2 * R * H + i] = d.y;
+    dH[3 * R * H + i] = -d.x;
+  }
+}
+
+// out[col] += sum_r x[r][col]  (x: [rows][ld], cols <= ld).  grid (ceil(cols/256), chunks)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long rows, int cols, int ld,
+                                                     int rows_per_chunk, float* __restrict__ out) {
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col >= cols) return;
+  long long r0 = (long long)blockIdx.y * rows_per_chunk, r1 = r0 + rows_per_chunk;
+  if (r1 > rows) r1 = rows;
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += __ldg(x + r * ld + col);
+  atomicAdd(out + col, s);
+}
+
+// dW[tap][part][n] += sum over (fo, rows) x[b][fi][ti][part] * dY[fo][r][n];  grid (Fout, chunks), block = N threads
+__global__ void enc0_wgrad_kernel(const float* __restrict__ stft, const float* __restrict__ dY, int NB, int Fin, int T,
+                                  int N, int Fout, int causal, int rows_per_chunk, float* __restrict__ dW) {
+  const int n = threadIdx.x, fo = blockIdx.x;
+  const int Tp = T + 1;
+  const long long R = (long long)NB * Tp;
+  long long r0 = (long long)blockIdx.y * rows_per_chunk, r1 = r0 + rows_per_chunk;
+  if (r1 > R) r1 = R;
+  float acc[20];
+#pragma unroll
+  for (int k = 0; k < 20; ++k) acc[k] = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const int b = (int)(r / Tp), t = (int)(r % Tp) - 1;
+    if (t < 0) continue;
+    const float g = __ldg(dY + ((long long)fo * R + r) * N + n);
+#pragma unroll
+    for (int tap = 0; tap < 10; ++tap) {
+      const int kf = tap >> 1, kt = tap & 1;
+      const int fi = 2 * fo + kf - 2, ti = causal ? t - 1 + kt : t + kt;
+      if (fi >= 0 && fi < Fin && ti >= 0 && ti < T) {
+        const float2 x = __ldg(reinterpret_cast<const float2*>(stft + ((long long)(b * Fin + fi) * T + ti) * 2));
+        acc[tap * 2] = fmaf(x.x, g, acc[tap * 2]);
+        acc[tap * 2 + 1] = fmaf(x.y, g, acc[tap * 2 + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 20; ++k) atomicAdd(dW + k * N + n, acc[k]);
+}
+
+__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, long long n,
+                                                        float lr, float b1, float b2, float eps, float wd, float bc1,
+                                                        float bc2_sqrt) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    const float gv = g[i] + wd * pv;                              // torch.optim.Adam: L2 penalty added to the gradient
+    const float mv = b1 * m[i] + (1.f - b1) * gv;
+    const float vv = b2 * v[i] + (1.f - b2) * gv * gv;
+    m[i] = mv;
+    v[i] = vv;
+    p[i] = pv - (lr / bc1) * mv / (sqrtf(vv) / bc2_sqrt + eps);
+  }
+}
+
+static inline int grid_for(long long n, int per_sm) {
+  const long long b = (n + 255) / 256;
+  return (int)(b < 148LL * per_sm ? (b > 0 ? b : 1) : 148LL * per_sm);
+}
+
+}  // namespace idv
+
+extern "C" int idv_planes_transpose_split(const void* planes, int in_split, int F, int R, int Cp, int Rpad, int shift,
+                                          void* out, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(planes && out && F > 0 && F <= 65535 && R > 0 && Cp > 0 && Rpad >= R && Rpad % 64 == 0,
+                "idv_planes_transpose_split: bad argument (Rpad must be a multiple of 64 >= R)");
+  dim3 grid(Rpad / 32, cdiv(Cp, 32), F), block(32, 8);
+  IDV_CHECK_ARG(grid.y <= 65535, "idv_planes_transpose_split: Cp too large");
+  planes_transpose_split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(planes, in_split, F, R, Cp, Rpad, shift,
+                                                                          reinterpret_cast<unsigned short*>(out));
+  IDV_LAUNCH_CHECK("planes_transpose_split_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_f32_to_split(const float* x, int64_t n, void* out, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(x && out && n > 0 && n % 4 == 0, "idv_f32_to_split: n must be a positive multiple of 4");
+  f32_to_split_kernel<<<grid_for(n / 4, 16), 256, 0, (cudaStream_t)stream>>>(x, n / 4,
+                                                                             reinterpret_cast<unsigned short*>(out));
+  IDV_LAUNCH_CHECK("f32_to_split_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_cbn_bwd_reduce(const void* y, int y_split, const void* g, int g_split, int NB, int C, int F, int T,
+                                  const float* stats, const float* zb, float slope, double* acc, int t_valid,
+                                  void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(y && g && stats && zb && acc && NB > 0 && C > 0 && C <= 1024 && F > 0 && F <= 65535 && T > 0,
+                "idv_cbn_bwd_reduce: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  IDV_CUDA(cudaMemsetAsync(acc, 0, (size_t)C * 8 * sizeof(double), st));
+  const long long R = (long long)NB * (T + 1);
+  int chunks = (int)(148LL * 8 / F);
+  if (chunks < 1) chunks = 1;
+  if (chunks > R) chunks = (int)R;
+  const int rows_per_chunk = (int)((R + chunks - 1) / chunks);
+  const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
+  dim3 grid(F, chunks);
+  cbn_bwd_reduce_kernel<<<grid, ((C + 31) / 32) * 32, 0, st>>>(y, y_split, g, g_split, NB, C, F, T, Tv, rows_per_chunk,
+                                                                stats, zb, slope, acc);
+  IDV_LAUNCH_CHECK("cbn_bwd_reduce_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_cbn_bwd_finalize(const double* acc, double count, int C, const float* stats, const float* gamma_rr,
+                                    const float* gamma_ri, const float* gamma_ii, float* coef, float* d_gamma_rr,
+                                    float* d_gamma_ri, float* d_gamma_ii, float* d_beta_r, float* d_beta_i,
+                                    double* d_slope, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(acc && stats && gamma_rr && gamma_ri && gamma_ii && coef && d_gamma_rr && d_gamma_ri && d_gamma_ii &&
+                    d_beta_r && d_beta_i && C > 0 && count > 0,
+                "idv_cbn_bwd_finalize: bad argument");
+  cbn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(acc, count, C, stats, gamma_rr, gamma_ri,
+                                                                          gamma_ii, coef, d_gamma_rr, d_gamma_ri,
+                                                                          d_gamma_ii, d_beta_r, d_beta_i, d_slope);
+  IDV_LAUNCH_CHECK("cbn_bwd_finalize_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_cbn_bwd_apply(const void* y, int y_split, const void* g, int g_split, int NB, int C, int F, int T,
+                                 const float* stats, const float* zb, const float* coef, float slope, void* dy,
+                                 int dy_split, int t_valid, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(y && g && stats && zb && coef && dy && NB > 0 && C > 0 && F > 0 && T > 0, "idv_cbn_bwd_apply: bad argument");
+  const long long n = (long long)F * NB * (T + 1) * ((C + 7) / 8 * 8);
+  const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
+  cbn_bwd_apply_kernel<<<grid_for(n, 32), 256, 0, (cudaStream_t)stream>>>(y, y_split, g, g_split, NB, C, F, T, Tv, stats,
+                                                                          zb, coef, slope, dy, dy_split);
+  IDV_LAUNCH_CHECK("cbn_bwd_apply_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_lstm_scan_c(const float* P, int NB, int T, int H, float* cst, int t_valid, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(P && cst && NB > 0 && T > 0 && H > 0, "idv_lstm_scan_c: bad argument");
+  const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
+  lstm_scan_c_kernel<<<grid_for(4LL * NB * H, 16), 256, 0, (cudaStream_t)stream>>>(P, NB, T, Tv, H, cst);
+  IDV_LAUNCH_CHECK("lstm_scan_c_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_lstm_cell_bwd_step(const float* P, const float* cst, const float* dH, const float* dh_rec, float* dc,
+                                      int NB, int T, int H, int t, int last, float* dP, void* dP_step, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(P && cst && dH && dc && dP && dP_step && (last || dh_rec) && NB > 0 && T > 0 && H > 0 && t >= 0 && t < T,
+                "idv_lstm_cell_bwd_step: bad argument");
+  lstm_cell_bwd_step_kernel<<<grid_for(4LL * NB * H, 8), 256, 0, (cudaStream_t)stream>>>(
+      P, cst, dH, dh_rec, dc, NB, T, H, t, last, dP, reinterpret_cast<unsigned short*>(dP_step));
+  IDV_LAUNCH_CHECK("lstm_cell_bwd_step_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_lstm_combine_bwd(const float* dlatent, int NB, int T, int H, float* dH, int t_valid, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(dlatent && dH && NB > 0 && T > 0 && H > 0, "idv_lstm_combine_bwd: bad argument");
+  const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
+  lstm_combine_bwd_kernel<<<grid_for((long long)NB * (T + 1) * H, 16), 256, 0, (cudaStream_t)stream>>>(dlatent, NB, T, Tv,
+                                                                                                    H, dH);
+  IDV_LAUNCH_CHECK("lstm_combine_bwd_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_colsum_add(const float* x, int64_t rows, int cols, int ld, float* out, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(x && out && rows > 0 && cols > 0 && ld >= cols, "idv_colsum_add: bad argument");
+  int chunks = 148 * 4 / cdiv(cols, 256);
+  if (chunks < 1) chunks = 1;
+  if (chunks > rows) chunks = (int)rows;
+  const int rpc = (int)((rows + chunks - 1) / chunks);
+  dim3 grid(cdiv(cols, 256), chunks);
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, rpc, out);
+  IDV_LAUNCH_CHECK("colsum_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_enc0_wgrad(const float* stft, const float* dY, int B, int Fin, int T, int Cout, int causal, float* dW,
+                              void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(stft && dY && dW && B > 0 && Fin >= 5 && T > 0 && Cout > 0 && 2 * Cout <= 1024, "idv_enc0_wgrad: bad argument");
+  const int Fout = (Fin + 4 - 5) / 2 + 1, N = 2 * Cout;
+  const long long R = (long long)B * (T + 1);
+  int chunks = 148 * 8 / Fout;
+  if (chunks < 1) chunks = 1;
+  if (chunks > R) chunks = (int)R;
+  const int rpc = (int)((R + chunks - 1) / chunks);
+  cudaStream_t st = (cudaStream_t)stream;
+  IDV_CUDA(cudaMemsetAsync(dW, 0, (size_t)20 * N * sizeof(float), st));
+  dim3 grid(Fout, chunks);
+  enc0_wgrad_kernel<<<grid, N, 0, st>>>(stft, dY, B, Fin, T, N, Fout, causal, rpc, dW);
+  IDV_LAUNCH_CHECK("enc0_wgrad_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, int step, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "idv_adam_step: bad argument");
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = sqrtf(1.f - powf(beta2, (float)step));
+  adam_step_kernel<<<grid_for(n, 16), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+                                                                      bc1, bc2);
+  IDV_LAUNCH_CHECK("adam_step_kernel");
+  return IDV_OK;
+}

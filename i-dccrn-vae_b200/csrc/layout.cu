@@ -232,7 +232,7 @@ __global__ void cbn_train_finalize_kernel(const double* __restrict__ acc, double
                                           const float* __restrict__ beta_i, float* __restrict__ run_mr,
                                           float* __restrict__ run_mi, float* __restrict__ run_vrr,
                                           float* __restrict__ run_vri, float* __restrict__ run_vii, float momentum,
-                                          int first, float* __restrict__ zb) {
+                                          int first, float* __restrict__ zb, float* __restrict__ stats) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float eps = 1e-5f;
@@ -242,6 +242,9 @@ __global__ void cbn_train_finalize_kernel(const double* __restrict__ acc, double
   const float vrr = (float)(acc[c * 5 + 2] / count - mr * mr) + eps;
   const float vii = (float)(acc[c * 5 + 3] / count - mi * mi) + eps;
   const float vri = (float)(acc[c * 5 + 4] / count - mr * mi);
+  if (stats) {                               // saved for the backward pass (idv_cbn_bwd_*)
+    stats[c * 5 + 0] = mu_r; stats[c * 5 + 1] = mu_i; stats[c * 5 + 2] = vrr; stats[c * 5 + 3] = vri; stats[c * 5 + 4] = vii;
+  }
   if (first) {
     run_mr[c] = mu_r; run_mi[c] = mu_i; run_vrr[c] = vrr; run_vri[c] = vri; run_vii[c] = vii;
   } else {
@@ -268,12 +271,14 @@ __global__ void cbn_train_finalize_kernel(const double* __restrict__ acc, double
 // grid-stride over (plane, row, channel)
 __global__ void __launch_bounds__(256) cbn_apply_planes_kernel(void* __restrict__ planesv, int split, int NB, int C,
                                                                int F, int T, int Tv, const float* __restrict__ zb,
-                                                               int apply_prelu, float slope) {
+                                                               int apply_prelu, float slope, void* __restrict__ outv) {
   const int Ch = round_up8(C), Cp = 2 * Ch, Tp = T + 1;
   const long long R = (long long)NB * Tp;
   const long long n = (long long)F * R * C;
   float* pf = reinterpret_cast<float*>(planesv);
   unsigned short* ps = reinterpret_cast<unsigned short*>(planesv);
+  float* of = reinterpret_cast<float*>(outv);
+  unsigned short* os = reinterpret_cast<unsigned short*>(outv);
   const long long hl = (long long)F * R * Cp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -298,11 +303,11 @@ __global__ void __launch_bounds__(256) cbn_apply_planes_kernel(void* __restrict_
       oi = prelu_f(oi, slope);
     }
     if (split) {
-      st_split1(ps, hl, idx + c, orr);
-      st_split1(ps, hl, idx + Ch + c, oi);
+      st_split1(os, hl, idx + c, orr);
+      st_split1(os, hl, idx + Ch + c, oi);
     } else {
-      pf[idx + c] = orr;
-      pf[idx + Ch + c] = oi;
+      of[idx + c] = orr;
+      of[idx + Ch + c] = oi;
     }
   }
 }
@@ -331,7 +336,7 @@ extern "C" int idv_cbn_train_finalize(const double* acc, double count, int C, co
                                       const float* gamma_ri, const float* gamma_ii, const float* beta_r,
                                       const float* beta_i, float* run_mean_r, float* run_mean_i, float* run_vrr,
                                       float* run_vri, float* run_vii, float momentum, int first, float* zb,
-                                      void* stream) {
+                                      float* stats, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(acc && gamma_rr && gamma_ri && gamma_ii && beta_r && beta_i && run_mean_r && run_mean_i && run_vrr &&
                     run_vri && run_vii && zb && C > 0 && count > 0,
@@ -339,19 +344,22 @@ extern "C" int idv_cbn_train_finalize(const double* acc, double count, int C, co
   cbn_train_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(acc, count, C, gamma_rr, gamma_ri, gamma_ii,
                                                                              beta_r, beta_i, run_mean_r, run_mean_i,
                                                                              run_vrr, run_vri, run_vii, momentum, first,
-                                                                             zb);
+                                                                             zb, stats);
   IDV_LAUNCH_CHECK("cbn_train_finalize_kernel");
   return IDV_OK;
 }
 
 extern "C" int idv_cbn_apply_planes(void* planes, int split, int NB, int C, int F, int T, const float* zb,
-                                    int apply_prelu, float prelu_slope, int t_valid, void* stream) {
+                                    int apply_prelu, float prelu_slope, int t_valid, void* out, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(planes && zb && NB > 0 && C > 0 && F > 0 && T > 0, "idv_cbn_apply_planes: bad argument");
   const long long n = (long long)F * NB * (T + 1) * C;
   const int blocks = (int)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
   const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
-  cbn_apply_planes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(planes, split, NB, C, F, T, Tv, zb, apply_prelu, prelu_slope);
+  if (out && out != planes)            // out of place (the raw values are kept for the backward pass): pad rows = 0
+    IDV_CUDA(cudaMemsetAsync(out, 0, (size_t)F * NB * (T + 1) * 2 * ((C + 7) / 8 * 8) * sizeof(float), (cudaStream_t)stream));
+  cbn_apply_planes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(planes, split, NB, C, F, T, Tv, zb, apply_prelu,
+                                                                    prelu_slope, out ? out : planes);
   IDV_LAUNCH_CHECK("cbn_apply_planes_kernel");
   return IDV_OK;
 }

@@ -490,8 +490,7 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
                   "idv_tapgemm_tc: head mode needs N == 32, Tp, predict (and stft_x for the mask head)");
   }
   IDV_CHECK_ARG(R > 0 && n_units > 0 && a0_planes > 0 && n_slots > 0, "idv_tapgemm_tc: empty problem");
-  IDV_CHECK_ARG(N >= 32 && N % 32 == 0 && (N <= 256 ? (N == 32 || N == 64 || N == 128 || N == 256) : N % 256 == 0),
-                "idv_tapgemm_tc: N=%d must be 32, 64, 128, 256 or a multiple of 256", N);
+  IDV_CHECK_ARG(N >= 32 && N % 32 == 0 && (N % 64 == 0 || N == 32), "idv_tapgemm_tc: N=%d must be 32 or a multiple of 64", N);
   IDV_CHECK_ARG(a0_cp % 8 == 0 && kc_max % 64 == 0 && (head || out_ld % 8 == 0) && (!a1 || a1_cp % 8 == 0),
                 "idv_tapgemm_tc: channel counts must be multiples of 8 and kc_max of 64");
   int dev = 0, sms = 0;
@@ -500,7 +499,7 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
   // Widest N tile by default (fewest A re-reads).  Small problems (streaming steps, short batches) would leave most
   // SMs idle and, with one CTA streaming a whole weight slice through a 2-stage ring, run at the latency of single
   // TMA round trips: narrow the tile (more CTAs, 3-4 stage ring) until every SM has a tile.
-  int BN = N < 256 ? N : 256;
+  int BN = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
   if (head == 0 || head == 3)
     while (BN > 64 && N % (BN / 2) == 0 && (long long)n_units * cdiv(R, BM) * (N / BN) < sms) BN /= 2;
   CUtensorMap mA0, mA1, mW;

@@ -40,8 +40,19 @@ SIGNATURES = {
     "idv_z_to_planes": [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp],
     "idv_cbn_eval_user": [vp, i64, i32, i64, vp, vp, vp],
     "idv_cbn_stats_planes": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
-    "idv_cbn_train_finalize": [vp, ctypes.c_double, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp],
-    "idv_cbn_apply_planes": [vp, i32, i32, i32, i32, i32, vp, i32, f32, i32, vp],
+    "idv_cbn_train_finalize": [vp, ctypes.c_double, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, vp],
+    "idv_cbn_apply_planes": [vp, i32, i32, i32, i32, i32, vp, i32, f32, i32, vp, vp],
+    "idv_planes_transpose_split": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    "idv_f32_to_split": [vp, i64, vp, vp],
+    "idv_cbn_bwd_reduce": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, f32, vp, i32, vp],
+    "idv_cbn_bwd_finalize": [vp, ctypes.c_double, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "idv_cbn_bwd_apply": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, i32, vp],
+    "idv_lstm_combine_bwd": [vp, i32, i32, i32, vp, i32, vp],
+    "idv_lstm_scan_c": [vp, i32, i32, i32, vp, i32, vp],
+    "idv_lstm_cell_bwd_step": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
+    "idv_colsum_add": [vp, i64, i32, i32, vp, vp],
+    "idv_enc0_wgrad": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
+    "idv_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp],
     "idv_cbn_stats_user": [vp, i64, i32, i64, vp, vp],
     "idv_head_user": [vp, i64, i64, f32, i32, vp, i32, vp],
     "idv_stream_frames_split": [vp, vp, i32, i32, i64, i32, i32, i32, vp, vp],

@@ -148,14 +148,15 @@ class _ComplexConvBase(nn.Module):
                                         pad_t=self._time_geometry()[0])
         return items[key]
 
-    def run_packed(self, pk, xp, out=None):
+    def run_packed(self, pk, xp, out=None, out_split=None):
         """One tap-GEMM launch of a pack built by pack.pack_conv for this layer's geometry (out: static
-        streaming-state tensor, see ops.tapgemm)."""
+        streaming-state tensor, see ops.tapgemm; out_split=False: fp32 planes from split inputs)."""
         tv = self.frames_out(xp.Tv)
         if not 0 < tv <= xp.T:
             raise RuntimeError("conv output has %d frames, the row layout holds %d" % (tv, xp.T))
-        out = ops.tapgemm(pk, xp, None, xp.NB, xp.T, t_valid=tv, out=out)
-        return Planes(out, xp.NB, pk.c_out, pk.f_out, xp.T, split=xp.split, Tv=tv)
+        out = ops.tapgemm(pk, xp, None, xp.NB, xp.T, t_valid=tv, out=out, out_split=out_split)
+        split = xp.split if out_split is None else bool(out_split)
+        return Planes(out, xp.NB, pk.c_out, pk.f_out, xp.T, split=split, Tv=tv)
 
     def forward_planes(self, xp, bn=None, slope=None):
         return self.run_packed(self._packed(xp.F, xp.data.device, bn, slope), xp)
@@ -432,9 +433,9 @@ class Encoder(nn.Module):
     def _slope(self):
         return float(self.prelu.weight.detach().reshape(-1)[0])
 
-    def forward_from_stft(self, stft_x, train=False, out=None, prev=None):
+    def forward_from_stft(self, stft_x, train=False, out=None, prev=None, raw_only=False):
         """First layer (in_channel == 1): reads the user-layout STFT (B, F, T, 2) directly.  out / prev: streaming
-        state (ops.enc0)."""
+        state (ops.enc0).  raw_only: return the conv output before ComplexBatchNormal / PReLU (training forward)."""
         items = self._cache.check(self)
         key = ("enc0", bool(train), str(stft_x.device))
         if key not in items:
@@ -446,11 +447,13 @@ class Encoder(nn.Module):
         w, b, cout, slope = items[key]
         if not self.conv.causal and self.conv._time_geometry() != (0, -1):
             raise NotImplementedError("first non-causal encoder layer: kernel (5,2) with time padding 0 expected")
-        out = ops.enc0(stft_x, w, b, cout, slope, out_split=ops.use_split(), causal=self.conv.causal, out=out,
-                       prev=prev)
+        out = ops.enc0(stft_x, w, b, cout, slope, out_split=ops.use_split() and not raw_only, causal=self.conv.causal,
+                       out=out, prev=prev)
+        if raw_only:                                   # fp32: the batch statistics and the backward pass need y - mean
+            return out                                 # at full precision (|mean| can be >> the channel's std)
         return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
-    def forward_planes(self, xp, train=False, out=None):
+    def forward_planes(self, xp, train=False, out=None, raw_only=False):
         items = self._cache.check(self)          # invalidates the child's fold when bn / prelu change
         key = ("raw" if train else "fold", xp.F, str(xp.data.device))
         if key not in items:
@@ -459,7 +462,9 @@ class Encoder(nn.Module):
             items[key] = pack.pack_conv(c.conv_re.weight, c.conv_re.bias, c.conv_im.weight, c.conv_im.bias,
                                         None if train else self.bn.fold_inputs(), None if train else self._slope(),
                                         xp.F, sf, pf, xp.data.device, pad_t=c._time_geometry()[0])
-        out = self.conv.run_packed(items[key], xp, out)
+        out = self.conv.run_packed(items[key], xp, out, out_split=False if raw_only else None)
+        if raw_only:
+            return out
         return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
     def forward(self, x, train):
@@ -636,10 +641,18 @@ class _VaeEncoderBase(nn.Module):
     def _encode(self, x, train, eps):
         if len(self.lstms) != 1:
             raise NotImplementedError("one ComplexLSTM stage expected (lstm_dim has two entries)")
-        stft_x = self.stft(x)
-        planes = _run_encoder_stack(self.encoders, stft_x, train)
-        top = planes[-1]
-        latent = self.lstms[0].forward_planes(top)                     # (B, T, 3*zdim*latent_num, 2)
+        if train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training step: the latent carries a grad_fn whose backward runs the C-ABI backward kernels (train.py);
+            # z is drawn from the detached latent (the phase-1 loss does not use it)
+            from . import train as _train
+            latent_g, stft_x, planes = _train.encoder_train_forward(self, x)
+            top, latent = planes[-1], latent_g.detach()
+        else:
+            latent_g = None
+            stft_x = self.stft(x)
+            planes = _run_encoder_stack(self.encoders, stft_x, train)
+            top = planes[-1]
+            latent = self.lstms[0].forward_planes(top)                 # (B, T, 3*zdim*latent_num, 2)
         z, S = self.zdim, self.num_samples
         zs = []
         for k in range(self.latent_num):
@@ -649,7 +662,7 @@ class _VaeEncoderBase(nn.Module):
                 er = ei = None
                 seed, off = _next_philox()
             zs.append(ops.reparam(latent, 3 * z * k, z, S, er, ei, seed, off))
-        return stft_x, SkipList(planes), latent, zs, top.C, top.F
+        return stft_x, SkipList(planes), (latent if latent_g is None else latent_g), zs, top.C, top.F
 
     def reparameterization(self, miu, log_sigma, delta, num_samples, eps=None):
         """model/pvae_module.py:L2177-2231; eps = (eps_real, eps_imag) of shape (B, S, T, zdim) or None."""

@@ -304,7 +304,7 @@ def cbn_eval_user(x, zb):
 
 
 # ---- ComplexBatchNormal(train=True), forward only ------------------------------------------------------------------
-def _cbn_finalize(bn, acc, count, device):
+def _cbn_finalize(bn, acc, count, device, stats=None):
     """Batch statistics -> running-buffer update (first call copies, then EMA: complex_progress.py:L144-159) and the
     per-channel affine of the batch statistics.  ``bn`` is a modules.ComplexBatchNormal."""
     C = bn.gamma_rr.numel()
@@ -312,7 +312,7 @@ def _cbn_finalize(bn, acc, count, device):
     first = bool(bn.init_flag)
     lib.call("idv_cbn_train_finalize", acc, float(count), C, bn.gamma_rr.detach(), bn.gamma_ri.detach(),
              bn.gamma_ii.detach(), bn.beta_r.detach(), bn.beta_i.detach(), bn.running_mean_real, bn.running_mean_imag,
-             bn.Vrr, bn.Vri, bn.Vii, float(bn.momentum), 1 if first else 0, zb)
+             bn.Vrr, bn.Vri, bn.Vii, float(bn.momentum), 1 if first else 0, zb, stats)
     if first and not bn.dis_cbn:
         bn.init_flag = False
     return zb
@@ -325,7 +325,7 @@ def cbn_train_planes(p, bn, slope):
     lib.call("idv_cbn_stats_planes", p.data, 1 if p.split else 0, p.NB, C, p.F, p.T, acc, p.Tv)
     zb = _cbn_finalize(bn, acc, p.NB * p.F * p.Tv, p.data.device)
     lib.call("idv_cbn_apply_planes", p.data, 1 if p.split else 0, p.NB, C, p.F, p.T, zb,
-             0 if slope is None else 1, 0.0 if slope is None else float(slope), p.Tv)
+             0 if slope is None else 1, 0.0 if slope is None else float(slope), p.Tv, None)
     return p
 
 

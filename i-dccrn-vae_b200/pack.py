@@ -36,7 +36,7 @@ class TapGemmPack:
         self._units_l, self._taps_l = [list(u) for u in units], [list(t) for t in taps]
 
     def tc_eligible(self):
-        n_ok = self.N in (32, 64, 128, 256) or (self.N > 256 and self.N % 256 == 0)
+        n_ok = self.N == 32 or self.N % 64 == 0
         return n_ok and all(t[4] % 64 == 0 and t[3] % 8 == 0 for t in self._taps_l) and self.out_ld % 8 == 0
 
     def tc(self):
@@ -484,3 +484,188 @@ def pack_istft_tc(n_fft, win, device):
                 bias=torch.zeros(N, device=device), wsq=wsq.to(device),
                 taps=torch.tensor([[0, 0, 0, 0, kpad, 0]], dtype=torch.int32, device=device),
                 units=torch.tensor([[0, 1, 0, 0, 0, kpad // 64]], dtype=torch.int32, device=device))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# backward (phase-1 training step): data-gradient packs and weight-gradient tap tables
+# ------------------------------------------------------------------------------------------------------------------
+def raw_block_weights(conv_re_w, conv_im_w, transposed=False):
+    """Block-real weights W (taps, 2*ch_in, 2*ch_out) of a complex (transposed) conv WITHOUT the CBN fold (the
+    training path keeps ComplexBatchNormal separate).  Returns (W, kh, kw, cin, cout)."""
+    wr, wi = _cpu(conv_re_w), _cpu(conv_im_w)
+    if transposed:
+        cin, cout, kh, kw = wr.shape
+        m_re, m_im = wr.permute(2, 3, 0, 1).reshape(kh * kw, cin, cout), wi.permute(2, 3, 0, 1).reshape(kh * kw, cin, cout)
+    else:
+        cout, cin, kh, kw = wr.shape
+        m_re, m_im = wr.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout), wi.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
+    Z, bp = _identity_fold(cout)
+    zero = torch.zeros(cout)
+    W, _ = _block_weights(m_re, m_im, zero, zero, Z, bp, round8(cin), round8(cout))
+    return W, kh, kw, cin, cout
+
+
+def pack_conv_dgrad(conv_re_w, conv_im_w, f_in, stride_f, pad_f, pad_t, device):
+    """Data gradient of the complex conv packed by pack_conv: dx[fi][r] = sum over (fo, kf, kt) with
+    fi = stride_f*fo + kf - pad_f of dy[fo][r + (pad_t - kt)] W_tap^T - a tap-GEMM over the planes of dy with the
+    mirrored time shifts (the transposed conv of model/complex_progress.py:L16-22's conv)."""
+    W, kh, kw, cin, cout = raw_block_weights(conv_re_w, conv_im_w)
+    f_out = (f_in + 2 * pad_f - kh) // stride_f + 1
+    K, N = 2 * round8(cout), 2 * round8(cin)
+    Wt = W.transpose(1, 2).contiguous()                              # (taps, 2ch_out, 2ch_in)
+    units, taps = [], []
+    for fi in range(f_in):
+        begin = len(taps)
+        for kf in range(kh):
+            num = fi + pad_f - kf
+            if num % stride_f:
+                continue
+            fo = num // stride_f
+            if fo < 0 or fo >= f_out:
+                continue
+            for kt in range(kw):
+                taps.append([0, fo, -(pad_t - kt), 0, K, (kf * kw + kt) * K * N])
+        units.append([begin, len(taps) - begin, fi, 0, 0, 0])
+    p = TapGemmPack(Wt.reshape(-1), torch.zeros(N), units, taps, N, f_in, N, False, 0.0, device)
+    p.f_out, p.c_out = f_in, cin
+    return p
+
+
+def wgrad_conv_tables(f_in, f_out, kh, kw, stride_f, pad_f, pad_t, rpad, groups, device):
+    """Tap tables of the weight-gradient GEMM of a complex conv: unit (kf, kt, g) sums, over the output planes fo of
+    group g, dyT[fo] (rows = output channels, K = rows of the activation, shifted by the tap's time offset: source
+    0 = shift 0, source 1 = shift 1) against xT[fi] (weight-operand slot fi): out[unit] = dW_tap^T (2ch_out, 2ch_in)."""
+    units, taps = [], []
+    # at least 3 output planes per group: every group then has an in-range input plane for every kf (no empty unit)
+    per = max(3, (f_out + groups - 1) // groups)
+    groups = (f_out + per - 1) // per
+    for kf in range(kh):
+        for kt in range(kw):
+            dt = pad_t - kt
+            if dt not in (0, 1):
+                raise NotImplementedError("weight gradients are built for time shifts 0 / 1 (causal taps)")
+            for g in range(groups):
+                begin = len(taps)
+                for fo in range(g * per, min(f_out, (g + 1) * per)):
+                    fi = stride_f * fo + kf - pad_f
+                    if 0 <= fi < f_in:
+                        taps.append([dt, fo, 0, 0, rpad, fi])
+                if len(taps) == begin:
+                    raise RuntimeError("empty weight-gradient unit (kf %d, group %d)" % (kf, g))
+                units.append([begin, len(taps) - begin, len(units), 0, 0, (len(taps) - begin) * (rpad // 64)])
+    return (torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(device),
+            torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(device), len(units), groups)
+
+
+def unfold_conv_wgrad(dwt, kh, kw, cin, cout):
+    """dwt: (kh*kw, 2ch_out, 2ch_in) = dW_tap^T of the block-real weights -> gradients of conv_re.weight and
+    conv_im.weight (Cout, Cin, kh, kw): W[:cin,:cout] = m_re, W[ch_in+ci, co] = -m_im, W[ci, ch_out+co] = m_im,
+    W[ch_in+ci, ch_out+co] = m_re (model/complex_progress.py:L17-19)."""
+    ch_in, ch_out = round8(cin), round8(cout)
+    d = dwt.transpose(1, 2)                                           # (taps, 2ch_in, 2ch_out)
+    d_re = d[:, :cin, :cout] + d[:, ch_in:ch_in + cin, ch_out:ch_out + cout]
+    d_im = d[:, :cin, ch_out:ch_out + cout] - d[:, ch_in:ch_in + cin, :cout]
+    f = lambda m: m.reshape(kh, kw, cin, cout).permute(3, 2, 0, 1).contiguous()
+    return f(d_re), f(d_im)
+
+
+def pack_lstm_gates(lstm_re, lstm_im, hidden, layer, c_in, f_in, device):
+    """Gate pre-activations of one nn.LSTM layer for ALL time steps as one two-source tap-GEMM (backward pass: the
+    forward kernels keep them on chip).  Unit s = (module m, part p), N = 4H:
+      layer 0: source 0 = the encoder output planes (f_in planes, channel half p), source 1 = this layer's h
+               planes [4][R][H] read one row back (h(t-1); the pad row is h(-1) = 0);
+      layer l: source 0 = h planes of the layer below, source 1 = this layer's h planes one row back."""
+    H = hidden
+    N = 4 * H
+    mats, bias = [], torch.zeros(2 * N, dtype=torch.float64)
+    units, taps = [], []
+    off = 0
+    offs = {}
+    for m, mod in enumerate((lstm_re, lstm_im)):
+        wih = _cpu(mod["weight_ih_l%d" % layer]).double()
+        if layer == 0:
+            ch = round8(c_in)
+            w = torch.zeros(f_in, ch, N, dtype=torch.float64)
+            w[:, :c_in] = wih.reshape(N, c_in, f_in).permute(2, 1, 0)
+            for f in range(f_in):
+                offs[("ih", m, f)] = off
+                mats.append(w[f].reshape(-1))
+                off += ch * N
+        else:
+            offs[("ih", m)] = off
+            mats.append(wih.t().contiguous().reshape(-1))
+            off += H * N
+        offs[("hh", m)] = off
+        mats.append(_cpu(mod["weight_hh_l%d" % layer]).double().t().contiguous().reshape(-1))
+        off += H * N
+        bias[m * N:(m + 1) * N] = _cpu(mod["bias_ih_l%d" % layer]).double() + _cpu(mod["bias_hh_l%d" % layer]).double()
+    for m in range(2):
+        for p in range(2):
+            s = m * 2 + p
+            begin = len(taps)
+            if layer == 0:
+                ch = round8(c_in)
+                for f in range(f_in):
+                    taps.append([0, f, 0, p * ch, ch, offs[("ih", m, f)]])
+            else:
+                taps.append([0, s, 0, 0, H, offs[("ih", m)]])
+            taps.append([1, s, 1, 0, H, offs[("hh", m)]])
+            units.append([begin, len(taps) - begin, s, 0, m * N, 0])
+    return TapGemmPack(torch.cat(mats), bias, units, taps, N, 4, N, False, 0.0, device)
+
+
+def pack_lstm_dgrad(lstm_re, lstm_im, hidden, layer, kind, device, c_in=0, f_in=0):
+    """Gate gradients dP [4][rows][4H] times a weight matrix (K = 4H):
+      kind 'hh'          -> dh(t-1) = dP W_hh^m, N = H, out [4][rows][H];
+      kind 'ih', layer>0 -> gradient of the layer below's h, N = H, out [4][rows][H];
+      kind 'ih', layer 0 -> gradient of the encoder output planes: unit (f, p) sums the two modules,
+                            N = ch, out planes [f_in][rows][2ch] at channel offset p*ch."""
+    H = hidden
+    K = 4 * H
+    if kind == "ih" and layer == 0:
+        ch = round8(c_in)
+        mats, units, taps = [], [], []
+        for m, mod in enumerate((lstm_re, lstm_im)):
+            w = _cpu(mod["weight_ih_l0"]).double().reshape(K, c_in, f_in)
+            for f in range(f_in):
+                wf = torch.zeros(K, ch, dtype=torch.float64)
+                wf[:, :c_in] = w[:, :, f]
+                mats.append(wf.reshape(-1))
+        for f in range(f_in):
+            for p in range(2):
+                begin = len(taps)
+                for m in range(2):
+                    taps.append([0, m * 2 + p, 0, 0, K, (m * f_in + f) * K * ch])
+                units.append([begin, 2, f, p * ch, 0, 0])
+        return TapGemmPack(torch.cat(mats), torch.zeros(ch), units, taps, ch, f_in, 2 * ch, False, 0.0, device)
+    mats, units, taps = [], [], []
+    for m, mod in enumerate((lstm_re, lstm_im)):
+        mats.append(_cpu(mod["weight_%s_l%d" % (kind, layer)]).double().reshape(-1))       # (4H, H) = [K][N]
+    for m in range(2):
+        for p in range(2):
+            taps.append([0, m * 2 + p, 0, 0, K, m * K * H])
+            units.append([len(taps) - 1, 1, m * 2 + p, 0, 0, 0])
+    return TapGemmPack(torch.cat(mats), torch.zeros(H), units, taps, H, 4, H, False, 0.0, device)
+
+
+def wgrad_lstm_tables(rpad, device, f_in=0):
+    """Weight-gradient GEMM of an LSTM matrix: unit m sums the two parts p: dPT[(m,p)] (rows = 4H gate columns,
+    K = rows of the sequence) against the transposed input slot.  f_in == 0: slots are the 4 streams (h planes) ->
+    out [2][4H][H]; f_in > 0 (layer-0 W_ih): the encoder planes transposed and viewed as slots f*2 + p of ch
+    channels -> units (m, f), out [2*f_in][4H][ch]."""
+    units, taps = [], []
+    ks = rpad // 64
+    if f_in == 0:
+        for m in range(2):
+            for p in range(2):
+                taps.append([0, m * 2 + p, 0, 0, rpad, m * 2 + p])
+            units.append([2 * m, 2, m, 0, 0, 2 * ks])
+    else:
+        for m in range(2):
+            for f in range(f_in):
+                begin = len(taps)
+                for p in range(2):
+                    taps.append([0, m * 2 + p, 0, 0, rpad, f * 2 + p])
+                units.append([begin, 2, m * f_in + f, 0, 0, 2 * ks])
+    return (torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(device),
+            torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(device), len(units))

@@ -87,7 +87,7 @@ int idv_tapgemm_f32(const float* a0, int a0_ld, int64_t a0_plane,
  * a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation.
  * wt: bf16 [2][n_slots][N][kc_max] (K-major), tap.w_off = slot index, tap.kc % 64 == 0,
  * unit.reserved = number of 64-wide K steps of the unit.  out: split bf16 (out_hl = elements between
- * the hi and lo sets) when out_split, else fp32.  N in {32,64,128,256} or a multiple of 256.        */
+ * the hi and lo sets) when out_split, else fp32.  N = 32 or a multiple of 64.                       */
 int idv_tapgemm_tc(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
                    int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias, int N,
                    const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
@@ -220,21 +220,63 @@ int idv_cbn_eval_user(const float* x, int64_t outer, int C, int64_t inner, const
  *   non-pad row of the planes tensor (fp32 or split bf16);
  * idv_cbn_train_finalize: batch mean / biased (co)variances (eps added to Vrr, Vii as the reference does), update
  *   of the running buffers (first != 0: copy, else EMA with `momentum`), zb[c][6] = Z, b' from the batch statistics;
- * idv_cbn_apply_planes: y <- act(Z y + b') in place (pad rows untouched).                                       */
+ * idv_cbn_apply_planes: y <- act(Z y + b') in place (pad rows untouched), or into `out` (same format, pad rows
+ *   zeroed) when out != NULL - the training forward keeps the raw values for the backward pass.
+ * idv_cbn_train_finalize also writes stats[c][5] = batch mean (re, im), Vrr, Vri, Vii (NULL = not wanted).           */
 int idv_cbn_stats_planes(const void* planes, int split, int NB, int C, int F, int T, double* acc, int t_valid,
                          void* stream);
 int idv_cbn_train_finalize(const double* acc, double count, int C, const float* gamma_rr, const float* gamma_ri,
                            const float* gamma_ii, const float* beta_r, const float* beta_i, float* run_mean_r,
                            float* run_mean_i, float* run_vrr, float* run_vri, float* run_vii, float momentum,
-                           int first, float* zb, void* stream);
+                           int first, float* zb, float* stats, void* stream);
 int idv_cbn_apply_planes(void* planes, int split, int NB, int C, int F, int T, const float* zb, int apply_prelu,
-                         float prelu_slope, int t_valid, void* stream);
+                         float prelu_slope, int t_valid, void* out, void* stream);
 /* statistics on the reference layout x (outer, C, inner, 2) (stand-alone ComplexBatchNormal(train=True); the last
  * decoder layer whose raw output is written in the reference layout) and the in-place recon head on
  * y (n_utt, n_per_utt, 2): PReLU(slope) then, if mask, the mask head with stft_x[b / s_rep].                       */
 int idv_cbn_stats_user(const float* x, int64_t outer, int C, int64_t inner, double* acc, void* stream);
 int idv_head_user(float* y, int64_t n_per_utt, int64_t n_utt, float prelu_slope, int mask, const float* stft_x,
                   int s_rep, void* stream);
+
+/* ---- backward of the NSVAE encoder (phase-1 training step, i_dccrn_vae/nsvae_dccrn/train_nsvae.py:L505-566) --------
+ * GEMM-shaped gradients run on idv_tapgemm_tc: data gradients with transposed weights and mirrored taps, weight
+ * gradients as GEMMs over the ROW dimension on the transposed copies made by idv_planes_transpose_split.
+ *   idv_planes_transpose_split: planes [F][R][Cp] (fp32 / split) -> split bf16 [2][F][Cp][Rpad],
+ *       out[f][c][k] = in[f][k + shift][c] (0 outside [0, R)), Rpad % 64 == 0;
+ *   idv_f32_to_split: fp32 [n] -> split bf16 [2][n];
+ *   idv_cbn_bwd_reduce / _finalize / _apply: ComplexBatchNormal(train=True) + PReLU backward
+ *       (model/complex_progress.py:L131-209 differentiated through the batch mean and covariance; model/pvae_module.py:L64-68).
+ *       y = raw conv output, g = gradient w.r.t. the layer output, stats / zb from idv_cbn_train_finalize;
+ *       reduce -> acc[C][8] (double); finalize -> parameter gradients (+=, d_slope double accumulator) and
+ *       coef[C][10]; apply -> dy = gradient w.r.t. y (planes, pad rows 0);
+ *   idv_lstm_combine_bwd: gradient of the latent (NB, T, H, 2) -> dH [4][R][H] (complex_progress.py:L62-73);
+ *   idv_lstm_scan_c: gate pre-activations P [4][R][4H] -> cell states [4][R][H];
+ *   idv_lstm_cell_bwd_step: one BPTT step t (t = T-1 first with last = 1): dP[t] (fp32 planes and the split-bf16
+ *       copy [2][4][NB][4H] for the dh = dP W_hh tap-GEMM of the next step), dc carried;
+ *   idv_colsum_add: out[col] += sum_rows x (bias gradients);
+ *   idv_enc0_wgrad: weight gradient of idv_enc0_fwd, dW [10][2][2*Cout];
+ *   idv_adam_step: torch.optim.Adam(lr, betas, eps, weight_decay) on a flat buffer (train_nsvae.py:L200).           */
+int idv_planes_transpose_split(const void* planes, int in_split, int F, int R, int Cp, int Rpad, int shift, void* out,
+                               void* stream);
+int idv_f32_to_split(const float* x, int64_t n, void* out, void* stream);
+int idv_cbn_bwd_reduce(const void* y, int y_split, const void* g, int g_split, int NB, int C, int F, int T,
+                       const float* stats, const float* zb, float slope, double* acc, int t_valid, void* stream);
+int idv_cbn_bwd_finalize(const double* acc, double count, int C, const float* stats, const float* gamma_rr,
+                         const float* gamma_ri, const float* gamma_ii, float* coef, float* d_gamma_rr,
+                         float* d_gamma_ri, float* d_gamma_ii, float* d_beta_r, float* d_beta_i, double* d_slope,
+                         void* stream);
+int idv_cbn_bwd_apply(const void* y, int y_split, const void* g, int g_split, int NB, int C, int F, int T,
+                      const float* stats, const float* zb, const float* coef, float slope, void* dy, int dy_split,
+                      int t_valid, void* stream);
+int idv_lstm_combine_bwd(const float* dlatent, int NB, int T, int H, float* dH, int t_valid, void* stream);
+int idv_lstm_scan_c(const float* P, int NB, int T, int H, float* cst, int t_valid, void* stream);
+int idv_lstm_cell_bwd_step(const float* P, const float* cst, const float* dH, const float* dh_rec, float* dc, int NB,
+                           int T, int H, int t, int last, float* dP, void* dP_step, void* stream);
+int idv_colsum_add(const float* x, int64_t rows, int cols, int ld, float* out, void* stream);
+int idv_enc0_wgrad(const float* stft, const float* dY, int B, int Fin, int T, int Cout, int causal, float* dW,
+                   void* stream);
+int idv_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, void* stream);
 
 /* ---- frame streaming (causal network; carried state instead of whole utterances) ------------------------------
  * Hop-synchronous streams: a step consumes hop*k new samples per stream and runs the same tap-GEMMs on k-frame

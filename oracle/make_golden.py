@@ -156,6 +156,85 @@ def case_vae_train(tag, B, L, seed):
     np.savez(os.path.join(OUT, tag + ".npz"), **g)
 
 
+def grad_probe(name, shape, seed=4242):
+    """Fixed pseudo-random direction per parameter: <grad, probe> + ||grad|| pin a gradient with two numbers."""
+    import zlib
+    g = torch.Generator().manual_seed(seed + zlib.crc32(name.encode()) % 100000)
+    return torch.randn(shape, generator=g, dtype=torch.float64)
+
+
+def case_train_step(tag, B, L, latent_num, seed):
+    """Phase-1 NSVAE training step of train_nsvae.py:L472-566: frozen clean / noise CVAE encoders (train=False), noisy
+    encoder train=True, closed-form KL loss (standard_nsvae_loss_true_kl, w_kl = 1), backward.  The fixture pins the
+    loss and, per noisy-encoder parameter, ||grad|| and <grad, probe>; small parameters are stored in full."""
+    import types
+    print("case", tag)
+    for m in ("matplotlib", "matplotlib.pyplot"):                    # unused import in model/nsvae_loss.py:L3
+        sys.modules.setdefault(m, types.ModuleType(m))
+    import model.nsvae_loss as ref_loss
+    net = ref_causal_cfg.get_net_params()
+    noisy = ref_mod.nsvae_pvae_dccrn_encoder_twophase(net, True, "cpu", ZDIM, NFFT, HOP, WIN, 1, latent_num)
+    noisy.load_state_dict(fill_state_dict(noisy.state_dict(), seed), strict=True)
+    frozen = []
+    for j in range(2):
+        e = ref_mod.pvae_dccrn_encoder_skip_prepare(net, True, "cpu", ZDIM, NFFT, HOP, WIN, 1)
+        e.load_state_dict(fill_state_dict(e.state_dict(), seed + 1 + j), strict=True)
+        frozen.append(e.eval())
+    xs = [synth_waveform(B, L, seed=1234 + seed + j) for j in range(3)]          # noisy, clean, noise
+    T = L // HOP + 1
+    eps = synth_eps((B, 1, T, ZDIM), seed=7 + seed, n=2 * latent_num)
+    with torch.no_grad():
+        with supplied_eps(synth_eps((B, 1, T, ZDIM), seed=8 + seed, n=2)):
+            rc = frozen[0](xs[1], train=False)
+        with supplied_eps(synth_eps((B, 1, T, ZDIM), seed=9 + seed, n=2)):
+            rn = frozen[1](xs[2], train=False)
+    with supplied_eps(eps):
+        r = noisy(xs[0], train=True)
+    lossf = ref_loss.standard_nsvae_loss_true_kl(1.0, 0, 1.0, 0, ZDIM, 1, latent_num, "twophase", "False",
+                                                 [0, 1, 2, 3, 4, 5], "latent")
+    # final_nsvae_loss (L448-473) = w_kl * kl_loss + w_dismiu * miu_dis_loss; with the shipped w_dismiu = 0 the step
+    # is kl_loss (L330-347) - called directly because miu_dis_loss cannot run with latent_num == 1 (None operands)
+    out = (None,) + tuple(lossf.kl_loss(rc[1], rn[1], r[1], r[5], rc[2], rn[2], r[2], r[6], rc[3], rn[3], r[3], r[7],
+                                        r[0], r[4]))
+    kl_loss = out[1]
+    kl_loss.backward()
+    # ---- the port, differentiated by autograd on the same tensors
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and k in dict(noisy.named_parameters()))
+          for k, v in noisy.state_dict().items()}
+    st = P.vae_encoder_forward(sd, xs[0], ZDIM, latent_num, 1, eps, train=True, grad=True)
+    with torch.no_grad():
+        sc = P.vae_encoder_forward(frozen[0].state_dict(), xs[1], ZDIM, 1, 1, synth_eps((B, 1, T, ZDIM), seed=8 + seed, n=2))
+        sn = P.vae_encoder_forward(frozen[1].state_dict(), xs[2], ZDIM, 1, 1, synth_eps((B, 1, T, ZDIM), seed=9 + seed, n=2))
+    pl, pc, pn = P.nsvae_kl_loss(st, sc, sn, ZDIM, latent_num, 1.0)
+    pl.backward()
+    check("kl loss", pl.detach(), kl_loss.detach(), 1e-4)     # latent_num 1: difference of two large means
+    g = {"B": B, "L": L, "latent_num": latent_num, "seed": seed, "loss": np32(kl_loss), "kl_clean": np32(out[2]),
+         "kl_noise": np32(out[3]), "miu": np32(r[1])}
+    worst = 0.0
+    for name, p in noisy.named_parameters():
+        if p.grad is None:
+            assert name.startswith("dense."), name                     # unused ComplexDense: no gradient
+            continue
+        if ".conv.conv_" in name and name.endswith(".bias"):
+            # a bias in front of a batch-statistics normalisation has an exactly zero gradient; autograd returns
+            # round-off (~1e-7), which only an absolute bound can pin
+            assert float(p.grad.abs().max()) < 1e-5 and float(sd[name].grad.abs().max()) < 1e-5, name
+            g["zero/" + name] = np.float64(p.grad.abs().max())
+            continue
+        e = P.rel_l2(sd[name].grad, p.grad)
+        if e > 1e-4:
+            print("   ", name, "rel %.2e  |ref| %.3e |port| %.3e" % (e, float(p.grad.norm()), float(sd[name].grad.norm())))
+        worst = max(worst, e)
+        gd = p.grad.double()
+        g["norm/" + name] = np.float64(gd.norm())
+        g["probe/" + name] = np.float64((gd * grad_probe(name, p.shape)).sum())
+        if p.numel() <= 1024:
+            g["full/" + name] = np32(p.grad)
+    print("  port-vs-reference gradients (autograd of the port): worst rel_l2 = %.2e" % worst)
+    assert worst < 2e-4, worst
+    np.savez(os.path.join(OUT, tag + ".npz"), **g)
+
+
 def case_dccrn(tag, B, L, seed, causal=True):
     print("case", tag)
     net = (ref_causal_cfg if causal else ref_noncausal_cfg).get_net_params()
@@ -240,6 +319,10 @@ def case_primitives(tag, seed):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-trainstep" in sys.argv:
+        case_train_step("train_step_l2", B=2, L=1200, latent_num=2, seed=13)
+        case_train_step("train_step_l1", B=3, L=700, latent_num=1, seed=14)
+        sys.exit(0)
     if "--only-noncausal" in sys.argv:
         noncausal_cases()
         sys.exit(0)
@@ -262,4 +345,6 @@ if __name__ == "__main__":
              recon_type="real_imag", seed=4, full=False)
     case_dccrn("dccrn_mask_e2e", B=2, L=8000, seed=5)
     noncausal_cases()
+    case_train_step("train_step_l2", B=2, L=1200, latent_num=2, seed=13)
+    case_train_step("train_step_l1", B=3, L=700, latent_num=1, seed=14)
     print("golden fixtures written to", OUT)

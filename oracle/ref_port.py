@@ -149,16 +149,34 @@ def cbn_eval(x, sd, pre):
     return torch.stack((out_r, out_i), dim=-1)
 
 
+def cbn_train(x, sd, pre):
+    """ComplexBatchNormal.forward(train=True) — model/complex_progress.py:L131-160 + cbn: batch mean / biased
+    (co)variances over (B, F, T), eps added to Vrr and Vii, differentiable through the statistics exactly like the
+    reference (running-buffer updates are a side effect the port does not reproduce)."""
+    C = x.shape[1]
+    re, im = x[..., 0], x[..., 1]
+    rc = re - re.mean((0, 2, 3), keepdim=True)
+    ic = im - im.mean((0, 2, 3), keepdim=True)
+    st = dict(sd)
+    st[pre + "Vrr"] = (rc * rc).mean((0, 2, 3), keepdim=True) + EPS_CBN
+    st[pre + "Vii"] = (ic * ic).mean((0, 2, 3), keepdim=True) + EPS_CBN
+    st[pre + "Vri"] = (rc * ic).mean((0, 2, 3), keepdim=True)
+    zrr, zri, zir, zii = cbn_whiten_affine(st, pre)
+    out_r = zrr * rc + zri * ic + sd[pre + "beta_r"].view(1, C, 1, 1)
+    out_i = zir * rc + zii * ic + sd[pre + "beta_i"].view(1, C, 1, 1)
+    return torch.stack((out_r, out_i), dim=-1)
+
+
 def prelu(x, sd, pre):
     """nn.PReLU() with one shared slope on the 5-D tensor — model/pvae_module.py:L58,L67."""
     return F.prelu(x, sd[pre + "weight"])
 
 
-def encoder_block(x, sd, pre, causal=True):
-    """Encoder.forward(x, train=False) — model/pvae_module.py:L64-68."""
+def encoder_block(x, sd, pre, causal=True, train=False):
+    """Encoder.forward(x, train) — model/pvae_module.py:L64-68."""
     pad = (2, 1) if causal else (2, 0)
     y = complex_conv2d(x, sd, pre + "conv.", (2, 1), pad, causal)
-    return prelu(cbn_eval(y, sd, pre + "bn."), sd, pre + "prelu.")
+    return prelu((cbn_train if train else cbn_eval)(y, sd, pre + "bn."), sd, pre + "prelu.")
 
 
 def decoder_block(x, sd, pre, causal=True):
@@ -175,9 +193,37 @@ def _lstm_module(sd, pre, input_size, hidden, layers, dtype):
     return m.eval()
 
 
-def complex_lstm(x, sd, pre, hidden, layers=2):
-    """ComplexLSTM.forward — model/complex_progress.py:L58-74.  x: (T, B, D, 2)."""
+def _lstm_functional(x, sd, pre, hidden, layers):
+    """nn.LSTM (unidirectional, zero initial state) written out with the tensors of ``sd`` so that autograd reaches
+    them (training-step oracle).  Gate order i, f, g, o; x: (T, B, D)."""
+    T, B, _ = x.shape
+    inp = x
+    for l in range(layers):
+        wih, whh = sd[pre + "weight_ih_l%d" % l], sd[pre + "weight_hh_l%d" % l]
+        b = sd[pre + "bias_ih_l%d" % l] + sd[pre + "bias_hh_l%d" % l]
+        gin = inp @ wih.t() + b
+        h = x.new_zeros(B, hidden)
+        c = x.new_zeros(B, hidden)
+        outs = []
+        for t in range(T):
+            a = gin[t] + h @ whh.t()
+            i, f, g, o = a[:, :hidden], a[:, hidden:2 * hidden], a[:, 2 * hidden:3 * hidden], a[:, 3 * hidden:]
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            outs.append(h)
+        inp = torch.stack(outs)
+    return inp
+
+
+def complex_lstm(x, sd, pre, hidden, layers=2, grad=False):
+    """ComplexLSTM.forward — model/complex_progress.py:L58-74.  x: (T, B, D, 2).  grad=True evaluates the same
+    recurrences functionally on the tensors of ``sd`` (differentiable w.r.t. them)."""
     d_in = x.shape[2]
+    if grad:
+        run_re = lambda v: _lstm_functional(v, sd, pre + "lstm_re.", hidden, layers)
+        run_im = lambda v: _lstm_functional(v, sd, pre + "lstm_im.", hidden, layers)
+        rr, ri, ii, ir = run_re(x[..., 0]), run_im(x[..., 0]), run_im(x[..., 1]), run_re(x[..., 1])
+        return torch.stack((rr - ii, ir + ri), dim=-1)
     lre = _lstm_module(sd, pre + "lstm_re.", d_in, hidden, layers, x.dtype)
     lim = _lstm_module(sd, pre + "lstm_im.", d_in, hidden, layers, x.dtype)
     with torch.no_grad():
@@ -238,16 +284,55 @@ def mask_head(mask, stft_x, num_samples=1):
 # ------------------------------------------------------------------------------------------------
 # model graphs
 # ------------------------------------------------------------------------------------------------
-def encoder_stack(x5, sd, n_layers=6, causal=True):
+def encoder_stack(x5, sd, n_layers=6, causal=True, train=False):
     skiper = []
     for i in range(n_layers):
-        x5 = encoder_block(x5, sd, "encoders.%d." % i, causal)
+        x5 = encoder_block(x5, sd, "encoders.%d." % i, causal, train)
         skiper.append(x5)
     return x5, skiper
 
 
+def cal_kl(miu1, miu2, log_sigma1, log_sigma2, delta1, delta2, zdim, eps=1e-10):
+    """standard_nsvae_loss_true_kl.cal_kl — model/nsvae_loss.py:L275-328: closed-form KL between two complex
+    Gaussians per (B, T) (distribution 1 = the noisy encoder's posterior, 2 = the frozen target's)."""
+    m1r, m1i, m2r, m2i = miu1[..., 0], miu1[..., 1], miu2[..., 0], miu2[..., 1]
+    s1, s2 = torch.exp(log_sigma1[..., 0]), torch.exp(log_sigma2[..., 0])
+
+    def protect(d, s):
+        dr, di = d[..., 0], d[..., 1]
+        ad = torch.sqrt(dr.pow(2) + di.pow(2) + eps)
+        tmp = s * 0.99 / (ad + eps)
+        cl = ad >= (s - 1e-3)
+        dr, di = torch.where(cl, dr * tmp, dr), torch.where(cl, di * tmp, di)
+        return dr, di, dr.pow(2) + di.pow(2)
+    d1r, d1i, a1 = protect(delta1, s1)
+    d2r, d2i, a2 = protect(delta2, s2)
+    log_det_c1 = torch.log(0.25 * (s1.pow(2) - a1) + eps)
+    log_det_c2 = torch.log(0.25 * (s2.pow(2) - a2) + eps)
+    coeff = 2 / (s2.pow(2) - a2 + eps)
+    trace_term = s1 * s2 - d2r * d1r - d2i * d1i
+    dr, di = m2r - m1r, m2i - m1i
+    quadra = dr.pow(2) * (s2 - d2r) - 2 * d2i * dr * di + di.pow(2) * (s2 + d2r)
+    return 0.5 * torch.sum(coeff * (trace_term + quadra) + log_det_c2 - log_det_c1, dim=2) - zdim
+
+
+def nsvae_kl_loss(noisy, clean, noise, zdim=128, latent_num=1, alpha=1.0):
+    """standard_nsvae_loss_true_kl.kl_loss — model/nsvae_loss.py:L330-347 (the phase-1 training loss of
+    train_nsvae.py:L539-544 with w_kl = 1, w_dismiu = 0).  noisy / clean / noise: encoder state dicts of
+    vae_encoder_forward.  Returns (loss, kl_clean, kl_noise)."""
+    kc = cal_kl(noisy["miu_speech"], clean["miu_speech"], noisy["log_sigma_speech"], clean["log_sigma_speech"],
+                noisy["delta_speech"], clean["delta_speech"], zdim)
+    if latent_num == 1:
+        kn = cal_kl(noisy["miu_speech"], noise["miu_speech"], noisy["log_sigma_speech"], noise["log_sigma_speech"],
+                    noisy["delta_speech"], noise["delta_speech"], zdim)
+        return kc.mean() - alpha * kn.mean(), kc.mean(), kn.mean()
+    kn = cal_kl(noisy["miu_noise"], noise["miu_speech"], noisy["log_sigma_noise"], noise["log_sigma_speech"],
+                noisy["delta_noise"], noise["delta_speech"], zdim)
+    return kc.mean() + alpha * kn.mean(), kc.mean(), kn.mean()
+
+
 def vae_encoder_forward(sd, signal, zdim=128, latent_num=1, num_samples=1, eps=None, causal=True,
-                        stft_params=(512, 100, 400)):
+                        stft_params=(512, 100, 400), train=False, grad=False):
     """nsvae_pvae_dccrn_encoder_twophase.forward(x, train=False) — model/pvae_module.py:L2233-2268;
     with latent_num == 1 it is also pvae_dccrn_encoder_skip_prepare.forward (L1888-1914).
     eps: list of (B,S,T,zdim) tensors in draw order [speech_r, speech_i, (noise_r, noise_i)].
@@ -255,12 +340,12 @@ def vae_encoder_forward(sd, signal, zdim=128, latent_num=1, num_samples=1, eps=N
     st = {}
     stft_x = stft(signal, *stft_params)
     st["stft_x"] = stft_x
-    x, skiper = encoder_stack(stft_x.unsqueeze(1), sd, 6, causal)
+    x, skiper = encoder_stack(stft_x.unsqueeze(1), sd, 6, causal, train)
     st["skiper"] = skiper
     B, C, Fq, T, D = x.shape
     lstm_in = x.reshape(B, -1, T, D).permute(2, 0, 1, 3)
     hidden = 3 * zdim * latent_num
-    lat = complex_lstm(lstm_in, sd, "lstms.0.", hidden, 2).permute(1, 0, 2, 3)   # (B,T,hidden,2)
+    lat = complex_lstm(lstm_in, sd, "lstms.0.", hidden, 2, grad).permute(1, 0, 2, 3)   # (B,T,hidden,2)
     st["latent"] = lat
     z = zdim
     st["miu_speech"], st["log_sigma_speech"], st["delta_speech"] = lat[:, :, 0:z], lat[:, :, z:2 * z], lat[:, :, 2 * z:3 * z]

@@ -496,7 +496,7 @@ def idv_cbn_stats_user(x, outer, C, inner, acc):
 
 
 def idv_cbn_train_finalize(acc, count, C, g_rr, g_ri, g_ii, beta_r, beta_i, run_mr, run_mi, run_vrr, run_vri, run_vii,
-                           momentum, first, zb):
+                           momentum, first, zb, stats=None):
     a = acc.view(C, 5).to(D)
     eps = 1e-5
     mr, mi = a[:, 0] / count, a[:, 1] / count
@@ -505,6 +505,8 @@ def idv_cbn_train_finalize(acc, count, C, g_rr, g_ri, g_ii, beta_r, beta_i, run_
     vrr = f32(a[:, 2] / count - mr * mr) + eps
     vii = f32(a[:, 3] / count - mi * mi) + eps
     vri = f32(a[:, 4] / count - mr * mi)
+    if stats is not None:
+        stats.view(C, 5).copy_(torch.stack((mu_r, mu_i, vrr, vri, vii), 1))
     for buf, val in ((run_mr, mu_r), (run_mi, mu_i), (run_vrr, vrr), (run_vri, vri), (run_vii, vii)):
         b = buf.view(-1)
         b.copy_(val if first else momentum * b + (1 - momentum) * val)
@@ -520,7 +522,7 @@ def idv_cbn_train_finalize(acc, count, C, g_rr, g_ri, g_ii, beta_r, beta_i, run_
                                      beta_i.view(-1) - (zir * mu_r + zii * mu_i)), 1))
 
 
-def idv_cbn_apply_planes(planes, split, NB, C, F, T, zb, apply_prelu, slope, t_valid=0):
+def idv_cbn_apply_planes(planes, split, NB, C, F, T, zb, apply_prelu, slope, t_valid=0, out=None):
     Ch, Tp = _r8(C), T + 1
     te = 1 + _tv(t_valid, T)
     n = F * NB * Tp * 2 * Ch
@@ -532,9 +534,11 @@ def idv_cbn_apply_planes(planes, split, NB, C, F, T, zb, apply_prelu, slope, t_v
     if apply_prelu:
         o_r = torch.where(o_r > 0, o_r, slope * o_r)
         o_i = torch.where(o_i > 0, o_i, slope * o_i)
+    if out is not None and out is not planes:
+        p = torch.zeros_like(p)
     p[:, :, 1:te, 0, :C] = o_r
     p[:, :, 1:te, 1, :C] = o_i
-    _wr(planes, split, p)
+    _wr(out if out is not None else planes, split, p)
 
 
 def idv_head_user(y, n_per_utt, n_utt, slope, mask, stft_x, s_rep):
@@ -549,6 +553,156 @@ def idv_head_user(y, n_per_utt, n_utt, slope, mask, stft_x, s_rep):
         in_ph = torch.atan2(X[..., 1], X[..., 0])
         yr, yi = in_mag * mag * torch.cos(in_ph + ph), in_mag * mag * torch.sin(in_ph + ph)
     y.view(n_utt, n_per_utt, 2).copy_(torch.stack((yr, yi), -1).to(torch.float32))
+
+
+# ---- backward of the encoder (csrc/backward.cu) -----------------------------------------------------------------------
+def idv_planes_transpose_split(planes, in_split, F, R, Cp, Rpad, shift, out):
+    x = _rd(planes, in_split, F * R * Cp).view(F, R, Cp)
+    o = torch.zeros(F, Cp, Rpad, dtype=D)
+    for k in range(Rpad):
+        r = k + shift
+        if 0 <= r < R:
+            o[:, :, k] = x[:, r, :]
+    _wr(out, 1, o)
+
+
+def idv_f32_to_split(x, n, out):
+    _wr(out, 1, _flat(x)[:n].to(D))
+
+
+def _cbn_bwd_common(y, y_split, g, g_split, NB, C, F, T, stats, zb, slope, t_valid):
+    Ch, Tp, Tv = _r8(C), T + 1, _tv(t_valid, T)
+    n = F * NB * Tp * 2 * Ch
+    yv = _rd(y, y_split, n).view(F, NB, Tp, 2, Ch)[:, :, 1:1 + Tv, :, :C]
+    gv = _rd(g, g_split, n).view(F, NB, Tp, 2, Ch)[:, :, 1:1 + Tv, :, :C]
+    k = zb.view(C, 6).to(D)
+    st = stats.view(C, 5).to(D)
+    yr, yi, gr, gi = yv[..., 0, :], yv[..., 1, :], gv[..., 0, :], gv[..., 1, :]
+    pr = k[:, 0] * yr + k[:, 1] * yi + k[:, 4]
+    pi = k[:, 2] * yr + k[:, 3] * yi + k[:, 5]
+    gpr = torch.where(pr > 0, gr, slope * gr)
+    gpi = torch.where(pi > 0, gi, slope * gi)
+    return pr, pi, gr, gi, gpr, gpi, yr - st[:, 0], yi - st[:, 1]
+
+
+def idv_cbn_bwd_reduce(y, y_split, g, g_split, NB, C, F, T, stats, zb, slope, acc, t_valid=0):
+    pr, pi, gr, gi, gpr, gpi, xr, xi = _cbn_bwd_common(y, y_split, g, g_split, NB, C, F, T, stats, zb, slope, t_valid)
+    sm = lambda v: v.sum((0, 1, 2))
+    sl = sm(torch.where(pr > 0, torch.zeros_like(pr), gr * pr)) + sm(torch.where(pi > 0, torch.zeros_like(pi), gi * pi))
+    acc.view(C, 8).copy_(torch.stack((sm(gpr), sm(gpi), sm(gpr * xr), sm(gpr * xi), sm(gpi * xr), sm(gpi * xi), sl,
+                                      torch.zeros(C, dtype=D)), 1))
+
+
+def idv_cbn_bwd_finalize(acc, count, C, stats, g_rr, g_ri, g_ii, coef, d_grr, d_gri, d_gii, d_br, d_bi, d_slope):
+    """Independent derivation: autograd through cbn()'s per-channel algebra (model/complex_progress.py:L168-205)."""
+    s = acc.view(C, 8).to(D)
+    st = stats.view(C, 5).to(D)
+    eps = 1e-5
+    with torch.enable_grad():                     # called from inside an autograd backward (grad mode is off there)
+        V = [st[:, 2].clone().requires_grad_(True), st[:, 3].clone().requires_grad_(True), st[:, 4].clone().requires_grad_(True)]
+        G = [g_rr.view(-1).to(D).clone().requires_grad_(True), g_ri.view(-1).to(D).clone().requires_grad_(True),
+             g_ii.view(-1).to(D).clone().requires_grad_(True)]
+        a, cri, b = V
+        delta = torch.clamp(a * b - cri * cri + eps, min=1e-8)
+        sq = torch.sqrt(delta)
+        t = torch.sqrt(a + b + 2 * sq + eps)
+        ist = 1.0 / (sq * t + eps)
+        wrr, wii, wri = (b + sq) * ist, (a + sq) * ist, -cri * ist
+        zrr, zri = G[0] * wrr + G[1] * wri, G[0] * wri + G[1] * wii
+        zir, zii = G[1] * wrr + G[2] * wri, G[1] * wri + G[2] * wii
+        # L(Z) = <dZ, Z> with dZ_ab = sum gp_a xc_b
+        obj = (s[:, 2] * zrr + s[:, 3] * zri + s[:, 4] * zir + s[:, 5] * zii).sum()
+        ga, gc, gb, dgrr, dgri, dgii = torch.autograd.grad(obj, V + G)
+    for dst, val in ((d_grr, dgrr), (d_gri, dgri), (d_gii, dgii), (d_br, s[:, 0]), (d_bi, s[:, 1])):
+        dst.view(-1).add_(val.to(torch.float32))
+    n = count
+    zrr, zri, zir, zii = zrr.detach(), zri.detach(), zir.detach(), zii.detach()
+    coef.view(C, 10).copy_(torch.stack((zrr, zir, zri, zii, 2 * ga / n, gc / n, 2 * gb / n,
+                                        (zrr * s[:, 0] + zir * s[:, 1]) / n, (zri * s[:, 0] + zii * s[:, 1]) / n,
+                                        torch.zeros(C, dtype=D)), 1).to(torch.float32))
+    if d_slope is not None:
+        d_slope += s[:, 6].sum()
+
+
+def idv_cbn_bwd_apply(y, y_split, g, g_split, NB, C, F, T, stats, zb, coef, slope, dy, dy_split, t_valid=0):
+    pr, pi, gr, gi, gpr, gpi, xr, xi = _cbn_bwd_common(y, y_split, g, g_split, NB, C, F, T, stats, zb, slope, t_valid)
+    k = coef.view(C, 10).to(D)
+    Ch, Tp, Tv = _r8(C), T + 1, _tv(t_valid, T)
+    o = torch.zeros(F, NB, Tp, 2, Ch, dtype=D)
+    o[:, :, 1:1 + Tv, 0, :C] = k[:, 0] * gpr + k[:, 1] * gpi + k[:, 4] * xr + k[:, 5] * xi - k[:, 7]
+    o[:, :, 1:1 + Tv, 1, :C] = k[:, 2] * gpr + k[:, 3] * gpi + k[:, 5] * xr + k[:, 6] * xi - k[:, 8]
+    _wr(dy, dy_split, o)
+
+
+def idv_lstm_combine_bwd(dlatent, NB, T, H, dH, t_valid=0):
+    Tp, Tv = T + 1, _tv(t_valid, T)
+    d = dlatent.view(NB, Tv, H, 2)
+    o = torch.zeros(4, NB, Tp, H)
+    o[0, :, 1:1 + Tv], o[1, :, 1:1 + Tv], o[2, :, 1:1 + Tv], o[3, :, 1:1 + Tv] = d[..., 0], d[..., 1], d[..., 1], -d[..., 0]
+    dH.view(4, NB, Tp, H).copy_(o)
+
+
+def idv_lstm_scan_c(P, NB, T, H, cst, t_valid=0):
+    Tp, Tv = T + 1, _tv(t_valid, T)
+    p = P.view(4, NB, Tp, 4 * H).to(D)
+    co = cst.view(4, NB, Tp, H)
+    c = torch.zeros(4, NB, H, dtype=D)
+    co[:, :, 0] = 0
+    for t in range(Tv):
+        a = p[:, :, 1 + t]
+        c = torch.sigmoid(a[..., H:2 * H]) * c + torch.sigmoid(a[..., :H]) * torch.tanh(a[..., 2 * H:3 * H])
+        co[:, :, 1 + t] = c.to(torch.float32)
+
+
+def idv_lstm_cell_bwd_step(P, cst, dH, dh_rec, dc, NB, T, H, t, last, dP, dP_step):
+    Tp = T + 1
+    a = P.view(4, NB, Tp, 4 * H)[:, :, 1 + t].to(D)
+    ig, fg, gg, og = torch.sigmoid(a[..., :H]), torch.sigmoid(a[..., H:2 * H]), torch.tanh(a[..., 2 * H:3 * H]), \
+        torch.sigmoid(a[..., 3 * H:])
+    cs = cst.view(4, NB, Tp, H).to(D)
+    c, cprev = cs[:, :, 1 + t], cs[:, :, t]
+    tc = torch.tanh(c)
+    dh = dH.view(4, NB, Tp, H)[:, :, 1 + t].to(D)
+    dcv = dh * og * (1 - tc * tc)
+    if not last:
+        dh = dh + dh_rec.view(4, NB, H).to(D)
+        dcv = dc.view(4, NB, H).to(D) + dh * og * (1 - tc * tc)
+    d = torch.cat((dcv * gg * ig * (1 - ig), dcv * cprev * fg * (1 - fg), dcv * ig * (1 - gg * gg),
+                   dh * tc * og * (1 - og)), -1)
+    dc.view(4, NB, H).copy_((dcv * fg).to(torch.float32))
+    dP.view(4, NB, Tp, 4 * H)[:, :, 1 + t] = d.to(torch.float32)
+    _wr(dP_step, 1, d)
+
+
+def idv_colsum_add(x, rows, cols, ld, out):
+    _flat(out)[:cols].add_(_flat(x)[:rows * ld].view(rows, ld)[:, :cols].to(D).sum(0).to(torch.float32))
+
+
+def idv_enc0_wgrad(stft, dY, B, Fin, T, Cout, causal, dW):
+    N = 2 * Cout
+    Fout = (Fin + 4 - 5) // 2 + 1
+    x = stft.view(B, Fin, T, 2).to(D)
+    xpad = torch.zeros(B, Fin + 4, T + 1, 2, dtype=D)
+    if causal:
+        xpad[:, 2:2 + Fin, 1:] = x
+    else:
+        xpad[:, 2:2 + Fin, :T] = x
+    g = dY.view(Fout, B, T + 1, N)[:, :, 1:].to(D)
+    o = torch.zeros(10, 2, N, dtype=D)
+    for kf in range(5):
+        for kt in range(2):
+            sl = xpad[:, kf:kf + 2 * Fout - 1:2, kt:kt + T]                       # (B, Fout, T, 2)
+            o[kf * 2 + kt] = torch.einsum("bftp,fbtn->pn", sl, g)
+    dW.view(10, 2, N).copy_(o.to(torch.float32))
+
+
+def idv_adam_step(p, g, m, v, n, lr, b1, b2, eps, wd, step):
+    pv, gv, mv, vv = (_flat(t)[:n] for t in (p, g, m, v))
+    gg = gv + wd * pv
+    mv.copy_(b1 * mv + (1 - b1) * gg)
+    vv.copy_(b2 * vv + (1 - b2) * gg * gg)
+    bc1, bc2 = 1 - b1 ** step, math.sqrt(1 - b2 ** step)
+    pv.sub_((lr / bc1) * mv / (vv.sqrt() / bc2 + eps))
 
 
 # ---- frame streaming --------------------------------------------------------------------------------------------
