@@ -155,7 +155,9 @@ def test_layout_roundtrip(NB, C_, F, T, tv):
     for split, buf in ((0, planes), (1, sp)):
         acc = torch.zeros(C_ * 5, dtype=torch.float64)
         assert _both("idv_cbn_stats_planes", [buf, split, NB, C_, F, T, acc, tv], [6]) < 1e-6
-        assert _both("idv_cbn_apply_planes", [buf.clone(), split, NB, C_, F, T, zb.reshape(-1), 1, 0.3, tv], [0]) < 1e-6
+        assert _both("idv_cbn_apply_planes", [buf.clone(), split, NB, C_, F, T, zb.reshape(-1), 1, 0.3, tv, None], [0]) < 1e-6
+        assert _both("idv_cbn_apply_planes", [buf.clone(), split, NB, C_, F, T, zb.reshape(-1), 1, 0.3, tv,
+                                              torch.full_like(buf, 2.0)], [10]) < 1e-6        # out of place
 
 
 def test_streaming_state_kernels():
@@ -209,6 +211,67 @@ def test_tapgemm_keeps_pad_rows_when_streaming():
     args = [a32, 72, R * 72, None, 0, 0, R, -Tp, w32, _rand(N, seed=4), N, torch.tensor([[0, 1, 0, 0, 0, 0]], dtype=torch.int32),
             torch.tensor([[0, 0, 1, 8, 64, 0]], dtype=torch.int32), 1, _rand(R * N, seed=6), N, R * N, 1, 0.2, 0]
     assert _both("idv_tapgemm_f32", args, [14]) < 1e-5
+
+
+@pytest.mark.parametrize("NB,C_,F,T", [(3, 32, 9, 8), (2, 5, 3, 33), (1, 256, 5, 64)])
+def test_cbn_prelu_backward_kernels(NB, C_, F, T):
+    """csrc/backward.cu: reduce / finalize / apply against the contract; the emulator's finalize differentiates cbn()'s
+    per-channel algebra by autograd, the kernel uses the hand-derived chain."""
+    Ch = (C_ + 7) // 8 * 8
+    n = F * NB * (T + 1) * 2 * Ch
+    y = _rand(n, seed=60) * 2 + 0.5
+    g = _rand(n, seed=61)
+    stats = torch.stack((_rand(C_, seed=62), _rand(C_, seed=63), 1 + _rand(C_, seed=64).abs(), 0.3 * _rand(C_, seed=65),
+                         0.8 + _rand(C_, seed=66).abs()), 1).contiguous()
+    zb = _rand(C_, 6, seed=67)
+    acc = torch.zeros(C_ * 8, dtype=torch.float64)
+    assert _both("idv_cbn_bwd_reduce", [y, 0, g, 0, NB, C_, F, T, stats, zb, 0.25, acc, 0], [11]) < 1e-6
+    E.call("idv_cbn_bwd_reduce", y, 0, g, 0, NB, C_, F, T, stats, zb, 0.25, acc, 0)
+    gam = [1 + 0.2 * _rand(C_, seed=68), _rand(C_, seed=69), 1 + 0.2 * _rand(C_, seed=70)]
+    outs = [torch.zeros(C_ * 10)] + [_rand(C_, seed=71 + i) for i in range(5)] + [torch.ones(1, dtype=torch.float64)]
+    args = [acc, float(NB * F * T), C_, stats] + gam + outs
+    assert _both("idv_cbn_bwd_finalize", args, [7, 8, 9, 10, 11, 12, 13]) < 2e-5
+    coef = torch.zeros(C_ * 10)
+    E.call("idv_cbn_bwd_finalize", acc, float(NB * F * T), C_, stats, *gam, coef, *[torch.zeros(C_) for _ in range(5)],
+           torch.zeros(1, dtype=torch.float64))
+    for dy_split in (0, 1):
+        dy = torch.zeros(2 * n, dtype=torch.bfloat16) if dy_split else torch.zeros(n)
+        ys = _to_split(y).reshape(-1)
+        assert _both("idv_cbn_bwd_apply", [ys, 1, g, 0, NB, C_, F, T, stats, zb, coef, 0.25, dy, dy_split, 0], [12]) < 2e-5
+
+
+def test_lstm_backward_and_misc_kernels():
+    NB, T, H = 3, 6, 64
+    R = NB * (T + 1)
+    P_ = _rand(4, R, 4 * H, seed=80)
+    cst = torch.zeros(4 * R * H)
+    assert _both("idv_lstm_scan_c", [P_, NB, T, H, cst, 0], [4]) < 1e-5
+    E.call("idv_lstm_scan_c", P_, NB, T, H, cst, 0)
+    dH = _rand(4, R, H, seed=81)
+    dP, dstep = torch.zeros(4 * R * 4 * H), torch.zeros(2 * 4 * NB * 4 * H, dtype=torch.bfloat16)
+    dc, dhr = _rand(4 * NB * H, seed=82), _rand(4 * NB * H, seed=83)
+    assert _both("idv_lstm_cell_bwd_step", [P_, cst, dH, None, dc.clone(), NB, T, H, T - 1, 1, dP, dstep], [4, 10, 11]) < 1e-5
+    assert _both("idv_lstm_cell_bwd_step", [P_, cst, dH, dhr, dc.clone(), NB, T, H, 2, 0, dP, dstep], [4, 10, 11]) < 1e-5
+    assert _both("idv_lstm_cell_bwd_step", [P_, cst, dH, dhr, dc.clone(), NB, T, H, 0, 0, dP, dstep], [4, 10, 11]) < 1e-5
+    dl = _rand(NB, T, H, 2, seed=84)
+    assert _both("idv_lstm_combine_bwd", [dl, NB, T, H, torch.full((4 * R * H,), 3.0), 0], [4]) < 1e-7
+    x = _rand(1000, 200, seed=85)
+    assert _both("idv_colsum_add", [x, 1000, 130, 200, _rand(130, seed=86)], [4]) < 1e-5
+    B, Fin, Tt, Cout = 2, 33, 19, 32
+    Fout = (Fin - 1) // 2 + 1
+    st = _rand(B, Fin, Tt, 2, seed=87)
+    dY = _rand(Fout, B, Tt + 1, 2 * Cout, seed=88)
+    dY[:, :, 0] = 0
+    assert _both("idv_enc0_wgrad", [st, dY, B, Fin, Tt, Cout, 1, torch.zeros(20 * 2 * Cout)], [7]) < 1e-5
+    n = 4096 + 12
+    pr, gr, m, v = _rand(n, seed=89), _rand(n, seed=90), _rand(n, seed=91) * 0.1, _rand(n, seed=92).abs() * 0.01
+    assert _both("idv_adam_step", [pr, gr, m, v, n, 1e-3, 0.9, 0.999, 1e-8, 1e-3, 7], [0, 2, 3]) < 1e-5
+    pl = _rand(3, 50, 24, seed=93)
+    for shift in (0, 1):
+        out = torch.zeros(2 * 3 * 24 * 64, dtype=torch.bfloat16)
+        assert _both("idv_planes_transpose_split", [pl, 0, 3, 50, 24, 64, shift, out], [7]) < 1e-7
+        assert _both("idv_planes_transpose_split", [_to_split(pl).reshape(-1), 1, 3, 50, 24, 64, shift, out], [7]) < 1e-7
+    assert _both("idv_f32_to_split", [pl, pl.numel(), torch.zeros(2 * pl.numel(), dtype=torch.bfloat16)], [2]) < 1e-7
 
 
 def test_bad_arguments_return_error_codes():

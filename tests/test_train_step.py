@@ -128,7 +128,11 @@ def run_layerwise_case(device, latent_num=1, B=3, L=700, seed=14, tol=5e-5):
         sl = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith(pre) and v.dtype.is_floating_point}
         y = P.complex_conv2d(a_prev, sl, pre + "conv.")
         y.retain_grad()
-        out = P.prelu(P.cbn_train(y, sl, pre + "bn."), sl, pre + "prelu.")
+        # PReLU branch per element taken from OUR forward (sign of our activation): the branch of an element whose
+        # pre-activation is within round-off of 0 is implementation-defined, everything else is compared exactly
+        mask = ops.planes_to_user(acts[layer]).cpu() > 0
+        pre_act = P.cbn_train(y, sl, pre + "bn.")
+        out = torch.where(mask, pre_act, sl[pre + "prelu.weight"] * pre_act)
         out.backward(gu)
         errs["dy%d" % layer] = C.rel_l2(dyu, y.grad)
         if layer:
