@@ -310,6 +310,76 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, c
   }
 }
 
+
+// ---- closed-form KL between two complex Gaussians, forward + gradient (model/nsvae_loss.py:L275-328) ------------------
+// lat1 (n_bt, H1, 2): (mu, log sigma, delta) of distribution 1 at channel ch1 (zdim each); lat2 likewise (constant).
+// acc[0] += scale * sum_bt kl, acc[1] += mean_scale * sum_bt kl; dlat1 += scale * d(sum kl)/dlat1.
+__global__ void __launch_bounds__(256) kl_fwd_bwd_kernel(const float* __restrict__ lat1, int H1, int ch1,
+                                                         const float* __restrict__ lat2, int H2, int ch2,
+                                                         long long n_bt, int zdim, float scale, float mean_scale,
+                                                         float* __restrict__ dlat1, double* __restrict__ acc) {
+  const float e = 1e-10f;                                      // standard_nsvae_loss_true_kl.epsilon (L250)
+  const long long n = n_bt * zdim;
+  double part = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % zdim);
+    const long long bt = i / zdim;
+    const float* a = lat1 + (bt * H1 + ch1 + j) * 2;
+    const float* b = lat2 + (bt * H2 + ch2 + j) * 2;
+    const float m1r = a[0], m1i = a[1], ls1 = a[2 * zdim], d1r = a[4 * zdim], d1i = a[4 * zdim + 1];
+    const float m2r = b[0], m2i = b[1], ls2 = b[2 * zdim];
+    float p2r = b[4 * zdim], p2i = b[4 * zdim + 1];
+    const float s1 = expf(ls1), s2 = expf(ls2);
+    const float ad1 = sqrtf(d1r * d1r + d1i * d1i + e), tmp1 = s1 * 0.99f / (ad1 + e);
+    const bool cl1 = ad1 >= s1 - 1e-3f;
+    const float p1r = cl1 ? d1r * tmp1 : d1r, p1i = cl1 ? d1i * tmp1 : d1i;
+    const float a1 = p1r * p1r + p1i * p1i;
+    const float ad2 = sqrtf(p2r * p2r + p2i * p2i + e), tmp2 = s2 * 0.99f / (ad2 + e);
+    if (ad2 >= s2 - 1e-3f) { p2r *= tmp2; p2i *= tmp2; }
+    const float a2 = p2r * p2r + p2i * p2i;
+    const float den1 = 0.25f * (s1 * s1 - a1) + e, den2 = 0.25f * (s2 * s2 - a2) + e;
+    const float coeff = 2.f / (s2 * s2 - a2 + e);
+    const float trace = s1 * s2 - p2r * p1r - p2i * p1i;
+    const float dr = m2r - m1r, di = m2i - m1i;
+    const float quad = dr * dr * (s2 - p2r) - 2.f * p2i * dr * di + di * di * (s2 + p2r);
+    part += (double)(coeff * (trace + quad) + logf(den2) - logf(den1));
+    if (dlat1) {
+      const float k = 0.5f * scale;
+      const float g_m1r = coeff * (-2.f * dr * (s2 - p2r) + 2.f * p2i * di);
+      const float g_m1i = coeff * (2.f * p2i * dr - 2.f * di * (s2 + p2r));
+      float g_s1 = coeff * s2 - 0.5f * s1 / den1;
+      const float g_p1r = -coeff * p2r + 0.5f * p1r / den1, g_p1i = -coeff * p2i + 0.5f * p1i / den1;
+      float g_d1r = g_p1r, g_d1i = g_p1i;
+      if (cl1) {                                               // p1 = d1 * 0.99 s1 / (|d1| + e)
+        const float dot = g_p1r * d1r + g_p1i * d1i;
+        g_s1 += dot * 0.99f / (ad1 + e);
+        const float dtmp = -0.99f * s1 / ((ad1 + e) * (ad1 + e)) / ad1;
+        g_d1r = g_p1r * tmp1 + dot * dtmp * d1r;
+        g_d1i = g_p1i * tmp1 + dot * dtmp * d1i;
+      }
+      float* d = dlat1 + (bt * H1 + ch1 + j) * 2;
+      d[0] += k * g_m1r;
+      d[1] += k * g_m1i;
+      d[2 * zdim] += k * g_s1 * s1;                            // log sigma: only the real part is used (L285)
+      d[4 * zdim] += k * g_d1r;
+      d[4 * zdim + 1] += k * g_d1i;
+    }
+  }
+  // block reduction of the partial sums
+  __shared__ double red[8];
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    t *= 0.5;
+    if (blockIdx.x == 0) t -= (double)zdim * (double)n_bt;      // kl = 0.5 sum_j(...) - zdim per (b, t)
+    atomicAdd(acc, t * (double)scale);
+    atomicAdd(acc + 1, t * (double)mean_scale);
+  }
+}
+
 static inline int grid_for(long long n, int per_sm) {
   const long long b = (n + 255) / 256;
   return (int)(b < 148LL * per_sm ? (b > 0 ? b : 1) : 148LL * per_sm);
@@ -457,5 +527,18 @@ extern "C" int idv_adam_step(float* p, const float* g, float* m, float* v, int64
   adam_step_kernel<<<grid_for(n, 16), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
                                                                       bc1, bc2);
   IDV_LAUNCH_CHECK("adam_step_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_kl_fwd_bwd(const float* lat1, int H1, int ch1, const float* lat2, int H2, int ch2, int64_t n_bt,
+                              int zdim, float scale, float mean_scale, float* dlat1, double* acc, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(lat1 && lat2 && acc && n_bt > 0 && zdim > 0 && ch1 >= 0 && ch1 + 3 * zdim <= H1 && ch2 >= 0 &&
+                    ch2 + 3 * zdim <= H2,
+                "idv_kl_fwd_bwd: bad argument");
+  kl_fwd_bwd_kernel<<<grid_for(n_bt * zdim, 8), 256, 0, (cudaStream_t)stream>>>(lat1, H1, ch1, lat2, H2, ch2,
+                                                                                (long long)n_bt, zdim, scale, mean_scale,
+                                                                                dlat1, acc);
+  IDV_LAUNCH_CHECK("kl_fwd_bwd_kernel");
   return IDV_OK;
 }

@@ -53,6 +53,7 @@ SIGNATURES = {
     "idv_colsum_add": [vp, i64, i32, i32, vp, vp],
     "idv_enc0_wgrad": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
     "idv_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp],
+    "idv_kl_fwd_bwd": [vp, i32, i32, vp, i32, i32, i64, i32, f32, f32, vp, vp, vp],
     "idv_cbn_stats_user": [vp, i64, i32, i64, vp, vp],
     "idv_head_user": [vp, i64, i64, f32, i32, vp, i32, vp],
     "idv_stream_frames_split": [vp, vp, i32, i32, i64, i32, i32, i32, vp, vp],

@@ -1,0 +1,52 @@
+"""Training losses as fused C-ABI kernels.
+
+``nsvae_kl_loss``: the phase-1 NSVAE loss of train_nsvae.py:L539-544 = standard_nsvae_loss_true_kl.kl_loss
+(model/nsvae_loss.py:L275-347, w_kl = 1, w_dismiu = 0): closed-form KL between the noisy encoder's complex-Gaussian
+posterior(s) and the frozen clean / noise encoders' posteriors, mean over (B, T).  One kernel pass per KL term computes
+the value and the gradient w.r.t. the noisy latent; autograd only carries that gradient to the encoder's backward."""
+import torch
+
+from . import lib
+
+
+class _KLFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lat, lat_clean, lat_noise, zdim, latent_num, alpha):
+        lat_c = lib.require_f32_cuda(lat.detach(), "noisy latent")
+        lat_clean = lib.require_f32_cuda(lat_clean.detach(), "clean latent")
+        lat_noise = lib.require_f32_cuda(lat_noise.detach(), "noise latent")
+        B, T, H1, _ = lat_c.shape
+        if H1 != 3 * zdim * latent_num or lat_clean.shape[2] < 3 * zdim or lat_noise.shape[2] < 3 * zdim:
+            raise RuntimeError("latent widths do not match zdim / latent_num")
+        n_bt = B * T
+        dlat = torch.zeros_like(lat_c)
+        acc = torch.zeros(4, dtype=torch.float64, device=lat_c.device)
+        inv = 1.0 / n_bt
+        lib.call("idv_kl_fwd_bwd", lat_c, H1, 0, lat_clean, lat_clean.shape[2], 0, n_bt, zdim, inv, inv, dlat, acc)
+        # latent_num 1: the speech posterior is pushed AWAY from the noise prior (minus sign, L336);
+        # latent_num 2: the second triplet is pulled towards it (L342)
+        ch, sign = (0, -1.0) if latent_num == 1 else (3 * zdim, 1.0)
+        lib.call("idv_kl_fwd_bwd", lat_c, H1, ch, lat_noise, lat_noise.shape[2], 0, n_bt, zdim, sign * alpha * inv, inv,
+                 dlat, acc[2:])
+        ctx.save_for_backward(dlat)
+        out = acc.to(torch.float32)
+        return out[0] + out[2], out[1], out[3]
+
+    @staticmethod
+    def backward(ctx, g_loss, g_kc, g_kn):
+        (dlat,) = ctx.saved_tensors
+        return g_loss * dlat, None, None, None, None, None
+
+
+def nsvae_kl_loss(noisy, clean, noise, zdim=128, latent_num=1, alpha=1.0):
+    """noisy / clean / noise: encoder return tuples (z, mu, log_sigma, delta, ...) or latents (B, T, H, 2).
+    Returns (loss, mean KL to the clean posterior, mean KL to the noise posterior) like kl_loss (L330-347)."""
+    def latent_of(r, n):
+        if isinstance(r, torch.Tensor):
+            return r
+        parts = [r[1], r[2], r[3]] + ([r[5], r[6], r[7]] if n == 2 else [])
+        base = parts[0]._base
+        if base is not None and all(p._base is base for p in parts) and base.shape[2] == sum(p.shape[2] for p in parts):
+            return base                                   # the slices of one latent tensor (no copy)
+        return torch.cat(parts, dim=2)
+    return _KLFn.apply(latent_of(noisy, latent_num), latent_of(clean, 1), latent_of(noise, 1), zdim, latent_num, alpha)

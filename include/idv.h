@@ -277,6 +277,12 @@ int idv_enc0_wgrad(const float* stft, const float* dY, int B, int Fin, int T, in
                    void* stream);
 int idv_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, void* stream);
+/* Closed-form KL(q1 || q2) between complex Gaussians, value and gradient in one pass (standard_nsvae_loss_true_kl.cal_kl,
+ * model/nsvae_loss.py:L275-328).  lat1 (n_bt, H1, 2) holds (mu, log sigma, delta) of q1 from channel ch1 (zdim each),
+ * lat2 the same for the fixed q2.  acc[0] += scale * sum_bt kl, acc[1] += mean_scale * sum_bt kl;
+ * dlat1 (may be NULL) += scale * d(sum_bt kl)/dlat1.                                                            */
+int idv_kl_fwd_bwd(const float* lat1, int H1, int ch1, const float* lat2, int H2, int ch2, int64_t n_bt, int zdim,
+                   float scale, float mean_scale, float* dlat1, double* acc, void* stream);
 
 /* ---- frame streaming (causal network; carried state instead of whole utterances) ------------------------------
  * Hop-synchronous streams: a step consumes hop*k new samples per stream and runs the same tap-GEMMs on k-frame

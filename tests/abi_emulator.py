@@ -696,6 +696,21 @@ def idv_enc0_wgrad(stft, dY, B, Fin, T, Cout, causal, dW):
     dW.view(10, 2, N).copy_(o.to(torch.float32))
 
 
+def idv_kl_fwd_bwd(lat1, H1, ch1, lat2, H2, ch2, n_bt, zdim, scale, mean_scale, dlat1, acc):
+    """Contract = the oracle's cal_kl restatement differentiated by autograd (test double only)."""
+    from oracle import ref_port as P
+    with torch.enable_grad():
+        a = lat1.view(1, n_bt, H1, 2).detach().clone().requires_grad_(True)
+        b = lat2.view(1, n_bt, H2, 2)
+        sl = lambda t, c, k: t[:, :, c + k * zdim:c + (k + 1) * zdim]
+        kl = P.cal_kl(sl(a, ch1, 0), sl(b, ch2, 0), sl(a, ch1, 1), sl(b, ch2, 1), sl(a, ch1, 2), sl(b, ch2, 2), zdim).sum()
+        (ga,) = torch.autograd.grad(kl, a)
+    acc[0] += float(kl) * scale
+    acc[1] += float(kl) * mean_scale
+    if dlat1 is not None:
+        dlat1.view(-1).add_((scale * ga).reshape(-1))
+
+
 def idv_adam_step(p, g, m, v, n, lr, b1, b2, eps, wd, step):
     pv, gv, mv, vv = (_flat(t)[:n] for t in (p, g, m, v))
     gg = gv + wd * pv

@@ -274,6 +274,17 @@ def test_lstm_backward_and_misc_kernels():
     assert _both("idv_f32_to_split", [pl, pl.numel(), torch.zeros(2 * pl.numel(), dtype=torch.bfloat16)], [2]) < 1e-7
 
 
+def test_kl_loss_kernel():
+    """Fused closed-form KL value + gradient against autograd of the oracle's cal_kl (incl. the |delta| <= sigma
+    protection branch on both distributions)."""
+    n_bt, z = 37, 128
+    lat1, lat2 = _rand(n_bt, 6 * z, 2, seed=95) * 0.7, _rand(n_bt, 3 * z, 2, seed=96) * 0.7
+    for ch1 in (0, 3 * z):
+        acc = torch.zeros(2, dtype=torch.float64)
+        dl = _rand(n_bt, 6 * z, 2, seed=97)
+        assert _both("idv_kl_fwd_bwd", [lat1, 6 * z, ch1, lat2, 3 * z, 0, n_bt, z, -0.3, 1.0 / n_bt, dl, acc], [10, 11]) < 2e-5
+
+
 def test_bad_arguments_return_error_codes():
     with pytest.raises(RuntimeError, match="idv_stft_fwd"):
         lib.call("idv_stft_fwd", torch.zeros(1, 100).cuda(), 1, 100, torch.zeros(4).cuda(), 512, 100, 400,

@@ -57,3 +57,46 @@ def test_two_rank_sharded_enhancement_matches_single_process(emulated_abi, tmp_p
     assert got["out"].shape == want.shape
     assert C.rel_l2(got["out"], want) < 1e-6            # ragged shards (2 + 1 utterances), same arithmetic
     assert got["t"] == 11.0                             # MAX over ranks
+
+
+def _train_worker(rank, world, port, tmp):
+    """Data-parallel training step: each rank back-propagates its own shard, FlatAdam all-reduces (mean) the flat
+    gradient bucket and applies the same update on every rank."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import abi_emulator
+    from idccrn_b200 import lib, ops, losses
+    from idccrn_b200.train import FlatAdam
+    import test_train_step as TS
+    lib.call = abi_emulator.call
+    lib.require_f32_cuda = lambda t, what: t.contiguous()
+    ops.set_gemm_mode("tc")
+    torch.set_num_threads(2)
+    noisy, frozen = TS.build_step(1, 3, "cpu")
+    opt = FlatAdam(noisy.parameters(), lr=1e-3, weight_decay=1e-3, process_group=dist.group.WORLD, world_size=world)
+    x = C.synth_waveform(2, 500, seed=50 + rank)                       # a different shard per rank
+    eps = [torch.zeros(2, 1, 6, C.ZDIM)] * 2                           # the emulator has no Philox: supply eps
+    with torch.no_grad():
+        rc, rn = frozen[0](x, train=False, eps=eps), frozen[1](x, train=False, eps=eps)
+    r = noisy(x, train=True, eps=eps)
+    loss, _, _ = losses.nsvae_kl_loss(r, rc, rn, C.ZDIM, 1, 1.0)
+    opt.zero_grad()
+    loss.backward()
+    local = torch.cat([p.grad.reshape(-1) for p in opt.params if p.grad is not None]).clone()
+    opt.step()
+    torch.save({"local": local, "reduced": opt.gflat.clone(), "flat": opt.flat.clone()}, tmp % rank)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_and_adam(emulated_abi, tmp_path):
+    tmp = str(tmp_path / "rank%d.pt")
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_train_worker, args=(2, port, tmp), nprocs=2, join=True)
+    a, b = torch.load(tmp % 0), torch.load(tmp % 1)
+    assert C.rel_l2(a["local"], b["local"]) > 1e-2                      # different shards, different gradients
+    want = (a["local"] + b["local"]) / 2
+    assert C.rel_l2(a["reduced"], want) < 1e-6 and torch.equal(a["reduced"], b["reduced"])
+    assert torch.equal(a["flat"], b["flat"])                            # identical parameters after the step

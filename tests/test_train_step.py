@@ -182,6 +182,42 @@ def test_train_step_gradients_emulated(emulated_abi, golden, tag):
         ops.set_gemm_mode(old)
 
 
+def run_kl_case(device, latent_num):
+    from idccrn_b200 import losses
+    B, T, z = 3, 9, C.ZDIM
+    gen = torch.Generator().manual_seed(3 + latent_num)
+    lat = (torch.randn(B, T, 3 * z * latent_num, 2, generator=gen) * 0.7).to(device).requires_grad_(True)
+    lc = (torch.randn(B, T, 3 * z, 2, generator=gen) * 0.7).to(device)
+    ln_ = (torch.randn(B, T, 3 * z, 2, generator=gen) * 0.7).to(device)
+    loss, kc, kn = losses.nsvae_kl_loss(lat, lc, ln_, z, latent_num, 0.7)
+    (2.0 * loss).backward()
+    ref_lat = lat.detach().cpu().double().requires_grad_(True)
+    sl = lambda t, k: {"miu": t[:, :, k * z:(k + 1) * z], "ls": t[:, :, (k + 1) * z:(k + 2) * z], "de": t[:, :, (k + 2) * z:(k + 3) * z]}
+    a, c, n = sl(ref_lat, 0), sl(lc.cpu().double(), 0), sl(ln_.cpu().double(), 0)
+    st = {"miu_speech": a["miu"], "log_sigma_speech": a["ls"], "delta_speech": a["de"]}
+    if latent_num == 2:
+        b = sl(ref_lat, 3)
+        st.update(miu_noise=b["miu"], log_sigma_noise=b["ls"], delta_noise=b["de"])
+    want, wc, wn = P.nsvae_kl_loss(st, {"miu_speech": c["miu"], "log_sigma_speech": c["ls"], "delta_speech": c["de"]},
+                                   {"miu_speech": n["miu"], "log_sigma_speech": n["ls"], "delta_speech": n["de"]}, z, latent_num, 0.7)
+    (2.0 * want).backward()
+    scale = max(abs(float(wc)), abs(float(wn)))
+    assert abs(float(loss) - float(want)) / scale < 2e-5 and abs(float(kc) - float(wc)) / scale < 2e-5
+    assert abs(float(kn) - float(wn)) / scale < 2e-5
+    assert C.rel_l2(lat.grad, ref_lat.grad) < 2e-5
+
+
+@pytest.mark.parametrize("latent_num", [1, 2])
+def test_kl_loss_matches_reference_formula_emulated(emulated_abi, latent_num):
+    run_kl_case("cpu", latent_num)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("latent_num", [1, 2])
+def test_kl_loss_matches_reference_formula_gpu(latent_num):
+    run_kl_case("cuda", latent_num)
+
+
 def test_layerwise_backward_emulated(emulated_abi):
     from idccrn_b200 import ops
     old = ops.GEMM_MODE[0]
