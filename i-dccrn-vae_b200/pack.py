@@ -46,7 +46,7 @@ class TapGemmPack:
             if not self.tc_eligible():
                 raise RuntimeError("tap-GEMM (N=%d) does not fit the tensor-core kernel's shape rules" % self.N)
             dev = self.w.device
-            w = self.w.detach().cpu()
+            w = self.w.detach() if PACK_ON_DEVICE[0] else self.w.detach().cpu()
             slots, taps = {}, []
             kc_max = max(t[4] for t in self._taps_l)
             for t in self._taps_l:
@@ -54,7 +54,7 @@ class TapGemmPack:
                 if key not in slots:
                     slots[key] = len(slots)
                 taps.append([t[0], t[1], t[2], t[3], t[4], slots[key]])
-            wt = torch.zeros(len(slots), self.N, kc_max, dtype=torch.float32)
+            wt = torch.zeros(len(slots), self.N, kc_max, dtype=torch.float32, device=w.device)
             for (w_off, kc), si in slots.items():
                 wt[si, :, :kc] = w[w_off:w_off + kc * self.N].view(kc, self.N).t()
             hi = wt.to(torch.bfloat16)
@@ -88,9 +88,9 @@ def cbn_fold(bn):
     return Z, bprime
 
 
-def _identity_fold(C):
-    Z = torch.eye(2, dtype=torch.float64).repeat(C, 1, 1)
-    return Z, torch.zeros(C, 2, dtype=torch.float64)
+def _identity_fold(C, device="cpu"):
+    Z = torch.eye(2, dtype=torch.float64, device=device).repeat(C, 1, 1)
+    return Z, torch.zeros(C, 2, dtype=torch.float64, device=device)
 
 
 def _block_weights(m_re, m_im, b_re, b_im, Z, bprime, ch_in, ch_out):
@@ -100,7 +100,7 @@ def _block_weights(m_re, m_im, b_re, b_im, Z, bprime, ch_in, ch_out):
     taps, cin, cout = m_re.shape
     m_re, m_im = m_re.double(), m_im.double()
     zrr, zri, zir, zii = (Z[:, 0, 0], Z[:, 0, 1], Z[:, 1, 0], Z[:, 1, 1])
-    W = torch.zeros(taps, 2 * ch_in, 2 * ch_out, dtype=torch.float64)
+    W = torch.zeros(taps, 2 * ch_in, 2 * ch_out, dtype=torch.float64, device=m_re.device)
     # rows: [re-in | im-in], cols: [re-out | im-out]
     W[:, :cin, :cout] = zrr * m_re + zri * m_im
     W[:, ch_in:ch_in + cin, :cout] = -zrr * m_im + zri * m_re
@@ -108,14 +108,30 @@ def _block_weights(m_re, m_im, b_re, b_im, Z, bprime, ch_in, ch_out):
     W[:, ch_in:ch_in + cin, ch_out:ch_out + cout] = -zir * m_im + zii * m_re
     yb_re = (b_re - b_im).double()
     yb_im = (b_re + b_im).double()
-    bias = torch.zeros(2 * ch_out, dtype=torch.float64)
+    bias = torch.zeros(2 * ch_out, dtype=torch.float64, device=m_re.device)
     bias[:cout] = zrr * yb_re + zri * yb_im + bprime[:, 0]
     bias[ch_out:ch_out + cout] = zir * yb_re + zii * yb_im + bprime[:, 1]
     return W, bias
 
 
+# Packs are computed on the CPU by default (inference: once per weight version).  A training step changes every
+# weight, so its packs are recomputed every step: `with on_device():` keeps the (O(parameters)) packing arithmetic
+# on the device the weights live on instead of round-tripping them through the host.
+PACK_ON_DEVICE = [False]
+
+
+class on_device:
+    def __enter__(self):
+        self.old = PACK_ON_DEVICE[0]
+        PACK_ON_DEVICE[0] = True
+
+    def __exit__(self, *a):
+        PACK_ON_DEVICE[0] = self.old
+
+
 def _cpu(t):
-    return t.detach().cpu()
+    t = t.detach()
+    return t if PACK_ON_DEVICE[0] else t.cpu()
 
 
 def pack_conv(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, f_in, stride_f, pad_f, device, pad_t=1):
@@ -129,7 +145,7 @@ def pack_conv(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, f_in, strid
         raise NotImplementedError("complex conv is built for 1- or 2-tap time kernels with time padding 0 or 1 "
                                   "(got kernel %d, padding %d)" % (kw, pad_t))
     ch_in, ch_out = round8(cin), round8(cout)
-    Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(cout)
+    Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(cout, wr.device)
     m_re = wr.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
     m_im = wi.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
     W, bias = _block_weights(m_re, m_im, _cpu(conv_re_b), _cpu(conv_im_b), Z, bp, ch_in, ch_out)
@@ -205,10 +221,10 @@ def pack_enc0(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, device):
     wr, wi = _cpu(conv_re_w), _cpu(conv_im_w)
     cout, cin, kh, kw = wr.shape
     assert cin == 1 and kh == 5 and kw == 2 and cout % 32 == 0
-    Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(cout)
+    Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(cout, wr.device)
     m_re = wr.permute(2, 3, 1, 0).reshape(10, 1, cout)
     m_im = wi.permute(2, 3, 1, 0).reshape(10, 1, cout)
-    W = torch.zeros(10, 2, 2 * cout, dtype=torch.float64)
+    W = torch.zeros(10, 2, 2 * cout, dtype=torch.float64, device=wr.device)
     Wb, bias = _block_weights(m_re, m_im, _cpu(conv_re_b), _cpu(conv_im_b), Z, bp, 8, cout)
     W[:, 0] = Wb[:, 0]           # re-in row
     W[:, 1] = Wb[:, 8]           # im-in row (ch_in = 8 padding of one channel)
@@ -293,8 +309,9 @@ def pack_lstm_inproj0(lstm_re, lstm_im, hidden, c_in, f_in, device):
     unit p (input part x_re / x_im) writes plane p of G0[2][R][8H]."""
     H, ch = hidden, round8(c_in)
     N = 8 * H
-    W = torch.zeros(f_in, ch, N, dtype=torch.float64)
-    bias = torch.zeros(N, dtype=torch.float64)
+    dev = _cpu(lstm_re["weight_ih_l0"]).device
+    W = torch.zeros(f_in, ch, N, dtype=torch.float64, device=dev)
+    bias = torch.zeros(N, dtype=torch.float64, device=dev)
     for m, mod in enumerate((lstm_re, lstm_im)):
         wih = _cpu(mod["weight_ih_l0"]).double()                     # (4H, c_in*f_in)
         W[:, :c_in, m * 4 * H:(m + 1) * 4 * H] = wih.reshape(4 * H, c_in, f_in).permute(2, 1, 0)
@@ -313,8 +330,9 @@ def pack_lstm_inproj1(lstm_re, lstm_im, hidden, device, layer=1):
     module m's weight_ih_l{layer} and writes plane m*2+p of G1[4][R][4H]."""
     H = hidden
     N = 4 * H
-    W = torch.zeros(2, H, N, dtype=torch.float64)
-    bias = torch.zeros(2 * N, dtype=torch.float64)
+    dev = _cpu(lstm_re["weight_ih_l%d" % layer]).device
+    W = torch.zeros(2, H, N, dtype=torch.float64, device=dev)
+    bias = torch.zeros(2 * N, dtype=torch.float64, device=dev)
     for m, mod in enumerate((lstm_re, lstm_im)):
         W[m] = _cpu(mod["weight_ih_l%d" % layer]).double().t()
         bias[m * N:(m + 1) * N] = _cpu(mod["bias_ih_l%d" % layer]).double() + _cpu(mod["bias_hh_l%d" % layer]).double()
@@ -499,8 +517,8 @@ def raw_block_weights(conv_re_w, conv_im_w, transposed=False):
     else:
         cout, cin, kh, kw = wr.shape
         m_re, m_im = wr.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout), wi.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
-    Z, bp = _identity_fold(cout)
-    zero = torch.zeros(cout)
+    Z, bp = _identity_fold(cout, wr.device)
+    zero = torch.zeros(cout, device=wr.device)
     W, _ = _block_weights(m_re, m_im, zero, zero, Z, bp, round8(cin), round8(cout))
     return W, kh, kw, cin, cout
 
@@ -577,7 +595,8 @@ def pack_lstm_gates(lstm_re, lstm_im, hidden, layer, c_in, f_in, device):
       layer l: source 0 = h planes of the layer below, source 1 = this layer's h planes one row back."""
     H = hidden
     N = 4 * H
-    mats, bias = [], torch.zeros(2 * N, dtype=torch.float64)
+    dev = _cpu(lstm_re["weight_hh_l%d" % layer]).device
+    mats, bias = [], torch.zeros(2 * N, dtype=torch.float64, device=dev)
     units, taps = [], []
     off = 0
     offs = {}
@@ -585,7 +604,7 @@ def pack_lstm_gates(lstm_re, lstm_im, hidden, layer, c_in, f_in, device):
         wih = _cpu(mod["weight_ih_l%d" % layer]).double()
         if layer == 0:
             ch = round8(c_in)
-            w = torch.zeros(f_in, ch, N, dtype=torch.float64)
+            w = torch.zeros(f_in, ch, N, dtype=torch.float64, device=dev)
             w[:, :c_in] = wih.reshape(N, c_in, f_in).permute(2, 1, 0)
             for f in range(f_in):
                 offs[("ih", m, f)] = off
@@ -628,7 +647,7 @@ def pack_lstm_dgrad(lstm_re, lstm_im, hidden, layer, kind, device, c_in=0, f_in=
         for m, mod in enumerate((lstm_re, lstm_im)):
             w = _cpu(mod["weight_ih_l0"]).double().reshape(K, c_in, f_in)
             for f in range(f_in):
-                wf = torch.zeros(K, ch, dtype=torch.float64)
+                wf = torch.zeros(K, ch, dtype=torch.float64, device=w.device)
                 wf[:, :c_in] = w[:, :, f]
                 mats.append(wf.reshape(-1))
         for f in range(f_in):

@@ -78,6 +78,10 @@ class EncoderTrainStep:
 
     # ---------------------------------------------------------------------------------------------- forward
     def forward(self, x):
+        with pack.on_device():                 # the weights change every step: repack on the GPU, not on the host
+            return self._forward(x)
+
+    def _forward(self, x):
         """x (B, L) -> latent (B, T, 3*zdim*latent_num, 2); keeps the tensors of the backward pass."""
         enc = self.enc
         stft_x = enc.stft(x)
@@ -136,10 +140,10 @@ class EncoderTrainStep:
         if sv is None:
             raise RuntimeError("backward() without a train-mode forward")
         dlatent = lib.require_f32_cuda(dlatent, "dlatent")
-        g_top = self._lstm_backward(dlatent)
-        g = g_top
-        for i in reversed(range(len(self.enc.encoders))):
-            g = self._conv_backward(i, g)
+        with pack.on_device():
+            g = self._lstm_backward(dlatent)
+            for i in reversed(range(len(self.enc.encoders))):
+                g = self._conv_backward(i, g)
         self.saved = None
 
     # ---- LSTM ----
