@@ -542,3 +542,175 @@ extern "C" int idv_kl_fwd_bwd(const float* lat1, int H1, int ch1, const float* l
   IDV_LAUNCH_CHECK("kl_fwd_bwd_kernel");
   return IDV_OK;
 }
+
+// ====================================================================================================================
+// decoder side (phase-2 training step, i_dccrn_vae/nsvae_dccrn/train_second_phase_decoder.py:L376-433: frozen encoder,
+// decoder train=True, SI-SNR loss): SI-SNR value + gradient, adjoint of the overlap-add, backward of the reconstruction
+// head.  The transposed convs / ComplexBatchNormal / PReLU / dense reuse the kernels above and the tap-GEMM.
+// ====================================================================================================================
+namespace idv {
+
+// sums[b][3] = <est, src>, |src|^2, |est|^2   (grid (chunks, B))
+__global__ void __launch_bounds__(256) sisnr_reduce_kernel(const float* __restrict__ src, const float* __restrict__ est,
+                                                           int L, double* __restrict__ sums) {
+  const int b = blockIdx.y;
+  double d = 0, ss = 0, ee = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    const float s = __ldg(src + (long long)b * L + i), e = __ldg(est + (long long)b * L + i);
+    d += (double)s * e; ss += (double)s * s; ee += (double)e * e;
+  }
+  __shared__ double red[3][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    d += __shfl_down_sync(0xffffffffu, d, o);
+    ss += __shfl_down_sync(0xffffffffu, ss, o);
+    ee += __shfl_down_sync(0xffffffffu, ee, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = d; red[1][threadIdx.x >> 5] = ss; red[2][threadIdx.x >> 5] = ee; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    atomicAdd(sums + b * 3 + threadIdx.x, t);
+  }
+}
+
+// model/nsvae_loss.py:L877-889: alpha = <est,src>/(|src|^2+eps), s_t = alpha src, e = est - s_t,
+// snr = 10 log10(|s_t|^2/(|e|^2+eps) + eps), loss = -mean_b snr.  d_est += scale * d(loss)/d(est); loss[0] += loss.
+__global__ void __launch_bounds__(256) sisnr_grad_kernel(const float* __restrict__ src, const float* __restrict__ est,
+                                                         int B, int L, const double* __restrict__ sums, float scale,
+                                                         float* __restrict__ d_est, double* __restrict__ loss) {
+  const int b = blockIdx.y;
+  const double eps = 1e-8;
+  const double dot = sums[b * 3], ss = sums[b * 3 + 1], ee = sums[b * 3 + 2];
+  const double alpha = dot / (ss + eps);
+  const double a = alpha * alpha * ss;                              // |s_target|^2
+  const double n = ee - 2 * alpha * dot + a;                        // |e_noise|^2
+  const double ratio = a / (n + eps) + eps;
+  // d snr / d est = k * [ (da/dest)/(n+eps) - a/(n+eps)^2 dn/dest ],  k = 10 / (ln10 * ratio)
+  const double k = 10.0 / (2.302585092994046 * ratio);
+  const double da_c = 2 * alpha * ss / (ss + eps);                  // da/dest = da_c * src
+  const double es = dot - alpha * ss;                               // <e, src>
+  const double c_src = k * (da_c / (n + eps) + a / ((n + eps) * (n + eps)) * 2 * (alpha + es / (ss + eps)));
+  const double c_est = -k * a / ((n + eps) * (n + eps)) * 2;        // dn/dest = 2 (est - alpha src) - 2 es/(ss+eps) src
+  const double w = -(double)scale / B;
+  if (d_est)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+      const long long idx = (long long)b * L + i;
+      d_est[idx] += (float)(w * (c_src * __ldg(src + idx) + c_est * __ldg(est + idx)));
+    }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(loss, -(10.0 * log10(ratio)) / B);
+}
+
+// adjoint of idv_ola_fwd: dframes[(b,t)][j] = dsig[b][hop*t - (n_fft/2 - off) + j] / env  for j < win (0 elsewhere / beyond)
+__global__ void __launch_bounds__(256) ola_bwd_kernel(const float* __restrict__ dsig, const float* __restrict__ wsq, int T,
+                                                      int n_fft, int hop, int win, int out_len, int frame_ld,
+                                                      float* __restrict__ dframes, long long n) {
+  const int off = (n_fft - win) / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % frame_ld);
+    const long long bt = i / frame_ld;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    float v = 0.f;
+    const int s = hop * t + off + j - n_fft / 2;                    // output sample this tap contributes to
+    if (j < win && s >= 0 && s < out_len) {
+      const int q = s + n_fft / 2 - off;
+      int t_hi = q / hop, t_lo = (q - win + hop) / hop;
+      if (q - win + 1 <= 0) t_lo = 0;
+      if (t_hi > T - 1) t_hi = T - 1;
+      float env = 0.f;
+      for (int tt = t_lo; tt <= t_hi; ++tt) {
+        const int jj = q - hop * tt;
+        if (jj >= 0 && jj < win) env += __ldg(wsq + jj);
+      }
+      v = __ldg(dsig + (long long)b * out_len + s) / env;
+    }
+    dframes[i] = v;
+  }
+}
+
+// Backward of the reconstruction head on the last decoder layer (Cout = 1).  raw (NB, F, T, 2): transposed-conv
+// output before ComplexBatchNormal; zb[6]: Z, b' of the batch statistics; pre = Z raw + b', m = PReLU(pre).
+//   real_imag head: S = m;   mask head (model/pvae_module.py:L2594-2609): S = X * tanh(|m|)/|m| * m.
+// drows[(b*T + t)][2k + part] = dL/dS.  Writes planes (C = 1, Cp = 16) y <- raw and g <- dL/dm for the cbn_bwd kernels.
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ zb,
+                                                       float slope, int mask, const float* __restrict__ stft_x,
+                                                       const float* __restrict__ drows, int drows_ld, int NB, int F, int T,
+                                                       float* __restrict__ y_planes, float* __restrict__ g_planes) {
+  const long long n = (long long)NB * F * T;
+  const int Tp = T + 1;
+  const long long R = (long long)NB * Tp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T);
+    const int f = (int)((i / T) % F);
+    const int b = (int)(i / ((long long)T * F));
+    const float2 y = __ldg(reinterpret_cast<const float2*>(raw + i * 2));
+    const float2 gs = __ldg(reinterpret_cast<const float2*>(drows + ((long long)b * T + t) * drows_ld + 2 * f));
+    float gr = gs.x, gi = gs.y;
+    if (mask) {
+      const float pr = fmaf(zb[0], y.x, fmaf(zb[1], y.y, zb[4])), pi = fmaf(zb[2], y.x, fmaf(zb[3], y.y, zb[5]));
+      const float mr = prelu_f(pr, slope), mi = prelu_f(pi, slope);
+      const float2 X = __ldg(reinterpret_cast<const float2*>(stft_x + i * 2));
+      // S = X u (complex), u = h(r) m, h = tanh(r)/r:  g_u = conj(X) g,  g_m = h g_u + h'(r)/r (g_u . m) m
+      const float gur = X.x * gr + X.y * gi, gui = X.x * gi - X.y * gr;
+      const float r = sqrtf(mr * mr + mi * mi);
+      float h = 1.f, hp_r = 0.f;
+      if (r > 1e-12f) {
+        const float th = tanhf(r);
+        h = th / r;
+        hp_r = ((1.f - th * th) * r - th) / (r * r * r);              // h'(r) / r
+      }
+      const float dotm = gur * mr + gui * mi;
+      gr = h * gur + hp_r * dotm * mr;
+      gi = h * gui + hp_r * dotm * mi;
+    }
+    const long long row = ((long long)f * R + (long long)b * Tp + 1 + t) * 16;
+    y_planes[row] = y.x; y_planes[row + 8] = y.y;
+    g_planes[row] = gr; g_planes[row + 8] = gi;
+  }
+}
+
+}  // namespace idv
+
+extern "C" int idv_sisnr_fwd_bwd(const float* src, const float* est, int B, int L, float scale, float* d_est,
+                                 double* sums, double* loss, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(src && est && sums && loss && B > 0 && B <= 65535 && L > 0, "idv_sisnr_fwd_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  IDV_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * 3 * sizeof(double), st));
+  int chunks = cdiv(L, 256 * 16);
+  if (chunks > 64) chunks = 64;
+  dim3 grid(chunks, B);
+  sisnr_reduce_kernel<<<grid, 256, 0, st>>>(src, est, L, sums);
+  IDV_LAUNCH_CHECK("sisnr_reduce_kernel");
+  sisnr_grad_kernel<<<grid, 256, 0, st>>>(src, est, B, L, sums, scale, d_est, loss);
+  IDV_LAUNCH_CHECK("sisnr_grad_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_ola_bwd(const float* dsig, const float* wsq, int B, int T, int n_fft, int hop, int win, int frame_ld,
+                           float* dframes, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(dsig && wsq && dframes && B > 0 && T > 1 && frame_ld >= win, "idv_ola_bwd: bad argument");
+  const long long n = (long long)B * T * frame_ld;
+  ola_bwd_kernel<<<grid_for(n, 16), 256, 0, (cudaStream_t)stream>>>(dsig, wsq, T, n_fft, hop, win, hop * (T - 1), frame_ld,
+                                                                    dframes, n);
+  IDV_LAUNCH_CHECK("ola_bwd_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_head_bwd(const float* raw, const float* zb, float slope, int mask, const float* stft_x,
+                            const float* drows, int drows_ld, int NB, int F, int T, float* y_planes, float* g_planes,
+                            void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(raw && zb && drows && y_planes && g_planes && (!mask || stft_x) && NB > 0 && F > 0 && T > 0 &&
+                    drows_ld >= 2 * F,
+                "idv_head_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bytes = (size_t)F * NB * (T + 1) * 16 * sizeof(float);
+  IDV_CUDA(cudaMemsetAsync(y_planes, 0, bytes, st));
+  IDV_CUDA(cudaMemsetAsync(g_planes, 0, bytes, st));
+  head_bwd_kernel<<<grid_for((long long)NB * F * T, 16), 256, 0, st>>>(raw, zb, slope, mask, stft_x, drows, drows_ld, NB, F,
+                                                                       T, y_planes, g_planes);
+  IDV_LAUNCH_CHECK("head_bwd_kernel");
+  return IDV_OK;
+}

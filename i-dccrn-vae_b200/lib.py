@@ -11,6 +11,7 @@ from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+ABI_VERSION = 3        # IDV_ABI_VERSION of include/idv.h this binding was written against
 
 c_f32p = ctypes.c_void_p
 i32, i64, u64, f32, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_void_p
@@ -54,6 +55,9 @@ SIGNATURES = {
     "idv_enc0_wgrad": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
     "idv_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp],
     "idv_kl_fwd_bwd": [vp, i32, i32, vp, i32, i32, i64, i32, f32, f32, vp, vp, vp],
+    "idv_sisnr_fwd_bwd": [vp, vp, i32, i32, f32, vp, vp, vp, vp],
+    "idv_ola_bwd": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    "idv_head_bwd": [vp, vp, f32, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp],
     "idv_cbn_stats_user": [vp, i64, i32, i64, vp, vp],
     "idv_head_user": [vp, i64, i64, f32, i32, vp, i32, vp],
     "idv_stream_frames_split": [vp, vp, i32, i32, i64, i32, i32, i32, vp, vp],
@@ -95,7 +99,7 @@ def load():
 
 
 # kernels launched by each entry point (memset nodes not counted)
-KERNELS_PER_CALL = {"idv_istft_fwd": 2}
+KERNELS_PER_CALL = {"idv_istft_fwd": 2, "idv_sisnr_fwd_bwd": 2}
 
 
 class CarryEntry(ctypes.Structure):

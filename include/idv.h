@@ -284,6 +284,21 @@ int idv_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
 int idv_kl_fwd_bwd(const float* lat1, int H1, int ch1, const float* lat2, int H2, int ch2, int64_t n_bt, int zdim,
                    float scale, float mean_scale, float* dlat1, double* acc, void* stream);
 
+/* ---- decoder side of the training step (train_second_phase_decoder.py:L376-433: SI-SNR through the decoder) -------
+ *   idv_sisnr_fwd_bwd: si_snr (model/nsvae_loss.py:L877-889) of est (B, L) against src (B, L): loss[0] += -mean_b snr_b,
+ *       d_est (may be NULL) += scale * d loss / d est; sums: B*3 doubles of workspace;
+ *   idv_ola_bwd: adjoint of idv_ola_fwd: dframes (B*T, frame_ld) <- dsig (B, hop*(T-1)) / window envelope;
+ *   idv_head_bwd: backward of the reconstruction head (real_imag: identity; mask: model/pvae_module.py:L2594-2609) for
+ *       the last decoder layer.  raw (NB, F, T, 2) = transposed-conv output before ComplexBatchNormal, zb[6] its batch
+ *       Z / b', drows[(b*T+t)][2k+part] = gradient of the spectrum; writes fp32 planes (C = 1: [F][NB*(T+1)][16])
+ *       y_planes <- raw and g_planes <- gradient w.r.t. the PReLU output, ready for idv_cbn_bwd_*.                  */
+int idv_sisnr_fwd_bwd(const float* src, const float* est, int B, int L, float scale, float* d_est, double* sums,
+                      double* loss, void* stream);
+int idv_ola_bwd(const float* dsig, const float* wsq, int B, int T, int n_fft, int hop, int win, int frame_ld,
+                float* dframes, void* stream);
+int idv_head_bwd(const float* raw, const float* zb, float slope, int mask, const float* stft_x, const float* drows,
+                 int drows_ld, int NB, int F, int T, float* y_planes, float* g_planes, void* stream);
+
 /* ---- frame streaming (causal network; carried state instead of whole utterances) ------------------------------
  * Hop-synchronous streams: a step consumes hop*k new samples per stream and runs the same tap-GEMMs on k-frame
  * planes (Tp = -(k+1): pad rows kept) whose pad rows hold the last frame of the previous step.  The state kernels:
