@@ -631,10 +631,11 @@ __global__ void __launch_bounds__(256) ola_bwd_kernel(const float* __restrict__ 
 // Backward of the reconstruction head on the last decoder layer (Cout = 1).  raw (NB, F, T, 2): transposed-conv
 // output before ComplexBatchNormal; zb[6]: Z, b' of the batch statistics; pre = Z raw + b', m = PReLU(pre).
 //   real_imag head: S = m;   mask head (model/pvae_module.py:L2594-2609): S = X * tanh(|m|)/|m| * m.
-// drows[(b*T + t)][2k + part] = dL/dS.  Writes planes (C = 1, Cp = 16) y <- raw and g <- dL/dm for the cbn_bwd kernels.
+// drows[(b*T + t)][2k + part] (+ dpred (NB, F, T, 2) if given) = dL/dS.  Writes planes (C = 1, Cp = 16) y <- raw and g <- dL/dm for the cbn_bwd kernels.
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ zb,
                                                        float slope, int mask, const float* __restrict__ stft_x,
-                                                       const float* __restrict__ drows, int drows_ld, int NB, int F, int T,
+                                                       const float* __restrict__ drows, int drows_ld,
+                                                       const float* __restrict__ dpred, int NB, int F, int T,
                                                        float* __restrict__ y_planes, float* __restrict__ g_planes) {
   const long long n = (long long)NB * F * T;
   const int Tp = T + 1;
@@ -646,6 +647,10 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     const float2 y = __ldg(reinterpret_cast<const float2*>(raw + i * 2));
     const float2 gs = __ldg(reinterpret_cast<const float2*>(drows + ((long long)b * T + t) * drows_ld + 2 * f));
     float gr = gs.x, gi = gs.y;
+    if (dpred) {                                                      // gradient that reached `predict` directly
+      const float2 gp = __ldg(reinterpret_cast<const float2*>(dpred + i * 2));
+      gr += gp.x; gi += gp.y;
+    }
     if (mask) {
       const float pr = fmaf(zb[0], y.x, fmaf(zb[1], y.y, zb[4])), pi = fmaf(zb[2], y.x, fmaf(zb[3], y.y, zb[5]));
       const float mr = prelu_f(pr, slope), mi = prelu_f(pi, slope);
@@ -666,6 +671,156 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     const long long row = ((long long)f * R + (long long)b * Tp + 1 + t) * 16;
     y_planes[row] = y.x; y_planes[row + 8] = y.y;
     g_planes[row] = gr; g_planes[row + 8] = gi;
+  }
+}
+
+
+// ---- last decoder layer (Cout = 1, kernel (5,2), stride (2,1), freq pad 2, causal) --------------------------------------
+// dy planes fp32 [Fout = 2 Fin - 1][R][16] (re at channel 0, im at 8), w10 [10 (kf*2+kt)][Ktot][2] (pack_dec5 without fold).
+// dx[fi][r][c] = sum_{kf,kt} dy[2fi - 2 + kf][r + kt] . w10[kf*2+kt][k_off + c]      grid (row tiles of 64, Fin)
+__global__ void __launch_bounds__(256) dec5_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w10,
+                                                         int Ktot, int k_off, int Cp, int Fin, int NB, int T,
+                                                         float* __restrict__ dx) {
+  extern __shared__ float ws[];                                       // [10][Cp][2]
+  for (int i = threadIdx.x; i < 10 * Cp * 2; i += 256) {
+    const int tap = i / (Cp * 2), rem = i % (Cp * 2);
+    ws[i] = __ldg(w10 + ((long long)tap * Ktot + k_off) * 2 + rem);
+  }
+  __syncthreads();
+  const int Tp = T + 1, Fout = 2 * Fin - 1, fi = blockIdx.y;
+  const long long R = (long long)NB * Tp;
+  const int q = Cp >> 2, lanes = 256 / q;
+  if ((int)threadIdx.x >= lanes * q) return;
+  const int c4 = (threadIdx.x % q) * 4;
+  long long r_end = (long long)(blockIdx.x + 1) * 64;
+  if (r_end > R) r_end = R;
+  for (long long r = (long long)blockIdx.x * 64 + threadIdx.x / q; r < r_end; r += lanes) {
+    const int tt = (int)(r % Tp);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tt != 0) {
+#pragma unroll
+      for (int kf = 0; kf < 5; ++kf) {
+        const int fo = 2 * fi - 2 + kf;
+        if (fo < 0 || fo >= Fout) continue;
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+          if (kt && tt == T) continue;                                // the frame after the last one is dropped
+          const float* g = dy + ((long long)fo * R + r + kt) * 16;
+          const float gr = __ldg(g), gi = __ldg(g + 8);
+          const float* w = ws + ((kf * 2 + kt) * Cp + c4) * 2;
+          a.x = fmaf(w[0], gr, fmaf(w[1], gi, a.x));
+          a.y = fmaf(w[2], gr, fmaf(w[3], gi, a.y));
+          a.z = fmaf(w[4], gr, fmaf(w[5], gi, a.z));
+          a.w = fmaf(w[6], gr, fmaf(w[7], gi, a.w));
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(dx + ((long long)fi * R + r) * Cp + c4) = a;
+  }
+}
+
+// dW[tap][k_off + c][part] += sum_{fi, r} x[fi][r][c] * dy[2fi - 2 + kf][r + kt][part]     grid (Fin, chunks), block 256
+__global__ void __launch_bounds__(256) dec5_wgrad_kernel(const void* __restrict__ x, int x_split,
+                                                         const float* __restrict__ dy, int Ktot, int k_off, int Cp,
+                                                         int Fin, int NB, int T, int rows_per_chunk,
+                                                         float* __restrict__ dW) {
+  __shared__ float red[256];
+  const int Tp = T + 1, Fout = 2 * Fin - 1, fi = blockIdx.x;
+  const long long R = (long long)NB * Tp, hl = (long long)Fin * R * Cp;
+  const int nj = 256 / Cp, c = threadIdx.x % Cp, j = threadIdx.x / Cp;
+  long long r0 = (long long)blockIdx.y * rows_per_chunk, r1 = r0 + rows_per_chunk;
+  if (r1 > R) r1 = R;
+  float acc[20];
+#pragma unroll
+  for (int k = 0; k < 20; ++k) acc[k] = 0.f;
+  if (j < nj)
+    for (long long r = r0 + j; r < r1; r += nj) {
+      const int tt = (int)(r % Tp);
+      if (tt == 0) continue;
+      const float xv = ld_act(x, x_split, hl, ((long long)fi * R + r) * Cp + c);
+#pragma unroll
+      for (int kf = 0; kf < 5; ++kf) {
+        const int fo = 2 * fi - 2 + kf;
+        if (fo < 0 || fo >= Fout) continue;
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+          if (kt && tt == T) continue;
+          const float* g = dy + ((long long)fo * R + r + kt) * 16;
+          acc[(kf * 2 + kt) * 2] = fmaf(xv, __ldg(g), acc[(kf * 2 + kt) * 2]);
+          acc[(kf * 2 + kt) * 2 + 1] = fmaf(xv, __ldg(g + 8), acc[(kf * 2 + kt) * 2 + 1]);
+        }
+      }
+    }
+#pragma unroll
+  for (int k = 0; k < 20; ++k) {
+    red[threadIdx.x] = acc[k];
+    __syncthreads();
+    if (j == 0) {
+      float t = 0.f;
+      for (int jj = 0; jj < nj; ++jj) t += red[jj * Cp + c];
+      atomicAdd(dW + ((long long)(k >> 1) * Ktot + k_off + c) * 2 + (k & 1), t);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- reparameterisation backward (model/pvae_module.py:L2177-2231, S = 1) ----------------------------------------------
+// dlatent[(bt)][ch0 + {0, zdim, 2 zdim} + j][2] += d z / d (mu, log sigma, delta) applied to dz (NB, T, zdim, 2).
+// The imaginary part of log sigma is ignored by the forward (its gradient is 0).
+__global__ void __launch_bounds__(256) reparam_bwd_kernel(const float* __restrict__ latent, long long n_bt, int Htot,
+                                                          int ch0, int zdim, const float* __restrict__ eps_r,
+                                                          const float* __restrict__ eps_i,
+                                                          const float* __restrict__ dz, float* __restrict__ dlat) {
+  const float e = 1e-6f;
+  const long long n = n_bt * zdim;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % zdim);
+    const long long bt = i / zdim;
+    const long long base = (bt * Htot + ch0 + j) * 2;
+    const float ls = latent[base + 2 * zdim];
+    const float d0r = latent[base + 4 * zdim], d0i = latent[base + 4 * zdim + 1];
+    const float er = eps_r[i], ei = eps_i[i];
+    const float gzr = dz[i * 2], gzi = dz[i * 2 + 1];
+    // forward (fp32 like the kernel), keeping what the chain rule needs
+    const float sig = expf(ls);
+    const float ad0 = sqrtf(d0r * d0r + d0i * d0i + e);
+    const bool clamp = ad0 >= sig - 1e-3f;
+    const float tmp = sig * 0.99f / (ad0 + e);
+    const float dr = clamp ? d0r * tmp : d0r, di = clamp ? d0i * tmp : d0i;
+    const float ad2 = dr * dr + di * di + e;                          // |delta|^2 + eps after the protection
+    const float den = sqrtf(2.f * (sig + dr) + e);
+    const float de = den + e;
+    const float num = sig + dr;
+    const float rad = sig * sig - ad2 + e;
+    const float sq = sqrtf(rad);
+    // z_r = mu_r + num/de * er;  z_i = mu_i + di/de * er + sq/de * ei
+    const float g_num = gzr * er / de;
+    const float g_di_direct = gzi * er / de;
+    const float g_sq = gzi * ei / de;
+    const float g_de = -(gzr * er * num + gzi * (er * di + ei * sq)) / (de * de);
+    const float g_rad = g_sq * 0.5f / sq;
+    const float g_den = g_de;                                         // de = den + e
+    const float g_two = g_den * 0.5f / den;                           // den = sqrt(2 (sig + dr) + e)
+    float g_sig = g_num + 2.f * g_two + g_rad * 2.f * sig;
+    float g_dr = g_num + 2.f * g_two - g_rad * 2.f * dr;
+    float g_di = g_di_direct - g_rad * 2.f * di;
+    float g_d0r, g_d0i;
+    if (clamp) {
+      // dr = d0r * tmp, di = d0i * tmp, tmp = 0.99 sig / (ad0 + e)
+      const float g_tmp = g_dr * d0r + g_di * d0i;
+      g_sig += g_tmp * 0.99f / (ad0 + e);
+      const float g_ad0 = -g_tmp * tmp / (ad0 + e);
+      g_d0r = g_dr * tmp + g_ad0 * d0r / ad0;
+      g_d0i = g_di * tmp + g_ad0 * d0i / ad0;
+    } else {
+      g_d0r = g_dr;
+      g_d0i = g_di;
+    }
+    dlat[base] += gzr;
+    dlat[base + 1] += gzi;
+    dlat[base + 2 * zdim] += g_sig * sig;                             // sig = exp(log sigma_re)
+    dlat[base + 4 * zdim] += g_d0r;
+    dlat[base + 4 * zdim + 1] += g_d0i;
   }
 }
 
@@ -699,8 +854,8 @@ extern "C" int idv_ola_bwd(const float* dsig, const float* wsq, int B, int T, in
 }
 
 extern "C" int idv_head_bwd(const float* raw, const float* zb, float slope, int mask, const float* stft_x,
-                            const float* drows, int drows_ld, int NB, int F, int T, float* y_planes, float* g_planes,
-                            void* stream) {
+                            const float* drows, int drows_ld, const float* dpred, int NB, int F, int T, float* y_planes,
+                            float* g_planes, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(raw && zb && drows && y_planes && g_planes && (!mask || stft_x) && NB > 0 && F > 0 && T > 0 &&
                     drows_ld >= 2 * F,
@@ -709,8 +864,50 @@ extern "C" int idv_head_bwd(const float* raw, const float* zb, float slope, int 
   const size_t bytes = (size_t)F * NB * (T + 1) * 16 * sizeof(float);
   IDV_CUDA(cudaMemsetAsync(y_planes, 0, bytes, st));
   IDV_CUDA(cudaMemsetAsync(g_planes, 0, bytes, st));
-  head_bwd_kernel<<<grid_for((long long)NB * F * T, 16), 256, 0, st>>>(raw, zb, slope, mask, stft_x, drows, drows_ld, NB, F,
-                                                                       T, y_planes, g_planes);
+  head_bwd_kernel<<<grid_for((long long)NB * F * T, 16), 256, 0, st>>>(raw, zb, slope, mask, stft_x, drows, drows_ld, dpred,
+                                                                       NB, F, T, y_planes, g_planes);
   IDV_LAUNCH_CHECK("head_bwd_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_dec5_dgrad(const float* dy, const float* w10, int Ktot, int k_off, int Cp, int Fin, int NB, int T,
+                              float* dx, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(dy && w10 && dx && Cp >= 4 && Cp % 4 == 0 && Cp <= 1024 && k_off >= 0 && k_off + Cp <= Ktot && Fin > 0 &&
+                    NB > 0 && T > 0,
+                "idv_dec5_dgrad: bad argument");
+  const long long R = (long long)NB * (T + 1);
+  dim3 grid((unsigned)cdiv64(R, 64), Fin);
+  dec5_dgrad_kernel<<<grid, 256, 10 * Cp * 2 * sizeof(float), (cudaStream_t)stream>>>(dy, w10, Ktot, k_off, Cp, Fin, NB, T, dx);
+  IDV_LAUNCH_CHECK("dec5_dgrad_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_dec5_wgrad(const void* x, int x_split, const float* dy, int Ktot, int k_off, int Cp, int Fin, int NB,
+                              int T, float* dW, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(x && dy && dW && Cp >= 8 && Cp <= 256 && 256 % Cp == 0 && k_off >= 0 && k_off + Cp <= Ktot && Fin > 0 &&
+                    NB > 0 && T > 0,
+                "idv_dec5_wgrad: bad argument (Cp must divide 256)");
+  const long long R = (long long)NB * (T + 1);
+  int chunks = cdiv(148 * 8, Fin);
+  const long long per = cdiv64(R, chunks);
+  chunks = (int)cdiv64(R, per);
+  dim3 grid(Fin, chunks);
+  dec5_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_split, dy, Ktot, k_off, Cp, Fin, NB, T, (int)per, dW);
+  IDV_LAUNCH_CHECK("dec5_wgrad_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_reparam_bwd(const float* latent, int NB, int T, int Htot, int ch0, int zdim, const float* eps_r,
+                               const float* eps_i, const float* dz, float* dlatent, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(latent && eps_r && eps_i && dz && dlatent && NB > 0 && T > 0 && zdim > 0 && ch0 >= 0 &&
+                    ch0 + 3 * zdim <= Htot,
+                "idv_reparam_bwd: bad argument");
+  const long long n = (long long)NB * T * zdim;
+  reparam_bwd_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(latent, (long long)NB * T, Htot, ch0, zdim, eps_r,
+                                                                        eps_i, dz, dlatent);
+  IDV_LAUNCH_CHECK("reparam_bwd_kernel");
   return IDV_OK;
 }

@@ -57,7 +57,10 @@ SIGNATURES = {
     "idv_kl_fwd_bwd": [vp, i32, i32, vp, i32, i32, i64, i32, f32, f32, vp, vp, vp],
     "idv_sisnr_fwd_bwd": [vp, vp, i32, i32, f32, vp, vp, vp, vp],
     "idv_ola_bwd": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
-    "idv_head_bwd": [vp, vp, f32, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp],
+    "idv_head_bwd": [vp, vp, f32, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp],
+    "idv_dec5_dgrad": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    "idv_dec5_wgrad": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    "idv_reparam_bwd": [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
     "idv_cbn_stats_user": [vp, i64, i32, i64, vp, vp],
     "idv_head_user": [vp, i64, i64, f32, i32, vp, i32, vp],
     "idv_stream_frames_split": [vp, vp, i32, i32, i64, i32, i32, i32, vp, vp],

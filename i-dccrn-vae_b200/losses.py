@@ -9,6 +9,33 @@ import torch
 from . import lib
 
 
+class _SiSnrFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, source, estimate):
+        src = lib.require_f32_cuda(source.detach(), "source")
+        est = lib.require_f32_cuda(estimate.detach(), "estimate")
+        if src.dim() != 2 or src.shape != est.shape:
+            raise RuntimeError("si_snr expects source and estimate of one shape (B, L)")
+        B, L = src.shape
+        d_est = torch.zeros_like(est)
+        sums = torch.empty(B * 3, dtype=torch.float64, device=est.device)
+        loss = torch.zeros(1, dtype=torch.float64, device=est.device)
+        lib.call("idv_sisnr_fwd_bwd", src, est, B, L, 1.0, d_est, sums, loss)
+        ctx.save_for_backward(d_est)
+        return loss.to(torch.float32)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_est,) = ctx.saved_tensors
+        return None, g * d_est
+
+
+def si_snr_loss(source, estimate):
+    """two_phase_loss.si_snr (model/nsvae_loss.py:L877-889): -mean_b SI-SNR(estimate_b, source_b) in dB; value and
+    gradient w.r.t. ``estimate`` from one fused pass (two kernels: per-utterance sums, then the gradient)."""
+    return _SiSnrFn.apply(source, estimate)
+
+
 class _KLFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, lat, lat_clean, lat_noise, zdim, latent_num, alpha):

@@ -202,16 +202,18 @@ class _ComplexConvTransposeBase(nn.Module):
     def frames_out(self, frames_in):
         return frames_in + _pair(self.tconv_re.kernel_size)[1] - 1 - (1 if self.causal else 0)
 
-    def run_packed(self, pk, pp, skip, out=None):
-        """One tap-GEMM launch of a pack built by pack.pack_conv_transpose for this layer."""
+    def run_packed(self, pk, pp, skip, out=None, out_split=None):
+        """One tap-GEMM launch of a pack built by pack.pack_conv_transpose for this layer (out_split=False: fp32
+        planes from split inputs)."""
         tv = self.frames_out(pp.Tv)
         if not 0 < tv <= pp.T:
             raise RuntimeError("transposed conv output has %d frames, the row layout holds %d" % (tv, pp.T))
         if skip is not None and (skip.T != pp.T or skip.NB != pp.NB or skip.Tv != pp.Tv):
             raise RuntimeError("skip tensor has %d/%d frames x %d utterances, the decoder activation %d/%d x %d"
                                % (skip.Tv, skip.T, skip.NB, pp.Tv, pp.T, pp.NB))
-        out = ops.tapgemm(pk, pp, skip, pp.NB, pp.T, t_valid=tv, out=out)
-        return Planes(out, pp.NB, pk.c_out, pk.f_out, pp.T, split=pp.split, Tv=tv)
+        out = ops.tapgemm(pk, pp, skip, pp.NB, pp.T, t_valid=tv, out=out, out_split=out_split)
+        split = pp.split if out_split is None else bool(out_split)
+        return Planes(out, pp.NB, pk.c_out, pk.f_out, pp.T, split=split, Tv=tv)
 
     def _packed(self, f_in, c_p, c_skip, device, bn=None, slope=None):
         items = self._cache.check(self)
@@ -489,7 +491,8 @@ class Decoder(nn.Module):
     def _fold(self):
         return (self.bn.fold_inputs(), self._slope()) if self.if_bn else (None, None)
 
-    def forward_planes(self, pp, skip=None, train=False, out=None):
+    def forward_planes(self, pp, skip=None, train=False, out=None, raw_only=False):
+        """raw_only: the transposed-conv output before ComplexBatchNormal / PReLU as fp32 planes (training forward)."""
         train = bool(train) and self.if_bn
         items = self._cache.check(self)
         c_skip = skip.C if skip is not None else 0
@@ -504,10 +507,14 @@ class Decoder(nn.Module):
             items[key] = pack.pack_conv_transpose(t.tconv_re.weight, t.tconv_re.bias, t.tconv_im.weight,
                                                   t.tconv_im.bias, bn, slope, pp.F, pp.C, c_skip,
                                                   pp.data.device, sf, pf)
+        if raw_only:
+            if not train:
+                raise RuntimeError("raw_only is the training forward (train=True with ComplexBatchNormal)")
+            return self.transconv.run_packed(items[key], pp, skip, out, out_split=False)
         out = self.transconv.run_packed(items[key], pp, skip, out)
         return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
-    def forward_head(self, pp, skip, mask, stft_x, predict, out_bmul, out_boff, train=False):
+    def forward_head(self, pp, skip, mask, stft_x, predict, out_bmul, out_boff, train=False, raw_only=False):
         """Last layer (out_channel == 1) fused with the reconstruction head; writes ``predict``.  train=True: the raw
         transposed conv is written first, then CBN with batch statistics + PReLU (+ mask head) run in place."""
         train = bool(train) and self.if_bn
@@ -538,7 +545,7 @@ class Decoder(nn.Module):
             ops.dec5_head_tc(items[tkey], pp, skip, fused_mask, stft_x, predict, out_bmul, out_boff)
         else:
             ops.dec5_head(pp, skip, w, b, slope, fused_mask, stft_x, predict, out_bmul, out_boff)
-        if train:
+        if train and not raw_only:
             ops.head_train_user(predict, self.bn, self._slope(), mask, stft_x, 1)
 
     def forward(self, x, train=True):
@@ -753,6 +760,11 @@ class _VaeDecoderBase(nn.Module):
                 raise RuntimeError("stft_x %s does not match the reconstructed spectrum (B, %d, %d, 2)"
                                    % (tuple(stft_x.shape), n_bins, t_alloc))
         self.decoder_outputs = []
+        if train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training step: (recon_sig, predict) carry a grad_fn whose backward runs the C-ABI backward kernels
+            from . import train as _train
+            recon_sig, predict = _train.decoder_train_forward(self, stft_x if mask else None, z, skiper, skips, C, F, mask)
+            return recon_sig, torch.view_as_complex(predict)
         for s in range(S):
             zp = ops.z_to_planes(z, B, S, s, split=split, t_alloc=t_alloc)
             p = self.dense.forward_planes(zp, C, F)

@@ -178,7 +178,7 @@ def pack_conv_transpose(t_re_w, t_re_b, t_im_w, t_im_b, bn, slope, f_in, c_p, c_
     if kw not in (1, 2):
         raise NotImplementedError("complex transposed conv is built for 1- or 2-tap time kernels")
     ch_out = round8(cout)
-    Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(cout)
+    Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(cout, wr.device)
     f_out = (f_in - 1) * stride_f - 2 * pad_f + kh
     N = 2 * ch_out
     srcs = [(0, 0, c_p)]
@@ -237,7 +237,7 @@ def pack_dec5(t_re_w, t_re_b, t_im_w, t_im_b, bn, slope, c_p, c_skip, device):
     wr, wi = _cpu(t_re_w), _cpu(t_im_w)
     cin_tot, cout, kh, kw = wr.shape
     assert cout == 1 and kh == 5 and kw == 2 and cin_tot >= c_p + c_skip
-    Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(1)
+    Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(1, wr.device)
     parts, bias = [], None
     for (c0, cn) in ((0, c_p), (c_p, c_skip)):
         if cn == 0:
@@ -251,6 +251,25 @@ def pack_dec5(t_re_w, t_re_b, t_im_w, t_im_b, bn, slope, c_p, c_skip, device):
     w = torch.cat(parts, 1).to(torch.float32).contiguous().to(device)
     b2 = torch.stack((bias[0], bias[8])).to(torch.float32).to(device)
     return w, b2, float(slope if slope is not None else 1.0)
+
+
+def unfold_dec5_wgrad(dW, c_p, c_skip, cin_tot):
+    """dW (10, 2 ch_p + 2 ch_skip, 2): gradient of pack_dec5's w10 (no fold) -> gradients of tconv_re / tconv_im.weight
+    (cin_tot, 1, 5, 2): w10[tap][ci][0] = m_re, [ch+ci][0] = -m_im, [ci][1] = m_im, [ch+ci][1] = m_re."""
+    d_re = torch.zeros(cin_tot, 1, 5, 2, dtype=dW.dtype, device=dW.device)
+    d_im = torch.zeros_like(d_re)
+    k0 = 0
+    for (c0, cn) in ((0, c_p), (c_p, c_skip)):
+        if cn == 0:
+            continue
+        ch = round8(cn)
+        blk = dW[:, k0:k0 + 2 * ch]
+        g_re = blk[:, :cn, 0] + blk[:, ch:ch + cn, 1]                 # (10, cn)
+        g_im = blk[:, :cn, 1] - blk[:, ch:ch + cn, 0]
+        d_re[c0:c0 + cn, 0] = g_re.t().reshape(cn, 5, 2)
+        d_im[c0:c0 + cn, 0] = g_im.t().reshape(cn, 5, 2)
+        k0 += 2 * ch
+    return d_re, d_im
 
 
 def pack_dec5_tc(w10, bias2, slope, f_in, kcs, device):
@@ -504,6 +523,21 @@ def pack_istft_tc(n_fft, win, device):
                 units=torch.tensor([[0, 1, 0, 0, 0, kpad // 64]], dtype=torch.int32, device=device))
 
 
+def pack_istft_adjoint_tc(n_fft, win, device):
+    """Adjoint of pack_istft_tc's DFT GEMM (backward of the iSTFT): gradient of the frames [R][kpad >= win] times the
+    synthesis basis transposed -> gradient rows [R][N >= 2 nbins] in idv_spec_rows_split's order (2k + part)."""
+    nb = n_fft // 2 + 1
+    kpad = (win + 63) // 64 * 64
+    N = (2 * nb + 255) // 256 * 256
+    basis, wsq = pack_istft_basis(n_fft, win, "cpu")                  # [>= 2nb][>= win]
+    w = torch.zeros(N, kpad)
+    w[:2 * nb, :win] = basis[:2 * nb, :win]
+    return dict(wt=_split_rows(w.unsqueeze(0)).to(device), kc_max=kpad, n_slots=1, N=N, kpad=kpad, nbins=nb,
+                bias=torch.zeros(N, device=device), wsq=wsq.to(device),
+                taps=torch.tensor([[0, 0, 0, 0, kpad, 0]], dtype=torch.int32, device=device),
+                units=torch.tensor([[0, 1, 0, 0, 0, kpad // 64]], dtype=torch.int32, device=device))
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # backward (phase-1 training step): data-gradient packs and weight-gradient tap tables
 # ------------------------------------------------------------------------------------------------------------------
@@ -549,23 +583,35 @@ def pack_conv_dgrad(conv_re_w, conv_im_w, f_in, stride_f, pad_f, pad_t, device):
     return p
 
 
-def wgrad_conv_tables(f_in, f_out, kh, kw, stride_f, pad_f, pad_t, rpad, groups, device):
+def wgrad_conv_tables(f_in, f_out, kh, kw, stride_f, pad_f, pad_t, rpad, groups, device, transposed=False):
     """Tap tables of the weight-gradient GEMM of a complex conv: unit (kf, kt, g) sums, over the output planes fo of
     group g, dyT[fo] (rows = output channels, K = rows of the activation, shifted by the tap's time offset: source
-    0 = shift 0, source 1 = shift 1) against xT[fi] (weight-operand slot fi): out[unit] = dW_tap^T (2ch_out, 2ch_in)."""
+    0 = shift 0, source 1 = shift 1) against xT[fi] (weight-operand slot fi): out[unit] = dW_tap^T (2ch_out, 2ch_in).
+    transposed: the complex transposed conv of pack_conv_transpose (fi = (fo + pad_f - kf) / stride_f, time tap kt
+    pairs x[t - kt] with dy[t])."""
+    def plane_in(fo, kf):
+        if not transposed:
+            return stride_f * fo + kf - pad_f
+        num = fo + pad_f - kf
+        return num // stride_f if num % stride_f == 0 else -1
+
     units, taps = [], []
-    # at least 3 output planes per group: every group then has an in-range input plane for every kf (no empty unit)
-    per = max(3, (f_out + groups - 1) // groups)
-    groups = (f_out + per - 1) // per
+    # enough consecutive output planes per group that every group has an in-range input plane for every kf
+    min_per = 4 if transposed else 3
+    per = max(min_per, (f_out + groups - 1) // groups)
+    bounds = list(range(0, f_out, per)) + [f_out]
+    if len(bounds) > 2 and bounds[-1] - bounds[-2] < min_per:
+        del bounds[-2]                                                # merge a short last group into its neighbour
+    groups = len(bounds) - 1
     for kf in range(kh):
         for kt in range(kw):
-            dt = pad_t - kt
+            dt = kt if transposed else pad_t - kt
             if dt not in (0, 1):
                 raise NotImplementedError("weight gradients are built for time shifts 0 / 1 (causal taps)")
             for g in range(groups):
                 begin = len(taps)
-                for fo in range(g * per, min(f_out, (g + 1) * per)):
-                    fi = stride_f * fo + kf - pad_f
+                for fo in range(bounds[g], bounds[g + 1]):
+                    fi = plane_in(fo, kf)
                     if 0 <= fi < f_in:
                         taps.append([dt, fo, 0, 0, rpad, fi])
                 if len(taps) == begin:
@@ -575,16 +621,72 @@ def wgrad_conv_tables(f_in, f_out, kh, kw, stride_f, pad_f, pad_t, rpad, groups,
             torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(device), len(units), groups)
 
 
-def unfold_conv_wgrad(dwt, kh, kw, cin, cout):
+def unfold_conv_wgrad(dwt, kh, kw, cin, cout, transposed=False):
     """dwt: (kh*kw, 2ch_out, 2ch_in) = dW_tap^T of the block-real weights -> gradients of conv_re.weight and
-    conv_im.weight (Cout, Cin, kh, kw): W[:cin,:cout] = m_re, W[ch_in+ci, co] = -m_im, W[ci, ch_out+co] = m_im,
-    W[ch_in+ci, ch_out+co] = m_re (model/complex_progress.py:L17-19)."""
+    conv_im.weight (Cout, Cin, kh, kw) - transposed: tconv_re / tconv_im.weight (Cin, Cout, kh, kw):
+    W[:cin,:cout] = m_re, W[ch_in+ci, co] = -m_im, W[ci, ch_out+co] = m_im, W[ch_in+ci, ch_out+co] = m_re
+    (model/complex_progress.py:L17-19, L245-247)."""
     ch_in, ch_out = round8(cin), round8(cout)
     d = dwt.transpose(1, 2)                                           # (taps, 2ch_in, 2ch_out)
     d_re = d[:, :cin, :cout] + d[:, ch_in:ch_in + cin, ch_out:ch_out + cout]
     d_im = d[:, :cin, ch_out:ch_out + cout] - d[:, ch_in:ch_in + cin, :cout]
-    f = lambda m: m.reshape(kh, kw, cin, cout).permute(3, 2, 0, 1).contiguous()
+    perm = (2, 3, 0, 1) if transposed else (3, 2, 0, 1)
+    f = lambda m: m.reshape(kh, kw, cin, cout).permute(*perm).contiguous()
     return f(d_re), f(d_im)
+
+
+def pack_convT_dgrad(t_re_w, t_im_w, c0, cn, f_in, stride_f, pad_f, device):
+    """Data gradient w.r.t. input channels [c0, c0 + cn) (the running activation or the skip tensor) of the complex
+    transposed conv packed by pack_conv_transpose: dx[fi][r] = sum over (kf, kt) of dy[stride_f*fi - pad_f + kf][r + kt]
+    W_tap^T - the strided conv that model/complex_progress.py:L244-250's transposed conv is the adjoint of."""
+    W, kh, kw, cin, cout = raw_block_weights(t_re_w[c0:c0 + cn], t_im_w[c0:c0 + cn], transposed=True)
+    f_out = (f_in - 1) * stride_f - 2 * pad_f + kh
+    K, N = 2 * round8(cout), 2 * round8(cn)
+    Wt = W.transpose(1, 2).contiguous()                              # (taps, 2ch_out, 2ch_in)
+    units, taps = [], []
+    for fi in range(f_in):
+        begin = len(taps)
+        for kf in range(kh):
+            fo = stride_f * fi - pad_f + kf
+            if fo < 0 or fo >= f_out:
+                continue
+            for kt in range(kw):
+                taps.append([0, fo, -kt, 0, K, (kf * kw + kt) * K * N])
+        units.append([begin, len(taps) - begin, fi, 0, 0, 0])
+    p = TapGemmPack(Wt.reshape(-1), torch.zeros(N), units, taps, N, f_in, N, False, 0.0, device)
+    p.f_out, p.c_out = f_in, cn
+    return p
+
+
+def pack_dense_dgrad(w_read, w_imag, c_out, f_out, device):
+    """Gradient of z from the gradient of the ComplexDense output planes [f_out][R][2 ch_c] (pack_dense's layout):
+    dz_part[r][k] = sum over (f, c) of g[f][r][part*ch_c + c] W_part[c*f_out + f][k].  Output: z planes [1][R][2 ch_z]."""
+    zdim = w_read.shape[1]
+    ch_z, ch_c = round8(zdim), round8(c_out)
+    dev = _cpu(w_read).device
+    W = torch.zeros(2, f_out, ch_c, ch_z, dtype=torch.float64, device=dev)
+    for part, w in enumerate((w_read, w_imag)):
+        W[part, :, :c_out, :zdim] = _cpu(w).double().reshape(c_out, f_out, zdim).permute(1, 0, 2)
+    units, taps = [], []
+    for part in range(2):
+        begin = len(taps)
+        for f in range(f_out):
+            taps.append([0, f, 0, part * ch_c, ch_c, (part * f_out + f) * ch_c * ch_z])
+        units.append([begin, f_out, 0, part * ch_z, 0, 0])
+    return TapGemmPack(W.reshape(-1), torch.zeros(ch_z), units, taps, ch_z, 1, 2 * ch_z, False, 0.0, device)
+
+
+def wgrad_dense_tables(f_out, rpad, device):
+    """Weight-gradient GEMM of ComplexDense: unit (f, part) = gT[f] (rows = the 2 ch_c output channels of plane f,
+    K = rows of the sequence) against slot `part` of zT ([2 ch_z][rpad] viewed as 2 slots of ch_z rows)."""
+    units, taps = [], []
+    ks = rpad // 64
+    for f in range(f_out):
+        for part in range(2):
+            taps.append([0, f, 0, 0, rpad, part])
+            units.append([len(taps) - 1, 1, len(units), 0, 0, ks])
+    return (torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(device),
+            torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(device), len(units))
 
 
 def pack_lstm_gates(lstm_re, lstm_im, hidden, layer, c_in, f_in, device):

@@ -319,6 +319,316 @@ def encoder_train_forward(enc, x):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# decoder (phase 2 of the reference: i_dccrn_vae/nsvae_dccrn/train_second_phase_decoder.py:L376-433 - frozen NSVAE
+# encoder, decoder train=True, SI-SNR / spectral reconstruction losses, backward through iSTFT, reconstruction head,
+# ComplexBatchNormal(train) + PReLU, complex transposed convs with skip concat, ComplexDense)
+# ------------------------------------------------------------------------------------------------------------------
+class DecoderTrainStep:
+    """Train-mode forward of a VAE decoder keeping what the backward needs, and the backward from the gradients of
+    (recon_sig, predict) into ``.grad`` of every decoder parameter; optionally also the gradients of ``z`` and of the
+    skip tensors (end-to-end step).  Same kernel plan as the encoder: data gradients of the
+    transposed convs = the tcgen05 tap-GEMM with transposed weights (the strided conv the layer is the adjoint of),
+    weight gradients = the tap-GEMM over the row dimension on transposed copies; the Cout = 1 last layer, whose output
+    gradient has only 2 channels, has SIMT kernels (idv_dec5_dgrad / idv_dec5_wgrad)."""
+
+    def __init__(self, dec):
+        if not dec.causal:
+            raise NotImplementedError("the backward pass is built for the causal network (model/causal_netconfig.py)")
+        if dec.num_samples != 1:
+            raise NotImplementedError("training is built for num_samples = 1 (the shipped training configs)")
+        if not ops.use_split():
+            raise RuntimeError("training runs on the tensor-core path (IDV_GEMM=tc)")
+        self.dec = dec
+        self.saved = None
+        self._packs = {}
+
+    # ---------------------------------------------------------------------------------------------- forward
+    def forward(self, stft_x, z, skips, C, F, mask):
+        with pack.on_device():
+            return self._forward(stft_x, z, skips, C, F, mask)
+
+    def _forward(self, stft_x, z, skips, C, F, mask):
+        """z (B, T, zdim, 2), skips {layer: Planes}.  Returns recon_sig (B, L), predict (B, F, T, 2)."""
+        dec = self.dec
+        z = lib.require_f32_cuda(z, "z")
+        B, T, zdim, _ = z.shape
+        dev = z.device
+        n = len(dec.decoders)
+        zp = ops.z_to_planes(z, B, 1, 0, split=True, t_alloc=T)
+        p = dec.dense.forward_planes(zp, C, F)
+        sv = {"zp": zp, "dense_out": p, "layers": [], "B": B, "T": T, "C": C, "F": F, "mask": mask}
+        for i in range(n - 1):
+            d = dec.decoders[i]
+            raw = d.forward_planes(p, skips.get(i), True, raw_only=True)
+            Cc = raw.C
+            acc = torch.empty(Cc * 5, dtype=torch.float64, device=dev)
+            lib.call("idv_cbn_stats_planes", raw.data, 0, raw.NB, Cc, raw.F, raw.T, acc, raw.Tv)
+            stats = torch.empty(Cc * 5, dtype=torch.float32, device=dev)
+            zb = ops._cbn_finalize(d.bn, acc, raw.NB * raw.F * raw.Tv, dev, stats)
+            slope = d._slope()
+            act32 = torch.empty_like(raw.data)
+            lib.call("idv_cbn_apply_planes", raw.data, 0, raw.NB, Cc, raw.F, raw.T, zb, 1, slope, raw.Tv, act32)
+            act = _to_split(act32)
+            del act32
+            a = Planes(act, raw.NB, Cc, raw.F, raw.T, split=True, Tv=raw.Tv)
+            sv["layers"].append({"x": p, "skip": skips.get(i), "raw": raw, "stats": stats, "zb": zb, "slope": slope})
+            p = a
+        d = dec.decoders[n - 1]
+        n_bins = 2 * p.F - 1
+        raw5 = torch.empty((B, n_bins, T, 2), dtype=torch.float32, device=dev)
+        d.forward_head(p, skips.get(n - 1), False, None, raw5, 1, 0, train=True, raw_only=True)
+        inner = n_bins * T
+        acc = torch.empty(5, dtype=torch.float64, device=dev)
+        lib.call("idv_cbn_stats_user", raw5, B, 1, inner, acc)
+        stats = torch.empty(5, dtype=torch.float32, device=dev)
+        zb = ops._cbn_finalize(d.bn, acc, B * inner, dev, stats)
+        predict = torch.empty_like(raw5)
+        lib.call("idv_cbn_eval_user", raw5, B, 1, inner, zb, predict)
+        if mask:
+            stft_x = lib.require_f32_cuda(stft_x, "stft_x")
+        lib.call("idv_head_user", predict, inner, B, float(d._slope()), 1 if mask else 0, stft_x if mask else None, 1)
+        sv["head"] = {"x": p, "skip": skips.get(n - 1), "raw": raw5, "stats": stats, "zb": zb, "slope": d._slope(),
+                      "stft_x": stft_x if mask else None}
+        self.saved = sv
+        recon_sig = dec.istft.forward_ri(predict)
+        return recon_sig, predict
+
+    # ---------------------------------------------------------------------------------------------- backward
+    def _grad(self, param, value):
+        value = value.to(param.dtype).reshape(param.shape)
+        param.grad = value if param.grad is None else param.grad + value
+
+    def backward(self, d_sig, d_pred=None, want_dz=False, want_dskip=False):
+        """d_sig (B, L) / d_pred (B, F, T, 2): gradients of recon_sig / predict (either may be None).  Accumulates
+        the parameter gradients; returns (dz or None, {layer: gradient planes of the skip tensor})."""
+        if self.saved is None:
+            raise RuntimeError("backward() without a train-mode forward")
+        with pack.on_device():
+            out = self._backward(d_sig, d_pred, want_dz, want_dskip)
+        self.saved = None
+        return out
+
+    def _bn_backward(self, d, raw_data, g, NB, C, F, T, stats, zb, slope, dy_split):
+        """ComplexBatchNormal(train) + PReLU backward of decoder block ``d`` on planes; returns dy (gradient of the raw
+        transposed-conv output) and writes the parameter gradients."""
+        dev = g.device
+        bn = d.bn
+        acc = torch.empty(C * 8, dtype=torch.float64, device=dev)
+        lib.call("idv_cbn_bwd_reduce", raw_data, 0, g, 0, NB, C, F, T, stats, zb, slope, acc, T)
+        coef = torch.empty(C * 10, dtype=torch.float32, device=dev)
+        dpar = [_zeros(C, dev) for _ in range(5)]
+        dslope = _zeros(1, dev, torch.float64)
+        lib.call("idv_cbn_bwd_finalize", acc, float(NB * F * T), C, stats, bn.gamma_rr.detach(), bn.gamma_ri.detach(),
+                 bn.gamma_ii.detach(), coef, dpar[0], dpar[1], dpar[2], dpar[3], dpar[4], dslope)
+        for prm, val in zip((bn.gamma_rr, bn.gamma_ri, bn.gamma_ii, bn.beta_r, bn.beta_i), dpar):
+            self._grad(prm, val)
+        self._grad(d.prelu.weight, dslope.to(torch.float32))
+        dy = torch.empty(raw_data.numel() * (2 if dy_split else 1), dtype=torch.bfloat16 if dy_split else torch.float32,
+                         device=dev)
+        lib.call("idv_cbn_bwd_apply", raw_data, 0, g, 0, NB, C, F, T, stats, zb, coef, slope, dy, 1 if dy_split else 0, T)
+        t = d.transconv
+        # a bias in front of a batch-statistics normalisation has an exactly zero gradient
+        self._grad(t.tconv_re.bias, torch.zeros_like(t.tconv_re.bias))
+        self._grad(t.tconv_im.bias, torch.zeros_like(t.tconv_im.bias))
+        return dy
+
+    def _backward(self, d_sig, d_pred, want_dz, want_dskip):
+        sv, dec = self.saved, self.dec
+        B, T = sv["B"], sv["T"]
+        hd = sv["head"]
+        dev = hd["raw"].device
+        n = len(dec.decoders)
+        n_bins = hd["raw"].shape[1]
+        dskips = {}
+        # ---- iSTFT adjoint: overlap-add adjoint, then the DFT GEMM with the transposed synthesis basis
+        ist = dec.istft
+        if d_sig is not None:
+            d_sig = lib.require_f32_cuda(d_sig, "gradient of recon_sig")
+            key = ("istft_adj", str(dev))
+            if key not in self._packs:
+                self._packs[key] = pack.pack_istft_adjoint_tc(ist.n_fft, ist.win_length, dev)
+            hp = self._packs[key]
+            R0 = B * T
+            dframes = torch.empty(R0 * hp["kpad"], dtype=torch.float32, device=dev)
+            lib.call("idv_ola_bwd", d_sig, hp["wsq"], B, T, ist.n_fft, ist.hop_length, ist.win_length, hp["kpad"], dframes)
+            dfs = _to_split(dframes)
+            drows = torch.empty(R0 * hp["N"], dtype=torch.float32, device=dev)
+            lib.call("idv_tapgemm_tc", dfs, hp["kpad"], 1, None, 0, 0, R0, 0, hp["wt"], hp["kc_max"], 1, hp["bias"],
+                     hp["N"], hp["units"], hp["taps"], 1, drows, hp["N"], R0 * hp["N"], 0, 0, 0, 0.0, 0)
+            ld = hp["N"]
+        else:
+            ld = 2 * n_bins
+            drows = _zeros(B * T * ld, dev)
+        if d_pred is not None:
+            d_pred = lib.require_f32_cuda(d_pred, "gradient of predict")
+        # ---- reconstruction head + last layer (Cout = 1)
+        d5 = dec.decoders[n - 1]
+        x5, sk5 = hd["x"], hd["skip"]
+        R = B * (T + 1)
+        yp = torch.empty(n_bins * R * 16, dtype=torch.float32, device=dev)
+        gp = torch.empty(n_bins * R * 16, dtype=torch.float32, device=dev)
+        lib.call("idv_head_bwd", hd["raw"], hd["zb"], float(hd["slope"]), 1 if sv["mask"] else 0, hd["stft_x"], drows, ld,
+                 d_pred, B, n_bins, T, yp, gp)
+        del drows
+        dy5 = self._bn_backward(d5, yp, gp, B, 1, n_bins, T, hd["stats"], hd["zb"], float(hd["slope"]), False)
+        del yp, gp
+        t5 = d5.transconv
+        c_skip = sk5.C if sk5 is not None else 0
+        w10, _, _ = pack.pack_dec5(t5.tconv_re.weight, t5.tconv_re.bias, t5.tconv_im.weight, t5.tconv_im.bias, None, None,
+                                   x5.C, c_skip, dev)
+        ktot = x5.Cp + (sk5.Cp if sk5 is not None else 0)
+        dW = _zeros(10 * ktot * 2, dev)
+        g = torch.empty(x5.F * R * x5.Cp, dtype=torch.float32, device=dev)
+        lib.call("idv_dec5_dgrad", dy5, w10, ktot, 0, x5.Cp, x5.F, B, T, g)
+        lib.call("idv_dec5_wgrad", x5.data, 1, dy5, ktot, 0, x5.Cp, x5.F, B, T, dW)
+        if sk5 is not None:
+            lib.call("idv_dec5_wgrad", sk5.data, 1, dy5, ktot, x5.Cp, sk5.Cp, sk5.F, B, T, dW)
+            if want_dskip:
+                gs = torch.empty(sk5.F * R * sk5.Cp, dtype=torch.float32, device=dev)
+                lib.call("idv_dec5_dgrad", dy5, w10, ktot, x5.Cp, sk5.Cp, sk5.F, B, T, gs)
+                dskips[n - 1] = gs
+        del dy5
+        d_re, d_im = pack.unfold_dec5_wgrad(dW.view(10, ktot, 2), x5.C, c_skip, t5.tconv_re.weight.shape[0])
+        self._grad(t5.tconv_re.weight, d_re)
+        self._grad(t5.tconv_im.weight, d_im)
+        # ---- layers n-2 .. 0
+        for i in reversed(range(n - 1)):
+            g, gs = self._tconv_backward(i, g, want_dskip)
+            if gs is not None:
+                dskips[i] = gs
+        # ---- ComplexDense: g = gradient of its output planes [F][R][2 ch_c]
+        dz = self._dense_backward(g, want_dz)
+        return dz, dskips
+
+    def _tconv_backward(self, i, g, want_dskip):
+        sv = self.saved["layers"][i]
+        d = self.dec.decoders[i]
+        raw, xin, skip = sv["raw"], sv["x"], sv["skip"]
+        NB, C, F, T = raw.NB, raw.C, raw.F, raw.T
+        dev = g.device
+        R = NB * (T + 1)
+        dy = self._bn_backward(d, raw.data, g, NB, C, F, T, sv["stats"], sv["zb"], sv["slope"], True)
+        t = d.transconv
+        wr, wi = t.tconv_re.weight, t.tconv_im.weight
+        cin_tot, cout, kh, kw = wr.shape
+        kh_, sf, pf = t._geometry()
+        dyp = Planes(dy, NB, C, F, T, split=True)
+        c_skip = skip.C if skip is not None else 0
+        key = ("dgrad", i, wr._version, wi._version)
+        if key not in self._packs:
+            self._packs[key] = pack.pack_convT_dgrad(wr, wi, 0, xin.C, xin.F, sf, pf, dev)
+        gin = ops.tapgemm(self._packs[key], dyp, None, NB, T, zero_pad_rows=True, out_split=False)
+        gskip = None
+        if skip is not None and want_dskip:
+            key = ("dgrad_skip", i, wr._version, wi._version)
+            if key not in self._packs:
+                self._packs[key] = pack.pack_convT_dgrad(wr, wi, xin.C, c_skip, xin.F, sf, pf, dev)
+            gskip = ops.tapgemm(self._packs[key], dyp, None, NB, T, zero_pad_rows=True, out_split=False)
+        # weight gradients: K = rows x output planes, one GEMM per source (weight rows [p | skip] like torch.cat)
+        rp = _rpad(R)
+        rows = 2 * round8(cout)
+        dyT0 = _transpose_split(dy, True, F, R, raw.Cp, 0)
+        dyT1 = _transpose_split(dy, True, F, R, raw.Cp, 1)
+        d_re, d_im = torch.zeros_like(wr), torch.zeros_like(wi)
+        for (src, c0) in ((xin, 0), (skip, xin.C)):
+            if src is None:
+                continue
+            N = src.Cp
+            tiles = kh * kw * ((rows + 127) // 128) * max(1, N // 256)
+            groups = max(1, min(F, -(-160 // tiles)))
+            tk = ("wgrad", i, rp, groups, src.F)
+            if tk not in self._packs:
+                self._packs[tk] = pack.wgrad_conv_tables(src.F, F, kh, kw, sf, pf, 0, rp, groups, dev, transposed=True)
+            u, tp, nu, ng = self._packs[tk]
+            xT = _transpose_split(src.data, True, src.F, R, src.Cp, 0)
+            o = _wgrad_gemm(dyT0, dyT1, F, rows, xT, src.F, N, rp, u, tp, nu)
+            dwt = o.view(kh * kw, ng, rows, N).sum(1)
+            g_re, g_im = pack.unfold_conv_wgrad(dwt, kh, kw, src.C, cout, transposed=True)
+            d_re[c0:c0 + src.C] = g_re
+            d_im[c0:c0 + src.C] = g_im
+            del xT, o
+        self._grad(wr, d_re)
+        self._grad(wi, d_im)
+        return gin, gskip
+
+    def _dense_backward(self, g, want_dz):
+        sv, dense = self.saved, self.dec.dense
+        zp, p0 = sv["zp"], sv["dense_out"]
+        NB, T, C, F = p0.NB, p0.T, p0.C, p0.F
+        dev = g.device
+        R = NB * (T + 1)
+        rp = _rpad(R)
+        ch_c, ch_z = round8(C), round8(zp.C)
+        zdim = zp.C
+        wr, wi = dense.linear_read.weight, dense.linear_imag.weight
+        # bias gradients: column sums of every output plane
+        db = _zeros(F * 2 * ch_c, dev)
+        for f in range(F):
+            lib.call("idv_colsum_add", g[f * R * 2 * ch_c:(f + 1) * R * 2 * ch_c], R, 2 * ch_c, 2 * ch_c,
+                     db[f * 2 * ch_c:(f + 1) * 2 * ch_c])
+        dbv = db.view(F, 2, ch_c)[:, :, :C]
+        self._grad(dense.linear_read.bias, dbv[:, 0].t().reshape(-1))
+        self._grad(dense.linear_imag.bias, dbv[:, 1].t().reshape(-1))
+        gT = _transpose_split(g, False, F, R, 2 * ch_c, 0)
+        zT = _transpose_split(zp.data, True, 1, R, 2 * ch_z, 0)
+        tk = ("wg_dense", rp, F)
+        if tk not in self._packs:
+            self._packs[tk] = pack.wgrad_dense_tables(F, rp, dev)
+        u, tp, nu = self._packs[tk]
+        o = _wgrad_gemm(gT, None, F, 2 * ch_c, zT, 2, ch_z, rp, u, tp, nu).view(F, 2, 2, ch_c, ch_z)   # [f][part][half]
+        self._grad(wr, o[:, 0, 0, :C, :zdim].permute(1, 0, 2).reshape(C * F, zdim))
+        self._grad(wi, o[:, 1, 1, :C, :zdim].permute(1, 0, 2).reshape(C * F, zdim))
+        if not want_dz:
+            return None
+        key = ("dgrad_dense", wr._version, wi._version)
+        if key not in self._packs:
+            self._packs[key] = pack.pack_dense_dgrad(wr, wi, C, F, dev)
+        gs = Planes(_to_split(g), NB, C, F, T, split=True)
+        dzp = ops.tapgemm(self._packs[key], gs, None, NB, T, zero_pad_rows=True, out_split=False)    # [1][R][2 ch_z]
+        dz = dzp.view(NB, T + 1, 2, ch_z)[:, 1:, :, :zdim].permute(0, 1, 3, 2).contiguous()           # (B, T, zdim, 2)
+        return dz
+
+
+class _DecoderTrainFn(torch.autograd.Function):
+    """Autograd plumbing of the decoder: forward = DecoderTrainStep.forward; backward receives the gradients of
+    (recon_sig, predict) and runs DecoderTrainStep.backward, which writes the parameter gradients itself.  ``token`` is
+    the encoder's ordering token (a scalar produced by the encoder's autograd node) when the skip tensors need
+    gradients: autograd then runs this node before the encoder's, and the skip gradients are handed over directly."""
+
+    @staticmethod
+    def forward(ctx, step, stft_x, z, token, skips, C, F, mask, enc_step, *params):
+        recon_sig, predict = step.forward(stft_x, z, skips, C, F, mask)
+        ctx.step, ctx.enc_step, ctx.n, ctx.dev = step, enc_step, len(params), z.device
+        ctx.set_materialize_grads(False)
+        return recon_sig, predict
+
+    @staticmethod
+    def backward(ctx, d_sig, d_pred):
+        want_dz = ctx.needs_input_grad[2]
+        want_dskip = ctx.enc_step is not None and ctx.needs_input_grad[3]
+        dz, dskips = ctx.step.backward(None if d_sig is None else d_sig.contiguous(),
+                                       None if d_pred is None else d_pred.contiguous(), want_dz, want_dskip)
+        if want_dskip:
+            ctx.enc_step.add_skip_grads(dskips, len(ctx.step.dec.decoders))
+        token_grad = torch.zeros((), device=ctx.dev) if ctx.needs_input_grad[3] else None
+        return (None, None, dz, token_grad, None, None, None, None, None) + (None,) * ctx.n
+
+
+def decoder_train_forward(dec, stft_x, z, skiper, skips, C, F, mask):
+    """(recon_sig, predict (B, F, T, 2)) with a grad_fn.  skiper: the encoder's SkipList (carries the encoder's train
+    step / ordering token when the encoder ran under autograd), skips: {layer: Planes}."""
+    step = getattr(dec, "_train_step", None)
+    if step is None:
+        step = dec._train_step = DecoderTrainStep(dec)
+    params = [p for p in dec.parameters() if p.requires_grad]
+    token = getattr(skiper, "grad_token", None) if skips else None
+    enc_step = getattr(skiper, "train_step", None) if token is not None else None
+    if token is None:
+        token = torch.zeros((), device=z.device)
+    return _DecoderTrainFn.apply(step, stft_x, z, token, skips, C, F, mask, enc_step, *params)
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # optimiser + gradient all-reduce (data-parallel training: SURVEY §8(e))
 # ------------------------------------------------------------------------------------------------------------------
 class FlatAdam:

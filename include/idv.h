@@ -290,14 +290,28 @@ int idv_kl_fwd_bwd(const float* lat1, int H1, int ch1, const float* lat2, int H2
  *   idv_ola_bwd: adjoint of idv_ola_fwd: dframes (B*T, frame_ld) <- dsig (B, hop*(T-1)) / window envelope;
  *   idv_head_bwd: backward of the reconstruction head (real_imag: identity; mask: model/pvae_module.py:L2594-2609) for
  *       the last decoder layer.  raw (NB, F, T, 2) = transposed-conv output before ComplexBatchNormal, zb[6] its batch
- *       Z / b', drows[(b*T+t)][2k+part] = gradient of the spectrum; writes fp32 planes (C = 1: [F][NB*(T+1)][16])
+ *       Z / b', drows[(b*T+t)][2k+part] (+ dpred (NB, F, T, 2) when not NULL: the gradient that reached `predict`
+ *       directly) = gradient of the spectrum; writes fp32 planes (C = 1: [F][NB*(T+1)][16])
  *       y_planes <- raw and g_planes <- gradient w.r.t. the PReLU output, ready for idv_cbn_bwd_*.                  */
 int idv_sisnr_fwd_bwd(const float* src, const float* est, int B, int L, float scale, float* d_est, double* sums,
                       double* loss, void* stream);
 int idv_ola_bwd(const float* dsig, const float* wsq, int B, int T, int n_fft, int hop, int win, int frame_ld,
                 float* dframes, void* stream);
 int idv_head_bwd(const float* raw, const float* zb, float slope, int mask, const float* stft_x, const float* drows,
-                 int drows_ld, int NB, int F, int T, float* y_planes, float* g_planes, void* stream);
+                 int drows_ld, const float* dpred, int NB, int F, int T, float* y_planes, float* g_planes, void* stream);
+/* Last decoder layer (Cout = 1; the tap-GEMM needs K % 64 == 0, its output gradient has K = 2), SIMT:
+ *   dy: fp32 planes [2 Fin - 1][NB*(T+1)][16] from idv_cbn_bwd_apply (re at channel 0, im at channel 8);
+ *   w10: [10 (kf*2+kt)][Ktot][2] raw block weights (pack_dec5 without the CBN fold), this source's channels at k_off;
+ *   idv_dec5_dgrad: dx fp32 planes [Fin][R][Cp] = gradient of the layer input (pad rows 0);
+ *   idv_dec5_wgrad: dW [10][Ktot][2] += x^T dy  (x: fp32 or split-bf16 planes [Fin][R][Cp], Cp divides 256).
+ * idv_reparam_bwd: gradient of the reparameterisation (model/pvae_module.py:L2177-2231, num_samples = 1) with the eps
+ *   of the forward: dlatent (NB, T, Htot, 2) += dz (NB, T, zdim, 2) . dz/d(mu, log sigma, delta) at channel ch0.     */
+int idv_dec5_dgrad(const float* dy, const float* w10, int Ktot, int k_off, int Cp, int Fin, int NB, int T, float* dx,
+                   void* stream);
+int idv_dec5_wgrad(const void* x, int x_split, const float* dy, int Ktot, int k_off, int Cp, int Fin, int NB, int T,
+                   float* dW, void* stream);
+int idv_reparam_bwd(const float* latent, int NB, int T, int Htot, int ch0, int zdim, const float* eps_r,
+                    const float* eps_i, const float* dz, float* dlatent, void* stream);
 
 /* ---- frame streaming (causal network; carried state instead of whole utterances) ------------------------------
  * Hop-synchronous streams: a step consumes hop*k new samples per stream and runs the same tap-GEMMs on k-frame

@@ -235,6 +235,65 @@ def case_train_step(tag, B, L, latent_num, seed):
     np.savez(os.path.join(OUT, tag + ".npz"), **g)
 
 
+def case_train_step_phase2(tag, B, L, latent_num, recon_type, weights, seed):
+    """Phase-2 decoder training step of train_second_phase_decoder.py:L376-433: frozen NSVAE encoder (train=False),
+    nsvae_pvae_dccrn_decoder_twophase(train=True, pad='sig'), two_phase_loss.multi_recon_loss (shipped weights '001' =
+    SI-SNR only), backward.  Pins the loss terms and, per decoder parameter, ||grad|| and <grad, probe>."""
+    import types
+    print("case", tag)
+    for m in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    import model.nsvae_loss as ref_loss
+    net, enc = build_vae(latent_num, 1, seed)
+    dec = ref_mod.nsvae_pvae_dccrn_decoder_twophase(net, True, "cpu", 1, ZDIM, NFFT, HOP, WIN, recon_type, True,
+                                                    [0, 1, 2, 3, 4, 5], False)
+    dec.load_state_dict(fill_state_dict(dec.state_dict(), seed + 1), strict=True)
+    xs = [synth_waveform(B, L, seed=1234 + seed + j) for j in range(2)]           # noisy, clean
+    T = L // HOP + 1
+    eps = synth_eps((B, 1, T, ZDIM), seed=7 + seed, n=2 * latent_num)
+    with torch.no_grad(), supplied_eps(eps):
+        r = enc(xs[0], train=False)
+    sig, pred = dec(r[11], r[0], r[8], r[9], r[10], train=True, pad="sig")
+    stft_clean = enc.stft(xs[1])
+    lossf = ref_loss.two_phase_loss(list(weights), 1.0, ZDIM, latent_num)
+    final, l_cpx, l_mag, l_si = lossf.multi_recon_loss(pred, stft_clean, xs[1], sig)
+    final.backward()
+    # ---- the port, differentiated by autograd
+    params = dict(dec.named_parameters())
+    sd = {k: v.detach().clone().requires_grad_(k in params) for k, v in fill_state_dict(dec.state_dict(), seed + 1).items()}
+    with torch.no_grad():
+        st = P.vae_encoder_forward(enc.state_dict(), xs[0], ZDIM, latent_num, 1, eps)
+    dd = P.vae_decoder_forward(sd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], 1, recon_type, "sig",
+                               train=True)
+    pf, pc, pm, ps = P.multi_recon_loss(dd["predict"], P.stft(xs[1]), xs[1], dd["recon_sig"], weights)
+    pf.backward()
+    check("phase2 recon_sig", dd["recon_sig"].detach(), sig.detach())
+    for nm, a, b in (("final", pf, final), ("cpx", pc, l_cpx), ("mag", pm, l_mag), ("sisnr", ps, l_si)):
+        assert abs(float(a) - float(b)) <= 1e-5 * max(1.0, abs(float(b))), (nm, float(a), float(b))
+    g = {"B": B, "L": L, "latent_num": latent_num, "seed": seed, "mask": int(recon_type == "mask"),
+         "weights": np.asarray(weights, dtype=np.float64), "loss": np32(final), "loss_cpx": np32(l_cpx),
+         "loss_mag": np32(l_mag), "loss_sisnr": np32(l_si), "recon_sig": np32(sig)}
+    worst = 0.0
+    for name, p in dec.named_parameters():
+        assert p.grad is not None, name
+        if ".transconv.tconv_" in name and name.endswith(".bias"):
+            assert float(p.grad.abs().max()) < 1e-4 * max(1.0, float(final.abs())), (name, float(p.grad.abs().max()))
+            g["zero/" + name] = np.float64(p.grad.abs().max())
+            continue
+        e = P.rel_l2(sd[name].grad, p.grad)
+        if e > 1e-4:
+            print("   ", name, "rel %.2e  |ref| %.3e |port| %.3e" % (e, float(p.grad.norm()), float(sd[name].grad.norm())))
+        worst = max(worst, e)
+        gd = p.grad.double()
+        g["norm/" + name] = np.float64(gd.norm())
+        g["probe/" + name] = np.float64((gd * grad_probe(name, p.shape)).sum())
+        if p.numel() <= 1024:
+            g["full/" + name] = np32(p.grad)
+    print("  port-vs-reference decoder gradients: worst rel_l2 = %.2e" % worst)
+    assert worst < 5e-4, worst
+    np.savez(os.path.join(OUT, tag + ".npz"), **g)
+
+
 def case_dccrn(tag, B, L, seed, causal=True):
     print("case", tag)
     net = (ref_causal_cfg if causal else ref_noncausal_cfg).get_net_params()
@@ -316,9 +375,19 @@ def case_primitives(tag, seed):
     np.savez(os.path.join(OUT, tag + ".npz"), **g)
 
 
+def phase2_cases():
+    case_train_step_phase2("train_phase2_mask_sisnr", B=2, L=1200, latent_num=2, recon_type="mask",
+                           weights=(0.0, 0.0, 1.0), seed=15)
+    case_train_step_phase2("train_phase2_ri_multi", B=3, L=700, latent_num=1, recon_type="real_imag",
+                           weights=(0.5, 0.25, 1.0), seed=16)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-phase2" in sys.argv:
+        phase2_cases()
+        sys.exit(0)
     if "--only-trainstep" in sys.argv:
         case_train_step("train_step_l2", B=2, L=1200, latent_num=2, seed=13)
         case_train_step("train_step_l1", B=3, L=700, latent_num=1, seed=14)
@@ -347,4 +416,5 @@ if __name__ == "__main__":
     noncausal_cases()
     case_train_step("train_step_l2", B=2, L=1200, latent_num=2, seed=13)
     case_train_step("train_step_l1", B=3, L=700, latent_num=1, seed=14)
+    phase2_cases()
     print("golden fixtures written to", OUT)

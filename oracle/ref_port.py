@@ -179,10 +179,10 @@ def encoder_block(x, sd, pre, causal=True, train=False):
     return prelu((cbn_train if train else cbn_eval)(y, sd, pre + "bn."), sd, pre + "prelu.")
 
 
-def decoder_block(x, sd, pre, causal=True):
-    """Decoder.forward(x, train=False) — model/pvae_module.py:L88-93 (if_bn always True)."""
+def decoder_block(x, sd, pre, causal=True, train=False):
+    """Decoder.forward(x, train) — model/pvae_module.py:L88-93 (if_bn always True)."""
     y = complex_conv_transpose2d(x, sd, pre + "transconv.", (2, 1), (2, 0), causal)
-    return prelu(cbn_eval(y, sd, pre + "bn."), sd, pre + "prelu.")
+    return prelu((cbn_train if train else cbn_eval)(y, sd, pre + "bn."), sd, pre + "prelu.")
 
 
 def _lstm_module(sd, pre, input_size, hidden, layers, dtype):
@@ -331,6 +331,29 @@ def nsvae_kl_loss(noisy, clean, noise, zdim=128, latent_num=1, alpha=1.0):
     return kc.mean() + alpha * kn.mean(), kc.mean(), kn.mean()
 
 
+def si_snr(source, estimate, eps=1e-8):
+    """two_phase_loss.si_snr — model/nsvae_loss.py:L877-889.  The reference builds the B x B matrix
+    ``estimate @ source.T`` and keeps its diagonal; the per-utterance dot product is the same number."""
+    dot = (estimate * source).sum(1, keepdim=True)
+    s_target = dot * source / ((source ** 2).sum(1, keepdim=True) + eps)
+    e_noise = estimate - s_target
+    snr = 10 * torch.log10((s_target ** 2).sum(1) / ((e_noise ** 2).sum(1) + eps) + eps)
+    return -snr.mean()
+
+
+def multi_recon_loss(predict, ori_stft, source, estimate, weights):
+    """two_phase_loss.multi_recon_loss — model/nsvae_loss.py:L891-913 (``ori_mag`` uses real^2 + real^2 like L899).
+    predict: complex (B,F,T); ori_stft: (B,F,T,2).  Returns (final, loss_cpx, loss_mag, loss_sisnr)."""
+    pr, pi = predict.real, predict.imag
+    p_mag = torch.sqrt(pr ** 2 + pi ** 2 + 1e-6)
+    o_r, o_i = ori_stft[..., 0], ori_stft[..., 1]
+    o_mag = torch.sqrt(o_r ** 2 + o_r ** 2 + 1e-6)
+    l_cpx = (((pr - o_r) ** 2).sum(1) + ((pi - o_i) ** 2).sum(1)).mean()
+    l_mag = ((p_mag - o_mag) ** 2).sum(1).mean()
+    l_si = si_snr(source, estimate)
+    return weights[0] * l_cpx + weights[1] * l_mag + weights[2] * l_si, l_cpx, l_mag, l_si
+
+
 def vae_encoder_forward(sd, signal, zdim=128, latent_num=1, num_samples=1, eps=None, causal=True,
                         stft_params=(512, 100, 400), train=False, grad=False):
     """nsvae_pvae_dccrn_encoder_twophase.forward(x, train=False) — model/pvae_module.py:L2233-2268;
@@ -361,7 +384,7 @@ def vae_encoder_forward(sd, signal, zdim=128, latent_num=1, num_samples=1, eps=N
 
 def vae_decoder_forward(sd, stft_x, z, skiper, C, Fq, num_samples=1, recon_type="real_imag",
                         skip_mode="zero", skip_to_use=(0, 1, 2, 3, 4, 5), causal=True,
-                        stft_params=(512, 100, 400)):
+                        stft_params=(512, 100, 400), train=False):
     """pvae_dccrn_decoder_skip_prepare.forward (skip_mode='zero', model/pvae_module.py:L2082-2122)
     and nsvae_pvae_dccrn_decoder_twophase.forward(pad='zero'|'sig', use_sc=True, L2548-2619)."""
     BS, T, zdim, D = z.shape
@@ -376,7 +399,7 @@ def vae_decoder_forward(sd, stft_x, z, skiper, C, Fq, num_samples=1, recon_type=
             else:
                 sk = sk.unsqueeze(1).repeat(1, num_samples, 1, 1, 1, 1).view((BS,) + tuple(sk.shape[1:]))
             p = torch.cat([p, sk], dim=1)
-        p = decoder_block(p, sd, "decoders.%d." % i, causal)
+        p = decoder_block(p, sd, "decoders.%d." % i, causal, train)
         outs.append(p)
     if recon_type == "real_imag":
         predict = torch.complex(p[..., 0], p[..., 1]).squeeze(1)

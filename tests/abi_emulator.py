@@ -792,6 +792,129 @@ def idv_stream_ola(frames, frame_ld, wsq, acc, NB, k, t0, hop, win, out):
     acc.view(NB, tl).copy_(buf[:, hop * k:hop * k + tl].to(torch.float32))
 
 
+# ---- decoder side of the training step (csrc/backward.cu) -------------------------------------------------------------
+def idv_sisnr_fwd_bwd(src, est, B, L, scale, d_est, sums, loss):
+    """Contract = si_snr of model/nsvae_loss.py:L877-889 (restated) differentiated by autograd."""
+    with torch.enable_grad():
+        s = src.view(B, L).to(D)
+        e = est.view(B, L).to(D).detach().clone().requires_grad_(True)
+        eps = 1e-8
+        alpha = (e * s).sum(1, keepdim=True) / ((s * s).sum(1, keepdim=True) + eps)
+        tgt = alpha * s
+        noise = e - tgt
+        snr = 10 * torch.log10((tgt ** 2).sum(1) / ((noise ** 2).sum(1) + eps) + eps)
+        lo = -snr.mean()
+        (g,) = torch.autograd.grad(lo, e)
+    loss[0] += float(lo)
+    if d_est is not None:
+        d_est.view(B, L).add_((scale * g).to(torch.float32))
+
+
+def idv_ola_bwd(dsig, wsq, B, T, n_fft, hop, win, frame_ld, dframes):
+    """Adjoint of idv_ola_fwd (autograd of its restatement)."""
+    off = (n_fft - win) // 2
+    total = n_fft + hop * (T - 1)
+    h = n_fft // 2
+    env = torch.zeros(total, dtype=D)
+    for t in range(T):
+        env[t * hop + off:t * hop + off + win] += wsq.to(D)
+    gy = torch.zeros(B, total, dtype=D)
+    gy[:, h:total - h] = dsig.view(B, hop * (T - 1)).to(D) / env[h:total - h]
+    o = torch.zeros(B, T, frame_ld, dtype=D)
+    for t in range(T):
+        o[:, t, :win] = gy[:, t * hop + off:t * hop + off + win]
+    dframes.view(B, T, frame_ld).copy_(o.to(torch.float32))
+
+
+def idv_head_bwd(raw, zb, slope, mask, stft_x, drows, drows_ld, dpred, NB, F, T, y_planes, g_planes):
+    """Contract: autograd of CBN-affine -> PReLU -> (mask head) on the raw last-layer output."""
+    k = zb.view(6).to(D)
+    y = raw.view(NB, F, T, 2).to(D)
+    gS = drows.view(NB, T, drows_ld)[:, :, :2 * F].reshape(NB, T, F, 2).permute(0, 2, 1, 3).to(D)
+    if dpred is not None:
+        gS = gS + dpred.view(NB, F, T, 2).to(D)
+    pr = k[0] * y[..., 0] + k[1] * y[..., 1] + k[4]
+    pi = k[2] * y[..., 0] + k[3] * y[..., 1] + k[5]
+    with torch.enable_grad():
+        m = torch.stack((torch.where(pr > 0, pr, slope * pr), torch.where(pi > 0, pi, slope * pi)), -1)
+        m = m.detach().clone().requires_grad_(True)
+        if mask:
+            mr, mi = m[..., 0], m[..., 1]
+            mag = torch.tanh(torch.sqrt(mr ** 2 + mi ** 2))
+            ph = torch.atan2(mi / (mag + 1e-8), mr / (mag + 1e-8))
+            X = stft_x.view(NB, F, T, 2).to(D)
+            in_mag = torch.sqrt(X[..., 0] ** 2 + X[..., 1] ** 2)
+            in_ph = torch.atan2(X[..., 1], X[..., 0])
+            S = torch.stack((in_mag * mag * torch.cos(in_ph + ph), in_mag * mag * torch.sin(in_ph + ph)), -1)
+            (gm,) = torch.autograd.grad((S * gS).sum(), m)
+        else:
+            gm = gS
+    Tp = T + 1
+    yp = torch.zeros(F, NB, Tp, 16)
+    gp = torch.zeros(F, NB, Tp, 16)
+    yp[:, :, 1:, 0], yp[:, :, 1:, 8] = y[..., 0].permute(1, 0, 2), y[..., 1].permute(1, 0, 2)
+    gp[:, :, 1:, 0], gp[:, :, 1:, 8] = gm[..., 0].permute(1, 0, 2), gm[..., 1].permute(1, 0, 2)
+    y_planes.view(F, NB, Tp, 16).copy_(yp)
+    g_planes.view(F, NB, Tp, 16).copy_(gp)
+
+
+def _dec5_taps(Fin):
+    Fout = 2 * Fin - 1
+    for fi in range(Fin):
+        for kf in range(5):
+            fo = 2 * fi - 2 + kf
+            if 0 <= fo < Fout:
+                yield fi, kf, fo
+
+
+def idv_dec5_dgrad(dy, w10, Ktot, k_off, Cp, Fin, NB, T, dx):
+    Tp = T + 1
+    Fout = 2 * Fin - 1
+    g = dy.view(Fout, NB, Tp, 16)[..., [0, 8]].to(D)                      # (Fout, NB, Tp, 2)
+    W = w10.view(10, Ktot, 2)[:, k_off:k_off + Cp].to(D)
+    o = torch.zeros(Fin, NB, Tp, Cp, dtype=D)
+    for fi, kf, fo in _dec5_taps(Fin):
+        o[fi, :, 1:] += g[fo, :, 1:] @ W[kf * 2].t()                       # out[t] uses x[t] through kt = 0
+        o[fi, :, 1:T] += g[fo, :, 2:] @ W[kf * 2 + 1].t()                  # and x[t-1] through kt = 1
+    dx.view(Fin, NB, Tp, Cp).copy_(o.to(torch.float32))
+
+
+def idv_dec5_wgrad(x, x_split, dy, Ktot, k_off, Cp, Fin, NB, T, dW):
+    Tp = T + 1
+    Fout = 2 * Fin - 1
+    g = dy.view(Fout, NB, Tp, 16)[..., [0, 8]].to(D)
+    xv = _rd(x, x_split, Fin * NB * Tp * Cp).view(Fin, NB, Tp, Cp)
+    o = torch.zeros(10, Cp, 2, dtype=D)
+    for fi, kf, fo in _dec5_taps(Fin):
+        o[kf * 2] += torch.einsum("btc,btp->cp", xv[fi, :, 1:], g[fo, :, 1:])
+        o[kf * 2 + 1] += torch.einsum("btc,btp->cp", xv[fi, :, 1:T], g[fo, :, 2:])
+    dW.view(10, Ktot, 2)[:, k_off:k_off + Cp].add_(o.to(torch.float32))
+
+
+def idv_reparam_bwd(latent, NB, T, Htot, ch0, zdim, eps_r, eps_i, dz, dlatent):
+    """Contract: autograd of the idv_reparam_fwd restatement (S = 1)."""
+    with torch.enable_grad():
+        lat = latent.view(NB, T, Htot, 2).to(D).detach().clone().requires_grad_(True)
+        z = torch.zeros(NB, T, zdim, 2, dtype=D)
+        e = 1e-6
+        mu, ls, dl = lat[:, :, ch0:ch0 + zdim], lat[:, :, ch0 + zdim:ch0 + 2 * zdim], lat[:, :, ch0 + 2 * zdim:ch0 + 3 * zdim]
+        sig = torch.exp(ls[..., 0])
+        dr, di = dl[..., 0], dl[..., 1]
+        ad = torch.sqrt(dr * dr + di * di + e)
+        tmp = sig * 0.99 / (ad + e)
+        cl = ad >= sig - 1e-3
+        dr, di = torch.where(cl, dr * tmp, dr), torch.where(cl, di * tmp, di)
+        ad = torch.sqrt(dr * dr + di * di + e)
+        den = torch.sqrt(2 * (sig + dr) + e)
+        er, ei = eps_r.view(NB, T, zdim).to(D), eps_i.view(NB, T, zdim).to(D)
+        zr = mu[..., 0] + ((sig + dr) / (den + e)) * er
+        zi = mu[..., 1] + (di / (den + e)) * er + (torch.sqrt(sig * sig - ad * ad + e) / (den + e)) * ei
+        z = torch.stack((zr, zi), -1)
+        (g,) = torch.autograd.grad((z * dz.view(NB, T, zdim, 2).to(D)).sum(), lat)
+    dlatent.view(NB, T, Htot, 2).add_(g.to(torch.float32))
+
+
+
 TABLE = {k: v for k, v in globals().items() if k.startswith("idv_")}
 
 

@@ -436,3 +436,72 @@ def test_stft_istft_tensor_core_pieces(B, L):
     assert _both("idv_spec_rows_split", [spec, B, 257, T, ip["kpad"], rows], [5]) < 1e-7
     fr = _rand(R, 512, seed=7)
     assert _both("idv_ola_fwd", [fr, 512, ip["wsq"], B, T, 512, 100, 400, torch.zeros(B, 100 * (T - 1))], [8]) < 1e-5
+
+
+@pytest.mark.parametrize("B,L", [(1, 300), (3, 6400), (5, 1999)])
+def test_sisnr_and_ola_backward(B, L):
+    src, est = _rand(B, L, seed=30), _rand(B, L, seed=31) * 0.5 + 0.3 * _rand(B, L, seed=30)
+    d_est = _rand(B, L, seed=32) * 0.01                       # accumulates (+=)
+    sums, loss = torch.zeros(B * 3, dtype=torch.float64), torch.full((1,), 0.5, dtype=torch.float64)
+    assert _both("idv_sisnr_fwd_bwd", [src, est, B, L, 0.7, d_est, sums, loss], [5, 7]) < 2e-5
+    from idccrn_b200 import pack as PK
+    hop = 100
+    Ls = L // hop * hop
+    T = Ls // hop + 1
+    wsq = PK.pack_istft_basis(512, 400, "cpu")[1]
+    dsig = _rand(B, Ls, seed=33)
+    for ld in (400, 448):
+        dfr = torch.full((B * T, ld), 7.0)
+        assert _both("idv_ola_bwd", [dsig, wsq, B, T, 512, hop, 400, ld, dfr], [8]) < 1e-6
+    # adjoint identity: <ola(f), s> == <f, ola_bwd(s)>
+    fr = _rand(B * T, 448, seed=34).cuda()
+    out = torch.zeros(B, Ls).cuda()
+    lib.call("idv_ola_fwd", fr, 448, wsq.cuda(), B, T, 512, hop, 400, out)
+    dfr = torch.zeros(B * T, 448).cuda()
+    lib.call("idv_ola_bwd", dsig.cuda(), wsq.cuda(), B, T, 512, hop, 400, 448, dfr)
+    lhs, rhs = float((out.double() * dsig.cuda().double()).sum()), float((fr[:, :400].double() * dfr[:, :400].double()).sum())
+    assert abs(lhs - rhs) < 1e-6 * max(1.0, abs(lhs))
+
+
+@pytest.mark.parametrize("NB,F,T,mask,with_dpred", [(2, 17, 9, 0, False), (3, 257, 13, 1, True), (1, 5, 1, 1, False)])
+def test_head_backward(NB, F, T, mask, with_dpred):
+    raw = _rand(NB, F, T, 2, seed=40)
+    zb = torch.tensor([0.9, 0.3, -0.2, 1.1, 0.05, -0.1])
+    stft_x = _rand(NB, F, T, 2, seed=41)
+    ld = 2 * F + 6
+    drows = _rand(NB * T, ld, seed=42)
+    dpred = _rand(NB, F, T, 2, seed=43) if with_dpred else None
+    R = NB * (T + 1)
+    yp, gp = torch.full((F * R * 16,), 3.0), torch.full((F * R * 16,), 3.0)
+    args = [raw, zb, 0.25, mask, stft_x if mask else None, drows, ld, dpred, NB, F, T, yp, gp]
+    assert _both("idv_head_bwd", args, [11, 12]) < 2e-5
+
+
+@pytest.mark.parametrize("NB,Fin,T,cp,cs", [(2, 5, 7, 64, 64), (1, 9, 1, 64, 0), (3, 129, 6, 64, 64), (2, 4, 5, 16, 32)])
+def test_dec5_backward(NB, Fin, T, cp, cs):
+    Fout, R, ktot = 2 * Fin - 1, NB * (T + 1), cp + cs
+    dy = _rand(Fout, NB, T + 1, 16, seed=50)
+    dy[:, :, 0] = 0                                            # pad rows of a gradient are zero
+    w10 = _rand(10, ktot, 2, seed=51)
+    for (k_off, c) in ((0, cp), (cp, cs)):
+        if c == 0:
+            continue
+        dx = torch.full((Fin * R * c,), 5.0)
+        assert _both("idv_dec5_dgrad", [dy, w10, ktot, k_off, c, Fin, NB, T, dx], [8]) < 1e-5
+        x = _rand(Fin, NB, T + 1, c, seed=52 + k_off)
+        x[:, :, 0] = 0
+        xs = torch.zeros(2 * x.numel(), dtype=torch.bfloat16)
+        E._wr(xs, 1, x)
+        dW = _rand(10, ktot, 2, seed=53)                       # accumulates (+=)
+        assert _both("idv_dec5_wgrad", [xs, 1, dy, ktot, k_off, c, Fin, NB, T, dW], [9]) < 1e-5
+        dW = torch.zeros(10, ktot, 2)
+        assert _both("idv_dec5_wgrad", [x, 0, dy, ktot, k_off, c, Fin, NB, T, dW], [9]) < 1e-5
+
+
+def test_reparam_backward():
+    NB, T, zdim, Htot, ch0 = 3, 11, 128, 768, 384
+    lat = _rand(NB, T, Htot, 2, seed=60) * 0.7
+    er, ei = _rand(NB, 1, T, zdim, seed=61), _rand(NB, 1, T, zdim, seed=62)
+    dz = _rand(NB, T, zdim, 2, seed=63)
+    dlat = _rand(NB, T, Htot, 2, seed=64) * 0.1               # accumulates (+=)
+    assert _both("idv_reparam_bwd", [lat, NB, T, Htot, ch0, zdim, er, ei, dz, dlat], [9]) < 2e-5

@@ -28,6 +28,8 @@ ap.add_argument("--seconds", type=float, default=4.0)
 ap.add_argument("--latent-num", type=int, default=2)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--phase", type=int, default=1, help="1: KL step of train_nsvae.py; 2: decoder step of "
+                "train_second_phase_decoder.py (frozen NSVAE encoder, decoder train=True, SI-SNR)")
 args = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -49,12 +51,41 @@ for j in range(2):
     e = M.pvae_dccrn_encoder_skip_prepare(net, True, dev, C.ZDIM, C.NFFT, C.HOP, C.WIN, 1)
     e.load_state_dict(fill_state_dict(e.state_dict(), 1 + j))
     frozen.append(e.to(dev).eval())
-opt = FlatAdam(noisy.parameters(), lr=1e-3, weight_decay=1e-3, process_group=group, world_size=world)
+dec = None
+if args.phase == 2:
+    dec = M.nsvae_pvae_dccrn_decoder_twophase(net, True, dev, 1, C.ZDIM, C.NFFT, C.HOP, C.WIN, "mask", True, C.SKIPS, False)
+    dec.load_state_dict(fill_state_dict(dec.state_dict(), 5))
+    dec = dec.to(dev)
+    noisy.eval()
+opt = FlatAdam((dec if dec is not None else noisy).parameters(), lr=1e-3, weight_decay=1e-3, process_group=group,
+               world_size=world)
 xs = [synth_waveform(B, L, seed=100 * rank + j).to(dev) for j in range(3)]
 ev = lambda: torch.cuda.Event(enable_timing=True)
 
 
+def step2(timers=None):
+    """train_second_phase_decoder.py:L376-433 with the shipped recon_loss_weight '001' (SI-SNR only)."""
+    marks = [ev() for _ in range(5)]
+    marks[0].record()
+    with torch.no_grad():
+        r = noisy(xs[0], train=False)
+    marks[1].record()
+    sig, pred = dec(r[11], r[0], r[8], r[9], r[10], train=True, pad="sig")
+    loss = losses.si_snr_loss(xs[1], sig)
+    marks[2].record()
+    opt.zero_grad()
+    loss.backward()
+    marks[3].record()
+    opt.step()
+    marks[4].record()
+    if timers is not None:
+        timers.append(marks)
+    return loss
+
+
 def step(timers=None):
+    if args.phase == 2:
+        return step2(timers)
     marks = [ev() for _ in range(5)]
     marks[0].record()
     with torch.no_grad():
@@ -93,15 +124,19 @@ if world > 1:
 ms = float(ms)
 if rank == 0:
     ph = [sum(t[i].elapsed_time(t[i + 1]) for t in timers) / len(timers) for i in range(4)]
-    out = {"workload": "phase-1 NSVAE training step: 2 frozen CVAE encoders fwd + noisy encoder (latent_num=%d) fwd/bwd + KL + "
-                       "Adam" % ln, "batch_per_gpu": B, "seconds": args.seconds, "n_gpus": world, "ms_per_step": ms,
+    wl = ("phase-1 NSVAE training step: 2 frozen CVAE encoders fwd + noisy encoder (latent_num=%d) fwd/bwd + KL + Adam" % ln
+          if args.phase == 1 else
+          "phase-2 decoder training step: frozen NSVAE encoder (latent_num=%d) fwd + twophase decoder (mask, real skips) "
+          "train fwd + SI-SNR + bwd + Adam" % ln)
+    names = (("frozen_encoders_fwd", "noisy_fwd_and_loss") if args.phase == 1 else ("frozen_encoder_fwd", "decoder_fwd_and_loss"))
+    out = {"workload": wl, "batch_per_gpu": B, "seconds": args.seconds, "n_gpus": world, "ms_per_step": ms,
            "audio_s_per_s": world * B * args.seconds / (ms / 1e3), "loss": float(loss),
-           "phase_ms": {"frozen_encoders_fwd": ph[0], "noisy_fwd_and_loss": ph[1], "backward": ph[2],
+           "phase_ms": {names[0]: ph[0], names[1]: ph[1], "backward": ph[2],
                         "allreduce_and_adam": ph[3]},
            "kernel_launches_per_step": (lib.LAUNCHES[0] - n0) / args.steps,
            "grad_bytes_allreduced": int(opt.gflat.numel() * 4), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
     print(json.dumps(out))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "train_step%s.json" % ("" if world == 1 else "_%d" % world)), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "train_step%s%s.json" % ("" if args.phase == 1 else "_phase2", "" if world == 1 else "_%d" % world)), "w"), indent=1)
 if world > 1:
     dist.destroy_process_group()
