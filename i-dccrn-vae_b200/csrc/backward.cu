@@ -764,6 +764,15 @@ __global__ void __launch_bounds__(256) dec5_wgrad_kernel(const void* __restrict_
   }
 }
 
+__global__ void __launch_bounds__(256) axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = *reinterpret_cast<float4*>(y + i * 4);
+    const float4 u = ldg4(x + i * 4);
+    v.x = fmaf(a, u.x, v.x); v.y = fmaf(a, u.y, v.y); v.z = fmaf(a, u.z, v.z); v.w = fmaf(a, u.w, v.w);
+    *reinterpret_cast<float4*>(y + i * 4) = v;
+  }
+}
+
 // ---- reparameterisation backward (model/pvae_module.py:L2177-2231, S = 1) ----------------------------------------------
 // dlatent[(bt)][ch0 + {0, zdim, 2 zdim} + j][2] += d z / d (mu, log sigma, delta) applied to dz (NB, T, zdim, 2).
 // The imaginary part of log sigma is ignored by the forward (its gradient is 0).
@@ -909,5 +918,13 @@ extern "C" int idv_reparam_bwd(const float* latent, int NB, int T, int Htot, int
   reparam_bwd_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(latent, (long long)NB * T, Htot, ch0, zdim, eps_r,
                                                                         eps_i, dz, dlatent);
   IDV_LAUNCH_CHECK("reparam_bwd_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_axpy(float* y, const float* x, float a, int64_t n, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(y && x && n > 0 && n % 4 == 0, "idv_axpy: n must be a positive multiple of 4");
+  axpy_kernel<<<grid_for(n / 4, 16), 256, 0, (cudaStream_t)stream>>>(y, x, a, n / 4);
+  IDV_LAUNCH_CHECK("axpy_kernel");
   return IDV_OK;
 }

@@ -60,6 +60,7 @@ SIGNATURES = {
     "idv_head_bwd": [vp, vp, f32, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp],
     "idv_dec5_dgrad": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "idv_dec5_wgrad": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    "idv_axpy": [vp, vp, f32, i64, vp],
     "idv_reparam_bwd": [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
     "idv_cbn_stats_user": [vp, i64, i32, i64, vp, vp],
     "idv_head_user": [vp, i64, i64, f32, i32, vp, i32, vp],

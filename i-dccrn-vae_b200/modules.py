@@ -648,11 +648,11 @@ class _VaeEncoderBase(nn.Module):
     def _encode(self, x, train, eps):
         if len(self.lstms) != 1:
             raise NotImplementedError("one ComplexLSTM stage expected (lstm_dim has two entries)")
+        token = step = None
         if train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            # training step: the latent carries a grad_fn whose backward runs the C-ABI backward kernels (train.py);
-            # z is drawn from the detached latent (the phase-1 loss does not use it)
+            # training step: the latent carries a grad_fn whose backward runs the C-ABI backward kernels (train.py)
             from . import train as _train
-            latent_g, stft_x, planes = _train.encoder_train_forward(self, x)
+            latent_g, stft_x, planes, token, step = _train.encoder_train_forward(self, x)
             top, latent = planes[-1], latent_g.detach()
         else:
             latent_g = None
@@ -668,8 +668,13 @@ class _VaeEncoderBase(nn.Module):
             else:
                 er = ei = None
                 seed, off = _next_philox()
-            zs.append(ops.reparam(latent, 3 * z * k, z, S, er, ei, seed, off))
-        return stft_x, SkipList(planes), (latent if latent_g is None else latent_g), zs, top.C, top.F
+            if latent_g is not None and S == 1:
+                zs.append(_train.reparam_train(latent_g, 3 * z * k, z, er, ei))    # differentiable z
+            else:
+                zs.append(ops.reparam(latent, 3 * z * k, z, S, er, ei, seed, off))
+        skiper = SkipList(planes)
+        skiper.grad_token, skiper.train_step = token, step
+        return stft_x, skiper, (latent if latent_g is None else latent_g), zs, top.C, top.F
 
     def reparameterization(self, miu, log_sigma, delta, num_samples, eps=None):
         """model/pvae_module.py:L2177-2231; eps = (eps_real, eps_imag) of shape (B, S, T, zdim) or None."""

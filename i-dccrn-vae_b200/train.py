@@ -75,9 +75,21 @@ class EncoderTrainStep:
         self.enc = enc
         self.saved = None
         self._packs = {}
+        self.skip_grads = {}
+
+    def add_skip_grads(self, dskips, n_dec):
+        """Gradients of the skip tensors from a decoder's backward (decoder layer i reads encoder layer n_dec-1-i:
+        model/pvae_module.py:L2556-2567); added to the layer's output gradient in ``backward``."""
+        for i, g in dskips.items():
+            k = n_dec - 1 - i
+            if k in self.skip_grads:
+                lib.call("idv_axpy", self.skip_grads[k], g, 1.0, g.numel())
+            else:
+                self.skip_grads[k] = g
 
     # ---------------------------------------------------------------------------------------------- forward
     def forward(self, x):
+        self.skip_grads = {}
         with pack.on_device():                 # the weights change every step: repack on the GPU, not on the host
             return self._forward(x)
 
@@ -143,6 +155,10 @@ class EncoderTrainStep:
         with pack.on_device():
             g = self._lstm_backward(dlatent)
             for i in reversed(range(len(self.enc.encoders))):
+                gs = self.skip_grads.pop(i, None)
+                if gs is not None:
+                    lib.call("idv_axpy", g, gs, 1.0, g.numel())
+                    del gs
                 g = self._conv_backward(i, g)
         self.saved = None
 
@@ -299,23 +315,58 @@ class _EncoderTrainFn(torch.autograd.Function):
         ctx.step = step
         ctx.n = len(params)
         step._aux = (stft_x, acts)
-        return latent
+        # ordering token: a decoder that back-propagates into the skip tensors takes it as an input, so autograd runs
+        # the decoder's backward (which hands the skip gradients to ``step``) before this node's
+        return latent, torch.zeros((), device=latent.device)
 
     @staticmethod
-    def backward(ctx, dlatent):
+    def backward(ctx, dlatent, dtoken):
         ctx.step.backward(dlatent.contiguous())
         return (None, None) + (None,) * ctx.n
 
 
+class _ReparamFn(torch.autograd.Function):
+    """z = reparameterization(mu, log sigma, delta) (model/pvae_module.py:L2177-2231, num_samples = 1) with the
+    gradient of the latent from idv_reparam_bwd (end-to-end training: the decoder's loss reaches the encoder through z)."""
+
+    @staticmethod
+    def forward(ctx, latent, ch0, zdim, eps_r, eps_i):
+        lat = lib.require_f32_cuda(latent.detach(), "latent")
+        z = ops.reparam(lat, ch0, zdim, 1, eps_r, eps_i, 0, 0)
+        ctx.save_for_backward(lat, eps_r, eps_i)
+        ctx.ch0, ctx.zdim = ch0, zdim
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lat, eps_r, eps_i = ctx.saved_tensors
+        NB, T, Htot, _ = lat.shape
+        dlat = torch.zeros_like(lat)
+        lib.call("idv_reparam_bwd", lat, NB, T, Htot, ctx.ch0, ctx.zdim, eps_r, eps_i,
+                 lib.require_f32_cuda(dz, "gradient of z"), dlat)
+        return dlat, None, None, None, None
+
+
+def reparam_train(latent, ch0, zdim, eps_r, eps_i):
+    """Differentiable z for the training step; eps drawn with torch.randn when not supplied (like the reference's
+    randn_like: the backward needs the same draw)."""
+    NB, T = latent.shape[0], latent.shape[1]
+    if eps_r is None:
+        eps_r = torch.randn((NB, 1, T, zdim), dtype=torch.float32, device=latent.device)
+        eps_i = torch.randn((NB, 1, T, zdim), dtype=torch.float32, device=latent.device)
+    eps_r, eps_i = lib.require_f32_cuda(eps_r, "eps_r"), lib.require_f32_cuda(eps_i, "eps_i")
+    return _ReparamFn.apply(latent, ch0, zdim, eps_r, eps_i)
+
+
 def encoder_train_forward(enc, x):
-    """latent (with a grad_fn), stft_x, encoder activation planes of one train-mode forward."""
+    """latent (with a grad_fn), stft_x, encoder activation planes, ordering token, train step of one train-mode forward."""
     step = getattr(enc, "_train_step", None)
     if step is None:
         step = enc._train_step = EncoderTrainStep(enc)
     params = [p for p in enc.parameters() if p.requires_grad]
-    latent = _EncoderTrainFn.apply(step, x, *params)
+    latent, token = _EncoderTrainFn.apply(step, x, *params)
     stft_x, acts = step._aux
-    return latent, stft_x, acts
+    return latent, stft_x, acts, token, step
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -310,6 +310,8 @@ int idv_dec5_dgrad(const float* dy, const float* w10, int Ktot, int k_off, int C
                    void* stream);
 int idv_dec5_wgrad(const void* x, int x_split, const float* dy, int Ktot, int k_off, int Cp, int Fin, int NB, int T,
                    float* dW, void* stream);
+/* y += a x (fp32, n % 4 == 0): adds the skip-connection gradient to an encoder layer's output gradient. */
+int idv_axpy(float* y, const float* x, float a, int64_t n, void* stream);
 int idv_reparam_bwd(const float* latent, int NB, int T, int Htot, int ch0, int zdim, const float* eps_r,
                     const float* eps_i, const float* dz, float* dlatent, void* stream);
 

@@ -294,6 +294,83 @@ def case_train_step_phase2(tag, B, L, latent_num, recon_type, weights, seed):
     np.savez(os.path.join(OUT, tag + ".npz"), **g)
 
 
+def case_train_step_e2e(tag, B, L, latent_num, seed):
+    """End-to-end training step: frozen clean / noise CVAE encoders, noisy NSVAE encoder
+    train=True, twophase decoder train=True (pad='sig', mask head) on z_speech, loss =
+    nsvae_loss_with_cvae_decoder_recon.kl_loss_and_recon_loss (model/nsvae_loss.py:L598-613) with recon weights
+    (0, 0, 1): KL + SI-SNR; backward into BOTH models (through z and through the skip tensors)."""
+    import types
+    print("case", tag)
+    for m in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    import model.nsvae_loss as ref_loss
+    net = ref_causal_cfg.get_net_params()
+    noisy = ref_mod.nsvae_pvae_dccrn_encoder_twophase(net, True, "cpu", ZDIM, NFFT, HOP, WIN, 1, latent_num)
+    noisy.load_state_dict(fill_state_dict(noisy.state_dict(), seed), strict=True)
+    dec = ref_mod.nsvae_pvae_dccrn_decoder_twophase(net, True, "cpu", 1, ZDIM, NFFT, HOP, WIN, "mask", True,
+                                                    [0, 1, 2, 3, 4, 5], False)
+    dec.load_state_dict(fill_state_dict(dec.state_dict(), seed + 3), strict=True)
+    frozen = []
+    for j in range(2):
+        e = ref_mod.pvae_dccrn_encoder_skip_prepare(net, True, "cpu", ZDIM, NFFT, HOP, WIN, 1)
+        e.load_state_dict(fill_state_dict(e.state_dict(), seed + 1 + j), strict=True)
+        frozen.append(e.eval())
+    xs = [synth_waveform(B, L, seed=1234 + seed + j) for j in range(3)]          # noisy, clean, noise
+    T = L // HOP + 1
+    eps = synth_eps((B, 1, T, ZDIM), seed=7 + seed, n=2 * latent_num)
+    with torch.no_grad():
+        with supplied_eps(synth_eps((B, 1, T, ZDIM), seed=8 + seed, n=2)):
+            rc = frozen[0](xs[1], train=False)
+        with supplied_eps(synth_eps((B, 1, T, ZDIM), seed=9 + seed, n=2)):
+            rn = frozen[1](xs[2], train=False)
+    with supplied_eps(eps):
+        r = noisy(xs[0], train=True)
+    sig, pred = dec(r[11], r[0], r[8], r[9], r[10], train=True, pad="sig")
+    lossf = ref_loss.nsvae_loss_with_cvae_decoder_recon(1.0, 1.0, 1.0, [0.0, 0.0, 1.0], latent_num, ZDIM)
+    out = lossf.kl_loss_and_recon_loss(rc[1], rn[1], r[1], r[5], rc[2], rn[2], r[2], r[6], rc[3], rn[3], r[3], r[7],
+                                       r[0], r[4], pred, noisy.stft(xs[1]), xs[1], sig)
+    loss, kl, sisnr = out[0], out[1], out[7]
+    loss.backward()
+    # ---- the port
+    ep, dp = dict(noisy.named_parameters()), dict(dec.named_parameters())
+    esd = {k: v.detach().clone().requires_grad_(k in ep) for k, v in fill_state_dict(noisy.state_dict(), seed).items()}
+    dsd = {k: v.detach().clone().requires_grad_(k in dp) for k, v in fill_state_dict(dec.state_dict(), seed + 3).items()}
+    st = P.vae_encoder_forward(esd, xs[0], ZDIM, latent_num, 1, eps, train=True, grad=True)
+    with torch.no_grad():
+        sc = P.vae_encoder_forward(frozen[0].state_dict(), xs[1], ZDIM, 1, 1, synth_eps((B, 1, T, ZDIM), seed=8 + seed, n=2))
+        sn = P.vae_encoder_forward(frozen[1].state_dict(), xs[2], ZDIM, 1, 1, synth_eps((B, 1, T, ZDIM), seed=9 + seed, n=2))
+    dd = P.vae_decoder_forward(dsd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], 1, "mask", "sig", train=True)
+    pkl, _, _ = P.nsvae_kl_loss(st, sc, sn, ZDIM, latent_num, 1.0)
+    psi = P.si_snr(xs[1], dd["recon_sig"])
+    (pkl + psi).backward()
+    for nm, a, b in (("kl", pkl, kl), ("sisnr", psi, sisnr)):
+        assert abs(float(a.detach()) - float(b.detach())) <= 1e-4 * max(1.0, abs(float(b.detach()))), (nm, float(a), float(b))
+    g = {"B": B, "L": L, "latent_num": latent_num, "seed": seed, "loss": np32(loss), "kl": np32(kl), "sisnr": np32(sisnr),
+         "recon_sig": np32(sig)}
+    worst = 0.0
+    for pre, mod, sd in (("enc/", noisy, esd), ("dec/", dec, dsd)):
+        for name, p in mod.named_parameters():
+            if p.grad is None:
+                assert pre == "enc/" and name.startswith("dense."), name
+                continue
+            if name.endswith(".bias") and (".conv.conv_" in name or ".transconv.tconv_" in name):
+                assert float(p.grad.abs().max()) < 1e-3, (name, float(p.grad.abs().max()))
+                g["zero/" + pre + name] = np.float64(p.grad.abs().max())
+                continue
+            e = P.rel_l2(sd[name].grad, p.grad)
+            if e > 1e-4:
+                print("   ", pre + name, "rel %.2e  |ref| %.3e |port| %.3e" % (e, float(p.grad.norm()), float(sd[name].grad.norm())))
+            worst = max(worst, e)
+            gd = p.grad.double()
+            g["norm/" + pre + name] = np.float64(gd.norm())
+            g["probe/" + pre + name] = np.float64((gd * grad_probe(name, p.shape)).sum())
+            if p.numel() <= 1024:
+                g["full/" + pre + name] = np32(p.grad)
+    print("  port-vs-reference end-to-end gradients: worst rel_l2 = %.2e" % worst)
+    assert worst < 2e-3, worst
+    np.savez(os.path.join(OUT, tag + ".npz"), **g)
+
+
 def case_dccrn(tag, B, L, seed, causal=True):
     print("case", tag)
     net = (ref_causal_cfg if causal else ref_noncausal_cfg).get_net_params()
@@ -375,6 +452,11 @@ def case_primitives(tag, seed):
     np.savez(os.path.join(OUT, tag + ".npz"), **g)
 
 
+def e2e_cases():
+    case_train_step_e2e("train_e2e_l2", B=2, L=1200, latent_num=2, seed=17)
+    case_train_step_e2e("train_e2e_l1", B=3, L=2300, latent_num=1, seed=18)
+
+
 def phase2_cases():
     case_train_step_phase2("train_phase2_mask_sisnr", B=2, L=1200, latent_num=2, recon_type="mask",
                            weights=(0.0, 0.0, 1.0), seed=15)
@@ -385,6 +467,9 @@ def phase2_cases():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-e2e" in sys.argv:
+        e2e_cases()
+        sys.exit(0)
     if "--only-phase2" in sys.argv:
         phase2_cases()
         sys.exit(0)
@@ -417,4 +502,5 @@ if __name__ == "__main__":
     case_train_step("train_step_l2", B=2, L=1200, latent_num=2, seed=13)
     case_train_step("train_step_l1", B=3, L=700, latent_num=1, seed=14)
     phase2_cases()
+    e2e_cases()
     print("golden fixtures written to", OUT)

@@ -891,6 +891,10 @@ def idv_dec5_wgrad(x, x_split, dy, Ktot, k_off, Cp, Fin, NB, T, dW):
     dW.view(10, Ktot, 2)[:, k_off:k_off + Cp].add_(o.to(torch.float32))
 
 
+def idv_axpy(y, x, a, n):
+    _flat(y)[:n].add_(a * _flat(x)[:n])
+
+
 def idv_reparam_bwd(latent, NB, T, Htot, ch0, zdim, eps_r, eps_i, dz, dlatent):
     """Contract: autograd of the idv_reparam_fwd restatement (S = 1)."""
     with torch.enable_grad():

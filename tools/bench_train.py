@@ -29,7 +29,8 @@ ap.add_argument("--latent-num", type=int, default=2)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--phase", type=int, default=1, help="1: KL step of train_nsvae.py; 2: decoder step of "
-                "train_second_phase_decoder.py (frozen NSVAE encoder, decoder train=True, SI-SNR)")
+                "train_second_phase_decoder.py (frozen NSVAE encoder, decoder train=True, SI-SNR); 3: end-to-end step of "
+                "BASELINE config 4 (KL + SI-SNR, gradients into the encoder AND the decoder)")
 args = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -52,12 +53,15 @@ for j in range(2):
     e.load_state_dict(fill_state_dict(e.state_dict(), 1 + j))
     frozen.append(e.to(dev).eval())
 dec = None
-if args.phase == 2:
+if args.phase in (2, 3):
     dec = M.nsvae_pvae_dccrn_decoder_twophase(net, True, dev, 1, C.ZDIM, C.NFFT, C.HOP, C.WIN, "mask", True, C.SKIPS, False)
     dec.load_state_dict(fill_state_dict(dec.state_dict(), 5))
     dec = dec.to(dev)
-    noisy.eval()
-opt = FlatAdam((dec if dec is not None else noisy).parameters(), lr=1e-3, weight_decay=1e-3, process_group=group,
+    if args.phase == 2:
+        noisy.eval()
+train_params = {1: lambda: list(noisy.parameters()), 2: lambda: list(dec.parameters()),
+                3: lambda: list(noisy.parameters()) + list(dec.parameters())}[args.phase]()
+opt = FlatAdam(train_params, lr=1e-3, weight_decay=1e-3, process_group=group,
                world_size=world)
 xs = [synth_waveform(B, L, seed=100 * rank + j).to(dev) for j in range(3)]
 ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -83,9 +87,34 @@ def step2(timers=None):
     return loss
 
 
+def step3(timers=None):
+    """nsvae_loss_with_cvae_decoder_recon.kl_loss_and_recon_loss (model/nsvae_loss.py:L598-613), recon weights (0,0,1)."""
+    marks = [ev() for _ in range(5)]
+    marks[0].record()
+    with torch.no_grad():
+        rc = frozen[0](xs[1], train=False)
+        rn = frozen[1](xs[2], train=False)
+    marks[1].record()
+    r = noisy(xs[0], train=True)
+    sig, pred = dec(r[11], r[0], r[8], r[9], r[10], train=True, pad="sig")
+    kl, kc, kn = losses.nsvae_kl_loss(r, rc, rn, C.ZDIM, ln, 1.0)
+    loss = kl + losses.si_snr_loss(xs[1], sig)
+    marks[2].record()
+    opt.zero_grad()
+    loss.backward()
+    marks[3].record()
+    opt.step()
+    marks[4].record()
+    if timers is not None:
+        timers.append(marks)
+    return loss
+
+
 def step(timers=None):
     if args.phase == 2:
         return step2(timers)
+    if args.phase == 3:
+        return step3(timers)
     marks = [ev() for _ in range(5)]
     marks[0].record()
     with torch.no_grad():
@@ -124,11 +153,13 @@ if world > 1:
 ms = float(ms)
 if rank == 0:
     ph = [sum(t[i].elapsed_time(t[i + 1]) for t in timers) / len(timers) for i in range(4)]
-    wl = ("phase-1 NSVAE training step: 2 frozen CVAE encoders fwd + noisy encoder (latent_num=%d) fwd/bwd + KL + Adam" % ln
-          if args.phase == 1 else
-          "phase-2 decoder training step: frozen NSVAE encoder (latent_num=%d) fwd + twophase decoder (mask, real skips) "
-          "train fwd + SI-SNR + bwd + Adam" % ln)
-    names = (("frozen_encoders_fwd", "noisy_fwd_and_loss") if args.phase == 1 else ("frozen_encoder_fwd", "decoder_fwd_and_loss"))
+    wl = {1: "phase-1 NSVAE training step: 2 frozen CVAE encoders fwd + noisy encoder (latent_num=%d) fwd/bwd + KL + Adam",
+          2: "phase-2 decoder training step: frozen NSVAE encoder (latent_num=%d) fwd + twophase decoder (mask, real skips) "
+             "train fwd + SI-SNR + bwd + Adam",
+          3: "end-to-end NSVAE training step (BASELINE config 4): 2 frozen CVAE encoders fwd + noisy encoder (latent_num=%d) "
+             "and twophase decoder (mask, real skips) fwd/bwd + KL + SI-SNR + Adam"}[args.phase] % ln
+    names = {1: ("frozen_encoders_fwd", "noisy_fwd_and_loss"), 2: ("frozen_encoder_fwd", "decoder_fwd_and_loss"),
+             3: ("frozen_encoders_fwd", "encoder_decoder_fwd_and_loss")}[args.phase]
     out = {"workload": wl, "batch_per_gpu": B, "seconds": args.seconds, "n_gpus": world, "ms_per_step": ms,
            "audio_s_per_s": world * B * args.seconds / (ms / 1e3), "loss": float(loss),
            "phase_ms": {names[0]: ph[0], names[1]: ph[1], "backward": ph[2],
@@ -137,6 +168,6 @@ if rank == 0:
            "grad_bytes_allreduced": int(opt.gflat.numel() * 4), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
     print(json.dumps(out))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "train_step%s%s.json" % ("" if args.phase == 1 else "_phase2", "" if world == 1 else "_%d" % world)), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "train_step%s%s.json" % ({1: "", 2: "_phase2", 3: "_e2e"}[args.phase], "" if world == 1 else "_%d" % world)), "w"), indent=1)
 if world > 1:
     dist.destroy_process_group()
