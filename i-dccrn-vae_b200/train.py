@@ -16,11 +16,16 @@ gradient over - every FLOP is a C-ABI kernel:
 Not differentiated: ``z`` (the phase-1 loss only uses mu / log sigma / delta, model/nsvae_loss.py:L275-328) and the
 skip tensors (``w_resi = 0`` in the shipped configs); the unused ``dense.*`` gets no gradient, like the reference.
 """
+import os
+
 import torch
 
 from . import lib, ops, pack
 from .ops import Planes
 from .pack import round8
+
+
+BPTT_GRAPH = [os.environ.get("IDV_BPTT_GRAPH", "1") != "0"]     # replay the BPTT loop as a CUDA graph
 
 
 def _rpad(R):
@@ -76,6 +81,7 @@ class EncoderTrainStep:
         self.saved = None
         self._packs = {}
         self.skip_grads = {}
+        self._bptt_state = {}
 
     def add_skip_grads(self, dskips, n_dec):
         """Gradients of the skip tensors from a decoder's backward (decoder layer i reads encoder layer n_dec-1-i:
@@ -192,17 +198,9 @@ class EncoderTrainStep:
             P = ops.tapgemm(pk_g, below, h_split[layer], NB, T, zero_pad_rows=False, out_split=False)
             cst = torch.empty(4 * R * H, dtype=torch.float32, device=dev)
             lib.call("idv_lstm_scan_c", P, NB, T, H, cst, T)
-            # BPTT: one cell kernel + one dh = dP W_hh tap-GEMM per step
-            dP = _zeros(4 * R * 4 * H, dev)
-            dP_step = torch.empty(2 * 4 * NB * 4 * H, dtype=torch.bfloat16, device=dev)
-            dc = torch.empty(4 * NB * H, dtype=torch.float32, device=dev)
-            step_planes = _HRows(dP_step, NB, 4 * H)
-            dh_rec = None
-            for t in range(T - 1, -1, -1):
-                lib.call("idv_lstm_cell_bwd_step", P, cst, dH, dh_rec, dc, NB, T, H, t, 1 if dh_rec is None else 0, dP,
-                         dP_step)
-                if t:
-                    dh_rec = ops.tapgemm(pk_hh, step_planes, None, NB, 0, zero_pad_rows=False, out_split=False)
+            # BPTT: one cell kernel + one dh = dP W_hh tap-GEMM per step, replayed as ONE CUDA graph per layer
+            dP = self._bptt(layer, P, cst, dH, pk_hh, NB, T, H)
+            del P, cst
             dPs = Planes(_to_split(dP), NB, 4 * H, 4, T, cp=4 * H, split=True)
             # gradient of the layer input
             gin = ops.tapgemm(pk_ih, dPs, None, NB, T, zero_pad_rows=True, out_split=False)
@@ -235,6 +233,55 @@ class EncoderTrainStep:
             else:
                 g_top = gin                                            # planes [F][R][2ch]: gradient of the encoder output
         return g_top
+
+    def _bptt(self, layer, P, cst, dH, pk_hh, NB, T, H):
+        """Back-propagation through time of one nn.LSTM layer (4 streams x NB rows): 2T - 1 dependent launches.  The
+        loop is launch-bound (a step is a few microseconds of GPU work), so it is captured once per (layer, shape) into
+        a CUDA graph over static buffers and replayed; the first call of a shape runs eagerly (lazy CUDA
+        initialisation must not happen under capture).  Returns dP fp32 [4][R][4H] (static, pad rows zero)."""
+        dev = P.device
+        R = NB * (T + 1)
+        key = (layer, NB, T, H, str(dev))
+        st = self._bptt_state.get(key)
+        tc = pk_hh.tc()
+        if st is None:
+            st = self._bptt_state[key] = {
+                "P": torch.empty_like(P), "cst": torch.empty_like(cst), "dH": torch.empty_like(dH),
+                "dP": _zeros(4 * R * 4 * H, dev), "dP_step": torch.empty(2 * 4 * NB * 4 * H, dtype=torch.bfloat16, device=dev),
+                "dc": torch.empty(4 * NB * H, dtype=torch.float32, device=dev),
+                "dh_rec": torch.empty(4 * NB * H, dtype=torch.float32, device=dev),
+                "wt": torch.empty_like(tc["wt"]), "units": tc["units"].clone(), "taps": tc["taps"].clone(),
+                "bias": pk_hh.bias.clone(), "graph": None, "calls": 0}
+        st["P"].copy_(P)
+        st["cst"].copy_(cst)
+        st["dH"].copy_(dH)
+        st["wt"].copy_(tc["wt"])                    # the weights are re-packed every optimiser step: static copy
+
+        def loop():
+            dh = None
+            for t in range(T - 1, -1, -1):
+                lib.call("idv_lstm_cell_bwd_step", st["P"], st["cst"], st["dH"], dh, st["dc"], NB, T, H, t,
+                         1 if dh is None else 0, st["dP"], st["dP_step"])
+                if t:
+                    lib.call("idv_tapgemm_tc", st["dP_step"], 4 * H, 4, None, 0, 0, NB, 0, st["wt"], tc["kc_max"],
+                             tc["n_slots"], st["bias"], pk_hh.N, st["units"], st["taps"], pk_hh.n_units, st["dh_rec"],
+                             pk_hh.out_ld, NB * pk_hh.out_ld, pk_hh.out_planes * NB * pk_hh.out_ld, 0, 0, 0.0, 0)
+                    dh = st["dh_rec"]
+        st["calls"] += 1
+        if not BPTT_GRAPH[0] or st["calls"] == 1 or not P.is_cuda:
+            loop()
+        else:
+            if st["graph"] is None:
+                n0 = lib.LAUNCHES[0]
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    loop()
+                st["graph"], st["launches"] = g, lib.LAUNCHES[0] - n0
+                lib.LAUNCHES[0] = n0
+            st["graph"].replay()
+            lib.LAUNCHES[0] += st["launches"]
+        return st["dP"]
 
     # ---- conv + ComplexBatchNormal + PReLU ----
     def _conv_backward(self, i, g):

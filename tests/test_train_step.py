@@ -237,3 +237,24 @@ def test_train_step_gradients_gpu(golden, tag):
 @pytest.mark.gpu
 def test_layerwise_backward_gpu():
     run_layerwise_case("cuda", B=4, L=2500, tol=1e-4)
+
+
+@pytest.mark.gpu
+def test_bptt_cuda_graph_replay_matches_eager():
+    """The BPTT loop runs eagerly on the first call of a shape, is captured on the second and replayed afterwards:
+    the three must give the same gradients (same kernels, same order)."""
+    noisy, frozen = build_step(2, 13, "cuda")
+    grads = []
+    for it in range(4):
+        for p in noisy.parameters():
+            p.grad = None
+        loss_and_backward(noisy, frozen, 2, 1200, 2, 13, "cuda")
+        grads.append({k: p.grad.detach().clone() for k, p in noisy.named_parameters() if p.grad is not None})
+    st = noisy._train_step._bptt_state
+    assert st and all(v["graph"] is not None and v["calls"] == 4 for v in st.values())
+    for it in (1, 2, 3):
+        for k, g0 in grads[0].items():
+            if float(g0.norm()) == 0:
+                continue
+            # batch statistics move the running buffers only, not the forward: identical inputs -> identical gradients
+            assert C.rel_l2(grads[it][k], g0) < 1e-6, (it, k)
