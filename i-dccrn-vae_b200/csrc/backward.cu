@@ -199,12 +199,13 @@ __global__ void __launch_bounds__(256) lstm_scan_c_kernel(const float* __restric
   }
 }
 
-// one BPTT step (time t): dh = dH[t] + dh_rec; dP[t] <- gate gradients; dc carried.
+// one BPTT step (time t): dh = dH[t] + sum over the dh_parts split-K partial planes of dh_rec; dP[t] <- gate
+// gradients; dc carried.
 __global__ void __launch_bounds__(256) lstm_cell_bwd_step_kernel(const float* __restrict__ P,
                                                                  const float* __restrict__ cst,
                                                                  const float* __restrict__ dH,
                                                                  const float* __restrict__ dh_rec, float* __restrict__ dc,
-                                                                 int NB, int T, int H, int t, int last,
+                                                                 int NB, int T, int H, int t, int last, int dh_parts,
                                                                  float* __restrict__ dP,
                                                                  unsigned short* __restrict__ dP_step) {
   const long long n = 4LL * NB * H;
@@ -218,7 +219,9 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_step_kernel(const float* __
                 og = sgm(__ldg(pt + 3 * H + j));
     const float c = __ldg(cst + row * H + j), cprev = __ldg(cst + (row - 1) * H + j);   // row - 1 = pad row (0) at t = 0
     const float tc = tanhf(c);
-    const float dh = __ldg(dH + row * H + j) + (last ? 0.f : __ldg(dh_rec + i));
+    float dh = __ldg(dH + row * H + j);
+    if (!last)
+      for (int q = 0; q < dh_parts; ++q) dh += __ldg(dh_rec + q * n + i);
     const float dcv = (last ? 0.f : dc[i]) + dh * og * (1.f - tc * tc);
     const float d_o = dh * tc * og * (1.f - og);
     const float d_i = dcv * gg * ig * (1.f - ig);
@@ -468,12 +471,14 @@ extern "C" int idv_lstm_scan_c(const float* P, int NB, int T, int H, float* cst,
 }
 
 extern "C" int idv_lstm_cell_bwd_step(const float* P, const float* cst, const float* dH, const float* dh_rec, float* dc,
-                                      int NB, int T, int H, int t, int last, float* dP, void* dP_step, void* stream) {
+                                      int NB, int T, int H, int t, int last, int dh_parts, float* dP, void* dP_step,
+                                      void* stream) {
   using namespace idv;
-  IDV_CHECK_ARG(P && cst && dH && dc && dP && dP_step && (last || dh_rec) && NB > 0 && T > 0 && H > 0 && t >= 0 && t < T,
+  IDV_CHECK_ARG(P && cst && dH && dc && dP && dP_step && (last || (dh_rec && dh_parts > 0)) && NB > 0 && T > 0 && H > 0 &&
+                    t >= 0 && t < T,
                 "idv_lstm_cell_bwd_step: bad argument");
   lstm_cell_bwd_step_kernel<<<grid_for(4LL * NB * H, 8), 256, 0, (cudaStream_t)stream>>>(
-      P, cst, dH, dh_rec, dc, NB, T, H, t, last, dP, reinterpret_cast<unsigned short*>(dP_step));
+      P, cst, dH, dh_rec, dc, NB, T, H, t, last, dh_parts, dP, reinterpret_cast<unsigned short*>(dP_step));
   IDV_LAUNCH_CHECK("lstm_cell_bwd_step_kernel");
   return IDV_OK;
 }

@@ -50,7 +50,7 @@ SIGNATURES = {
     "idv_cbn_bwd_apply": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, i32, vp],
     "idv_lstm_combine_bwd": [vp, i32, i32, i32, vp, i32, vp],
     "idv_lstm_scan_c": [vp, i32, i32, i32, vp, i32, vp],
-    "idv_lstm_cell_bwd_step": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
+    "idv_lstm_cell_bwd_step": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],
     "idv_colsum_add": [vp, i64, i32, i32, vp, vp],
     "idv_enc0_wgrad": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
     "idv_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp],

@@ -735,9 +735,22 @@ def pack_lstm_gates(lstm_re, lstm_im, hidden, layer, c_in, f_in, device):
     return TapGemmPack(torch.cat(mats), bias, units, taps, N, 4, N, False, 0.0, device)
 
 
-def pack_lstm_dgrad(lstm_re, lstm_im, hidden, layer, kind, device, c_in=0, f_in=0):
+def bptt_split_k(hidden, sms=148):
+    """Split-K factor of the per-step dh = dP W_hh GEMM (2 modules x H/64 column tiles x split CTAs <= SMs)."""
+    ksteps = 4 * hidden // 64
+    best = 1
+    for s in range(1, ksteps + 1):
+        if ksteps % s == 0 and 2 * max(1, hidden // 64) * s <= sms:
+            best = s
+    return best
+
+
+def pack_lstm_dgrad(lstm_re, lstm_im, hidden, layer, kind, device, c_in=0, f_in=0, split_k=0):
     """Gate gradients dP [4][rows][4H] times a weight matrix (K = 4H):
       kind 'hh'          -> dh(t-1) = dP W_hh^m, N = H, out [4][rows][H];
+      kind 'hh', split_k -> the one-time-step form of the BPTT loop: the two streams of a module are ONE plane of
+                            2*rows rows (they share W_hh^m), K is cut into split_k slices so that 2 x H/64 x split_k
+                            CTAs stream the weights instead of 4 x H/64: out [split_k][4][rows][H] partial sums;
       kind 'ih', layer>0 -> gradient of the layer below's h, N = H, out [4][rows][H];
       kind 'ih', layer 0 -> gradient of the encoder output planes: unit (f, p) sums the two modules,
                             N = ch, out planes [f_in][rows][2ch] at channel offset p*ch."""
@@ -762,6 +775,15 @@ def pack_lstm_dgrad(lstm_re, lstm_im, hidden, layer, kind, device, c_in=0, f_in=
     mats, units, taps = [], [], []
     for m, mod in enumerate((lstm_re, lstm_im)):
         mats.append(_cpu(mod["weight_%s_l%d" % (kind, layer)]).double().reshape(-1))       # (4H, H) = [K][N]
+    if split_k:
+        if kind != "hh" or K % (64 * split_k):
+            raise ValueError("split_k must divide the 64-wide K steps of the recurrent matrix")
+        kc = K // split_k
+        for j in range(split_k):
+            for m in range(2):
+                taps.append([0, m, 0, j * kc, kc, m * K * H + j * kc * H])
+                units.append([len(taps) - 1, 1, j * 2 + m, 0, 0, 0])
+        return TapGemmPack(torch.cat(mats), torch.zeros(H), units, taps, H, 2 * split_k, H, False, 0.0, device)
     for m in range(2):
         for p in range(2):
             taps.append([0, m * 2 + p, 0, 0, K, m * K * H])

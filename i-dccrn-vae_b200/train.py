@@ -192,7 +192,8 @@ class EncoderTrainStep:
         for layer in (1, 0):
             below = h_split[0] if layer == 1 else top
             pk_g = self._lstm_pack(("gates", layer), lambda: pack.pack_lstm_gates(re, im, H, layer, top.C, top.F, dev))
-            pk_hh = self._lstm_pack(("hh", layer), lambda: pack.pack_lstm_dgrad(re, im, H, layer, "hh", dev))
+            sk = pack.bptt_split_k(H)
+            pk_hh = self._lstm_pack(("hh", layer), lambda: pack.pack_lstm_dgrad(re, im, H, layer, "hh", dev, split_k=sk))
             pk_ih = self._lstm_pack(("ih", layer), lambda: pack.pack_lstm_dgrad(re, im, H, layer, "ih", dev, top.C, top.F))
             # gate pre-activations of every step, cell states
             P = ops.tapgemm(pk_g, below, h_split[layer], NB, T, zero_pad_rows=False, out_split=False)
@@ -249,7 +250,7 @@ class EncoderTrainStep:
                 "P": torch.empty_like(P), "cst": torch.empty_like(cst), "dH": torch.empty_like(dH),
                 "dP": _zeros(4 * R * 4 * H, dev), "dP_step": torch.empty(2 * 4 * NB * 4 * H, dtype=torch.bfloat16, device=dev),
                 "dc": torch.empty(4 * NB * H, dtype=torch.float32, device=dev),
-                "dh_rec": torch.empty(4 * NB * H, dtype=torch.float32, device=dev),
+                "dh_rec": torch.empty(pk_hh.out_planes // 2 * 4 * NB * H, dtype=torch.float32, device=dev),
                 "wt": torch.empty_like(tc["wt"]), "units": tc["units"].clone(), "taps": tc["taps"].clone(),
                 "bias": pk_hh.bias.clone(), "graph": None, "calls": 0}
         st["P"].copy_(P)
@@ -257,15 +258,18 @@ class EncoderTrainStep:
         st["dH"].copy_(dH)
         st["wt"].copy_(tc["wt"])                    # the weights are re-packed every optimiser step: static copy
 
+        parts = pk_hh.out_planes // 2
+
         def loop():
             dh = None
             for t in range(T - 1, -1, -1):
                 lib.call("idv_lstm_cell_bwd_step", st["P"], st["cst"], st["dH"], dh, st["dc"], NB, T, H, t,
-                         1 if dh is None else 0, st["dP"], st["dP_step"])
+                         1 if dh is None else 0, parts, st["dP"], st["dP_step"])
                 if t:
-                    lib.call("idv_tapgemm_tc", st["dP_step"], 4 * H, 4, None, 0, 0, NB, 0, st["wt"], tc["kc_max"],
+                    # dP_step [4 streams][NB][4H] read as [2 modules][2 NB rows][4H]: one unit per (module, K slice)
+                    lib.call("idv_tapgemm_tc", st["dP_step"], 4 * H, 2, None, 0, 0, 2 * NB, 0, st["wt"], tc["kc_max"],
                              tc["n_slots"], st["bias"], pk_hh.N, st["units"], st["taps"], pk_hh.n_units, st["dh_rec"],
-                             pk_hh.out_ld, NB * pk_hh.out_ld, pk_hh.out_planes * NB * pk_hh.out_ld, 0, 0, 0.0, 0)
+                             pk_hh.out_ld, 2 * NB * pk_hh.out_ld, pk_hh.out_planes * 2 * NB * pk_hh.out_ld, 0, 0, 0.0, 0)
                     dh = st["dh_rec"]
         st["calls"] += 1
         if not BPTT_GRAPH[0] or st["calls"] == 1 or not P.is_cuda:

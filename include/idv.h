@@ -40,7 +40,7 @@ extern "C" {
 #define IDV_E_CUDA 2     /* CUDA runtime error (message has the cudaError string) */
 #define IDV_E_RESOURCE 3 /* kernel cannot be made resident (cooperative launch too large) */
 
-#define IDV_ABI_VERSION 3
+#define IDV_ABI_VERSION 4
 
 int idv_abi_version(void);
 const char* idv_last_error(void);
@@ -252,7 +252,8 @@ int idv_head_user(float* y, int64_t n_per_utt, int64_t n_utt, float prelu_slope,
  *   idv_lstm_combine_bwd: gradient of the latent (NB, T, H, 2) -> dH [4][R][H] (complex_progress.py:L62-73);
  *   idv_lstm_scan_c: gate pre-activations P [4][R][4H] -> cell states [4][R][H];
  *   idv_lstm_cell_bwd_step: one BPTT step t (t = T-1 first with last = 1): dP[t] (fp32 planes and the split-bf16
- *       copy [2][4][NB][4H] for the dh = dP W_hh tap-GEMM of the next step), dc carried;
+ *       copy [2][4][NB][4H] for the dh = dP W_hh tap-GEMM of the next step), dc carried; dh_rec holds dh_parts
+ *       partial planes [dh_parts][4][NB][H] (the recurrent tap-GEMM is split along K to fill the GPU) that are summed;
  *   idv_colsum_add: out[col] += sum_rows x (bias gradients);
  *   idv_enc0_wgrad: weight gradient of idv_enc0_fwd, dW [10][2][2*Cout];
  *   idv_adam_step: torch.optim.Adam(lr, betas, eps, weight_decay) on a flat buffer (train_nsvae.py:L200).           */
@@ -271,7 +272,7 @@ int idv_cbn_bwd_apply(const void* y, int y_split, const void* g, int g_split, in
 int idv_lstm_combine_bwd(const float* dlatent, int NB, int T, int H, float* dH, int t_valid, void* stream);
 int idv_lstm_scan_c(const float* P, int NB, int T, int H, float* cst, int t_valid, void* stream);
 int idv_lstm_cell_bwd_step(const float* P, const float* cst, const float* dH, const float* dh_rec, float* dc, int NB,
-                           int T, int H, int t, int last, float* dP, void* dP_step, void* stream);
+                           int T, int H, int t, int last, int dh_parts, float* dP, void* dP_step, void* stream);
 int idv_colsum_add(const float* x, int64_t rows, int cols, int ld, float* out, void* stream);
 int idv_enc0_wgrad(const float* stft, const float* dY, int B, int Fin, int T, int Cout, int causal, float* dW,
                    void* stream);

@@ -654,7 +654,7 @@ def idv_lstm_scan_c(P, NB, T, H, cst, t_valid=0):
         co[:, :, 1 + t] = c.to(torch.float32)
 
 
-def idv_lstm_cell_bwd_step(P, cst, dH, dh_rec, dc, NB, T, H, t, last, dP, dP_step):
+def idv_lstm_cell_bwd_step(P, cst, dH, dh_rec, dc, NB, T, H, t, last, dh_parts, dP, dP_step):
     Tp = T + 1
     a = P.view(4, NB, Tp, 4 * H)[:, :, 1 + t].to(D)
     ig, fg, gg, og = torch.sigmoid(a[..., :H]), torch.sigmoid(a[..., H:2 * H]), torch.tanh(a[..., 2 * H:3 * H]), \
@@ -665,7 +665,7 @@ def idv_lstm_cell_bwd_step(P, cst, dH, dh_rec, dc, NB, T, H, t, last, dP, dP_ste
     dh = dH.view(4, NB, Tp, H)[:, :, 1 + t].to(D)
     dcv = dh * og * (1 - tc * tc)
     if not last:
-        dh = dh + dh_rec.view(4, NB, H).to(D)
+        dh = dh + _flat(dh_rec)[:dh_parts * 4 * NB * H].view(dh_parts, 4, NB, H).to(D).sum(0)
         dcv = dc.view(4, NB, H).to(D) + dh * og * (1 - tc * tc)
     d = torch.cat((dcv * gg * ig * (1 - ig), dcv * cprev * fg * (1 - fg), dcv * ig * (1 - gg * gg),
                    dh * tc * og * (1 - og)), -1)

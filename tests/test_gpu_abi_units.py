@@ -249,10 +249,10 @@ def test_lstm_backward_and_misc_kernels():
     E.call("idv_lstm_scan_c", P_, NB, T, H, cst, 0)
     dH = _rand(4, R, H, seed=81)
     dP, dstep = torch.zeros(4 * R * 4 * H), torch.zeros(2 * 4 * NB * 4 * H, dtype=torch.bfloat16)
-    dc, dhr = _rand(4 * NB * H, seed=82), _rand(4 * NB * H, seed=83)
-    assert _both("idv_lstm_cell_bwd_step", [P_, cst, dH, None, dc.clone(), NB, T, H, T - 1, 1, dP, dstep], [4, 10, 11]) < 1e-5
-    assert _both("idv_lstm_cell_bwd_step", [P_, cst, dH, dhr, dc.clone(), NB, T, H, 2, 0, dP, dstep], [4, 10, 11]) < 1e-5
-    assert _both("idv_lstm_cell_bwd_step", [P_, cst, dH, dhr, dc.clone(), NB, T, H, 0, 0, dP, dstep], [4, 10, 11]) < 1e-5
+    dc, dhr = _rand(4 * NB * H, seed=82), _rand(3 * 4 * NB * H, seed=83)
+    assert _both("idv_lstm_cell_bwd_step", [P_, cst, dH, None, dc.clone(), NB, T, H, T - 1, 1, 0, dP, dstep], [4, 11, 12]) < 1e-5
+    assert _both("idv_lstm_cell_bwd_step", [P_, cst, dH, dhr, dc.clone(), NB, T, H, 2, 0, 1, dP, dstep], [4, 11, 12]) < 1e-5
+    assert _both("idv_lstm_cell_bwd_step", [P_, cst, dH, dhr, dc.clone(), NB, T, H, 0, 0, 3, dP, dstep], [4, 11, 12]) < 1e-5   # split-K partial planes
     dl = _rand(NB, T, H, 2, seed=84)
     assert _both("idv_lstm_combine_bwd", [dl, NB, T, H, torch.full((4 * R * H,), 3.0), 0], [4]) < 1e-7
     x = _rand(1000, 200, seed=85)
