@@ -22,22 +22,46 @@ __device__ __forceinline__ float ld_act(const void* p, int split, long long hl, 
                : __ldg(reinterpret_cast<const float*>(p) + idx);
 }
 
-// out[f][c][k] = in[f][k + shift][c] for 0 <= k + shift < R, else 0;  k < Rpad.  grid (Rpad/32, Cp/32, F), block (32, 8)
+// out[f][c][k] = in[f][k + shift][c] for 0 <= k + shift < R, else 0;  k < Rpad.  grid (Rpad/64, ceil(Cp/64), F), block 256.
+// 64 x 64 tiles; channel pairs are read and row pairs are written as 32-bit words (Cp even, Rpad % 64 == 0).
 __global__ void __launch_bounds__(256) planes_transpose_split_kernel(const void* __restrict__ in, int in_split, int F,
                                                                      int R, int Cp, int Rpad, int shift,
                                                                      unsigned short* __restrict__ out) {
-  __shared__ float tile[32][33];
-  const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32, f = blockIdx.z;
-  const int tx = threadIdx.x, ty = threadIdx.y;
+  __shared__ float tile[64][65];
+  const int k0 = blockIdx.x * 64, c0 = blockIdx.y * 64, f = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long hl_in = (long long)F * R * Cp, hl_out = (long long)F * Cp * Rpad;
-  for (int i = ty; i < 32; i += 8) {
-    const int r = k0 + i + shift, c = c0 + tx;
-    tile[i][tx] = (r >= 0 && r < R && c < Cp) ? ld_act(in, in_split, hl_in, ((long long)f * R + r) * Cp + c) : 0.f;
+  const float* inf = reinterpret_cast<const float*>(in);
+  const unsigned short* ins = reinterpret_cast<const unsigned short*>(in);
+  for (int i = ty; i < 64; i += 8) {
+    const int r = k0 + i + shift, c = c0 + 2 * tx;
+    float v0 = 0.f, v1 = 0.f;
+    if (r >= 0 && r < R && c < Cp) {
+      const long long idx = ((long long)f * R + r) * Cp + c;
+      if (in_split) {
+        const unsigned h = __ldg(reinterpret_cast<const unsigned*>(ins + idx));
+        const unsigned l = __ldg(reinterpret_cast<const unsigned*>(ins + hl_in + idx));
+        v0 = __uint_as_float(h << 16) + __uint_as_float(l << 16);
+        v1 = __uint_as_float(h & 0xffff0000u) + __uint_as_float(l & 0xffff0000u);
+      } else {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(inf + idx));
+        v0 = v.x; v1 = v.y;
+      }
+    }
+    tile[i][2 * tx] = v0;
+    tile[i][2 * tx + 1] = v1;
   }
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i, k = k0 + tx;
-    if (c < Cp && k < Rpad) st_split1(out, hl_out, ((long long)f * Cp + c) * Rpad + k, tile[tx][i]);
+  for (int j = ty; j < 64; j += 8) {
+    const int c = c0 + j, k = k0 + 2 * tx;
+    if (c < Cp) {                                                    // k + 1 < Rpad: Rpad is a multiple of 64
+      unsigned short h0, l0, h1, l1;
+      split_bf16(tile[2 * tx][j], h0, l0);
+      split_bf16(tile[2 * tx + 1][j], h1, l1);
+      const long long o = ((long long)f * Cp + c) * Rpad + k;
+      *reinterpret_cast<unsigned*>(out + o) = (unsigned)h0 | ((unsigned)h1 << 16);
+      *reinterpret_cast<unsigned*>(out + hl_out + o) = (unsigned)l0 | ((unsigned)l1 << 16);
+    }
   }
 }
 
@@ -50,37 +74,49 @@ __global__ void __launch_bounds__(256) f32_to_split_kernel(const float* __restri
 // ---- ComplexBatchNormal(train) + PReLU backward --------------------------------------------------------------------
 // pre = Z y + b' (b' = beta - Z mu), act = PReLU(pre).  gp = g * (pre > 0 ? 1 : slope), xc = y - mu.
 // acc[c][8] (double): sum gp_r, gp_i, gp_r xc_r, gp_r xc_i, gp_i xc_r, gp_i xc_i, sum g*pre over pre <= 0, (unused)
-// grid (F, chunks), block = round32(C) threads (one complex channel per thread)
-__global__ void cbn_bwd_reduce_kernel(const void* __restrict__ y, int y_split, const void* __restrict__ g, int g_split,
-                                      int NB, int C, int F, int T, int Tv, int rows_per_chunk,
-                                      const float* __restrict__ stats, const float* __restrict__ zb, float slope,
-                                      double* __restrict__ acc) {
-  const int c = threadIdx.x;
+// grid (F, chunks), block (round32(C), 256 / round32(C)): thread = (complex channel, row lane)
+__global__ void __launch_bounds__(256) cbn_bwd_reduce_kernel(const void* __restrict__ y, int y_split,
+                                                             const void* __restrict__ g, int g_split, int NB, int C,
+                                                             int F, int T, int Tv, int rows_per_chunk,
+                                                             const float* __restrict__ stats, const float* __restrict__ zb,
+                                                             float slope, double* __restrict__ acc) {
+  __shared__ double red[256];
+  const int c = threadIdx.x, ly = threadIdx.y, ny = blockDim.y, Cw = blockDim.x;
   const int Ch = r8(C), Cp = 2 * Ch, Tp = T + 1;
   const long long R = (long long)NB * Tp, hl = (long long)F * R * Cp;
   const int f = blockIdx.x;
   long long r_begin = (long long)blockIdx.y * rows_per_chunk, r_end = r_begin + rows_per_chunk;
   if (r_end > R) r_end = R;
-  if (c >= C) return;
-  const float mu_r = stats[c * 5 + 0], mu_i = stats[c * 5 + 1];
-  const float zrr = zb[c * 6 + 0], zri = zb[c * 6 + 1], zir = zb[c * 6 + 2], zii = zb[c * 6 + 3];
-  const float br = zb[c * 6 + 4], bi = zb[c * 6 + 5];
   double s[7] = {0, 0, 0, 0, 0, 0, 0};
-  for (long long r = r_begin; r < r_end; ++r) {
-    const int tt = (int)(r % Tp);
-    if (tt == 0 || tt > Tv) continue;
-    const long long idx = ((long long)f * R + r) * Cp;
-    const float yr = ld_act(y, y_split, hl, idx + c), yi = ld_act(y, y_split, hl, idx + Ch + c);
-    const float gr = ld_act(g, g_split, hl, idx + c), gi = ld_act(g, g_split, hl, idx + Ch + c);
-    const float pr = fmaf(zrr, yr, fmaf(zri, yi, br)), pi = fmaf(zir, yr, fmaf(zii, yi, bi));
-    const float gpr = pr > 0.f ? gr : slope * gr, gpi = pi > 0.f ? gi : slope * gi;
-    const float xr = yr - mu_r, xi = yi - mu_i;
-    s[0] += gpr; s[1] += gpi;
-    s[2] += (double)gpr * xr; s[3] += (double)gpr * xi; s[4] += (double)gpi * xr; s[5] += (double)gpi * xi;
-    s[6] += (pr > 0.f ? 0.0 : (double)gr * pr) + (pi > 0.f ? 0.0 : (double)gi * pi);
+  if (c < C) {
+    const float mu_r = stats[c * 5 + 0], mu_i = stats[c * 5 + 1];
+    const float zrr = zb[c * 6 + 0], zri = zb[c * 6 + 1], zir = zb[c * 6 + 2], zii = zb[c * 6 + 3];
+    const float br = zb[c * 6 + 4], bi = zb[c * 6 + 5];
+    for (long long r = r_begin + ly; r < r_end; r += ny) {
+      const int tt = (int)(r % Tp);
+      if (tt == 0 || tt > Tv) continue;
+      const long long idx = ((long long)f * R + r) * Cp;
+      const float yr = ld_act(y, y_split, hl, idx + c), yi = ld_act(y, y_split, hl, idx + Ch + c);
+      const float gr = ld_act(g, g_split, hl, idx + c), gi = ld_act(g, g_split, hl, idx + Ch + c);
+      const float pr = fmaf(zrr, yr, fmaf(zri, yi, br)), pi = fmaf(zir, yr, fmaf(zii, yi, bi));
+      const float gpr = pr > 0.f ? gr : slope * gr, gpi = pi > 0.f ? gi : slope * gi;
+      const float xr = yr - mu_r, xi = yi - mu_i;
+      s[0] += gpr; s[1] += gpi;
+      s[2] += (double)gpr * xr; s[3] += (double)gpr * xi; s[4] += (double)gpi * xr; s[5] += (double)gpi * xi;
+      s[6] += (pr > 0.f ? 0.0 : (double)gr * pr) + (pi > 0.f ? 0.0 : (double)gi * pi);
+    }
   }
 #pragma unroll
-  for (int k = 0; k < 7; ++k) atomicAdd(acc + c * 8 + k, s[k]);
+  for (int k = 0; k < 7; ++k) {
+    red[ly * Cw + c] = s[k];
+    __syncthreads();
+    if (ly == 0 && c < C) {
+      double t = 0.0;
+      for (int q = 0; q < ny; ++q) t += red[q * Cw + c];
+      atomicAdd(acc + c * 8 + k, t);
+    }
+    __syncthreads();
+  }
 }
 
 // per channel: parameter gradients (+=) and the coefficients of the element-wise pass
@@ -393,9 +429,9 @@ static inline int grid_for(long long n, int per_sm) {
 extern "C" int idv_planes_transpose_split(const void* planes, int in_split, int F, int R, int Cp, int Rpad, int shift,
                                           void* out, void* stream) {
   using namespace idv;
-  IDV_CHECK_ARG(planes && out && F > 0 && F <= 65535 && R > 0 && Cp > 0 && Rpad >= R && Rpad % 64 == 0,
-                "idv_planes_transpose_split: bad argument (Rpad must be a multiple of 64 >= R)");
-  dim3 grid(Rpad / 32, cdiv(Cp, 32), F), block(32, 8);
+  IDV_CHECK_ARG(planes && out && F > 0 && F <= 65535 && R > 0 && Cp > 0 && Cp % 2 == 0 && Rpad >= R && Rpad % 64 == 0,
+                "idv_planes_transpose_split: bad argument (Cp even, Rpad a multiple of 64 >= R)");
+  dim3 grid(Rpad / 64, cdiv(Cp, 64), F), block(256);
   IDV_CHECK_ARG(grid.y <= 65535, "idv_planes_transpose_split: Cp too large");
   planes_transpose_split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(planes, in_split, F, R, Cp, Rpad, shift,
                                                                           reinterpret_cast<unsigned short*>(out));
@@ -421,14 +457,17 @@ extern "C" int idv_cbn_bwd_reduce(const void* y, int y_split, const void* g, int
   cudaStream_t st = (cudaStream_t)stream;
   IDV_CUDA(cudaMemsetAsync(acc, 0, (size_t)C * 8 * sizeof(double), st));
   const long long R = (long long)NB * (T + 1);
+  IDV_CHECK_ARG(C <= 256, "idv_cbn_bwd_reduce: at most 256 complex channels");
   int chunks = (int)(148LL * 8 / F);
   if (chunks < 1) chunks = 1;
   if (chunks > R) chunks = (int)R;
   const int rows_per_chunk = (int)((R + chunks - 1) / chunks);
   const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
   dim3 grid(F, chunks);
-  cbn_bwd_reduce_kernel<<<grid, ((C + 31) / 32) * 32, 0, st>>>(y, y_split, g, g_split, NB, C, F, T, Tv, rows_per_chunk,
-                                                                stats, zb, slope, acc);
+  const int Cw = ((C + 31) / 32) * 32;
+  dim3 block(Cw, 256 / Cw);
+  cbn_bwd_reduce_kernel<<<grid, block, 0, st>>>(y, y_split, g, g_split, NB, C, F, T, Tv, rows_per_chunk, stats, zb, slope,
+                                                acc);
   IDV_LAUNCH_CHECK("cbn_bwd_reduce_kernel");
   return IDV_OK;
 }
@@ -725,24 +764,29 @@ __global__ void __launch_bounds__(256) dec5_dgrad_kernel(const float* __restrict
 }
 
 // dW[tap][k_off + c][part] += sum_{fi, r} x[fi][r][c] * dy[2fi - 2 + kf][r + kt][part]     grid (Fin, chunks), block 256
+// thread = (4 channels, row lane): the 20 gradient values of a row are loaded once per 80 FMAs.
 __global__ void __launch_bounds__(256) dec5_wgrad_kernel(const void* __restrict__ x, int x_split,
                                                          const float* __restrict__ dy, int Ktot, int k_off, int Cp,
                                                          int Fin, int NB, int T, int rows_per_chunk,
                                                          float* __restrict__ dW) {
-  __shared__ float red[256];
+  extern __shared__ float red[];                                     // [nj][Cp][20]
   const int Tp = T + 1, Fout = 2 * Fin - 1, fi = blockIdx.x;
   const long long R = (long long)NB * Tp, hl = (long long)Fin * R * Cp;
-  const int nj = 256 / Cp, c = threadIdx.x % Cp, j = threadIdx.x / Cp;
+  const int q = Cp >> 2, nj = 256 / q, c4 = (threadIdx.x % q) * 4, j = threadIdx.x / q;
   long long r0 = (long long)blockIdx.y * rows_per_chunk, r1 = r0 + rows_per_chunk;
   if (r1 > R) r1 = R;
-  float acc[20];
+  float acc[4][20];
 #pragma unroll
-  for (int k = 0; k < 20; ++k) acc[k] = 0.f;
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int k = 0; k < 20; ++k) acc[a][k] = 0.f;
   if (j < nj)
     for (long long r = r0 + j; r < r1; r += nj) {
       const int tt = (int)(r % Tp);
       if (tt == 0) continue;
-      const float xv = ld_act(x, x_split, hl, ((long long)fi * R + r) * Cp + c);
+      const long long idx = ((long long)fi * R + r) * Cp + c4;
+      const float4 xv = x_split ? ld_split4(reinterpret_cast<const unsigned short*>(x), hl, idx)
+                                : ldg4(reinterpret_cast<const float*>(x) + idx);
 #pragma unroll
       for (int kf = 0; kf < 5; ++kf) {
         const int fo = 2 * fi - 2 + kf;
@@ -750,22 +794,27 @@ __global__ void __launch_bounds__(256) dec5_wgrad_kernel(const void* __restrict_
 #pragma unroll
         for (int kt = 0; kt < 2; ++kt) {
           if (kt && tt == T) continue;
-          const float* g = dy + ((long long)fo * R + r + kt) * 16;
-          acc[(kf * 2 + kt) * 2] = fmaf(xv, __ldg(g), acc[(kf * 2 + kt) * 2]);
-          acc[(kf * 2 + kt) * 2 + 1] = fmaf(xv, __ldg(g + 8), acc[(kf * 2 + kt) * 2 + 1]);
+          const float* gp = dy + ((long long)fo * R + r + kt) * 16;
+          const float gr = __ldg(gp), gi = __ldg(gp + 8);
+          const int k = (kf * 2 + kt) * 2;
+          acc[0][k] = fmaf(xv.x, gr, acc[0][k]); acc[0][k + 1] = fmaf(xv.x, gi, acc[0][k + 1]);
+          acc[1][k] = fmaf(xv.y, gr, acc[1][k]); acc[1][k + 1] = fmaf(xv.y, gi, acc[1][k + 1]);
+          acc[2][k] = fmaf(xv.z, gr, acc[2][k]); acc[2][k + 1] = fmaf(xv.z, gi, acc[2][k + 1]);
+          acc[3][k] = fmaf(xv.w, gr, acc[3][k]); acc[3][k + 1] = fmaf(xv.w, gi, acc[3][k + 1]);
         }
       }
     }
+  if (j < nj)
 #pragma unroll
-  for (int k = 0; k < 20; ++k) {
-    red[threadIdx.x] = acc[k];
-    __syncthreads();
-    if (j == 0) {
-      float t = 0.f;
-      for (int jj = 0; jj < nj; ++jj) t += red[jj * Cp + c];
-      atomicAdd(dW + ((long long)(k >> 1) * Ktot + k_off + c) * 2 + (k & 1), t);
-    }
-    __syncthreads();
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int k = 0; k < 20; ++k) red[((long long)j * Cp + c4 + a) * 20 + k] = acc[a][k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cp * 20; i += 256) {
+    float t = 0.f;
+    for (int jj = 0; jj < nj; ++jj) t += red[(long long)jj * Cp * 20 + i];
+    const int c = i / 20, k = i % 20;
+    atomicAdd(dW + ((long long)(k >> 1) * Ktot + k_off + c) * 2 + (k & 1), t);
   }
 }
 
@@ -900,15 +949,19 @@ extern "C" int idv_dec5_dgrad(const float* dy, const float* w10, int Ktot, int k
 extern "C" int idv_dec5_wgrad(const void* x, int x_split, const float* dy, int Ktot, int k_off, int Cp, int Fin, int NB,
                               int T, float* dW, void* stream) {
   using namespace idv;
-  IDV_CHECK_ARG(x && dy && dW && Cp >= 8 && Cp <= 256 && 256 % Cp == 0 && k_off >= 0 && k_off + Cp <= Ktot && Fin > 0 &&
+  IDV_CHECK_ARG(x && dy && dW && Cp >= 8 && Cp <= 512 && Cp % 8 == 0 && k_off >= 0 && k_off + Cp <= Ktot && Fin > 0 &&
                     NB > 0 && T > 0,
-                "idv_dec5_wgrad: bad argument (Cp must divide 256)");
+                "idv_dec5_wgrad: bad argument (Cp a multiple of 8, <= 512)");
   const long long R = (long long)NB * (T + 1);
   int chunks = cdiv(148 * 8, Fin);
   const long long per = cdiv64(R, chunks);
   chunks = (int)cdiv64(R, per);
   dim3 grid(Fin, chunks);
-  dec5_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_split, dy, Ktot, k_off, Cp, Fin, NB, T, (int)per, dW);
+  const int nj = 256 / (Cp / 4);
+  const size_t smem = (size_t)nj * Cp * 20 * sizeof(float);
+  if (smem > 48 * 1024)
+    IDV_CUDA(cudaFuncSetAttribute(dec5_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dec5_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, x_split, dy, Ktot, k_off, Cp, Fin, NB, T, (int)per, dW);
   IDV_LAUNCH_CHECK("dec5_wgrad_kernel");
   return IDV_OK;
 }

@@ -190,9 +190,12 @@ extern "C" int idv_z_to_planes(const float* z, int NB, int S, int s, int T, int 
 namespace idv {
 
 // grid (F, chunks), block = Ch threads (one complex channel per thread; Ch <= 1024)
-__global__ void cbn_stats_planes_kernel(const void* __restrict__ planesv, int split, int NB, int C, int F, int T,
-                                        int Tv, int rows_per_chunk, double* __restrict__ acc) {
-  const int c = threadIdx.x;
+__global__ void __launch_bounds__(256) cbn_stats_planes_kernel(const void* __restrict__ planesv, int split, int NB, int C,
+                                                               int F, int T, int Tv, int rows_per_chunk,
+                                                               double* __restrict__ acc) {
+  // block (round32(C), 256 / round32(C)): thread = (complex channel, row lane), shared-memory reduce over the lanes
+  __shared__ double red[256];
+  const int c = threadIdx.x, ly = threadIdx.y, ny = blockDim.y, Cw = blockDim.x;
   const int Ch = round_up8(C), Cp = 2 * Ch, Tp = T + 1;
   const long long R = (long long)NB * Tp;
   const int f = blockIdx.x;
@@ -201,9 +204,9 @@ __global__ void cbn_stats_planes_kernel(const void* __restrict__ planesv, int sp
   const float* pf = reinterpret_cast<const float*>(planesv);
   const unsigned short* ps = reinterpret_cast<const unsigned short*>(planesv);
   const long long hl = (long long)F * R * Cp;
-  double sr = 0, si = 0, srr = 0, sii = 0, sri = 0;
+  double s[5] = {0, 0, 0, 0, 0};
   if (c < C) {
-    for (long long r = r_begin; r < r_end; ++r) {
+    for (long long r = r_begin + ly; r < r_end; r += ny) {
       const int tt = (int)(r % Tp);
       if (tt == 0 || tt > Tv) continue;                  // causal pad row / beyond the valid frames
       const long long idx = ((long long)f * R + r) * Cp;
@@ -215,14 +218,20 @@ __global__ void cbn_stats_planes_kernel(const void* __restrict__ planesv, int sp
         re = __ldg(pf + idx + c);
         im = __ldg(pf + idx + Ch + c);
       }
-      sr += re; si += im;
-      srr += (double)re * re; sii += (double)im * im; sri += (double)re * im;
+      s[0] += re; s[1] += im;
+      s[2] += (double)re * re; s[3] += (double)im * im; s[4] += (double)re * im;
     }
-    atomicAdd(acc + c * 5 + 0, sr);
-    atomicAdd(acc + c * 5 + 1, si);
-    atomicAdd(acc + c * 5 + 2, srr);
-    atomicAdd(acc + c * 5 + 3, sii);
-    atomicAdd(acc + c * 5 + 4, sri);
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    red[ly * Cw + c] = s[k];
+    __syncthreads();
+    if (ly == 0 && c < C) {
+      double t = 0.0;
+      for (int q = 0; q < ny; ++q) t += red[q * Cw + c];
+      atomicAdd(acc + c * 5 + k, t);
+    }
+    __syncthreads();
   }
 }
 
@@ -271,38 +280,44 @@ __global__ void cbn_train_finalize_kernel(const double* __restrict__ acc, double
 // grid-stride over (plane, row, channel)
 __global__ void __launch_bounds__(256) cbn_apply_planes_kernel(void* __restrict__ planesv, int split, int NB, int C,
                                                                int F, int T, int Tv, const float* __restrict__ zb,
-                                                               int apply_prelu, float slope, void* __restrict__ outv) {
+                                                               int apply_prelu, float slope, void* __restrict__ outv,
+                                                               int out_split, int in_place) {
+  // one thread per (row, complex channel incl. the padding channels); out of place: pad rows / channels written as 0
   const int Ch = round_up8(C), Cp = 2 * Ch, Tp = T + 1;
   const long long R = (long long)NB * Tp;
-  const long long n = (long long)F * R * C;
+  const long long n = (long long)F * R * Ch;
   float* pf = reinterpret_cast<float*>(planesv);
   unsigned short* ps = reinterpret_cast<unsigned short*>(planesv);
   float* of = reinterpret_cast<float*>(outv);
   unsigned short* os = reinterpret_cast<unsigned short*>(outv);
   const long long hl = (long long)F * R * Cp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const long long fr = i / C;
+    const int c = (int)(i % Ch);
+    const long long fr = i / Ch;
     const long long r = fr % R;
     const int tt = (int)(r % Tp);
-    if (tt == 0 || tt > Tv) continue;
+    const bool live = c < C && tt != 0 && tt <= Tv;
+    if (!live && in_place) continue;
     const long long idx = fr * Cp;
-    float re, im;
-    if (split) {
-      re = ld_split1(ps, hl, idx + c);
-      im = ld_split1(ps, hl, idx + Ch + c);
-    } else {
-      re = pf[idx + c];
-      im = pf[idx + Ch + c];
+    float orr = 0.f, oi = 0.f;
+    if (live) {
+      float re, im;
+      if (split) {
+        re = ld_split1(ps, hl, idx + c);
+        im = ld_split1(ps, hl, idx + Ch + c);
+      } else {
+        re = pf[idx + c];
+        im = pf[idx + Ch + c];
+      }
+      const float* k = zb + c * 6;
+      orr = fmaf(k[0], re, fmaf(k[1], im, k[4]));
+      oi = fmaf(k[2], re, fmaf(k[3], im, k[5]));
+      if (apply_prelu) {
+        orr = prelu_f(orr, slope);
+        oi = prelu_f(oi, slope);
+      }
     }
-    const float* k = zb + c * 6;
-    float orr = fmaf(k[0], re, fmaf(k[1], im, k[4]));
-    float oi = fmaf(k[2], re, fmaf(k[3], im, k[5]));
-    if (apply_prelu) {
-      orr = prelu_f(orr, slope);
-      oi = prelu_f(oi, slope);
-    }
-    if (split) {
+    if (out_split) {
       st_split1(os, hl, idx + c, orr);
       st_split1(os, hl, idx + Ch + c, oi);
     } else {
@@ -317,17 +332,18 @@ __global__ void __launch_bounds__(256) cbn_apply_planes_kernel(void* __restrict_
 extern "C" int idv_cbn_stats_planes(const void* planes, int split, int NB, int C, int F, int T, double* acc,
                                     int t_valid, void* stream) {
   using namespace idv;
-  IDV_CHECK_ARG(planes && acc && NB > 0 && C > 0 && C <= 1024 && F > 0 && F <= 65535 && T > 0, "idv_cbn_stats_planes: bad argument");
+  IDV_CHECK_ARG(planes && acc && NB > 0 && C > 0 && C <= 256 && F > 0 && F <= 65535 && T > 0, "idv_cbn_stats_planes: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   IDV_CUDA(cudaMemsetAsync(acc, 0, (size_t)C * 5 * sizeof(double), st));
   const long long R = (long long)NB * (T + 1);
-  int chunks = (int)(R / 512 > 0 ? R / 512 : 1);
-  if (chunks > 256) chunks = 256;
+  int chunks = (int)(148LL * 8 / F);
+  if (chunks < 1) chunks = 1;
+  if (chunks > R) chunks = (int)R;
   const int rows_per_chunk = (int)((R + chunks - 1) / chunks);
-  const int threads = ((C + 31) / 32) * 32;
-  dim3 grid(F, chunks);
+  const int Cw = ((C + 31) / 32) * 32;
+  dim3 grid(F, chunks), block(Cw, 256 / Cw);
   const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
-  cbn_stats_planes_kernel<<<grid, threads, 0, st>>>(planes, split, NB, C, F, T, Tv, rows_per_chunk, acc);
+  cbn_stats_planes_kernel<<<grid, block, 0, st>>>(planes, split, NB, C, F, T, Tv, rows_per_chunk, acc);
   IDV_LAUNCH_CHECK("cbn_stats_planes_kernel");
   return IDV_OK;
 }
@@ -350,16 +366,18 @@ extern "C" int idv_cbn_train_finalize(const double* acc, double count, int C, co
 }
 
 extern "C" int idv_cbn_apply_planes(void* planes, int split, int NB, int C, int F, int T, const float* zb,
-                                    int apply_prelu, float prelu_slope, int t_valid, void* out, void* stream) {
+                                    int apply_prelu, float prelu_slope, int t_valid, void* out, int out_split,
+                                    void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(planes && zb && NB > 0 && C > 0 && F > 0 && T > 0, "idv_cbn_apply_planes: bad argument");
-  const long long n = (long long)F * NB * (T + 1) * C;
+  const int in_place = (!out || out == planes) ? 1 : 0;
+  if (in_place) out_split = split;
+  const long long n = (long long)F * NB * (T + 1) * ((C + 7) / 8 * 8);
   const int blocks = (int)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
   const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
-  if (out && out != planes)            // out of place (the raw values are kept for the backward pass): pad rows = 0
-    IDV_CUDA(cudaMemsetAsync(out, 0, (size_t)F * NB * (T + 1) * 2 * ((C + 7) / 8 * 8) * sizeof(float), (cudaStream_t)stream));
   cbn_apply_planes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(planes, split, NB, C, F, T, Tv, zb, apply_prelu,
-                                                                    prelu_slope, out ? out : planes);
+                                                                    prelu_slope, in_place ? planes : out, out_split ? 1 : 0,
+                                                                    in_place);
   IDV_LAUNCH_CHECK("cbn_apply_planes_kernel");
   return IDV_OK;
 }

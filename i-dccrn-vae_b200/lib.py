@@ -42,7 +42,7 @@ SIGNATURES = {
     "idv_cbn_eval_user": [vp, i64, i32, i64, vp, vp, vp],
     "idv_cbn_stats_planes": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "idv_cbn_train_finalize": [vp, ctypes.c_double, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, vp],
-    "idv_cbn_apply_planes": [vp, i32, i32, i32, i32, i32, vp, i32, f32, i32, vp, vp],
+    "idv_cbn_apply_planes": [vp, i32, i32, i32, i32, i32, vp, i32, f32, i32, vp, i32, vp],
     "idv_planes_transpose_split": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "idv_f32_to_split": [vp, i64, vp, vp],
     "idv_cbn_bwd_reduce": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, f32, vp, i32, vp],

@@ -114,12 +114,10 @@ class EncoderTrainStep:
             stats = torch.empty(C * 5, dtype=torch.float32, device=dev)
             zb = ops._cbn_finalize(e.bn, acc, raw.NB * raw.F * raw.Tv, dev, stats)
             slope = e._slope()
-            # out of place and into the split format in one pass would need a second kernel variant: normalise in
-            # fp32 (raw is kept for the backward pass), then split for the next layer's tensor-core GEMM
-            act32 = torch.empty_like(raw.data)
-            lib.call("idv_cbn_apply_planes", raw.data, 0, raw.NB, C, raw.F, raw.T, zb, 1, slope, raw.Tv, act32)
-            act = _to_split(act32)
-            del act32
+            # raw stays fp32 for the backward pass; the normalised activation goes straight into the split format of
+            # the next layer's tensor-core GEMM
+            act = torch.empty(2 * raw.data.numel(), dtype=torch.bfloat16, device=dev)
+            lib.call("idv_cbn_apply_planes", raw.data, 0, raw.NB, C, raw.F, raw.T, zb, 1, slope, raw.Tv, act, 1)
             a = Planes(act, raw.NB, C, raw.F, raw.T, split=True, Tv=raw.Tv)
             sv["layers"].append({"x": p, "raw": raw, "stats": stats, "zb": zb, "slope": slope, "act": a})
             p = a
@@ -468,10 +466,8 @@ class DecoderTrainStep:
             stats = torch.empty(Cc * 5, dtype=torch.float32, device=dev)
             zb = ops._cbn_finalize(d.bn, acc, raw.NB * raw.F * raw.Tv, dev, stats)
             slope = d._slope()
-            act32 = torch.empty_like(raw.data)
-            lib.call("idv_cbn_apply_planes", raw.data, 0, raw.NB, Cc, raw.F, raw.T, zb, 1, slope, raw.Tv, act32)
-            act = _to_split(act32)
-            del act32
+            act = torch.empty(2 * raw.data.numel(), dtype=torch.bfloat16, device=dev)
+            lib.call("idv_cbn_apply_planes", raw.data, 0, raw.NB, Cc, raw.F, raw.T, zb, 1, slope, raw.Tv, act, 1)
             a = Planes(act, raw.NB, Cc, raw.F, raw.T, split=True, Tv=raw.Tv)
             sv["layers"].append({"x": p, "skip": skips.get(i), "raw": raw, "stats": stats, "zb": zb, "slope": slope})
             p = a

@@ -220,8 +220,9 @@ int idv_cbn_eval_user(const float* x, int64_t outer, int C, int64_t inner, const
  *   non-pad row of the planes tensor (fp32 or split bf16);
  * idv_cbn_train_finalize: batch mean / biased (co)variances (eps added to Vrr, Vii as the reference does), update
  *   of the running buffers (first != 0: copy, else EMA with `momentum`), zb[c][6] = Z, b' from the batch statistics;
- * idv_cbn_apply_planes: y <- act(Z y + b') in place (pad rows untouched), or into `out` (same format, pad rows
- *   zeroed) when out != NULL - the training forward keeps the raw values for the backward pass.
+ * idv_cbn_apply_planes: y <- act(Z y + b') in place (pad rows untouched), or into `out` (fp32 or split bf16 per
+ *   out_split; pad rows, invalid frames and padding channels written as 0) when out != NULL - the training forward
+ *   keeps the raw fp32 values for the backward pass and feeds the next layer's tensor-core GEMM the split copy.
  * idv_cbn_train_finalize also writes stats[c][5] = batch mean (re, im), Vrr, Vri, Vii (NULL = not wanted).           */
 int idv_cbn_stats_planes(const void* planes, int split, int NB, int C, int F, int T, double* acc, int t_valid,
                          void* stream);
@@ -230,7 +231,7 @@ int idv_cbn_train_finalize(const double* acc, double count, int C, const float* 
                            float* run_mean_i, float* run_vrr, float* run_vri, float* run_vii, float momentum,
                            int first, float* zb, float* stats, void* stream);
 int idv_cbn_apply_planes(void* planes, int split, int NB, int C, int F, int T, const float* zb, int apply_prelu,
-                         float prelu_slope, int t_valid, void* out, void* stream);
+                         float prelu_slope, int t_valid, void* out, int out_split, void* stream);
 /* statistics on the reference layout x (outer, C, inner, 2) (stand-alone ComplexBatchNormal(train=True); the last
  * decoder layer whose raw output is written in the reference layout) and the in-place recon head on
  * y (n_utt, n_per_utt, 2): PReLU(slope) then, if mask, the mask head with stft_x[b / s_rep].                       */

@@ -522,7 +522,7 @@ def idv_cbn_train_finalize(acc, count, C, g_rr, g_ri, g_ii, beta_r, beta_i, run_
                                      beta_i.view(-1) - (zir * mu_r + zii * mu_i)), 1))
 
 
-def idv_cbn_apply_planes(planes, split, NB, C, F, T, zb, apply_prelu, slope, t_valid=0, out=None):
+def idv_cbn_apply_planes(planes, split, NB, C, F, T, zb, apply_prelu, slope, t_valid=0, out=None, out_split=0):
     Ch, Tp = _r8(C), T + 1
     te = 1 + _tv(t_valid, T)
     n = F * NB * Tp * 2 * Ch
@@ -538,7 +538,10 @@ def idv_cbn_apply_planes(planes, split, NB, C, F, T, zb, apply_prelu, slope, t_v
         p = torch.zeros_like(p)
     p[:, :, 1:te, 0, :C] = o_r
     p[:, :, 1:te, 1, :C] = o_i
-    _wr(out if out is not None else planes, split, p)
+    if out is not None and out is not planes:
+        _wr(out, out_split, p)
+    else:
+        _wr(planes, split, p)
 
 
 def idv_head_user(y, n_per_utt, n_utt, slope, mask, stft_x, s_rep):

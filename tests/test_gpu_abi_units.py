@@ -155,9 +155,12 @@ def test_layout_roundtrip(NB, C_, F, T, tv):
     for split, buf in ((0, planes), (1, sp)):
         acc = torch.zeros(C_ * 5, dtype=torch.float64)
         assert _both("idv_cbn_stats_planes", [buf, split, NB, C_, F, T, acc, tv], [6]) < 1e-6
-        assert _both("idv_cbn_apply_planes", [buf.clone(), split, NB, C_, F, T, zb.reshape(-1), 1, 0.3, tv, None], [0]) < 1e-6
+        assert _both("idv_cbn_apply_planes", [buf.clone(), split, NB, C_, F, T, zb.reshape(-1), 1, 0.3, tv, None, 0], [0]) < 1e-6
         assert _both("idv_cbn_apply_planes", [buf.clone(), split, NB, C_, F, T, zb.reshape(-1), 1, 0.3, tv,
-                                              torch.full_like(buf, 2.0)], [10]) < 1e-6        # out of place
+                                              torch.full_like(buf, 2.0), split], [10]) < 1e-6        # out of place
+        other = torch.full_like(sp if not split else planes, 2.0)                     # out of place, other format
+        assert _both("idv_cbn_apply_planes", [buf.clone(), split, NB, C_, F, T, zb.reshape(-1), 1, 0.3, tv, other,
+                                              1 - split], [10]) < 1e-5
 
 
 def test_streaming_state_kernels():
