@@ -325,7 +325,7 @@ def cbn_train_planes(p, bn, slope):
     lib.call("idv_cbn_stats_planes", p.data, 1 if p.split else 0, p.NB, C, p.F, p.T, acc, p.Tv)
     zb = _cbn_finalize(bn, acc, p.NB * p.F * p.Tv, p.data.device)
     lib.call("idv_cbn_apply_planes", p.data, 1 if p.split else 0, p.NB, C, p.F, p.T, zb,
-             0 if slope is None else 1, 0.0 if slope is None else float(slope), p.Tv, None)
+             0 if slope is None else 1, 0.0 if slope is None else float(slope), p.Tv, None, 0)
     return p
 
 

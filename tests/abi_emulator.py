@@ -522,7 +522,7 @@ def idv_cbn_train_finalize(acc, count, C, g_rr, g_ri, g_ii, beta_r, beta_i, run_
                                      beta_i.view(-1) - (zir * mu_r + zii * mu_i)), 1))
 
 
-def idv_cbn_apply_planes(planes, split, NB, C, F, T, zb, apply_prelu, slope, t_valid=0, out=None, out_split=0):
+def idv_cbn_apply_planes(planes, split, NB, C, F, T, zb, apply_prelu, slope, t_valid, out, out_split):
     Ch, Tp = _r8(C), T + 1
     te = 1 + _tv(t_valid, T)
     n = F * NB * Tp * 2 * Ch
