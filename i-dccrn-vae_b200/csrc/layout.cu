@@ -327,7 +327,33 @@ __global__ void __launch_bounds__(256) cbn_apply_planes_kernel(void* __restrict_
   }
 }
 
+// out[b][f][t][p] = x * scale[f][p] + shift[f][p]; zero_edge_imag: the imaginary part of bins 0 and F-1 is set to 0
+__global__ void __launch_bounds__(256) bin_affine_kernel(const float* __restrict__ x, long long n, int F, int T,
+                                                         const float* __restrict__ scale, const float* __restrict__ shift,
+                                                         int zero_edge_imag, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)((i / T) % F);
+    const float2 v = *reinterpret_cast<const float2*>(x + i * 2);
+    float2 o;
+    o.x = fmaf(v.x, scale[2 * f], shift[2 * f]);
+    o.y = fmaf(v.y, scale[2 * f + 1], shift[2 * f + 1]);
+    if (zero_edge_imag && (f == 0 || f == F - 1)) o.y = 0.f;
+    *reinterpret_cast<float2*>(out + i * 2) = o;
+  }
+}
+
 }  // namespace idv
+
+extern "C" int idv_bin_affine(const float* x, int B, int F, int T, const float* scale, const float* shift,
+                              int zero_edge_imag, float* out, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(x && scale && shift && out && B > 0 && F > 0 && T > 0, "idv_bin_affine: bad argument");
+  const long long n = (long long)B * F * T;
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  bin_affine_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, F, T, scale, shift, zero_edge_imag, out);
+  IDV_LAUNCH_CHECK("bin_affine_kernel");
+  return IDV_OK;
+}
 
 extern "C" int idv_cbn_stats_planes(const void* planes, int split, int NB, int C, int F, int T, double* acc,
                                     int t_valid, void* stream) {

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) reparam_kernel(const float* __restrict__ 
                                                       int ch0, int zdim, int S, const float* __restrict__ eps_r,
                                                       const float* __restrict__ eps_i, uint64_t seed,
                                                       uint64_t offset, const unsigned long long* __restrict__ offset_dev,
-                                                      float* __restrict__ z) {
+                                                      int variant, float* __restrict__ z) {
   const int64_t n = (int64_t)NB * S * T * zdim;
   const float e = 1e-6f;
   if (offset_dev) offset += *offset_dev;               // device-side draw counter (CUDA-graph replays)
@@ -207,8 +207,9 @@ __global__ void __launch_bounds__(256) reparam_kernel(const float* __restrict__ 
       er = nrm.x;
       ei = nrm.y;
     }
-    // model/pvae_module.py:L2177-2231, same operation order
-    const float sig = expf(ls.x);
+    // model/pvae_module.py:L2177-2231, same operation order; variant 1 = the *_fc_latent encoders (L2403-2450:
+    // log sigma clamped to [-13, 13], square-root arguments clamped at eps, no eps in the denominators)
+    const float sig = expf(variant ? fminf(fmaxf(ls.x, -13.f), 13.f) : ls.x);
     float dr = dl.x, di = dl.y;
     float ad = sqrtf(dr * dr + di * di + e);
     const float tmp = sig * 0.99f / (ad + e);
@@ -217,12 +218,20 @@ __global__ void __launch_bounds__(256) reparam_kernel(const float* __restrict__ 
       di *= tmp;
     }
     ad = sqrtf(dr * dr + di * di + e);
-    const float den = sqrtf(2.f * (sig + dr) + e);
     const float num_r = sig + dr;
-    const float sx = di / (den + e);
-    const float sy = sqrtf(sig * sig - ad * ad + e) / (den + e);
-    const float zr = mu.x + (num_r / (den + e)) * er;
-    const float zi = mu.y + sx * er + sy * ei;
+    float zr, zi;
+    if (variant) {
+      const float den = sqrtf(fmaxf(2.f * (sig + dr), e));
+      const float sy = sqrtf(fmaxf(sig * sig - ad * ad, e)) / den;
+      zr = mu.x + (num_r / den) * er;
+      zi = mu.y + (di / den) * er + sy * ei;
+    } else {
+      const float den = sqrtf(2.f * (sig + dr) + e);
+      const float sx = di / (den + e);
+      const float sy = sqrtf(sig * sig - ad * ad + e) / (den + e);
+      zr = mu.x + (num_r / (den + e)) * er;
+      zi = mu.y + sx * er + sy * ei;
+    }
     *reinterpret_cast<float2*>(z + i * 2) = make_float2(zr, zi);
   }
 }
@@ -326,16 +335,17 @@ extern "C" int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, flo
 
 extern "C" int idv_reparam_fwd(const float* latent, int NB, int T, int Htot, int ch0, int zdim, int S,
                                const float* eps_r, const float* eps_i, uint64_t seed, uint64_t offset,
-                               const uint64_t* offset_dev, float* z, void* stream) {
+                               const uint64_t* offset_dev, int variant, float* z, void* stream) {
   using namespace idv;
-  IDV_CHECK_ARG(latent && z && NB > 0 && T > 0 && S > 0 && zdim > 0, "idv_reparam_fwd: bad argument");
+  IDV_CHECK_ARG(latent && z && NB > 0 && T > 0 && S > 0 && zdim > 0 && (variant == 0 || variant == 1),
+                "idv_reparam_fwd: bad argument");
   IDV_CHECK_ARG(ch0 >= 0 && ch0 + 3 * zdim <= Htot, "idv_reparam_fwd: latent slice out of range");
   IDV_CHECK_ARG((eps_r == nullptr) == (eps_i == nullptr), "idv_reparam_fwd: supply both eps tensors or neither");
   const int64_t n = (int64_t)NB * S * T * zdim;
   const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
   reparam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, seed,
                                                            offset, reinterpret_cast<const unsigned long long*>(offset_dev),
-                                                           z);
+                                                           variant, z);
   IDV_LAUNCH_CHECK("reparam_kernel");
   return IDV_OK;
 }

@@ -35,7 +35,8 @@ SIGNATURES = {
     "idv_lstm_recurrent_tc": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp],
     "idv_lstm2_wave_tc": [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],
     "idv_lstm_combine_fwd": [vp, i32, i32, i32, vp, i32, vp],
-    "idv_reparam_fwd": [vp, i32, i32, i32, i32, i32, i32, vp, vp, u64, u64, vp, vp, vp],
+    "idv_reparam_fwd": [vp, i32, i32, i32, i32, i32, i32, vp, vp, u64, u64, vp, i32, vp, vp],
+    "idv_bin_affine": [vp, i32, i32, i32, vp, vp, i32, vp, vp],
     "idv_planes_to_user": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "idv_user_to_planes": [vp, i32, i32, i32, i32, vp, i32, i32, vp],
     "idv_z_to_planes": [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp],

@@ -627,23 +627,69 @@ def _next_philox():
 # --------------------------------------------------------------------------------------------------
 # VAE encoders — model/pvae_module.py:L1791-1914, L2131-2268
 # --------------------------------------------------------------------------------------------------
+def _norm_consts(mean, std):
+    """(scale, shift) of the data_mean / data_std normalisation and of its inverse, each (F, 2) fp32:
+    (x - mean) / (std + 1e-6) = x * scale + shift (model/pvae_module.py:L367-368); std * y + mean (L483-484)."""
+    m = mean.detach().to(torch.float32).reshape(-1, 2)
+    sd = std.detach().to(torch.float32).reshape(-1, 2)
+    scale = 1.0 / (sd + 1e-6)
+    return (scale.contiguous(), (-m * scale).contiguous()), (sd.contiguous(), m.contiguous())
+
+
 class _VaeEncoderBase(nn.Module):
-    def _init_common(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num):
+    def _init_common(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num,
+                     heads=None, data_mean=None, data_std=None, channels=None, chw=None, lstm_in=None):
+        """heads: names of the ComplexDense(zdim, zdim) latent heads of the *_fc_latent variants in the order
+        (mean, logvar, delta) per latent (the LSTM then has zdim hidden units and there is no unused ``dense``);
+        channels / chw / lstm_in: overrides of the channel-doubling variants."""
         self.device = device
         self.causal = causal
         self.latent_num = latent_num
         self.stft = STFT(n_fft, hop_len, win_length=win_length, device=device)
-        self.dense = ComplexDense(zdim, net_params["dense"][1])          # unused, present in the state_dict
+        self._heads = list(heads) if heads else None
+        if self._heads is None:
+            self.dense = ComplexDense(zdim, net_params["dense"][1])          # unused, present in the state_dict
+        else:
+            for name in self._heads:
+                setattr(self, name, ComplexDense(zdim, zdim))
+            self._head_cache = _PackCache()
         self.zdim = zdim
         self.num_samples = num_samples
-        encoders = _build_encoders(net_params, causal)
-        lstm_dims = net_params["lstm_dim"]
-        lstms = [ComplexLSTM(input_size=lstm_dims[i], hidden_size=int(3 * zdim * latent_num),
+        if channels is None:
+            encoders = _build_encoders(net_params, causal)
+        else:
+            ks, st, pd = net_params["encoder_kernel_sizes"], net_params["encoder_strides"], net_params["encoder_paddings"]
+            encoders = [Encoder(in_channel=channels[i], out_channel=channels[i + 1], kernel_size=ks[i], stride=st[i],
+                                padding=pd[i], chw=chw[i], causal=causal) for i in range(len(channels) - 1)]
+        lstm_dims = list(net_params["lstm_dim"]) if lstm_in is None else [lstm_in] + list(net_params["lstm_dim"][1:])
+        hidden = int(zdim if self._heads is not None else 3 * zdim * latent_num)
+        lstms = [ComplexLSTM(input_size=lstm_dims[i], hidden_size=hidden,
                              num_layers=net_params["lstm_layer_num"], device=device)
                  for i in range(len(lstm_dims) - 1)]
         self.encoders = nn.ModuleList(encoders)
         self.lstms = nn.ModuleList(lstms)
         self.epsilon = 1e-6
+        self.register_buffer("data_mean", data_mean)
+        self.register_buffer("data_std", data_std)
+        self.datanorm = data_mean is not None and data_std is not None
+
+    def _apply_heads(self, lat):
+        """(B, T, zdim, 2) LSTM output -> (B, T, 3 * latent_num * zdim, 2): all ComplexDense heads as ONE tap-GEMM
+        (model/pvae_module.py:L2478-2494; heads concatenated in (mean, logvar, delta) order per latent)."""
+        B, T, H, _ = lat.shape
+        mods = [getattr(self, n) for n in self._heads]
+        n_out = len(mods) * self.zdim
+        items = self._head_cache.check(nn.ModuleList(mods))
+        key = str(lat.device)
+        if key not in items:
+            cat = lambda f: torch.cat([f(m) for m in mods])
+            items[key] = pack.pack_dense(cat(lambda m: m.linear_read.weight), cat(lambda m: m.linear_read.bias),
+                                         cat(lambda m: m.linear_imag.weight), cat(lambda m: m.linear_imag.bias),
+                                         n_out, 1, lat.device)
+        zp = ops.z_to_planes(lat, B, 1, 0, split=ops.use_split(), t_alloc=T)
+        out = ops.tapgemm(items[key], zp, None, B, T, out_split=False if zp.split else None)
+        u = ops.planes_to_user(Planes(out, B, n_out, 1, T, split=False))             # (B, n_out, 1, T, 2)
+        return u[:, :, 0].permute(0, 2, 1, 3).contiguous()
 
     def _encode(self, x, train, eps):
         if len(self.lstms) != 1:
@@ -651,16 +697,27 @@ class _VaeEncoderBase(nn.Module):
         token = step = None
         if train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # training step: the latent carries a grad_fn whose backward runs the C-ABI backward kernels (train.py)
+            if self._heads is not None or self.datanorm:
+                raise NotImplementedError("the backward pass is built for the encoders without latent heads / data_norm "
+                                          "(nsvae_pvae_dccrn_encoder_twophase, pvae_dccrn_encoder_skip_prepare)")
             from . import train as _train
             latent_g, stft_x, planes, token, step = _train.encoder_train_forward(self, x)
             top, latent = planes[-1], latent_g.detach()
         else:
             latent_g = None
             stft_x = self.stft(x)
+            if self.datanorm:                                          # model/pvae_module.py:L367-371
+                key = (self.data_mean._version, self.data_std._version, str(stft_x.device))
+                if getattr(self, "_norm_key", None) != key:
+                    self._norm_key, self._norm = key, _norm_consts(self.data_mean, self.data_std)[0]
+                stft_x = ops.bin_affine(stft_x, self._norm[0], self._norm[1], zero_edge_imag=True, out=stft_x)
             planes = _run_encoder_stack(self.encoders, stft_x, train)
             top = planes[-1]
-            latent = self.lstms[0].forward_planes(top)                 # (B, T, 3*zdim*latent_num, 2)
+            latent = self.lstms[0].forward_planes(top)                 # (B, T, hidden, 2)
+            if self._heads is not None:
+                latent = self._apply_heads(latent)                     # (B, T, 3*zdim*latent_num, 2)
         z, S = self.zdim, self.num_samples
+        variant = 1 if self._heads is not None else 0
         zs = []
         for k in range(self.latent_num):
             if eps is not None:
@@ -671,17 +728,44 @@ class _VaeEncoderBase(nn.Module):
             if latent_g is not None and S == 1:
                 zs.append(_train.reparam_train(latent_g, 3 * z * k, z, er, ei))    # differentiable z
             else:
-                zs.append(ops.reparam(latent, 3 * z * k, z, S, er, ei, seed, off))
+                zs.append(ops.reparam(latent, 3 * z * k, z, S, er, ei, seed, off, variant=variant))
         skiper = SkipList(planes)
         skiper.grad_token, skiper.train_step = token, step
         return stft_x, skiper, (latent if latent_g is None else latent_g), zs, top.C, top.F
+
+    def _forward12(self, x, train, eps):
+        """The NSVAE 12-tuple (model/pvae_module.py:L2268)."""
+        stft_x, skiper, lat, zs, C, F = self._encode(x, train, eps)
+        z = self.zdim
+        miu_s, ls_s, de_s = lat[:, :, 0:z, :], lat[:, :, z:2 * z, :], lat[:, :, 2 * z:3 * z, :]
+        if self.latent_num == 1:
+            return zs[0], miu_s, ls_s, de_s, None, None, None, None, skiper, C, F, stft_x
+        miu_n, ls_n, de_n = lat[:, :, 3 * z:4 * z, :], lat[:, :, 4 * z:5 * z, :], lat[:, :, 5 * z:6 * z, :]
+        return zs[0], miu_s, ls_s, de_s, zs[1], miu_n, ls_n, de_n, skiper, C, F, stft_x
+
+    def _forward8(self, x, train, eps):
+        """The CVAE 8-tuple (model/pvae_module.py:L1914)."""
+        stft_x, skiper, lat, zs, C, F = self._encode(x, train, eps)
+        z = self.zdim
+        return zs[0], lat[:, :, 0:z, :], lat[:, :, z:2 * z, :], lat[:, :, 2 * z:, :], skiper, C, F, stft_x
 
     def reparameterization(self, miu, log_sigma, delta, num_samples, eps=None):
         """model/pvae_module.py:L2177-2231; eps = (eps_real, eps_imag) of shape (B, S, T, zdim) or None."""
         latent = torch.cat((miu, log_sigma, delta), dim=2).contiguous()
         er, ei = eps if eps is not None else (None, None)
         seed, off = (0, 0) if eps is not None else _next_philox()
-        return ops.reparam(latent, 0, miu.shape[2], num_samples, er, ei, seed, off)
+        return ops.reparam(latent, 0, miu.shape[2], num_samples, er, ei, seed, off,
+                           variant=1 if self._heads is not None else 0)
+
+
+def _check_latent_num(latent_num):
+    if latent_num not in (1, 2):
+        raise ValueError("latent_num must be 1 or 2")
+
+
+_NS_HEADS = ("speech_dense_mean", "speech_dense_logvar", "speech_dense_delta",
+             "noise_dense_mean", "noise_dense_logvar", "noise_dense_delta")
+_CVAE_HEADS = ("dense_mean", "dense_logvar", "dense_delta")
 
 
 class nsvae_pvae_dccrn_encoder_twophase(_VaeEncoderBase):
@@ -690,18 +774,69 @@ class nsvae_pvae_dccrn_encoder_twophase(_VaeEncoderBase):
 
     def __init__(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num):
         super().__init__()
-        if latent_num not in (1, 2):
-            raise ValueError("latent_num must be 1 or 2")
+        _check_latent_num(latent_num)
         self._init_common(net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num)
 
     def forward(self, x, train=True, eps=None):
-        stft_x, skiper, lat, zs, C, F = self._encode(x, train, eps)
-        z = self.zdim
-        miu_s, ls_s, de_s = lat[:, :, 0:z, :], lat[:, :, z:2 * z, :], lat[:, :, 2 * z:3 * z, :]
-        if self.latent_num == 1:
-            return zs[0], miu_s, ls_s, de_s, None, None, None, None, skiper, C, F, stft_x
-        miu_n, ls_n, de_n = lat[:, :, 3 * z:4 * z, :], lat[:, :, 4 * z:5 * z, :], lat[:, :, 5 * z:6 * z, :]
-        return zs[0], miu_s, ls_s, de_s, zs[1], miu_n, ls_n, de_n, skiper, C, F, stft_x
+        return self._forward12(x, train, eps)
+
+
+class nsvae_dccrn_encoder_original(nsvae_pvae_dccrn_encoder_twophase):
+    """model/pvae_module.py:L930-1076: the same computation as nsvae_pvae_dccrn_encoder_twophase."""
+
+
+class nsvae_pvae_dccrn_encoder_twophase_fc_latent(_VaeEncoderBase):
+    """model/pvae_module.py:L2353-2503: LSTM with zdim hidden units, ComplexDense heads for (mu, log sigma, delta) of
+    the speech (and noise) latent, clamped reparameterisation (L2403-2450)."""
+
+    def __init__(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num):
+        super().__init__()
+        _check_latent_num(latent_num)
+        self._init_common(net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num,
+                          heads=_NS_HEADS[:3 * latent_num])
+
+    def forward(self, x, train=True, eps=None):
+        return self._forward12(x, train, eps)
+
+
+class nsvae_dccrn_encoder_original_fc_latent(nsvae_pvae_dccrn_encoder_twophase_fc_latent):
+    """model/pvae_module.py:L1077-1235: the same computation as nsvae_pvae_dccrn_encoder_twophase_fc_latent."""
+
+
+class nsvae_dccrn_encoder_double_channel(_VaeEncoderBase):
+    """model/pvae_module.py:L1236-1393: every encoder layer has twice the channels (the LSTM input too)."""
+
+    def __init__(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num):
+        super().__init__()
+        _check_latent_num(latent_num)
+        ch = list(net_params["encoder_channels"])
+        channels = [ch[0]] + [2 * c for c in ch[1:]]
+        chw = [tuple(2 * t for t in c) for c in net_params["encoder_chw"]]
+        self._init_common(net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num,
+                          channels=channels, chw=chw, lstm_in=2 * net_params["lstm_dim"][0])
+
+    def forward(self, x, train=True, eps=None):
+        return self._forward12(x, train, eps)
+
+
+class nsvae_dccrn_encoder_adapt_channel(_VaeEncoderBase):
+    """model/pvae_module.py:L1394-1555: the encoder layers whose output is used as a skip tensor have twice the
+    channels.  Like the reference, the constructor doubles the entries of ``net_params`` IN PLACE (L1411-1414)."""
+
+    def __init__(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num, skip_to_use):
+        super().__init__()
+        _check_latent_num(latent_num)
+        ch, chw = net_params["encoder_channels"], net_params["encoder_chw"]
+        for idx, c_num in enumerate(ch[1:]):
+            if (len(ch) - 2 - idx) in skip_to_use:
+                ch[idx + 1] = c_num * 2
+                chw[idx] = tuple(t * 2 for t in chw[idx])
+        lstm_in = 2 * net_params["lstm_dim"][0] if 0 in skip_to_use else net_params["lstm_dim"][0]
+        self._init_common(net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, latent_num,
+                          channels=list(ch), chw=list(chw), lstm_in=lstm_in)
+
+    def forward(self, x, train=True, eps=None):
+        return self._forward12(x, train, eps)
 
 
 class pvae_dccrn_encoder_skip_prepare(_VaeEncoderBase):
@@ -712,9 +847,60 @@ class pvae_dccrn_encoder_skip_prepare(_VaeEncoderBase):
         self._init_common(net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, 1)
 
     def forward(self, x, train=True, eps=None):
-        stft_x, skiper, lat, zs, C, F = self._encode(x, train, eps)
-        z = self.zdim
-        return zs[0], lat[:, :, 0:z, :], lat[:, :, z:2 * z, :], lat[:, :, 2 * z:, :], skiper, C, F, stft_x
+        return self._forward8(x, train, eps)
+
+
+class pvae_dccrn_encoder_prob_skip(pvae_dccrn_encoder_skip_prepare):
+    """model/pvae_module.py:L1556-1680: the same computation as pvae_dccrn_encoder_skip_prepare."""
+
+
+class pvae_dccrn_encoder_skip_prepare_fc_latent(_VaeEncoderBase):
+    """model/pvae_module.py:L1917-2043"""
+
+    def __init__(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples):
+        super().__init__()
+        self._init_common(net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, 1,
+                          heads=_CVAE_HEADS)
+
+    def forward(self, x, train=True, eps=None):
+        return self._forward8(x, train, eps)
+
+
+class pvae_dccrn_encoder(_VaeEncoderBase):
+    """model/pvae_module.py:L259-394: the CVAE encoder with the optional data_mean / data_std normalisation."""
+
+    def __init__(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, data_mean=None,
+                 data_std=None):
+        super().__init__()
+        self._init_common(net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, 1,
+                          data_mean=data_mean, data_std=data_std)
+
+    def forward(self, x, train=True, eps=None):
+        return self._forward8(x, train, eps)
+
+
+class pvae_dccrn_encoder_no_skip(_VaeEncoderBase):
+    """model/pvae_module.py:L523-660 (data_mean / data_std are positional here)"""
+
+    def __init__(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, data_mean, data_std):
+        super().__init__()
+        self._init_common(net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, 1,
+                          data_mean=data_mean, data_std=data_std)
+
+    def forward(self, x, train=True, eps=None):
+        return self._forward8(x, train, eps)
+
+
+class pvae_dccrn_encoder_no_skip_fc_latent(_VaeEncoderBase):
+    """model/pvae_module.py:L662-803"""
+
+    def __init__(self, net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, data_mean, data_std):
+        super().__init__()
+        self._init_common(net_params, causal, device, zdim, n_fft, hop_len, win_length, num_samples, 1,
+                          heads=_CVAE_HEADS, data_mean=data_mean, data_std=data_std)
+
+    def forward(self, x, train=True, eps=None):
+        return self._forward8(x, train, eps)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -722,7 +908,7 @@ class pvae_dccrn_encoder_skip_prepare(_VaeEncoderBase):
 # --------------------------------------------------------------------------------------------------
 class _VaeDecoderBase(nn.Module):
     def _init_common(self, net_params, causal, device, num_samples, zdim, n_fft, hop_len, win_length, recon_type,
-                     skip_to_use, use_sc):
+                     skip_to_use, use_sc, data_mean=None, data_std=None):
         if recon_type not in ("real_imag", "mask"):
             raise ValueError("recon_type must be 'real_imag' or 'mask'")
         self.device = device
@@ -736,6 +922,9 @@ class _VaeDecoderBase(nn.Module):
         self.decoders = nn.ModuleList(_build_decoders(net_params, causal, skip_to_use, use_sc))
         self.istft = ISTFT(n_fft, hop_len, win_length=win_length, device=device)
         self.keep_decoder_outputs = False
+        self.register_buffer("data_mean", data_mean)
+        self.register_buffer("data_std", data_std)
+        self.datanorm = data_mean is not None and data_std is not None
 
     def _decode(self, stft_x, z, skiper, C, F, train, real_skips, mask):
         BS, T, zdim, D = z.shape
@@ -767,6 +956,8 @@ class _VaeDecoderBase(nn.Module):
         self.decoder_outputs = []
         if train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # training step: (recon_sig, predict) carry a grad_fn whose backward runs the C-ABI backward kernels
+            if self.datanorm:
+                raise NotImplementedError("the backward pass is built for the decoders without data_norm")
             from . import train as _train
             recon_sig, predict = _train.decoder_train_forward(self, stft_x if mask else None, z, skiper, skips, C, F, mask)
             return recon_sig, torch.view_as_complex(predict)
@@ -781,6 +972,11 @@ class _VaeDecoderBase(nn.Module):
                                               train)
         if self.keep_decoder_outputs and S == 1:
             self.decoder_outputs = SkipList(self.decoder_outputs)
+        if self.datanorm:                                              # model/pvae_module.py:L483-484, L507-510
+            key = (self.data_mean._version, self.data_std._version, str(predict.device))
+            if getattr(self, "_norm_key", None) != key:
+                self._norm_key, self._norm = key, _norm_consts(self.data_mean, self.data_std)[1]
+            ops.bin_affine(predict, self._norm[0], self._norm[1], out=predict)
         recon_sig = self.istft.forward_ri(predict)
         return recon_sig, torch.view_as_complex(predict)
 
@@ -800,6 +996,41 @@ class pvae_dccrn_decoder_skip_prepare(_VaeDecoderBase):
 
     def forward(self, stft_x, z, skiper, C, F, train=True):
         return self._decode(stft_x, z, skiper, C, F, train, real_skips=False, mask=False)
+
+
+class pvae_dccrn_decoder(_VaeDecoderBase):
+    """model/pvae_module.py:L396-521: real skip tensors (repeated num_samples times), optional data_norm."""
+
+    def __init__(self, net_params, causal, device, num_samples, zdim, n_fft, hop_len, win_length, recon_type,
+                 skip_to_use, resynthesis=False, data_mean=None, data_std=None):
+        super().__init__()
+        self._init_common(net_params, causal, device, num_samples, zdim, n_fft, hop_len, win_length, recon_type,
+                          skip_to_use, True, data_mean, data_std)
+        self.resynthesis = resynthesis
+        if resynthesis:
+            raise NotImplementedError("resynthesis=True calls self.stft, which this class does not have in the "
+                                      "reference either (model/pvae_module.py:L488)")
+
+    def forward(self, stft_x, z, skiper, C, F, train=True):
+        return self._decode(stft_x, z, skiper, C, F, train, real_skips=True, mask=(self.recon_type == 'mask'))
+
+
+class pvae_dccrn_decoder_no_skip(_VaeDecoderBase):
+    """model/pvae_module.py:L805-928: no skip inputs at all, optional data_norm / resynthesis."""
+
+    def __init__(self, net_params, causal, device, num_samples, zdim, n_fft, hop_len, win_length, recon_type,
+                 resynthesis=False, data_mean=None, data_std=None):
+        super().__init__()
+        self._init_common(net_params, causal, device, num_samples, zdim, n_fft, hop_len, win_length, recon_type,
+                          [], False, data_mean, data_std)
+        self.resynthesis = resynthesis
+        self.stft = STFT(n_fft, hop_len, win_length=win_length, device=device)
+
+    def forward(self, stft_x, z, skiper, C, F, train=True):
+        sig, predict = self._decode(stft_x, z, skiper, C, F, train, real_skips=False, mask=(self.recon_type == 'mask'))
+        if self.resynthesis:
+            predict = torch.view_as_complex(self.stft(sig))
+        return sig, predict
 
 
 class nsvae_pvae_dccrn_decoder_twophase(_VaeDecoderBase):
@@ -879,15 +1110,19 @@ class DCCRN_(nn.Module):
         self.register_buffer("data_mean", data_mean)
         self.register_buffer("data_std", data_std)
         self.datanorm = self.data_mean is not None and self.data_std is not None
-        if self.datanorm:
-            raise NotImplementedError("data_norm (model/pvae_module.py:L217-221) is off in every shipped run and "
-                                      "is not built")
         if recon_type not in ("mask", "real_imag"):
             raise ValueError("recon_type must be 'mask' or 'real_imag'")
 
     def forward(self, signal, train=True):
         stft_x = self.stft(signal)
+        if self.datanorm:                                              # model/pvae_module.py:L217-221, L236-239, L248-249
+            key = (self.data_mean._version, self.data_std._version, str(stft_x.device))
+            if getattr(self, "_norm_key", None) != key:
+                self._norm_key, self._norm = key, _norm_consts(self.data_mean, self.data_std)
+            stft_x = ops.bin_affine(stft_x, self._norm[0][0], self._norm[0][1], zero_edge_imag=True, out=stft_x)
         predict = self.std_DCCRN.forward_spec(stft_x, train, mask=(self.recon_type == 'mask'))
+        if self.datanorm:
+            ops.bin_affine(predict, self._norm[1][0], self._norm[1][1], out=predict)
         clean = self.istft.forward_ri(predict)
         if self.resynthesis:
             predict = self.stft(clean)

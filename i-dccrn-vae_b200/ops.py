@@ -251,7 +251,8 @@ def lstm_combine(hseq, NB, T, H, t_valid=0):
     return latent
 
 
-def reparam(latent, ch0, zdim, S, eps_r, eps_i, seed, offset, offset_dev=None, out=None):
+def reparam(latent, ch0, zdim, S, eps_r, eps_i, seed, offset, offset_dev=None, out=None, variant=0):
+    """variant 1: the clamped formula of the *_fc_latent encoders (model/pvae_module.py:L2403-2450)."""
     NB, T, Htot, _ = latent.shape
     z = out if out is not None else torch.empty((NB * S, T, zdim, 2), dtype=torch.float32, device=latent.device)
     if eps_r is not None:
@@ -259,8 +260,18 @@ def reparam(latent, ch0, zdim, S, eps_r, eps_i, seed, offset, offset_dev=None, o
         eps_i = lib.require_f32_cuda(eps_i, "eps_i")
         if tuple(eps_r.shape) != (NB, S, T, zdim) or tuple(eps_i.shape) != (NB, S, T, zdim):
             raise RuntimeError("eps must have shape (B, S, T, zdim) = %s" % ((NB, S, T, zdim),))
-    lib.call("idv_reparam_fwd", latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, int(seed), int(offset), offset_dev, z)
+    lib.call("idv_reparam_fwd", latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, int(seed), int(offset), offset_dev,
+             int(variant), z)
     return z
+
+
+def bin_affine(x, scale, shift, zero_edge_imag=False, out=None):
+    """x (B, F, T, 2) * scale (F, 2) + shift (F, 2) (data_mean / data_std normalisation and its inverse)."""
+    x = lib.require_f32_cuda(x, "spectrum")
+    B, F, T, _ = x.shape
+    out = torch.empty_like(x) if out is None else out
+    lib.call("idv_bin_affine", x, B, F, T, scale, shift, 1 if zero_edge_imag else 0, out)
+    return out
 
 
 def planes_to_user(p):

@@ -193,10 +193,16 @@ int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, float* latent,
 /* reparameterization (model/pvae_module.py:L2177-2231).  latent: (NB,T,Htot,2); the (mu, log
  * sigma, delta) triplet starts at channel ch0 (zdim each).  eps_r/eps_i: (NB,S,T,zdim) or NULL ->
  * Philox4x32-10 N(0,1) from (seed, offset + *offset_dev); offset_dev (device, may be NULL) lets a captured CUDA
- * graph draw fresh noise on every replay.  z: (NB*S, T, zdim, 2).                                */
+ * graph draw fresh noise on every replay.  z: (NB*S, T, zdim, 2).  variant 1 = the clamped formula of the
+ * *_fc_latent encoders (model/pvae_module.py:L2403-2450).                                          */
 int idv_reparam_fwd(const float* latent, int NB, int T, int Htot, int ch0, int zdim, int S,
                     const float* eps_r, const float* eps_i, uint64_t seed, uint64_t offset,
-                    const uint64_t* offset_dev, float* z, void* stream);
+                    const uint64_t* offset_dev, int variant, float* z, void* stream);
+/* Per-bin affine on a spectrum (B, F, T, 2): out = x * scale[f][part] + shift[f][part] (in place allowed) - the
+ * data_mean / data_std normalisation of the CVAE encoders (model/pvae_module.py:L367-371: zero_edge_imag = 1 clears
+ * the imaginary part of the first and last bin afterwards) and its inverse in the decoders (L483-484). */
+int idv_bin_affine(const float* x, int B, int F, int T, const float* scale, const float* shift, int zero_edge_imag,
+                   float* out, void* stream);
 
 /* ---- layout conversion at the module boundary --------------------------------------------------*/
 /* planes [F][R][Cp] (fp32, or split bf16 when in_split) -> user (NB, C, F, T, 2) */

@@ -371,6 +371,61 @@ def case_train_step_e2e(tag, B, L, latent_num, seed):
     np.savez(os.path.join(OUT, tag + ".npz"), **g)
 
 
+def case_variant(tag):
+    """One of the class variants of oracle/variants.py: the unmodified reference classes on seeded weights / inputs /
+    eps (train=False); pins latents, z, the deepest skip tensor and - when the variant has a decoder - the outputs."""
+    import copy
+    from oracle.variants import VARIANTS, run_variant
+    print("case", tag)
+    v = VARIANTS[tag]
+    net = copy.deepcopy(ref_causal_cfg.get_net_params())             # adapt_channel mutates its net_params
+    torch.manual_seed(0)
+    enc, dec = v["build"](ref_mod, net, "cpu")
+    enc.load_state_dict(fill_state_dict(enc.state_dict(), v["seed"]), strict=True)
+    enc.eval()
+    if dec is not None:
+        dec.load_state_dict(fill_state_dict(dec.state_dict(), v["seed"] + 1), strict=True)
+        dec.eval()
+    x = synth_waveform(v["B"], v["L"], seed=1234 + v["seed"])
+    T = v["L"] // HOP + 1
+    eps = synth_eps((v["B"], v["S"], T, ZDIM), seed=7 + v["seed"], n=2 * v["latent_num"])
+    with torch.no_grad(), supplied_eps(eps):
+        out = run_variant(v, enc, dec, x, None)
+    g = {k: np32(t) for k, t in out.items()}
+    g.update(B=v["B"], L=v["L"], S=v["S"], latent_num=v["latent_num"], seed=v["seed"])
+    np.savez(os.path.join(OUT, tag + ".npz"), **g)
+    print("   stored", sorted(k for k in g if k not in ("B", "L", "S", "latent_num", "seed")))
+
+
+def case_dccrn_datanorm(tag, seed=31):
+    """DCCRN_ with data_mean / data_std (model/pvae_module.py:L217-221, L236-249), both heads."""
+    import copy
+    print("case", tag)
+    x = synth_waveform(2, 900, seed=1234 + seed)
+    g = {"seed": seed}
+    for recon_type in ("mask", "real_imag"):
+        net = copy.deepcopy(ref_causal_cfg.get_net_params())
+        m = ref_mod.DCCRN_(NFFT, HOP, net, True, "cpu", WIN, [0, 1, 2, 3, 4, 5], recon_type, False,
+                           torch.zeros(1, 257, 1, 2), torch.ones(1, 257, 1, 2))
+        m.load_state_dict(fill_state_dict(m.state_dict(), seed), strict=True)
+        m.eval()
+        with torch.no_grad():
+            clean, pred = m(x, train=False)
+            sd = m.state_dict()
+            d = P.dccrn_forward(sd, x, recon_type=recon_type, data_norm=(sd["data_mean"], sd["data_std"]))
+        check("dccrn datanorm %s predict" % recon_type, d["predict"], pred)
+        check("dccrn datanorm %s clean" % recon_type, d["clean"], clean)
+        g["clean_" + recon_type], g["predict_" + recon_type] = np32(clean), np32(pred)
+    np.savez(os.path.join(OUT, tag + ".npz"), **g)
+
+
+def variant_cases():
+    from oracle.variants import VARIANTS
+    for tag in VARIANTS:
+        case_variant(tag)
+    case_dccrn_datanorm("dccrn_datanorm")
+
+
 def case_dccrn(tag, B, L, seed, causal=True):
     print("case", tag)
     net = (ref_causal_cfg if causal else ref_noncausal_cfg).get_net_params()
@@ -467,6 +522,9 @@ def phase2_cases():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-variants" in sys.argv:
+        variant_cases()
+        sys.exit(0)
     if "--only-e2e" in sys.argv:
         e2e_cases()
         sys.exit(0)
@@ -503,4 +561,5 @@ if __name__ == "__main__":
     case_train_step("train_step_l1", B=3, L=700, latent_num=1, seed=14)
     phase2_cases()
     e2e_cases()
+    variant_cases()
     print("golden fixtures written to", OUT)

@@ -410,12 +410,16 @@ def vae_decoder_forward(sd, stft_x, z, skiper, C, Fq, num_samples=1, recon_type=
 
 
 def dccrn_forward(sd, signal, skip_to_use=(0, 1, 2, 3, 4, 5), recon_type="mask", causal=True,
-                  hidden=128, stft_params=(512, 100, 400)):
+                  hidden=128, stft_params=(512, 100, 400), data_norm=None):
     """DCCRN_.forward(signal, train=False) + standard_DCCRN.forward — model/pvae_module.py:L215-255,
     L174-198 (data_norm off, resynthesis off).  Keys are prefixed ``std_DCCRN.``."""
     pre = "std_DCCRN."
     sub = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
     stft_x = stft(signal, *stft_params)
+    if data_norm is not None:                                   # model/pvae_module.py:L217-221
+        stft_x = ((stft_x - data_norm[0]) / (data_norm[1] + 1e-6)).clone()
+        stft_x[:, 0, :, 1] = 0
+        stft_x[:, -1, :, 1] = 0
     x, skiper = encoder_stack(stft_x.unsqueeze(1), sub, 6, causal)
     B, C, Fq, T, D = x.shape
     lstm_in = x.reshape(B, -1, T, D).permute(2, 0, 1, 3)
@@ -430,6 +434,9 @@ def dccrn_forward(sd, signal, skip_to_use=(0, 1, 2, 3, 4, 5), recon_type="mask",
         predict = mask_head(p, stft_x, 1)
     else:
         predict = torch.complex(p[..., 0], p[..., 1]).squeeze(1)
+    if data_norm is not None:                                   # L236-239, L248-249
+        pr = data_norm[1] * torch.view_as_real(predict) + data_norm[0]
+        predict = torch.complex(pr[..., 0], pr[..., 1])
     return {"clean": istft(predict, *stft_params), "predict": predict, "latent": lat,
             "stft_x": stft_x, "skiper": skiper}
 

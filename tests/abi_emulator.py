@@ -427,23 +427,37 @@ def idv_lstm_combine_fwd(hseq, NB, T, H, latent, t_valid=0):
     latent.copy_(torch.stack((rr - ii, ir + ri), -1))
 
 
-def idv_reparam_fwd(latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, seed, offset, offset_dev, z):
+def idv_reparam_fwd(latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, seed, offset, offset_dev, variant, z):
     assert eps_r is not None, "the emulator only supports supplied eps"
     e = 1e-6
     lat = latent.view(NB, T, Htot, 2)
     mu, ls, dl = lat[:, :, ch0:ch0 + zdim], lat[:, :, ch0 + zdim:ch0 + 2 * zdim], lat[:, :, ch0 + 2 * zdim:ch0 + 3 * zdim]
-    sig = torch.exp(ls[..., 0])
+    sig = torch.exp(torch.clamp(ls[..., 0], -13, 13) if variant else ls[..., 0])
     dr, di = dl[..., 0], dl[..., 1]
     ad = torch.sqrt(dr * dr + di * di + e)
     tmp = sig * 0.99 / (ad + e)
     cl = ad >= sig - 1e-3
     dr, di = torch.where(cl, dr * tmp, dr), torch.where(cl, di * tmp, di)
     ad = torch.sqrt(dr * dr + di * di + e)
-    den = torch.sqrt(2 * (sig + dr) + e)
-    zr = mu[..., 0][:, None] + ((sig + dr) / (den + e))[:, None] * eps_r.view(NB, S, T, zdim)
-    zi = mu[..., 1][:, None] + (di / (den + e))[:, None] * eps_r.view(NB, S, T, zdim) + \
-        (torch.sqrt(sig * sig - ad * ad + e) / (den + e))[:, None] * eps_i.view(NB, S, T, zdim)
+    er, ei = eps_r.view(NB, S, T, zdim), eps_i.view(NB, S, T, zdim)
+    if variant:
+        den = torch.sqrt(torch.clamp(2 * (sig + dr), min=e))
+        zr = mu[..., 0][:, None] + ((sig + dr) / den)[:, None] * er
+        zi = mu[..., 1][:, None] + (di / den)[:, None] * er + (torch.sqrt(torch.clamp(sig * sig - ad * ad, min=e)) / den)[:, None] * ei
+    else:
+        den = torch.sqrt(2 * (sig + dr) + e)
+        zr = mu[..., 0][:, None] + ((sig + dr) / (den + e))[:, None] * er
+        zi = mu[..., 1][:, None] + (di / (den + e))[:, None] * er + \
+            (torch.sqrt(sig * sig - ad * ad + e) / (den + e))[:, None] * ei
     z.copy_(torch.stack((zr, zi), -1).view(NB * S, T, zdim, 2))
+
+
+def idv_bin_affine(x, B, F, T, scale, shift, zero_edge_imag, out):
+    v = x.view(B, F, T, 2).to(D) * scale.view(1, F, 1, 2).to(D) + shift.view(1, F, 1, 2).to(D)
+    if zero_edge_imag:
+        v[:, 0, :, 1] = 0
+        v[:, -1, :, 1] = 0
+    out.view(B, F, T, 2).copy_(v.to(torch.float32))
 
 
 def _r8(c):

@@ -126,9 +126,14 @@ def test_lstm_recurrent_and_combine(NB, T, H, tv):
 def test_reparam_supplied_eps():
     NB, T, z, S = 3, 11, 128, 2
     lat = _rand(NB, T, 6 * z, 2, seed=18)
-    args = [lat, NB, T, 6 * z, 3 * z, z, S, _rand(NB, S, T, z, seed=19), _rand(NB, S, T, z, seed=20), 0, 0, None,
-            torch.zeros(NB * S, T, z, 2)]
-    assert _both("idv_reparam_fwd", args, [12]) < 1e-5
+    for variant in (0, 1):
+        args = [lat * (1 + 9 * variant), NB, T, 6 * z, 3 * z, z, S, _rand(NB, S, T, z, seed=19), _rand(NB, S, T, z, seed=20),
+                0, 0, None, variant, torch.zeros(NB * S, T, z, 2)]
+        assert _both("idv_reparam_fwd", args, [13]) < 1e-5
+    x = _rand(NB, 257, T, 2, seed=21)
+    sc, sh = _rand(257, 2, seed=22), _rand(257, 2, seed=23)
+    for ze in (0, 1):
+        assert _both("idv_bin_affine", [x, NB, 257, T, sc, sh, ze, torch.zeros_like(x)], [7]) < 1e-6
 
 
 @pytest.mark.parametrize("NB,C_,F,T,tv", [(2, 3, 5, 7, 0), (1, 32, 129, 33, 0), (3, 1, 4, 65, 0), (2, 5, 3, 40, 34)])
