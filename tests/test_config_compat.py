@@ -53,3 +53,33 @@ def test_build_enhancer_matches_reference_pairing(tmp_path):
     enc2, dec2 = CFG.build_enhancer(cfg, "cpu", latent_num=2, finetuned_decoder=True)
     assert enc2.lstms[0].hidden_size == 768 and isinstance(dec2, M.nsvae_pvae_dccrn_decoder_twophase)
     assert dec2.recon_type == "mask"
+
+
+def test_reference_import_shim():
+    """``from model.pvae_module import *`` (what the reference's scripts do) resolves to this package's classes."""
+    import sys
+    from idccrn_b200 import compat
+    saved = {n: sys.modules.pop(n) for n in list(sys.modules) if n == "model" or n.startswith("model.")}
+    try:
+        compat.install()
+        ns = {}
+        exec("from model.pvae_module import *\nimport model.causal_netconfig as cfgmod\n"
+             "from model.complex_progress import ComplexBatchNormal as CBN", ns)
+        assert ns["nsvae_pvae_dccrn_encoder_twophase"] is M.nsvae_pvae_dccrn_encoder_twophase
+        assert ns["pvae_dccrn_decoder_no_skip"] is M.pvae_dccrn_decoder_no_skip and ns["DCCRN_"] is M.DCCRN_
+        assert ns["CBN"] is M.ComplexBatchNormal
+        net = ns["cfgmod"].get_net_params()
+        assert net["encoder_paddings"][0] == (2, 1) and net["lstm_dim"][0] == 1280
+        enc = ns["nsvae_pvae_dccrn_encoder_twophase"](net, True, "cpu", 128, 512, 100, 400, 1, 2)
+        assert enc.lstms[0].hidden_size == 768
+        import pytest
+        with pytest.raises(RuntimeError):
+            sys.modules["model.pvae_module"].__idccrn_b200_shim__ = False
+            compat.install()
+        sys.modules["model.pvae_module"].__idccrn_b200_shim__ = True
+    finally:
+        compat.uninstall()
+        for n in list(sys.modules):
+            if n == "model" or n.startswith("model."):
+                del sys.modules[n]
+        sys.modules.update(saved)
