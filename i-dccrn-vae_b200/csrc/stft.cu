@@ -162,10 +162,20 @@ __global__ void __launch_bounds__(ST_THREADS) istft_frames_kernel(const float* _
 // overlap-add + window-envelope normalisation + centre trim (HBM-bound)
 __global__ void __launch_bounds__(256) ola_kernel(const float* __restrict__ frames, int frame_ld,
                                                   const float* __restrict__ wsq, int T, int n_fft, int hop, int win,
-                                                  int out_len, float* __restrict__ out) {
+                                                  int out_len, const int* __restrict__ lengths,
+                                                  float* __restrict__ out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (s >= out_len) return;
+  const int T_all = T;
+  if (lengths) {                                     // ragged batch: utterance b has lengths[b] / hop + 1 frames
+    T = lengths[b] / hop + 1;
+    if (T > T_all) T = T_all;
+    if (s >= hop * (T - 1)) {
+      out[(int64_t)b * out_len + s] = 0.f;
+      return;
+    }
+  }
   const int off = (n_fft - win) / 2;
   const int q = s + n_fft / 2 - off;                 // position relative to the first window tap
   int t_hi = q / hop;
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__(256) ola_kernel(const float* __restrict__ fram
   if (q - win + 1 <= 0) t_lo = 0;
   if (t_hi > T - 1) t_hi = T - 1;
   float acc = 0.f, env = 0.f;
-  const float* fb = frames + (int64_t)b * T * frame_ld;
+  const float* fb = frames + (int64_t)b * T_all * frame_ld;
   for (int t = t_lo; t <= t_hi; ++t) {
     const int j = q - hop * t;
     if (j >= 0 && j < win) {
@@ -188,6 +198,7 @@ __global__ void __launch_bounds__(256) ola_kernel(const float* __restrict__ fram
 // frames[(b*T + t)][j] = xp[b][hop*t + off + j] for j < win, 0 for win <= j < kpad   (hi / lo planes)
 __global__ void __launch_bounds__(256) stft_frames_split_kernel(const float* __restrict__ x, int B, int L, int T,
                                                                 int n_fft, int hop, int win, int kpad,
+                                                                const int* __restrict__ lengths,
                                                                 unsigned short* __restrict__ out) {
   const long long n = (long long)B * T * (kpad / 4);
   const long long hl = (long long)B * T * kpad;
@@ -196,14 +207,17 @@ __global__ void __launch_bounds__(256) stft_frames_split_kernel(const float* __r
     const int j4 = (int)(i % (kpad / 4)) * 4;
     const long long bt = i / (kpad / 4);
     const int t = (int)(bt % T), b = (int)(bt / T);
+    // ragged batch: utterance b holds lengths[b] samples (reflect padding at ITS end), frames beyond its last are 0
+    const int Lb = lengths ? min(lengths[b], L) : L;
+    const bool live = t <= Lb / hop;
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int j = j4 + e;
       int idx = hop * t + off + j - half;
       if (idx < 0) idx = -idx;
-      if (idx >= L) idx = 2 * (L - 1) - idx;
-      v[e] = (j < win && idx >= 0 && idx < L) ? __ldg(x + (long long)b * L + idx) : 0.f;
+      if (idx >= Lb) idx = 2 * (Lb - 1) - idx;
+      v[e] = (live && j < win && idx >= 0 && idx < Lb) ? __ldg(x + (long long)b * L + idx) : 0.f;
     }
     st_split4(out, hl, bt * kpad + j4, make_float4(v[0], v[1], v[2], v[3]));
   }
@@ -240,8 +254,8 @@ __global__ void __launch_bounds__(256) spec_rows_split_kernel(const float* __res
 
 }  // namespace idv
 
-extern "C" int idv_stft_frames_split(const float* x, int B, int L, int n_fft, int hop, int win, int kpad, void* out,
-                                     void* stream) {
+extern "C" int idv_stft_frames_split(const float* x, int B, int L, int n_fft, int hop, int win, int kpad,
+                                     const int* lengths, void* out, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(x && out && B > 0 && hop > 0 && win > 0 && n_fft >= win && kpad >= win && kpad % 64 == 0,
                 "idv_stft_frames_split: bad argument");
@@ -249,7 +263,7 @@ extern "C" int idv_stft_frames_split(const float* x, int B, int L, int n_fft, in
   const int T = L / hop + 1;
   const long long n = (long long)B * T * (kpad / 4);
   const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-  stft_frames_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, B, L, T, n_fft, hop, win, kpad,
+  stft_frames_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, B, L, T, n_fft, hop, win, kpad, lengths,
                                                                       reinterpret_cast<unsigned short*>(out));
   IDV_LAUNCH_CHECK("stft_frames_split_kernel");
   return IDV_OK;
@@ -269,12 +283,12 @@ extern "C" int idv_spec_rows_split(const float* spec, int B, int nbins, int T, i
 }
 
 extern "C" int idv_ola_fwd(const float* frames, int frame_ld, const float* wsq, int B, int T, int n_fft, int hop,
-                           int win, float* out, void* stream) {
+                           int win, const int* lengths, float* out, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(frames && wsq && out && B > 0 && B <= 65535 && T > 1 && frame_ld >= win, "idv_ola_fwd: bad argument");
   const int out_len = hop * (T - 1);
   dim3 g2(cdiv(out_len, 256), B);
-  ola_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(frames, frame_ld, wsq, T, n_fft, hop, win, out_len, out);
+  ola_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(frames, frame_ld, wsq, T, n_fft, hop, win, out_len, lengths, out);
   IDV_LAUNCH_CHECK("ola_kernel");
   return IDV_OK;
 }
@@ -314,7 +328,7 @@ extern "C" int idv_istft_fwd(const float* spec, int B, int T, const float* basis
   IDV_LAUNCH_CHECK("istft_frames_kernel");
   const int out_len = hop * (T - 1);
   dim3 g2(cdiv(out_len, 256), B);
-  ola_kernel<<<g2, 256, 0, st>>>(frames, win, wsq, T, n_fft, hop, win, out_len, out);
+  ola_kernel<<<g2, 256, 0, st>>>(frames, win, wsq, T, n_fft, hop, win, out_len, nullptr, out);
   IDV_LAUNCH_CHECK("ola_kernel");
   return IDV_OK;
 }

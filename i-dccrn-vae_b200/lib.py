@@ -11,7 +11,7 @@ from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
-ABI_VERSION = 3        # IDV_ABI_VERSION of include/idv.h this binding was written against
+ABI_VERSION = 5        # IDV_ABI_VERSION of include/idv.h this binding was written against
 
 c_f32p = ctypes.c_void_p
 i32, i64, u64, f32, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_void_p
@@ -26,9 +26,9 @@ SIGNATURES = {
                        i32, i32, f32, i32, vp],
     "idv_tapgemm_tc_head": [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, vp, vp, i32, vp, i32, i64, i64,
                             i32, i32, f32, i32, i32, i32, i32, vp, vp, i32, vp],
-    "idv_stft_frames_split": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    "idv_stft_frames_split": [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],
     "idv_spec_rows_split": [vp, i32, i32, i32, i32, vp, vp],
-    "idv_ola_fwd": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp],
+    "idv_ola_fwd": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp],
     "idv_enc0_fwd": [vp, i32, i32, i32, vp, vp, i32, f32, vp, i32, i32, i32, vp, i32, vp],
     "idv_dec5_head_fwd": [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, i32, i32, vp],
     "idv_lstm_recurrent_fwd": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, i32, vp],

@@ -60,12 +60,15 @@ class STFT(nn.Module):
         self.win_length = win_length
         self.window = torch.hann_window(self.win_length).to(device)   # plain attribute like the reference
         self._basis = None
+        self.lengths = None        # int32 (B,) true sample counts of a zero-padded ragged batch (pipeline.enhance_ragged)
 
     def forward(self, signal):
         if ops.use_split():                            # tensor-core DFT GEMM
             if getattr(self, "_tc", None) is None or self._tc["bias"].device != signal.device:
                 self._tc = pack.pack_stft_tc(self.n_fft, self.win_length, signal.device)
-            return ops.stft_tc(signal, self._tc, self.n_fft, self.hop_length, self.win_length)
+            return ops.stft_tc(signal, self._tc, self.n_fft, self.hop_length, self.win_length, self.lengths)
+        if self.lengths is not None:
+            raise NotImplementedError("ragged batches run on the tensor-core path (IDV_GEMM=tc)")
         if self._basis is None or self._basis.device != signal.device:
             self._basis = pack.pack_stft_basis(self.n_fft, self.win_length, signal.device)
         return ops.stft(signal, self._basis, self.n_fft, self.hop_length, self.win_length)
@@ -77,6 +80,7 @@ class ISTFT(nn.Module):
         self.n_fft, self.hop_length, self.win_length = n_fft, hop_length, win_length
         self.window = torch.hann_window(self.win_length).to(device)
         self._basis = None
+        self.lengths = None        # see STFT.lengths
 
     def _ensure(self, device):
         if self._basis is None or self._basis[0].device != device:
@@ -87,7 +91,9 @@ class ISTFT(nn.Module):
         if ops.use_split():
             if getattr(self, "_tc", None) is None or self._tc["bias"].device != spec_ri.device:
                 self._tc = pack.pack_istft_tc(self.n_fft, self.win_length, spec_ri.device)
-            return ops.istft_tc(spec_ri, self._tc, self.n_fft, self.hop_length, self.win_length)
+            return ops.istft_tc(spec_ri, self._tc, self.n_fft, self.hop_length, self.win_length, self.lengths)
+        if self.lengths is not None:
+            raise NotImplementedError("ragged batches run on the tensor-core path (IDV_GEMM=tc)")
         basis, wsq = self._ensure(spec_ri.device)
         return ops.istft(spec_ri, basis, wsq, self.n_fft, self.hop_length, self.win_length)
 

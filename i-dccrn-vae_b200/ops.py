@@ -93,9 +93,18 @@ def istft(spec_ri, basis, wsq, n_fft, hop, win):
     return out
 
 
-def stft_tc(x, hp, n_fft, hop, win):
+def _lengths_arg(lengths, B, device):
+    if lengths is None:
+        return None
+    if not isinstance(lengths, torch.Tensor) or lengths.dtype != torch.int32 or lengths.numel() != B:
+        raise RuntimeError("lengths must be an int32 tensor with one entry per utterance")
+    return lengths.to(device).contiguous()
+
+
+def stft_tc(x, hp, n_fft, hop, win, lengths=None):
     """STFT on the tensor cores: frames (split bf16) -> one tap-GEMM against the windowed DFT basis whose
-    epilogue writes the reference layout (B, nbins, T, 2)."""
+    epilogue writes the reference layout (B, nbins, T, 2).  lengths: int32 (B,) true sample counts of a zero-padded
+    ragged batch (reflect padding at every utterance's own end)."""
     x = lib.require_f32_cuda(x, "signal")
     if x.dim() != 2:
         raise RuntimeError("signal must be (B, L), got %s" % (tuple(x.shape),))
@@ -103,14 +112,14 @@ def stft_tc(x, hp, n_fft, hop, win):
     T = L // hop + 1
     R = B * T
     frames = torch.empty(2 * R * hp["kpad"], dtype=torch.bfloat16, device=x.device)
-    lib.call("idv_stft_frames_split", x, B, L, n_fft, hop, win, hp["kpad"], frames)
+    lib.call("idv_stft_frames_split", x, B, L, n_fft, hop, win, hp["kpad"], _lengths_arg(lengths, B, x.device), frames)
     out = torch.empty((B, hp["nbins"], T, 2), dtype=torch.float32, device=x.device)
     lib.call("idv_tapgemm_tc_head", frames, hp["kpad"], 1, None, 0, 0, R, T, hp["wt"], hp["kc_max"], 1, hp["bias"],
              hp["N"], hp["units"], hp["taps"], 1, None, 0, 0, 0, 0, 0, 0.0, 3, hp["nbins"], 1, 0, None, out, 0)
     return out
 
 
-def istft_tc(spec_ri, hp, n_fft, hop, win):
+def istft_tc(spec_ri, hp, n_fft, hop, win, lengths=None):
     spec_ri = lib.require_f32_cuda(spec_ri, "spectrum")
     B, nb, T, _ = spec_ri.shape
     if nb != hp["nbins"]:
@@ -123,7 +132,7 @@ def istft_tc(spec_ri, hp, n_fft, hop, win):
     lib.call("idv_tapgemm_tc", rows, hp["kpad"], 1, None, 0, 0, R, 0, hp["wt"], hp["kc_max"], 1, hp["bias"], N,
              hp["units"], hp["taps"], 1, frames, N, R * N, 0, 0, 0, 0.0, 0)
     out = torch.empty((B, hop * (T - 1)), dtype=torch.float32, device=spec_ri.device)
-    lib.call("idv_ola_fwd", frames, N, hp["wsq"], B, T, n_fft, hop, win, out)
+    lib.call("idv_ola_fwd", frames, N, hp["wsq"], B, T, n_fft, hop, win, _lengths_arg(lengths, B, spec_ri.device), out)
     return out
 
 

@@ -40,7 +40,7 @@ extern "C" {
 #define IDV_E_CUDA 2     /* CUDA runtime error (message has the cudaError string) */
 #define IDV_E_RESOURCE 3 /* kernel cannot be made resident (cooperative launch too large) */
 
-#define IDV_ABI_VERSION 4
+#define IDV_ABI_VERSION 5
 
 int idv_abi_version(void);
 const char* idv_last_error(void);
@@ -125,12 +125,16 @@ int idv_istft_fwd(const float* spec, int B, int T, const float* basis, const flo
  *   idv_tapgemm_tc_head(head = 3): D = frames . basis^T, column pair (2k, 2k+1) of row (b,t) is written to
  *                          predict[(b*head_fout + k)*Tp + t] (Tp = frames per utterance; no bias, no pad rows);
  *   idv_spec_rows_split:   spec (B, nbins, T, 2) -> split-bf16 rows [2][B*T][kpad], rows[(b,t)][2k+part];
- *   idv_ola_fwd:           frames (B*T, frame_ld) -> overlap-add / window envelope / centre trim -> (B, hop*(T-1)). */
-int idv_stft_frames_split(const float* x, int B, int L, int n_fft, int hop, int win, int kpad, void* out,
-                          void* stream);
+ *   idv_ola_fwd:           frames (B*T, frame_ld) -> overlap-add / window envelope / centre trim -> (B, hop*(T-1)).
+ * Ragged batches: lengths (device int32 [B], NULL = all L) gives the true sample count of every utterance of the
+ * zero-padded batch: the framing reflects at each utterance's own end and zeroes the frames beyond its last one, the
+ * overlap-add uses each utterance's own frame count for the envelope and zeroes the samples beyond hop*(T_b-1) - so a
+ * padded batch of the causal network reproduces the per-utterance results exactly.                              */
+int idv_stft_frames_split(const float* x, int B, int L, int n_fft, int hop, int win, int kpad, const int* lengths,
+                          void* out, void* stream);
 int idv_spec_rows_split(const float* spec, int B, int nbins, int T, int kpad, void* out, void* stream);
 int idv_ola_fwd(const float* frames, int frame_ld, const float* wsq, int B, int T, int n_fft, int hop, int win,
-                float* out, void* stream);
+                const int* lengths, float* out, void* stream);
 
 /* ---- first encoder layer (Cin = 1) -------------------------------------------------------------
  * Encoder 0: ComplexConv2d(1 -> Cout, (5,2), stride (2,1), freq pad 2) + CBN(eval) + PReLU,

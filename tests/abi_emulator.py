@@ -212,12 +212,15 @@ def idv_istft_fwd(spec, B, T, basis, wsq, n_fft, hop, win, frames, out):
     out.copy_((y[:, h:total - h] / env[h:total - h]).to(torch.float32))
 
 
-def idv_stft_frames_split(x, B, L, n_fft, hop, win, kpad, out):
+def idv_stft_frames_split(x, B, L, n_fft, hop, win, kpad, lengths, out):
     T = L // hop + 1
     off = (n_fft - win) // 2
-    xp = torch.nn.functional.pad(x.view(B, 1, L).to(D), (n_fft // 2, n_fft // 2), mode="reflect")[:, 0]
     fr = torch.zeros(B, T, kpad, dtype=D)
-    fr[:, :, :win] = xp.unfold(1, n_fft, hop)[:, :T, off:off + win]
+    for b in range(B):
+        Lb = L if lengths is None else min(int(lengths[b]), L)
+        Tb = Lb // hop + 1
+        xp = torch.nn.functional.pad(x.view(B, 1, L)[b:b + 1, :, :Lb].to(D), (n_fft // 2, n_fft // 2), mode="reflect")[0, 0]
+        fr[b, :Tb, :win] = xp.unfold(0, n_fft, hop)[:Tb, off:off + win]
     _wr(out, 1, fr)
 
 
@@ -227,17 +230,21 @@ def idv_spec_rows_split(spec, B, nbins, T, kpad, out):
     _wr(out, 1, rows)
 
 
-def idv_ola_fwd(frames, frame_ld, wsq, B, T, n_fft, hop, win, out):
+def idv_ola_fwd(frames, frame_ld, wsq, B, T, n_fft, hop, win, lengths, out):
     off = (n_fft - win) // 2
     fr = frames.view(B, T, frame_ld)[:, :, :win].to(D)
-    total = n_fft + hop * (T - 1)
-    y = torch.zeros(B, total, dtype=D)
-    env = torch.zeros(total, dtype=D)
-    for t in range(T):
-        y[:, t * hop + off:t * hop + off + win] += fr[:, t]
-        env[t * hop + off:t * hop + off + win] += wsq.to(D)
     h = n_fft // 2
-    out.copy_((y[:, h:total - h] / env[h:total - h]).to(torch.float32))
+    res = torch.zeros(B, hop * (T - 1), dtype=D)
+    for b in range(B):
+        Tb = T if lengths is None else min(int(lengths[b]) // hop + 1, T)
+        total = n_fft + hop * (Tb - 1)
+        y = torch.zeros(total, dtype=D)
+        env = torch.zeros(total, dtype=D)
+        for t in range(Tb):
+            y[t * hop + off:t * hop + off + win] += fr[b, t]
+            env[t * hop + off:t * hop + off + win] += wsq.to(D)
+        res[b, :hop * (Tb - 1)] = y[h:total - h] / env[h:total - h]
+    out.copy_(res.to(torch.float32))
 
 
 def idv_enc0_fwd(stft, B, Fin, T, w, bias, Cout, slope, out, out_split=0, causal=1, t_valid=0, prev=None, keep_pad=0):

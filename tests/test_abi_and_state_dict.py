@@ -29,7 +29,8 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     assert set(syms) == set(lib.EXPORTS), set(syms) ^ set(lib.EXPORTS)
     cdll.idv_abi_version.restype = ctypes.c_int
-    assert cdll.idv_abi_version() == 4
+    from idccrn_b200 import lib as _lib
+    assert cdll.idv_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_product_has_no_cpu_fallback():

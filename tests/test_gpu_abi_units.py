@@ -432,8 +432,10 @@ def test_stft_istft_tensor_core_pieces(B, L):
     hp = PK.pack_stft_tc(512, 400, "cpu")
     x = _rand(B, L, seed=5)
     frames = torch.zeros(2 * R * hp["kpad"], dtype=torch.bfloat16)
-    assert _both("idv_stft_frames_split", [x, B, L, 512, 100, 400, hp["kpad"], frames], [7]) < 1e-7
-    E.call("idv_stft_frames_split", x, B, L, 512, 100, 400, hp["kpad"], frames)
+    assert _both("idv_stft_frames_split", [x, B, L, 512, 100, 400, hp["kpad"], None, frames], [8]) < 1e-7
+    lens = torch.tensor([max(257, L - 173 * b) for b in range(B)], dtype=torch.int32)          # ragged batch
+    assert _both("idv_stft_frames_split", [x, B, L, 512, 100, 400, hp["kpad"], lens, frames], [8]) < 1e-7
+    E.call("idv_stft_frames_split", x, B, L, 512, 100, 400, hp["kpad"], None, frames)
     out = torch.zeros(B, 257, T, 2)
     args = [frames, hp["kpad"], 1, None, 0, 0, R, T, hp["wt"], hp["kc_max"], 1, hp["bias"], hp["N"], hp["units"],
             hp["taps"], 1, None, 0, 0, 0, 0, 0, 0.0, 3, 257, 1, 0, None, out, 0]
@@ -443,7 +445,8 @@ def test_stft_istft_tensor_core_pieces(B, L):
     rows = torch.zeros(2 * R * ip["kpad"], dtype=torch.bfloat16)
     assert _both("idv_spec_rows_split", [spec, B, 257, T, ip["kpad"], rows], [5]) < 1e-7
     fr = _rand(R, 512, seed=7)
-    assert _both("idv_ola_fwd", [fr, 512, ip["wsq"], B, T, 512, 100, 400, torch.zeros(B, 100 * (T - 1))], [8]) < 1e-5
+    assert _both("idv_ola_fwd", [fr, 512, ip["wsq"], B, T, 512, 100, 400, None, torch.zeros(B, 100 * (T - 1))], [9]) < 1e-5
+    assert _both("idv_ola_fwd", [fr, 512, ip["wsq"], B, T, 512, 100, 400, lens, torch.full((B, 100 * (T - 1)), 3.0)], [9]) < 1e-5
 
 
 @pytest.mark.parametrize("B,L", [(1, 300), (3, 6400), (5, 1999)])
@@ -464,7 +467,7 @@ def test_sisnr_and_ola_backward(B, L):
     # adjoint identity: <ola(f), s> == <f, ola_bwd(s)>
     fr = _rand(B * T, 448, seed=34).cuda()
     out = torch.zeros(B, Ls).cuda()
-    lib.call("idv_ola_fwd", fr, 448, wsq.cuda(), B, T, 512, hop, 400, out)
+    lib.call("idv_ola_fwd", fr, 448, wsq.cuda(), B, T, 512, hop, 400, None, out)
     dfr = torch.zeros(B * T, 448).cuda()
     lib.call("idv_ola_bwd", dsig.cuda(), wsq.cuda(), B, T, 512, hop, 400, 448, dfr)
     lhs, rhs = float((out.double() * dsig.cuda().double()).sum()), float((fr[:, :400].double() * dfr[:, :400].double()).sum())

@@ -42,7 +42,7 @@ def _sisnr_gap_db(ours, ref, anchor):
 def test_extension_is_loaded_and_native():
     from idccrn_b200 import lib
     l = lib.load()
-    assert l.idv_abi_version() == 4
+    assert l.idv_abi_version() == lib.ABI_VERSION
     import ctypes
     n = ctypes.c_int(0)
     assert l.idv_device_sm_count(ctypes.byref(n)) == 0 and n.value > 0

@@ -1,0 +1,69 @@
+"""Ragged batches: utterances of different lengths, zero-padded into length buckets, must give exactly
+what the reference gives for each utterance ALONE (it never batches inference): the STFT reflects at each utterance's
+own end and the iSTFT normalises / trims with its own frame count.  Checked against the oracle run per utterance."""
+import pytest
+import torch
+
+import common as C
+from idccrn_b200 import ragged
+from idccrn_b200.synth import synth_eps, synth_waveform
+from oracle import ref_port as P
+
+
+def test_bucket_batches_host_logic():
+    lens = [64000, 63000, 16000, 15900, 15000, 700, 64000]
+    b = ragged.bucket_batches(lens, max_batch=3, max_pad_frac=0.1)
+    assert sorted(i for idx, _ in b for i in idx) == list(range(len(lens)))          # every utterance exactly once
+    for idx, L in b:
+        assert len(idx) <= 3 and L % 100 == 0 and L >= max(lens[i] for i in idx)
+        assert 1.0 - sum(lens[i] for i in idx) / float(L * len(idx)) <= 0.1 + 1e-9
+    assert ragged.bucket_batches([500], 8, 0.0) == [([0], 500)]
+    assert ragged.bucket_batches([], 8) == []
+    with pytest.raises(ValueError):
+        ragged.bucket_batches([100, 0], 8)
+
+
+def run_ragged(device, dec_kind, recon_type, tol):
+    lens = [2350, 1200, 2312, 777, 1999]                                             # not multiples of the hop
+    seed = 40
+    enc, dec = C.build_vae(1, 1, dec_kind, recon_type, seed, device)
+    waves = [synth_waveform(1, L, seed=900 + i)[0] for i, L in enumerate(lens)]
+    eps_all = {i: synth_eps((1, 1, L // C.HOP + 1, C.ZDIM), seed=50 + i, n=2) for i, L in enumerate(lens)}
+
+    def eps_fn(idx, frames):
+        out = [torch.zeros(len(idx), 1, frames, C.ZDIM) for _ in range(2)]
+        for r, i in enumerate(idx):
+            for k in range(2):
+                out[k][r, :, :eps_all[i][k].shape[2]] = eps_all[i][k][0]
+        return [o.to(device) for o in out]
+
+    kw = {"pad": "sig"} if dec_kind == "twophase" else {}
+    got = ragged.enhance_ragged(waves, enc, dec, device, max_batch=3, max_pad_frac=0.5, decoder_kwargs=kw, eps_fn=eps_fn)
+    assert enc.stft.lengths is None and dec.istft.lengths is None
+    esd = {k: v.cpu() for k, v in enc.state_dict().items()}
+    dsd = {k: v.cpu() for k, v in dec.state_dict().items()}
+    for i, w in enumerate(waves):
+        with torch.no_grad():
+            st = P.vae_encoder_forward(esd, w[None], C.ZDIM, 1, 1, eps_all[i])
+            dd = P.vae_decoder_forward(dsd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], 1, recon_type,
+                                       "sig" if dec_kind == "twophase" else "zero")
+        assert got[i].shape == dd["recon_sig"][0].shape == (C.HOP * (lens[i] // C.HOP),)
+        err = C.rel_l2(got[i], dd["recon_sig"][0])
+        assert err < tol, (i, lens[i], err)
+
+
+@pytest.mark.parametrize("dec_kind,recon_type", [("skip_prepare", "real_imag"), ("twophase", "mask")])
+def test_ragged_batch_equals_per_utterance_oracle_emulated(emulated_abi, dec_kind, recon_type):
+    from idccrn_b200 import ops
+    old = ops.GEMM_MODE[0]
+    ops.set_gemm_mode("tc")
+    try:
+        run_ragged("cpu", dec_kind, recon_type, 5e-5)
+    finally:
+        ops.set_gemm_mode(old)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dec_kind,recon_type", [("skip_prepare", "real_imag"), ("twophase", "mask")])
+def test_ragged_batch_equals_per_utterance_oracle_gpu(dec_kind, recon_type):
+    run_ragged("cuda", dec_kind, recon_type, 1e-4)
