@@ -1,6 +1,6 @@
 """idccrn_b200 — B200-native (sm_100a) implementation of the I-DCCRN-VAE enhancement forward path behind
 the reference's torch.nn.Module API.  See DESIGN.md / INTEGRATION.md."""
-from . import build, compat, config, lib, netconfig, ops, pack, pipeline, ragged, shard, synth, modules  # noqa: F401
+from . import build, compat, config, lib, metrics, netconfig, ops, pack, pipeline, ragged, shard, synth, wavio, modules  # noqa: F401
 from .modules import *  # noqa: F401,F403
 from .modules import (STFT, ISTFT, ConvSTFT, ConviSTFT, ComplexConv2d, causal_complex_conv2d,  # noqa: F401
                       ComplexConvTranspose2d, causal_ComplexConvTranspose2d, ComplexBatchNormal,

@@ -645,6 +645,44 @@ __global__ void __launch_bounds__(256) sisnr_grad_kernel(const float* __restrict
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(loss, -(10.0 * log10(ratio)) / B);
 }
 
+// two_phase_loss.multi_recon_loss (model/nsvae_loss.py:L891-913) without its SI-SNR term: per bin of pred / ori (n bins,
+// (re, im) interleaved)  cpx = (pr-or)^2 + (pi-oi)^2,  mag = (sqrt(pr^2+pi^2+1e-6) - sqrt(or^2+or^2+1e-6))^2 - the
+// reference's ori magnitude squares the REAL part twice (L899) and that is kept.  acc[0] += inv_bt * sum cpx,
+// acc[1] += inv_bt * sum mag,  d_pred += inv_bt * (w_cpx d cpx + w_mag d mag).  HBM-bound: 16 B read (+ 8 B
+// read-modify-write of d_pred) per bin.
+__global__ void __launch_bounds__(256) spec_loss_kernel(const float2* __restrict__ pred, const float2* __restrict__ ori,
+                                                        long long n, float w_cpx, float w_mag, float inv_bt,
+                                                        float2* __restrict__ d_pred, double* __restrict__ acc) {
+  double s_c = 0, s_m = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float2 p = __ldg(pred + i), o = __ldg(ori + i);
+    const float dr = p.x - o.x, di = p.y - o.y;
+    const float pm = sqrtf(p.x * p.x + p.y * p.y + 1e-6f), om = sqrtf(o.x * o.x + o.x * o.x + 1e-6f);
+    const float dm = pm - om;
+    s_c += (double)(dr * dr + di * di);
+    s_m += (double)(dm * dm);
+    if (d_pred) {
+      const float k = 2.f * w_mag * dm / pm;
+      float2 g = d_pred[i];
+      g.x += inv_bt * (2.f * w_cpx * dr + k * p.x);
+      g.y += inv_bt * (2.f * w_cpx * di + k * p.y);
+      d_pred[i] = g;
+    }
+  }
+  __shared__ double red[2][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    s_c += __shfl_down_sync(0xffffffffu, s_c, o);
+    s_m += __shfl_down_sync(0xffffffffu, s_m, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s_c; red[1][threadIdx.x >> 5] = s_m; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    atomicAdd(acc + threadIdx.x, t * (double)inv_bt);
+  }
+}
+
 // adjoint of idv_ola_fwd: dframes[(b,t)][j] = dsig[b][hop*t - (n_fft/2 - off) + j] / env  for j < win (0 elsewhere / beyond)
 __global__ void __launch_bounds__(256) ola_bwd_kernel(const float* __restrict__ dsig, const float* __restrict__ wsq, int T,
                                                       int n_fft, int hop, int win, int out_len, int frame_ld,
@@ -902,6 +940,19 @@ extern "C" int idv_sisnr_fwd_bwd(const float* src, const float* est, int B, int 
   IDV_LAUNCH_CHECK("sisnr_reduce_kernel");
   sisnr_grad_kernel<<<grid, 256, 0, st>>>(src, est, B, L, sums, scale, d_est, loss);
   IDV_LAUNCH_CHECK("sisnr_grad_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_spec_loss_fwd_bwd(const float* pred, const float* ori, int64_t n_bins, float w_cpx, float w_mag,
+                                     float inv_bt, float* d_pred, double* acc, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(pred && ori && acc && n_bins > 0, "idv_spec_loss_fwd_bwd: bad argument");
+  long long blocks = (n_bins + 256 * 4 - 1) / (256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  spec_loss_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(pred), reinterpret_cast<const float2*>(ori), n_bins, w_cpx, w_mag, inv_bt,
+      reinterpret_cast<float2*>(d_pred), acc);
+  IDV_LAUNCH_CHECK("spec_loss_kernel");
   return IDV_OK;
 }
 

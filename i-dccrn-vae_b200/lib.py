@@ -57,6 +57,7 @@ SIGNATURES = {
     "idv_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp],
     "idv_kl_fwd_bwd": [vp, i32, i32, vp, i32, i32, i64, i32, f32, f32, vp, vp, vp],
     "idv_sisnr_fwd_bwd": [vp, vp, i32, i32, f32, vp, vp, vp, vp],
+    "idv_spec_loss_fwd_bwd": [vp, vp, i64, f32, f32, f32, vp, vp, vp],
     "idv_ola_bwd": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "idv_head_bwd": [vp, vp, f32, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp],
     "idv_dec5_dgrad": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],

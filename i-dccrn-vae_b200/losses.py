@@ -77,3 +77,39 @@ def nsvae_kl_loss(noisy, clean, noise, zdim=128, latent_num=1, alpha=1.0):
             return base                                   # the slices of one latent tensor (no copy)
         return torch.cat(parts, dim=2)
     return _KLFn.apply(latent_of(noisy, latent_num), latent_of(clean, 1), latent_of(noise, 1), zdim, latent_num, alpha)
+
+
+class _SpecLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_ri, ori_ri, w_cpx, w_mag):
+        pred = lib.require_f32_cuda(pred_ri.detach(), "predicted spectrum")
+        ori = lib.require_f32_cuda(ori_ri.detach(), "target spectrum")
+        if pred.dim() != 4 or pred.shape[-1] != 2 or pred.shape != ori.shape:
+            raise RuntimeError("multi_recon_loss expects spectra of one shape (B, F, T, 2), got %s and %s" % (
+                tuple(pred.shape), tuple(ori.shape)))
+        B, F, T, _ = pred.shape
+        d_pred = torch.zeros_like(pred)
+        acc = torch.zeros(2, dtype=torch.float64, device=pred.device)
+        lib.call("idv_spec_loss_fwd_bwd", pred, ori, B * F * T, float(w_cpx), float(w_mag), 1.0 / (B * T), d_pred, acc)
+        ctx.save_for_backward(d_pred)
+        out = acc.to(torch.float32)
+        return w_cpx * out[0] + w_mag * out[1], out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g, g_cpx, g_mag):
+        (d_pred,) = ctx.saved_tensors
+        return g * d_pred, None, None, None
+
+
+def multi_recon_loss(predict_cpx_stft, ori_cpx_stft, source, est_source, recon_loss_weight=(0.0, 0.0, 1.0)):
+    """two_phase_loss.multi_recon_loss (model/nsvae_loss.py:L891-913): ``w0 * loss_cpx + w1 * loss_mag + w2 * si_snr``;
+    returns (final, loss_cpx, loss_mag, sisnr) like the reference.  predict_cpx_stft: (B, F, T) complex64 (the decoder's
+    ``predict``), ori_cpx_stft: (B, F, T, 2) fp32 (the STFT of the clean signal).  The spectral terms (value and the
+    gradient w.r.t. ``predict``) are ONE fused pass, ``idv_spec_loss_fwd_bwd``; the reference's ori magnitude
+    ``sqrt(re^2 + re^2 + 1e-6)`` (L899) is reproduced.  Gradients reach ``predict`` (weights 0 and 1) and ``est_source``
+    (weight 2) only - the reference's targets carry no gradient either."""
+    w = [float(v) for v in recon_loss_weight]
+    pred_ri = torch.view_as_real(predict_cpx_stft) if predict_cpx_stft.is_complex() else predict_cpx_stft
+    spec, l_cpx, l_mag = _SpecLossFn.apply(pred_ri, ori_cpx_stft, w[0], w[1])
+    l_si = si_snr_loss(source, est_source)
+    return spec + w[2] * l_si, l_cpx, l_mag, l_si

@@ -298,7 +298,13 @@ int idv_kl_fwd_bwd(const float* lat1, int H1, int ch1, const float* lat2, int H2
 
 /* ---- decoder side of the training step (train_second_phase_decoder.py:L376-433: SI-SNR through the decoder) -------
  *   idv_sisnr_fwd_bwd: si_snr (model/nsvae_loss.py:L877-889) of est (B, L) against src (B, L): loss[0] += -mean_b snr_b,
- *       d_est (may be NULL) += scale * d loss / d est; sums: B*3 doubles of workspace;
+ *       d_est (may be NULL) += scale * d loss / d est; sums (B*3 doubles, overwritten) <- per utterance <est,src>, |src|^2,
+ *       |est|^2 (what a per-utterance SI-SDR score needs, utils/eval_metrics.py:L49-64);
+ *   idv_spec_loss_fwd_bwd: the two spectral terms of two_phase_loss.multi_recon_loss (model/nsvae_loss.py:L891-906):
+ *       pred / ori = n_bins (re, im) pairs ((B, F, T, 2) fp32); acc[0] += inv_bt * sum |pred - ori|^2,
+ *       acc[1] += inv_bt * sum (|pred|_eps - |ori|_quirk)^2 with |ori|_quirk = sqrt(or^2 + or^2 + 1e-6) (the reference
+ *       squares the real part twice, L899); d_pred (may be NULL) += inv_bt * (w_cpx d/dpred cpx + w_mag d/dpred mag);
+ *       inv_bt = 1 / (B * T) (the reference averages over batch and frames, sums over bins);
  *   idv_ola_bwd: adjoint of idv_ola_fwd: dframes (B*T, frame_ld) <- dsig (B, hop*(T-1)) / window envelope;
  *   idv_head_bwd: backward of the reconstruction head (real_imag: identity; mask: model/pvae_module.py:L2594-2609) for
  *       the last decoder layer.  raw (NB, F, T, 2) = transposed-conv output before ComplexBatchNormal, zb[6] its batch
@@ -307,6 +313,8 @@ int idv_kl_fwd_bwd(const float* lat1, int H1, int ch1, const float* lat2, int H2
  *       y_planes <- raw and g_planes <- gradient w.r.t. the PReLU output, ready for idv_cbn_bwd_*.                  */
 int idv_sisnr_fwd_bwd(const float* src, const float* est, int B, int L, float scale, float* d_est, double* sums,
                       double* loss, void* stream);
+int idv_spec_loss_fwd_bwd(const float* pred, const float* ori, int64_t n_bins, float w_cpx, float w_mag, float inv_bt,
+                          float* d_pred, double* acc, void* stream);
 int idv_ola_bwd(const float* dsig, const float* wsq, int B, int T, int n_fft, int hop, int win, int frame_ld,
                 float* dframes, void* stream);
 int idv_head_bwd(const float* raw, const float* zb, float slope, int mask, const float* stft_x, const float* drows,

@@ -830,8 +830,26 @@ def idv_sisnr_fwd_bwd(src, est, B, L, scale, d_est, sums, loss):
         lo = -snr.mean()
         (g,) = torch.autograd.grad(lo, e)
     loss[0] += float(lo)
+    sums.view(B, 3).copy_(torch.stack([(e * s).sum(1), (s * s).sum(1), (e * e).sum(1)], 1).detach())
     if d_est is not None:
         d_est.view(B, L).add_((scale * g).to(torch.float32))
+
+
+def idv_spec_loss_fwd_bwd(pred, ori, n_bins, w_cpx, w_mag, inv_bt, d_pred, acc):
+    """Contract = the two spectral terms of multi_recon_loss (model/nsvae_loss.py:L891-906, restated, the ori-magnitude
+    quirk of L899 included) differentiated by autograd."""
+    with torch.enable_grad():
+        p = pred.reshape(n_bins, 2).to(D).detach().clone().requires_grad_(True)
+        o = ori.reshape(n_bins, 2).to(D)
+        cpx = (((p[:, 0] - o[:, 0]) ** 2).sum() + ((p[:, 1] - o[:, 1]) ** 2).sum()) * inv_bt
+        pm = torch.sqrt(p[:, 0] ** 2 + p[:, 1] ** 2 + 1e-6)
+        om = torch.sqrt(o[:, 0] ** 2 + o[:, 0] ** 2 + 1e-6)
+        mag = ((pm - om) ** 2).sum() * inv_bt
+        (g,) = torch.autograd.grad(w_cpx * cpx + w_mag * mag, p)
+    acc[0] += float(cpx)
+    acc[1] += float(mag)
+    if d_pred is not None:
+        d_pred.view(n_bins, 2).add_(g.to(torch.float32))
 
 
 def idv_ola_bwd(dsig, wsq, B, T, n_fft, hop, win, frame_ld, dframes):

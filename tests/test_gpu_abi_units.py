@@ -449,12 +449,23 @@ def test_stft_istft_tensor_core_pieces(B, L):
     assert _both("idv_ola_fwd", [fr, 512, ip["wsq"], B, T, 512, 100, 400, lens, torch.full((B, 100 * (T - 1)), 3.0)], [9]) < 1e-5
 
 
+@pytest.mark.parametrize("n,w", [(1, (1.0, 1.0)), (257 * 33 * 2, (0.3, 0.7)), (100003, (1.0, 0.0)), (4099, (0.0, 0.0))])
+def test_spec_loss(n, w):
+    pred, ori = _rand(n, 2, seed=40), _rand(n, 2, seed=41)
+    pred[: n // 7] = 0.0                                       # |pred| = 0: the 1e-6 under the root keeps d|pred| finite
+    d_pred = _rand(n, 2, seed=42) * 0.01                       # accumulates (+=)
+    acc = torch.full((2,), 0.25, dtype=torch.float64)
+    assert _both("idv_spec_loss_fwd_bwd", [pred, ori, n, w[0], w[1], 1.0 / 66, d_pred, acc], [6, 7]) < 2e-5
+    acc2 = torch.zeros(2, dtype=torch.float64)
+    assert _both("idv_spec_loss_fwd_bwd", [pred, ori, n, w[0], w[1], 1.0 / 66, None, acc2], [7]) < 2e-5
+
+
 @pytest.mark.parametrize("B,L", [(1, 300), (3, 6400), (5, 1999)])
 def test_sisnr_and_ola_backward(B, L):
     src, est = _rand(B, L, seed=30), _rand(B, L, seed=31) * 0.5 + 0.3 * _rand(B, L, seed=30)
     d_est = _rand(B, L, seed=32) * 0.01                       # accumulates (+=)
     sums, loss = torch.zeros(B * 3, dtype=torch.float64), torch.full((1,), 0.5, dtype=torch.float64)
-    assert _both("idv_sisnr_fwd_bwd", [src, est, B, L, 0.7, d_est, sums, loss], [5, 7]) < 2e-5
+    assert _both("idv_sisnr_fwd_bwd", [src, est, B, L, 0.7, d_est, sums, loss], [5, 6, 7]) < 2e-5
     from idccrn_b200 import pack as PK
     hop = 100
     Ls = L // hop * hop

@@ -67,3 +67,46 @@ def test_ragged_batch_equals_per_utterance_oracle_emulated(emulated_abi, dec_kin
 @pytest.mark.parametrize("dec_kind,recon_type", [("skip_prepare", "real_imag"), ("twophase", "mask")])
 def test_ragged_batch_equals_per_utterance_oracle_gpu(dec_kind, recon_type):
     run_ragged("cuda", dec_kind, recon_type, 1e-4)
+
+
+def test_wav_round_trip(tmp_path):
+    import numpy as np
+    import wave
+    from idccrn_b200 import wavio
+    x = (0.3 * np.sin(np.arange(4321) * 0.05)).astype(np.float32)
+    p = str(tmp_path / "a.wav")
+    wavio.write_wav(p, x)
+    with wave.open(p) as w:                                                  # the stdlib reader accepts what we wrote
+        assert (w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()) == (16000, 1, 2, 4321)
+        ref = np.frombuffer(w.readframes(4321), dtype="<i2").astype(np.float32) / 32768.0
+    y, fs = wavio.read_wav(p)
+    assert fs == 16000 and y.dtype == np.float32 and np.array_equal(y, ref) and np.abs(y - x).max() <= 0.5 / 32768 + 1e-7
+    with wave.open(str(tmp_path / "st.wav"), "w") as w:                      # stereo 8 kHz written by the stdlib
+        w.setnchannels(2), w.setsampwidth(2), w.setframerate(8000)
+        w.writeframes(np.stack([ref, -ref], 1).astype(np.float32).__mul__(32768).astype("<i2").tobytes())
+    y2, fs2 = wavio.read_wav(str(tmp_path / "st.wav"))
+    assert fs2 == 8000 and len(y2) == 4321 and np.abs(y2).max() == 0.0       # mono = mean of the channels
+    with pytest.raises(ValueError):
+        wavio.load_utterances([str(tmp_path / "st.wav")])
+    assert wavio.load_utterances([p])[0].shape == (4321,)
+
+
+def run_si_sdr(device):
+    from idccrn_b200 import metrics
+    ref = synth_waveform(4, 3000, seed=5)
+    est = 0.7 * ref + 0.05 * synth_waveform(4, 3000, seed=6)
+    ref[2, 2000:] = 0
+    est[2, 2000:] = 0                                                        # a zero-padded shorter utterance
+    got = metrics.si_sdr(est.to(device), ref.to(device)).cpu()
+    want = P.si_sdr_db(est, ref)
+    want[2] = P.si_sdr_db(est[2, :2000], ref[2, :2000])
+    assert torch.allclose(got, want, atol=1e-4), (got, want)
+
+
+def test_si_sdr_emulated(emulated_abi):
+    run_si_sdr("cpu")
+
+
+@pytest.mark.gpu
+def test_si_sdr_gpu():
+    run_si_sdr("cuda")

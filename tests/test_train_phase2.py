@@ -28,10 +28,11 @@ def run_phase2(golden, tag, device, fused_sisnr=False):
         stft_clean = enc.stft(xs[1])
     sig, pred = dec(r[11], r[0], r[8], r[9], r[10], train=True, pad="sig")
     assert sig.grad_fn is not None and pred.grad_fn is not None
-    if fused_sisnr:
+    if fused_sisnr:                     # the product's fused loss kernels (idv_spec_loss_fwd_bwd + idv_sisnr_fwd_bwd)
         from idccrn_b200 import losses
-        assert weights[0] == 0 and weights[1] == 0
-        loss = weights[2] * losses.si_snr_loss(xs[1], sig)
+        loss, l_cpx, l_mag, l_si = losses.multi_recon_loss(pred, stft_clean, xs[1], sig, weights)
+        for k, v in (("loss_cpx", l_cpx), ("loss_mag", l_mag), ("loss_sisnr", l_si)):
+            assert abs(float(v) - float(g[k])) <= 2e-5 * max(1.0, abs(float(g[k]))), (k, float(v), float(g[k]))
     else:
         loss, l_cpx, l_mag, l_si = P.multi_recon_loss(pred, stft_clean, xs[1], sig, weights)   # the reference's formula
     loss.backward()
@@ -112,11 +113,12 @@ def test_phase2_gradients_emulated(emulated_abi, golden, tag):
         ops.set_gemm_mode(old)
 
 
-def test_phase2_fused_sisnr_emulated(emulated_abi, golden):
+@pytest.mark.parametrize("tag", ["train_phase2_mask_sisnr", "train_phase2_ri_multi"])
+def test_phase2_fused_loss_emulated(emulated_abi, golden, tag):
     from idccrn_b200 import ops
     old = _tc_mode()
     try:
-        check_phase2(*run_phase2(golden, "train_phase2_mask_sisnr", "cpu", fused_sisnr=True), tol=2e-4)
+        check_phase2(*run_phase2(golden, tag, "cpu", fused_sisnr=True), tol=2e-4)
     finally:
         ops.set_gemm_mode(old)
 
@@ -128,5 +130,6 @@ def test_phase2_gradients_gpu(golden, tag):
 
 
 @pytest.mark.gpu
-def test_phase2_fused_sisnr_gpu(golden):
-    check_phase2(*run_phase2(golden, "train_phase2_mask_sisnr", "cuda", fused_sisnr=True), tol=5e-4)
+@pytest.mark.parametrize("tag", ["train_phase2_mask_sisnr", "train_phase2_ri_multi"])
+def test_phase2_fused_loss_gpu(golden, tag):
+    check_phase2(*run_phase2(golden, tag, "cuda", fused_sisnr=True), tol=5e-4)
