@@ -12,6 +12,7 @@ namespace idv {
 void set_error(const char* fmt, ...);
 int option_lstm_ncols();
 int option_dynamic_tiles();
+int option_gemm_pairs();
 
 #define IDV_CHECK_ARG(cond, ...)             \
   do {                                       \

@@ -47,23 +47,33 @@ struct Params {
   unsigned int* sched;        // [0] next tile, [1] CTAs finished (dynamic tile scheduler; self-resetting)
 };
 
-template <int BN>
+// TWO: the kernel runs as CTA PAIRS (thread-block clusters of 2, tcgen05 cta_group::2).  A pair computes a 256 x BN
+// tile: each CTA stages its own 128 activation rows and HALF of the weight tile (BN/2 rows), one thread of the even
+// CTA issues M = 256 MMAs that read both CTAs' shared memory and write both CTAs' TMEM.  Per MMA a CTA's shared
+// memory serves 4 KB (A) + BN/2 x 32 B (B) instead of 4 KB + BN x 32 B, and TMA writes half the weight bytes: the
+// shared-memory traffic (TMA writes + UMMA reads) that bounds the 1-CTA kernel drops below the math time.
+template <int BN, bool TWO = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;              // one of hi / lo
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 2 : (BN >= 128 ? 3 : 4);
+  static constexpr int STAGES = TWO ? 3 : ((BN >= 256) ? 2 : (BN >= 128 ? 3 : 4));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages, power of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // DYN = false: tile i of CTA b is b + i*gridDim.x (lock-step CTAs, best when the kernel owns the GPU);
 // DYN = true : tiles are claimed from a global counter (kernels of other streams may hold SMs).
-template <int BN, bool DYN>
+template <int BN, bool DYN, bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW, const Params p) {
-  using C = Cfg<BN>;
+  static_assert(!(TWO && DYN), "the CTA-pair kernel uses the static tile schedule");
+  using C = Cfg<BN, TWO>;
+  // TWO: rank of this CTA in its pair, index / count of pairs; a "tile" is then a PAIR of row tiles (2*rt + rank)
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;
+  const int wid = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nwork = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -77,7 +87,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.n_units * p.n_row_tiles * p.n_col_tiles;
+  const int n_row_tiles = TWO ? (p.n_row_tiles + 1) / 2 : p.n_row_tiles;
+  const int total_tiles = p.n_units * n_row_tiles * p.n_col_tiles;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0);
@@ -91,7 +102,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 4);      // one arrive per epilogue warp
+      mbar_init(tempty0 + 8 * a, TWO ? 8 : 4);      // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int qi = 0; qi < 4; ++qi) {
       mbar_init(qfull0 + 8 * qi, 1);
@@ -100,11 +111,17 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     fence_barrier_init();
   }
   if (warp == EPI_WARP0) {
-    tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
-    tmem_relinquish();
+    if (TWO) {
+      tmem_alloc_2sm(smem_u32(tmem_slot), C::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();            // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -115,7 +132,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       // dynamic tile scheduler: tiles are claimed from a global counter so that any number of co-resident CTAs
       // (other kernels may hold SMs) share the work evenly; the claimed ids are handed to the MMA / epilogue
       // warps through a 4-entry shared-memory queue (-1 terminates)
-      int t_next = DYN ? (int)atomicAdd(p.sched, 1u) : (int)blockIdx.x;
+      int t_next = DYN ? (int)atomicAdd(p.sched, 1u) : wid;
       for (uint32_t qi = 0;; ++qi) {
         int t = t_next;
         if (t >= total_tiles) t = -1;
@@ -127,13 +144,14 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
         if (t < 0) break;
         // DYN: claimed one tile ahead, the atomic's latency hides behind this tile's loads
-        t_next = DYN ? (int)atomicAdd(p.sched, 1u) : t + (int)gridDim.x;
+        t_next = DYN ? (int)atomicAdd(p.sched, 1u) : t + nwork;
         const int nt = t % p.n_col_tiles;
-        const int rt = (t / p.n_col_tiles) % p.n_row_tiles;
-        const idv_unit_t unit = p.units[t / (p.n_col_tiles * p.n_row_tiles)];
+        const int rt = TWO ? 2 * ((t / p.n_col_tiles) % n_row_tiles) + (int)rank : (t / p.n_col_tiles) % n_row_tiles;
+        const idv_unit_t unit = p.units[t / (p.n_col_tiles * n_row_tiles)];
         // co-resident CTAs work on the same unit: start each at a different tap so they do not all request the
         // same weight tile (same L2 lines) at the same moment; the accumulation order is per-CTA but fixed
-        const int rot = (int)(blockIdx.x % (unsigned)unit.n_taps);
+        // (both CTAs of a pair walk the taps in the same order)
+        const int rot = (int)((unsigned)wid % (unsigned)unit.n_taps);
         for (int ti0 = 0; ti0 < unit.n_taps; ++ti0) {
           const int ti = ti0 + rot < unit.n_taps ? ti0 + rot : ti0 + rot - unit.n_taps;
           const idv_tap_t tap = p.taps[unit.tap_begin + ti];
@@ -141,9 +159,17 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           for (int k0 = 0; k0 < tap.kc; k0 += BK) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-            mbar_expect_tx(full0 + 8 * stage, C::STAGE_BYTES);
-            tma_load_4d(am, full0 + 8 * stage, sa, tap.ch_off + k0, rt * BM - tap.dt, tap.f_in, 0);
-            tma_load_4d(&tmW, full0 + 8 * stage, sa + 2 * C::A_BYTES, k0, nt * BN, tap.w_off, 0);
+            if (TWO) {
+              // the full barrier of a stage lives in the even CTA and collects the bytes of BOTH CTAs' loads
+              const uint32_t fb = (full0 + 8 * stage) & PEER_BIT_MASK;
+              if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * C::STAGE_BYTES);
+              tma_load_4d_2sm(am, fb, sa, tap.ch_off + k0, rt * BM - tap.dt, tap.f_in, 0);
+              tma_load_4d_2sm(&tmW, fb, sa + 2 * C::A_BYTES, k0, nt * BN + (int)rank * (BN / 2), tap.w_off, 0);
+            } else {
+              mbar_expect_tx(full0 + 8 * stage, C::STAGE_BYTES);
+              tma_load_4d(am, full0 + 8 * stage, sa, tap.ch_off + k0, rt * BM - tap.dt, tap.f_in, 0);
+              tma_load_4d(&tmW, full0 + 8 * stage, sa + 2 * C::A_BYTES, k0, nt * BN, tap.w_off, 0);
+            }
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -151,8 +177,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = TWO ? make_idesc_m256(BN) : make_idesc(BN);
       uint32_t stage = 0, phase = 0;
       for (uint32_t local = 0;; ++local) {
         int t;
@@ -162,11 +188,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           t = tq[qs];
           mbar_arrive(qempty0 + 8 * qs);
         } else {
-          t = (int)(blockIdx.x + local * gridDim.x);
+          t = (int)(wid + local * nwork);
           if (t >= total_tiles) t = -1;
         }
         if (t < 0) break;
-        const idv_unit_t unit = p.units[t / (p.n_col_tiles * p.n_row_tiles)];
+        const idv_unit_t unit = p.units[t / (p.n_col_tiles * n_row_tiles)];
         const int ksteps = unit.reserved;
         const uint32_t acc = local & 1, aphase = (local >> 1) & 1;
         mbar_wait(tempty0 + 8 * acc, aphase ^ 1);
@@ -182,14 +208,22 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);      // +32 B per K step inside the swizzle row
-            umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, (ks | k) != 0);
-            umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
-            umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1);
+            if (TWO) {
+              umma_bf16_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, (ks | k) != 0);
+              umma_bf16_2sm(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+              umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc, 1);
+            } else {
+              umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, (ks | k) != 0);
+              umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+              umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1);
+            }
           }
-          umma_commit(empty0 + 8 * stage);            // frees the smem slot when these MMAs retire
+          if (TWO) umma_commit_2sm(empty0 + 8 * stage, 3);   // frees the slot in BOTH CTAs when these MMAs retire
+          else umma_commit(empty0 + 8 * stage);       // frees the smem slot when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull0 + 8 * acc);                // accumulator complete -> epilogue
+        if (TWO) umma_commit_2sm(tfull0 + 8 * acc, 3);
+        else umma_commit(tfull0 + 8 * acc);           // accumulator complete -> epilogue
       }
     }
   } else {
@@ -204,13 +238,15 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(qempty0 + 8 * qs);
       } else {
-        t = (int)(blockIdx.x + local * gridDim.x);
+        t = (int)(wid + local * nwork);
         if (t >= total_tiles) t = -1;
       }
       if (t < 0) break;
       const int nt = t % p.n_col_tiles;
-      const int rt = (t / p.n_col_tiles) % p.n_row_tiles;
-      const idv_unit_t unit = p.units[t / (p.n_col_tiles * p.n_row_tiles)];
+      const int rt = TWO ? 2 * ((t / p.n_col_tiles) % n_row_tiles) + (int)rank : (t / p.n_col_tiles) % n_row_tiles;
+      const idv_unit_t unit = p.units[t / (p.n_col_tiles * n_row_tiles)];
+      // the accumulator-empty barrier the MMA issuer waits on (TWO: the even CTA's, 8 warps arrive)
+      const uint32_t tempty_bar = TWO ? ((tempty0 + 8 * (local & 1)) & PEER_BIT_MASK) : (tempty0 + 8 * (local & 1));
       const uint32_t acc = local & 1, aphase = (local >> 1) & 1;
       mbar_wait(tfull0 + 8 * acc, aphase);
       tc_fence_after();
@@ -241,7 +277,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        if (lane == 0) { if (TWO) mbar_arrive_cluster(tempty_bar); else mbar_arrive(tempty_bar); }
         continue;
       }
       if (p.head) {
@@ -251,7 +287,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        if (lane == 0) { if (TWO) mbar_arrive_cluster(tempty_bar); else mbar_arrive(tempty_bar); }
         if (row_ok && !pad_row) {
           const int T = p.Tp - 1;
           const int b = r / p.Tp, t = r % p.Tp - 1;
@@ -322,15 +358,17 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (lane == 0) { if (TWO) mbar_arrive_cluster(tempty_bar); else mbar_arrive(tempty_bar); }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();            // neither CTA leaves (or frees TMEM) while its peer may still touch it
   if (warp == EPI_WARP0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (TWO) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
   if (DYN && threadIdx.x == 0) {
     // last CTA out re-arms the scheduler slot for its next user
@@ -440,11 +478,44 @@ template <int BN, bool DYN>
 static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const Params& p, int sms,
                    cudaStream_t st) {
   using C = Cfg<BN>;
-  IDV_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<BN, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  IDV_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<BN, DYN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                C::SMEM_BYTES));
   const int total = p.n_units * p.n_row_tiles * p.n_col_tiles;
   const int grid = total < sms ? total : sms;
-  tapgemm_tc_kernel<BN, DYN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(a0, a1, w, p);
+  tapgemm_tc_kernel<BN, DYN, false><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(a0, a1, w, p);
   IDV_LAUNCH_CHECK("tapgemm_tc_kernel");
+  return IDV_OK;
+}
+
+// CTA-pair kernel: clusters of 2, as many as fit the device at once (persistent)
+template <int BN>
+static int launch_pairs(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, Params& p, cudaStream_t st) {
+  using C = Cfg<BN, true>;
+  static_assert(C::SMEM_BYTES <= 232448, "stage ring exceeds the shared memory of one SM");
+  auto kern = tapgemm_tc_kernel<BN, false, true>;
+  IDV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  static int max_pairs[64] = {0};
+  int dev = 0;
+  IDV_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!max_pairs[dev]) {
+    cfg.gridDim = dim3(2);
+    int n = 0;
+    IDV_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    IDV_CHECK_ARG(n > 0, "idv_tapgemm_tc: no CTA pair fits the device");
+    max_pairs[dev] = n;
+  }
+  const int total = p.n_units * ((p.n_row_tiles + 1) / 2) * p.n_col_tiles;
+  const int pairs = total < max_pairs[dev] ? total : max_pairs[dev];
+  cfg.gridDim = dim3(2 * pairs);
+  p.sched = nullptr;
+  IDV_CUDA(cudaLaunchKernelEx(&cfg, kern, a0, a1, w, p));
   return IDV_OK;
 }
 
@@ -511,7 +582,9 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
   } else {
     mA1 = mA0;
   }
-  rc = encode_map_4d(&mW, wt, kc_max, N, n_slots, (uint64_t)n_slots * N * kc_max, BK, BN);
+  // CTA pairs for the wide tiles (every CTA stages half of the weight tile) unless tiles are claimed dynamically
+  const bool pairs = BN == 256 && option_gemm_pairs() && !option_dynamic_tiles() && cdiv(R, BM) >= 2;
+  rc = encode_map_4d(&mW, wt, kc_max, N, n_slots, (uint64_t)n_slots * N * kc_max, BK, pairs ? BN / 2 : BN);
   if (rc) return rc;
   Params p;
   p.R = R; p.Tp = Tp < 0 ? -Tp : Tp; p.keep_pad = Tp < 0; p.N = N; p.n_units = n_units; p.t_valid = t_valid;
@@ -521,6 +594,7 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
   p.head = head; p.head_fout = head_fout; p.head_bmul = head_bmul; p.head_boff = head_boff;
   p.stft_x = stft_x; p.predict = predict;
   cudaStream_t st = (cudaStream_t)stream;
+  if (pairs) return launch_pairs<256>(mA0, mA1, mW, p, st);
   switch (BN) {
     case 256: return launch<256>(mA0, mA1, mW, p, sms, st);
     case 128: return launch<128>(mA0, mA1, mW, p, sms, st);

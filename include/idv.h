@@ -47,7 +47,9 @@ const char* idv_last_error(void);
 /* Process-wide tuning options.  "lstm_ncols": gate columns per CTA of idv_lstm_recurrent_tc (0 = auto; 64 = half as
  * many CTAs, leaves SMs free for kernels running concurrently on other streams).  "gemm_dynamic_tiles": 1 = the
  * tensor-core tap-GEMM claims its tiles from a global counter (for kernels sharing the GPU across streams),
- * 0 (default) = static round-robin tiles.                                                                      */
+ * 0 (default) = static round-robin tiles.  "gemm_cta_pairs": 1 (default) = tiles of width 256 run as CTA pairs
+ * (thread-block clusters of 2, tcgen05 cta_group::2: M = 256 MMAs, every CTA stages half of the weight tile) when the
+ * tiles are static; 0 = one CTA per tile everywhere.                                                          */
 int idv_set_option(const char* name, int value);
 /* SM count of the current device (grids are sized against it). */
 int idv_device_sm_count(int* out);

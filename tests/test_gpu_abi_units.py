@@ -316,14 +316,20 @@ def test_bad_arguments_return_error_codes():
     (1284, 642, 256, [128, 128], [-1, 0], True, True, 0, 640),  # row+1 tap at the end of the tensor (zero fill)
     (256, 2, 512, [128, 64], [1, 0], False, True, 1, 0),        # streaming-sized: few tiles -> narrow N tiles (BN 64)
     (128, 0, 1536, [192, 64], [0, 0], False, False, 0, 0),        # one LSTM step: N = 4H in 24 narrow tiles
+    (10300, 103, 256, [128, 64], [1, 0], True, True, 1, 0),     # >= 148 wide tiles: BN = 256 (CTA pairs), odd row-tile count
+    (6000, 0, 512, [64, 128], [0, 1], False, False, 0, 0),      # BN = 256, two N tiles, fp32 out
 ])
-@pytest.mark.parametrize("dynamic_tiles", [0, 1])
+@pytest.mark.parametrize("dynamic_tiles", [0, 1, 2])
 def test_tapgemm_tc(R, Tp, N, kcs, dts, two_src, prelu, out_split, tv, dynamic_tiles):
-    lib.set_option("gemm_dynamic_tiles", dynamic_tiles)
+    """dynamic_tiles: 0 = static tiles (wide tiles run as CTA pairs, cta_group::2), 1 = tiles claimed from a global
+    counter, 2 = static tiles with the CTA pairs switched off."""
+    lib.set_option("gemm_dynamic_tiles", 1 if dynamic_tiles == 1 else 0)
+    lib.set_option("gemm_cta_pairs", 0 if dynamic_tiles == 2 else 1)
     try:
         _tapgemm_tc_case(R, Tp, N, kcs, dts, two_src, prelu, out_split, tv)
     finally:
         lib.set_option("gemm_dynamic_tiles", 0)
+        lib.set_option("gemm_cta_pairs", 1)
 
 
 def _tapgemm_tc_case(R, Tp, N, kcs, dts, two_src, prelu, out_split, tv=0):
