@@ -57,7 +57,7 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;              // one of hi / lo
   static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = TWO ? 3 : ((BN >= 256) ? 2 : (BN >= 128 ? 3 : 4));
+  static constexpr int STAGES = TWO ? (BN >= 256 ? 3 : (BN >= 128 ? 4 : 5)) : ((BN >= 256) ? 2 : (BN >= 128 ? 3 : 4));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages, power of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -583,7 +583,8 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
     mA1 = mA0;
   }
   // CTA pairs for the wide tiles (every CTA stages half of the weight tile) unless tiles are claimed dynamically
-  const bool pairs = BN == 256 && option_gemm_pairs() && !option_dynamic_tiles() && cdiv(R, BM) >= 2;
+  // (large problems only: a streaming step with a handful of row tiles keeps one CTA per tile)
+  const bool pairs = option_gemm_pairs() && !option_dynamic_tiles() && cdiv(R, BM) >= 8;
   rc = encode_map_4d(&mW, wt, kc_max, N, n_slots, (uint64_t)n_slots * N * kc_max, BK, pairs ? BN / 2 : BN);
   if (rc) return rc;
   Params p;
@@ -594,7 +595,14 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
   p.head = head; p.head_fout = head_fout; p.head_bmul = head_bmul; p.head_boff = head_boff;
   p.stft_x = stft_x; p.predict = predict;
   cudaStream_t st = (cudaStream_t)stream;
-  if (pairs) return launch_pairs<256>(mA0, mA1, mW, p, st);
+  if (pairs) {
+    switch (BN) {
+      case 256: return launch_pairs<256>(mA0, mA1, mW, p, st);
+      case 128: return launch_pairs<128>(mA0, mA1, mW, p, st);
+      case 64: return launch_pairs<64>(mA0, mA1, mW, p, st);
+      default: return launch_pairs<32>(mA0, mA1, mW, p, st);
+    }
+  }
   switch (BN) {
     case 256: return launch<256>(mA0, mA1, mW, p, sms, st);
     case 128: return launch<128>(mA0, mA1, mW, p, sms, st);
