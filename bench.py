@@ -316,16 +316,20 @@ def run_ours(args):
 
 def ncu_dram_traffic(B, tc_mode):
     """DRAM bytes of the dominant kernel's launches in one step, from the committed `ncu --set full` capture of this
-    workload (profiles/r01_ncu_tapgemm_tc_full.csv, taken at batch 64): a profiler figure, never measured here."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_tapgemm_tc_full.csv")
+    workload (profiles/r01_ncu_tapgemm_tc_pairs_full.csv, taken at batch 64): a profiler figure, never measured here.
+    The capture lists all 15 tcgen05 tap-GEMM launches of a step; the 13 behind idv_tapgemm_tc (the kernel the roofline
+    object describes) are the rows that are not marked "head API"."""
+    name = "r01_ncu_tapgemm_tc_pairs_full.csv"
+    path = os.path.join(ROOT, "profiles", name)
     if not tc_mode or B != 64 or not os.path.exists(path):
         return None, "no ncu capture for this configuration"
     import csv
     rows = list(csv.reader(open(path)))
     hdr = rows[0]
     ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-    gb = sum(float(r[ir]) + float(r[iw]) for r in rows[2:] if len(r) > iw)
-    return gb, "profiles/r01_ncu_tapgemm_tc_full.csv (%d launches)" % (len(rows) - 2)
+    sel = [r for r in rows[2:] if len(r) > iw and "head API" not in r[0]]
+    gb = sum(float(r[ir]) + float(r[iw]) for r in sel)
+    return gb, "profiles/%s (%d launches)" % (name, len(sel))
 
 
 def main():

@@ -9,6 +9,7 @@ import common as C
 import idccrn_b200 as M
 from idccrn_b200 import lib, losses
 from idccrn_b200.synth import fill_state_dict, synth_waveform
+lib.set_option("gemm_cta_pairs", int(os.environ.get("IDV_PAIRS", "1")))      # A/B of the CTA-pair tap-GEMM
 B, L, ln = int(sys.argv[1]) if len(sys.argv) > 1 else 32, 64000, int(sys.argv[2]) if len(sys.argv) > 2 else 2
 phase = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 net = M.get_net_params()
