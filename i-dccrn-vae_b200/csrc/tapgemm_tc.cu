@@ -317,9 +317,18 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
         continue;
       }
-      const long long obase = (long long)unit.out_f * p.out_plane + (long long)r * p.out_ld + unit.out_ch_off + nt * BN;
+      const long long obase0 = (long long)unit.out_f * p.out_plane + (long long)r * p.out_ld + unit.out_ch_off + nt * BN;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        // N > out_ld: the unit's columns wrap into consecutive output planes, out_ld columns each (two output planes of a
+        // narrow transposed conv computed as ONE tile from the input planes they share); planes past the tensor are dropped
+        long long obase = obase0;
+        bool plane_ok = true;
+        if (p.N > p.out_ld) {
+          const int n0 = nt * BN + c0, pa = n0 / p.out_ld;
+          obase = (long long)(unit.out_f + pa) * p.out_plane + (long long)r * p.out_ld + (n0 - pa * p.out_ld) - c0;
+          plane_ok = p.out_hl <= 0 || (long long)(unit.out_f + pa + 1) * p.out_plane <= p.out_hl;
+        }
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
         tmem_ld_wait();
@@ -330,7 +339,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           if (p.apply_prelu) x = prelu_f(x, p.slope);
           f[j] = pad_row ? 0.f : x;
         }
-        if (row_ok && !(p.keep_pad && tt_row == 0)) {     // keep_pad: the pad row carries x[t-1] of the last step
+        if (row_ok && plane_ok && !(p.keep_pad && tt_row == 0)) {   // keep_pad: the pad row carries x[t-1] of the last step
           if (p.out_split) {
             __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + c0;
             __nv_bfloat16* ol = oh + p.out_hl;
@@ -562,6 +571,8 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
   }
   IDV_CHECK_ARG(R > 0 && n_units > 0 && a0_planes > 0 && n_slots > 0, "idv_tapgemm_tc: empty problem");
   IDV_CHECK_ARG(N >= 32 && N % 32 == 0 && (N % 64 == 0 || N == 32), "idv_tapgemm_tc: N=%d must be 32 or a multiple of 64", N);
+  IDV_CHECK_ARG(head || N <= out_ld || (out_ld % 32 == 0 && N % out_ld == 0),
+                "idv_tapgemm_tc: N=%d > out_ld=%d wraps into consecutive planes and needs out_ld %% 32 == 0, N %% out_ld == 0", N, out_ld);
   IDV_CHECK_ARG(a0_cp % 8 == 0 && kc_max % 64 == 0 && (head || out_ld % 8 == 0) && (!a1 || a1_cp % 8 == 0),
                 "idv_tapgemm_tc: channel counts must be multiples of 8 and kc_max of 64");
   int dev = 0, sms = 0;

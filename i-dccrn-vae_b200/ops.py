@@ -155,8 +155,8 @@ def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None, t_valid=0, 
             raise RuntimeError("static tap-GEMM output has %d elements, expected %d" % (out.numel(), n_out))
         lib.call("idv_tapgemm_tc", a0.data, a0.Cp, a0.F, a1.data if a1 is not None else None,
                  a1.Cp if a1 is not None else 0, a1.F if a1 is not None else 0, R,
-                 tp, tc["wt"], tc["kc_max"], tc["n_slots"], pack.bias, pack.N,
-                 tc["units"], tc["taps"], pack.n_units, out, pack.out_ld, R * pack.out_ld, n_out,
+                 tp, tc["wt"], tc["kc_max"], tc["n_slots"], tc.get("bias", pack.bias), tc.get("N", pack.N),
+                 tc["units"], tc["taps"], tc.get("n_units", pack.n_units), out, pack.out_ld, R * pack.out_ld, n_out,
                  1 if out_split else 0, 1 if pack.prelu else 0, pack.slope, int(t_valid))
         return out
     if out_split:

@@ -18,6 +18,9 @@ def round8(c):
     return (c + 7) // 8 * 8
 
 
+PAIR_PLANES = [True]      # narrow transposed convs: two output planes per tensor-core tile (TapGemmPack._tc_paired)
+
+
 class TapGemmPack:
     """Operands of one idv_tapgemm_* launch (weights, bias, unit/tap tables)."""
 
@@ -47,6 +50,9 @@ class TapGemmPack:
                 raise RuntimeError("tap-GEMM (N=%d) does not fit the tensor-core kernel's shape rules" % self.N)
             dev = self.w.device
             w = self.w.detach() if PACK_ON_DEVICE[0] else self.w.detach().cpu()
+            if getattr(self, "pair_planes", False):
+                self._tc = self._tc_paired(w, dev)
+                return self._tc
             slots, taps = {}, []
             kc_max = max(t[4] for t in self._taps_l)
             for t in self._taps_l:
@@ -134,6 +140,48 @@ def _cpu(t):
     return t if PACK_ON_DEVICE[0] else t.cpu()
 
 
+def _tc_paired(self, w, dev):
+    """Tensor-core tables of a NARROW transposed conv with two output planes per unit (N_tc = 2N, columns [0, N) =
+    plane 2q, [N, 2N) = plane 2q+1; the kernel wraps them into the two planes because N_tc > out_ld): the even and the
+    odd output plane read the same two or three input planes, so one tile loads each activation box once for both -
+    at N = 64 the kernel is bound by operand ingest (L2 -> shared memory), not by the tensor pipe.  Taps of the pair are
+    merged by (source, plane, dt, K range); a plane that lacks a tap gets a zero weight block."""
+    import collections
+    N, N2 = self.N, 2 * self.N
+    kc_max = max(t[4] for t in self._taps_l)
+    units, taps, slots = [], [], {}
+    for q in range((len(self._units_l) + 1) // 2):
+        pair = self._units_l[2 * q:2 * q + 2]
+        assert pair[0][2] == 2 * q and all(u[3] == 0 and u[4] == 0 for u in pair)
+        groups = collections.OrderedDict()
+        for half, u in enumerate(pair):
+            assert u[2] == 2 * q + half
+            for t in self._taps_l[u[0]:u[0] + u[1]]:
+                groups.setdefault((t[0], t[1], t[2], t[3], t[4]), [None, None])[half] = t[5]
+        begin = len(taps)
+        for key, (we, wo) in groups.items():
+            skey = (we, wo, key[4])
+            if skey not in slots:
+                slots[skey] = len(slots)
+            taps.append([key[0], key[1], key[2], key[3], key[4], slots[skey]])
+        units.append([begin, len(groups), 2 * q, 0, 0, sum(k[4] // 64 for k in groups)])
+    wt = torch.zeros(len(slots), N2, kc_max, dtype=torch.float32, device=w.device)
+    for (we, wo, kc), si in slots.items():
+        if we is not None:
+            wt[si, :N, :kc] = w[we:we + kc * N].view(kc, N).t()
+        if wo is not None:
+            wt[si, N:, :kc] = w[wo:wo + kc * N].view(kc, N).t()
+    hi = wt.to(torch.bfloat16)
+    lo = (wt - hi.to(torch.float32)).to(torch.bfloat16)
+    return dict(wt=torch.stack((hi, lo)).contiguous().to(dev), kc_max=kc_max, n_slots=len(slots),
+                taps=torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(dev),
+                units=torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(dev),
+                N=N2, n_units=len(units), bias=torch.cat((self.bias, self.bias)).contiguous())
+
+
+TapGemmPack._tc_paired = _tc_paired
+
+
 def pack_conv(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, f_in, stride_f, pad_f, device, pad_t=1):
     """Complex conv (kernel (kh,kw), stride (stride_f,1), pad (pad_f,pad_t)) [+ CBN + PReLU].
     weights: (Cout, Cin, kh, kw).  Time tap kt reads x[t-pad_t+kt]: the causal layer (pad_t = 1, last column
@@ -213,6 +261,7 @@ def pack_conv_transpose(t_re_w, t_re_b, t_im_w, t_im_b, bn, slope, f_in, c_p, c_
         units.append([begin, len(taps) - begin, fo, 0, 0, 0])
     p = TapGemmPack(torch.cat(Ws), bias, units, taps, N, f_out, N, slope is not None, slope or 0.0, device)
     p.f_out, p.c_out = f_out, cout
+    p.pair_planes = PAIR_PLANES[0] and N == 64 and stride_f == 2     # two output planes per tensor-core tile (_tc_paired)
     return p
 
 

@@ -89,7 +89,10 @@ int idv_tapgemm_f32(const float* a0, int a0_ld, int64_t a0_plane,
  * a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation.
  * wt: bf16 [2][n_slots][N][kc_max] (K-major), tap.w_off = slot index, tap.kc % 64 == 0,
  * unit.reserved = number of 64-wide K steps of the unit.  out: split bf16 (out_hl = elements between
- * the hi and lo sets) when out_split, else fp32.  N = 32 or a multiple of 64.                       */
+ * the hi and lo sets) when out_split, else fp32.  N = 32 or a multiple of 64.  N > out_ld (out_ld % 32 == 0,
+ * N % out_ld == 0, unit.out_ch_off = 0): the columns of a unit wrap into CONSECUTIVE output planes, column n goes to
+ * plane unit.out_f + n / out_ld, column n % out_ld - two output planes of a narrow transposed conv as one tile over
+ * the input planes they share; planes at or past out_hl / out_plane (out_hl > 0) are not written.            */
 int idv_tapgemm_tc(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
                    int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias, int N,
                    const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,

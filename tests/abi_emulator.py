@@ -143,6 +143,15 @@ def idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max
         if apply_prelu:
             acc = torch.where(acc > 0, acc, slope * acc)
         _mask_rows(acc, R, Tp, t_valid)
+        if N > out_ld:                                      # columns wrap into consecutive output planes
+            assert out_ld % 32 == 0 and N % out_ld == 0 and out_ch_off == 0
+            for j in range(N // out_ld):
+                o0 = (out_f + j) * out_plane
+                if out_hl > 0 and o0 + out_plane > out_hl:
+                    continue
+                res[o0:o0 + R * out_ld].view(R, out_ld)[:] = acc[:, j * out_ld:(j + 1) * out_ld]
+                written[o0:o0 + R * out_ld].view(R, out_ld)[:] = _written_rows(R, Tp)[:, None]
+            continue
         view = res[out_f * out_plane:out_f * out_plane + R * out_ld].view(R, out_ld)
         view[:, out_ch_off:out_ch_off + N] = acc
         written[out_f * out_plane:out_f * out_plane + R * out_ld].view(R, out_ld)[:, out_ch_off:out_ch_off + N] = \

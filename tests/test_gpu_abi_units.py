@@ -357,6 +357,23 @@ def _tapgemm_tc_case(R, Tp, N, kcs, dts, two_src, prelu, out_split, tv=0):
     assert _both("idv_tapgemm_tc", args, [16]) < 1e-5
 
 
+@pytest.mark.parametrize("R,Tp,out_split", [(300, 13, 1), (1300, 0, 0)])
+def test_tapgemm_tc_columns_wrap_into_planes(R, Tp, out_split):
+    """N > out_ld: column n of a unit goes to plane out_f + n / out_ld (two output planes of a narrow transposed conv
+    as one tile); the plane past the end of the tensor (odd plane count) is not written."""
+    F0, cp0, N, ld, kc, n_planes = 3, 136, 128, 64, 64, 5
+    a0 = _to_split(_rand(F0, R, cp0, seed=1))
+    taps = [[0, 0, 0, 8, kc, 0], [0, 1, 1, 8, kc, 1], [0, 2, 1, 0, kc, 2], [0, 1, 0, 0, kc, 1]]
+    units = [[0, 2, 0, 0, 0, 2], [2, 2, 2, 0, 0, 2], [1, 2, 4, 0, 0, 2]]      # planes (0,1), (2,3), (4, -)
+    wt = _to_split(_rand(3, N, kc, seed=3) * 0.1)
+    bias = _rand(N, seed=4)
+    n_out = n_planes * R * ld
+    out = torch.full((2 * n_out,), 3.0, dtype=torch.bfloat16) if out_split else torch.full((n_out,), 3.0)
+    args = [a0, cp0, F0, None, 0, 0, R, Tp, wt, kc, 3, bias, N, torch.tensor(units, dtype=torch.int32),
+            torch.tensor(taps, dtype=torch.int32), 3, out, ld, R * ld, n_out, out_split, 1, 0.2, 0]
+    assert _both("idv_tapgemm_tc", args, [16]) < 1e-5
+
+
 @pytest.mark.parametrize("NB,T,H,tv", [(3, 6, 128, 0), (64, 40, 384, 0), (5, 9, 768, 0), (70, 5, 128, 0), (3, 12, 128, 7)])
 def test_lstm_recurrent_tc(NB, T, H, tv):
     from idccrn_b200 import pack as PK
