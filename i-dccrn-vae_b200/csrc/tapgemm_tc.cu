@@ -594,8 +594,10 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
     mA1 = mA0;
   }
   // CTA pairs for the wide tiles (every CTA stages half of the weight tile) unless tiles are claimed dynamically
-  // (large problems only: a streaming step with a handful of row tiles keeps one CTA per tile)
-  const bool pairs = option_gemm_pairs() && !option_dynamic_tiles() && cdiv(R, BM) >= 8;
+  // (large problems only: a streaming step with a handful of row tiles keeps one CTA per tile - measured: 9 row tiles
+  // as 5 pairs were 10 % slower - and a small odd tile count would waste a tenth of the pairs)
+  const int n_rt = cdiv(R, BM);
+  const bool pairs = option_gemm_pairs() && !option_dynamic_tiles() && n_rt >= 8 && (n_rt % 2 == 0 || n_rt >= 32);
   rc = encode_map_4d(&mW, wt, kc_max, N, n_slots, (uint64_t)n_slots * N * kc_max, BK, pairs ? BN / 2 : BN);
   if (rc) return rc;
   Params p;
