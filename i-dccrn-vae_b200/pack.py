@@ -261,7 +261,7 @@ def pack_conv_transpose(t_re_w, t_re_b, t_im_w, t_im_b, bn, slope, f_in, c_p, c_
         units.append([begin, len(taps) - begin, fo, 0, 0, 0])
     p = TapGemmPack(torch.cat(Ws), bias, units, taps, N, f_out, N, slope is not None, slope or 0.0, device)
     p.f_out, p.c_out = f_out, cout
-    p.pair_planes = PAIR_PLANES[0] and N == 64 and stride_f == 2     # two output planes per tensor-core tile (_tc_paired)
+    p.pair_planes = PAIR_PLANES[0] and N in (64, 128) and stride_f == 2     # two output planes per tensor-core tile (_tc_paired)
     return p
 
 
