@@ -15,6 +15,8 @@ void set_error(const char* fmt, ...) {
 static int g_lstm_ncols = 0;
 static int g_dynamic_tiles = 0;
 static int g_gemm_pairs = 1;
+static int g_wave_pairs = 1;
+int option_lstm_wave_pairs() { return g_wave_pairs; }
 int option_gemm_pairs() { return g_gemm_pairs; }
 int option_lstm_ncols() { return g_lstm_ncols; }
 int option_dynamic_tiles() { return g_dynamic_tiles; }
@@ -30,6 +32,10 @@ extern "C" int idv_set_option(const char* name, int value) {
   }
   if (strcmp(name, "gemm_dynamic_tiles") == 0) {
     g_dynamic_tiles = value != 0;
+    return IDV_OK;
+  }
+  if (strcmp(name, "lstm_wave_cta_pairs") == 0) {
+    g_wave_pairs = value != 0;
     return IDV_OK;
   }
   if (strcmp(name, "gemm_cta_pairs") == 0) {

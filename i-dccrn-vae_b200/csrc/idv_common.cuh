@@ -13,6 +13,7 @@ void set_error(const char* fmt, ...);
 int option_lstm_ncols();
 int option_dynamic_tiles();
 int option_gemm_pairs();
+int option_lstm_wave_pairs();
 
 #define IDV_CHECK_ARG(cond, ...)             \
   do {                                       \

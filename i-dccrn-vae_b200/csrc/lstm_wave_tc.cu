@@ -14,6 +14,12 @@
 //   L0(t) waits A >= 8NC*t           and B >= 8NC*(t-3)  (slot t%4 of hxA was last read by IP(t-4))
 //   IP(t) waits A >= 8NC*(t+1)       and C >= 8NC*(t-3)  (slot t%4 of G1x was last read by L1(t-4))
 //   L1(t) waits C >= 8NC*t           and B >= 8NC*(t+1)
+// PAIR (default): neighbouring CTAs of one (module, role) run as a CTA pair (cluster of 2, tcgen05 cta_group::2, M = 128
+// = 64 rows of each CTA, N = 128 = the 64 gate columns of each CTA): a CTA streams only ITS 64 rows of h (98 KB instead
+// of 196 KB per step - the streaming phase is bound by the ~68 GB/s of TMA ingest one SM gets) and its MMAs read 2 KB of
+// A instead of 4 KB.  The even CTA issues the MMAs; a CTA's TMEM then holds its 64 rows x 128 columns as lanes 0-63 =
+// columns 0-63 (the even CTA's hidden units), lanes 64-127 = columns 64-127 (the odd CTA's), so epilogue thread L works
+// on row 64*rank + L%64 and the units of CTA (c & ~1) + L/64.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -75,7 +81,7 @@ __device__ __forceinline__ void wait_counter(const unsigned int* ctr, long long 
 __device__ __forceinline__ float wsig(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float wtanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
-template <int N>
+template <int N, bool PAIR>
 __global__ void __launch_bounds__(W_THREADS, 1)
 lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmWi,
                     const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmHA,
@@ -88,7 +94,10 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
   const int KC = p.KC, stages = p.stages;
   const int w_bytes = 2 * KC * W_TILE;
   uint8_t* ring = smem + w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + stages * 2 * W_HTILE);
+  constexpr int ROWS_C = PAIR ? W_ROWS / 2 : W_ROWS;          // rows of h this CTA streams
+  constexpr int HT = ROWS_C * BK * 2;                         // bytes of the hi (or lo) rows of one K chunk
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + stages * 2 * HT);
   const uint32_t wfull = smem_u32(bars), hfull0 = wfull + 8, hempty0 = hfull0 + 8 * 8, accfull = hempty0 + 8 * 8,
                  accempty = accfull + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
@@ -118,25 +127,36 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       mbar_init(hempty0 + 8 * s, 1);
     }
     mbar_init(accfull, 1);
-    mbar_init(accempty, W_EPI_WARPS);
+    mbar_init(accempty, PAIR ? 2 * W_EPI_WARPS : W_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == W_EPI_WARP0) {
-    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      mbar_expect_tx(wfull, (uint32_t)w_bytes);
+      // PAIR: the barriers the MMA issuer waits on live in the even CTA and collect the bytes of both CTAs' loads
+      if (!PAIR || rank == 0) mbar_expect_tx(wfull, (uint32_t)w_bytes * (PAIR ? 2 : 1));
       for (int hl = 0; hl < 2; ++hl)
-        for (int kc = 0; kc < KC; ++kc)
-          tma_load_2d(tmW, wfull, smem_w + (hl * KC + kc) * W_TILE, kc * BK, ((hl * 2 + m) * NC + c) * N);
+        for (int kc = 0; kc < KC; ++kc) {
+          if (PAIR)
+            tma_load_2d_2sm(tmW, wfull & PEER_BIT_MASK, smem_w + (hl * KC + kc) * W_TILE, kc * BK, ((hl * 2 + m) * NC + c) * N);
+          else
+            tma_load_2d(tmW, wfull, smem_w + (hl * KC + kc) * W_TILE, kc * BK, ((hl * 2 + m) * NC + c) * N);
+        }
       uint32_t stage = 0, phase = 0;
       for (int t = 0; t < T; ++t) {
         int slot;
@@ -160,9 +180,14 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         for (int kc0 = 0; kc0 < KC; ++kc0) {
           const int kc = kc0;                  // same order in every CTA (measured: rotating the order does not help)
           mbar_wait(hempty0 + 8 * stage, phase ^ 1);
-          const uint32_t sa = smem_ring + stage * 2 * W_HTILE;
-          mbar_expect_tx(hfull0 + 8 * stage, 2 * W_HTILE);
-          tma_load_3d(tmH, hfull0 + 8 * stage, sa, kc * BK, 0, blk);        // {64 k, 128 rows, hi+lo} = 32 KB
+          const uint32_t sa = smem_ring + stage * 2 * HT;
+          if (PAIR) {
+            if (rank == 0) mbar_expect_tx(hfull0 + 8 * stage, 4 * HT);
+            tma_load_3d_2sm(tmH, (hfull0 + 8 * stage) & PEER_BIT_MASK, sa, kc * BK, (int)rank * ROWS_C, blk);   // my 64 rows
+          } else {
+            mbar_expect_tx(hfull0 + 8 * stage, 2 * HT);
+            tma_load_3d(tmH, hfull0 + 8 * stage, sa, kc * BK, 0, blk);      // {64 k, 128 rows, hi+lo} = 32 KB
+          }
           if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
         }
         WAVE_DBG(1);
@@ -170,8 +195,8 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(N);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = PAIR ? make_idesc_mn(128, 2 * N) : make_idesc(N);
       mbar_wait(wfull, 0);
       uint32_t stage = 0, phase = 0;
       for (int t = 0; t < T; ++t) {
@@ -184,21 +209,29 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
           if (kc0 == 0) WAVE_DBG(2);
           if (p.dbg && blockIdx.x == 0 && m == 0 && role == 0 && t >= 300 && t < 304 && kc0 < 8)
             p.dbg[96 + (t - 300) * 8 + kc0] = wgtime();
-          const uint32_t sa = smem_ring + stage * 2 * W_HTILE;
-          const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + W_HTILE);
+          const uint32_t sa = smem_ring + stage * 2 * HT;
+          const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + HT);
           const uint64_t b_hi = make_desc_sw128(smem_w + kc * W_TILE);
           const uint64_t b_lo = make_desc_sw128(smem_w + (KC + kc) * W_TILE);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-            umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, (kc0 | k) != 0);
-            umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
-            umma_bf16(tmem_base, a_hi + koff, b_hi + koff, idesc, 1);
+            if (PAIR) {
+              umma_bf16_2sm(tmem_base, a_lo + koff, b_hi + koff, idesc, (kc0 | k) != 0);
+              umma_bf16_2sm(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
+              umma_bf16_2sm(tmem_base, a_hi + koff, b_hi + koff, idesc, 1);
+            } else {
+              umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, (kc0 | k) != 0);
+              umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
+              umma_bf16(tmem_base, a_hi + koff, b_hi + koff, idesc, 1);
+            }
           }
-          umma_commit(hempty0 + 8 * stage);
+          if (PAIR) umma_commit_2sm(hempty0 + 8 * stage, 3);
+          else umma_commit(hempty0 + 8 * stage);
           if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(accfull);
+        if (PAIR) umma_commit_2sm(accfull, 3);
+        else umma_commit(accfull);
         WAVE_DBG(3);
       }
     }
@@ -207,11 +240,14 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
     const int q = warp & 3;                           // TMEM lane quarter (rows q*32 .. q*32+31)
     const int half = (warp - W_EPI_WARP0) >> 2;       // which half of the HS hidden units
     constexpr int HU = HS / 2;                        // units per thread
-    const int r = q * 32 + lane;
+    // TMEM lane -> (row, owner of the gate columns): one CTA per tile: lane = row, own columns; PAIR: see the header
+    const int tl = q * 32 + lane;
+    const int r = PAIR ? (int)rank * 64 + (tl & 63) : tl;
+    const int c_own = PAIR ? (c & ~1) + (tl >> 6) : c;
     const int part = r >> 6;
     const int b = r & 63;
     const bool valid = b < p.NB;
-    const int u0 = c * HS + half * HU;                // first hidden unit of this thread
+    const int u0 = c_own * HS + half * HU;            // first hidden unit of this thread
     float cst[HU];
 #pragma unroll
     for (int j = 0; j < HU; ++j) cst[j] = 0.f;
@@ -221,7 +257,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
         for (int j = 0; j < HU; ++j)
-          bias[gt * HU + j] = __ldg(p.bias1 + ((long long)m * NC + c) * N + gt * HS + half * HU + j);
+          bias[gt * HU + j] = __ldg(p.bias1 + ((long long)m * NC + c_own) * N + gt * HS + half * HU + j);
     }
     for (int t = 0; t < T; ++t) {
       const long long rcur = (long long)b * Tp + 1 + t;
@@ -263,7 +299,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(accempty);
+      if (lane == 0) { if (PAIR) mbar_arrive_cluster(accempty & PEER_BIT_MASK); else mbar_arrive(accempty); }
       if (warp == W_EPI_WARP0 && lane == 0) WAVE_DBG(5);
       if (role == 1) {
         // ---- layer-1 input projection: G1(t) rows -> exchange buffer slot t%4
@@ -321,18 +357,34 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   if (warp == W_EPI_WARP0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int N>
+template <int N, bool PAIR>
 static int launch_wave(const CUtensorMap* maps, const WaveParams& p, size_t smem, cudaStream_t st) {
-  IDV_CUDA(cudaFuncSetAttribute(lstm_wave_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  IDV_CUDA(cudaFuncSetAttribute(lstm_wave_tc_kernel<N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.NC, 6, 1), block(W_THREADS);
-  void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&maps[4], (void*)&p};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)lstm_wave_tc_kernel<N>, grid, block, args, smem, st);
+  cudaError_t e;
+  if (PAIR) {
+    // cooperative (all 6 * NC CTAs co-resident: they wait on one another) AND clusters of 2 along x
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    e = cudaLaunchKernelEx(&cfg, lstm_wave_tc_kernel<N, PAIR>, maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  } else {
+    void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&maps[4], (void*)&p};
+    e = cudaLaunchCooperativeKernel((const void*)lstm_wave_tc_kernel<N, PAIR>, grid, block, args, smem, st);
+  }
   if (e == cudaErrorCooperativeLaunchTooLarge) {
     set_error("idv_lstm2_wave_tc: cooperative grid %dx6 is not co-resident", p.NC);
     return IDV_E_RESOURCE;
@@ -384,11 +436,13 @@ extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_o
   IDV_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   IDV_CHECK_ARG(6 * NC <= sms, "idv_lstm2_wave_tc: %d CTAs exceed the %d SMs", 6 * NC, sms);
   const size_t w_bytes = (size_t)2 * KC * N * BK * 2;
-  int stages = (int)(((size_t)smem_optin - w_bytes - 1024 - 256) / (2 * W_HTILE));
-  if (stages > 8) stages = 8;
+  const bool pair = option_lstm_wave_pairs() && NC % 2 == 0;
+  const size_t stage_bytes = (size_t)2 * W_HTILE / (pair ? 2 : 1);
+  int stages = (int)(((size_t)smem_optin - w_bytes - 1024 - 256) / stage_bytes);
+  if (stages > (pair ? 7 : 8)) stages = pair ? 7 : 8;
   if (stages > KC) stages = KC;
   IDV_CHECK_ARG(stages >= 1, "idv_lstm2_wave_tc: not enough shared memory for H=%d", H);
-  const size_t smem = w_bytes + (size_t)stages * 2 * W_HTILE + 1024 + 256;
+  const size_t smem = w_bytes + (size_t)stages * stage_bytes + 1024 + 256;
   uint8_t* wk = reinterpret_cast<uint8_t*>(work);
   const size_t hxA_bytes = (size_t)W_REP * 4 * 2 * 2 * 128 * H * 2, hxC_bytes = (size_t)W_REP * 2 * 2 * 2 * 128 * H * 2;
   CUtensorMap maps[5];
@@ -397,9 +451,9 @@ extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_o
     rc = encode_map_2d(&maps[i], wp[i], H, (uint64_t)2 * 2 * NC * N, BK, N);
     if (rc) return rc;
   }
-  rc = encode_map_3d(&maps[3], wk, H, W_ROWS, (uint64_t)W_REP * 4 * 2 * 2, BK, W_ROWS, 2);
+  rc = encode_map_3d(&maps[3], wk, H, W_ROWS, (uint64_t)W_REP * 4 * 2 * 2, BK, pair ? W_ROWS / 2 : W_ROWS, 2);
   if (rc) return rc;
-  rc = encode_map_3d(&maps[4], wk + hxA_bytes, H, W_ROWS, (uint64_t)W_REP * 2 * 2 * 2, BK, W_ROWS, 2);
+  rc = encode_map_3d(&maps[4], wk + hxA_bytes, H, W_ROWS, (uint64_t)W_REP * 2 * 2 * 2, BK, pair ? W_ROWS / 2 : W_ROWS, 2);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   IDV_CUDA(cudaMemsetAsync(work, 0, (size_t)work_bytes, st));
@@ -419,7 +473,7 @@ extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_o
     IDV_CUDA(cudaMalloc(&p.dbg, (96 + 32) * sizeof(unsigned long long)));
     IDV_CUDA(cudaMemsetAsync(p.dbg, 0, (96 + 32) * sizeof(unsigned long long), st));
   }
-  rc = launch_wave<64>(maps, p, smem, st);
+  rc = pair ? launch_wave<64, true>(maps, p, smem, st) : launch_wave<64, false>(maps, p, smem, st);
   if (dbg && rc == IDV_OK) {
     unsigned long long h[96 + 32];
     IDV_CUDA(cudaStreamSynchronize(st));

@@ -49,7 +49,8 @@ const char* idv_last_error(void);
  * tensor-core tap-GEMM claims its tiles from a global counter (for kernels sharing the GPU across streams),
  * 0 (default) = static round-robin tiles.  "gemm_cta_pairs": 1 (default) = tiles of width 256 run as CTA pairs
  * (thread-block clusters of 2, tcgen05 cta_group::2: M = 256 MMAs, every CTA stages half of the weight tile) when the
- * tiles are static; 0 = one CTA per tile everywhere.                                                          */
+ * tiles are static; 0 = one CTA per tile everywhere.  "lstm_wave_cta_pairs": 1 (default) = neighbouring CTAs of
+ * idv_lstm2_wave_tc run as pairs (each streams 64 of the 128 rows of h), 0 = every CTA streams all 128 rows.      */
 int idv_set_option(const char* name, int value);
 /* SM count of the current device (grids are sized against it). */
 int idv_device_sm_count(int* out);
