@@ -87,7 +87,9 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
                     const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmHA,
                     const __grid_constant__ CUtensorMap tmHC, const WaveParams p) {
   constexpr int HS = N / 4;
-  constexpr int TMEM_COLS = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  // PAIR: the split runs as TWO MMAs per K step, A_hi x [W_hi | W_lo] (width 2 * 2N: the hi and lo weight tiles of a K
+  // chunk are adjacent in shared memory) and A_lo x W_hi on top of its first half; the epilogue adds the two halves
+  constexpr int TMEM_COLS = PAIR ? 2 * N : (N <= 32 ? 32 : (N <= 64 ? 64 : 128));
   constexpr int W_TILE = N * BK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -152,8 +154,8 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       if (!PAIR || rank == 0) mbar_expect_tx(wfull, (uint32_t)w_bytes * (PAIR ? 2 : 1));
       for (int hl = 0; hl < 2; ++hl)
         for (int kc = 0; kc < KC; ++kc) {
-          if (PAIR)
-            tma_load_2d_2sm(tmW, wfull & PEER_BIT_MASK, smem_w + (hl * KC + kc) * W_TILE, kc * BK, ((hl * 2 + m) * NC + c) * N);
+          if (PAIR)      // [kc][hi | lo]
+            tma_load_2d_2sm(tmW, wfull & PEER_BIT_MASK, smem_w + (kc * 2 + hl) * W_TILE, kc * BK, ((hl * 2 + m) * NC + c) * N);
           else
             tma_load_2d(tmW, wfull, smem_w + (hl * KC + kc) * W_TILE, kc * BK, ((hl * 2 + m) * NC + c) * N);
         }
@@ -197,6 +199,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
     // ================================ MMA issuer ================================
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = PAIR ? make_idesc_mn(128, 2 * N) : make_idesc(N);
+      constexpr uint32_t idesc_cat = make_idesc_mn(128, 4 * N);
       mbar_wait(wfull, 0);
       uint32_t stage = 0, phase = 0;
       for (int t = 0; t < T; ++t) {
@@ -211,15 +214,14 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
             p.dbg[96 + (t - 300) * 8 + kc0] = wgtime();
           const uint32_t sa = smem_ring + stage * 2 * HT;
           const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + HT);
-          const uint64_t b_hi = make_desc_sw128(smem_w + kc * W_TILE);
-          const uint64_t b_lo = make_desc_sw128(smem_w + (KC + kc) * W_TILE);
+          const uint64_t b_hi = make_desc_sw128(smem_w + (PAIR ? 2 * kc : kc) * W_TILE);
+          const uint64_t b_lo = make_desc_sw128(smem_w + (KC + kc) * W_TILE);          // (not used by PAIR)
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
             if (PAIR) {
-              umma_bf16_2sm(tmem_base, a_lo + koff, b_hi + koff, idesc, (kc0 | k) != 0);
-              umma_bf16_2sm(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
-              umma_bf16_2sm(tmem_base, a_hi + koff, b_hi + koff, idesc, 1);
+              umma_bf16_2sm(tmem_base, a_hi + koff, b_hi + koff, idesc_cat, (kc0 | k) != 0);   // [hi*hi | hi*lo]
+              umma_bf16_2sm(tmem_base, a_lo + koff, b_hi + koff, idesc, 1);                      // + lo*hi
             } else {
               umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, (kc0 | k) != 0);
               umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
@@ -296,6 +298,15 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
 #pragma unroll
       for (int gt = 0; gt < 4; ++gt)
         tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + gt * HS + half * HU, v + gt * HU);
+      if (PAIR) {
+        uint32_t v2[4 * HU];
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt)
+          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + N + gt * HS + half * HU, v2 + gt * HU);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4 * HU; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+      }
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
