@@ -9,11 +9,11 @@
 // Every role is the same pipeline as csrc/lstm_tc.cu: its N = 4*Hs gate columns of the weight matrix resident in
 // shared memory (bf16 hi/lo), the 128 x H input rows streamed by TMA from an L2-resident exchange buffer, 3 MMAs
 // per K step into TMEM, thread = row epilogue.  Exchange buffers are 4 deep in time (hxA, G1x) / 2 deep (hxC) and
-// the per-(module, role) step counters (one increment per epilogue warp: 8*NC per step) carry both the data
-// dependencies and the buffer-reuse back-pressure:
-//   L0(t) waits A >= 8NC*t           and B >= 8NC*(t-3)  (slot t%4 of hxA was last read by IP(t-4))
-//   IP(t) waits A >= 8NC*(t+1)       and C >= 8NC*(t-3)  (slot t%4 of G1x was last read by L1(t-4))
-//   L1(t) waits C >= 8NC*t           and B >= 8NC*(t+1)
+// the per-(module, role) step counters (one increment per CTA and step) carry both the data dependencies and the
+// buffer-reuse back-pressure:
+//   L0(t) waits A >= NC*t           and B >= NC*(t-3)  (slot t%4 of hxA was last read by IP(t-4))
+//   IP(t) waits A >= NC*(t+1)       and C >= NC*(t-3)  (slot t%4 of G1x was last read by L1(t-4))
+//   L1(t) waits C >= NC*t           and B >= NC*(t+1)
 // PAIR (default): neighbouring CTAs of one (module, role) run as a CTA pair (cluster of 2, tcgen05 cta_group::2, M = 128
 // = 64 rows of each CTA, N = 128 = the 64 gate columns of each CTA): a CTA streams only ITS 64 rows of h (98 KB instead
 // of 196 KB per step - the streaming phase is bound by the ~68 GB/s of TMA ingest one SM gets) and its MMAs read 2 KB of
@@ -163,16 +163,16 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       for (int t = 0; t < T; ++t) {
         int slot;
         if (role == 0) {            // input h0(t-1): slot (t)%4 holds h0(t-1) (h0(t) is written to slot (t+1)%4)
-          wait_counter(cA, (long long)NC * W_EPI_WARPS * t);
-          wait_counter(cB, (long long)NC * W_EPI_WARPS * (t - 3));
+          wait_counter(cA, (long long)NC * t);
+          wait_counter(cB, (long long)NC * (t - 3));
           slot = t & 3;
         } else if (role == 1) {     // input h0(t): slot (t+1)%4
-          wait_counter(cA, (long long)NC * W_EPI_WARPS * (t + 1));
-          wait_counter(cC, (long long)NC * W_EPI_WARPS * (t - 3));
+          wait_counter(cA, (long long)NC * (t + 1));
+          wait_counter(cC, (long long)NC * (t - 3));
           slot = (t + 1) & 3;
         } else {                    // input h1(t-1): slot t%2
-          wait_counter(cC, (long long)NC * W_EPI_WARPS * t);
-          wait_counter(cB, (long long)NC * W_EPI_WARPS * (t + 1));
+          wait_counter(cC, (long long)NC * t);
+          wait_counter(cB, (long long)NC * (t + 1));
           slot = t & 1;
         }
         fence_proxy_async_global();
@@ -280,7 +280,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         }
       } else if (role == 2) {
         // G1(t) is produced inside this kernel: acquire counter B, then coherent (L2) loads
-        if (lane == 0) wait_counter(cB, (long long)NC * W_EPI_WARPS * (t + 1));
+        if (lane == 0) wait_counter(cB, (long long)NC * (t + 1));
         __syncwarp();
         const float* gp = p.g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
 #pragma unroll
@@ -324,9 +324,15 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
                             __uint_as_float(v[gt * HU + j + 1]) + bias[gt * HU + j + 1],
                             __uint_as_float(v[gt * HU + j + 2]) + bias[gt * HU + j + 2],
                             __uint_as_float(v[gt * HU + j + 3]) + bias[gt * HU + j + 3]);
-        __threadfence();                               // every warp publishes on its own (counters count warps)
-        __syncwarp();
-        if (lane == 0) atomicAdd(my_ctr, 1u);
+        // publish: ONE counter increment per CTA and step (same-address atomics serialise in the L2, ~27 clk each:
+        // 8 per CTA x 24 CTAs took 2.4 us to drain): the epilogue warps meet at a named barrier, then one thread
+        // fences - cumulative over the stores it has synchronised with, the pattern of a cooperative-groups grid
+        // sync - and increments.  (Every thread fencing BEFORE the barrier measured the same step time.)
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * W_EPI_WARPS) : "memory");
+        if (warp == W_EPI_WARP0 && lane == 0) {
+          __threadfence();
+          atomicAdd(my_ctr, 1u);
+        }
         continue;
       }
       float hn[HU];
@@ -353,10 +359,12 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         }
       }
       if (warp == W_EPI_WARP0 && lane == 0) WAVE_DBG(6);
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) atomicAdd(my_ctr, 1u);
-      if (warp == W_EPI_WARP0 && lane == 0) WAVE_DBG(7);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * W_EPI_WARPS) : "memory");
+      if (warp == W_EPI_WARP0 && lane == 0) {
+        __threadfence();
+        atomicAdd(my_ctr, 1u);
+        WAVE_DBG(7);
+      }
       if (role == 2 && valid) {
         const long long oidx = ((long long)(m * 2 + part) * R + rcur) * H + u0;
 #pragma unroll
