@@ -390,15 +390,20 @@ static int launch_wave(const CUtensorMap* maps, const WaveParams& p, size_t smem
   dim3 grid(p.NC, 6, 1), block(W_THREADS);
   cudaError_t e;
   if (PAIR) {
-    // cooperative (all 6 * NC CTAs co-resident: they wait on one another) AND clusters of 2 along x
+    // clusters of 2 along x.  All 6 * NC CTAs wait on one another and must be co-resident; that is checked against
+    // cudaOccupancyMaxActiveClusters (the caller falls back to the one-CTA-per-tile cooperative kernel otherwise)
+    // instead of asked for with the cooperative attribute: Nsight Compute cannot replay a launch that carries both the
+    // cooperative and the cluster attribute (LaunchFailed), and every CTA that has not started yet only ever waits for
+    // SMs held by OTHER kernels.  Every spin in the kernel has a timeout that traps.
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cfg.attrs = attr; cfg.numAttrs = 2;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int max_clusters = 0;
+    IDV_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, lstm_wave_tc_kernel<N, PAIR>, &cfg));
+    if (2 * max_clusters < (int)(grid.x * grid.y)) return IDV_E_RESOURCE;
     e = cudaLaunchKernelEx(&cfg, lstm_wave_tc_kernel<N, PAIR>, maps[0], maps[1], maps[2], maps[3], maps[4], p);
   } else {
     void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&maps[4], (void*)&p};
@@ -437,9 +442,9 @@ extern "C" int idv_lstm2_wave_config(int H, int* n_cols, int* n_ctas, int64_t* w
   return IDV_OK;
 }
 
-extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
-                                 const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
-                                 float* hseq1, void* work, unsigned int* sync, int t_valid, void* stream) {
+static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
+                    const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H, float* hseq1,
+                    void* work, unsigned int* sync, int t_valid, void* stream) {
   using namespace idv;
   using namespace idv::tc;
   IDV_CHECK_ARG(g0 && w_hh0 && w_ih1 && w_hh1 && bias1 && hseq1 && work && sync, "idv_lstm2_wave_tc: null pointer");
@@ -455,7 +460,7 @@ extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_o
   IDV_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   IDV_CHECK_ARG(6 * NC <= sms, "idv_lstm2_wave_tc: %d CTAs exceed the %d SMs", 6 * NC, sms);
   const size_t w_bytes = (size_t)2 * KC * N * BK * 2;
-  const bool pair = option_lstm_wave_pairs() && NC % 2 == 0;
+  pair = pair && NC % 2 == 0;
   const size_t stage_bytes = (size_t)2 * W_HTILE / (pair ? 2 : 1);
   int stages = (int)(((size_t)smem_optin - w_bytes - 1024 - 256) / stage_bytes);
   if (stages > (pair ? 7 : 8)) stages = pair ? 7 : 8;
@@ -511,5 +516,16 @@ extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_o
       fprintf(stderr, "\n");
     }
   }
+  return rc;
+}
+
+extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
+                                 const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
+                                 float* hseq1, void* work, unsigned int* sync, int t_valid, void* stream) {
+  int rc = IDV_E_RESOURCE;
+  if (idv::option_lstm_wave_pairs())
+    rc = wave_run(true, g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq1, work, sync, t_valid, stream);
+  if (rc == IDV_E_RESOURCE)        // the CTA pairs do not all fit the device at once: one CTA per tile, cooperative launch
+    rc = wave_run(false, g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq1, work, sync, t_valid, stream);
   return rc;
 }
