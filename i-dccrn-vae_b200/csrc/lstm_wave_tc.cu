@@ -523,7 +523,9 @@ extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_o
                                  const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
                                  float* hseq1, void* work, unsigned int* sync, int t_valid, void* stream) {
   int rc = IDV_E_RESOURCE;
-  if (idv::option_lstm_wave_pairs())
+  // pairs are launched without the cooperative guarantee (see launch_wave): not when kernels of several streams share
+  // the GPU ("gemm_dynamic_tiles" is the multi-stream switch) - two half-resident grids could wait for each other's SMs
+  if (idv::option_lstm_wave_pairs() && !idv::option_dynamic_tiles())
     rc = wave_run(true, g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq1, work, sync, t_valid, stream);
   if (rc == IDV_E_RESOURCE)        // the CTA pairs do not all fit the device at once: one CTA per tile, cooperative launch
     rc = wave_run(false, g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq1, work, sync, t_valid, stream);
