@@ -283,6 +283,7 @@ def run_ours(args):
         achieved_tf = tg_flops / (tg["ms"] / 1e3) / 1e12 if tg["launches"] else None
         cpu_val, cpu_dt, cores, sample = cpu_oracle_throughput(2, 1) if not args.no_cpu else (None, None, 0, "skipped")
         traffic, traffic_src = ncu_dram_traffic(B, tc_mode)
+        hbm_stages = hbm_stage_rooflines(per_kernel, B, L, T, peaks) if tc_mode else None
         line = {
             "metric": "audio_seconds_enhanced_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -307,11 +308,36 @@ def run_ours(args):
                                   "`achieved` counts ALGORITHMIC flops (SURVEY 8(d)), the tensor pipe executes 3x that")
                          if tc_mode else "fp32 SIMT implementation measured against the bf16 tensor-pipe peak"},
             "per_kernel_ms": per_kernel,
+            "hbm_stages": hbm_stages,
             "cpu_baseline": {"value": cpu_val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def hbm_stage_rooflines(per_kernel, B, L, T, peaks, H=384, zdim=128, kpad_stft=448, kpad_istft=576, n_istft=512, c0=32):
+    """Achieved HBM GB/s of the elementwise / framing / overlap-add stages (north_star): ALGORITHMIC bytes = the tensors
+    a stage must read and write once (fp32 = 4 B, split bf16 = 2 x 2 B per value), divided by its live CUDA-event time."""
+    R, Rf, nb = B * (T + 1), B * T, 257
+    f1 = (nb + 4 - 5) // 2 + 1
+    by = {
+        "idv_stft_frames_split": B * L * 4 + Rf * kpad_stft * 4,                    # waveform -> split-bf16 frames
+        "idv_enc0_fwd": B * nb * T * 2 * 4 + f1 * R * 2 * c0 * 4,                   # STFT (B,257,T,2) -> 129 planes x 64 ch
+        "idv_lstm_combine_fwd": 4 * R * H * 4 + B * T * H * 2 * 4,                  # 4 streams -> latent (B,T,H,2)
+        "idv_reparam_fwd": B * T * H * 2 * 4 + B * T * zdim * 2 * 4,                # latent -> z
+        "idv_z_to_planes": B * T * zdim * 2 * 4 + R * 2 * zdim * 4,                 # z -> split-bf16 rows
+        "idv_spec_rows_split": B * nb * T * 2 * 4 + Rf * kpad_istft * 4,            # spectrum -> split-bf16 K-major rows
+        "idv_ola_fwd": Rf * n_istft * 4 + B * L * 4,                                # frames -> waveform
+    }
+    peak = peaks.get("hbm_gbs") or 6548.8            # MEASURED_PEAKS.json copy bandwidth, else the recipe fallback
+    out = {}
+    for k, b in by.items():
+        if k in per_kernel and per_kernel[k]["ms"] > 0:
+            gbs = b / (per_kernel[k]["ms"] / 1e3) / 1e9
+            out[k] = {"ms": per_kernel[k]["ms"], "algorithmic_mb": b / 1e6, "achieved_gbps": gbs, "frac_of_hbm_peak": gbs / peak}
+    out["peak_gbps"] = peak
+    return out
 
 
 def ncu_dram_traffic(B, tc_mode):
