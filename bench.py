@@ -33,26 +33,8 @@ CPU_SAMPLE_BATCH = 4
 
 
 def algorithmic_gmac_per_utt(T, H=384, real_skip=False):
-    """SURVEY §8(d) formulae (real MACs; complex conv = 4 real convs; zero-skip decoder counted at its
-    effective, halved K)."""
-    enc_c = [1, 32, 64, 128, 128, 256, 256]
-    f = [257, 129, 65, 33, 17, 9, 5]
-    dec_c = [256, 256, 128, 128, 64, 32, 1]
-    g = {}
-    g["enc"] = [4 * enc_c[i] * enc_c[i + 1] * 10 * f[i + 1] * T / 1e9 for i in range(6)]
-    g["dec"] = [4 * (dec_c[i] + (enc_c[6 - i] if real_skip else 0)) * dec_c[i + 1] * 10 * f[6 - i] * T / 1e9
-                for i in range(6)]
-    g["lstm_inproj0"] = 4 * (4 * H * 1280) * T / 1e9
-    g["lstm_inproj1"] = 4 * (4 * H * H) * T / 1e9            # runs inside the wavefront LSTM kernel
-    g["lstm_inproj"] = g["lstm_inproj0"] + g["lstm_inproj1"]
-    g["lstm_rec"] = 4 * (4 * H * 2 * H) * T / 1e9
-    g["dense"] = 2 * 128 * 1280 * T / 1e9
-    g["stft"] = T * 512 * 514 / 1e9
-    g["istft"] = T * 512 * 514 / 1e9
-    # launches of idv_tapgemm_tc in one step: enc1-5, LSTM layer-0 in-proj, dense, dec0-4, iSTFT frames GEMM
-    g["tapgemm"] = sum(g["enc"][1:]) + sum(g["dec"][:5]) + g["lstm_inproj0"] + g["dense"] + g["istft"]
-    g["total"] = sum(g["enc"]) + sum(g["dec"]) + g["lstm_inproj"] + g["lstm_rec"] + g["dense"] + g["stft"] + g["istft"]
-    return g
+    from idccrn_b200.workloads import algorithmic_gmac_per_utt as f
+    return f(T, H, real_skip)
 
 
 class ClockSampler:
@@ -132,7 +114,12 @@ def workload_config(B, world, T, g):
             "batch_per_gpu": B, "global_batch": B * world, "utterance_s": SECONDS, "fs": FS, "frames": T,
             "eps": "on-device Philox", "parallelism": "replica x%d (utterance shards)" % world,
             "l2": "per-step activation working set ~12 GB >> 126 MB L2 (no flush needed)",
-            "gflop_per_utt_algorithmic": 2 * g["total"]}
+            "gflop_per_utt_algorithmic": 2 * g["total"],
+            # identical in both arms: the CPU legs (this arm's cpu_baseline and the whole --impl reference arm) time
+            # cpu_sample_batch utterances per step, not batch_per_gpu (CPU throughput is flat in the batch size)
+            "cpu_sample_batch": CPU_SAMPLE_BATCH,
+            "reference_arm": "oracle/ref_port.py (the reference's own torch ops) on the host cores, "
+                             "%d x %d s utterances per step" % (CPU_SAMPLE_BATCH, SECONDS)}
 
 
 def run_reference(args):
@@ -269,12 +256,25 @@ def run_ours(args):
     per_kernel = {k: {"launches": len(v), "ms": sum(v)} for k, v in lib.resolve_profile(prof).items()}
     step_ms_prof = sum(v["ms"] for v in per_kernel.values())
 
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    # ---- the other BASELINE configurations (all ranks take part; config 3 is split over them)
+    enc = dec = None                 # (the step closure holds the only other reference)
+    torch.cuda.empty_cache()
+    which = [c for c in args.configs.split(",") if c]
+    configs = measure_configs(args, dev, world, rank, dist.group.WORLD if world > 1 else None, peaks, which) if which else {}
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager:
+        try:
+            eager = eager_b200()
+        except Exception as e:
+            eager = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        torch.cuda.empty_cache()
+
     if rank == 0:
         g = algorithmic_gmac_per_utt(T)
-        peaks = {}
-        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(pk):
-            peaks = json.load(open(pk))
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
         tc_mode = "idv_tapgemm_tc" in per_kernel
@@ -309,11 +309,168 @@ def run_ours(args):
                          if tc_mode else "fp32 SIMT implementation measured against the bf16 tensor-pipe peak"},
             "per_kernel_ms": per_kernel,
             "hbm_stages": hbm_stages,
+            "configs": configs,
+            "eager_b200": eager,
             "cpu_baseline": {"value": cpu_val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_configs(args, dev, world, rank, group, peaks, which):
+    """The other BASELINE configurations on the same ranks (``configs`` object of the JSON line): device-resident
+    inputs, >= 3 warm-up steps, CUDA events bracketed by barrier + synchronize, MAX over ranks.  Each entry:
+    ms_per_step, whole-job audio-s/s and the algorithmic-FLOP fraction of the measured sustained bf16 peak
+    (SURVEY 8(d) MAC counts; the tensor pipe executes 3x that with the bf16x3 split)."""
+    import gc
+    import torch.distributed as dist
+    from idccrn_b200 import lib, shard, workloads as W
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    out = {}
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(step, steps, warm=3):
+        for _ in range(warm):
+            step()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.LAUNCHES[0]
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = shard.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+        sync_all()
+        return ms, (lib.LAUNCHES[0] - n0) / steps
+
+    def inference(tag, maker, **kw):
+        step, info = maker(dev, **kw)
+        ms, launches = timed(step, min(args.steps, 5))
+        T = info["utterance_s"] * FS // HOP + 1
+        g = algorithmic_gmac_per_utt(T, info["H"], info["real_skip"])
+        strong = info.get("scaling") == "strong"
+        utts = info["global_batch"] if strong else info["batch_per_gpu"] * world
+        flops = 2 * g["total"] * 1e9 * info["batch_per_gpu"]                 # per GPU and step
+        e = {"workload": info["workload"], "batch_per_gpu": info["batch_per_gpu"], "utterance_s": info["utterance_s"],
+             "frames": T, "scaling": info.get("scaling", "weak"), "ms_per_step": ms,
+             "audio_s_per_s": utts * info["utterance_s"] / (ms / 1e3), "gpu_launches_per_step": launches,
+             "gflop_per_utt_algorithmic": 2 * g["total"],
+             "algorithmic_tflops_per_gpu": flops / (ms / 1e3) / 1e12,
+             "algorithmic_flop_frac_of_bf16_peak": flops / (ms / 1e3) / 1e12 / peak_tf}
+        if args.config_kernels:
+            pk = W.profile_step(step)
+            e["per_kernel_ms"] = {k: round(v["ms"], 4) for k, v in sorted(pk.items(), key=lambda kv: -kv[1]["ms"])}
+        out[tag] = e
+        del step
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    def guarded(tag, fn):
+        if tag not in which:
+            return
+        try:
+            fn()
+        except Exception as e:                      # a failing side config must not take the headline line with it
+            out[tag] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            gc.collect()
+            torch.cuda.empty_cache()
+
+    guarded("1", lambda: inference("1", W.config1, rank=rank))
+    guarded("2b", lambda: inference("2b", W.config2b, rank=rank))
+    guarded("3", lambda: inference("3", W.config3, world=world, rank=rank))
+
+    def training():
+        step, info, opt = W.config4(dev, world=world, rank=rank, group=group)
+        ms, launches = timed(step, min(args.steps, 3), warm=3)
+        out["4"] = {"workload": info["workload"], "batch_per_gpu": info["batch_per_gpu"], "utterance_s": info["utterance_s"],
+                    "scaling": "weak", "ms_per_step": ms,
+                    "audio_s_per_s": world * info["batch_per_gpu"] * info["utterance_s"] / (ms / 1e3),
+                    "gpu_launches_per_step": launches, "grad_bytes_allreduced": int(opt.gflat.numel() * 4),
+                    "allreduce": "NCCL all_reduce of one flat fp32 bucket, mean over ranks" if world > 1 else "single rank"}
+        del step, opt
+        gc.collect()
+        torch.cuda.empty_cache()
+    guarded("4", training)
+
+    def streaming():
+        se, chunk, info = W.config5(dev, rank=rank)
+        n0 = lib.LAUNCHES[0]
+        se._step_impl(1 << 40, 1 << 20)               # one eager step to count our kernels per step
+        launches = lib.LAUNCHES[0] - n0
+        se.steps += 1
+        sync_all()
+        lat, b2b = W.time_streaming(se, chunk, 300)
+        b2b = shard.max_over_ranks(b2b, dev)
+        p50 = shard.max_over_ranks(lat[len(lat) // 2], dev)
+        p99 = shard.max_over_ranks(lat[int(len(lat) * 0.99)], dev)
+        hop_s = se.hop * se.k / float(FS)
+        out["5"] = {"workload": info["workload"], "streams_per_gpu": se.NB, "streams_total": se.NB * world,
+                    "frames_per_step": se.k, "scaling": "weak", "kernels_per_step": launches,
+                    "latency_ms_p50": p50, "latency_ms_p99": p99, "ms_per_step_back_to_back": b2b,
+                    "audio_s_per_s": world * se.NB * hop_s / (b2b / 1e3), "realtime_factor_per_stream": hop_s / (b2b / 1e3),
+                    "algorithmic_delay_ms": se.output_delay / 16.0,
+                    "note": "latencies: MAX over ranks of the per-rank p50 / p99 of 300 graph replays (CUDA events)"}
+        del se
+        gc.collect()
+        torch.cuda.empty_cache()
+    guarded("5", streaming)
+    return out
+
+
+def eager_b200(steps=2, batch=8):
+    """Baseline leg, never the product: the reference-equivalent PyTorch modules (oracle/ref_port.py = the reference's
+    own torch ops: cuDNN convs, nn.LSTM, torch.stft) run EAGERLY on this B200 for config 2, with PyTorch's default TF32
+    convolution setting and in true fp32 - the practical bar of SURVEY 8(d), since the reference ships no Blackwell
+    kernel.  Bounded sample: `batch` x 4 s utterances (throughput scaled to audio-s/s)."""
+    from oracle import ref_port as P
+    import idccrn_b200 as M
+    from idccrn_b200.synth import fill_state_dict, synth_eps, synth_waveform
+    net = M.get_net_params()
+    enc = M.nsvae_pvae_dccrn_encoder_twophase(net, True, "cpu", ZDIM, NFFT, HOP, WIN, 1, 1)
+    dec = M.pvae_dccrn_decoder_skip_prepare(net, True, "cpu", 1, ZDIM, NFFT, HOP, WIN, "real_imag", list(range(6)))
+    esd = {k: v.cuda() for k, v in fill_state_dict(enc.state_dict(), 0).items()}
+    dsd = {k: v.cuda() for k, v in fill_state_dict(dec.state_dict(), 1).items()}
+    L = FS * SECONDS
+    x = synth_waveform(batch, L).cuda()
+    eps = [e.cuda() for e in synth_eps((batch, 1, L // HOP + 1, ZDIM))]
+
+    def step():
+        with torch.no_grad():
+            st = P.vae_encoder_forward(esd, x, ZDIM, 1, 1, eps)
+            return P.vae_decoder_forward(dsd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], 1,
+                                         "real_imag", "zero")["recon_sig"]
+
+    def run():
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"ms_per_step": ms, "audio_s_per_s": batch * SECONDS / (ms / 1e3)}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    out = {"what": "oracle port (the reference's torch ops) eager on this GPU, config 2, %d x %d s utterances per step"
+                   % (batch, SECONDS), "batch": batch}
+    try:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = True, False       # PyTorch defaults
+        out["tf32_default"] = run()
+        out["tf32_default"]["note"] = "TF32 convolutions miss the 1e-4 waveform gate (SURVEY F9: 9.7e-4)"
+        torch.backends.cudnn.allow_tf32 = False
+        out["fp32"] = run()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return out
 
 
 def hbm_stage_rooflines(per_kernel, B, L, T, peaks, H=384, zdim=128, kpad_stft=448, kpad_istft=576, n_istft=512, c0=32):
@@ -366,6 +523,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="utterances per GPU (config 2: 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager_b200 baseline leg (N = 1 only)")
+    ap.add_argument("--configs", default="1,2b,3,4,5",
+                    help="other BASELINE configurations to add to the line's `configs` object ('' = none)")
+    ap.add_argument("--config-kernels", action="store_true", help="per-kernel device times inside every `configs` entry")
     ap.add_argument("--streams", type=int, default=1,
                     help="batches in flight: consecutive steps alternate over this many CUDA streams (1 = serial)")
     args = ap.parse_args()

@@ -8,5 +8,7 @@ from .modules import (STFT, ISTFT, ConvSTFT, ConviSTFT, ComplexConv2d, causal_co
                       SkipList, nsvae_pvae_dccrn_encoder_twophase, pvae_dccrn_encoder_skip_prepare,
                       pvae_dccrn_decoder_skip_prepare, nsvae_pvae_dccrn_decoder_twophase, standard_DCCRN, DCCRN_)
 from .netconfig import get_net_params  # noqa: F401
+# imported eagerly (after modules) so that the ``idccrn_b200`` alias covers them: one module object per file
+from . import losses, streaming, train  # noqa: F401,E402
 
 __version__ = "0.1.0"

@@ -16,6 +16,8 @@ static int g_lstm_ncols = 0;
 static int g_dynamic_tiles = 0;
 static int g_gemm_pairs = 1;
 static int g_wave_pairs = 1;
+static int g_tile_order = 1;
+int option_tile_order() { return g_tile_order; }
 int option_lstm_wave_pairs() { return g_wave_pairs; }
 int option_gemm_pairs() { return g_gemm_pairs; }
 int option_lstm_ncols() { return g_lstm_ncols; }
@@ -36,6 +38,11 @@ extern "C" int idv_set_option(const char* name, int value) {
   }
   if (strcmp(name, "lstm_wave_cta_pairs") == 0) {
     g_wave_pairs = value != 0;
+    return IDV_OK;
+  }
+  if (strcmp(name, "gemm_tile_order") == 0) {
+    IDV_CHECK_ARG(value == 0 || value == 1, "idv_set_option: gemm_tile_order must be 0 (unit-major) or 1 (row-major)");
+    g_tile_order = value;
     return IDV_OK;
   }
   if (strcmp(name, "gemm_cta_pairs") == 0) {

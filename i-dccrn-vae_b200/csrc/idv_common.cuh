@@ -14,6 +14,7 @@ int option_lstm_ncols();
 int option_dynamic_tiles();
 int option_gemm_pairs();
 int option_lstm_wave_pairs();
+int option_tile_order();
 
 #define IDV_CHECK_ARG(cond, ...)             \
   do {                                       \
@@ -74,6 +75,12 @@ __device__ __forceinline__ void st_split4(unsigned short* hi, long long hl, long
   split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
   *reinterpret_cast<uint2*>(hi + idx) = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
   *reinterpret_cast<uint2*>(hi + hl + idx) = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+}
+__device__ __forceinline__ void st_split2(unsigned short* hi, long long hl, long long idx, float2 v) {
+  unsigned short h[2], l[2];
+  split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]);
+  *reinterpret_cast<unsigned*>(hi + idx) = (unsigned)h[0] | ((unsigned)h[1] << 16);
+  *reinterpret_cast<unsigned*>(hi + hl + idx) = (unsigned)l[0] | ((unsigned)l[1] << 16);
 }
 __device__ __forceinline__ float ld_split1(const unsigned short* hi, long long hl, long long idx) {
   return bf16_bits_to_float(__ldg(hi + idx)) + bf16_bits_to_float(__ldg(hi + hl + idx));

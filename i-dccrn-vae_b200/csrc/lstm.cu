@@ -202,7 +202,9 @@ __global__ void __launch_bounds__(256) reparam_kernel(const float* __restrict__ 
       ei = __ldg(eps_i + i);
     } else {
       curandStatePhilox4_32_10_t st;
-      curand_init((unsigned long long)seed, (unsigned long long)i, (unsigned long long)offset, &st);
+      // Philox's `offset` counts single 32-bit outputs and curand_normal2 consumes two of them: one draw = one whole
+      // Philox block (4 outputs), so consecutive draws (counter + 1) never share a uniform
+      curand_init((unsigned long long)seed, (unsigned long long)i, 4ULL * (unsigned long long)offset, &st);
       const float2 nrm = curand_normal2(&st);
       er = nrm.x;
       ei = nrm.y;
@@ -233,6 +235,134 @@ __global__ void __launch_bounds__(256) reparam_kernel(const float* __restrict__ 
       zi = mu.y + sx * er + sy * ei;
     }
     *reinterpret_cast<float2*>(z + i * 2) = make_float2(zr, zi);
+  }
+}
+
+// reparameterisation of one element (model/pvae_module.py:L2177-2231, same operation order as reparam_kernel, variant 0)
+__device__ __forceinline__ float2 reparam_one(float2 mu, float2 ls, float2 dl, float er, float ei) {
+  const float e = 1e-6f;
+  const float sig = expf(ls.x);
+  float dr = dl.x, di = dl.y;
+  float ad = sqrtf(dr * dr + di * di + e);
+  const float tmp = sig * 0.99f / (ad + e);
+  if (ad >= sig - 1e-3f) {
+    dr *= tmp;
+    di *= tmp;
+  }
+  ad = sqrtf(dr * dr + di * di + e);
+  const float den = sqrtf(2.f * (sig + dr) + e);
+  const float sx = di / (den + e);
+  const float sy = sqrtf(sig * sig - ad * ad + e) / (den + e);
+  return make_float2(mu.x + ((sig + dr) / (den + e)) * er, mu.y + sx * er + sy * ei);
+}
+
+// Fused latent stage: thread = (plane row r, latent channel j < zdim).  A valid row (b, t) combines the four LSTM
+// streams into the 3 * latent_num latent values of channel j, writes them to `latent`, draws / reads eps, writes z of
+// every sample and (latent 0) the decoder's z planes; pad rows and rows beyond the valid frames only zero the z planes.
+__global__ void __launch_bounds__(256) latent_fused_kernel(const float* __restrict__ hseq, int NB, int Talloc, int Tv, int H,
+                                                           int zdim, int latent_num, int S,
+                                                           const float* __restrict__ eps_r0, const float* __restrict__ eps_i0,
+                                                           const float* __restrict__ eps_r1, const float* __restrict__ eps_i1,
+                                                           uint64_t seed, uint64_t offset,
+                                                           const unsigned long long* __restrict__ offset_dev,
+                                                           float* __restrict__ latent, float* __restrict__ z0,
+                                                           float* __restrict__ z1, void* __restrict__ zplanes, int out_split) {
+  const int Tp = Talloc + 1;
+  const int64_t R = (int64_t)NB * Tp;
+  const int Ch = (zdim + 7) & ~7, Cp = 2 * Ch;
+  const int64_t n = R * Ch;
+  if (offset_dev) offset += *offset_dev;
+  float* pf = reinterpret_cast<float*>(zplanes);
+  unsigned short* ps = reinterpret_cast<unsigned short*>(zplanes);
+  const int64_t plane_el = R * Cp;                       // elements of one sample's plane (per hi / lo half)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % Ch);
+    const int64_t r = i / Ch;
+    const int tt = (int)(r % Tp), b = (int)(r / Tp);
+    const bool live = tt >= 1 && tt <= Tv && j < zdim;
+    float2 zs0[8];                                        // z of latent 0 for up to 8 samples per pass
+    for (int s0 = 0; s0 < S; s0 += 8) {
+      const int ns = S - s0 < 8 ? S - s0 : 8;
+      if (live) {
+        const int t = tt - 1;
+        for (int k = 0; k < latent_num; ++k) {
+          float2 tri[3];
+#pragma unroll
+          for (int c3 = 0; c3 < 3; ++c3) {
+            const int col = (3 * k + c3) * zdim + j;
+            const int64_t idx = r * H + col;
+            const float rr = __ldg(hseq + idx), ir = __ldg(hseq + R * H + idx);
+            const float ri = __ldg(hseq + 2 * R * H + idx), ii = __ldg(hseq + 3 * R * H + idx);
+            tri[c3] = make_float2(rr - ii, ir + ri);
+            if (s0 == 0)
+              *reinterpret_cast<float2*>(latent + (((int64_t)b * Tv + t) * H + col) * 2) = tri[c3];
+          }
+          const float* er_p = k ? eps_r1 : eps_r0;
+          const float* ei_p = k ? eps_i1 : eps_i0;
+          float* zk = k ? z1 : z0;
+          for (int si = 0; si < ns; ++si) {
+            const int s = s0 + si;
+            const int64_t e_idx = (((int64_t)b * S + s) * Tv + t) * zdim + j;
+            float er, ei;
+            if (er_p) {
+              er = __ldg(er_p + e_idx);
+              ei = __ldg(ei_p + e_idx);
+            } else {
+              curandStatePhilox4_32_10_t st;
+              curand_init((unsigned long long)seed, (unsigned long long)(e_idx + (int64_t)k * NB * S * Tv * zdim),
+                          4ULL * (unsigned long long)offset, &st);
+              const float2 nrm = curand_normal2(&st);
+              er = nrm.x;
+              ei = nrm.y;
+            }
+            const float2 zv = reparam_one(tri[0], tri[1], tri[2], er, ei);
+            *reinterpret_cast<float2*>(zk + e_idx * 2) = zv;
+            if (k == 0) zs0[si] = zv;
+          }
+        }
+      }
+      for (int si = 0; si < ns; ++si) {
+        const float2 zv = live ? zs0[si] : make_float2(0.f, 0.f);
+        const int64_t base = (int64_t)(s0 + si) * plane_el * (out_split ? 2 : 1) + r * Cp;
+        if (out_split) {
+          st_split1(ps, plane_el, base + j, zv.x);
+          st_split1(ps, plane_el, base + Ch + j, zv.y);
+        } else {
+          pf[base + j] = zv.x;
+          pf[base + Ch + j] = zv.y;
+        }
+      }
+    }
+  }
+}
+
+// lstm_combine_kernel + z_to_planes_kernel in one pass: thread = (plane row r, channel j)
+__global__ void __launch_bounds__(256) combine_planes_kernel(const float* __restrict__ hseq, int NB, int Talloc, int Tv,
+                                                             int H, float* __restrict__ latent, void* __restrict__ planes,
+                                                             int out_split) {
+  const int Tp = Talloc + 1;
+  const int64_t R = (int64_t)NB * Tp;
+  const int Ch = (H + 7) & ~7, Cp = 2 * Ch;
+  const int64_t n = R * Ch;
+  float* pf = reinterpret_cast<float*>(planes);
+  unsigned short* ps = reinterpret_cast<unsigned short*>(planes);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % Ch);
+    const int64_t r = i / Ch;
+    const int tt = (int)(r % Tp), b = (int)(r / Tp);
+    float2 v = make_float2(0.f, 0.f);
+    if (tt >= 1 && tt <= Tv && j < H) {
+      const int64_t idx = r * H + j;
+      v = make_float2(__ldg(hseq + idx) - __ldg(hseq + 3 * R * H + idx), __ldg(hseq + R * H + idx) + __ldg(hseq + 2 * R * H + idx));
+      *reinterpret_cast<float2*>(latent + (((int64_t)b * Tv + (tt - 1)) * H + j) * 2) = v;
+    }
+    if (out_split) {
+      st_split1(ps, R * Cp, r * Cp + j, v.x);
+      st_split1(ps, R * Cp, r * Cp + Ch + j, v.y);
+    } else {
+      pf[r * Cp + j] = v.x;
+      pf[r * Cp + Ch + j] = v.y;
+    }
   }
 }
 
@@ -347,5 +477,39 @@ extern "C" int idv_reparam_fwd(const float* latent, int NB, int T, int Htot, int
                                                            offset, reinterpret_cast<const unsigned long long*>(offset_dev),
                                                            variant, z);
   IDV_LAUNCH_CHECK("reparam_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_latent_fwd(const float* hseq, int NB, int T, int H, int t_valid, int zdim, int latent_num, int S,
+                              const float* eps_r0, const float* eps_i0, const float* eps_r1, const float* eps_i1,
+                              uint64_t seed, uint64_t offset, const uint64_t* offset_dev, float* latent, float* z0,
+                              float* z1, void* zplanes, int out_split, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(hseq && latent && z0 && zplanes && NB > 0 && T > 0 && S > 0 && zdim > 0, "idv_latent_fwd: bad argument");
+  IDV_CHECK_ARG((latent_num == 1 || latent_num == 2) && H == 3 * zdim * latent_num,
+                "idv_latent_fwd: H = %d must equal 3 * zdim (%d) * latent_num (%d)", H, zdim, latent_num);
+  IDV_CHECK_ARG((latent_num == 2) == (z1 != nullptr), "idv_latent_fwd: z1 is the second latent's output");
+  IDV_CHECK_ARG((eps_r0 == nullptr) == (eps_i0 == nullptr) && (eps_r1 == nullptr) == (eps_i1 == nullptr) &&
+                    (latent_num == 1 ? eps_r1 == nullptr : (eps_r1 == nullptr) == (eps_r0 == nullptr)),
+                "idv_latent_fwd: supply eps for every latent (real and imaginary draw) or for none");
+  const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
+  const int64_t n = (int64_t)NB * (T + 1) * ((zdim + 7) / 8 * 8);
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  latent_fused_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      hseq, NB, T, Tv, H, zdim, latent_num, S, eps_r0, eps_i0, eps_r1, eps_i1, seed, offset,
+      reinterpret_cast<const unsigned long long*>(offset_dev), latent, z0, z1, zplanes, out_split);
+  IDV_LAUNCH_CHECK("latent_fused_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_lstm_combine_planes(const float* hseq, int NB, int T, int H, int t_valid, float* latent, void* planes,
+                                       int out_split, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(hseq && latent && planes && NB > 0 && T > 0 && H > 0, "idv_lstm_combine_planes: bad argument");
+  const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
+  const int64_t n = (int64_t)NB * (T + 1) * ((H + 7) / 8 * 8);
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  combine_planes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(hseq, NB, T, Tv, H, latent, planes, out_split);
+  IDV_LAUNCH_CHECK("combine_planes_kernel");
   return IDV_OK;
 }

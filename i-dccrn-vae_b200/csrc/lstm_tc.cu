@@ -35,6 +35,8 @@ struct LstmTcParams {
   unsigned short* hx;                       // bf16 [n_rg][2 parity][2 m][2 hl][128][H]
   unsigned int* sync;                       // [n_rg][2 m] step counters (zeroed by the host)
   unsigned long long* dbg;                  // optional phase timestamps (IDV_LSTM_DBG=1), CTA (0,0,0), steps [200,208)
+  int rg0;                                  // first row group of this launch (batches whose row groups do not all fit the
+                                            // device at once run as consecutive launches)
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -78,7 +80,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   const uint32_t smem_w = smem_u32(smem), smem_ring = smem_u32(ring);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x, m = blockIdx.y, rg = blockIdx.z;
+  const int c = blockIdx.x, m = blockIdx.y, rg = p.rg0 + blockIdx.z;
   const int NC = p.NC, H = p.H, T = p.Tsteps;
   const int Tp = p.T + 1;
   const long long R = (long long)p.NB * Tp;
@@ -329,8 +331,8 @@ extern "C" int idv_lstm_recurrent_tc(const float* g, int64_t g_m_off, int64_t g_
   IDV_CHECK_ARG(stages >= 2 || (stages >= 1 && KC == 1), "idv_lstm_recurrent_tc: not enough shared memory for H=%d", H);
   const size_t smem = w_bytes + (size_t)stages * 2 * L_HTILE + 1024 + 256;
   IDV_CHECK_ARG((int)smem <= smem_optin, "idv_lstm_recurrent_tc: needs %zu B of shared memory", smem);
-  IDV_CHECK_ARG(NC * 2 * n_rg <= sms, "idv_lstm_recurrent_tc: %d CTAs exceed the %d SMs (batch %d too large for one launch)",
-                NC * 2 * n_rg, sms, NB);
+  IDV_CHECK_ARG(NC * 2 <= sms, "idv_lstm_recurrent_tc: %d CTAs per row group exceed the %d SMs", NC * 2, sms);
+  const int rg_per_launch = sms / (NC * 2);           // row groups (64 utterances each) that are co-resident
   CUtensorMap mW, mH;
   rc = encode_map_2d(&mW, wpack, H, (uint64_t)2 * 2 * NC * N, BK, N);
   if (rc) return rc;
@@ -351,10 +353,14 @@ extern "C" int idv_lstm_recurrent_tc(const float* g, int64_t g_m_off, int64_t g_
     IDV_CUDA(cudaMalloc(&p.dbg, 8 * 16 * sizeof(unsigned long long)));
     IDV_CUDA(cudaMemsetAsync(p.dbg, 0, 8 * 16 * sizeof(unsigned long long), st));
   }
-  switch (N) {
-    case 64: rc = launch_lstm_tc<64>(mW, mH, p, n_rg, smem, st); break;
-    case 48: rc = launch_lstm_tc<48>(mW, mH, p, n_rg, smem, st); break;
-    default: rc = launch_lstm_tc<32>(mW, mH, p, n_rg, smem, st); break;
+  for (int rg0 = 0; rg0 < n_rg && rc == IDV_OK; rg0 += rg_per_launch) {
+    p.rg0 = rg0;
+    const int nz = n_rg - rg0 < rg_per_launch ? n_rg - rg0 : rg_per_launch;
+    switch (N) {
+      case 64: rc = launch_lstm_tc<64>(mW, mH, p, nz, smem, st); break;
+      case 48: rc = launch_lstm_tc<48>(mW, mH, p, nz, smem, st); break;
+      default: rc = launch_lstm_tc<32>(mW, mH, p, nz, smem, st); break;
+    }
   }
   if (dbg && rc == IDV_OK) {
     unsigned long long h[8 * 16];

@@ -40,6 +40,10 @@ struct WaveParams {
   int g_ld;
   const float* bias1;                       // [2 m][NC][N] CTA-major (gate*Hs + j)
   int NB, T, H, NC, KC, stages, Tsteps;     // T = allocated frames (row layout), Tsteps = valid steps
+  int b0, NBc;                              // this launch works on utterances [b0, b0 + NBc) of the NB (chunks of <= 64)
+  int n_roles;                              // 3 = two-layer wavefront (L0 | IP | L1), 1 = ONE nn.LSTM layer per launch (role L0 only)
+  unsigned short* hsplit;                   // single-layer mode: optional bf16 [2][4][R][H] output (next layer's in-proj input)
+  float* hseq0;                             // single-layer mode: optional fp32 [4][R][H] output
   float* hseq1;                             // fp32 [4][R][H] layer-1 output
   unsigned short* hxA;                      // bf16 [W_REP][4 slot][2 m][2 hl][128][H]   h0
   unsigned short* hxC;                      // bf16 [W_REP][2 slot][2 m][2 hl][128][H]   h1
@@ -89,7 +93,8 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
   constexpr int HS = N / 4;
   // PAIR: the split runs as TWO MMAs per K step, A_hi x [W_hi | W_lo] (width 2 * 2N: the hi and lo weight tiles of a K
   // chunk are adjacent in shared memory) and A_lo x W_hi on top of its first half; the epilogue adds the two halves
-  constexpr int TMEM_COLS = PAIR ? 2 * N : (N <= 32 ? 32 : (N <= 64 ? 64 : 128));
+  constexpr int ACC_COLS = PAIR ? 2 * N : N;
+  constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : 256));
   constexpr int W_TILE = N * BK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -107,7 +112,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x;
-  const int m = blockIdx.y / 3, role = blockIdx.y % 3;        // 0 = L0, 1 = IP, 2 = L1
+  const int m = blockIdx.y / p.n_roles, role = blockIdx.y % p.n_roles;        // 0 = L0, 1 = IP, 2 = L1
   const int NC = p.NC, H = p.H, T = p.Tsteps;
   const int Tp = p.T + 1;
   const long long R = (long long)p.NB * Tp;
@@ -164,8 +169,8 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         int slot;
         if (role == 0) {            // input h0(t-1): slot (t)%4 holds h0(t-1) (h0(t) is written to slot (t+1)%4)
           wait_counter(cA, (long long)NC * t);
-          wait_counter(cB, (long long)NC * (t - 3));
-          slot = t & 3;
+          if (p.n_roles == 3) wait_counter(cB, (long long)NC * (t - 3));   // (single layer: all readers of a slot are L0 CTAs,
+          slot = t & 3;                                                    //  at most one step apart)
         } else if (role == 1) {     // input h0(t): slot (t+1)%4
           wait_counter(cA, (long long)NC * (t + 1));
           wait_counter(cC, (long long)NC * (t - 3));
@@ -242,13 +247,15 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
     const int q = warp & 3;                           // TMEM lane quarter (rows q*32 .. q*32+31)
     const int half = (warp - W_EPI_WARP0) >> 2;       // which half of the HS hidden units
     constexpr int HU = HS / 2;                        // units per thread
+    constexpr int VW = (HU % 4 == 0) ? 4 : 2;         // vector width of the global accesses (N = 48: 6 units per thread)
+    static_assert(HU % VW == 0 && HU <= 8, "units per epilogue thread");
     // TMEM lane -> (row, owner of the gate columns): one CTA per tile: lane = row, own columns; PAIR: see the header
     const int tl = q * 32 + lane;
     const int r = PAIR ? (int)rank * 64 + (tl & 63) : tl;
     const int c_own = PAIR ? (c & ~1) + (tl >> 6) : c;
     const int part = r >> 6;
-    const int b = r & 63;
-    const bool valid = b < p.NB;
+    const bool valid = (r & 63) < p.NBc;
+    const int b = p.b0 + (r & 63);                    // utterance of the whole batch (row layout, outputs)
     const int u0 = c_own * HS + half * HU;            // first hidden unit of this thread
     float cst[HU];
 #pragma unroll
@@ -270,9 +277,14 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
 #pragma unroll
           for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
-            for (int j = 0; j < HU; j += 4) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(gp + gt * H + j));
-              gin[gt * HU + j] = v.x; gin[gt * HU + j + 1] = v.y; gin[gt * HU + j + 2] = v.z; gin[gt * HU + j + 3] = v.w;
+            for (int j = 0; j < HU; j += VW) {
+              if (VW == 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(gp + gt * H + j));
+                gin[gt * HU + j] = v.x; gin[gt * HU + j + 1] = v.y; gin[gt * HU + j + 2] = v.z; gin[gt * HU + j + 3] = v.w;
+              } else {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(gp + gt * H + j));
+                gin[gt * HU + j] = v.x; gin[gt * HU + j + 1] = v.y;
+              }
             }
         } else {
 #pragma unroll
@@ -282,27 +294,45 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         // G1(t) is produced inside this kernel: acquire counter B, then coherent (L2) loads
         if (lane == 0) wait_counter(cB, (long long)NC * (t + 1));
         __syncwarp();
-        const float* gp = p.g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
+        if constexpr (VW == 4) {                      // (the wavefront roles only exist for N = 64)
+          const float* gp = p.g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
 #pragma unroll
-        for (int gt = 0; gt < 4; ++gt)
+          for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
-          for (int j = 0; j < HU; j += 4) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(gp + gt * H + j));
-            gin[gt * HU + j] = v.x; gin[gt * HU + j + 1] = v.y; gin[gt * HU + j + 2] = v.z; gin[gt * HU + j + 3] = v.w;
-          }
+            for (int j = 0; j < HU; j += 4) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(gp + gt * H + j));
+              gin[gt * HU + j] = v.x; gin[gt * HU + j + 1] = v.y; gin[gt * HU + j + 2] = v.z; gin[gt * HU + j + 3] = v.w;
+            }
+        }
       }
       mbar_wait(accfull, t & 1);
       tc_fence_after();
       if (warp == W_EPI_WARP0 && lane == 0) WAVE_DBG(4);
       uint32_t v[4 * HU];                             // [gate][unit]: accumulator columns gate*HS + half*HU + j
 #pragma unroll
-      for (int gt = 0; gt < 4; ++gt)
-        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + gt * HS + half * HU, v + gt * HU);
+      for (int gt = 0; gt < 4; ++gt) {
+        if (HU == 8) {
+          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + gt * HS + half * HU, v + gt * HU);
+        } else {                                      // 8 columns are read, the first HU kept (all inside the allocation)
+          uint32_t w8[8];
+          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + gt * HS + half * HU, w8);
+#pragma unroll
+          for (int j = 0; j < HU; ++j) v[gt * HU + j] = w8[j];
+        }
+      }
       if (PAIR) {
         uint32_t v2[4 * HU];
 #pragma unroll
-        for (int gt = 0; gt < 4; ++gt)
-          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + N + gt * HS + half * HU, v2 + gt * HU);
+        for (int gt = 0; gt < 4; ++gt) {
+          if (HU == 8) {
+            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + N + gt * HS + half * HU, v2 + gt * HU);
+          } else {
+            uint32_t w8[8];
+            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + N + gt * HS + half * HU, w8);
+#pragma unroll
+            for (int j = 0; j < HU; ++j) v2[gt * HU + j] = w8[j];
+          }
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4 * HU; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
@@ -314,16 +344,18 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       if (warp == W_EPI_WARP0 && lane == 0) WAVE_DBG(5);
       if (role == 1) {
         // ---- layer-1 input projection: G1(t) rows -> exchange buffer slot t%4
-        float* gp = p.g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
+        if constexpr (VW == 4) {
+          float* gp = p.g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
 #pragma unroll
-        for (int gt = 0; gt < 4; ++gt)
+          for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
-          for (int j = 0; j < HU; j += 4)
-            *reinterpret_cast<float4*>(gp + gt * H + j) =
-                make_float4(__uint_as_float(v[gt * HU + j]) + bias[gt * HU + j],
-                            __uint_as_float(v[gt * HU + j + 1]) + bias[gt * HU + j + 1],
-                            __uint_as_float(v[gt * HU + j + 2]) + bias[gt * HU + j + 2],
-                            __uint_as_float(v[gt * HU + j + 3]) + bias[gt * HU + j + 3]);
+            for (int j = 0; j < HU; j += 4)
+              *reinterpret_cast<float4*>(gp + gt * H + j) =
+                  make_float4(__uint_as_float(v[gt * HU + j]) + bias[gt * HU + j],
+                              __uint_as_float(v[gt * HU + j + 1]) + bias[gt * HU + j + 1],
+                              __uint_as_float(v[gt * HU + j + 2]) + bias[gt * HU + j + 2],
+                              __uint_as_float(v[gt * HU + j + 3]) + bias[gt * HU + j + 3]);
+        }
         // publish: ONE counter increment per CTA and step (same-address atomics serialise in the L2, ~27 clk each:
         // 8 per CTA x 24 CTAs took 2.4 us to drain): the epilogue warps meet at a named barrier, then one thread
         // fences - cumulative over the stores it has synchronised with, the pattern of a cooperative-groups grid
@@ -354,8 +386,10 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
           unsigned short* hx = (role == 0 ? p.hxA : p.hxC) +
                                (((((long long)rep * nslot + slot) * 2 + m) * 2) * W_ROWS + r) * H + u0;
 #pragma unroll
-          for (int j = 0; j < HU; j += 4)
-            st_split4(hx, (long long)W_ROWS * H, j, make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]));
+          for (int j = 0; j < HU; j += VW) {
+            if constexpr (VW == 4) st_split4(hx, (long long)W_ROWS * H, j, make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]));
+            else st_split2(hx, (long long)W_ROWS * H, j, make_float2(hn[j], hn[j + 1]));
+          }
         }
       }
       if (warp == W_EPI_WARP0 && lane == 0) WAVE_DBG(6);
@@ -366,10 +400,27 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         WAVE_DBG(7);
       }
       if (role == 2 && valid) {
+        if constexpr (VW == 4) {
+          const long long oidx = ((long long)(m * 2 + part) * R + rcur) * H + u0;
+#pragma unroll
+          for (int j = 0; j < HU; j += 4)
+            *reinterpret_cast<float4*>(p.hseq1 + oidx + j) = make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]);
+        }
+      }
+      if (p.n_roles == 1 && valid) {                  // one layer per launch: the sequence outputs, off the critical path
         const long long oidx = ((long long)(m * 2 + part) * R + rcur) * H + u0;
 #pragma unroll
-        for (int j = 0; j < HU; j += 4)
-          *reinterpret_cast<float4*>(p.hseq1 + oidx + j) = make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]);
+        for (int j = 0; j < HU; j += VW) {
+          if constexpr (VW == 4) {
+            const float4 hv = make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]);
+            if (p.hsplit) st_split4(p.hsplit, 4 * R * H, oidx + j, hv);
+            if (p.hseq0) *reinterpret_cast<float4*>(p.hseq0 + oidx + j) = hv;
+          } else {
+            const float2 hv = make_float2(hn[j], hn[j + 1]);
+            if (p.hsplit) st_split2(p.hsplit, 4 * R * H, oidx + j, hv);
+            if (p.hseq0) *reinterpret_cast<float2*>(p.hseq0 + oidx + j) = hv;
+          }
+        }
       }
     }
   }
@@ -387,7 +438,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
 template <int N, bool PAIR>
 static int launch_wave(const CUtensorMap* maps, const WaveParams& p, size_t smem, cudaStream_t st) {
   IDV_CUDA(cudaFuncSetAttribute(lstm_wave_tc_kernel<N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(p.NC, 6, 1), block(W_THREADS);
+  dim3 grid(p.NC, 2 * p.n_roles, 1), block(W_THREADS);
   cudaError_t e;
   if (PAIR) {
     // clusters of 2 along x.  All 6 * NC CTAs wait on one another and must be co-resident; that is checked against
@@ -448,7 +499,7 @@ static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off
   using namespace idv;
   using namespace idv::tc;
   IDV_CHECK_ARG(g0 && w_hh0 && w_ih1 && w_hh1 && bias1 && hseq1 && work && sync, "idv_lstm2_wave_tc: null pointer");
-  IDV_CHECK_ARG(NB > 0 && NB <= 64 && T > 0, "idv_lstm2_wave_tc: needs 1 <= NB <= 64 (got %d)", NB);
+  IDV_CHECK_ARG(NB > 0 && T > 0, "idv_lstm2_wave_tc: empty problem (NB %d, T %d)", NB, T);
   int N = 0, NC = 0;
   int64_t work_bytes = 0;
   int rc = idv_lstm2_wave_config(H, &N, &NC, &work_bytes);
@@ -480,8 +531,6 @@ static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off
   rc = encode_map_3d(&maps[4], wk + hxA_bytes, H, W_ROWS, (uint64_t)W_REP * 2 * 2 * 2, BK, pair ? W_ROWS / 2 : W_ROWS, 2);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  IDV_CUDA(cudaMemsetAsync(work, 0, (size_t)work_bytes, st));
-  IDV_CUDA(cudaMemsetAsync(sync, 0, 6 * sizeof(unsigned int), st));
   WaveParams p;
   p.g0 = g0; p.g_m_off = g_m_off; p.g_p_off = g_p_off; p.g_ld = g_ld; p.bias1 = bias1;
   p.NB = NB; p.T = T; p.H = H; p.NC = NC; p.KC = KC; p.stages = stages;
@@ -491,13 +540,22 @@ static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off
   p.hxC = reinterpret_cast<unsigned short*>(wk + hxA_bytes);
   p.g1x = reinterpret_cast<float*>(wk + hxA_bytes + hxC_bytes);
   p.sync = sync;
+  p.n_roles = 3; p.hsplit = nullptr; p.hseq0 = nullptr;
   p.dbg = nullptr;
   const bool dbg = getenv("IDV_LSTM_DBG") != nullptr && p.Tsteps > 304;
   if (dbg) {
     IDV_CUDA(cudaMalloc(&p.dbg, (96 + 32) * sizeof(unsigned long long)));
     IDV_CUDA(cudaMemsetAsync(p.dbg, 0, (96 + 32) * sizeof(unsigned long long), st));
   }
-  rc = pair ? launch_wave<64, true>(maps, p, smem, st) : launch_wave<64, false>(maps, p, smem, st);
+  // a launch holds 64 utterances (M = 128 rows = 2 input parts x 64): larger batches run as consecutive launches on
+  // the same stream, each with freshly zeroed exchange buffers / counters (h(-1) = 0)
+  for (int b0 = 0; b0 < NB && rc == IDV_OK; b0 += 64) {
+    p.b0 = b0;
+    p.NBc = NB - b0 < 64 ? NB - b0 : 64;
+    IDV_CUDA(cudaMemsetAsync(work, 0, (size_t)work_bytes, st));
+    IDV_CUDA(cudaMemsetAsync(sync, 0, 6 * sizeof(unsigned int), st));
+    rc = pair ? launch_wave<64, true>(maps, p, smem, st) : launch_wave<64, false>(maps, p, smem, st);
+  }
   if (dbg && rc == IDV_OK) {
     unsigned long long h[96 + 32];
     IDV_CUDA(cudaStreamSynchronize(st));
@@ -529,5 +587,88 @@ extern "C" int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_o
     rc = wave_run(true, g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq1, work, sync, t_valid, stream);
   if (rc == IDV_E_RESOURCE)        // the CTA pairs do not all fit the device at once: one CTA per tile, cooperative launch
     rc = wave_run(false, g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq1, work, sync, t_valid, stream);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ONE nn.LSTM layer of both modules per launch on the same kernel (role L0 only): the CTA-pair recurrence for hidden
+// sizes whose two layers do not fit the device at once (H = 768: the three weight matrices of the wavefront are 56.6 MB
+// of bf16 hi/lo against 33.6 MB of shared memory on 148 SMs - at most one layer's W_hh, 18.9 MB, can be resident) and
+// for the training forward, which needs the per-layer sequences.  Against idv_lstm_recurrent_tc (one CTA per tile): a
+// CTA streams 64 instead of 128 rows of h per step, two MMAs per K step, one counter increment per CTA and step.
+// ---------------------------------------------------------------------------------------------------------------------
+static int layer_cols(int H) {
+  if (H % 64 != 0) return 0;
+  if (H <= 512 && H % 16 == 0 && (H / 16) % 2 == 0) return 64;
+  if (H <= 768 && H % 12 == 0 && (H / 12) % 2 == 0) return 48;
+  return 0;
+}
+
+extern "C" int idv_lstm_layer_pair_config(int H, int* n_cols, int* n_ctas, int64_t* work_bytes) {
+  using namespace idv;
+  IDV_CHECK_ARG(n_cols && n_ctas && work_bytes, "idv_lstm_layer_pair_config: null pointer");
+  const int N = layer_cols(H);
+  IDV_CHECK_ARG(N > 0, "idv_lstm_layer_pair_config: hidden size %d is not supported by the CTA-pair recurrence", H);
+  *n_cols = N;
+  *n_ctas = H / (N / 4);
+  *work_bytes = (int64_t)4 * 2 * 2 * 128 * H * 2;          // h exchange buffer: bf16 [4 slots][2 m][2 hl][128][H]
+  return IDV_OK;
+}
+
+extern "C" int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* wpack, int NB,
+                                      int T, int H, float* hseq, void* hsplit, void* work, unsigned int* sync, int t_valid,
+                                      void* stream) {
+  using namespace idv;
+  using namespace idv::tc;
+  IDV_CHECK_ARG(g && wpack && work && sync && (hseq || hsplit), "idv_lstm_layer_pair_tc: null pointer");
+  IDV_CHECK_ARG(NB > 0 && T > 0, "idv_lstm_layer_pair_tc: empty problem");
+  int N = 0, NC = 0;
+  int64_t work_bytes = 0;
+  int rc = idv_lstm_layer_pair_config(H, &N, &NC, &work_bytes);
+  if (rc) return rc;
+  const int KC = H / 64;
+  int dev = 0, sms = 0, smem_optin = 0;
+  IDV_CUDA(cudaGetDevice(&dev));
+  IDV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  IDV_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  IDV_CHECK_ARG(2 * NC <= sms, "idv_lstm_layer_pair_tc: %d CTAs exceed the %d SMs", 2 * NC, sms);
+  const size_t w_bytes = (size_t)2 * KC * N * BK * 2;
+  // (no cooperative guarantee for clusters: not when kernels of several streams share the GPU, see idv_lstm2_wave_tc)
+  bool pair = option_lstm_wave_pairs() && !option_dynamic_tiles();
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const size_t stage_bytes = (size_t)2 * W_HTILE / (pair ? 2 : 1);
+    int stages = (int)(((size_t)smem_optin - w_bytes - 1024 - 256) / stage_bytes);
+    if (stages > (pair ? 7 : 8)) stages = pair ? 7 : 8;
+    if (stages > KC) stages = KC;
+    IDV_CHECK_ARG(stages >= 2 || (stages >= 1 && KC == 1), "idv_lstm_layer_pair_tc: not enough shared memory for H=%d", H);
+    const size_t smem = w_bytes + (size_t)stages * stage_bytes + 1024 + 256;
+    CUtensorMap maps[5];
+    rc = encode_map_2d(&maps[0], wpack, H, (uint64_t)2 * 2 * NC * N, BK, N);
+    if (rc) return rc;
+    rc = encode_map_3d(&maps[3], work, H, W_ROWS, (uint64_t)4 * 2 * 2, BK, pair ? W_ROWS / 2 : W_ROWS, 2);
+    if (rc) return rc;
+    maps[1] = maps[0]; maps[2] = maps[0]; maps[4] = maps[3];
+    WaveParams p;
+    p.g0 = g; p.g_m_off = g_m_off; p.g_p_off = g_p_off; p.g_ld = g_ld; p.bias1 = nullptr;
+    p.NB = NB; p.T = T; p.H = H; p.NC = NC; p.KC = KC; p.stages = stages;
+    p.Tsteps = (t_valid > 0 && t_valid < T) ? t_valid : T;
+    p.hseq1 = nullptr;
+    p.hxA = reinterpret_cast<unsigned short*>(work); p.hxC = nullptr; p.g1x = nullptr;
+    p.sync = sync; p.dbg = nullptr;
+    p.n_roles = 1; p.hsplit = reinterpret_cast<unsigned short*>(hsplit); p.hseq0 = hseq;
+    rc = IDV_OK;
+    for (int b0 = 0; b0 < NB && rc == IDV_OK; b0 += 64) {
+      p.b0 = b0;
+      p.NBc = NB - b0 < 64 ? NB - b0 : 64;
+      IDV_CUDA(cudaMemsetAsync(work, 0, (size_t)work_bytes, st));
+      IDV_CUDA(cudaMemsetAsync(sync, 0, 6 * sizeof(unsigned int), st));
+      if (N == 64) rc = pair ? launch_wave<64, true>(maps, p, smem, st) : launch_wave<64, false>(maps, p, smem, st);
+      else rc = pair ? launch_wave<48, true>(maps, p, smem, st) : launch_wave<48, false>(maps, p, smem, st);
+      if (rc == IDV_E_RESOURCE && b0 == 0) break;
+    }
+    if (rc != IDV_E_RESOURCE || !pair) break;
+    pair = false;                 // the CTA pairs are not all co-resident: one CTA per tile, cooperative launch
+  }
   return rc;
 }

@@ -45,7 +45,28 @@ struct Params {
   const float* stft_x;
   float* predict;
   unsigned int* sched;        // [0] next tile, [1] CTAs finished (dynamic tile scheduler; self-resetting)
+  int order;                  // tile order: 0 = (unit, row tile, N tile), 1 = (row tile, unit, N tile) - see decode_tile
 };
+
+// Tile index -> (unit, row tile, N tile).  The CTAs that run at the same time work on CONSECUTIVE tile indices, so the
+// order decides what they share in the L2:
+//   order 0: unit outermost - co-resident CTAs walk the rows of ONE output plane; the input planes it reads (5 for a
+//            stride-2 conv, 84 MB each at batch 64) are evicted from the 126 MB L2 before the next output plane, which
+//            shares 3 of them, comes round: every input plane is read from DRAM 2-3 times (ncu: 39.8 GB per step for
+//            23 GB of compulsory traffic);
+//   order 1: row tile outermost, unit inner - co-resident CTAs compute ALL output planes of the same few row tiles,
+//            so an input box is fetched from DRAM once and served from the L2 to the 2-5 units that read it.
+__device__ __forceinline__ void decode_tile(const Params& p, int t, int n_row_tiles, int& u, int& rt, int& nt) {
+  nt = t % p.n_col_tiles;
+  const int q = t / p.n_col_tiles;
+  if (p.order) {
+    u = q % p.n_units;
+    rt = q / p.n_units;
+  } else {
+    rt = q % n_row_tiles;
+    u = q / n_row_tiles;
+  }
+}
 
 // TWO: the kernel runs as CTA PAIRS (thread-block clusters of 2, tcgen05 cta_group::2).  A pair computes a 256 x BN
 // tile: each CTA stages its own 128 activation rows and HALF of the weight tile (BN/2 rows), one thread of the even
@@ -145,9 +166,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         if (t < 0) break;
         // DYN: claimed one tile ahead, the atomic's latency hides behind this tile's loads
         t_next = DYN ? (int)atomicAdd(p.sched, 1u) : t + nwork;
-        const int nt = t % p.n_col_tiles;
-        const int rt = TWO ? 2 * ((t / p.n_col_tiles) % n_row_tiles) + (int)rank : (t / p.n_col_tiles) % n_row_tiles;
-        const idv_unit_t unit = p.units[t / (p.n_col_tiles * n_row_tiles)];
+        int ui, rt, nt;
+        decode_tile(p, t, n_row_tiles, ui, rt, nt);
+        if (TWO) rt = 2 * rt + (int)rank;
+        const idv_unit_t unit = p.units[ui];
         // co-resident CTAs work on the same unit: start each at a different tap so they do not all request the
         // same weight tile (same L2 lines) at the same moment; the accumulation order is per-CTA but fixed
         // (both CTAs of a pair walk the taps in the same order)
@@ -192,8 +214,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           if (t >= total_tiles) t = -1;
         }
         if (t < 0) break;
-        const idv_unit_t unit = p.units[t / (p.n_col_tiles * n_row_tiles)];
-        const int ksteps = unit.reserved;
+        int ui, rt_, nt_;
+        decode_tile(p, t, n_row_tiles, ui, rt_, nt_);
+        const int ksteps = p.units[ui].reserved;
         const uint32_t acc = local & 1, aphase = (local >> 1) & 1;
         mbar_wait(tempty0 + 8 * acc, aphase ^ 1);
         tc_fence_after();
@@ -242,9 +265,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         if (t >= total_tiles) t = -1;
       }
       if (t < 0) break;
-      const int nt = t % p.n_col_tiles;
-      const int rt = TWO ? 2 * ((t / p.n_col_tiles) % n_row_tiles) + (int)rank : (t / p.n_col_tiles) % n_row_tiles;
-      const idv_unit_t unit = p.units[t / (p.n_col_tiles * n_row_tiles)];
+      int ui, rt, nt;
+      decode_tile(p, t, n_row_tiles, ui, rt, nt);
+      if (TWO) rt = 2 * rt + (int)rank;
+      const idv_unit_t unit = p.units[ui];
       // the accumulator-empty barrier the MMA issuer waits on (TWO: the even CTA's, 8 warps arrive)
       const uint32_t tempty_bar = TWO ? ((tempty0 + 8 * (local & 1)) & PEER_BIT_MASK) : (tempty0 + 8 * (local & 1));
       const uint32_t acc = local & 1, aphase = (local >> 1) & 1;
@@ -607,6 +631,7 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
   p.out_plane = out_plane; p.out_hl = out_hl; p.out_split = out_split; p.apply_prelu = apply_prelu; p.slope = prelu_slope;
   p.head = head; p.head_fout = head_fout; p.head_bmul = head_bmul; p.head_boff = head_boff;
   p.stft_x = stft_x; p.predict = predict;
+  p.order = option_tile_order();
   cudaStream_t st = (cudaStream_t)stream;
   if (pairs) {
     switch (BN) {

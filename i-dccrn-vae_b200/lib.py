@@ -11,7 +11,7 @@ from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
-ABI_VERSION = 5        # IDV_ABI_VERSION of include/idv.h this binding was written against
+ABI_VERSION = 6        # IDV_ABI_VERSION of include/idv.h this binding was written against
 
 c_f32p = ctypes.c_void_p
 i32, i64, u64, f32, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_void_p
@@ -34,8 +34,11 @@ SIGNATURES = {
     "idv_lstm_recurrent_fwd": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, i32, vp],
     "idv_lstm_recurrent_tc": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp],
     "idv_lstm2_wave_tc": [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],
+    "idv_lstm_layer_pair_tc": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp],
     "idv_lstm_combine_fwd": [vp, i32, i32, i32, vp, i32, vp],
     "idv_reparam_fwd": [vp, i32, i32, i32, i32, i32, i32, vp, vp, u64, u64, vp, i32, vp, vp],
+    "idv_latent_fwd": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, i32, vp],
+    "idv_lstm_combine_planes": [vp, i32, i32, i32, i32, vp, vp, i32, vp],
     "idv_bin_affine": [vp, i32, i32, i32, vp, vp, i32, vp, vp],
     "idv_planes_to_user": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "idv_user_to_planes": [vp, i32, i32, i32, i32, vp, i32, i32, vp],
@@ -73,7 +76,8 @@ SIGNATURES = {
     "idv_stream_last_frame": [vp, i32, i32, i32, vp, vp],
     "idv_stream_ola": [vp, i32, vp, vp, i32, i32, i64, i32, i32, vp, vp],
 }
-EXPORTS = ["idv_abi_version", "idv_last_error", "idv_lstm_tc_config", "idv_lstm2_wave_config", "idv_set_option"] + \
+EXPORTS = ["idv_abi_version", "idv_last_error", "idv_lstm_tc_config", "idv_lstm2_wave_config",
+           "idv_lstm_layer_pair_config", "idv_set_option"] + \
     list(SIGNATURES)
 
 
@@ -101,6 +105,10 @@ def load():
         fn.argtypes = args
         fn.restype = ctypes.c_int
     _LIB = lib
+    # IDV_OPTIONS="name=value,name=value": idv_set_option switches for A/B measurements (tools, bench runs)
+    for item in filter(None, os.environ.get("IDV_OPTIONS", "").split(",")):
+        name, _, value = item.partition("=")
+        set_option(name.strip(), int(value))
     return lib
 
 
@@ -175,6 +183,18 @@ def lstm2_wave_config(H):
                                           ctypes.POINTER(ctypes.c_int64)]
     lib.idv_lstm2_wave_config.restype = ctypes.c_int
     if lib.idv_lstm2_wave_config(int(H), ctypes.byref(n), ctypes.byref(c), ctypes.byref(w)) != 0:
+        return None
+    return n.value, c.value, w.value
+
+
+def lstm_layer_pair_config(H):
+    """(gate columns per CTA, CTAs per module, workspace bytes) of the one-layer CTA-pair recurrence, or None."""
+    lib = load()
+    n, c, w = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int64(0)
+    lib.idv_lstm_layer_pair_config.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                               ctypes.POINTER(ctypes.c_int64)]
+    lib.idv_lstm_layer_pair_config.restype = ctypes.c_int
+    if lib.idv_lstm_layer_pair_config(int(H), ctypes.byref(n), ctypes.byref(c), ctypes.byref(w)) != 0:
         return None
     return n.value, c.value, w.value
 

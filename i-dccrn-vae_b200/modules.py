@@ -10,23 +10,27 @@ goes through the C ABI (ops.py), and there is no CPU or eager fallback.
 North-star aliases: ConvSTFT = STFT, ConviSTFT = ISTFT, ComplexBatchNorm = ComplexBatchNormal,
 NavieComplexLSTM = ComplexLSTM.
 
-``train=True`` runs the reference's train-mode FORWARD (ComplexBatchNormal batch statistics and running-buffer
-updates, model/complex_progress.py:L131-160) without building an autograd graph.  Both time geometries are built:
-the causal one (model/causal_netconfig.py: time pad 1, last column dropped, T frames everywhere) and the
-non-causal one (model/net_config.py: no time pad, one frame fewer per encoder layer and one more per decoder
-layer); activations keep the row layout of the STFT's T frames and carry their valid frame count (ops.Planes.Tv).
-Not built (raise NotImplementedError): backward / optimiser, data_norm.
+``train=True`` runs the reference's train-mode forward (ComplexBatchNormal batch statistics and running-buffer
+updates, model/complex_progress.py:L131-160).  Under ``torch.no_grad()`` that is all; with autograd enabled and
+trainable parameters the encoders / decoders dispatch to train.py, whose single autograd node per model runs the
+C-ABI backward kernels and writes the parameter gradients (phase 1, phase 2 and the end-to-end step; ``num_samples``
+>= 1).  Both time geometries are built: the causal one (model/causal_netconfig.py: time pad 1, last column dropped, T
+frames everywhere) and the non-causal one (model/net_config.py: no time pad, one frame fewer per encoder layer and
+one more per decoder layer); activations keep the row layout of the STFT's T frames and carry their valid frame count
+(ops.Planes.Tv).  Not built (raise NotImplementedError): the backward pass through the ``*_fc_latent`` / ``data_norm``
+variants and through the non-causal net.
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from . import ops, pack
 from .ops import Planes
 
-_TRAIN_MSG = ("train=True with num_samples > 1 is not built (the batch statistics would span the sample passes); "
-              "use num_samples == 1 or train=False")
-# train=True is FORWARD ONLY: ComplexBatchNormal uses batch statistics and updates its running buffers exactly like
-# the reference (first call copies, later calls EMA), but no autograd graph is built (backward kernels: next round).
+_TRAIN_MSG = ("train=True with num_samples > 1 outside autograd is not built (the batch statistics span the sample "
+              "passes: that forward lives in train.DecoderTrainStep); run it with gradients enabled, use "
+              "num_samples == 1, or train=False")
 
 
 def _sd(module):
@@ -321,7 +325,7 @@ class ComplexLSTM(nn.Module):
 
     def _packed_tc(self, cfg, device):
         items = self._cache.check(self)
-        key = ("whh_tc", cfg, str(device))
+        key = ("whh_tc", cfg[0], cfg[1], str(device))
         if key not in items:
             re, im = _sd(self.lstm_re), _sd(self.lstm_im)
             items[key] = [pack.pack_lstm_whh_tc(re, im, l, cfg[0], cfg[1], device) for l in range(self.num_layer)]
@@ -337,8 +341,10 @@ class ComplexLSTM(nn.Module):
                           pack.pack_lstm_whh_tc(re, im, 1, n, c, device), pack.pack_lstm_bias_tc(re, im, 1, n, c, device))
         return items[key]
 
-    def forward_planes(self, xp):
-        """xp: Planes with C*F == input_size (feature d = c*F + f).  Returns the latent (NB, T, H, 2)."""
+    def forward_planes(self, xp, combine=True):
+        """xp: Planes with C*F == input_size (feature d = c*F + f).  Returns the latent (NB, T, H, 2), or with
+        combine=False the four uncombined streams ``(hseq fp32 [4][R][H], NB, T, H, Tv)`` for a fused consumer
+        (ops.latent_fused / ops.lstm_combine_planes)."""
         layers = self._packed(xp.C, xp.F, xp.data.device)
         NB, T, H, Tv = xp.NB, xp.T, self.hidden_size, xp.Tv
         R = NB * (T + 1)
@@ -351,7 +357,7 @@ class ComplexLSTM(nn.Module):
             if ops.GATE_HOOK[0] is not None:
                 ops.GATE_HOOK[0]()
             hseq = ops.lstm2_wave_tc(g, 4 * H, R * 8 * H, 8 * H, w0, wi1, w1, b1, NB, T, H, wave[2], t_valid=Tv)
-            return ops.lstm_combine(hseq, NB, T, H, Tv)
+            return ops.lstm_combine(hseq, NB, T, H, Tv) if combine else (hseq, NB, T, H, Tv)
         # tensor-core recurrence when the planes are split-bf16 and the cooperative grid fits the device;
         # otherwise the fp32 SIMT recurrence (any batch size)
         cfg = ops.lstm_tc_supported(H, NB, xp.data.device) if split else None
@@ -365,7 +371,7 @@ class ComplexLSTM(nn.Module):
             offs = (4 * H, R * 8 * H, 8 * H) if l == 0 else (2 * R * 4 * H, R * 4 * H, 4 * H)
             if cfg:
                 hseq, hsp = ops.lstm_recurrent_tc(g, offs[0], offs[1], offs[2], whh_tc[l], NB, T, H,
-                                                  want_f32=last, want_split=more, t_valid=Tv)
+                                                  want_f32=last, want_split=more, t_valid=Tv, cfg=cfg)
             else:
                 hseq, hsp = ops.lstm_recurrent(g, offs[0], offs[1], offs[2], whh, NB, T, H, want_split=more,
                                                t_valid=Tv)
@@ -373,7 +379,7 @@ class ComplexLSTM(nn.Module):
             if not last:
                 src = Planes(hsp, NB, H, 4, T, cp=H, split=True, Tv=Tv) if split else \
                     Planes(hseq, NB, H, 4, T, cp=H, Tv=Tv)
-        return ops.lstm_combine(hseq, NB, T, H, Tv)
+        return ops.lstm_combine(hseq, NB, T, H, Tv) if combine else (hseq, NB, T, H, Tv)
 
     def forward(self, x):
         """x: (T, B, D, 2) -> (T, B, H, 2)"""
@@ -623,11 +629,34 @@ def _run_encoder_stack(encoders, stft_x, train=False):
 
 
 _philox_calls = [0]
+FUSED_LATENT = [os.environ.get("IDV_FUSED_LATENT", "1") != "0"]      # one idv_latent_fwd launch instead of lstm_combine + reparam + z_to_planes (A/B switch)
+
+
+def _z_planes(z, B, S, s, split, t_alloc):
+    """Decoder input planes of sample s of z (B*S, T, zdim, 2).  When z is the (unmodified) z_speech an encoder of
+    this package returned, the planes idv_latent_fwd already wrote are used; any other tensor is converted."""
+    tag = getattr(z, "_idv_planes", None)
+    if tag is not None and tag[1] == z._version and len(tag[0]) == S:
+        p = tag[0][s]
+        if p.split == split and p.T == t_alloc and p.NB == B and p.data.device == z.device:
+            return p
+    return ops.z_to_planes(z, B, S, s, split=split, t_alloc=t_alloc)
+
+
+def philox_seed():
+    """Seed of the on-device Philox draws: torch's seed mixed with the rank, so the ranks of a data-parallel job draw
+    different eps for their different utterances (every rank usually sets the same torch seed)."""
+    seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        seed ^= ((torch.distributed.get_rank() + 1) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    return seed
 
 
 def _next_philox():
+    """(seed, draw counter): every draw advances the counter by one; the kernels turn a counter into its own block of
+    Philox outputs (4 x 32 bit per element), so draws never share a uniform."""
     _philox_calls[0] += 1
-    return torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, _philox_calls[0]
+    return philox_seed(), _philox_calls[0]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -719,6 +748,17 @@ class _VaeEncoderBase(nn.Module):
                 stft_x = ops.bin_affine(stft_x, self._norm[0], self._norm[1], zero_edge_imag=True, out=stft_x)
             planes = _run_encoder_stack(self.encoders, stft_x, train)
             top = planes[-1]
+            if self._heads is None and FUSED_LATENT[0]:
+                # ONE launch: combine of the four LSTM streams, latent split, reparameterisation of every latent and the
+                # z planes the decoder's ComplexDense reads (they ride on z_speech: see _z_planes)
+                hs = self.lstms[0].forward_planes(top, combine=False)
+                seed, off = (0, 0) if eps is not None else _next_philox()
+                latent, zs, zpl = ops.latent_fused(*hs, self.zdim, self.latent_num, self.num_samples, eps, seed, off,
+                                                   top.split)
+                zs[0]._idv_planes = (zpl, zs[0]._version)
+                skiper = SkipList(planes)
+                skiper.grad_token, skiper.train_step = None, None
+                return stft_x, skiper, latent, zs, top.C, top.F
             latent = self.lstms[0].forward_planes(top)                 # (B, T, hidden, 2)
             if self._heads is not None:
                 latent = self._apply_heads(latent)                     # (B, T, 3*zdim*latent_num, 2)
@@ -968,16 +1008,18 @@ class _VaeDecoderBase(nn.Module):
             recon_sig, predict = _train.decoder_train_forward(self, stft_x if mask else None, z, skiper, skips, C, F, mask)
             return recon_sig, torch.view_as_complex(predict)
         for s in range(S):
-            zp = ops.z_to_planes(z, B, S, s, split=split, t_alloc=t_alloc)
+            zp = _z_planes(z, B, S, s, split, t_alloc)
             p = self.dense.forward_planes(zp, C, F)
             for i in range(n - 1):
                 p = self.decoders[i].forward_planes(p, skips.get(i), train)
-                if self.keep_decoder_outputs and S == 1:
+                if S == 1:
                     self.decoder_outputs.append(p)
             self.decoders[n - 1].forward_head(p, skips.get(n - 1), mask, stft_x if mask else None, predict, S, s,
                                               train)
-        if self.keep_decoder_outputs and S == 1:
-            self.decoder_outputs = SkipList(self.decoder_outputs)
+        # model/pvae_module.py:L2090,L2099: the per-layer outputs (B*S, C, F, T, 2) are kept on the module.  Here they
+        # stay activation planes and are converted on access (SkipList); with num_samples > 1 the sample passes run
+        # one after the other on (B, ...) planes, so the list is only kept for num_samples == 1.
+        self.decoder_outputs = SkipList(self.decoder_outputs) if S == 1 else []
         if self.datanorm:                                              # model/pvae_module.py:L483-484, L507-510
             key = (self.data_mean._version, self.data_std._version, str(predict.device))
             if getattr(self, "_norm_key", None) != key:
@@ -1085,11 +1127,11 @@ class standard_DCCRN(nn.Module):
         stft_x = ops.lib.require_f32_cuda(stft_x, "stft_x")
         planes = _run_encoder_stack(self.encoders, stft_x, train)
         top = planes[-1]
-        lat = self.lstms[0].forward_planes(top)                         # (B, T, H, 2)
+        hs = self.lstms[0].forward_planes(top, combine=False)
+        lat, zp = ops.lstm_combine_planes(*hs, top.split)               # (B, T, H, 2) + the dense layer's input plane
         if not train:
             self.latent = lat                                           # model/pvae_module.py:L187-188
         B, T = lat.shape[0], top.T
-        zp = ops.z_to_planes(lat, B, 1, 0, split=top.split, t_alloc=top.T)
         p = self.dense.forward_planes(zp, top.C, top.F)
         n = len(self.decoders)
         for i in range(n - 1):

@@ -213,20 +213,37 @@ def lstm_recurrent(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, want_split=False, t
     return hseq, hsplit
 
 
+LSTM_LAYER_PAIRS = [os.environ.get("IDV_LSTM_LAYER_PAIRS", "1") != "0"]   # one-layer recurrence as CTA pairs (else one CTA per tile)
+
+
 def lstm_tc_supported(H, NB, device):
-    cfg = lib.lstm_tc_config(H)
-    if cfg is None:
-        return None
-    n_rg = (NB + 63) // 64
+    """Configuration of the one-layer-per-launch tensor-core recurrence: (gate columns per CTA, CTAs per module, kind,
+    workspace bytes) with kind "pair" (idv_lstm_layer_pair_tc: CTA pairs, half of h streamed per CTA) or "tc"
+    (idv_lstm_recurrent_tc), or None when the hidden size fits neither.  Batches of more than 64 utterances run as
+    consecutive launches inside the entry points."""
     sms = torch.cuda.get_device_properties(device).multi_processor_count if torch.cuda.is_available() else 148
-    return cfg if n_rg * 2 * cfg[1] <= sms else None
+    if LSTM_LAYER_PAIRS[0]:
+        cfg = lib.lstm_layer_pair_config(H)
+        if cfg is not None and 2 * cfg[1] <= sms:
+            return cfg[0], cfg[1], "pair", cfg[2]
+    cfg = lib.lstm_tc_config(H)
+    if cfg is None or 2 * cfg[1] > sms:
+        return None
+    return cfg[0], cfg[1], "tc", 0
 
 
-def lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, want_f32=True, want_split=False, t_valid=0):
-    """Tensor-core recurrence.  Returns (hseq fp32 or None, hsplit bf16 or None)."""
+def lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, want_f32=True, want_split=False, t_valid=0, cfg=None):
+    """Tensor-core recurrence of one layer; cfg from lstm_tc_supported (wpack packed with its first two entries).
+    Returns (hseq fp32 or None, hsplit bf16 or None)."""
     n = 4 * NB * (T + 1) * H
     hseq = _empty(n, g.device) if want_f32 else None
     hsplit = _empty_act(n, g.device, True) if want_split else None
+    if cfg is not None and cfg[2] == "pair":
+        work = torch.empty(int(cfg[3]), dtype=torch.uint8, device=g.device)
+        sync = torch.empty(6, dtype=torch.int32, device=g.device)
+        lib.call("idv_lstm_layer_pair_tc", g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, work, sync,
+                 int(t_valid))
+        return hseq, hsplit
     n_rg = (NB + 63) // 64
     hx = torch.empty(n_rg * 2 * 2 * 2 * 128 * H, dtype=torch.bfloat16, device=g.device)
     sync = torch.empty(n_rg * 2, dtype=torch.int32, device=g.device)
@@ -237,7 +254,7 @@ def lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, want_f32=True,
 
 def lstm2_wave_supported(H, NB, device):
     cfg = lib.lstm2_wave_config(H)
-    if cfg is None or NB > 64:
+    if cfg is None:                       # (NB > 64: the entry point loops over chunks of 64 utterances)
         return None
     sms = torch.cuda.get_device_properties(device).multi_processor_count if torch.cuda.is_available() else 148
     return cfg if 6 * cfg[1] <= sms else None
@@ -272,6 +289,42 @@ def reparam(latent, ch0, zdim, S, eps_r, eps_i, seed, offset, offset_dev=None, o
     lib.call("idv_reparam_fwd", latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, int(seed), int(offset), offset_dev,
              int(variant), z)
     return z
+
+
+def latent_fused(hseq, NB, T, H, t_valid, zdim, latent_num, S, eps, seed, offset, split, offset_dev=None):
+    """ONE launch for the latent stage of the VAE encoders without heads: combine of the four LSTM streams, latent
+    split, reparameterisation of every latent and the decoder's z planes (idv_latent_fwd).  eps: None (Philox) or the
+    list [real_0, imag_0(, real_1, imag_1)] of (NB, S, Tv, zdim) tensors.  Returns (latent, [z_k], [Planes per sample])."""
+    Tv = t_valid if 0 < t_valid < T else T
+    dev = hseq.device
+    latent = torch.empty((NB, Tv, H, 2), dtype=torch.float32, device=dev)
+    zs = [torch.empty((NB * S, Tv, zdim, 2), dtype=torch.float32, device=dev) for _ in range(latent_num)]
+    e = [None] * 4
+    if eps is not None:
+        if len(eps) != 2 * latent_num:
+            raise RuntimeError("eps must hold %d tensors (real, imaginary draw per latent)" % (2 * latent_num))
+        for i, t in enumerate(eps):
+            t = lib.require_f32_cuda(t, "eps")
+            if tuple(t.shape) != (NB, S, Tv, zdim):
+                raise RuntimeError("eps must have shape (B, S, T, zdim) = %s" % ((NB, S, Tv, zdim),))
+            e[i] = t
+    Cp = 2 * round8(zdim)
+    n_plane = NB * (T + 1) * Cp
+    zpl = _empty_act(S * n_plane, dev, split)
+    lib.call("idv_latent_fwd", hseq, NB, T, H, Tv, zdim, latent_num, S, e[0], e[1], e[2], e[3], int(seed), int(offset),
+             offset_dev, latent, zs[0], zs[1] if latent_num == 2 else None, zpl, 1 if split else 0)
+    per = n_plane * (2 if split else 1)
+    planes = [Planes(zpl[s * per:(s + 1) * per], NB, zdim, 1, T, split=split, Tv=Tv) for s in range(S)]
+    return latent, zs, planes
+
+
+def lstm_combine_planes(hseq, NB, T, H, t_valid, split):
+    """lstm_combine + z_to_planes in one launch: returns (latent (NB, Tv, H, 2), Planes [1][R][2 round8(H)])."""
+    Tv = t_valid if 0 < t_valid < T else T
+    latent = torch.empty((NB, Tv, H, 2), dtype=torch.float32, device=hseq.device)
+    data = _empty_act(NB * (T + 1) * 2 * round8(H), hseq.device, split)
+    lib.call("idv_lstm_combine_planes", hseq, NB, T, H, Tv, latent, data, 1 if split else 0)
+    return latent, Planes(data, NB, H, 1, T, split=split, Tv=Tv)
 
 
 def bin_affine(x, scale, shift, zero_edge_imag=False, out=None):
@@ -333,6 +386,10 @@ def _cbn_finalize(bn, acc, count, device, stats=None):
     lib.call("idv_cbn_train_finalize", acc, float(count), C, bn.gamma_rr.detach(), bn.gamma_ri.detach(),
              bn.gamma_ii.detach(), bn.beta_r.detach(), bn.beta_i.detach(), bn.running_mean_real, bn.running_mean_imag,
              bn.Vrr, bn.Vri, bn.Vii, float(bn.momentum), 1 if first else 0, zb, stats)
+    # the kernel rewrote the running buffers through raw pointers: bump their versions so every cached eval-mode fold
+    # of this layer (modules._PackCache stamps are (data_ptr, _version)) is rebuilt from the new statistics
+    for buf in (bn.running_mean_real, bn.running_mean_imag, bn.Vrr, bn.Vri, bn.Vii):
+        torch.autograd.graph.increment_version(buf)
     if first and not bn.dis_cbn:
         bn.init_flag = False
     return zb

@@ -57,6 +57,11 @@ def enhance_ragged(waves, encoder, decoder, device, max_batch=64, max_pad_frac=0
     hop = encoder.stft.hop_length
     decoder_kwargs = decoder_kwargs or {}
     lens = [int(w.numel()) for w in waves]
+    n_fft = encoder.stft.n_fft
+    short = [i for i, n in enumerate(lens) if n <= n_fft // 2]
+    if short:          # torch.stft's reflect padding (model/pvae_module.py:L22) raises for these; so do we
+        raise RuntimeError("utterance(s) %s have %s samples: the STFT's reflect padding needs more than n_fft/2 = %d"
+                           % (short[:8], [lens[i] for i in short[:8]], n_fft // 2))
     buckets = bucket_batches(lens, max_batch, max_pad_frac, hop)
     dev = torch.device(device)
     copy_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None

@@ -116,6 +116,7 @@ class StreamingEnhancer:
         self.primed = False
         self._graph = None
         self._lstm_packs = None
+        self._mods, self._stamp = None, None
 
     def reset(self):
         """Forget all streams (state back to the start of a signal).  A captured graph stays valid."""
@@ -216,7 +217,7 @@ class StreamingEnhancer:
         if tuple(x0.shape) != (self.NB, self.hop):
             raise RuntimeError("prime expects (%d, %d) samples" % (self.NB, self.hop))
         self.hist[:, -self.hop:].copy_(x0)
-        self._seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        self._seed = modules.philox_seed()
         self.primed = True
 
     def step(self, x, eps=None):
@@ -227,6 +228,7 @@ class StreamingEnhancer:
         x = lib.require_f32_cuda(x, "x")
         if tuple(x.shape) != (self.NB, self.hop * self.k):
             raise RuntimeError("step expects (%d, %d) samples" % (self.NB, self.hop * self.k))
+        self._check_weights()
         self.x_in.copy_(x)
         if eps is not None:
             if self.eps_in is None:
@@ -249,6 +251,20 @@ class StreamingEnhancer:
             self._step_impl(base, t0)
         self.steps += 1
         return self.y_out.clone()
+
+    def _check_weights(self):
+        """The LSTM step packs and the captured graph bake weight-pack pointers in: drop both when any parameter or
+        buffer of the two models changed identity or version (load_state_dict, an optimiser step, .to()) - the same
+        (data_ptr, _version) stamp modules._PackCache uses for the per-layer packs.  Parameters and buffers are looked
+        up through their modules on every call, so re-bound tensors are seen too."""
+        if self._mods is None:
+            self._mods = list(self.enc.modules()) + list(self.dec.modules())
+        stamp = tuple((t.data_ptr(), t._version) for m in self._mods for d in (m._parameters, m._buffers)
+                      for t in d.values() if t is not None)
+        if stamp != self._stamp:
+            if self._stamp is not None:
+                self._lstm_packs, self._graph = None, None
+            self._stamp = stamp
 
     def _capture(self):
         """Capture one steady-state step (base >= 0: no reflect; t0 large: interior envelope) as a CUDA graph.  The

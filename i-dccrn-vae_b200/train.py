@@ -130,11 +130,12 @@ class EncoderTrainStep:
             raise NotImplementedError("training needs the tensor-core LSTM recurrence (H %% 64 == 0, batch fits the GPU)")
         whh_tc = lstm._packed_tc(cfg, dev)
         g = ops.tapgemm(layers[0][0], p, None, NB, T, zero_pad_rows=False, out_split=False)
-        h0, h0s = ops.lstm_recurrent_tc(g, 4 * H, R * 8 * H, 8 * H, whh_tc[0], NB, T, H, want_f32=True, want_split=True)
+        h0, h0s = ops.lstm_recurrent_tc(g, 4 * H, R * 8 * H, 8 * H, whh_tc[0], NB, T, H, want_f32=True, want_split=True,
+                                        cfg=cfg)
         src = Planes(h0s, NB, H, 4, T, cp=H, split=True)
         g = ops.tapgemm(layers[1][0], src, None, NB, T, zero_pad_rows=False, out_split=False)
         h1, h1s = ops.lstm_recurrent_tc(g, 2 * R * 4 * H, R * 4 * H, 4 * H, whh_tc[1], NB, T, H, want_f32=True,
-                                        want_split=True)
+                                        want_split=True, cfg=cfg)
         # pad rows of the h planes are h(-1) = 0 for the recompute of the gates (the recurrence leaves them unwritten)
         for t in (h0, h1):
             t.view(4, NB, T + 1, H)[:, :, 0].zero_()
@@ -729,53 +730,158 @@ def decoder_train_forward(dec, stft_x, z, skiper, skips, C, F, mask):
 # ------------------------------------------------------------------------------------------------------------------
 # optimiser + gradient all-reduce (data-parallel training: SURVEY §8(e))
 # ------------------------------------------------------------------------------------------------------------------
-class FlatAdam:
+class FlatAdam(torch.optim.Optimizer):
     """torch.optim.Adam(lr, betas, eps, weight_decay) semantics (train_nsvae.py:L200: lr from the config,
     weight_decay = 0.001) on ONE flat fp32 buffer: the parameters that receive gradients are re-pointed into a flat
     tensor, their gradients are gathered into a flat bucket (one NCCL all-reduce per step when a process group is
-    given: mean over ranks, DDP semantics), the update is one ``idv_adam_step`` launch."""
+    given: mean over ranks, DDP semantics), the update is one ``idv_adam_step`` launch per run of parameters that share
+    a step count (normally one).
+
+    It IS a ``torch.optim.Optimizer``: ``param_groups`` (one group; ``lr`` is read from it every step, so torch's lr
+    schedulers drive it), ``zero_grad``, and ``state_dict()`` / ``load_state_dict()`` in torch.optim.Adam's own format
+    (per parameter ``step`` / ``exp_avg`` / ``exp_avg_sq``), so the reference's checkpoints of optimiser state
+    (train_nsvae.py:L318-330) load into it and its checkpoints load into ``torch.optim.Adam``.  Like torch.optim.Adam a
+    parameter whose ``.grad`` is None in a step is skipped in that step (no update, no moment decay, no step count):
+    the flat layout is rebuilt when the set of parameters with gradients changes."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None,
                  world_size=1):
-        self.params = [p for p in params if p.requires_grad]
-        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        params = [p for p in params if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        if len(self.param_groups) != 1:
+            raise NotImplementedError("FlatAdam holds one parameter group")
         self.group, self.world = process_group, world_size
-        self.step_count = 0
         self.flat = None
+        self.live = []                 # parameters in the flat layout, in param_groups order
+        self._steps = {}               # id(param) -> number of updates applied
+        self._pending = None           # (m, v) per parameter from load_state_dict, applied at the next layout build
 
-    def _build(self):
-        # parameters without a gradient after the first backward (the unused dense.*) are left out, like
-        # torch.optim.Adam skips parameters whose .grad is None
-        self.live = [p for p in self.params if p.grad is not None]
-        n = sum(p.numel() for p in self.live)
-        dev = self.live[0].device
-        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+    # ---- convenience views of the single group (the round-1 attribute names)
+    @property
+    def params(self):
+        return self.param_groups[0]["params"]
+
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, v):
+        self.param_groups[0]["lr"] = v
+
+    @property
+    def step_count(self):
+        return max(self._steps.values()) if self._steps else 0
+
+    def _moments(self):
+        """{id(param): (exp_avg, exp_avg_sq)} views of the current layout (+ moments loaded but not laid out yet)."""
+        out = dict(self._pending or {})
+        if self.flat is not None:
+            for p, (off, k) in zip(self.live, self.views):
+                out[id(p)] = (self.m[off:off + k].view(p.shape), self.v[off:off + k].view(p.shape))
+        return out
+
+    def _build(self, live):
+        old = self._moments()
+        n = sum(p.numel() for p in live)
+        dev = live[0].device
+        flat = torch.empty(n, dtype=torch.float32, device=dev)
         self.gflat = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
-        self.views = []
-        for p in self.live:
+        m = torch.zeros(n, dtype=torch.float32, device=dev)
+        v = torch.zeros(n, dtype=torch.float32, device=dev)
+        off, views = 0, []
+        for p in live:
             k = p.numel()
-            self.flat[off:off + k].copy_(p.data.reshape(-1))
-            p.data = self.flat[off:off + k].view(p.shape)
-            self.views.append((off, k))
+            flat[off:off + k].copy_(p.data.reshape(-1))
+            if id(p) in old:
+                m[off:off + k].copy_(old[id(p)][0].reshape(-1))
+                v[off:off + k].copy_(old[id(p)][1].reshape(-1))
+            views.append((off, k))
             off += k
+        in_new = {id(p) for p in live}
+        for p in self.live:                          # parameters that leave the layout get storage of their own back
+            if id(p) not in in_new:
+                p.data = p.data.clone()
+        # moments of parameters outside the new layout (left it, or loaded and never laid out) wait in _pending
+        pending = {k: (mv[0].clone(), mv[1].clone()) for k, mv in old.items() if k not in in_new}
+        for p, (off, k) in zip(live, views):
+            p.data = flat[off:off + k].view(p.shape)
+        self.flat, self.m, self.v, self.live, self.views = flat, m, v, list(live), views
+        self._pending = pending or None
 
-    def zero_grad(self):
-        for p in self.params:
-            p.grad = None
-
-    def step(self):
-        if self.flat is None:
-            self._build()
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        live = [p for p in self.params if p.grad is not None]
+        if not live:
+            return loss
+        if self.flat is None or len(live) != len(self.live) or any(a is not b for a, b in zip(live, self.live)):
+            self._build(live)
         for p, (off, k) in zip(self.live, self.views):
             self.gflat[off:off + k].copy_(p.grad.reshape(-1))
         if self.group is not None and self.world > 1:
             torch.distributed.all_reduce(self.gflat, group=self.group)
             self.gflat.div_(self.world)
-        self.step_count += 1
-        lib.call("idv_adam_step", self.flat, self.gflat, self.m, self.v, self.flat.numel(), float(self.lr),
-                 float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd), self.step_count)
+        g = self.param_groups[0]
+        # one launch per run of consecutive parameters with the same step count (bias corrections differ otherwise)
+        i = 0
+        while i < len(self.live):
+            st = self._steps.get(id(self.live[i]), 0)
+            j = i
+            while j + 1 < len(self.live) and self._steps.get(id(self.live[j + 1]), 0) == st:
+                j += 1
+            a, b = self.views[i][0], self.views[j][0] + self.views[j][1]
+            lib.call("idv_adam_step", self.flat[a:b], self.gflat[a:b], self.m[a:b], self.v[a:b], b - a, float(g["lr"]),
+                     float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), st + 1)
+            i = j + 1
         for p in self.live:                          # the kernel wrote the parameters behind autograd's back:
+            self._steps[id(p)] = self._steps.get(id(p), 0) + 1
             torch.autograd.graph.increment_version(p)    # bump the versions so the weight-pack caches rebuild
+        return loss
+
+    def state_dict(self):
+        """torch.optim.Adam's format: {'state': {index: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]}."""
+        mom = self._moments()
+        state = {}
+        for i, p in enumerate(self.params):
+            if id(p) in mom and self._steps.get(id(p), 0) > 0:
+                state[i] = {"step": torch.tensor(float(self._steps[id(p)])), "exp_avg": mom[id(p)][0].clone(),
+                            "exp_avg_sq": mom[id(p)][1].clone()}
+        g = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        g.update(amsgrad=False, maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                 params=list(range(len(self.params))))
+        return {"state": state, "param_groups": [g]}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("optimizer state has %d group(s) / %d parameters, this optimiser 1 / %d"
+                             % (len(groups), len(groups[0]["params"]), len(self.params)))
+        if groups[0].get("amsgrad") or groups[0].get("maximize"):
+            raise NotImplementedError("FlatAdam implements plain Adam (amsgrad / maximize off)")
+        for k in ("lr", "betas", "eps", "weight_decay"):
+            if k in groups[0]:
+                self.param_groups[0][k] = tuple(groups[0][k]) if k == "betas" else groups[0][k]
+        index = {pid: i for i, pid in enumerate(groups[0]["params"])}
+        pending, self._steps = {}, {}
+        for pid, st in sd["state"].items():
+            p = self.params[index[pid] if pid in index else int(pid)]
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError("optimizer state of parameter %s has shape %s, the parameter %s"
+                                 % (pid, tuple(st["exp_avg"].shape), tuple(p.shape)))
+            pending[id(p)] = (st["exp_avg"].detach().to(p.device, torch.float32).clone(),
+                              st["exp_avg_sq"].detach().to(p.device, torch.float32).clone())
+            self._steps[id(p)] = int(float(st["step"]))
+        if self.flat is not None:                    # keep the current layout, overwrite its moments
+            for p, (off, k) in zip(self.live, self.views):
+                if id(p) in pending:
+                    self.m[off:off + k].copy_(pending[id(p)][0].reshape(-1))
+                    self.v[off:off + k].copy_(pending[id(p)][1].reshape(-1))
+                else:
+                    self.m[off:off + k].zero_()
+                    self.v[off:off + k].zero_()
+            pending = {k: v for k, v in pending.items() if all(id(p) != k for p in self.live)}
+        self._pending = pending or None

@@ -1,6 +1,7 @@
 """Import alias: the package directory is ``i-dccrn-vae_b200/`` (not a Python identifier), so
-``import idccrn_b200`` resolves to it here.  All submodules are aliased too, so there is exactly one
-copy of every class regardless of which name was used to import it."""
+``import idccrn_b200`` resolves to it here.  The package imports every one of its submodules in ``__init__`` and all of
+them are aliased below, so there is exactly one module object (one copy of every class and of every module-level
+switch) regardless of which name was used to import it."""
 import importlib
 import os
 import sys

@@ -40,7 +40,7 @@ extern "C" {
 #define IDV_E_CUDA 2     /* CUDA runtime error (message has the cudaError string) */
 #define IDV_E_RESOURCE 3 /* kernel cannot be made resident (cooperative launch too large) */
 
-#define IDV_ABI_VERSION 5
+#define IDV_ABI_VERSION 6
 
 int idv_abi_version(void);
 const char* idv_last_error(void);
@@ -197,6 +197,13 @@ int idv_lstm2_wave_config(int H, int* n_cols, int* n_ctas, int64_t* work_bytes);
 int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
                       const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
                       float* hseq1, void* work, unsigned int* sync, int t_valid, void* stream);
+/* ONE nn.LSTM layer of both modules per launch as CTA pairs (the kernel of idv_lstm2_wave_tc restricted to its first
+ * role): same contract as idv_lstm_recurrent_tc, wpack packed with (n_cols, n_ctas) from idv_lstm_layer_pair_config
+ * (H = 768: 48 gate columns x 64 CTAs per module).  work: work_bytes workspace, sync: 6 x uint32 (both zeroed by the
+ * call).  Any NB (chunks of 64 utterances run as consecutive launches).                                          */
+int idv_lstm_layer_pair_config(int H, int* n_cols, int* n_ctas, int64_t* work_bytes);
+int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* wpack, int NB, int T,
+                           int H, float* hseq, void* hsplit, void* work, unsigned int* sync, int t_valid, void* stream);
 /* Combine the four streams (real = rr - ii, imag = ir + ri), emit the user-layout latent
  * (NB, T, H, 2).  Replaces the stack/permute at complex_progress.py:L62-73, pvae_module.py:L2247. */
 int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, float* latent, int t_valid, void* stream);
@@ -208,6 +215,25 @@ int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, float* latent,
 int idv_reparam_fwd(const float* latent, int NB, int T, int Htot, int ch0, int zdim, int S,
                     const float* eps_r, const float* eps_i, uint64_t seed, uint64_t offset,
                     const uint64_t* offset_dev, int variant, float* z, void* stream);
+/* Fused latent stage of the VAE encoders: the four LSTM streams hseq [4][R][H] (R = NB*(T+1)) ->
+ *   latent  (NB, Tv, H, 2)            combine of complex_progress.py:L62-73 (re = rr - ii, im = ir + ri),
+ *   z0 / z1 (NB*S, Tv, zdim, 2)       reparameterisation of latent k = 0 / 1 (model/pvae_module.py:L2177-2231;
+ *                                     triplet k at channels [3k zdim, 3(k+1) zdim); z1 and its eps NULL when latent_num = 1),
+ *   zplanes [S][1 plane][R][2*round8(zdim)]   z0 of sample s in the activation-plane layout the decoder's ComplexDense
+ *                                     tap-GEMM reads (fp32, or bf16 hi/lo [S][2][R][Cp] when out_split; pad rows and
+ *                                     rows of frames >= Tv written as zero) - replaces idv_lstm_combine_fwd +
+ *                                     idv_reparam_fwd (x latent_num) + idv_z_to_planes (x S) by ONE launch.
+ * eps_*: (NB, S, Tv, zdim) or all NULL -> Philox4x32-10 from (seed, offset + *offset_dev), one Philox block per
+ * element and draw.  H == 3 * zdim * latent_num.                                                              */
+int idv_latent_fwd(const float* hseq, int NB, int T, int H, int t_valid, int zdim, int latent_num, int S,
+                   const float* eps_r0, const float* eps_i0, const float* eps_r1, const float* eps_i1,
+                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, float* latent, float* z0, float* z1,
+                   void* zplanes, int out_split, void* stream);
+/* idv_lstm_combine_fwd that ALSO writes the combined latent as one activation plane [1][R][2*round8(H)] (the input
+ * of the supervised DCCRN's ComplexDense, model/pvae_module.py:L189-192): replaces idv_lstm_combine_fwd +
+ * idv_z_to_planes.  planes: fp32, or bf16 hi/lo [2][R][Cp] when out_split; pad rows / rows >= Tv are zeroed. */
+int idv_lstm_combine_planes(const float* hseq, int NB, int T, int H, int t_valid, float* latent, void* planes,
+                            int out_split, void* stream);
 /* Per-bin affine on a spectrum (B, F, T, 2): out = x * scale[f][part] + shift[f][part] (in place allowed) - the
  * data_mean / data_std normalisation of the CVAE encoders (model/pvae_module.py:L367-371: zero_edge_imag = 1 clears
  * the imaginary part of the first and last bin afterwards) and its inverse in the decoders (L483-484). */

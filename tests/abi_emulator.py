@@ -354,7 +354,17 @@ def _bf16_split(x):
 
 def idv_lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, hx, sync, t_valid=0):
     """Contract of the tensor-core recurrence: the recurrent product uses the split value of h(t-1)."""
-    n_cols, n_ctas = _lstm_tc_config(H)
+    _lstm_rec_tc(_lstm_tc_config(H), g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, t_valid)
+
+
+def idv_lstm_layer_pair_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, work, sync, t_valid=0):
+    """Same contract as idv_lstm_recurrent_tc with the weight pack in the CTA-pair kernel's (n_cols, n_ctas) order."""
+    from idccrn_b200 import lib
+    _lstm_rec_tc(lib.lstm_layer_pair_config(H)[:2], g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, t_valid)
+
+
+def _lstm_rec_tc(cfg, g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, t_valid):
+    n_cols, n_ctas = cfg
     hs = n_cols // 4
     Tp = T + 1
     R = NB * Tp
@@ -466,6 +476,24 @@ def idv_reparam_fwd(latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, seed, offse
         zi = mu[..., 1][:, None] + (di / (den + e))[:, None] * er + \
             (torch.sqrt(sig * sig - ad * ad + e) / (den + e))[:, None] * ei
     z.copy_(torch.stack((zr, zi), -1).view(NB * S, T, zdim, 2))
+
+
+def idv_latent_fwd(hseq, NB, T, H, t_valid, zdim, latent_num, S, eps_r0, eps_i0, eps_r1, eps_i1, seed, offset, offset_dev,
+                   latent, z0, z1, zplanes, out_split):
+    """Contract = idv_lstm_combine_fwd, then idv_reparam_fwd per latent, then idv_z_to_planes per sample."""
+    Tv = _tv(t_valid, T)
+    idv_lstm_combine_fwd(hseq, NB, T, H, latent, t_valid)
+    for k, (er, ei, z) in enumerate(((eps_r0, eps_i0, z0), (eps_r1, eps_i1, z1))[:latent_num]):
+        idv_reparam_fwd(latent, NB, Tv, H, 3 * zdim * k, zdim, S, er, ei, seed, offset, offset_dev, 0, z)
+    per = NB * (T + 1) * 2 * _r8(zdim) * (2 if out_split else 1)
+    zp = _flat(zplanes)
+    for s in range(S):
+        idv_z_to_planes(z0, NB, S, s, T, zdim, zp[s * per:(s + 1) * per], out_split, t_valid)
+
+
+def idv_lstm_combine_planes(hseq, NB, T, H, t_valid, latent, planes, out_split):
+    idv_lstm_combine_fwd(hseq, NB, T, H, latent, t_valid)
+    idv_z_to_planes(latent, NB, 1, 0, T, H, planes, out_split, t_valid)
 
 
 def idv_bin_affine(x, B, F, T, scale, shift, zero_edge_imag, out):

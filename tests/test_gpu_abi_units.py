@@ -357,6 +357,105 @@ def _tapgemm_tc_case(R, Tp, N, kcs, dts, two_src, prelu, out_split, tv=0):
     assert _both("idv_tapgemm_tc", args, [16]) < 1e-5
 
 
+@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("R,Tp,N,n_units", [(2600, 13, 256, 7), (5000, 0, 128, 5), (1100, 11, 512, 3)])
+def test_tapgemm_tc_tile_orders(order, R, Tp, N, n_units):
+    """Both tile orders (unit-major / row-major with the units as the inner loop) on problems with many units, several
+    row tiles per CTA (pairs and tails) and, for N = 512, two N tiles: every unit reads its own planes / writes its own."""
+    F0, cp0, kc = n_units + 1, 136, 128
+    a0 = _to_split(_rand(F0, R, cp0, seed=1))
+    taps, units = [], []
+    for u in range(n_units):
+        taps += [[0, u, 1, 0, kc, 0], [0, u + 1, 0, 8, kc, 1 + u % 2]]
+        units.append([2 * u, 2, n_units - 1 - u, 0, (u % 2) * N, 4])
+    wt = _to_split(_rand(3, N, kc, seed=3) * 0.1)
+    bias = _rand(2 * N, seed=4)
+    n_out = n_units * R * N
+    out = torch.zeros(2 * n_out, dtype=torch.bfloat16)
+    args = [a0, cp0, F0, None, 0, 0, R, Tp, wt, kc, 3, bias, N, torch.tensor(units, dtype=torch.int32),
+            torch.tensor(taps, dtype=torch.int32), n_units, out, N, R * N, n_out, 1, 1, 0.2, 0]
+    lib.set_option("gemm_tile_order", order)
+    try:
+        assert _both("idv_tapgemm_tc", args, [16]) < 1e-5
+    finally:
+        lib.set_option("gemm_tile_order", 1)
+
+
+@pytest.mark.parametrize("NB,T,zdim,latent_num,S,tv,split", [(3, 7, 128, 1, 1, 0, 1), (2, 5, 128, 2, 3, 0, 1), (5, 9, 16, 2, 1, 6, 0),
+                                                             (1, 3, 128, 1, 10, 0, 1)])
+def test_latent_fused(NB, T, zdim, latent_num, S, tv, split):
+    """idv_latent_fwd = lstm_combine + reparam (per latent) + z_to_planes (per sample) of the contract emulator."""
+    H = 3 * zdim * latent_num
+    R = NB * (T + 1)
+    Tv = tv if 0 < tv < T else T
+    hseq = _rand(4, R, H, seed=31) * 0.5
+    eps = [_rand(NB, S, Tv, zdim, seed=40 + i) for i in range(4)]
+    latent = torch.zeros(NB, Tv, H, 2)
+    z0, z1 = torch.zeros(NB * S, Tv, zdim, 2), (torch.zeros(NB * S, Tv, zdim, 2) if latent_num == 2 else None)
+    n_pl = S * R * 2 * ((zdim + 7) // 8 * 8)
+    zpl = torch.full((2 * n_pl,), 3.0, dtype=torch.bfloat16) if split else torch.full((n_pl,), 3.0)
+    args = [hseq, NB, T, H, tv, zdim, latent_num, S, eps[0], eps[1], eps[2] if latent_num == 2 else None,
+            eps[3] if latent_num == 2 else None, 0, 0, None, latent, z0, z1, zpl, split]
+    outs = [15, 16, 18] + ([17] if latent_num == 2 else [])
+    # the split planes of several samples are compared sample by sample (hi | lo halves per sample)
+    cpu = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
+    E.call("idv_latent_fwd", *cpu)
+    gpu = [a.cuda() if isinstance(a, torch.Tensor) else a for a in args]
+    lib.call("idv_latent_fwd", *gpu)
+    torch.cuda.synchronize()
+    for i in outs:
+        a, b = gpu[i].cpu(), cpu[i]
+        if a.dtype == torch.bfloat16:
+            a, b = a.view(S, 2, -1).double().sum(1), b.view(S, 2, -1).double().sum(1)
+        assert C.rel_l2(a, b) < 2e-6, (i, C.rel_l2(a, b))
+
+
+def test_latent_fused_philox_draws_are_independent():
+    """No eps supplied: N(0,1) draws; consecutive draw counters must not share a uniform (the radius uniform of one
+    draw used to be the angle uniform of the next: |eps| correlated across draws), ranks / latents differ."""
+    NB, T, zdim = 4, 50, 128
+    H, R = 3 * zdim, 4 * 51
+    hseq = torch.zeros(4, R, H).cuda()                     # mu = 0, log sigma = 0, delta = 0 -> z = eps / sqrt(2)-ish scale
+    def draw(offset, seed=1234):
+        latent = torch.zeros(NB, T, H, 2).cuda()
+        z0 = torch.zeros(NB, T, zdim, 2).cuda()
+        zpl = torch.zeros(R * 2 * zdim).cuda()
+        lib.call("idv_latent_fwd", hseq, NB, T, H, 0, zdim, 1, 1, None, None, None, None, seed, offset, None, latent, z0,
+                 None, zpl, 0)
+        torch.cuda.synchronize()
+        return z0.cpu().double()
+    a, b, c = draw(1), draw(2), draw(1)
+    assert torch.equal(a, c)                               # same (seed, counter) -> same draw
+    assert abs(float(a.mean())) < 0.02 and 0.4 < float(a[..., 0].var()) < 0.6      # sigma = 1, delta = 0: var = 1/2
+    ra, rb = a.pow(2).sum(-1).flatten(), b.pow(2).sum(-1).flatten()
+    corr = float(torch.corrcoef(torch.stack((ra, rb)))[0, 1])
+    assert abs(corr) < 0.02, corr                          # |eps|^2 of consecutive draws uncorrelated
+    assert abs(float(torch.corrcoef(torch.stack((a[..., 0].flatten(), b[..., 1].flatten())))[0, 1])) < 0.02
+    d = draw(1, seed=99)
+    assert C.rel_l2(d, a) > 0.5
+    # the stand-alone kernel (streaming, reparameterization()) follows the same rule
+    lat = torch.zeros(NB, T, H, 2).cuda()
+    def draw2(offset):
+        z = torch.zeros(NB, T, zdim, 2).cuda()
+        lib.call("idv_reparam_fwd", lat, NB, T, H, 0, zdim, 1, None, None, 1234, offset, None, 0, z)
+        torch.cuda.synchronize()
+        return z.cpu().double()
+    x, y = draw2(5), draw2(6)
+    corr = float(torch.corrcoef(torch.stack((x.pow(2).sum(-1).flatten(), y.pow(2).sum(-1).flatten())))[0, 1])
+    assert abs(corr) < 0.02, corr
+
+
+@pytest.mark.parametrize("NB,T,H,tv,split", [(3, 7, 128, 0, 1), (2, 9, 20, 5, 0)])
+def test_lstm_combine_planes(NB, T, H, tv, split):
+    R = NB * (T + 1)
+    Tv = tv if 0 < tv < T else T
+    hseq = _rand(4, R, H, seed=33)
+    latent = torch.zeros(NB, Tv, H, 2)
+    n = R * 2 * ((H + 7) // 8 * 8)
+    pl = torch.full((2 * n,), 3.0, dtype=torch.bfloat16) if split else torch.full((n,), 3.0)
+    assert _both("idv_lstm_combine_planes", [hseq, NB, T, H, tv, latent, pl, split], [5, 6]) < 2e-6
+
+
 @pytest.mark.parametrize("R,Tp,out_split", [(300, 13, 1), (1300, 0, 0)])
 def test_tapgemm_tc_columns_wrap_into_planes(R, Tp, out_split):
     """N > out_ld: column n of a unit goes to plane out_f + n / out_ld (two output planes of a narrow transposed conv
@@ -374,7 +473,8 @@ def test_tapgemm_tc_columns_wrap_into_planes(R, Tp, out_split):
     assert _both("idv_tapgemm_tc", args, [16]) < 1e-5
 
 
-@pytest.mark.parametrize("NB,T,H,tv", [(3, 6, 128, 0), (64, 40, 384, 0), (5, 9, 768, 0), (70, 5, 128, 0), (3, 12, 128, 7)])
+@pytest.mark.parametrize("NB,T,H,tv", [(3, 6, 128, 0), (64, 40, 384, 0), (5, 9, 768, 0), (70, 5, 128, 0), (3, 12, 128, 7),
+                                       (130, 4, 768, 0), (200, 3, 384, 2)])      # row groups that are not co-resident: consecutive launches
 def test_lstm_recurrent_tc(NB, T, H, tv):
     from idccrn_b200 import pack as PK
     n_cols, n_ctas = lib.lstm_tc_config(H)
@@ -390,6 +490,31 @@ def test_lstm_recurrent_tc(NB, T, H, tv):
     sync = torch.zeros(n_rg * 2, dtype=torch.int32)
     args = [g, 4 * H, R * 8 * H, 8 * H, wp, NB, T, H, hseq, hsplit, hx, sync, tv]
     assert _both("idv_lstm_recurrent_tc", args, [8, 9]) < 2e-5
+
+
+@pytest.mark.parametrize("pairs", [1, 0])
+@pytest.mark.parametrize("NB,T,H,tv", [(3, 6, 128, 0), (64, 30, 768, 0), (5, 9, 768, 4), (64, 12, 384, 0), (130, 4, 768, 0),
+                                       (70, 5, 512, 0)])
+def test_lstm_layer_pair_tc(NB, T, H, tv, pairs):
+    """One nn.LSTM layer per launch on the CTA-pair kernel (48 gate columns per CTA at H = 768), both as pairs and as
+    its one-CTA-per-tile cooperative fallback."""
+    from idccrn_b200 import pack as PK
+    n_cols, n_ctas, work_bytes = lib.lstm_layer_pair_config(H)
+    assert n_cols == (48 if H == 768 else 64) and n_ctas * (n_cols // 4) == H
+    R = NB * (T + 1)
+    g = _rand(2, R, 8 * H, seed=15)
+    whh = _rand(2, 4 * H, H, seed=16) / (H ** 0.5)
+    wp = PK.pack_lstm_whh_tc({"weight_hh_l0": whh[0]}, {"weight_hh_l0": whh[1]}, 0, n_cols, n_ctas, "cpu")
+    hseq = torch.zeros(4, R, H)
+    hsplit = torch.zeros(2 * 4 * R * H, dtype=torch.bfloat16)
+    work = torch.zeros(work_bytes, dtype=torch.uint8)
+    sync = torch.zeros(6, dtype=torch.int32)
+    args = [g, 4 * H, R * 8 * H, 8 * H, wp, NB, T, H, hseq, hsplit, work, sync, tv]
+    lib.set_option("lstm_wave_cta_pairs", pairs)
+    try:
+        assert _both("idv_lstm_layer_pair_tc", args, [8, 9]) < 2e-5
+    finally:
+        lib.set_option("lstm_wave_cta_pairs", 1)
 
 
 @pytest.mark.parametrize("NB,Fin,T,two_src,mask,S", [(2, 9, 40, True, 2, 1), (3, 5, 130, False, 1, 2)])
@@ -423,7 +548,8 @@ def test_tapgemm_tc_head(NB, Fin, T, two_src, mask, S):
     assert C.rel_l2(cpu, ref) < 2e-5
 
 
-@pytest.mark.parametrize("NB,T,H,tv", [(3, 9, 128, 0), (64, 30, 384, 0), (17, 2, 384, 0), (4, 16, 128, 10)])
+@pytest.mark.parametrize("NB,T,H,tv", [(3, 9, 128, 0), (64, 30, 384, 0), (17, 2, 384, 0), (4, 16, 128, 10),
+                                       (70, 7, 128, 0), (130, 5, 384, 3)])       # > 64 utterances: chunks of 64 inside the entry point
 def test_lstm2_wave_tc(NB, T, H, tv):
     from idccrn_b200 import pack as PK
     n_cols, n_ctas, work_bytes = lib.lstm2_wave_config(H)

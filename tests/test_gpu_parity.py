@@ -209,6 +209,133 @@ def test_full_size_batch_rows_match_small_oracle_run(gemm_mode):
     assert wave < WAVE_TOL and mu < WAVE_TOL and gap < 0.01
 
 
+@pytest.mark.parametrize("B", [32, 64])
+def test_dccrn_config3_full_length_rows_match_oracle(B):
+    """BASELINE config 3 shape: supervised DCCRN_ (causal, mask head, real skips, H = 128) on 10-s utterances
+    (L = 160 000, T = 1 601 frames: 1 603 dependent steps of the wavefront LSTM), at the per-GPU shard sizes of the
+    8- and 4-GPU split (32 / 64 utterances).  Rows {0, last} of the CUDA run against the live oracle on those rows
+    (supervised_dccrn/test.py:L129,L413; model/pvae_module.py:L200-255)."""
+    seed, L = 31, 160000
+    m = M.DCCRN_(C.NFFT, C.HOP, M.get_net_params(True), True, "cuda", C.WIN, C.SKIPS, "mask", False, None, None)
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed), strict=True)
+    m = m.cuda().eval()
+    x = synth_waveform(B, L, seed=1234 + seed).cuda()
+    with torch.no_grad():
+        clean, pred = m(x, train=False)
+    torch.cuda.synchronize()
+    assert clean.shape == (B, L) and pred.shape == (B, 257, 1601) and torch.isfinite(clean).all()
+    rows = [0, B - 1]
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = P.dccrn_forward(sd, x[rows].cpu())
+    errs = {"latent": C.rel_l2(m.std_DCCRN.latent[rows], ref["latent"]),
+            "predict": C.rel_l2(torch.view_as_real(pred)[rows], torch.view_as_real(ref["predict"])),
+            "clean": C.rel_l2(clean[rows], ref["clean"])}
+    # error growth along the sequence: the last second of the waveform on its own
+    tail = C.rel_l2(clean[rows][:, -16000:], ref["clean"][:, -16000:])
+    gap, sdr = _sisnr_gap_db(clean[rows], ref["clean"], x[rows])
+    print("config3 B=%d T=1601:" % B, errs, "tail %.2e gap %.4f dB sdr %.1f" % (tail, gap, sdr))
+    assert errs["latent"] < STAGE_TOL["tc"] and errs["predict"] < WAVE_TOL
+    assert errs["clean"] < WAVE_TOL and tail < WAVE_TOL and gap < 0.01
+
+
+def test_config2b_full_size_rows_match_oracle():
+    """BASELINE config 2b (the shipped final system, test_se_cvaefinetune.py:L263-312,L678): NSVAE encoder with
+    latent_num = 2 (H = 768 LSTM) + nsvae_pvae_dccrn_decoder_twophase(use_sc, pad='sig', mask head) at B = 64 x 4 s -
+    the batch size where the H = 768 recurrence runs its 64-utterance row group with all CTAs busy."""
+    seed, B, L = 23, 64, 64000
+    enc, dec = C.build_vae(2, 1, "twophase", "mask", seed, "cuda")
+    x, eps = C.vae_inputs(B, L, 1, 2, seed, "cuda")
+    out = C.run_vae(enc, dec, x, eps, "twophase")
+    torch.cuda.synchronize()
+    rows = [0, 63]
+    esd = {k: v.cpu() for k, v in enc.state_dict().items()}
+    dsd = {k: v.cpu() for k, v in dec.state_dict().items()}
+    with torch.no_grad():
+        st = P.vae_encoder_forward(esd, x[rows].cpu(), C.ZDIM, 2, 1, [e[rows].cpu() for e in eps])
+        dd = P.vae_decoder_forward(dsd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], 1, "mask", "sig")
+    errs = {"miu": C.rel_l2(out["miu"][rows], st["miu_speech"]), "z": C.rel_l2(out["z_speech"][rows], st["z_speech"]),
+            "z_noise": C.rel_l2(out["z_noise"][rows], st["z_noise"]),
+            "predict": C.rel_l2(out["predict"][rows], torch.view_as_real(dd["predict"]))}
+    wave = C.rel_l2(out["recon_sig"][rows], dd["recon_sig"])
+    gap, sdr = _sisnr_gap_db(out["recon_sig"][rows], dd["recon_sig"], x[rows])
+    print("config2b B=64:", errs, "wave %.2e gap %.4f dB sdr %.1f" % (wave, gap, sdr))
+    assert torch.isfinite(out["recon_sig"]).all()
+    assert all(v < STAGE_TOL["tc"] for v in errs.values()), errs
+    assert wave < WAVE_TOL and gap < 0.01
+
+
+@pytest.mark.parametrize("latent_num,dec_kind,recon", [(1, "skip_prepare", "real_imag"), (2, "twophase", "mask")])
+def test_num_samples_10_single_utterance(latent_num, dec_kind, recon):
+    """Every shipped test_*.sh runs --num_samples 10 on ONE utterance and averages the 10 enhanced signals
+    (test_nsvae_se.sh:L4-12, test_nsvae_se.py:L352): B = 1, S = 10, all samples and their mean against the oracle."""
+    seed, B, L, S = 41, 1, 48000, 10
+    enc, dec = C.build_vae(latent_num, S, dec_kind, recon, seed, "cuda")
+    x, eps = C.vae_inputs(B, L, S, latent_num, seed, "cuda")
+    out = C.run_vae(enc, dec, x, eps, dec_kind)
+    esd = {k: v.cpu() for k, v in enc.state_dict().items()}
+    dsd = {k: v.cpu() for k, v in dec.state_dict().items()}
+    with torch.no_grad():
+        st = P.vae_encoder_forward(esd, x.cpu(), C.ZDIM, latent_num, S, [e.cpu() for e in eps])
+        dd = P.vae_decoder_forward(dsd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], S, recon,
+                                   "zero" if dec_kind == "skip_prepare" else "sig")
+    assert out["recon_sig"].shape == (S, L) and out["z_speech"].shape[0] == S
+    errs = {"z": C.rel_l2(out["z_speech"], st["z_speech"]),
+            "predict": C.rel_l2(out["predict"], torch.view_as_real(dd["predict"]))}
+    wave = C.rel_l2(out["recon_sig"], dd["recon_sig"])
+    mean = C.rel_l2(out["recon_sig"].mean(0), dd["recon_sig"].mean(0))        # the averaged output the script scores
+    gap, sdr = _sisnr_gap_db(out["recon_sig"], dd["recon_sig"], x.repeat_interleave(S, 0))
+    print("S=10:", errs, "wave %.2e mean %.2e gap %.4f dB" % (wave, mean, gap))
+    assert all(v < STAGE_TOL["tc"] for v in errs.values()), errs
+    assert wave < WAVE_TOL and mean < WAVE_TOL and gap < 0.01
+
+
+def test_cbn_fold_follows_running_statistics_updated_by_a_train_forward():
+    """eval -> train-mode forward with FROZEN parameters (running buffers change, no optimiser step) -> eval: the
+    second eval must use the new running statistics (the folded weights are cached per weight version; the train
+    kernel rewrites the buffers through raw pointers)."""
+    seed = 5
+    enc = M.Encoder(3, 5, (5, 2), (2, 1), (5, 9, 1), padding=(2, 1), causal=True)
+    enc.load_state_dict(fill_state_dict(enc.state_dict(), seed))
+    enc = enc.cuda()
+    for p_ in enc.parameters():
+        p_.requires_grad_(False)
+    g = torch.Generator().manual_seed(3)
+    x1 = torch.randn(2, 3, 17, 12, 2, generator=g).cuda()
+    x2 = (2.5 * torch.randn(2, 3, 17, 12, 2, generator=g) + 0.7).cuda()
+    def oracle(x):
+        sd = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
+        return P.encoder_block(x.cpu(), sd, "", causal=True, train=False)
+    with torch.no_grad():
+        y0 = enc(x1, False)
+        assert C.rel_l2(y0, oracle(x1)) < 2e-5
+        enc(x2, True)                                   # batch statistics of x2 -> running buffers (first call copies)
+        y1 = enc(x1, False)
+        assert C.rel_l2(y1, oracle(x1)) < 2e-5          # oracle reads the UPDATED buffers from the state_dict
+        assert C.rel_l2(y1, y0) > 1e-2                  # and they really changed the output
+        enc(x1, True)                                   # EMA update
+        assert C.rel_l2(enc(x2, False), oracle(x2)) < 2e-5
+    # stand-alone ComplexBatchNormal: eval, train, eval
+    bn = M.ComplexBatchNormal(5, 1, 1)
+    bn.load_state_dict(fill_state_dict(bn.state_dict(), seed))
+    bn = bn.cuda()
+    xa = torch.randn(2, 5, 7, 9, 2, generator=g).cuda()
+    with torch.no_grad():
+        bn(xa, train=False)
+        bn(3.0 * xa + 1.0, train=True)
+        want = P.cbn_eval(xa.cpu(), {k: v.detach().cpu() for k, v in bn.state_dict().items()}, "")
+        assert C.rel_l2(bn(xa, train=False), want) < 1e-5
+
+
+def test_decoder_outputs_are_kept_by_default():
+    """model/pvae_module.py:L2090,L2099: ``self.decoder_outputs`` after every forward."""
+    enc, dec = C.build_vae(1, 1, "twophase", "mask", 2, "cuda")
+    x, eps = C.vae_inputs(2, 3200, 1, 1, 2, "cuda")
+    C.run_vae(enc, dec, x, eps, "twophase")
+    assert len(dec.decoder_outputs) == 5
+    assert tuple(dec.decoder_outputs[0].shape) == (2, 256, 9, 33, 2) and tuple(dec.decoder_outputs[4].shape) == (2, 32, 129, 33, 2)
+
+
 def test_philox_eps_statistics():
     """Default (no eps supplied) path: on-device Philox N(0,1); z - mu must have the closed-form scale."""
     enc, dec = C.build_vae(1, 1, "skip_prepare", "real_imag", 0, "cuda")
