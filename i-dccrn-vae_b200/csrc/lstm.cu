@@ -366,6 +366,37 @@ __global__ void __launch_bounds__(256) combine_planes_kernel(const float* __rest
   }
 }
 
+// nn.LSTM with one hidden unit: thread = utterance, all layers advanced step by step (exact expf / tanhf)
+__global__ void __launch_bounds__(64) lstm_h1_kernel(const float* __restrict__ g, int g_ld, const float* __restrict__ wrec,
+                                                     int L, int NB, int Talloc, int Tv, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= NB) return;
+  float w[4][12], h[4] = {0.f, 0.f, 0.f, 0.f}, c[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int l = 0; l < L; ++l)
+    for (int k = 0; k < 12; ++k) w[l][k] = __ldg(wrec + l * 12 + k);
+  const int Tp = Talloc + 1;
+  for (int t = 0; t < Tv; ++t) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + ((long long)b * Tp + 1 + t) * g_ld));
+    float x = 0.f;
+    for (int l = 0; l < L; ++l) {
+      float a[4];
+      if (l == 0) {
+        a[0] = g0.x; a[1] = g0.y; a[2] = g0.z; a[3] = g0.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = w[l][k] * x + w[l][8 + k];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] += w[l][4 + k] * h[l];
+      const float ig = sigmoid_f(a[0]), fg = sigmoid_f(a[1]), gg = tanhf(a[2]), og = sigmoid_f(a[3]);
+      c[l] = fg * c[l] + ig * gg;
+      h[l] = og * tanhf(c[l]);
+      x = h[l];
+    }
+    out[(long long)b * Tv + t] = x;
+  }
+}
+
 struct RecCfg {
   int NU, NR, Hs, RC, UT;
   size_t smem;
@@ -511,5 +542,17 @@ extern "C" int idv_lstm_combine_planes(const float* hseq, int NB, int T, int H, 
   const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
   combine_planes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(hseq, NB, T, Tv, H, latent, planes, out_split);
   IDV_LAUNCH_CHECK("combine_planes_kernel");
+  return IDV_OK;
+}
+
+extern "C" int idv_lstm_h1_fwd(const float* g, int g_ld, const float* wrec, int num_layers, int NB, int T, int t_valid,
+                               float* out, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(g && wrec && out && NB > 0 && T > 0, "idv_lstm_h1_fwd: bad argument");
+  IDV_CHECK_ARG(num_layers >= 1 && num_layers <= 4 && g_ld >= 4 && g_ld % 4 == 0,
+                "idv_lstm_h1_fwd: 1..4 layers and a gate row stride that is a multiple of 4 expected");
+  const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
+  lstm_h1_kernel<<<(NB + 63) / 64, 64, 0, (cudaStream_t)stream>>>(g, g_ld, wrec, num_layers, NB, T, Tv, out);
+  IDV_LAUNCH_CHECK("lstm_h1_kernel");
   return IDV_OK;
 }

@@ -35,6 +35,7 @@ SIGNATURES = {
     "idv_lstm_recurrent_tc": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp],
     "idv_lstm2_wave_tc": [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],
     "idv_lstm_layer_pair_tc": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp],
+    "idv_lstm_h1_fwd": [vp, i32, vp, i32, i32, i32, i32, vp, vp],
     "idv_lstm_combine_fwd": [vp, i32, i32, i32, vp, i32, vp],
     "idv_reparam_fwd": [vp, i32, i32, i32, i32, i32, i32, vp, vp, u64, u64, vp, i32, vp, vp],
     "idv_latent_fwd": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, i32, vp],

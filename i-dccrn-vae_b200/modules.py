@@ -28,9 +28,7 @@ import torch.nn as nn
 from . import ops, pack
 from .ops import Planes
 
-_TRAIN_MSG = ("train=True with num_samples > 1 outside autograd is not built (the batch statistics span the sample "
-              "passes: that forward lives in train.DecoderTrainStep); run it with gradients enabled, use "
-              "num_samples == 1, or train=False")
+_TRAIN_MSG = "the fused reconstruction head runs its train-mode ComplexBatchNormal on one batch (out_bmul == 1)"
 
 
 def _sd(module):
@@ -972,35 +970,45 @@ class _VaeDecoderBase(nn.Module):
         self.register_buffer("data_std", data_std)
         self.datanorm = data_mean is not None and data_std is not None
 
-    def _decode(self, stft_x, z, skiper, C, F, train, real_skips, mask):
+    def _decode(self, stft_x, z, skiper, C, F, train, real_skips, mask, self_skip=False):
+        """self_skip: every skip slot is fed the layer's own input (pvae_dccrn_decoder_prob_skip, skip_prob = 2)."""
         BS, T, zdim, D = z.shape
         S = self.num_samples
-        if train and S != 1:
-            raise NotImplementedError(_TRAIN_MSG)
+        autograd = train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if BS % S:
             raise RuntimeError("z batch %d is not a multiple of num_samples %d" % (BS, S))
         B = BS // S
+        # train-mode forward with num_samples > 1: the batch statistics of every ComplexBatchNormal span all B*S rows
+        # (model/pvae_module.py:L2550-2567), so the samples run as ONE batch with the skip tensors / noisy STFT repeated
+        # per sample (row b*S + s <- utterance b) instead of the eval path's per-sample passes
+        repeat = S if (train and S != 1 and not autograd) else 1
+        if repeat > 1:
+            B, S = BS, 1
         n = len(self.decoders)
         # frames of the row layout = frames of the reconstructed spectrum (the non-causal layers add one each)
         t_alloc = T
         for dec in self.decoders:
             t_alloc = dec.transconv.frames_out(t_alloc)
         skips, split = {}, ops.use_split()
-        if real_skips:
+        if real_skips or self_skip:
             for i in range(n):
                 if self.use_sc and i in self.skip_to_use:
-                    skips[i] = _skip_planes(skiper, len(skiper) - i - 1, split, t_alloc)
+                    skips[i] = "self" if self_skip else _skip_planes(skiper, len(skiper) - i - 1, split, t_alloc)
+                    if repeat > 1 and not self_skip:
+                        skips[i] = ops.repeat_planes(skips[i], repeat)
         n_bins = F
         for _ in range(n):
             n_bins = 2 * n_bins - 1          # kernel 5 / stride 2 / pad 2 transposed conv
         predict = torch.empty((BS, n_bins, t_alloc, 2), dtype=torch.float32, device=z.device)
         if mask:
             stft_x = ops.lib.require_f32_cuda(stft_x, "stft_x")
+            if repeat > 1:
+                stft_x = stft_x.repeat_interleave(repeat, 0)
             if tuple(stft_x.shape[1:]) != (n_bins, t_alloc, 2):
                 raise RuntimeError("stft_x %s does not match the reconstructed spectrum (B, %d, %d, 2)"
                                    % (tuple(stft_x.shape), n_bins, t_alloc))
         self.decoder_outputs = []
-        if train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if autograd:
             # training step: (recon_sig, predict) carry a grad_fn whose backward runs the C-ABI backward kernels
             if self.datanorm:
                 raise NotImplementedError("the backward pass is built for the decoders without data_norm")
@@ -1011,11 +1019,11 @@ class _VaeDecoderBase(nn.Module):
             zp = _z_planes(z, B, S, s, split, t_alloc)
             p = self.dense.forward_planes(zp, C, F)
             for i in range(n - 1):
-                p = self.decoders[i].forward_planes(p, skips.get(i), train)
+                p = self.decoders[i].forward_planes(p, p if self_skip and i in skips else skips.get(i), train)
                 if S == 1:
                     self.decoder_outputs.append(p)
-            self.decoders[n - 1].forward_head(p, skips.get(n - 1), mask, stft_x if mask else None, predict, S, s,
-                                              train)
+            self.decoders[n - 1].forward_head(p, p if self_skip and (n - 1) in skips else skips.get(n - 1), mask,
+                                              stft_x if mask else None, predict, S, s, train)
         # model/pvae_module.py:L2090,L2099: the per-layer outputs (B*S, C, F, T, 2) are kept on the module.  Here they
         # stay activation planes and are converted on access (SkipList); with num_samples > 1 the sample passes run
         # one after the other on (B, ...) planes, so the list is only kept for num_samples == 1.
@@ -1079,6 +1087,37 @@ class pvae_dccrn_decoder_no_skip(_VaeDecoderBase):
         if self.resynthesis:
             predict = torch.view_as_complex(self.stft(sig))
         return sig, predict
+
+
+class pvae_dccrn_decoder_prob_skip(_VaeDecoderBase):
+    """model/pvae_module.py:L1681-1788: the CVAE decoder whose skip connections are dropped at random while training.
+    Every forward draws ``torch.rand(1)`` from torch's global CPU generator like the reference (L1729; also in eval, so
+    the generator advances identically); with train=True and a draw >= 0.5 the skip slots are fed zeros (skip_prob = 1)
+    or the layer's own input (skip_prob = 2), otherwise - and always with train=False - the real skip tensors, repeated
+    ``num_samples`` times.  Only recon_type 'real_imag' defines an output in the reference (L1783-1786).
+    Extra keyword ``sc_flag``: force the draw's outcome (True = real skips) for parity runs."""
+
+    def __init__(self, net_params, causal, device, num_samples, zdim, n_fft, hop_len, win_length, recon_type,
+                 skip_to_use, skip_prob):
+        super().__init__()
+        self._init_common(net_params, causal, device, num_samples, zdim, n_fft, hop_len, win_length, recon_type,
+                          skip_to_use, True)
+        if recon_type != "real_imag":
+            raise NotImplementedError("pvae_dccrn_decoder_prob_skip only defines recon_type='real_imag' "
+                                      "(model/pvae_module.py:L1783-1786)")
+        if skip_prob not in (1, 2):
+            raise ValueError("skip_prob must be 1 (zero skips) or 2 (the layer's own input as its skip) - the reference "
+                             "leaves zero_flag undefined otherwise (model/pvae_module.py:L1691-1694)")
+        self.skip_prob = skip_prob
+        self.zero_flag = skip_prob == 1
+
+    def forward(self, stft_x, z, skiper, C, F, train=True, sc_flag=None):
+        draw = torch.rand(1)
+        if sc_flag is None:
+            sc_flag = bool(draw[0] < 0.5) if train else True
+        if sc_flag:
+            return self._decode(stft_x, z, skiper, C, F, train, real_skips=True, mask=False)
+        return self._decode(stft_x, z, skiper, C, F, train, real_skips=False, mask=False, self_skip=not self.zero_flag)
 
 
 class nsvae_pvae_dccrn_decoder_twophase(_VaeDecoderBase):
@@ -1175,6 +1214,61 @@ class DCCRN_(nn.Module):
         if self.resynthesis:
             predict = self.stft(clean)
         return clean, torch.view_as_complex(predict)
+
+
+# --------------------------------------------------------------------------------------------------
+# GAN discriminator of train_second_phase_adversarial.py — model/pvae_module.py:L2271-2350
+# --------------------------------------------------------------------------------------------------
+class dis_Encoder(Encoder):
+    """model/pvae_module.py:L2271-2293: Encoder whose ComplexBatchNormal keeps ``init_flag`` set (dis_cbn=True: the
+    running statistics are overwritten by every train-mode batch instead of averaged)."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, stride, chw, padding=None, causal=False):
+        super().__init__(in_channel, out_channel, kernel_size, stride, chw, padding, causal)
+        self.bn = ComplexBatchNormal(chw[0], chw[1], chw[2], dis_cbn=True)
+
+
+class distinguisher(nn.Module):
+    """model/pvae_module.py:L2294-2350: STFT -> 6 dis_Encoder blocks -> a REAL nn.LSTM over the flattened (C, F, re/im)
+    features with ONE hidden unit -> (B, T, 1) score per frame.  The encoder stack runs on the tap-GEMM kernels; the
+    LSTM's input projection (2560 -> 4 gates) is one more tap-GEMM (N = 32, 4 live columns) and its scalar recurrence
+    one small kernel (idv_lstm_h1_fwd, one thread per utterance)."""
+
+    def __init__(self, net_params, causal, device, zdim, n_fft, hop_len, win_length):
+        super().__init__()
+        self.device = device
+        self.causal = causal
+        self.stft = STFT(n_fft, hop_len, win_length=win_length, device=device)
+        ch, ks = net_params["encoder_channels"], net_params["encoder_kernel_sizes"]
+        st, pd, chw = net_params["encoder_strides"], net_params["encoder_paddings"], net_params["encoder_chw"]
+        self.encoders = nn.ModuleList([dis_Encoder(in_channel=ch[i], out_channel=ch[i + 1], kernel_size=ks[i], stride=st[i],
+                                                   padding=pd[i], chw=chw[i], causal=causal) for i in range(len(ch) - 1)])
+        lstm_dims = net_params["lstm_dim"]
+        self.lstms = nn.ModuleList([nn.LSTM(input_size=lstm_dims[i] * 2, hidden_size=1,
+                                            num_layers=net_params["lstm_layer_num"], device=device)
+                                    for i in range(len(lstm_dims) - 1)])
+        self.epsilon = 1e-6
+        self._cache = _PackCache()
+
+    def forward(self, x, train=True):
+        if len(self.lstms) != 1:
+            raise NotImplementedError("one LSTM stage expected (lstm_dim has two entries)")
+        if train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("the distinguisher is built forward-only (eval and train-mode statistics); its "
+                                      "backward pass (train_second_phase_adversarial.py) is not - call it under "
+                                      "torch.no_grad() or freeze its parameters")
+        stft_x = self.stft(x)
+        top = _run_encoder_stack(self.encoders, stft_x, train)[-1]
+        lstm = self.lstms[0]
+        if top.C * top.F * 2 != lstm.input_size:
+            raise RuntimeError("LSTM input size %d != 2*C*F = 2*%d*%d" % (lstm.input_size, top.C, top.F))
+        items = self._cache.check(lstm)
+        key = (top.C, top.F, str(top.data.device))
+        if key not in items:
+            items[key] = pack.pack_lstm_h1(_sd(lstm), lstm.num_layers, top.C, top.F, top.data.device)
+        inproj, wrec = items[key]
+        g = ops.tapgemm(inproj, top, None, top.NB, top.T, zero_pad_rows=False, out_split=False)      # [1][R][32]
+        return ops.lstm_h1(g, inproj.out_ld, wrec, lstm.num_layers, top.NB, top.T, top.Tv)           # (B, T, 1)
 
 
 # north-star aliases (SURVEY §0 F4)

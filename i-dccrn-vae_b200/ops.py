@@ -270,6 +270,15 @@ def lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T,
     return hseq
 
 
+def lstm_h1(g, g_ld, wrec, num_layers, NB, T, t_valid=0):
+    """Real nn.LSTM with one hidden unit (the GAN distinguisher's head): g = layer-0 gate pre-activations [R][g_ld]
+    (columns 0-3), wrec = pack.pack_lstm_h1's recurrent parameters.  Returns (NB, Tv, 1)."""
+    Tv = t_valid if 0 < t_valid < T else T
+    out = torch.empty((NB, Tv, 1), dtype=torch.float32, device=g.device)
+    lib.call("idv_lstm_h1_fwd", g, g_ld, wrec, num_layers, NB, T, Tv, out)
+    return out
+
+
 def lstm_combine(hseq, NB, T, H, t_valid=0):
     Tv = t_valid if 0 < t_valid < T else T
     latent = torch.empty((NB, Tv, H, 2), dtype=torch.float32, device=hseq.device)
@@ -365,6 +374,16 @@ def z_to_planes(z, NB, S, s, split=False, t_alloc=None):
     data = _empty_act(NB * (T + 1) * 2 * round8(zdim), z.device, split)
     lib.call("idv_z_to_planes", z, NB, S, s, T, zdim, data, 1 if split else 0, Tv)
     return Planes(data, NB, zdim, 1, T, split=split, Tv=Tv)
+
+
+def repeat_planes(p, S):
+    """Rows b -> b*S + s (the unsqueeze(1).repeat(1, S, ...).view of model/pvae_module.py:L2564-2566) on activation
+    planes: the skip tensors of a train-mode decoder pass with num_samples = S > 1, whose batch statistics span all
+    B*S rows (device-memory copy; the eval path never materialises the repeat)."""
+    Tp = p.T + 1
+    lead = 2 if p.split else 1
+    data = p.data.view(lead, p.F, p.NB, Tp, p.Cp).repeat_interleave(S, dim=2).reshape(-1).contiguous()
+    return Planes(data, p.NB * S, p.C, p.F, p.T, cp=p._cp, split=p.split, Tv=p.Tv)
 
 
 def cbn_eval_user(x, zb):

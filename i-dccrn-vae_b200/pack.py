@@ -443,6 +443,32 @@ def pack_lstm_step(lstm_re, lstm_im, hidden, layer, device):
     return TapGemmPack(W.reshape(-1), bias, units, taps, N, 4, N, False, 0.0, device)
 
 
+def pack_lstm_h1(lstm, num_layers, c_in, f_in, device):
+    """nn.LSTM with ONE hidden unit over the features (c, f, part) flattened as (c*f_in + f)*2 + part (the reshape at
+    model/pvae_module.py:L2336-2339): layer-0 input projection as a tap-GEMM (N = 32, columns 0-3 = gates i, f, g, o
+    with b_ih_l0 + b_hh_l0 folded in) and the scalar recurrent parameters fp32 [num_layers][12] =
+    (w_ih[4] (layers >= 1), w_hh[4], b_ih + b_hh [4] (layers >= 1)) for idv_lstm_h1_fwd."""
+    ch, N = round8(c_in), 32
+    wih = _cpu(lstm["weight_ih_l0"]).double()                          # (4, c_in*f_in*2)
+    dev = wih.device
+    w = wih.reshape(4, c_in, f_in, 2)
+    W = torch.zeros(f_in, 2 * ch, N, dtype=torch.float64, device=dev)
+    W[:, :c_in, :4] = w[..., 0].permute(2, 1, 0)
+    W[:, ch:ch + c_in, :4] = w[..., 1].permute(2, 1, 0)
+    bias = torch.zeros(N, dtype=torch.float64, device=dev)
+    bias[:4] = _cpu(lstm["bias_ih_l0"]).double() + _cpu(lstm["bias_hh_l0"]).double()
+    taps = [[0, f, 0, 0, 2 * ch, f * 2 * ch * N] for f in range(f_in)]
+    units = [[0, f_in, 0, 0, 0, 0]]
+    inproj = TapGemmPack(W.reshape(-1), bias, units, taps, N, 1, N, False, 0.0, device)
+    rec = torch.zeros(num_layers, 12, dtype=torch.float64, device=dev)
+    for l in range(num_layers):
+        rec[l, 4:8] = _cpu(lstm["weight_hh_l%d" % l]).double().reshape(4)
+        if l > 0:
+            rec[l, 0:4] = _cpu(lstm["weight_ih_l%d" % l]).double().reshape(4)
+            rec[l, 8:12] = _cpu(lstm["bias_ih_l%d" % l]).double() + _cpu(lstm["bias_hh_l%d" % l]).double()
+    return inproj, rec.to(torch.float32).contiguous().to(device)
+
+
 def pack_lstm_whh(lstm_re, lstm_im, layer, device):
     return torch.stack((_cpu(lstm_re["weight_hh_l%d" % layer]), _cpu(lstm_im["weight_hh_l%d" % layer]))) \
         .to(torch.float32).contiguous().to(device)

@@ -435,8 +435,6 @@ class DecoderTrainStep:
     def __init__(self, dec):
         if not dec.causal:
             raise NotImplementedError("the backward pass is built for the causal network (model/causal_netconfig.py)")
-        if dec.num_samples != 1:
-            raise NotImplementedError("training is built for num_samples = 1 (the shipped training configs)")
         if not ops.use_split():
             raise RuntimeError("training runs on the tensor-core path (IDV_GEMM=tc)")
         self.dec = dec
@@ -449,18 +447,31 @@ class DecoderTrainStep:
             return self._forward(stft_x, z, skips, C, F, mask)
 
     def _forward(self, stft_x, z, skips, C, F, mask):
-        """z (B, T, zdim, 2), skips {layer: Planes}.  Returns recon_sig (B, L), predict (B, F, T, 2)."""
+        """z (B*S, T, zdim, 2), skips {layer: Planes of B utterances, or "self"}.  Returns recon_sig (B*S, L), predict
+        (B*S, F, T, 2).  With num_samples = S > 1 (train_second_phase_decoder.sh:L6 runs --num_samples 2) the S samples of
+        an utterance are rows b*S + s of ONE batch, exactly like the reference (model/pvae_module.py:L2550-2567): the
+        batch statistics of every ComplexBatchNormal span all B*S rows, the skip tensors and the noisy STFT of the mask
+        head are repeated per sample (row b*S + s reads utterance b).  "self" = the layer's own input as its skip tensor
+        (pvae_dccrn_decoder_prob_skip with skip_prob = 2, L1757-1758)."""
         dec = self.dec
         z = lib.require_f32_cuda(z, "z")
-        B, T, zdim, _ = z.shape
+        B, T, zdim, _ = z.shape                     # B = utterances x samples from here on
+        S = dec.num_samples
+        if B % S:
+            raise RuntimeError("z batch %d is not a multiple of num_samples %d" % (B, S))
         dev = z.device
         n = len(dec.decoders)
+        if S > 1:
+            skips = {i: (sk if isinstance(sk, str) else ops.repeat_planes(sk, S)) for i, sk in skips.items()}
+            if mask:
+                stft_x = lib.require_f32_cuda(stft_x, "stft_x").repeat_interleave(S, 0)
         zp = ops.z_to_planes(z, B, 1, 0, split=True, t_alloc=T)
         p = dec.dense.forward_planes(zp, C, F)
-        sv = {"zp": zp, "dense_out": p, "layers": [], "B": B, "T": T, "C": C, "F": F, "mask": mask}
+        sv = {"zp": zp, "dense_out": p, "layers": [], "B": B, "T": T, "C": C, "F": F, "mask": mask, "S": S}
+        _skip = lambda i, cur: cur if isinstance(skips.get(i), str) else skips.get(i)
         for i in range(n - 1):
             d = dec.decoders[i]
-            raw = d.forward_planes(p, skips.get(i), True, raw_only=True)
+            raw = d.forward_planes(p, _skip(i, p), True, raw_only=True)
             Cc = raw.C
             acc = torch.empty(Cc * 5, dtype=torch.float64, device=dev)
             lib.call("idv_cbn_stats_planes", raw.data, 0, raw.NB, Cc, raw.F, raw.T, acc, raw.Tv)
@@ -470,12 +481,12 @@ class DecoderTrainStep:
             act = torch.empty(2 * raw.data.numel(), dtype=torch.bfloat16, device=dev)
             lib.call("idv_cbn_apply_planes", raw.data, 0, raw.NB, Cc, raw.F, raw.T, zb, 1, slope, raw.Tv, act, 1)
             a = Planes(act, raw.NB, Cc, raw.F, raw.T, split=True, Tv=raw.Tv)
-            sv["layers"].append({"x": p, "skip": skips.get(i), "raw": raw, "stats": stats, "zb": zb, "slope": slope})
+            sv["layers"].append({"x": p, "skip": _skip(i, p), "raw": raw, "stats": stats, "zb": zb, "slope": slope})
             p = a
         d = dec.decoders[n - 1]
         n_bins = 2 * p.F - 1
         raw5 = torch.empty((B, n_bins, T, 2), dtype=torch.float32, device=dev)
-        d.forward_head(p, skips.get(n - 1), False, None, raw5, 1, 0, train=True, raw_only=True)
+        d.forward_head(p, _skip(n - 1, p), False, None, raw5, 1, 0, train=True, raw_only=True)
         inner = n_bins * T
         acc = torch.empty(5, dtype=torch.float64, device=dev)
         lib.call("idv_cbn_stats_user", raw5, B, 1, inner, acc)
@@ -486,7 +497,7 @@ class DecoderTrainStep:
         if mask:
             stft_x = lib.require_f32_cuda(stft_x, "stft_x")
         lib.call("idv_head_user", predict, inner, B, float(d._slope()), 1 if mask else 0, stft_x if mask else None, 1)
-        sv["head"] = {"x": p, "skip": skips.get(n - 1), "raw": raw5, "stats": stats, "zb": zb, "slope": d._slope(),
+        sv["head"] = {"x": p, "skip": _skip(n - 1, p), "raw": raw5, "stats": stats, "zb": zb, "slope": d._slope(),
                       "stft_x": stft_x if mask else None}
         self.saved = sv
         recon_sig = dec.istft.forward_ri(predict)
@@ -582,10 +593,13 @@ class DecoderTrainStep:
         lib.call("idv_dec5_wgrad", x5.data, 1, dy5, ktot, 0, x5.Cp, x5.F, B, T, dW)
         if sk5 is not None:
             lib.call("idv_dec5_wgrad", sk5.data, 1, dy5, ktot, x5.Cp, sk5.Cp, sk5.F, B, T, dW)
-            if want_dskip:
+            if want_dskip or sk5 is x5:
                 gs = torch.empty(sk5.F * R * sk5.Cp, dtype=torch.float32, device=dev)
                 lib.call("idv_dec5_dgrad", dy5, w10, ktot, x5.Cp, sk5.Cp, sk5.F, B, T, gs)
-                dskips[n - 1] = gs
+                if sk5 is x5:                        # the layer's input was also its skip tensor: both gradients are dL/dx
+                    lib.call("idv_axpy", g, gs, 1.0, g.numel())
+                else:
+                    dskips[n - 1] = self._sum_samples(gs, sk5)
         del dy5
         d_re, d_im = pack.unfold_dec5_wgrad(dW.view(10, ktot, 2), x5.C, c_skip, t5.tconv_re.weight.shape[0])
         self._grad(t5.tconv_re.weight, d_re)
@@ -618,11 +632,16 @@ class DecoderTrainStep:
             self._packs[key] = pack.pack_convT_dgrad(wr, wi, 0, xin.C, xin.F, sf, pf, dev)
         gin = ops.tapgemm(self._packs[key], dyp, None, NB, T, zero_pad_rows=True, out_split=False)
         gskip = None
-        if skip is not None and want_dskip:
+        if skip is not None and (want_dskip or skip is xin):
             key = ("dgrad_skip", i, wr._version, wi._version)
             if key not in self._packs:
                 self._packs[key] = pack.pack_convT_dgrad(wr, wi, xin.C, c_skip, xin.F, sf, pf, dev)
             gskip = ops.tapgemm(self._packs[key], dyp, None, NB, T, zero_pad_rows=True, out_split=False)
+            if skip is xin:                          # self skip: both halves of the concatenated input are the same tensor
+                lib.call("idv_axpy", gin, gskip, 1.0, gin.numel())
+                gskip = None
+            else:
+                gskip = self._sum_samples(gskip, skip)
         # weight gradients: K = rows x output planes, one GEMM per source (weight rows [p | skip] like torch.cat)
         rp = _rpad(R)
         rows = 2 * round8(cout)
@@ -649,6 +668,15 @@ class DecoderTrainStep:
         self._grad(wr, d_re)
         self._grad(wi, d_im)
         return gin, gskip
+
+    def _sum_samples(self, g, planes):
+        """Gradient planes [F][B*S*(T+1)][Cp] of a skip tensor that was repeated per sample -> [F][B*(T+1)][Cp]: the
+        encoder's skip tensor of utterance b feeds rows b*S .. b*S + S - 1."""
+        S = self.saved["S"]
+        if S == 1:
+            return g
+        Tp = planes.T + 1
+        return g.view(planes.F, planes.NB // S, S, Tp, planes.Cp).sum(2).reshape(-1).contiguous()
 
     def _dense_backward(self, g, want_dz):
         sv, dense = self.saved, self.dec.dense

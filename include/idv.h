@@ -204,6 +204,12 @@ int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_l
 int idv_lstm_layer_pair_config(int H, int* n_cols, int* n_ctas, int64_t* work_bytes);
 int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* wpack, int NB, int T,
                            int H, float* hseq, void* hsplit, void* work, unsigned int* sync, int t_valid, void* stream);
+/* Real nn.LSTM with ONE hidden unit and num_layers <= 4 layers (the GAN distinguisher, model/pvae_module.py:L2319-2345).
+ * g: layer-0 gate pre-activations fp32 [R][g_ld] (columns 0-3 = i, f, g, o with both layer-0 biases), R = NB*(T+1),
+ * row b*(T+1)+1+t.  wrec: fp32 [num_layers][12] = (w_ih[4], w_hh[4], bias[4]) (w_ih / bias unused for layer 0).
+ * out: (NB, Tv, 1) = the top layer's h.  One thread per utterance (the recurrence is scalar).                  */
+int idv_lstm_h1_fwd(const float* g, int g_ld, const float* wrec, int num_layers, int NB, int T, int t_valid, float* out,
+                    void* stream);
 /* Combine the four streams (real = rr - ii, imag = ir + ri), emit the user-layout latent
  * (NB, T, H, 2).  Replaces the stack/permute at complex_progress.py:L62-73, pvae_module.py:L2247. */
 int idv_lstm_combine_fwd(const float* hseq, int NB, int T, int H, float* latent, int t_valid, void* stream);

@@ -235,7 +235,7 @@ def case_train_step(tag, B, L, latent_num, seed):
     np.savez(os.path.join(OUT, tag + ".npz"), **g)
 
 
-def case_train_step_phase2(tag, B, L, latent_num, recon_type, weights, seed):
+def case_train_step_phase2(tag, B, L, latent_num, recon_type, weights, seed, S=1):
     """Phase-2 decoder training step of train_second_phase_decoder.py:L376-433: frozen NSVAE encoder (train=False),
     nsvae_pvae_dccrn_decoder_twophase(train=True, pad='sig'), two_phase_loss.multi_recon_loss (shipped weights '001' =
     SI-SNR only), backward.  Pins the loss terms and, per decoder parameter, ||grad|| and <grad, probe>."""
@@ -244,33 +244,36 @@ def case_train_step_phase2(tag, B, L, latent_num, recon_type, weights, seed):
     for m in ("matplotlib", "matplotlib.pyplot"):
         sys.modules.setdefault(m, types.ModuleType(m))
     import model.nsvae_loss as ref_loss
-    net, enc = build_vae(latent_num, 1, seed)
-    dec = ref_mod.nsvae_pvae_dccrn_decoder_twophase(net, True, "cpu", 1, ZDIM, NFFT, HOP, WIN, recon_type, True,
+    net, enc = build_vae(latent_num, S, seed)
+    dec = ref_mod.nsvae_pvae_dccrn_decoder_twophase(net, True, "cpu", S, ZDIM, NFFT, HOP, WIN, recon_type, True,
                                                     [0, 1, 2, 3, 4, 5], False)
     dec.load_state_dict(fill_state_dict(dec.state_dict(), seed + 1), strict=True)
     xs = [synth_waveform(B, L, seed=1234 + seed + j) for j in range(2)]           # noisy, clean
     T = L // HOP + 1
-    eps = synth_eps((B, 1, T, ZDIM), seed=7 + seed, n=2 * latent_num)
+    eps = synth_eps((B, S, T, ZDIM), seed=7 + seed, n=2 * latent_num)
     with torch.no_grad(), supplied_eps(eps):
         r = enc(xs[0], train=False)
     sig, pred = dec(r[11], r[0], r[8], r[9], r[10], train=True, pad="sig")
-    stft_clean = enc.stft(xs[1])
+    # train_second_phase_decoder.py:L383-390: the clean targets are repeated per sample (row b*S + s <- utterance b)
+    clean_rep = xs[1].unsqueeze(1).repeat(1, S, 1).view(B * S, L)
+    stft_clean = enc.stft(xs[1]).unsqueeze(1).repeat(1, S, 1, 1, 1).view(B * S, NFFT // 2 + 1, T, 2)
     lossf = ref_loss.two_phase_loss(list(weights), 1.0, ZDIM, latent_num)
-    final, l_cpx, l_mag, l_si = lossf.multi_recon_loss(pred, stft_clean, xs[1], sig)
+    final, l_cpx, l_mag, l_si = lossf.multi_recon_loss(pred, stft_clean, clean_rep, sig)
     final.backward()
     # ---- the port, differentiated by autograd
     params = dict(dec.named_parameters())
     sd = {k: v.detach().clone().requires_grad_(k in params) for k, v in fill_state_dict(dec.state_dict(), seed + 1).items()}
     with torch.no_grad():
-        st = P.vae_encoder_forward(enc.state_dict(), xs[0], ZDIM, latent_num, 1, eps)
-    dd = P.vae_decoder_forward(sd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], 1, recon_type, "sig",
+        st = P.vae_encoder_forward(enc.state_dict(), xs[0], ZDIM, latent_num, S, eps)
+    dd = P.vae_decoder_forward(sd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], S, recon_type, "sig",
                                train=True)
-    pf, pc, pm, ps = P.multi_recon_loss(dd["predict"], P.stft(xs[1]), xs[1], dd["recon_sig"], weights)
+    pf, pc, pm, ps = P.multi_recon_loss(dd["predict"], P.stft(xs[1]).repeat_interleave(S, 0), clean_rep, dd["recon_sig"],
+                                        weights)
     pf.backward()
     check("phase2 recon_sig", dd["recon_sig"].detach(), sig.detach())
     for nm, a, b in (("final", pf, final), ("cpx", pc, l_cpx), ("mag", pm, l_mag), ("sisnr", ps, l_si)):
         assert abs(float(a) - float(b)) <= 1e-5 * max(1.0, abs(float(b))), (nm, float(a), float(b))
-    g = {"B": B, "L": L, "latent_num": latent_num, "seed": seed, "mask": int(recon_type == "mask"),
+    g = {"B": B, "L": L, "latent_num": latent_num, "seed": seed, "mask": int(recon_type == "mask"), "S": S,
          "weights": np.asarray(weights, dtype=np.float64), "loss": np32(final), "loss_cpx": np32(l_cpx),
          "loss_mag": np32(l_mag), "loss_sisnr": np32(l_si), "recon_sig": np32(sig)}
     worst = 0.0
@@ -426,6 +429,29 @@ def variant_cases():
     case_dccrn_datanorm("dccrn_datanorm")
 
 
+def n2_cases():
+    """pvae_dccrn_decoder_prob_skip and distinguisher of the unmodified reference (oracle/variants.py runners)."""
+    from oracle import variants as V
+    v = V.PROB_SKIP
+    print("case var_prob_skip_dec")
+    x = synth_waveform(v["B"], v["L"], seed=1234 + v["seed"])
+    T = v["L"] // HOP + 1
+    eps = synth_eps((v["B"], v["S"], T, ZDIM), seed=7 + v["seed"], n=2)
+    with supplied_eps(eps):
+        out = V.run_prob_skip(ref_mod, ref_causal_cfg.get_net_params, fill_state_dict, "cpu", x, None)
+    g = {}
+    for case, (sig, pred) in out.items():
+        g[case + "_sig"], g[case + "_predict"] = np32(sig), np32(pred)
+    assert P.rel_l2(g["train_real_sig"], g["train_zero_sig"]) > 1e-2 and P.rel_l2(g["train_zero_sig"], g["train_self_sig"]) > 1e-2
+    np.savez(os.path.join(OUT, "var_prob_skip_dec.npz"), **g)
+    v = V.DISTINGUISHER
+    print("case distinguisher")
+    x = synth_waveform(v["B"], v["L"], seed=1234 + v["seed"])
+    out = V.run_distinguisher(ref_mod, ref_causal_cfg.get_net_params, fill_state_dict, "cpu", x)
+    assert tuple(out["eval0"].shape) == (v["B"], v["L"] // HOP + 1, 1)
+    np.savez(os.path.join(OUT, "distinguisher.npz"), **{k: np32(t) for k, t in out.items()})
+
+
 def case_dccrn(tag, B, L, seed, causal=True):
     print("case", tag)
     net = (ref_causal_cfg if causal else ref_noncausal_cfg).get_net_params()
@@ -517,16 +543,26 @@ def phase2_cases():
                            weights=(0.0, 0.0, 1.0), seed=15)
     case_train_step_phase2("train_phase2_ri_multi", B=3, L=700, latent_num=1, recon_type="real_imag",
                            weights=(0.5, 0.25, 1.0), seed=16)
+    # the shipped phase-2 script runs --num_samples 2 (train_second_phase_decoder.sh:L6)
+    case_train_step_phase2("train_phase2_mask_sisnr_s2", B=2, L=1300, latent_num=2, recon_type="mask",
+                           weights=(0.0, 0.0, 1.0), seed=19, S=2)
 
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-n2" in sys.argv:
+        n2_cases()
+        sys.exit(0)
     if "--only-variants" in sys.argv:
         variant_cases()
         sys.exit(0)
     if "--only-e2e" in sys.argv:
         e2e_cases()
+        sys.exit(0)
+    if "--only-phase2-s2" in sys.argv:
+        case_train_step_phase2("train_phase2_mask_sisnr_s2", B=2, L=1300, latent_num=2, recon_type="mask",
+                               weights=(0.0, 0.0, 1.0), seed=19, S=2)
         sys.exit(0)
     if "--only-phase2" in sys.argv:
         phase2_cases()
@@ -562,4 +598,5 @@ if __name__ == "__main__":
     phase2_cases()
     e2e_cases()
     variant_cases()
+    n2_cases()
     print("golden fixtures written to", OUT)

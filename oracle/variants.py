@@ -103,3 +103,61 @@ def run_variant(v, enc, dec, x, eps):
             sig, pred = dec(stft_x, r[0], skiper, C, F, train=False)
         out["recon_sig"], out["predict"] = sig, pred
     return out
+
+
+# ---- N2 remainder: pvae_dccrn_decoder_prob_skip (model/pvae_module.py:L1681-1788) and the GAN distinguisher
+# (L2271-2350).  One runner for the reference classes (make_golden.py --only-n2) and for idccrn_b200 (tests).
+# case -> (train, torch seed whose first torch.rand(1) decides the skip drop, skip_prob)
+PROB_SKIP_CASES = {
+    "eval": (False, 0, 1),
+    "train_real": (True, None, 1),          # seed chosen below: draw < 0.5 -> real skips
+    "train_zero": (True, None, 1),          # draw >= 0.5, skip_prob 1 -> zero skips
+    "train_self": (True, None, 2),          # draw >= 0.5, skip_prob 2 -> the layer's own input as its skip
+}
+PROB_SKIP = dict(B=2, L=700, S=2, seed=33)
+
+
+def _seed_for(want_real):
+    """Smallest torch seed whose first torch.rand(1) is < 0.5 (want_real) / >= 0.5."""
+    for sd in range(1000):
+        torch.manual_seed(sd)
+        if bool(torch.rand(1)[0] < 0.5) == want_real:
+            return sd
+    raise RuntimeError("no seed found")
+
+
+def run_prob_skip(mod, net_fn, fill, device, x, eps):
+    """{case: (recon_sig, predict)}.  Every case builds a fresh decoder (train-mode forwards rewrite the CBN buffers);
+    the CVAE encoder (pvae_dccrn_encoder_prob_skip, eval) is shared.  The train-mode forwards run under no_grad."""
+    v = PROB_SKIP
+    enc = mod.pvae_dccrn_encoder_prob_skip(net_fn(), True, device, ZDIM, NFFT, HOP, WIN, v["S"])
+    enc.load_state_dict(fill(enc.state_dict(), v["seed"]), strict=True)
+    enc = enc.to(device).eval()
+    out = {}
+    with torch.no_grad():
+        r = enc(x, train=False, eps=eps) if eps is not None else enc(x, train=False)
+        z, skiper, C, F, stft_x = r[0], r[4], r[5], r[6], r[7]
+        for case, (train, sd, skip_prob) in PROB_SKIP_CASES.items():
+            dec = mod.pvae_dccrn_decoder_prob_skip(net_fn(), True, device, v["S"], ZDIM, NFFT, HOP, WIN, "real_imag", SKIPS,
+                                                   skip_prob)
+            dec.load_state_dict(fill(dec.state_dict(), v["seed"] + 1), strict=True)
+            dec = dec.to(device)
+            torch.manual_seed(_seed_for(case == "train_real") if sd is None else sd)
+            out[case] = dec(stft_x, z, skiper, C, F, train=train)
+    return out
+
+
+DISTINGUISHER = dict(B=3, L=900, seed=34)
+
+
+def run_distinguisher(mod, net_fn, fill, device, x):
+    """eval score, then two train-mode forwards (dis_cbn: the running statistics are overwritten both times), then eval
+    again with the statistics of the second batch."""
+    v = DISTINGUISHER
+    d = mod.distinguisher(net_fn(), True, device, ZDIM, NFFT, HOP, WIN)
+    d.load_state_dict(fill(d.state_dict(), v["seed"]), strict=True)
+    d = d.to(device)
+    with torch.no_grad():
+        out = {"eval0": d(x, train=False), "train1": d(x, train=True), "train2": d(0.5 * x.flip(0), train=True),
+               "eval1": d(x, train=False)}
+    return out

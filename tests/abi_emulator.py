@@ -446,6 +446,25 @@ def _lstm_tc_config(H):
     return lib.lstm_tc_config(H)          # pure host function of the real library (no GPU needed)
 
 
+def idv_lstm_h1_fwd(g, g_ld, wrec, num_layers, NB, T, t_valid, out):
+    Tp, Tv = T + 1, _tv(t_valid, T)
+    gv = _flat(g).view(NB, Tp, g_ld)[:, 1:1 + Tv, :4].to(D)
+    w = wrec.view(num_layers, 12).to(D)
+    h = torch.zeros(num_layers, NB, dtype=D)
+    c = torch.zeros(num_layers, NB, dtype=D)
+    res = torch.zeros(NB, Tv, dtype=D)
+    for t in range(Tv):
+        x = None
+        for l in range(num_layers):
+            a = gv[:, t] if l == 0 else x[:, None] * w[l, 0:4][None] + w[l, 8:12][None]
+            a = a + h[l][:, None] * w[l, 4:8][None]
+            c[l] = torch.sigmoid(a[:, 1]) * c[l] + torch.sigmoid(a[:, 0]) * torch.tanh(a[:, 2])
+            h[l] = torch.sigmoid(a[:, 3]) * torch.tanh(c[l])
+            x = h[l]
+        res[:, t] = x
+    out.copy_(res.view(NB, Tv, 1).to(torch.float32))
+
+
 def idv_lstm_combine_fwd(hseq, NB, T, H, latent, t_valid=0):
     Tp = T + 1
     hs = hseq.view(4, NB, Tp, H)[:, :, 1:1 + _tv(t_valid, T)]

@@ -19,15 +19,17 @@ def run_phase2(golden, tag, device, fused_sisnr=False):
     B, L, latent_num, seed = int(g["B"]), int(g["L"]), int(g["latent_num"]), int(g["seed"])
     recon_type = "mask" if int(g["mask"]) else "real_imag"
     weights = [float(w) for w in g["weights"]]
-    enc, dec = C.build_vae(latent_num, 1, "twophase", recon_type, seed, device)
+    S = int(g["S"]) if "S" in g else 1            # num_samples: rows b*S + s of one batch (train_second_phase_decoder.sh:L6)
+    enc, dec = C.build_vae(latent_num, S, "twophase", recon_type, seed, device)
     xs = [synth_waveform(B, L, seed=1234 + seed + j).to(device) for j in range(2)]
     T = L // C.HOP + 1
-    eps = [e.to(device) for e in synth_eps((B, 1, T, C.ZDIM), seed=7 + seed, n=2 * latent_num)]
+    eps = [e.to(device) for e in synth_eps((B, S, T, C.ZDIM), seed=7 + seed, n=2 * latent_num)]
     with torch.no_grad():
         r = enc(xs[0], train=False, eps=eps)
-        stft_clean = enc.stft(xs[1])
+        stft_clean = enc.stft(xs[1]).repeat_interleave(S, 0)
+    xs[1] = xs[1].repeat_interleave(S, 0)
     sig, pred = dec(r[11], r[0], r[8], r[9], r[10], train=True, pad="sig")
-    assert sig.grad_fn is not None and pred.grad_fn is not None
+    assert sig.grad_fn is not None and pred.grad_fn is not None and sig.shape[0] == B * S
     if fused_sisnr:                     # the product's fused loss kernels (idv_spec_loss_fwd_bwd + idv_sisnr_fwd_bwd)
         from idccrn_b200 import losses
         loss, l_cpx, l_mag, l_si = losses.multi_recon_loss(pred, stft_clean, xs[1], sig, weights)
@@ -103,7 +105,7 @@ def _tc_mode():
     return old
 
 
-@pytest.mark.parametrize("tag", ["train_phase2_mask_sisnr", "train_phase2_ri_multi"])
+@pytest.mark.parametrize("tag", ["train_phase2_mask_sisnr", "train_phase2_ri_multi", "train_phase2_mask_sisnr_s2"])
 def test_phase2_gradients_emulated(emulated_abi, golden, tag):
     from idccrn_b200 import ops
     old = _tc_mode()
@@ -124,12 +126,12 @@ def test_phase2_fused_loss_emulated(emulated_abi, golden, tag):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag", ["train_phase2_mask_sisnr", "train_phase2_ri_multi"])
+@pytest.mark.parametrize("tag", ["train_phase2_mask_sisnr", "train_phase2_ri_multi", "train_phase2_mask_sisnr_s2"])
 def test_phase2_gradients_gpu(golden, tag):
     check_phase2(*run_phase2(golden, tag, "cuda"), tol=5e-4)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag", ["train_phase2_mask_sisnr", "train_phase2_ri_multi"])
+@pytest.mark.parametrize("tag", ["train_phase2_mask_sisnr", "train_phase2_ri_multi", "train_phase2_mask_sisnr_s2"])
 def test_phase2_fused_loss_gpu(golden, tag):
     check_phase2(*run_phase2(golden, tag, "cuda", fused_sisnr=True), tol=5e-4)

@@ -10,6 +10,7 @@ import torch
 import common as C
 import idccrn_b200 as M
 from idccrn_b200.synth import fill_state_dict, synth_eps, synth_waveform
+from oracle import variants as V
 from oracle.variants import VARIANTS, run_variant
 
 
@@ -98,3 +99,65 @@ def test_dccrn_datanorm_emulated(emulated_abi, gemm_mode, golden):
 @pytest.mark.gpu
 def test_dccrn_datanorm_gpu(golden):
     run_dccrn_datanorm(golden, "cuda", 1e-4)
+
+
+# ---- N2 remainder: pvae_dccrn_decoder_prob_skip (model/pvae_module.py:L1681-1788), distinguisher (L2271-2350) ---------
+def run_prob_skip(golden, device, tol):
+    """eval + the three train-mode skip modes (real / zero / the layer's own input), decided by the same torch.rand(1)
+    draw as in the reference (the runner seeds torch's global generator identically on both sides); num_samples = 2."""
+    g = golden("var_prob_skip_dec")
+    v = V.PROB_SKIP
+    x = synth_waveform(v["B"], v["L"], seed=1234 + v["seed"]).to(device)
+    T = v["L"] // C.HOP + 1
+    eps = [e.to(device) for e in synth_eps((v["B"], v["S"], T, C.ZDIM), seed=7 + v["seed"], n=2)]
+    out = V.run_prob_skip(M, lambda: copy.deepcopy(M.get_net_params()), fill_state_dict, device, x, eps)
+    errs = {}
+    for case, (sig, pred) in out.items():
+        assert tuple(sig.shape) == g[case + "_sig"].shape
+        errs[case + "_sig"] = C.rel_l2(sig, g[case + "_sig"])
+        errs[case + "_predict"] = C.rel_l2(torch.view_as_real(pred), g[case + "_predict"])
+    print("prob_skip", device, errs)
+    assert all(e < tol for e in errs.values()), errs
+
+
+def run_distinguisher(golden, device, tol):
+    g = golden("distinguisher")
+    v = V.DISTINGUISHER
+    x = synth_waveform(v["B"], v["L"], seed=1234 + v["seed"]).to(device)
+    out = V.run_distinguisher(M, lambda: copy.deepcopy(M.get_net_params()), fill_state_dict, device, x)
+    errs = {}
+    for k, t in out.items():
+        assert tuple(t.shape) == g[k].shape, (k, tuple(t.shape), g[k].shape)
+        errs[k] = C.rel_l2(t, g[k])
+    print("distinguisher", device, errs)
+    assert all(e < tol for e in errs.values()), errs
+
+
+def test_n2_state_dict_keys():
+    net = copy.deepcopy(M.get_net_params())
+    d = M.distinguisher(net, True, "cpu", 128, 512, 100, 400)
+    sd = d.state_dict()
+    assert sd["lstms.0.weight_ih_l0"].shape == (4, 2560) and sd["lstms.0.weight_hh_l1"].shape == (4, 1)
+    assert "encoders.5.bn.Vri" in sd and d.encoders[0].bn.dis_cbn is True
+    p = M.pvae_dccrn_decoder_prob_skip(net, True, "cpu", 2, 128, 512, 100, 400, "real_imag", C.SKIPS, 2)
+    assert p.state_dict()["decoders.5.transconv.tconv_re.weight"].shape == (64, 1, 5, 2) and p.zero_flag is False
+    with pytest.raises(ValueError):
+        M.pvae_dccrn_decoder_prob_skip(net, True, "cpu", 1, 128, 512, 100, 400, "real_imag", C.SKIPS, 0)
+
+
+def test_prob_skip_decoder_emulated(emulated_abi, gemm_mode, golden):
+    run_prob_skip(golden, "cpu", 2e-5 if gemm_mode == "simt" else 5e-5)
+
+
+def test_distinguisher_emulated(emulated_abi, gemm_mode, golden):
+    run_distinguisher(golden, "cpu", 2e-5 if gemm_mode == "simt" else 5e-5)
+
+
+@pytest.mark.gpu
+def test_prob_skip_decoder_gpu(golden):
+    run_prob_skip(golden, "cuda", 1e-4)
+
+
+@pytest.mark.gpu
+def test_distinguisher_gpu(golden):
+    run_distinguisher(golden, "cuda", 1e-4)
