@@ -15,6 +15,7 @@ int option_dynamic_tiles();
 int option_gemm_pairs();
 int option_lstm_wave_pairs();
 int option_tile_order();
+int option_tma_store();
 
 #define IDV_CHECK_ARG(cond, ...)             \
   do {                                       \

@@ -30,6 +30,9 @@ struct Params {
   const idv_unit_t* units;
   const idv_tap_t* taps;
   const float* bias;
+  const float* bias2;         // optional: bias of the FIRST frame of every utterance (rows with r % Tp == 1) - a layer
+                              // composed with the affine map in front of it (dense + first decoder layer) loses the
+                              // bias terms of the time taps that read the zero pad row
   void* out;
   int out_ld;
   long long out_plane;        // elements between output planes
@@ -37,15 +40,16 @@ struct Params {
   int out_split;              // 1: bf16 hi/lo planes, 0: fp32
   int apply_prelu;
   float slope;
-  // head mode (last decoder layer, Cout = 1): unit q holds output bins fo = 2q (columns 0,1 = re,im) and
-  // fo = 2q+1 (columns 16,17); the epilogue applies bias + PReLU (+ mask head) and writes `predict`
-  // (NBtot, head_fout, T, 2) directly.  0 = off, 1 = real/imag, 2 = mask.
+  // head mode (last decoder layer, Cout = 1): a unit holds unit.out_ch_off (<= 16) consecutive output bins starting at
+  // fo = unit.out_f, bin e in accumulator columns (2e, 2e+1) = (re, im); the epilogue applies bias + PReLU (+ mask
+  // head) and writes `predict` (NBtot, head_fout, T, 2) directly.  0 = off, 1 = real/imag, 2 = mask.
   int head;
   int head_fout, head_bmul, head_boff;
   const float* stft_x;
   float* predict;
   unsigned int* sched;        // [0] next tile, [1] CTAs finished (dynamic tile scheduler; self-resetting)
   int order;                  // tile order: 0 = (unit, row tile, N tile), 1 = (row tile, unit, N tile) - see decode_tile
+  int tma_out;                // 1: split-bf16 tiles leave through shared memory + TMA stores (tmO), see the epilogue
 };
 
 // Tile index -> (unit, row tile, N tile).  The CTAs that run at the same time work on CONSECUTIVE tile indices, so the
@@ -78,9 +82,11 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;              // one of hi / lo
   static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = TWO ? (BN >= 256 ? 3 : (BN >= 128 ? 4 : 5)) : ((BN >= 256) ? 2 : (BN >= 128 ? 3 : 4));
+  static constexpr int STAGES = TWO ? (BN >= 256 ? 3 : (BN >= 64 ? 4 : 5)) : ((BN >= 256) ? 2 : (BN >= 128 ? 3 : 4));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages, power of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // epilogue staging for the TMA stores: per epilogue warp [hi | lo][32 rows][64 bf16] = 8 KB, 1024-byte aligned
+  static constexpr int OUT_STAGE_BYTES = 4 * 8192;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers, padded*/ + OUT_STAGE_BYTES;
 };
 
 // DYN = false: tile i of CTA b is b + i*gridDim.x (lock-step CTAs, best when the kernel owns the GPU);
@@ -88,7 +94,7 @@ struct Cfg {
 template <int BN, bool DYN, bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                  const __grid_constant__ CUtensorMap tmW, const Params p) {
+                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Params p) {
   static_assert(!(TWO && DYN), "the CTA-pair kernel uses the static tile schedule");
   using C = Cfg<BN, TWO>;
   // TWO: rank of this CTA in its pair, index / count of pairs; a "tile" is then a PAIR of row tiles (2*rt + rank)
@@ -106,6 +112,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 12);
   volatile int* tq = reinterpret_cast<volatile int*>(tmem_slot + 1);
   const uint32_t smem_base = smem_u32(smem);
+  const uint32_t out_stage0 = smem_base + C::STAGES * C::STAGE_BYTES + 1024;      // (stage ring is a multiple of 1024 B)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_row_tiles = TWO ? (p.n_row_tiles + 1) / 2 : p.n_row_tiles;
@@ -115,6 +122,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     prefetch_tmap(&tmA0);
     prefetch_tmap(&tmA1);
     prefetch_tmap(&tmW);
+    if (p.tma_out) prefetch_tmap(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -278,7 +286,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const bool row_ok = r < p.R;
       const int tt_row = p.Tp > 0 ? r % p.Tp : 1;
       const bool pad_row = p.Tp > 0 && p.head != 3 && (tt_row == 0 || (p.t_valid > 0 && tt_row > p.t_valid));
-      const float* bias = p.bias + unit.bias_off + nt * BN;
+      const float* bias = ((p.bias2 != nullptr && tt_row == 1) ? p.bias2 : p.bias) + unit.bias_off + nt * BN;
       if (p.head == 3) {
         // ---- STFT epilogue: rows are (b, t) frames (Tp = frames per utterance, no pad rows), column pair
         //      (2k, 2k+1) = (re, im) of bin k; written to the reference layout (B, nbins, T, 2)
@@ -305,7 +313,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         continue;
       }
       if (p.head) {
-        // ---- fused reconstruction head: 2 output bins per unit, written to the reference layout
+        // ---- fused reconstruction head: up to 16 output bins per unit, written to the reference layout
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, v);
         tmem_ld_wait();
@@ -316,12 +324,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const int T = p.Tp - 1;
           const int b = r / p.Tp, t = r % p.Tp - 1;
           const float b_r = __ldg(bias), b_i = __ldg(bias + 1);
+          const int nbins = unit.out_ch_off;          // head units: out_f = first output bin, out_ch_off = bins (<= 16)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int fo = 2 * unit.out_f + e;
-            if (fo >= p.head_fout) continue;
-            float yr = prelu_f(__uint_as_float(v[16 * e]) + b_r, p.slope);
-            float yi = prelu_f(__uint_as_float(v[16 * e + 1]) + b_i, p.slope);
+          for (int e = 0; e < 16; ++e) {
+            const int fo = unit.out_f + e;
+            if (e >= nbins || fo >= p.head_fout) continue;
+            float yr = prelu_f(__uint_as_float(v[2 * e]) + b_r, p.slope);
+            float yi = prelu_f(__uint_as_float(v[2 * e + 1]) + b_i, p.slope);
             if (p.head == 2) {
               // model/pvae_module.py:L2594-2609 — operation order kept
               const float mag = tanhf(sqrtf(yr * yr + yi * yi));
@@ -339,6 +348,64 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             *reinterpret_cast<float2*>(p.predict + ((long long)(bo * p.head_fout + fo) * T + t) * 2) = make_float2(yr, yi);
           }
         }
+        continue;
+      }
+      if (BN >= 64 && p.tma_out && (unit.out_ch_off & 63) == 0) {
+        // ---- split-bf16 tile through shared memory and TMA stores.  A thread owns a ROW of the accumulator, so direct
+        // stores scatter every 16-byte vector of a warp over 32 rows (32 L1 lines per store instruction: the narrow
+        // layers, whose main loop is short, were bound by this epilogue).  Instead each epilogue warp stages its 32 rows
+        // x 64 columns (hi and lo) in a 128B-swizzled buffer and one lane issues a tensor store of the box
+        // {64 ch, 32 rows, 1 plane, hi|lo}; rows past R are clipped by the tensor map, pad rows carry zeros.
+        const uint32_t stg = out_stage0 + (uint32_t)q * 8192u;
+        const int r0 = rt * BM + q * 32;
+        const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          if (lane == 0) bulk_wait_read_all();               // the previous box has left the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0 + 32 * h, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x0 = __uint_as_float(v[j + 2 * e]) + __ldg(bias + c0 + 32 * h + j + 2 * e);
+                float x1 = __uint_as_float(v[j + 2 * e + 1]) + __ldg(bias + c0 + 32 * h + j + 2 * e + 1);
+                if (p.apply_prelu) { x0 = prelu_f(x0, p.slope); x1 = prelu_f(x1, p.slope); }
+                if (pad_row) { x0 = 0.f; x1 = 0.f; }
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              const uint32_t chunk = (uint32_t)(4 * h + (j >> 3));                    // 16-byte chunk of the 128-byte row
+              const uint32_t a = stg + (uint32_t)lane * 128u + ((chunk ^ sw) << 4);
+              st_shared_v4(a, hw[0], hw[1], hw[2], hw[3]);
+              st_shared_v4(a + 4096u, lw[0], lw[1], lw[2], lw[3]);
+            }
+          }
+          fence_proxy_async();                               // generic-proxy writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0 && r0 < p.R) {
+            const int n0 = nt * BN + c0;
+            int plane = unit.out_f, col = unit.out_ch_off + n0;
+            if (p.N > p.out_ld) {                            // columns wrap into consecutive output planes
+              const int pa = n0 / p.out_ld;
+              plane += pa;
+              col = n0 - pa * p.out_ld;
+            }
+            if ((long long)(plane + 1) * p.out_plane <= p.out_hl) tma_store_4d(&tmO, stg, col, r0, plane, 0);
+            bulk_commit_group();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (TWO) mbar_arrive_cluster(tempty_bar); else mbar_arrive(tempty_bar); }
         continue;
       }
       const long long obase0 = (long long)unit.out_f * p.out_plane + (long long)r * p.out_ld + unit.out_ch_off + nt * BN;
@@ -395,6 +462,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   }
 
+  if (warp >= EPI_WARP0 && lane == 0) bulk_wait_all();      // this warp's tensor stores are complete
   tc_fence_before();
   __syncthreads();
   if (TWO) cluster_sync_all();            // neither CTA leaves (or frees TMEM) while its peer may still touch it
@@ -469,10 +537,10 @@ int encode_map_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows
 }
 
 static int encode_map_4d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t hl_stride_el,
-                         uint32_t b0, uint32_t b1) {
+                         uint32_t b0, uint32_t b1, uint64_t plane_stride_el = 0) {
   // dims (elements): {d0 = channels/k, d1 = rows/n, d2 = planes/slots, 2 = hi/lo}
   cuuint64_t dims[4] = {d0, d1, d2, 2};
-  cuuint64_t strides[3] = {d0 * 2, d0 * d1 * 2, hl_stride_el * 2};
+  cuuint64_t strides[3] = {d0 * 2, (plane_stride_el ? plane_stride_el : d0 * d1) * 2, hl_stride_el * 2};
   cuuint32_t box[4] = {b0, b1, 1, 2};
   cuuint32_t es[4] = {1, 1, 1, 1};
   EncodeTiledFn enc = get_encode_fn();
@@ -508,21 +576,22 @@ static unsigned int* sched_slot() {
 }
 
 template <int BN, bool DYN>
-static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const Params& p, int sms,
-                   cudaStream_t st) {
+static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o, const Params& p,
+                   int sms, cudaStream_t st) {
   using C = Cfg<BN>;
   IDV_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<BN, DYN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 C::SMEM_BYTES));
   const int total = p.n_units * p.n_row_tiles * p.n_col_tiles;
   const int grid = total < sms ? total : sms;
-  tapgemm_tc_kernel<BN, DYN, false><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(a0, a1, w, p);
+  tapgemm_tc_kernel<BN, DYN, false><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(a0, a1, w, o, p);
   IDV_LAUNCH_CHECK("tapgemm_tc_kernel");
   return IDV_OK;
 }
 
 // CTA-pair kernel: clusters of 2, as many as fit the device at once (persistent)
 template <int BN>
-static int launch_pairs(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, Params& p, cudaStream_t st) {
+static int launch_pairs(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o, Params& p,
+                        cudaStream_t st) {
   using C = Cfg<BN, true>;
   static_assert(C::SMEM_BYTES <= 232448, "stage ring exceeds the shared memory of one SM");
   auto kern = tapgemm_tc_kernel<BN, false, true>;
@@ -548,20 +617,20 @@ static int launch_pairs(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   const int pairs = total < max_pairs[dev] ? total : max_pairs[dev];
   cfg.gridDim = dim3(2 * pairs);
   p.sched = nullptr;
-  IDV_CUDA(cudaLaunchKernelEx(&cfg, kern, a0, a1, w, p));
+  IDV_CUDA(cudaLaunchKernelEx(&cfg, kern, a0, a1, w, o, p));
   return IDV_OK;
 }
 
 template <int BN>
-static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, Params& p, int sms,
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o, Params& p, int sms,
                   cudaStream_t st) {
   if (option_dynamic_tiles()) {
     p.sched = sched_slot();
     IDV_CHECK_ARG(p.sched != nullptr, "idv_tapgemm_tc: could not allocate the tile-scheduler pool");
-    return launch2<BN, true>(a0, a1, w, p, sms, st);
+    return launch2<BN, true>(a0, a1, w, o, p, sms, st);
   }
   p.sched = nullptr;
-  return launch2<BN, false>(a0, a1, w, p, sms, st);
+  return launch2<BN, false>(a0, a1, w, o, p, sms, st);
 }
 
 }  // namespace tc
@@ -577,12 +646,42 @@ extern "C" int idv_tapgemm_tc(const void* a0, int a0_cp, int a0_planes, const vo
                              1, 0, nullptr, nullptr, t_valid, stream);
 }
 
+static int tapgemm_tc_impl(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
+                           int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias, const float* bias2,
+                           int N, const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
+                           int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu,
+                           float prelu_slope, int head, int head_fout, int head_bmul, int head_boff,
+                           const float* stft_x, float* predict, int t_valid, void* stream);
+
 extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
                                    int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias, int N,
                                    const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
                                    int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu,
                                    float prelu_slope, int head, int head_fout, int head_bmul, int head_boff,
                                    const float* stft_x, float* predict, int t_valid, void* stream) {
+  return tapgemm_tc_impl(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, nullptr, N, units,
+                         taps, n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, prelu_slope, head,
+                         head_fout, head_bmul, head_boff, stft_x, predict, t_valid, stream);
+}
+
+extern "C" int idv_tapgemm_tc_b2(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
+                                 int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias,
+                                 const float* bias_first, int N, const idv_unit_t* units, const idv_tap_t* taps,
+                                 int n_units, void* out, int out_ld, int64_t out_plane, int64_t out_hl, int out_split,
+                                 int apply_prelu, float prelu_slope, int t_valid, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(bias_first && Tp > 1, "idv_tapgemm_tc_b2: needs the first-frame bias and Tp = frames per utterance + 1");
+  return tapgemm_tc_impl(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, bias_first, N,
+                         units, taps, n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, prelu_slope, 0, 0,
+                         1, 0, nullptr, nullptr, t_valid, stream);
+}
+
+static int tapgemm_tc_impl(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
+                           int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias, const float* bias2,
+                           int N, const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
+                           int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu,
+                           float prelu_slope, int head, int head_fout, int head_bmul, int head_boff,
+                           const float* stft_x, float* predict, int t_valid, void* stream) {
   using namespace idv;
   using namespace idv::tc;
   IDV_CHECK_ARG(a0 && wt && bias && units && taps && (out || head), "idv_tapgemm_tc: null pointer");
@@ -627,24 +726,36 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
   Params p;
   p.R = R; p.Tp = Tp < 0 ? -Tp : Tp; p.keep_pad = Tp < 0; p.N = N; p.n_units = n_units; p.t_valid = t_valid;
   p.n_row_tiles = cdiv(R, BM); p.n_col_tiles = N / BN;
-  p.units = units; p.taps = taps; p.bias = bias; p.out = out; p.out_ld = out_ld;
+  p.units = units; p.taps = taps; p.bias = bias; p.bias2 = bias2; p.out = out; p.out_ld = out_ld;
   p.out_plane = out_plane; p.out_hl = out_hl; p.out_split = out_split; p.apply_prelu = apply_prelu; p.slope = prelu_slope;
   p.head = head; p.head_fout = head_fout; p.head_bmul = head_bmul; p.head_boff = head_boff;
   p.stft_x = stft_x; p.predict = predict;
   p.order = option_tile_order();
+  // TMA-store epilogue: split-bf16 outputs whose rows are 128-byte multiples, not the streaming steps (their pad rows
+  // must stay untouched: a tensor store writes whole boxes); units with a column offset that is not a multiple of 64
+  // fall back to direct stores inside the kernel
+  CUtensorMap mO = mA0;
+  p.tma_out = 0;
+  if (option_tma_store() && head == 0 && out_split && Tp >= 0 && BN >= 64 && out_ld % 64 == 0 && out_plane > 0 && out_hl > 0 &&
+      out_hl % out_plane == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    rc = encode_map_4d(&mO, out, (uint64_t)out_ld, (uint64_t)R, (uint64_t)(out_hl / out_plane), (uint64_t)out_hl, BK, 32,
+                       (uint64_t)out_plane);
+    if (rc) return rc;
+    p.tma_out = 1;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (pairs) {
     switch (BN) {
-      case 256: return launch_pairs<256>(mA0, mA1, mW, p, st);
-      case 128: return launch_pairs<128>(mA0, mA1, mW, p, st);
-      case 64: return launch_pairs<64>(mA0, mA1, mW, p, st);
-      default: return launch_pairs<32>(mA0, mA1, mW, p, st);
+      case 256: return launch_pairs<256>(mA0, mA1, mW, mO, p, st);
+      case 128: return launch_pairs<128>(mA0, mA1, mW, mO, p, st);
+      case 64: return launch_pairs<64>(mA0, mA1, mW, mO, p, st);
+      default: return launch_pairs<32>(mA0, mA1, mW, mO, p, st);
     }
   }
   switch (BN) {
-    case 256: return launch<256>(mA0, mA1, mW, p, sms, st);
-    case 128: return launch<128>(mA0, mA1, mW, p, sms, st);
-    case 64: return launch<64>(mA0, mA1, mW, p, sms, st);
-    default: return launch<32>(mA0, mA1, mW, p, sms, st);
+    case 256: return launch<256>(mA0, mA1, mW, mO, p, sms, st);
+    case 128: return launch<128>(mA0, mA1, mW, mO, p, sms, st);
+    case 64: return launch<64>(mA0, mA1, mW, mO, p, sms, st);
+    default: return launch<32>(mA0, mA1, mW, mO, p, sms, st);
   }
 }

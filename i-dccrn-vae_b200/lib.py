@@ -24,6 +24,8 @@ SIGNATURES = {
     "idv_istft_fwd": [vp, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp],
     "idv_tapgemm_tc": [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, vp, vp, i32, vp, i32, i64, i64,
                        i32, i32, f32, i32, vp],
+    "idv_tapgemm_tc_b2": [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp, i32, vp, i32, i64, i64,
+                          i32, i32, f32, i32, vp],
     "idv_tapgemm_tc_head": [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, vp, vp, i32, vp, i32, i64, i64,
                             i32, i32, f32, i32, i32, i32, i32, vp, vp, i32, vp],
     "idv_stft_frames_split": [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],

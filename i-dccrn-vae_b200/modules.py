@@ -524,6 +524,35 @@ class Decoder(nn.Module):
         out = self.transconv.run_packed(items[key], pp, skip, out)
         return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
+    def forward_after_dense(self, dense, zp, c_p, f_in, skip=None):
+        """ComplexDense ``dense`` + this (first, causal) decoder layer as ONE tap-GEMM on the z planes ``zp``
+        (pack.pack_dense_conv_transpose: the two maps are composed at pack time; eval mode).  c_p, f_in: channels /
+        planes of the dense output (model/pvae_module.py:L2085-2088).  Returns this layer's output planes."""
+        if not self.transconv.causal or not zp.split:
+            raise RuntimeError("the dense + first-layer composition runs on the causal tensor-core path")
+        items = self._cache.check(self)
+        c_skip = skip.C if skip is not None else 0
+        dstamp = tuple((t.data_ptr(), t._version) for t in dense.state_dict(keep_vars=True).values())
+        key = ("dense_fused", dstamp, c_p, f_in, c_skip, str(zp.data.device))
+        if key not in items:
+            for k in [k for k in items if k[0] == "dense_fused"]:          # an older dense version's pack
+                del items[k]
+            kh, sf, pf = self.transconv._geometry()
+            t = self.transconv
+            if c_p + c_skip > t.tconv_re.in_channels or c_p * f_in != dense.linear_read.out_features:
+                raise RuntimeError("dense output %d x %d (+ %d skip channels) does not fit this layer" % (c_p, f_in, c_skip))
+            bn, slope = self._fold()
+            items[key] = pack.pack_dense_conv_transpose(
+                dense.linear_read.weight, dense.linear_read.bias, dense.linear_imag.weight, dense.linear_imag.bias,
+                t.tconv_re.weight, t.tconv_re.bias, t.tconv_im.weight, t.tconv_im.bias, bn, slope, f_in, c_p, c_skip,
+                zp.data.device, sf, pf)
+        pk = items[key]
+        if skip is not None and (skip.T != zp.T or skip.NB != zp.NB or skip.Tv != zp.Tv):
+            raise RuntimeError("skip tensor has %d/%d frames x %d utterances, z %d/%d x %d"
+                               % (skip.Tv, skip.T, skip.NB, zp.Tv, zp.T, zp.NB))
+        out = ops.tapgemm(pk, zp, skip, zp.NB, zp.T, t_valid=zp.Tv)
+        return Planes(out, zp.NB, pk.c_out, pk.f_out, zp.T, split=True, Tv=zp.Tv)
+
     def forward_head(self, pp, skip, mask, stft_x, predict, out_bmul, out_boff, train=False, raw_only=False):
         """Last layer (out_channel == 1) fused with the reconstruction head; writes ``predict``.  train=True: the raw
         transposed conv is written first, then CBN with batch statistics + PReLU (+ mask head) run in place."""
@@ -627,6 +656,7 @@ def _run_encoder_stack(encoders, stft_x, train=False):
 
 
 _philox_calls = [0]
+FUSED_DENSE = [os.environ.get("IDV_FUSED_DENSE", "1") != "0"]     # ComplexDense composed into the first decoder layer (A/B switch)
 FUSED_LATENT = [os.environ.get("IDV_FUSED_LATENT", "1") != "0"]      # one idv_latent_fwd launch instead of lstm_combine + reparam + z_to_planes (A/B switch)
 
 
@@ -1017,8 +1047,16 @@ class _VaeDecoderBase(nn.Module):
             return recon_sig, torch.view_as_complex(predict)
         for s in range(S):
             zp = _z_planes(z, B, S, s, split, t_alloc)
-            p = self.dense.forward_planes(zp, C, F)
-            for i in range(n - 1):
+            first = 0
+            if FUSED_DENSE[0] and split and self.causal and not train and not self_skip and n > 1:
+                # dense + decoders[0] as one launch on the z planes (composed at pack time)
+                p = self.decoders[0].forward_after_dense(self.dense, zp, C, F, skips.get(0))
+                if S == 1:
+                    self.decoder_outputs.append(p)
+                first = 1
+            else:
+                p = self.dense.forward_planes(zp, C, F)
+            for i in range(first, n - 1):
                 p = self.decoders[i].forward_planes(p, p if self_skip and i in skips else skips.get(i), train)
                 if S == 1:
                     self.decoder_outputs.append(p)
@@ -1171,9 +1209,15 @@ class standard_DCCRN(nn.Module):
         if not train:
             self.latent = lat                                           # model/pvae_module.py:L187-188
         B, T = lat.shape[0], top.T
-        p = self.dense.forward_planes(zp, top.C, top.F)
         n = len(self.decoders)
-        for i in range(n - 1):
+        first = 0
+        if FUSED_DENSE[0] and top.split and self.causal and not train and n > 1:
+            p = self.decoders[0].forward_after_dense(self.dense, zp, top.C, top.F,
+                                                     planes[n - 1] if 0 in self.skip_to_use else None)
+            first = 1
+        else:
+            p = self.dense.forward_planes(zp, top.C, top.F)
+        for i in range(first, n - 1):
             p = self.decoders[i].forward_planes(p, planes[n - 1 - i] if i in self.skip_to_use else None, train)
         predict = torch.empty((B, stft_x.shape[1], T, 2), dtype=torch.float32, device=stft_x.device)
         self.decoders[n - 1].forward_head(p, planes[0] if (n - 1) in self.skip_to_use else None, mask,

@@ -153,6 +153,16 @@ def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None, t_valid=0, 
             out = _empty_act(n_out, a0.data.device, out_split)
         elif out.numel() != (2 * n_out if out_split else n_out):
             raise RuntimeError("static tap-GEMM output has %d elements, expected %d" % (out.numel(), n_out))
+        b2 = getattr(pack, "bias_first", None)
+        if b2 is not None:        # layer composed with the dense map in front of it: own bias for every first frame
+            if tp <= 1:
+                raise RuntimeError("a composed (dense + transposed conv) pack needs the causal row layout")
+            lib.call("idv_tapgemm_tc_b2", a0.data, a0.Cp, a0.F, a1.data if a1 is not None else None,
+                     a1.Cp if a1 is not None else 0, a1.F if a1 is not None else 0, R,
+                     tp, tc["wt"], tc["kc_max"], tc["n_slots"], pack.bias, b2, pack.N,
+                     tc["units"], tc["taps"], pack.n_units, out, pack.out_ld, R * pack.out_ld, n_out,
+                     1 if out_split else 0, 1 if pack.prelu else 0, pack.slope, int(t_valid))
+            return out
         lib.call("idv_tapgemm_tc", a0.data, a0.Cp, a0.F, a1.data if a1 is not None else None,
                  a1.Cp if a1 is not None else 0, a1.F if a1 is not None else 0, R,
                  tp, tc["wt"], tc["kc_max"], tc["n_slots"], tc.get("bias", pack.bias), tc.get("N", pack.N),

@@ -8,6 +8,7 @@ Turns reference-layout parameters into the operands of the kernels in include/id
 All folding is done in float64 and rounded once to float32.
 """
 import math
+import os
 
 import torch
 
@@ -265,6 +266,85 @@ def pack_conv_transpose(t_re_w, t_re_b, t_im_w, t_im_b, bn, slope, f_in, c_p, c_
     return p
 
 
+def pack_dense_conv_transpose(w_read, b_read, w_imag, b_imag, t_re_w, t_re_b, t_im_w, t_im_b, bn, slope, f_in, c_p, c_skip,
+                              device, stride_f=2, pad_f=2):
+    """ComplexDense followed by the first CAUSAL complex transposed conv, composed in float64 into ONE tap-GEMM on the z
+    planes (model/pvae_module.py:L2085-2099: dense -> reshape (B, T, C, F, 2) -> permute -> decoders[0]):
+        out[fo][t] = sum_kt C[fo,kt] z[t-kt] + (sum over the kt whose frame t-kt exists of e[fo,kt]) + b
+        C[fo,kt] = sum over (kf, fi) feeding fo of D_fi W[kf,kt],   e[fo,kt] = sum d_fi W[kf,kt]
+    with D_fi / d_fi the dense layer's matrix / bias for plane fi.  K per time tap is 2*zdim instead of 2*C per (input
+    plane, time tap): at C = 256, F = 5 the layer runs 1.5 instead of 8.4 GMAC per 4-s utterance and the dense launch,
+    its 5 output planes and their re-read disappear.  The frame t = 0 only sees the kt = 0 constant (x[-1] is the zero
+    pad row, not d): ``bias_first``.  The skip source (c_skip > 0) keeps its taps.  Sources: 0 = z planes, 1 = skip."""
+    wr, wi = _cpu(t_re_w), _cpu(t_im_w)
+    cin_tot, cout, kh, kw = wr.shape
+    if kw != 2:
+        raise NotImplementedError("the dense + transposed-conv composition is built for the 2-tap causal time kernel")
+    dev = wr.device
+    zdim = w_read.shape[1]
+    ch_z, ch_p, ch_out = round8(zdim), round8(c_p), round8(cout)
+    Z, bp = cbn_fold(bn) if bn is not None else _identity_fold(cout, dev)
+    f_out = (f_in - 1) * stride_f - 2 * pad_f + kh
+    N = 2 * ch_out
+    m_re = wr[:c_p].permute(2, 3, 0, 1).reshape(kh * kw, c_p, cout)
+    m_im = wi[:c_p].permute(2, 3, 0, 1).reshape(kh * kw, c_p, cout)
+    Wp, bias = _block_weights(m_re, m_im, _cpu(t_re_b), _cpu(t_im_b), Z, bp, ch_p, ch_out)       # (taps, 2 ch_p, N), (N)
+    # dense: p[f][r] = z[r] Dm[f] + d[f]   (re and im parts are independent real linears: complex_progress.py:L83-89)
+    Dm = torch.zeros(f_in, 2 * ch_z, 2 * ch_p, dtype=torch.float64, device=dev)
+    d = torch.zeros(f_in, 2 * ch_p, dtype=torch.float64, device=dev)
+    for part, (w, b) in enumerate(((w_read, b_read), (w_imag, b_imag))):
+        w = _cpu(w).double().reshape(c_p, f_in, zdim)                  # [c][f][k]
+        Dm[:, part * ch_z:part * ch_z + zdim, part * ch_p:part * ch_p + c_p] = w.permute(1, 2, 0)
+        d[:, part * ch_p:part * ch_p + c_p] = _cpu(b).double().reshape(c_p, f_in).t()
+    kz = 2 * ch_z
+    Ws, units, taps = [], [], []
+    bias_full = torch.zeros(f_out, N, dtype=torch.float64, device=dev)
+    bias_first = torch.zeros(f_out, N, dtype=torch.float64, device=dev)
+    off = 0
+    # skip source weights (unchanged taps of pack_conv_transpose)
+    if c_skip:
+        ch_s = round8(c_skip)
+        s_re = wr[c_p:c_p + c_skip].permute(2, 3, 0, 1).reshape(kh * kw, c_skip, cout)
+        s_im = wi[c_p:c_p + c_skip].permute(2, 3, 0, 1).reshape(kh * kw, c_skip, cout)
+        Wsk, _ = _block_weights(s_re, s_im, _cpu(t_re_b), _cpu(t_im_b), Z, bp, ch_s, ch_out)
+        Ws.append(Wsk.reshape(-1))
+        skip_off, ks = 0, 2 * ch_s
+        off = Wsk.numel()
+    for fo in range(f_out):
+        begin = len(taps)
+        feeds = []
+        for kf in range(kh):
+            num = fo + pad_f - kf
+            if num % stride_f:
+                continue
+            fi = num // stride_f
+            if 0 <= fi < f_in:
+                feeds.append((kf, fi))
+        e = []
+        for kt in range(kw):
+            Cm = torch.zeros(kz, N, dtype=torch.float64, device=dev)
+            ev = torch.zeros(N, dtype=torch.float64, device=dev)
+            for kf, fi in feeds:
+                Cm += Dm[fi] @ Wp[kf * kw + kt]
+                ev += d[fi] @ Wp[kf * kw + kt]
+            e.append(ev)
+            Ws.append(Cm.reshape(-1))
+            taps.append([0, 0, kt, 0, kz, off])
+            off += kz * N
+        if c_skip:
+            for kf, fi in feeds:
+                for kt in range(kw):
+                    taps.append([1, fi, kt, 0, ks, skip_off + (kf * kw + kt) * ks * N])
+        bias_full[fo] = bias + e[0] + e[1]
+        bias_first[fo] = bias + e[0]
+        units.append([begin, len(taps) - begin, fo, 0, fo * N, 0])
+    p = TapGemmPack(torch.cat(Ws), bias_full.reshape(-1), units, taps, N, f_out, N, slope is not None, slope or 0.0, device)
+    p.bias_first = bias_first.reshape(-1).to(torch.float32).contiguous().to(device)
+    p.f_out, p.c_out = f_out, cout
+    p.pair_planes = False
+    return p
+
+
 def pack_enc0(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, device):
     """First encoder layer (Cin = 1): w [10][2][2*Cout], bias [2*Cout] for idv_enc0_fwd."""
     wr, wi = _cpu(conv_re_w), _cpu(conv_im_w)
@@ -321,11 +401,20 @@ def unfold_dec5_wgrad(dW, c_p, c_skip, cin_tot):
     return d_re, d_im
 
 
-def pack_dec5_tc(w10, bias2, slope, f_in, kcs, device):
+HEAD_BINS = [int(os.environ.get("IDV_HEAD_BINS", "8"))]           # output bins per unit of the fused last-layer + head tap-GEMM (1..16)
+
+
+def pack_dec5_tc(w10, bias2, slope, f_in, kcs, device, bins=None):
     """Last decoder layer on the tensor-core kernel with the head fused (idv_tapgemm_tc_head).
     w10: [10 (kf*2+kt)][sum(kcs)][2] folded weights of pack_dec5 (sources concatenated along k), bias2: [2].
-    Unit q -> output bins 2q (columns 0,1) and 2q+1 (columns 16,17); per source and time tap three weight slots
-    (input plane q+1, q, q-1):  q+1 feeds kf=0 (even) / kf=1 (odd), q feeds kf=2 / kf=3, q-1 feeds kf=4 (even)."""
+    A unit holds ``bins`` consecutive output bins fo0 .. fo0+bins-1, bin e in columns (2e, 2e+1) of the N = 32 tile.
+    Output bin fo reads input plane fi with kernel row kf = fo + 2 - 2 fi (kernel 5, stride 2, pad 2): the bins of a
+    unit read the input planes fo0/2 - 1 .. (fo0 + bins - 1)/2 + 1, one weight slot per (source, plane offset, time tap)
+    with the rows of the bins that plane does not feed left zero.  More bins per unit = fewer activation reads per bin
+    (the layer is bound by them): 6 planes for 8 bins against 3 planes for 2."""
+    bins = HEAD_BINS[0] if bins is None else bins
+    if not 1 <= bins <= 16 or bins % 2:
+        raise ValueError("bins per head unit must be even and <= 16")
     w10 = w10.detach().cpu().to(torch.float32)
     N = 32
     ksum = sum(kcs)
@@ -334,35 +423,40 @@ def pack_dec5_tc(w10, bias2, slope, f_in, kcs, device):
     for k in kcs:
         k_off.append(k_off[-1] + k)
     kc_max = max(kcs)
-    rel = (+1, 0, -1)
-    kf_even, kf_odd = {+1: 0, 0: 2, -1: 4}, {+1: 1, 0: 3}
+    f_out = 2 * f_in - 1
+    offs = list(range(-1, bins // 2 + 1))                  # input plane = fo0/2 + d
     slots, slot_id = [], {}
     for si in range(len(kcs)):
-        for d in rel:
+        ks = slice(k_off[si], k_off[si + 1])
+        for d in offs:
             for kt in range(2):
                 W = torch.zeros(N, kc_max)
-                ks = slice(k_off[si], k_off[si + 1])
-                W[0:2, :kcs[si]] = w10[kf_even[d] * 2 + kt, ks].t()
-                if d in kf_odd:
-                    W[16:18, :kcs[si]] = w10[kf_odd[d] * 2 + kt, ks].t()
+                for e in range(bins):
+                    kf = e + 2 - 2 * d
+                    if 0 <= kf < 5:
+                        W[2 * e:2 * e + 2, :kcs[si]] = w10[kf * 2 + kt, ks].t()
                 slot_id[(si, d, kt)] = len(slots)
                 slots.append(W)
     wt = torch.stack(slots)
     hi = wt.to(torch.bfloat16)
     lo = (wt - hi.to(torch.float32)).to(torch.bfloat16)
-    n_units = (2 * f_in - 1 + 1) // 2
+    n_units = (f_out + bins - 1) // bins
     units, taps = [], []
     for q in range(n_units):
         begin = len(taps)
-        for d in rel:
-            fi = q + d
+        fo0 = q * bins
+        nb = min(bins, f_out - fo0)
+        for d in offs:
+            fi = fo0 // 2 + d
             if fi < 0 or fi >= f_in:
+                continue
+            if not any(0 <= e + 2 - 2 * d < 5 for e in range(nb)):      # the plane feeds none of the unit's live bins
                 continue
             for kt in range(2):
                 for si in range(len(kcs)):
                     taps.append([si, fi, kt, 0, kcs[si], slot_id[(si, d, kt)]])
         ks = sum(t[4] // 64 for t in taps[begin:])
-        units.append([begin, len(taps) - begin, q, 0, 0, ks])
+        units.append([begin, len(taps) - begin, fo0, nb, 0, ks])
     bias = torch.zeros(N)
     bias[0:2] = bias2.detach().cpu().to(torch.float32)
     return dict(wt=torch.stack((hi, lo)).contiguous().to(device), kc_max=kc_max, n_slots=len(slots),

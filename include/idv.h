@@ -101,8 +101,9 @@ int idv_tapgemm_tc(const void* a0, int a0_cp, int a0_planes, const void* a1, int
                    int t_valid, void* stream);
 
 /* Same kernel with the reconstruction head fused into the epilogue (last decoder layer, Cout = 1):
- * N == 32, unit q produces the output bins fo = 2q (accumulator columns 0,1 = re,im) and fo = 2q+1 (columns
- * 16,17); bias[unit.bias_off + {0,1}] = (re, im); PReLU(slope) is always applied; head = 1 writes the complex
+ * N == 32, a unit produces unit.out_ch_off (1..16) consecutive output bins starting at bin unit.out_f, bin e in the
+ * accumulator columns (2e, 2e+1) = (re, im) - 8 bins per unit read 6 input planes where 2 bins read 3: the layer is
+ * bound by its activation reads; bias[unit.bias_off + {0,1}] = (re, im); PReLU(slope) is always applied; head = 1 writes the complex
  * spectrum, head = 2 the mask head of model/pvae_module.py:L2594-2609 (needs stft_x (NB, head_fout, T, 2)).
  * predict: (NBtot, head_fout, T, 2), utterance index b*head_bmul + head_boff.  `out` is unused (may be NULL).
  * Replaces idv_dec5_head_fwd on split-bf16 planes.                                                        */
@@ -112,6 +113,16 @@ int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, const void* a1
                         int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu, float prelu_slope,
                         int head, int head_fout, int head_bmul, int head_boff, const float* stft_x,
                         float* predict, int t_valid, void* stream);
+/* idv_tapgemm_tc with a second bias vector for the FIRST frame of every utterance (rows r with r % Tp == 1, same
+ * per-unit offsets as `bias`): a layer composed at pack time with the affine map in front of it - ComplexDense followed
+ * by the first causal transposed conv (model/pvae_module.py:L2085-2099: dense -> reshape -> decoders[0]) as ONE tap-GEMM
+ * on the z planes with K = 2*zdim per time tap instead of 2*C per (plane, time tap) - has a different constant there:
+ * the time tap that reads the zero pad row x[-1] does not see the dense layer's bias.                            */
+int idv_tapgemm_tc_b2(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes, int R, int Tp,
+                      const void* wt, int kc_max, int n_slots, const float* bias, const float* bias_first, int N,
+                      const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
+                      int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu, float prelu_slope, int t_valid,
+                      void* stream);
 
 /* ---- STFT / iSTFT -----------------------------------------------------------------------------
  * replaces torch.stft at model/pvae_module.py:L22 (n_fft 512, hop, win, periodic Hann, center,

@@ -79,7 +79,7 @@ def idv_tapgemm_tc_head(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, k
     un = units.clone()
     un[:, 2] = torch.arange(n_units)          # plane per unit in the scratch output
     un[:, 3] = 0
-    idv_tapgemm_tc._head_bias = True          # the head applies bias (re, im) to both bin pairs
+    idv_tapgemm_tc._head_bias = True          # the head applies bias (re, im) to every bin's column pair
     try:
         idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, 0, wt, kc_max, n_slots, bias, N, un, taps,
                        n_units, tmp, 32, R * 32, 0, 0, 1, slope)
@@ -89,12 +89,13 @@ def idv_tapgemm_tc_head(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, k
     NB = R // Tp
     acc = tmp.view(n_units, NB, Tp, 32)[:, :, 1:].to(D)             # (units, NB, T, 32), bias + PReLU applied
     pv = predict.view(-1, head_fout, T, 2)
-    for ui, (tb, nt, q, _, _, _) in enumerate(units.tolist()):
-        for e in range(2):
-            fo = 2 * q + e
+    for ui, (tb, nt, fo0, nbins, _, _) in enumerate(units.tolist()):
+        assert 1 <= nbins <= 16
+        for e in range(nbins):
+            fo = fo0 + e
             if fo >= head_fout:
                 continue
-            yr, yi = acc[ui, :, :, 16 * e], acc[ui, :, :, 16 * e + 1]
+            yr, yi = acc[ui, :, :, 2 * e], acc[ui, :, :, 2 * e + 1]
             if head == 2:
                 mag = torch.tanh(torch.sqrt(yr ** 2 + yi ** 2))
                 ph = torch.atan2(yi / (mag + 1e-8), yr / (mag + 1e-8))
@@ -103,6 +104,17 @@ def idv_tapgemm_tc_head(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, k
                 in_ph = torch.atan2(X[..., 1], X[..., 0])
                 yr, yi = in_mag * mag * torch.cos(in_ph + ph), in_mag * mag * torch.sin(in_ph + ph)
             pv[head_boff::head_bmul][:NB, fo] = torch.stack((yr, yi), -1).to(torch.float32)
+
+
+def idv_tapgemm_tc_b2(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, bias_first, N, units,
+                      taps, n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, slope, t_valid=0):
+    """idv_tapgemm_tc whose rows r % Tp == 1 (first frame of every utterance) use ``bias_first`` instead of ``bias``."""
+    idv_tapgemm_tc._bias_first = bias_first
+    try:
+        idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, N, units, taps,
+                       n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, slope, t_valid)
+    finally:
+        idv_tapgemm_tc._bias_first = None
 
 
 def idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, N, units, taps,
@@ -138,8 +150,12 @@ def idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max
             acc += ah @ wh + ah @ wl + al @ wh
         bvec = _flat(bias)[bias_off:bias_off + N].to(D).clone()
         if getattr(idv_tapgemm_tc, "_head_bias", False):
-            bvec[16:18] = bvec[0:2]
+            bvec = bvec[0:2].repeat(N // 2)
         acc += bvec
+        b1 = getattr(idv_tapgemm_tc, "_bias_first", None)
+        if b1 is not None:
+            first = (torch.arange(R) % abs(Tp)) == 1
+            acc[first] += (_flat(b1)[bias_off:bias_off + N].to(D) - bvec)
         if apply_prelu:
             acc = torch.where(acc > 0, acc, slope * acc)
         _mask_rows(acc, R, Tp, t_valid)

@@ -381,6 +381,34 @@ def test_tapgemm_tc_tile_orders(order, R, Tp, N, n_units):
         lib.set_option("gemm_tile_order", 1)
 
 
+@pytest.mark.parametrize("tma", [1, 0])
+@pytest.mark.parametrize("R,Tp,N,tv,pairs", [(2600, 13, 128, 0, 1), (1111, 11, 64, 7, 1), (130, 13, 256, 0, 0), (4160, 65, 192, 60, 1)])
+def test_tapgemm_tc_tma_store_epilogue(tma, R, Tp, N, tv, pairs):
+    """Split-bf16 outputs leave through shared memory + tensor stores (gemm_tma_store = 1, the default) or through
+    per-thread stores (0): same values.  Units at column offsets 0 / N of rows twice as wide (the dense layer's layout),
+    row tails that are not multiples of the 32-row store boxes, valid-frame masks, and a first-frame bias (b2 entry)."""
+    F0, cp0, kc = 3, 136, 128
+    a0 = _to_split(_rand(F0, R, cp0, seed=1))
+    taps = [[0, 0, 1, 0, kc, 0], [0, 1, 0, 8, kc, 1], [0, 2, 0, 0, kc, 2], [0, 1, 1, 8, kc, 0]]
+    units = [[0, 2, 0, 0, 0, 4], [2, 2, 0, N, N, 4], [1, 2, 1, N, 0, 4], [0, 1, 1, 0, N, 2]]
+    wt = _to_split(_rand(3, N, kc, seed=3) * 0.1)
+    bias, bias1 = _rand(2 * N, seed=4), _rand(2 * N, seed=5)
+    ld = 2 * N
+    n_out = 2 * R * ld
+    out = torch.full((2 * n_out,), 3.0, dtype=torch.bfloat16)
+    base = [a0, cp0, F0, None, 0, 0, R, Tp, wt, kc, 3, bias]
+    tail = [N, torch.tensor(units, dtype=torch.int32), torch.tensor(taps, dtype=torch.int32), 4, out, ld, R * ld, n_out, 1, 1,
+            0.2, tv]
+    lib.set_option("gemm_tma_store", tma)
+    lib.set_option("gemm_cta_pairs", pairs)
+    try:
+        assert _both("idv_tapgemm_tc", base + tail, [16]) < 1e-5
+        assert _both("idv_tapgemm_tc_b2", base + [bias1] + tail, [17]) < 1e-5
+    finally:
+        lib.set_option("gemm_tma_store", 1)
+        lib.set_option("gemm_cta_pairs", 1)
+
+
 @pytest.mark.parametrize("NB,T,zdim,latent_num,S,tv,split", [(3, 7, 128, 1, 1, 0, 1), (2, 5, 128, 2, 3, 0, 1), (5, 9, 16, 2, 1, 6, 0),
                                                              (1, 3, 128, 1, 10, 0, 1)])
 def test_latent_fused(NB, T, zdim, latent_num, S, tv, split):

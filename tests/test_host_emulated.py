@@ -142,9 +142,18 @@ def test_train_mode_forward_matches_reference(emulated_abi, gemm_mode, golden):
     run_train_case(golden, "cpu", 5e-5)
 
 
-def test_train_mode_rejects_multi_sample_decoder(emulated_abi):
+def test_train_mode_multi_sample_decoder_matches_oracle(emulated_abi):
+    """train=True with num_samples = 2 (no autograd): the batch statistics of every ComplexBatchNormal span all B*S rows
+    (model/pvae_module.py:L2550-2567), so the samples run as one batch with repeated skip tensors / noisy STFT."""
+    from oracle import ref_port as P
     enc, dec = C.build_vae(1, 2, "twophase", "mask", 0, "cpu")
-    x, eps = C.vae_inputs(1, 400, 2, 1, 0, "cpu")
-    r = enc(x, train=True, eps=eps)
-    with pytest.raises(NotImplementedError):
-        dec(r[11], r[0], r[8], r[9], r[10], train=True, pad="sig")
+    x, eps = C.vae_inputs(2, 900, 2, 1, 0, "cpu")
+    dsd = {k: v.clone() for k, v in dec.state_dict().items()}
+    with torch.no_grad():
+        r = enc(x, train=False, eps=eps)
+        sig, pred = dec(r[11], r[0], r[8], r[9], r[10], train=True, pad="sig")
+        st = P.vae_encoder_forward(enc.state_dict(), x, C.ZDIM, 1, 2, eps)
+        dd = P.vae_decoder_forward(dsd, st["stft_x"], st["z_speech"], st["skiper"], st["C"], st["F"], 2, "mask", "sig",
+                                   train=True)
+    assert sig.shape[0] == 4
+    assert C.rel_l2(sig, dd["recon_sig"]) < 5e-5 and C.rel_l2(torch.view_as_real(pred), torch.view_as_real(dd["predict"])) < 5e-5
