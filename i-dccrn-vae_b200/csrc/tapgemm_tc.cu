@@ -346,6 +346,17 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             }
             const int bo = b * p.head_bmul + p.head_boff;
             *reinterpret_cast<float2*>(p.predict + ((long long)(bo * p.head_fout + fo) * T + t) * 2) = make_float2(yr, yi);
+            if (p.out) {
+              // the same value as the K-major split-bf16 spectrum row the iSTFT's DFT GEMM reads (idv_spec_rows_split's
+              // layout: row bo*T + t, columns 2*bin + part): no separate transpose pass over `predict`
+              unsigned short h0, l0, h1, l1;
+              split_bf16(yr, h0, l0);
+              split_bf16(yi, h1, l1);
+              unsigned short* rows = reinterpret_cast<unsigned short*>(p.out);
+              const long long idx = ((long long)bo * T + t) * p.out_ld + 2 * fo;
+              *reinterpret_cast<unsigned int*>(rows + idx) = (unsigned)h0 | ((unsigned)h1 << 16);
+              *reinterpret_cast<unsigned int*>(rows + p.out_hl + idx) = (unsigned)l0 | ((unsigned)l1 << 16);
+            }
           }
         }
         continue;
@@ -691,6 +702,8 @@ static int tapgemm_tc_impl(const void* a0, int a0_cp, int a0_planes, const void*
   } else if (head) {
     IDV_CHECK_ARG(N == 32 && Tp > 1 && predict && head_fout > 0 && head_bmul > 0 && head_boff >= 0 && (head != 2 || stft_x),
                   "idv_tapgemm_tc: head mode needs N == 32, Tp, predict (and stft_x for the mask head)");
+    IDV_CHECK_ARG(!out || (out_ld >= 2 * head_fout && out_ld % 2 == 0 && out_hl > 0),
+                  "idv_tapgemm_tc: head mode with spectrum rows needs out_ld >= 2 * head_fout and the hi/lo stride out_hl");
   }
   IDV_CHECK_ARG(R > 0 && n_units > 0 && a0_planes > 0 && n_slots > 0, "idv_tapgemm_tc: empty problem");
   IDV_CHECK_ARG(N >= 32 && N % 32 == 0 && (N % 64 == 0 || N == 32), "idv_tapgemm_tc: N=%d must be 32 or a multiple of 64", N);

@@ -202,6 +202,54 @@ def lstm_layer_pair_config(H):
     return n.value, c.value, w.value
 
 
+_EXCLUSIVE = {}
+
+
+def check_exclusive_device(device_index):
+    """The CTA-pair LSTM kernels (clusters of 2) are launched WITHOUT the cooperative guarantee (Nsight Compute cannot
+    replay a launch that carries both the cooperative and the cluster attribute): their CTAs wait on one another, so the
+    whole grid must be resident, which holds when this process has the GPU to itself.  Checked once per device through
+    NVML: if other compute processes are on the device (MPS clients, a second job), the pair kernels are switched off
+    process-wide ("lstm_wave_cta_pairs" = 0) and the recurrences run on the cooperative one-CTA-per-tile kernels, whose
+    launch fails cleanly instead of waiting when the grid cannot be co-resident.  Kernels of several streams of THIS
+    process sharing the GPU: set the "gemm_dynamic_tiles" option (pipeline.StreamPipeline does), which has the same
+    effect.  Returns True when the device is exclusive (or NVML is unavailable: nothing is known, nothing is changed)."""
+    if device_index in _EXCLUSIVE:
+        return _EXCLUSIVE[device_index]
+    ok = True
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        h = None
+        uuid = getattr(props, "uuid", None)
+        if uuid is not None:
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                h = None
+        if h is None:
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = device_index
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if device_index < len(ids) and ids[device_index].isdigit():
+                    phys = int(ids[device_index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        others = [p for p in pynvml.nvmlDeviceGetComputeRunningProcesses(h) if p.pid != os.getpid()]
+        if others:
+            ok = False
+            import warnings
+            warnings.warn("idccrn_b200: %d other compute process(es) share GPU %d - the CTA-pair LSTM kernels need the "
+                          "device to themselves and are switched off (cooperative one-CTA kernels are used instead)"
+                          % (len(others), device_index))
+            set_option("lstm_wave_cta_pairs", 0)
+    except Exception:
+        ok = True
+    _EXCLUSIVE[device_index] = ok
+    return ok
+
+
 def ptr(t):
     """Device pointer of a contiguous fp32/int32 CUDA tensor (None -> NULL)."""
     if t is None:

@@ -99,6 +99,21 @@ class ISTFT(nn.Module):
         basis, wsq = self._ensure(spec_ri.device)
         return ops.istft(spec_ri, basis, wsq, self.n_fft, self.hop_length, self.win_length)
 
+    def spectrum_rows(self, B, T, device):
+        """Zero-initialised split-bf16 K-major spectrum rows [2][B*T][kpad] for the fused head to fill (its padding
+        columns must be zero: they meet zero weights in the DFT GEMM, and 0 * NaN garbage would not be 0).  One buffer
+        per (B, T, device) is kept and reused: the head rewrites every live column on every call."""
+        if getattr(self, "_tc", None) is None or self._tc["bias"].device != device:
+            self._tc = pack.pack_istft_tc(self.n_fft, self.win_length, device)
+        key = (B, T, str(device))
+        cache = getattr(self, "_rows", None)
+        if cache is None or cache[0] != key:
+            self._rows = (key, torch.zeros(2 * B * T * self._tc["kpad"], dtype=torch.bfloat16, device=device))
+        return self._rows[1]
+
+    def forward_rows(self, rows, B, T):
+        return ops.istft_rows_tc(rows, B, T, self._tc, self.n_fft, self.hop_length, self.win_length, self.lengths)
+
     def forward(self, x):
         """x: complex (B, F, T) like torch.istft's input at model/pvae_module.py:L41."""
         if not x.is_complex():
@@ -553,9 +568,14 @@ class Decoder(nn.Module):
         out = ops.tapgemm(pk, zp, skip, zp.NB, zp.T, t_valid=zp.Tv)
         return Planes(out, zp.NB, pk.c_out, pk.f_out, zp.T, split=True, Tv=zp.Tv)
 
-    def forward_head(self, pp, skip, mask, stft_x, predict, out_bmul, out_boff, train=False, raw_only=False):
+    def head_on_tensor_cores(self, pp, skip):
+        kcs = [pp.Cp] + ([skip.Cp] if skip is not None else [])
+        return pp.split and all(k % 64 == 0 for k in kcs)
+
+    def forward_head(self, pp, skip, mask, stft_x, predict, out_bmul, out_boff, train=False, raw_only=False, rows=None):
         """Last layer (out_channel == 1) fused with the reconstruction head; writes ``predict``.  train=True: the raw
-        transposed conv is written first, then CBN with batch statistics + PReLU (+ mask head) run in place."""
+        transposed conv is written first, then CBN with batch statistics + PReLU (+ mask head) run in place.
+        rows: ISTFT.spectrum_rows buffer the tensor-core head also fills (only with head_on_tensor_cores, eval)."""
         train = bool(train) and self.if_bn
         if train and out_bmul != 1:
             raise NotImplementedError(_TRAIN_MSG)
@@ -581,8 +601,11 @@ class Decoder(nn.Module):
             tkey = ("head_tc", train, pp.C, c_skip, pp.F, str(pp.data.device))
             if tkey not in items:
                 items[tkey] = pack.pack_dec5_tc(w, b, slope, pp.F, kcs, pp.data.device)
-            ops.dec5_head_tc(items[tkey], pp, skip, fused_mask, stft_x, predict, out_bmul, out_boff)
+            ops.dec5_head_tc(items[tkey], pp, skip, fused_mask, stft_x, predict, out_bmul, out_boff,
+                             rows if not train else None)
         else:
+            if rows is not None:
+                raise RuntimeError("spectrum rows are written by the tensor-core head only")
             ops.dec5_head(pp, skip, w, b, slope, fused_mask, stft_x, predict, out_bmul, out_boff)
         if train and not raw_only:
             ops.head_train_user(predict, self.bn, self._slope(), mask, stft_x, 1)
@@ -656,6 +679,7 @@ def _run_encoder_stack(encoders, stft_x, train=False):
 
 
 _philox_calls = [0]
+FUSED_SPEC_ROWS = [os.environ.get("IDV_FUSED_SPEC_ROWS", "1") != "0"]   # head epilogue writes the iSTFT GEMM's rows (A/B switch)
 FUSED_DENSE = [os.environ.get("IDV_FUSED_DENSE", "1") != "0"]     # ComplexDense composed into the first decoder layer (A/B switch)
 FUSED_LATENT = [os.environ.get("IDV_FUSED_LATENT", "1") != "0"]      # one idv_latent_fwd launch instead of lstm_combine + reparam + z_to_planes (A/B switch)
 
@@ -1038,6 +1062,9 @@ class _VaeDecoderBase(nn.Module):
                 raise RuntimeError("stft_x %s does not match the reconstructed spectrum (B, %d, %d, 2)"
                                    % (tuple(stft_x.shape), n_bins, t_alloc))
         self.decoder_outputs = []
+        rows = None          # the head also writes the iSTFT GEMM's operand rows when nothing touches predict in between
+        if FUSED_SPEC_ROWS[0] and split and not train and not self.datanorm:
+            rows = self.istft.spectrum_rows(BS, t_alloc, z.device)
         if autograd:
             # training step: (recon_sig, predict) carry a grad_fn whose backward runs the C-ABI backward kernels
             if self.datanorm:
@@ -1060,8 +1087,11 @@ class _VaeDecoderBase(nn.Module):
                 p = self.decoders[i].forward_planes(p, p if self_skip and i in skips else skips.get(i), train)
                 if S == 1:
                     self.decoder_outputs.append(p)
-            self.decoders[n - 1].forward_head(p, p if self_skip and (n - 1) in skips else skips.get(n - 1), mask,
-                                              stft_x if mask else None, predict, S, s, train)
+            last_skip = p if self_skip and (n - 1) in skips else skips.get(n - 1)
+            if rows is not None and not self.decoders[n - 1].head_on_tensor_cores(p, last_skip):
+                rows = None
+            self.decoders[n - 1].forward_head(p, last_skip, mask, stft_x if mask else None, predict, S, s, train,
+                                              rows=rows)
         # model/pvae_module.py:L2090,L2099: the per-layer outputs (B*S, C, F, T, 2) are kept on the module.  Here they
         # stay activation planes and are converted on access (SkipList); with num_samples > 1 the sample passes run
         # one after the other on (B, ...) planes, so the list is only kept for num_samples == 1.
@@ -1071,7 +1101,7 @@ class _VaeDecoderBase(nn.Module):
             if getattr(self, "_norm_key", None) != key:
                 self._norm_key, self._norm = key, _norm_consts(self.data_mean, self.data_std)[1]
             ops.bin_affine(predict, self._norm[0], self._norm[1], out=predict)
-        recon_sig = self.istft.forward_ri(predict)
+        recon_sig = self.istft.forward_rows(rows, BS, t_alloc) if rows is not None else self.istft.forward_ri(predict)
         return recon_sig, torch.view_as_complex(predict)
 
 
@@ -1199,8 +1229,9 @@ class standard_DCCRN(nn.Module):
         self.linear = ComplexConv2d(in_channel=1, out_channel=1, kernel_size=1, stride=1)   # unused, in state_dict
         self.detect_anormal = True
 
-    def forward_spec(self, stft_x, train, mask):
-        """stft_x (B, F, T, 2) -> predict (B, F, T, 2): decoder output, optionally through the mask head."""
+    def forward_spec(self, stft_x, train, mask, rows=None):
+        """stft_x (B, F, T, 2) -> predict (B, F, T, 2): decoder output, optionally through the mask head.
+        rows: ISTFT.spectrum_rows buffer the fused head fills as well (eval, tensor-core path)."""
         stft_x = ops.lib.require_f32_cuda(stft_x, "stft_x")
         planes = _run_encoder_stack(self.encoders, stft_x, train)
         top = planes[-1]
@@ -1220,8 +1251,10 @@ class standard_DCCRN(nn.Module):
         for i in range(first, n - 1):
             p = self.decoders[i].forward_planes(p, planes[n - 1 - i] if i in self.skip_to_use else None, train)
         predict = torch.empty((B, stft_x.shape[1], T, 2), dtype=torch.float32, device=stft_x.device)
-        self.decoders[n - 1].forward_head(p, planes[0] if (n - 1) in self.skip_to_use else None, mask,
-                                          stft_x if mask else None, predict, 1, 0, train)
+        last_skip = planes[0] if (n - 1) in self.skip_to_use else None
+        self.rows_written = rows is not None and not train and self.decoders[n - 1].head_on_tensor_cores(p, last_skip)
+        self.decoders[n - 1].forward_head(p, last_skip, mask, stft_x if mask else None, predict, 1, 0, train,
+                                          rows=rows if self.rows_written else None)
         return predict
 
     def forward(self, x, train=True):
@@ -1251,10 +1284,16 @@ class DCCRN_(nn.Module):
             if getattr(self, "_norm_key", None) != key:
                 self._norm_key, self._norm = key, _norm_consts(self.data_mean, self.data_std)
             stft_x = ops.bin_affine(stft_x, self._norm[0][0], self._norm[0][1], zero_edge_imag=True, out=stft_x)
-        predict = self.std_DCCRN.forward_spec(stft_x, train, mask=(self.recon_type == 'mask'))
+        rows = None
+        if FUSED_SPEC_ROWS[0] and ops.use_split() and not train and not self.datanorm:
+            rows = self.istft.spectrum_rows(stft_x.shape[0], stft_x.shape[2], stft_x.device)
+        predict = self.std_DCCRN.forward_spec(stft_x, train, mask=(self.recon_type == 'mask'), rows=rows)
         if self.datanorm:
             ops.bin_affine(predict, self._norm[1][0], self._norm[1][1], out=predict)
-        clean = self.istft.forward_ri(predict)
+        if rows is not None and self.std_DCCRN.rows_written:
+            clean = self.istft.forward_rows(rows, stft_x.shape[0], stft_x.shape[2])
+        else:
+            clean = self.istft.forward_ri(predict)
         if self.resynthesis:
             predict = self.stft(clean)
         return clean, torch.view_as_complex(predict)

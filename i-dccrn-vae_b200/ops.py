@@ -204,14 +204,28 @@ def dec5_head(p, skip, w, bias, slope, mask, stft_x, predict, out_bmul, out_boff
              1 if mask else 0, stft_x if mask else None, predict, out_bmul, out_boff)   # writes all p.T frames
 
 
-def dec5_head_tc(hp, p, skip, mask, stft_x, predict, out_bmul, out_boff):
-    """Last decoder layer + head on the tensor-core kernel (hp = pack.pack_dec5_tc)."""
+def dec5_head_tc(hp, p, skip, mask, stft_x, predict, out_bmul, out_boff, rows=None):
+    """Last decoder layer + head on the tensor-core kernel (hp = pack.pack_dec5_tc).  rows: optional bf16
+    [2][NBtot*T][kpad] spectrum rows for istft_rows_tc (written next to ``predict``; padding columns stay untouched)."""
     R = p.NB * (p.T + 1)
+    kpad = 0 if rows is None else rows.numel() // (2 * predict.shape[0] * predict.shape[2])
     lib.call("idv_tapgemm_tc_head", p.data, p.Cp, p.F, skip.data if skip is not None else None,
              skip.Cp if skip is not None else 0, skip.F if skip is not None else 0, R, p.T + 1,
              hp["wt"], hp["kc_max"], hp["n_slots"], hp["bias"], hp["N"], hp["units"], hp["taps"], hp["n_units"],
-             None, 0, 0, 0, 0, 1, hp["slope"], 2 if mask else 1, predict.shape[1], out_bmul, out_boff,
-             stft_x if mask else None, predict, 0)
+             rows, kpad, 0, rows.numel() // 2 if rows is not None else 0, 0, 1, hp["slope"], 2 if mask else 1,
+             predict.shape[1], out_bmul, out_boff, stft_x if mask else None, predict, 0)
+
+
+def istft_rows_tc(rows, B, T, hp, n_fft, hop, win, lengths=None):
+    """iSTFT from spectrum rows the fused head already wrote (no idv_spec_rows_split pass): DFT tap-GEMM + overlap-add."""
+    R = B * T
+    N = hp["N"]
+    frames = _empty(R * N, rows.device)
+    lib.call("idv_tapgemm_tc", rows, hp["kpad"], 1, None, 0, 0, R, 0, hp["wt"], hp["kc_max"], 1, hp["bias"], N,
+             hp["units"], hp["taps"], 1, frames, N, R * N, 0, 0, 0, 0.0, 0)
+    out = torch.empty((B, hop * (T - 1)), dtype=torch.float32, device=rows.device)
+    lib.call("idv_ola_fwd", frames, N, hp["wsq"], B, T, n_fft, hop, win, _lengths_arg(lengths, B, rows.device), out)
+    return out
 
 
 def lstm_recurrent(g, g_m_off, g_p_off, g_ld, whh, NB, T, H, want_split=False, t_valid=0):
@@ -249,6 +263,8 @@ def lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, want_f32=True,
     hseq = _empty(n, g.device) if want_f32 else None
     hsplit = _empty_act(n, g.device, True) if want_split else None
     if cfg is not None and cfg[2] == "pair":
+        if g.is_cuda:
+            lib.check_exclusive_device(g.device.index if g.device.index is not None else torch.cuda.current_device())
         work = torch.empty(int(cfg[3]), dtype=torch.uint8, device=g.device)
         sync = torch.empty(6, dtype=torch.int32, device=g.device)
         lib.call("idv_lstm_layer_pair_tc", g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, work, sync,
@@ -272,6 +288,8 @@ def lstm2_wave_supported(H, NB, device):
 
 def lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, work_bytes, t_valid=0):
     """Both layers of the ComplexLSTM as one wavefront kernel.  Returns hseq1 fp32 [4][R][H]."""
+    if g0.is_cuda:
+        lib.check_exclusive_device(g0.device.index if g0.device.index is not None else torch.cuda.current_device())
     hseq = _empty(4 * NB * (T + 1) * H, g0.device)
     work = torch.empty(int(work_bytes), dtype=torch.uint8, device=g0.device)
     sync = torch.empty(6, dtype=torch.int32, device=g0.device)

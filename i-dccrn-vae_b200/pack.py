@@ -401,7 +401,7 @@ def unfold_dec5_wgrad(dW, c_p, c_skip, cin_tot):
     return d_re, d_im
 
 
-HEAD_BINS = [int(os.environ.get("IDV_HEAD_BINS", "8"))]           # output bins per unit of the fused last-layer + head tap-GEMM (1..16)
+HEAD_BINS = [int(os.environ.get("IDV_HEAD_BINS", "16"))]           # output bins per unit of the fused last-layer + head tap-GEMM (1..16)
 
 
 def pack_dec5_tc(w10, bias2, slope, f_in, kcs, device, bins=None):

@@ -105,7 +105,10 @@ int idv_tapgemm_tc(const void* a0, int a0_cp, int a0_planes, const void* a1, int
  * accumulator columns (2e, 2e+1) = (re, im) - 8 bins per unit read 6 input planes where 2 bins read 3: the layer is
  * bound by its activation reads; bias[unit.bias_off + {0,1}] = (re, im); PReLU(slope) is always applied; head = 1 writes the complex
  * spectrum, head = 2 the mask head of model/pvae_module.py:L2594-2609 (needs stft_x (NB, head_fout, T, 2)).
- * predict: (NBtot, head_fout, T, 2), utterance index b*head_bmul + head_boff.  `out` is unused (may be NULL).
+ * predict: (NBtot, head_fout, T, 2), utterance index bo = b*head_bmul + head_boff.  `out` (optional, may be NULL): the
+ * same spectrum as split-bf16 K-major rows bf16 [2][NBtot*T][out_ld] (row bo*T + t, columns 2*bin + part; hi / lo sets
+ * out_hl elements apart) = the operand of the iSTFT's DFT GEMM (idv_spec_rows_split's layout; columns >= 2*head_fout
+ * are not written: the caller keeps them zero).
  * Replaces idv_dec5_head_fwd on split-bf16 planes.                                                        */
 int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
                         int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias, int N,

@@ -103,7 +103,14 @@ def idv_tapgemm_tc_head(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, k
                 in_mag = torch.sqrt(X[..., 0] ** 2 + X[..., 1] ** 2)
                 in_ph = torch.atan2(X[..., 1], X[..., 0])
                 yr, yi = in_mag * mag * torch.cos(in_ph + ph), in_mag * mag * torch.sin(in_ph + ph)
-            pv[head_boff::head_bmul][:NB, fo] = torch.stack((yr, yi), -1).to(torch.float32)
+            val = torch.stack((yr, yi), -1).to(torch.float32)
+            pv[head_boff::head_bmul][:NB, fo] = val
+            if out is not None:                           # split-bf16 K-major spectrum rows for the iSTFT GEMM
+                rows = _flat(out).view(2, -1, T, out_ld)
+                hi = val.to(torch.bfloat16)
+                lo = (val - hi.to(torch.float32)).to(torch.bfloat16)
+                rows[0][head_boff::head_bmul][:NB, :, 2 * fo:2 * fo + 2] = hi
+                rows[1][head_boff::head_bmul][:NB, :, 2 * fo:2 * fo + 2] = lo
 
 
 def idv_tapgemm_tc_b2(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, bias_first, N, units,
