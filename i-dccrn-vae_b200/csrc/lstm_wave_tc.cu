@@ -32,6 +32,7 @@ constexpr int W_THREADS = 64 + 32 * W_EPI_WARPS;
 constexpr int W_EPI_WARP0 = 2;
 constexpr int W_ROWS = 128;
 constexpr int W_HTILE = W_ROWS * BK * 2;
+constexpr int W_SYNC_STRIDE = 32;            // uint32 between the step counters (one 128-byte line each)
 constexpr int W_REP = 1;                     // replicas of the h exchange buffers (measured on B200: replication does not help)
 
 struct WaveParams {
@@ -48,7 +49,7 @@ struct WaveParams {
   unsigned short* hxA;                      // bf16 [W_REP][4 slot][2 m][2 hl][128][H]   h0
   unsigned short* hxC;                      // bf16 [W_REP][2 slot][2 m][2 hl][128][H]   h1
   float* g1x;                               // fp32 [4 slot][2 m][128][4H]        layer-1 gate pre-activations
-  unsigned int* sync;                       // [2 m][3] counters A, B, C
+  unsigned int* sync;                       // [2 m][3] counters A, B, C, W_SYNC_STRIDE uint32 apart
   unsigned long long* dbg;                  // optional phase timestamps (IDV_LSTM_DBG): CTA 0 of each role, module 0
 };
 
@@ -116,9 +117,11 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
   const int NC = p.NC, H = p.H, T = p.Tsteps;
   const int Tp = p.T + 1;
   const long long R = (long long)p.NB * Tp;
-  unsigned int* cA = p.sync + m * 3 + 0;
-  unsigned int* cB = p.sync + m * 3 + 1;
-  unsigned int* cC = p.sync + m * 3 + 2;
+  // every counter on a 128-byte line of its own: the pollers of one counter (ld.acquire of ~48 producer threads) and
+  // the increments of another must not queue up on the same L2 line
+  unsigned int* cA = p.sync + (m * 3 + 0) * W_SYNC_STRIDE;
+  unsigned int* cB = p.sync + (m * 3 + 1) * W_SYNC_STRIDE;
+  unsigned int* cC = p.sync + (m * 3 + 2) * W_SYNC_STRIDE;
   unsigned int* my_ctr = role == 0 ? cA : (role == 1 ? cB : cC);
   const CUtensorMap* tmW = role == 0 ? &tmW0 : (role == 1 ? &tmWi : &tmW1);
   const CUtensorMap* tmH = role == 2 ? &tmHC : &tmHA;
@@ -553,7 +556,7 @@ static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off
     p.b0 = b0;
     p.NBc = NB - b0 < 64 ? NB - b0 : 64;
     IDV_CUDA(cudaMemsetAsync(work, 0, (size_t)work_bytes, st));
-    IDV_CUDA(cudaMemsetAsync(sync, 0, 6 * sizeof(unsigned int), st));
+    IDV_CUDA(cudaMemsetAsync(sync, 0, 6 * W_SYNC_STRIDE * sizeof(unsigned int), st));
     rc = pair ? launch_wave<64, true>(maps, p, smem, st) : launch_wave<64, false>(maps, p, smem, st);
   }
   if (dbg && rc == IDV_OK) {
@@ -662,7 +665,7 @@ extern "C" int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g
       p.b0 = b0;
       p.NBc = NB - b0 < 64 ? NB - b0 : 64;
       IDV_CUDA(cudaMemsetAsync(work, 0, (size_t)work_bytes, st));
-      IDV_CUDA(cudaMemsetAsync(sync, 0, 6 * sizeof(unsigned int), st));
+      IDV_CUDA(cudaMemsetAsync(sync, 0, 6 * W_SYNC_STRIDE * sizeof(unsigned int), st));
       if (N == 64) rc = pair ? launch_wave<64, true>(maps, p, smem, st) : launch_wave<64, false>(maps, p, smem, st);
       else rc = pair ? launch_wave<48, true>(maps, p, smem, st) : launch_wave<48, false>(maps, p, smem, st);
       if (rc == IDV_E_RESOURCE && b0 == 0) break;

@@ -298,12 +298,24 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
           tmem_ld_wait();
           if (row_ok) {
+            // optional second copy for the first encoder layer's tap-GEMM: split-bf16 activation rows of ONE plane,
+            // row b*(T+1)+1+t (causal pad row in front of every utterance), column head_boff + 2*bin + part
+            unsigned short* rows = reinterpret_cast<unsigned short*>(p.out);
+            const long long ridx = ((long long)r + b + 1) * p.out_ld + p.head_boff;
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const int bin = (nt * BN + c0 + j) >> 1;
-              if (bin < p.head_fout)
-                *reinterpret_cast<float2*>(p.predict + ((long long)(b * p.head_fout + bin) * T + t) * 2) =
-                    make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+              if (bin < p.head_fout) {
+                const float xr = __uint_as_float(v[j]), xi = __uint_as_float(v[j + 1]);
+                *reinterpret_cast<float2*>(p.predict + ((long long)(b * p.head_fout + bin) * T + t) * 2) = make_float2(xr, xi);
+                if (rows) {
+                  unsigned short h0, l0, h1, l1;
+                  split_bf16(xr, h0, l0);
+                  split_bf16(xi, h1, l1);
+                  *reinterpret_cast<unsigned int*>(rows + ridx + 2 * bin) = (unsigned)h0 | ((unsigned)h1 << 16);
+                  *reinterpret_cast<unsigned int*>(rows + p.out_hl + ridx + 2 * bin) = (unsigned)l0 | ((unsigned)l1 << 16);
+                }
+              }
             }
           }
         }
@@ -699,6 +711,8 @@ static int tapgemm_tc_impl(const void* a0, int a0_cp, int a0_planes, const void*
   IDV_CHECK_ARG(head >= 0 && head <= 3, "idv_tapgemm_tc: epilogue mode must be 0..3");
   if (head == 3) {
     IDV_CHECK_ARG(Tp > 0 && predict && head_fout > 0 && R % Tp == 0, "idv_tapgemm_tc: STFT epilogue needs Tp = frames per utterance");
+    IDV_CHECK_ARG(!out || (head_boff >= 0 && head_boff % 2 == 0 && out_ld >= head_boff + 2 * head_fout && out_ld % 2 == 0 && out_hl > 0),
+                  "idv_tapgemm_tc: STFT epilogue with activation rows needs out_ld >= head_boff + 2 * head_fout and out_hl");
   } else if (head) {
     IDV_CHECK_ARG(N == 32 && Tp > 1 && predict && head_fout > 0 && head_bmul > 0 && head_boff >= 0 && (head != 2 || stft_x),
                   "idv_tapgemm_tc: head mode needs N == 32, Tp, predict (and stft_x for the mask head)");

@@ -64,6 +64,23 @@ class STFT(nn.Module):
         self._basis = None
         self.lengths = None        # int32 (B,) true sample counts of a zero-padded ragged batch (pipeline.enhance_ragged)
 
+    def forward_with_rows(self, signal):
+        """(stft_x, Planes): the spectrum in the reference layout AND as split-bf16 activation rows [1][B*(T+1)][576]
+        for the first encoder layer's tap-GEMM (Encoder.forward_from_stft(rows=...)), both written by the STFT GEMM's
+        epilogue.  The rows buffer is kept per (B, T, device): its pad rows / padding columns stay zero."""
+        if not ops.use_split():
+            raise RuntimeError("activation rows are written by the tensor-core STFT (IDV_GEMM=tc)")
+        if getattr(self, "_tc", None) is None or self._tc["bias"].device != signal.device:
+            self._tc = pack.pack_stft_tc(self.n_fft, self.win_length, signal.device)
+        B, T = signal.shape[0], signal.shape[1] // self.hop_length + 1
+        key = (B, T, str(signal.device))
+        if getattr(self, "_rows", None) is None or self._rows[0] != key:
+            self._rows = (key, torch.zeros(2 * B * (T + 1) * pack.ENC0_ROWS_LD, dtype=torch.bfloat16, device=signal.device))
+        rows = self._rows[1]
+        stft_x = ops.stft_tc(signal, self._tc, self.n_fft, self.hop_length, self.win_length, self.lengths, rows,
+                             pack.ENC0_ROWS_LD, pack.ENC0_COL0)
+        return stft_x, Planes(rows, B, 1, 1, T, cp=pack.ENC0_ROWS_LD, split=True)
+
     def forward(self, signal):
         if ops.use_split():                            # tensor-core DFT GEMM
             if getattr(self, "_tc", None) is None or self._tc["bias"].device != signal.device:
@@ -460,10 +477,22 @@ class Encoder(nn.Module):
     def _slope(self):
         return float(self.prelu.weight.detach().reshape(-1)[0])
 
-    def forward_from_stft(self, stft_x, train=False, out=None, prev=None, raw_only=False):
+    def forward_from_stft(self, stft_x, train=False, out=None, prev=None, raw_only=False, rows=None):
         """First layer (in_channel == 1): reads the user-layout STFT (B, F, T, 2) directly.  out / prev: streaming
-        state (ops.enc0).  raw_only: return the conv output before ComplexBatchNormal / PReLU (training forward)."""
+        state (ops.enc0).  raw_only: return the conv output before ComplexBatchNormal / PReLU (training forward).
+        rows: the STFT's activation rows (STFT.forward_with_rows) - the causal eval layer then runs as a tap-GEMM on the
+        tensor cores (pack.pack_enc0_tc) instead of the SIMT kernel."""
         items = self._cache.check(self)
+        if rows is not None and not train and not raw_only and out is None and self.conv.causal:
+            key = ("enc0_tc", stft_x.shape[1], str(stft_x.device))
+            if key not in items:
+                self.conv._geometry()
+                c = self.conv
+                items[key] = pack.pack_enc0_tc(c.conv_re.weight, c.conv_re.bias, c.conv_im.weight, c.conv_im.bias,
+                                               self.bn.fold_inputs(), self._slope(), stft_x.shape[1], stft_x.device)
+            pk = items[key]
+            data = ops.tapgemm(pk, rows, None, rows.NB, rows.T, t_valid=rows.T)
+            return Planes(data, rows.NB, pk.c_out, pk.f_out, rows.T, split=True)
         key = ("enc0", bool(train), str(stft_x.device))
         if key not in items:
             self.conv._geometry()
@@ -671,14 +700,15 @@ def _build_decoders(net_params, causal, skip_to_use, use_sc=True):
     return out
 
 
-def _run_encoder_stack(encoders, stft_x, train=False):
-    planes = [encoders[0].forward_from_stft(stft_x, train)]
+def _run_encoder_stack(encoders, stft_x, train=False, rows=None):
+    planes = [encoders[0].forward_from_stft(stft_x, train, rows=rows)]
     for enc in encoders[1:]:
         planes.append(enc.forward_planes(planes[-1], train))
     return planes
 
 
 _philox_calls = [0]
+ENC0_TC = [os.environ.get("IDV_ENC0_TC", "1") != "0"]        # first encoder layer as a tap-GEMM on STFT activation rows (A/B switch)
 FUSED_SPEC_ROWS = [os.environ.get("IDV_FUSED_SPEC_ROWS", "1") != "0"]   # head epilogue writes the iSTFT GEMM's rows (A/B switch)
 FUSED_DENSE = [os.environ.get("IDV_FUSED_DENSE", "1") != "0"]     # ComplexDense composed into the first decoder layer (A/B switch)
 FUSED_LATENT = [os.environ.get("IDV_FUSED_LATENT", "1") != "0"]      # one idv_latent_fwd launch instead of lstm_combine + reparam + z_to_planes (A/B switch)
@@ -792,13 +822,17 @@ class _VaeEncoderBase(nn.Module):
             top, latent = planes[-1], latent_g.detach()
         else:
             latent_g = None
-            stft_x = self.stft(x)
+            rows = None
+            if ENC0_TC[0] and ops.use_split() and self.causal and not train and not self.datanorm:
+                stft_x, rows = self.stft.forward_with_rows(x)          # + activation rows for the first layer's tap-GEMM
+            else:
+                stft_x = self.stft(x)
             if self.datanorm:                                          # model/pvae_module.py:L367-371
                 key = (self.data_mean._version, self.data_std._version, str(stft_x.device))
                 if getattr(self, "_norm_key", None) != key:
                     self._norm_key, self._norm = key, _norm_consts(self.data_mean, self.data_std)[0]
                 stft_x = ops.bin_affine(stft_x, self._norm[0], self._norm[1], zero_edge_imag=True, out=stft_x)
-            planes = _run_encoder_stack(self.encoders, stft_x, train)
+            planes = _run_encoder_stack(self.encoders, stft_x, train, rows)
             top = planes[-1]
             if self._heads is None and FUSED_LATENT[0]:
                 # ONE launch: combine of the four LSTM streams, latent split, reparameterisation of every latent and the
@@ -1229,11 +1263,11 @@ class standard_DCCRN(nn.Module):
         self.linear = ComplexConv2d(in_channel=1, out_channel=1, kernel_size=1, stride=1)   # unused, in state_dict
         self.detect_anormal = True
 
-    def forward_spec(self, stft_x, train, mask, rows=None):
+    def forward_spec(self, stft_x, train, mask, rows=None, enc_rows=None):
         """stft_x (B, F, T, 2) -> predict (B, F, T, 2): decoder output, optionally through the mask head.
         rows: ISTFT.spectrum_rows buffer the fused head fills as well (eval, tensor-core path)."""
         stft_x = ops.lib.require_f32_cuda(stft_x, "stft_x")
-        planes = _run_encoder_stack(self.encoders, stft_x, train)
+        planes = _run_encoder_stack(self.encoders, stft_x, train, enc_rows)
         top = planes[-1]
         hs = self.lstms[0].forward_planes(top, combine=False)
         lat, zp = ops.lstm_combine_planes(*hs, top.split)               # (B, T, H, 2) + the dense layer's input plane
@@ -1278,7 +1312,11 @@ class DCCRN_(nn.Module):
             raise ValueError("recon_type must be 'mask' or 'real_imag'")
 
     def forward(self, signal, train=True):
-        stft_x = self.stft(signal)
+        enc_rows = None
+        if ENC0_TC[0] and ops.use_split() and self.std_DCCRN.causal and not train and not self.datanorm:
+            stft_x, enc_rows = self.stft.forward_with_rows(signal)
+        else:
+            stft_x = self.stft(signal)
         if self.datanorm:                                              # model/pvae_module.py:L217-221, L236-239, L248-249
             key = (self.data_mean._version, self.data_std._version, str(stft_x.device))
             if getattr(self, "_norm_key", None) != key:
@@ -1287,7 +1325,7 @@ class DCCRN_(nn.Module):
         rows = None
         if FUSED_SPEC_ROWS[0] and ops.use_split() and not train and not self.datanorm:
             rows = self.istft.spectrum_rows(stft_x.shape[0], stft_x.shape[2], stft_x.device)
-        predict = self.std_DCCRN.forward_spec(stft_x, train, mask=(self.recon_type == 'mask'), rows=rows)
+        predict = self.std_DCCRN.forward_spec(stft_x, train, mask=(self.recon_type == 'mask'), rows=rows, enc_rows=enc_rows)
         if self.datanorm:
             ops.bin_affine(predict, self._norm[1][0], self._norm[1][1], out=predict)
         if rows is not None and self.std_DCCRN.rows_written:

@@ -101,10 +101,11 @@ def _lengths_arg(lengths, B, device):
     return lengths.to(device).contiguous()
 
 
-def stft_tc(x, hp, n_fft, hop, win, lengths=None):
+def stft_tc(x, hp, n_fft, hop, win, lengths=None, rows=None, rows_ld=0, rows_col0=0):
     """STFT on the tensor cores: frames (split bf16) -> one tap-GEMM against the windowed DFT basis whose
     epilogue writes the reference layout (B, nbins, T, 2).  lengths: int32 (B,) true sample counts of a zero-padded
-    ragged batch (reflect padding at every utterance's own end)."""
+    ragged batch (reflect padding at every utterance's own end).  rows: optional zero-initialised bf16
+    [2][B*(T+1)][rows_ld] buffer that also receives the spectrum as split activation rows (first encoder layer)."""
     x = lib.require_f32_cuda(x, "signal")
     if x.dim() != 2:
         raise RuntimeError("signal must be (B, L), got %s" % (tuple(x.shape),))
@@ -115,7 +116,8 @@ def stft_tc(x, hp, n_fft, hop, win, lengths=None):
     lib.call("idv_stft_frames_split", x, B, L, n_fft, hop, win, hp["kpad"], _lengths_arg(lengths, B, x.device), frames)
     out = torch.empty((B, hp["nbins"], T, 2), dtype=torch.float32, device=x.device)
     lib.call("idv_tapgemm_tc_head", frames, hp["kpad"], 1, None, 0, 0, R, T, hp["wt"], hp["kc_max"], 1, hp["bias"],
-             hp["N"], hp["units"], hp["taps"], 1, None, 0, 0, 0, 0, 0, 0.0, 3, hp["nbins"], 1, 0, None, out, 0)
+             hp["N"], hp["units"], hp["taps"], 1, rows, rows_ld, 0, rows.numel() // 2 if rows is not None else 0, 0, 0, 0.0,
+             3, hp["nbins"], 1, rows_col0, None, out, 0)
     return out
 
 
@@ -266,7 +268,7 @@ def lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, want_f32=True,
         if g.is_cuda:
             lib.check_exclusive_device(g.device.index if g.device.index is not None else torch.cuda.current_device())
         work = torch.empty(int(cfg[3]), dtype=torch.uint8, device=g.device)
-        sync = torch.empty(6, dtype=torch.int32, device=g.device)
+        sync = torch.empty(192, dtype=torch.int32, device=g.device)
         lib.call("idv_lstm_layer_pair_tc", g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, work, sync,
                  int(t_valid))
         return hseq, hsplit
@@ -292,7 +294,7 @@ def lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T,
         lib.check_exclusive_device(g0.device.index if g0.device.index is not None else torch.cuda.current_device())
     hseq = _empty(4 * NB * (T + 1) * H, g0.device)
     work = torch.empty(int(work_bytes), dtype=torch.uint8, device=g0.device)
-    sync = torch.empty(6, dtype=torch.int32, device=g0.device)
+    sync = torch.empty(192, dtype=torch.int32, device=g0.device)
     lib.call("idv_lstm2_wave_tc", g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq, work, sync,
              int(t_valid))
     return hseq

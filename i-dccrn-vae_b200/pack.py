@@ -19,7 +19,7 @@ def round8(c):
     return (c + 7) // 8 * 8
 
 
-PAIR_PLANES = [True]      # narrow transposed convs: two output planes per tensor-core tile (TapGemmPack._tc_paired)
+PAIR_PLANES = [os.environ.get("IDV_PAIR_PLANES", "1") != "0"]   # narrow (transposed) convs: 256 / N output planes per tensor-core tile (TapGemmPack._tc_paired)
 
 
 class TapGemmPack:
@@ -142,42 +142,45 @@ def _cpu(t):
 
 
 def _tc_paired(self, w, dev):
-    """Tensor-core tables of a NARROW transposed conv with two output planes per unit (N_tc = 2N, columns [0, N) =
-    plane 2q, [N, 2N) = plane 2q+1; the kernel wraps them into the two planes because N_tc > out_ld): the even and the
-    odd output plane read the same two or three input planes, so one tile loads each activation box once for both -
-    at N = 64 the kernel is bound by operand ingest (L2 -> shared memory), not by the tensor pipe.  Taps of the pair are
-    merged by (source, plane, dt, K range); a plane that lacks a tap gets a zero weight block."""
+    """Tensor-core tables of a NARROW (transposed) conv with G = 256 / N consecutive output planes per unit (N_tc = G N,
+    columns [g N, (g+1) N) = plane G q + g; the kernel wraps them into the planes because N_tc > out_ld): neighbouring
+    output planes read overlapping input planes (a stride-2 conv: planes 2fo-2 .. 2fo+2; the transposed conv: fo/2 - 1 ..
+    fo/2 + 1), so one tile loads each activation box once for all of them and issues N = 256 MMAs - the narrow tiles were
+    bound by operand ingest and by their epilogue, not by the tensor pipe.  Taps of the group are merged by (source,
+    plane, dt, K range); a plane that lacks a tap gets a zero weight block."""
     import collections
-    N, N2 = self.N, 2 * self.N
+    N = self.N
+    G = max(2, 256 // N)
+    NG = G * N
     kc_max = max(t[4] for t in self._taps_l)
     units, taps, slots = [], [], {}
-    for q in range((len(self._units_l) + 1) // 2):
-        pair = self._units_l[2 * q:2 * q + 2]
-        assert pair[0][2] == 2 * q and all(u[3] == 0 and u[4] == 0 for u in pair)
+    for q in range((len(self._units_l) + G - 1) // G):
+        grp = self._units_l[G * q:G * q + G]
+        assert grp[0][2] == G * q and all(u[3] == 0 and u[4] == 0 for u in grp)
         groups = collections.OrderedDict()
-        for half, u in enumerate(pair):
-            assert u[2] == 2 * q + half
+        for g, u in enumerate(grp):
+            assert u[2] == G * q + g
             for t in self._taps_l[u[0]:u[0] + u[1]]:
-                groups.setdefault((t[0], t[1], t[2], t[3], t[4]), [None, None])[half] = t[5]
+                groups.setdefault((t[0], t[1], t[2], t[3], t[4]), [None] * G)[g] = t[5]
         begin = len(taps)
-        for key, (we, wo) in groups.items():
-            skey = (we, wo, key[4])
+        for key, offs in groups.items():
+            skey = tuple(offs) + (key[4],)
             if skey not in slots:
                 slots[skey] = len(slots)
             taps.append([key[0], key[1], key[2], key[3], key[4], slots[skey]])
-        units.append([begin, len(groups), 2 * q, 0, 0, sum(k[4] // 64 for k in groups)])
-    wt = torch.zeros(len(slots), N2, kc_max, dtype=torch.float32, device=w.device)
-    for (we, wo, kc), si in slots.items():
-        if we is not None:
-            wt[si, :N, :kc] = w[we:we + kc * N].view(kc, N).t()
-        if wo is not None:
-            wt[si, N:, :kc] = w[wo:wo + kc * N].view(kc, N).t()
+        units.append([begin, len(groups), G * q, 0, 0, sum(k[4] // 64 for k in groups)])
+    wt = torch.zeros(len(slots), NG, kc_max, dtype=torch.float32, device=w.device)
+    for skey, si in slots.items():
+        kc = skey[-1]
+        for g, off in enumerate(skey[:-1]):
+            if off is not None:
+                wt[si, g * N:(g + 1) * N, :kc] = w[off:off + kc * N].view(kc, N).t()
     hi = wt.to(torch.bfloat16)
     lo = (wt - hi.to(torch.float32)).to(torch.bfloat16)
     return dict(wt=torch.stack((hi, lo)).contiguous().to(dev), kc_max=kc_max, n_slots=len(slots),
                 taps=torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(dev),
                 units=torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(dev),
-                N=N2, n_units=len(units), bias=torch.cat((self.bias, self.bias)).contiguous())
+                N=NG, n_units=len(units), bias=torch.cat([self.bias] * G).contiguous())
 
 
 TapGemmPack._tc_paired = _tc_paired
@@ -212,6 +215,7 @@ def pack_conv(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, f_in, strid
         units.append([begin, len(taps) - begin, fo, 0, 0, 0])
     p = TapGemmPack(W.reshape(-1), bias, units, taps, N, f_out, N, slope is not None, slope or 0.0, device)
     p.f_out, p.c_out = f_out, cout
+    p.pair_planes = PAIR_PLANES[0] and N in (64, 128) and stride_f == 2     # 256 / N output planes per tensor-core tile
     return p
 
 
@@ -359,6 +363,46 @@ def pack_enc0(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, device):
     W[:, 1] = Wb[:, 8]           # im-in row (ch_in = 8 padding of one channel)
     return (W.to(torch.float32).contiguous().to(device), bias.to(torch.float32).to(device), cout,
             float(slope if slope is not None else 1.0))
+
+
+ENC0_ROWS_LD = 576        # columns of the STFT activation rows: 4 (two zero bins below bin 0) + 2*257 + zero padding
+ENC0_COL0 = 4             # column of (bin 0, re)
+
+
+def pack_enc0_tc(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, f_in, device):
+    """First encoder layer (Cin = 1, kernel (5, 2), stride (2, 1), causal) as a tap-GEMM on the STFT's activation rows
+    [1 plane][R][ENC0_ROWS_LD] (column ENC0_COL0 + 2*bin + part; written by the STFT GEMM's epilogue): output plane fo
+    reads the bins 2fo-2 .. 2fo+2 = the 10 columns from 4*fo on.  Four consecutive output planes 4q .. 4q+3 read 22
+    neighbouring columns, so they share ONE 64-column box starting at 16q - 8 (a TMA box starts at a multiple of 8
+    columns; the box of q = 0 starts at -8: out-of-range columns are zero-filled) and run as one N = 256 unit
+    (TapGemmPack._tc_paired): plane g of the group has its 10 live K rows at 8 + 4g.  2 time taps, K = 64 per tap of which
+    22 are live - the layer was a 0.85 ms issue-bound SIMT kernel; the dead MMA columns cost nothing next to its 1.3 GB
+    of output."""
+    w, bias, cout, sl = pack_enc0(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, "cpu")    # [10][2][2 cout]
+    N = 2 * cout
+    f_out = (f_in + 4 - 5) // 2 + 1
+    if ENC0_COL0 + 2 * f_in > ENC0_ROWS_LD or 16 * ((f_out - 1) // 4) - 8 + 64 > ENC0_ROWS_LD:
+        raise RuntimeError("STFT rows of %d columns do not hold %d bins" % (ENC0_ROWS_LD, f_in))
+    mats = []
+    for g in range(4):                                    # position of the plane in its group of 4
+        for kt in range(2):
+            m = torch.zeros(64, N, dtype=torch.float32)
+            for kf in range(5):
+                for part in range(2):
+                    m[8 + 4 * g + 2 * kf + part] = w[kf * 2 + kt, part]
+            mats.append(m.reshape(-1))
+    units, taps = [], []
+    for fo in range(f_out):
+        q, g = fo // 4, fo % 4
+        begin = len(taps)
+        for kt in range(2):                               # time tap kt reads x[t - 1 + kt]
+            taps.append([0, 0, 1 - kt, 16 * q - 8, 64, (g * 2 + kt) * 64 * N])
+        units.append([begin, 2, fo, 0, 0, 0])
+    p = TapGemmPack(torch.cat(mats), bias.cpu(), units, taps, N, f_out, N, slope is not None, sl if slope is not None else 0.0,
+                    device)
+    p.f_out, p.c_out = f_out, cout
+    p.pair_planes = PAIR_PLANES[0] and N == 64
+    return p
 
 
 def pack_dec5(t_re_w, t_re_b, t_im_w, t_im_b, bn, slope, c_p, c_skip, device):

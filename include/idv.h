@@ -143,7 +143,11 @@ int idv_istft_fwd(const float* spec, int B, int T, const float* basis, const flo
  *   idv_stft_frames_split: x (B, L) -> split-bf16 frames [2][B*T][kpad], frames[(b,t)][j] = reflect-padded signal
  *                          at hop*t + (n_fft-win)/2 + j for j < win, 0 up to kpad (kpad % 64 == 0);
  *   idv_tapgemm_tc_head(head = 3): D = frames . basis^T, column pair (2k, 2k+1) of row (b,t) is written to
- *                          predict[(b*head_fout + k)*Tp + t] (Tp = frames per utterance; no bias, no pad rows);
+ *                          predict[(b*head_fout + k)*Tp + t] (Tp = frames per utterance; no bias, no pad rows); with
+ *                          `out` != NULL the same values also go to split-bf16 activation rows bf16 [2][B*(Tp+1)][out_ld]
+ *                          (row b*(Tp+1)+1+t, column head_boff + 2k + part, hi / lo sets out_hl apart; everything the
+ *                          kernel does not write - pad rows, padding columns - is kept zero by the caller): the input
+ *                          of the first encoder layer run as a tap-GEMM (pack.pack_enc0_tc);
  *   idv_spec_rows_split:   spec (B, nbins, T, 2) -> split-bf16 rows [2][B*T][kpad], rows[(b,t)][2k+part];
  *   idv_ola_fwd:           frames (B*T, frame_ld) -> overlap-add / window envelope / centre trim -> (B, hop*(T-1)).
  * Ragged batches: lengths (device int32 [B], NULL = all L) gives the true sample count of every utterance of the
@@ -205,15 +209,17 @@ int idv_lstm_recurrent_tc(const float* g, int64_t g_m_off, int64_t g_p_off, int 
  * input projection, without materialising the layer-1 gate pre-activations.  g0: layer-0 input projection
  * (as for idv_lstm_recurrent_tc).  w_hh0 / w_ih1 / w_hh1: packs in the layout of idv_lstm_recurrent_tc's wpack
  * with (n_cols, n_ctas) from idv_lstm2_wave_config; bias1: fp32 [2][n_ctas][n_cols] = b_ih_l1 + b_hh_l1 in the
- * same CTA-major order.  hseq1: fp32 [4][R][H] layer-1 output.  work: work_bytes workspace, sync: 6 x uint32
- * (both zeroed by the call).  NB <= 64; 6 * n_ctas CTAs must be co-resident.                                  */
+ * same CTA-major order.  hseq1: fp32 [4][R][H] layer-1 output.  work: work_bytes workspace, sync: 192 x uint32 (6
+ * step counters, one 128-byte line each)
+ * (both zeroed by the call).  Any NB (chunks of 64 utterances run as consecutive launches); 6 * n_ctas CTAs must be
+ * co-resident.                                                                                                  */
 int idv_lstm2_wave_config(int H, int* n_cols, int* n_ctas, int64_t* work_bytes);
 int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
                       const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
                       float* hseq1, void* work, unsigned int* sync, int t_valid, void* stream);
 /* ONE nn.LSTM layer of both modules per launch as CTA pairs (the kernel of idv_lstm2_wave_tc restricted to its first
  * role): same contract as idv_lstm_recurrent_tc, wpack packed with (n_cols, n_ctas) from idv_lstm_layer_pair_config
- * (H = 768: 48 gate columns x 64 CTAs per module).  work: work_bytes workspace, sync: 6 x uint32 (both zeroed by the
+ * (H = 768: 48 gate columns x 64 CTAs per module).  work: work_bytes workspace, sync: 192 x uint32 (both zeroed by the
  * call).  Any NB (chunks of 64 utterances run as consecutive launches).                                          */
 int idv_lstm_layer_pair_config(int H, int* n_cols, int* n_ctas, int64_t* work_bytes);
 int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* wpack, int NB, int T,

@@ -71,8 +71,14 @@ def idv_tapgemm_tc_head(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, k
                        n_units, tmp, N, R * N, 0, 0, 0, 0.0)
         T = Tp
         B = R // T
-        predict.view(B, head_fout, T, 2).copy_(tmp.view(B, T, N)[:, :, :2 * head_fout].reshape(B, T, head_fout, 2)
-                                               .permute(0, 2, 1, 3))
+        vals = tmp.view(B, T, N)[:, :, :2 * head_fout]
+        predict.view(B, head_fout, T, 2).copy_(vals.reshape(B, T, head_fout, 2).permute(0, 2, 1, 3))
+        if out is not None:                               # split-bf16 activation rows (one plane, causal row layout)
+            rows = _flat(out).view(2, B, T + 1, out_ld)
+            hi = vals.to(torch.bfloat16)
+            lo = (vals - hi.to(torch.float32)).to(torch.bfloat16)
+            rows[0][:, 1:, head_boff:head_boff + 2 * head_fout] = hi
+            rows[1][:, 1:, head_boff:head_boff + 2 * head_fout] = lo
         return
     assert head in (1, 2) and N == 32
     tmp = torch.zeros(n_units * R * 32)
@@ -146,7 +152,9 @@ def idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max
             hi, lo = (A0 if src == 0 else A1)
 
             def shifted(x):
-                x = x[f_in][:, ch_off:ch_off + kc]
+                x = x[f_in]
+                lo_c, hi_c = max(ch_off, 0), min(ch_off + kc, x.shape[1])      # channels outside the tensor read as zero
+                x = torch.nn.functional.pad(x[:, lo_c:hi_c], (lo_c - ch_off, ch_off + kc - hi_c))
                 if dt > 0:
                     x = torch.cat((torch.zeros(dt, kc, dtype=D), x[:R - dt]), 0)
                 elif dt < 0:

@@ -536,7 +536,7 @@ def test_lstm_layer_pair_tc(NB, T, H, tv, pairs):
     hseq = torch.zeros(4, R, H)
     hsplit = torch.zeros(2 * 4 * R * H, dtype=torch.bfloat16)
     work = torch.zeros(work_bytes, dtype=torch.uint8)
-    sync = torch.zeros(6, dtype=torch.int32)
+    sync = torch.zeros(192, dtype=torch.int32)
     args = [g, 4 * H, R * 8 * H, 8 * H, wp, NB, T, H, hseq, hsplit, work, sync, tv]
     lib.set_option("lstm_wave_cta_pairs", pairs)
     try:
@@ -595,7 +595,7 @@ def test_lstm2_wave_tc(NB, T, H, tv):
     b1 = PK.pack_lstm_bias_tc(mods[0], mods[1], 1, n_cols, n_ctas, "cpu")
     hseq = torch.zeros(4, R, H)
     work = torch.zeros(work_bytes, dtype=torch.uint8)
-    sync = torch.zeros(6, dtype=torch.int32)
+    sync = torch.zeros(192, dtype=torch.int32)
     args = [g, 4 * H, R * 8 * H, 8 * H, w0, wi, w1, b1, NB, T, H, hseq, work, sync, tv]
     assert _both("idv_lstm2_wave_tc", args, [11]) < 2e-5
 
@@ -617,6 +617,34 @@ def test_stft_istft_tensor_core_pieces(B, L):
     args = [frames, hp["kpad"], 1, None, 0, 0, R, T, hp["wt"], hp["kc_max"], 1, hp["bias"], hp["N"], hp["units"],
             hp["taps"], 1, None, 0, 0, 0, 0, 0, 0.0, 3, 257, 1, 0, None, out, 0]
     assert _both("idv_tapgemm_tc_head", args, [28]) < 1e-5
+    # the same launch also writing the split-bf16 activation rows of the first encoder layer (causal row layout)
+    ld, col0 = PK.ENC0_ROWS_LD, PK.ENC0_COL0
+    erows = torch.zeros(2 * B * (T + 1) * ld, dtype=torch.bfloat16)
+    args2 = list(args)
+    args2[16], args2[17], args2[19], args2[26] = erows, ld, B * (T + 1) * ld, col0
+    assert _both("idv_tapgemm_tc_head", args2, [16, 28]) < 1e-5
+    # ... and the first encoder layer as a tap-GEMM on those rows against the SIMT kernel's contract on the spectrum
+    E.call("idv_tapgemm_tc_head", *args2)
+    Cout = 32
+    w20 = _rand(10, 2, 2 * Cout, seed=8)
+    want = torch.zeros(129 * B * (T + 1) * 2 * Cout)
+    wre = w20[:, 0, :Cout].t().reshape(Cout, 1, 5, 2).contiguous()       # undo pack_enc0's layout: re-in -> re-out = conv_re
+    wim = w20[:, 0, Cout:].t().reshape(Cout, 1, 5, 2).contiguous()       #                          re-in -> im-out = conv_im
+    pk = PK.pack_enc0_tc(wre, torch.zeros(Cout), wim, torch.zeros(Cout), None, 0.3, 257, "cpu")
+    tc = pk.tc()
+    Rp = B * (T + 1)
+    got = torch.zeros(2 * 129 * Rp * 64, dtype=torch.bfloat16)
+    a = [erows, ld, 1, None, 0, 0, Rp, T + 1, tc["wt"], tc["kc_max"], tc["n_slots"], tc["bias"], tc["N"], tc["units"], tc["taps"],
+         tc["n_units"], got, 64, Rp * 64, 129 * Rp * 64, 1, 1, 0.3, T]
+    assert _both("idv_tapgemm_tc", a, [16]) < 1e-5
+    # same numbers as the SIMT contract evaluated with the complex weights (w_re, w_im) the pack was built from
+    w_ref = torch.zeros(10, 2, 2 * Cout)
+    w_ref[:, 0, :Cout], w_ref[:, 0, Cout:] = w20[:, 0, :Cout], w20[:, 0, Cout:]
+    w_ref[:, 1, :Cout], w_ref[:, 1, Cout:] = -w20[:, 0, Cout:], w20[:, 0, :Cout]
+    E.call("idv_enc0_fwd", out, B, 257, T, w_ref, torch.zeros(2 * Cout), Cout, 0.3, want, 0, 1, T, None, 0)
+    E.call("idv_tapgemm_tc", *a)
+    gf = got.view(2, -1).double().sum(0)
+    assert C.rel_l2(gf, want) < 2e-5
     ip = PK.pack_istft_tc(512, 400, "cpu")
     spec = _rand(B, 257, T, 2, seed=6)
     rows = torch.zeros(2 * R * ip["kpad"], dtype=torch.bfloat16)
