@@ -113,6 +113,12 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   volatile int* tq = reinterpret_cast<volatile int*>(tmem_slot + 1);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t out_stage0 = smem_base + C::STAGES * C::STAGE_BYTES + 1024;      // (stage ring is a multiple of 1024 B)
+  // Layers with a short K loop (the first encoder layer on the STFT rows: 2 chunks; dense + first decoder layer: 8) are
+  // bound by their epilogue, not by the main loop: they give up one ring stage, and the freed shared memory holds extra
+  // output staging buffers so that several tensor stores per epilogue warp are in flight instead of one.
+  const int nst = (p.tma_out && C::STAGES > 2 && p.units[0].reserved <= 8) ? C::STAGES - 1 : C::STAGES;
+  const int n_obufs = 1 + ((C::STAGES - nst) * C::STAGE_BYTES) / C::OUT_STAGE_BYTES;   // 1, 2 or 3
+  const uint32_t out_stage_x = smem_base + nst * C::STAGE_BYTES;                 // extra staging buffers (freed stage)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_row_tiles = TWO ? (p.n_row_tiles + 1) / 2 : p.n_row_tiles;
@@ -200,7 +206,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               tma_load_4d(am, full0 + 8 * stage, sa, tap.ch_off + k0, rt * BM - tap.dt, tap.f_in, 0);
               tma_load_4d(&tmW, full0 + 8 * stage, sa + 2 * C::A_BYTES, k0, nt * BN, tap.w_off, 0);
             }
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -251,7 +257,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           if (TWO) umma_commit_2sm(empty0 + 8 * stage, 3);   // frees the slot in BOTH CTAs when these MMAs retire
           else umma_commit(empty0 + 8 * stage);       // frees the smem slot when these MMAs retire
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }
         if (TWO) umma_commit_2sm(tfull0 + 8 * acc, 3);
         else umma_commit(tfull0 + 8 * acc);           // accumulator complete -> epilogue
@@ -260,6 +266,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   } else {
     // ================================ epilogue (4 warps) ================================
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
+    uint32_t oslab = 0;                               // tensor stores issued by this warp (staging-buffer rotation)
     for (uint32_t local = 0;; ++local) {
       int t;
       if (DYN) {
@@ -302,13 +309,33 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             // row b*(T+1)+1+t (causal pad row in front of every utterance), column head_boff + 2*bin + part
             unsigned short* rows = reinterpret_cast<unsigned short*>(p.out);
             const long long ridx = ((long long)r + b + 1) * p.out_ld + p.head_boff;
+            const int n0 = nt * BN + c0;
+            // 32 consecutive columns of a row = 64 bytes of hi and of lo: 16-byte vectors when the column offset allows
+            // (columns past 2*head_fout hold exact zeros - zero basis rows, no bias - which is what the padding needs)
+            const bool vec = rows != nullptr && (p.head_boff & 7) == 0 && (p.out_ld & 7) == 0 && p.head_boff + n0 + 32 <= p.out_ld;
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  unsigned short h0, l0, h1, l1;
+                  split_bf16(__uint_as_float(v[j + 2 * e]), h0, l0);
+                  split_bf16(__uint_as_float(v[j + 2 * e + 1]), h1, l1);
+                  hw[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                  lw[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                }
+                *reinterpret_cast<uint4*>(rows + ridx + n0 + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(rows + p.out_hl + ridx + n0 + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              const int bin = (nt * BN + c0 + j) >> 1;
+              const int bin = (n0 + j) >> 1;
               if (bin < p.head_fout) {
                 const float xr = __uint_as_float(v[j]), xi = __uint_as_float(v[j + 1]);
                 *reinterpret_cast<float2*>(p.predict + ((long long)(b * p.head_fout + bin) * T + t) * 2) = make_float2(xr, xi);
-                if (rows) {
+                if (rows && !vec) {
                   unsigned short h0, l0, h1, l1;
                   split_bf16(xr, h0, l0);
                   split_bf16(xi, h1, l1);
@@ -379,12 +406,17 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         // layers, whose main loop is short, were bound by this epilogue).  Instead each epilogue warp stages its 32 rows
         // x 64 columns (hi and lo) in a 128B-swizzled buffer and one lane issues a tensor store of the box
         // {64 ch, 32 rows, 1 plane, hi|lo}; rows past R are clipped by the tensor map, pad rows carry zeros.
-        const uint32_t stg = out_stage0 + (uint32_t)q * 8192u;
         const int r0 = rt * BM + q * 32;
         const uint32_t sw = (uint32_t)(lane & 7);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 64) {
-          if (lane == 0) bulk_wait_read_all();               // the previous box has left the staging buffer
+        for (int c0 = 0; c0 < BN; c0 += 64, ++oslab) {
+          const uint32_t ob = oslab % (uint32_t)n_obufs;
+          const uint32_t stg = (ob == 0 ? out_stage0 : out_stage_x + (ob - 1) * (uint32_t)C::OUT_STAGE_BYTES) + (uint32_t)q * 8192u;
+          if (lane == 0) {                                   // the box that used this staging buffer last has left it
+            if (n_obufs == 1) bulk_wait_read<0>();
+            else if (n_obufs == 2) bulk_wait_read<1>();
+            else bulk_wait_read<2>();
+          }
           __syncwarp();
 #pragma unroll
           for (int h = 0; h < 2; ++h) {

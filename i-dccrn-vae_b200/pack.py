@@ -142,7 +142,8 @@ def _cpu(t):
 
 
 def _tc_paired(self, w, dev):
-    """Tensor-core tables of a NARROW (transposed) conv with G = 256 / N consecutive output planes per unit (N_tc = G N,
+    """Tensor-core tables of a NARROW (transposed) conv with G = ``plane_group`` (default 2; measured: 4 planes of the
+    N = 64 transposed conv are no faster than 2) consecutive output planes per unit (N_tc = G N,
     columns [g N, (g+1) N) = plane G q + g; the kernel wraps them into the planes because N_tc > out_ld): neighbouring
     output planes read overlapping input planes (a stride-2 conv: planes 2fo-2 .. 2fo+2; the transposed conv: fo/2 - 1 ..
     fo/2 + 1), so one tile loads each activation box once for all of them and issues N = 256 MMAs - the narrow tiles were
@@ -150,7 +151,7 @@ def _tc_paired(self, w, dev):
     plane, dt, K range); a plane that lacks a tap gets a zero weight block."""
     import collections
     N = self.N
-    G = max(2, 256 // N)
+    G = getattr(self, "plane_group", 2)
     NG = G * N
     kc_max = max(t[4] for t in self._taps_l)
     units, taps, slots = [], [], {}
@@ -215,7 +216,9 @@ def pack_conv(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, f_in, strid
         units.append([begin, len(taps) - begin, fo, 0, 0, 0])
     p = TapGemmPack(W.reshape(-1), bias, units, taps, N, f_out, N, slope is not None, slope or 0.0, device)
     p.f_out, p.c_out = f_out, cout
-    p.pair_planes = PAIR_PLANES[0] and N in (64, 128) and stride_f == 2     # 256 / N output planes per tensor-core tile
+    # (measured on B200: grouping the output planes of the strided conv 32 -> 64, N = 128, into N = 256 units makes the
+    #  tile MMA-bound at 97 % tensor-pipe active but 7 % slower - 14 instead of 10 K chunks per plane pair with zero
+    #  weight blocks; the layer stays one plane per unit)
     return p
 
 
@@ -365,23 +368,22 @@ def pack_enc0(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, device):
             float(slope if slope is not None else 1.0))
 
 
-ENC0_ROWS_LD = 576        # columns of the STFT activation rows: 4 (two zero bins below bin 0) + 2*257 + zero padding
-ENC0_COL0 = 4             # column of (bin 0, re)
+ENC0_ROWS_LD = 576        # columns of the STFT activation rows: 8 (zero bins below bin 0) + 2*257 + zero padding
+ENC0_COL0 = 8             # column of (bin 0, re): a multiple of 8 so the STFT epilogue writes 16-byte vectors
 
 
 def pack_enc0_tc(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, f_in, device):
     """First encoder layer (Cin = 1, kernel (5, 2), stride (2, 1), causal) as a tap-GEMM on the STFT's activation rows
     [1 plane][R][ENC0_ROWS_LD] (column ENC0_COL0 + 2*bin + part; written by the STFT GEMM's epilogue): output plane fo
-    reads the bins 2fo-2 .. 2fo+2 = the 10 columns from 4*fo on.  Four consecutive output planes 4q .. 4q+3 read 22
-    neighbouring columns, so they share ONE 64-column box starting at 16q - 8 (a TMA box starts at a multiple of 8
-    columns; the box of q = 0 starts at -8: out-of-range columns are zero-filled) and run as one N = 256 unit
-    (TapGemmPack._tc_paired): plane g of the group has its 10 live K rows at 8 + 4g.  2 time taps, K = 64 per tap of which
-    22 are live - the layer was a 0.85 ms issue-bound SIMT kernel; the dead MMA columns cost nothing next to its 1.3 GB
+    reads the bins 2fo-2 .. 2fo+2 = the 10 columns from 4*fo + 4 on.  Four consecutive output planes 4q .. 4q+3 read 22
+    neighbouring columns, so they share ONE 64-column box starting at 16q (a TMA box starts at a multiple of 8
+    columns) and run as one N = 256 unit (TapGemmPack._tc_paired): plane g of the group has its 10 live K rows at
+    4 + 4g.  2 time taps, K = 64 per tap of which 22 are live - the layer was a 0.85 ms issue-bound SIMT kernel; the dead MMA columns cost nothing next to its 1.3 GB
     of output."""
     w, bias, cout, sl = pack_enc0(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, "cpu")    # [10][2][2 cout]
     N = 2 * cout
     f_out = (f_in + 4 - 5) // 2 + 1
-    if ENC0_COL0 + 2 * f_in > ENC0_ROWS_LD or 16 * ((f_out - 1) // 4) - 8 + 64 > ENC0_ROWS_LD:
+    if ENC0_COL0 != 8 or ENC0_COL0 + 2 * f_in > ENC0_ROWS_LD or 16 * ((f_out - 1) // 4) + 64 > ENC0_ROWS_LD:
         raise RuntimeError("STFT rows of %d columns do not hold %d bins" % (ENC0_ROWS_LD, f_in))
     mats = []
     for g in range(4):                                    # position of the plane in its group of 4
@@ -389,19 +391,20 @@ def pack_enc0_tc(conv_re_w, conv_re_b, conv_im_w, conv_im_b, bn, slope, f_in, de
             m = torch.zeros(64, N, dtype=torch.float32)
             for kf in range(5):
                 for part in range(2):
-                    m[8 + 4 * g + 2 * kf + part] = w[kf * 2 + kt, part]
+                    m[4 + 4 * g + 2 * kf + part] = w[kf * 2 + kt, part]
             mats.append(m.reshape(-1))
     units, taps = [], []
     for fo in range(f_out):
         q, g = fo // 4, fo % 4
         begin = len(taps)
         for kt in range(2):                               # time tap kt reads x[t - 1 + kt]
-            taps.append([0, 0, 1 - kt, 16 * q - 8, 64, (g * 2 + kt) * 64 * N])
+            taps.append([0, 0, 1 - kt, 16 * q, 64, (g * 2 + kt) * 64 * N])
         units.append([begin, 2, fo, 0, 0, 0])
     p = TapGemmPack(torch.cat(mats), bias.cpu(), units, taps, N, f_out, N, slope is not None, sl if slope is not None else 0.0,
                     device)
     p.f_out, p.c_out = f_out, cout
     p.pair_planes = PAIR_PLANES[0] and N == 64
+    p.plane_group = 4
     return p
 
 

@@ -355,6 +355,17 @@ class EncoderTrainStep:
         return gin
 
 
+# Callables(list of parameters) invoked when a model's backward node has written ALL of its parameter gradients for this
+# backward pass: FlatAdam starts the all-reduce of that model's slice of the gradient bucket there, so the collective
+# runs on the NCCL stream while the rest of the backward pass (the other model) still computes.
+GRADS_FINAL_HOOKS = []
+
+
+def _notify_grads_final(params):
+    for h in list(GRADS_FINAL_HOOKS):
+        h(params)
+
+
 class _EncoderTrainFn(torch.autograd.Function):
     """Autograd plumbing: forward = EncoderTrainStep.forward, backward hands dL/dlatent to EncoderTrainStep.backward,
     which writes the parameter gradients itself (the parameters are inputs only so that autograd calls backward)."""
@@ -372,6 +383,7 @@ class _EncoderTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlatent, dtoken):
         ctx.step.backward(dlatent.contiguous())
+        _notify_grads_final([p for p in ctx.step.enc.parameters() if p.requires_grad])
         return (None, None) + (None,) * ctx.n
 
 
@@ -737,6 +749,7 @@ class _DecoderTrainFn(torch.autograd.Function):
                                        None if d_pred is None else d_pred.contiguous(), want_dz, want_dskip)
         if want_dskip:
             ctx.enc_step.add_skip_grads(dskips, len(ctx.step.dec.decoders))
+        _notify_grads_final([p for p in ctx.step.dec.parameters() if p.requires_grad])
         token_grad = torch.zeros((), device=ctx.dev) if ctx.needs_input_grad[3] else None
         return (None, None, dz, token_grad, None, None, None, None, None) + (None,) * ctx.n
 
@@ -773,7 +786,7 @@ class FlatAdam(torch.optim.Optimizer):
     the flat layout is rebuilt when the set of parameters with gradients changes."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None,
-                 world_size=1):
+                 world_size=1, overlap=True):
         params = [p for p in params if p.requires_grad]
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         if len(self.param_groups) != 1:
@@ -781,6 +794,22 @@ class FlatAdam(torch.optim.Optimizer):
         self.group, self.world = process_group, world_size
         self.flat = None
         self.live = []                 # parameters in the flat layout, in param_groups order
+        # overlapped all-reduce: slices of the bucket whose gradients a backward node declared final (GRADS_FINAL_HOOKS)
+        # are reduced asynchronously while the backward pass continues; step() reduces what is left and waits
+        self.overlap = bool(overlap) and process_group is not None and world_size > 1
+        self._inflight = []            # (begin, end, work handle, [(param, grad tensor, version)])
+        self.overlapped_elements = 0   # bucket elements whose all-reduce was started during a backward pass (diagnostic)
+        if self.overlap:
+            import weakref
+            ref = weakref.ref(self)
+
+            def hook(params, _ref=ref):
+                me = _ref()
+                if me is None:
+                    GRADS_FINAL_HOOKS.remove(hook)
+                else:
+                    me._on_grads_final(params)
+            GRADS_FINAL_HOOKS.append(hook)
         self._steps = {}               # id(param) -> number of updates applied
         self._pending = None           # (m, v) per parameter from load_state_dict, applied at the next layout build
 
@@ -838,6 +867,28 @@ class FlatAdam(torch.optim.Optimizer):
         self._pending = pending or None
 
     @torch.no_grad()
+    def _on_grads_final(self, params):
+        """A backward node finished writing the gradients of ``params``: if they form one contiguous run of the flat
+        layout, gather them into the bucket and start its all-reduce now (async, on the collective's own stream)."""
+        if self.flat is None or not self.live:
+            return
+        index = {id(p): i for i, p in enumerate(self.live)}
+        idx = sorted(index[id(p)] for p in params if id(p) in index and p.grad is not None)
+        if not idx or idx != list(range(idx[0], idx[-1] + 1)):
+            return
+        a, b = self.views[idx[0]][0], self.views[idx[-1]][0] + self.views[idx[-1]][1]
+        if any(not (e <= a or s >= b) for s, e, _, _ in self._inflight):
+            return
+        stamp = []
+        for i in idx:
+            p, (off, k) = self.live[i], self.views[i]
+            self.gflat[off:off + k].copy_(p.grad.reshape(-1))
+            stamp.append((p, p.grad, p.grad._version))
+        work = torch.distributed.all_reduce(self.gflat[a:b], group=self.group, async_op=True)
+        self._inflight.append((a, b, work, stamp))
+        self.overlapped_elements += b - a
+
+    @torch.no_grad()
     def step(self, closure=None):
         loss = None
         if closure is not None:
@@ -846,12 +897,27 @@ class FlatAdam(torch.optim.Optimizer):
         live = [p for p in self.params if p.grad is not None]
         if not live:
             return loss
-        if self.flat is None or len(live) != len(self.live) or any(a is not b for a, b in zip(live, self.live)):
+        rebuilt = self.flat is None or len(live) != len(self.live) or any(a is not b for a, b in zip(live, self.live))
+        inflight, self._inflight = self._inflight, []
+        for _, _, work, _ in inflight:
+            work.wait()
+        # a slice reduced early is only valid if nothing touched those gradients afterwards (a module used twice in one
+        # graph accumulates into .grad after its first backward node ran) and the layout is still the same
+        valid = [(a, b) for a, b, _, stamp in inflight
+                 if not rebuilt and all(p.grad is g and g._version == v for p, g, v in stamp)]
+        if rebuilt:
             self._build(live)
+        done = lambda off: any(a <= off < b for a, b in valid)
         for p, (off, k) in zip(self.live, self.views):
-            self.gflat[off:off + k].copy_(p.grad.reshape(-1))
+            if not done(off):
+                self.gflat[off:off + k].copy_(p.grad.reshape(-1))
         if self.group is not None and self.world > 1:
-            torch.distributed.all_reduce(self.gflat, group=self.group)
+            # reduce the runs of the bucket that were not reduced during the backward pass
+            n, pos = self.gflat.numel(), 0
+            for a, b in sorted(valid) + [(n, n)]:
+                if a > pos:
+                    torch.distributed.all_reduce(self.gflat[pos:a], group=self.group)
+                pos = max(pos, b)
             self.gflat.div_(self.world)
         g = self.param_groups[0]
         # one launch per run of consecutive parameters with the same step count (bias corrections differ otherwise)

@@ -77,8 +77,8 @@ def idv_tapgemm_tc_head(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, k
             rows = _flat(out).view(2, B, T + 1, out_ld)
             hi = vals.to(torch.bfloat16)
             lo = (vals - hi.to(torch.float32)).to(torch.bfloat16)
-            rows[0][:, 1:, head_boff:head_boff + 2 * head_fout] = hi
-            rows[1][:, 1:, head_boff:head_boff + 2 * head_fout] = lo
+            rows[0][:, 1:, head_boff:head_boff + 2 * head_fout] = hi        # (the kernel may also write the exact
+            rows[1][:, 1:, head_boff:head_boff + 2 * head_fout] = lo        #  zeros of the padding columns)
         return
     assert head in (1, 2) and N == 32
     tmp = torch.zeros(n_units * R * 32)

@@ -59,7 +59,7 @@ def test_two_rank_sharded_enhancement_matches_single_process(emulated_abi, tmp_p
     assert got["t"] == 11.0                             # MAX over ranks
 
 
-def _train_worker(rank, world, port, tmp):
+def _train_worker(rank, world, port, tmp, overlap=True, steps=1):
     """Data-parallel training step: each rank back-propagates its own shard, FlatAdam all-reduces (mean) the flat
     gradient bucket and applies the same update on every rank."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -75,18 +75,21 @@ def _train_worker(rank, world, port, tmp):
     ops.set_gemm_mode("tc")
     torch.set_num_threads(2)
     noisy, frozen = TS.build_step(1, 3, "cpu")
-    opt = FlatAdam(noisy.parameters(), lr=1e-3, weight_decay=1e-3, process_group=dist.group.WORLD, world_size=world)
+    opt = FlatAdam(noisy.parameters(), lr=1e-3, weight_decay=1e-3, process_group=dist.group.WORLD, world_size=world,
+                   overlap=overlap)
     x = C.synth_waveform(2, 500, seed=50 + rank)                       # a different shard per rank
     eps = [torch.zeros(2, 1, 6, C.ZDIM)] * 2                           # the emulator has no Philox: supply eps
     with torch.no_grad():
         rc, rn = frozen[0](x, train=False, eps=eps), frozen[1](x, train=False, eps=eps)
-    r = noisy(x, train=True, eps=eps)
-    loss, _, _ = losses.nsvae_kl_loss(r, rc, rn, C.ZDIM, 1, 1.0)
-    opt.zero_grad()
-    loss.backward()
-    local = torch.cat([p.grad.reshape(-1) for p in opt.params if p.grad is not None]).clone()
-    opt.step()
-    torch.save({"local": local, "reduced": opt.gflat.clone(), "flat": opt.flat.clone()}, tmp % rank)
+    for _ in range(steps):
+        r = noisy(x, train=True, eps=eps)
+        loss, _, _ = losses.nsvae_kl_loss(r, rc, rn, C.ZDIM, 1, 1.0)
+        opt.zero_grad()
+        loss.backward()
+        local = torch.cat([p.grad.reshape(-1) for p in opt.params if p.grad is not None]).clone()
+        opt.step()
+    torch.save({"local": local, "reduced": opt.gflat.clone(), "flat": opt.flat.clone(),
+                "overlapped": opt.overlapped_elements}, tmp % rank)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -100,3 +103,19 @@ def test_two_rank_gradient_allreduce_and_adam(emulated_abi, tmp_path):
     want = (a["local"] + b["local"]) / 2
     assert C.rel_l2(a["reduced"], want) < 1e-6 and torch.equal(a["reduced"], b["reduced"])
     assert torch.equal(a["flat"], b["flat"])                            # identical parameters after the step
+
+
+def test_overlapped_allreduce_gives_the_same_update(emulated_abi, tmp_path):
+    """From the second step on (the flat layout exists) the encoder's slice of the gradient bucket is all-reduced
+    asynchronously as soon as its backward node has written the gradients; the parameters after two steps must equal
+    those of the non-overlapped optimiser bit for bit."""
+    res = {}
+    for overlap in (True, False):
+        tmp = str(tmp_path / ("ov%d_rank%%d.pt" % overlap))
+        port = 33500 + os.getpid() % 2000 + (7 if overlap else 0)
+        mp.spawn(_train_worker, args=(2, port, tmp, overlap, 2), nprocs=2, join=True)
+        res[overlap] = [torch.load(tmp % r) for r in range(2)]
+    assert res[True][0]["overlapped"] > 0 and res[False][0]["overlapped"] == 0
+    assert torch.equal(res[True][0]["flat"], res[True][1]["flat"])
+    assert torch.equal(res[True][0]["flat"], res[False][0]["flat"])
+    assert torch.equal(res[True][0]["reduced"], res[False][0]["reduced"])
