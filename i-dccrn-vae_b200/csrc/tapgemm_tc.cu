@@ -21,8 +21,14 @@
 namespace idv {
 namespace tc {
 
-constexpr int NUM_THREADS = 192;
 constexpr int EPI_WARP0 = 2;
+// Epilogue warps: 4 (one per TMEM lane quarter) for the 256-wide tiles, whose main loop hides the epilogue; 8 for
+// BN <= 128 (two warps per lane quarter, each taking every other 64-column slab / half of the head's bins): with the
+// short main loops of the narrow layers a 4-warp epilogue (TMEM load -> bias / PReLU / bf16 split -> staging -> tensor
+// store, ~2 us per slab and warp, mostly latency) was longer than the MMAs of a tile (enc1 / dec4: 68-70 % tensor-pipe
+// active).
+template <int BN> struct EpiWarps { static constexpr int value = BN <= 128 ? 8 : 4; };
+constexpr int MAX_THREADS = 64 + 32 * 8;
 
 struct Params {
   int R, Tp, N, t_valid, keep_pad;
@@ -82,17 +88,22 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;              // one of hi / lo
   static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = TWO ? (BN >= 256 ? 3 : (BN >= 64 ? 4 : 5)) : ((BN >= 256) ? 2 : (BN >= 128 ? 3 : 4));
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages, power of two
+  static constexpr int EPI_WARPS = EpiWarps<BN>::value;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   // epilogue staging for the TMA stores: per epilogue warp [hi | lo][32 rows][64 bf16] = 8 KB, 1024-byte aligned
-  static constexpr int OUT_STAGE_BYTES = 4 * 8192;
+  static constexpr int OUT_STAGE_BYTES = BN >= 64 ? EPI_WARPS * 8192 : 0;      // (N = 32 tiles never leave through TMA)
+  // ring depth: as many stages as fit next to the staging buffers (227 KB per SM)
+  static constexpr int STAGES = TWO ? (BN >= 256 ? 3 : (BN >= 128 ? 3 : (BN >= 64 ? 4 : 5)))
+                                    : (BN >= 256 ? 2 : (BN >= 128 ? 2 : (BN >= 64 ? 3 : 4)));
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages, power of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers, padded*/ + OUT_STAGE_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "stage ring + output staging exceed the shared memory of one SM");
 };
 
 // DYN = false: tile i of CTA b is b + i*gridDim.x (lock-step CTAs, best when the kernel owns the GPU);
 // DYN = true : tiles are claimed from a global counter (kernels of other streams may hold SMs).
 template <int BN, bool DYN, bool TWO>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(MAX_THREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Params p) {
   static_assert(!(TWO && DYN), "the CTA-pair kernel uses the static tile schedule");
@@ -117,7 +128,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   // bound by their epilogue, not by the main loop: they give up one ring stage, and the freed shared memory holds extra
   // output staging buffers so that several tensor stores per epilogue warp are in flight instead of one.
   const int nst = (p.tma_out && C::STAGES > 2 && p.units[0].reserved <= 8) ? C::STAGES - 1 : C::STAGES;
-  const int n_obufs = 1 + ((C::STAGES - nst) * C::STAGE_BYTES) / C::OUT_STAGE_BYTES;   // 1, 2 or 3
+  const int n_obufs = C::OUT_STAGE_BYTES ? 1 + ((C::STAGES - nst) * C::STAGE_BYTES) / C::OUT_STAGE_BYTES : 1;   // 1, 2 or 3
   const uint32_t out_stage_x = smem_base + nst * C::STAGE_BYTES;                 // extra staging buffers (freed stage)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,11 +148,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, TWO ? 8 : 4);      // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(tempty0 + 8 * a, (TWO ? 2 : 1) * C::EPI_WARPS);      // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int qi = 0; qi < 4; ++qi) {
       mbar_init(qfull0 + 8 * qi, 1);
-      mbar_init(qempty0 + 8 * qi, 5);     // MMA thread + 4 epilogue warps
+      mbar_init(qempty0 + 8 * qi, 1 + C::EPI_WARPS);     // MMA thread + the epilogue warps
     }
     fence_barrier_init();
   }
@@ -264,8 +275,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
     }
   } else {
-    // ================================ epilogue (4 warps) ================================
+    // ================================ epilogue (4 or 8 warps) ================================
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
+    const int ew = warp - EPI_WARP0;                  // epilogue warp index (staging buffer)
+    constexpr int NH = C::EPI_WARPS / 4;              // warps per lane quarter: each takes every NH-th column slab
+    const int half = ew >> 2;
     uint32_t oslab = 0;                               // tensor stores issued by this warp (staging-buffer rotation)
     for (uint32_t local = 0;; ++local) {
       int t;
@@ -300,7 +314,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int T = p.Tp;
         const int b = r / T, t = r % T;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = half * 32; c0 < BN; c0 += 32 * NH) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
           tmem_ld_wait();
@@ -367,7 +381,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             const int fo = unit.out_f + e;
-            if (e >= nbins || fo >= p.head_fout) continue;
+            if (e >= nbins || fo >= p.head_fout || (e * NH) / 16 != half) continue;      // bins split over the warps of a quarter
             float yr = prelu_f(__uint_as_float(v[2 * e]) + b_r, p.slope);
             float yi = prelu_f(__uint_as_float(v[2 * e + 1]) + b_i, p.slope);
             if (p.head == 2) {
@@ -409,9 +423,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int r0 = rt * BM + q * 32;
         const uint32_t sw = (uint32_t)(lane & 7);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 64, ++oslab) {
+        for (int c0 = half * 64; c0 < BN; c0 += 64 * NH, ++oslab) {
           const uint32_t ob = oslab % (uint32_t)n_obufs;
-          const uint32_t stg = (ob == 0 ? out_stage0 : out_stage_x + (ob - 1) * (uint32_t)C::OUT_STAGE_BYTES) + (uint32_t)q * 8192u;
+          const uint32_t stg = (ob == 0 ? out_stage0 : out_stage_x + (ob - 1) * (uint32_t)C::OUT_STAGE_BYTES) + (uint32_t)ew * 8192u;
           if (lane == 0) {                                   // the box that used this staging buffer last has left it
             if (n_obufs == 1) bulk_wait_read<0>();
             else if (n_obufs == 2) bulk_wait_read<1>();
@@ -465,7 +479,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
       const long long obase0 = (long long)unit.out_f * p.out_plane + (long long)r * p.out_ld + unit.out_ch_off + nt * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < BN; c0 += 32 * NH) {
         // N > out_ld: the unit's columns wrap into consecutive output planes, out_ld columns each (two output planes of a
         // narrow transposed conv computed as ONE tile from the input planes they share); planes past the tensor are dropped
         long long obase = obase0;
@@ -638,7 +652,7 @@ static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorM
                                 C::SMEM_BYTES));
   const int total = p.n_units * p.n_row_tiles * p.n_col_tiles;
   const int grid = total < sms ? total : sms;
-  tapgemm_tc_kernel<BN, DYN, false><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(a0, a1, w, o, p);
+  tapgemm_tc_kernel<BN, DYN, false><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a0, a1, w, o, p);
   IDV_LAUNCH_CHECK("tapgemm_tc_kernel");
   return IDV_OK;
 }
@@ -648,14 +662,13 @@ template <int BN>
 static int launch_pairs(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o, Params& p,
                         cudaStream_t st) {
   using C = Cfg<BN, true>;
-  static_assert(C::SMEM_BYTES <= 232448, "stage ring exceeds the shared memory of one SM");
   auto kern = tapgemm_tc_kernel<BN, false, true>;
   IDV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+  cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
   cfg.attrs = attr; cfg.numAttrs = 1;
   static int max_pairs[64] = {0};
   int dev = 0;
