@@ -22,12 +22,11 @@ namespace idv {
 namespace tc {
 
 constexpr int EPI_WARP0 = 2;
-// Epilogue warps: 4 (one per TMEM lane quarter) for the 256-wide tiles, whose main loop hides the epilogue; 8 for
-// BN <= 128 (two warps per lane quarter, each taking every other 64-column slab / half of the head's bins): with the
-// short main loops of the narrow layers a 4-warp epilogue (TMEM load -> bias / PReLU / bf16 split -> staging -> tensor
-// store, ~2 us per slab and warp, mostly latency) was longer than the MMAs of a tile (enc1 / dec4: 68-70 % tensor-pipe
-// active).
-template <int BN> struct EpiWarps { static constexpr int value = BN <= 128 ? 8 : 4; };
+// Epilogue warps per TMEM lane quarter.  Measured on B200 with 8 warps (two per quarter, each taking every other
+// 64-column slab) for BN <= 128: the narrow layers got SLOWER (enc1 1.07 -> 1.29 ms, dec4 1.21 -> 1.34 ms) because the
+// doubled staging buffers cost a ring stage - those layers are bound by operand ingest (L2 -> shared memory: 80 KB per
+// K chunk and CTA pair for 0.33 us of MMAs), not by their epilogue; the kernel keeps the generality, the count stays 4.
+template <int BN> struct EpiWarps { static constexpr int value = 4; };
 constexpr int MAX_THREADS = 64 + 32 * 8;
 
 struct Params {
@@ -93,8 +92,7 @@ struct Cfg {
   // epilogue staging for the TMA stores: per epilogue warp [hi | lo][32 rows][64 bf16] = 8 KB, 1024-byte aligned
   static constexpr int OUT_STAGE_BYTES = BN >= 64 ? EPI_WARPS * 8192 : 0;      // (N = 32 tiles never leave through TMA)
   // ring depth: as many stages as fit next to the staging buffers (227 KB per SM)
-  static constexpr int STAGES = TWO ? (BN >= 256 ? 3 : (BN >= 128 ? 3 : (BN >= 64 ? 4 : 5)))
-                                    : (BN >= 256 ? 2 : (BN >= 128 ? 2 : (BN >= 64 ? 3 : 4)));
+  static constexpr int STAGES = TWO ? (BN >= 256 ? 3 : (BN >= 64 ? 4 : 5)) : (BN >= 256 ? 2 : (BN >= 128 ? 3 : 4));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages, power of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers, padded*/ + OUT_STAGE_BYTES;
   static_assert(SMEM_BYTES <= 232448, "stage ring + output staging exceed the shared memory of one SM");

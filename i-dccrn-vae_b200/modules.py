@@ -55,6 +55,22 @@ class _PackCache:
 # --------------------------------------------------------------------------------------------------
 # STFT / ISTFT — model/pvae_module.py:L12-42
 # --------------------------------------------------------------------------------------------------
+def _cached_zero_rows(owner, numel, shape_key, device):
+    """Zero-initialised bf16 buffer kept on ``owner`` per (shape, device, CUDA stream): GEMM operand rows whose padding
+    (pad rows, padding columns) must stay zero while the producing epilogue rewrites every live element on each call.
+    One buffer per stream, so forwards in flight on different streams (pipeline.StreamPipeline) never share one; at most
+    4 buffers are kept."""
+    stream = torch.cuda.current_stream(device).cuda_stream if torch.device(device).type == "cuda" else 0
+    key = (shape_key, str(device), stream)
+    cache = owner.__dict__.setdefault("_rows_cache", {})
+    buf = cache.get(key)
+    if buf is None or buf.numel() != numel:
+        if len(cache) >= 4:
+            cache.pop(next(iter(cache)))
+        buf = cache[key] = torch.zeros(numel, dtype=torch.bfloat16, device=device)
+    return buf
+
+
 class STFT(nn.Module):
     def __init__(self, n_fft, hop_length, win_length, device):
         super().__init__()
@@ -73,10 +89,7 @@ class STFT(nn.Module):
         if getattr(self, "_tc", None) is None or self._tc["bias"].device != signal.device:
             self._tc = pack.pack_stft_tc(self.n_fft, self.win_length, signal.device)
         B, T = signal.shape[0], signal.shape[1] // self.hop_length + 1
-        key = (B, T, str(signal.device))
-        if getattr(self, "_rows", None) is None or self._rows[0] != key:
-            self._rows = (key, torch.zeros(2 * B * (T + 1) * pack.ENC0_ROWS_LD, dtype=torch.bfloat16, device=signal.device))
-        rows = self._rows[1]
+        rows = _cached_zero_rows(self, 2 * B * (T + 1) * pack.ENC0_ROWS_LD, (B, T), signal.device)
         stft_x = ops.stft_tc(signal, self._tc, self.n_fft, self.hop_length, self.win_length, self.lengths, rows,
                              pack.ENC0_ROWS_LD, pack.ENC0_COL0)
         return stft_x, Planes(rows, B, 1, 1, T, cp=pack.ENC0_ROWS_LD, split=True)
@@ -122,11 +135,7 @@ class ISTFT(nn.Module):
         per (B, T, device) is kept and reused: the head rewrites every live column on every call."""
         if getattr(self, "_tc", None) is None or self._tc["bias"].device != device:
             self._tc = pack.pack_istft_tc(self.n_fft, self.win_length, device)
-        key = (B, T, str(device))
-        cache = getattr(self, "_rows", None)
-        if cache is None or cache[0] != key:
-            self._rows = (key, torch.zeros(2 * B * T * self._tc["kpad"], dtype=torch.bfloat16, device=device))
-        return self._rows[1]
+        return _cached_zero_rows(self, 2 * B * T * self._tc["kpad"], (B, T), device)
 
     def forward_rows(self, rows, B, T):
         return ops.istft_rows_tc(rows, B, T, self._tc, self.n_fft, self.hop_length, self.win_length, self.lengths)

@@ -58,14 +58,29 @@ def write_wav(path, x, fs=16000):
         f.write(hdr + b"data" + struct.pack("<I", len(pcm)) + pcm)
 
 
-def load_utterances(paths, fs=16000):
-    """[float32 CPU tensors] for ragged.enhance_ragged; a file at another rate is an error (the reference never
-    resamples: sr=None, and its models are trained at 16 kHz)."""
+def resample(x, fs_in, fs_out):
+    """Polyphase rational resampling (scipy.signal.resample_poly: Kaiser-windowed FIR, up / down by the reduced ratio)
+    - the host-side step of dataset/cal_mean_std.py:L52-55 (``librosa.resample``).  librosa's default kernel (soxr_hq) is a
+    different low-pass design, so outputs agree to the filters' pass-band accuracy, not bit for bit."""
+    if fs_in == fs_out:
+        return np.asarray(x, dtype=np.float32)
+    from math import gcd
+    from scipy.signal import resample_poly
+    g = gcd(int(fs_in), int(fs_out))
+    return resample_poly(np.asarray(x, dtype=np.float64), int(fs_out) // g, int(fs_in) // g).astype(np.float32)
+
+
+def load_utterances(paths, fs=16000, allow_resample=False):
+    """[float32 CPU tensors] for ragged.enhance_ragged.  The reference's loaders never resample
+    (dataset/dataload_nsvae.py:L183: ``sr=None``; its models are trained at 16 kHz), so by default a file at another
+    rate is an error; allow_resample=True converts it with ``resample``."""
     import torch
     out = []
     for p in paths:
         x, r = read_wav(p)
         if r != fs:
-            raise ValueError("%s is sampled at %d Hz, the network expects %d Hz" % (p, r, fs))
+            if not allow_resample:
+                raise ValueError("%s is sampled at %d Hz, the network expects %d Hz" % (p, r, fs))
+            x = resample(x, r, fs)
         out.append(torch.from_numpy(x.copy()))
     return out

@@ -89,6 +89,15 @@ def test_wav_round_trip(tmp_path):
     with pytest.raises(ValueError):
         wavio.load_utterances([str(tmp_path / "st.wav")])
     assert wavio.load_utterances([p])[0].shape == (4321,)
+    # optional resampling (dataset/cal_mean_std.py:L52-55): an 8 kHz file enters the 16 kHz network at twice the length,
+    # a tone keeps its frequency and amplitude
+    assert wavio.load_utterances([str(tmp_path / "st.wav")], allow_resample=True)[0].shape == (8642,)
+    t = np.arange(8000) / 8000.0
+    tone = (0.5 * np.sin(2 * np.pi * 440.0 * t)).astype(np.float32)
+    up = wavio.resample(tone, 8000, 16000)
+    want = 0.5 * np.sin(2 * np.pi * 440.0 * np.arange(16000) / 16000.0)
+    assert up.dtype == np.float32 and len(up) == 16000 and np.abs(up[200:-200] - want[200:-200]).max() < 2e-3
+    assert wavio.resample(tone, 8000, 8000) is not None and len(wavio.resample(tone, 48000, 16000)) == 2667
 
 
 def run_si_sdr(device):
