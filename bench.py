@@ -492,6 +492,8 @@ def hbm_stage_rooflines(per_kernel, B, L, T, peaks, H=384, zdim=128, kpad_stft=4
         "idv_stft_frames_split": B * L * 4 + Rf * kpad_stft * 4,                    # waveform -> split-bf16 frames
         "idv_enc0_fwd": B * nb * T * 2 * 4 + f1 * R * 2 * c0 * 4,                   # STFT (B,257,T,2) -> 129 planes x 64 ch
         "idv_lstm_combine_fwd": 4 * R * H * 4 + B * T * H * 2 * 4,                  # 4 streams -> latent (B,T,H,2)
+        # fused latent stage: 4 LSTM streams -> latent (B,T,H,2) + z (B,T,zdim,2) + split-bf16 z planes
+        "idv_latent_fwd": 4 * R * H * 4 + B * T * H * 2 * 4 + B * T * zdim * 2 * 4 + R * 2 * zdim * 4,
         "idv_reparam_fwd": B * T * H * 2 * 4 + B * T * zdim * 2 * 4,                # latent -> z
         "idv_z_to_planes": B * T * zdim * 2 * 4 + R * 2 * zdim * 4,                 # z -> split-bf16 rows
         "idv_spec_rows_split": B * nb * T * 2 * 4 + Rf * kpad_istft * 4,            # spectrum -> split-bf16 K-major rows

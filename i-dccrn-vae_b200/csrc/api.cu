@@ -18,6 +18,8 @@ static int g_gemm_pairs = 1;
 static int g_wave_pairs = 1;
 static int g_tile_order = 1;
 static int g_tma_store = 1;
+static int g_lstm_interleave = 1;
+int option_lstm_interleave() { return g_lstm_interleave; }
 int option_tma_store() { return g_tma_store; }
 int option_tile_order() { return g_tile_order; }
 int option_lstm_wave_pairs() { return g_wave_pairs; }
@@ -45,6 +47,10 @@ extern "C" int idv_set_option(const char* name, int value) {
   if (strcmp(name, "gemm_tile_order") == 0) {
     IDV_CHECK_ARG(value == 0 || value == 1, "idv_set_option: gemm_tile_order must be 0 (unit-major) or 1 (row-major)");
     g_tile_order = value;
+    return IDV_OK;
+  }
+  if (strcmp(name, "lstm_interleave") == 0) {
+    g_lstm_interleave = value != 0;
     return IDV_OK;
   }
   if (strcmp(name, "gemm_tma_store") == 0) {

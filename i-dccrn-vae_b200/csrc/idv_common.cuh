@@ -16,6 +16,7 @@ int option_gemm_pairs();
 int option_lstm_wave_pairs();
 int option_tile_order();
 int option_tma_store();
+int option_lstm_interleave();
 
 #define IDV_CHECK_ARG(cond, ...)             \
   do {                                       \

@@ -22,6 +22,8 @@
 // on row 64*rank + L%64 and the units of CTA (c & ~1) + L/64.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace idv {
@@ -41,7 +43,13 @@ struct WaveParams {
   int g_ld;
   const float* bias1;                       // [2 m][NC][N] CTA-major (gate*Hs + j)
   int NB, T, H, NC, KC, stages, Tsteps;     // T = allocated frames (row layout), Tsteps = valid steps
-  int b0, NBc;                              // this launch works on utterances [b0, b0 + NBc) of the NB (chunks of <= 64)
+  // A launch works on ONE or TWO chunks of <= 64 utterances: chunk ch = utterances [b0[ch], b0[ch] + NBc[ch]).  Two chunks
+  // are two independent recurrences INTERLEAVED in the same CTAs (same resident weights; own exchange buffers, step
+  // counters, TMEM accumulator and cell state): while the h(t) of one chunk travels through the L2 (publish +
+  // propagation: 3.5 of the 8 us of a step) the CTA runs step t of the other chunk.
+  int nch, b0[2], NBc[2];
+  long long hxA_ch, hxC_ch, g1x_ch;         // elements between the two chunks' exchange buffers
+  int blkA_ch, blkC_ch;                     // ... and the same distance in blocks of the tensor maps
   int n_roles;                              // 3 = two-layer wavefront (L0 | IP | L1), 1 = ONE nn.LSTM layer per launch (role L0 only)
   unsigned short* hsplit;                   // single-layer mode: optional bf16 [2][4][R][H] output (next layer's in-proj input)
   float* hseq0;                             // single-layer mode: optional fp32 [4][R][H] output
@@ -62,7 +70,7 @@ __device__ __forceinline__ unsigned long long wgtime() {
 // 5 TMEM drained, 6 stores done, 7 published
 #define WAVE_DBG(slot)                                                                      \
   do {                                                                                      \
-    if (p.dbg && blockIdx.x == 0 && m == 0 && t >= 300 && t < 304)                          \
+    if (p.dbg && blockIdx.x == 0 && m == 0 && ch == 0 && t >= 300 && t < 304)               \
       p.dbg[(role * 4 + (t - 300)) * 8 + (slot)] = wgtime();                                \
   } while (0)
 
@@ -95,7 +103,9 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
   // PAIR: the split runs as TWO MMAs per K step, A_hi x [W_hi | W_lo] (width 2 * 2N: the hi and lo weight tiles of a K
   // chunk are adjacent in shared memory) and A_lo x W_hi on top of its first half; the epilogue adds the two halves
   constexpr int ACC_COLS = PAIR ? 2 * N : N;
-  constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : 256));
+  constexpr int ACC_STRIDE = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : 128);     // TMEM columns between the chunks' accumulators
+  constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static_assert(ACC_COLS <= 128, "two accumulators must fit the 512 TMEM columns (and the allocation a power of two)");
   constexpr int W_TILE = N * BK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -106,9 +116,9 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
   constexpr int HT = ROWS_C * BK * 2;                         // bytes of the hi (or lo) rows of one K chunk
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + stages * 2 * HT);
-  const uint32_t wfull = smem_u32(bars), hfull0 = wfull + 8, hempty0 = hfull0 + 8 * 8, accfull = hempty0 + 8 * 8,
-                 accempty = accfull + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  const uint32_t wfull = smem_u32(bars), hfull0 = wfull + 8, hempty0 = hfull0 + 8 * 8, accfull0 = hempty0 + 8 * 8,
+                 accempty0 = accfull0 + 16;                   // accumulator barriers: one pair per chunk
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
   const uint32_t smem_w = smem_u32(smem), smem_ring = smem_u32(ring);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,10 +129,10 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
   const long long R = (long long)p.NB * Tp;
   // every counter on a 128-byte line of its own: the pollers of one counter (ld.acquire of ~48 producer threads) and
   // the increments of another must not queue up on the same L2 line
-  unsigned int* cA = p.sync + (m * 3 + 0) * W_SYNC_STRIDE;
-  unsigned int* cB = p.sync + (m * 3 + 1) * W_SYNC_STRIDE;
-  unsigned int* cC = p.sync + (m * 3 + 2) * W_SYNC_STRIDE;
-  unsigned int* my_ctr = role == 0 ? cA : (role == 1 ? cB : cC);
+  // counters of chunk ch: p.sync + ch * 6 * W_SYNC_STRIDE + (m * 3 + {A, B, C}) * W_SYNC_STRIDE
+  unsigned int* const sync_m = p.sync + m * 3 * W_SYNC_STRIDE;
+  constexpr int CH_SYNC = 6 * W_SYNC_STRIDE;
+  const int nch = p.nch;
   const CUtensorMap* tmW = role == 0 ? &tmW0 : (role == 1 ? &tmWi : &tmW1);
   const CUtensorMap* tmH = role == 2 ? &tmHC : &tmHA;
 
@@ -136,8 +146,10 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       mbar_init(hfull0 + 8 * s, 1);
       mbar_init(hempty0 + 8 * s, 1);
     }
-    mbar_init(accfull, 1);
-    mbar_init(accempty, PAIR ? 2 * W_EPI_WARPS : W_EPI_WARPS);
+    for (int ch = 0; ch < 2; ++ch) {
+      mbar_init(accfull0 + 8 * ch, 1);
+      mbar_init(accempty0 + 8 * ch, PAIR ? 2 * W_EPI_WARPS : W_EPI_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == W_EPI_WARP0) {
@@ -168,7 +180,11 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
             tma_load_2d(tmW, wfull, smem_w + (hl * KC + kc) * W_TILE, kc * BK, ((hl * 2 + m) * NC + c) * N);
         }
       uint32_t stage = 0, phase = 0;
-      for (int t = 0; t < T; ++t) {
+      for (int t = 0; t < T; ++t)
+      for (int ch = 0; ch < nch; ++ch) {
+        const unsigned int* cA = sync_m + ch * CH_SYNC;
+        const unsigned int* cB = cA + W_SYNC_STRIDE;
+        const unsigned int* cC = cB + W_SYNC_STRIDE;
         int slot;
         if (role == 0) {            // input h0(t-1): slot (t)%4 holds h0(t-1) (h0(t) is written to slot (t+1)%4)
           wait_counter(cA, (long long)NC * t);
@@ -186,7 +202,8 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         fence_proxy_async_global();
         WAVE_DBG(0);
         const int nslot = role == 2 ? 2 : 4;
-        const int blk = ((((c % W_REP) * nslot + slot) * 2 + m) * 2);      // block index of the hi tile (lo = +1)
+        const int blk = ((((c % W_REP) * nslot + slot) * 2 + m) * 2) +     // block index of the hi tile (lo = +1)
+                        ch * (role == 2 ? p.blkC_ch : p.blkA_ch);
         for (int kc0 = 0; kc0 < KC; ++kc0) {
           const int kc = kc0;                  // same order in every CTA (measured: rotating the order does not help)
           mbar_wait(hempty0 + 8 * stage, phase ^ 1);
@@ -210,15 +227,17 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       constexpr uint32_t idesc_cat = make_idesc_mn(128, 4 * N);
       mbar_wait(wfull, 0);
       uint32_t stage = 0, phase = 0;
-      for (int t = 0; t < T; ++t) {
-        mbar_wait(accempty, (t & 1) ^ 1);
+      for (int t = 0; t < T; ++t)
+      for (int ch = 0; ch < nch; ++ch) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ch * ACC_STRIDE);
+        mbar_wait(accempty0 + 8 * ch, (t & 1) ^ 1);
         tc_fence_after();
         for (int kc0 = 0; kc0 < KC; ++kc0) {
           const int kc = kc0;
           mbar_wait(hfull0 + 8 * stage, phase);
           tc_fence_after();
           if (kc0 == 0) WAVE_DBG(2);
-          if (p.dbg && blockIdx.x == 0 && m == 0 && role == 0 && t >= 300 && t < 304 && kc0 < 8)
+          if (p.dbg && blockIdx.x == 0 && m == 0 && role == 0 && ch == 0 && t >= 300 && t < 304 && kc0 < 8)
             p.dbg[96 + (t - 300) * 8 + kc0] = wgtime();
           const uint32_t sa = smem_ring + stage * 2 * HT;
           const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + HT);
@@ -228,20 +247,20 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
             if (PAIR) {
-              umma_bf16_2sm(tmem_base, a_hi + koff, b_hi + koff, idesc_cat, (kc0 | k) != 0);   // [hi*hi | hi*lo]
-              umma_bf16_2sm(tmem_base, a_lo + koff, b_hi + koff, idesc, 1);                      // + lo*hi
+              umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc_cat, (kc0 | k) != 0);   // [hi*hi | hi*lo]
+              umma_bf16_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);                      // + lo*hi
             } else {
-              umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, (kc0 | k) != 0);
-              umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
-              umma_bf16(tmem_base, a_hi + koff, b_hi + koff, idesc, 1);
+              umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, (kc0 | k) != 0);
+              umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+              umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1);
             }
           }
           if (PAIR) umma_commit_2sm(hempty0 + 8 * stage, 3);
           else umma_commit(hempty0 + 8 * stage);
           if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
         }
-        if (PAIR) umma_commit_2sm(accfull, 3);
-        else umma_commit(accfull);
+        if (PAIR) umma_commit_2sm(accfull0 + 8 * ch, 3);
+        else umma_commit(accfull0 + 8 * ch);
         WAVE_DBG(3);
       }
     }
@@ -257,12 +276,10 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
     const int r = PAIR ? (int)rank * 64 + (tl & 63) : tl;
     const int c_own = PAIR ? (c & ~1) + (tl >> 6) : c;
     const int part = r >> 6;
-    const bool valid = (r & 63) < p.NBc;
-    const int b = p.b0 + (r & 63);                    // utterance of the whole batch (row layout, outputs)
     const int u0 = c_own * HS + half * HU;            // first hidden unit of this thread
-    float cst[HU];
+    float cst[2][HU];                                 // cell state of this thread's units, per chunk
 #pragma unroll
-    for (int j = 0; j < HU; ++j) cst[j] = 0.f;
+    for (int j = 0; j < HU; ++j) cst[0][j] = cst[1][j] = 0.f;
     float bias[4 * HU];
     if (role == 1) {
 #pragma unroll
@@ -271,7 +288,16 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         for (int j = 0; j < HU; ++j)
           bias[gt * HU + j] = __ldg(p.bias1 + ((long long)m * NC + c_own) * N + gt * HS + half * HU + j);
     }
-    for (int t = 0; t < T; ++t) {
+    // one time step of chunk CH (compile-time index: the per-chunk cell state stays in registers)
+    auto step = [&](const int t, auto CH) {
+      constexpr int ch = decltype(CH)::value;
+      const bool valid = (r & 63) < p.NBc[ch];
+      const int b = p.b0[ch] + (r & 63);              // utterance of the whole batch (row layout, outputs)
+      unsigned int* const cB = sync_m + ch * CH_SYNC + W_SYNC_STRIDE;
+      unsigned int* const my_ctr = sync_m + ch * CH_SYNC + role * W_SYNC_STRIDE;
+      const uint32_t accfull = accfull0 + 8 * ch, accempty = accempty0 + 8 * ch;
+      const uint32_t tacc = tmem_base + (uint32_t)(ch * ACC_STRIDE);
+      float* const g1x = p.g1x + ch * p.g1x_ch;
       const long long rcur = (long long)b * Tp + 1 + t;
       float gin[4 * HU];
       if (role == 0) {
@@ -298,7 +324,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         if (lane == 0) wait_counter(cB, (long long)NC * (t + 1));
         __syncwarp();
         if constexpr (VW == 4) {                      // (the wavefront roles only exist for N = 64)
-          const float* gp = p.g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
+          const float* gp = g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
 #pragma unroll
           for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
@@ -315,10 +341,10 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
 #pragma unroll
       for (int gt = 0; gt < 4; ++gt) {
         if (HU == 8) {
-          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + gt * HS + half * HU, v + gt * HU);
+          tmem_ld8(tacc + ((uint32_t)(q * 32) << 16) + gt * HS + half * HU, v + gt * HU);
         } else {                                      // 8 columns are read, the first HU kept (all inside the allocation)
           uint32_t w8[8];
-          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + gt * HS + half * HU, w8);
+          tmem_ld8(tacc + ((uint32_t)(q * 32) << 16) + gt * HS + half * HU, w8);
 #pragma unroll
           for (int j = 0; j < HU; ++j) v[gt * HU + j] = w8[j];
         }
@@ -328,10 +354,10 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
 #pragma unroll
         for (int gt = 0; gt < 4; ++gt) {
           if (HU == 8) {
-            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + N + gt * HS + half * HU, v2 + gt * HU);
+            tmem_ld8(tacc + ((uint32_t)(q * 32) << 16) + N + gt * HS + half * HU, v2 + gt * HU);
           } else {
             uint32_t w8[8];
-            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + N + gt * HS + half * HU, w8);
+            tmem_ld8(tacc + ((uint32_t)(q * 32) << 16) + N + gt * HS + half * HU, w8);
 #pragma unroll
             for (int j = 0; j < HU; ++j) v2[gt * HU + j] = w8[j];
           }
@@ -348,7 +374,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       if (role == 1) {
         // ---- layer-1 input projection: G1(t) rows -> exchange buffer slot t%4
         if constexpr (VW == 4) {
-          float* gp = p.g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
+          float* gp = g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
 #pragma unroll
           for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
@@ -368,7 +394,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
           __threadfence();
           atomicAdd(my_ctr, 1u);
         }
-        continue;
+        return;
       }
       float hn[HU];
 #pragma unroll
@@ -377,8 +403,8 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         const float fg = wsig(__uint_as_float(v[HU + j]) + gin[HU + j]);
         const float gg = wtanh(__uint_as_float(v[2 * HU + j]) + gin[2 * HU + j]);
         const float og = wsig(__uint_as_float(v[3 * HU + j]) + gin[3 * HU + j]);
-        cst[j] = fg * cst[j] + ig * gg;
-        hn[j] = og * wtanh(cst[j]);
+        cst[ch][j] = fg * cst[ch][j] + ig * gg;
+        hn[j] = og * wtanh(cst[ch][j]);
       }
       if (valid) {
         // h(t) goes to the slot the consumers of step t+1 read: (t+1)%4 for h0, (t+1)%2 for h1
@@ -386,7 +412,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         const int nslot = role == 0 ? 4 : 2;
 #pragma unroll
         for (int rep = 0; rep < W_REP; ++rep) {
-          unsigned short* hx = (role == 0 ? p.hxA : p.hxC) +
+          unsigned short* hx = (role == 0 ? p.hxA + ch * p.hxA_ch : p.hxC + ch * p.hxC_ch) +
                                (((((long long)rep * nslot + slot) * 2 + m) * 2) * W_ROWS + r) * H + u0;
 #pragma unroll
           for (int j = 0; j < HU; j += VW) {
@@ -425,6 +451,10 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
           }
         }
       }
+    };
+    for (int t = 0; t < T; ++t) {
+      step(t, std::integral_constant<int, 0>{});
+      if (nch > 1) step(t, std::integral_constant<int, 1>{});
     }
   }
 
@@ -474,6 +504,14 @@ static int launch_wave(const CUtensorMap* maps, const WaveParams& p, size_t smem
   return IDV_OK;
 }
 
+// utterances [b0, b0 + per_launch) of the batch as one or two chunks of <= 64
+static void set_chunks(WaveParams& p, int b0, int NB, int per_launch) {
+  const int n = NB - b0 < per_launch ? NB - b0 : per_launch;
+  p.nch = n > 64 ? 2 : 1;
+  p.b0[0] = b0; p.NBc[0] = n < 64 ? n : 64;
+  p.b0[1] = b0 + 64; p.NBc[1] = n > 64 ? n - 64 : 0;
+}
+
 static int wave_cols(int H) {
   // gate columns per CTA such that 6 * (H / Hs) CTAs fit the device (148 SMs): N = 64 for H = 384, 128
   if (H % 64 != 0) return 0;
@@ -491,8 +529,8 @@ extern "C" int idv_lstm2_wave_config(int H, int* n_cols, int* n_ctas, int64_t* w
   IDV_CHECK_ARG(N > 0, "idv_lstm2_wave_config: hidden size %d is not supported by the wavefront kernel", H);
   *n_cols = N;
   *n_ctas = H / (N / 4);
-  // hxA (4 slots) + hxC (2 slots) bf16 [slot][2][2][128][H]  +  g1x fp32 [4][2][128][4H]
-  *work_bytes = (int64_t)tc::W_REP * (4 + 2) * 2 * 2 * 128 * H * 2 + (int64_t)4 * 2 * 128 * 4 * H * 4;
+  // per chunk: hxA (4 slots) + hxC (2 slots) bf16 [slot][2][2][128][H]  +  g1x fp32 [4][2][128][4H]; two chunks per launch
+  *work_bytes = 2 * ((int64_t)tc::W_REP * (4 + 2) * 2 * 2 * 128 * H * 2 + (int64_t)4 * 2 * 128 * 4 * H * 4);
   return IDV_OK;
 }
 
@@ -522,16 +560,18 @@ static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off
   IDV_CHECK_ARG(stages >= 1, "idv_lstm2_wave_tc: not enough shared memory for H=%d", H);
   const size_t smem = w_bytes + (size_t)stages * stage_bytes + 1024 + 256;
   uint8_t* wk = reinterpret_cast<uint8_t*>(work);
+  // workspace: [hxA chunk 0 | hxA chunk 1][hxC chunk 0 | hxC chunk 1][g1x chunk 0 | g1x chunk 1]
   const size_t hxA_bytes = (size_t)W_REP * 4 * 2 * 2 * 128 * H * 2, hxC_bytes = (size_t)W_REP * 2 * 2 * 2 * 128 * H * 2;
+  const size_t g1x_bytes = (size_t)4 * 2 * 128 * 4 * H * 4;
   CUtensorMap maps[5];
   const void* wp[3] = {w_hh0, w_ih1, w_hh1};
   for (int i = 0; i < 3; ++i) {
     rc = encode_map_2d(&maps[i], wp[i], H, (uint64_t)2 * 2 * NC * N, BK, N);
     if (rc) return rc;
   }
-  rc = encode_map_3d(&maps[3], wk, H, W_ROWS, (uint64_t)W_REP * 4 * 2 * 2, BK, pair ? W_ROWS / 2 : W_ROWS, 2);
+  rc = encode_map_3d(&maps[3], wk, H, W_ROWS, (uint64_t)2 * W_REP * 4 * 2 * 2, BK, pair ? W_ROWS / 2 : W_ROWS, 2);
   if (rc) return rc;
-  rc = encode_map_3d(&maps[4], wk + hxA_bytes, H, W_ROWS, (uint64_t)W_REP * 2 * 2 * 2, BK, pair ? W_ROWS / 2 : W_ROWS, 2);
+  rc = encode_map_3d(&maps[4], wk + 2 * hxA_bytes, H, W_ROWS, (uint64_t)2 * W_REP * 2 * 2 * 2, BK, pair ? W_ROWS / 2 : W_ROWS, 2);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   WaveParams p;
@@ -540,8 +580,10 @@ static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off
   p.Tsteps = (t_valid > 0 && t_valid < T) ? t_valid : T;
   p.hseq1 = hseq1;
   p.hxA = reinterpret_cast<unsigned short*>(wk);
-  p.hxC = reinterpret_cast<unsigned short*>(wk + hxA_bytes);
-  p.g1x = reinterpret_cast<float*>(wk + hxA_bytes + hxC_bytes);
+  p.hxC = reinterpret_cast<unsigned short*>(wk + 2 * hxA_bytes);
+  p.g1x = reinterpret_cast<float*>(wk + 2 * hxA_bytes + 2 * hxC_bytes);
+  p.hxA_ch = (long long)(hxA_bytes / 2); p.hxC_ch = (long long)(hxC_bytes / 2); p.g1x_ch = (long long)(g1x_bytes / 4);
+  p.blkA_ch = W_REP * 4 * 2 * 2; p.blkC_ch = W_REP * 2 * 2 * 2;
   p.sync = sync;
   p.n_roles = 3; p.hsplit = nullptr; p.hseq0 = nullptr;
   p.dbg = nullptr;
@@ -550,13 +592,14 @@ static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off
     IDV_CUDA(cudaMalloc(&p.dbg, (96 + 32) * sizeof(unsigned long long)));
     IDV_CUDA(cudaMemsetAsync(p.dbg, 0, (96 + 32) * sizeof(unsigned long long), st));
   }
-  // a launch holds 64 utterances (M = 128 rows = 2 input parts x 64): larger batches run as consecutive launches on
-  // the same stream, each with freshly zeroed exchange buffers / counters (h(-1) = 0)
-  for (int b0 = 0; b0 < NB && rc == IDV_OK; b0 += 64) {
-    p.b0 = b0;
-    p.NBc = NB - b0 < 64 ? NB - b0 : 64;
+  // a chunk holds 64 utterances (M = 128 rows = 2 input parts x 64); a launch interleaves up to two chunks (128
+  // utterances); larger batches run as consecutive launches on the same stream, each with freshly zeroed exchange
+  // buffers / counters (h(-1) = 0)
+  const int per_launch = option_lstm_interleave() ? 128 : 64;
+  for (int b0 = 0; b0 < NB && rc == IDV_OK; b0 += per_launch) {
+    set_chunks(p, b0, NB, per_launch);
     IDV_CUDA(cudaMemsetAsync(work, 0, (size_t)work_bytes, st));
-    IDV_CUDA(cudaMemsetAsync(sync, 0, 6 * W_SYNC_STRIDE * sizeof(unsigned int), st));
+    IDV_CUDA(cudaMemsetAsync(sync, 0, 2 * 6 * W_SYNC_STRIDE * sizeof(unsigned int), st));
     rc = pair ? launch_wave<64, true>(maps, p, smem, st) : launch_wave<64, false>(maps, p, smem, st);
   }
   if (dbg && rc == IDV_OK) {
@@ -614,7 +657,7 @@ extern "C" int idv_lstm_layer_pair_config(int H, int* n_cols, int* n_ctas, int64
   IDV_CHECK_ARG(N > 0, "idv_lstm_layer_pair_config: hidden size %d is not supported by the CTA-pair recurrence", H);
   *n_cols = N;
   *n_ctas = H / (N / 4);
-  *work_bytes = (int64_t)4 * 2 * 2 * 128 * H * 2;          // h exchange buffer: bf16 [4 slots][2 m][2 hl][128][H]
+  *work_bytes = 2 * (int64_t)4 * 2 * 2 * 128 * H * 2;      // h exchange buffers: bf16 [2 chunks][4 slots][2 m][2 hl][128][H]
   return IDV_OK;
 }
 
@@ -649,7 +692,7 @@ extern "C" int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g
     CUtensorMap maps[5];
     rc = encode_map_2d(&maps[0], wpack, H, (uint64_t)2 * 2 * NC * N, BK, N);
     if (rc) return rc;
-    rc = encode_map_3d(&maps[3], work, H, W_ROWS, (uint64_t)4 * 2 * 2, BK, pair ? W_ROWS / 2 : W_ROWS, 2);
+    rc = encode_map_3d(&maps[3], work, H, W_ROWS, (uint64_t)2 * 4 * 2 * 2, BK, pair ? W_ROWS / 2 : W_ROWS, 2);
     if (rc) return rc;
     maps[1] = maps[0]; maps[2] = maps[0]; maps[4] = maps[3];
     WaveParams p;
@@ -658,14 +701,16 @@ extern "C" int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g
     p.Tsteps = (t_valid > 0 && t_valid < T) ? t_valid : T;
     p.hseq1 = nullptr;
     p.hxA = reinterpret_cast<unsigned short*>(work); p.hxC = nullptr; p.g1x = nullptr;
+    p.hxA_ch = (long long)4 * 2 * 2 * 128 * H; p.hxC_ch = 0; p.g1x_ch = 0;
+    p.blkA_ch = 4 * 2 * 2; p.blkC_ch = 0;
     p.sync = sync; p.dbg = nullptr;
     p.n_roles = 1; p.hsplit = reinterpret_cast<unsigned short*>(hsplit); p.hseq0 = hseq;
     rc = IDV_OK;
-    for (int b0 = 0; b0 < NB && rc == IDV_OK; b0 += 64) {
-      p.b0 = b0;
-      p.NBc = NB - b0 < 64 ? NB - b0 : 64;
+    const int per_launch = option_lstm_interleave() ? 128 : 64;
+    for (int b0 = 0; b0 < NB && rc == IDV_OK; b0 += per_launch) {
+      set_chunks(p, b0, NB, per_launch);
       IDV_CUDA(cudaMemsetAsync(work, 0, (size_t)work_bytes, st));
-      IDV_CUDA(cudaMemsetAsync(sync, 0, 6 * W_SYNC_STRIDE * sizeof(unsigned int), st));
+      IDV_CUDA(cudaMemsetAsync(sync, 0, 2 * 6 * W_SYNC_STRIDE * sizeof(unsigned int), st));
       if (N == 64) rc = pair ? launch_wave<64, true>(maps, p, smem, st) : launch_wave<64, false>(maps, p, smem, st);
       else rc = pair ? launch_wave<48, true>(maps, p, smem, st) : launch_wave<48, false>(maps, p, smem, st);
       if (rc == IDV_E_RESOURCE && b0 == 0) break;

@@ -268,7 +268,7 @@ def lstm_recurrent_tc(g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, want_f32=True,
         if g.is_cuda:
             lib.check_exclusive_device(g.device.index if g.device.index is not None else torch.cuda.current_device())
         work = torch.empty(int(cfg[3]), dtype=torch.uint8, device=g.device)
-        sync = torch.empty(192, dtype=torch.int32, device=g.device)
+        sync = torch.empty(384, dtype=torch.int32, device=g.device)
         lib.call("idv_lstm_layer_pair_tc", g, g_m_off, g_p_off, g_ld, wpack, NB, T, H, hseq, hsplit, work, sync,
                  int(t_valid))
         return hseq, hsplit
@@ -294,7 +294,7 @@ def lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T,
         lib.check_exclusive_device(g0.device.index if g0.device.index is not None else torch.cuda.current_device())
     hseq = _empty(4 * NB * (T + 1) * H, g0.device)
     work = torch.empty(int(work_bytes), dtype=torch.uint8, device=g0.device)
-    sync = torch.empty(192, dtype=torch.int32, device=g0.device)
+    sync = torch.empty(384, dtype=torch.int32, device=g0.device)
     lib.call("idv_lstm2_wave_tc", g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq, work, sync,
              int(t_valid))
     return hseq

@@ -98,8 +98,9 @@ def config2b(device, rank=0, batch=64, seconds=4):
                             "batch_per_gpu": batch, "utterance_s": seconds, "H": 768, "real_skip": True}
 
 
-def config3(device, world=1, rank=0, total_batch=256, seconds=10, chunk=64):
-    """Strong scaling: the 256 utterances are split over the ranks; a rank runs its shard in passes of <= ``chunk``."""
+def config3(device, world=1, rank=0, total_batch=256, seconds=10, chunk=128):
+    """Strong scaling: the 256 utterances are split over the ranks; a rank runs its shard in passes of <= ``chunk``
+    utterances (128: two 64-utterance LSTM chunks interleaved in one launch; ~75 GB of activations per pass)."""
     m = M.DCCRN_(NFFT, HOP, get_net_params(True), True, device, WIN, SKIPS, "mask", False, None, None)
     m.load_state_dict(fill_state_dict(m.state_dict(), 5), strict=True)
     m = m.to(device).eval()

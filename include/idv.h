@@ -209,17 +209,18 @@ int idv_lstm_recurrent_tc(const float* g, int64_t g_m_off, int64_t g_p_off, int 
  * input projection, without materialising the layer-1 gate pre-activations.  g0: layer-0 input projection
  * (as for idv_lstm_recurrent_tc).  w_hh0 / w_ih1 / w_hh1: packs in the layout of idv_lstm_recurrent_tc's wpack
  * with (n_cols, n_ctas) from idv_lstm2_wave_config; bias1: fp32 [2][n_ctas][n_cols] = b_ih_l1 + b_hh_l1 in the
- * same CTA-major order.  hseq1: fp32 [4][R][H] layer-1 output.  work: work_bytes workspace, sync: 192 x uint32 (6
- * step counters, one 128-byte line each)
- * (both zeroed by the call).  Any NB (chunks of 64 utterances run as consecutive launches); 6 * n_ctas CTAs must be
- * co-resident.                                                                                                  */
+ * same CTA-major order.  hseq1: fp32 [4][R][H] layer-1 output.  work: work_bytes workspace, sync: 384 x uint32 (2 chunks x
+ * 6 step counters, one 128-byte line each)
+ * (both zeroed by the call).  Any NB: a launch interleaves up to two chunks of 64 utterances (two independent
+ * recurrences in the same CTAs; option "lstm_interleave"), larger batches run as consecutive launches; 6 * n_ctas CTAs
+ * must be co-resident.                                                                                                  */
 int idv_lstm2_wave_config(int H, int* n_cols, int* n_ctas, int64_t* work_bytes);
 int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
                       const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
                       float* hseq1, void* work, unsigned int* sync, int t_valid, void* stream);
 /* ONE nn.LSTM layer of both modules per launch as CTA pairs (the kernel of idv_lstm2_wave_tc restricted to its first
  * role): same contract as idv_lstm_recurrent_tc, wpack packed with (n_cols, n_ctas) from idv_lstm_layer_pair_config
- * (H = 768: 48 gate columns x 64 CTAs per module).  work: work_bytes workspace, sync: 192 x uint32 (both zeroed by the
+ * (H = 768: 48 gate columns x 64 CTAs per module).  work: work_bytes workspace, sync: 384 x uint32 (both zeroed by the
  * call).  Any NB (chunks of 64 utterances run as consecutive launches).                                          */
 int idv_lstm_layer_pair_config(int H, int* n_cols, int* n_ctas, int64_t* work_bytes);
 int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* wpack, int NB, int T,

@@ -536,7 +536,7 @@ def test_lstm_layer_pair_tc(NB, T, H, tv, pairs):
     hseq = torch.zeros(4, R, H)
     hsplit = torch.zeros(2 * 4 * R * H, dtype=torch.bfloat16)
     work = torch.zeros(work_bytes, dtype=torch.uint8)
-    sync = torch.zeros(192, dtype=torch.int32)
+    sync = torch.zeros(384, dtype=torch.int32)
     args = [g, 4 * H, R * 8 * H, 8 * H, wp, NB, T, H, hseq, hsplit, work, sync, tv]
     lib.set_option("lstm_wave_cta_pairs", pairs)
     try:
@@ -595,9 +595,23 @@ def test_lstm2_wave_tc(NB, T, H, tv):
     b1 = PK.pack_lstm_bias_tc(mods[0], mods[1], 1, n_cols, n_ctas, "cpu")
     hseq = torch.zeros(4, R, H)
     work = torch.zeros(work_bytes, dtype=torch.uint8)
-    sync = torch.zeros(192, dtype=torch.int32)
+    sync = torch.zeros(384, dtype=torch.int32)
     args = [g, 4 * H, R * 8 * H, 8 * H, w0, wi, w1, b1, NB, T, H, hseq, work, sync, tv]
     assert _both("idv_lstm2_wave_tc", args, [11]) < 2e-5
+
+
+@pytest.mark.parametrize("interleave", [1, 0])
+@pytest.mark.parametrize("NB,T,H", [(128, 9, 384), (70, 12, 128), (200, 4, 384)])
+def test_lstm2_wave_tc_two_interleaved_chunks(NB, T, H, interleave):
+    """More than 64 utterances: two chunks of 64 run as two interleaved recurrences inside one launch
+    (lstm_interleave = 1, default) or as consecutive launches (0): same numbers either way, and the same as the contract."""
+    lib.set_option("lstm_interleave", interleave)
+    try:
+        test_lstm2_wave_tc(NB, T, H, 0)
+        if H == 384:
+            test_lstm_layer_pair_tc(NB, T, 768, 0, 1)
+    finally:
+        lib.set_option("lstm_interleave", 1)
 
 
 @pytest.mark.parametrize("B,L", [(1, 300), (3, 6400), (2, 12799)])

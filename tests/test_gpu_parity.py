@@ -209,11 +209,12 @@ def test_full_size_batch_rows_match_small_oracle_run(gemm_mode):
     assert wave < WAVE_TOL and mu < WAVE_TOL and gap < 0.01
 
 
-@pytest.mark.parametrize("B", [32, 64])
+@pytest.mark.parametrize("B", [32, 64, 128])
 def test_dccrn_config3_full_length_rows_match_oracle(B):
     """BASELINE config 3 shape: supervised DCCRN_ (causal, mask head, real skips, H = 128) on 10-s utterances
     (L = 160 000, T = 1 601 frames: 1 603 dependent steps of the wavefront LSTM), at the per-GPU shard sizes of the
-    8- and 4-GPU split (32 / 64 utterances).  Rows {0, last} of the CUDA run against the live oracle on those rows
+    8-, 4- and 2-GPU split (32 / 64 / 128 utterances; 128 = two 64-utterance LSTM chunks interleaved in one launch).
+    Rows {0, last} of the CUDA run against the live oracle on those rows
     (supervised_dccrn/test.py:L129,L413; model/pvae_module.py:L200-255)."""
     seed, L = 31, 160000
     m = M.DCCRN_(C.NFFT, C.HOP, M.get_net_params(True), True, "cuda", C.WIN, C.SKIPS, "mask", False, None, None)
