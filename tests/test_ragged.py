@@ -119,3 +119,23 @@ def test_si_sdr_emulated(emulated_abi):
 @pytest.mark.gpu
 def test_si_sdr_gpu():
     run_si_sdr("cuda")
+
+
+def test_estoi_properties():
+    import numpy as np
+    """metrics.stoi restates the published (E)STOI algorithm (pystoi is not in the image: parity unpinned): identical
+    signals score 1, the score falls monotonically with the noise level, and resampling to 10 kHz is part of it."""
+    from idccrn_b200 import metrics
+    rng = np.random.default_rng(0)
+    t = np.arange(48000) / 16000.0
+    x = (np.sin(2 * np.pi * 3 * t) ** 2) * rng.standard_normal(48000)          # amplitude-modulated noise ("speech-like")
+    assert abs(metrics.stoi(x, x, 16000, True) - 1.0) < 1e-9 and abs(metrics.stoi(x, x, 16000, False) - 1.0) < 1e-9
+    prev_e, prev_s = 1.0, 1.0
+    for snr in (30, 10, 0, -10):
+        n = rng.standard_normal(48000) * np.sqrt((x ** 2).mean() / 10 ** (snr / 10))
+        e, s_ = metrics.stoi(x, x + n, 16000, True), metrics.stoi(x, x + n, 16000, False)
+        assert e < prev_e and s_ <= prev_s and -0.1 < e < 1.0
+        prev_e, prev_s = e, s_
+    assert prev_e < 0.2
+    with pytest.raises(ValueError):
+        metrics.stoi(x[:2000], x[:2000], 16000)                                  # fewer than 30 non-silent frames
