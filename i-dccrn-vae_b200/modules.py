@@ -36,6 +36,39 @@ def _sd(module):
     return dict(module.state_dict(keep_vars=True))
 
 
+class _SlopeCache:
+    """PReLU slopes are kernel ARGUMENTS (floats), so reading one is a device -> host copy that drains the GPU queue.  A
+    training step changes every slope, and reading them block by block (13 syncs per step, each followed by that block's
+    host-side weight re-packing with an empty queue) left the GPU idle for a fifth of the step.  All blocks register
+    here; the first stale read refreshes EVERY stale block on that device with ONE copy."""
+
+    def __init__(self):
+        import weakref
+        self.blocks = weakref.WeakSet()
+
+    @staticmethod
+    def _stamp(block):
+        w = block.prelu.weight
+        return (w.data_ptr(), w._version)
+
+    def get(self, block):
+        c = block.__dict__.get("_slope_cached")
+        if c is not None and c[0] == self._stamp(block):
+            return c[1]
+        dev = block.prelu.weight.device
+        stale = [b for b in self.blocks if b.prelu.weight.device == dev and
+                 (b.__dict__.get("_slope_cached") is None or b.__dict__["_slope_cached"][0] != self._stamp(b))]
+        if all(b is not block for b in stale):
+            stale.append(block)
+        vals = torch.stack([b.prelu.weight.detach().reshape(-1)[0] for b in stale]).cpu().tolist()
+        for b, v in zip(stale, vals):
+            b.__dict__["_slope_cached"] = (self._stamp(b), float(v))
+        return block.__dict__["_slope_cached"][1]
+
+
+_SLOPES = _SlopeCache()
+
+
 class _PackCache:
     """Caches packed operands; rebuilt when any watched parameter/buffer changes identity or version."""
 
@@ -482,9 +515,10 @@ class Encoder(nn.Module):
         self.bn = ComplexBatchNormal(chw[0], chw[1], chw[2])
         self.prelu = nn.PReLU()
         self._cache = _PackCache()
+        _SLOPES.blocks.add(self)
 
     def _slope(self):
-        return float(self.prelu.weight.detach().reshape(-1)[0])
+        return _SLOPES.get(self)
 
     def forward_from_stft(self, stft_x, train=False, out=None, prev=None, raw_only=False, rows=None):
         """First layer (in_channel == 1): reads the user-layout STFT (B, F, T, 2) directly.  out / prev: streaming
@@ -547,9 +581,10 @@ class Decoder(nn.Module):
         self.prelu = nn.PReLU()
         self.if_bn = if_bn
         self._cache = _PackCache()
+        _SLOPES.blocks.add(self)
 
     def _slope(self):
-        return float(self.prelu.weight.detach().reshape(-1)[0])
+        return _SLOPES.get(self)
 
     def _fold(self):
         return (self.bn.fold_inputs(), self._slope()) if self.if_bn else (None, None)
