@@ -19,6 +19,36 @@ def round8(c):
     return (c + 7) // 8 * 8
 
 
+_TABLES = {}
+
+
+def dev_table(rows, device):
+    """int32 [n][6] unit / tap table on ``device``.  Tables depend on the layer geometry only, not on the weights, but a
+    training step re-packs every layer - and a host -> device copy from pageable memory blocks the host until every
+    kernel queued before it has run (188 such copies made one training step host-bound).  Identical tables are therefore
+    uploaded once per device and shared."""
+    import array
+    flat = array.array("i", [int(v) for r in rows for v in r])
+    key = (str(device), flat.tobytes())
+    t = _TABLES.get(key)
+    if t is None:
+        if len(_TABLES) > 4096:
+            _TABLES.clear()
+        t = _TABLES[key] = torch.tensor(flat, dtype=torch.int32).reshape(-1, 6).to(device)
+    return t
+
+
+_ZEROS = {}
+
+
+def dev_zeros(n, device):
+    """Shared read-only fp32 zero vector (bias of the gradient packs) - no host -> device copy per pack."""
+    key = (str(device), int(n))
+    if key not in _ZEROS:
+        _ZEROS[key] = torch.zeros(int(n), dtype=torch.float32, device=device)
+    return _ZEROS[key]
+
+
 PAIR_PLANES = [os.environ.get("IDV_PAIR_PLANES", "1") != "0"]   # narrow (transposed) convs: 256 / N output planes per tensor-core tile (TapGemmPack._tc_paired)
 
 
@@ -26,10 +56,10 @@ class TapGemmPack:
     """Operands of one idv_tapgemm_* launch (weights, bias, unit/tap tables)."""
 
     def __init__(self, w, bias, units, taps, N, out_planes, out_ld, prelu, slope, device):
-        self.w = w.to(device=device, dtype=torch.float32).contiguous()
+        self.w = w.to(device=device, dtype=torch.float32).contiguous()          # (no copy / no sync when already there)
         self.bias = bias.to(device=device, dtype=torch.float32).contiguous()
-        self.units = torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(device)
-        self.taps = torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(device)
+        self.units = dev_table(units, device)
+        self.taps = dev_table(taps, device)
         self.n_units = len(units)
         self.N = N
         self.out_planes = out_planes
@@ -71,8 +101,8 @@ class TapGemmPack:
                 ks = sum(t[4] // 64 for t in self._taps_l[u[0]:u[0] + u[1]])
                 units.append([u[0], u[1], u[2], u[3], u[4], ks])
             self._tc = dict(wt=torch.stack((hi, lo)).contiguous().to(dev), kc_max=kc_max, n_slots=len(slots),
-                            taps=torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(dev),
-                            units=torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(dev))
+                            taps=dev_table(taps, dev),
+                            units=dev_table(units, dev))
         return self._tc
 
 
@@ -179,8 +209,8 @@ def _tc_paired(self, w, dev):
     hi = wt.to(torch.bfloat16)
     lo = (wt - hi.to(torch.float32)).to(torch.bfloat16)
     return dict(wt=torch.stack((hi, lo)).contiguous().to(dev), kc_max=kc_max, n_slots=len(slots),
-                taps=torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(dev),
-                units=torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(dev),
+                taps=dev_table(taps, dev),
+                units=dev_table(units, dev),
                 N=NG, n_units=len(units), bias=torch.cat([self.bias] * G).contiguous())
 
 
@@ -462,7 +492,8 @@ def pack_dec5_tc(w10, bias2, slope, f_in, kcs, device, bins=None):
     bins = HEAD_BINS[0] if bins is None else bins
     if not 1 <= bins <= 16 or bins % 2:
         raise ValueError("bins per head unit must be even and <= 16")
-    w10 = w10.detach().cpu().to(torch.float32)
+    w10 = _cpu(w10).to(torch.float32)
+    wdev = w10.device
     N = 32
     ksum = sum(kcs)
     assert w10.shape == (10, ksum, 2) and all(k % 64 == 0 for k in kcs)
@@ -477,7 +508,7 @@ def pack_dec5_tc(w10, bias2, slope, f_in, kcs, device, bins=None):
         ks = slice(k_off[si], k_off[si + 1])
         for d in offs:
             for kt in range(2):
-                W = torch.zeros(N, kc_max)
+                W = torch.zeros(N, kc_max, device=wdev)
                 for e in range(bins):
                     kf = e + 2 - 2 * d
                     if 0 <= kf < 5:
@@ -504,11 +535,11 @@ def pack_dec5_tc(w10, bias2, slope, f_in, kcs, device, bins=None):
                     taps.append([si, fi, kt, 0, kcs[si], slot_id[(si, d, kt)]])
         ks = sum(t[4] // 64 for t in taps[begin:])
         units.append([begin, len(taps) - begin, fo0, nb, 0, ks])
-    bias = torch.zeros(N)
-    bias[0:2] = bias2.detach().cpu().to(torch.float32)
+    bias = torch.zeros(N, device=wdev)
+    bias[0:2] = _cpu(bias2).to(torch.float32)
     return dict(wt=torch.stack((hi, lo)).contiguous().to(device), kc_max=kc_max, n_slots=len(slots),
-                taps=torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(device),
-                units=torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(device), n_units=n_units,
+                taps=dev_table(taps, device),
+                units=dev_table(units, device), n_units=n_units,
                 bias=bias.to(device), slope=float(slope), N=N)
 
 
@@ -649,8 +680,9 @@ def pack_dense(w_read, b_read, w_imag, b_imag, c_out, f_out, device):
     zdim = w_read.shape[1]
     ch_z, ch_c = round8(zdim), round8(c_out)
     N = ch_c
-    W = torch.zeros(2, f_out, ch_z, N, dtype=torch.float64)
-    bias = torch.zeros(2, f_out, N, dtype=torch.float64)
+    dev = _cpu(w_read).device
+    W = torch.zeros(2, f_out, ch_z, N, dtype=torch.float64, device=dev)
+    bias = torch.zeros(2, f_out, N, dtype=torch.float64, device=dev)
     for part, (w, b) in enumerate(((w_read, b_read), (w_imag, b_imag))):
         w = _cpu(w).double().reshape(c_out, f_out, zdim)             # [c][f][k]
         W[part, :, :zdim, :c_out] = w.permute(1, 2, 0)
@@ -794,7 +826,7 @@ def pack_conv_dgrad(conv_re_w, conv_im_w, f_in, stride_f, pad_f, pad_t, device):
             for kt in range(kw):
                 taps.append([0, fo, -(pad_t - kt), 0, K, (kf * kw + kt) * K * N])
         units.append([begin, len(taps) - begin, fi, 0, 0, 0])
-    p = TapGemmPack(Wt.reshape(-1), torch.zeros(N), units, taps, N, f_in, N, False, 0.0, device)
+    p = TapGemmPack(Wt.reshape(-1), dev_zeros(N, device), units, taps, N, f_in, N, False, 0.0, device)
     p.f_out, p.c_out = f_in, cin
     return p
 
@@ -833,8 +865,8 @@ def wgrad_conv_tables(f_in, f_out, kh, kw, stride_f, pad_f, pad_t, rpad, groups,
                 if len(taps) == begin:
                     raise RuntimeError("empty weight-gradient unit (kf %d, group %d)" % (kf, g))
                 units.append([begin, len(taps) - begin, len(units), 0, 0, (len(taps) - begin) * (rpad // 64)])
-    return (torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(device),
-            torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(device), len(units), groups)
+    return (dev_table(units, device),
+            dev_table(taps, device), len(units), groups)
 
 
 def unfold_conv_wgrad(dwt, kh, kw, cin, cout, transposed=False):
@@ -869,7 +901,7 @@ def pack_convT_dgrad(t_re_w, t_im_w, c0, cn, f_in, stride_f, pad_f, device):
             for kt in range(kw):
                 taps.append([0, fo, -kt, 0, K, (kf * kw + kt) * K * N])
         units.append([begin, len(taps) - begin, fi, 0, 0, 0])
-    p = TapGemmPack(Wt.reshape(-1), torch.zeros(N), units, taps, N, f_in, N, False, 0.0, device)
+    p = TapGemmPack(Wt.reshape(-1), dev_zeros(N, device), units, taps, N, f_in, N, False, 0.0, device)
     p.f_out, p.c_out = f_in, cn
     return p
 
@@ -889,7 +921,7 @@ def pack_dense_dgrad(w_read, w_imag, c_out, f_out, device):
         for f in range(f_out):
             taps.append([0, f, 0, part * ch_c, ch_c, (part * f_out + f) * ch_c * ch_z])
         units.append([begin, f_out, 0, part * ch_z, 0, 0])
-    return TapGemmPack(W.reshape(-1), torch.zeros(ch_z), units, taps, ch_z, 1, 2 * ch_z, False, 0.0, device)
+    return TapGemmPack(W.reshape(-1), dev_zeros(ch_z, device), units, taps, ch_z, 1, 2 * ch_z, False, 0.0, device)
 
 
 def wgrad_dense_tables(f_out, rpad, device):
@@ -901,8 +933,8 @@ def wgrad_dense_tables(f_out, rpad, device):
         for part in range(2):
             taps.append([0, f, 0, 0, rpad, part])
             units.append([len(taps) - 1, 1, len(units), 0, 0, ks])
-    return (torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(device),
-            torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(device), len(units))
+    return (dev_table(units, device),
+            dev_table(taps, device), len(units))
 
 
 def pack_lstm_gates(lstm_re, lstm_im, hidden, layer, c_in, f_in, device):
@@ -987,7 +1019,7 @@ def pack_lstm_dgrad(lstm_re, lstm_im, hidden, layer, kind, device, c_in=0, f_in=
                 for m in range(2):
                     taps.append([0, m * 2 + p, 0, 0, K, (m * f_in + f) * K * ch])
                 units.append([begin, 2, f, p * ch, 0, 0])
-        return TapGemmPack(torch.cat(mats), torch.zeros(ch), units, taps, ch, f_in, 2 * ch, False, 0.0, device)
+        return TapGemmPack(torch.cat(mats), dev_zeros(ch, device), units, taps, ch, f_in, 2 * ch, False, 0.0, device)
     mats, units, taps = [], [], []
     for m, mod in enumerate((lstm_re, lstm_im)):
         mats.append(_cpu(mod["weight_%s_l%d" % (kind, layer)]).double().reshape(-1))       # (4H, H) = [K][N]
@@ -999,12 +1031,12 @@ def pack_lstm_dgrad(lstm_re, lstm_im, hidden, layer, kind, device, c_in=0, f_in=
             for m in range(2):
                 taps.append([0, m, 0, j * kc, kc, m * K * H + j * kc * H])
                 units.append([len(taps) - 1, 1, j * 2 + m, 0, 0, 0])
-        return TapGemmPack(torch.cat(mats), torch.zeros(H), units, taps, H, 2 * split_k, H, False, 0.0, device)
+        return TapGemmPack(torch.cat(mats), dev_zeros(H, device), units, taps, H, 2 * split_k, H, False, 0.0, device)
     for m in range(2):
         for p in range(2):
             taps.append([0, m * 2 + p, 0, 0, K, m * K * H])
             units.append([len(taps) - 1, 1, m * 2 + p, 0, 0, 0])
-    return TapGemmPack(torch.cat(mats), torch.zeros(H), units, taps, H, 4, H, False, 0.0, device)
+    return TapGemmPack(torch.cat(mats), dev_zeros(H, device), units, taps, H, 4, H, False, 0.0, device)
 
 
 def wgrad_lstm_tables(rpad, device, f_in=0):
@@ -1026,5 +1058,5 @@ def wgrad_lstm_tables(rpad, device, f_in=0):
                 for p in range(2):
                     taps.append([0, m * 2 + p, 0, 0, rpad, f * 2 + p])
                 units.append([begin, 2, m * f_in + f, 0, 0, 2 * ks])
-    return (torch.tensor(units, dtype=torch.int32).reshape(-1, 6).to(device),
-            torch.tensor(taps, dtype=torch.int32).reshape(-1, 6).to(device), len(units))
+    return (dev_table(units, device),
+            dev_table(taps, device), len(units))
