@@ -84,16 +84,23 @@ class TapGemmPack:
             if getattr(self, "pair_planes", False):
                 self._tc = self._tc_paired(w, dev)
                 return self._tc
-            slots, taps = {}, []
             kc_max = max(t[4] for t in self._taps_l)
-            for t in self._taps_l:
-                key = (t[5], t[4])
-                if key not in slots:
-                    slots[key] = len(slots)
-                taps.append([t[0], t[1], t[2], t[3], t[4], slots[key]])
+            # slot ids in (K width, weight offset) order: the slots of one K width whose blocks follow one another in
+            # ``w`` (the usual case: tap blocks of one source) are then filled by ONE strided view instead of one copy
+            # per slot - a training step re-packs every layer, and every tiny torch op is ~15 us of host time
+            keys = sorted({(t[4], t[5]) for t in self._taps_l})
+            slots = {(w_off, kc): i for i, (kc, w_off) in enumerate(keys)}
+            taps = [[t[0], t[1], t[2], t[3], t[4], slots[(t[5], t[4])]] for t in self._taps_l]
             wt = torch.zeros(len(slots), self.N, kc_max, dtype=torch.float32, device=w.device)
-            for (w_off, kc), si in slots.items():
-                wt[si, :, :kc] = w[w_off:w_off + kc * self.N].view(kc, self.N).t()
+            i = 0
+            while i < len(keys):
+                kc, o0 = keys[i]
+                blk = kc * self.N
+                j = i + 1
+                while j < len(keys) and keys[j] == (kc, o0 + (j - i) * blk):
+                    j += 1
+                wt[i:j, :, :kc] = w.as_strided((j - i, kc, self.N), (blk, self.N, 1), w.storage_offset() + o0).transpose(1, 2)
+                i = j
             hi = wt.to(torch.bfloat16)
             lo = (wt - hi.to(torch.float32)).to(torch.bfloat16)
             units = []
@@ -126,8 +133,8 @@ def cbn_fold(bn):
 
 
 def _identity_fold(C, device="cpu"):
-    Z = torch.eye(2, dtype=torch.float64, device=device).repeat(C, 1, 1)
-    return Z, torch.zeros(C, 2, dtype=torch.float64, device=device)
+    """(Z, b') of "no ComplexBatchNormal": None selects _block_weights' copy-only path."""
+    return None, None
 
 
 def _block_weights(m_re, m_im, b_re, b_im, Z, bprime, ch_in, ch_out):
@@ -135,6 +142,18 @@ def _block_weights(m_re, m_im, b_re, b_im, Z, bprime, ch_in, ch_out):
     Returns W (taps, 2*ch_in, 2*ch_out) and bias (2*ch_out) with the 2x2 fold applied.
     Raw block: y_re = m_re x_re - m_im x_im, y_im = m_re x_im + m_im x_re (complex_progress.py:L17-19)."""
     taps, cin, cout = m_re.shape
+    if Z is None:
+        # no fold (the training path keeps ComplexBatchNormal separate): the four blocks are copies of +-m_re / +-m_im -
+        # a handful of ops in the weights' own precision instead of the fp64 fold arithmetic (re-done every step)
+        W = torch.zeros(taps, 2 * ch_in, 2 * ch_out, dtype=torch.float64, device=m_re.device)
+        W[:, :cin, :cout] = m_re
+        W[:, ch_in:ch_in + cin, :cout] = -m_im
+        W[:, :cin, ch_out:ch_out + cout] = m_im
+        W[:, ch_in:ch_in + cin, ch_out:ch_out + cout] = m_re
+        bias = torch.zeros(2 * ch_out, dtype=torch.float64, device=m_re.device)
+        bias[:cout] = b_re - b_im
+        bias[ch_out:ch_out + cout] = b_re + b_im
+        return W, bias
     m_re, m_im = m_re.double(), m_im.double()
     zrr, zri, zir, zii = (Z[:, 0, 0], Z[:, 0, 1], Z[:, 1, 0], Z[:, 1, 1])
     W = torch.zeros(taps, 2 * ch_in, 2 * ch_out, dtype=torch.float64, device=m_re.device)
@@ -503,19 +522,25 @@ def pack_dec5_tc(w10, bias2, slope, f_in, kcs, device, bins=None):
     kc_max = max(kcs)
     f_out = 2 * f_in - 1
     offs = list(range(-1, bins // 2 + 1))                  # input plane = fo0/2 + d
-    slots, slot_id = [], {}
+    slot_id = {}
     for si in range(len(kcs)):
-        ks = slice(k_off[si], k_off[si + 1])
         for d in offs:
             for kt in range(2):
-                W = torch.zeros(N, kc_max, device=wdev)
-                for e in range(bins):
-                    kf = e + 2 - 2 * d
-                    if 0 <= kf < 5:
-                        W[2 * e:2 * e + 2, :kcs[si]] = w10[kf * 2 + kt, ks].t()
-                slot_id[(si, d, kt)] = len(slots)
-                slots.append(W)
-    wt = torch.stack(slots)
+                slot_id[(si, d, kt)] = len(slot_id)
+    # wt[slot][2e + part][k] = w10[kf*2 + kt][k_off[si] + k][part] with kf = e + 2 - 2d: ONE gather through an index
+    # table that depends on the geometry only (kept on the device: a training step re-packs this layer every step)
+    gkey = ("dec5_tc", bins, tuple(kcs), str(wdev))
+    if gkey not in _TABLES:
+        idx = torch.full((len(slot_id), N, kc_max), 10 * ksum * 2, dtype=torch.int64)       # -> the appended zero
+        for (si, d, kt), sl in slot_id.items():
+            k = torch.arange(kcs[si])
+            for e in range(bins):
+                kf = e + 2 - 2 * d
+                if 0 <= kf < 5:
+                    for part in range(2):
+                        idx[sl, 2 * e + part, :kcs[si]] = ((kf * 2 + kt) * ksum + k_off[si] + k) * 2 + part
+        _TABLES[gkey] = idx.to(wdev)
+    wt = torch.cat((w10.reshape(-1), w10.new_zeros(1)))[_TABLES[gkey]]
     hi = wt.to(torch.bfloat16)
     lo = (wt - hi.to(torch.float32)).to(torch.bfloat16)
     n_units = (f_out + bins - 1) // bins
@@ -537,7 +562,7 @@ def pack_dec5_tc(w10, bias2, slope, f_in, kcs, device, bins=None):
         units.append([begin, len(taps) - begin, fo0, nb, 0, ks])
     bias = torch.zeros(N, device=wdev)
     bias[0:2] = _cpu(bias2).to(torch.float32)
-    return dict(wt=torch.stack((hi, lo)).contiguous().to(device), kc_max=kc_max, n_slots=len(slots),
+    return dict(wt=torch.stack((hi, lo)).contiguous().to(device), kc_max=kc_max, n_slots=len(slot_id),
                 taps=dev_table(taps, device),
                 units=dev_table(units, device), n_units=n_units,
                 bias=bias.to(device), slope=float(slope), N=N)

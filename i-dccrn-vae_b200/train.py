@@ -879,11 +879,8 @@ class FlatAdam(torch.optim.Optimizer):
         a, b = self.views[idx[0]][0], self.views[idx[-1]][0] + self.views[idx[-1]][1]
         if any(not (e <= a or s >= b) for s, e, _, _ in self._inflight):
             return
-        stamp = []
-        for i in idx:
-            p, (off, k) = self.live[i], self.views[i]
-            self.gflat[off:off + k].copy_(p.grad.reshape(-1))
-            stamp.append((p, p.grad, p.grad._version))
+        torch.cat([self.live[i].grad.reshape(-1) for i in idx], out=self.gflat[a:b])       # one gather for the run
+        stamp = [(self.live[i], self.live[i].grad, self.live[i].grad._version) for i in idx]
         work = torch.distributed.all_reduce(self.gflat[a:b], group=self.group, async_op=True)
         self._inflight.append((a, b, work, stamp))
         self.overlapped_elements += b - a
@@ -908,9 +905,17 @@ class FlatAdam(torch.optim.Optimizer):
         if rebuilt:
             self._build(live)
         done = lambda off: any(a <= off < b for a, b in valid)
-        for p, (off, k) in zip(self.live, self.views):
-            if not done(off):
-                self.gflat[off:off + k].copy_(p.grad.reshape(-1))
+        i = 0
+        while i < len(self.live):                    # one gather (torch.cat) per run of parameters still to be copied
+            if done(self.views[i][0]):
+                i += 1
+                continue
+            j = i
+            while j + 1 < len(self.live) and not done(self.views[j + 1][0]):
+                j += 1
+            a, b = self.views[i][0], self.views[j][0] + self.views[j][1]
+            torch.cat([p.grad.reshape(-1) for p in self.live[i:j + 1]], out=self.gflat[a:b])
+            i = j + 1
         if self.group is not None and self.world > 1:
             # reduce the runs of the bucket that were not reduced during the backward pass
             n, pos = self.gflat.numel(), 0
