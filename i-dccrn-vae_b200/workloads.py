@@ -143,6 +143,12 @@ def config4(device, world=1, rank=0, group=None, batch=32, seconds=4, latent_num
                    world_size=world)
     L = int(seconds * FS)
     xs = [synth_waveform(batch, L, seed=100 * rank + j).to(device) for j in range(3)]
+    # the step is GPU-bound by a small margin (host ~60 ms ahead of 168 ms of kernels): a full (generation-2) garbage
+    # collection over the long-lived module / pack objects is a 60-100 ms host pause that stalls the GPU every few steps.
+    # Freezing what exists now keeps later collections to the per-step garbage.
+    import gc
+    gc.collect()
+    gc.freeze()
 
     def step():
         with torch.no_grad():
