@@ -11,7 +11,7 @@ import idccrn_b200  # noqa: F401
 from idccrn_b200 import workloads as W
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "2"
-maker = {"1": W.config1, "2": W.config2, "2b": W.config2b, "3": lambda d: W.config3(d, total_batch=64)}[cfg]
+maker = {"1": W.config1, "2": W.config2, "2b": W.config2b, "3": lambda d: W.config3(d, total_batch=128)}[cfg]
 step, info = maker(torch.device("cuda", 0))
 for _ in range(3):
     step()
