@@ -19,6 +19,8 @@ static int g_wave_pairs = 1;
 static int g_tile_order = 1;
 static int g_tma_store = 1;
 static int g_lstm_interleave = 1;
+static int g_lstm_sync_mode = 0;
+int option_lstm_sync_mode() { return g_lstm_sync_mode; }
 int option_lstm_interleave() { return g_lstm_interleave; }
 int option_tma_store() { return g_tma_store; }
 int option_tile_order() { return g_tile_order; }
@@ -47,6 +49,11 @@ extern "C" int idv_set_option(const char* name, int value) {
   if (strcmp(name, "gemm_tile_order") == 0) {
     IDV_CHECK_ARG(value == 0 || value == 1, "idv_set_option: gemm_tile_order must be 0 (unit-major) or 1 (row-major)");
     g_tile_order = value;
+    return IDV_OK;
+  }
+  if (strcmp(name, "lstm_sync_mode") == 0) {
+    IDV_CHECK_ARG(value == 0 || value == 1, "idv_set_option: lstm_sync_mode must be 0 or 1");
+    g_lstm_sync_mode = value;
     return IDV_OK;
   }
   if (strcmp(name, "lstm_interleave") == 0) {

@@ -17,6 +17,7 @@ int option_lstm_wave_pairs();
 int option_tile_order();
 int option_tma_store();
 int option_lstm_interleave();
+int option_lstm_sync_mode();
 
 #define IDV_CHECK_ARG(cond, ...)             \
   do {                                       \

@@ -50,6 +50,7 @@ struct WaveParams {
   int nch, b0[2], NBc[2];
   long long hxA_ch, hxC_ch, g1x_ch;         // elements between the two chunks' exchange buffers
   int blkA_ch, blkC_ch;                     // ... and the same distance in blocks of the tensor maps
+  int sync_mode;                            // 0: acquire polls, fence + atomic; 1: relaxed polls + one fence, red.release (option lstm_sync_mode)
   int n_roles;                              // 3 = two-layer wavefront (L0 | IP | L1), 1 = ONE nn.LSTM layer per launch (role L0 only)
   unsigned short* hsplit;                   // single-layer mode: optional bf16 [2][4][R][H] output (next layer's in-proj input)
   float* hseq0;                             // single-layer mode: optional fp32 [4][R][H] output
@@ -79,16 +80,33 @@ __device__ __forceinline__ unsigned int ldacq(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void wait_counter(const unsigned int* ctr, long long target) {
+__device__ __forceinline__ unsigned int ldrlx(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// relaxed: spin with relaxed loads and acquire once at the end (experiment: an acquire load per spin iteration is a
+// load + fence)
+__device__ __forceinline__ void wait_counter(const unsigned int* ctr, long long target, bool relaxed = false) {
   if (target <= 0) return;
   long long t0 = 0;
   unsigned int spins = 0;
-  while ((long long)ldacq(ctr) < target) {
+  while ((long long)(relaxed ? ldrlx(ctr) : ldacq(ctr)) < target) {
     if ((++spins & 255u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > WAIT_TIMEOUT_CYCLES) __trap();
     }
+  }
+  if (relaxed) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+// publish one step: release the CTA's h stores (the caller's warps met at a named barrier) and count the CTA in
+__device__ __forceinline__ void publish_step(unsigned int* ctr, int mode) {
+  if (mode == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+  } else {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
   }
 }
 __device__ __forceinline__ float wsig(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
@@ -133,6 +151,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
   unsigned int* const sync_m = p.sync + m * 3 * W_SYNC_STRIDE;
   constexpr int CH_SYNC = 6 * W_SYNC_STRIDE;
   const int nch = p.nch;
+  const bool rlx = p.sync_mode != 0;
   const CUtensorMap* tmW = role == 0 ? &tmW0 : (role == 1 ? &tmWi : &tmW1);
   const CUtensorMap* tmH = role == 2 ? &tmHC : &tmHA;
 
@@ -187,16 +206,16 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         const unsigned int* cC = cB + W_SYNC_STRIDE;
         int slot;
         if (role == 0) {            // input h0(t-1): slot (t)%4 holds h0(t-1) (h0(t) is written to slot (t+1)%4)
-          wait_counter(cA, (long long)NC * t);
-          if (p.n_roles == 3) wait_counter(cB, (long long)NC * (t - 3));   // (single layer: all readers of a slot are L0 CTAs,
+          wait_counter(cA, (long long)NC * t, rlx);
+          if (p.n_roles == 3) wait_counter(cB, (long long)NC * (t - 3), rlx);   // (single layer: all readers of a slot are L0 CTAs,
           slot = t & 3;                                                    //  at most one step apart)
         } else if (role == 1) {     // input h0(t): slot (t+1)%4
-          wait_counter(cA, (long long)NC * (t + 1));
-          wait_counter(cC, (long long)NC * (t - 3));
+          wait_counter(cA, (long long)NC * (t + 1), rlx);
+          wait_counter(cC, (long long)NC * (t - 3), rlx);
           slot = (t + 1) & 3;
         } else {                    // input h1(t-1): slot t%2
-          wait_counter(cC, (long long)NC * t);
-          wait_counter(cB, (long long)NC * (t + 1));
+          wait_counter(cC, (long long)NC * t, rlx);
+          wait_counter(cB, (long long)NC * (t + 1), rlx);
           slot = t & 1;
         }
         fence_proxy_async_global();
@@ -321,7 +340,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         }
       } else if (role == 2) {
         // G1(t) is produced inside this kernel: acquire counter B, then coherent (L2) loads
-        if (lane == 0) wait_counter(cB, (long long)NC * (t + 1));
+        if (lane == 0) wait_counter(cB, (long long)NC * (t + 1), rlx);
         __syncwarp();
         if constexpr (VW == 4) {                      // (the wavefront roles only exist for N = 64)
           const float* gp = g1x + ((((long long)(t & 3) * 2 + m) * W_ROWS + r) * 4) * H + u0;
@@ -391,8 +410,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         // sync - and increments.  (Every thread fencing BEFORE the barrier measured the same step time.)
         asm volatile("bar.sync 1, %0;" ::"n"(32 * W_EPI_WARPS) : "memory");
         if (warp == W_EPI_WARP0 && lane == 0) {
-          __threadfence();
-          atomicAdd(my_ctr, 1u);
+          publish_step(my_ctr, p.sync_mode);
         }
         return;
       }
@@ -424,8 +442,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       if (warp == W_EPI_WARP0 && lane == 0) WAVE_DBG(6);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * W_EPI_WARPS) : "memory");
       if (warp == W_EPI_WARP0 && lane == 0) {
-        __threadfence();
-        atomicAdd(my_ctr, 1u);
+        publish_step(my_ctr, p.sync_mode);
         WAVE_DBG(7);
       }
       if (role == 2 && valid) {
@@ -586,6 +603,7 @@ static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off
   p.blkA_ch = W_REP * 4 * 2 * 2; p.blkC_ch = W_REP * 2 * 2 * 2;
   p.sync = sync;
   p.n_roles = 3; p.hsplit = nullptr; p.hseq0 = nullptr;
+  p.sync_mode = option_lstm_sync_mode();
   p.dbg = nullptr;
   const bool dbg = getenv("IDV_LSTM_DBG") != nullptr && p.Tsteps > 304;
   if (dbg) {
@@ -705,6 +723,7 @@ extern "C" int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g
     p.blkA_ch = 4 * 2 * 2; p.blkC_ch = 0;
     p.sync = sync; p.dbg = nullptr;
     p.n_roles = 1; p.hsplit = reinterpret_cast<unsigned short*>(hsplit); p.hseq0 = hseq;
+    p.sync_mode = option_lstm_sync_mode();
     rc = IDV_OK;
     const int per_launch = option_lstm_interleave() ? 128 : 64;
     for (int b0 = 0; b0 < NB && rc == IDV_OK; b0 += per_launch) {
