@@ -20,6 +20,10 @@ static int g_tile_order = 1;
 static int g_tma_store = 1;
 static int g_lstm_interleave = 1;
 static int g_lstm_sync_mode = 0;
+static int g_launch_pdl = 1;
+static int g_splitk = 1;
+int option_splitk() { return g_splitk; }
+int option_launch_pdl() { return g_launch_pdl; }
 int option_lstm_sync_mode() { return g_lstm_sync_mode; }
 int option_lstm_interleave() { return g_lstm_interleave; }
 int option_tma_store() { return g_tma_store; }
@@ -54,6 +58,14 @@ extern "C" int idv_set_option(const char* name, int value) {
   if (strcmp(name, "lstm_sync_mode") == 0) {
     IDV_CHECK_ARG(value == 0 || value == 1, "idv_set_option: lstm_sync_mode must be 0 or 1");
     g_lstm_sync_mode = value;
+    return IDV_OK;
+  }
+  if (strcmp(name, "gemm_splitk") == 0) {
+    g_splitk = value != 0;
+    return IDV_OK;
+  }
+  if (strcmp(name, "launch_pdl") == 0) {
+    g_launch_pdl = value != 0;
     return IDV_OK;
   }
   if (strcmp(name, "lstm_interleave") == 0) {

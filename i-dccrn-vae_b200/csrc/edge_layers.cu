@@ -19,12 +19,14 @@ __global__ void __launch_bounds__(256, 2) enc0_kernel(const float* __restrict__ 
   // [cg*4 + j | 32 + cg*4 + j] so that the two float4 of channel group cg are bank-conflict free
   extern __shared__ __align__(16) float ws[];
   const int tid = threadIdx.x;
+  pdl_trigger();
   for (int i = tid; i < 21 * N; i += 256) {
     const int k = i / N, n = i % N;
     const int slab = n & ~63, c = n & 63;
     const int phys = slab + ((c & 4) ? 32 : 0) + (c >> 3) * 4 + (c & 3);
     ws[k * N + phys] = (k < 20) ? __ldg(w + i) : __ldg(bias + n);
   }
+  pdl_wait();           // (the weights are launch-invariant; the spectrum is the predecessor's output)
   const int Tp = T + 1;
   const int R = NB * Tp;
   const int cg = tid & 7;
@@ -241,9 +243,8 @@ extern "C" int idv_enc0_fwd(const float* stft, int B, int Fin, int T, const floa
   IDV_CUDA(cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_tiles = cdiv(R, E0_ROWS);
   dim3 grid(n_tiles < 16 ? n_tiles : cdiv(n_tiles, 8), Fout);      // ~8 row tiles per block
-  enc0_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(stft, B, Fin, T, w, bias, N, prelu_slope, out, Fout,
-                                                         out_split, causal, t_valid, prev, keep_pad);
-  IDV_LAUNCH_CHECK("enc0_kernel");
+  IDV_CUDA(launch_pdl(enc0_kernel, grid, dim3(256), smem, (cudaStream_t)stream, stft, B, Fin, T, w, bias, N, prelu_slope, out,
+                      Fout, out_split, causal, t_valid, prev, keep_pad));
   return IDV_OK;
 }
 

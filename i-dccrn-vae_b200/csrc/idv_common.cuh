@@ -18,6 +18,8 @@ int option_tile_order();
 int option_tma_store();
 int option_lstm_interleave();
 int option_lstm_sync_mode();
+int option_launch_pdl();
+int option_splitk();
 
 #define IDV_CHECK_ARG(cond, ...)             \
   do {                                       \
@@ -45,6 +47,31 @@ int option_lstm_sync_mode();
       return IDV_E_CUDA;                                                        \
     }                                                                           \
   } while (0)
+
+// ---- programmatic dependent launch (option launch_pdl) ----------------------------------------------------------------
+// A kernel launched through launch_pdl may start while its predecessor on the stream is still running (the predecessor
+// triggers with pdl_trigger(), or implicitly when it exits): its launch latency, block scheduling and set-up (barrier
+// initialisation, TMEM allocation, descriptor prefetch) overlap the predecessor's tail.  Contract of every kernel
+// launched this way: EVERY thread of EVERY block executes pdl_wait() before its first global-memory access that is not
+// to launch-invariant data (weights, tables); pdl_wait() returns when all predecessor grids have completed and their
+// writes are visible.  Both instructions are no-ops in a normal launch.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  if (option_launch_pdl()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -266,7 +266,10 @@ __global__ void __launch_bounds__(256) latent_fused_kernel(const float* __restri
                                                            uint64_t seed, uint64_t offset,
                                                            const unsigned long long* __restrict__ offset_dev,
                                                            float* __restrict__ latent, float* __restrict__ z0,
-                                                           float* __restrict__ z1, void* __restrict__ zplanes, int out_split) {
+                                                           float* __restrict__ z1, void* __restrict__ zplanes, int out_split,
+                                                           int keep_pad) {
+  pdl_trigger();
+  pdl_wait();
   const int Tp = Talloc + 1;
   const int64_t R = (int64_t)NB * Tp;
   const int Ch = (zdim + 7) & ~7, Cp = 2 * Ch;
@@ -321,6 +324,7 @@ __global__ void __launch_bounds__(256) latent_fused_kernel(const float* __restri
           }
         }
       }
+      if (keep_pad && tt == 0) continue;                  // streaming: the pad row carries z of the previous step's last frame
       for (int si = 0; si < ns; ++si) {
         const float2 zv = live ? zs0[si] : make_float2(0.f, 0.f);
         const int64_t base = (int64_t)(s0 + si) * plane_el * (out_split ? 2 : 1) + r * Cp;
@@ -514,7 +518,7 @@ extern "C" int idv_reparam_fwd(const float* latent, int NB, int T, int Htot, int
 extern "C" int idv_latent_fwd(const float* hseq, int NB, int T, int H, int t_valid, int zdim, int latent_num, int S,
                               const float* eps_r0, const float* eps_i0, const float* eps_r1, const float* eps_i1,
                               uint64_t seed, uint64_t offset, const uint64_t* offset_dev, float* latent, float* z0,
-                              float* z1, void* zplanes, int out_split, void* stream) {
+                              float* z1, void* zplanes, int out_split, int keep_pad, void* stream) {
   using namespace idv;
   IDV_CHECK_ARG(hseq && latent && z0 && zplanes && NB > 0 && T > 0 && S > 0 && zdim > 0, "idv_latent_fwd: bad argument");
   IDV_CHECK_ARG((latent_num == 1 || latent_num == 2) && H == 3 * zdim * latent_num,
@@ -526,10 +530,10 @@ extern "C" int idv_latent_fwd(const float* hseq, int NB, int T, int H, int t_val
   const int Tv = (t_valid > 0 && t_valid < T) ? t_valid : T;
   const int64_t n = (int64_t)NB * (T + 1) * ((zdim + 7) / 8 * 8);
   const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-  latent_fused_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      hseq, NB, T, Tv, H, zdim, latent_num, S, eps_r0, eps_i0, eps_r1, eps_i1, seed, offset,
-      reinterpret_cast<const unsigned long long*>(offset_dev), latent, z0, z1, zplanes, out_split);
-  IDV_LAUNCH_CHECK("latent_fused_kernel");
+  IDV_CUDA(launch_pdl(latent_fused_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, hseq, NB, T, Tv, H, zdim,
+                      latent_num, S, eps_r0, eps_i0, eps_r1, eps_i1, seed, offset,
+                      reinterpret_cast<const unsigned long long*>(offset_dev), latent, z0, z1, zplanes, out_split,
+                      keep_pad));
   return IDV_OK;
 }
 

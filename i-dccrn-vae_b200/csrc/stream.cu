@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(256) stream_frames_split_kernel(const float* _
                                                                   const float* __restrict__ xnew, int NB, int k,
                                                                   long long base, int hop, int win, int kpad,
                                                                   unsigned short* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int hl_len = win - hop, wlen = hl_len + hop * k;
   const long long n = (long long)NB * k * (kpad / 4);
   const long long hl = (long long)NB * k * kpad;
@@ -46,16 +48,20 @@ __global__ void __launch_bounds__(256) stream_frames_split_kernel(const float* _
 }
 
 // one block per stream: hist <- window[hop*k .. hop*k + win - hop)
-__global__ void stream_hist_shift_kernel(float* __restrict__ hist, const float* __restrict__ xnew, int k, int hop,
-                                         int win) {
-  extern __shared__ float tmp[];
-  const int hl_len = win - hop, b = blockIdx.x;
+__device__ __forceinline__ void hist_shift_stream(float* __restrict__ hist, const float* __restrict__ xnew, int b, int k,
+                                                  int hop, int win, float* tmp) {
+  const int hl_len = win - hop;
   for (int i = threadIdx.x; i < hl_len; i += blockDim.x) {
     const int w = hop * k + i;
     tmp[i] = w < hl_len ? hist[(long long)b * hl_len + w] : __ldg(xnew + (long long)b * hop * k + (w - hl_len));
   }
   __syncthreads();
   for (int i = threadIdx.x; i < hl_len; i += blockDim.x) hist[(long long)b * hl_len + i] = tmp[i];
+}
+__global__ void stream_hist_shift_kernel(float* __restrict__ hist, const float* __restrict__ xnew, int k, int hop,
+                                         int win) {
+  extern __shared__ float tmp[];
+  hist_shift_stream(hist, xnew, blockIdx.x, k, hop, win, tmp);
 }
 
 // gates = g_in[stream row (b, frame)] + g_rec[stream][b]; c, h update in place; h also to the frame's hseq row
@@ -65,6 +71,8 @@ __global__ void __launch_bounds__(256) lstm_cell_step_kernel(const float* __rest
                                                              int frame, float* __restrict__ c,
                                                              unsigned short* __restrict__ h_split,
                                                              float* __restrict__ hseq) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = 4LL * NB * H;
   const long long hl = n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -98,9 +106,7 @@ struct CarryEntry {
 
 // grid (chunks, entries): a chunk walks over (plane, stream) rows, the threads of a block over the 16-byte vectors of
 // 256/vec rows at a time; four independent row copies in flight per thread
-__global__ void __launch_bounds__(256) carry_rows_kernel(const CarryEntry* __restrict__ table,
-                                                         unsigned long long* __restrict__ counter) {
-  const CarryEntry e = table[blockIdx.y];
+__device__ __forceinline__ void carry_rows_entry(const CarryEntry& e) {
   const int vec = e.row_bytes / 16;                        // vectors per row
   const int rows_per_pass = 256 / vec > 0 ? 256 / vec : 1;
   const int v = threadIdx.x % vec, rsub = threadIdx.x / vec;
@@ -127,18 +133,20 @@ __global__ void __launch_bounds__(256) carry_rows_kernel(const CarryEntry* __res
       *reinterpret_cast<uint4*>(p + v * 16) = *reinterpret_cast<const uint4*>(p + src_off);
     }
   }
+}
+__global__ void __launch_bounds__(256) carry_rows_kernel(const CarryEntry* __restrict__ table,
+                                                         unsigned long long* __restrict__ counter) {
+  carry_rows_entry(table[blockIdx.y]);
   if (counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *counter += 1ULL;
 }
 
 // acc: carried tail (NB, win - hop) of partial sums for the outputs o0 + hop*k .. ; frames (NB*k, frame_ld).
 // Position i of this step is output sample o = o0 + i, o0 = hop*t0 - (win/2) (t0 = global index of the first new
 // frame): the frames t0 + f cover i - hop*f in [0, win).  Emits i < hop*k, keeps the rest as the new tail.
-__global__ void __launch_bounds__(256) stream_ola_kernel(const float* __restrict__ frames, int frame_ld,
-                                                         const float* __restrict__ wsq, float* __restrict__ acc,
-                                                         int k, long long t0, int hop, int win,
-                                                         float* __restrict__ out) {
-  extern __shared__ float tail[];
-  const int tl = win - hop, b = blockIdx.x, total = hop * k + tl;
+__device__ __forceinline__ void ola_stream(const float* __restrict__ frames, int frame_ld, const float* __restrict__ wsq,
+                                           float* __restrict__ acc, int b, int k, long long t0, int hop, int win,
+                                           float* __restrict__ out, float* tail) {
+  const int tl = win - hop, total = hop * k + tl;
   const float* fb = frames + (long long)b * k * frame_ld;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     float a = i < tl ? acc[(long long)b * tl + i] : 0.f;
@@ -168,8 +176,77 @@ __global__ void __launch_bounds__(256) stream_ola_kernel(const float* __restrict
   __syncthreads();
   for (int i = threadIdx.x; i < tl; i += blockDim.x) acc[(long long)b * tl + i] = tail[i];
 }
+__global__ void __launch_bounds__(256) stream_ola_kernel(const float* __restrict__ frames, int frame_ld,
+                                                         const float* __restrict__ wsq, float* __restrict__ acc,
+                                                         int k, long long t0, int hop, int win,
+                                                         float* __restrict__ out) {
+  extern __shared__ float tail[];
+  ola_stream(frames, frame_ld, wsq, acc, blockIdx.x, k, t0, hop, win, out, tail);
+}
+
+// Everything of a step that only updates carried state or emits the output, in ONE launch (the step is a chain of
+// dependent small kernels: every launch costs its latency): blockIdx.y < n_entries: carry_rows of that entry;
+// n_entries: history shift; n_entries + 1: last STFT frame -> prev; n_entries + 2: overlap-add + output.
+struct TailParams {
+  const CarryEntry* table;
+  int n_entries;
+  unsigned long long* counter;
+  float* hist; const float* xnew;
+  const float* stft; int F; float* prev;
+  const float* frames; int frame_ld; const float* wsq; float* acc; long long t0; float* out;
+  int NB, k, hop, win;
+};
+__global__ void __launch_bounds__(256) stream_tail_kernel(const TailParams p) {
+  extern __shared__ float tmp[];
+  pdl_trigger();
+  pdl_wait();
+  const int job = (int)blockIdx.y - p.n_entries;
+  if (job < 0) {
+    carry_rows_entry(p.table[blockIdx.y]);
+    if (p.counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.counter += 1ULL;
+  } else if (job == 0) {
+    if (p.hist)
+      for (int b = blockIdx.x; b < p.NB; b += gridDim.x) {
+        hist_shift_stream(p.hist, p.xnew, b, p.k, p.hop, p.win, tmp);
+        __syncthreads();
+      }
+  } else if (job == 1) {
+    if (p.prev) {
+      const int n = p.NB * p.F;
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        *reinterpret_cast<float2*>(p.prev + (long long)i * 2) =
+            __ldg(reinterpret_cast<const float2*>(p.stft + ((long long)i * p.k + (p.k - 1)) * 2));
+    }
+  } else {
+    for (int b = blockIdx.x; b < p.NB; b += gridDim.x) {
+      ola_stream(p.frames, p.frame_ld, p.wsq, p.acc, b, p.k, p.t0, p.hop, p.win, p.out, tmp);
+      __syncthreads();
+    }
+  }
+}
 
 }  // namespace idv
+
+extern "C" int idv_stream_tail(const idv_carry_t* table, int n_entries, uint64_t* counter, float* hist, const float* x_new,
+                               const float* stft, int F, float* prev, const float* frames, int frame_ld, const float* wsq,
+                               float* acc, int64_t t0, float* out, int NB, int k, int hop, int win, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(table && n_entries > 0 && n_entries <= 65000, "idv_stream_tail: bad carry table");
+  IDV_CHECK_ARG(frames && wsq && acc && out && NB > 0 && k > 0 && t0 >= 0 && hop > 0 && win > hop && frame_ld >= win &&
+                    win - hop <= 8192,
+                "idv_stream_tail: bad argument");
+  IDV_CHECK_ARG((hist == nullptr) == (x_new == nullptr) && (prev == nullptr || (stft && F > 0)),
+                "idv_stream_tail: hist needs x_new, prev needs stft");
+  TailParams p;
+  p.table = reinterpret_cast<const CarryEntry*>(table); p.n_entries = n_entries;
+  p.counter = reinterpret_cast<unsigned long long*>(counter);
+  p.hist = hist; p.xnew = x_new; p.stft = stft; p.F = F; p.prev = prev;
+  p.frames = frames; p.frame_ld = frame_ld; p.wsq = wsq; p.acc = acc; p.t0 = (long long)t0; p.out = out;
+  p.NB = NB; p.k = k; p.hop = hop; p.win = win;
+  dim3 grid(48, n_entries + 3);
+  IDV_CUDA(launch_pdl(stream_tail_kernel, grid, dim3(256), (size_t)(win - hop) * sizeof(float), (cudaStream_t)stream, p));
+  return IDV_OK;
+}
 
 extern "C" int idv_stream_frames_split(const float* hist, const float* x_new, int NB, int k, int64_t base, int hop,
                                        int win, int kpad, void* frames, void* stream) {
@@ -178,9 +255,8 @@ extern "C" int idv_stream_frames_split(const float* hist, const float* x_new, in
                 "idv_stream_frames_split: bad argument");
   const long long n = (long long)NB * k * (kpad / 4);
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  stream_frames_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(hist, x_new, NB, k, (long long)base, hop, win,
-                                                                       kpad, reinterpret_cast<unsigned short*>(frames));
-  IDV_LAUNCH_CHECK("stream_frames_split_kernel");
+  IDV_CUDA(launch_pdl(stream_frames_split_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, hist, x_new, NB, k,
+                      (long long)base, hop, win, kpad, reinterpret_cast<unsigned short*>(frames)));
   return IDV_OK;
 }
 
@@ -202,10 +278,9 @@ extern "C" int idv_lstm_cell_step(const float* g_in, int64_t g_m_off, int64_t g_
                 "idv_lstm_cell_step: bad argument");
   const long long n = 4LL * NB * H;
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  lstm_cell_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g_in, g_m_off, g_p_off, g_ld, g_rec, NB, H, T + 1,
-                                                                  frame, c, reinterpret_cast<unsigned short*>(h_split),
-                                                                  hseq);
-  IDV_LAUNCH_CHECK("lstm_cell_step_kernel");
+  IDV_CUDA(launch_pdl(lstm_cell_step_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, g_in, (long long)g_m_off,
+                      (long long)g_p_off, g_ld, g_rec, NB, H, T + 1, frame, c, reinterpret_cast<unsigned short*>(h_split),
+                      hseq));
   return IDV_OK;
 }
 

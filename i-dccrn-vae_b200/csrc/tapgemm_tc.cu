@@ -55,6 +55,14 @@ struct Params {
   unsigned int* sched;        // [0] next tile, [1] CTAs finished (dynamic tile scheduler; self-resetting)
   int order;                  // tile order: 0 = (unit, row tile, N tile), 1 = (row tile, unit, N tile) - see decode_tile
   int tma_out;                // 1: split-bf16 tiles leave through shared memory + TMA stores (tmO), see the epilogue
+  // split-K (small problems: a frame-streaming step has 10-40 output tiles for 148 SMs, and ONE CTA streaming the whole K
+  // range of a tile - megabytes of weights and activation rows - is bound by the L2 -> shared-memory rate of a single
+  // SM): a tile's 64-wide K steps are divided over `ksplit` CTAs, every CTA adds its partial accumulator to the fp32
+  // workspace of the tile (red.global.add.v4.f32), the CTA that arrives last reads the sums back, clears them for
+  // the next launch and runs the epilogue.  Tile index = (output tile) * ksplit + part.
+  int ksplit;
+  float* ws;                  // [output tiles][128 rows][BN] partial sums, all zero between launches
+  unsigned int* ws_cnt;       // [output tiles] CTAs that have added their part, zero between launches
 };
 
 // Tile index -> (unit, row tile, N tile).  The CTAs that run at the same time work on CONSECUTIVE tile indices, so the
@@ -131,8 +139,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_row_tiles = TWO ? (p.n_row_tiles + 1) / 2 : p.n_row_tiles;
-  const int total_tiles = p.n_units * n_row_tiles * p.n_col_tiles;
+  const int total_tiles = p.n_units * n_row_tiles * p.n_col_tiles * p.ksplit;
+  volatile unsigned int* ks_flag = reinterpret_cast<volatile unsigned int*>(tmem_slot + 6);   // split-K: "this CTA arrived last"
 
+  pdl_trigger();          // the next kernel of the stream may be scheduled; it waits for this grid at its own pdl_wait()
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0);
     prefetch_tmap(&tmA1);
@@ -168,6 +178,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (TWO) cluster_sync_all();            // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the predecessor's tail; its outputs (this kernel's
+  // activation planes) may only be read, and this kernel's outputs written, from here on
+  pdl_wait();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -190,18 +203,23 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         // DYN: claimed one tile ahead, the atomic's latency hides behind this tile's loads
         t_next = DYN ? (int)atomicAdd(p.sched, 1u) : t + nwork;
         int ui, rt, nt;
-        decode_tile(p, t, n_row_tiles, ui, rt, nt);
+        decode_tile(p, t / p.ksplit, n_row_tiles, ui, rt, nt);
         if (TWO) rt = 2 * rt + (int)rank;
         const idv_unit_t unit = p.units[ui];
+        // split-K: this CTA's part of the unit's K steps (counted over the taps in table order)
+        const int part = t % p.ksplit;
+        const int c_begin = unit.reserved * part / p.ksplit, c_end = unit.reserved * (part + 1) / p.ksplit;
+        int ci = 0;
         // co-resident CTAs work on the same unit: start each at a different tap so they do not all request the
         // same weight tile (same L2 lines) at the same moment; the accumulation order is per-CTA but fixed
         // (both CTAs of a pair walk the taps in the same order)
-        const int rot = (int)((unsigned)wid % (unsigned)unit.n_taps);
+        const int rot = p.ksplit > 1 ? 0 : (int)((unsigned)wid % (unsigned)unit.n_taps);
         for (int ti0 = 0; ti0 < unit.n_taps; ++ti0) {
           const int ti = ti0 + rot < unit.n_taps ? ti0 + rot : ti0 + rot - unit.n_taps;
           const idv_tap_t tap = p.taps[unit.tap_begin + ti];
           const CUtensorMap* am = tap.src ? &tmA1 : &tmA0;
-          for (int k0 = 0; k0 < tap.kc; k0 += BK) {
+          for (int k0 = 0; k0 < tap.kc; k0 += BK, ++ci) {
+            if (ci < c_begin || ci >= c_end) continue;
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
             if (TWO) {
@@ -238,8 +256,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
         if (t < 0) break;
         int ui, rt_, nt_;
-        decode_tile(p, t, n_row_tiles, ui, rt_, nt_);
-        const int ksteps = p.units[ui].reserved;
+        decode_tile(p, t / p.ksplit, n_row_tiles, ui, rt_, nt_);
+        const int ks_unit = p.units[ui].reserved, part = t % p.ksplit;
+        const int ksteps = ks_unit * (part + 1) / p.ksplit - ks_unit * part / p.ksplit;
         const uint32_t acc = local & 1, aphase = (local >> 1) & 1;
         mbar_wait(tempty0 + 8 * acc, aphase ^ 1);
         tc_fence_after();
@@ -293,7 +312,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
       if (t < 0) break;
       int ui, rt, nt;
-      decode_tile(p, t, n_row_tiles, ui, rt, nt);
+      decode_tile(p, t / p.ksplit, n_row_tiles, ui, rt, nt);
       if (TWO) rt = 2 * rt + (int)rank;
       const idv_unit_t unit = p.units[ui];
       // the accumulator-empty barrier the MMA issuer waits on (TWO: the even CTA's, 8 warps arrive)
@@ -476,6 +495,36 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         continue;
       }
       const long long obase0 = (long long)unit.out_f * p.out_plane + (long long)r * p.out_ld + unit.out_ch_off + nt * BN;
+      float* ws_row = nullptr;
+      if (p.ksplit > 1) {
+        // ---- split-K: add this CTA's partial accumulator to the tile's workspace, count the CTA in; only the CTA that
+        // arrives last goes on (with the complete sums instead of its own accumulator)
+        const int tb = t / p.ksplit;
+        ws_row = p.ws + ((long long)tb * BM + q * 32 + lane) * BN;
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < BN; c0 += 32 * NH) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ws_row + c0 + j), "f"(__uint_as_float(v[j])),
+                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                         : "memory");
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (TWO) mbar_arrive_cluster(tempty_bar); else mbar_arrive(tempty_bar); }
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * C::EPI_WARPS) : "memory");
+        if (ew == 0 && lane == 0) *ks_flag = atomicAdd(p.ws_cnt + tb, 1u);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * C::EPI_WARPS) : "memory");
+        const bool last = *ks_flag == (unsigned int)(p.ksplit - 1);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * C::EPI_WARPS) : "memory");      // (the flag is rewritten by the next tile)
+        if (!last) continue;
+        __threadfence();
+        if (ew == 0 && lane == 0) p.ws_cnt[tb] = 0u;
+      }
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BN; c0 += 32 * NH) {
         // N > out_ld: the unit's columns wrap into consecutive output planes, out_ld columns each (two output planes of a
@@ -488,8 +537,18 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           plane_ok = p.out_hl <= 0 || (long long)(unit.out_f + pa + 1) * p.out_plane <= p.out_hl;
         }
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
-        tmem_ld_wait();
+        if (ws_row) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sv = __ldcg(reinterpret_cast<const float4*>(ws_row + c0 + j));
+            *reinterpret_cast<float4*>(ws_row + c0 + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j] = __float_as_uint(sv.x); v[j + 1] = __float_as_uint(sv.y);
+            v[j + 2] = __float_as_uint(sv.z); v[j + 3] = __float_as_uint(sv.w);
+          }
+        } else {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
+          tmem_ld_wait();
+        }
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -523,6 +582,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
         }
       }
+      if (ws_row) continue;               // (split-K: the accumulator was released before the partial sums were published)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (TWO) mbar_arrive_cluster(tempty_bar); else mbar_arrive(tempty_bar); }
@@ -642,16 +702,37 @@ static unsigned int* sched_slot() {
   return pool[dev] + 2 * i;
 }
 
+// split-K workspace, one per device: partial sums of up to KS_TILES output tiles (128 x 256 fp32 each) + their arrival
+// counters.  Zeroed once; every launch leaves it zero (the CTA that arrives last clears what it reads).  Launches of one
+// stream are ordered (a dependent launch touches it after its pdl_wait()); several streams: split-K is off
+// (gemm_dynamic_tiles).
+constexpr int KS_TILES = 160;
+static int ks_workspace(float** ws, unsigned int** cnt) {
+  static float* pool[64] = {nullptr};
+  int dev = 0;
+  IDV_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!pool[dev]) {
+    const size_t bytes = (size_t)KS_TILES * BM * 256 * sizeof(float) + KS_TILES * sizeof(unsigned int);
+    float* p = nullptr;
+    IDV_CUDA(cudaMalloc(&p, bytes));
+    IDV_CUDA(cudaMemset(p, 0, bytes));
+    pool[dev] = p;
+  }
+  *ws = pool[dev];
+  *cnt = reinterpret_cast<unsigned int*>(pool[dev] + (size_t)KS_TILES * BM * 256);
+  return IDV_OK;
+}
+
 template <int BN, bool DYN>
 static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o, const Params& p,
                    int sms, cudaStream_t st) {
   using C = Cfg<BN>;
   IDV_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<BN, DYN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 C::SMEM_BYTES));
-  const int total = p.n_units * p.n_row_tiles * p.n_col_tiles;
+  const int total = p.n_units * p.n_row_tiles * p.n_col_tiles * p.ksplit;
   const int grid = total < sms ? total : sms;
-  tapgemm_tc_kernel<BN, DYN, false><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a0, a1, w, o, p);
-  IDV_LAUNCH_CHECK("tapgemm_tc_kernel");
+  IDV_CUDA(launch_pdl(tapgemm_tc_kernel<BN, DYN, false>, dim3(grid), dim3(C::THREADS), (size_t)C::SMEM_BYTES, st, a0, a1, w, o, p));
   return IDV_OK;
 }
 
@@ -663,9 +744,11 @@ static int launch_pairs(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   auto kern = tapgemm_tc_kernel<BN, false, true>;
   IDV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
   cfg.attrs = attr; cfg.numAttrs = 1;
   static int max_pairs[64] = {0};
@@ -682,6 +765,7 @@ static int launch_pairs(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   const int total = p.n_units * ((p.n_row_tiles + 1) / 2) * p.n_col_tiles;
   const int pairs = total < max_pairs[dev] ? total : max_pairs[dev];
   cfg.gridDim = dim3(2 * pairs);
+  cfg.numAttrs = option_launch_pdl() ? 2 : 1;
   p.sched = nullptr;
   IDV_CUDA(cudaLaunchKernelEx(&cfg, kern, a0, a1, w, o, p));
   return IDV_OK;
@@ -717,7 +801,7 @@ static int tapgemm_tc_impl(const void* a0, int a0_cp, int a0_planes, const void*
                            int N, const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
                            int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu,
                            float prelu_slope, int head, int head_fout, int head_bmul, int head_boff,
-                           const float* stft_x, float* predict, int t_valid, void* stream);
+                           const float* stft_x, float* predict, int t_valid, int min_ksteps, void* stream);
 
 extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
                                    int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias, int N,
@@ -727,7 +811,20 @@ extern "C" int idv_tapgemm_tc_head(const void* a0, int a0_cp, int a0_planes, con
                                    const float* stft_x, float* predict, int t_valid, void* stream) {
   return tapgemm_tc_impl(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, nullptr, N, units,
                          taps, n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, prelu_slope, head,
-                         head_fout, head_bmul, head_boff, stft_x, predict, t_valid, stream);
+                         head_fout, head_bmul, head_boff, stft_x, predict, t_valid, 0, stream);
+}
+
+extern "C" int idv_tapgemm_tc_splitk(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
+                                     int R, int Tp, const void* wt, int kc_max, int n_slots, const float* bias,
+                                     const float* bias_first, int N, const idv_unit_t* units, const idv_tap_t* taps,
+                                     int n_units, void* out, int out_ld, int64_t out_plane, int64_t out_hl, int out_split,
+                                     int apply_prelu, float prelu_slope, int t_valid, int min_ksteps, void* stream) {
+  using namespace idv;
+  IDV_CHECK_ARG(!bias_first || Tp > 1 || Tp < -1, "idv_tapgemm_tc_splitk: a first-frame bias needs |Tp| = frames per utterance + 1");
+  IDV_CHECK_ARG(min_ksteps >= 0, "idv_tapgemm_tc_splitk: min_ksteps = the smallest unit.reserved of the table (0: no split)");
+  return tapgemm_tc_impl(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, bias_first, N,
+                         units, taps, n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, prelu_slope, 0, 0,
+                         1, 0, nullptr, nullptr, t_valid, min_ksteps, stream);
 }
 
 extern "C" int idv_tapgemm_tc_b2(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
@@ -736,10 +833,10 @@ extern "C" int idv_tapgemm_tc_b2(const void* a0, int a0_cp, int a0_planes, const
                                  int n_units, void* out, int out_ld, int64_t out_plane, int64_t out_hl, int out_split,
                                  int apply_prelu, float prelu_slope, int t_valid, void* stream) {
   using namespace idv;
-  IDV_CHECK_ARG(bias_first && Tp > 1, "idv_tapgemm_tc_b2: needs the first-frame bias and Tp = frames per utterance + 1");
+  IDV_CHECK_ARG(bias_first && (Tp > 1 || Tp < -1), "idv_tapgemm_tc_b2: needs the first-frame bias and |Tp| = frames per utterance + 1");
   return tapgemm_tc_impl(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, bias_first, N,
                          units, taps, n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, prelu_slope, 0, 0,
-                         1, 0, nullptr, nullptr, t_valid, stream);
+                         1, 0, nullptr, nullptr, t_valid, 0, stream);
 }
 
 static int tapgemm_tc_impl(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes,
@@ -747,7 +844,7 @@ static int tapgemm_tc_impl(const void* a0, int a0_cp, int a0_planes, const void*
                            int N, const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
                            int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu,
                            float prelu_slope, int head, int head_fout, int head_bmul, int head_boff,
-                           const float* stft_x, float* predict, int t_valid, void* stream) {
+                           const float* stft_x, float* predict, int t_valid, int min_ksteps, void* stream) {
   using namespace idv;
   using namespace idv::tc;
   IDV_CHECK_ARG(a0 && wt && bias && units && taps && (out || head), "idv_tapgemm_tc: null pointer");
@@ -775,7 +872,19 @@ static int tapgemm_tc_impl(const void* a0, int a0_cp, int a0_planes, const void*
   // SMs idle and, with one CTA streaming a whole weight slice through a 2-stage ring, run at the latency of single
   // TMA round trips: narrow the tile (more CTAs, 3-4 stage ring) until every SM has a tile.
   int BN = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
-  if (head == 0 || head == 3)
+  // split-K (Params::ksplit) instead of narrow tiles when the caller knows the K steps of its units: the WIDEST tile
+  // (fewest re-reads of the activation rows) whose K range divides over enough CTAs to fill the device
+  int ksplit = 1;
+  if (head == 0 && min_ksteps >= 2 && option_splitk() && !option_dynamic_tiles() && BN >= 64) {
+    const long long base = (long long)n_units * cdiv(R, BM) * (N / BN);
+    if (base * 2 <= sms && base <= KS_TILES) {
+      long long s = sms / base;
+      if (s > min_ksteps) s = min_ksteps;
+      if (s > 32) s = 32;
+      ksplit = (int)s;
+    }
+  }
+  if ((head == 0 || head == 3) && ksplit == 1)
     while (BN > 64 && N % (BN / 2) == 0 && (long long)n_units * cdiv(R, BM) * (N / BN) < sms) BN /= 2;
   CUtensorMap mA0, mA1, mW;
   int rc = encode_map_4d(&mA0, a0, a0_cp, R, a0_planes, (uint64_t)a0_planes * R * a0_cp, BK, BM);
@@ -790,7 +899,7 @@ static int tapgemm_tc_impl(const void* a0, int a0_cp, int a0_planes, const void*
   // (large problems only: a streaming step with a handful of row tiles keeps one CTA per tile - measured: 9 row tiles
   // as 5 pairs were 10 % slower - and a small odd tile count would waste a tenth of the pairs)
   const int n_rt = cdiv(R, BM);
-  const bool pairs = option_gemm_pairs() && !option_dynamic_tiles() && n_rt >= 8 && (n_rt % 2 == 0 || n_rt >= 32);
+  const bool pairs = ksplit == 1 && option_gemm_pairs() && !option_dynamic_tiles() && n_rt >= 8 && (n_rt % 2 == 0 || n_rt >= 32);
   rc = encode_map_4d(&mW, wt, kc_max, N, n_slots, (uint64_t)n_slots * N * kc_max, BK, pairs ? BN / 2 : BN);
   if (rc) return rc;
   Params p;
@@ -801,12 +910,17 @@ static int tapgemm_tc_impl(const void* a0, int a0_cp, int a0_planes, const void*
   p.head = head; p.head_fout = head_fout; p.head_bmul = head_bmul; p.head_boff = head_boff;
   p.stft_x = stft_x; p.predict = predict;
   p.order = option_tile_order();
+  p.ksplit = ksplit; p.ws = nullptr; p.ws_cnt = nullptr;
+  if (ksplit > 1) {
+    rc = ks_workspace(&p.ws, &p.ws_cnt);
+    if (rc) return rc;
+  }
   // TMA-store epilogue: split-bf16 outputs whose rows are 128-byte multiples, not the streaming steps (their pad rows
   // must stay untouched: a tensor store writes whole boxes); units with a column offset that is not a multiple of 64
   // fall back to direct stores inside the kernel
   CUtensorMap mO = mA0;
   p.tma_out = 0;
-  if (option_tma_store() && head == 0 && out_split && Tp >= 0 && BN >= 64 && out_ld % 64 == 0 && out_plane > 0 && out_hl > 0 &&
+  if (option_tma_store() && ksplit == 1 && head == 0 && out_split && Tp >= 0 && BN >= 64 && out_ld % 64 == 0 && out_plane > 0 && out_hl > 0 &&
       out_hl % out_plane == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     rc = encode_map_4d(&mO, out, (uint64_t)out_ld, (uint64_t)R, (uint64_t)(out_hl / out_plane), (uint64_t)out_hl, BK, 32,
                        (uint64_t)out_plane);

@@ -11,7 +11,7 @@ from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
-ABI_VERSION = 6        # IDV_ABI_VERSION of include/idv.h this binding was written against
+ABI_VERSION = 7        # IDV_ABI_VERSION of include/idv.h this binding was written against
 
 c_f32p = ctypes.c_void_p
 i32, i64, u64, f32, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_void_p
@@ -26,6 +26,8 @@ SIGNATURES = {
                        i32, i32, f32, i32, vp],
     "idv_tapgemm_tc_b2": [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp, i32, vp, i32, i64, i64,
                           i32, i32, f32, i32, vp],
+    "idv_tapgemm_tc_splitk": [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp, i32, vp, i32, i64,
+                              i64, i32, i32, f32, i32, i32, vp],
     "idv_tapgemm_tc_head": [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, vp, vp, i32, vp, i32, i64, i64,
                             i32, i32, f32, i32, i32, i32, i32, vp, vp, i32, vp],
     "idv_stft_frames_split": [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],
@@ -40,7 +42,7 @@ SIGNATURES = {
     "idv_lstm_h1_fwd": [vp, i32, vp, i32, i32, i32, i32, vp, vp],
     "idv_lstm_combine_fwd": [vp, i32, i32, i32, vp, i32, vp],
     "idv_reparam_fwd": [vp, i32, i32, i32, i32, i32, i32, vp, vp, u64, u64, vp, i32, vp, vp],
-    "idv_latent_fwd": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, i32, vp],
+    "idv_latent_fwd": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, i32, i32, vp],
     "idv_lstm_combine_planes": [vp, i32, i32, i32, i32, vp, vp, i32, vp],
     "idv_bin_affine": [vp, i32, i32, i32, vp, vp, i32, vp, vp],
     "idv_planes_to_user": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
@@ -78,6 +80,7 @@ SIGNATURES = {
     "idv_carry_rows": [vp, i32, vp, vp],
     "idv_stream_last_frame": [vp, i32, i32, i32, vp, vp],
     "idv_stream_ola": [vp, i32, vp, vp, i32, i32, i64, i32, i32, vp, vp],
+    "idv_stream_tail": [vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, i64, vp, i32, i32, i32, i32, vp],
 }
 EXPORTS = ["idv_abi_version", "idv_last_error", "idv_lstm_tc_config", "idv_lstm2_wave_config",
            "idv_lstm_layer_pair_config", "idv_set_option"] + \

@@ -612,10 +612,11 @@ class Decoder(nn.Module):
         out = self.transconv.run_packed(items[key], pp, skip, out)
         return ops.cbn_train_planes(out, self.bn, self._slope()) if train else out
 
-    def forward_after_dense(self, dense, zp, c_p, f_in, skip=None):
+    def forward_after_dense(self, dense, zp, c_p, f_in, skip=None, out=None, first_frame=True):
         """ComplexDense ``dense`` + this (first, causal) decoder layer as ONE tap-GEMM on the z planes ``zp``
         (pack.pack_dense_conv_transpose: the two maps are composed at pack time; eval mode).  c_p, f_in: channels /
-        planes of the dense output (model/pvae_module.py:L2085-2088).  Returns this layer's output planes."""
+        planes of the dense output (model/pvae_module.py:L2085-2088).  Returns this layer's output planes.
+        out / first_frame: frame streaming (static output planes; a step that does not start the signal)."""
         if not self.transconv.causal or not zp.split:
             raise RuntimeError("the dense + first-layer composition runs on the causal tensor-core path")
         items = self._cache.check(self)
@@ -638,7 +639,7 @@ class Decoder(nn.Module):
         if skip is not None and (skip.T != zp.T or skip.NB != zp.NB or skip.Tv != zp.Tv):
             raise RuntimeError("skip tensor has %d/%d frames x %d utterances, z %d/%d x %d"
                                % (skip.Tv, skip.T, skip.NB, zp.Tv, zp.T, zp.NB))
-        out = ops.tapgemm(pk, zp, skip, zp.NB, zp.T, t_valid=zp.Tv)
+        out = ops.tapgemm(pk, zp, skip, zp.NB, zp.T, t_valid=zp.Tv, out=out, first_frame=first_frame)
         return Planes(out, zp.NB, pk.c_out, pk.f_out, zp.T, split=True, Tv=zp.Tv)
 
     def head_on_tensor_cores(self, pp, skip):

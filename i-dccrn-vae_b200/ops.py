@@ -138,11 +138,20 @@ def istft_tc(spec_ri, hp, n_fft, hop, win, lengths=None):
     return out
 
 
-def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None, t_valid=0, out=None):
+STREAM_LIVE_ROWS = [os.environ.get("IDV_STREAM_LIVE_ROWS", "1") != "0"]      # A/B switch of TapGemmPack.tc_stream
+
+
+def pack_has_overrides(tc):
+    return "bias" in tc or "N" in tc or "n_units" in tc
+
+
+def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None, t_valid=0, out=None, first_frame=True):
     """Run one packed tap-GEMM.  a0/a1: Planes (a1 may be None).  Returns the flat output tensor
     [pack.out_planes][R][pack.out_ld] (fp32, or bf16 [2][...] when out_split).  Split inputs run on the
     tcgen05 kernel, fp32 inputs on the SIMT kernel.  t_valid: valid frames of the OUTPUT (0 = all T).
-    out: write into this (static) tensor and leave its pad rows untouched (streaming state, Tp < 0 in the ABI)."""
+    out: write into this (static) tensor and leave its pad rows untouched (streaming state, Tp < 0 in the ABI).
+    first_frame=False (composed dense + first decoder layer in a stream): frame 0 of the step is not the first frame of
+    the signal, so every frame gets the regular bias."""
     R = NB * (T + 1)
     tp = ((T + 1) if zero_pad_rows else 0) if out is None else -(T + 1)
     if a0.split:
@@ -156,14 +165,33 @@ def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None, t_valid=0, 
         elif out.numel() != (2 * n_out if out_split else n_out):
             raise RuntimeError("static tap-GEMM output has %d elements, expected %d" % (out.numel(), n_out))
         b2 = getattr(pack, "bias_first", None)
+        if STREAM_LIVE_ROWS[0] and tp <= 0 and T >= 1 and (b2 is None or not first_frame) and not pack_has_overrides(tc):
+            # frame-streaming step (static output / no pad-row handling): the GEMM over the live rows only
+            st = pack.tc_stream(T, a0.Cp, a1.Cp if a1 is not None else 0)
+            if st is not None:
+                lib.call("idv_tapgemm_tc_splitk", a0.data, a0.Cp * (T + 1), a0.F, a1.data if a1 is not None else None,
+                         a1.Cp * (T + 1) if a1 is not None else 0, a1.F if a1 is not None else 0, NB,
+                         0, tc["wt"], tc["kc_max"], tc["n_slots"], pack.bias, None, pack.N,
+                         st["units"], st["taps"], st["n_units"], out, pack.out_ld * (T + 1), R * pack.out_ld, n_out,
+                         1 if out_split else 0, 1 if pack.prelu else 0, pack.slope, 0, tc.get("min_ksteps", 0))
+                return out
         if b2 is not None:        # layer composed with the dense map in front of it: own bias for every first frame
-            if tp <= 1:
+            if abs(tp) <= 1:
                 raise RuntimeError("a composed (dense + transposed conv) pack needs the causal row layout")
+            if not first_frame:
+                b2 = pack.bias
             lib.call("idv_tapgemm_tc_b2", a0.data, a0.Cp, a0.F, a1.data if a1 is not None else None,
                      a1.Cp if a1 is not None else 0, a1.F if a1 is not None else 0, R,
                      tp, tc["wt"], tc["kc_max"], tc["n_slots"], pack.bias, b2, pack.N,
                      tc["units"], tc["taps"], pack.n_units, out, pack.out_ld, R * pack.out_ld, n_out,
                      1 if out_split else 0, 1 if pack.prelu else 0, pack.slope, int(t_valid))
+            return out
+        if tp <= 0 and tc.get("min_ksteps", 0) >= 2:          # small problems (streaming steps): split-K when tiles are few
+            lib.call("idv_tapgemm_tc_splitk", a0.data, a0.Cp, a0.F, a1.data if a1 is not None else None,
+                     a1.Cp if a1 is not None else 0, a1.F if a1 is not None else 0, R,
+                     tp, tc["wt"], tc["kc_max"], tc["n_slots"], pack.bias, None, pack.N,
+                     tc["units"], tc["taps"], pack.n_units, out, pack.out_ld, R * pack.out_ld, n_out,
+                     1 if out_split else 0, 1 if pack.prelu else 0, pack.slope, int(t_valid), tc["min_ksteps"])
             return out
         lib.call("idv_tapgemm_tc", a0.data, a0.Cp, a0.F, a1.data if a1 is not None else None,
                  a1.Cp if a1 is not None else 0, a1.F if a1 is not None else 0, R,
@@ -330,10 +358,11 @@ def reparam(latent, ch0, zdim, S, eps_r, eps_i, seed, offset, offset_dev=None, o
     return z
 
 
-def latent_fused(hseq, NB, T, H, t_valid, zdim, latent_num, S, eps, seed, offset, split, offset_dev=None):
+def latent_fused(hseq, NB, T, H, t_valid, zdim, latent_num, S, eps, seed, offset, split, offset_dev=None, zplanes_out=None):
     """ONE launch for the latent stage of the VAE encoders without heads: combine of the four LSTM streams, latent
     split, reparameterisation of every latent and the decoder's z planes (idv_latent_fwd).  eps: None (Philox) or the
-    list [real_0, imag_0(, real_1, imag_1)] of (NB, S, Tv, zdim) tensors.  Returns (latent, [z_k], [Planes per sample])."""
+    list [real_0, imag_0(, real_1, imag_1)] of (NB, S, Tv, zdim) tensors.  Returns (latent, [z_k], [Planes per sample]).
+    zplanes_out: write the z planes into this static tensor and keep its pad rows (frame streaming)."""
     Tv = t_valid if 0 < t_valid < T else T
     dev = hseq.device
     latent = torch.empty((NB, Tv, H, 2), dtype=torch.float32, device=dev)
@@ -349,9 +378,12 @@ def latent_fused(hseq, NB, T, H, t_valid, zdim, latent_num, S, eps, seed, offset
             e[i] = t
     Cp = 2 * round8(zdim)
     n_plane = NB * (T + 1) * Cp
-    zpl = _empty_act(S * n_plane, dev, split)
+    zpl = _empty_act(S * n_plane, dev, split) if zplanes_out is None else zplanes_out
+    if zpl.numel() != S * n_plane * (2 if split else 1):
+        raise RuntimeError("static z planes have %d elements, expected %d" % (zpl.numel(), S * n_plane * (2 if split else 1)))
     lib.call("idv_latent_fwd", hseq, NB, T, H, Tv, zdim, latent_num, S, e[0], e[1], e[2], e[3], int(seed), int(offset),
-             offset_dev, latent, zs[0], zs[1] if latent_num == 2 else None, zpl, 1 if split else 0)
+             offset_dev, latent, zs[0], zs[1] if latent_num == 2 else None, zpl, 1 if split else 0,
+             0 if zplanes_out is None else 1)
     per = n_plane * (2 if split else 1)
     planes = [Planes(zpl[s * per:(s + 1) * per], NB, zdim, 1, T, split=split, Tv=Tv) for s in range(S)]
     return latent, zs, planes

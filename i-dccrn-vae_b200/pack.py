@@ -109,8 +109,41 @@ class TapGemmPack:
                 units.append([u[0], u[1], u[2], u[3], u[4], ks])
             self._tc = dict(wt=torch.stack((hi, lo)).contiguous().to(dev), kc_max=kc_max, n_slots=len(slots),
                             taps=dev_table(taps, dev),
-                            units=dev_table(units, dev))
+                            units=dev_table(units, dev), min_ksteps=min(u[5] for u in units))
         return self._tc
+
+    def tc_stream(self, k, cp0, cp1):
+        """Tables of the same tap-GEMM for a frame-streaming step of k frames, on LIVE rows only.  A streaming plane set
+        holds k + 1 rows per stream (row 0 = the carried x[t-1], rows 1..k = the new frames); read as ONE row of
+        (k + 1) * cp channels per stream it makes the time tap a channel offset: output frame j of unit u becomes its own
+        unit whose taps read channel offset ch_off + (j + 1 - dt) * cp at dt = 0 and write column offset
+        out_ch_off + (j + 1) * out_ld of an output row of (k + 1) * out_ld columns.  The GEMM then has n_streams rows
+        instead of n_streams * (k + 1): no tile row is spent on pad rows (half of all rows at k = 1) and the weights
+        stream through half as many tiles.  Same memory layouts, same arithmetic; None when the pack does not fit
+        (several output planes per tile)."""
+        if getattr(self, "pair_planes", False) or self.N > self.out_ld:
+            return None
+        cache = self.__dict__.setdefault("_tc_stream", {})
+        key = (k, cp0, cp1)
+        if key not in cache:
+            tc = self.tc()
+            taps_tc = tc["taps"].cpu().tolist()
+            units_tc = tc["units"].cpu().tolist()
+            cps = (cp0, cp1)
+            taps, units = [], []
+            for u in units_tc:
+                if any(not 0 <= taps_tc[i][2] <= 1 for i in range(u[0], u[0] + u[1])):
+                    cache[key] = None                      # a time tap outside the carried frame
+                    return None
+                for j in range(k):
+                    begin = len(taps)
+                    for i in range(u[0], u[0] + u[1]):
+                        t = taps_tc[i]
+                        taps.append([t[0], t[1], 0, t[3] + (j + 1 - t[2]) * cps[t[0]], t[4], t[5]])
+                    units.append([begin, u[1], u[2], u[3] + (j + 1) * self.out_ld, u[4], u[5]])
+            dev = tc["wt"].device
+            cache[key] = dict(units=dev_table(units, dev), taps=dev_table(taps, dev), n_units=len(units))
+        return cache[key]
 
 
 def cbn_fold(bn):

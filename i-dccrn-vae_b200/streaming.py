@@ -90,7 +90,7 @@ class StreamingEnhancer:
         self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.x_in = torch.zeros(NB, self.hop * k, device=dev)
         self.y_out = torch.zeros(NB, self.hop * k, device=dev)
-        self.eps_in = None
+        self.eps_in, self._eps_zero, self.spec_rows = None, None, None
         # encoder outputs (also the skip tensors), dense output, decoder outputs 0..n-2
         f, self.enc_bufs = nb, []
         for e in self.enc.encoders:
@@ -99,7 +99,10 @@ class StreamingEnhancer:
             self.enc_bufs.append(self._planes(c.out_channels, f))
         top = self.enc_bufs[-1]
         self.C, self.F = top.C, top.F
-        self.dense_buf = self._planes(self.C, self.F)
+        # the decoder's first layer runs composed with the dense layer on the z planes (pack.pack_dense_conv_transpose): the
+        # carried x[t-1] of that layer is z of the previous frame
+        self.fused_dense = modules.FUSED_DENSE[0] and len(self.dec.decoders) > 1
+        self.dense_buf = self._planes(self.enc.zdim if self.fused_dense else self.C, 1 if self.fused_dense else self.F)
         f, self.dec_bufs = self.F, []
         for d in list(self.dec.decoders)[:-1]:
             f = 2 * f - 1
@@ -149,14 +152,12 @@ class StreamingEnhancer:
         # ---- STFT of the k new frames
         frames = torch.empty(2 * NB * k * hp["kpad"], dtype=torch.bfloat16, device=self.device)
         lib.call("idv_stream_frames_split", self.hist, self.x_in, NB, k, int(base), hop, win, hp["kpad"], frames)
-        lib.call("idv_stream_hist_shift", self.hist, self.x_in, NB, k, hop, win)
         stft_x = torch.empty((NB, hp["nbins"], k, 2), dtype=torch.float32, device=self.device)
         lib.call("idv_tapgemm_tc_head", frames, hp["kpad"], 1, None, 0, 0, NB * k, k, hp["wt"], hp["kc_max"], 1,
                  hp["bias"], hp["N"], hp["units"], hp["taps"], 1, None, 0, 0, 0, 0, 0, 0.0, 3, hp["nbins"], 1, 0, None,
                  stft_x, 0)
         # ---- encoder stack (state = pad rows of the static plane sets)
         p = enc.encoders[0].forward_from_stft(stft_x, False, out=self.enc_bufs[0].data, prev=self.stft_prev)
-        lib.call("idv_stream_last_frame", stft_x, NB, hp["nbins"], k, self.stft_prev)
         for i in range(1, len(enc.encoders)):
             p = enc.encoders[i].forward_planes(p, False, out=self.enc_bufs[i].data)
         # ---- ComplexLSTM, one time step per frame on the carried (h, c)
@@ -172,40 +173,62 @@ class StreamingEnhancer:
                      self.h_state[0], None)
             g1 = ops.tapgemm(pk1, hp0, hp1, NB, 0, zero_pad_rows=False, out_split=False)
             lib.call("idv_lstm_cell_step", None, 0, 0, 0, g1, NB, H, k, f, self.c_state[1], self.h_state[1], self.hseq)
-        latent = ops.lstm_combine(self.hseq, NB, k, H)
-        # ---- reparameterisation (speech latent), dense, decoder stack
-        zd = enc.zdim
+        # ---- combine + reparameterisation + z planes in one launch (only the speech latent feeds the decoder; a supplied
+        # eps covers the speech latent, the noise latent of a two-latent encoder then draws with eps = 0)
+        zd, ln = enc.zdim, enc.latent_num
         if self.eps_in is not None:
-            z = ops.reparam(latent, 0, zd, 1, self.eps_in[0], self.eps_in[1], 0, 0)
+            eps = list(self.eps_in[:2])
+            if ln == 2:
+                if self._eps_zero is None or self._eps_zero.shape != eps[0].shape:
+                    self._eps_zero = torch.zeros_like(eps[0])
+                eps += [self._eps_zero, self._eps_zero]
+            _, _, zpl = ops.latent_fused(self.hseq, NB, k, H, k, zd, ln, 1, eps, 0, 0, True,
+                                         zplanes_out=self.dense_buf.data if self.fused_dense else None)
         else:
-            z = ops.reparam(latent, 0, zd, 1, None, None, self._seed, 0, offset_dev=self.counter)
-        zp = ops.z_to_planes(z, NB, 1, 0, split=True)
-        q = dec.dense.forward_planes(zp, self.C, self.F, out=self.dense_buf.data)
+            _, _, zpl = ops.latent_fused(self.hseq, NB, k, H, k, zd, ln, 1, None, self._seed, 0, True,
+                                         offset_dev=self.counter,
+                                         zplanes_out=self.dense_buf.data if self.fused_dense else None)
         n = len(dec.decoders)
         skips = {}
         if self.real_skips:
             for i in range(n):
                 if i in dec.skip_to_use:
                     skips[i] = self.enc_bufs[n - 1 - i]
-        for i in range(n - 1):
+        first = 0
+        if self.fused_dense:
+            # dense + decoders[0] as one tap-GEMM on the z planes; only the very first frame of a signal lacks the dense
+            # bias behind its x[t-1] tap (zero padding of the dense OUTPUT in the reference)
+            q = dec.decoders[0].forward_after_dense(dec.dense, zpl[0], self.C, self.F, skips.get(0),
+                                                    out=self.dec_bufs[0].data, first_frame=(t0 == 0))
+            first = 1
+        else:
+            q = dec.dense.forward_planes(zpl[0], self.C, self.F, out=self.dense_buf.data)
+        for i in range(first, n - 1):
             q = dec.decoders[i].forward_planes(q, skips.get(i), False, out=self.dec_bufs[i].data)
         predict = torch.empty((NB, hp["nbins"], k, 2), dtype=torch.float32, device=self.device)
-        dec.decoders[n - 1].forward_head(q, skips.get(n - 1), self.mask, stft_x if self.mask else None, predict, 1, 0,
-                                         False)
-        # ---- iSTFT: synthesis frames + carried overlap-add
+        # ---- last layer + head; its epilogue also writes the K-major split rows of the synthesis GEMM
         ist = dec.istft
         if getattr(ist, "_tc", None) is None or ist._tc["bias"].device != self.device:
             ist._tc = pack.pack_istft_tc(n_fft, win, self.device)
         ip = ist._tc
-        rows = torch.empty(2 * NB * k * ip["kpad"], dtype=torch.bfloat16, device=self.device)
-        lib.call("idv_spec_rows_split", predict, NB, hp["nbins"], k, ip["kpad"], rows)
+        if self.spec_rows is None:          # padding columns stay zero: the head rewrites every live column per step
+            self.spec_rows = torch.zeros(2 * NB * k * ip["kpad"], dtype=torch.bfloat16, device=self.device)
+        rows = self.spec_rows
+        last = dec.decoders[n - 1]
+        fused_rows = last.head_on_tensor_cores(q, skips.get(n - 1))
+        last.forward_head(q, skips.get(n - 1), self.mask, stft_x if self.mask else None, predict, 1, 0, False,
+                          rows=rows if fused_rows else None)
+        if not fused_rows:
+            lib.call("idv_spec_rows_split", predict, NB, hp["nbins"], k, ip["kpad"], rows)
+        # ---- iSTFT: synthesis frames + carried overlap-add
         N = ip["N"]
         fr = torch.empty(NB * k * N, dtype=torch.float32, device=self.device)
         lib.call("idv_tapgemm_tc", rows, ip["kpad"], 1, None, 0, 0, NB * k, 0, ip["wt"], ip["kc_max"], 1, ip["bias"], N,
                  ip["units"], ip["taps"], 1, fr, N, NB * k * N, 0, 0, 0, 0.0, 0)
-        lib.call("idv_stream_ola", fr, N, ip["wsq"], self.ola, NB, k, int(t0), hop, win, self.y_out)
-        # ---- carry x[t-1] of every layer input to the pad rows, bump the noise counter
-        lib.call("idv_carry_rows", self.carry, self.n_carry, self.counter)
+        # ---- everything that only updates carried state or emits the output, in one launch: overlap-add, x[t-1] of every
+        # layer input to the pad rows, sample history, last STFT frame, noise counter
+        lib.call("idv_stream_tail", self.carry, self.n_carry, self.counter, self.hist, self.x_in, stft_x, hp["nbins"],
+                 self.stft_prev, fr, N, ip["wsq"], self.ola, int(t0), self.y_out, NB, k, hop, win)
         self.predict = predict
 
     # ------------------------------------------------------------------------------------------ public

@@ -40,7 +40,7 @@ extern "C" {
 #define IDV_E_CUDA 2     /* CUDA runtime error (message has the cudaError string) */
 #define IDV_E_RESOURCE 3 /* kernel cannot be made resident (cooperative launch too large) */
 
-#define IDV_ABI_VERSION 6
+#define IDV_ABI_VERSION 7
 
 int idv_abi_version(void);
 const char* idv_last_error(void);
@@ -126,6 +126,17 @@ int idv_tapgemm_tc_b2(const void* a0, int a0_cp, int a0_planes, const void* a1, 
                       const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
                       int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu, float prelu_slope, int t_valid,
                       void* stream);
+/* idv_tapgemm_tc_b2 (bias_first may be NULL) for SMALL problems, with split-K: min_ksteps = the smallest unit.reserved
+ * of the unit table (the caller packed it; 0 = never split).  When the output tiles would leave more than half of the
+ * SMs idle (a frame-streaming step: 10-40 tiles, each streaming megabytes of weights and activation rows through ONE
+ * SM's L2 port), the 64-wide K steps of every tile are divided over up to min_ksteps CTAs; partial accumulators are added
+ * in an fp32 workspace owned by the library (red.global.add), the CTA that arrives last applies bias / PReLU and stores.
+ * Same results up to fp32 summation order.  Not with gemm_dynamic_tiles (several streams).                       */
+int idv_tapgemm_tc_splitk(const void* a0, int a0_cp, int a0_planes, const void* a1, int a1_cp, int a1_planes, int R,
+                          int Tp, const void* wt, int kc_max, int n_slots, const float* bias, const float* bias_first,
+                          int N, const idv_unit_t* units, const idv_tap_t* taps, int n_units, void* out, int out_ld,
+                          int64_t out_plane, int64_t out_hl, int out_split, int apply_prelu, float prelu_slope,
+                          int t_valid, int min_ksteps, void* stream);
 
 /* ---- STFT / iSTFT -----------------------------------------------------------------------------
  * replaces torch.stft at model/pvae_module.py:L22 (n_fft 512, hop, win, periodic Hann, center,
@@ -251,11 +262,12 @@ int idv_reparam_fwd(const float* latent, int NB, int T, int Htot, int ch0, int z
  *                                     rows of frames >= Tv written as zero) - replaces idv_lstm_combine_fwd +
  *                                     idv_reparam_fwd (x latent_num) + idv_z_to_planes (x S) by ONE launch.
  * eps_*: (NB, S, Tv, zdim) or all NULL -> Philox4x32-10 from (seed, offset + *offset_dev), one Philox block per
- * element and draw.  H == 3 * zdim * latent_num.                                                              */
+ * element and draw.  H == 3 * zdim * latent_num.  keep_pad (frame streaming): the pad rows of zplanes are left
+ * untouched (they carry z of the previous step's last frame, refreshed by idv_carry_rows).                      */
 int idv_latent_fwd(const float* hseq, int NB, int T, int H, int t_valid, int zdim, int latent_num, int S,
                    const float* eps_r0, const float* eps_i0, const float* eps_r1, const float* eps_i1,
                    uint64_t seed, uint64_t offset, const uint64_t* offset_dev, float* latent, float* z0, float* z1,
-                   void* zplanes, int out_split, void* stream);
+                   void* zplanes, int out_split, int keep_pad, void* stream);
 /* idv_lstm_combine_fwd that ALSO writes the combined latent as one activation plane [1][R][2*round8(H)] (the input
  * of the supervised DCCRN's ComplexDense, model/pvae_module.py:L189-192): replaces idv_lstm_combine_fwd +
  * idv_z_to_planes.  planes: fp32, or bf16 hi/lo [2][R][Cp] when out_split; pad rows / rows >= Tv are zeroed. */
@@ -427,6 +439,13 @@ int idv_carry_rows(const idv_carry_t* table, int n_entries, uint64_t* counter, v
 int idv_stream_last_frame(const float* stft, int NB, int F, int k, float* prev, void* stream);
 int idv_stream_ola(const float* frames, int frame_ld, const float* wsq, float* acc, int NB, int k, int64_t t0,
                    int hop, int win, float* out, void* stream);
+/* Everything of a step that only updates carried state or emits its output, as ONE launch (a step is a chain of small
+ * dependent kernels: every launch costs its latency): idv_carry_rows(table, n_entries, counter) + idv_stream_hist_shift
+ * (hist, x_new; both NULL = skip) + idv_stream_last_frame(stft (NB, F, k, 2), prev; prev NULL = skip) +
+ * idv_stream_ola(frames, frame_ld, wsq, acc, t0, out).  Same contracts as the four entry points above.           */
+int idv_stream_tail(const idv_carry_t* table, int n_entries, uint64_t* counter, float* hist, const float* x_new,
+                    const float* stft, int F, float* prev, const float* frames, int frame_ld, const float* wsq,
+                    float* acc, int64_t t0, float* out, int NB, int k, int hop, int win, void* stream);
 
 #ifdef __cplusplus
 }

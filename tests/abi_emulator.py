@@ -130,6 +130,18 @@ def idv_tapgemm_tc_b2(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_
         idv_tapgemm_tc._bias_first = None
 
 
+def idv_tapgemm_tc_splitk(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, bias_first, N,
+                          units, taps, n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, slope, t_valid=0,
+                          min_ksteps=0):
+    """Contract = idv_tapgemm_tc / idv_tapgemm_tc_b2 (how the K range is divided over CTAs is not part of it)."""
+    if bias_first is not None:
+        return idv_tapgemm_tc_b2(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, bias_first,
+                                 N, units, taps, n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, slope,
+                                 t_valid)
+    return idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, N, units, taps,
+                          n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, slope, t_valid)
+
+
 def idv_tapgemm_tc(a0, a0_cp, a0_planes, a1, a1_cp, a1_planes, R, Tp, wt, kc_max, n_slots, bias, N, units, taps,
                    n_units, out, out_ld, out_plane, out_hl, out_split, apply_prelu, slope, t_valid=0):
     """Contract of the tensor-core tap-GEMM incl. its arithmetic: a_hi*w_hi + a_hi*w_lo + a_lo*w_hi."""
@@ -529,9 +541,11 @@ def idv_reparam_fwd(latent, NB, T, Htot, ch0, zdim, S, eps_r, eps_i, seed, offse
 
 
 def idv_latent_fwd(hseq, NB, T, H, t_valid, zdim, latent_num, S, eps_r0, eps_i0, eps_r1, eps_i1, seed, offset, offset_dev,
-                   latent, z0, z1, zplanes, out_split):
-    """Contract = idv_lstm_combine_fwd, then idv_reparam_fwd per latent, then idv_z_to_planes per sample."""
+                   latent, z0, z1, zplanes, out_split, keep_pad=0):
+    """Contract = idv_lstm_combine_fwd, then idv_reparam_fwd per latent, then idv_z_to_planes per sample; keep_pad: the
+    pad rows of zplanes keep their content."""
     Tv = _tv(t_valid, T)
+    old = _flat(zplanes).clone() if keep_pad else None
     idv_lstm_combine_fwd(hseq, NB, T, H, latent, t_valid)
     for k, (er, ei, z) in enumerate(((eps_r0, eps_i0, z0), (eps_r1, eps_i1, z1))[:latent_num]):
         idv_reparam_fwd(latent, NB, Tv, H, 3 * zdim * k, zdim, S, er, ei, seed, offset, offset_dev, 0, z)
@@ -539,6 +553,11 @@ def idv_latent_fwd(hseq, NB, T, H, t_valid, zdim, latent_num, S, eps_r0, eps_i0,
     zp = _flat(zplanes)
     for s in range(S):
         idv_z_to_planes(z0, NB, S, s, T, zdim, zp[s * per:(s + 1) * per], out_split, t_valid)
+    if keep_pad:
+        # planes [S][hl][NB][T + 1][Cp]: row 0 of every utterance back to what it was
+        cp = 2 * _r8(zdim)
+        new, prev = zp.view(-1, NB, T + 1, cp), old.view(-1, NB, T + 1, cp)
+        new[:, :, 0] = prev[:, :, 0]
 
 
 def idv_lstm_combine_planes(hseq, NB, T, H, t_valid, latent, planes, out_split):
@@ -901,6 +920,17 @@ def idv_stream_ola(frames, frame_ld, wsq, acc, NB, k, t0, hop, win, out):
     o = torch.where(env > 0, buf[:, :hop * k] / torch.where(env > 0, env, torch.ones_like(env)), torch.zeros_like(env))
     out.view(NB, hop * k).copy_(o.to(torch.float32))
     acc.view(NB, tl).copy_(buf[:, hop * k:hop * k + tl].to(torch.float32))
+
+
+def idv_stream_tail(table, n_entries, counter, hist, x_new, stft, F, prev, frames, frame_ld, wsq, acc, t0, out, NB, k,
+                    hop, win):
+    """Contract = the four state entry points above in one launch."""
+    idv_carry_rows(table, n_entries, counter)
+    if hist is not None:
+        idv_stream_hist_shift(hist, x_new, NB, k, hop, win)
+    if prev is not None:
+        idv_stream_last_frame(stft, NB, F, k, prev)
+    idv_stream_ola(frames, frame_ld, wsq, acc, NB, k, t0, hop, win, out)
 
 
 # ---- decoder side of the training step (csrc/backward.cu) -------------------------------------------------------------

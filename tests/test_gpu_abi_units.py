@@ -357,6 +357,68 @@ def _tapgemm_tc_case(R, Tp, N, kcs, dts, two_src, prelu, out_split, tv=0):
     assert _both("idv_tapgemm_tc", args, [16]) < 1e-5
 
 
+@pytest.mark.parametrize("R,Tp,N,kcs,dts,two_src,prelu,out_split,splitk", [
+    (128, 0, 512, [512, 512, 256, 192], [0, 0, 0, 0], False, True, 1, 1),      # one row tile, 23 K steps over up to 23 CTAs
+    (128, 0, 512, [512, 512, 256, 192], [0, 0, 0, 0], False, True, 1, 0),      # same with the switch off
+    (256, -2, 256, [256, 128], [1, 0], True, True, 1, 1),                       # streaming layout, pad rows kept, two sources
+    (200, 0, 1536, [384, 384], [0, 0], False, False, 0, 1),                     # fp32 out (LSTM step projection), row tail
+    (128, 0, 64, [64, 64, 64], [0, 0, 0], False, False, 1, 1),                  # 3 K steps, narrow tile
+])
+def test_tapgemm_tc_splitk(R, Tp, N, kcs, dts, two_src, prelu, out_split, splitk):
+    """idv_tapgemm_tc_splitk: the K steps of every tile divided over several CTAs (partial sums in the library's
+    workspace) - same contract; run twice: the workspace must be left clean."""
+    lib.set_option("gemm_splitk", splitk)
+    try:
+        F0, cp0, cp1 = 3, 520, 264
+        a0 = _to_split(_rand(F0, R, cp0, seed=1))
+        a1 = _to_split(_rand(2, R, cp1, seed=2)) if two_src else None
+        kc_max = max(kcs)
+        taps, nk = [], 0
+        for i, (kc, dt) in enumerate(zip(kcs, dts)):
+            src = 1 if (two_src and i % 2) else 0
+            taps.append([src, i % (2 if src else F0), dt, 8, kc, i])
+            nk += kc // 64
+        units = [[0, len(taps), 1, 8, N, nk], [0, 1, 0, 8, 0, kcs[0] // 64]]
+        w = _rand(len(taps), N, kc_max, seed=3) * 0.1
+        for i, kc in enumerate(kcs):
+            w[i, :, kc:] = 0
+        out_ld = N + 16
+        n_out = 2 * R * out_ld
+        for rep in range(2):
+            out = _to_split(_rand(n_out, seed=7)).reshape(-1) if out_split else _rand(n_out, seed=7)
+            args = [a0, cp0, F0, a1, cp1 if two_src else 0, 2 if two_src else 0, R, Tp, _to_split(w), kc_max, len(taps),
+                    _rand(2 * N, seed=4), None, N, torch.tensor(units, dtype=torch.int32),
+                    torch.tensor(taps, dtype=torch.int32), 2, out, out_ld, R * out_ld, n_out, out_split, 1 if prelu else 0,
+                    0.2, 0, min(u[5] for u in units)]
+            assert _both("idv_tapgemm_tc_splitk", args, [17]) < 1e-5
+    finally:
+        lib.set_option("gemm_splitk", 1)
+
+
+def test_tapgemm_stream_tables_equal_the_row_layout():
+    """TapGemmPack.tc_stream: the same tap-GEMM on the live rows of a k-frame streaming plane set ((k + 1) * cp channels
+    per stream, time taps as channel offsets) writes what the row layout with kept pad rows writes."""
+    from idccrn_b200 import ops
+    from idccrn_b200.ops import Planes
+    NB, k, C0, C1, F, N = 5, 3, 32, 64, 4, 128
+    taps = [[0, 1, 1, 0, 64, 0], [0, 2, 0, 0, 64, 64 * N], [1, 0, 1, 0, 128, 128 * N], [1, 3, 0, 0, 128, 256 * N]]
+    units = [[0, 4, 0, 0, 0, 0], [1, 3, 1, 0, N, 0]]
+    pk = pack.TapGemmPack(_rand(384 * N, seed=1) * 0.1, _rand(2 * N, seed=2), units, taps, N, 2, N, True, 0.1, "cuda")
+    R = NB * (k + 1)
+    a0 = Planes(_to_split(_rand(F, R, 64, seed=3)).reshape(-1).cuda(), NB, C0, F, k, split=True)
+    a1 = Planes(_to_split(_rand(F, R, 128, seed=4)).reshape(-1).cuda(), NB, C1, F, k, split=True)
+    outs = []
+    for live in (True, False):
+        ops.STREAM_LIVE_ROWS[0] = live
+        try:
+            out = _to_split(_rand(2 * R * N, seed=5)).reshape(-1).cuda()
+            ops.tapgemm(pk, a0, a1, NB, k, out=out)
+        finally:
+            ops.STREAM_LIVE_ROWS[0] = True
+        outs.append(out.view(2, -1).float().sum(0).cpu())
+    assert C.rel_l2(outs[0], outs[1]) < 1e-6, C.rel_l2(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("order", [0, 1])
 @pytest.mark.parametrize("R,Tp,N,n_units", [(2600, 13, 256, 7), (5000, 0, 128, 5), (1100, 11, 512, 3)])
 def test_tapgemm_tc_tile_orders(order, R, Tp, N, n_units):
@@ -409,10 +471,12 @@ def test_tapgemm_tc_tma_store_epilogue(tma, R, Tp, N, tv, pairs):
         lib.set_option("gemm_cta_pairs", 1)
 
 
-@pytest.mark.parametrize("NB,T,zdim,latent_num,S,tv,split", [(3, 7, 128, 1, 1, 0, 1), (2, 5, 128, 2, 3, 0, 1), (5, 9, 16, 2, 1, 6, 0),
-                                                             (1, 3, 128, 1, 10, 0, 1)])
-def test_latent_fused(NB, T, zdim, latent_num, S, tv, split):
-    """idv_latent_fwd = lstm_combine + reparam (per latent) + z_to_planes (per sample) of the contract emulator."""
+@pytest.mark.parametrize("NB,T,zdim,latent_num,S,tv,split,keep_pad", [
+    (3, 7, 128, 1, 1, 0, 1, 0), (2, 5, 128, 2, 3, 0, 1, 0), (5, 9, 16, 2, 1, 6, 0, 0), (1, 3, 128, 1, 10, 0, 1, 0),
+    (4, 2, 128, 1, 1, 0, 1, 1)])
+def test_latent_fused(NB, T, zdim, latent_num, S, tv, split, keep_pad):
+    """idv_latent_fwd = lstm_combine + reparam (per latent) + z_to_planes (per sample) of the contract emulator;
+    keep_pad: the pad rows of the z planes (3.0 here) survive."""
     H = 3 * zdim * latent_num
     R = NB * (T + 1)
     Tv = tv if 0 < tv < T else T
@@ -423,7 +487,7 @@ def test_latent_fused(NB, T, zdim, latent_num, S, tv, split):
     n_pl = S * R * 2 * ((zdim + 7) // 8 * 8)
     zpl = torch.full((2 * n_pl,), 3.0, dtype=torch.bfloat16) if split else torch.full((n_pl,), 3.0)
     args = [hseq, NB, T, H, tv, zdim, latent_num, S, eps[0], eps[1], eps[2] if latent_num == 2 else None,
-            eps[3] if latent_num == 2 else None, 0, 0, None, latent, z0, z1, zpl, split]
+            eps[3] if latent_num == 2 else None, 0, 0, None, latent, z0, z1, zpl, split, keep_pad]
     outs = [15, 16, 18] + ([17] if latent_num == 2 else [])
     # the split planes of several samples are compared sample by sample (hi | lo halves per sample)
     cpu = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
@@ -449,7 +513,7 @@ def test_latent_fused_philox_draws_are_independent():
         z0 = torch.zeros(NB, T, zdim, 2).cuda()
         zpl = torch.zeros(R * 2 * zdim).cuda()
         lib.call("idv_latent_fwd", hseq, NB, T, H, 0, zdim, 1, 1, None, None, None, None, seed, offset, None, latent, z0,
-                 None, zpl, 0)
+                 None, zpl, 0, 0)
         torch.cuda.synchronize()
         return z0.cpu().double()
     a, b, c = draw(1), draw(2), draw(1)
