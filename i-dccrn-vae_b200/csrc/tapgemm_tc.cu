@@ -57,12 +57,14 @@ struct Params {
   int tma_out;                // 1: split-bf16 tiles leave through shared memory + TMA stores (tmO), see the epilogue
   // split-K (small problems: a frame-streaming step has 10-40 output tiles for 148 SMs, and ONE CTA streaming the whole K
   // range of a tile - megabytes of weights and activation rows - is bound by the L2 -> shared-memory rate of a single
-  // SM): a tile's 64-wide K steps are divided over `ksplit` CTAs, every CTA adds its partial accumulator to the fp32
-  // workspace of the tile (red.global.add.v4.f32), the CTA that arrives last reads the sums back, clears them for
-  // the next launch and runs the epilogue.  Tile index = (output tile) * ksplit + part.
+  // SM): a tile's 64-wide K steps are divided over `ksplit` CTAs; every CTA stores its partial accumulator in the fp32
+  // workspace, waits until all parts of its tile are there and then reduces + finishes every ksplit-th 32-column slab
+  // (fixed summation order: deterministic).  Tile index = (output tile) * ksplit + part; ksplit <= BN / 32.
+  // (First version, measured: partial sums added with red.global.add.v4.f32 and the last CTA finishing the tile - the
+  // 1.1 M vector reductions of a layer took 100-150 us, four times the unsplit kernel.)
   int ksplit;
-  float* ws;                  // [output tiles][128 rows][BN] partial sums, all zero between launches
-  unsigned int* ws_cnt;       // [output tiles] CTAs that have added their part, zero between launches
+  float* ws;                  // [output tiles][ksplit][128 rows][BN] partial accumulators
+  unsigned int* ws_cnt;       // [output tiles][2] parts stored / parts finished, zero between launches
 };
 
 // Tile index -> (unit, row tile, N tile).  The CTAs that run at the same time work on CONSECUTIVE tile indices, so the
@@ -140,7 +142,6 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_row_tiles = TWO ? (p.n_row_tiles + 1) / 2 : p.n_row_tiles;
   const int total_tiles = p.n_units * n_row_tiles * p.n_col_tiles * p.ksplit;
-  volatile unsigned int* ks_flag = reinterpret_cast<volatile unsigned int*>(tmem_slot + 6);   // split-K: "this CTA arrived last"
 
   pdl_trigger();          // the next kernel of the stream may be scheduled; it waits for this grid at its own pdl_wait()
   if (warp == 0 && lane == 0) {
@@ -495,35 +496,48 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         continue;
       }
       const long long obase0 = (long long)unit.out_f * p.out_plane + (long long)r * p.out_ld + unit.out_ch_off + nt * BN;
-      float* ws_row = nullptr;
+      const float* ws_row = nullptr;
+      long long ws_part = 0;              // elements between the partial tiles of one output tile
+      int my_part = 0;
       if (p.ksplit > 1) {
-        // ---- split-K: add this CTA's partial accumulator to the tile's workspace, count the CTA in; only the CTA that
-        // arrives last goes on (with the complete sums instead of its own accumulator)
+        // ---- split-K: every CTA stores its partial accumulator (plain stores), the ksplit CTAs of an output tile wait for
+        // one another (they are co-resident: the grid is at most one CTA per SM), then CTA `part` reduces and finishes
+        // the 32-column slabs j with j % ksplit == part - a reduce-scatter through the L2, summed in a fixed order
         const int tb = t / p.ksplit;
-        ws_row = p.ws + ((long long)tb * BM + q * 32 + lane) * BN;
+        my_part = t % p.ksplit;
+        ws_part = (long long)BM * BN;
+        // partial tile layout [BN / 4 column vectors][128 rows] float4: the 32 lanes (rows) of a warp store / load 512
+        // consecutive bytes per instruction (row-major, one row per thread, scattered every 16-byte piece over its own line)
+        float* ws_tile = p.ws + (long long)tb * p.ksplit * ws_part;
+        float* mine = ws_tile + my_part * ws_part + (long long)(q * 32 + lane) * 4;
 #pragma unroll 1
         for (int c0 = half * 32; c0 < BN; c0 += 32 * NH) {
+          if ((c0 >> 5) % p.ksplit == my_part) continue;          // my own slabs stay in TMEM
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ws_row + c0 + j), "f"(__uint_as_float(v[j])),
-                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
-                         : "memory");
+            *reinterpret_cast<float4*>(mine + (long long)((c0 + j) >> 2) * (BM * 4)) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { if (TWO) mbar_arrive_cluster(tempty_bar); else mbar_arrive(tempty_bar); }
         __threadfence();
         asm volatile("bar.sync 1, %0;" ::"n"(32 * C::EPI_WARPS) : "memory");
-        if (ew == 0 && lane == 0) *ks_flag = atomicAdd(p.ws_cnt + tb, 1u);
+        if (ew == 0 && lane == 0) {
+          atomicAdd(p.ws_cnt + 2 * tb, 1u);
+          long long t0 = 0;
+          unsigned int spins = 0;
+          while (*reinterpret_cast<volatile unsigned int*>(p.ws_cnt + 2 * tb) < (unsigned int)p.ksplit) {
+            if ((++spins & 255u) == 0) {
+              const long long now = clock64();
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > WAIT_TIMEOUT_CYCLES) __trap();
+            }
+          }
+          __threadfence();
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * C::EPI_WARPS) : "memory");
-        const bool last = *ks_flag == (unsigned int)(p.ksplit - 1);
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * C::EPI_WARPS) : "memory");      // (the flag is rewritten by the next tile)
-        if (!last) continue;
-        __threadfence();
-        if (ew == 0 && lane == 0) p.ws_cnt[tb] = 0u;
+        ws_row = ws_tile + (long long)(q * 32 + lane) * 4;
       }
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BN; c0 += 32 * NH) {
@@ -536,18 +550,32 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           obase = (long long)(unit.out_f + pa) * p.out_plane + (long long)r * p.out_ld + (n0 - pa * p.out_ld) - c0;
           plane_ok = p.out_hl <= 0 || (long long)(unit.out_f + pa + 1) * p.out_plane <= p.out_hl;
         }
+        if (ws_row && (c0 >> 5) % p.ksplit != my_part) continue;   // split-K: another CTA of the tile finishes this slab
         uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
+        tmem_ld_wait();
         if (ws_row) {
+          // own part from TMEM, the others from the workspace in part order 0, 1, ... (the own one takes its place: the
+          // sum does not depend on which CTA computes it)
+          float sum[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 sv = __ldcg(reinterpret_cast<const float4*>(ws_row + c0 + j));
-            *reinterpret_cast<float4*>(ws_row + c0 + j) = make_float4(0.f, 0.f, 0.f, 0.f);
-            v[j] = __float_as_uint(sv.x); v[j + 1] = __float_as_uint(sv.y);
-            v[j + 2] = __float_as_uint(sv.z); v[j + 3] = __float_as_uint(sv.w);
+          for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+#pragma unroll 1
+          for (int pp = 0; pp < p.ksplit; ++pp) {
+            if (pp == my_part) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(v[j]);
+            } else {
+              const float* src = ws_row + pp * ws_part + (long long)(c0 >> 2) * (BM * 4);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 sv = __ldcg(reinterpret_cast<const float4*>(src + (long long)(j >> 2) * (BM * 4)));
+                sum[j] += sv.x; sum[j + 1] += sv.y; sum[j + 2] += sv.z; sum[j + 3] += sv.w;
+              }
+            }
           }
-        } else {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
-          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(sum[j]);
         }
         float f[32];
 #pragma unroll
@@ -582,10 +610,20 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
         }
       }
-      if (ws_row) continue;               // (split-K: the accumulator was released before the partial sums were published)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (TWO) mbar_arrive_cluster(tempty_bar); else mbar_arrive(tempty_bar); }
+      if (ws_row) {
+        // the CTA of the tile that finishes last re-arms the tile's two counters for the next launch
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * C::EPI_WARPS) : "memory");
+        if (ew == 0 && lane == 0) {
+          const int tb = t / p.ksplit;
+          if (atomicAdd(p.ws_cnt + 2 * tb + 1, 1u) == (unsigned int)(p.ksplit - 1)) {
+            p.ws_cnt[2 * tb] = 0u;
+            p.ws_cnt[2 * tb + 1] = 0u;
+          }
+        }
+      }
     }
   }
 
@@ -702,10 +740,9 @@ static unsigned int* sched_slot() {
   return pool[dev] + 2 * i;
 }
 
-// split-K workspace, one per device: partial sums of up to KS_TILES output tiles (128 x 256 fp32 each) + their arrival
-// counters.  Zeroed once; every launch leaves it zero (the CTA that arrives last clears what it reads).  Launches of one
-// stream are ordered (a dependent launch touches it after its pdl_wait()); several streams: split-K is off
-// (gemm_dynamic_tiles).
+// split-K workspace, one per device: the partial accumulators of up to KS_TILES CTAs (128 x 256 fp32 each) + two counters
+// per output tile (zeroed once; the CTA that finishes a tile last re-arms them).  Launches of one stream are ordered (a
+// dependent launch touches the workspace after its pdl_wait()); several streams: split-K is off (gemm_dynamic_tiles).
 constexpr int KS_TILES = 160;
 static int ks_workspace(float** ws, unsigned int** cnt) {
   static float* pool[64] = {nullptr};
@@ -713,7 +750,7 @@ static int ks_workspace(float** ws, unsigned int** cnt) {
   IDV_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) dev = 0;
   if (!pool[dev]) {
-    const size_t bytes = (size_t)KS_TILES * BM * 256 * sizeof(float) + KS_TILES * sizeof(unsigned int);
+    const size_t bytes = (size_t)KS_TILES * BM * 256 * sizeof(float) + 2 * KS_TILES * sizeof(unsigned int);
     float* p = nullptr;
     IDV_CUDA(cudaMalloc(&p, bytes));
     IDV_CUDA(cudaMemset(p, 0, bytes));
@@ -877,10 +914,13 @@ static int tapgemm_tc_impl(const void* a0, int a0_cp, int a0_planes, const void*
   int ksplit = 1;
   if (head == 0 && min_ksteps >= 2 && option_splitk() && !option_dynamic_tiles() && BN >= 64) {
     const long long base = (long long)n_units * cdiv(R, BM) * (N / BN);
-    if (base * 2 <= sms && base <= KS_TILES) {
-      long long s = sms / base;
+    // (measured: with 64-column tiles on more than half of the SMs the unsplit kernel is as fast - the reduction costs a
+    // few microseconds per launch)
+    const long long narrow = (long long)n_units * cdiv(R, BM) * (N / 64);
+    if (base * 2 <= sms && narrow * 2 <= sms) {
+      long long s = sms / base;                    // (base * s CTAs <= sms <= KS_TILES partial tiles)
       if (s > min_ksteps) s = min_ksteps;
-      if (s > 32) s = 32;
+      if (s > BN / 32) s = BN / 32;                // a CTA finishes whole 32-column slabs
       ksplit = (int)s;
     }
   }

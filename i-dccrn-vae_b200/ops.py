@@ -141,10 +141,6 @@ def istft_tc(spec_ri, hp, n_fft, hop, win, lengths=None):
 STREAM_LIVE_ROWS = [os.environ.get("IDV_STREAM_LIVE_ROWS", "1") != "0"]      # A/B switch of TapGemmPack.tc_stream
 
 
-def pack_has_overrides(tc):
-    return "bias" in tc or "N" in tc or "n_units" in tc
-
-
 def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None, t_valid=0, out=None, first_frame=True):
     """Run one packed tap-GEMM.  a0/a1: Planes (a1 may be None).  Returns the flat output tensor
     [pack.out_planes][R][pack.out_ld] (fp32, or bf16 [2][...] when out_split).  Split inputs run on the
@@ -158,23 +154,23 @@ def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None, t_valid=0, 
         if a1 is not None and not a1.split:
             raise RuntimeError("tap-GEMM sources must share one activation format")
         out_split = True if out_split is None else out_split
-        tc = pack.tc()
         n_out = pack.out_planes * R * pack.out_ld
         if out is None:
             out = _empty_act(n_out, a0.data.device, out_split)
         elif out.numel() != (2 * n_out if out_split else n_out):
             raise RuntimeError("static tap-GEMM output has %d elements, expected %d" % (out.numel(), n_out))
         b2 = getattr(pack, "bias_first", None)
-        if STREAM_LIVE_ROWS[0] and tp <= 0 and T >= 1 and (b2 is None or not first_frame) and not pack_has_overrides(tc):
+        if STREAM_LIVE_ROWS[0] and tp <= 0 and T >= 1 and (b2 is None or not first_frame):
             # frame-streaming step (static output / no pad-row handling): the GEMM over the live rows only
             st = pack.tc_stream(T, a0.Cp, a1.Cp if a1 is not None else 0)
             if st is not None:
                 lib.call("idv_tapgemm_tc_splitk", a0.data, a0.Cp * (T + 1), a0.F, a1.data if a1 is not None else None,
                          a1.Cp * (T + 1) if a1 is not None else 0, a1.F if a1 is not None else 0, NB,
-                         0, tc["wt"], tc["kc_max"], tc["n_slots"], pack.bias, None, pack.N,
+                         0, st["wt"], st["kc_max"], st["n_slots"], pack.bias, None, pack.N,
                          st["units"], st["taps"], st["n_units"], out, pack.out_ld * (T + 1), R * pack.out_ld, n_out,
-                         1 if out_split else 0, 1 if pack.prelu else 0, pack.slope, 0, tc.get("min_ksteps", 0))
+                         1 if out_split else 0, 1 if pack.prelu else 0, pack.slope, 0, st["min_ksteps"])
                 return out
+        tc = pack.tc()
         if b2 is not None:        # layer composed with the dense map in front of it: own bias for every first frame
             if abs(tp) <= 1:
                 raise RuntimeError("a composed (dense + transposed conv) pack needs the causal row layout")

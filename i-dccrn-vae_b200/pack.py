@@ -79,11 +79,21 @@ class TapGemmPack:
         if self._tc is None:
             if not self.tc_eligible():
                 raise RuntimeError("tap-GEMM (N=%d) does not fit the tensor-core kernel's shape rules" % self.N)
+            if getattr(self, "pair_planes", False):
+                dev = self.w.device
+                w = self.w.detach() if PACK_ON_DEVICE[0] else self.w.detach().cpu()
+                self._tc = self._tc_paired(w, dev)
+            else:
+                self._tc = self.tc_plain()
+        return self._tc
+
+    def tc_plain(self):
+        """The one-output-plane-per-unit tables (what tc() returns unless the pack computes several planes per tile)."""
+        if self.__dict__.get("_tc_plain_cache") is None:
+            if not self.tc_eligible():
+                raise RuntimeError("tap-GEMM (N=%d) does not fit the tensor-core kernel's shape rules" % self.N)
             dev = self.w.device
             w = self.w.detach() if PACK_ON_DEVICE[0] else self.w.detach().cpu()
-            if getattr(self, "pair_planes", False):
-                self._tc = self._tc_paired(w, dev)
-                return self._tc
             kc_max = max(t[4] for t in self._taps_l)
             # slot ids in (K width, weight offset) order: the slots of one K width whose blocks follow one another in
             # ``w`` (the usual case: tap blocks of one source) are then filled by ONE strided view instead of one copy
@@ -107,10 +117,10 @@ class TapGemmPack:
             for u in self._units_l:
                 ks = sum(t[4] // 64 for t in self._taps_l[u[0]:u[0] + u[1]])
                 units.append([u[0], u[1], u[2], u[3], u[4], ks])
-            self._tc = dict(wt=torch.stack((hi, lo)).contiguous().to(dev), kc_max=kc_max, n_slots=len(slots),
-                            taps=dev_table(taps, dev),
-                            units=dev_table(units, dev), min_ksteps=min(u[5] for u in units))
-        return self._tc
+            self._tc_plain_cache = dict(wt=torch.stack((hi, lo)).contiguous().to(dev), kc_max=kc_max, n_slots=len(slots),
+                                        taps=dev_table(taps, dev), units=dev_table(units, dev),
+                                        min_ksteps=min(u[5] for u in units), taps_l=taps, units_l=units)
+        return self._tc_plain_cache
 
     def tc_stream(self, k, cp0, cp1):
         """Tables of the same tap-GEMM for a frame-streaming step of k frames, on LIVE rows only.  A streaming plane set
@@ -119,16 +129,17 @@ class TapGemmPack:
         unit whose taps read channel offset ch_off + (j + 1 - dt) * cp at dt = 0 and write column offset
         out_ch_off + (j + 1) * out_ld of an output row of (k + 1) * out_ld columns.  The GEMM then has n_streams rows
         instead of n_streams * (k + 1): no tile row is spent on pad rows (half of all rows at k = 1) and the weights
-        stream through half as many tiles.  Same memory layouts, same arithmetic; None when the pack does not fit
-        (several output planes per tile)."""
-        if getattr(self, "pair_planes", False) or self.N > self.out_ld:
+        stream through half as many tiles.  Same memory layouts, same arithmetic.  Built from the one-plane-per-unit
+        tables (tc_plain) also for the packs that compute several output planes per tile in the batched path.  Returns
+        the full operand set (wt, kc_max, n_slots, units, taps, n_units, min_ksteps) or None."""
+        if self.N > self.out_ld:
             return None
         cache = self.__dict__.setdefault("_tc_stream", {})
         key = (k, cp0, cp1)
         if key not in cache:
-            tc = self.tc()
-            taps_tc = tc["taps"].cpu().tolist()
-            units_tc = tc["units"].cpu().tolist()
+            tc = self.tc_plain()
+            taps_tc = tc["taps_l"]
+            units_tc = tc["units_l"]
             cps = (cp0, cp1)
             taps, units = [], []
             for u in units_tc:
@@ -142,7 +153,8 @@ class TapGemmPack:
                         taps.append([t[0], t[1], 0, t[3] + (j + 1 - t[2]) * cps[t[0]], t[4], t[5]])
                     units.append([begin, u[1], u[2], u[3] + (j + 1) * self.out_ld, u[4], u[5]])
             dev = tc["wt"].device
-            cache[key] = dict(units=dev_table(units, dev), taps=dev_table(taps, dev), n_units=len(units))
+            cache[key] = dict(units=dev_table(units, dev), taps=dev_table(taps, dev), n_units=len(units), wt=tc["wt"],
+                              kc_max=tc["kc_max"], n_slots=tc["n_slots"], min_ksteps=tc["min_ksteps"])
         return cache[key]
 
 

@@ -1,4 +1,9 @@
-"""Throughput mode: consecutive batches alternate over several CUDA streams.
+"""Throughput modes.
+
+HostPipeline: batches that live in host memory - the host -> device copy of batch i+1 and the device -> host copy of
+batch i-1 run on two copy streams while batch i computes on the caller's stream (the kernels keep the whole GPU).
+
+StreamPipeline: consecutive batches alternate over several CUDA streams.
 
 A single forward is a dependency chain  encoder GEMMs -> LSTM recurrence (latency-bound, few SMs) -> decoder
 GEMMs, so on one stream the tensor pipe idles during the recurrence.  With two batches in flight the recurrence of
@@ -80,3 +85,54 @@ class StreamPipeline:
         cur = torch.cuda.current_stream(self.device)
         for s in self.streams:
             cur.wait_stream(s)
+
+
+class HostPipeline:
+    """Enhance batches held in (pinned) host memory with the copies overlapped:
+
+        hp = HostPipeline(lambda x: enhance(x), device)       # x: device tensor -> device tensor
+        for x_host, y_host in batches:
+            hp.submit(x_host, y_host)                         # returns at once; y_host is filled asynchronously
+        hp.join()                                             # current stream waits for every copy; then synchronise
+
+    ``depth`` input buffers rotate: the copy of batch i + 1 starts as soon as the compute of batch i + 1 - depth has
+    finished with its buffer.  One compute stream (the caller's current stream): nothing competes with the kernels for
+    SMs, only the copy engines run beside them."""
+
+    def __init__(self, fn, device, depth=2):
+        self.fn, self.device, self.depth = fn, torch.device(device), int(depth)
+        self.s_in = torch.cuda.Stream(device=self.device)
+        self.s_out = torch.cuda.Stream(device=self.device)
+        self._x = [None] * self.depth
+        self._free = [None] * self.depth          # event: the compute that read input buffer i is done
+        self._i = 0
+
+    def submit(self, x_host, out_host):
+        i = self._i % self.depth
+        self._i += 1
+        cur = torch.cuda.current_stream(self.device)
+        if self._x[i] is None or self._x[i].shape != x_host.shape or self._x[i].dtype != x_host.dtype:
+            self._x[i] = torch.empty(x_host.shape, dtype=x_host.dtype, device=self.device)
+            self.s_in.wait_stream(cur)                         # (allocated on the compute stream)
+        with torch.cuda.stream(self.s_in):
+            if self._free[i] is not None:
+                self.s_in.wait_event(self._free[i])
+            self._x[i].copy_(x_host, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.s_in)
+        cur.wait_event(ready)
+        y = self.fn(self._x[i])
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._free[i] = done
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(done)
+            out_host.copy_(y, non_blocking=True)
+        y.record_stream(self.s_out)
+        return out_host
+
+    def join(self):
+        """The caller's current stream waits for every submitted copy (synchronise it to read the host buffers)."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.s_in)
+        cur.wait_stream(self.s_out)
