@@ -139,6 +139,7 @@ def istft_tc(spec_ri, hp, n_fft, hop, win, lengths=None):
 
 
 STREAM_LIVE_ROWS = [os.environ.get("IDV_STREAM_LIVE_ROWS", "1") != "0"]      # A/B switch of TapGemmPack.tc_stream
+STREAM_MAX_FRAMES = 16       # frames per step up to which a step's tap-GEMMs run on live rows (one unit per frame)
 
 
 def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None, t_valid=0, out=None, first_frame=True):
@@ -160,8 +161,10 @@ def tapgemm(pack, a0, a1, NB, T, zero_pad_rows=True, out_split=None, t_valid=0, 
         elif out.numel() != (2 * n_out if out_split else n_out):
             raise RuntimeError("static tap-GEMM output has %d elements, expected %d" % (out.numel(), n_out))
         b2 = getattr(pack, "bias_first", None)
-        if STREAM_LIVE_ROWS[0] and tp <= 0 and T >= 1 and (b2 is None or not first_frame):
-            # frame-streaming step (static output / no pad-row handling): the GEMM over the live rows only
+        if STREAM_LIVE_ROWS[0] and tp <= 0 and 1 <= T <= STREAM_MAX_FRAMES and (b2 is None or not first_frame):
+            # frame-streaming step (static output / no pad-row handling, a few frames): the GEMM over the live rows only
+            # (a whole utterance without pad-row handling - the LSTM input projection - keeps the row layout: one unit
+            # per frame would leave it NB rows per tile)
             st = pack.tc_stream(T, a0.Cp, a1.Cp if a1 is not None else 0)
             if st is not None:
                 lib.call("idv_tapgemm_tc_splitk", a0.data, a0.Cp * (T + 1), a0.F, a1.data if a1 is not None else None,
