@@ -22,7 +22,9 @@ static int g_lstm_interleave = 1;
 static int g_lstm_sync_mode = 0;
 static int g_launch_pdl = 1;
 static int g_splitk = 1;
+static int g_lstm_cluster_alt = 0;
 int option_splitk() { return g_splitk; }
+int option_lstm_cluster_alt() { return g_lstm_cluster_alt; }
 int option_launch_pdl() { return g_launch_pdl; }
 int option_lstm_sync_mode() { return g_lstm_sync_mode; }
 int option_lstm_interleave() { return g_lstm_interleave; }
@@ -62,6 +64,11 @@ extern "C" int idv_set_option(const char* name, int value) {
   }
   if (strcmp(name, "gemm_splitk") == 0) {
     g_splitk = value != 0;
+    return IDV_OK;
+  }
+  if (strcmp(name, "lstm_cluster_alt") == 0) {
+    IDV_CHECK_ARG(value == 0 || value == 1, "idv_set_option: lstm_cluster_alt must be 0 (largest CTAs) or 1 (second choice)");
+    g_lstm_cluster_alt = value;
     return IDV_OK;
   }
   if (strcmp(name, "launch_pdl") == 0) {

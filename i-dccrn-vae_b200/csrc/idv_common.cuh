@@ -20,6 +20,7 @@ int option_lstm_interleave();
 int option_lstm_sync_mode();
 int option_launch_pdl();
 int option_splitk();
+int option_lstm_cluster_alt();
 
 #define IDV_CHECK_ARG(cond, ...)             \
   do {                                       \

@@ -11,7 +11,7 @@ from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
-ABI_VERSION = 7        # IDV_ABI_VERSION of include/idv.h this binding was written against
+ABI_VERSION = 8        # IDV_ABI_VERSION of include/idv.h this binding was written against
 
 c_f32p = ctypes.c_void_p
 i32, i64, u64, f32, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_void_p
@@ -39,6 +39,7 @@ SIGNATURES = {
     "idv_lstm_recurrent_tc": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp],
     "idv_lstm2_wave_tc": [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],
     "idv_lstm_layer_pair_tc": [vp, i64, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp],
+    "idv_lstm2_cluster_tc": [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],
     "idv_lstm_h1_fwd": [vp, i32, vp, i32, i32, i32, i32, vp, vp],
     "idv_lstm_combine_fwd": [vp, i32, i32, i32, vp, i32, vp],
     "idv_reparam_fwd": [vp, i32, i32, i32, i32, i32, i32, vp, vp, u64, u64, vp, i32, vp, vp],
@@ -83,7 +84,7 @@ SIGNATURES = {
     "idv_stream_tail": [vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, i64, vp, i32, i32, i32, i32, vp],
 }
 EXPORTS = ["idv_abi_version", "idv_last_error", "idv_lstm_tc_config", "idv_lstm2_wave_config",
-           "idv_lstm_layer_pair_config", "idv_set_option"] + \
+           "idv_lstm_layer_pair_config", "idv_lstm2_cluster_config", "idv_set_option"] + \
     list(SIGNATURES)
 
 
@@ -143,9 +144,14 @@ def resolve_profile(prof):
     return {k: [e0.elapsed_time(e1) for (e0, e1) in v] for k, v in prof.items()}
 
 
-def call(name, *args):
+E_RESOURCE = 3         # IDV_E_RESOURCE
+
+
+def call(name, *args, soft_resource=False):
     """Call a C-ABI entry point.  torch tensors are passed as device pointers (they must be contiguous
-    CUDA tensors); the current CUDA stream is appended as the trailing ``stream`` argument."""
+    CUDA tensors); the current CUDA stream is appended as the trailing ``stream`` argument.  With ``soft_resource`` an
+    IDV_E_RESOURCE status (the kernel cannot be made resident on this device) is returned as False instead of raised, for
+    entry points whose contract names another entry point to use in that case."""
     lib = load()
     conv = [ptr(a) if isinstance(a, torch.Tensor) else a for a in args]
     conv.append(torch.cuda.current_stream().cuda_stream)
@@ -154,12 +160,18 @@ def call(name, *args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     rc = getattr(lib, name)(*conv)
+    if rc == E_RESOURCE and soft_resource:
+        return False
     if rc != 0:
         raise RuntimeError("%s failed (code %d): %s" % (name, rc, lib.idv_last_error().decode()))
     LAUNCHES[0] += KERNELS_PER_CALL.get(name, 1)
     if hook is not None:
         e1.record()
         hook(name, (e0, e1))
+    return True
+
+
+OPTIONS = {}            # options set through set_option in this process (name -> value)
 
 
 def set_option(name, value):
@@ -168,6 +180,7 @@ def set_option(name, value):
     lib.idv_set_option.restype = ctypes.c_int
     if lib.idv_set_option(name.encode(), int(value)) != 0:
         raise RuntimeError("idv_set_option failed: %s" % lib.idv_last_error().decode())
+    OPTIONS[name] = int(value)
 
 
 def lstm_tc_config(H):
@@ -203,6 +216,18 @@ def lstm_layer_pair_config(H):
     if lib.idv_lstm_layer_pair_config(int(H), ctypes.byref(n), ctypes.byref(c), ctypes.byref(w)) != 0:
         return None
     return n.value, c.value, w.value
+
+
+def lstm2_cluster_config(H, NB, T):
+    """(hidden units per CTA, CTAs per cluster, workspace bytes) of the small-batch cluster recurrence, or None."""
+    lib = load()
+    u, c, w = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int64(0)
+    lib.idv_lstm2_cluster_config.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                             ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64)]
+    lib.idv_lstm2_cluster_config.restype = ctypes.c_int
+    if lib.idv_lstm2_cluster_config(int(H), int(NB), int(T), ctypes.byref(u), ctypes.byref(c), ctypes.byref(w)) != 0:
+        return None
+    return u.value, c.value, w.value
 
 
 _EXCLUSIVE = {}

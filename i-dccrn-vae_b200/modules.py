@@ -413,6 +413,16 @@ class ComplexLSTM(nn.Module):
                           pack.pack_lstm_whh_tc(re, im, 1, n, c, device), pack.pack_lstm_bias_tc(re, im, 1, n, c, device))
         return items[key]
 
+    def _packed_cluster(self, cfg, device):
+        items = self._cache.check(self)
+        key = ("cluster", cfg[0], cfg[1], str(device))
+        if key not in items:
+            re, im = _sd(self.lstm_re), _sd(self.lstm_im)
+            u, c = cfg[0], cfg[1]
+            items[key] = (pack.pack_lstm_cluster_tc(re, im, 0, u, c, device), pack.pack_lstm_cluster_tc(re, im, 1, u, c, device, "ih"),
+                          pack.pack_lstm_cluster_tc(re, im, 1, u, c, device), pack.pack_lstm_cluster_bias(re, im, 1, u, c, device))
+        return items[key]
+
     def forward_planes(self, xp, combine=True):
         """xp: Planes with C*F == input_size (feature d = c*F + f).  Returns the latent (NB, T, H, 2), or with
         combine=False the four uncombined streams ``(hseq fp32 [4][R][H], NB, T, H, Tv)`` for a fused consumer
@@ -423,12 +433,20 @@ class ComplexLSTM(nn.Module):
         src, hseq, split = xp, None, xp.split
         # two layers, batch <= 64: one wavefront kernel (layer 0 | layer-1 input projection | layer 1)
         wave = ops.lstm2_wave_supported(H, NB, xp.data.device) if (split and self.num_layer == 2 and ops.LSTM_WAVE[0]) else None
+        # ... and <= 16 utterances (ops.LSTM_CLUSTER_MAX_NB): one thread-block cluster per (module, role), h exchanged through distributed shared memory
+        clus = ops.lstm2_cluster_supported(H, NB, T, xp.data.device) if wave else None
         if wave:
-            w0, wi1, w1, b1 = self._packed_wave(wave, xp.data.device)
             g = ops.tapgemm(layers[0][0], xp, None, NB, T, zero_pad_rows=False, out_split=False)
             if ops.GATE_HOOK[0] is not None:
                 ops.GATE_HOOK[0]()
-            hseq = ops.lstm2_wave_tc(g, 4 * H, R * 8 * H, 8 * H, w0, wi1, w1, b1, NB, T, H, wave[2], t_valid=Tv)
+            while clus:
+                w0, wi1, w1, b1 = self._packed_cluster(clus, xp.data.device)
+                hseq = ops.lstm2_cluster_tc(g, 4 * H, R * 8 * H, 8 * H, w0, wi1, w1, b1, NB, T, H, clus[2], t_valid=Tv)
+                # not co-resident: the second cluster shape if there is one, else the wavefront kernel below
+                clus = ops.lstm2_cluster_next(H, NB, T, xp.data.device, clus) if hseq is None else None
+            if hseq is None:                # (no clusters, or they are not co-resident on this device)
+                w0, wi1, w1, b1 = self._packed_wave(wave, xp.data.device)
+                hseq = ops.lstm2_wave_tc(g, 4 * H, R * 8 * H, 8 * H, w0, wi1, w1, b1, NB, T, H, wave[2], t_valid=Tv)
             return ops.lstm_combine(hseq, NB, T, H, Tv) if combine else (hseq, NB, T, H, Tv)
         # tensor-core recurrence when the planes are split-bf16 and the cooperative grid fits the device;
         # otherwise the fp32 SIMT recurrence (any batch size)

@@ -327,6 +327,45 @@ def lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T,
     return hseq
 
 
+LSTM_CLUSTER = [os.environ.get("IDV_LSTM_CLUSTER", "1") != "0"]   # small batches: cluster recurrence (DSMEM exchange)
+LSTM_CLUSTER_MAX_NB = [int(os.environ.get("IDV_LSTM_CLUSTER_MAX_NB", "16"))]   # ... up to this many utterances
+_CLUSTER_OFF = set()                                                 # (device, H): the clusters are not co-resident here
+
+
+def lstm2_cluster_supported(H, NB, T, device):
+    """(units per CTA, CTAs per cluster, workspace bytes) of idv_lstm2_cluster_tc for this problem, or None."""
+    if not LSTM_CLUSTER[0] or NB > LSTM_CLUSTER_MAX_NB[0] or (str(device), H) in _CLUSTER_OFF:
+        return None
+    if lib.OPTIONS.get("gemm_dynamic_tiles", 0) or not lib.OPTIONS.get("lstm_wave_cta_pairs", 1):
+        return None                       # kernels of several streams / processes share the GPU (see lib.check_exclusive_device)
+    return lib.lstm2_cluster_config(H, NB, T)
+
+
+def lstm2_cluster_next(H, NB, T, device, failed_cfg):
+    """After lstm2_cluster_tc returned None for `failed_cfg`: the second cluster shape (option "lstm_cluster_alt") if the
+    hidden size has one, else None (and the cluster recurrence stays off for this device and hidden size)."""
+    if not lib.OPTIONS.get("lstm_cluster_alt", 0):
+        lib.set_option("lstm_cluster_alt", 1)
+        cfg = lib.lstm2_cluster_config(H, NB, T)
+        if cfg is not None and cfg[:2] != failed_cfg[:2]:
+            return cfg
+    _CLUSTER_OFF.add((str(device), H))
+    return None
+
+
+def lstm2_cluster_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, work_bytes, t_valid=0):
+    """Both layers of the ComplexLSTM for <= 32 utterances, one thread-block cluster per (module, role).  Returns hseq1
+    fp32 [4][R][H], or None when the clusters cannot be co-resident on this device (see lstm2_cluster_next)."""
+    if g0.is_cuda:
+        lib.check_exclusive_device(g0.device.index if g0.device.index is not None else torch.cuda.current_device())
+    hseq = _empty(4 * NB * (T + 1) * H, g0.device)
+    work = torch.empty(int(work_bytes), dtype=torch.uint8, device=g0.device)
+    sync = torch.empty(128, dtype=torch.int32, device=g0.device)
+    ok = lib.call("idv_lstm2_cluster_tc", g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq, work, sync,
+                  int(t_valid), soft_resource=True)
+    return hseq if ok is not False else None
+
+
 def lstm_h1(g, g_ld, wrec, num_layers, NB, T, t_valid=0):
     """Real nn.LSTM with one hidden unit (the GAN distinguisher's head): g = layer-0 gate pre-activations [R][g_ld]
     (columns 0-3), wrec = pack.pack_lstm_h1's recurrent parameters.  Returns (NB, Tv, 1)."""

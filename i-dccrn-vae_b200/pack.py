@@ -743,6 +743,32 @@ def pack_lstm_whh_tc(lstm_re, lstm_im, layer, n_cols, n_ctas, device, kind="hh")
     return torch.stack((hi, lo)).contiguous().to(device)
 
 
+def pack_lstm_cluster_tc(lstm_re, lstm_im, layer, upc, cs, device, kind="hh"):
+    """Weights for the small-batch cluster recurrence (csrc/lstm_cluster_tc.cu): bf16 [2 (hi,lo)][2 (module)][cs][4*upc][H],
+    CTA c holds row W[gate*H + c*upc + j] at 4*j + gate (the four gates of a hidden unit in neighbouring TMEM lanes)."""
+    mats = []
+    for mod in (lstm_re, lstm_im):
+        w = _cpu(mod["weight_%s_l%d" % (kind, layer)]).to(torch.float32)          # (4H, H)
+        H = w.shape[1]
+        assert upc * cs == H
+        mats.append(w.view(4, cs, upc, H).permute(1, 2, 0, 3).reshape(cs, 4 * upc, H))
+    w = torch.stack(mats)
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.to(torch.float32)).to(torch.bfloat16)
+    return torch.stack((hi, lo)).contiguous().to(device)
+
+
+def pack_lstm_cluster_bias(lstm_re, lstm_im, layer, upc, cs, device):
+    """b_ih + b_hh of one layer in the lane order of pack_lstm_cluster_tc: fp32 [2][cs][128]."""
+    out = []
+    for mod in (lstm_re, lstm_im):
+        b = (_cpu(mod["bias_ih_l%d" % layer]).double() + _cpu(mod["bias_hh_l%d" % layer]).double())
+        o = torch.zeros(cs, 128, dtype=torch.float64, device=b.device)
+        o[:, :4 * upc] = b.view(4, cs, upc).permute(1, 2, 0).reshape(cs, 4 * upc)
+        out.append(o)
+    return torch.stack(out).to(torch.float32).contiguous().to(device)
+
+
 def pack_dense(w_read, b_read, w_imag, b_imag, c_out, f_out, device):
     """ComplexDense (no cross terms, model/complex_progress.py:L83-89) followed by the reshape/permute
     to (B, C, F, T) (model/pvae_module.py:L2085-2088): output feature n = c*f_out + f goes to plane f,

@@ -40,7 +40,7 @@ extern "C" {
 #define IDV_E_CUDA 2     /* CUDA runtime error (message has the cudaError string) */
 #define IDV_E_RESOURCE 3 /* kernel cannot be made resident (cooperative launch too large) */
 
-#define IDV_ABI_VERSION 7
+#define IDV_ABI_VERSION 8
 
 int idv_abi_version(void);
 const char* idv_last_error(void);
@@ -50,7 +50,9 @@ const char* idv_last_error(void);
  * 0 (default) = static round-robin tiles.  "gemm_cta_pairs": 1 (default) = tiles of width 256 run as CTA pairs
  * (thread-block clusters of 2, tcgen05 cta_group::2: M = 256 MMAs, every CTA stages half of the weight tile) when the
  * tiles are static; 0 = one CTA per tile everywhere.  "lstm_wave_cta_pairs": 1 (default) = neighbouring CTAs of
- * idv_lstm2_wave_tc run as pairs (each streams 64 of the 128 rows of h), 0 = every CTA streams all 128 rows.      */
+ * idv_lstm2_wave_tc run as pairs (each streams 64 of the 128 rows of h), 0 = every CTA streams all 128 rows.
+ * "lstm_cluster_alt": 0 (default) = idv_lstm2_cluster_tc uses the largest CTAs (32 hidden units: H = 384 as clusters of
+ * 12), 1 = the second choice (24 units: clusters of 16), for devices on which the first cannot be scheduled.          */
 int idv_set_option(const char* name, int value);
 /* SM count of the current device (grids are sized against it). */
 int idv_device_sm_count(int* out);
@@ -229,6 +231,20 @@ int idv_lstm2_wave_config(int H, int* n_cols, int* n_ctas, int64_t* work_bytes);
 int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
                       const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
                       float* hseq1, void* work, unsigned int* sync, int t_valid, void* stream);
+/* Small-batch form of idv_lstm2_wave_tc (1 <= NB <= 32 utterances; a step works on 16, 32 or 64 rows = 2 input parts x
+ * 8, 16 or 32 utterance slots): same arithmetic and contract, but every (module, role)
+ * is ONE thread-block cluster (cs CTAs of upc hidden units each) that exchanges h(t) through distributed shared memory
+ * instead of the L2 (csrc/lstm_cluster_tc.cu): ~2.5x shorter dependent step.  idv_lstm2_cluster_config gives (upc, cs,
+ * work_bytes) for (H, NB, T) or fails when the hidden size / batch is not supported (H = 384: 32 x 12 or, with option
+ * "lstm_cluster_alt", 24 x 16; H = 128: 32 x 4; H + 32 <= 512 TMEM columns: the weights stay in tensor memory).
+ * w_hh0 / w_ih1 / w_hh1: bf16 [2 (hi,lo)][2 (module)][cs][4*upc][H], CTA c holds row W[gate*H + c*upc + j] at 4*j + gate;
+ * bias1: fp32 [2][cs][128] = b_ih_l1 + b_hh_l1 in the same order (entries >= 4*upc unused).  work: work_bytes, sync: 128 x
+ * uint32 (zeroed by the call).  Returns IDV_E_RESOURCE when the 6 clusters cannot be co-resident or the GPU is shared
+ * (options "gemm_dynamic_tiles", "lstm_wave_cta_pairs" = 0): the caller then uses idv_lstm2_wave_tc.              */
+int idv_lstm2_cluster_config(int H, int NB, int T, int* upc, int* cs, int64_t* work_bytes);
+int idv_lstm2_cluster_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
+                         const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
+                         float* hseq1, void* work, unsigned int* sync, int t_valid, void* stream);
 /* ONE nn.LSTM layer of both modules per launch as CTA pairs (the kernel of idv_lstm2_wave_tc restricted to its first
  * role): same contract as idv_lstm_recurrent_tc, wpack packed with (n_cols, n_ctas) from idv_lstm_layer_pair_config
  * (H = 768: 48 gate columns x 64 CTAs per module).  work: work_bytes workspace, sync: 384 x uint32 (both zeroed by the

@@ -447,14 +447,31 @@ def idv_lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB
     layer-1 recurrence (split h1)."""
     n_cols, n_ctas = 64, H // 16
     hs = n_cols // 4
-    Tp = T + 1
-    R = NB * Tp
 
     def unpack(wp):
         w = wp.view(2, 2, n_ctas, 4, hs, H).to(D)
         return w.permute(0, 1, 3, 2, 4, 5).reshape(2, 2, 4 * H, H)
-    W0, Wi, W1 = unpack(w_hh0), unpack(w_ih1), unpack(w_hh1)
     b1 = bias1.view(2, n_ctas, 4, hs).to(D).permute(0, 2, 1, 3).reshape(2, 4 * H)
+    _lstm2_tc(g0, g_m_off, g_p_off, g_ld, unpack(w_hh0), unpack(w_ih1), unpack(w_hh1), b1, NB, T, H, hseq1, t_valid)
+
+
+def idv_lstm2_cluster_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq1, work, sync,
+                         t_valid=0):
+    """Same contract as idv_lstm2_wave_tc for NB <= 8, with the packs in the cluster kernel's order: CTA c holds row
+    W[gate*H + c*upc + j] at 4*j + gate, bias fp32 [2][cs][128]."""
+    from idccrn_b200 import lib
+    upc, cs, _ = lib.lstm2_cluster_config(H, NB, T)
+
+    def unpack(wp):
+        w = wp.view(2, 2, cs, upc, 4, H).to(D)                         # [hl][m][c][j][gate][k]
+        return w.permute(0, 1, 4, 2, 3, 5).reshape(2, 2, 4 * H, H)
+    b1 = bias1.view(2, cs, 128)[:, :, :4 * upc].reshape(2, cs, upc, 4).to(D).permute(0, 3, 1, 2).reshape(2, 4 * H)
+    _lstm2_tc(g0, g_m_off, g_p_off, g_ld, unpack(w_hh0), unpack(w_ih1), unpack(w_hh1), b1, NB, T, H, hseq1, t_valid)
+
+
+def _lstm2_tc(g0, g_m_off, g_p_off, g_ld, W0, Wi, W1, b1, NB, T, H, hseq1, t_valid):
+    Tp = T + 1
+    R = NB * Tp
     gf = _flat(g0)
     rows0 = torch.arange(NB) * Tp
     out = hseq1.view(4, R, H)
@@ -1081,5 +1098,6 @@ def idv_reparam_bwd(latent, NB, T, Htot, ch0, zdim, eps_r, eps_i, dz, dlatent):
 TABLE = {k: v for k, v in globals().items() if k.startswith("idv_")}
 
 
-def call(name, *args):
+def call(name, *args, soft_resource=False):
     TABLE[name](*args)
+    return True

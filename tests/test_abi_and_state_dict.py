@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert set(syms) == set(lib.EXPORTS), set(syms) ^ set(lib.EXPORTS)
     cdll.idv_abi_version.restype = ctypes.c_int
     from idccrn_b200 import lib as _lib
-    assert cdll.idv_abi_version() == _lib.ABI_VERSION == 7
+    assert cdll.idv_abi_version() == _lib.ABI_VERSION == 8
 
 
 def test_product_has_no_cpu_fallback():

@@ -664,6 +664,33 @@ def test_lstm2_wave_tc(NB, T, H, tv):
     assert _both("idv_lstm2_wave_tc", args, [11]) < 2e-5
 
 
+@pytest.mark.parametrize("NB,T,H,tv", [(4, 40, 384, 0), (8, 9, 384, 0), (1, 3, 384, 0), (1, 1, 384, 0), (2, 2, 384, 0),
+                                       (5, 33, 128, 20), (8, 12, 256, 0), (3, 700, 384, 0),
+                                       (9, 11, 384, 0), (16, 40, 128, 0), (17, 9, 384, 0), (32, 21, 384, 0), (32, 30, 128, 7),
+                                       (24, 5, 256, 0)])
+def test_lstm2_cluster_tc(NB, T, H, tv):
+    """Small-batch cluster recurrence (DSMEM exchange) against the contract it shares with the wavefront kernel."""
+    from idccrn_b200 import pack as PK
+    upc, cs, work_bytes = lib.lstm2_cluster_config(H, NB, T)
+    R = NB * (T + 1)
+    g = _rand(2, R, 8 * H, seed=15)
+    mods = []
+    for mi in range(2):
+        mods.append({"weight_hh_l0": _rand(4 * H, H, seed=20 + mi) / (H ** 0.5),
+                     "weight_ih_l1": _rand(4 * H, H, seed=22 + mi) / (H ** 0.5),
+                     "weight_hh_l1": _rand(4 * H, H, seed=24 + mi) / (H ** 0.5),
+                     "bias_ih_l1": _rand(4 * H, seed=26 + mi) * 0.1, "bias_hh_l1": _rand(4 * H, seed=28 + mi) * 0.1})
+    w0 = PK.pack_lstm_cluster_tc(mods[0], mods[1], 0, upc, cs, "cpu")
+    wi = PK.pack_lstm_cluster_tc(mods[0], mods[1], 1, upc, cs, "cpu", "ih")
+    w1 = PK.pack_lstm_cluster_tc(mods[0], mods[1], 1, upc, cs, "cpu")
+    b1 = PK.pack_lstm_cluster_bias(mods[0], mods[1], 1, upc, cs, "cpu")
+    hseq = torch.zeros(4, R, H)
+    work = torch.zeros(work_bytes, dtype=torch.uint8)
+    sync = torch.zeros(128, dtype=torch.int32)
+    args = [g, 4 * H, R * 8 * H, 8 * H, w0, wi, w1, b1, NB, T, H, hseq, work, sync, tv]
+    assert _both("idv_lstm2_cluster_tc", args, [11]) < 2e-5
+
+
 @pytest.mark.parametrize("interleave", [1, 0])
 @pytest.mark.parametrize("NB,T,H", [(128, 9, 384), (70, 12, 128), (200, 4, 384)])
 def test_lstm2_wave_tc_two_interleaved_chunks(NB, T, H, interleave):

@@ -102,10 +102,11 @@ def run_layerwise_case(device, latent_num=1, B=3, L=700, seed=14, tol=5e-5):
     rec = {"dy": [], "g": {}, "gin": {}}
     orig_call, orig_cb = lib.call, train.EncoderTrainStep._conv_backward
 
-    def spy(name, *a):
-        orig_call(name, *a)
+    def spy(name, *a, **kw):
+        ret = orig_call(name, *a, **kw)
         if name == "idv_cbn_bwd_apply":
             rec["dy"].append((a[4:8], a[12].clone(), a[13]))
+        return ret
 
     def hook(self, i, g):
         rec["g"][i] = g.clone()

@@ -37,10 +37,10 @@ step(); torch.cuda.synchronize()
 prof = []
 shapes = []
 _orig_call = lib.call
-def _spy(name, *a):
+def _spy(name, *a, **kw):
     if name == "idv_tapgemm_tc":
         shapes.append((a[6], a[12], a[15], a[9]))          # rows, N, units, kc_max
-    _orig_call(name, *a)
+    return _orig_call(name, *a, **kw)
 lib.call = _spy
 import idccrn_b200.ops as _ops, idccrn_b200.train as _tr
 lib.set_profile_hook(lambda name, ev: prof.append((name, ev)))
