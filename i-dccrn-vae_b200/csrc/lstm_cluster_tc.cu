@@ -122,11 +122,6 @@ __device__ __forceinline__ void cl_wait_counter(const unsigned int* ctr, long lo
     }
   }
 }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ float sel4(int i, float a, float b, float c, float d) {
   return i == 0 ? a : (i == 1 ? b : (i == 2 ? c : d));
 }
@@ -236,7 +231,7 @@ lstm_cluster_tc_kernel(const ClusterParams p) {
       }
       mbar_wait(accempty, (t & 1) ^ 1);
       tc_fence_after();
-      if (elect_one()) {
+      if (elect_one_sync()) {
         CL_DBG(0);
         if (role != 1 && t > 0 && t + 2 < T) mbar_expect_tx(full0 + 8 * b, (uint32_t)BB);   // arm the next fill of this buffer (h(t+1))
         if (role != 1 && t == 0) {
@@ -419,7 +414,7 @@ lstm_cluster_tc_kernel(const ClusterParams p) {
       asm volatile("bar.sync 1, %0;" ::"n"(32 * N_EPI_WARPS) : "memory");
       if (warp == CL_EPI_WARP0 && lane == 0) CL_DBG(3);
       // this CTA's block of h(t) -> buffer (t+1)&1 of every CTA of the cluster (h(T-1) has no consumer here)
-      if (t + 1 < T && elect_one()) {
+      if (t + 1 < T && elect_one_sync()) {
         for (int d = ew; d < CS; d += N_EPI_WARPS)
           dsmem_bulk_copy(mapa_u32(my_blk + (b ? 0 : BB), (uint32_t)d), smem_s + b * SB, (uint32_t)SB,
                           mapa_u32(full0 + (b ? 0 : 8), (uint32_t)d));

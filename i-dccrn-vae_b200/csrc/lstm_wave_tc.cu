@@ -241,7 +241,9 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0 && rank == 0) {
+    // the whole warp runs the loop, the tcgen05 instructions are issued under elect.sync (from a `lane == 0` branch ptxas
+    // wraps every tcgen05.mma in an elect / R2UR / branch loop: ~37 ns of issue per MMA, measured in lstm_cluster_tc.cu)
+    if (rank == 0) {
       constexpr uint32_t idesc = PAIR ? make_idesc_mn(128, 2 * N) : make_idesc(N);
       constexpr uint32_t idesc_cat = make_idesc_mn(128, 4 * N);
       mbar_wait(wfull, 0);
@@ -255,32 +257,37 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
           const int kc = kc0;
           mbar_wait(hfull0 + 8 * stage, phase);
           tc_fence_after();
-          if (kc0 == 0) WAVE_DBG(2);
-          if (p.dbg && blockIdx.x == 0 && m == 0 && role == 0 && ch == 0 && t >= 300 && t < 304 && kc0 < 8)
-            p.dbg[96 + (t - 300) * 8 + kc0] = wgtime();
-          const uint32_t sa = smem_ring + stage * 2 * HT;
-          const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + HT);
-          const uint64_t b_hi = make_desc_sw128(smem_w + (PAIR ? 2 * kc : kc) * W_TILE);
-          const uint64_t b_lo = make_desc_sw128(smem_w + (KC + kc) * W_TILE);          // (not used by PAIR)
+          if (elect_one_sync()) {
+            if (kc0 == 0) WAVE_DBG(2);
+            if (p.dbg && blockIdx.x == 0 && m == 0 && role == 0 && ch == 0 && t >= 300 && t < 304 && kc0 < 8)
+              p.dbg[96 + (t - 300) * 8 + kc0] = wgtime();
+            const uint32_t sa = smem_ring + stage * 2 * HT;
+            const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + HT);
+            const uint64_t b_hi = make_desc_sw128(smem_w + (PAIR ? 2 * kc : kc) * W_TILE);
+            const uint64_t b_lo = make_desc_sw128(smem_w + (KC + kc) * W_TILE);          // (not used by PAIR)
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-            if (PAIR) {
-              umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc_cat, (kc0 | k) != 0);   // [hi*hi | hi*lo]
-              umma_bf16_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);                      // + lo*hi
-            } else {
-              umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, (kc0 | k) != 0);
-              umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
-              umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+              if (PAIR) {
+                umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc_cat, (kc0 | k) != 0);   // [hi*hi | hi*lo]
+                umma_bf16_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);                      // + lo*hi
+              } else {
+                umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, (kc0 | k) != 0);
+                umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+                umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1);
+              }
+            }
+            if (PAIR) umma_commit_2sm(hempty0 + 8 * stage, 3);
+            else umma_commit(hempty0 + 8 * stage);
+            if (kc0 + 1 == KC) {
+              if (PAIR) umma_commit_2sm(accfull0 + 8 * ch, 3);
+              else umma_commit(accfull0 + 8 * ch);
+              WAVE_DBG(3);
             }
           }
-          if (PAIR) umma_commit_2sm(hempty0 + 8 * stage, 3);
-          else umma_commit(hempty0 + 8 * stage);
+          __syncwarp();
           if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
         }
-        if (PAIR) umma_commit_2sm(accfull0 + 8 * ch, 3);
-        else umma_commit(accfull0 + 8 * ch);
-        WAVE_DBG(3);
       }
     }
   } else {

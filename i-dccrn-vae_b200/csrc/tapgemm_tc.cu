@@ -241,7 +241,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0 && rank == 0) {
+    // The whole warp runs the loop and the tcgen05 instructions are issued under elect.sync.  (Issued from a
+    // `lane == 0` branch ptxas cannot know that one thread is active and wraps EVERY tcgen05.mma in an elect / R2UR /
+    // branch loop - ~50 clocks of issue per MMA, more than a 128 x 64 MMA takes: the narrow tiles were issue-bound.)
+    if (rank == 0) {
       constexpr uint32_t idesc = TWO ? make_idesc_m256(BN) : make_idesc(BN);
       uint32_t stage = 0, phase = 0;
       for (uint32_t local = 0;; ++local) {
@@ -250,7 +253,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const uint32_t qs = local & 3, qph = (local >> 2) & 1;
           mbar_wait(qfull0 + 8 * qs, qph);
           t = tq[qs];
-          mbar_arrive(qempty0 + 8 * qs);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(qempty0 + 8 * qs);
         } else {
           t = (int)(wid + local * nwork);
           if (t >= total_tiles) t = -1;
@@ -267,29 +271,41 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + C::A_BYTES);
-          const uint64_t b_hi = make_desc_sw128(sa + 2 * C::A_BYTES);
-          const uint64_t b_lo = make_desc_sw128(sa + 2 * C::A_BYTES + C::B_BYTES);
+          if (elect_one_sync()) {
+            const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+            const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + C::A_BYTES);
+            const uint64_t b_hi = make_desc_sw128(sa + 2 * C::A_BYTES);
+            const uint64_t b_lo = make_desc_sw128(sa + 2 * C::A_BYTES + C::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);      // +32 B per K step inside the swizzle row
-            if (TWO) {
-              umma_bf16_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, (ks | k) != 0);
-              umma_bf16_2sm(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
-              umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc, 1);
-            } else {
-              umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, (ks | k) != 0);
-              umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
-              umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);      // +32 B per K step inside the swizzle row
+              if (TWO) {
+                umma_bf16_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, (ks | k) != 0);
+                umma_bf16_2sm(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+                umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc, 1);
+              } else {
+                umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, (ks | k) != 0);
+                umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+                umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1);
+              }
+            }
+            if (TWO) umma_commit_2sm(empty0 + 8 * stage, 3);   // frees the slot in BOTH CTAs when these MMAs retire
+            else umma_commit(empty0 + 8 * stage);       // frees the smem slot when these MMAs retire
+            if (ks + 1 == ksteps) {
+              if (TWO) umma_commit_2sm(tfull0 + 8 * acc, 3);
+              else umma_commit(tfull0 + 8 * acc);         // accumulator complete -> epilogue
             }
           }
-          if (TWO) umma_commit_2sm(empty0 + 8 * stage, 3);   // frees the slot in BOTH CTAs when these MMAs retire
-          else umma_commit(empty0 + 8 * stage);       // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }
-        if (TWO) umma_commit_2sm(tfull0 + 8 * acc, 3);
-        else umma_commit(tfull0 + 8 * acc);           // accumulator complete -> epilogue
+        if (ksteps == 0) {                              // (a unit without taps: the epilogue still gets its signal)
+          if (elect_one_sync()) {
+            if (TWO) umma_commit_2sm(tfull0 + 8 * acc, 3);
+            else umma_commit(tfull0 + 8 * acc);
+          }
+          __syncwarp();
+        }
       }
     }
   } else {
