@@ -188,16 +188,20 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      // PAIR: the barriers the MMA issuer waits on live in the even CTA and collect the bytes of both CTAs' loads
-      if (!PAIR || rank == 0) mbar_expect_tx(wfull, (uint32_t)w_bytes * (PAIR ? 2 : 1));
-      for (int hl = 0; hl < 2; ++hl)
-        for (int kc = 0; kc < KC; ++kc) {
-          if (PAIR)      // [kc][hi | lo]
-            tma_load_2d_2sm(tmW, wfull & PEER_BIT_MASK, smem_w + (kc * 2 + hl) * W_TILE, kc * BK, ((hl * 2 + m) * NC + c) * N);
-          else
-            tma_load_2d(tmW, wfull, smem_w + (hl * KC + kc) * W_TILE, kc * BK, ((hl * 2 + m) * NC + c) * N);
-        }
+    // (whole warp in the loop, TMA instructions under elect.sync: see the MMA issuer)
+    {
+      if (elect_one_sync()) {
+        // PAIR: the barriers the MMA issuer waits on live in the even CTA and collect the bytes of both CTAs' loads
+        if (!PAIR || rank == 0) mbar_expect_tx(wfull, (uint32_t)w_bytes * (PAIR ? 2 : 1));
+        for (int hl = 0; hl < 2; ++hl)
+          for (int kc = 0; kc < KC; ++kc) {
+            if (PAIR)      // [kc][hi | lo]
+              tma_load_2d_2sm(tmW, wfull & PEER_BIT_MASK, smem_w + (kc * 2 + hl) * W_TILE, kc * BK, ((hl * 2 + m) * NC + c) * N);
+            else
+              tma_load_2d(tmW, wfull, smem_w + (hl * KC + kc) * W_TILE, kc * BK, ((hl * 2 + m) * NC + c) * N);
+          }
+      }
+      __syncwarp();
       uint32_t stage = 0, phase = 0;
       for (int t = 0; t < T; ++t)
       for (int ch = 0; ch < nch; ++ch) {
@@ -205,38 +209,42 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         const unsigned int* cB = cA + W_SYNC_STRIDE;
         const unsigned int* cC = cB + W_SYNC_STRIDE;
         int slot;
-        if (role == 0) {            // input h0(t-1): slot (t)%4 holds h0(t-1) (h0(t) is written to slot (t+1)%4)
-          wait_counter(cA, (long long)NC * t, rlx);
-          if (p.n_roles == 3) wait_counter(cB, (long long)NC * (t - 3), rlx);   // (single layer: all readers of a slot are L0 CTAs,
-          slot = t & 3;                                                    //  at most one step apart)
-        } else if (role == 1) {     // input h0(t): slot (t+1)%4
-          wait_counter(cA, (long long)NC * (t + 1), rlx);
-          wait_counter(cC, (long long)NC * (t - 3), rlx);
-          slot = (t + 1) & 3;
-        } else {                    // input h1(t-1): slot t%2
-          wait_counter(cC, (long long)NC * t, rlx);
-          wait_counter(cB, (long long)NC * (t + 1), rlx);
-          slot = t & 1;
+        if (lane == 0) {
+          if (role == 0) {            // input h0(t-1): slot (t)%4 holds h0(t-1) (h0(t) is written to slot (t+1)%4)
+            wait_counter(cA, (long long)NC * t, rlx);
+            if (p.n_roles == 3) wait_counter(cB, (long long)NC * (t - 3), rlx);   // (single layer: all readers of a slot are L0 CTAs,
+          } else if (role == 1) {     // input h0(t): slot (t+1)%4                //  at most one step apart)
+            wait_counter(cA, (long long)NC * (t + 1), rlx);
+            wait_counter(cC, (long long)NC * (t - 3), rlx);
+          } else {                    // input h1(t-1): slot t%2
+            wait_counter(cC, (long long)NC * t, rlx);
+            wait_counter(cB, (long long)NC * (t + 1), rlx);
+          }
+          WAVE_DBG(0);
         }
+        __syncwarp();
         fence_proxy_async_global();
-        WAVE_DBG(0);
+        slot = role == 0 ? (t & 3) : (role == 1 ? ((t + 1) & 3) : (t & 1));
         const int nslot = role == 2 ? 2 : 4;
         const int blk = ((((c % W_REP) * nslot + slot) * 2 + m) * 2) +     // block index of the hi tile (lo = +1)
                         ch * (role == 2 ? p.blkC_ch : p.blkA_ch);
         for (int kc0 = 0; kc0 < KC; ++kc0) {
           const int kc = kc0;                  // same order in every CTA (measured: rotating the order does not help)
           mbar_wait(hempty0 + 8 * stage, phase ^ 1);
-          const uint32_t sa = smem_ring + stage * 2 * HT;
-          if (PAIR) {
-            if (rank == 0) mbar_expect_tx(hfull0 + 8 * stage, 4 * HT);
-            tma_load_3d_2sm(tmH, (hfull0 + 8 * stage) & PEER_BIT_MASK, sa, kc * BK, (int)rank * ROWS_C, blk);   // my 64 rows
-          } else {
-            mbar_expect_tx(hfull0 + 8 * stage, 2 * HT);
-            tma_load_3d(tmH, hfull0 + 8 * stage, sa, kc * BK, 0, blk);      // {64 k, 128 rows, hi+lo} = 32 KB
+          if (elect_one_sync()) {
+            const uint32_t sa = smem_ring + stage * 2 * HT;
+            if (PAIR) {
+              if (rank == 0) mbar_expect_tx(hfull0 + 8 * stage, 4 * HT);
+              tma_load_3d_2sm(tmH, (hfull0 + 8 * stage) & PEER_BIT_MASK, sa, kc * BK, (int)rank * ROWS_C, blk);   // my 64 rows
+            } else {
+              mbar_expect_tx(hfull0 + 8 * stage, 2 * HT);
+              tma_load_3d(tmH, hfull0 + 8 * stage, sa, kc * BK, 0, blk);      // {64 k, 128 rows, hi+lo} = 32 KB
+            }
+            if (kc0 + 1 == KC) WAVE_DBG(1);
           }
+          __syncwarp();
           if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
         }
-        WAVE_DBG(1);
       }
     }
   } else if (warp == 1) {
