@@ -32,7 +32,6 @@
 namespace idv {
 namespace tc {
 
-constexpr int CL_NR_MAX = 64;             // rows of a step NR = 2 input parts x NR/2 utterance slots: 16, 32 or 64
 constexpr int CL_EPI_WARP0 = 4;           // warp 0 loader, 1 MMA issuer, 2 publisher, 3 idle, 4 .. 4 + 4 * EPW epilogue
 constexpr int CL_SYNC_STRIDE = 32;        // uint32 between the two counters of a module (one 128-byte line each)
                                           // TMEM: [accumulator 2 * NR][W_hi H/2][W_lo H/2] columns
@@ -44,6 +43,11 @@ struct ClusterParams {
   const float* bias1;                     // fp32 [2 m][CS][128 lanes]
   const unsigned short* w[3];             // W_hh0, W_ih1, W_hh1: bf16 [2 hl][2 m][CS][4*UPC][H]
   int NB, T, Tsteps, H, CS, KC;
+  // a launch runs ceil(NB / (NR/2)) independent CHUNKS of NR/2 utterances: blockIdx.y = chunk * 6 + (module, role); every
+  // chunk has its own six clusters, counters and exchange buffers.  The dependencies inside a chunk are acyclic (L0 -> IP ->
+  // L1, T-deep buffers, no back-pressure), so any number of chunks is deadlock-free whatever the block scheduler does; the
+  // chunks that are co-resident (6 * cs CTAs each: 6 chunks at H = 128, 2 at H = 384) run concurrently.
+  long long hx0_chunk, g1x_chunk;         // elements between the chunks' buffers
   float* hseq1;                           // fp32 [4][R][H]
   unsigned short* hx0;                    // bf16 [T][2 m][H/8 k-cores][2 hi,lo][NRG][8 rows][8 k]
   float* g1x;                             // fp32 [T][2 m][CS][128 lanes][16 rows]
@@ -129,7 +133,7 @@ __device__ __forceinline__ float sel4(int i, float a, float b, float c, float d)
 // 4 block pushed to the cluster, 5 published to the next role
 #define CL_DBG(slot)                                                                         \
   do {                                                                                       \
-    if (p.dbg && rank == 0 && m == 0 && t >= 300 && t < 304) p.dbg[(role * 4 + (t - 300)) * 8 + (slot)] = cgtime(); \
+    if (p.dbg && rank == 0 && m == 0 && chunk == 0 && t >= 300 && t < 304) p.dbg[(role * 4 + (t - 300)) * 8 + (slot)] = cgtime(); \
   } while (0)
 
 // EPW epilogue warps per TMEM lane quarter: a thread owns RPT = 16 / EPW of the 16 rows of its gate column (a single warp per
@@ -163,10 +167,15 @@ lstm_cluster_tc_kernel(const ClusterParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();             // = blockIdx.x (clusters span x)
-  const int m = blockIdx.y / 3, role = blockIdx.y % 3; // 0 = L0, 1 = IP, 2 = L1
+  const int chunk = blockIdx.y / 6, mr = blockIdx.y % 6;
+  const int m = mr / 3, role = mr % 3;                 // 0 = L0, 1 = IP, 2 = L1
   const int Tp = p.T + 1;
   const long long R = (long long)p.NB * Tp;
-  unsigned int* const ctrA = p.sync + (m * 2) * CL_SYNC_STRIDE;
+  const int b0 = chunk * (NR / 2);                     // first utterance of this chunk
+  const int NBc = p.NB - b0 < NR / 2 ? p.NB - b0 : NR / 2;
+  unsigned short* const hx0 = p.hx0 + chunk * p.hx0_chunk;
+  float* const g1x = p.g1x + chunk * p.g1x_chunk;
+  unsigned int* const ctrA = p.sync + (chunk * 4 + m * 2) * CL_SYNC_STRIDE;
   unsigned int* const ctrB = ctrA + CL_SYNC_STRIDE;
 
   if (warp == 1 && lane == 0) {
@@ -208,7 +217,7 @@ lstm_cluster_tc_kernel(const ClusterParams p) {
         fence_proxy_async_global();
         mbar_wait(empty0 + 8 * b, ((t >> 1) & 1) ^ 1);
         mbar_expect_tx(full0 + 8 * b, (uint32_t)BB);
-        bulk_load_g2s(smem_b + b * BB, reinterpret_cast<const uint8_t*>(p.hx0) + ((long long)t * 2 + m) * BB, (uint32_t)BB,
+        bulk_load_g2s(smem_b + b * BB, reinterpret_cast<const uint8_t*>(hx0) + ((long long)t * 2 + m) * BB, (uint32_t)BB,
                       full0 + 8 * b);
       }
     }
@@ -259,7 +268,7 @@ lstm_cluster_tc_kernel(const ClusterParams p) {
       if (lane == 0) {
         if (role == 0) {
           // this CTA's block of h0(t) for the input-projection cluster
-          bulk_store_s2g(reinterpret_cast<uint8_t*>(p.hx0) + ((long long)t * 2 + m) * BB + rank * SB, smem_s + b * SB, (uint32_t)SB);
+          bulk_store_s2g(reinterpret_cast<uint8_t*>(hx0) + ((long long)t * 2 + m) * BB + rank * SB, smem_s + b * SB, (uint32_t)SB);
           bulk_commit_group();
           bulk_wait_all();
           fence_proxy_async_global();
@@ -323,12 +332,12 @@ lstm_cluster_tc_kernel(const ClusterParams p) {
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
           const int n = row0 + i, part = n / (NR / 2), utt = n % (NR / 2);
-          gin[i] = (lane_ok && utt < p.NB) ? __ldg(gp + part * p.g_p_off + ((long long)utt * Tp + 1 + t) * p.g_ld) : 0.f;
+          gin[i] = (lane_ok && utt < NBc) ? __ldg(gp + part * p.g_p_off + ((long long)(b0 + utt) * Tp + 1 + t) * p.g_ld) : 0.f;
         }
       } else if (role == 2) {
         if (lane == 0) cl_wait_counter(ctrB, (long long)CS * (t + 1));
         __syncwarp();
-        const float* gp = p.g1x + ((((long long)t * 2 + m) * CS + rank) * 128 + L) * NR + row0;
+        const float* gp = g1x + ((((long long)t * 2 + m) * CS + rank) * 128 + L) * NR + row0;
 #pragma unroll
         for (int i = 0; i < RPT; i += 4) {
           const float4 v = ldcg4(gp + i);
@@ -359,7 +368,7 @@ lstm_cluster_tc_kernel(const ClusterParams p) {
       if (t >= 2) mbar_wait(pubdone0 + 8 * b, ((t >> 1) - 1) & 1);
       if (role == 1) {
         if (lane_ok) {
-          float* gp = p.g1x + ((((long long)t * 2 + m) * CS + rank) * 128 + L) * NR + row0;
+          float* gp = g1x + ((((long long)t * 2 + m) * CS + rank) * 128 + L) * NR + row0;
 #pragma unroll
           for (int i = 0; i < RPT; i += 4)
             *reinterpret_cast<float4*>(gp + i) = make_float4(acc[i] + bias, acc[i + 1] + bias, acc[i + 2] + bias, acc[i + 3] + bias);
@@ -426,7 +435,7 @@ lstm_cluster_tc_kernel(const ClusterParams p) {
 #pragma unroll
         for (int j = 0; j < KEEP; ++j) {
           const int n = row0 + KEEP * g + j, part = n / (NR / 2), utt = n % (NR / 2);
-          if (utt < p.NB) p.hseq1[((long long)(m * 2 + part) * R + (long long)utt * Tp + 1 + t) * H + unit] = hn[j];
+          if (utt < NBc) p.hseq1[((long long)(m * 2 + part) * R + (long long)(b0 + utt) * Tp + 1 + t) * H + unit] = hn[j];
         }
       }
     }
@@ -442,8 +451,10 @@ lstm_cluster_tc_kernel(const ClusterParams p) {
 }
 
 static size_t cluster_smem(int H, int upc, int nr) { return (size_t)2 * H * 4 * nr + (size_t)2 * upc * 4 * nr + 256 + 1024; }
-// rows of a step for NB utterances (2 input parts x NB, rounded up to 16 / 32 / 64), 0 if too many
-static int cluster_rows(int NB) { return NB <= 8 ? 16 : (NB <= 16 ? 32 : (NB <= 32 ? 64 : 0)); }
+// rows of a step: 16 (2 input parts x 8 utterance slots) for <= 8 utterances, else chunks of 16 utterances = 32 rows
+// (64 rows per chunk measured slower than the wavefront kernel: the exchange is bound by the DSMEM ingest of an SM)
+static int cluster_rows(int NB) { return NB <= 8 ? 16 : 32; }
+static int cluster_chunks(int NB) { const int ch = cluster_rows(NB) / 2; return (NB + ch - 1) / ch; }
 
 // hidden units per CTA: a multiple of 8 (whole k-cores), <= 32 (M = 128 lanes); cluster of <= 16 CTAs; W hi + lo + the
 // accumulator within the 512 TMEM columns.  `alt` selects the second choice (smaller CTAs, larger cluster).
@@ -464,30 +475,52 @@ static int cluster_upc(int H, int nr, int alt, int* cs_out) {
 }
 
 template <int UPC, int EPW, int NR>
-static int launch_cluster(const ClusterParams& p, size_t smem, cudaStream_t st) {
+static int cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int cs, size_t smem, int n_chunks, cudaStream_t st) {
   IDV_CUDA(cudaFuncSetAttribute(lstm_cluster_tc_kernel<UPC, EPW, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (p.CS > 8) IDV_CUDA(cudaFuncSetAttribute(lstm_cluster_tc_kernel<UPC, EPW, NR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  if (cs > 8) IDV_CUDA(cudaFuncSetAttribute(lstm_cluster_tc_kernel<UPC, EPW, NR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(cs, 6 * n_chunks, 1); cfg.blockDim = dim3(32 * (CL_EPI_WARP0 + 4 * EPW)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return IDV_OK;
+}
+
+// clusters of this shape that can be resident at once (0 + IDV_E_RESOURCE when the cluster cannot be scheduled at all)
+template <int UPC, int EPW, int NR>
+static int cluster_occupancy(int cs, size_t smem, int* max_clusters) {
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)p.CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.gridDim = dim3(p.CS, 6, 1); cfg.blockDim = dim3(32 * (CL_EPI_WARP0 + 4 * EPW)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  // the six clusters wait on one another (L0 -> IP -> L1): all of them must be resident at once.  No cooperative
-  // attribute (Nsight Compute cannot replay cooperative + cluster launches): same precondition as the CTA-pair kernels
-  // (the process has the GPU to itself; every wait has a timeout that traps)
-  int max_clusters = 0;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, lstm_cluster_tc_kernel<UPC, EPW, NR>, &cfg);
+  int rc = cluster_cfg<UPC, EPW, NR>(cfg, attr, cs, smem, 1, nullptr);
+  if (rc) return rc;
+  *max_clusters = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(max_clusters, lstm_cluster_tc_kernel<UPC, EPW, NR>, &cfg);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    set_error("idv_lstm2_cluster_tc: cluster of %d CTAs cannot be scheduled: %s", p.CS, cudaGetErrorString(e));
+    set_error("idv_lstm2_cluster_tc: cluster of %d CTAs cannot be scheduled: %s", cs, cudaGetErrorString(e));
+    *max_clusters = 0;
     return IDV_E_RESOURCE;
   }
+  return IDV_OK;
+}
+
+template <int UPC, int EPW, int NR>
+static int launch_cluster(const ClusterParams& p, size_t smem, int n_chunks, cudaStream_t st) {
+  // the six clusters of a chunk wait on one another (L0 -> IP -> L1): they should be resident at once (for speed; the
+  // waits are acyclic, see ClusterParams).  No cooperative attribute (Nsight Compute cannot replay cooperative + cluster
+  // launches): same precondition as the CTA-pair kernels (the process has the GPU to itself; every wait has a timeout that
+  // traps)
+  int max_clusters = 0;
+  int rc = cluster_occupancy<UPC, EPW, NR>(p.CS, smem, &max_clusters);
+  if (rc) return rc;
   if (max_clusters < 6) {
     set_error("idv_lstm2_cluster_tc: only %d of 6 clusters of %d CTAs are co-resident", max_clusters, p.CS);
     return IDV_E_RESOURCE;
   }
-  e = cudaLaunchKernelEx(&cfg, lstm_cluster_tc_kernel<UPC, EPW, NR>, p);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  rc = cluster_cfg<UPC, EPW, NR>(cfg, attr, p.CS, smem, n_chunks, st);
+  if (rc) return rc;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_cluster_tc_kernel<UPC, EPW, NR>, p);
   if (e != cudaSuccess) {
     set_error("idv_lstm2_cluster_tc: launch failed: %s", cudaGetErrorString(e));
     return IDV_E_CUDA;
@@ -501,18 +534,31 @@ static int launch_cluster(const ClusterParams& p, size_t smem, cudaStream_t st) 
 extern "C" int idv_lstm2_cluster_config(int H, int NB, int T, int* upc, int* cs, int64_t* work_bytes) {
   using namespace idv;
   IDV_CHECK_ARG(upc && cs && work_bytes, "idv_lstm2_cluster_config: null pointer");
-  IDV_CHECK_ARG(NB >= 1 && NB <= tc::CL_NR_MAX / 2, "idv_lstm2_cluster_config: the cluster recurrence takes 1 to %d utterances (got %d)",
-                tc::CL_NR_MAX / 2, NB);
-  const int nr = tc::cluster_rows(NB);
+  IDV_CHECK_ARG(NB >= 1, "idv_lstm2_cluster_config: empty batch");
+  const int nr = tc::cluster_rows(NB), nch = tc::cluster_chunks(NB);
   IDV_CHECK_ARG(T >= 1, "idv_lstm2_cluster_config: T must be positive");
   int c = 0;
   const int u = tc::cluster_upc(H, nr, option_lstm_cluster_alt(), &c);
   IDV_CHECK_ARG(u > 0, "idv_lstm2_cluster_config: hidden size %d is not supported by the cluster recurrence", H);
   *upc = u;
   *cs = c;
-  // hx0 bf16 [T][2][H * 2 * nr] + g1x fp32 [T][2][cs][128][nr]
-  *work_bytes = (int64_t)T * 2 * H * 4 * nr + (int64_t)T * 2 * c * 128 * nr * 4;
+  // per chunk: hx0 bf16 [T][2][H * 2 * nr] + g1x fp32 [T][2][cs][128][nr]
+  *work_bytes = (int64_t)nch * ((int64_t)T * 2 * H * 4 * nr + (int64_t)T * 2 * c * 128 * nr * 4);
   return IDV_OK;
+}
+
+extern "C" int idv_lstm2_cluster_concurrency(int H, int NB, int* max_clusters) {
+  using namespace idv;
+  using namespace idv::tc;
+  IDV_CHECK_ARG(max_clusters, "idv_lstm2_cluster_concurrency: null pointer");
+  int upc = 0, cs = 0;
+  int64_t work_bytes = 0;
+  int rc = idv_lstm2_cluster_config(H, NB, 1, &upc, &cs, &work_bytes);
+  if (rc) return rc;
+  const int nr = cluster_rows(NB);
+  const size_t smem = cluster_smem(H, upc, nr);
+  if (nr == 16) return upc == 32 ? cluster_occupancy<32, 4, 16>(cs, smem, max_clusters) : cluster_occupancy<24, 4, 16>(cs, smem, max_clusters);
+  return upc == 32 ? cluster_occupancy<32, 4, 32>(cs, smem, max_clusters) : cluster_occupancy<24, 4, 32>(cs, smem, max_clusters);
 }
 
 extern "C" int idv_lstm2_cluster_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
@@ -549,8 +595,11 @@ extern "C" int idv_lstm2_cluster_tc(const float* g0, int64_t g_m_off, int64_t g_
   p.w[2] = reinterpret_cast<const unsigned short*>(w_hh1);
   p.NB = NB; p.T = T; p.Tsteps = (t_valid > 0 && t_valid < T) ? t_valid : T; p.H = H; p.CS = cs; p.KC = H / 64;
   p.hseq1 = hseq1;
+  const int nch = cluster_chunks(NB);
   p.hx0 = reinterpret_cast<unsigned short*>(work);
-  p.g1x = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(work) + (size_t)T * 2 * H * 4 * nr);
+  p.hx0_chunk = (long long)T * 2 * H * 2 * nr;
+  p.g1x = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(work) + (size_t)nch * (size_t)T * 2 * H * 4 * nr);
+  p.g1x_chunk = (long long)T * 2 * cs * 128 * nr;
   p.sync = sync;
   p.dbg = nullptr;
   const bool dbg = getenv("IDV_LSTM_DBG") != nullptr && p.Tsteps > 304;
@@ -558,10 +607,9 @@ extern "C" int idv_lstm2_cluster_tc(const float* g0, int64_t g_m_off, int64_t g_
     IDV_CUDA(cudaMalloc(&p.dbg, 96 * sizeof(unsigned long long)));
     IDV_CUDA(cudaMemsetAsync(p.dbg, 0, 96 * sizeof(unsigned long long), st));
   }
-  IDV_CUDA(cudaMemsetAsync(sync, 0, 4 * CL_SYNC_STRIDE * sizeof(unsigned int), st));
-  if (nr == 16) rc = upc == 32 ? launch_cluster<32, 4, 16>(p, smem, st) : launch_cluster<24, 4, 16>(p, smem, st);
-  else if (nr == 32) rc = upc == 32 ? launch_cluster<32, 4, 32>(p, smem, st) : launch_cluster<24, 4, 32>(p, smem, st);
-  else rc = upc == 32 ? launch_cluster<32, 4, 64>(p, smem, st) : launch_cluster<24, 4, 64>(p, smem, st);
+  IDV_CUDA(cudaMemsetAsync(sync, 0, (size_t)nch * 4 * CL_SYNC_STRIDE * sizeof(unsigned int), st));
+  if (nr == 16) rc = upc == 32 ? launch_cluster<32, 4, 16>(p, smem, nch, st) : launch_cluster<24, 4, 16>(p, smem, nch, st);
+  else rc = upc == 32 ? launch_cluster<32, 4, 32>(p, smem, nch, st) : launch_cluster<24, 4, 32>(p, smem, nch, st);
   if (dbg && rc == IDV_OK) {
     unsigned long long h[96];
     IDV_CUDA(cudaStreamSynchronize(st));

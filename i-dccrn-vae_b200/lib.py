@@ -84,7 +84,7 @@ SIGNATURES = {
     "idv_stream_tail": [vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, i64, vp, i32, i32, i32, i32, vp],
 }
 EXPORTS = ["idv_abi_version", "idv_last_error", "idv_lstm_tc_config", "idv_lstm2_wave_config",
-           "idv_lstm_layer_pair_config", "idv_lstm2_cluster_config", "idv_set_option"] + \
+           "idv_lstm_layer_pair_config", "idv_lstm2_cluster_config", "idv_lstm2_cluster_concurrency", "idv_set_option"] + \
     list(SIGNATURES)
 
 
@@ -228,6 +228,17 @@ def lstm2_cluster_config(H, NB, T):
     if lib.idv_lstm2_cluster_config(int(H), int(NB), int(T), ctypes.byref(u), ctypes.byref(c), ctypes.byref(w)) != 0:
         return None
     return u.value, c.value, w.value
+
+
+def lstm2_cluster_concurrency(H, NB):
+    """Clusters of the (H, NB) shape the CURRENT CUDA device holds at once, or None (unsupported shape / no device)."""
+    lib = load()
+    n = ctypes.c_int(0)
+    lib.idv_lstm2_cluster_concurrency.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.idv_lstm2_cluster_concurrency.restype = ctypes.c_int
+    if lib.idv_lstm2_cluster_concurrency(int(H), int(NB), ctypes.byref(n)) != 0:
+        return None
+    return n.value
 
 
 _EXCLUSIVE = {}

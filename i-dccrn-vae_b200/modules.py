@@ -433,7 +433,7 @@ class ComplexLSTM(nn.Module):
         src, hseq, split = xp, None, xp.split
         # two layers, batch <= 64: one wavefront kernel (layer 0 | layer-1 input projection | layer 1)
         wave = ops.lstm2_wave_supported(H, NB, xp.data.device) if (split and self.num_layer == 2 and ops.LSTM_WAVE[0]) else None
-        # ... and <= 16 utterances (ops.LSTM_CLUSTER_MAX_NB): one thread-block cluster per (module, role), h exchanged through distributed shared memory
+        # ... or, when faster (few utterances, or chunks of 16 that run concurrently): one thread-block cluster per (module, role), h exchanged through distributed shared memory
         clus = ops.lstm2_cluster_supported(H, NB, T, xp.data.device) if wave else None
         if wave:
             g = ops.tapgemm(layers[0][0], xp, None, NB, T, zero_pad_rows=False, out_split=False)

@@ -327,18 +327,48 @@ def lstm2_wave_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T,
     return hseq
 
 
-LSTM_CLUSTER = [os.environ.get("IDV_LSTM_CLUSTER", "1") != "0"]   # small batches: cluster recurrence (DSMEM exchange)
-LSTM_CLUSTER_MAX_NB = [int(os.environ.get("IDV_LSTM_CLUSTER_MAX_NB", "16"))]   # ... up to this many utterances
+LSTM_CLUSTER = [os.environ.get("IDV_LSTM_CLUSTER", "1") != "0"]   # cluster recurrence (weights in TMEM, DSMEM exchange)
+LSTM_CLUSTER_MULTI = [os.environ.get("IDV_LSTM_CLUSTER_MULTI", "1") != "0"]   # ... also as several concurrent chunks of 16 utterances
 _CLUSTER_OFF = set()                                                 # (device, H): the clusters are not co-resident here
 
 
+_CLUSTER_CHUNKS = {}                                                 # (device, H, cs) -> chunks that run concurrently
+
+
+def _cluster_concurrent_chunks(device, H, NB, cs):
+    key = (str(device), H, cs)
+    if key not in _CLUSTER_CHUNKS:
+        n = None
+        if torch.cuda.is_available() and torch.device(device).type == "cuda":
+            with torch.cuda.device(device):
+                n = lib.lstm2_cluster_concurrency(H, NB)
+        if n is None:                     # no device (host-logic tests): clusters do not span GPCs (8 GPCs of ~18 SMs on a B200)
+            n = 8 * (18 // cs)
+        _CLUSTER_CHUNKS[key] = max(1, n // 6)
+    return _CLUSTER_CHUNKS[key]
+
+
 def lstm2_cluster_supported(H, NB, T, device):
-    """(units per CTA, CTAs per cluster, workspace bytes) of idv_lstm2_cluster_tc for this problem, or None."""
-    if not LSTM_CLUSTER[0] or NB > LSTM_CLUSTER_MAX_NB[0] or (str(device), H) in _CLUSTER_OFF:
+    """(units per CTA, CTAs per cluster, workspace bytes) of idv_lstm2_cluster_tc when it is the faster recurrence for this
+    problem, else None.  <= 16 utterances: always (1.58 / 2.64 ms against 4.0-4.25 ms of the wavefront kernel at H = 384, 4-s
+    utterances).  More: the entry point runs chunks of 16 utterances, each on its own six clusters; the chunks whose clusters
+    fit the device together run concurrently (clusters do not span GPCs: 5 chunks at H = 128, 1 at H = 384), so the choice is
+    by estimated microseconds per time step (measured on B200, profiles/r02_lstm_chunks_vs_wave.json): a round of chunks
+    2.2 + H / 200, a wavefront launch of <= 64 utterances 5.3 (H <= 128) or 7.3, of 65-128 interleaved utterances 1.3 x that."""
+    if not LSTM_CLUSTER[0] or (str(device), H) in _CLUSTER_OFF:
         return None
     if lib.OPTIONS.get("gemm_dynamic_tiles", 0) or not lib.OPTIONS.get("lstm_wave_cta_pairs", 1):
         return None                       # kernels of several streams / processes share the GPU (see lib.check_exclusive_device)
-    return lib.lstm2_cluster_config(H, NB, T)
+    cfg = lib.lstm2_cluster_config(H, NB, T)
+    if cfg is None or NB <= 16:
+        return cfg
+    if not LSTM_CLUSTER_MULTI[0] or cfg[2] > (8 << 30):
+        return None
+    n_chunks = -(-NB // 16)
+    rounds = -(-n_chunks // _cluster_concurrent_chunks(device, H, NB, cfg[1]))
+    full, rem = divmod(NB, 128)
+    wave = (1.3 * full + (0.0 if rem == 0 else (1.0 if rem <= 64 else 1.3))) * (5.3 if H <= 128 else 7.3)
+    return cfg if rounds * (2.2 + H / 200.0) < wave else None
 
 
 def lstm2_cluster_next(H, NB, T, device, failed_cfg):
@@ -354,13 +384,13 @@ def lstm2_cluster_next(H, NB, T, device, failed_cfg):
 
 
 def lstm2_cluster_tc(g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, work_bytes, t_valid=0):
-    """Both layers of the ComplexLSTM for <= 32 utterances, one thread-block cluster per (module, role).  Returns hseq1
+    """Both layers of the ComplexLSTM, one thread-block cluster per (module, role) and chunk of <= 16 utterances.  Returns hseq1
     fp32 [4][R][H], or None when the clusters cannot be co-resident on this device (see lstm2_cluster_next)."""
     if g0.is_cuda:
         lib.check_exclusive_device(g0.device.index if g0.device.index is not None else torch.cuda.current_device())
     hseq = _empty(4 * NB * (T + 1) * H, g0.device)
     work = torch.empty(int(work_bytes), dtype=torch.uint8, device=g0.device)
-    sync = torch.empty(128, dtype=torch.int32, device=g0.device)
+    sync = torch.empty(128 * max(1, -(-NB // 8)), dtype=torch.int32, device=g0.device)
     ok = lib.call("idv_lstm2_cluster_tc", g0, g_m_off, g_p_off, g_ld, w_hh0, w_ih1, w_hh1, bias1, NB, T, H, hseq, work, sync,
                   int(t_valid), soft_resource=True)
     return hseq if ok is not False else None

@@ -231,17 +231,23 @@ int idv_lstm2_wave_config(int H, int* n_cols, int* n_ctas, int64_t* work_bytes);
 int idv_lstm2_wave_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
                       const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
                       float* hseq1, void* work, unsigned int* sync, int t_valid, void* stream);
-/* Small-batch form of idv_lstm2_wave_tc (1 <= NB <= 32 utterances; a step works on 16, 32 or 64 rows = 2 input parts x
- * 8, 16 or 32 utterance slots): same arithmetic and contract, but every (module, role)
- * is ONE thread-block cluster (cs CTAs of upc hidden units each) that exchanges h(t) through distributed shared memory
- * instead of the L2 (csrc/lstm_cluster_tc.cu): ~2.5x shorter dependent step.  idv_lstm2_cluster_config gives (upc, cs,
- * work_bytes) for (H, NB, T) or fails when the hidden size / batch is not supported (H = 384: 32 x 12 or, with option
- * "lstm_cluster_alt", 24 x 16; H = 128: 32 x 4; H + 32 <= 512 TMEM columns: the weights stay in tensor memory).
+/* Cluster form of idv_lstm2_wave_tc: same arithmetic and contract, but every (module, role) is ONE thread-block cluster
+ * (cs CTAs of upc hidden units each) with its weights resident in tensor memory that exchanges h(t) through distributed
+ * shared memory instead of the L2 (csrc/lstm_cluster_tc.cu): 2.4 us instead of 7-8 us per dependent step for <= 8
+ * utterances (a step works on 16 rows = 2 input parts x 8 utterance slots), 4.1 us for <= 16 (32 rows).  Larger batches run
+ * as independent chunks of 16 utterances inside ONE launch, each chunk on its own six clusters (the chunks whose clusters
+ * fit the device together run concurrently: 6 at H = 128, 2 at H = 384).  idv_lstm2_cluster_config gives (upc, cs,
+ * work_bytes) for (H, NB, T) or fails when the hidden size is not supported (H = 384: 32 x 12 or, with option
+ * "lstm_cluster_alt", 24 x 16; H = 128: 32 x 4; H + 64 <= 512 TMEM columns).
  * w_hh0 / w_ih1 / w_hh1: bf16 [2 (hi,lo)][2 (module)][cs][4*upc][H], CTA c holds row W[gate*H + c*upc + j] at 4*j + gate;
- * bias1: fp32 [2][cs][128] = b_ih_l1 + b_hh_l1 in the same order (entries >= 4*upc unused).  work: work_bytes, sync: 128 x
- * uint32 (zeroed by the call).  Returns IDV_E_RESOURCE when the 6 clusters cannot be co-resident or the GPU is shared
- * (options "gemm_dynamic_tiles", "lstm_wave_cta_pairs" = 0): the caller then uses idv_lstm2_wave_tc.              */
+ * bias1: fp32 [2][cs][128] = b_ih_l1 + b_hh_l1 in the same order (entries >= 4*upc unused).  work: work_bytes, sync:
+ * 128 * ceil(NB / 8) x uint32 (zeroed by the call).  Returns IDV_E_RESOURCE when the 6 clusters of a chunk cannot be
+ * co-resident or the GPU is shared (options "gemm_dynamic_tiles", "lstm_wave_cta_pairs" = 0): the caller then uses
+ * idv_lstm2_wave_tc.                                                                                                 */
 int idv_lstm2_cluster_config(int H, int NB, int T, int* upc, int* cs, int64_t* work_bytes);
+/* Clusters of the (H, NB) shape that the current device can hold at once (cudaOccupancyMaxActiveClusters): / 6 = chunks of
+ * idv_lstm2_cluster_tc that run concurrently (clusters do not span GPCs: 5 chunks at H = 128, 1 at H = 384 on a B200). */
+int idv_lstm2_cluster_concurrency(int H, int NB, int* max_clusters);
 int idv_lstm2_cluster_tc(const float* g0, int64_t g_m_off, int64_t g_p_off, int g_ld, const void* w_hh0,
                          const void* w_ih1, const void* w_hh1, const float* bias1, int NB, int T, int H,
                          float* hseq1, void* work, unsigned int* sync, int t_valid, void* stream);

@@ -667,7 +667,7 @@ def test_lstm2_wave_tc(NB, T, H, tv):
 @pytest.mark.parametrize("NB,T,H,tv", [(4, 40, 384, 0), (8, 9, 384, 0), (1, 3, 384, 0), (1, 1, 384, 0), (2, 2, 384, 0),
                                        (5, 33, 128, 20), (8, 12, 256, 0), (3, 700, 384, 0),
                                        (9, 11, 384, 0), (16, 40, 128, 0), (17, 9, 384, 0), (32, 21, 384, 0), (32, 30, 128, 7),
-                                       (24, 5, 256, 0)])
+                                       (24, 5, 256, 0), (100, 6, 128, 0), (70, 4, 384, 3)])
 def test_lstm2_cluster_tc(NB, T, H, tv):
     """Small-batch cluster recurrence (DSMEM exchange) against the contract it shares with the wavefront kernel."""
     from idccrn_b200 import pack as PK
@@ -686,7 +686,7 @@ def test_lstm2_cluster_tc(NB, T, H, tv):
     b1 = PK.pack_lstm_cluster_bias(mods[0], mods[1], 1, upc, cs, "cpu")
     hseq = torch.zeros(4, R, H)
     work = torch.zeros(work_bytes, dtype=torch.uint8)
-    sync = torch.zeros(128, dtype=torch.int32)
+    sync = torch.zeros(128 * -(-NB // 8), dtype=torch.int32)
     args = [g, 4 * H, R * 8 * H, 8 * H, w0, wi, w1, b1, NB, T, H, hseq, work, sync, tv]
     assert _both("idv_lstm2_cluster_tc", args, [11]) < 2e-5
 

@@ -19,11 +19,17 @@ for model, H in (("vae", 384), ("dccrn", 128)):
         net.load_state_dict(fill_state_dict(net.state_dict(), 3), strict=True)
         net = net.cuda().eval()
         run = lambda x: net(x)
-    for NB in (1, 2, 4, 8, 12, 16, 24, 32):
+    for NB in (4, 8, 16, 32, 48, 64, 96, 128):
         x = C.synth_waveform(NB, 64000, seed=1).cuda()
         row = {"model": model, "H": H, "NB": NB}
         for name, flag in (("cluster", True), ("wave", False)):
             ops.LSTM_CLUSTER[0] = flag
+            if flag and ops.lstm2_cluster_supported(H, NB, 641, x.device) is None:
+                # force the chunked cluster launch even where the heuristic prefers the wavefront kernel
+                _sup = ops.lstm2_cluster_supported
+                ops.lstm2_cluster_supported = lambda H_, NB_, T_, d_: lib.lstm2_cluster_config(H_, NB_, T_)
+            else:
+                _sup = None
             with torch.no_grad():
                 for _ in range(3):
                     run(x)
@@ -38,6 +44,9 @@ for model, H in (("vae", 384), ("dccrn", 128)):
             names = sorted({n for n, _ in prof if "lstm2" in n})
             row[name + "_ms"] = round(sum(ms) / max(len(ms), 1), 4)
             row[name + "_kernel"] = names
+            if _sup is not None:
+                ops.lstm2_cluster_supported = _sup
+                row["cluster_forced"] = True
         ops.LSTM_CLUSTER[0] = True
         out["cases"].append(row)
         print(row, flush=True)
