@@ -526,11 +526,11 @@ def hbm_stage_rooflines(per_kernel, B, L, T, peaks, H=384, zdim=128, kpad_stft=4
 
 def ncu_dram_traffic(B, tc_mode):
     """DRAM bytes of the dominant kernel's launches in one step, from the committed `ncu --set full` capture of this
-    workload (profiles/r02_ncu_tapgemm_full_final.csv: `ncu --set full -k regex:tapgemm_tc` of ONE step of the final build
+    workload (profiles/r02_ncu_tapgemm_full_final2.csv: `ncu --set full -k regex:tapgemm_tc` of ONE step of the final build
     at batch 64, tools/step_launches.py): a profiler figure, never measured here.  The capture lists every tcgen05 tap-GEMM
     launch of the step; the STFT DFT and the fused head (entry point idv_tapgemm_tc_head: the first launch and the
     N = 32 one) are not part of the kernel the roofline object describes and are left out."""
-    name = "r02_ncu_tapgemm_full_final.csv"
+    name = "r02_ncu_tapgemm_full_final2.csv"
     path = os.path.join(ROOT, "profiles", name)
     if not tc_mode or B != 64 or not os.path.exists(path):
         return None, "no ncu capture for this configuration"
