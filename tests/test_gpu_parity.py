@@ -383,3 +383,48 @@ def test_standalone_cbn_train_vs_oracle_formula():
     got = cbn(x.cuda(), train=True)
     assert C.rel_l2(got, want) < 1e-5
     assert C.rel_l2(cbn.Vri, sd["Vri"]) < 1e-4 and cbn.init_flag is False
+
+
+@pytest.mark.parametrize("B", [3, 12, 40])
+def test_lstm_recurrence_choices_agree(B):
+    """The recurrences behind ComplexLSTM (the default choice, the wavefront kernel, the cluster kernel as chunks of 16
+    utterances) give the same latent; a shared GPU (option gemm_dynamic_tiles) makes the cluster entry point decline."""
+    from idccrn_b200 import lib, ops
+    enc, _ = C.build_vae(1, 1, "skip_prepare", "real_imag", 5, "cuda")
+    x, eps = C.vae_inputs(B, 6400, 1, 1, 5, "cuda")
+    calls = []
+    lib.set_profile_hook(lambda n, ev: calls.append(n))
+    try:
+        with torch.no_grad():
+            ref = enc(x, train=False, eps=eps)[1]
+            used_default = [n for n in calls if "lstm2" in n]
+            del calls[:]
+            ops.LSTM_CLUSTER[0] = False
+            wave = enc(x, train=False, eps=eps)[1]
+            ops.LSTM_CLUSTER[0] = True
+            assert [n for n in calls if "lstm2" in n] == ["idv_lstm2_wave_tc"]
+            del calls[:]
+            multi = ops.LSTM_CLUSTER_MULTI[0]
+            ops.LSTM_CLUSTER_MULTI[0] = True
+            forced = ops.lstm2_cluster_supported
+            ops.lstm2_cluster_supported = lambda H, NB, T, d: lib.lstm2_cluster_config(H, NB, T)   # chunked launch even where slower
+            try:
+                chunks = enc(x, train=False, eps=eps)[1]
+            finally:
+                ops.lstm2_cluster_supported = forced
+                ops.LSTM_CLUSTER_MULTI[0] = multi
+            assert [n for n in calls if "lstm2" in n] == ["idv_lstm2_cluster_tc"]
+    finally:
+        lib.set_profile_hook(None)
+    assert used_default == (["idv_lstm2_cluster_tc"] if B <= 16 else ["idv_lstm2_wave_tc"])
+    lib.set_option("gemm_dynamic_tiles", 1)
+    try:
+        assert ops.lstm2_cluster_supported(384, B, 65, x.device) is None
+        cfg = lib.lstm2_cluster_config(384, B, 8)
+        g = torch.zeros(2 * B * 9 * 8 * 384, device="cuda")
+        packs = enc.lstms[0]._packed_cluster(cfg, x.device)
+        if packs is not None:
+            assert ops.lstm2_cluster_tc(g, 4 * 384, B * 9 * 8 * 384, 8 * 384, *packs, B, 8, 384, cfg[2]) is None   # IDV_E_RESOURCE
+    finally:
+        lib.set_option("gemm_dynamic_tiles", 0)
+    assert C.rel_l2(wave, ref) < 2e-5 and C.rel_l2(chunks, ref) < 2e-5
