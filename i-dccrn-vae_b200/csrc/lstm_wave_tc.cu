@@ -29,9 +29,17 @@
 namespace idv {
 namespace tc {
 
-constexpr int W_EPI_WARPS = 8;
-constexpr int W_THREADS = 64 + 32 * W_EPI_WARPS;
+// epilogue warps: a thread = (row, HS / (warps / 4) of the CTA's hidden units): 8 warps = 8 units per thread at N = 64, 6 at
+// N = 48.  Measured on B200 with 16 warps at N = 64 (-DIDV_WAVE_EPI_WARPS_N64=16): the gate math + stores of a step got
+// shorter (1.28 -> 1.02 us) but the publish (named barrier of 512 threads + fence + counter) longer (1.15 -> 1.9 us): step
+// 7.2 -> 8.2 us, config-2 LSTM 5.9 -> 6.5 ms (profiles/r02_lstm_dbg_s_16_epilogue_warps.log).  Stays 8.
 constexpr int W_EPI_WARP0 = 2;
+#ifndef IDV_WAVE_EPI_WARPS_N64
+#define IDV_WAVE_EPI_WARPS_N64 8
+#endif
+constexpr int W_EPI_WARPS_N64 = IDV_WAVE_EPI_WARPS_N64;
+__host__ __device__ constexpr int wave_epi_warps(int n_cols) { return n_cols == 64 ? W_EPI_WARPS_N64 : 8; }
+__host__ __device__ constexpr int wave_threads(int n_cols) { return 64 + 32 * wave_epi_warps(n_cols); }
 constexpr int W_ROWS = 128;
 constexpr int W_HTILE = W_ROWS * BK * 2;
 constexpr int W_SYNC_STRIDE = 32;            // uint32 between the step counters (one 128-byte line each)
@@ -113,11 +121,12 @@ __device__ __forceinline__ float wsig(float x) { return __fdividef(1.f, 1.f + __
 __device__ __forceinline__ float wtanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
 template <int N, bool PAIR>
-__global__ void __launch_bounds__(W_THREADS, 1)
+__global__ void __launch_bounds__(wave_threads(N), 1)
 lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmWi,
                     const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmHA,
                     const __grid_constant__ CUtensorMap tmHC, const WaveParams p) {
   constexpr int HS = N / 4;
+  constexpr int W_EPI_WARPS = wave_epi_warps(N);
   // PAIR: the split runs as TWO MMAs per K step, A_hi x [W_hi | W_lo] (width 2 * 2N: the hi and lo weight tiles of a K
   // chunk are adjacent in shared memory) and A_lo x W_hi on top of its first half; the epilogue adds the two halves
   constexpr int ACC_COLS = PAIR ? 2 * N : N;
@@ -301,8 +310,8 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
   } else {
     // ================================ epilogue: 8 warps, thread = (row, half of the CTA's units) ===========
     const int q = warp & 3;                           // TMEM lane quarter (rows q*32 .. q*32+31)
-    const int half = (warp - W_EPI_WARP0) >> 2;       // which half of the HS hidden units
-    constexpr int HU = HS / 2;                        // units per thread
+    const int half = (warp - W_EPI_WARP0) >> 2;       // which part of the HS hidden units
+    constexpr int HU = HS / (W_EPI_WARPS / 4);        // units per thread
     constexpr int VW = (HU % 4 == 0) ? 4 : 2;         // vector width of the global accesses (N = 48: 6 units per thread)
     static_assert(HU % VW == 0 && HU <= 8, "units per epilogue thread");
     // TMEM lane -> (row, owner of the gate columns): one CTA per tile: lane = row, own columns; PAIR: see the header
@@ -376,6 +385,8 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       for (int gt = 0; gt < 4; ++gt) {
         if (HU == 8) {
           tmem_ld8(tacc + ((uint32_t)(q * 32) << 16) + gt * HS + half * HU, v + gt * HU);
+        } else if (HU == 4) {
+          tmem_ld4(tacc + ((uint32_t)(q * 32) << 16) + gt * HS + half * HU, v + gt * HU);
         } else {                                      // 8 columns are read, the first HU kept (all inside the allocation)
           uint32_t w8[8];
           tmem_ld8(tacc + ((uint32_t)(q * 32) << 16) + gt * HS + half * HU, w8);
@@ -389,6 +400,8 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         for (int gt = 0; gt < 4; ++gt) {
           if (HU == 8) {
             tmem_ld8(tacc + ((uint32_t)(q * 32) << 16) + N + gt * HS + half * HU, v2 + gt * HU);
+          } else if (HU == 4) {
+            tmem_ld4(tacc + ((uint32_t)(q * 32) << 16) + N + gt * HS + half * HU, v2 + gt * HU);
           } else {
             uint32_t w8[8];
             tmem_ld8(tacc + ((uint32_t)(q * 32) << 16) + N + gt * HS + half * HU, w8);
@@ -503,7 +516,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
 template <int N, bool PAIR>
 static int launch_wave(const CUtensorMap* maps, const WaveParams& p, size_t smem, cudaStream_t st) {
   IDV_CUDA(cudaFuncSetAttribute(lstm_wave_tc_kernel<N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(p.NC, 2 * p.n_roles, 1), block(W_THREADS);
+  dim3 grid(p.NC, 2 * p.n_roles, 1), block(wave_threads(N));
   cudaError_t e;
   if (PAIR) {
     // clusters of 2 along x.  All 6 * NC CTAs wait on one another and must be co-resident; that is checked against
