@@ -2,7 +2,7 @@
 # Round-2 final multi-GPU session (gpurun --gpus 8): the bench line of the final build at 8 GPUs, launched the way the driver
 # launches it (torchrun, one rank per GPU, NCCL).
 mkdir -p gpurun_out
-for n in 8; do
+for n in ${NLIST:-8}; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29510 + n)) \
     bench.py --gpus $n --steps 10 --warmup 3 --no-eager > gpurun_out/r02_bench_${n}gpu_final2.json 2> gpurun_out/r02_bench_${n}gpu_final2.err
   tail -c 300 gpurun_out/r02_bench_${n}gpu_final2.err
