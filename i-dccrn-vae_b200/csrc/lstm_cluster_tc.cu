@@ -1,30 +1,31 @@
-// Small-batch two-layer complex-LSTM recurrence (<= 32 utterances): one thread-block CLUSTER per (module, role) and the
-// hidden state exchanged between the CTAs of a cluster through distributed shared memory.
+// Two-layer complex-LSTM recurrence for FEW utterances per chunk (8 or 16): one thread-block CLUSTER per (module, role) and
+// chunk, the weights resident in tensor memory, the hidden state exchanged between the CTAs of a cluster through distributed
+// shared memory.  Larger batches run as independent chunks of 16 utterances in the same launch (see ClusterParams).
 //
 // Why a second kernel: the wavefront kernel (csrc/lstm_wave_tc.cu) moves h(t) through the L2 - stores, fence, counter,
-// poll, TMA load: 3.5 of its 8 us per step are publish + propagation, whatever the batch.  With <= 8 utterances a step's
-// h is 16 rows x H, i.e. 24 KB as split bf16 (H = 384): small enough that EVERY CTA of a (module, role) can receive all
-// of it in its own shared memory each step.  So here
-//   * the problem is transposed: D[gate columns (M = 128 TMEM lanes)][rows (N = 16)] = W[gate cols][K = H] x h^T[K][rows];
+// poll, TMA load: 4.5 of its 7-8 us per step are gate math + publish + propagation, whatever the batch.  With <= 8 utterances
+// a step's h is NR = 16 rows x H (32 rows for <= 16 utterances), i.e. 24 KB as split bf16 (H = 384): small enough that EVERY
+// CTA of a (module, role) can receive all of it in its own shared memory each step.  So here
+//   * the problem is transposed: D[gate columns (M = 128 TMEM lanes)][rows (N = NR)] = W[gate cols][K = H] x h^T[K][rows];
 //     W (bf16 hi AND lo, this CTA's 4 * UPC gate columns) is the A operand and stays in TENSOR MEMORY for the whole
 //     sequence (tcgen05.mma with A from TMEM: lane = gate column, two K elements per 32-bit column: H/2 columns each for
-//     hi and lo next to the 32 accumulator columns) - with W in shared memory the 48 small MMAs of a step were bound by
-//     re-reading its 147 KB (1.9 us per step, measured); h^T is the B operand in the no-swizzle K-major canonical layout
-//     ([k-core][hi | lo][8-row group][8 rows][8 k]), in which the UPC hidden units a CTA produces are ONE contiguous
-//     block of UPC * 64 bytes;
+//     hi and lo next to the 2 * NR accumulator columns) - with W in shared memory (first version) the 48 small MMAs of a
+//     step took 1.9 us; h^T is the B operand in the no-swizzle K-major canonical layout ([k-core][hi | lo][8-row group]
+//     [8 rows][8 k]), in which the UPC hidden units a CTA produces are ONE contiguous block of UPC * 4 * NR bytes;
 //   * after the gates a CTA pushes its block into the B buffer of every CTA of the cluster with one
-//     cp.async.bulk.shared::cluster per destination, completing on the DESTINATION's mbarrier: the consumer's MMA thread
-//     simply waits for H * 64 bytes of transactions - no fence, no counter, no poll on the recurrence chain;
-//   * the split product runs as 2 MMAs per K step: W_hi x [h_hi | h_lo] (N = 32: the hi and lo row groups of a k-core
-//     are adjacent) and W_lo x h_hi on top of its first half; the epilogue adds the two halves;
-//   * epilogue thread = gate column (TMEM lane 4 * unit + gate) holding the 16 rows; the four gates of a unit sit in
-//     four neighbouring lanes and are exchanged with 12 warp shuffles, after which lane `gate` owns rows [4*gate, 4*gate+4)
-//     of the unit (cell state in registers).
-// Roles as in the wavefront kernel: L0 | IP (layer-1 input projection) | L1, one cluster each per module = 6 clusters.
-// Between clusters the data goes through global memory once (L0 -> IP: h0(t) as a bulk store of the staged block + a
-// release counter; IP -> L1: G1(t) fp32 + counter), T deep, so there is no back-pressure between the roles and the
-// latency of these hops only fills the pipeline.  All 6 clusters must be co-resident (checked with
-// cudaOccupancyMaxActiveClusters; the caller falls back to the wavefront kernel otherwise).
+//     cp.async.bulk.shared::cluster per destination, completing on the DESTINATION's mbarrier: the consumer's MMA warp
+//     simply waits for H * 4 * NR bytes of transactions - no fence, no counter, no poll on the recurrence chain;
+//   * the split product runs as 2 MMAs per K step: W_hi x [h_hi | h_lo] (N = 2 NR: the hi and lo row groups of a k-core
+//     are adjacent) and W_lo x h_hi on top of its first half; the epilogue adds the two halves.  TMEM addresses are
+//     compile-time constants and the issue runs under elect.sync (48 MMAs in 0.48 us; 1.76 us from a `lane == 0` branch);
+//   * epilogue thread = (gate column = TMEM lane 4 * unit + gate, RPT = NR / EPW rows), EPW = 4 warps per lane quarter;
+//     the four gates of a unit sit in four neighbouring lanes and are exchanged with 3 warp shuffles per kept row, after
+//     which lane `gate` owns RPT / 4 rows of the unit (cell state in registers).
+// Roles as in the wavefront kernel: L0 | IP (layer-1 input projection) | L1, one cluster each per module = 6 clusters per
+// chunk.  Between clusters the data goes through global memory once (L0 -> IP: h0(t) as a bulk store of the staged block +
+// a release counter; IP -> L1: G1(t) fp32 + counter), T deep, so there is no back-pressure between the roles and the
+// latency of these hops only fills the pipeline.  The 6 clusters of a chunk should be co-resident (checked with
+// cudaOccupancyMaxActiveClusters; the caller falls back to the wavefront kernel otherwise).  Measurements: DESIGN.md 4.2b.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -42,16 +43,16 @@ struct ClusterParams {
   int g_ld;
   const float* bias1;                     // fp32 [2 m][CS][128 lanes]
   const unsigned short* w[3];             // W_hh0, W_ih1, W_hh1: bf16 [2 hl][2 m][CS][4*UPC][H]
-  int NB, T, Tsteps, H, CS, KC;
+  int NB, T, Tsteps, H, CS;
   // a launch runs ceil(NB / (NR/2)) independent CHUNKS of NR/2 utterances: blockIdx.y = chunk * 6 + (module, role); every
   // chunk has its own six clusters, counters and exchange buffers.  The dependencies inside a chunk are acyclic (L0 -> IP ->
   // L1, T-deep buffers, no back-pressure), so any number of chunks is deadlock-free whatever the block scheduler does; the
-  // chunks that are co-resident (6 * cs CTAs each: 6 chunks at H = 128, 2 at H = 384) run concurrently.
+  // chunks that are co-resident (clusters do not span GPCs: 5 chunks at H = 128, 1 at H = 384 on a B200) run concurrently.
   long long hx0_chunk, g1x_chunk;         // elements between the chunks' buffers
   float* hseq1;                           // fp32 [4][R][H]
   unsigned short* hx0;                    // bf16 [T][2 m][H/8 k-cores][2 hi,lo][NRG][8 rows][8 k]
-  float* g1x;                             // fp32 [T][2 m][CS][128 lanes][16 rows]
-  unsigned int* sync;                     // [2 m][A, B] step counters
+  float* g1x;                             // fp32 [T][2 m][CS][128 lanes][NR rows]
+  unsigned int* sync;                     // [chunk][2 m][A, B] step counters
   unsigned long long* dbg;
 };
 
@@ -593,7 +594,7 @@ extern "C" int idv_lstm2_cluster_tc(const float* g0, int64_t g_m_off, int64_t g_
   p.w[0] = reinterpret_cast<const unsigned short*>(w_hh0);
   p.w[1] = reinterpret_cast<const unsigned short*>(w_ih1);
   p.w[2] = reinterpret_cast<const unsigned short*>(w_hh1);
-  p.NB = NB; p.T = T; p.Tsteps = (t_valid > 0 && t_valid < T) ? t_valid : T; p.H = H; p.CS = cs; p.KC = H / 64;
+  p.NB = NB; p.T = T; p.Tsteps = (t_valid > 0 && t_valid < T) ? t_valid : T; p.H = H; p.CS = cs;
   p.hseq1 = hseq1;
   const int nch = cluster_chunks(NB);
   p.hx0 = reinterpret_cast<unsigned short*>(work);
