@@ -23,8 +23,12 @@ static int g_lstm_sync_mode = 0;
 static int g_launch_pdl = 1;
 static int g_splitk = 1;
 static int g_lstm_cluster_alt = 0;
+static int g_lstm_chunk_sync = 1;
+static int g_lstm_tma_publish = 0;
 int option_splitk() { return g_splitk; }
 int option_lstm_cluster_alt() { return g_lstm_cluster_alt; }
+int option_lstm_chunk_sync() { return g_lstm_chunk_sync; }
+int option_lstm_tma_publish() { return g_lstm_tma_publish; }
 int option_launch_pdl() { return g_launch_pdl; }
 int option_lstm_sync_mode() { return g_lstm_sync_mode; }
 int option_lstm_interleave() { return g_lstm_interleave; }
@@ -64,6 +68,14 @@ extern "C" int idv_set_option(const char* name, int value) {
   }
   if (strcmp(name, "gemm_splitk") == 0) {
     g_splitk = value != 0;
+    return IDV_OK;
+  }
+  if (strcmp(name, "lstm_tma_publish") == 0) {
+    g_lstm_tma_publish = value != 0;
+    return IDV_OK;
+  }
+  if (strcmp(name, "lstm_chunk_sync") == 0) {
+    g_lstm_chunk_sync = value != 0;
     return IDV_OK;
   }
   if (strcmp(name, "lstm_cluster_alt") == 0) {

@@ -21,6 +21,8 @@ int option_lstm_sync_mode();
 int option_launch_pdl();
 int option_splitk();
 int option_lstm_cluster_alt();
+int option_lstm_chunk_sync();
+int option_lstm_tma_publish();
 
 #define IDV_CHECK_ARG(cond, ...)             \
   do {                                       \

@@ -67,6 +67,19 @@ struct WaveParams {
   unsigned short* hxC;                      // bf16 [W_REP][2 slot][2 m][2 hl][128][H]   h1
   float* g1x;                               // fp32 [4 slot][2 m][128][4H]        layer-1 gate pre-activations
   unsigned int* sync;                       // [2 m][3] counters A, B, C, W_SYNC_STRIDE uint32 apart
+  // single-layer mode (n_roles = 1), optional: one step counter per 64-wide K CHUNK of h instead of one per module,
+  // [2 chunks of utterances][2 m][KC] x W_SYNC_STRIDE.  A CTA increments the counter(s) of the chunk(s) its hidden units
+  // fall into; a consumer polls all KC counters at once (one lane each) and loads chunk k as soon as ITS ~6 producers
+  // have published, instead of waiting for all 64 CTAs of the module: the 64 same-address atomics no longer serialise
+  // (H = 768: published -> seen by the next step took 3.6 of 11.2 us) and the ingest overlaps the stragglers' publish.
+  unsigned int* kcsync;
+  // experiment (option "lstm_tma_publish", OFF by default): h(t) leaves through shared memory + ONE tensor store per CTA
+  // and step (box {units of the CTA / pair, its rows, hi | lo}) instead of 4-byte stores scattered over 64 rows, and the
+  // publisher waits for the bulk group.  Measured on B200 (profiles/r02_lstm_dbg_*_tma_publish.log): staging is quick
+  // (gates + stores 1.25 -> 0.64 us at H = 768) but a box of 128 rows x 48 bytes takes the TMA unit ~4.5 us to complete:
+  // step 11.0 -> 11.1 us at H = 768, 7.2 -> 8.5 us at H = 384.  The narrow column strip per producer is the problem, not
+  // the store instruction.
+  int tma_pub;
   unsigned long long* dbg;                  // optional phase timestamps (IDV_LSTM_DBG): CTA 0 of each role, module 0
 };
 
@@ -124,7 +137,8 @@ template <int N, bool PAIR>
 __global__ void __launch_bounds__(wave_threads(N), 1)
 lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmWi,
                     const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmHA,
-                    const __grid_constant__ CUtensorMap tmHC, const WaveParams p) {
+                    const __grid_constant__ CUtensorMap tmHC, const __grid_constant__ CUtensorMap tmSA,
+                    const __grid_constant__ CUtensorMap tmSC, const WaveParams p) {
   constexpr int HS = N / 4;
   constexpr int W_EPI_WARPS = wave_epi_warps(N);
   // PAIR: the split runs as TWO MMAs per K step, A_hi x [W_hi | W_lo] (width 2 * 2N: the hi and lo weight tiles of a K
@@ -142,7 +156,10 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
   constexpr int ROWS_C = PAIR ? W_ROWS / 2 : W_ROWS;          // rows of h this CTA streams
   constexpr int HT = ROWS_C * BK * 2;                         // bytes of the hi (or lo) rows of one K chunk
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + stages * 2 * HT);
+  constexpr int UW = (PAIR ? 2 : 1) * HS;                     // hidden units this CTA stores per row (its pair's)
+  constexpr int STG = 2 * ROWS_C * UW * 2;                    // staging of one chunk's h block: [hi | lo][rows][UW] bf16
+  uint8_t* stg = ring + stages * 2 * HT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + (p.tma_pub ? 2 * STG : 0));
   const uint32_t wfull = smem_u32(bars), hfull0 = wfull + 8, hempty0 = hfull0 + 8 * 8, accfull0 = hempty0 + 8 * 8,
                  accempty0 = accfull0 + 16;                   // accumulator barriers: one pair per chunk
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
@@ -211,6 +228,13 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
           }
       }
       __syncwarp();
+      // (per-chunk counters) CTAs whose published units fall into K chunk `lane`: a CTA publishes the units of its pair
+      int kc_cnt = 0;
+      if (p.n_roles == 1 && p.kcsync != nullptr && lane < KC)
+        for (int cc = 0; cc < NC; ++cc) {
+          const int ulo = (PAIR ? (cc & ~1) : cc) * HS, uhi = ulo + (PAIR ? 2 : 1) * HS - 1;
+          if ((ulo >> 6) <= lane && lane <= (uhi >> 6)) ++kc_cnt;
+        }
       uint32_t stage = 0, phase = 0;
       for (int t = 0; t < T; ++t)
       for (int ch = 0; ch < nch; ++ch) {
@@ -218,7 +242,8 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         const unsigned int* cB = cA + W_SYNC_STRIDE;
         const unsigned int* cC = cB + W_SYNC_STRIDE;
         int slot;
-        if (lane == 0) {
+        const bool by_chunk = p.n_roles == 1 && p.kcsync != nullptr;
+        if (lane == 0 && !by_chunk) {
           if (role == 0) {            // input h0(t-1): slot (t)%4 holds h0(t-1) (h0(t) is written to slot (t+1)%4)
             wait_counter(cA, (long long)NC * t, rlx);
             if (p.n_roles == 3) wait_counter(cB, (long long)NC * (t - 3), rlx);   // (single layer: all readers of a slot are L0 CTAs,
@@ -237,8 +262,27 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         const int nslot = role == 2 ? 2 : 4;
         const int blk = ((((c % W_REP) * nslot + slot) * 2 + m) * 2) +     // block index of the hi tile (lo = +1)
                         ch * (role == 2 ? p.blkC_ch : p.blkA_ch);
+        // by_chunk: lane k polls the counter of K chunk k; chunk k is loaded as soon as it and every chunk before it is ready
+        const unsigned int* kb = by_chunk ? p.kcsync + (long long)((ch * 2 + m) * KC) * W_SYNC_STRIDE : nullptr;
+        const long long kc_target = (long long)kc_cnt * t;
+        uint32_t ready = by_chunk ? 0u : 0xffffffffu;
+        long long poll_t0 = 0;
+        unsigned int polls = 0;
         for (int kc0 = 0; kc0 < KC; ++kc0) {
           const int kc = kc0;                  // same order in every CTA (measured: rotating the order does not help)
+          while (!((ready >> kc) & 1u)) {
+            bool ok = true;
+            if (lane < KC && !((ready >> lane) & 1u)) ok = kc_target <= 0 || (long long)ldacq(kb + lane * W_SYNC_STRIDE) >= kc_target;
+            ready = __ballot_sync(0xffffffffu, ok);
+            if ((ready >> kc) & 1u) {
+              fence_proxy_async_global();
+              if (lane == 0 && kc == 0) WAVE_DBG(0);
+            } else if ((++polls & 63u) == 0) {
+              const long long now = clock64();
+              if (poll_t0 == 0) poll_t0 = now;
+              else if (now - poll_t0 > WAIT_TIMEOUT_CYCLES) __trap();
+            }
+          }
           mbar_wait(hempty0 + 8 * stage, phase ^ 1);
           if (elect_one_sync()) {
             const uint32_t sa = smem_ring + stage * 2 * HT;
@@ -452,14 +496,40 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
         cst[ch][j] = fg * cst[ch][j] + ig * gg;
         hn[j] = og * wtanh(cst[ch][j]);
       }
-      if (valid) {
-        // h(t) goes to the slot the consumers of step t+1 read: (t+1)%4 for h0, (t+1)%2 for h1
-        const int slot = role == 0 ? ((t + 1) & 3) : ((t + 1) & 1);
+      // h(t) goes to the slot the consumers of step t+1 read: (t+1)%4 for h0, (t+1)%2 for h1
+      const int wslot = role == 0 ? ((t + 1) & 3) : ((t + 1) & 1);
+      if (p.tma_pub) {
+        // block of this CTA in shared memory: [hi | lo][its rows][the UW units of its pair] (all rows: the unused ones
+        // hold finite values nobody reads), written with one tensor store by the publishing thread below
+        const int row_l = PAIR ? (tl & 63) : tl;
+        const int uoff = (PAIR ? (tl >> 6) * HS : 0) + half * HU;
+        uint8_t* sp = stg + ch * STG + (row_l * UW + uoff) * 2;
+        unsigned short hi[HU], lo[HU];
+#pragma unroll
+        for (int j = 0; j < HU; ++j) split_bf16(hn[j], hi[j], lo[j]);
+        if constexpr (HU % 8 == 0) {
+#pragma unroll
+          for (int j = 0; j < HU; j += 8) {
+            *reinterpret_cast<uint4*>(sp + j * 2) = make_uint4((unsigned)hi[j] | ((unsigned)hi[j + 1] << 16), (unsigned)hi[j + 2] | ((unsigned)hi[j + 3] << 16),
+                                                              (unsigned)hi[j + 4] | ((unsigned)hi[j + 5] << 16), (unsigned)hi[j + 6] | ((unsigned)hi[j + 7] << 16));
+            *reinterpret_cast<uint4*>(sp + ROWS_C * UW * 2 + j * 2) =
+                make_uint4((unsigned)lo[j] | ((unsigned)lo[j + 1] << 16), (unsigned)lo[j + 2] | ((unsigned)lo[j + 3] << 16),
+                           (unsigned)lo[j + 4] | ((unsigned)lo[j + 5] << 16), (unsigned)lo[j + 6] | ((unsigned)lo[j + 7] << 16));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < HU; j += 2) {
+            *reinterpret_cast<unsigned*>(sp + j * 2) = (unsigned)hi[j] | ((unsigned)hi[j + 1] << 16);
+            *reinterpret_cast<unsigned*>(sp + ROWS_C * UW * 2 + j * 2) = (unsigned)lo[j] | ((unsigned)lo[j + 1] << 16);
+          }
+        }
+        fence_proxy_async();
+      } else if (valid) {
         const int nslot = role == 0 ? 4 : 2;
 #pragma unroll
         for (int rep = 0; rep < W_REP; ++rep) {
           unsigned short* hx = (role == 0 ? p.hxA + ch * p.hxA_ch : p.hxC + ch * p.hxC_ch) +
-                               (((((long long)rep * nslot + slot) * 2 + m) * 2) * W_ROWS + r) * H + u0;
+                               (((((long long)rep * nslot + wslot) * 2 + m) * 2) * W_ROWS + r) * H + u0;
 #pragma unroll
           for (int j = 0; j < HU; j += VW) {
             if constexpr (VW == 4) st_split4(hx, (long long)W_ROWS * H, j, make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]));
@@ -470,7 +540,23 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
       if (warp == W_EPI_WARP0 && lane == 0) WAVE_DBG(6);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * W_EPI_WARPS) : "memory");
       if (warp == W_EPI_WARP0 && lane == 0) {
-        publish_step(my_ctr, p.sync_mode);
+        if (p.tma_pub) {
+          const int blk = ((wslot * 2 + m) * 2) + ch * (role == 2 ? p.blkC_ch : p.blkA_ch);
+          tma_store_3d(role == 2 ? &tmSC : &tmSA, smem_u32(stg + ch * STG), (PAIR ? (c & ~1) : c) * HS, PAIR ? (int)rank * ROWS_C : 0, blk);
+          bulk_commit_group();
+          bulk_wait_all();                 // the block is written (not merely read out of shared memory)
+          fence_proxy_async_global();
+        }
+        if (p.n_roles == 1 && p.kcsync != nullptr) {
+          // one increment per K chunk this CTA's stores belong to (the units of its pair: 1 or 2 chunks)
+          unsigned int* kb = p.kcsync + (long long)((ch * 2 + m) * KC) * W_SYNC_STRIDE;
+          const int ulo = (PAIR ? (c & ~1) : c) * HS, uhi = ulo + (PAIR ? 2 : 1) * HS - 1;
+          __threadfence();
+          atomicAdd(kb + (ulo >> 6) * W_SYNC_STRIDE, 1u);
+          if ((uhi >> 6) != (ulo >> 6)) atomicAdd(kb + (uhi >> 6) * W_SYNC_STRIDE, 1u);
+        } else {
+          publish_step(my_ctr, p.sync_mode);
+        }
         WAVE_DBG(7);
       }
       if (role == 2 && valid) {
@@ -533,9 +619,10 @@ static int launch_wave(const CUtensorMap* maps, const WaveParams& p, size_t smem
     int max_clusters = 0;
     IDV_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, lstm_wave_tc_kernel<N, PAIR>, &cfg));
     if (2 * max_clusters < (int)(grid.x * grid.y)) return IDV_E_RESOURCE;
-    e = cudaLaunchKernelEx(&cfg, lstm_wave_tc_kernel<N, PAIR>, maps[0], maps[1], maps[2], maps[3], maps[4], p);
+    e = cudaLaunchKernelEx(&cfg, lstm_wave_tc_kernel<N, PAIR>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], p);
   } else {
-    void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&maps[4], (void*)&p};
+    void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&maps[4], (void*)&maps[5],
+                    (void*)&maps[6], (void*)&p};
     e = cudaLaunchCooperativeKernel((const void*)lstm_wave_tc_kernel<N, PAIR>, grid, block, args, smem, st);
   }
   if (e == cudaErrorCooperativeLaunchTooLarge) {
@@ -599,16 +686,20 @@ static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off
   const size_t w_bytes = (size_t)2 * KC * N * BK * 2;
   pair = pair && NC % 2 == 0;
   const size_t stage_bytes = (size_t)2 * W_HTILE / (pair ? 2 : 1);
-  int stages = (int)(((size_t)smem_optin - w_bytes - 1024 - 256) / stage_bytes);
+  // tensor-store publish: staging of two chunks' h blocks [hi | lo][rows of the CTA][units of the CTA / pair]
+  const int uw = (pair ? 2 : 1) * (N / 4), rows_c = pair ? W_ROWS / 2 : W_ROWS;
+  const int tma_pub = option_lstm_tma_publish() && (uw * 2) % 16 == 0;
+  const size_t stg_bytes = tma_pub ? (size_t)2 * 2 * rows_c * uw * 2 : 0;
+  int stages = (int)(((size_t)smem_optin - w_bytes - stg_bytes - 1024 - 256) / stage_bytes);
   if (stages > (pair ? 7 : 8)) stages = pair ? 7 : 8;
   if (stages > KC) stages = KC;
   IDV_CHECK_ARG(stages >= 1, "idv_lstm2_wave_tc: not enough shared memory for H=%d", H);
-  const size_t smem = w_bytes + (size_t)stages * stage_bytes + 1024 + 256;
+  const size_t smem = w_bytes + (size_t)stages * stage_bytes + stg_bytes + 1024 + 256;
   uint8_t* wk = reinterpret_cast<uint8_t*>(work);
   // workspace: [hxA chunk 0 | hxA chunk 1][hxC chunk 0 | hxC chunk 1][g1x chunk 0 | g1x chunk 1]
   const size_t hxA_bytes = (size_t)W_REP * 4 * 2 * 2 * 128 * H * 2, hxC_bytes = (size_t)W_REP * 2 * 2 * 2 * 128 * H * 2;
   const size_t g1x_bytes = (size_t)4 * 2 * 128 * 4 * H * 4;
-  CUtensorMap maps[5];
+  CUtensorMap maps[7];
   const void* wp[3] = {w_hh0, w_ih1, w_hh1};
   for (int i = 0; i < 3; ++i) {
     rc = encode_map_2d(&maps[i], wp[i], H, (uint64_t)2 * 2 * NC * N, BK, N);
@@ -618,8 +709,16 @@ static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off
   if (rc) return rc;
   rc = encode_map_3d(&maps[4], wk + 2 * hxA_bytes, H, W_ROWS, (uint64_t)2 * W_REP * 2 * 2 * 2, BK, pair ? W_ROWS / 2 : W_ROWS, 2);
   if (rc) return rc;
+  maps[5] = maps[3]; maps[6] = maps[4];
+  if (tma_pub) {        // the same buffers for the tensor stores: boxes {units of the CTA / pair, its rows, hi | lo}, no swizzle
+    rc = encode_map_3d(&maps[5], wk, H, W_ROWS, (uint64_t)2 * W_REP * 4 * 2 * 2, uw, rows_c, 2, false);
+    if (rc) return rc;
+    rc = encode_map_3d(&maps[6], wk + 2 * hxA_bytes, H, W_ROWS, (uint64_t)2 * W_REP * 2 * 2 * 2, uw, rows_c, 2, false);
+    if (rc) return rc;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   WaveParams p;
+  p.tma_pub = tma_pub;
   p.g0 = g0; p.g_m_off = g_m_off; p.g_p_off = g_p_off; p.g_ld = g_ld; p.bias1 = bias1;
   p.NB = NB; p.T = T; p.H = H; p.NC = NC; p.KC = KC; p.stages = stages;
   p.Tsteps = (t_valid > 0 && t_valid < T) ? t_valid : T;
@@ -629,7 +728,7 @@ static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off
   p.g1x = reinterpret_cast<float*>(wk + 2 * hxA_bytes + 2 * hxC_bytes);
   p.hxA_ch = (long long)(hxA_bytes / 2); p.hxC_ch = (long long)(hxC_bytes / 2); p.g1x_ch = (long long)(g1x_bytes / 4);
   p.blkA_ch = W_REP * 4 * 2 * 2; p.blkC_ch = W_REP * 2 * 2 * 2;
-  p.sync = sync;
+  p.sync = sync; p.kcsync = nullptr;
   p.n_roles = 3; p.hsplit = nullptr; p.hseq0 = nullptr;
   p.sync_mode = option_lstm_sync_mode();
   p.dbg = nullptr;
@@ -703,7 +802,8 @@ extern "C" int idv_lstm_layer_pair_config(int H, int* n_cols, int* n_ctas, int64
   IDV_CHECK_ARG(N > 0, "idv_lstm_layer_pair_config: hidden size %d is not supported by the CTA-pair recurrence", H);
   *n_cols = N;
   *n_ctas = H / (N / 4);
-  *work_bytes = 2 * (int64_t)4 * 2 * 2 * 128 * H * 2;      // h exchange buffers: bf16 [2 chunks][4 slots][2 m][2 hl][128][H]
+  // h exchange buffers: bf16 [2 chunks][4 slots][2 m][2 hl][128][H], then the per-K-chunk step counters [2][2][H/64] lines
+  *work_bytes = 2 * (int64_t)4 * 2 * 2 * 128 * H * 2 + (int64_t)2 * 2 * (H / 64) * tc::W_SYNC_STRIDE * 4;
   return IDV_OK;
 }
 
@@ -730,18 +830,28 @@ extern "C" int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g
   cudaStream_t st = (cudaStream_t)stream;
   for (int attempt = 0; attempt < 2; ++attempt) {
     const size_t stage_bytes = (size_t)2 * W_HTILE / (pair ? 2 : 1);
-    int stages = (int)(((size_t)smem_optin - w_bytes - 1024 - 256) / stage_bytes);
+    const int uw = (pair ? 2 : 1) * (N / 4), rows_c = pair ? W_ROWS / 2 : W_ROWS;
+    const int tma_pub = option_lstm_tma_publish() && (uw * 2) % 16 == 0;
+    const size_t stg_bytes = tma_pub ? (size_t)2 * 2 * rows_c * uw * 2 : 0;
+    int stages = (int)(((size_t)smem_optin - w_bytes - stg_bytes - 1024 - 256) / stage_bytes);
     if (stages > (pair ? 7 : 8)) stages = pair ? 7 : 8;
     if (stages > KC) stages = KC;
     IDV_CHECK_ARG(stages >= 2 || (stages >= 1 && KC == 1), "idv_lstm_layer_pair_tc: not enough shared memory for H=%d", H);
-    const size_t smem = w_bytes + (size_t)stages * stage_bytes + 1024 + 256;
-    CUtensorMap maps[5];
+    const size_t smem = w_bytes + (size_t)stages * stage_bytes + stg_bytes + 1024 + 256;
+    CUtensorMap maps[7];
     rc = encode_map_2d(&maps[0], wpack, H, (uint64_t)2 * 2 * NC * N, BK, N);
     if (rc) return rc;
     rc = encode_map_3d(&maps[3], work, H, W_ROWS, (uint64_t)2 * 4 * 2 * 2, BK, pair ? W_ROWS / 2 : W_ROWS, 2);
     if (rc) return rc;
     maps[1] = maps[0]; maps[2] = maps[0]; maps[4] = maps[3];
+    maps[5] = maps[3];
+    if (tma_pub) {
+      rc = encode_map_3d(&maps[5], work, H, W_ROWS, (uint64_t)2 * 4 * 2 * 2, uw, rows_c, 2, false);
+      if (rc) return rc;
+    }
+    maps[6] = maps[5];
     WaveParams p;
+    p.tma_pub = tma_pub;
     p.g0 = g; p.g_m_off = g_m_off; p.g_p_off = g_p_off; p.g_ld = g_ld; p.bias1 = nullptr;
     p.NB = NB; p.T = T; p.H = H; p.NC = NC; p.KC = KC; p.stages = stages;
     p.Tsteps = (t_valid > 0 && t_valid < T) ? t_valid : T;
@@ -750,8 +860,16 @@ extern "C" int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g
     p.hxA_ch = (long long)4 * 2 * 2 * 128 * H; p.hxC_ch = 0; p.g1x_ch = 0;
     p.blkA_ch = 4 * 2 * 2; p.blkC_ch = 0;
     p.sync = sync; p.dbg = nullptr;
+    p.kcsync = option_lstm_chunk_sync()
+                   ? reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(work) + (size_t)2 * 4 * 2 * 2 * 128 * H * 2)
+                   : nullptr;
     p.n_roles = 1; p.hsplit = reinterpret_cast<unsigned short*>(hsplit); p.hseq0 = hseq;
     p.sync_mode = option_lstm_sync_mode();
+    const bool dbg = getenv("IDV_LSTM_DBG") != nullptr && p.Tsteps > 304;
+    if (dbg) {
+      IDV_CUDA(cudaMalloc(&p.dbg, (96 + 32) * sizeof(unsigned long long)));
+      IDV_CUDA(cudaMemsetAsync(p.dbg, 0, (96 + 32) * sizeof(unsigned long long), st));
+    }
     rc = IDV_OK;
     const int per_launch = option_lstm_interleave() ? 128 : 64;
     for (int b0 = 0; b0 < NB && rc == IDV_OK; b0 += per_launch) {
@@ -761,6 +879,27 @@ extern "C" int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g
       if (N == 64) rc = pair ? launch_wave<64, true>(maps, p, smem, st) : launch_wave<64, false>(maps, p, smem, st);
       else rc = pair ? launch_wave<48, true>(maps, p, smem, st) : launch_wave<48, false>(maps, p, smem, st);
       if (rc == IDV_E_RESOURCE && b0 == 0) break;
+    }
+    if (dbg) {
+      if (rc == IDV_OK) {
+        unsigned long long h[96 + 32];
+        IDV_CUDA(cudaStreamSynchronize(st));
+        IDV_CUDA(cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        // slots: 0 deps satisfied, 1 loads issued, 2 first tile landed, 3 MMAs issued, 4 accumulator ready, 5 TMEM drained,
+        // 6 stores done, 7 published
+        for (int i = 0; i < 4; ++i) {
+          fprintf(stderr, "[layer dbg] H=%d N=%d t=%d:", H, N, 300 + i);
+          for (int sl = 0; sl < 8; ++sl) fprintf(stderr, " %lld", (long long)(h[i * 8 + sl] - h[0]));
+          fprintf(stderr, "\n");
+        }
+        for (int i = 0; i < 2; ++i) {
+          fprintf(stderr, "[layer dbg] tile arrivals t=%d:", 300 + i);
+          for (int k = 0; k < 8; ++k) fprintf(stderr, " %lld", (long long)(h[96 + i * 8 + k] - h[0]));
+          fprintf(stderr, "\n");
+        }
+      }
+      cudaFree(p.dbg);
+      p.dbg = nullptr;
     }
     if (rc != IDV_E_RESOURCE || !pair) break;
     pair = false;                 // the CTA pairs are not all co-resident: one CTA per tile, cooperative launch

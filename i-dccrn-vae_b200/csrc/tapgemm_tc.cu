@@ -697,7 +697,7 @@ int encode_map_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows
 }
 
 int encode_map_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t blocks, uint32_t box_cols,
-                  uint32_t box_rows, uint32_t box_blocks) {
+                  uint32_t box_rows, uint32_t box_blocks, bool swizzle128) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -708,8 +708,8 @@ int encode_map_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows
   cuuint32_t box[3] = {box_cols, box_rows, box_blocks};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(3d) failed: CUresult %d", (int)rc);
     return IDV_E_CUDA;

@@ -72,6 +72,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the shared-memory source of every committed bulk store has been read (it may be overwritten)
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -257,8 +262,9 @@ EncodeTiledFn get_encode_fn();
 // bf16 2-D map over [rows][cols] (cols contiguous), 128B-swizzled boxes {box_cols, box_rows}
 int encode_map_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows);
 // bf16 3-D map over [blocks][rows][cols], boxes {box_cols, box_rows, box_blocks}
+// (swizzle128 = false: plain row-major boxes, e.g. for tensor stores from an unswizzled staging buffer)
 int encode_map_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t blocks, uint32_t box_cols,
-                  uint32_t box_rows, uint32_t box_blocks);
+                  uint32_t box_rows, uint32_t box_blocks, bool swizzle128 = true);
 
 }  // namespace tc
 }  // namespace idv
