@@ -24,7 +24,7 @@ static int g_launch_pdl = 1;
 static int g_splitk = 1;
 static int g_lstm_cluster_alt = 0;
 static int g_lstm_chunk_sync = 1;
-static int g_lstm_tma_publish = 0;
+static int g_lstm_tma_publish = -1;
 int option_splitk() { return g_splitk; }
 int option_lstm_cluster_alt() { return g_lstm_cluster_alt; }
 int option_lstm_chunk_sync() { return g_lstm_chunk_sync; }
@@ -71,7 +71,8 @@ extern "C" int idv_set_option(const char* name, int value) {
     return IDV_OK;
   }
   if (strcmp(name, "lstm_tma_publish") == 0) {
-    g_lstm_tma_publish = value != 0;
+    IDV_CHECK_ARG(value >= -1 && value <= 2, "idv_set_option: lstm_tma_publish must be -1 (auto), 0 (direct stores), 1 (tensor store) or 2 (staged 16-byte stores)");
+    g_lstm_tma_publish = value;
     return IDV_OK;
   }
   if (strcmp(name, "lstm_chunk_sync") == 0) {

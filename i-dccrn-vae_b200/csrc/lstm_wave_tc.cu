@@ -73,12 +73,14 @@ struct WaveParams {
   // have published, instead of waiting for all 64 CTAs of the module: the 64 same-address atomics no longer serialise
   // (H = 768: published -> seen by the next step took 3.6 of 11.2 us) and the ingest overlaps the stragglers' publish.
   unsigned int* kcsync;
-  // experiment (option "lstm_tma_publish", OFF by default): h(t) leaves through shared memory + ONE tensor store per CTA
-  // and step (box {units of the CTA / pair, its rows, hi | lo}) instead of 4-byte stores scattered over 64 rows, and the
-  // publisher waits for the bulk group.  Measured on B200 (profiles/r02_lstm_dbg_*_tma_publish.log): staging is quick
-  // (gates + stores 1.25 -> 0.64 us at H = 768) but a box of 128 rows x 48 bytes takes the TMA unit ~4.5 us to complete:
-  // step 11.0 -> 11.1 us at H = 768, 7.2 -> 8.5 us at H = 384.  The narrow column strip per producer is the problem, not
-  // the store instruction.
+  // how h(t) leaves the CTA (option "lstm_tma_publish"): 0 = every epilogue thread stores its units of its row (4-byte
+  // stores at N = 48: 1 536 partial-sector writes per CTA and step, whose drain the publishing fence waits for); 2 = the
+  // block is staged in shared memory and leaves with 16-byte stores (384 per CTA and step): step 10.9 -> 9.7 us at H = 768
+  // (config 2b 46.1 -> 44.4 ms), but 7.2 -> 8.2 us at N = 64 / H = 384, whose direct stores are 16 bytes already (the extra
+  // barrier costs more than it saves) - so auto = 2 for the 48-column one-layer kernel only; 1 = staged + ONE tensor store
+  // per CTA and step, the publisher waiting for the bulk group: a box of 128 rows x 48 bytes takes the TMA unit ~4.5 us
+  // (step 11.1 us at H = 768, 8.5 us at H = 384) - measured, kept as a switch.  profiles/r02_lstm_dbg_*_{tma_publish,
+  // staged_stores}.log
   int tma_pub;
   unsigned long long* dbg;                  // optional phase timestamps (IDV_LSTM_DBG): CTA 0 of each role, module 0
 };
@@ -523,7 +525,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
             *reinterpret_cast<unsigned*>(sp + ROWS_C * UW * 2 + j * 2) = (unsigned)lo[j] | ((unsigned)lo[j + 1] << 16);
           }
         }
-        fence_proxy_async();
+        if (p.tma_pub == 1) fence_proxy_async();
       } else if (valid) {
         const int nslot = role == 0 ? 4 : 2;
 #pragma unroll
@@ -537,10 +539,24 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
           }
         }
       }
+      if (p.tma_pub == 2) {
+        // mode 2: the staged block leaves with 16-byte stores (a row's strip of UW units = UW / 8 vectors per plane): a
+        // quarter of the store transactions of the 4-byte stores above
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * W_EPI_WARPS) : "memory");
+        constexpr int VPR = UW * 2 / 16;                      // vectors per row strip
+        const int blk = ((wslot * 2 + m) * 2) + ch * (role == 2 ? p.blkC_ch : p.blkA_ch);
+        unsigned short* hx0 = role == 0 ? p.hxA : p.hxC;      // block 0 of the exchange buffer ([block][128 rows][H])
+        const int ubase = (PAIR ? (c & ~1) : c) * HS;
+        for (int i = threadIdx.x - 32 * W_EPI_WARP0; i < 2 * ROWS_C * VPR; i += 32 * W_EPI_WARPS) {
+          const int pl = i / (ROWS_C * VPR), rr = (i / VPR) % ROWS_C, vv = i % VPR;
+          const uint4 x = *reinterpret_cast<const uint4*>(stg + ch * STG + ((pl * ROWS_C + rr) * UW) * 2 + vv * 16);
+          *reinterpret_cast<uint4*>(hx0 + ((long long)(blk + pl) * W_ROWS + (PAIR ? (int)rank * ROWS_C : 0) + rr) * H + ubase + vv * 8) = x;
+        }
+      }
       if (warp == W_EPI_WARP0 && lane == 0) WAVE_DBG(6);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * W_EPI_WARPS) : "memory");
       if (warp == W_EPI_WARP0 && lane == 0) {
-        if (p.tma_pub) {
+        if (p.tma_pub == 1) {
           const int blk = ((wslot * 2 + m) * 2) + ch * (role == 2 ? p.blkC_ch : p.blkA_ch);
           tma_store_3d(role == 2 ? &tmSC : &tmSA, smem_u32(stg + ch * STG), (PAIR ? (c & ~1) : c) * HS, PAIR ? (int)rank * ROWS_C : 0, blk);
           bulk_commit_group();
@@ -688,7 +704,8 @@ static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off
   const size_t stage_bytes = (size_t)2 * W_HTILE / (pair ? 2 : 1);
   // tensor-store publish: staging of two chunks' h blocks [hi | lo][rows of the CTA][units of the CTA / pair]
   const int uw = (pair ? 2 : 1) * (N / 4), rows_c = pair ? W_ROWS / 2 : W_ROWS;
-  const int tma_pub = option_lstm_tma_publish() && (uw * 2) % 16 == 0;
+  // how h(t) leaves the CTA (option "lstm_tma_publish"; auto = direct stores here: the staged forms measured slower at N = 64)
+  const int tma_pub = (uw * 2) % 16 == 0 && option_lstm_tma_publish() > 0 ? option_lstm_tma_publish() : 0;
   const size_t stg_bytes = tma_pub ? (size_t)2 * 2 * rows_c * uw * 2 : 0;
   int stages = (int)(((size_t)smem_optin - w_bytes - stg_bytes - 1024 - 256) / stage_bytes);
   if (stages > (pair ? 7 : 8)) stages = pair ? 7 : 8;
@@ -710,7 +727,7 @@ static int wave_run(bool pair, const float* g0, int64_t g_m_off, int64_t g_p_off
   rc = encode_map_3d(&maps[4], wk + 2 * hxA_bytes, H, W_ROWS, (uint64_t)2 * W_REP * 2 * 2 * 2, BK, pair ? W_ROWS / 2 : W_ROWS, 2);
   if (rc) return rc;
   maps[5] = maps[3]; maps[6] = maps[4];
-  if (tma_pub) {        // the same buffers for the tensor stores: boxes {units of the CTA / pair, its rows, hi | lo}, no swizzle
+  if (tma_pub == 1) {   // the same buffers for the tensor stores: boxes {units of the CTA / pair, its rows, hi | lo}, no swizzle
     rc = encode_map_3d(&maps[5], wk, H, W_ROWS, (uint64_t)2 * W_REP * 4 * 2 * 2, uw, rows_c, 2, false);
     if (rc) return rc;
     rc = encode_map_3d(&maps[6], wk + 2 * hxA_bytes, H, W_ROWS, (uint64_t)2 * W_REP * 2 * 2 * 2, uw, rows_c, 2, false);
@@ -831,7 +848,10 @@ extern "C" int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g
   for (int attempt = 0; attempt < 2; ++attempt) {
     const size_t stage_bytes = (size_t)2 * W_HTILE / (pair ? 2 : 1);
     const int uw = (pair ? 2 : 1) * (N / 4), rows_c = pair ? W_ROWS / 2 : W_ROWS;
-    const int tma_pub = option_lstm_tma_publish() && (uw * 2) % 16 == 0;
+    // auto: staged 16-byte stores for the 48-column kernel (H = 768: 4-byte stores of 6 units per thread otherwise), direct
+    // stores for the 64-column one (16-byte stores already)
+    const int tma_opt = option_lstm_tma_publish() < 0 ? (N == 48 ? 2 : 0) : option_lstm_tma_publish();
+    const int tma_pub = (uw * 2) % 16 == 0 ? tma_opt : 0;
     const size_t stg_bytes = tma_pub ? (size_t)2 * 2 * rows_c * uw * 2 : 0;
     int stages = (int)(((size_t)smem_optin - w_bytes - stg_bytes - 1024 - 256) / stage_bytes);
     if (stages > (pair ? 7 : 8)) stages = pair ? 7 : 8;
@@ -845,7 +865,7 @@ extern "C" int idv_lstm_layer_pair_tc(const float* g, int64_t g_m_off, int64_t g
     if (rc) return rc;
     maps[1] = maps[0]; maps[2] = maps[0]; maps[4] = maps[3];
     maps[5] = maps[3];
-    if (tma_pub) {
+    if (tma_pub == 1) {
       rc = encode_map_3d(&maps[5], work, H, W_ROWS, (uint64_t)2 * 4 * 2 * 2, uw, rows_c, 2, false);
       if (rc) return rc;
     }

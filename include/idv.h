@@ -53,8 +53,9 @@ const char* idv_last_error(void);
  * idv_lstm2_wave_tc run as pairs (each streams 64 of the 128 rows of h), 0 = every CTA streams all 128 rows.
  * "lstm_chunk_sync": 1 (default) = idv_lstm_layer_pair_tc publishes / polls one step counter per 64-wide K chunk of h (a
  * consumer loads chunk k as soon as its producers have published) instead of one per module, 0 = one counter per module.
- * "lstm_tma_publish": 0 (default) / 1 = the wavefront / CTA-pair LSTM kernels publish h(t) with one tensor store per CTA and step
- * (measured slower, kept as a switch).
+ * "lstm_tma_publish": how the wavefront / CTA-pair LSTM kernels write h(t): -1 (default) = auto (staged 16-byte stores for the
+ * 48-column one-layer kernel of H = 768, direct stores otherwise), 0 = direct stores, 2 = staged 16-byte stores, 1 = one
+ * tensor store per CTA and step (measured slower, kept as a switch).
  * "lstm_cluster_alt": 0 (default) = idv_lstm2_cluster_tc uses the largest CTAs (32 hidden units: H = 384 as clusters of
  * 12), 1 = the second choice (24 units: clusters of 16), for devices on which the first cannot be scheduled.          */
 int idv_set_option(const char* name, int value);
