@@ -62,7 +62,7 @@ extern "C" int idv_set_option(const char* name, int value) {
     return IDV_OK;
   }
   if (strcmp(name, "lstm_sync_mode") == 0) {
-    IDV_CHECK_ARG(value == 0 || value == 1, "idv_set_option: lstm_sync_mode must be 0 or 1");
+    IDV_CHECK_ARG(value >= 0 && value <= 2, "idv_set_option: lstm_sync_mode must be 0 (fence + atomic, acquire polls), 1 (red.release, relaxed polls + fence) or 2 (red.release, acquire polls)");
     g_lstm_sync_mode = value;
     return IDV_OK;
   }

@@ -58,7 +58,8 @@ struct WaveParams {
   int nch, b0[2], NBc[2];
   long long hxA_ch, hxC_ch, g1x_ch;         // elements between the two chunks' exchange buffers
   int blkA_ch, blkC_ch;                     // ... and the same distance in blocks of the tensor maps
-  int sync_mode;                            // 0: acquire polls, fence + atomic; 1: relaxed polls + one fence, red.release (option lstm_sync_mode)
+  int sync_mode;                            // 0: acquire polls, fence + atomic; 1: relaxed polls + one fence, red.release; 2: acquire polls,
+                                            // red.release (option lstm_sync_mode; 1 and 2 measured slower than 0)
   int n_roles;                              // 3 = two-layer wavefront (L0 | IP | L1), 1 = ONE nn.LSTM layer per launch (role L0 only)
   unsigned short* hsplit;                   // single-layer mode: optional bf16 [2][4][R][H] output (next layer's in-proj input)
   float* hseq0;                             // single-layer mode: optional fp32 [4][R][H] output
@@ -179,7 +180,7 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
   unsigned int* const sync_m = p.sync + m * 3 * W_SYNC_STRIDE;
   constexpr int CH_SYNC = 6 * W_SYNC_STRIDE;
   const int nch = p.nch;
-  const bool rlx = p.sync_mode != 0;
+  const bool rlx = p.sync_mode == 1;
   const CUtensorMap* tmW = role == 0 ? &tmW0 : (role == 1 ? &tmWi : &tmW1);
   const CUtensorMap* tmH = role == 2 ? &tmHC : &tmHA;
 
@@ -567,9 +568,14 @@ lstm_wave_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_const
           // one increment per K chunk this CTA's stores belong to (the units of its pair: 1 or 2 chunks)
           unsigned int* kb = p.kcsync + (long long)((ch * 2 + m) * KC) * W_SYNC_STRIDE;
           const int ulo = (PAIR ? (c & ~1) : c) * HS, uhi = ulo + (PAIR ? 2 : 1) * HS - 1;
-          __threadfence();
-          atomicAdd(kb + (ulo >> 6) * W_SYNC_STRIDE, 1u);
-          if ((uhi >> 6) != (ulo >> 6)) atomicAdd(kb + (uhi >> 6) * W_SYNC_STRIDE, 1u);
+          if (p.sync_mode == 0) {
+            __threadfence();
+            atomicAdd(kb + (ulo >> 6) * W_SYNC_STRIDE, 1u);
+            if ((uhi >> 6) != (ulo >> 6)) atomicAdd(kb + (uhi >> 6) * W_SYNC_STRIDE, 1u);
+          } else {
+            publish_step(kb + (ulo >> 6) * W_SYNC_STRIDE, p.sync_mode);
+            if ((uhi >> 6) != (ulo >> 6)) publish_step(kb + (uhi >> 6) * W_SYNC_STRIDE, p.sync_mode);
+          }
         } else {
           publish_step(my_ctr, p.sync_mode);
         }
