@@ -609,6 +609,24 @@ def test_lstm_layer_pair_tc(NB, T, H, tv, pairs):
         lib.set_option("lstm_wave_cta_pairs", 1)
 
 
+@pytest.mark.parametrize("chunk_sync,publish,sync_mode", [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 2, 0), (1, 2, 2), (1, -1, 1)])
+@pytest.mark.parametrize("NB,T,H", [(64, 20, 768), (100, 7, 768), (9, 12, 384)])
+def test_lstm_layer_pair_tc_switches(NB, T, H, chunk_sync, publish, sync_mode):
+    """Every combination of the publish / poll switches of the one-layer kernel (per-K-chunk counters, how h(t) is
+    written, release forms) computes the same thing; the two-layer wavefront kernel under the same switches as well."""
+    lib.set_option("lstm_chunk_sync", chunk_sync)
+    lib.set_option("lstm_tma_publish", publish)
+    lib.set_option("lstm_sync_mode", sync_mode)
+    try:
+        test_lstm_layer_pair_tc(NB, T, H, 0, 1)
+        if H == 384:
+            test_lstm2_wave_tc(NB if NB <= 64 else 64, T, H, 0)
+    finally:
+        lib.set_option("lstm_chunk_sync", 1)
+        lib.set_option("lstm_tma_publish", -1)
+        lib.set_option("lstm_sync_mode", 0)
+
+
 @pytest.mark.parametrize("NB,Fin,T,two_src,mask,S", [(2, 9, 40, True, 2, 1), (3, 5, 130, False, 1, 2)])
 def test_tapgemm_tc_head(NB, Fin, T, two_src, mask, S):
     """Last decoder layer + head fused in the tensor-core epilogue, packed by pack.pack_dec5_tc."""
